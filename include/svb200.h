@@ -1,0 +1,242 @@
+/* svb200.h — C ABI of the B200-native "assemble + FSILS solve" engine.
+ *
+ * This is the drop-in boundary for the one hot path of svMultiPhysics that this repository
+ * accelerates: per Newton iteration, (1) element residual/tangent assembly, (2) the scatter into
+ * the FSILS block-CSR system (rowPtr/colPtr/Val, R) and (3) the FSILS Krylov solve.
+ *
+ * Conventions (identical to the reference):
+ *   - all arrays are column-major ("Fortran order"), 0-based, int32 indices, FP64 values;
+ *   - nodal state arrays are (tDof, nNo): dof fastest, node slowest;
+ *   - Val is (dof*dof, nnz): block k holds 16 (dof=4) contiguous doubles, entry dof*i+j
+ *     (row-major inside the block), see Code/Source/solver/FsilsLinearAlgebra.cpp:35;
+ *   - every pointer argument is a HOST pointer that is only borrowed for the duration of the call
+ *     unless the function name ends in `_dev`.
+ *
+ * Every function returns 0 on success and a non-zero svb200_status on failure; the message is
+ * available from svb200_last_error().  The library never falls back to a CPU path: when no CUDA
+ * device is usable svb200_create() fails.
+ *
+ * Reference interfaces replaced (file:line are into /root/reference at the surveyed snapshot):
+ *   LinearAlgebra::{alloc,assemble,solve}            Code/Source/solver/LinearAlgebra.h:22-29
+ *   FsilsLinearAlgebra::{alloc,assemble,solve}       Code/Source/solver/FsilsLinearAlgebra.cpp:26-128
+ *   eq_assem::global_eq_assem                        Code/Source/solver/eq_assem.cpp:377-455
+ *   fluid::construct_fluid                           Code/Source/solver/fluid.cpp:480-762
+ *   struct_ns::construct_dsolid                      Code/Source/solver/sv_struct.cpp:184-341
+ *   lhsa_ns::lhsa / do_assem                         Code/Source/solver/lhsa.cpp:126-381 / 70-114
+ *   fsi_linear_solver::fsils_lhs_create              Code/Source/linear_solver/lhs.cpp:30-348
+ *   fsi_linear_solver::fsils_bc_create               Code/Source/linear_solver/bc.cpp:18-102
+ *   fsi_linear_solver::fsils_solve                   Code/Source/linear_solver/solve.cpp:23-166
+ *   fsi_linear_solver::fsils_commuv                  Code/Source/linear_solver/in_commu.cpp:84-143
+ *   all_fun::commu                                   Code/Source/solver/all_fun.cpp:95-119
+ */
+#ifndef SVB200_H
+#define SVB200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVB200_ABI_VERSION 1
+
+typedef struct svb200_ctx svb200_ctx;
+
+typedef enum {
+  SVB200_OK = 0,
+  SVB200_ERR_INVALID = 1,     /* bad argument / call order */
+  SVB200_ERR_CUDA = 2,        /* CUDA runtime error */
+  SVB200_ERR_NCCL = 3,        /* NCCL error */
+  SVB200_ERR_NUMERIC = 4,     /* what the reference throws std::runtime_error for: zero residual
+                                 norm (linear_solver/gmres.cpp:500-502), non-positive Jacobian
+                                 (solver/fluid.cpp:637-639) */
+  SVB200_ERR_UNSUPPORTED = 5
+} svb200_status;
+
+/* Equation / domain physics: the subset of consts::EquationType on the hot path
+ * (Code/Source/solver/consts.h). */
+typedef enum {
+  SVB200_PHYS_FLUID = 0,
+  SVB200_PHYS_STRUCT = 1,
+  SVB200_PHYS_FSI = 2,
+  SVB200_PHYS_MESH = 3
+} svb200_phys;
+
+/* consts::FluidViscosityModelType (solver/fluid.cpp:2254-2297). */
+typedef enum { SVB200_VISC_CONST = 0, SVB200_VISC_CY = 1, SVB200_VISC_CASSON = 2 } svb200_visc;
+
+/* consts::ConstitutiveModelType, isochoric part (solver/mat_models.cpp:435-581). */
+typedef enum { SVB200_ISO_NHK = 0, SVB200_ISO_MR = 1, SVB200_ISO_GUCCIONE = 2, SVB200_ISO_STVK = 3 } svb200_iso;
+/* volumetric part (solver/mat_models.cpp:1441-1464). */
+typedef enum { SVB200_VOL_NONE = 0, SVB200_VOL_QUAD = 1, SVB200_VOL_ST91 = 2, SVB200_VOL_M94 = 3 } svb200_vol;
+
+/* fsi_linear_solver::LinearSolverType (linear_solver/fils_struct.hpp). */
+typedef enum { SVB200_LS_NS = 0, SVB200_LS_GMRES = 1, SVB200_LS_CG = 2, SVB200_LS_BICGS = 3 } svb200_ls_type;
+/* consts::PreconditionerType: only the FSILS diagonal (Jacobi) preconditioner is on the path. */
+typedef enum { SVB200_PREC_FSILS = 0 } svb200_prec;
+/* fsi_linear_solver::BcType. */
+typedef enum { SVB200_BC_DIR = 0, SVB200_BC_NEU = 1 } svb200_bc_type;
+/* Scatter mode of the element assembly. */
+typedef enum {
+  SVB200_SCATTER_ATOMIC = 0,  /* FP64 red.global.add; fastest, last-bit non-deterministic */
+  SVB200_SCATTER_COLORED = 1  /* graph-coloured, conflict-free, bitwise reproducible */
+} svb200_scatter;
+/* What svb200_download / svb200_upload move. */
+typedef enum { SVB200_ARRAY_R = 0, SVB200_ARRAY_VAL = 1, SVB200_ARRAY_W = 2 } svb200_array;
+
+/* Per-equation time-integration parameters (eqType af/am/gam/beta, ComMod dt/tDof/dof/mvMsh). */
+typedef struct {
+  double dt;
+  double af, am, gam, beta;
+  int32_t phys;      /* svb200_phys of the equation */
+  int32_t dof;       /* unknowns per node of this equation (com_mod.dof) */
+  int32_t tDof;      /* state dofs per node (com_mod.tDof) */
+  int32_t s;         /* eq.s: first state dof of this equation */
+  int32_t mvMsh;     /* com_mod.mvMsh: ALE convective velocity (solver/fluid.cpp:1909-1915) */
+  int32_t vmsStab;   /* lM.nFs == 1 (solver/fluid.cpp:496-500); only 1 is supported */
+  int32_t scatter;   /* svb200_scatter */
+  int32_t reserved;
+} svb200_eqparams;
+
+/* Per-domain material parameters (dmnType, stModelType, fluidViscModelType). */
+typedef struct {
+  int32_t Id;        /* dmn.Id; -1 = whole mesh, else bit index tested against eId (all_fun.cpp:122) */
+  int32_t phys;      /* svb200_phys of the domain */
+  double rho;        /* fluid_density or solid_density */
+  double f[3];       /* f_x, f_y, f_z body force per unit mass */
+  /* fluid */
+  double K_darcy;    /* inverse_darcy_permeability */
+  int32_t viscType;  /* svb200_visc */
+  int32_t isoType;   /* svb200_iso */
+  double mu_i, mu_o, lam, a, n;
+  /* solid */
+  int32_t volType;   /* svb200_vol */
+  int32_t reserved;
+  double Kpen;
+  double C10, C01;
+  double bff, bss, bfs;     /* Guccione exponents (stModelType bff/bss/bfs) */
+  double dmp;               /* damping */
+  double E, nu;             /* elasticity_modulus, poisson_ratio (mesh / linear elasticity) */
+  double solid_visc_mu;     /* 0 = no solid viscosity */
+} svb200_dmnparams;
+
+/* FSILS_subLsType inputs (linear_solver/fils_struct.hpp:198-242). */
+typedef struct {
+  int32_t mItr;
+  int32_t sD;
+  double relTol;
+  double absTol;
+} svb200_sublsparams;
+
+typedef struct {
+  svb200_sublsparams RI, GM, CG;
+} svb200_lsparams;
+
+/* FSILS_subLsType outputs. */
+typedef struct {
+  int32_t success;
+  int32_t itr;
+  double iNorm, fNorm, dB, callD;
+} svb200_sublsresult;
+
+typedef struct {
+  svb200_sublsresult RI, GM, CG;
+  int32_t Resm, Resc;
+  /* residual history of the outermost Krylov loop: |err(i+1)| after each inner iteration
+   * (what linear_solver/gmres.cpp prints under debug_gmres_v); at most hist_cap entries kept. */
+  int32_t hist_n;
+  int32_t hist_cap;
+  double* hist;      /* caller-provided buffer of hist_cap doubles, or NULL */
+} svb200_lsresult;
+
+/* ---- lifecycle -------------------------------------------------------------------------- */
+int svb200_abi_version(void);
+const char* svb200_last_error(void);
+int svb200_create(svb200_ctx** out, int device);
+int svb200_destroy(svb200_ctx* ctx);
+
+/* One process per GPU: rank/nranks of this context and the 128-byte ncclUniqueId generated by
+ * svb200_comm_unique_id() on rank 0 and broadcast by the host (torch.distributed / MPI).
+ * Replaces fsils_commu_create (linear_solver/commu.cpp:17-46). */
+int svb200_comm_unique_id(void* id128);
+int svb200_comm_init(svb200_ctx* ctx, int nranks, int rank, const void* id128);
+
+/* ---- structure (once) ------------------------------------------------------------------- */
+/* CSR graph in INPUT node order exactly as lhsa_ns::lhsa builds it (columns ascending per row).
+ * map/mynNo and the shared-node lists are what fsils_lhs_create computes (linear_solver/lhs.cpp);
+ * pass map=NULL, mynNo=nNo, nReq=0 for a single partition.  neigh_ptr is the concatenation of the
+ * per-neighbour lists cS[i].ptr (FSILS-order local ids), neigh_n[i] entries each. */
+int svb200_set_graph(svb200_ctx* ctx, int32_t nNo, int32_t nnz, const int32_t* rowPtr, const int32_t* colPtr,
+                     int32_t mynNo, const int32_t* map,
+                     int32_t nReq, const int32_t* neigh_rank, const int32_t* neigh_n, const int32_t* neigh_ptr);
+
+/* One mesh (mshType): connectivity IEN(eNoN,nEl) in input node ids, optional domain bitmask
+ * eId(nEl), optional fibres fN(3*nFn,nEl), and the reference-element tables of fs[0]:
+ * w(nG), N(eNoN,nG), Nx(3,eNoN,nG).  eNoN = 4 (TET4) or 8 (HEX8). */
+int svb200_set_mesh(svb200_ctx* ctx, int32_t iM, int32_t eNoN, int32_t nEl, const int32_t* IEN,
+                    const int32_t* eId, int32_t nFn, const double* fN,
+                    int32_t nG, const double* w, const double* N, const double* Nx);
+
+/* Reference coordinates com_mod.x(3,nNo). */
+int svb200_set_coords(svb200_ctx* ctx, const double* x);
+
+/* Linear-solver faces (fsils_bc_create): glob are INPUT-order node ids, val(face_dof,nNo). */
+int svb200_set_num_faces(svb200_ctx* ctx, int32_t nFaces);
+int svb200_set_face(svb200_ctx* ctx, int32_t faIn, int32_t bGrp, int32_t face_dof, int32_t nNo,
+                    const int32_t* glob, const double* val, int32_t sharedFlag);
+
+/* ---- per Newton iteration --------------------------------------------------------------- */
+/* ls_alloc (solver/ls.cpp:24-40): R(dof,nNo) and Val(dof*dof,nnz) are (re)zeroed on the device. */
+int svb200_alloc(svb200_ctx* ctx, int32_t dof);
+
+/* Upload the generalised-alpha intermediate state (Ag,Yg,Dg)(tDof,nNo) and body force Bf(3,nNo).
+ * NULL pointers leave the device copy unchanged (Dg, Bf may never be set: treated as zero). */
+int svb200_set_state(svb200_ctx* ctx, int32_t tDof, const double* Ag, const double* Yg, const double* Dg,
+                     const double* Bf);
+
+/* global_eq_assem for mesh iM: element loop + scatter, R/Val stay on the device. */
+int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq,
+                    const svb200_dmnparams* dmn, int32_t nDmn);
+
+/* Host-assembled surface terms (Neumann/backflow faces): R(:,rows[k]) += R_add(:,k),
+ * Val(:,slot(rows_k,cols_k)) += K_add(:,k). */
+int svb200_add_host_contrib(svb200_ctx* ctx, int32_t dof, int32_t nR, const int32_t* rows, const double* R_add,
+                            int32_t nK, const int32_t* krows, const int32_t* kcols, const double* K_add);
+
+/* all_fun::commu(R): shared-node sum of the residual across partitions (no-op for one rank). */
+int svb200_commu_R(svb200_ctx* ctx);
+
+/* fsils_solve: preconditions in place, runs the Krylov solver, writes the increment to R_out
+ * (dof,nNo, INPUT node order; may be NULL to keep it on the device only). */
+int svb200_solve(svb200_ctx* ctx, int32_t dof, int32_t ls_type, int32_t prec, const svb200_lsparams* ls,
+                 int32_t nFaces, const int32_t* incL, const double* res,
+                 double* R_out, svb200_lsresult* result);
+
+/* ---- debug / parity --------------------------------------------------------------------- */
+/* R(dof,nNo) and Val(dof*dof,nnz) are returned in INPUT node order / input CSR slot order. */
+int svb200_download(svb200_ctx* ctx, int32_t what, double* dst);
+int svb200_upload(svb200_ctx* ctx, int32_t what, int32_t dof, const double* src);
+
+/* Stand-alone operators on the current device Val, for tests and the bench:
+ * KU = K*U (+ halo sum), both (dof,nNo) host arrays in INPUT order. */
+int svb200_spmv(svb200_ctx* ctx, int32_t dof, const double* U, double* KU);
+
+/* Device-side timing of the last svb200_assemble / svb200_solve call in milliseconds
+ * (CUDA events on the library's stream). */
+int svb200_last_timing(svb200_ctx* ctx, double* assemble_ms, double* solve_ms);
+
+/* Repeat the assembly kernel(s) / SpMV n times on resident data and return the average device
+ * time per launch in ms (CUDA events on the launching stream); used by bench.py for the roofline. */
+int svb200_bench_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, const svb200_dmnparams* dmn,
+                          int32_t nDmn, int32_t reps, double* ms_per_launch);
+int svb200_bench_spmv(svb200_ctx* ctx, int32_t dof, int32_t reps, double* ms_per_launch);
+/* Measured FP64 FMA peak (independent DFMA chains) in TFLOP/s. */
+int svb200_measure_fp64_peak(svb200_ctx* ctx, double* tflops);
+/* Number of CUDA kernels this library has launched on ctx since creation. */
+int64_t svb200_launch_count(svb200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVB200_H */

@@ -1,0 +1,422 @@
+// ref_harness.cpp — flat C entry points around the UNMODIFIED reference hot path.
+//
+// TEST INFRASTRUCTURE ONLY.  This file is compiled (by oracle/Makefile, target `ref`) together with
+// the reference's own sources where they lie under /root/reference into oracle/_ref/libsvref.so.
+// It fills a reference `ComMod` by hand for a synthetic mesh (the way the reference's unit tests
+// do with MockComMod, tests/unitTests/test_common.h:78-96) and calls the reference routines:
+//
+//   nn::select_ele / fs::init_fs_msh            solver/nn.cpp:1302, solver/fs.cpp:271
+//   lhsa_ns::add_col (the loop of lhsa_ns::lhsa) solver/lhsa.cpp:13-54,155-166,352-380
+//   fsils_commu_create / fsils_lhs_create       linear_solver/commu.cpp:17, linear_solver/lhs.cpp:30
+//   fsils_bc_create                             linear_solver/bc.cpp:18
+//   fluid::construct_fluid                      solver/fluid.cpp:480
+//   struct_ns::construct_dsolid                 solver/sv_struct.cpp:184
+//   fsi::construct_fsi, mesh::construct_mesh    solver/fsi.cpp:24, solver/mesh.cpp:22
+//   fsi_linear_solver::fsils_solve              linear_solver/solve.cpp:23
+//   spar_mul::fsils_spar_mul_vv                 linear_solver/spar_mul.cpp:164
+//
+// Parameter structs are shared with the product ABI (include/svb200.h) so that parity tests feed
+// both sides the same bytes.  Nothing here is linked into libsvb200.so.
+
+#include "ComMod.h"
+#include "CepMod.h"
+#include "SolutionStates.h"
+#include "FsilsLinearAlgebra.h"
+#include "fluid.h"
+#include "sv_struct.h"
+#include "fsi.h"
+#include "mesh.h"
+#include "fs.h"
+#include "nn.h"
+#include "lhsa.h"
+#include "fsils_api.hpp"
+#include "commu.h"
+#include "lhs.h"
+#include "spar_mul.h"
+#include "consts.h"
+
+#include "../include/svb200.h"
+
+#include <chrono>
+#include <cstring>
+#include <string>
+#include <stdexcept>
+
+namespace {
+
+thread_local std::string g_err;
+
+struct RefCase {
+  ComMod com_mod;
+  CepMod cep_mod;
+  SolutionStates sol;
+  FsilsLinearAlgebra* la = nullptr;
+  bool graph_built = false;
+  double last_assemble_s = 0.0;
+  double last_solve_s = 0.0;
+};
+
+consts::EquationType to_phys(int p)
+{
+  switch (p) {
+    case SVB200_PHYS_FLUID: return consts::EquationType::phys_fluid;
+    case SVB200_PHYS_STRUCT: return consts::EquationType::phys_struct;
+    case SVB200_PHYS_FSI: return consts::EquationType::phys_FSI;
+    case SVB200_PHYS_MESH: return consts::EquationType::phys_mesh;
+  }
+  throw std::runtime_error("[ref_harness] unknown physics");
+}
+
+void fill_domain(dmnType& d, const svb200_dmnparams& p)
+{
+  using namespace consts;
+  d.Id = p.Id;
+  d.phys = to_phys(p.phys);
+  d.prop[PhysicalProperyType::fluid_density] = p.rho;
+  d.prop[PhysicalProperyType::solid_density] = p.rho;
+  d.prop[PhysicalProperyType::f_x] = p.f[0];
+  d.prop[PhysicalProperyType::f_y] = p.f[1];
+  d.prop[PhysicalProperyType::f_z] = p.f[2];
+  d.prop[PhysicalProperyType::inverse_darcy_permeability] = p.K_darcy;
+  d.prop[PhysicalProperyType::backflow_stab] = 0.0;
+  d.prop[PhysicalProperyType::damping] = p.dmp;
+  d.prop[PhysicalProperyType::elasticity_modulus] = p.E;
+  d.prop[PhysicalProperyType::poisson_ratio] = p.nu;
+  switch (p.viscType) {
+    case SVB200_VISC_CONST: d.fluid_visc.viscType = FluidViscosityModelType::viscType_Const; break;
+    case SVB200_VISC_CY: d.fluid_visc.viscType = FluidViscosityModelType::viscType_CY; break;
+    case SVB200_VISC_CASSON: d.fluid_visc.viscType = FluidViscosityModelType::viscType_Cass; break;
+  }
+  d.fluid_visc.mu_i = p.mu_i; d.fluid_visc.mu_o = p.mu_o; d.fluid_visc.lam = p.lam;
+  d.fluid_visc.a = p.a; d.fluid_visc.n = p.n;
+  switch (p.isoType) {
+    case SVB200_ISO_NHK: d.stM.isoType = ConstitutiveModelType::stIso_nHook; break;
+    case SVB200_ISO_MR: d.stM.isoType = ConstitutiveModelType::stIso_MR; break;
+    case SVB200_ISO_GUCCIONE: d.stM.isoType = ConstitutiveModelType::stIso_Gucci; break;
+    case SVB200_ISO_STVK: d.stM.isoType = ConstitutiveModelType::stIso_StVK; break;
+  }
+  switch (p.volType) {
+    case SVB200_VOL_NONE: d.stM.volType = ConstitutiveModelType::stVol_NA; break;
+    case SVB200_VOL_QUAD: d.stM.volType = ConstitutiveModelType::stVol_Quad; break;
+    case SVB200_VOL_ST91: d.stM.volType = ConstitutiveModelType::stVol_ST91; break;
+    case SVB200_VOL_M94: d.stM.volType = ConstitutiveModelType::stVol_M94; break;
+  }
+  d.stM.Kpen = p.Kpen; d.stM.C10 = p.C10; d.stM.C01 = p.C01;
+  d.stM.bff = p.bff; d.stM.bss = p.bss; d.stM.bfs = p.bfs;
+  if (p.solid_visc_mu != 0.0) {
+    d.solid_visc.viscType = SolidViscosityModelType::viscType_Newtonian;
+    d.solid_visc.mu = p.solid_visc_mu;
+  } else {
+    d.solid_visc.viscType = SolidViscosityModelType::viscType_NA;
+  }
+}
+
+void fill_eq(RefCase& c, const svb200_eqparams& e, const svb200_dmnparams* dmn, int nDmn)
+{
+  auto& cm = c.com_mod;
+  if (cm.eq.size() == 0) { cm.eq = std::vector<eqType>(1); cm.nEq = 1; }
+  auto& eq = cm.eq[0];
+  cm.cEq = 0;
+  cm.dt = e.dt;
+  cm.dof = e.dof;
+  cm.tDof = e.tDof;
+  cm.mvMsh = (e.mvMsh != 0);
+  eq.phys = to_phys(e.phys);
+  eq.af = e.af; eq.am = e.am; eq.gam = e.gam; eq.beta = e.beta;
+  eq.dof = e.dof; eq.s = e.s; eq.e = e.s + e.dof - 1;
+  eq.nDmn = nDmn;
+  eq.dmn.resize(nDmn);
+  for (int i = 0; i < nDmn; i++) fill_domain(eq.dmn[i], dmn[i]);
+  if (!c.la) c.la = new FsilsLinearAlgebra();
+  eq.linear_algebra = c.la;
+  eq.linear_algebra_preconditioner = consts::PreconditionerType::PREC_FSILS;
+}
+
+template <class F> int guarded(F&& f)
+{
+  try { f(); return 0; }
+  catch (const std::exception& ex) { g_err = ex.what(); return SVB200_ERR_NUMERIC; }
+  catch (...) { g_err = "unknown exception"; return SVB200_ERR_NUMERIC; }
+}
+
+} // namespace
+
+extern "C" {
+
+const char* svref_last_error(void) { return g_err.c_str(); }
+
+void* svref_create(void)
+{
+  auto c = new RefCase();
+  c->com_mod.nsd = 3;
+  c->com_mod.nsymd = 6;
+  return c;
+}
+
+void svref_destroy(void* h) { delete static_cast<RefCase*>(h); }
+
+/// com_mod.x(3,nNo); also sizes Bf to zero.
+int svref_set_coords(void* h, int nNo, const double* x)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    auto& cm = c.com_mod;
+    cm.tnNo = nNo;
+    cm.x.resize(3, nNo);
+    std::memcpy(cm.x.data(), x, sizeof(double)*3*nNo);
+    cm.Bf.resize(3, nNo);
+  });
+}
+
+/// Append one mesh; the reference fills its own Gauss/shape tables (select_ele, init_fs_msh).
+int svref_add_mesh(void* h, int eNoN, int nEl, const int* IEN, const int* eId, int nFn, const double* fN)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    auto& cm = c.com_mod;
+    cm.msh.emplace_back();
+    cm.nMsh = (int)cm.msh.size();
+    auto& m = cm.msh.back();
+    m.eNoN = eNoN; m.nEl = nEl; m.gnEl = nEl; m.nNo = cm.tnNo; m.gnNo = cm.tnNo;
+    m.lShl = false; m.lFib = false;
+    m.nFs = 1;     // P1-P1 / Q1-Q1 with VMS stabilisation (vmsStab = true, solver/fluid.cpp:496)
+    m.IEN.resize(eNoN, nEl);
+    std::memcpy(m.IEN.data(), IEN, sizeof(int)*eNoN*nEl);
+    if (eId) { m.eId.resize(nEl); std::memcpy(m.eId.data(), eId, sizeof(int)*nEl); }
+    m.nFn = nFn;
+    if (nFn > 0 && fN) { m.fN.resize(3*nFn, nEl); std::memcpy(m.fN.data(), fN, sizeof(double)*3*nFn*nEl); }
+    nn::select_ele(cm, m);
+    fs::init_fs_msh(cm, m);
+  });
+}
+
+int svref_get_mesh_tables(void* h, int iM, int* nG, double* w, double* N, double* Nx)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    auto& m = c.com_mod.msh.at(iM);
+    *nG = m.nG;
+    if (w) std::memcpy(w, m.w.data(), sizeof(double)*m.nG);
+    if (N) std::memcpy(N, m.N.data(), sizeof(double)*m.eNoN*m.nG);
+    if (Nx) std::memcpy(Nx, m.Nx.data(), sizeof(double)*3*m.eNoN*m.nG);
+  });
+}
+
+/// The element loop of lhsa_ns::lhsa (solver/lhsa.cpp:155-166) through the reference's own add_col,
+/// then its compaction (:352-380), then fsils_commu_create + fsils_lhs_create as initialize() does.
+int svref_build_graph(void* h, int nFaces, int* nnz_out)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    auto& cm = c.com_mod;
+    int tnNo = cm.tnNo;
+    int max_enon = 0;
+    for (auto& m : cm.msh) max_enon = std::max(max_enon, m.eNoN);
+    int mnnzeic = 10*max_enon;
+    Array<int> uInd(mnnzeic, tnNo);
+    uInd = -1;
+    for (auto& m : cm.msh) {
+      for (int e = 0; e < m.nEl; e++) {
+        for (int a = 0; a < m.eNoN; a++) {
+          int rowN = m.IEN(a,e);
+          for (int b = 0; b < m.eNoN; b++) {
+            lhsa_ns::add_col(tnNo, rowN, m.IEN(b,e), mnnzeic, uInd);
+          }
+        }
+      }
+    }
+    int nnz = 0;
+    for (int r = 0; r < tnNo; r++) {
+      if (uInd(0,r) == -1) throw std::runtime_error("isolated node " + std::to_string(r));
+      for (int i = 0; i < mnnzeic; i++) if (uInd(i,r) != -1) nnz++;
+    }
+    cm.colPtr.resize(nnz);
+    cm.rowPtr.resize(tnNo+1);
+    int j = 0;
+    cm.rowPtr(0) = 0;
+    for (int r = 0; r < tnNo; r++) {
+      for (int i = 0; i < mnnzeic; i++) if (uInd(i,r) != -1) cm.colPtr(j++) = uInd(i,r);
+      cm.rowPtr(r+1) = j;
+    }
+    cm.idMap.resize(tnNo);
+    for (int a = 0; a < tnNo; a++) cm.idMap[a] = a;
+    cm.ltg.resize(tnNo);
+    for (int a = 0; a < tnNo; a++) cm.ltg[a] = a;
+
+    fsi_linear_solver::FSILS_commuType communicator;
+    fsi_linear_solver::fsils_commu_create(communicator, MPI_COMM_WORLD);
+    fsi_linear_solver::fsils_lhs_create(cm.lhs, communicator, tnNo, tnNo, nnz, cm.ltg, cm.rowPtr, cm.colPtr, nFaces);
+    c.graph_built = true;
+    *nnz_out = nnz;
+  });
+}
+
+int svref_get_graph(void* h, int* rowPtr, int* colPtr)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    auto& cm = c.com_mod;
+    std::memcpy(rowPtr, cm.rowPtr.data(), sizeof(int)*(cm.tnNo+1));
+    std::memcpy(colPtr, cm.colPtr.data(), sizeof(int)*cm.colPtr.size());
+  });
+}
+
+int svref_set_face(void* h, int faIn, int bGrp, int face_dof, int nNo, const int* glob, const double* val)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    Vector<int> gNodes(nNo);
+    for (int a = 0; a < nNo; a++) gNodes(a) = glob[a];
+    Array<double> sVl(face_dof, nNo);
+    if (val) std::memcpy(sVl.data(), val, sizeof(double)*face_dof*nNo);
+    auto t = (bGrp == SVB200_BC_DIR) ? fsi_linear_solver::BcType::BC_TYPE_Dir : fsi_linear_solver::BcType::BC_TYPE_Neu;
+    fsi_linear_solver::fsils_bc_create(c.com_mod.lhs, faIn, nNo, face_dof, t, gNodes, sVl);
+  });
+}
+
+/// ls_alloc (solver/ls.cpp:24-40): fresh zero R(dof,tnNo), Val(dof*dof,nnz).
+int svref_alloc(void* h, int dof)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    auto& cm = c.com_mod;
+    cm.dof = dof;
+    cm.R.resize(dof, cm.tnNo);
+    cm.Val.resize(dof*dof, cm.lhs.nnz);
+    cm.R = 0.0;
+    cm.Val = 0.0;
+  });
+}
+
+int svref_set_state(void* h, int tDof, const double* Ag, const double* Yg, const double* Dg, const double* Bf)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    auto& cm = c.com_mod;
+    int n = cm.tnNo;
+    cm.tDof = tDof;
+    auto& A = c.sol.intermediate.get_acceleration();
+    auto& Y = c.sol.intermediate.get_velocity();
+    auto& D = c.sol.intermediate.get_displacement();
+    if (A.nrows() != tDof || A.ncols() != n) { A.resize(tDof, n); Y.resize(tDof, n); D.resize(tDof, n); }
+    if (Ag) std::memcpy(A.data(), Ag, sizeof(double)*tDof*n);
+    if (Yg) std::memcpy(Y.data(), Yg, sizeof(double)*tDof*n);
+    if (Dg) std::memcpy(D.data(), Dg, sizeof(double)*tDof*n);
+    if (Bf) std::memcpy(cm.Bf.data(), Bf, sizeof(double)*3*n);
+    // Old displacement (used by the mesh equation, solver/mesh.cpp) mirrors Dg in the harness.
+    auto& Do = c.sol.old.get_displacement();
+    if (Do.nrows() != tDof || Do.ncols() != n) Do.resize(tDof, n);
+    if (Dg) std::memcpy(Do.data(), Dg, sizeof(double)*tDof*n);
+  });
+}
+
+/// The switch of eq_assem::global_eq_assem (solver/eq_assem.cpp:397-449) for the in-scope physics.
+int svref_assemble(void* h, int iM, const svb200_eqparams* e, const svb200_dmnparams* dmn, int nDmn)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    fill_eq(c, *e, dmn, nDmn);
+    auto& cm = c.com_mod;
+    auto& m = cm.msh.at(iM);
+    auto t0 = std::chrono::steady_clock::now();
+    switch (e->phys) {
+      case SVB200_PHYS_FLUID: fluid::construct_fluid(cm, m, c.sol); break;
+      case SVB200_PHYS_STRUCT: struct_ns::construct_dsolid(cm, c.cep_mod, m, c.sol); break;
+      case SVB200_PHYS_FSI: fsi::construct_fsi(cm, c.cep_mod, m, c.sol); break;
+      case SVB200_PHYS_MESH: mesh::construct_mesh(cm, c.cep_mod, m, c.sol); break;
+      default: throw std::runtime_error("[ref_harness] physics not supported");
+    }
+    c.last_assemble_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  });
+}
+
+int svref_get(void* h, int what, double* dst)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    auto& cm = c.com_mod;
+    if (what == SVB200_ARRAY_R) std::memcpy(dst, cm.R.data(), sizeof(double)*cm.R.size());
+    else if (what == SVB200_ARRAY_VAL) std::memcpy(dst, cm.Val.data(), sizeof(double)*cm.Val.size());
+    else throw std::runtime_error("[ref_harness] bad array id");
+  });
+}
+
+int svref_put(void* h, int what, int dof, const double* src)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    auto& cm = c.com_mod;
+    cm.dof = dof;
+    if (what == SVB200_ARRAY_R) {
+      cm.R.resize(dof, cm.tnNo);
+      std::memcpy(cm.R.data(), src, sizeof(double)*cm.R.size());
+    } else if (what == SVB200_ARRAY_VAL) {
+      cm.Val.resize(dof*dof, cm.lhs.nnz);
+      std::memcpy(cm.Val.data(), src, sizeof(double)*cm.Val.size());
+    } else throw std::runtime_error("[ref_harness] bad array id");
+  });
+}
+
+/// fsils_ls_create defaults are bypassed: every parameter comes from `ls` (as read_ls does after XML).
+int svref_solve(void* h, int dof, int ls_type, int prec, const svb200_lsparams* ls, int nFaces, const int* incL,
+    const double* res, double* R_out, svb200_lsresult* out)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    using namespace fsi_linear_solver;
+    auto& cm = c.com_mod;
+    FSILS_lsType fls;
+    LinearSolverType t;
+    switch (ls_type) {
+      case SVB200_LS_NS: t = LinearSolverType::LS_TYPE_NS; break;
+      case SVB200_LS_GMRES: t = LinearSolverType::LS_TYPE_GMRES; break;
+      case SVB200_LS_CG: t = LinearSolverType::LS_TYPE_CG; break;
+      case SVB200_LS_BICGS: t = LinearSolverType::LS_TYPE_BICGS; break;
+      default: throw std::runtime_error("bad ls_type");
+    }
+    fsils_ls_create(fls, t);
+    auto cp = [](FSILS_subLsType& d, const svb200_sublsparams& s) {
+      d.mItr = s.mItr; d.sD = s.sD; d.relTol = s.relTol; d.absTol = s.absTol;
+    };
+    cp(fls.RI, ls->RI); cp(fls.GM, ls->GM); cp(fls.CG, ls->CG);
+    Vector<int> incLv(nFaces);
+    Vector<double> resv(nFaces);
+    for (int i = 0; i < nFaces; i++) { incLv(i) = incL ? incL[i] : 1; resv(i) = res ? res[i] : 0.0; }
+    (void)prec;
+    auto t0 = std::chrono::steady_clock::now();
+    fsils_solve(cm.lhs, fls, dof, cm.R, cm.Val, consts::PreconditionerType::PREC_FSILS, incLv, resv);
+    c.last_solve_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (R_out) std::memcpy(R_out, cm.R.data(), sizeof(double)*cm.R.size());
+    if (out) {
+      auto co = [](svb200_sublsresult& d, const FSILS_subLsType& s) {
+        d.success = s.success; d.itr = s.itr; d.iNorm = s.iNorm; d.fNorm = s.fNorm; d.dB = s.dB; d.callD = s.callD;
+      };
+      co(out->RI, fls.RI); co(out->GM, fls.GM); co(out->CG, fls.CG);
+      out->Resm = fls.Resm; out->Resc = fls.Resc;
+      out->hist_n = 0;
+    }
+  });
+}
+
+/// KU = K U with the reference SpMV on the current com_mod.Val.
+int svref_spmv(void* h, int dof, const double* U, double* KU)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    auto& cm = c.com_mod;
+    Array<double> u(dof, cm.tnNo), ku(dof, cm.tnNo);
+    std::memcpy(u.data(), U, sizeof(double)*dof*cm.tnNo);
+    spar_mul::fsils_spar_mul_vv(cm.lhs, cm.lhs.rowPtr, cm.lhs.colPtr, dof, cm.Val, u, ku);
+    std::memcpy(KU, ku.data(), sizeof(double)*dof*cm.tnNo);
+  });
+}
+
+int svref_last_timing(void* h, double* assemble_s, double* solve_s)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  if (assemble_s) *assemble_s = c.last_assemble_s;
+  if (solve_s) *solve_s = c.last_solve_s;
+  return 0;
+}
+
+} // extern "C"

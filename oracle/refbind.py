@@ -1,0 +1,191 @@
+"""ctypes bindings of the two CPU checkers (TEST INFRASTRUCTURE ONLY).
+
+* ``RefCase``    -> oracle/_ref/libsvref.so : the unmodified reference hot path (oracle/ref_harness.cpp)
+* ``OracleCase`` -> oracle/libsvoracle.so  : our C restatement of the same algorithms (oracle/sv_oracle.c)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  The product package (svmultiphysics_b200) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from svmultiphysics_b200 import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(_HERE, "_ref", "libsvref.so")
+ORACLE_SO = os.path.join(_HERE, "libsvoracle.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+def _f64(a):
+    return None if a is None else np.asfortranarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return None if a is None else np.asfortranarray(a, dtype=np.int32)
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_SO)
+
+
+class _FlatCase:
+    """Shared driver for both checkers: they export the same flat entry points under a prefix."""
+    prefix = ""
+    so_path = ""
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            lib = C.CDLL(cls.so_path)
+            p = cls.prefix
+            getattr(lib, p + "create").restype = C.c_void_p
+            getattr(lib, p + "last_error").restype = C.c_char_p
+            for name in ("destroy", "set_coords", "add_mesh", "get_mesh_tables", "build_graph", "get_graph",
+                         "set_face", "alloc", "set_state", "assemble", "get", "put", "solve", "spmv", "last_timing"):
+                getattr(lib, p + name).argtypes = None
+            cls._lib = lib
+        return cls._lib
+
+    def _call(self, name, *args):
+        fn = getattr(self.lib(), self.prefix + name)
+        rc = fn(C.c_void_p(self.h), *args)
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}{name}: {getattr(self.lib(), self.prefix + 'last_error')().decode()}")
+
+    def __init__(self):
+        self.h = getattr(self.lib(), self.prefix + "create")()
+        self.nNo = 0
+        self.nnz = 0
+        self.meshes = []
+
+    def close(self):
+        if self.h:
+            getattr(self.lib(), self.prefix + "destroy")(C.c_void_p(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_coords(self, x):
+        x = _f64(x)
+        self.nNo = x.shape[1]
+        self._call("set_coords", C.c_int(self.nNo), _d(x))
+
+    def add_mesh(self, IEN, eId=None, nFn=0, fN=None):
+        IEN = _i32(IEN)
+        eId = _i32(eId)
+        fN = _f64(fN)
+        self._call("add_mesh", C.c_int(IEN.shape[0]), C.c_int(IEN.shape[1]), _i(IEN), _i(eId), C.c_int(nFn), _d(fN))
+        self.meshes.append((IEN.shape[0], IEN.shape[1]))
+        return len(self.meshes) - 1
+
+    def mesh_tables(self, iM):
+        eNoN = self.meshes[iM][0]
+        nG = C.c_int(0)
+        self._call("get_mesh_tables", C.c_int(iM), C.byref(nG), None, None, None)
+        w = np.zeros(nG.value)
+        N = np.zeros((eNoN, nG.value), order="F")
+        Nx = np.zeros((3, eNoN, nG.value), order="F")
+        self._call("get_mesh_tables", C.c_int(iM), C.byref(nG), _d(w), _d(N), _d(Nx))
+        return w, N, Nx
+
+    def build_graph(self, nFaces=0):
+        nnz = C.c_int(0)
+        self._call("build_graph", C.c_int(nFaces), C.byref(nnz))
+        self.nnz = nnz.value
+        rowPtr = np.zeros(self.nNo + 1, dtype=np.int32)
+        colPtr = np.zeros(self.nnz, dtype=np.int32)
+        self._call("get_graph", _i(rowPtr), _i(colPtr))
+        return rowPtr, colPtr
+
+    def set_face(self, faIn, bGrp, glob, val):
+        glob = _i32(glob)
+        val = _f64(val)
+        self._call("set_face", C.c_int(faIn), C.c_int(bGrp), C.c_int(val.shape[0]), C.c_int(len(glob)), _i(glob), _d(val))
+
+    def alloc(self, dof):
+        self.dof = dof
+        self._call("alloc", C.c_int(dof))
+
+    def set_state(self, Ag, Yg, Dg=None, Bf=None):
+        Ag, Yg, Dg, Bf = _f64(Ag), _f64(Yg), _f64(Dg), _f64(Bf)
+        self._call("set_state", C.c_int(Ag.shape[0]), _d(Ag), _d(Yg), _d(Dg), _d(Bf))
+
+    def assemble(self, iM, eq: abi.EqParams, dmns):
+        arr = (abi.DmnParams * len(dmns))(*dmns)
+        self._call("assemble", C.c_int(iM), C.byref(eq), arr, C.c_int(len(dmns)))
+
+    def get_R(self):
+        R = np.zeros((self.dof, self.nNo), order="F")
+        self._call("get", C.c_int(abi.ARRAY_R), _d(R))
+        return R
+
+    def get_Val(self):
+        V = np.zeros((self.dof * self.dof, self.nnz), order="F")
+        self._call("get", C.c_int(abi.ARRAY_VAL), _d(V))
+        return V
+
+    def put_R(self, R):
+        R = _f64(R)
+        self.dof = R.shape[0]
+        self._call("put", C.c_int(abi.ARRAY_R), C.c_int(self.dof), _d(R))
+
+    def put_Val(self, V, dof):
+        V = _f64(V)
+        self.dof = dof
+        self._call("put", C.c_int(abi.ARRAY_VAL), C.c_int(dof), _d(V))
+
+    def solve(self, dof, ls_type, ls: abi.LsParams, incL=None, res=None, hist_cap=0):
+        nFaces = 0 if incL is None else len(incL)
+        incL = _i32(incL)
+        res = _f64(res)
+        out = abi.LsResult()
+        hist = np.zeros(max(hist_cap, 1))
+        out.hist = hist.ctypes.data_as(_dp)
+        out.hist_cap = hist_cap
+        X = np.zeros((dof, self.nNo), order="F")
+        self._call("solve", C.c_int(dof), C.c_int(ls_type), C.c_int(abi.PREC_FSILS), C.byref(ls), C.c_int(nFaces),
+                   _i(incL), _d(res), _d(X), C.byref(out))
+        return X, out, hist[:out.hist_n].copy()
+
+    def spmv(self, dof, U):
+        U = _f64(U)
+        KU = np.zeros_like(U, order="F")
+        self._call("spmv", C.c_int(dof), _d(U), _d(KU))
+        return KU
+
+    def last_timing(self):
+        a, s = C.c_double(0), C.c_double(0)
+        self._call("last_timing", C.byref(a), C.byref(s))
+        return a.value, s.value
+
+
+class RefCase(_FlatCase):
+    prefix = "svref_"
+    so_path = REF_SO
+    _lib = None
+
+
+class OracleCase(_FlatCase):
+    prefix = "svorc_"
+    so_path = ORACLE_SO
+    _lib = None

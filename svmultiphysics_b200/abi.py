@@ -1,0 +1,121 @@
+"""ctypes mirror of include/svb200.h (structs and enums only; no library loading here)."""
+from __future__ import annotations
+
+import ctypes as C
+
+ABI_VERSION = 1
+
+# svb200_phys
+PHYS_FLUID, PHYS_STRUCT, PHYS_FSI, PHYS_MESH = 0, 1, 2, 3
+# svb200_visc
+VISC_CONST, VISC_CY, VISC_CASSON = 0, 1, 2
+# svb200_iso / svb200_vol
+ISO_NHK, ISO_MR, ISO_GUCCIONE, ISO_STVK = 0, 1, 2, 3
+VOL_NONE, VOL_QUAD, VOL_ST91, VOL_M94 = 0, 1, 2, 3
+# svb200_ls_type
+LS_NS, LS_GMRES, LS_CG, LS_BICGS = 0, 1, 2, 3
+PREC_FSILS = 0
+BC_DIR, BC_NEU = 0, 1
+SCATTER_ATOMIC, SCATTER_COLORED = 0, 1
+ARRAY_R, ARRAY_VAL, ARRAY_W = 0, 1, 2
+
+
+class EqParams(C.Structure):
+    _fields_ = [
+        ("dt", C.c_double),
+        ("af", C.c_double), ("am", C.c_double), ("gam", C.c_double), ("beta", C.c_double),
+        ("phys", C.c_int32), ("dof", C.c_int32), ("tDof", C.c_int32), ("s", C.c_int32),
+        ("mvMsh", C.c_int32), ("vmsStab", C.c_int32), ("scatter", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class DmnParams(C.Structure):
+    _fields_ = [
+        ("Id", C.c_int32), ("phys", C.c_int32),
+        ("rho", C.c_double),
+        ("f", C.c_double * 3),
+        ("K_darcy", C.c_double),
+        ("viscType", C.c_int32), ("isoType", C.c_int32),
+        ("mu_i", C.c_double), ("mu_o", C.c_double), ("lam", C.c_double), ("a", C.c_double), ("n", C.c_double),
+        ("volType", C.c_int32), ("reserved", C.c_int32),
+        ("Kpen", C.c_double),
+        ("C10", C.c_double), ("C01", C.c_double),
+        ("bff", C.c_double), ("bss", C.c_double), ("bfs", C.c_double),
+        ("dmp", C.c_double),
+        ("E", C.c_double), ("nu", C.c_double),
+        ("solid_visc_mu", C.c_double),
+    ]
+
+
+class SubLsParams(C.Structure):
+    _fields_ = [("mItr", C.c_int32), ("sD", C.c_int32), ("relTol", C.c_double), ("absTol", C.c_double)]
+
+
+class LsParams(C.Structure):
+    _fields_ = [("RI", SubLsParams), ("GM", SubLsParams), ("CG", SubLsParams)]
+
+
+class SubLsResult(C.Structure):
+    _fields_ = [("success", C.c_int32), ("itr", C.c_int32),
+                ("iNorm", C.c_double), ("fNorm", C.c_double), ("dB", C.c_double), ("callD", C.c_double)]
+
+
+class LsResult(C.Structure):
+    _fields_ = [("RI", SubLsResult), ("GM", SubLsResult), ("CG", SubLsResult),
+                ("Resm", C.c_int32), ("Resc", C.c_int32),
+                ("hist_n", C.c_int32), ("hist_cap", C.c_int32),
+                ("hist", C.POINTER(C.c_double))]
+
+
+def gen_alpha(rho_inf: float):
+    """Generalised-alpha coefficients from the spectral radius (Code/Source/solver/initialize.cpp:484-486)."""
+    am = 0.5 * (3.0 - rho_inf) / (1.0 + rho_inf)
+    af = 1.0 / (1.0 + rho_inf)
+    gam = 0.5 + am - af
+    beta = 0.25 * (1.0 + am - af) ** 2
+    return af, am, gam, beta
+
+
+def fluid_eq(dt: float, rho_inf: float = 0.5, tDof: int = 4, scatter: int = SCATTER_ATOMIC, mvMsh: int = 0) -> EqParams:
+    af, am, gam, beta = gen_alpha(rho_inf)
+    return EqParams(dt=dt, af=af, am=am, gam=gam, beta=beta, phys=PHYS_FLUID, dof=4, tDof=tDof, s=0,
+                    mvMsh=mvMsh, vmsStab=1, scatter=scatter, reserved=0)
+
+
+def fluid_domain(rho: float = 1.06, mu: float = 0.04, f=(0.0, 0.0, 0.0), K_darcy: float = 0.0,
+                 viscType: int = VISC_CONST, mu_o: float = 0.0, lam: float = 0.0, a: float = 0.0, n: float = 0.0,
+                 Id: int = -1) -> DmnParams:
+    d = DmnParams()
+    d.Id = Id
+    d.phys = PHYS_FLUID
+    d.rho = rho
+    d.f[0], d.f[1], d.f[2] = f
+    d.K_darcy = K_darcy
+    d.viscType = viscType
+    d.mu_i, d.mu_o, d.lam, d.a, d.n = mu, mu_o, lam, a, n
+    return d
+
+
+def ls_params(ls_type: int, mItr=None, sD=None, relTol=None, absTol=1e-10, gm=None, cg=None) -> LsParams:
+    """Defaults of fsils_ls_create (Code/Source/linear_solver/ls.cpp:22-59), overridable like read_ls does."""
+    p = LsParams()
+    if ls_type == LS_NS:
+        p.RI = SubLsParams(10, 100, 0.4, 1e-10)
+        p.GM = SubLsParams(2, 100, 1e-2, 1e-10)
+        p.CG = SubLsParams(500, 0, 0.2, 1e-10)
+    elif ls_type == LS_GMRES:
+        p.RI = SubLsParams(1000, 250, 0.1, 1e-10)
+    else:
+        p.RI = SubLsParams(1000, 250, 1e-2, 1e-10)
+    if mItr is not None:
+        p.RI.mItr = mItr
+    if sD is not None:
+        p.RI.sD = sD
+    if relTol is not None:
+        p.RI.relTol = relTol
+    p.RI.absTol = absTol
+    if gm:
+        p.GM = SubLsParams(*gm)
+    if cg:
+        p.CG = SubLsParams(*cg)
+    return p

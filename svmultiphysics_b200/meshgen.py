@@ -1,0 +1,146 @@
+"""Deterministic synthetic meshes for the hot-path configs.
+
+Nothing here reads external files: the reference's own test meshes are Git-LFS pointers that are
+not available offline, so every config is generated from a structured hex lattice.
+
+* ``cylinder_tet4``  — the ``pipe_RCR_3d`` analogue (C1) and the 10 M / 80 M tet4 cylinders (C2/C3):
+  a (n x n) square lattice mapped smoothly onto a disc, extruded along z, every hex Kuhn-split into
+  6 tet4 sharing the (0,0,0)-(1,1,1) diagonal so that face diagonals match between neighbours.
+* ``box_hex8``       — the ``block_compression`` analogue (C4).
+
+Node order per tet obeys the solver's convention det[x0-x3, x1-x3, x2-x3] > 0
+(tet4 shape functions are "origin-last", Code/Source/solver/nn.cpp:174; the Jacobian is the
+determinant computed in nn::gnn, Code/Source/solver/nn.cpp:871).
+"""
+from __future__ import annotations
+
+import itertools
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+@dataclass
+class Mesh:
+    """Column-major (Fortran-order) arrays exactly as the reference holds them."""
+    x: np.ndarray            # (3, nNo) float64
+    IEN: np.ndarray          # (eNoN, nEl) int32
+    eNoN: int
+    faces: dict = field(default_factory=dict)   # name -> int32 node ids
+    eId: np.ndarray | None = None               # (nEl,) int32 domain bitmask
+    lattice: tuple | None = None                # (nx, ny, nz) cells
+
+    @property
+    def nNo(self) -> int:
+        return self.x.shape[1]
+
+    @property
+    def nEl(self) -> int:
+        return self.IEN.shape[1]
+
+
+def _lattice_nodes(nx, ny, nz):
+    i, j, k = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
+    # node id = i + (nx+1)*(j + (ny+1)*k): i fastest
+    order = np.argsort((i + (nx + 1) * (j + (ny + 1) * k)).ravel(), kind="stable")
+    return i.ravel()[order], j.ravel()[order], k.ravel()[order]
+
+
+def _hex_cells(nx, ny, nz):
+    """(8, nCells) node ids in VTK hexahedron order, cells ordered i fastest."""
+    ci, cj, ck = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    cid = (ci + nx * (cj + ny * ck)).ravel()
+    order = np.argsort(cid, kind="stable")
+    ci, cj, ck = ci.ravel()[order], cj.ravel()[order], ck.ravel()[order]
+
+    def nid(di, dj, dk):
+        return (ci + di) + (nx + 1) * ((cj + dj) + (ny + 1) * (ck + dk))
+
+    corners = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]
+    return np.stack([nid(*c) for c in corners]).astype(np.int64)
+
+
+def _kuhn_tets(hexes):
+    """Split VTK-ordered hexes (8,n) into 6 tets each: (4, 6n), tets of one hex adjacent."""
+    corner_of = {(0, 0, 0): 0, (1, 0, 0): 1, (1, 1, 0): 2, (0, 1, 0): 3,
+                 (0, 0, 1): 4, (1, 0, 1): 5, (1, 1, 1): 6, (0, 1, 1): 7}
+    local = []
+    for perm in itertools.permutations(range(3)):
+        v = [0, 0, 0]
+        tet = [corner_of[tuple(v)]]
+        for ax in perm:
+            v[ax] = 1
+            tet.append(corner_of[tuple(v)])
+        local.append(tet)
+    local = np.array(local)                       # (6,4)
+    tets = hexes[local.T.reshape(4, 6), :]        # (4,6,n)
+    n = hexes.shape[1]
+    return tets.transpose(0, 2, 1).reshape(4, 6 * n)
+
+
+def _fix_orientation(x, IEN):
+    p = x[:, IEN]                                 # (3,4,nEl)
+    d = p[:, :3, :] - p[:, 3:4, :]
+    det = np.einsum("ie,ie->e", d[:, 0, :], np.cross(d[:, 1, :], d[:, 2, :], axis=0))
+    neg = det < 0
+    IEN = IEN.copy()
+    IEN[0, neg], IEN[1, neg] = IEN[1, neg].copy(), IEN[0, neg].copy()
+    return IEN
+
+
+def cylinder_tet4(n: int, nz: int, R: float = 2.0, L: float = 30.0) -> Mesh:
+    """Cylinder of radius R, length L along z: (n x n x nz) hexes -> 6*n*n*nz tet4."""
+    i, j, k = _lattice_nodes(n, n, nz)
+    u = 2.0 * i / n - 1.0
+    v = 2.0 * j / n - 1.0
+    # elliptical square -> disc map (smooth, bijective, boundary -> circle)
+    xs = R * u * np.sqrt(1.0 - 0.5 * v * v)
+    ys = R * v * np.sqrt(1.0 - 0.5 * u * u)
+    zs = L * k / nz
+    x = np.asfortranarray(np.stack([xs, ys, zs]).astype(np.float64))
+    IEN = _fix_orientation(x, _kuhn_tets(_hex_cells(n, n, nz)))
+    ids = np.arange(x.shape[1], dtype=np.int32)
+    wall = (i == 0) | (i == n) | (j == 0) | (j == n)
+    faces = {
+        "wall": ids[wall],
+        "inlet": ids[(k == 0) & ~wall],
+        "outlet": ids[(k == nz) & ~wall],
+        "outlet_all": ids[k == nz],
+    }
+    return Mesh(x=x, IEN=np.asfortranarray(IEN.astype(np.int32)), eNoN=4, faces=faces, lattice=(n, n, nz))
+
+
+def box_tet4(nx: int, ny: int, nz: int, lengths=(1.0, 1.0, 1.0)) -> Mesh:
+    i, j, k = _lattice_nodes(nx, ny, nz)
+    x = np.asfortranarray(np.stack([lengths[0] * i / nx, lengths[1] * j / ny, lengths[2] * k / nz]).astype(np.float64))
+    IEN = _fix_orientation(x, _kuhn_tets(_hex_cells(nx, ny, nz)))
+    ids = np.arange(x.shape[1], dtype=np.int32)
+    faces = {"X0": ids[i == 0], "X1": ids[i == nx], "Y0": ids[j == 0], "Y1": ids[j == ny],
+             "Z0": ids[k == 0], "Z1": ids[k == nz]}
+    return Mesh(x=x, IEN=np.asfortranarray(IEN.astype(np.int32)), eNoN=4, faces=faces, lattice=(nx, ny, nz))
+
+
+def box_hex8(nx: int, ny: int, nz: int, lengths=(1.0, 1.0, 1.0)) -> Mesh:
+    i, j, k = _lattice_nodes(nx, ny, nz)
+    x = np.asfortranarray(np.stack([lengths[0] * i / nx, lengths[1] * j / ny, lengths[2] * k / nz]).astype(np.float64))
+    IEN = _hex_cells(nx, ny, nz)
+    ids = np.arange(x.shape[1], dtype=np.int32)
+    faces = {"X0": ids[i == 0], "X1": ids[i == nx], "Y0": ids[j == 0], "Y1": ids[j == ny],
+             "Z0": ids[k == 0], "Z1": ids[k == nz]}
+    return Mesh(x=x, IEN=np.asfortranarray(IEN.astype(np.int32)), eNoN=8, faces=faces, lattice=(nx, ny, nz))
+
+
+def poiseuille_state(mesh: Mesh, R: float = 2.0, U: float = 10.0, seed: int = 1234, tDof: int = 4,
+                     noise: float = 0.01, dpdz: float = -1.0):
+    """Seeded synthetic state of SURVEY §8(d) C2: Poiseuille u_z + 1 % noise, linear p, Ag ~ N(0,1)e-2."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n = mesh.nNo
+    r2 = (mesh.x[0] ** 2 + mesh.x[1] ** 2) / (R * R)
+    Yg = np.zeros((tDof, n), order="F")
+    Yg[2] = U * (1.0 - r2)
+    Yg[:3] += noise * U * rng.uniform(-1.0, 1.0, size=(3, n))
+    Yg[3] = dpdz * mesh.x[2] + noise * rng.uniform(-1.0, 1.0, size=n)
+    rng2 = np.random.Generator(np.random.PCG64(seed + 1))
+    Ag = np.asfortranarray(1e-2 * rng2.standard_normal((tDof, n)))
+    Dg = np.zeros((tDof, n), order="F")
+    return np.asfortranarray(Ag), np.asfortranarray(Yg), Dg
