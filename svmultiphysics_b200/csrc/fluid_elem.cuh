@@ -1,0 +1,316 @@
+// fluid_elem.cuh — per-element VMS Navier-Stokes residual/tangent for linear tetrahedra, written for
+// one CUDA thread per element.
+//
+// What it computes is what the reference computes in fluid::construct_fluid for a TET4 element
+// (Code/Source/solver/fluid.cpp:545-749): nn::gnn once (solver/nn.cpp:862-899), then per Gauss
+// point fluid_3d_m (fluid.cpp:1768-2237) and fluid_3d_c (fluid.cpp:1443-1760).  It is NOT a
+// transcription: for a linear tetrahedron the shape-function gradients, the velocity/pressure
+// gradients, the strain rate, the viscosity and the element metric are constant over the element
+// and the second derivatives vanish, so the 16 (a,b) tangent blocks are not accumulated Gauss
+// point by Gauss point.  Instead the Gauss loop only accumulates a small set of element scalars
+// and per-node vectors ("moments" of the Gauss-point dependent stabilisation terms):
+//
+//   K_uu(i,j;a,b) = A1 Nx(j,a) Nx(i,b) + A2 Nx(i,a) Nx(j,b) + A3 esNx(i,a) esNx(j,b)
+//                   + delta_ij ( D(a,b) + A1 gradNa.gradNb )
+//   K_up(i;a,b)   = -Nx(i,a) Sb(b) + Nx(i,b) S2(a)
+//   K_pu(j;a,b)   =  Nx(j,b) Sb(a) - Nx(j,a) S3(b)
+//   K_pp(a,b)     =  Spp gradNa.gradNb
+//
+// with A1 = mu sum_g wl_g, A2 = sum_g wl_g tauC_g, A3 = (dmu/dgamma)/gamma sum_g wl_g,
+// Sb(b) = sum_g wl_g N_b(g), S2(a) = sum_g wl_g rho tauM_g uaNx_a(g),
+// S3(b) = sum_g wl_g tauM_g (T1_b(g) - rho amd N_b(g)), Spp = sum_g wl_g tauM_g and
+// D(a,b) = sum_g of four rank-1 terms (see tet4_gauss below).  The 256 tangent entries are then
+// emitted block by block from these ~60 numbers (tet4_block), which is what makes one element per
+// thread fit in registers.  Results agree with the reference to FP64 round-off (different
+// summation order), tested at 1e-12 relative.
+#pragma once
+#include "svb200_internal.h"
+
+#ifndef SVB_HD
+#ifdef __CUDACC__
+#define SVB_HD __host__ __device__ __forceinline__
+#else
+#define SVB_HD inline
+#endif
+#endif
+
+namespace svb {
+
+// utils::is_zero(v) of the reference (Code/Source/solver/utils.cpp:141-160) for value2 = 0 reduces to
+// |v| < 10*eps*max(|v|,eps)  <=>  |v| < 10*eps^2.
+SVB_HD bool is_zero(double v)
+{
+  const double eps = 2.220446049250313e-16;
+  return fabs(v) < 10.0 * eps * eps;
+}
+
+// fluid::get_viscosity (fluid.cpp:2240-2298).  `gam` may be modified (Casson clips it), exactly as the
+// reference does through its by-reference argument; mu_g is d(mu)/d(gamma).
+SVB_HD void viscosity(const FluidDmn& d, double& gam, double& mu, double& mu_g)
+{
+  if (d.viscType == SVB200_VISC_CONST) {
+    mu = d.mu_i;
+    mu_g = 0.0;
+  } else if (d.viscType == SVB200_VISC_CY) {
+    double T1 = 1.0 + pow(d.lam * gam, d.a);
+    double T2 = pow(T1, (d.n - 1.0) / d.a);
+    mu = d.mu_i + (d.mu_o - d.mu_i) * T2;
+    T1 = T2 / T1;
+    T2 = pow(d.lam, d.a) * pow(gam, d.a - 1.0) * T1;
+    mu_g = (d.mu_o - d.mu_i) * (d.n - 1.0) * T2;
+  } else {
+    double mu_o;
+    if (gam < d.lam) {
+      mu_o = d.mu_o / sqrt(d.lam);
+      gam = d.lam;
+    } else {
+      mu_o = d.mu_o / sqrt(gam);
+    }
+    mu = (d.mu_i + mu_o) * (d.mu_i + mu_o);
+    mu_g = 2.0 * mu_o * (mu_o + d.mu_i) / gam;
+  }
+}
+
+// Everything the block emitter needs, ~90 doubles.
+struct Tet4Elem {
+  double Nx[4][3];     // physical gradient of N_a
+  double esNx[4][3];   // es . grad N_a (only used when A3 != 0)
+  double D[4][4];
+  double Sb[4], S2[4], S3[4];
+  double A1, A2, A3, Spp;
+  double lR[4][4];     // lR[a][i]
+};
+
+// Geometry + Gauss loop.  xl[a][i], yl[a][0..3] = (u,v,w,p), uc[a][i] = convective nodal velocity
+// (= yl - mesh velocity when mvMsh), ab[a][i] = al - bfl.  Returns the Jacobian determinant.
+SVB_HD double tet4_element(const FluidArgs& P, const FluidDmn& dm, const double xl[4][3], const double yl[4][4],
+                           const double uc[4][3], const double ab[4][3], Tet4Elem& E)
+{
+  // ---- nn::gnn -------------------------------------------------------------------------------
+  double xXi[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < 4; a++) s += xl[a][i] * P.Nxi[0][a][k];
+      xXi[i][k] = s;
+    }
+  const double Jac = xXi[0][0] * xXi[1][1] * xXi[2][2] + xXi[0][1] * xXi[1][2] * xXi[2][0] +
+                     xXi[0][2] * xXi[1][0] * xXi[2][1] - xXi[0][0] * xXi[1][2] * xXi[2][1] -
+                     xXi[0][1] * xXi[1][0] * xXi[2][2] - xXi[0][2] * xXi[1][1] * xXi[2][0];
+  const double iJ = 1.0 / Jac;
+  double xiX[3][3];
+  xiX[0][0] = (xXi[1][1] * xXi[2][2] - xXi[1][2] * xXi[2][1]) * iJ;
+  xiX[0][1] = (xXi[2][1] * xXi[0][2] - xXi[2][2] * xXi[0][1]) * iJ;
+  xiX[0][2] = (xXi[0][1] * xXi[1][2] - xXi[0][2] * xXi[1][1]) * iJ;
+  xiX[1][0] = (xXi[1][2] * xXi[2][0] - xXi[1][0] * xXi[2][2]) * iJ;
+  xiX[1][1] = (xXi[2][2] * xXi[0][0] - xXi[2][0] * xXi[0][2]) * iJ;
+  xiX[1][2] = (xXi[0][2] * xXi[1][0] - xXi[0][0] * xXi[1][2]) * iJ;
+  xiX[2][0] = (xXi[1][0] * xXi[2][1] - xXi[1][1] * xXi[2][0]) * iJ;
+  xiX[2][1] = (xXi[2][0] * xXi[0][1] - xXi[2][1] * xXi[0][0]) * iJ;
+  xiX[2][2] = (xXi[0][0] * xXi[1][1] - xXi[0][1] * xXi[1][0]) * iJ;
+  // metric ks = xiX^T xiX (symmetric): k00,k01,k02,k11,k12,k22
+  const double k00 = xiX[0][0] * xiX[0][0] + xiX[1][0] * xiX[1][0] + xiX[2][0] * xiX[2][0];
+  const double k01 = xiX[0][1] * xiX[0][0] + xiX[1][1] * xiX[1][0] + xiX[2][1] * xiX[2][0];
+  const double k02 = xiX[0][2] * xiX[0][0] + xiX[1][2] * xiX[1][0] + xiX[2][2] * xiX[2][0];
+  const double k11 = xiX[0][1] * xiX[0][1] + xiX[1][1] * xiX[1][1] + xiX[2][1] * xiX[2][1];
+  const double k12 = xiX[0][1] * xiX[0][2] + xiX[1][1] * xiX[1][2] + xiX[2][1] * xiX[2][2];
+  const double k22 = xiX[0][2] * xiX[0][2] + xiX[1][2] * xiX[1][2] + xiX[2][2] * xiX[2][2];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+      E.Nx[a][i] = P.Nxi[0][a][0] * xiX[0][i] + P.Nxi[0][a][1] * xiX[1][i] + P.Nxi[0][a][2] * xiX[2][i];
+
+  // ---- element-constant kinematics (fluid.cpp:1827-1980) ----------------------------------------
+  double ux[3][3], px[3];   // ux[i][j] = d u_j / d x_i
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < 4; a++) s += E.Nx[a][i] * yl[a][j];
+      ux[i][j] = s;
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; a++) s += E.Nx[a][i] * yl[a][3];
+    px[i] = s;
+  }
+  const double divU = ux[0][0] + ux[1][1] + ux[2][2];
+  double es[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) es[i][j] = ux[i][j] + ux[j][i];
+  double gam = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) gam += es[i][j] * es[i][j];
+  gam = sqrt(0.5 * gam);
+  double mu, mu_g;
+  viscosity(dm, gam, mu, mu_g);
+  mu_g = is_zero(gam) ? 0.0 : mu_g / gam;
+  if (mu_g != 0.0) {
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+        E.esNx[a][j] = es[0][j] * E.Nx[a][0] + es[1][j] * E.Nx[a][1] + es[2][j] * E.Nx[a][2];
+  }
+
+  const double rho = dm.rho;
+  const double T = P.af * P.gam * P.dt;
+  const double amd = P.am / T;
+  const double muKd = mu * dm.Kd;
+  const double nu = mu / rho;
+  double kT = 4.0 / (P.dt * P.dt) + (dm.Kd * nu) * (dm.Kd * nu);
+  const double kS = 36.0 * (k00 * k00 + k11 * k11 + k22 * k22 + 2.0 * (k01 * k01 + k02 * k02 + k12 * k12)) * nu * nu;
+  const double kTS = kT + kS;
+  const double trK = k00 + k11 + k22;
+  const double q1c = rho * amd + muKd;
+
+  // ---- Gauss loop: accumulate moments --------------------------------------------------------------
+  double RM[3][3], UP[3] = {0.0, 0.0, 0.0};
+  double sPa = 0.0, sW = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) RM[i][j] = 0.0;
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    E.Sb[a] = 0.0; E.S2[a] = 0.0; E.S3[a] = 0.0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) { E.D[a][b] = 0.0; E.lR[a][b] = 0.0; }
+  }
+  double sA2 = 0.0, sPP = 0.0;
+
+#pragma unroll 1
+  for (int g = 0; g < 4; g++) {
+    const double wJ = P.w[g] * Jac;
+    const double wl = wJ * T;
+    double u[3] = {0.0, 0.0, 0.0}, ud[3] = {-dm.f[0], -dm.f[1], -dm.f[2]}, p = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const double Na = P.N[g][a];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        u[i] += Na * uc[a][i];
+        ud[i] += Na * ab[a][i];
+      }
+      p += Na * yl[a][3];
+    }
+    const double kU = u[0] * u[0] * k00 + u[1] * u[1] * k11 + u[2] * u[2] * k22 +
+                      2.0 * (u[0] * u[1] * k01 + u[0] * u[2] * k02 + u[1] * u[2] * k12);
+    const double tauM = 1.0 / (rho * sqrt(kTS + kU));
+    double up[3], ua[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const double rV = ud[j] + u[0] * ux[0][j] + u[1] * ux[1][j] + u[2] * ux[2][j];
+      up[j] = -tauM * (rho * rV + px[j] + muKd * u[j]);
+    }
+    const double tauC = 1.0 / (tauM * trK);
+    double tauB = up[0] * up[0] * k00 + up[1] * up[1] * k11 + up[2] * up[2] * k22 +
+                  2.0 * (up[0] * up[1] * k01 + up[0] * up[2] * k02 + up[1] * up[2] * k12);
+    if (is_zero(tauB)) tauB = 2.220446049250313e-16;
+    tauB = rho / sqrt(tauB);
+#pragma unroll
+    for (int i = 0; i < 3; i++) ua[i] = u[i] + up[i];
+    const double pa = p - tauC * divU;
+    sPa += wJ * pa;
+    sW += wJ;
+    sA2 += wl * tauC;
+    sPP += wl * tauM;
+    double Aj[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const double rVb = tauB * (up[0] * ux[0][j] + up[1] * ux[1][j] + up[2] * ux[2][j]);
+      const double rV2 = ud[j] + ua[0] * ux[0][j] + ua[1] * ux[1][j] + ua[2] * ux[2][j];
+      Aj[j] = rho * rV2 + muKd * ua[j];
+#pragma unroll
+      for (int i = 0; i < 3; i++) RM[i][j] += wJ * (rVb * up[i] - rho * up[j] * ua[i]);
+      UP[j] += wJ * up[j];
+    }
+    double P1[4], P2[4], P3[4], P4[4], Q1[4], Q2[4], Q3[4], Q4[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const double Na = P.N[g][a];
+      const double uNx = u[0] * E.Nx[a][0] + u[1] * E.Nx[a][1] + u[2] * E.Nx[a][2];
+      const double upNx = up[0] * E.Nx[a][0] + up[1] * E.Nx[a][1] + up[2] * E.Nx[a][2];
+      const double uaNx = uNx + upNx;
+      const double c = rho * tauM * uaNx;
+      P1[a] = wl * (Na + c);
+      P2[a] = wl * rho * Na;
+      P3[a] = wl * tauB * upNx;
+      P4[a] = wl * c;
+      Q1[a] = q1c * Na;
+      Q2[a] = uaNx;
+      Q3[a] = upNx;
+      Q4[a] = rho * uNx;
+      E.Sb[a] += wl * Na;
+      E.S2[a] += P4[a];
+      E.S3[a] -= wl * tauM * (Q4[a] + Q1[a]);
+      const double wN = wJ * Na;
+#pragma unroll
+      for (int j = 0; j < 3; j++) E.lR[a][j] += wN * Aj[j];
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++)
+        E.D[a][b] += P1[a] * Q1[b] + P2[a] * Q2[b] + P3[a] * Q3[b] + P4[a] * Q4[b];
+  }
+
+  // ---- finish residual ------------------------------------------------------------------------------
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) RM[i][j] += mu * es[i][j] * sW;
+    RM[i][i] -= sPa;
+  }
+  const double iT = 1.0 / T;
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+      E.lR[a][j] += E.Nx[a][0] * RM[0][j] + E.Nx[a][1] * RM[1][j] + E.Nx[a][2] * RM[2][j];
+    E.lR[a][3] = divU * (E.Sb[a] * iT) - (UP[0] * E.Nx[a][0] + UP[1] * E.Nx[a][1] + UP[2] * E.Nx[a][2]);
+  }
+  const double sWl = sW * T;
+  E.A1 = mu * sWl;
+  E.A2 = sA2;
+  E.A3 = mu_g * sWl;
+  E.Spp = sPP;
+  return Jac;
+}
+
+// One 4x4 tangent block lK(:,a,b), row-major (entry 4*i+j), fluid.cpp:2146-2224 and :1733-1759.
+SVB_HD void tet4_block(const Tet4Elem& E, int a, int b, double K[16])
+{
+  const double nn = E.Nx[a][0] * E.Nx[b][0] + E.Nx[a][1] * E.Nx[b][1] + E.Nx[a][2] * E.Nx[b][2];
+  const double dd = E.D[a][b] + E.A1 * nn;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      double v = E.A1 * E.Nx[a][j] * E.Nx[b][i] + E.A2 * E.Nx[a][i] * E.Nx[b][j];
+      if (i == j) v += dd;
+      K[4 * i + j] = v;
+    }
+    K[4 * i + 3] = E.Nx[b][i] * E.S2[a] - E.Nx[a][i] * E.Sb[b];
+    K[12 + i] = E.Nx[b][i] * E.Sb[a] - E.Nx[a][i] * E.S3[b];
+  }
+  K[15] = E.Spp * nn;
+  if (E.A3 != 0.0) {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) K[4 * i + j] += E.A3 * E.esNx[a][i] * E.esNx[b][j];
+  }
+}
+
+}  // namespace svb

@@ -1,0 +1,172 @@
+// svb200_internal.h — device-side state behind the opaque svb200_ctx (include/svb200.h).
+//
+// Data layout in HBM (all FP64 / int32, column-major like the reference):
+//   * nodes are stored in FSILS order (lhs.map of linear_solver/lhs.cpp:215-218): interface nodes
+//     shared with lower ranks first, interior nodes, interface nodes shared with higher ranks last,
+//     so "owned" dots run over [0,mynNo) and halo packs touch two contiguous-ish ends;
+//   * the block-CSR matrix (rowPtr/colPtr/Val) is stored with rows in that same order, the columns
+//     of a row kept in the input order, one dof x dof block = dof*dof contiguous doubles
+//     (row-major inside the block, Code/Source/solver/FsilsLinearAlgebra.cpp:35);
+//   * nodal state (x, Ag, Yg, Dg, Bf, R) is (rows, nNo), node-major AoS exactly like the reference.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "../../include/svb200.h"
+
+namespace svb {
+
+constexpr int MAX_DMN = 8;
+constexpr int MAX_ENON = 8;
+constexpr int MAX_NG = 8;
+
+struct Mesh {
+  int eNoN = 0, nEl = 0, nG = 0, nFn = 0;
+  int* d_IEN = nullptr;      // (eNoN, nEl) internal node ids
+  int* d_eId = nullptr;      // (nEl) or null
+  double* d_fN = nullptr;    // (3*nFn, nEl) or null
+  int* d_slot = nullptr;     // (eNoN*eNoN, nEl): CSR slot of pair (a,b) = entry a*eNoN+b
+  int* d_color_perm = nullptr;   // element ids sorted by colour (coloured scatter)
+  std::vector<int> color_off;    // offsets into d_color_perm per colour
+  std::vector<double> w, N, Nx;  // host copies of the reference-element tables
+  bool set = false;
+};
+
+struct Face {
+  int bGrp = 0, dof = 0, nNo = 0, shared = 0;
+  bool set = false;
+  int* d_glob = nullptr;     // internal node ids
+  double* d_val = nullptr;   // (dof, nNo)
+  double* d_valM = nullptr;  // (dof, nNo): val * W (precond_diag)
+  double nS = 0.0;           // sum of val^2 over owned nodes (fsils_bc_create)
+  // per-solve flags (fsils_solve)
+  bool incFlag = true, coupledFlag = false;
+  double res = 0.0;
+};
+
+struct Neighbor {
+  int rank = 0, n = 0;
+  int* d_ptr = nullptr;       // internal node ids shared with that rank (same order on both sides)
+  double* d_send = nullptr;   // (maxdof, n)
+  double* d_recv = nullptr;
+};
+
+// Kernel argument block of the fluid assembly kernels (passed by value as __grid_constant__).
+struct FluidDmn {
+  double rho, f[3], Kd;
+  double mu_i, mu_o, lam, a, n;
+  int viscType, Id, isFluid, pad;
+};
+
+struct FluidArgs {
+  const int* IEN;
+  const int* eId;
+  const int* slot;
+  const int* perm;      // optional element permutation (coloured scatter) or null
+  const double* x;
+  const double* Ag;
+  const double* Yg;
+  const double* Bf;
+  double* R;
+  double* Val;
+  int e0, e1;           // element range [e0,e1) (indices into perm when perm != null)
+  int tDof, mvMsh, nDmn, atomic;
+  double dt, af, am, gam;
+  double w[MAX_NG];
+  double N[MAX_NG][MAX_ENON];        // N[g][a]
+  double Nxi[MAX_NG][MAX_ENON][3];   // Nxi[g][a][k] = d N_a / d xi_k at Gauss point g
+  FluidDmn dmn[MAX_DMN];
+};
+
+}  // namespace svb
+
+struct svb200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t launches = 0;
+
+  // graph
+  int nNo = 0, nnz = 0, mynNo = 0;
+  bool has_map = false;
+  std::vector<int> h_map;        // input -> internal node id
+  std::vector<int> h_rowPtr_in;  // input CSR (kept for slot translation on download)
+  std::vector<int> h_rowPtr;     // internal CSR row pointer
+  int* d_map = nullptr;
+  int* d_rowPtr = nullptr;       // (nNo+1) internal
+  int* d_colPtr = nullptr;       // (nnz) internal column ids
+  int* d_diagPtr = nullptr;      // (nNo)
+  int* d_slot_in2int = nullptr;  // unused when has_map == false
+
+  // coordinates and state (internal order)
+  int tDof = 0;
+  double* d_x = nullptr;
+  double* d_Ag = nullptr;
+  double* d_Yg = nullptr;
+  double* d_Dg = nullptr;
+  double* d_Bf = nullptr;
+  double* d_stage = nullptr;     // staging buffer for permuted uploads/downloads
+  size_t stage_bytes = 0;
+
+  // linear system
+  int dof = 0;
+  double* d_R = nullptr;
+  double* d_Val = nullptr;
+  size_t R_cap = 0, Val_cap = 0;   // capacities in doubles
+  double* d_W = nullptr;           // (dof,nNo) preconditioner scaling
+  size_t W_cap = 0;
+
+  std::vector<svb::Mesh> mesh;
+  std::vector<svb::Face> face;
+
+  // Krylov workspace
+  double* d_work = nullptr;
+  size_t work_cap = 0;
+  double* d_red = nullptr;         // partial-reduction scratch
+  double* h_pinned = nullptr;      // pinned host scratch for scalar read-back
+  size_t red_cap = 0;
+
+  // multi-GPU
+  int nranks = 1, rank = 0;
+  void* nccl_comm = nullptr;
+  std::vector<svb::Neighbor> neigh;
+
+  double last_assemble_ms = 0.0, last_solve_ms = 0.0;
+};
+
+namespace svb {
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define SVB_CUDA(call)                                                             \
+  do {                                                                             \
+    cudaError_t e__ = (call);                                                      \
+    if (e__ != cudaSuccess) return svb::cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+
+#define SVB_REQUIRE(cond, msg)                 \
+  do {                                         \
+    if (!(cond)) {                             \
+      svb::set_error(std::string("svb200: ") + (msg)); \
+      return SVB200_ERR_INVALID;               \
+    }                                          \
+  } while (0)
+
+// assemble_fluid.cu
+int launch_assemble_fluid(svb200_ctx* ctx, const Mesh& m, const FluidArgs& args);
+// graph_kernels.cu
+int launch_build_slot_map(svb200_ctx* ctx, Mesh& m);
+int launch_find_diag(svb200_ctx* ctx);
+int launch_permute_cols(svb200_ctx* ctx, int rows, int n, const int* d_map, const double* src, double* dst, bool inverse);
+// fsils_kernels.cu
+int launch_spmv(svb200_ctx* ctx, int dof, const double* Val, const double* U, double* KU);
+int launch_dots(svb200_ctx* ctx, int n, int nvec, const double* const* d_vec_list, const double* base, size_t stride,
+                const double* v, double* d_out);
+// fsils_solvers.cu
+int fsils_solve_device(svb200_ctx* ctx, int dof, int ls_type, const svb200_lsparams* ls, int nFaces, const int* incL,
+                       const double* res, svb200_lsresult* result);
+int fp64_peak(svb200_ctx* ctx, double* tflops);
+
+}  // namespace svb

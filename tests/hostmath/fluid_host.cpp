@@ -1,0 +1,46 @@
+// fluid_host.cpp — TEST-ONLY host build of the device element routines (fluid_elem.cuh).
+// Lets the CPU-only test suite check the hoisted tet4 element algebra against the reference oracle
+// without a GPU.  Never linked into libsvb200.so; the product has no CPU path.
+#include <cmath>
+#include <cstring>
+#include <vector>
+using std::fabs; using std::sqrt; using std::pow;
+#define SVB_HD inline
+#include "../../svmultiphysics_b200/csrc/fluid_elem.cuh"
+
+extern "C" int hostmath_fluid_tet4(const svb::FluidArgs* P, int nNo, const int* rowPtr, const int* colPtr,
+                                   double* R, double* Val)
+{
+  using namespace svb;
+  for (int e = P->e0; e < P->e1; e++) {
+    int n[4];
+    double xl[4][3], yl[4][4], uc[4][3], ab[4][3];
+    for (int a = 0; a < 4; a++) {
+      n[a] = P->IEN[4*e + a];
+      for (int i = 0; i < 3; i++) {
+        xl[a][i] = P->x[3*n[a] + i];
+        ab[a][i] = P->Ag[P->tDof*n[a] + i] - P->Bf[3*n[a] + i];
+        uc[a][i] = P->Yg[P->tDof*n[a] + i] - (P->mvMsh ? P->Yg[P->tDof*n[a] + 4 + i] : 0.0);
+      }
+      for (int i = 0; i < 4; i++) yl[a][i] = P->Yg[P->tDof*n[a] + i];
+    }
+    int iD = 0;
+    for (int d = 0; d < P->nDmn; d++) { iD = d; if (P->dmn[d].Id == -1) break; if (P->eId && ((P->eId[e] >> P->dmn[d].Id) & 1)) break; }
+    if (!P->dmn[iD].isFluid) continue;
+    Tet4Elem E;
+    tet4_element(*P, P->dmn[iD], xl, yl, uc, ab, E);
+    for (int a = 0; a < 4; a++) {
+      for (int i = 0; i < 4; i++) R[4*n[a] + i] += E.lR[a][i];
+      for (int b = 0; b < 4; b++) {
+        double K[16];
+        tet4_block(E, a, b, K);
+        int s = -1;
+        for (int k = rowPtr[n[a]]; k < rowPtr[n[a]+1]; k++) if (colPtr[k] == n[b]) { s = k; break; }
+        if (s < 0) return 1;
+        for (int i = 0; i < 16; i++) Val[16*(size_t)s + i] += K[i];
+      }
+    }
+  }
+  return 0;
+}
+extern "C" int hostmath_sizeof_fluidargs() { return (int)sizeof(svb::FluidArgs); }
