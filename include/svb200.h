@@ -41,6 +41,12 @@ extern "C" {
 
 #define SVB200_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define SVB200_API __attribute__((visibility("default")))
+#else
+#define SVB200_API
+#endif
+
 typedef struct svb200_ctx svb200_ctx;
 
 typedef enum {
@@ -151,90 +157,99 @@ typedef struct {
 } svb200_lsresult;
 
 /* ---- lifecycle -------------------------------------------------------------------------- */
-int svb200_abi_version(void);
-const char* svb200_last_error(void);
-int svb200_create(svb200_ctx** out, int device);
-int svb200_destroy(svb200_ctx* ctx);
+SVB200_API int svb200_abi_version(void);
+SVB200_API const char* svb200_last_error(void);
+SVB200_API int svb200_create(svb200_ctx** out, int device);
+SVB200_API int svb200_destroy(svb200_ctx* ctx);
 
 /* One process per GPU: rank/nranks of this context and the 128-byte ncclUniqueId generated by
  * svb200_comm_unique_id() on rank 0 and broadcast by the host (torch.distributed / MPI).
  * Replaces fsils_commu_create (linear_solver/commu.cpp:17-46). */
-int svb200_comm_unique_id(void* id128);
-int svb200_comm_init(svb200_ctx* ctx, int nranks, int rank, const void* id128);
+SVB200_API int svb200_comm_unique_id(void* id128);
+SVB200_API int svb200_comm_init(svb200_ctx* ctx, int nranks, int rank, const void* id128);
 
 /* ---- structure (once) ------------------------------------------------------------------- */
 /* CSR graph in INPUT node order exactly as lhsa_ns::lhsa builds it (columns ascending per row).
  * map/mynNo and the shared-node lists are what fsils_lhs_create computes (linear_solver/lhs.cpp);
  * pass map=NULL, mynNo=nNo, nReq=0 for a single partition.  neigh_ptr is the concatenation of the
  * per-neighbour lists cS[i].ptr (FSILS-order local ids), neigh_n[i] entries each. */
-int svb200_set_graph(svb200_ctx* ctx, int32_t nNo, int32_t nnz, const int32_t* rowPtr, const int32_t* colPtr,
+SVB200_API int svb200_set_graph(svb200_ctx* ctx, int32_t nNo, int32_t nnz, const int32_t* rowPtr, const int32_t* colPtr,
                      int32_t mynNo, const int32_t* map,
                      int32_t nReq, const int32_t* neigh_rank, const int32_t* neigh_n, const int32_t* neigh_ptr);
+
+/* lhsa_ns::lhsa (solver/lhsa.cpp:126-381) on the device: the sorted node-to-node adjacency of all
+ * meshes as CSR (columns ascending per row, every node pair of every element, diagonal included).
+ * begin -> add_mesh (once per mesh, IEN(eNoN,nEl) in caller node ids) -> finish (returns nnz) -> get.
+ * The result is bit-identical to the reference's rowPtr/colPtr; pass it to svb200_set_graph. */
+SVB200_API int svb200_lhsa_begin(svb200_ctx* ctx, int32_t nNo);
+SVB200_API int svb200_lhsa_add_mesh(svb200_ctx* ctx, int32_t eNoN, int32_t nEl, const int32_t* IEN);
+SVB200_API int svb200_lhsa_finish(svb200_ctx* ctx, int32_t* nnz);
+SVB200_API int svb200_lhsa_get(svb200_ctx* ctx, int32_t* rowPtr, int32_t* colPtr);
 
 /* One mesh (mshType): connectivity IEN(eNoN,nEl) in input node ids, optional domain bitmask
  * eId(nEl), optional fibres fN(3*nFn,nEl), and the reference-element tables of fs[0]:
  * w(nG), N(eNoN,nG), Nx(3,eNoN,nG).  eNoN = 4 (TET4) or 8 (HEX8). */
-int svb200_set_mesh(svb200_ctx* ctx, int32_t iM, int32_t eNoN, int32_t nEl, const int32_t* IEN,
+SVB200_API int svb200_set_mesh(svb200_ctx* ctx, int32_t iM, int32_t eNoN, int32_t nEl, const int32_t* IEN,
                     const int32_t* eId, int32_t nFn, const double* fN,
                     int32_t nG, const double* w, const double* N, const double* Nx);
 
 /* Reference coordinates com_mod.x(3,nNo). */
-int svb200_set_coords(svb200_ctx* ctx, const double* x);
+SVB200_API int svb200_set_coords(svb200_ctx* ctx, const double* x);
 
 /* Linear-solver faces (fsils_bc_create): glob are INPUT-order node ids, val(face_dof,nNo). */
-int svb200_set_num_faces(svb200_ctx* ctx, int32_t nFaces);
-int svb200_set_face(svb200_ctx* ctx, int32_t faIn, int32_t bGrp, int32_t face_dof, int32_t nNo,
+SVB200_API int svb200_set_num_faces(svb200_ctx* ctx, int32_t nFaces);
+SVB200_API int svb200_set_face(svb200_ctx* ctx, int32_t faIn, int32_t bGrp, int32_t face_dof, int32_t nNo,
                     const int32_t* glob, const double* val, int32_t sharedFlag);
 
 /* ---- per Newton iteration --------------------------------------------------------------- */
 /* ls_alloc (solver/ls.cpp:24-40): R(dof,nNo) and Val(dof*dof,nnz) are (re)zeroed on the device. */
-int svb200_alloc(svb200_ctx* ctx, int32_t dof);
+SVB200_API int svb200_alloc(svb200_ctx* ctx, int32_t dof);
 
 /* Upload the generalised-alpha intermediate state (Ag,Yg,Dg)(tDof,nNo) and body force Bf(3,nNo).
  * NULL pointers leave the device copy unchanged (Dg, Bf may never be set: treated as zero). */
-int svb200_set_state(svb200_ctx* ctx, int32_t tDof, const double* Ag, const double* Yg, const double* Dg,
+SVB200_API int svb200_set_state(svb200_ctx* ctx, int32_t tDof, const double* Ag, const double* Yg, const double* Dg,
                      const double* Bf);
 
 /* global_eq_assem for mesh iM: element loop + scatter, R/Val stay on the device. */
-int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq,
+SVB200_API int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq,
                     const svb200_dmnparams* dmn, int32_t nDmn);
 
 /* Host-assembled surface terms (Neumann/backflow faces): R(:,rows[k]) += R_add(:,k),
  * Val(:,slot(rows_k,cols_k)) += K_add(:,k). */
-int svb200_add_host_contrib(svb200_ctx* ctx, int32_t dof, int32_t nR, const int32_t* rows, const double* R_add,
+SVB200_API int svb200_add_host_contrib(svb200_ctx* ctx, int32_t dof, int32_t nR, const int32_t* rows, const double* R_add,
                             int32_t nK, const int32_t* krows, const int32_t* kcols, const double* K_add);
 
 /* all_fun::commu(R): shared-node sum of the residual across partitions (no-op for one rank). */
-int svb200_commu_R(svb200_ctx* ctx);
+SVB200_API int svb200_commu_R(svb200_ctx* ctx);
 
 /* fsils_solve: preconditions in place, runs the Krylov solver, writes the increment to R_out
  * (dof,nNo, INPUT node order; may be NULL to keep it on the device only). */
-int svb200_solve(svb200_ctx* ctx, int32_t dof, int32_t ls_type, int32_t prec, const svb200_lsparams* ls,
+SVB200_API int svb200_solve(svb200_ctx* ctx, int32_t dof, int32_t ls_type, int32_t prec, const svb200_lsparams* ls,
                  int32_t nFaces, const int32_t* incL, const double* res,
                  double* R_out, svb200_lsresult* result);
 
 /* ---- debug / parity --------------------------------------------------------------------- */
 /* R(dof,nNo) and Val(dof*dof,nnz) are returned in INPUT node order / input CSR slot order. */
-int svb200_download(svb200_ctx* ctx, int32_t what, double* dst);
-int svb200_upload(svb200_ctx* ctx, int32_t what, int32_t dof, const double* src);
+SVB200_API int svb200_download(svb200_ctx* ctx, int32_t what, double* dst);
+SVB200_API int svb200_upload(svb200_ctx* ctx, int32_t what, int32_t dof, const double* src);
 
 /* Stand-alone operators on the current device Val, for tests and the bench:
  * KU = K*U (+ halo sum), both (dof,nNo) host arrays in INPUT order. */
-int svb200_spmv(svb200_ctx* ctx, int32_t dof, const double* U, double* KU);
+SVB200_API int svb200_spmv(svb200_ctx* ctx, int32_t dof, const double* U, double* KU);
 
 /* Device-side timing of the last svb200_assemble / svb200_solve call in milliseconds
  * (CUDA events on the library's stream). */
-int svb200_last_timing(svb200_ctx* ctx, double* assemble_ms, double* solve_ms);
+SVB200_API int svb200_last_timing(svb200_ctx* ctx, double* assemble_ms, double* solve_ms);
 
 /* Repeat the assembly kernel(s) / SpMV n times on resident data and return the average device
  * time per launch in ms (CUDA events on the launching stream); used by bench.py for the roofline. */
-int svb200_bench_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, const svb200_dmnparams* dmn,
+SVB200_API int svb200_bench_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, const svb200_dmnparams* dmn,
                           int32_t nDmn, int32_t reps, double* ms_per_launch);
-int svb200_bench_spmv(svb200_ctx* ctx, int32_t dof, int32_t reps, double* ms_per_launch);
+SVB200_API int svb200_bench_spmv(svb200_ctx* ctx, int32_t dof, int32_t reps, double* ms_per_launch);
 /* Measured FP64 FMA peak (independent DFMA chains) in TFLOP/s. */
-int svb200_measure_fp64_peak(svb200_ctx* ctx, double* tflops);
+SVB200_API int svb200_measure_fp64_peak(svb200_ctx* ctx, double* tflops);
 /* Number of CUDA kernels this library has launched on ctx since creation. */
-int64_t svb200_launch_count(svb200_ctx* ctx);
+SVB200_API int64_t svb200_launch_count(svb200_ctx* ctx);
 
 #ifdef __cplusplus
 }

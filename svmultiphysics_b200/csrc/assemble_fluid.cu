@@ -1,0 +1,156 @@
+// assemble_fluid.cu — fused element loop + scatter for fluid TET4 (K1 of SURVEY.md §7).
+//
+// Replaces, per Newton iteration, fluid::construct_fluid (Code/Source/solver/fluid.cpp:480-762),
+// nn::gnn (solver/nn.cpp:862-899), fluid_3d_m / fluid_3d_c (fluid.cpp:1768-2237 / 1443-1760) and the
+// lhsa_ns::do_assem scatter (solver/lhsa.cpp:70-114).
+//
+// Mapping: one thread per element computes the ~60 element moments of fluid_elem.cuh in registers;
+// the 16 tangent blocks are then emitted one (a,b) pair at a time, transposed through a per-warp
+// shared-memory tile so that a half-warp adds the 16 contiguous doubles of ONE 128-byte CSR block
+// with one fully coalesced REDG.F64 (measured on B200: 554 G red/s coalesced vs 174 G red/s when
+// every lane walks its own block, profiles/r1_microbench_fp64_red.txt).  The CSR slot of every
+// (a,b) pair comes from a precomputed element->slot map, so the binary search of do_assem is gone.
+// Scatter modes: ATOMIC (red.global.add.f64, all elements in one launch) and COLORED (one launch per
+// colour, plain read-modify-write, bitwise reproducible).
+#include "fluid_elem.cuh"
+
+namespace svb {
+
+constexpr int ASM_THREADS = 128;
+constexpr int TILE_LD = 17;   // 16 doubles + 1 pad: conflict-free 64-bit column reads
+
+template <bool ATOMIC>
+__device__ __forceinline__ void add_f64(double* p, double v)
+{
+  if (ATOMIC) {
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+  } else {
+    *p += v;
+  }
+}
+
+__device__ __forceinline__ int pick_domain(const FluidArgs& P, int e)
+{
+  int iD = 0;
+  for (int d = 0; d < P.nDmn; d++) {
+    iD = d;
+    if (P.dmn[d].Id == -1) break;
+    if (P.eId != nullptr && ((P.eId[e] >> P.dmn[d].Id) & 1)) break;
+  }
+  return iD;
+}
+
+template <bool ATOMIC>
+__global__ void __launch_bounds__(ASM_THREADS)
+assemble_fluid_tet4_kernel(const __grid_constant__ FluidArgs P)
+{
+  __shared__ double tile[ASM_THREADS / 32][32 * TILE_LD];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  double* T = tile[warp];
+
+  const int idx = P.e0 + blockIdx.x * ASM_THREADS + threadIdx.x;
+  bool active = idx < P.e1;
+  int e = 0;
+  if (active) e = P.perm ? P.perm[idx] : idx;
+
+  Tet4Elem E;
+  int node[4] = {0, 0, 0, 0};
+  if (active) {
+    const int iD = pick_domain(P, e);
+    if (!P.dmn[iD].isFluid) {
+      active = false;
+    } else {
+      const int4 n4 = *reinterpret_cast<const int4*>(P.IEN + 4 * (size_t)e);
+      node[0] = n4.x; node[1] = n4.y; node[2] = n4.z; node[3] = n4.w;
+      double xl[4][3], yl[4][4], uc[4][3], ab[4][3];
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const size_t n = (size_t)node[a];
+        const double* xp = P.x + 3 * n;
+        const double* bp = P.Bf + 3 * n;
+        const double* ap = P.Ag + (size_t)P.tDof * n;
+        const double* yp = P.Yg + (size_t)P.tDof * n;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          xl[a][i] = __ldg(xp + i);
+          ab[a][i] = __ldg(ap + i) - __ldg(bp + i);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) yl[a][i] = __ldg(yp + i);
+#pragma unroll
+        for (int i = 0; i < 3; i++) uc[a][i] = yl[a][i] - (P.mvMsh ? __ldg(yp + 4 + i) : 0.0);
+      }
+      tet4_element(P, P.dmn[iD], xl, yl, uc, ab, E);
+    }
+  }
+
+  // ---- residual: R(:,node_a) += lR(:,a); 16 doubles per element through the tile -------------------
+  const int half = lane >> 4, j = lane & 15;
+  if (active) {
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int i = 0; i < 4; i++) T[lane * TILE_LD + 4 * a + i] = E.lR[a][i];
+  }
+  __syncwarp();
+#pragma unroll 4
+  for (int r = 0; r < 16; r++) {
+    const int src = 2 * r + half;
+    const int n0 = __shfl_sync(0xffffffffu, node[0], src);
+    const int n1 = __shfl_sync(0xffffffffu, node[1], src);
+    const int n2 = __shfl_sync(0xffffffffu, node[2], src);
+    const int n3 = __shfl_sync(0xffffffffu, node[3], src);
+    const bool act = __shfl_sync(0xffffffffu, (int)active, src);
+    const int a = j >> 2;
+    const int n = a == 0 ? n0 : (a == 1 ? n1 : (a == 2 ? n2 : n3));
+    if (act) add_f64<ATOMIC>(P.R + 4 * (size_t)n + (j & 3), T[src * TILE_LD + j]);
+  }
+  __syncwarp();
+
+  // ---- tangent: one (a,b) block per step ------------------------------------------------------------
+  const int* slotp = P.slot + 16 * (size_t)e;
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    int4 s4 = make_int4(-1, -1, -1, -1);
+    if (active) s4 = *reinterpret_cast<const int4*>(slotp + 4 * a);
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const int myslot = b == 0 ? s4.x : (b == 1 ? s4.y : (b == 2 ? s4.z : s4.w));
+      if (active) {
+        double K[16];
+        tet4_block(E, a, b, K);
+#pragma unroll
+        for (int i = 0; i < 16; i++) T[lane * TILE_LD + i] = K[i];
+      }
+      __syncwarp();
+#pragma unroll 4
+      for (int r = 0; r < 16; r++) {
+        const int src = 2 * r + half;
+        const int s = __shfl_sync(0xffffffffu, myslot, src);
+        if (s >= 0) add_f64<ATOMIC>(P.Val + 16 * (size_t)s + j, T[src * TILE_LD + j]);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+int launch_assemble_fluid(svb200_ctx* ctx, const Mesh& m, const FluidArgs& args)
+{
+  if (m.eNoN != 4) {
+    set_error("svb200: fluid assembly is implemented for TET4 meshes (eNoN=4)");
+    return SVB200_ERR_UNSUPPORTED;
+  }
+  const int n = args.e1 - args.e0;
+  if (n <= 0) return SVB200_OK;
+  const int blocks = (n + ASM_THREADS - 1) / ASM_THREADS;
+  if (args.atomic)
+    assemble_fluid_tet4_kernel<true><<<blocks, ASM_THREADS, 0, ctx->stream>>>(args);
+  else
+    assemble_fluid_tet4_kernel<false><<<blocks, ASM_THREADS, 0, ctx->stream>>>(args);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
+}  // namespace svb

@@ -1,0 +1,449 @@
+// fsils_kernels.cu — device building blocks of the FSILS Krylov solvers.
+//
+//   bsr_spmv           spar_mul::fsils_spar_mul_vv   Code/Source/linear_solver/spar_mul.cpp:164-231
+//   multi_dot          dot::fsils_nc_dot_v           linear_solver/dot.cpp:107-146  (i+2 dots in ONE pass)
+//   cgs_update         the Gram-Schmidt sweep + scale of gmres_v, linear_solver/gmres.cpp:541-549
+//   lincomb            X += sum_j y_j u_j            linear_solver/gmres.cpp:590-592
+//   axpby & friends    omp_la::omp_sum_v / omp_mul_v linear_solver/omp_la.cpp:21-122
+//   precond_*          precond::precond_diag         linear_solver/precond.cpp:95-242
+//
+// All of them are HBM-bandwidth bound; vectors are (dof,nNo) node-major, the matrix is block-CSR
+// with dof*dof contiguous doubles per block.  Reductions are two-stage and run in a fixed order, so
+// results are bitwise reproducible from run to run.
+#include "svb200_internal.h"
+#include "fsils_kernels.h"
+
+namespace svb {
+
+// ----------------------------------------------------------------------------------------------
+// SpMV, dof = 4: 8 lanes per row, each lane owns two adjacent entries (one double2 = 16 B) of every
+// 4x4 block of that row, so that a lane group reads one whole 128-byte block per load instruction.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bsr_spmv4_kernel(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ colPtr,
+                 const double* __restrict__ Val, const double* __restrict__ U, double* __restrict__ KU)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = t >> 3;
+  const int l = t & 7;
+  const int i = l >> 1, j0 = (l & 1) << 1;
+  double acc = 0.0;
+  if (row < nNo) {
+    const int k0 = rowPtr[row], k1 = rowPtr[row + 1];
+    const double2* V2 = reinterpret_cast<const double2*>(Val) + l;
+    int k = k0;
+    for (; k + 4 <= k1; k += 4) {
+      const int c0 = __ldg(colPtr + k), c1 = __ldg(colPtr + k + 1), c2 = __ldg(colPtr + k + 2), c3 = __ldg(colPtr + k + 3);
+      const double2 v0 = __ldcs(V2 + 8 * (size_t)k), v1 = __ldcs(V2 + 8 * (size_t)(k + 1));
+      const double2 v2 = __ldcs(V2 + 8 * (size_t)(k + 2)), v3 = __ldcs(V2 + 8 * (size_t)(k + 3));
+      const double2 u0 = *reinterpret_cast<const double2*>(U + 4 * (size_t)c0 + j0);
+      const double2 u1 = *reinterpret_cast<const double2*>(U + 4 * (size_t)c1 + j0);
+      const double2 u2 = *reinterpret_cast<const double2*>(U + 4 * (size_t)c2 + j0);
+      const double2 u3 = *reinterpret_cast<const double2*>(U + 4 * (size_t)c3 + j0);
+      acc += v0.x * u0.x + v0.y * u0.y;
+      acc += v1.x * u1.x + v1.y * u1.y;
+      acc += v2.x * u2.x + v2.y * u2.y;
+      acc += v3.x * u3.x + v3.y * u3.y;
+    }
+    for (; k < k1; k++) {
+      const int c0 = __ldg(colPtr + k);
+      const double2 v0 = __ldcs(V2 + 8 * (size_t)k);
+      const double2 u0 = *reinterpret_cast<const double2*>(U + 4 * (size_t)c0 + j0);
+      acc += v0.x * u0.x + v0.y * u0.y;
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  if (row < nNo && (l & 1) == 0) KU[4 * (size_t)row + i] = acc;
+}
+
+// Generic dof: one thread per (row, i).
+template <int DOF>
+__global__ void __launch_bounds__(256)
+bsr_spmv_kernel(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ colPtr,
+                const double* __restrict__ Val, const double* __restrict__ U, double* __restrict__ KU)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)nNo * DOF) return;
+  const int row = (int)(t / DOF), i = (int)(t % DOF);
+  double acc = 0.0;
+  for (int k = rowPtr[row]; k < rowPtr[row + 1]; k++) {
+    const int c = colPtr[k];
+    const double* v = Val + (size_t)k * DOF * DOF + i * DOF;
+    const double* u = U + (size_t)c * DOF;
+#pragma unroll
+    for (int j = 0; j < DOF; j++) acc += v[j] * u[j];
+  }
+  KU[t] = acc;
+}
+
+int launch_spmv(svb200_ctx* ctx, int dof, const double* Val, const double* U, double* KU)
+{
+  const int nNo = ctx->nNo;
+  if (nNo == 0) return SVB200_OK;
+  if (dof == 4) {
+    const long long threads = (long long)nNo * 8;
+    bsr_spmv4_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(nNo, ctx->d_rowPtr, ctx->d_colPtr, Val, U, KU);
+  } else {
+    const long long threads = (long long)nNo * dof;
+    const unsigned blocks = (unsigned)((threads + 255) / 256);
+    switch (dof) {
+      case 1: bsr_spmv_kernel<1><<<blocks, 256, 0, ctx->stream>>>(nNo, ctx->d_rowPtr, ctx->d_colPtr, Val, U, KU); break;
+      case 2: bsr_spmv_kernel<2><<<blocks, 256, 0, ctx->stream>>>(nNo, ctx->d_rowPtr, ctx->d_colPtr, Val, U, KU); break;
+      case 3: bsr_spmv_kernel<3><<<blocks, 256, 0, ctx->stream>>>(nNo, ctx->d_rowPtr, ctx->d_colPtr, Val, U, KU); break;
+      default:
+        set_error("svb200: SpMV supports dof 1..4");
+        return SVB200_ERR_UNSUPPORTED;
+    }
+  }
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// multi_dot: out[j] = sum_{k<n} u_j[k] * v[k], j = 0..nvec-1, u_j = ubase + j*stride.
+// A CTA keeps a tile of v in registers and streams the matching tile of every u_j past it, so v and
+// each u_j are read from HBM exactly once.  Stage 1 leaves per-CTA partials in `part`
+// (gridDim.x, nvec); stage 2 (one CTA) adds them in CTA order.
+// ----------------------------------------------------------------------------------------------
+constexpr int DOT_THREADS = 256;
+constexpr int DOT_PER_THREAD = 4;   // doubles of v per thread per tile (2 x double2)
+constexpr int DOT_TILE = DOT_THREADS * DOT_PER_THREAD;
+
+__global__ void __launch_bounds__(DOT_THREADS)
+multi_dot_stage1(long long n, int nvec, const double* __restrict__ ubase, long long stride,
+                 const double* __restrict__ v, double* __restrict__ part)
+{
+  extern __shared__ double sm[];   // [DOT_THREADS/32][nvec]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* mine = sm + (size_t)warp * nvec;
+  for (int j = lane; j < nvec; j += 32) mine[j] = 0.0;
+  __syncwarp();
+  const long long ntiles = (n + DOT_TILE - 1) / DOT_TILE;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long k0 = tile * DOT_TILE + (long long)threadIdx.x * 2;
+    const long long k1 = k0 + DOT_TILE / 2;
+    double2 va = make_double2(0.0, 0.0), vb = make_double2(0.0, 0.0);
+    const bool fa = k0 + 1 < n, fb = k1 + 1 < n;
+    if (fa) va = *reinterpret_cast<const double2*>(v + k0);
+    else if (k0 < n) va.x = v[k0];
+    if (fb) vb = *reinterpret_cast<const double2*>(v + k1);
+    else if (k1 < n) vb.x = v[k1];
+    for (int j = 0; j < nvec; j++) {
+      const double* u = ubase + (long long)j * stride;
+      double2 ua = make_double2(0.0, 0.0), ub = make_double2(0.0, 0.0);
+      if (fa) ua = *reinterpret_cast<const double2*>(u + k0);
+      else if (k0 < n) ua.x = u[k0];
+      if (fb) ub = *reinterpret_cast<const double2*>(u + k1);
+      else if (k1 < n) ub.x = u[k1];
+      double s = va.x * ua.x + va.y * ua.y + vb.x * ub.x + vb.y * ub.y;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) mine[j] += s;
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < nvec; j += DOT_THREADS) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < DOT_THREADS / 32; w++) s += sm[(size_t)w * nvec + j];
+    part[(size_t)blockIdx.x * nvec + j] = s;
+  }
+}
+
+__global__ void multi_dot_stage2(int nblocks, int nvec, const double* __restrict__ part, double* __restrict__ out)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nvec) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; b++) s += part[(size_t)b * nvec + j];
+  out[j] = s;
+}
+
+int multi_dot(svb200_ctx* ctx, long long n, int nvec, const double* ubase, long long stride, const double* v, double* d_out)
+{
+  if (nvec <= 0) return SVB200_OK;
+  const long long ntiles = (n + DOT_TILE - 1) / DOT_TILE;
+  int blocks = (int)std::min<long long>(std::max<long long>(ntiles, 1), 148 * 4);
+  const size_t need = (size_t)blocks * nvec;
+  if (need > ctx->red_cap) {
+    if (ctx->d_red) cudaFree(ctx->d_red);
+    ctx->red_cap = need * 2;
+    SVB_CUDA(cudaMalloc(&ctx->d_red, sizeof(double) * ctx->red_cap));
+  }
+  const size_t smem = sizeof(double) * (DOT_THREADS / 32) * nvec;
+  multi_dot_stage1<<<blocks, DOT_THREADS, smem, ctx->stream>>>(n, nvec, ubase, stride, v, ctx->d_red);
+  multi_dot_stage2<<<(nvec + 127) / 128, 128, 0, ctx->stream>>>(blocks, nvec, ctx->d_red, d_out);
+  ctx->launches += 2;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// cgs_update: classical Gram-Schmidt sweep of gmres_v fused with the normalisation:
+//   v <- (v - sum_{j<=i} h_j u_j) / hn,   hn = sqrt|h_{i+1} - sum_j h_j^2|
+// h (i+2 doubles) is read from device memory (it may just have been all-reduced); every thread
+// recomputes hn with the reference's sequential order, thread 0 of block 0 stores it to h[i+1].
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cgs_update_kernel(long long n, int nprev, const double* __restrict__ ubase, long long stride, double* __restrict__ v,
+                  double* __restrict__ h, double* __restrict__ hn_out)
+{
+  extern __shared__ double hs[];   // nprev + 1
+  for (int j = threadIdx.x; j <= nprev; j += blockDim.x) hs[j] = h[j];
+  __syncthreads();
+  double hn = hs[nprev];
+  for (int j = 0; j < nprev; j++) hn = __dsub_rn(hn, __dmul_rn(hs[j], hs[j]));   // no FMA: host repeats this bit for bit
+  hn = sqrt(fabs(hn));
+  const double inv = 1.0 / hn;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *hn_out = hn;
+  const long long k0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (k0 >= n) return;
+  if (k0 + 1 < n) {
+    double2 x = *reinterpret_cast<double2*>(v + k0);
+    for (int j = 0; j < nprev; j++) {
+      const double2 u = *reinterpret_cast<const double2*>(ubase + (long long)j * stride + k0);
+      x.x -= hs[j] * u.x;
+      x.y -= hs[j] * u.y;
+    }
+    x.x *= inv;
+    x.y *= inv;
+    *reinterpret_cast<double2*>(v + k0) = x;
+  } else {
+    double x = v[k0];
+    for (int j = 0; j < nprev; j++) x -= hs[j] * ubase[(long long)j * stride + k0];
+    v[k0] = x * inv;
+  }
+}
+
+int cgs_update(svb200_ctx* ctx, long long n, int nprev, const double* ubase, long long stride, double* v, double* d_h,
+               double* d_hn)
+{
+  const long long threads = (n + 1) / 2;
+  cgs_update_kernel<<<(unsigned)((threads + 255) / 256), 256, sizeof(double) * (nprev + 1), ctx->stream>>>(
+      n, nprev, ubase, stride, v, d_h, d_hn);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
+// X += sum_{j<ny} y_j u_j with y passed by value (<= 256 coefficients).
+__global__ void __launch_bounds__(256)
+lincomb_kernel(long long n, int ny, const __grid_constant__ Coefs y, const double* __restrict__ ubase, long long stride,
+               double* __restrict__ X)
+{
+  const long long k0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (k0 >= n) return;
+  if (k0 + 1 < n) {
+    double2 x = *reinterpret_cast<double2*>(X + k0);
+    for (int j = 0; j < ny; j++) {
+      const double2 u = *reinterpret_cast<const double2*>(ubase + (long long)j * stride + k0);
+      x.x += y.c[j] * u.x;
+      x.y += y.c[j] * u.y;
+    }
+    *reinterpret_cast<double2*>(X + k0) = x;
+  } else {
+    double x = X[k0];
+    for (int j = 0; j < ny; j++) x += y.c[j] * ubase[(long long)j * stride + k0];
+    X[k0] = x;
+  }
+}
+
+int lincomb(svb200_ctx* ctx, long long n, int ny, const Coefs& y, const double* ubase, long long stride, double* X)
+{
+  if (ny <= 0) return SVB200_OK;
+  const long long threads = (n + 1) / 2;
+  lincomb_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(n, ny, y, ubase, stride, X);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
+// z = a*x + b*y (any of the pointers may alias); x or y may be null when its factor is zero.
+__global__ void __launch_bounds__(256)
+axpby_kernel(long long n, double a, const double* x, double b, const double* y, double* z)
+{
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  double r = 0.0;
+  if (x) r = a * x[k];
+  if (y) r += b * y[k];
+  z[k] = r;
+}
+
+int axpby(svb200_ctx* ctx, long long n, double a, const double* x, double b, const double* y, double* z)
+{
+  if (n == 0) return SVB200_OK;
+  axpby_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, a, x, b, y, z);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
+// z = x * y element-wise.
+__global__ void __launch_bounds__(256) hadamard_kernel(long long n, const double* x, const double* y, double* z)
+{
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) z[k] = x[k] * y[k];
+}
+
+int hadamard(svb200_ctx* ctx, long long n, const double* x, const double* y, double* z)
+{
+  if (n == 0) return SVB200_OK;
+  hadamard_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, x, y, z);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// precond_diag pieces.
+// ----------------------------------------------------------------------------------------------
+__global__ void diag_extract_kernel(int nNo, int dof, const int* __restrict__ diagPtr, const double* __restrict__ Val,
+                                    double* __restrict__ W)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)nNo * dof) return;
+  const int r = (int)(t / dof), i = (int)(t % dof);
+  W[t] = Val[(size_t)diagPtr[r] * dof * dof + i * dof + i];
+}
+
+__global__ void w_invsqrt_kernel(long long n, double* __restrict__ W)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  double w = W[t];
+  if (w == 0.0) w = 1.0;
+  W[t] = 1.0 / sqrt(fabs(w));
+}
+
+// W(i,glob(a)) *= val(i,a), i < nd  (Dirichlet faces, precond.cpp:177-198)
+__global__ void face_scale_w_kernel(int fnNo, int fdof, int nd, int dof, const int* __restrict__ glob,
+                                    const double* __restrict__ val, double* __restrict__ W)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= fnNo * nd) return;
+  const int a = t / nd, i = t % nd;
+  W[(size_t)glob[a] * dof + i] *= val[(size_t)a * fdof + i];
+}
+
+// valM(i,a) = val(i,a) * W(i,glob(a))  (coupled faces, precond.cpp:218-241)
+__global__ void face_valm_kernel(int fnNo, int fdof, int nd, int dof, const int* __restrict__ glob,
+                                 const double* __restrict__ val, const double* __restrict__ W, double* __restrict__ valM)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= fnNo * fdof) return;
+  const int a = t / fdof, i = t % fdof;
+  valM[t] = (i < nd) ? val[t] * W[(size_t)glob[a] * dof + i] : 0.0;
+}
+
+// Val(dof*i+j, k) = (Val * W(i,row)) * W(j,col(k)) — pre_mul then pos_mul in ONE pass (same rounding
+// sequence as the reference's two passes); one thread per matrix entry, coalesced over Val.
+__global__ void __launch_bounds__(256)
+scale_matrix_kernel(int nNo, int dof, const int* __restrict__ rowPtr, const int* __restrict__ colPtr,
+                    const double* __restrict__ W, double* __restrict__ Val)
+{
+  // one warp per row
+  const int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= nNo) return;
+  const int d2 = dof * dof;
+  const long long e0 = (long long)rowPtr[row] * d2, e1 = (long long)rowPtr[row + 1] * d2;
+  for (long long e = e0 + lane; e < e1; e += 32) {
+    const int k = (int)(e / d2), r = (int)(e % d2);
+    const int i = r / dof, j = r % dof;
+    const double wi = W[(size_t)row * dof + i];
+    const double wj = W[(size_t)colPtr[k] * dof + j];
+    Val[e] = (Val[e] * wi) * wj;
+  }
+}
+
+int precond_extract_diag(svb200_ctx* ctx, int dof, const double* Val, double* W)
+{
+  const long long n = (long long)ctx->nNo * dof;
+  if (n == 0) return SVB200_OK;
+  diag_extract_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->nNo, dof, ctx->d_diagPtr, Val, W);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
+int precond_invsqrt(svb200_ctx* ctx, int dof, double* W)
+{
+  const long long n = (long long)ctx->nNo * dof;
+  if (n == 0) return SVB200_OK;
+  w_invsqrt_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, W);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
+int precond_face_scale(svb200_ctx* ctx, const Face& f, int dof, double* W)
+{
+  const int nd = f.dof < dof ? f.dof : dof;
+  const int n = f.nNo * nd;
+  if (n == 0) return SVB200_OK;
+  face_scale_w_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(f.nNo, f.dof, nd, dof, f.d_glob, f.d_val, W);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
+int precond_face_valm(svb200_ctx* ctx, const Face& f, int dof, const double* W)
+{
+  const int nd = f.dof < dof ? f.dof : dof;
+  const int n = f.nNo * f.dof;
+  if (n == 0) return SVB200_OK;
+  face_valm_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(f.nNo, f.dof, nd, dof, f.d_glob, f.d_val, W, f.d_valM);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
+int precond_scale_matrix(svb200_ctx* ctx, int dof, const double* W, double* Val)
+{
+  if (ctx->nNo == 0) return SVB200_OK;
+  const long long threads = (long long)ctx->nNo * 32;
+  scale_matrix_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(ctx->nNo, dof, ctx->d_rowPtr, ctx->d_colPtr, W, Val);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// FP64 FMA peak (independent DFMA chains), for the roofline denominator of the assembly kernel.
+// ----------------------------------------------------------------------------------------------
+__global__ void fma_peak_kernel(double* out, int iters, double a, double b)
+{
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+int fp64_peak(svb200_ctx* ctx, double* tflops)
+{
+  int nsm = 0;
+  SVB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
+  const int blocks = nsm * 8, threads = 256, iters = 20000;
+  double* out = nullptr;
+  SVB_CUDA(cudaMalloc(&out, sizeof(double) * blocks * threads));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    SVB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    fma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(out, iters, 1.0000001, 1e-9);
+    ctx->launches++;
+    SVB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    SVB_CUDA(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    SVB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  SVB_CUDA(cudaFree(out));
+  *tflops = 2.0 * 8 * iters * (double)blocks * threads / (best * 1e-3) * 1e-12;
+  return SVB200_OK;
+}
+
+}  // namespace svb

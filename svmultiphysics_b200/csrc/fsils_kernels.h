@@ -1,0 +1,24 @@
+// fsils_kernels.h — launch wrappers of fsils_kernels.cu / comm.cu used by the solver drivers.
+#pragma once
+#include "svb200_internal.h"
+
+namespace svb {
+
+struct Coefs { double c[256]; };
+
+int multi_dot(svb200_ctx* ctx, long long n, int nvec, const double* ubase, long long stride, const double* v, double* d_out);
+int cgs_update(svb200_ctx* ctx, long long n, int nprev, const double* ubase, long long stride, double* v, double* d_h, double* d_hn);
+int lincomb(svb200_ctx* ctx, long long n, int ny, const Coefs& y, const double* ubase, long long stride, double* X);
+int axpby(svb200_ctx* ctx, long long n, double a, const double* x, double b, const double* y, double* z);
+int hadamard(svb200_ctx* ctx, long long n, const double* x, const double* y, double* z);
+int precond_extract_diag(svb200_ctx* ctx, int dof, const double* Val, double* W);
+int precond_invsqrt(svb200_ctx* ctx, int dof, double* W);
+int precond_face_scale(svb200_ctx* ctx, const Face& f, int dof, double* W);
+int precond_face_valm(svb200_ctx* ctx, const Face& f, int dof, const double* W);
+int precond_scale_matrix(svb200_ctx* ctx, int dof, const double* W, double* Val);
+
+// comm.cu: shared-node sums and scalar all-reduces (no-ops for a single partition)
+int halo_sum(svb200_ctx* ctx, int dof, double* V);
+int allreduce_sum(svb200_ctx* ctx, double* d_buf, int n);
+
+}  // namespace svb

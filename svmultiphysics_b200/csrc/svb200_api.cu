@@ -1,0 +1,734 @@
+// svb200_api.cu — the C ABI of include/svb200.h: host-side orchestration only, every number is
+// produced by the CUDA kernels of this library.  There is no CPU fallback anywhere in this file: when
+// no usable CUDA device exists svb200_create fails and nothing else can be called.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include "svb200_internal.h"
+#include "fsils_kernels.h"
+
+namespace svb {
+
+static thread_local std::string g_error;
+
+void set_error(const std::string& msg) { g_error = msg; }
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
+{
+  g_error = std::string("svb200: CUDA error '") + cudaGetErrorString(e) + "' in " + what + " (" + file + ":" +
+            std::to_string(line) + ")";
+  return SVB200_ERR_CUDA;
+}
+
+int nccl_unique_id(void* id128);
+int nccl_init(svb200_ctx* ctx, int nranks, int rank, const void* id128);
+void nccl_destroy(svb200_ctx* ctx);
+int add_bc_mul_device(svb200_ctx* ctx, int op, int dof, const double* X, double* Y, double* d_scal);
+
+template <class T>
+static int upload(svb200_ctx* ctx, T** d, const T* h, size_t n)
+{
+  if (*d) { cudaFree(*d); *d = nullptr; }
+  if (n == 0) return SVB200_OK;
+  SVB_CUDA(cudaMalloc(d, sizeof(T) * n));
+  SVB_CUDA(cudaMemcpyAsync(*d, h, sizeof(T) * n, cudaMemcpyHostToDevice, ctx->stream));
+  SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SVB200_OK;
+}
+
+static int ensure_stage(svb200_ctx* ctx, size_t bytes)
+{
+  if (bytes > ctx->stage_bytes) {
+    if (ctx->d_stage) cudaFree(ctx->d_stage);
+    ctx->d_stage = nullptr;
+    ctx->stage_bytes = 0;
+    SVB_CUDA(cudaMalloc(&ctx->d_stage, bytes));
+    ctx->stage_bytes = bytes;
+  }
+  return SVB200_OK;
+}
+
+// Host (rows, nNo) array in caller node order -> device array in internal order.
+static int upload_nodal(svb200_ctx* ctx, int rows, const double* h, double** d)
+{
+  const size_t n = (size_t)rows * ctx->nNo;
+  if (!*d) SVB_CUDA(cudaMalloc(d, sizeof(double) * std::max<size_t>(n, 1)));
+  if (n == 0) return SVB200_OK;
+  if (!ctx->has_map) {
+    SVB_CUDA(cudaMemcpyAsync(*d, h, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    int rc = ensure_stage(ctx, sizeof(double) * n);
+    if (rc) return rc;
+    SVB_CUDA(cudaMemcpyAsync(ctx->d_stage, h, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch_permute_cols(ctx, rows, ctx->nNo, ctx->d_map, ctx->d_stage, *d, false);
+    if (rc) return rc;
+  }
+  SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SVB200_OK;
+}
+
+static int download_nodal(svb200_ctx* ctx, int rows, const double* d, double* h)
+{
+  const size_t n = (size_t)rows * ctx->nNo;
+  if (n == 0) return SVB200_OK;
+  if (!ctx->has_map) {
+    SVB_CUDA(cudaMemcpyAsync(h, d, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  } else {
+    int rc = ensure_stage(ctx, sizeof(double) * n);
+    if (rc) return rc;
+    rc = launch_permute_cols(ctx, rows, ctx->nNo, ctx->d_map, d, ctx->d_stage, true);
+    if (rc) return rc;
+    SVB_CUDA(cudaMemcpyAsync(h, ctx->d_stage, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SVB200_OK;
+}
+
+static void free_mesh(Mesh& m)
+{
+  cudaFree(m.d_IEN); cudaFree(m.d_eId); cudaFree(m.d_fN); cudaFree(m.d_slot); cudaFree(m.d_color_perm);
+  m = Mesh();
+}
+
+static void free_face(Face& f)
+{
+  cudaFree(f.d_glob); cudaFree(f.d_val); cudaFree(f.d_valM);
+  f = Face();
+}
+
+// Greedy element colouring: two elements of one colour never share a node, so a colour can be
+// scattered with plain read-modify-write (deterministic mode).
+static int build_coloring(svb200_ctx* ctx, Mesh& m, const std::vector<int>& ien)
+{
+  std::vector<uint64_t> mask(ctx->nNo, 0), mask2(ctx->nNo, 0);   // 128 colours max
+  std::vector<int> color(m.nEl);
+  int ncol = 0;
+  for (int e = 0; e < m.nEl; e++) {
+    uint64_t u0 = 0, u1 = 0;
+    for (int a = 0; a < m.eNoN; a++) {
+      const int n = ien[(size_t)e * m.eNoN + a];
+      u0 |= mask[n];
+      u1 |= mask2[n];
+    }
+    int c;
+    if (~u0) c = __builtin_ctzll(~u0);
+    else if (~u1) c = 64 + __builtin_ctzll(~u1);
+    else {
+      set_error("svb200: more than 128 colours needed for the coloured scatter");
+      return SVB200_ERR_UNSUPPORTED;
+    }
+    color[e] = c;
+    ncol = std::max(ncol, c + 1);
+    for (int a = 0; a < m.eNoN; a++) {
+      const int n = ien[(size_t)e * m.eNoN + a];
+      if (c < 64) mask[n] |= (1ull << c);
+      else mask2[n] |= (1ull << (c - 64));
+    }
+  }
+  m.color_off.assign(ncol + 1, 0);
+  for (int e = 0; e < m.nEl; e++) m.color_off[color[e] + 1]++;
+  for (int c = 0; c < ncol; c++) m.color_off[c + 1] += m.color_off[c];
+  std::vector<int> pos(m.color_off.begin(), m.color_off.end() - 1), perm(m.nEl);
+  for (int e = 0; e < m.nEl; e++) perm[pos[color[e]]++] = e;
+  return upload(ctx, &m.d_color_perm, perm.data(), perm.size());
+}
+
+}  // namespace svb
+
+using namespace svb;
+
+#define CTX_GUARD(ctx)                                        \
+  do {                                                        \
+    if (!(ctx)) { set_error("svb200: null context"); return SVB200_ERR_INVALID; } \
+    cudaError_t e__ = cudaSetDevice((ctx)->device);           \
+    if (e__ != cudaSuccess) return cuda_fail(e__, "cudaSetDevice", __FILE__, __LINE__); \
+  } while (0)
+
+#define TRY(call)                      \
+  do {                                 \
+    int rc__ = (call);                 \
+    if (rc__ != SVB200_OK) return rc__; \
+  } while (0)
+
+extern "C" {
+
+int svb200_abi_version(void) { return SVB200_ABI_VERSION; }
+
+const char* svb200_last_error(void) { return g_error.c_str(); }
+
+int svb200_create(svb200_ctx** out, int device)
+{
+  if (!out) { set_error("svb200_create: null output pointer"); return SVB200_ERR_INVALID; }
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_error(std::string("svb200_create: no usable CUDA device (") + cudaGetErrorString(e) +
+              "); this library has no CPU path");
+    return SVB200_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) { set_error("svb200_create: bad device index"); return SVB200_ERR_INVALID; }
+  SVB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SVB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    set_error(std::string("svb200_create: device '") + prop.name + "' is not a Blackwell (sm_100a) GPU");
+    return SVB200_ERR_UNSUPPORTED;
+  }
+  auto* ctx = new svb200_ctx();
+  ctx->device = device;
+  SVB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  SVB_CUDA(cudaEventCreate(&ctx->ev0));
+  SVB_CUDA(cudaEventCreate(&ctx->ev1));
+  SVB_CUDA(cudaMallocHost(&ctx->h_pinned, sizeof(double) * 1024));
+  *out = ctx;
+  return SVB200_OK;
+}
+
+int svb200_destroy(svb200_ctx* ctx)
+{
+  if (!ctx) return SVB200_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  nccl_destroy(ctx);
+  for (auto& m : ctx->mesh) free_mesh(m);
+  for (auto& f : ctx->face) free_face(f);
+  for (auto& nb : ctx->neigh) { cudaFree(nb.d_ptr); cudaFree(nb.d_send); cudaFree(nb.d_recv); }
+  cudaFree(ctx->d_map); cudaFree(ctx->d_rowPtr); cudaFree(ctx->d_colPtr); cudaFree(ctx->d_diagPtr);
+  cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf);
+  cudaFree(ctx->d_stage); cudaFree(ctx->d_R); cudaFree(ctx->d_Val); cudaFree(ctx->d_W);
+  cudaFree(ctx->d_work); cudaFree(ctx->d_red);
+  cudaFreeHost(ctx->h_pinned);
+  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return SVB200_OK;
+}
+
+int svb200_comm_unique_id(void* id128)
+{
+  if (!id128) { set_error("svb200_comm_unique_id: null buffer"); return SVB200_ERR_INVALID; }
+  return nccl_unique_id(id128);
+}
+
+int svb200_comm_init(svb200_ctx* ctx, int nranks, int rank, const void* id128)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks && id128, "svb200_comm_init: bad arguments");
+  return nccl_init(ctx, nranks, rank, id128);
+}
+
+int svb200_set_graph(svb200_ctx* ctx, int32_t nNo, int32_t nnz, const int32_t* rowPtr, const int32_t* colPtr,
+                     int32_t mynNo, const int32_t* map, int32_t nReq, const int32_t* neigh_rank,
+                     const int32_t* neigh_n, const int32_t* neigh_ptr)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(nNo >= 0 && nnz >= 0 && rowPtr && (colPtr || nnz == 0), "svb200_set_graph: bad arguments");
+  SVB_REQUIRE(rowPtr[0] == 0 && rowPtr[nNo] == nnz, "svb200_set_graph: rowPtr does not span [0,nnz]");
+  SVB_REQUIRE(mynNo >= 0 && mynNo <= nNo, "svb200_set_graph: mynNo out of range");
+  ctx->nNo = nNo;
+  ctx->nnz = nnz;
+  ctx->mynNo = mynNo;
+  ctx->has_map = (map != nullptr);
+  ctx->h_rowPtr_in.assign(rowPtr, rowPtr + nNo + 1);
+  ctx->h_map.resize(nNo);
+  if (map) {
+    std::vector<char> seen(nNo, 0);
+    for (int a = 0; a < nNo; a++) {
+      SVB_REQUIRE(map[a] >= 0 && map[a] < nNo && !seen[map[a]], "svb200_set_graph: map is not a permutation");
+      seen[map[a]] = 1;
+      ctx->h_map[a] = map[a];
+    }
+  } else {
+    std::iota(ctx->h_map.begin(), ctx->h_map.end(), 0);
+  }
+  // internal CSR: rows in FSILS order, columns of a row kept in caller order
+  std::vector<int> len(nNo);
+  for (int a = 0; a < nNo; a++) {
+    SVB_REQUIRE(rowPtr[a + 1] >= rowPtr[a], "svb200_set_graph: rowPtr is not monotone");
+    len[ctx->h_map[a]] = rowPtr[a + 1] - rowPtr[a];
+  }
+  ctx->h_rowPtr.assign(nNo + 1, 0);
+  for (int r = 0; r < nNo; r++) ctx->h_rowPtr[r + 1] = ctx->h_rowPtr[r] + len[r];
+  std::vector<int> col(nnz);
+  for (int a = 0; a < nNo; a++) {
+    const int base = ctx->h_rowPtr[ctx->h_map[a]];
+    for (int k = rowPtr[a]; k < rowPtr[a + 1]; k++) {
+      SVB_REQUIRE(colPtr[k] >= 0 && colPtr[k] < nNo, "svb200_set_graph: column index out of range");
+      col[base + (k - rowPtr[a])] = ctx->h_map[colPtr[k]];
+    }
+  }
+  TRY(upload(ctx, &ctx->d_rowPtr, ctx->h_rowPtr.data(), (size_t)nNo + 1));
+  TRY(upload(ctx, &ctx->d_colPtr, col.data(), (size_t)nnz));
+  TRY(upload(ctx, &ctx->d_map, ctx->h_map.data(), (size_t)nNo));
+  if (ctx->d_diagPtr) { cudaFree(ctx->d_diagPtr); ctx->d_diagPtr = nullptr; }
+  SVB_CUDA(cudaMalloc(&ctx->d_diagPtr, sizeof(int) * std::max(nNo, 1)));
+  if (nNo > 0) TRY(launch_find_diag(ctx));
+
+  for (auto& nb : ctx->neigh) { cudaFree(nb.d_ptr); cudaFree(nb.d_send); cudaFree(nb.d_recv); }
+  ctx->neigh.clear();
+  size_t off = 0;
+  for (int i = 0; i < nReq; i++) {
+    SVB_REQUIRE(neigh_rank && neigh_n && neigh_ptr, "svb200_set_graph: neighbour lists missing");
+    Neighbor nb;
+    nb.rank = neigh_rank[i];
+    nb.n = neigh_n[i];
+    for (int k = 0; k < nb.n; k++)
+      SVB_REQUIRE(neigh_ptr[off + k] >= 0 && neigh_ptr[off + k] < nNo, "svb200_set_graph: shared node id out of range");
+    TRY(upload(ctx, &nb.d_ptr, neigh_ptr + off, (size_t)nb.n));
+    SVB_CUDA(cudaMalloc(&nb.d_send, sizeof(double) * 4 * std::max(nb.n, 1)));
+    SVB_CUDA(cudaMalloc(&nb.d_recv, sizeof(double) * 4 * std::max(nb.n, 1)));
+    off += nb.n;
+    ctx->neigh.push_back(nb);
+  }
+  std::sort(ctx->neigh.begin(), ctx->neigh.end(), [](const Neighbor& a, const Neighbor& b) { return a.rank < b.rank; });
+  // state arrays depend on nNo
+  cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf);
+  ctx->d_x = ctx->d_Ag = ctx->d_Yg = ctx->d_Dg = ctx->d_Bf = nullptr;
+  ctx->tDof = 0;
+  return SVB200_OK;
+}
+
+int svb200_set_mesh(svb200_ctx* ctx, int32_t iM, int32_t eNoN, int32_t nEl, const int32_t* IEN, const int32_t* eId,
+                    int32_t nFn, const double* fN, int32_t nG, const double* w, const double* N, const double* Nx)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(ctx->d_rowPtr, "svb200_set_mesh: call svb200_set_graph first");
+  SVB_REQUIRE(iM >= 0 && iM < 64, "svb200_set_mesh: bad mesh index");
+  SVB_REQUIRE(eNoN >= 1 && eNoN <= MAX_ENON && nG >= 1 && nG <= MAX_NG, "svb200_set_mesh: unsupported eNoN / nG");
+  SVB_REQUIRE(nEl >= 0 && (IEN || nEl == 0) && w && N && Nx, "svb200_set_mesh: bad arguments");
+  if ((int)ctx->mesh.size() <= iM) ctx->mesh.resize(iM + 1);
+  Mesh& m = ctx->mesh[iM];
+  free_mesh(m);
+  m.eNoN = eNoN; m.nEl = nEl; m.nG = nG; m.nFn = nFn;
+  std::vector<int> ien((size_t)eNoN * nEl);
+  for (size_t k = 0; k < ien.size(); k++) {
+    SVB_REQUIRE(IEN[k] >= 0 && IEN[k] < ctx->nNo, "svb200_set_mesh: IEN entry out of range");
+    ien[k] = ctx->h_map[IEN[k]];
+  }
+  TRY(upload(ctx, &m.d_IEN, ien.data(), ien.size()));
+  if (eId) TRY(upload(ctx, &m.d_eId, eId, (size_t)nEl));
+  if (fN && nFn > 0) TRY(upload(ctx, &m.d_fN, fN, (size_t)3 * nFn * nEl));
+  m.w.assign(w, w + nG);
+  m.N.assign(N, N + (size_t)eNoN * nG);
+  m.Nx.assign(Nx, Nx + (size_t)3 * eNoN * nG);
+  TRY(launch_build_slot_map(ctx, m));
+  TRY(build_coloring(ctx, m, ien));
+  m.set = true;
+  return SVB200_OK;
+}
+
+int svb200_set_coords(svb200_ctx* ctx, const double* x)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(ctx->d_rowPtr && x, "svb200_set_coords: call svb200_set_graph first");
+  return upload_nodal(ctx, 3, x, &ctx->d_x);
+}
+
+int svb200_set_num_faces(svb200_ctx* ctx, int32_t nFaces)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(nFaces >= 0, "svb200_set_num_faces: negative count");
+  for (auto& f : ctx->face) free_face(f);
+  ctx->face.assign(nFaces, Face());
+  return SVB200_OK;
+}
+
+int svb200_set_face(svb200_ctx* ctx, int32_t faIn, int32_t bGrp, int32_t face_dof, int32_t nNo, const int32_t* glob,
+                    const double* val, int32_t sharedFlag)
+{
+  CTX_GUARD(ctx);
+  // same messages as fsils_bc_create (linear_solver/bc.cpp:25-32)
+  if (faIn >= (int)ctx->face.size()) {
+    set_error("FSILS: faIn is exceeding lhs structure maximum number of faces (" + std::to_string(ctx->face.size()) +
+              ") is less than " + std::to_string(faIn) + ".");
+    return SVB200_ERR_INVALID;
+  }
+  if (faIn <= -1) { set_error("FSILS: faIn is smaller than zero"); return SVB200_ERR_INVALID; }
+  SVB_REQUIRE(face_dof >= 1 && face_dof <= 4 && nNo >= 0 && (glob || nNo == 0), "svb200_set_face: bad arguments");
+  Face& f = ctx->face[faIn];
+  free_face(f);
+  f.bGrp = bGrp; f.dof = face_dof; f.nNo = nNo; f.shared = sharedFlag;
+  std::vector<int> g(nNo);
+  for (int a = 0; a < nNo; a++) {
+    SVB_REQUIRE(glob[a] >= 0 && glob[a] < ctx->nNo, "svb200_set_face: node id out of range");
+    g[a] = ctx->h_map[glob[a]];
+  }
+  std::vector<double> v((size_t)face_dof * nNo, 0.0);
+  if (val) std::copy(val, val + v.size(), v.begin());
+  TRY(upload(ctx, &f.d_glob, g.data(), g.size()));
+  TRY(upload(ctx, &f.d_val, v.data(), v.size()));
+  if (!v.empty()) {
+    SVB_CUDA(cudaMalloc(&f.d_valM, sizeof(double) * v.size()));
+    SVB_CUDA(cudaMemsetAsync(f.d_valM, 0, sizeof(double) * v.size(), ctx->stream));
+  }
+  if (sharedFlag && ctx->nranks > 1 && val) {
+    // fsils_bc_create sums the face values of shared nodes across partitions (bc.cpp:70-102).
+    const size_t n = (size_t)face_dof * ctx->nNo;
+    TRY(ensure_stage(ctx, sizeof(double) * n));
+    SVB_CUDA(cudaMemsetAsync(ctx->d_stage, 0, sizeof(double) * n, ctx->stream));
+    std::vector<double> full(n, 0.0);
+    for (int a = 0; a < nNo; a++)
+      for (int i = 0; i < face_dof; i++) full[(size_t)g[a] * face_dof + i] = v[(size_t)a * face_dof + i];
+    SVB_CUDA(cudaMemcpyAsync(ctx->d_stage, full.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(halo_sum(ctx, face_dof, ctx->d_stage));
+    SVB_CUDA(cudaMemcpyAsync(full.data(), ctx->d_stage, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int a = 0; a < nNo; a++)
+      for (int i = 0; i < face_dof; i++) v[(size_t)a * face_dof + i] = full[(size_t)g[a] * face_dof + i];
+    SVB_CUDA(cudaMemcpyAsync(f.d_val, v.data(), sizeof(double) * v.size(), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  f.set = true;
+  return SVB200_OK;
+}
+
+int svb200_alloc(svb200_ctx* ctx, int32_t dof)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(ctx->d_rowPtr, "svb200_alloc: call svb200_set_graph first");
+  SVB_REQUIRE(dof >= 1 && dof <= 4, "svb200_alloc: dof must be in [1,4]");
+  const size_t nR = (size_t)dof * ctx->nNo, nV = (size_t)dof * dof * ctx->nnz;
+  if (nR > ctx->R_cap) {
+    cudaFree(ctx->d_R); ctx->d_R = nullptr;
+    SVB_CUDA(cudaMalloc(&ctx->d_R, sizeof(double) * std::max<size_t>(nR, 1)));
+    ctx->R_cap = nR;
+  }
+  if (nV > ctx->Val_cap) {
+    cudaFree(ctx->d_Val); ctx->d_Val = nullptr;
+    SVB_CUDA(cudaMalloc(&ctx->d_Val, sizeof(double) * std::max<size_t>(nV, 1)));
+    ctx->Val_cap = nV;
+  }
+  ctx->dof = dof;
+  if (nR) SVB_CUDA(cudaMemsetAsync(ctx->d_R, 0, sizeof(double) * nR, ctx->stream));
+  if (nV) SVB_CUDA(cudaMemsetAsync(ctx->d_Val, 0, sizeof(double) * nV, ctx->stream));
+  return SVB200_OK;
+}
+
+int svb200_set_state(svb200_ctx* ctx, int32_t tDof, const double* Ag, const double* Yg, const double* Dg,
+                     const double* Bf)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(ctx->d_rowPtr, "svb200_set_state: call svb200_set_graph first");
+  SVB_REQUIRE(tDof >= 1 && tDof <= 16, "svb200_set_state: bad tDof");
+  if (tDof != ctx->tDof) {
+    cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg);
+    ctx->d_Ag = ctx->d_Yg = ctx->d_Dg = nullptr;
+    ctx->tDof = tDof;
+  }
+  const size_t n = (size_t)tDof * ctx->nNo;
+  auto zero_if_new = [&](double** d, size_t cnt) -> int {
+    if (!*d) {
+      SVB_CUDA(cudaMalloc(d, sizeof(double) * std::max<size_t>(cnt, 1)));
+      SVB_CUDA(cudaMemsetAsync(*d, 0, sizeof(double) * cnt, ctx->stream));
+    }
+    return SVB200_OK;
+  };
+  TRY(zero_if_new(&ctx->d_Ag, n));
+  TRY(zero_if_new(&ctx->d_Yg, n));
+  TRY(zero_if_new(&ctx->d_Dg, n));
+  TRY(zero_if_new(&ctx->d_Bf, (size_t)3 * ctx->nNo));
+  if (Ag) TRY(upload_nodal(ctx, tDof, Ag, &ctx->d_Ag));
+  if (Yg) TRY(upload_nodal(ctx, tDof, Yg, &ctx->d_Yg));
+  if (Dg) TRY(upload_nodal(ctx, tDof, Dg, &ctx->d_Dg));
+  if (Bf) TRY(upload_nodal(ctx, 3, Bf, &ctx->d_Bf));
+  return SVB200_OK;
+}
+
+static int fill_fluid_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn,
+                           int nDmn, FluidArgs& A)
+{
+  SVB_REQUIRE(nDmn >= 1 && nDmn <= MAX_DMN, "svb200_assemble: between 1 and 8 domains are supported");
+  SVB_REQUIRE(eq->dof == 4 && ctx->dof == 4, "svb200_assemble: the fluid equation has dof = 4 (call svb200_alloc(4))");
+  SVB_REQUIRE(eq->vmsStab == 1, "svb200_assemble: only VMS-stabilised equal-order elements are supported");
+  SVB_REQUIRE(eq->tDof == ctx->tDof && ctx->d_Yg, "svb200_assemble: state not set (svb200_set_state) or tDof mismatch");
+  SVB_REQUIRE(!eq->mvMsh || eq->tDof >= 7, "svb200_assemble: mvMsh needs the mesh velocity in state dofs 4..6");
+  SVB_REQUIRE(ctx->d_x, "svb200_assemble: coordinates not set");
+  memset(&A, 0, sizeof(A));
+  A.IEN = m.d_IEN; A.eId = m.d_eId; A.slot = m.d_slot; A.perm = nullptr;
+  A.x = ctx->d_x; A.Ag = ctx->d_Ag; A.Yg = ctx->d_Yg; A.Bf = ctx->d_Bf;
+  A.R = ctx->d_R; A.Val = ctx->d_Val;
+  A.e0 = 0; A.e1 = m.nEl;
+  A.tDof = eq->tDof; A.mvMsh = eq->mvMsh; A.nDmn = nDmn;
+  A.atomic = (eq->scatter == SVB200_SCATTER_ATOMIC);
+  A.dt = eq->dt; A.af = eq->af; A.am = eq->am; A.gam = eq->gam;
+  for (int g = 0; g < m.nG; g++) {
+    A.w[g] = m.w[g];
+    for (int a = 0; a < m.eNoN; a++) {
+      A.N[g][a] = m.N[(size_t)g * m.eNoN + a];
+      for (int k = 0; k < 3; k++) A.Nxi[g][a][k] = m.Nx[((size_t)g * m.eNoN + a) * 3 + k];
+    }
+  }
+  bool needEId = false;
+  for (int d = 0; d < nDmn; d++) {
+    FluidDmn& o = A.dmn[d];
+    o.rho = dmn[d].rho;
+    for (int k = 0; k < 3; k++) o.f[k] = dmn[d].f[k];
+    o.Kd = dmn[d].K_darcy;
+    o.mu_i = dmn[d].mu_i; o.mu_o = dmn[d].mu_o; o.lam = dmn[d].lam; o.a = dmn[d].a; o.n = dmn[d].n;
+    o.viscType = dmn[d].viscType;
+    o.Id = dmn[d].Id;
+    o.isFluid = (dmn[d].phys == SVB200_PHYS_FLUID);
+    if (o.Id != -1) needEId = true;
+    SVB_REQUIRE(o.Id >= -1 && o.Id < 31, "svb200_assemble: domain Id out of range");
+    if (o.Id == -1) break;
+  }
+  // all_fun::domain throws "eId is not allocated" when no domain covers the whole mesh (all_fun.cpp:137-139)
+  if (needEId && A.dmn[0].Id != -1) {
+    bool whole = false;
+    for (int d = 0; d < nDmn; d++) whole |= (dmn[d].Id == -1);
+    if (!whole && !m.d_eId) { set_error("eId is not allocated"); return SVB200_ERR_INVALID; }
+  }
+  return SVB200_OK;
+}
+
+static int run_assemble(svb200_ctx* ctx, const Mesh& m, FluidArgs& A)
+{
+  if (A.atomic) return launch_assemble_fluid(ctx, m, A);
+  A.perm = m.d_color_perm;
+  for (size_t c = 0; c + 1 < m.color_off.size(); c++) {
+    A.e0 = m.color_off[c];
+    A.e1 = m.color_off[c + 1];
+    TRY(launch_assemble_fluid(ctx, m, A));
+  }
+  return SVB200_OK;
+}
+
+int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int32_t nDmn)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(eq && dmn, "svb200_assemble: null parameters");
+  SVB_REQUIRE(iM >= 0 && iM < (int)ctx->mesh.size() && ctx->mesh[iM].set, "svb200_assemble: mesh not set");
+  SVB_REQUIRE(ctx->d_R && ctx->d_Val, "svb200_assemble: call svb200_alloc first");
+  const Mesh& m = ctx->mesh[iM];
+  if (eq->phys != SVB200_PHYS_FLUID) {
+    set_error("svb200_assemble: only the fluid equation is implemented in this build");
+    return SVB200_ERR_UNSUPPORTED;
+  }
+  FluidArgs A;
+  TRY(fill_fluid_args(ctx, m, eq, dmn, nDmn, A));
+  SVB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  TRY(run_assemble(ctx, m, A));
+  SVB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  SVB_CUDA(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f;
+  SVB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  ctx->last_assemble_ms = ms;
+  return SVB200_OK;
+}
+
+__global__ void add_rows_kernel(int n, int dof, const int* __restrict__ rows, const double* __restrict__ add,
+                                double* __restrict__ dst)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * dof) return;
+  atomicAdd(dst + (size_t)rows[t / dof] * dof + t % dof, add[t]);
+}
+
+int svb200_add_host_contrib(svb200_ctx* ctx, int32_t dof, int32_t nR, const int32_t* rows, const double* R_add,
+                            int32_t nK, const int32_t* krows, const int32_t* kcols, const double* K_add)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(dof == ctx->dof && ctx->d_R && ctx->d_Val, "svb200_add_host_contrib: call svb200_alloc(dof) first");
+  if (nR > 0) {
+    SVB_REQUIRE(rows && R_add, "svb200_add_host_contrib: null residual arrays");
+    std::vector<int> r(nR);
+    for (int k = 0; k < nR; k++) {
+      SVB_REQUIRE(rows[k] >= 0 && rows[k] < ctx->nNo, "svb200_add_host_contrib: row out of range");
+      r[k] = ctx->h_map[rows[k]];
+    }
+    int* d_r = nullptr; double* d_a = nullptr;
+    TRY(upload(ctx, &d_r, r.data(), r.size()));
+    TRY(upload(ctx, &d_a, R_add, (size_t)nR * dof));
+    add_rows_kernel<<<(nR * dof + 255) / 256, 256, 0, ctx->stream>>>(nR, dof, d_r, d_a, ctx->d_R);
+    ctx->launches++;
+    SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_r); cudaFree(d_a);
+  }
+  if (nK > 0) {
+    SVB_REQUIRE(krows && kcols && K_add, "svb200_add_host_contrib: null tangent arrays");
+    std::vector<int> col(ctx->nnz);
+    SVB_CUDA(cudaMemcpy(col.data(), ctx->d_colPtr, sizeof(int) * ctx->nnz, cudaMemcpyDeviceToHost));
+    std::vector<int> s(nK);
+    for (int k = 0; k < nK; k++) {
+      SVB_REQUIRE(krows[k] >= 0 && krows[k] < ctx->nNo && kcols[k] >= 0 && kcols[k] < ctx->nNo,
+                  "svb200_add_host_contrib: index out of range");
+      const int r = ctx->h_map[krows[k]], c = ctx->h_map[kcols[k]];
+      int slot = -1;
+      for (int q = ctx->h_rowPtr[r]; q < ctx->h_rowPtr[r + 1]; q++)
+        if (col[q] == c) { slot = q; break; }
+      SVB_REQUIRE(slot >= 0, "svb200_add_host_contrib: (row,col) pair is not in the CSR graph");
+      s[k] = slot;
+    }
+    int* d_s = nullptr; double* d_a = nullptr;
+    TRY(upload(ctx, &d_s, s.data(), s.size()));
+    TRY(upload(ctx, &d_a, K_add, (size_t)nK * dof * dof));
+    add_rows_kernel<<<(nK * dof * dof + 255) / 256, 256, 0, ctx->stream>>>(nK, dof * dof, d_s, d_a, ctx->d_Val);
+    ctx->launches++;
+    SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_s); cudaFree(d_a);
+  }
+  return SVB200_OK;
+}
+
+int svb200_commu_R(svb200_ctx* ctx)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(ctx->d_R, "svb200_commu_R: call svb200_alloc first");
+  return halo_sum(ctx, ctx->dof, ctx->d_R);
+}
+
+int svb200_solve(svb200_ctx* ctx, int32_t dof, int32_t ls_type, int32_t prec, const svb200_lsparams* ls,
+                 int32_t nFaces, const int32_t* incL, const double* res, double* R_out, svb200_lsresult* result)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(ls, "svb200_solve: null solver parameters");
+  SVB_REQUIRE(dof == ctx->dof && ctx->d_R && ctx->d_Val, "svb200_solve: call svb200_alloc(dof) and assemble first");
+  SVB_REQUIRE(prec == SVB200_PREC_FSILS, "svb200_solve: only the FSILS diagonal preconditioner is implemented");
+  SVB_REQUIRE(nFaces <= (int)ctx->face.size(), "svb200_solve: nFaces exceeds svb200_set_num_faces");
+  SVB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  TRY(fsils_solve_device(ctx, dof, ls_type, ls, nFaces, incL, res, result));
+  SVB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  SVB_CUDA(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f;
+  SVB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  ctx->last_solve_ms = ms;
+  if (R_out) TRY(download_nodal(ctx, dof, ctx->d_R, R_out));
+  return SVB200_OK;
+}
+
+// Val is returned in the caller's CSR slot order: caller row a occupies internal row map[a].
+static int copy_val(svb200_ctx* ctx, int dof, double* host, bool to_host)
+{
+  const size_t d2 = (size_t)dof * dof;
+  if (!ctx->has_map) {
+    if (to_host)
+      SVB_CUDA(cudaMemcpyAsync(host, ctx->d_Val, sizeof(double) * d2 * ctx->nnz, cudaMemcpyDeviceToHost, ctx->stream));
+    else
+      SVB_CUDA(cudaMemcpyAsync(ctx->d_Val, host, sizeof(double) * d2 * ctx->nnz, cudaMemcpyHostToDevice, ctx->stream));
+    SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SVB200_OK;
+  }
+  for (int a = 0; a < ctx->nNo; a++) {
+    const size_t len = (size_t)(ctx->h_rowPtr_in[a + 1] - ctx->h_rowPtr_in[a]) * d2;
+    double* h = host + (size_t)ctx->h_rowPtr_in[a] * d2;
+    double* d = ctx->d_Val + (size_t)ctx->h_rowPtr[ctx->h_map[a]] * d2;
+    if (to_host) SVB_CUDA(cudaMemcpyAsync(h, d, sizeof(double) * len, cudaMemcpyDeviceToHost, ctx->stream));
+    else SVB_CUDA(cudaMemcpyAsync(d, h, sizeof(double) * len, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SVB200_OK;
+}
+
+int svb200_download(svb200_ctx* ctx, int32_t what, double* dst)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(dst, "svb200_download: null destination");
+  switch (what) {
+    case SVB200_ARRAY_R:
+      SVB_REQUIRE(ctx->d_R, "svb200_download: R not allocated");
+      return download_nodal(ctx, ctx->dof, ctx->d_R, dst);
+    case SVB200_ARRAY_VAL:
+      SVB_REQUIRE(ctx->d_Val, "svb200_download: Val not allocated");
+      return copy_val(ctx, ctx->dof, dst, true);
+    case SVB200_ARRAY_W:
+      SVB_REQUIRE(ctx->d_W, "svb200_download: W not computed yet");
+      return download_nodal(ctx, ctx->dof, ctx->d_W, dst);
+  }
+  set_error("svb200_download: unknown array id");
+  return SVB200_ERR_INVALID;
+}
+
+int svb200_upload(svb200_ctx* ctx, int32_t what, int32_t dof, const double* src)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(src, "svb200_upload: null source");
+  SVB_REQUIRE(dof == ctx->dof && ctx->d_R && ctx->d_Val, "svb200_upload: call svb200_alloc(dof) first");
+  switch (what) {
+    case SVB200_ARRAY_R: return upload_nodal(ctx, dof, src, &ctx->d_R);
+    case SVB200_ARRAY_VAL: return copy_val(ctx, dof, const_cast<double*>(src), false);
+  }
+  set_error("svb200_upload: unknown array id");
+  return SVB200_ERR_INVALID;
+}
+
+int svb200_spmv(svb200_ctx* ctx, int32_t dof, const double* U, double* KU)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(U && KU, "svb200_spmv: null vectors");
+  SVB_REQUIRE(dof == ctx->dof && ctx->d_Val, "svb200_spmv: call svb200_alloc(dof) first");
+  const size_t n = (size_t)dof * ctx->nNo;
+  double* d_u = nullptr; double* d_ku = nullptr;
+  SVB_CUDA(cudaMalloc(&d_u, sizeof(double) * std::max<size_t>(n, 1)));
+  SVB_CUDA(cudaMalloc(&d_ku, sizeof(double) * std::max<size_t>(n, 1)));
+  int rc = upload_nodal(ctx, dof, U, &d_u);
+  if (!rc) rc = launch_spmv(ctx, dof, ctx->d_Val, d_u, d_ku);
+  if (!rc) rc = halo_sum(ctx, dof, d_ku);
+  if (!rc) rc = download_nodal(ctx, dof, d_ku, KU);
+  cudaFree(d_u); cudaFree(d_ku);
+  return rc;
+}
+
+int svb200_last_timing(svb200_ctx* ctx, double* assemble_ms, double* solve_ms)
+{
+  if (!ctx) { set_error("svb200: null context"); return SVB200_ERR_INVALID; }
+  if (assemble_ms) *assemble_ms = ctx->last_assemble_ms;
+  if (solve_ms) *solve_ms = ctx->last_solve_ms;
+  return SVB200_OK;
+}
+
+int svb200_bench_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, const svb200_dmnparams* dmn,
+                          int32_t nDmn, int32_t reps, double* ms_per_launch)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(eq && dmn && ms_per_launch && reps >= 1, "svb200_bench_assemble: bad arguments");
+  SVB_REQUIRE(iM >= 0 && iM < (int)ctx->mesh.size() && ctx->mesh[iM].set, "svb200_bench_assemble: mesh not set");
+  SVB_REQUIRE(ctx->d_R && ctx->d_Val, "svb200_bench_assemble: call svb200_alloc first");
+  const Mesh& m = ctx->mesh[iM];
+  FluidArgs A;
+  TRY(fill_fluid_args(ctx, m, eq, dmn, nDmn, A));
+  SVB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  for (int r = 0; r < reps; r++) {
+    FluidArgs B = A;
+    TRY(run_assemble(ctx, m, B));
+  }
+  SVB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  SVB_CUDA(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f;
+  SVB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *ms_per_launch = ms / reps;
+  return SVB200_OK;
+}
+
+int svb200_bench_spmv(svb200_ctx* ctx, int32_t dof, int32_t reps, double* ms_per_launch)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(ms_per_launch && reps >= 1, "svb200_bench_spmv: bad arguments");
+  SVB_REQUIRE(dof == ctx->dof && ctx->d_Val, "svb200_bench_spmv: call svb200_alloc(dof) first");
+  const size_t n = (size_t)dof * ctx->nNo;
+  double* d_u = nullptr; double* d_ku = nullptr;
+  SVB_CUDA(cudaMalloc(&d_u, sizeof(double) * std::max<size_t>(n, 1)));
+  SVB_CUDA(cudaMalloc(&d_ku, sizeof(double) * std::max<size_t>(n, 1)));
+  SVB_CUDA(cudaMemsetAsync(d_u, 0, sizeof(double) * n, ctx->stream));
+  int rc = launch_spmv(ctx, dof, ctx->d_Val, d_u, d_ku);   // warm-up
+  SVB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  for (int r = 0; r < reps && !rc; r++) rc = launch_spmv(ctx, dof, ctx->d_Val, d_u, d_ku);
+  SVB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  SVB_CUDA(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f;
+  SVB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *ms_per_launch = ms / reps;
+  cudaFree(d_u); cudaFree(d_ku);
+  return rc;
+}
+
+int svb200_measure_fp64_peak(svb200_ctx* ctx, double* tflops)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(tflops, "svb200_measure_fp64_peak: null output");
+  return fp64_peak(ctx, tflops);
+}
+
+int64_t svb200_launch_count(svb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -133,6 +133,12 @@ struct svb200_ctx {
   std::vector<svb::Neighbor> neigh;
 
   double last_assemble_ms = 0.0, last_solve_ms = 0.0;
+
+  // lhsa scratch (svb200_lhsa_*)
+  int lhsa_nNo = 0;
+  unsigned long long* d_lhsa_keys = nullptr;
+  size_t lhsa_n = 0, lhsa_cap = 0;
+  std::vector<int> lhsa_rowPtr, lhsa_colPtr;
 };
 
 namespace svb {

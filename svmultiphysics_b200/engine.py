@@ -1,0 +1,272 @@
+"""ctypes host layer over the C ABI (include/svb200.h -> lib/libsvb200.so).
+
+``Engine`` mirrors, call for call, what the reference host does around its linear-algebra plugin
+(Code/Source/solver/LinearAlgebra.h:13-37, FsilsLinearAlgebra.cpp:26-128) and its element loops
+(eq_assem::global_eq_assem, Code/Source/solver/eq_assem.cpp:377-455):
+
+    lhsa            -> Engine.lhsa(meshes)                     (solver/lhsa.cpp:126)
+    fsils_lhs_create-> Engine.set_graph(rowPtr, colPtr, ...)   (linear_solver/lhs.cpp:30)
+    fsils_bc_create -> Engine.set_face(...)                    (linear_solver/bc.cpp:18)
+    ls_alloc        -> Engine.alloc(dof)                       (solver/ls.cpp:24)
+    global_eq_assem -> Engine.assemble(iM, eq, domains)
+    all_fun::commu  -> Engine.commu_R()                        (solver/all_fun.cpp:95)
+    ls_solve        -> Engine.solve(...)                       (solver/ls.cpp:45 -> fsils_solve)
+
+There is no CPU implementation behind this class: if the CUDA library is missing or no B200 is
+visible, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsvb200.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+# every symbol include/svb200.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "svb200_abi_version", "svb200_last_error", "svb200_create", "svb200_destroy",
+    "svb200_comm_unique_id", "svb200_comm_init",
+    "svb200_set_graph", "svb200_lhsa_begin", "svb200_lhsa_add_mesh", "svb200_lhsa_finish", "svb200_lhsa_get",
+    "svb200_set_mesh", "svb200_set_coords", "svb200_set_num_faces", "svb200_set_face",
+    "svb200_alloc", "svb200_set_state", "svb200_assemble", "svb200_add_host_contrib", "svb200_commu_R",
+    "svb200_solve", "svb200_download", "svb200_upload", "svb200_spmv", "svb200_last_timing",
+    "svb200_bench_assemble", "svb200_bench_spmv", "svb200_measure_fp64_peak", "svb200_launch_count",
+]
+
+_lib = None
+
+
+class Svb200Error(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(message)
+        self.status = status
+
+
+def load_library():
+    """Load libsvb200.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Svb200Error(-1, f"{LIB_PATH} is missing: build it with `make -C svmultiphysics_b200/csrc` "
+                                  "(or python -c 'import __graft_entry__ as g; g.build()'); there is no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        lib.svb200_last_error.restype = C.c_char_p
+        lib.svb200_launch_count.restype = C.c_int64
+        lib.svb200_launch_count.argtypes = [C.c_void_p]
+        _lib = lib
+    return _lib
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+def _f64(a):
+    return None if a is None else np.asfortranarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return None if a is None else np.asfortranarray(a, dtype=np.int32)
+
+
+class Engine:
+    """One mesh partition on one B200 (one svb200_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        self.nNo = 0
+        self.nnz = 0
+        self.dof = 0
+        self.meshes = []
+        rc = self.lib.svb200_create(C.byref(self.h), C.c_int(device))
+        if rc != 0:
+            raise Svb200Error(rc, self.lib.svb200_last_error().decode())
+
+    # ---- plumbing ------------------------------------------------------------------------------
+    def _call(self, name, *args):
+        rc = getattr(self.lib, name)(self.h, *args)
+        if rc != 0:
+            raise Svb200Error(rc, self.lib.svb200_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.svb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.svb200_launch_count(self.h))
+
+    # ---- multi-GPU -----------------------------------------------------------------------------
+    @staticmethod
+    def unique_id() -> bytes:
+        lib = load_library()
+        buf = C.create_string_buffer(128)
+        rc = lib.svb200_comm_unique_id(buf)
+        if rc != 0:
+            raise Svb200Error(rc, lib.svb200_last_error().decode())
+        return buf.raw
+
+    def comm_init(self, nranks: int, rank: int, uid: bytes):
+        self._call("svb200_comm_init", C.c_int(nranks), C.c_int(rank), C.c_char_p(uid))
+
+    # ---- structure -----------------------------------------------------------------------------
+    def lhsa(self, nNo: int, IENs):
+        """Sparse structure of all meshes (lhsa_ns::lhsa): returns (rowPtr, colPtr)."""
+        self._call("svb200_lhsa_begin", C.c_int32(nNo))
+        for IEN in IENs:
+            IEN = _i32(IEN)
+            self._call("svb200_lhsa_add_mesh", C.c_int32(IEN.shape[0]), C.c_int32(IEN.shape[1]), _i(IEN))
+        nnz = C.c_int32(0)
+        self._call("svb200_lhsa_finish", C.byref(nnz))
+        rowPtr = np.zeros(nNo + 1, dtype=np.int32)
+        colPtr = np.zeros(max(nnz.value, 1), dtype=np.int32)
+        self._call("svb200_lhsa_get", _i(rowPtr), _i(colPtr))
+        return rowPtr, colPtr[:nnz.value]
+
+    def set_graph(self, rowPtr, colPtr, mynNo=None, node_map=None, neighbours=None):
+        """neighbours: list of (rank, ptr) with ptr = FSILS-order local ids shared with that rank."""
+        rowPtr, colPtr = _i32(rowPtr), _i32(colPtr)
+        self.nNo = len(rowPtr) - 1
+        self.nnz = len(colPtr)
+        node_map = _i32(node_map)
+        neighbours = neighbours or []
+        ranks = np.array([r for r, _ in neighbours], dtype=np.int32)
+        counts = np.array([len(p) for _, p in neighbours], dtype=np.int32)
+        ptrs = np.concatenate([np.asarray(p, dtype=np.int32) for _, p in neighbours]) if neighbours else np.zeros(0, np.int32)
+        self._call("svb200_set_graph", C.c_int32(self.nNo), C.c_int32(self.nnz), _i(rowPtr), _i(colPtr),
+                   C.c_int32(self.nNo if mynNo is None else mynNo), _i(node_map),
+                   C.c_int32(len(neighbours)), _i(ranks), _i(counts), _i(np.ascontiguousarray(ptrs)))
+
+    def set_mesh(self, iM, IEN, w, N, Nx, eId=None, nFn=0, fN=None):
+        IEN, eId, fN = _i32(IEN), _i32(eId), _f64(fN)
+        w, N, Nx = _f64(w), _f64(N), _f64(Nx)
+        self._call("svb200_set_mesh", C.c_int32(iM), C.c_int32(IEN.shape[0]), C.c_int32(IEN.shape[1]), _i(IEN), _i(eId),
+                   C.c_int32(nFn), _d(fN), C.c_int32(len(w)), _d(w), _d(N), _d(Nx))
+        while len(self.meshes) <= iM:
+            self.meshes.append(None)
+        self.meshes[iM] = (IEN.shape[0], IEN.shape[1])
+
+    def set_coords(self, x):
+        x = _f64(x)
+        assert x.shape == (3, self.nNo)
+        self._call("svb200_set_coords", _d(x))
+
+    def set_num_faces(self, n):
+        self._call("svb200_set_num_faces", C.c_int32(n))
+
+    def set_face(self, faIn, bGrp, glob, val, shared=0):
+        glob, val = _i32(glob), _f64(val)
+        self._call("svb200_set_face", C.c_int32(faIn), C.c_int32(bGrp), C.c_int32(val.shape[0]), C.c_int32(len(glob)),
+                   _i(glob), _d(val), C.c_int32(shared))
+
+    # ---- per Newton iteration ------------------------------------------------------------------
+    def alloc(self, dof):
+        self.dof = dof
+        self._call("svb200_alloc", C.c_int32(dof))
+
+    def set_state(self, Ag, Yg, Dg=None, Bf=None):
+        Ag, Yg, Dg, Bf = _f64(Ag), _f64(Yg), _f64(Dg), _f64(Bf)
+        tDof = (Ag if Ag is not None else Yg).shape[0]
+        self._call("svb200_set_state", C.c_int32(tDof), _d(Ag), _d(Yg), _d(Dg), _d(Bf))
+
+    def assemble(self, iM, eq: abi.EqParams, dmns):
+        arr = (abi.DmnParams * len(dmns))(*dmns)
+        self._call("svb200_assemble", C.c_int32(iM), C.byref(eq), arr, C.c_int32(len(dmns)))
+
+    def add_host_contrib(self, dof, rows=None, R_add=None, krows=None, kcols=None, K_add=None):
+        rows, krows, kcols = _i32(rows), _i32(krows), _i32(kcols)
+        R_add, K_add = _f64(R_add), _f64(K_add)
+        self._call("svb200_add_host_contrib", C.c_int32(dof), C.c_int32(0 if rows is None else len(rows)), _i(rows),
+                   _d(R_add), C.c_int32(0 if krows is None else len(krows)), _i(krows), _i(kcols), _d(K_add))
+
+    def commu_R(self):
+        self._call("svb200_commu_R")
+
+    def solve(self, dof, ls_type, ls: abi.LsParams, incL=None, res=None, hist_cap=0, want_solution=True):
+        nFaces = 0 if incL is None else len(incL)
+        incL, res = _i32(incL), _f64(res)
+        out = abi.LsResult()
+        hist = np.zeros(max(hist_cap, 1))
+        out.hist = hist.ctypes.data_as(_dp)
+        out.hist_cap = hist_cap
+        X = np.zeros((dof, self.nNo), order="F") if want_solution else None
+        self._call("svb200_solve", C.c_int32(dof), C.c_int32(ls_type), C.c_int32(abi.PREC_FSILS), C.byref(ls),
+                   C.c_int32(nFaces), _i(incL), _d(res), _d(X), C.byref(out))
+        return X, out, hist[:out.hist_n].copy()
+
+    # ---- debug / parity / bench ----------------------------------------------------------------
+    def get_R(self):
+        R = np.zeros((self.dof, self.nNo), order="F")
+        self._call("svb200_download", C.c_int32(abi.ARRAY_R), _d(R))
+        return R
+
+    def get_Val(self):
+        V = np.zeros((self.dof * self.dof, self.nnz), order="F")
+        self._call("svb200_download", C.c_int32(abi.ARRAY_VAL), _d(V))
+        return V
+
+    def get_W(self):
+        W = np.zeros((self.dof, self.nNo), order="F")
+        self._call("svb200_download", C.c_int32(abi.ARRAY_W), _d(W))
+        return W
+
+    def put_R(self, R):
+        R = _f64(R)
+        self._call("svb200_upload", C.c_int32(abi.ARRAY_R), C.c_int32(R.shape[0]), _d(R))
+
+    def put_Val(self, V, dof):
+        V = _f64(V)
+        self._call("svb200_upload", C.c_int32(abi.ARRAY_VAL), C.c_int32(dof), _d(V))
+
+    def spmv(self, dof, U):
+        U = _f64(U)
+        KU = np.zeros_like(U, order="F")
+        self._call("svb200_spmv", C.c_int32(dof), _d(U), _d(KU))
+        return KU
+
+    def last_timing(self):
+        a, s = C.c_double(0), C.c_double(0)
+        self._call("svb200_last_timing", C.byref(a), C.byref(s))
+        return a.value, s.value
+
+    def bench_assemble(self, iM, eq, dmns, reps):
+        arr = (abi.DmnParams * len(dmns))(*dmns)
+        ms = C.c_double(0)
+        self._call("svb200_bench_assemble", C.c_int32(iM), C.byref(eq), arr, C.c_int32(len(dmns)), C.c_int32(reps), C.byref(ms))
+        return ms.value
+
+    def bench_spmv(self, dof, reps):
+        ms = C.c_double(0)
+        self._call("svb200_bench_spmv", C.c_int32(dof), C.c_int32(reps), C.byref(ms))
+        return ms.value
+
+    def fp64_peak(self):
+        t = C.c_double(0)
+        self._call("svb200_measure_fp64_peak", C.byref(t))
+        return t.value

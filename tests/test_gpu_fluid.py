@@ -1,0 +1,114 @@
+"""GPU parity tests (run on a B200 with -m gpu): CUDA path through the C ABI vs the oracle."""
+import numpy as np
+import pytest
+
+from svmultiphysics_b200 import abi
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+ASM_TOL = 1e-12   # north_star: assembled R / Val within 1e-12 relative
+
+
+def _oracle():
+    from oracle import refbind
+    return refbind.RefCase if refbind.have_ref() else refbind.OracleCase
+
+
+CASES = [
+    ("newtonian", {}, 0.0, (0.0, 0.0, 0.0), 4, 0),
+    ("darcy_bodyforce", {}, 3.0, (0.1, -0.2, 0.3), 4, 0),
+    ("carreau_yasuda", dict(viscType=abi.VISC_CY, mu=0.035, mu_o=0.16, lam=8.2, a=0.64, n=0.2128), 0.0, (0, 0, 0), 4, 0),
+    ("casson", dict(viscType=abi.VISC_CASSON, mu=0.3, mu_o=0.1, lam=0.5), 0.5, (0, 0, 1.0), 4, 0),
+    ("moving_mesh", {}, 0.0, (0, 0, 0), 7, 1),
+]
+
+
+@pytest.mark.parametrize("scatter", [abi.SCATTER_ATOMIC, abi.SCATTER_COLORED])
+@pytest.mark.parametrize("name,visc,Kd,f,tDof,mv", CASES, ids=[c[0] for c in CASES])
+def test_fluid_assembly_parity(name, visc, Kd, f, tDof, mv, scatter):
+    m, Ag, Yg, Dg, Bf = common.fluid_case(tDof=tDof)
+    orc, rowPtr, colPtr = common.make_oracle(_oracle(), m)
+    dmn = [abi.fluid_domain(K_darcy=Kd, f=f, **visc)]
+    eq = abi.fluid_eq(0.005, tDof=tDof, mvMsh=mv, scatter=scatter)
+    orc.alloc(4)
+    orc.set_state(Ag, Yg, Dg, Bf)
+    orc.assemble(0, eq, dmn)
+    R0, V0 = orc.get_R(), orc.get_Val()
+
+    eng = common.make_engine(m, rowPtr, colPtr)
+    eng.alloc(4)
+    eng.set_state(Ag, Yg, Dg, Bf)
+    eng.assemble(0, eq, dmn)
+    R1, V1 = eng.get_R(), eng.get_Val()
+    assert common.rel_err(R1, R0) < ASM_TOL
+    assert common.rel_err(V1, V0) < ASM_TOL
+    if scatter == abi.SCATTER_COLORED:
+        # deterministic mode: bitwise reproducible
+        eng.alloc(4)
+        eng.assemble(0, eq, dmn)
+        assert np.array_equal(eng.get_Val(), V1) and np.array_equal(eng.get_R(), R1)
+    assert eng.launch_count > 0
+    eng.close()
+
+
+def test_lhsa_matches_reference():
+    m, *_ = common.fluid_case()
+    orc, rowPtr, colPtr = common.make_oracle(_oracle(), m)
+    from svmultiphysics_b200.engine import Engine
+    eng = Engine(0)
+    rp, cp = eng.lhsa(m.nNo, [m.IEN])
+    assert np.array_equal(rp, rowPtr) and np.array_equal(cp, colPtr)
+    eng.close()
+
+
+def test_spmv_parity():
+    m, Ag, Yg, Dg, Bf = common.fluid_case()
+    orc, rowPtr, colPtr = common.make_oracle(_oracle(), m)
+    eq, dmn = abi.fluid_eq(0.005), [abi.fluid_domain()]
+    orc.alloc(4); orc.set_state(Ag, Yg, Dg, Bf); orc.assemble(0, eq, dmn)
+    V0 = orc.get_Val()
+    U = np.asfortranarray(np.random.default_rng(3).standard_normal((4, m.nNo)))
+    KU0 = orc.spmv(4, U)
+    eng = common.make_engine(m, rowPtr, colPtr)
+    eng.alloc(4)
+    eng.put_Val(V0, 4)
+    KU1 = eng.spmv(4, U)
+    assert common.rel_err(KU1, KU0) < 1e-13
+    eng.close()
+
+
+@pytest.mark.parametrize("ls_type,kw", [
+    (abi.LS_GMRES, dict(mItr=100, sD=50, relTol=1e-8)),
+    (abi.LS_GMRES, dict(mItr=20, sD=10, relTol=1e-10)),    # restarts
+    (abi.LS_BICGS, dict(mItr=400, relTol=1e-8)),
+], ids=["gmres50", "gmres10_restart", "bicgs"])
+def test_fluid_solve_parity(ls_type, kw):
+    m, Ag, Yg, Dg, Bf = common.fluid_case()
+    faces = common.dirichlet_faces(m)
+    orc, rowPtr, colPtr = common.make_oracle(_oracle(), m, nFaces=len(faces))
+    eq, dmn = abi.fluid_eq(0.005), [abi.fluid_domain()]
+    for i, (g, nodes, val) in enumerate(faces):
+        orc.set_face(i, g, nodes, val)
+    orc.alloc(4); orc.set_state(Ag, Yg, Dg, Bf); orc.assemble(0, eq, dmn)
+    ls = abi.ls_params(ls_type, **kw)
+    incL = np.ones(len(faces), dtype=np.int32)
+    res = np.zeros(len(faces))
+    X0, out0, _ = orc.solve(4, ls_type, ls, incL, res)
+
+    eng = common.make_engine(m, rowPtr, colPtr)
+    eng.set_num_faces(len(faces))
+    for i, (g, nodes, val) in enumerate(faces):
+        eng.set_face(i, g, nodes, val)
+    eng.alloc(4); eng.set_state(Ag, Yg, Dg, Bf); eng.assemble(0, eq, dmn)
+    X1, out1, hist = eng.solve(4, ls_type, ls, incL, res, hist_cap=512)
+    assert out1.RI.success == out0.RI.success == 1
+    assert out1.RI.itr == out0.RI.itr
+    assert abs(out1.RI.iNorm - out0.RI.iNorm) <= 1e-10 * out0.RI.iNorm
+    # residual history: classical Gram-Schmidt amplifies summation-order differences; the contract is
+    # 'matched to the set tolerance' (relTol * iNorm); we hold it to 1 % of the final residual itself
+    assert abs(out1.RI.fNorm - out0.RI.fNorm) <= 1e-2 * out0.RI.fNorm
+    assert abs(out1.RI.dB - out0.RI.dB) <= 0.2
+    # solution agrees to the solver tolerance (both are relTol-accurate solutions of the same system)
+    assert common.rel_err(X1, X0) < 1e-6
+    eng.close()
