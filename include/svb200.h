@@ -241,6 +241,16 @@ SVB200_API int svb200_spmv(svb200_ctx* ctx, int32_t dof, const double* U, double
  * (CUDA events on the library's stream). */
 SVB200_API int svb200_last_timing(svb200_ctx* ctx, double* assemble_ms, double* solve_ms);
 
+/* Page-lock / unlock a caller buffer so that the H2D/D2H copies of svb200_set_state, svb200_solve and
+ * svb200_download run at full PCIe rate (cudaHostRegister / cudaHostUnregister). */
+SVB200_API int svb200_host_register(svb200_ctx* ctx, void* ptr, size_t bytes);
+SVB200_API int svb200_host_unregister(svb200_ctx* ctx, void* ptr);
+
+/* CUDA-event stopwatch on the library's stream: mark(0) ... mark(1), then elapsed gives the device
+ * time in ms between the two marks (synchronises on the second). */
+SVB200_API int svb200_timer_mark(svb200_ctx* ctx, int32_t which);
+SVB200_API int svb200_timer_elapsed(svb200_ctx* ctx, double* ms);
+
 /* Repeat the assembly kernel(s) / SpMV n times on resident data and return the average device
  * time per launch in ms (CUDA events on the launching stream); used by bench.py for the roofline. */
 SVB200_API int svb200_bench_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, const svb200_dmnparams* dmn,

@@ -180,6 +180,8 @@ int svb200_create(svb200_ctx** out, int device)
   SVB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   SVB_CUDA(cudaEventCreate(&ctx->ev0));
   SVB_CUDA(cudaEventCreate(&ctx->ev1));
+  SVB_CUDA(cudaEventCreate(&ctx->tm0));
+  SVB_CUDA(cudaEventCreate(&ctx->tm1));
   SVB_CUDA(cudaMallocHost(&ctx->h_pinned, sizeof(double) * 1024));
   *out = ctx;
   return SVB200_OK;
@@ -730,5 +732,38 @@ int svb200_measure_fp64_peak(svb200_ctx* ctx, double* tflops)
 }
 
 int64_t svb200_launch_count(svb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int svb200_host_register(svb200_ctx* ctx, void* ptr, size_t bytes)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(ptr && bytes > 0, "svb200_host_register: bad arguments");
+  SVB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  return SVB200_OK;
+}
+
+int svb200_host_unregister(svb200_ctx* ctx, void* ptr)
+{
+  CTX_GUARD(ctx);
+  SVB_CUDA(cudaHostUnregister(ptr));
+  return SVB200_OK;
+}
+
+int svb200_timer_mark(svb200_ctx* ctx, int32_t which)
+{
+  CTX_GUARD(ctx);
+  SVB_CUDA(cudaEventRecord(which == 0 ? ctx->tm0 : ctx->tm1, ctx->stream));
+  return SVB200_OK;
+}
+
+int svb200_timer_elapsed(svb200_ctx* ctx, double* ms)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(ms, "svb200_timer_elapsed: null output");
+  SVB_CUDA(cudaEventSynchronize(ctx->tm1));
+  float f = 0.f;
+  SVB_CUDA(cudaEventElapsedTime(&f, ctx->tm0, ctx->tm1));
+  *ms = f;
+  return SVB200_OK;
+}
 
 }  // extern "C"

@@ -85,6 +85,7 @@ struct svb200_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t tm0 = nullptr, tm1 = nullptr;   // svb200_timer_*
   int64_t launches = 0;
 
   // graph

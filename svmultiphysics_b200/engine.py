@@ -38,6 +38,7 @@ ABI_SYMBOLS = [
     "svb200_set_mesh", "svb200_set_coords", "svb200_set_num_faces", "svb200_set_face",
     "svb200_alloc", "svb200_set_state", "svb200_assemble", "svb200_add_host_contrib", "svb200_commu_R",
     "svb200_solve", "svb200_download", "svb200_upload", "svb200_spmv", "svb200_last_timing",
+    "svb200_host_register", "svb200_host_unregister", "svb200_timer_mark", "svb200_timer_elapsed",
     "svb200_bench_assemble", "svb200_bench_spmv", "svb200_measure_fp64_peak", "svb200_launch_count",
 ]
 
@@ -264,6 +265,21 @@ class Engine:
     def bench_spmv(self, dof, reps):
         ms = C.c_double(0)
         self._call("svb200_bench_spmv", C.c_int32(dof), C.c_int32(reps), C.byref(ms))
+        return ms.value
+
+    def pin(self, arr: np.ndarray):
+        """Page-lock a numpy buffer that is repeatedly copied to / from the device."""
+        self._call("svb200_host_register", C.c_void_p(arr.ctypes.data), C.c_size_t(arr.nbytes))
+
+    def unpin(self, arr: np.ndarray):
+        self._call("svb200_host_unregister", C.c_void_p(arr.ctypes.data))
+
+    def timer_mark(self, which: int):
+        self._call("svb200_timer_mark", C.c_int32(which))
+
+    def timer_elapsed(self) -> float:
+        ms = C.c_double(0)
+        self._call("svb200_timer_elapsed", C.byref(ms))
         return ms.value
 
     def fp64_peak(self):

@@ -144,3 +144,23 @@ def poiseuille_state(mesh: Mesh, R: float = 2.0, U: float = 10.0, seed: int = 12
     Ag = np.asfortranarray(1e-2 * rng2.standard_normal((tDof, n)))
     Dg = np.zeros((tDof, n), order="F")
     return np.asfortranarray(Ag), np.asfortranarray(Yg), Dg
+
+
+def cylinder_slab(n: int, nz: int, rank: int, nranks: int, R: float = 2.0, Lseg: float = 30.0):
+    """Weak-scaling partition used by bench.py: rank r owns the z-slab [r*Lseg,(r+1)*Lseg] of a cylinder of
+    nranks*nz cell layers (one 6*n*n*nz-tet slab per GPU).  Returns (mesh, max_other_rank, plane_lo,
+    plane_hi): the local mesh in local node ids, for every local node the highest other rank holding
+    it (-1 = interior), and the local ids of the two interface planes in (i,j) order.  This geometric
+    slab partition stands in for the reference's ParMETIS element partition (Code/Source/solver/SPLIT.c),
+    which needs MPI; any other partition can be fed through partition.partition_mesh."""
+    m = cylinder_tet4(n, nz, R=R, L=Lseg)
+    m.x[2] += rank * Lseg
+    P = (n + 1) * (n + 1)
+    plane_lo = np.arange(P, dtype=np.int32)                      # k = 0
+    plane_hi = (np.arange(P) + P * nz).astype(np.int32)          # k = nz
+    other = -np.ones(m.nNo, dtype=np.int32)
+    if rank > 0:
+        other[plane_lo] = rank - 1
+    if rank < nranks - 1:
+        other[plane_hi] = rank + 1
+    return m, other, plane_lo, plane_hi

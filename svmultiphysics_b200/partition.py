@@ -1,0 +1,99 @@
+"""Element-partition -> per-rank local meshes and FSILS communication structure (host logic).
+
+Mirrors what the reference does once at start-up:
+
+* ``part_msh`` (Code/Source/solver/distribute.cpp:1972) splits the ELEMENTS among ranks (ParMETIS there;
+  any ``part[e]`` array here) and duplicates interface nodes on every rank that touches them;
+* ``fsils_lhs_create`` (Code/Source/linear_solver/lhs.cpp:30-348) reorders the local nodes of a rank as
+  ``[shared only with lower ranks | interior | shared with a higher rank]``, sets ``mynNo`` so that the
+  last group is excluded (a node is "owned" by the highest rank holding it, lhs.cpp:139-160), and
+  builds per-neighbour lists of shared nodes in the same order on both sides (the order of the
+  higher rank's FSILS numbering, lhs.cpp:281-347).
+
+Everything here is integer bookkeeping on the host (numpy); the numbers it produces are fed to
+``svb200_set_graph``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+@dataclass
+class LocalPart:
+    rank: int
+    ltg: np.ndarray                 # (nNo,) local (input order) -> global node id
+    IEN: np.ndarray                 # (eNoN, nEl) local node ids (input order)
+    elems: np.ndarray               # global element ids of this rank
+    node_map: np.ndarray            # (nNo,) input order -> FSILS order (lhs.map)
+    mynNo: int
+    neighbours: list = field(default_factory=list)   # [(rank, ptr)] ptr = FSILS-order local ids
+
+    @property
+    def nNo(self):
+        return len(self.ltg)
+
+
+def fsils_order(max_other_rank: np.ndarray, rank: int):
+    """lhs.map and mynNo for one rank.  ``max_other_rank[a]`` = highest OTHER rank that also holds
+    local node a, or -1 when the node is interior to this rank."""
+    n = len(max_other_rank)
+    group = np.where(max_other_rank < 0, 1, np.where(max_other_rank > rank, 2, 0)).astype(np.int8)
+    order = np.argsort(group, kind="stable")     # FSILS position -> input id
+    node_map = np.empty(n, dtype=np.int32)
+    node_map[order] = np.arange(n, dtype=np.int32)
+    mynNo = int(np.count_nonzero(group < 2))
+    return node_map, mynNo
+
+
+def partition_mesh(IEN: np.ndarray, nNo: int, part: np.ndarray, nranks: int):
+    """Split a global mesh by the element partition ``part`` (values in [0,nranks))."""
+    node_sets = []
+    for r in range(nranks):
+        el = np.flatnonzero(part == r)
+        node_sets.append(np.unique(IEN[:, el]))
+    # highest and second-highest rank holding each global node
+    max1 = -np.ones(nNo, dtype=np.int32)
+    max2 = -np.ones(nNo, dtype=np.int32)
+    for r, nodes in enumerate(node_sets):          # ascending r: the new rank is always the largest so far
+        max2[nodes] = max1[nodes]
+        max1[nodes] = r
+    parts = []
+    for r in range(nranks):
+        nodes = node_sets[r]
+        gtl = -np.ones(nNo, dtype=np.int64)
+        gtl[nodes] = np.arange(len(nodes))
+        el = np.flatnonzero(part == r).astype(np.int64)
+        lIEN = np.asfortranarray(gtl[IEN[:, el]].astype(np.int32))
+        other = np.where(max1[nodes] != r, max1[nodes], max2[nodes])
+        # a node held by lower ranks only besides r: max1 == r and max2 = highest lower rank (or -1)
+        node_map, mynNo = fsils_order(other, r)
+        parts.append(LocalPart(rank=r, ltg=nodes.astype(np.int64), IEN=lIEN, elems=el, node_map=node_map, mynNo=mynNo))
+    # neighbour lists: shared nodes of (lo,hi) in the order of hi's FSILS numbering
+    for hi in range(nranks):
+        for lo in range(hi):
+            common = np.intersect1d(node_sets[lo], node_sets[hi], assume_unique=True)
+            if len(common) == 0:
+                continue
+            ph, pl = parts[hi], parts[lo]
+            fs_hi = ph.node_map[np.searchsorted(ph.ltg, common)]
+            o = np.argsort(fs_hi, kind="stable")
+            common = common[o]
+            ptr_hi = fs_hi[o].astype(np.int32)
+            ptr_lo = pl.node_map[np.searchsorted(pl.ltg, common)].astype(np.int32)
+            ph.neighbours.append((lo, ptr_hi))
+            pl.neighbours.append((hi, ptr_lo))
+    for p in parts:
+        p.neighbours.sort(key=lambda t: t[0])
+    return parts
+
+
+def glue_nodal(parts, arrays, nNo_global):
+    """Assemble a global (rows, nNo) array from per-rank local arrays (input order); shared nodes
+    must agree across ranks after a halo sum, the highest rank's copy is kept."""
+    rows = arrays[0].shape[0]
+    out = np.zeros((rows, nNo_global), order="F")
+    for p, a in zip(parts, arrays):
+        out[:, p.ltg] = a
+    return out
