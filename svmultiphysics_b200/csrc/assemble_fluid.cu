@@ -12,6 +12,7 @@
 // (a,b) pair comes from a precomputed element->slot map, so the binary search of do_assem is gone.
 // Scatter modes: ATOMIC (red.global.add.f64, all elements in one launch) and COLORED (one launch per
 // colour, plain read-modify-write, bitwise reproducible).
+#include <cstdlib>
 #include "fluid_elem.cuh"
 
 namespace svb {
@@ -40,8 +41,8 @@ __device__ __forceinline__ int pick_domain(const FluidArgs& P, int e)
   return iD;
 }
 
-template <bool ATOMIC>
-__global__ void __launch_bounds__(ASM_THREADS)
+template <bool ATOMIC, int MINB>
+__global__ void __launch_bounds__(ASM_THREADS, MINB)
 assemble_fluid_tet4_kernel(const __grid_constant__ FluidArgs P)
 {
   __shared__ double tile[ASM_THREADS / 32][32 * TILE_LD];
@@ -144,10 +145,14 @@ int launch_assemble_fluid(svb200_ctx* ctx, const Mesh& m, const FluidArgs& args)
   const int n = args.e1 - args.e0;
   if (n <= 0) return SVB200_OK;
   const int blocks = (n + ASM_THREADS - 1) / ASM_THREADS;
-  if (args.atomic)
-    assemble_fluid_tet4_kernel<true><<<blocks, ASM_THREADS, 0, ctx->stream>>>(args);
-  else
-    assemble_fluid_tet4_kernel<false><<<blocks, ASM_THREADS, 0, ctx->stream>>>(args);
+  static const int variant = getenv("SVB200_ASM_MINB") ? atoi(getenv("SVB200_ASM_MINB")) : 2;   // tuning knob
+  if (args.atomic) {
+    if (variant == 4) assemble_fluid_tet4_kernel<true, 4><<<blocks, ASM_THREADS, 0, ctx->stream>>>(args);
+    else if (variant == 3) assemble_fluid_tet4_kernel<true, 3><<<blocks, ASM_THREADS, 0, ctx->stream>>>(args);
+    else assemble_fluid_tet4_kernel<true, 2><<<blocks, ASM_THREADS, 0, ctx->stream>>>(args);
+  } else {
+    assemble_fluid_tet4_kernel<false, 2><<<blocks, ASM_THREADS, 0, ctx->stream>>>(args);
+  }
   ctx->launches++;
   SVB_CUDA(cudaGetLastError());
   return SVB200_OK;

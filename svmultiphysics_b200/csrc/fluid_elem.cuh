@@ -293,11 +293,13 @@ SVB_HD void tet4_block(const Tet4Elem& E, int a, int b, double K[16])
 {
   const double nn = E.Nx[a][0] * E.Nx[b][0] + E.Nx[a][1] * E.Nx[b][1] + E.Nx[a][2] * E.Nx[b][2];
   const double dd = E.D[a][b] + E.A1 * nn;
+  const double q1[3] = {E.A1 * E.Nx[b][0], E.A1 * E.Nx[b][1], E.A1 * E.Nx[b][2]};
+  const double q2[3] = {E.A2 * E.Nx[b][0], E.A2 * E.Nx[b][1], E.A2 * E.Nx[b][2]};
 #pragma unroll
   for (int i = 0; i < 3; i++) {
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-      double v = E.A1 * E.Nx[a][j] * E.Nx[b][i] + E.A2 * E.Nx[a][i] * E.Nx[b][j];
+      double v = E.Nx[a][j] * q1[i] + E.Nx[a][i] * q2[j];
       if (i == j) v += dd;
       K[4 * i + j] = v;
     }
@@ -307,9 +309,11 @@ SVB_HD void tet4_block(const Tet4Elem& E, int a, int b, double K[16])
   K[15] = E.Spp * nn;
   if (E.A3 != 0.0) {
 #pragma unroll
-    for (int i = 0; i < 3; i++)
+    for (int i = 0; i < 3; i++) {
+      const double t = E.A3 * E.esNx[a][i];
 #pragma unroll
-      for (int j = 0; j < 3; j++) K[4 * i + j] += E.A3 * E.esNx[a][i] * E.esNx[b][j];
+      for (int j = 0; j < 3; j++) K[4 * i + j] += t * E.esNx[b][j];
+    }
   }
 }
 
