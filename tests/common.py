@@ -4,6 +4,34 @@ import numpy as np
 from svmultiphysics_b200 import abi, elements, meshgen
 
 
+GOLDEN_N, GOLDEN_NZ = 3, 2      # mesh of the committed golden vectors (tests/golden/make_golden.py)
+
+# (name, viscosity kwargs, K_darcy, body force, tDof, mvMsh)
+FLUID_CASES = [
+    ("newtonian", {}, 0.0, (0.0, 0.0, 0.0), 4, 0),
+    ("darcy_bodyforce", {}, 3.0, (0.1, -0.2, 0.3), 4, 0),
+    ("carreau_yasuda", dict(viscType=abi.VISC_CY, mu=0.035, mu_o=0.16, lam=8.2, a=0.64, n=0.2128), 0.0, (0.0, 0.0, 0.0), 4, 0),
+    ("casson", dict(viscType=abi.VISC_CASSON, mu=0.3, mu_o=0.1, lam=0.5), 0.5, (0.0, 0.0, 1.0), 4, 0),
+    ("moving_mesh", {}, 0.0, (0.0, 0.0, 0.0), 7, 1),
+]
+
+# (name, LS type, parameter overrides)
+LS_CASES = [
+    ("gmres", abi.LS_GMRES, dict(mItr=100, sD=50, relTol=1e-8)),
+    ("gmres_restart", abi.LS_GMRES, dict(mItr=20, sD=10, relTol=1e-10)),
+    ("bicgs", abi.LS_BICGS, dict(mItr=400, relTol=1e-8)),
+]
+
+
+def spmv_vector(nNo, dof=4):
+    return np.asfortranarray(np.random.default_rng(3).standard_normal((dof, nNo)))
+
+
+def load_golden(name="fluid_tet4.npz"):
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
+
+
 def rel_err(a, b):
     """max |a-b| / max |b| : the FP64 parity measure used for assembled R / Val (tolerance 1e-12)."""
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))

@@ -1,0 +1,56 @@
+"""Generate the golden vectors under tests/golden/ from the UNMODIFIED reference (oracle/_ref/libsvref.so).
+
+Run in the build container (needs /root/reference to have been compiled by `make -C oracle ref`):
+    python tests/golden/make_golden.py
+Inputs are regenerated deterministically by tests/common.py (seeded), only the reference OUTPUTS are
+stored: CSR structure, assembled R / Val, GMRES / BiCGStab / CG results, SpMV product, element tables.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle.refbind import RefCase, have_ref  # noqa: E402
+from svmultiphysics_b200 import abi, meshgen  # noqa: E402
+from tests import common  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def fluid_golden():
+    out = {}
+    for name, visc, Kd, f, tDof, mv in common.FLUID_CASES:
+        m, Ag, Yg, Dg, Bf = common.fluid_case(n=common.GOLDEN_N, nz=common.GOLDEN_NZ, tDof=tDof)
+        faces = common.dirichlet_faces(m)
+        c, rowPtr, colPtr = common.make_oracle(RefCase, m, nFaces=len(faces))
+        for i, (g, nodes, val) in enumerate(faces):
+            c.set_face(i, g, nodes, val)
+        eq = abi.fluid_eq(0.005, tDof=tDof, mvMsh=mv)
+        dmn = [abi.fluid_domain(K_darcy=Kd, f=f, **visc)]
+        c.alloc(4); c.set_state(Ag, Yg, Dg, Bf); c.assemble(0, eq, dmn)
+        out[f"{name}/R"], out[f"{name}/Val"] = c.get_R(), c.get_Val()
+        U = common.spmv_vector(m.nNo)
+        out[f"{name}/KU"] = c.spmv(4, U)
+        for ls_name, ls_type, kw in common.LS_CASES:
+            c.put_R(out[f"{name}/R"]); c.put_Val(out[f"{name}/Val"], 4)
+            ls = abi.ls_params(ls_type, **kw)
+            X, o, _ = c.solve(4, ls_type, ls, np.ones(len(faces), np.int32), np.zeros(len(faces)))
+            out[f"{name}/{ls_name}/X"] = X
+            out[f"{name}/{ls_name}/stats"] = np.array([o.RI.itr, o.RI.success, o.RI.iNorm, o.RI.fNorm, o.RI.dB])
+        out["rowPtr"], out["colPtr"] = rowPtr, colPtr
+    for eNoN, mk in ((4, lambda: meshgen.cylinder_tet4(2, 2)), (8, lambda: meshgen.box_hex8(2, 2, 2))):
+        m = mk()
+        c = RefCase(); c.set_coords(m.x); c.add_mesh(m.IEN)
+        w, N, Nx = c.mesh_tables(0)
+        out[f"tables{eNoN}/w"], out[f"tables{eNoN}/N"], out[f"tables{eNoN}/Nx"] = w, N, Nx
+    np.savez_compressed(os.path.join(HERE, "fluid_tet4.npz"), **out)
+    print("wrote fluid_tet4.npz with", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    if not have_ref():
+        raise SystemExit("oracle/_ref/libsvref.so is missing: run `make -C oracle ref` first")
+    fluid_golden()

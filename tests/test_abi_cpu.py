@@ -1,0 +1,66 @@
+"""CPU tests of the drop-in boundary: the C-ABI library builds, loads and exports exactly what
+include/svb200.h declares; without a GPU it fails loudly instead of falling back."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from svmultiphysics_b200 import abi, engine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(engine.LIB_PATH):
+        subprocess.check_call(["make", "-j", "8"], cwd=os.path.join(ROOT, "svmultiphysics_b200", "csrc"))
+    return engine.load_library()
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "svb200.h")).read()
+    return sorted(set(re.findall(r"SVB200_API\s+[\w\s\*]+?\b(svb200_\w+)\s*\(", src)))
+
+
+def test_header_and_library_agree(lib):
+    declared = header_symbols()
+    assert len(declared) >= 30
+    assert sorted(engine.ABI_SYMBOLS) == declared
+    for s in declared:
+        assert hasattr(lib, s), f"libsvb200.so does not export {s}"
+    lib.svb200_abi_version.restype = C.c_int
+    assert lib.svb200_abi_version() == abi.ABI_VERSION
+
+
+def test_struct_layouts_match_header():
+    # sizes implied by include/svb200.h (natural alignment, LP64)
+    assert C.sizeof(abi.EqParams) == 5 * 8 + 8 * 4
+    assert C.sizeof(abi.DmnParams) == 8 + 8 * 5 + 8 + 8 * 5 + 8 + 8 * 10
+    assert C.sizeof(abi.SubLsParams) == 24 and C.sizeof(abi.LsParams) == 72
+    assert C.sizeof(abi.SubLsResult) == 40 and C.sizeof(abi.LsResult) == 3 * 40 + 8 + 8 + 8
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible; the no-GPU failure path cannot be exercised")
+    with pytest.raises(engine.Svb200Error, match="no usable CUDA device"):
+        engine.Engine(0)
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under svmultiphysics_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "svmultiphysics_b200")
+    for dp, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dp, fn)).read()
+                assert "oracle" not in text.replace("the oracle", "").lower() or fn == "meshgen.py", f"{fn} mentions the oracle"
+
+
+def test_gen_alpha_matches_reference_formula():
+    # rho_inf = 0.5 (pipe_RCR_3d): am = 5/6, af = 2/3, gam = 2/3 (Code/Source/solver/initialize.cpp:484-486)
+    af, am, gam, beta = abi.gen_alpha(0.5)
+    assert abs(am - 5.0 / 6.0) < 1e-15 and abs(af - 2.0 / 3.0) < 1e-15 and abs(gam - 2.0 / 3.0) < 1e-15

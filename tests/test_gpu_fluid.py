@@ -15,13 +15,7 @@ def _oracle():
     return refbind.RefCase if refbind.have_ref() else refbind.OracleCase
 
 
-CASES = [
-    ("newtonian", {}, 0.0, (0.0, 0.0, 0.0), 4, 0),
-    ("darcy_bodyforce", {}, 3.0, (0.1, -0.2, 0.3), 4, 0),
-    ("carreau_yasuda", dict(viscType=abi.VISC_CY, mu=0.035, mu_o=0.16, lam=8.2, a=0.64, n=0.2128), 0.0, (0, 0, 0), 4, 0),
-    ("casson", dict(viscType=abi.VISC_CASSON, mu=0.3, mu_o=0.1, lam=0.5), 0.5, (0, 0, 1.0), 4, 0),
-    ("moving_mesh", {}, 0.0, (0, 0, 0), 7, 1),
-]
+CASES = common.FLUID_CASES
 
 
 @pytest.mark.parametrize("scatter", [abi.SCATTER_ATOMIC, abi.SCATTER_COLORED])

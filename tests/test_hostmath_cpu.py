@@ -1,0 +1,70 @@
+"""CPU test of the DEVICE element algebra: svmultiphysics_b200/csrc/fluid_elem.cuh compiled for the host
+(tests/hostmath, test-only) must reproduce the reference's assembled R / Val to 1e-12."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from svmultiphysics_b200 import abi, elements
+from tests import common
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class FluidDmn(C.Structure):
+    _fields_ = [("rho", C.c_double), ("f", C.c_double * 3), ("Kd", C.c_double), ("mu_i", C.c_double), ("mu_o", C.c_double),
+                ("lam", C.c_double), ("a", C.c_double), ("n", C.c_double),
+                ("viscType", C.c_int), ("Id", C.c_int), ("isFluid", C.c_int), ("pad", C.c_int)]
+
+
+class FluidArgs(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("IEN", "eId", "slot", "perm", "x", "Ag", "Yg", "Bf", "R", "Val")] + \
+               [(k, C.c_int) for k in ("e0", "e1", "tDof", "mvMsh", "nDmn", "atomic")] + \
+               [(k, C.c_double) for k in ("dt", "af", "am", "gam")] + \
+               [("w", C.c_double * 8), ("N", (C.c_double * 8) * 8), ("Nxi", ((C.c_double * 3) * 8) * 8), ("dmn", FluidDmn * 8)]
+
+
+@pytest.fixture(scope="module")
+def hostmath():
+    so = os.path.join(HERE, "hostmath", "libhostmath.so")
+    subprocess.check_call(["make"], cwd=os.path.join(HERE, "hostmath"))
+    lib = C.CDLL(so)
+    assert lib.hostmath_sizeof_fluidargs() == C.sizeof(FluidArgs)
+    return lib
+
+
+@pytest.mark.parametrize("case", common.FLUID_CASES, ids=[c[0] for c in common.FLUID_CASES])
+def test_device_element_algebra_matches_golden(hostmath, case):
+    golden = common.load_golden()
+    name, visc, Kd, f, tDof, mv = case
+    m, Ag, Yg, Dg, Bf = common.fluid_case(n=common.GOLDEN_N, nz=common.GOLDEN_NZ, tDof=tDof)
+    eq = abi.fluid_eq(0.005, tDof=tDof, mvMsh=mv)
+    d = abi.fluid_domain(K_darcy=Kd, f=f, **visc)
+    w, N, Nx = elements.tables(4)
+    A = FluidArgs()
+    keep = [np.ascontiguousarray(m.IEN.T.astype(np.int32)), np.ascontiguousarray(m.x.T), np.ascontiguousarray(Ag.T),
+            np.ascontiguousarray(Yg.T), np.ascontiguousarray(Bf.T)]
+    A.IEN, A.x, A.Ag, A.Yg, A.Bf = (k.ctypes.data for k in keep)
+    A.e0, A.e1, A.tDof, A.mvMsh, A.nDmn = 0, m.nEl, tDof, mv, 1
+    A.dt, A.af, A.am, A.gam = eq.dt, eq.af, eq.am, eq.gam
+    for g in range(4):
+        A.w[g] = w[g]
+        for a in range(4):
+            A.N[g][a] = N[a, g]
+            for k in range(3):
+                A.Nxi[g][a][k] = Nx[k, a, g]
+    A.dmn[0].rho, A.dmn[0].Kd = d.rho, d.K_darcy
+    for i in range(3):
+        A.dmn[0].f[i] = d.f[i]
+    A.dmn[0].mu_i, A.dmn[0].mu_o, A.dmn[0].lam, A.dmn[0].a, A.dmn[0].n = d.mu_i, d.mu_o, d.lam, d.a, d.n
+    A.dmn[0].viscType, A.dmn[0].Id, A.dmn[0].isFluid = d.viscType, -1, 1
+    rowPtr, colPtr = golden["rowPtr"], golden["colPtr"]
+    R = np.zeros((m.nNo, 4))
+    V = np.zeros((len(colPtr), 16))
+    rc = hostmath.hostmath_fluid_tet4(C.byref(A), m.nNo, rowPtr.ctypes.data_as(C.c_void_p), colPtr.ctypes.data_as(C.c_void_p),
+                                      R.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    assert common.rel_err(R.T, golden[f"{name}/R"]) < 1e-12
+    assert common.rel_err(V.T, golden[f"{name}/Val"]) < 1e-12

@@ -1,0 +1,104 @@
+"""CPU tests of the multi-GPU host logic: element partition -> local meshes, FSILS node order, shared-node
+lists (svmultiphysics_b200/partition.py), incl. a world_size-2 gloo run of the halo-sum exchange pattern."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from svmultiphysics_b200 import meshgen, partition
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _parts(nranks, n=4, nz=6, mode="slab"):
+    m = meshgen.cylinder_tet4(n, nz)
+    if mode == "slab":
+        hexid = np.arange(m.nEl) // 6
+        k = hexid // (n * n)
+        part = (k * nranks // nz).astype(np.int32)
+    else:
+        part = np.random.default_rng(7).integers(0, nranks, m.nEl).astype(np.int32)
+    return m, part, partition.partition_mesh(m.IEN, m.nNo, part, nranks)
+
+
+@pytest.mark.parametrize("nranks,mode", [(2, "slab"), (3, "slab"), (4, "random")])
+def test_partition_invariants(nranks, mode):
+    m, part, parts = _parts(nranks, mode=mode)
+    owned = np.zeros(m.nNo, dtype=np.int32)
+    for p in parts:
+        assert sorted(p.node_map.tolist()) == list(range(p.nNo))           # a permutation
+        inv = np.empty(p.nNo, dtype=np.int64); inv[p.node_map] = np.arange(p.nNo)
+        owned[p.ltg[inv[:p.mynNo]]] += 1                                    # FSILS positions [0,mynNo) are "owned"
+        assert np.array_equal(p.ltg[p.IEN], m.IEN[:, p.elems])              # local connectivity maps back
+    assert np.all(owned == 1), "every global node must be owned by exactly one rank (dots count it once)"
+    # neighbour lists: same global nodes in the same order on both sides
+    for p in parts:
+        inv = np.empty(p.nNo, dtype=np.int64); inv[p.node_map] = np.arange(p.nNo)
+        for (q, ptr) in p.neighbours:
+            other = parts[q]
+            inv_o = np.empty(other.nNo, dtype=np.int64); inv_o[other.node_map] = np.arange(other.nNo)
+            ptr_o = dict(other.neighbours)[p.rank]
+            assert np.array_equal(p.ltg[inv[ptr]], other.ltg[inv_o[ptr_o]])
+
+
+def test_slab_generator_matches_general_partition():
+    n, nz, nranks = 3, 2, 3
+    for r in range(nranks):
+        m, other, plo, phi = meshgen.cylinder_slab(n, nz, r, nranks)
+        node_map, mynNo = partition.fsils_order(other, r)
+        nshared_hi = len(phi) if r < nranks - 1 else 0
+        assert mynNo == m.nNo - nshared_hi
+        if r > 0:
+            assert np.array_equal(np.sort(node_map[plo]), np.arange(len(plo)))      # low group first
+        if r < nranks - 1:
+            assert node_map[phi].min() == mynNo                                       # high group last
+
+
+WORKER = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from svmultiphysics_b200 import meshgen, partition
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+n, nz = 3, 4
+m = meshgen.cylinder_tet4(n, nz)
+part = ((np.arange(m.nEl) // 6) // (n * n) * world // nz).astype(np.int32)
+parts = partition.partition_mesh(m.IEN, m.nNo, part, world)
+p = parts[rank]
+# a nodal field that is a partial sum on every rank: value = number of local elements touching the node
+inv = np.empty(p.nNo, dtype=np.int64); inv[p.node_map] = np.arange(p.nNo)
+v = np.zeros(p.nNo)                         # FSILS order
+np.add.at(v, p.node_map[p.IEN.ravel()], 1.0)
+# halo sum exactly as fsils_commuv: send my partial values of the shared nodes, add what I receive
+reqs, recv = [], {}
+for (q, ptr) in p.neighbours:
+    recv[q] = torch.zeros(len(ptr), dtype=torch.float64)
+    reqs.append(dist.isend(torch.from_numpy(v[ptr].copy()), q))
+    reqs.append(dist.irecv(recv[q], q))
+for r in reqs: r.wait()
+for (q, ptr) in p.neighbours:
+    v[ptr] += recv[q].numpy()
+# compare with the global count
+g = np.zeros(m.nNo); np.add.at(g, m.IEN.ravel(), 1.0)
+ok = np.array_equal(v[p.node_map], g[p.ltg])
+# owned-node dot: sum over ranks of sum_{a<mynNo} v_a must equal the global sum
+loc = torch.tensor([v[:p.mynNo].sum()], dtype=torch.float64)
+dist.all_reduce(loc)
+ok = ok and abs(loc.item() - g.sum()) < 1e-9
+flag = torch.tensor([1 if ok else 0]); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+dist.destroy_process_group()
+sys.exit(0 if flag.item() == 1 else 1)
+'''
+
+
+def test_halo_sum_pattern_gloo_world2(tmp_path):
+    import subprocess
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", str(script), ROOT]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
