@@ -153,11 +153,14 @@ multi_dot_stage1(long long n, int nvec, const double* __restrict__ ubase, long l
 
 __global__ void multi_dot_stage2(int nblocks, int nvec, const double* __restrict__ part, double* __restrict__ out)
 {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per output
+  const int lane = threadIdx.x & 31;
   if (j >= nvec) return;
   double s = 0.0;
-  for (int b = 0; b < nblocks; b++) s += part[(size_t)b * nvec + j];
-  out[j] = s;
+  for (int b = lane; b < nblocks; b += 32) s += part[(size_t)b * nvec + j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[j] = s;
 }
 
 int multi_dot(svb200_ctx* ctx, long long n, int nvec, const double* ubase, long long stride, const double* v, double* d_out)
@@ -173,7 +176,7 @@ int multi_dot(svb200_ctx* ctx, long long n, int nvec, const double* ubase, long 
   }
   const size_t smem = sizeof(double) * (DOT_THREADS / 32) * nvec;
   multi_dot_stage1<<<blocks, DOT_THREADS, smem, ctx->stream>>>(n, nvec, ubase, stride, v, ctx->d_red);
-  multi_dot_stage2<<<(nvec + 127) / 128, 128, 0, ctx->stream>>>(blocks, nvec, ctx->d_red, d_out);
+  multi_dot_stage2<<<(nvec * 32 + 127) / 128, 128, 0, ctx->stream>>>(blocks, nvec, ctx->d_red, d_out);
   ctx->launches += 2;
   SVB_CUDA(cudaGetLastError());
   return SVB200_OK;
@@ -405,6 +408,140 @@ int precond_scale_matrix(svb200_ctx* ctx, int dof, const double* W, double* Val)
   if (ctx->nNo == 0) return SVB200_OK;
   const long long threads = (long long)ctx->nNo * 32;
   scale_matrix_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(ctx->nNo, dof, ctx->d_rowPtr, ctx->d_colPtr, W, Val);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// NS (Schur complement) solver pieces, linear_solver/ns_solver.cpp.
+// ----------------------------------------------------------------------------------------------
+// Rectangular-block SpMV: blocks are R x C (row-major), U is (C,nNo), KU is (R,nNo).  Covers
+// fsils_spar_mul_vv on the momentum block (3x3), _sv on G (3x1), _vs on D / Gt (1x3) and _ss on L (1x1),
+// linear_solver/spar_mul.cpp:19-231.
+template <int R, int C>
+__global__ void __launch_bounds__(256)
+bsr_spmv_rc_kernel(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ colPtr, const double* __restrict__ K,
+                   const double* __restrict__ U, double* __restrict__ KU)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)nNo * R) return;
+  const int row = (int)(t / R), i = (int)(t % R);
+  double acc = 0.0;
+  for (int k = rowPtr[row]; k < rowPtr[row + 1]; k++) {
+    const int c = colPtr[k];
+    const double* v = K + (size_t)k * R * C + i * C;
+    const double* u = U + (size_t)c * C;
+#pragma unroll
+    for (int j = 0; j < C; j++) acc += v[j] * u[j];
+  }
+  KU[t] = acc;
+}
+
+int spmv_rc(svb200_ctx* ctx, int R, int C, const double* K, const double* U, double* KU)
+{
+  const int nNo = ctx->nNo;
+  if (nNo == 0) return SVB200_OK;
+  const unsigned blocks = (unsigned)(((long long)nNo * R + 255) / 256);
+#define SVB_RC(r, c)                                                                                              \
+  if (R == r && C == c) {                                                                                          \
+    bsr_spmv_rc_kernel<r, c><<<blocks, 256, 0, ctx->stream>>>(nNo, ctx->d_rowPtr, ctx->d_colPtr, K, U, KU);        \
+    ctx->launches++;                                                                                               \
+    SVB_CUDA(cudaGetLastError());                                                                                  \
+    return SVB200_OK;                                                                                              \
+  }
+  SVB_RC(3, 3) SVB_RC(3, 1) SVB_RC(1, 3) SVB_RC(1, 1) SVB_RC(2, 2) SVB_RC(2, 1) SVB_RC(1, 2)
+#undef SVB_RC
+  set_error("svb200: unsupported block shape in spmv_rc");
+  return SVB200_ERR_UNSUPPORTED;
+}
+
+// tslot[j] = slot l of row col(j) whose column is the row of j (the transposed entry), or -1.
+__global__ void transpose_slot_kernel(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ colPtr,
+                                      int* __restrict__ tslot)
+{
+  const int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3);
+  const int l8 = threadIdx.x & 7;
+  if (row >= nNo) return;
+  for (int j = rowPtr[row] + l8; j < rowPtr[row + 1]; j += 8) {
+    const int k = colPtr[j];
+    int t = -1;
+    for (int l = rowPtr[k]; l < rowPtr[k + 1]; l++)
+      if (colPtr[l] == row) { t = l; break; }
+    tslot[j] = t;
+  }
+}
+
+int build_transpose_slots(svb200_ctx* ctx, int* d_tslot)
+{
+  if (ctx->nNo == 0) return SVB200_OK;
+  const long long threads = (long long)ctx->nNo * 8;
+  transpose_slot_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(ctx->nNo, ctx->d_rowPtr, ctx->d_colPtr, d_tslot);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
+// ns_solver::depart (ns_solver.cpp:64-132): split the (nsd+1)^2 blocks of Val into mK, mG, mD, mL and
+// Gt(:, tslot(j)) = -mG(:, j).  Gt must be zeroed by the caller (entries without a transposed slot).
+__global__ void __launch_bounds__(256)
+depart_kernel(long long nnz, int nsd, const double* __restrict__ Val, const int* __restrict__ tslot, double* __restrict__ mK,
+              double* __restrict__ mG, double* __restrict__ mD, double* __restrict__ mL, double* __restrict__ Gt)
+{
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nnz) return;
+  const int dof = nsd + 1;
+  const double* v = Val + (size_t)j * dof * dof;
+  const int t = tslot[j];
+  for (int a = 0; a < nsd; a++) {
+    for (int b = 0; b < nsd; b++) mK[(size_t)j * nsd * nsd + a * nsd + b] = v[a * dof + b];
+    const double g = v[a * dof + nsd];
+    mG[(size_t)j * nsd + a] = g;
+    if (t >= 0) Gt[(size_t)t * nsd + a] = -g;
+    mD[(size_t)j * nsd + a] = v[nsd * dof + a];
+  }
+  mL[j] = v[nsd * dof + nsd];
+}
+
+int ns_depart(svb200_ctx* ctx, int nsd, const double* Val, const int* d_tslot, double* mK, double* mG, double* mD, double* mL,
+              double* Gt)
+{
+  const long long nnz = ctx->nnz;
+  if (nnz == 0) return SVB200_OK;
+  SVB_CUDA(cudaMemsetAsync(Gt, 0, sizeof(double) * nnz * nsd, ctx->stream));
+  depart_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, ctx->stream>>>(nnz, nsd, Val, d_tslot, mK, mG, mD, mL, Gt);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
+// Split Ri(dof,nNo) into Rm(nsd,nNo), Rc(nNo) and merge back.
+__global__ void split_kernel(long long nNo, int dof, const double* __restrict__ Ri, double* __restrict__ Rm, double* __restrict__ Rc)
+{
+  const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nNo) return;
+  for (int i = 0; i < dof - 1; i++) Rm[a * (dof - 1) + i] = Ri[a * dof + i];
+  Rc[a] = Ri[a * dof + dof - 1];
+}
+__global__ void merge_kernel(long long nNo, int dof, const double* __restrict__ Rm, const double* __restrict__ Rc, double* __restrict__ Ri)
+{
+  const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nNo) return;
+  for (int i = 0; i < dof - 1; i++) Ri[a * dof + i] = Rm[a * (dof - 1) + i];
+  Ri[a * dof + dof - 1] = Rc[a];
+}
+int ns_split(svb200_ctx* ctx, int dof, const double* Ri, double* Rm, double* Rc)
+{
+  if (ctx->nNo == 0) return SVB200_OK;
+  split_kernel<<<(ctx->nNo + 255) / 256, 256, 0, ctx->stream>>>(ctx->nNo, dof, Ri, Rm, Rc);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+int ns_merge(svb200_ctx* ctx, int dof, const double* Rm, const double* Rc, double* Ri)
+{
+  if (ctx->nNo == 0) return SVB200_OK;
+  merge_kernel<<<(ctx->nNo + 255) / 256, 256, 0, ctx->stream>>>(ctx->nNo, dof, Rm, Rc, Ri);
   ctx->launches++;
   SVB_CUDA(cudaGetLastError());
   return SVB200_OK;

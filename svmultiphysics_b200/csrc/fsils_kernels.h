@@ -17,6 +17,12 @@ int precond_face_scale(svb200_ctx* ctx, const Face& f, int dof, double* W);
 int precond_face_valm(svb200_ctx* ctx, const Face& f, int dof, const double* W);
 int precond_scale_matrix(svb200_ctx* ctx, int dof, const double* W, double* Val);
 
+int spmv_rc(svb200_ctx* ctx, int R, int C, const double* K, const double* U, double* KU);
+int build_transpose_slots(svb200_ctx* ctx, int* d_tslot);
+int ns_depart(svb200_ctx* ctx, int nsd, const double* Val, const int* d_tslot, double* mK, double* mG, double* mD, double* mL, double* Gt);
+int ns_split(svb200_ctx* ctx, int dof, const double* Ri, double* Rm, double* Rc);
+int ns_merge(svb200_ctx* ctx, int dof, const double* Rm, const double* Rc, double* Ri);
+
 // comm.cu: shared-node sums and scalar all-reduces (no-ops for a single partition)
 int halo_sum(svb200_ctx* ctx, int dof, double* V);
 int allreduce_sum(svb200_ctx* ctx, double* d_buf, int n);

@@ -183,77 +183,96 @@ static int precond_diag_device(svb200_ctx* ctx, int dof, double* Val, double* R,
 }
 
 // ---- GMRES -------------------------------------------------------------------------------------
-static int gmres_device(svb200_ctx* ctx, int dof, const svb200_sublsparams& p, svb200_sublsresult& r, const double* Val,
-                        double* R, svb200_lsresult* full)
+// One routine for both reference variants:
+//   ns_inner == false: gmres_v / gmres_s (gmres.cpp:425-609 / 257-412): R is overwritten by the solution, the
+//                      tolerance comes from |R|, every SpMV is counted, early return when |R| <= absTol;
+//   ns_inner == true : gmres (gmres.cpp:65-250), the momentum solve inside the NS solver: R is read only, X is
+//                      the output, no SpMV on the first restart, eps fixed by the first restart, itr and callD
+//                      ACCUMULATE over calls, and the BCOP_TYPE_PRE correction is applied when a coupled face
+//                      exists (it is dead code in gmres_v, `flag = false`, gmres.cpp:437).
+// u: workspace of (sD+1) vectors, d_scal: >= sD+16 doubles of device scratch.
+static int gmres_core(svb200_ctx* ctx, int dof, const svb200_sublsparams& p, svb200_sublsresult& r, const double* Val,
+                      double* R, double* X, double* u, double* d_scal, bool ns_inner, svb200_lsresult* full)
 {
   const long long n = (long long)ctx->nNo * dof;
+  const long long us = (n + 1) & ~1ll;     // 16-byte aligned stride between Krylov vectors (double2 kernels)
   const int sD = p.sD;
-  if (sD < 1 || sD > 250) {
-    set_error("svb200: Krylov space dimension must be in [1,250]");
-    return SVB200_ERR_INVALID;
-  }
-  // workspace: u (sD+1 vectors) | X | scalars
-  SVB_TRY(ensure_work(ctx, (size_t)n * (sD + 2) + SCAL_N));
-  double* u = ctx->d_work;
-  double* X = u + (size_t)n * (sD + 1);
-  double* d_scal = X + n;
-  double* d_h = d_scal + 8;        // Hessenberg column (sD+2)
+  double* d_h = d_scal + 8;
   double* d_hn = d_scal + 4;
   double* hp = ctx->h_pinned;
-
   std::vector<double> h((size_t)(sD + 1) * sD, 0.0), y(sD), c(sD), s(sD), err(sD + 1, 0.0);
   auto H = [&](int i, int j) -> double& { return h[(size_t)j * (sD + 1) + i]; };
+  bool anyCoupled = false;
+  for (auto& f : ctx->face) anyCoupled |= (f.set && f.coupledFlag);
 
   const double t0 = now_s();
   r.success = 0;
-  double eps;
-  SVB_TRY(norm_owned(ctx, dof, R, d_scal, &eps));
-  r.iNorm = eps;
-  r.fNorm = eps;
-  eps = std::max(p.absTol, p.relTol * eps);
-  r.itr = 0;
+  double eps = 0.0;
   int last_i = 0;
-  SVB_TRY(bc_pre_device(ctx, dof, d_scal));
-  if (full) full->hist_n = 0;
-
-  if (r.iNorm <= p.absTol) {
-    r.callD = std::numeric_limits<double>::epsilon();
-    r.dB = 0.0;
-    r.success = 1;
-    return SVB200_OK;     // R is left untouched, as in the reference (gmres.cpp:470-475)
+  if (!ns_inner) {
+    SVB_TRY(norm_owned(ctx, dof, R, d_scal, &eps));
+    r.iNorm = eps;
+    r.fNorm = eps;
+    eps = std::max(p.absTol, p.relTol * eps);
+    r.itr = 0;
+    SVB_TRY(bc_pre_device(ctx, dof, d_scal));
+    if (full) full->hist_n = 0;
+    if (r.iNorm <= p.absTol) {
+      r.callD = std::numeric_limits<double>::epsilon();
+      r.dB = 0.0;
+      r.success = 1;
+      return SVB200_OK;     // R is left untouched, as in the reference (gmres.cpp:470-475)
+    }
   }
   SVB_CUDA(cudaMemsetAsync(X, 0, sizeof(double) * n, ctx->stream));
 
   for (int l = 0; l < p.mItr; l++) {
-    r.dB = r.fNorm;
-    r.itr++;
+    if (!ns_inner) {
+      r.dB = r.fNorm;
+      r.itr++;
+    }
     if (l == 0) {
       // X = 0: K X (+ coupled-face term) is exactly zero, u0 = R.
       SVB_CUDA(cudaMemcpyAsync(u, R, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
     } else {
       SVB_TRY(spmv_halo(ctx, dof, Val, X, u));
       SVB_TRY(add_bc_mul_device(ctx, 0, dof, X, u, d_scal));
+      if (ns_inner) r.itr++;
       SVB_TRY(axpby(ctx, n, 1.0, R, -1.0, u, u));
     }
+    if (ns_inner && anyCoupled) SVB_TRY(add_bc_mul_device(ctx, 1, dof, u, u, d_scal));
     SVB_TRY(norm_owned(ctx, dof, u, d_scal, &err[0]));
     if (err[0] == 0.0) {
       set_error("FSILS: A zero matrix norm has been computed. This is probably caused by ill-posed boundary conditions.");
       return SVB200_ERR_NUMERIC;
     }
+    if (ns_inner) {
+      if (l == 0) {
+        eps = err[0];
+        r.iNorm = eps;
+        r.fNorm = eps;
+        eps = std::max(p.absTol, p.relTol * eps);
+      }
+      r.dB = r.fNorm;
+    }
     SVB_TRY(axpby(ctx, n, 1.0 / err[0], u, 0.0, nullptr, u));
 
     for (int i = 0; i < sD; i++) {
-      r.itr++;
+      if (!ns_inner) r.itr++;
       last_i = i;
-      double* ui = u + (size_t)n * i;
-      double* ui1 = u + (size_t)n * (i + 1);
+      double* ui = u + (size_t)us * i;
+      double* ui1 = u + (size_t)us * (i + 1);
       SVB_TRY(spmv_halo(ctx, dof, Val, ui, ui1));
       SVB_TRY(add_bc_mul_device(ctx, 0, dof, ui, ui1, d_scal));
-      SVB_TRY(multi_dot(ctx, (long long)ctx->mynNo * dof, i + 2, u, n, ui1, d_h));
+      if (ns_inner) {
+        r.itr++;
+        if (anyCoupled) SVB_TRY(add_bc_mul_device(ctx, 1, dof, ui1, ui1, d_scal));
+      }
+      SVB_TRY(multi_dot(ctx, (long long)ctx->mynNo * dof, i + 2, u, us, ui1, d_h));
       SVB_TRY(allreduce_sum(ctx, d_h, i + 2));
       SVB_CUDA(cudaMemcpyAsync(hp, d_h, sizeof(double) * (i + 2), cudaMemcpyDeviceToHost, ctx->stream));
       SVB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-      SVB_TRY(cgs_update(ctx, n, i + 1, u, n, ui1, d_h, d_hn));
+      SVB_TRY(cgs_update(ctx, n, i + 1, u, us, ui1, d_h, d_hn));
       SVB_CUDA(cudaEventSynchronize(ctx->ev1));
 
       for (int j = 0; j <= i + 1; j++) H(j, i) = hp[j];
@@ -272,7 +291,7 @@ static int gmres_device(svb200_ctx* ctx, int dof, const svb200_sublsparams& p, s
       H(i + 1, i) = 0.0;
       err[i + 1] = -s[i] * err[i];
       err[i] = c[i] * err[i];
-      if (full && full->hist && full->hist_n < full->hist_cap) full->hist[full->hist_n++] = std::fabs(err[i + 1]);
+      if (!ns_inner && full && full->hist && full->hist_n < full->hist_cap) full->hist[full->hist_n++] = std::fabs(err[i + 1]);
       if (std::fabs(err[i + 1]) < eps) {
         r.success = 1;
         break;
@@ -286,15 +305,36 @@ static int gmres_device(svb200_ctx* ctx, int dof, const svb200_sublsparams& p, s
     }
     Coefs cf;
     for (int j = 0; j <= last_i; j++) cf.c[j] = y[j];
-    SVB_TRY(lincomb(ctx, n, last_i + 1, cf, u, n, X));
+    SVB_TRY(lincomb(ctx, n, last_i + 1, cf, u, us, X));
     r.fNorm = std::fabs(err[last_i + 1]);
     if (r.success) break;
   }
-  SVB_CUDA(cudaMemcpyAsync(R, X, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
-  SVB_CUDA(cudaStreamSynchronize(ctx->stream));
-  r.callD = now_s() - t0;
+  if (!ns_inner) {
+    SVB_CUDA(cudaMemcpyAsync(R, X, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+    r.callD = now_s() - t0;
+  } else {
+    SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+    r.callD = now_s() - t0 + r.callD;
+  }
   r.dB = 10.0 * std::log(r.fNorm / r.dB);
   return SVB200_OK;
+}
+
+static int gmres_device(svb200_ctx* ctx, int dof, const svb200_sublsparams& p, svb200_sublsresult& r, const double* Val,
+                        double* R, svb200_lsresult* full)
+{
+  const long long n = (long long)ctx->nNo * dof;
+  if (p.sD < 1 || p.sD > 250) {
+    set_error("svb200: Krylov space dimension must be in [1,250]");
+    return SVB200_ERR_INVALID;
+  }
+  const long long us = (n + 1) & ~1ll;
+  SVB_TRY(ensure_work(ctx, (size_t)us * (p.sD + 2) + SCAL_N));
+  double* u = ctx->d_work;
+  double* X = u + (size_t)us * (p.sD + 1);
+  double* d_scal = X + us;
+  return gmres_core(ctx, dof, p, r, Val, R, X, u, d_scal, false, full);
 }
 
 // ---- CG ------------------------------------------------------------------------------------------
@@ -302,11 +342,12 @@ static int cg_device(svb200_ctx* ctx, int dof, const svb200_sublsparams& p, svb2
                      double* R, svb200_lsresult* full)
 {
   const long long n = (long long)ctx->nNo * dof;
-  SVB_TRY(ensure_work(ctx, (size_t)n * 3 + SCAL_N));
+  const long long ns = (n + 1) & ~1ll;
+  SVB_TRY(ensure_work(ctx, (size_t)ns * 3 + SCAL_N));
   double* P = ctx->d_work;
-  double* KP = P + n;
-  double* X = KP + n;
-  double* d_scal = X + n;
+  double* KP = P + ns;
+  double* X = KP + ns;
+  double* d_scal = X + ns;
   const double t0 = now_s();
   r.success = 0;
   SVB_TRY(norm_owned(ctx, dof, R, d_scal, &r.iNorm));
@@ -352,14 +393,15 @@ static int bicgs_device(svb200_ctx* ctx, int dof, const svb200_sublsparams& p, s
                         double* R, svb200_lsresult* full)
 {
   const long long n = (long long)ctx->nNo * dof;
-  SVB_TRY(ensure_work(ctx, (size_t)n * 6 + SCAL_N));
+  const long long ns = (n + 1) & ~1ll;
+  SVB_TRY(ensure_work(ctx, (size_t)ns * 6 + SCAL_N));
   double* P = ctx->d_work;
-  double* Rh = P + n;
-  double* X = Rh + n;
-  double* V = X + n;
-  double* S = V + n;
-  double* T = S + n;
-  double* d_scal = T + n;
+  double* Rh = P + ns;
+  double* X = Rh + ns;
+  double* V = X + ns;
+  double* S = V + ns;
+  double* T = S + ns;
+  double* d_scal = T + ns;
   const double t0 = now_s();
   r.success = 0;
   double err;
@@ -481,11 +523,295 @@ int fsils_solve_device(svb200_ctx* ctx, int dof, int ls_type, const svb200_lspar
   return SVB200_OK;
 }
 
-// Placeholder until the NS (Schur complement) solver lands: fail loudly, never fall back.
-int ns_solver_device(svb200_ctx*, int, const svb200_lsparams*, svb200_lsresult*, double*, double*)
+// ---- NS solver (Schur complement) -------------------------------------------------------------------
+// ge::ge (linear_solver/ge.cpp:13-112): diagonally scaled Gaussian elimination with partial pivoting on the
+// leading N x N part of the (nV x nV, column-major) Gram matrix; tiny, stays on the host.
+static bool ge_host(int nV, int N, const std::vector<double>& A, std::vector<double>& B)
 {
-  set_error("svb200: LS type NS is not implemented yet");
-  return SVB200_ERR_UNSUPPORTED;
+  auto a = [&](int i, int j) { return A[(size_t)j * nV + i]; };
+  std::vector<double> W(std::max(N, 1));
+  const double tol = std::numeric_limits<double>::denorm_min();
+  const double eps = std::numeric_limits<double>::epsilon();
+  for (int i = 0; i < N; i++) {
+    if (std::fabs(a(i, i)) < tol) { std::fill(B.begin(), B.end(), 0.0); return false; }
+    W[i] = 1.0 / std::sqrt(std::fabs(a(i, i)));
+  }
+  std::vector<double> Cm((size_t)std::max(N, 1) * (N + 1));
+  auto C = [&](int i, int j) -> double& { return Cm[(size_t)j * N + i]; };
+  for (int i = 0; i < N; i++) {
+    for (int j = 0; j < N; j++) C(i, j) = W[i] * W[j] * a(i, j);
+    C(i, N) = W[i] * B[i];
+  }
+  if (N <= 0) return false;
+  if (N == 1) {
+    B[0] = C(0, 1) / C(0, 0);
+    B[0] = B[0] * W[0];
+    return true;
+  }
+  if (N == 2) {
+    const double pivot = C(0, 0) * C(1, 1) - C(1, 0) * C(0, 1);
+    if (std::fabs(pivot) < eps) { std::fill(B.begin(), B.end(), 0.0); return false; }
+    B[0] = (C(0, 2) * C(1, 1) - C(1, 2) * C(0, 1)) / pivot;
+    B[1] = (C(1, 2) * C(0, 0) - C(0, 2) * C(1, 0)) / pivot;
+    B[0] = W[0] * B[0];
+    B[1] = W[1] * B[1];
+    return true;
+  }
+  for (int m = 0; m < N - 1; m++) {
+    int ipv = m;
+    double pivot = std::fabs(C(m, m));
+    for (int i = m + 1; i < N; i++)
+      if (std::fabs(C(i, m)) > pivot) { ipv = i; pivot = std::fabs(C(i, m)); }
+    if (std::fabs(pivot) < eps) { std::fill(B.begin(), B.end(), 0.0); return false; }
+    if (ipv != m)
+      for (int j = m; j < N + 1; j++) std::swap(C(m, j), C(ipv, j));
+    for (int i = m + 1; i < N; i++) {
+      const double saveEl = C(i, m) / C(m, m);
+      C(i, m) = 0.0;
+      for (int j = m + 1; j < N + 1; j++) C(i, j) = C(i, j) - saveEl * C(m, j);
+    }
+  }
+  for (int j = N - 1; j >= 0; j--) {
+    for (int i = j + 1; i < N; i++) C(j, N) = C(j, N) - C(j, i) * C(i, N);
+    C(j, N) = C(j, N) / C(j, j);
+  }
+  for (int i = 0; i < N; i++) B[i] = W[i] * C(i, N);
+  return true;
+}
+
+// cgrad::schur (cgrad.cpp:23-133): CG on S p = L p - Gt (G p); R(nNo) in/out.
+// work: X, P, SP, DGP (nNo each) and GP (nsd*nNo).
+static int schur_device(svb200_ctx* ctx, int nsd, const svb200_sublsparams& p, svb200_sublsresult& r, const double* Gt,
+                        const double* mG, const double* mL, double* R, double* work, double* d_scal)
+{
+  const long long nNo = ctx->nNo;
+  const long long nns = (nNo + 1) & ~1ll;
+  double* X = work;
+  double* P = X + nns;
+  double* SP = P + nns;
+  double* DGP = SP + nns;
+  double* GP = DGP + nns;
+  bool anyCoupled = false;
+  for (auto& f : ctx->face) anyCoupled |= (f.set && f.coupledFlag);
+  const double t0 = now_s();
+  r.success = 0;
+  SVB_TRY(norm_owned(ctx, 1, R, d_scal, &r.iNorm));
+  const double tol = std::max(p.absTol, p.relTol * r.iNorm);
+  const double eps = tol * tol;
+  double errO = r.iNorm * r.iNorm;
+  double err = errO;
+  SVB_CUDA(cudaMemsetAsync(X, 0, sizeof(double) * nNo, ctx->stream));
+  SVB_CUDA(cudaMemcpyAsync(P, R, sizeof(double) * nNo, cudaMemcpyDeviceToDevice, ctx->stream));
+  int last_i = 0;
+  for (int i = 0; i < p.mItr; i++) {
+    last_i = i;
+    if (err < eps) {
+      r.success = 1;
+      break;
+    }
+    errO = err;
+    SVB_TRY(spmv_rc(ctx, nsd, 1, mG, P, GP));
+    SVB_TRY(halo_sum(ctx, nsd, GP));
+    if (anyCoupled) SVB_TRY(add_bc_mul_device(ctx, 1, nsd, GP, GP, d_scal));
+    SVB_TRY(spmv_rc(ctx, 1, nsd, Gt, GP, DGP));
+    SVB_TRY(halo_sum(ctx, 1, DGP));
+    SVB_TRY(spmv_rc(ctx, 1, 1, mL, P, SP));
+    SVB_TRY(halo_sum(ctx, 1, SP));
+    SVB_TRY(axpby(ctx, nNo, -1.0, DGP, 1.0, SP, SP));
+    double psp;
+    SVB_TRY(dot_owned(ctx, 1, P, SP, d_scal, &psp));
+    const double alpha = errO / psp;
+    SVB_TRY(axpby(ctx, nNo, alpha, P, 1.0, X, X));
+    SVB_TRY(axpby(ctx, nNo, -alpha, SP, 1.0, R, R));
+    SVB_TRY(norm_owned(ctx, 1, R, d_scal, &err));
+    err = err * err;
+    SVB_TRY(axpby(ctx, nNo, errO / err, R, 1.0, P, P));
+    SVB_TRY(axpby(ctx, nNo, err / errO, P, 0.0, nullptr, P));
+  }
+  SVB_CUDA(cudaMemcpyAsync(R, X, sizeof(double) * nNo, cudaMemcpyDeviceToDevice, ctx->stream));
+  SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  r.fNorm = std::sqrt(err);
+  r.callD = now_s() - t0 + r.callD;
+  r.itr = r.itr + last_i;
+  r.dB = (errO < std::numeric_limits<double>::epsilon()) ? 0.0 : 5.0 * std::log(err / errO);
+  return SVB200_OK;
+}
+
+// ns_solver::ns_solver (ns_solver.cpp:140-472).
+int ns_solver_device(svb200_ctx* ctx, int dof, const svb200_lsparams* ls, svb200_lsresult* res, double* Val, double* Ri)
+{
+  const long long nNo = ctx->nNo, nnz = ctx->nnz;
+  const int nsd = dof - 1;
+  if (nsd != 3 && nsd != 2) {
+    set_error("svb200: the NS solver needs dof = 3 (2-D) or 4 (3-D)");
+    return SVB200_ERR_INVALID;
+  }
+  const int iBmax = ls->RI.mItr;
+  const int nB = 2 * iBmax;
+  const int sD = ls->GM.sD;
+  if (sD < 1 || sD > 250 || iBmax < 1 || iBmax > 100) {
+    set_error("svb200: NS solver needs 1 <= Krylov dimension <= 250 and 1 <= Max_iterations <= 100");
+    return SVB200_ERR_INVALID;
+  }
+  const long long nv = nsd * nNo;
+  const long long nvs = (nv + 1) & ~1ll, nns = (nNo + 1) & ~1ll;   // 16-byte aligned strides
+  // workspace layout (doubles)
+  size_t need = 0;
+  auto take = [&](size_t cnt) { size_t o = need; need += (cnt + 1) & ~(size_t)1; return o; };
+  const size_t oRm = take(nv), oRmi = take(nv), oRc = take(nNo), oRci = take(nNo);
+  const size_t oU = take((size_t)nvs * iBmax), oMU = take((size_t)nvs * nB), oP = take((size_t)nns * iBmax), oMP = take((size_t)nns * nB);
+  const size_t oK = take((size_t)nnz * nsd * nsd), oG = take((size_t)nnz * nsd), oD = take((size_t)nnz * nsd), oL = take(nnz),
+               oGt = take((size_t)nnz * nsd);
+  const size_t oGm = take((size_t)nvs * (sD + 1)), oSch = take((size_t)nns * 4 + nvs), oScal = take(SCAL_N);
+  SVB_TRY(ensure_work(ctx, need));
+  double* W = ctx->d_work;
+  double *Rm = W + oRm, *Rmi = W + oRmi, *Rc = W + oRc, *Rci = W + oRci, *U = W + oU, *MU = W + oMU, *P = W + oP, *MP = W + oMP;
+  double *mK = W + oK, *mG = W + oG, *mD = W + oD, *mL = W + oL, *Gt = W + oGt, *gm_u = W + oGm, *sch = W + oSch, *d_scal = W + oScal;
+  double* d_gram = d_scal + 300;     // Gram-matrix partial results (<= 2*(nB+1) + ... doubles)
+  if (!ctx->d_tslot) {
+    SVB_CUDA(cudaMalloc(&ctx->d_tslot, sizeof(int) * std::max<long long>(nnz, 1)));
+    SVB_TRY(build_transpose_slots(ctx, ctx->d_tslot));
+  }
+  svb200_sublsresult &RI = res->RI, &GM = res->GM, &CG = res->CG;
+  const double t0 = now_s();
+
+  SVB_TRY(ns_split(ctx, dof, Ri, Rmi, Rci));
+  SVB_CUDA(cudaMemcpyAsync(Rm, Rmi, sizeof(double) * nv, cudaMemcpyDeviceToDevice, ctx->stream));
+  SVB_CUDA(cudaMemcpyAsync(Rc, Rci, sizeof(double) * nNo, cudaMemcpyDeviceToDevice, ctx->stream));
+  double nm, nc;
+  SVB_TRY(norm_owned(ctx, nsd, Rm, d_scal, &nm));
+  SVB_TRY(norm_owned(ctx, 1, Rc, d_scal, &nc));
+  double eps = std::sqrt(nm * nm + nc * nc);
+  RI.iNorm = eps;
+  RI.fNorm = eps * eps;
+  CG.callD = 0.0; GM.callD = 0.0;
+  CG.itr = 0; GM.itr = 0;
+  RI.success = 0;
+  eps = std::max(ls->RI.absTol, ls->RI.relTol * eps);
+  SVB_TRY(ns_depart(ctx, nsd, Val, ctx->d_tslot, mK, mG, mD, mL, Gt));
+  SVB_TRY(bc_pre_device(ctx, dof, d_scal));     // nS over the first nsd = dof-1 components (ns_solver.cpp:29-58)
+
+  std::vector<double> A((size_t)nB * nB, 0.0), B(nB, 0.0), xB(nB, 0.0), oldxB(nB, 0.0);
+  int iBB = 0, i_count = 0;
+  for (int i = 0; i < iBmax; i++) {
+    int iB = 2 * i;
+    iBB = 2 * i + 1;
+    RI.dB = RI.fNorm;
+    i_count = i;
+    double* Ui = U + (size_t)nvs * i;
+    double* Pi = P + (size_t)nns * i;
+    double* MU_iB = MU + (size_t)nvs * iB;
+    double* MU_iBB = MU + (size_t)nvs * iBB;
+    double* MP_iB = MP + (size_t)nns * iB;
+    double* MP_iBB = MP + (size_t)nns * iBB;
+    // U = K^-1 Rm
+    SVB_TRY(gmres_core(ctx, nsd, ls->GM, GM, mK, Rm, Ui, gm_u, d_scal, true, nullptr));
+    // P = Rc - D U ; P = S^-1 P
+    SVB_TRY(spmv_rc(ctx, 1, nsd, mD, Ui, Pi));
+    SVB_TRY(halo_sum(ctx, 1, Pi));
+    SVB_TRY(axpby(ctx, nNo, 1.0, Rc, -1.0, Pi, Pi));
+    SVB_TRY(schur_device(ctx, nsd, ls->CG, CG, Gt, mG, mL, Pi, sch, d_scal));
+    // MU(iB) = G P ; MU(iBB) = Rm - G P ; U = K^-1 MU(iBB)
+    SVB_TRY(spmv_rc(ctx, nsd, 1, mG, Pi, MU_iB));
+    SVB_TRY(halo_sum(ctx, nsd, MU_iB));
+    SVB_TRY(axpby(ctx, nv, 1.0, Rm, -1.0, MU_iB, MU_iBB));
+    SVB_TRY(gmres_core(ctx, nsd, ls->GM, GM, mK, MU_iBB, Ui, gm_u, d_scal, true, nullptr));
+    // MU(iBB) = K U + bc(U) ; MP(iB) = L P ; MP(iBB) = D U
+    SVB_TRY(launch_spmv(ctx, nsd, mK, Ui, MU_iBB));
+    SVB_TRY(halo_sum(ctx, nsd, MU_iBB));
+    SVB_TRY(add_bc_mul_device(ctx, 0, nsd, Ui, MU_iBB, d_scal));
+    SVB_TRY(spmv_rc(ctx, 1, 1, mL, Pi, MP_iB));
+    SVB_TRY(halo_sum(ctx, 1, MP_iB));
+    SVB_TRY(spmv_rc(ctx, 1, nsd, mD, Ui, MP_iBB));
+    SVB_TRY(halo_sum(ctx, 1, MP_iBB));
+    // Gram matrix columns iB, iBB: [ <MU_j,MU_k> (j<=k), <MU_k,Rmi> ] and the same with MP / Rci
+    int cnt = 0;
+    for (int k = iB; k <= iBB; k++) {
+      SVB_TRY(multi_dot(ctx, (long long)ctx->mynNo * nsd, k + 1, MU, nvs, MU + (size_t)nvs * k, d_gram + cnt));
+      SVB_TRY(multi_dot(ctx, (long long)ctx->mynNo * nsd, 1, Rmi, 0, MU + (size_t)nvs * k, d_gram + cnt + k + 1));
+      cnt += k + 2;
+    }
+    const int half = cnt;
+    for (int k = iB; k <= iBB; k++) {
+      SVB_TRY(multi_dot(ctx, (long long)ctx->mynNo, k + 1, MP, nns, MP + (size_t)nns * k, d_gram + cnt));
+      SVB_TRY(multi_dot(ctx, (long long)ctx->mynNo, 1, Rci, 0, MP + (size_t)nns * k, d_gram + cnt + k + 1));
+      cnt += k + 2;
+    }
+    if (cnt > SCAL_N - 300) {
+      set_error("svb200: NS Gram buffer overflow");
+      return SVB200_ERR_INVALID;
+    }
+    SVB_TRY(allreduce_sum(ctx, d_gram, cnt));
+    SVB_TRY(fetch(ctx, d_gram, cnt, ctx->h_pinned));
+    {
+      const double* g = ctx->h_pinned;
+      int c = 0;
+      for (int k = iB; k <= iBB; k++) {
+        for (int j = 0; j <= k; j++) {
+          const double v = g[c] + g[half + c];
+          A[(size_t)k * nB + j] = v;
+          A[(size_t)j * nB + k] = v;
+          c++;
+        }
+        B[k] = g[c] + g[half + c];
+        c++;
+      }
+    }
+    xB = B;
+    if (ge_host(nB, iBB + 1, A, xB)) {
+      oldxB = xB;
+    } else {
+      // the reference throws on the master rank (ns_solver.cpp:346-348), which aborts the run
+      set_error("FSILS: Singular matrix detected");
+      return SVB200_ERR_NUMERIC;
+    }
+    double sum = 0.0;
+    for (int q = 0; q <= iBB; q++) sum += xB[q] * B[q];
+    RI.fNorm = RI.iNorm * RI.iNorm - sum;
+    if (RI.fNorm < eps * eps) {
+      RI.success = 1;
+      break;
+    }
+    // Rm = Rmi - sum_j xB_j MU_j ; Rc = Rci - sum_j xB_j MP_j
+    Coefs cf;
+    for (int j = 0; j <= iBB; j++) cf.c[j] = -xB[j];
+    SVB_CUDA(cudaMemcpyAsync(Rm, Rmi, sizeof(double) * nv, cudaMemcpyDeviceToDevice, ctx->stream));
+    SVB_CUDA(cudaMemcpyAsync(Rc, Rci, sizeof(double) * nNo, cudaMemcpyDeviceToDevice, ctx->stream));
+    SVB_TRY(lincomb(ctx, nv, iBB + 1, cf, MU, nvs, Rm));
+    SVB_TRY(lincomb(ctx, nNo, iBB + 1, cf, MP, nns, Rc));
+  }
+  RI.itr = i_count;
+  {
+    Coefs cf;
+    for (int j = 0; j <= iBB; j++) cf.c[j] = -xB[j];
+    SVB_CUDA(cudaMemcpyAsync(Rc, Rci, sizeof(double) * nNo, cudaMemcpyDeviceToDevice, ctx->stream));
+    SVB_TRY(lincomb(ctx, nNo, iBB + 1, cf, MP, nns, Rc));
+  }
+  double nrc;
+  SVB_TRY(norm_owned(ctx, 1, Rc, d_scal, &nrc));
+  res->Resc = static_cast<int>(100.0 * nrc * nrc / RI.fNorm);
+  res->Resm = 100 - res->Resc;
+  // solution: Rmi = sum_i xB(2i+1) U_i ; Rci = sum_i xB(2i) P_i
+  {
+    Coefs cu, cp;
+    for (int i = 0; i <= RI.itr; i++) { cu.c[i] = xB[2 * i + 1]; cp.c[i] = xB[2 * i]; }
+    SVB_CUDA(cudaMemsetAsync(Rmi, 0, sizeof(double) * nv, ctx->stream));
+    SVB_CUDA(cudaMemsetAsync(Rci, 0, sizeof(double) * nNo, ctx->stream));
+    SVB_TRY(lincomb(ctx, nv, RI.itr + 1, cu, U, nvs, Rmi));
+    SVB_TRY(lincomb(ctx, nNo, RI.itr + 1, cp, P, nns, Rci));
+  }
+  SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  RI.callD = now_s() - t0;
+  RI.dB = 5.0 * std::log(RI.fNorm / RI.dB);
+  if (res->Resc < 0 || res->Resm < 0) {
+    res->Resc = 0;
+    res->Resm = 0;
+    RI.dB = 0;
+    RI.fNorm = 0.0;
+  }
+  RI.fNorm = std::sqrt(RI.fNorm);
+  SVB_TRY(ns_merge(ctx, dof, Rmi, Rci, Ri));
+  return SVB200_OK;
 }
 
 }  // namespace svb

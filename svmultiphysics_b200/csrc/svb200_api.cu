@@ -199,7 +199,7 @@ int svb200_destroy(svb200_ctx* ctx)
   cudaFree(ctx->d_map); cudaFree(ctx->d_rowPtr); cudaFree(ctx->d_colPtr); cudaFree(ctx->d_diagPtr);
   cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf);
   cudaFree(ctx->d_stage); cudaFree(ctx->d_R); cudaFree(ctx->d_Val); cudaFree(ctx->d_W);
-  cudaFree(ctx->d_work); cudaFree(ctx->d_red);
+  cudaFree(ctx->d_work); cudaFree(ctx->d_red); cudaFree(ctx->d_tslot);
   cudaFreeHost(ctx->h_pinned);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
@@ -264,6 +264,7 @@ int svb200_set_graph(svb200_ctx* ctx, int32_t nNo, int32_t nnz, const int32_t* r
   TRY(upload(ctx, &ctx->d_colPtr, col.data(), (size_t)nnz));
   TRY(upload(ctx, &ctx->d_map, ctx->h_map.data(), (size_t)nNo));
   if (ctx->d_diagPtr) { cudaFree(ctx->d_diagPtr); ctx->d_diagPtr = nullptr; }
+  if (ctx->d_tslot) { cudaFree(ctx->d_tslot); ctx->d_tslot = nullptr; }
   SVB_CUDA(cudaMalloc(&ctx->d_diagPtr, sizeof(int) * std::max(nNo, 1)));
   if (nNo > 0) TRY(launch_find_diag(ctx));
 

@@ -98,7 +98,7 @@ struct svb200_ctx {
   int* d_rowPtr = nullptr;       // (nNo+1) internal
   int* d_colPtr = nullptr;       // (nnz) internal column ids
   int* d_diagPtr = nullptr;      // (nNo)
-  int* d_slot_in2int = nullptr;  // unused when has_map == false
+  int* d_tslot = nullptr;        // (nnz) slot of the transposed entry (NS solver: Gt), built on first use
 
   // coordinates and state (internal order)
   int tDof = 0;
