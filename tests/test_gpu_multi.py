@@ -1,0 +1,27 @@
+"""Multi-GPU parity (needs >= 2 B200s; skipped otherwise): partitioned assembly + NCCL halo sums + Krylov solve
+against the single-partition oracle."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("mode,ls", [("slab", "gmres"), ("scattered", "gmres"), ("slab", "ns")])
+def test_two_gpu_parity(mode, ls):
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    n = min(_ngpu(), 4) if mode == "scattered" else 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(ROOT, "tests", "mgpu_worker.py"), mode, ls]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    print(r.stdout[-2000:])
+    assert r.returncode == 0, r.stdout[-4000:]
