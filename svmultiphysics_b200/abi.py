@@ -96,6 +96,33 @@ def fluid_domain(rho: float = 1.06, mu: float = 0.04, f=(0.0, 0.0, 0.0), K_darcy
     return d
 
 
+def struct_eq(dt: float, rho_inf: float = 0.5, tDof: int = 3, dof: int = 3, s: int = 0, scatter: int = SCATTER_ATOMIC) -> EqParams:
+    af, am, gam, beta = gen_alpha(rho_inf)
+    return EqParams(dt=dt, af=af, am=am, gam=gam, beta=beta, phys=PHYS_STRUCT, dof=dof, tDof=tDof, s=s,
+                    mvMsh=0, vmsStab=1, scatter=scatter, reserved=0)
+
+
+def struct_domain(rho: float = 1000.0, isoType: int = ISO_NHK, volType: int = VOL_ST91, E: float = 240.56596e6, nu: float = 0.5,
+                  Kpen: float = 4.0e9, C10=None, C01: float = 0.0, bff: float = 0.0, bss: float = 0.0, bfs: float = 0.0,
+                  dmp: float = 0.0, f=(0.0, 0.0, 0.0), Id: int = -1) -> DmnParams:
+    """Solid domain; C10 defaults to mu/2 with mu = E/(2(1+nu)) as set_material_props does for nHK
+    (Code/Source/solver/set_material_props.h)."""
+    d = DmnParams()
+    d.Id = Id
+    d.phys = PHYS_STRUCT
+    d.rho = rho
+    d.f[0], d.f[1], d.f[2] = f
+    d.isoType, d.volType = isoType, volType
+    d.Kpen = Kpen
+    mu = E / (2.0 * (1.0 + nu))
+    d.C10 = 0.5 * mu if C10 is None else C10
+    d.C01 = C01
+    d.bff, d.bss, d.bfs = bff, bss, bfs
+    d.dmp = dmp
+    d.E, d.nu = E, nu
+    return d
+
+
 def ls_params(ls_type: int, mItr=None, sD=None, relTol=None, absTol=1e-10, gm=None, cg=None) -> LsParams:
     """Defaults of fsils_ls_create (Code/Source/linear_solver/ls.cpp:22-59), overridable like read_ls does."""
     p = LsParams()

@@ -74,7 +74,7 @@ assemble_fluid_tet4_kernel(const __grid_constant__ FluidArgs P)
         const double* yp = P.Yg + (size_t)P.tDof * n;
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-          xl[a][i] = __ldg(xp + i);
+          xl[a][i] = __ldg(xp + i) + (P.ale ? __ldg(P.Dg + (size_t)P.tDof * n + 4 + i) : 0.0);
           ab[a][i] = __ldg(ap + i) - __ldg(bp + i);
         }
 #pragma unroll

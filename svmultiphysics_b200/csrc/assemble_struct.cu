@@ -1,0 +1,303 @@
+// assemble_struct.cu — fused element loop + scatter for the displacement-based solid (K2 of SURVEY.md §7).
+//
+// Replaces struct_ns::construct_dsolid / struct_3d (Code/Source/solver/sv_struct.cpp:184-341, 541-826),
+// mat_models::compute_pk2cc (Code/Source/solver/mat_models.cpp:291-817), nn::gnn per Gauss point
+// (Code/Source/solver/nn.cpp:862-899) and the do_assem scatter (Code/Source/solver/lhsa.cpp:70-114), for
+// TET4 and HEX8 meshes, neo-Hookean / Mooney-Rivlin / Guccione / St.Venant-Kirchhoff with Quad/ST91/M94
+// penalties, as a struct equation (dof = 3) or as the solid part of an FSI equation (dof = 4).
+//
+// Mapping: ENON lanes per element (lane = element node a), 32/ENON elements per warp.  Per Gauss point every
+// lane computes its own grad N_a, Bm_a and DBm_a = Dm Bm_a and publishes them through shared memory; the
+// element matrix is symmetric for a hyperelastic solid (K_ab = K_ba^T), so lane a only accumulates the blocks
+// (a, a+k mod ENON), k = 0..ENON/2, in registers (5 x 9 doubles for HEX8) and scatters each of them twice
+// (as is, and transposed) — 36 of 64 block products instead of 64.
+#include <cstdlib>
+#include "struct_elem.cuh"
+
+namespace svb {
+
+struct StructArgs {
+  const int* IEN;
+  const int* eId;
+  const int* slot;
+  const int* perm;
+  const double* fN;
+  const double* x;
+  const double* Ag;
+  const double* Yg;
+  const double* Dg;
+  const double* Bf;
+  double* R;
+  double* Val;
+  int e0, e1;
+  int tDof, dof, s, nFn, nDmn, atomic, nG, pad;
+  double dt, af, am, gam, beta;
+  double w[MAX_NG];
+  double N[MAX_NG][MAX_ENON];
+  double Nxi[MAX_NG][MAX_ENON][3];
+  StructDmn dmn[MAX_DMN];
+};
+
+template <bool ATOMIC>
+__device__ __forceinline__ void add64(double* p, double v)
+{
+  if (ATOMIC) asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+  else *p += v;
+}
+
+constexpr int STRUCT_THREADS = 128;
+
+template <int ENON, bool ATOMIC>
+__global__ void __launch_bounds__(STRUCT_THREADS)
+assemble_struct_kernel(const __grid_constant__ StructArgs P)
+{
+  constexpr int EPW = 32 / ENON;            // elements per warp
+  constexpr int KMAX = ENON / 2;            // lane a owns blocks (a, a+k), k = 0..KMAX (k = KMAX only for a < KMAX)
+  constexpr int PER_EL = ENON * (3 + 3 + 3 + 3 + 18);   // x, d, q, Nx, DBm
+  __shared__ double sm[(STRUCT_THREADS / 32) * EPW * PER_EL];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int a = lane % ENON, el = lane / ENON;
+  double* se = sm + (size_t)(warp * EPW + el) * PER_EL;
+  double(*sx)[3] = reinterpret_cast<double(*)[3]>(se);
+  double(*sd)[3] = reinterpret_cast<double(*)[3]>(se + 3 * ENON);
+  double(*sq)[3] = reinterpret_cast<double(*)[3]>(se + 6 * ENON);
+  double(*sNx)[3] = reinterpret_cast<double(*)[3]>(se + 9 * ENON);
+  double(*sDB)[18] = reinterpret_cast<double(*)[18]>(se + 12 * ENON);
+
+  const long long idx = (long long)P.e0 + ((long long)blockIdx.x * (STRUCT_THREADS / 32) + warp) * EPW + el;
+  bool active = idx < P.e1;
+  int e = 0;
+  if (active) e = P.perm ? P.perm[idx] : (int)idx;
+  int iD = 0;
+  if (active) {
+    for (int d = 0; d < P.nDmn; d++) {
+      iD = d;
+      if (P.dmn[d].Id == -1) break;
+      if (P.eId != nullptr && ((P.eId[e] >> P.dmn[d].Id) & 1)) break;
+    }
+    if (!P.dmn[iD].isStruct) active = false;
+  }
+  const StructDmn& dm = P.dmn[iD];
+  const int DOF = P.dof;
+  int node = 0;
+  double fN[2][3] = {{0, 0, 0}, {0, 0, 0}};
+  if (active) {
+    node = P.IEN[(size_t)e * ENON + a];
+    const size_t n = (size_t)node;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      sx[a][i] = __ldg(P.x + 3 * n + i);
+      sd[a][i] = __ldg(P.Dg + (size_t)P.tDof * n + P.s + i);
+      sq[a][i] = dm.rho * (__ldg(P.Ag + (size_t)P.tDof * n + P.s + i) - __ldg(P.Bf + 3 * n + i)) +
+                 dm.dmp * __ldg(P.Yg + (size_t)P.tDof * n + P.s + i);
+    }
+    if (P.fN != nullptr)
+      for (int k = 0; k < P.nFn && k < 2; k++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) fN[k][i] = __ldg(P.fN + (size_t)3 * P.nFn * e + 3 * k + i);
+  }
+  __syncwarp();
+
+  const double afu = P.af * P.beta * P.dt * P.dt;
+  const double amd = P.am * dm.rho + P.af * P.gam * P.dt * dm.dmp;
+  double acc[KMAX + 1][3][3];
+  double lR[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k <= KMAX; k++)
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) acc[k][i][j] = 0.0;
+
+#pragma unroll 1
+  for (int g = 0; g < P.nG; g++) {
+    double F[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, S[3][3], Bm[6][3], SNx[3], Nxa[3];
+    double w = 0.0;
+    if (active) {
+      // nn::gnn at this Gauss point (all lanes of the element repeat the 3x3 Jacobian)
+      double xXi[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+      for (int b = 0; b < ENON; b++)
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int k = 0; k < 3; k++) xXi[i][k] += sx[b][i] * P.Nxi[g][b][k];
+      const double Jac = xXi[0][0] * xXi[1][1] * xXi[2][2] + xXi[0][1] * xXi[1][2] * xXi[2][0] + xXi[0][2] * xXi[1][0] * xXi[2][1] -
+                         xXi[0][0] * xXi[1][2] * xXi[2][1] - xXi[0][1] * xXi[1][0] * xXi[2][2] - xXi[0][2] * xXi[1][1] * xXi[2][0];
+      const double iJ = 1.0 / Jac;
+      double xiX[3][3];
+      xiX[0][0] = (xXi[1][1] * xXi[2][2] - xXi[1][2] * xXi[2][1]) * iJ;
+      xiX[0][1] = (xXi[2][1] * xXi[0][2] - xXi[2][2] * xXi[0][1]) * iJ;
+      xiX[0][2] = (xXi[0][1] * xXi[1][2] - xXi[0][2] * xXi[1][1]) * iJ;
+      xiX[1][0] = (xXi[1][2] * xXi[2][0] - xXi[1][0] * xXi[2][2]) * iJ;
+      xiX[1][1] = (xXi[2][2] * xXi[0][0] - xXi[2][0] * xXi[0][2]) * iJ;
+      xiX[1][2] = (xXi[0][2] * xXi[1][0] - xXi[0][0] * xXi[1][2]) * iJ;
+      xiX[2][0] = (xXi[1][0] * xXi[2][1] - xXi[1][1] * xXi[2][0]) * iJ;
+      xiX[2][1] = (xXi[2][0] * xXi[0][1] - xXi[2][1] * xXi[0][0]) * iJ;
+      xiX[2][2] = (xXi[0][0] * xXi[1][1] - xXi[0][1] * xXi[1][0]) * iJ;
+      w = P.w[g] * Jac;
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        Nxa[i] = P.Nxi[g][a][0] * xiX[0][i] + P.Nxi[g][a][1] * xiX[1][i] + P.Nxi[g][a][2] * xiX[2][i];
+        sNx[a][i] = Nxa[i];
+      }
+    }
+    __syncwarp();
+    if (active) {
+      double ud[3] = {-dm.rho * dm.f[0], -dm.rho * dm.f[1], -dm.rho * dm.f[2]};
+#pragma unroll
+      for (int b = 0; b < ENON; b++) {
+        const double Nb = P.N[g][b];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          ud[i] += Nb * sq[b][i];
+#pragma unroll
+          for (int j = 0; j < 3; j++) F[i][j] += sNx[b][j] * sd[b][i];
+        }
+      }
+      double Dm[6][6];
+      pk2cc_voigt(dm, F, fN, S, Dm);
+      make_Bm(Nxa, F, Bm);
+      double DBm[6][3];
+      make_DBm(Dm, Bm, DBm);
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) sDB[a][3 * r + j] = DBm[r][j];
+      const double Na = P.N[g][a];
+#pragma unroll
+      for (int i = 0; i < 3; i++) SNx[i] = Nxa[0] * S[0][i] + Nxa[1] * S[1][i] + Nxa[2] * S[2][i];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        // P = F S ; lR(i,a) += w (N_a ud_i + sum_j Nx(j,a) P(i,j))
+        const double PNx = F[i][0] * SNx[0] + F[i][1] * SNx[1] + F[i][2] * SNx[2];
+        lR[i] += w * (Na * ud[i] + PNx);
+      }
+    }
+    __syncwarp();
+    if (active) {
+      const double Na = P.N[g][a];
+#pragma unroll
+      for (int k = 0; k <= KMAX; k++) {
+        if (k == KMAX && a >= KMAX) continue;
+        const int b = (a + k) % ENON;
+        double DB[6][3], Nxb[3];
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+          for (int j = 0; j < 3; j++) DB[r][j] = sDB[b][3 * r + j];
+#pragma unroll
+        for (int i = 0; i < 3; i++) Nxb[i] = sNx[b][i];
+        struct_block(acc[k], w, amd * Na * P.N[g][b], afu, SNx, Nxb, Bm, DB);
+      }
+    }
+    __syncwarp();
+  }
+
+  if (!active) return;
+  // ---- scatter ------------------------------------------------------------------------------------------
+#pragma unroll
+  for (int i = 0; i < 3; i++) add64<ATOMIC>(P.R + (size_t)DOF * node + i, lR[i]);
+  const int* sl = P.slot + (size_t)e * ENON * ENON;
+#pragma unroll
+  for (int k = 0; k <= KMAX; k++) {
+    if (k == KMAX && a >= KMAX) continue;
+    const int b = (a + k) % ENON;
+    double* v = P.Val + (size_t)DOF * DOF * sl[a * ENON + b];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) add64<ATOMIC>(v + DOF * i + j, acc[k][i][j]);
+    if (k > 0) {
+      double* vt = P.Val + (size_t)DOF * DOF * sl[b * ENON + a];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) add64<ATOMIC>(vt + DOF * j + i, acc[k][i][j]);
+    }
+  }
+}
+
+int fill_struct_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn, StructArgs& A)
+{
+  SVB_REQUIRE(nDmn >= 1 && nDmn <= MAX_DMN, "svb200_assemble: between 1 and 8 domains are supported");
+  SVB_REQUIRE(eq->dof == ctx->dof && (eq->dof == 3 || eq->dof == 4), "svb200_assemble: the solid needs dof = 3 (struct) or 4 (FSI)");
+  SVB_REQUIRE(eq->tDof == ctx->tDof && ctx->d_Dg && ctx->d_Yg && ctx->d_Ag, "svb200_assemble: state not set or tDof mismatch");
+  SVB_REQUIRE(eq->s >= 0 && eq->s + 3 <= eq->tDof, "svb200_assemble: eq.s out of range");
+  SVB_REQUIRE(ctx->d_x, "svb200_assemble: coordinates not set");
+  SVB_REQUIRE(m.eNoN == 4 || m.eNoN == 8, "svb200_assemble: the solid is implemented for TET4 and HEX8 meshes");
+  memset(&A, 0, sizeof(A));
+  A.IEN = m.d_IEN; A.eId = m.d_eId; A.slot = m.d_slot; A.perm = nullptr; A.fN = m.d_fN;
+  A.x = ctx->d_x; A.Ag = ctx->d_Ag; A.Yg = ctx->d_Yg; A.Dg = ctx->d_Dg; A.Bf = ctx->d_Bf;
+  A.R = ctx->d_R; A.Val = ctx->d_Val;
+  A.e0 = 0; A.e1 = m.nEl;
+  A.tDof = eq->tDof; A.dof = eq->dof; A.s = eq->s; A.nFn = m.nFn; A.nDmn = nDmn; A.nG = m.nG;
+  A.atomic = (eq->scatter == SVB200_SCATTER_ATOMIC);
+  A.dt = eq->dt; A.af = eq->af; A.am = eq->am; A.gam = eq->gam; A.beta = eq->beta;
+  for (int g = 0; g < m.nG; g++) {
+    A.w[g] = m.w[g];
+    for (int a = 0; a < m.eNoN; a++) {
+      A.N[g][a] = m.N[(size_t)g * m.eNoN + a];
+      for (int k = 0; k < 3; k++) A.Nxi[g][a][k] = m.Nx[((size_t)g * m.eNoN + a) * 3 + k];
+    }
+  }
+  bool whole = false;
+  for (int d = 0; d < nDmn; d++) {
+    StructDmn& o = A.dmn[d];
+    o.rho = dmn[d].rho;
+    for (int k = 0; k < 3; k++) o.f[k] = dmn[d].f[k];
+    o.dmp = dmn[d].dmp;
+    o.Kpen = dmn[d].Kpen; o.C10 = dmn[d].C10; o.C01 = dmn[d].C01;
+    o.bff = dmn[d].bff; o.bss = dmn[d].bss; o.bfs = dmn[d].bfs;
+    o.isoType = dmn[d].isoType; o.volType = dmn[d].volType;
+    o.Id = dmn[d].Id;
+    o.isStruct = (dmn[d].phys == SVB200_PHYS_STRUCT);
+    SVB_REQUIRE(o.Id >= -1 && o.Id < 31, "svb200_assemble: domain Id out of range");
+    if (o.isStruct) {
+      SVB_REQUIRE(dmn[d].solid_visc_mu == 0.0, "svb200_assemble: solid viscosity is not implemented");
+      SVB_REQUIRE(o.isoType == SVB200_ISO_NHK || o.isoType == SVB200_ISO_MR || o.isoType == SVB200_ISO_GUCCIONE ||
+                      o.isoType == SVB200_ISO_STVK, "svb200_assemble: constitutive model not implemented");
+      // compute_pk2cc throws for Guccione without two fibre families (mat_models.cpp:514-516)
+      if (o.isoType == SVB200_ISO_GUCCIONE && (m.nFn != 2 || !m.d_fN)) {
+        set_error("[compute_pk2cc] Min fiber directions not defined for Guccione material model.");
+        return SVB200_ERR_INVALID;
+      }
+    }
+    whole |= (o.Id == -1);
+  }
+  if (!whole && !m.d_eId) { set_error("eId is not allocated"); return SVB200_ERR_INVALID; }
+  return SVB200_OK;
+}
+
+template <int ENON>
+static int launch_one(svb200_ctx* ctx, const StructArgs& A)
+{
+  constexpr int EPB = (STRUCT_THREADS / 32) * (32 / ENON);   // elements per CTA
+  const long long n = (long long)A.e1 - A.e0;
+  if (n <= 0) return SVB200_OK;
+  const unsigned blocks = (unsigned)((n + EPB - 1) / EPB);
+  if (A.atomic) assemble_struct_kernel<ENON, true><<<blocks, STRUCT_THREADS, 0, ctx->stream>>>(A);
+  else assemble_struct_kernel<ENON, false><<<blocks, STRUCT_THREADS, 0, ctx->stream>>>(A);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
+int run_assemble_struct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn)
+{
+  StructArgs A;
+  int rc = fill_struct_args(ctx, m, eq, dmn, nDmn, A);
+  if (rc) return rc;
+  auto launch = [&](const StructArgs& B) { return m.eNoN == 8 ? launch_one<8>(ctx, B) : launch_one<4>(ctx, B); };
+  if (A.atomic) return launch(A);
+  A.perm = m.d_color_perm;
+  for (size_t c = 0; c + 1 < m.color_off.size(); c++) {
+    A.e0 = m.color_off[c];
+    A.e1 = m.color_off[c + 1];
+    rc = launch(A);
+    if (rc) return rc;
+  }
+  return SVB200_OK;
+}
+
+}  // namespace svb

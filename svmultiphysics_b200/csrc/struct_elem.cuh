@@ -1,0 +1,299 @@
+// struct_elem.cuh — Gauss-point algebra of the displacement-based solid (struct_3d) in closed Voigt form.
+//
+// Reference: struct_ns::struct_3d (Code/Source/solver/sv_struct.cpp:541-826) and
+// mat_models::compute_pk2cc<3> (Code/Source/solver/mat_models.cpp:291-817) with bar_to_iso (:232-255),
+// compute_svol_p (:1441-1464) and cc_to_voigt_eigen (:104-155).
+//
+// The reference builds the 3x3x3x3 elasticity tensor with Eigen tensor contractions
+// (P : CC_bar : P^T costs 2 x 81 x 9 FMAs even when CC_bar = 0).  Here every model is written directly
+// on the 6x6 Voigt matrix (order 11,22,33,12,23,31):
+//   * volumetric      S += p J Ci ;  Dm += -2 p J (Ci (.) Ci) + pl J (Ci x Ci)
+//   * isochoric       S_iso = J2d S_bar - r1 Ci,  r1 = J2d (C : S_bar)/3
+//                     Dm += sum_k c_k (A~_k x A~_k)            with CC_bar = sum_k c_k A_k x A_k,
+//                                                              A~ = A - (C:A)/3 Ci   (= P : A)
+//                           - 2/3 (Ci x S_iso + S_iso x Ci) + 2 r1 (Ci (.) Ci) - 2 r1/3 (Ci x Ci)
+//   nHK: CC_bar = 0; Guccione: 7 dyads; Mooney-Rivlin: I x I and the symmetric identity handled in closed form.
+// (x = dyadic product, (.) = symmetric dyadic product 1/2(A_ik B_jl + A_il B_jk), mat_fun.h:201-223).
+#pragma once
+#include "fluid_elem.cuh"   // SVB_HD, is_zero
+
+namespace svb {
+
+struct StructDmn {
+  double rho, f[3], dmp;
+  double Kpen, C10, C01, bff, bss, bfs;
+  int isoType, volType, Id, isStruct;
+};
+
+#define SVB_VI(a) ((a) < 3 ? (a) : ((a) == 3 ? 0 : ((a) == 4 ? 1 : 2)))
+#define SVB_VJ(a) ((a) < 3 ? (a) : ((a) == 3 ? 1 : ((a) == 4 ? 2 : 0)))
+
+// Dm += c * (A x B + B x A)/2-free helpers on full 3x3 symmetric inputs.
+SVB_HD void dm_add_dyad(double Dm[6][6], double c, const double A[3][3], const double B[3][3])
+{
+#pragma unroll
+  for (int a = 0; a < 6; a++)
+#pragma unroll
+    for (int b = 0; b < 6; b++) Dm[a][b] += c * A[SVB_VI(a)][SVB_VJ(a)] * B[SVB_VI(b)][SVB_VJ(b)];
+}
+
+SVB_HD void dm_add_symdyad(double Dm[6][6], double c, const double A[3][3])
+{
+#pragma unroll
+  for (int a = 0; a < 6; a++)
+#pragma unroll
+    for (int b = 0; b < 6; b++) {
+      const int i = SVB_VI(a), j = SVB_VJ(a), k = SVB_VI(b), l = SVB_VJ(b);
+      Dm[a][b] += c * 0.5 * (A[i][k] * A[j][l] + A[i][l] * A[j][k]);
+    }
+}
+
+SVB_HD double ddot(const double A[3][3], const double B[3][3])
+{
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) s += A[i][j] * B[i][j];
+  return s;
+}
+
+// compute_pk2cc<3> without active stress / prestress / viscosity: F -> S (3x3), Dm (6x6).
+// fN[0] = fibre, fN[1] = sheet direction (Guccione only).  Returns 0, or 1 for an unsupported model.
+SVB_HD int pk2cc_voigt(const StructDmn& dm, const double F[3][3], const double fN[2][3], double S[3][3], double Dm[6][6])
+{
+#pragma unroll
+  for (int a = 0; a < 6; a++)
+#pragma unroll
+    for (int b = 0; b < 6; b++) Dm[a][b] = 0.0;
+  const double J = F[0][0] * (F[1][1] * F[2][2] - F[1][2] * F[2][1]) - F[0][1] * (F[1][0] * F[2][2] - F[1][2] * F[2][0]) +
+                   F[0][2] * (F[1][0] * F[2][1] - F[1][1] * F[2][0]);
+  const double J2d = pow(J, -2.0 / 3.0);
+  const double J4d = J2d * J2d;
+  double C[3][3], Ci[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      C[i][j] = F[0][i] * F[0][j] + F[1][i] * F[1][j] + F[2][i] * F[2][j];
+      S[i][j] = 0.0;
+    }
+  {
+    const double dC = J * J;   // det C
+    Ci[0][0] = (C[1][1] * C[2][2] - C[1][2] * C[2][1]) / dC;
+    Ci[0][1] = (C[0][2] * C[2][1] - C[0][1] * C[2][2]) / dC;
+    Ci[0][2] = (C[0][1] * C[1][2] - C[0][2] * C[1][1]) / dC;
+    Ci[1][1] = (C[0][0] * C[2][2] - C[0][2] * C[2][0]) / dC;
+    Ci[1][2] = (C[0][2] * C[1][0] - C[0][0] * C[1][2]) / dC;
+    Ci[2][2] = (C[0][0] * C[1][1] - C[0][1] * C[1][0]) / dC;
+    Ci[1][0] = Ci[0][1]; Ci[2][0] = Ci[0][2]; Ci[2][1] = Ci[1][2];
+  }
+  const double trC = C[0][0] + C[1][1] + C[2][2];
+
+  // volumetric part (mat_models.cpp:397-405, 1441-1464)
+  if (!is_zero(dm.Kpen)) {
+    double p = 0.0, pl = 0.0;
+    if (dm.volType == SVB200_VOL_QUAD) { p = dm.Kpen * (J - 1.0); pl = dm.Kpen * (2.0 * J - 1.0); }
+    else if (dm.volType == SVB200_VOL_ST91) { p = 0.5 * dm.Kpen * (J - 1.0 / J); pl = dm.Kpen * J; }
+    else if (dm.volType == SVB200_VOL_M94) { p = dm.Kpen * (1.0 - 1.0 / J); pl = dm.Kpen; }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) S[i][j] += p * J * Ci[i][j];
+    dm_add_symdyad(Dm, -2.0 * p * J, Ci);
+    dm_add_dyad(Dm, pl * J, Ci, Ci);
+  }
+
+  double Idm[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  if (dm.isoType == SVB200_ISO_STVK) {        // mat_models.cpp:415-421
+    const double g1 = dm.C10, g2 = dm.C01 * 2.0;
+    const double trE = 0.5 * (trC - 3.0);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) S[i][j] += g1 * trE * Idm[i][j] + g2 * 0.5 * (C[i][j] - Idm[i][j]);
+    dm_add_dyad(Dm, g1, Idm, Idm);
+    dm_add_symdyad(Dm, g2, Idm);
+    return 0;
+  }
+
+  double Sb[3][3];
+  if (dm.isoType == SVB200_ISO_NHK) {         // mat_models.cpp:435-450
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) Sb[i][j] = 2.0 * dm.C10 * Idm[i][j];
+  } else if (dm.isoType == SVB200_ISO_MR) {   // mat_models.cpp:453-468
+    const double Inv1 = J2d * trC;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) Sb[i][j] = 2.0 * (dm.C10 + Inv1 * dm.C01) * Idm[i][j] - 2.0 * dm.C01 * J2d * C[i][j];
+    // CC_bar = c (I x I - Isym), c = 4 J4d C01:  P:(I x I):P^T = I~ x I~ ;
+    // P:Isym:P^T = Isym - 1/3 (Ci x C + C x Ci) + (C:C)/9 Ci x Ci
+    const double c = 4.0 * J4d * dm.C01;
+    double It[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) It[i][j] = Idm[i][j] - (trC / 3.0) * Ci[i][j];
+    dm_add_dyad(Dm, c, It, It);
+    dm_add_symdyad(Dm, -c, Idm);
+    dm_add_dyad(Dm, c / 3.0, Ci, C);
+    dm_add_dyad(Dm, c / 3.0, C, Ci);
+    dm_add_dyad(Dm, -c * ddot(C, C) / 9.0, Ci, Ci);
+  } else if (dm.isoType == SVB200_ISO_GUCCIONE) {   // mat_models.cpp:513-581
+    double R[3][3];   // R[k] = k-th local axis (fibre, sheet, normal)
+#pragma unroll
+    for (int i = 0; i < 3; i++) { R[0][i] = fN[0][i]; R[1][i] = fN[1][i]; }
+    R[2][0] = R[0][1] * R[1][2] - R[0][2] * R[1][1];
+    R[2][1] = R[0][2] * R[1][0] - R[0][0] * R[1][2];
+    R[2][2] = R[0][0] * R[1][1] - R[0][1] * R[1][0];
+    const double nn = sqrt(R[2][0] * R[2][0] + R[2][1] * R[2][1] + R[2][2] * R[2][2]);
+#pragma unroll
+    for (int i = 0; i < 3; i++) R[2][i] /= nn;
+    double E[3][3], Es[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) E[i][j] = 0.5 * (J2d * C[i][j] - Idm[i][j]);
+#pragma unroll
+    for (int p = 0; p < 3; p++)
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = 0; j < 3; j++) s += R[p][i] * E[i][j] * R[q][j];
+        Es[p][q] = s;
+      }
+    const double g1 = dm.bff, g2 = dm.bss, g3 = dm.bfs;
+    const double QQ = g1 * Es[0][0] * Es[0][0] +
+                      g2 * (Es[1][1] * Es[1][1] + Es[2][2] * Es[2][2] + Es[1][2] * Es[1][2] + Es[2][1] * Es[2][1]) +
+                      g3 * (Es[0][1] * Es[0][1] + Es[1][0] * Es[1][0] + Es[0][2] * Es[0][2] + Es[2][0] * Es[2][0]);
+    const double r2 = dm.C10 * exp(QQ);
+    // symmetrised dyads H[k]: 00, 11, 22, 12, 01, 20 with their weights in S_hat and CC_bar
+    const int pa[6] = {0, 1, 2, 1, 0, 2}, pb[6] = {0, 1, 2, 2, 1, 0};
+    const double ws[6] = {g1 * Es[0][0], g2 * Es[1][1], g2 * Es[2][2], 2.0 * g2 * Es[1][2], 2.0 * g3 * Es[0][1], 2.0 * g3 * Es[0][2]};
+    const double wc[6] = {g1, g2, g2, 2.0 * g2, 2.0 * g3, 2.0 * g3};
+    double Sh[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    const double cbar = r2 * J4d;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      double H[3][3], Ht[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) H[i][j] = 0.5 * (R[pa[k]][i] * R[pb[k]][j] + R[pb[k]][i] * R[pa[k]][j]);
+      const double cH = ddot(C, H) / 3.0;
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) { Sh[i][j] += ws[k] * H[i][j]; Ht[i][j] = H[i][j] - cH * Ci[i][j]; }
+      dm_add_dyad(Dm, cbar * wc[k], Ht, Ht);
+    }
+    {
+      double St[3][3];
+      const double cS = ddot(C, Sh) / 3.0;
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) { St[i][j] = Sh[i][j] - cS * Ci[i][j]; Sb[i][j] = r2 * Sh[i][j]; }
+      dm_add_dyad(Dm, 2.0 * cbar, St, St);
+    }
+  } else {
+    return 1;
+  }
+  // bar_to_iso (mat_models.cpp:232-255)
+  const double r1 = J2d * ddot(C, Sb) / 3.0;
+  double Siso[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      Siso[i][j] = J2d * Sb[i][j] - r1 * Ci[i][j];
+      S[i][j] += Siso[i][j];
+    }
+  dm_add_dyad(Dm, -2.0 / 3.0, Ci, Siso);
+  dm_add_dyad(Dm, -2.0 / 3.0, Siso, Ci);
+  dm_add_symdyad(Dm, 2.0 * r1, Ci);
+  dm_add_dyad(Dm, -2.0 * r1 / 3.0, Ci, Ci);
+  return 0;
+}
+
+// nn::gnn for insd = 3 and any eNoN (Code/Source/solver/nn.cpp:862-899): Nxi[a][k] -> Nx[a][i], Jac.
+template <int ENON>
+SVB_HD double gnn3(const double Nxi[][3], const double xl[][3], double Nx[][3])
+{
+  double xXi[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, xiX[3][3];
+#pragma unroll
+  for (int a = 0; a < ENON; a++)
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) xXi[i][k] += xl[a][i] * Nxi[a][k];
+  const double Jac = xXi[0][0] * xXi[1][1] * xXi[2][2] + xXi[0][1] * xXi[1][2] * xXi[2][0] + xXi[0][2] * xXi[1][0] * xXi[2][1] -
+                     xXi[0][0] * xXi[1][2] * xXi[2][1] - xXi[0][1] * xXi[1][0] * xXi[2][2] - xXi[0][2] * xXi[1][1] * xXi[2][0];
+  const double iJ = 1.0 / Jac;
+  xiX[0][0] = (xXi[1][1] * xXi[2][2] - xXi[1][2] * xXi[2][1]) * iJ;
+  xiX[0][1] = (xXi[2][1] * xXi[0][2] - xXi[2][2] * xXi[0][1]) * iJ;
+  xiX[0][2] = (xXi[0][1] * xXi[1][2] - xXi[0][2] * xXi[1][1]) * iJ;
+  xiX[1][0] = (xXi[1][2] * xXi[2][0] - xXi[1][0] * xXi[2][2]) * iJ;
+  xiX[1][1] = (xXi[2][2] * xXi[0][0] - xXi[2][0] * xXi[0][2]) * iJ;
+  xiX[1][2] = (xXi[0][2] * xXi[1][0] - xXi[0][0] * xXi[1][2]) * iJ;
+  xiX[2][0] = (xXi[1][0] * xXi[2][1] - xXi[1][1] * xXi[2][0]) * iJ;
+  xiX[2][1] = (xXi[2][0] * xXi[0][1] - xXi[2][1] * xXi[0][0]) * iJ;
+  xiX[2][2] = (xXi[0][0] * xXi[1][1] - xXi[0][1] * xXi[1][0]) * iJ;
+#pragma unroll
+  for (int a = 0; a < ENON; a++)
+#pragma unroll
+    for (int i = 0; i < 3; i++) Nx[a][i] = Nxi[a][0] * xiX[0][i] + Nxi[a][1] * xiX[1][i] + Nxi[a][2] * xiX[2][i];
+  return Jac;
+}
+
+// Bm(:,i) for node a (sv_struct.cpp:705-729): Bm[r][i], r = Voigt row, i = displacement component.
+SVB_HD void make_Bm(const double Nx[3], const double F[3][3], double Bm[6][3])
+{
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    Bm[0][i] = Nx[0] * F[i][0];
+    Bm[1][i] = Nx[1] * F[i][1];
+    Bm[2][i] = Nx[2] * F[i][2];
+    Bm[3][i] = Nx[0] * F[i][1] + F[i][0] * Nx[1];
+    Bm[4][i] = Nx[1] * F[i][2] + F[i][1] * Nx[2];
+    Bm[5][i] = Nx[2] * F[i][0] + F[i][2] * Nx[0];
+  }
+}
+
+SVB_HD void make_DBm(const double Dm[6][6], const double Bm[6][3], double DBm[6][3])
+{
+#pragma unroll
+  for (int r = 0; r < 6; r++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < 6; q++) s += Dm[r][q] * Bm[q][j];
+      DBm[r][j] = s;
+    }
+}
+
+// K(i,j) += w [ delta_ij (amd Na Nb + afu gradNa.S.gradNb) + afu Bm_a(:,i).DBm_b(:,j) ]  (sv_struct.cpp:736-825)
+SVB_HD void struct_block(double K[3][3], double w, double amdNaNb, double afu, const double SNxa[3], const double Nxb[3],
+                         const double Bma[6][3], const double DBmb[6][3])
+{
+  const double NxSNx = SNxa[0] * Nxb[0] + SNxa[1] * Nxb[1] + SNxa[2] * Nxb[2];
+  const double T1 = amdNaNb + afu * NxSNx;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      double s = 0.0;
+#pragma unroll
+      for (int r = 0; r < 6; r++) s += Bma[r][i] * DBmb[r][j];
+      K[i][j] += w * ((i == j ? T1 : 0.0) + afu * s);
+    }
+}
+
+}  // namespace svb

@@ -443,16 +443,19 @@ static int fill_fluid_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams
 {
   SVB_REQUIRE(nDmn >= 1 && nDmn <= MAX_DMN, "svb200_assemble: between 1 and 8 domains are supported");
   SVB_REQUIRE(eq->dof == 4 && ctx->dof == 4, "svb200_assemble: the fluid equation has dof = 4 (call svb200_alloc(4))");
+  SVB_REQUIRE(m.eNoN == 4, "svb200_assemble: fluid assembly is implemented for TET4 meshes");
   SVB_REQUIRE(eq->vmsStab == 1, "svb200_assemble: only VMS-stabilised equal-order elements are supported");
   SVB_REQUIRE(eq->tDof == ctx->tDof && ctx->d_Yg, "svb200_assemble: state not set (svb200_set_state) or tDof mismatch");
   SVB_REQUIRE(!eq->mvMsh || eq->tDof >= 7, "svb200_assemble: mvMsh needs the mesh velocity in state dofs 4..6");
   SVB_REQUIRE(ctx->d_x, "svb200_assemble: coordinates not set");
   memset(&A, 0, sizeof(A));
   A.IEN = m.d_IEN; A.eId = m.d_eId; A.slot = m.d_slot; A.perm = nullptr;
-  A.x = ctx->d_x; A.Ag = ctx->d_Ag; A.Yg = ctx->d_Yg; A.Bf = ctx->d_Bf;
+  A.x = ctx->d_x; A.Ag = ctx->d_Ag; A.Yg = ctx->d_Yg; A.Bf = ctx->d_Bf; A.Dg = ctx->d_Dg;
   A.R = ctx->d_R; A.Val = ctx->d_Val;
   A.e0 = 0; A.e1 = m.nEl;
   A.tDof = eq->tDof; A.mvMsh = eq->mvMsh; A.nDmn = nDmn;
+  A.ale = (eq->phys == SVB200_PHYS_FSI);
+  SVB_REQUIRE(!A.ale || (eq->tDof >= 7 && ctx->d_Dg), "svb200_assemble: FSI needs tDof >= 7 and the displacement state");
   A.atomic = (eq->scatter == SVB200_SCATTER_ATOMIC);
   A.dt = eq->dt; A.af = eq->af; A.am = eq->am; A.gam = eq->gam;
   for (int g = 0; g < m.nG; g++) {
@@ -467,7 +470,7 @@ static int fill_fluid_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams
     FluidDmn& o = A.dmn[d];
     o.rho = dmn[d].rho;
     for (int k = 0; k < 3; k++) o.f[k] = dmn[d].f[k];
-    o.Kd = dmn[d].K_darcy;
+    o.Kd = A.ale ? 0.0 : dmn[d].K_darcy;   // construct_fsi passes K_inverse_darcy_permeability = 0 (fsi.cpp:215,313)
     o.mu_i = dmn[d].mu_i; o.mu_o = dmn[d].mu_o; o.lam = dmn[d].lam; o.a = dmn[d].a; o.n = dmn[d].n;
     o.viscType = dmn[d].viscType;
     o.Id = dmn[d].Id;
@@ -504,14 +507,35 @@ int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, cons
   SVB_REQUIRE(iM >= 0 && iM < (int)ctx->mesh.size() && ctx->mesh[iM].set, "svb200_assemble: mesh not set");
   SVB_REQUIRE(ctx->d_R && ctx->d_Val, "svb200_assemble: call svb200_alloc first");
   const Mesh& m = ctx->mesh[iM];
-  if (eq->phys != SVB200_PHYS_FLUID) {
-    set_error("svb200_assemble: only the fluid equation is implemented in this build");
-    return SVB200_ERR_UNSUPPORTED;
-  }
-  FluidArgs A;
-  TRY(fill_fluid_args(ctx, m, eq, dmn, nDmn, A));
   SVB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-  TRY(run_assemble(ctx, m, A));
+  switch (eq->phys) {
+    case SVB200_PHYS_FLUID: {
+      FluidArgs A;
+      TRY(fill_fluid_args(ctx, m, eq, dmn, nDmn, A));
+      TRY(run_assemble(ctx, m, A));
+    } break;
+    case SVB200_PHYS_STRUCT:
+      TRY(run_assemble_struct(ctx, m, eq, dmn, nDmn));
+      break;
+    case SVB200_PHYS_FSI: {
+      // fsi::construct_fsi (fsi.cpp:24-362): per-element domain switch; fluid elements on the moved mesh
+      // (ALE), solid elements through struct_3d writing the 3x3 part of the 4x4 blocks.
+      bool anyFluid = false, anySolid = false;
+      for (int d = 0; d < nDmn; d++) {
+        anyFluid |= (dmn[d].phys == SVB200_PHYS_FLUID);
+        anySolid |= (dmn[d].phys == SVB200_PHYS_STRUCT);
+      }
+      if (anyFluid) {
+        FluidArgs A;
+        TRY(fill_fluid_args(ctx, m, eq, dmn, nDmn, A));
+        TRY(run_assemble(ctx, m, A));
+      }
+      if (anySolid) TRY(run_assemble_struct(ctx, m, eq, dmn, nDmn));
+    } break;
+    default:
+      set_error("svb200_assemble: this physics is not implemented in this build");
+      return SVB200_ERR_UNSUPPORTED;
+  }
   SVB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
   SVB_CUDA(cudaEventSynchronize(ctx->ev1));
   float ms = 0.f;

@@ -68,10 +68,12 @@ struct FluidArgs {
   const double* Ag;
   const double* Yg;
   const double* Bf;
+  const double* Dg;     // displacement state; dofs 4..6 = mesh displacement (FSI / ALE geometry)
   double* R;
   double* Val;
   int e0, e1;           // element range [e0,e1) (indices into perm when perm != null)
   int tDof, mvMsh, nDmn, atomic;
+  int ale, pad0;        // ale: element geometry is x + Dg(4..6) (fsi::construct_fsi, fsi.cpp:140-146)
   double dt, af, am, gam;
   double w[MAX_NG];
   double N[MAX_NG][MAX_ENON];        // N[g][a]
@@ -163,6 +165,8 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 // assemble_fluid.cu
 int launch_assemble_fluid(svb200_ctx* ctx, const Mesh& m, const FluidArgs& args);
+// assemble_struct.cu
+int run_assemble_struct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);
 // graph_kernels.cu
 int launch_build_slot_map(svb200_ctx* ctx, Mesh& m);
 int launch_find_diag(svb200_ctx* ctx);

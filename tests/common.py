@@ -73,3 +73,56 @@ def dirichlet_faces(m):
         g = m.faces[name]
         faces.append((abi.BC_DIR, g, np.zeros((3, len(g)), order="F")))
     return faces
+
+
+# ---- solid / FSI cases -------------------------------------------------------------------------------
+# (name, mesh factory, struct_domain kwargs, number of fibre families)
+def _hex():
+    return meshgen.box_hex8(4, 3, 3, (1e-3, 1e-3, 1e-3))
+
+
+def _tet():
+    return meshgen.box_tet4(3, 3, 2, (1.0, 1.0, 1.0))
+
+
+STRUCT_CASES = [
+    ("hex8_nHK_ST91", _hex, dict(), 0),                                         # struct/block_compression
+    ("hex8_nHK_M94_damped", _hex, dict(volType=abi.VOL_M94, E=1e7, nu=0.3, Kpen=1e7 / (3 * (1 - 0.6)), dmp=5.0, f=(0.1, 0.2, 0.3)), 0),
+    ("tet4_nHK_Quad", _tet, dict(volType=abi.VOL_QUAD, E=1e6, nu=0.4, Kpen=1e6, rho=1.0), 0),
+    ("hex8_MR", _hex, dict(isoType=abi.ISO_MR, C10=1e5, C01=3e4, Kpen=1e7, rho=1.0), 0),
+    ("hex8_StVK", _hex, dict(isoType=abi.ISO_STVK, C10=2e5, C01=1e5, Kpen=0.0, rho=1.0), 0),
+    ("hex8_Guccione", _hex, dict(isoType=abi.ISO_GUCCIONE, C10=440.0, bff=8.0, bss=6.0, bfs=12.0, Kpen=1e6, rho=1e-3), 2),   # struct/LV_Guccione_passive
+]
+
+
+def struct_state(m, nFn=0, seed=11, tDof=3):
+    rng = np.random.default_rng(seed)
+    L = m.x.max()
+    Dg = np.zeros((tDof, m.nNo), order="F")
+    Dg[:3] = 0.01 * L * (m.x / L) * np.array([[1.0], [-0.5], [0.3]]) + 1e-3 * L * rng.standard_normal((3, m.nNo))
+    Yg = np.asfortranarray(0.1 * rng.standard_normal((tDof, m.nNo)))
+    Ag = np.asfortranarray(rng.standard_normal((tDof, m.nNo)))
+    Bf = np.asfortranarray(0.1 * rng.standard_normal((3, m.nNo)))
+    fN = None
+    if nFn:
+        f = rng.standard_normal((3, m.nEl)); f /= np.linalg.norm(f, axis=0)
+        s = rng.standard_normal((3, m.nEl)); s -= (s * f).sum(0) * f; s /= np.linalg.norm(s, axis=0)
+        fN = np.asfortranarray(np.vstack([f, s]))
+    return Ag, Yg, Dg, Bf, fN
+
+
+def fsi_case(n=4, nz=6):
+    """Pipe with a fluid core (domain Id 0) and a solid outer ring (domain Id 1) sharing interface nodes, like
+    tests/cases/fsi/pipe_3d: tDof = 7 (u,v,w,p + mesh displacement/velocity in dofs 4..6)."""
+    m = meshgen.cylinder_tet4(n, nz, R=1.0, L=3.0)
+    c = m.x[:, m.IEN].mean(axis=1)                      # element centroids
+    solid = (c[0] ** 2 + c[1] ** 2) > 0.55 ** 2
+    m.eId = np.where(solid, 2, 1).astype(np.int32)      # bit 1 = solid, bit 0 = fluid
+    rng = np.random.default_rng(21)
+    Ag, Yg, _ = meshgen.poiseuille_state(m, R=1.0, U=5.0, tDof=7)
+    Yg[4:7] = 0.2 * rng.standard_normal((3, m.nNo))
+    Dg = np.zeros((7, m.nNo), order="F")
+    Dg[:3] = 2e-3 * rng.standard_normal((3, m.nNo))
+    Dg[4:7] = 5e-3 * rng.standard_normal((3, m.nNo))
+    Bf = np.asfortranarray(0.1 * rng.standard_normal((3, m.nNo)))
+    return m, Ag, Yg, Dg, Bf

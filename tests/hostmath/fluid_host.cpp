@@ -18,7 +18,7 @@ extern "C" int hostmath_fluid_tet4(const svb::FluidArgs* P, int nNo, const int* 
     for (int a = 0; a < 4; a++) {
       n[a] = P->IEN[4*e + a];
       for (int i = 0; i < 3; i++) {
-        xl[a][i] = P->x[3*n[a] + i];
+        xl[a][i] = P->x[3*n[a] + i] + (P->ale ? P->Dg[P->tDof*n[a] + 4 + i] : 0.0);
         ab[a][i] = P->Ag[P->tDof*n[a] + i] - P->Bf[3*n[a] + i];
         uc[a][i] = P->Yg[P->tDof*n[a] + i] - (P->mvMsh ? P->Yg[P->tDof*n[a] + 4 + i] : 0.0);
       }

@@ -20,8 +20,8 @@ class FluidDmn(C.Structure):
 
 
 class FluidArgs(C.Structure):
-    _fields_ = [(k, C.c_void_p) for k in ("IEN", "eId", "slot", "perm", "x", "Ag", "Yg", "Bf", "R", "Val")] + \
-               [(k, C.c_int) for k in ("e0", "e1", "tDof", "mvMsh", "nDmn", "atomic")] + \
+    _fields_ = [(k, C.c_void_p) for k in ("IEN", "eId", "slot", "perm", "x", "Ag", "Yg", "Bf", "Dg", "R", "Val")] + \
+               [(k, C.c_int) for k in ("e0", "e1", "tDof", "mvMsh", "nDmn", "atomic", "ale", "pad0")] + \
                [(k, C.c_double) for k in ("dt", "af", "am", "gam")] + \
                [("w", C.c_double * 8), ("N", (C.c_double * 8) * 8), ("Nxi", ((C.c_double * 3) * 8) * 8), ("dmn", FluidDmn * 8)]
 
