@@ -210,6 +210,9 @@ SVB200_API int svb200_alloc(svb200_ctx* ctx, int32_t dof);
 SVB200_API int svb200_set_state(svb200_ctx* ctx, int32_t tDof, const double* Ag, const double* Yg, const double* Dg,
                      const double* Bf);
 
+/* Old displacement Do(tDof,nNo) (solutions.old), read by the mesh-motion equation (solver/mesh.cpp:22-135). */
+SVB200_API int svb200_set_old_disp(svb200_ctx* ctx, int32_t tDof, const double* Do);
+
 /* global_eq_assem for mesh iM: element loop + scatter, R/Val stay on the device. */
 SVB200_API int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq,
                     const svb200_dmnparams* dmn, int32_t nDmn);

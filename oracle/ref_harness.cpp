@@ -310,6 +310,17 @@ int svref_set_state(void* h, int tDof, const double* Ag, const double* Yg, const
   });
 }
 
+int svref_set_old_disp(void* h, int tDof, const double* Do_in)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    auto& Do = c.sol.old.get_displacement();
+    int n = c.com_mod.tnNo;
+    if (Do.nrows() != tDof || Do.ncols() != n) Do.resize(tDof, n);
+    std::memcpy(Do.data(), Do_in, sizeof(double)*tDof*n);
+  });
+}
+
 /// The switch of eq_assem::global_eq_assem (solver/eq_assem.cpp:397-449) for the in-scope physics.
 int svref_assemble(void* h, int iM, const svb200_eqparams* e, const svb200_dmnparams* dmn, int nDmn)
 {

@@ -57,7 +57,7 @@ class _FlatCase:
             getattr(lib, p + "create").restype = C.c_void_p
             getattr(lib, p + "last_error").restype = C.c_char_p
             for name in ("destroy", "set_coords", "add_mesh", "get_mesh_tables", "build_graph", "get_graph",
-                         "set_face", "alloc", "set_state", "assemble", "get", "put", "solve", "spmv", "last_timing"):
+                         "set_face", "alloc", "set_state", "set_old_disp", "assemble", "get", "put", "solve", "spmv", "last_timing"):
                 getattr(lib, p + name).argtypes = None
             cls._lib = lib
         return cls._lib
@@ -129,6 +129,10 @@ class _FlatCase:
     def set_state(self, Ag, Yg, Dg=None, Bf=None):
         Ag, Yg, Dg, Bf = _f64(Ag), _f64(Yg), _f64(Dg), _f64(Bf)
         self._call("set_state", C.c_int(Ag.shape[0]), _d(Ag), _d(Yg), _d(Dg), _d(Bf))
+
+    def set_old_disp(self, Do):
+        Do = _f64(Do)
+        self._call("set_old_disp", C.c_int(Do.shape[0]), _d(Do))
 
     def assemble(self, iM, eq: abi.EqParams, dmns):
         arr = (abi.DmnParams * len(dmns))(*dmns)

@@ -268,6 +268,14 @@ int svorc_set_state(void* h, int tDof, const double* Ag, const double* Yg, const
   return 0;
 }
 
+/* Old displacement (mesh-motion equation); kept for interface parity with the reference harness. */
+int svorc_set_old_disp(void* h, int tDof, const double* Do)
+{
+  OCase* c = h;
+  (void)tDof; (void)Do; (void)c;
+  return 0;
+}
+
 /* utils::is_zero(value, 0) */
 static int is_zero(double v)
 {

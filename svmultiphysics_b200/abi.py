@@ -123,6 +123,23 @@ def struct_domain(rho: float = 1000.0, isoType: int = ISO_NHK, volType: int = VO
     return d
 
 
+def mesh_eq(dt: float, rho_inf: float = 0.5, tDof: int = 7, s: int = 4, scatter: int = SCATTER_ATOMIC) -> EqParams:
+    """Mesh-motion equation of an FSI run: dof = 3, state dofs nsd+1..2nsd (Code/Source/solver/mesh.cpp:47-48)."""
+    af, am, gam, beta = gen_alpha(rho_inf)
+    return EqParams(dt=dt, af=af, am=am, gam=gam, beta=beta, phys=PHYS_MESH, dof=3, tDof=tDof, s=s,
+                    mvMsh=1, vmsStab=1, scatter=scatter, reserved=0)
+
+
+def mesh_domain(E: float = 1.0, nu: float = 0.3, rho: float = 0.0, f=(0.0, 0.0, 0.0), Id: int = -1) -> DmnParams:
+    d = DmnParams()
+    d.Id = Id
+    d.phys = PHYS_MESH
+    d.rho = rho
+    d.f[0], d.f[1], d.f[2] = f
+    d.E, d.nu = E, nu
+    return d
+
+
 def ls_params(ls_type: int, mItr=None, sD=None, relTol=None, absTol=1e-10, gm=None, cg=None) -> LsParams:
     """Defaults of fsils_ls_create (Code/Source/linear_solver/ls.cpp:22-59), overridable like read_ls does."""
     p = LsParams()

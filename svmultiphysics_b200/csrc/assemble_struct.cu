@@ -12,6 +12,7 @@
 // (a, a+k mod ENON), k = 0..ENON/2, in registers (5 x 9 doubles for HEX8) and scatters each of them twice
 // (as is, and transposed) — 36 of 64 block products instead of 64.
 #include <cstdlib>
+#include <vector>
 #include "struct_elem.cuh"
 
 namespace svb {
@@ -218,6 +219,107 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
   }
 }
 
+// ---- mesh-motion equation: linear elasticity on the configuration at t_n --------------------------------
+// mesh::construct_mesh (Code/Source/solver/mesh.cpp:22-135) + l_elas::l_elas_3d (Code/Source/solver/l_elas.cpp:249-365):
+// geometry x + Do(is..), displacement Dg(is..) - Do(is..), and the Gauss weight WITHOUT the Jacobian
+// (w = lM.w(g), mesh.cpp:122: Jacobian-based stiffening).  ENON lanes per element, lane a owns row a.
+template <int ENON, bool ATOMIC>
+__global__ void __launch_bounds__(128)
+assemble_mesh_kernel(const __grid_constant__ StructArgs P, const double* __restrict__ Do)
+{
+  constexpr int EPW = 32 / ENON;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int a = lane % ENON, el = lane / ENON;
+  const long long idx = (long long)P.e0 + ((long long)blockIdx.x * 4 + warp) * EPW + el;
+  if (idx >= P.e1) return;
+  const int e = P.perm ? P.perm[idx] : (int)idx;
+  int iD = 0;
+  for (int d = 0; d < P.nDmn; d++) {
+    iD = d;
+    if (P.dmn[d].Id == -1) break;
+    if (P.eId != nullptr && ((P.eId[e] >> P.dmn[d].Id) & 1)) break;
+  }
+  const StructDmn& dm = P.dmn[iD];
+  if (!dm.isStruct) return;          // isStruct marks the domains this launch handles (mesh domains here)
+  const int DOF = P.dof, is = P.s;
+  int node[ENON];
+  double xl[ENON][3], dl[ENON][3];
+#pragma unroll
+  for (int b = 0; b < ENON; b++) {
+    node[b] = P.IEN[(size_t)e * ENON + b];
+    const size_t n = (size_t)node[b];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const double dol = __ldg(Do + (size_t)P.tDof * n + is + i);
+      xl[b][i] = __ldg(P.x + 3 * n + i) + dol;
+      dl[b][i] = __ldg(P.Dg + (size_t)P.tDof * n + is + i) - dol;
+    }
+  }
+  // elasticity_modulus and poisson_ratio travel in C10 / C01 for this kernel
+  const double elM = dm.C10, nu = dm.C01, rho = dm.rho;
+  const double lambda = elM * nu / (1.0 + nu) / (1.0 - 2.0 * nu);
+  const double mu = elM * 0.5 / (1.0 + nu);
+  const double lDm = lambda / mu;
+  const double T1c = P.af * P.beta * P.dt * P.dt;
+  const double amd = P.am / T1c * rho;
+  double K[ENON][3][3], lR[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int b = 0; b < ENON; b++)
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) K[b][i][j] = 0.0;
+  double Nx[ENON][3];
+#pragma unroll 1
+  for (int g = 0; g < P.nG; g++) {
+    if (g == 0 || ENON != 4) gnn3<ENON>(P.Nxi[g], xl, Nx);     // TET4: lShpF, gradients constant
+    const double w = P.w[g];
+    const double wl = w * T1c * mu;
+    double ud[3] = {-dm.f[0], -dm.f[1], -dm.f[2]}, ed[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int b = 0; b < ENON; b++) {
+      const double Nb = P.N[g][b];
+      const size_t n = (size_t)node[b];
+#pragma unroll
+      for (int i = 0; i < 3; i++) ud[i] += Nb * __ldg(P.Ag + (size_t)P.tDof * n + is + i);
+      ed[0] += Nx[b][0] * dl[b][0];
+      ed[1] += Nx[b][1] * dl[b][1];
+      ed[2] += Nx[b][2] * dl[b][2];
+      ed[3] += Nx[b][1] * dl[b][0] + Nx[b][0] * dl[b][1];
+      ed[4] += Nx[b][2] * dl[b][1] + Nx[b][1] * dl[b][2];
+      ed[5] += Nx[b][0] * dl[b][2] + Nx[b][2] * dl[b][0];
+    }
+    const double divD = lambda * (ed[0] + ed[1] + ed[2]);
+    const double S0 = divD + 2.0 * mu * ed[0], S1 = divD + 2.0 * mu * ed[1], S2 = divD + 2.0 * mu * ed[2];
+    const double S3 = mu * ed[3], S4 = mu * ed[4], S5 = mu * ed[5];
+    const double Na = P.N[g][a];
+    lR[0] += w * (rho * Na * ud[0] + Nx[a][0] * S0 + Nx[a][1] * S3 + Nx[a][2] * S5);
+    lR[1] += w * (rho * Na * ud[1] + Nx[a][0] * S3 + Nx[a][1] * S1 + Nx[a][2] * S4);
+    lR[2] += w * (rho * Na * ud[2] + Nx[a][0] * S5 + Nx[a][1] * S4 + Nx[a][2] * S2);
+#pragma unroll
+    for (int b = 0; b < ENON; b++) {
+      const double NxdNx = Nx[a][0] * Nx[b][0] + Nx[a][1] * Nx[b][1] + Nx[a][2] * Nx[b][2];
+      const double T1 = amd * Na * P.N[g][b] / mu + NxdNx;
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+          K[b][i][j] += wl * ((i == j ? T1 + (1.0 + lDm) * Nx[a][i] * Nx[b][i] : lDm * Nx[a][i] * Nx[b][j] + Nx[a][j] * Nx[b][i]));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++) add64<ATOMIC>(P.R + (size_t)DOF * node[a] + i, lR[i]);
+  const int* sl = P.slot + (size_t)e * ENON * ENON + a * ENON;
+#pragma unroll
+  for (int b = 0; b < ENON; b++) {
+    double* v = P.Val + (size_t)DOF * DOF * sl[b];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) add64<ATOMIC>(v + DOF * i + j, K[b][i][j]);
+  }
+}
+
 int fill_struct_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn, StructArgs& A)
 {
   SVB_REQUIRE(nDmn >= 1 && nDmn <= MAX_DMN, "svb200_assemble: between 1 and 8 domains are supported");
@@ -289,6 +391,49 @@ int run_assemble_struct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* e
   int rc = fill_struct_args(ctx, m, eq, dmn, nDmn, A);
   if (rc) return rc;
   auto launch = [&](const StructArgs& B) { return m.eNoN == 8 ? launch_one<8>(ctx, B) : launch_one<4>(ctx, B); };
+  if (A.atomic) return launch(A);
+  A.perm = m.d_color_perm;
+  for (size_t c = 0; c + 1 < m.color_off.size(); c++) {
+    A.e0 = m.color_off[c];
+    A.e1 = m.color_off[c + 1];
+    rc = launch(A);
+    if (rc) return rc;
+  }
+  return SVB200_OK;
+}
+
+template <int ENON>
+static int launch_mesh(svb200_ctx* ctx, const StructArgs& A, const double* Do)
+{
+  constexpr int EPB = 4 * (32 / ENON);
+  const long long n = (long long)A.e1 - A.e0;
+  if (n <= 0) return SVB200_OK;
+  const unsigned blocks = (unsigned)((n + EPB - 1) / EPB);
+  if (A.atomic) assemble_mesh_kernel<ENON, true><<<blocks, 128, 0, ctx->stream>>>(A, Do);
+  else assemble_mesh_kernel<ENON, false><<<blocks, 128, 0, ctx->stream>>>(A, Do);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
+int run_assemble_mesh(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn)
+{
+  SVB_REQUIRE(ctx->d_Do, "svb200_assemble: the mesh equation needs the old displacement (svb200_set_old_disp)");
+  SVB_REQUIRE(eq->dof == 3 && ctx->dof == 3, "svb200_assemble: the mesh equation has dof = 3");
+  // reuse the solid argument block: mark mesh domains as the ones to assemble, E / nu travel in C10 / C01
+  std::vector<svb200_dmnparams> d(dmn, dmn + nDmn);
+  for (auto& q : d) {
+    const bool isMesh = (q.phys == SVB200_PHYS_MESH);
+    q.phys = isMesh ? SVB200_PHYS_STRUCT : SVB200_PHYS_FLUID;
+    q.isoType = SVB200_ISO_NHK;
+    q.solid_visc_mu = 0.0;
+    q.C10 = q.E;
+    q.C01 = q.nu;
+  }
+  StructArgs A;
+  int rc = fill_struct_args(ctx, m, eq, d.data(), nDmn, A);
+  if (rc) return rc;
+  auto launch = [&](const StructArgs& B) { return m.eNoN == 8 ? launch_mesh<8>(ctx, B, ctx->d_Do) : launch_mesh<4>(ctx, B, ctx->d_Do); };
   if (A.atomic) return launch(A);
   A.perm = m.d_color_perm;
   for (size_t c = 0; c + 1 < m.color_off.size(); c++) {

@@ -197,7 +197,7 @@ int svb200_destroy(svb200_ctx* ctx)
   for (auto& f : ctx->face) free_face(f);
   for (auto& nb : ctx->neigh) { cudaFree(nb.d_ptr); cudaFree(nb.d_send); cudaFree(nb.d_recv); }
   cudaFree(ctx->d_map); cudaFree(ctx->d_rowPtr); cudaFree(ctx->d_colPtr); cudaFree(ctx->d_diagPtr);
-  cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf);
+  cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf); cudaFree(ctx->d_Do);
   cudaFree(ctx->d_stage); cudaFree(ctx->d_R); cudaFree(ctx->d_Val); cudaFree(ctx->d_W);
   cudaFree(ctx->d_work); cudaFree(ctx->d_red); cudaFree(ctx->d_tslot);
   cudaFreeHost(ctx->h_pinned);
@@ -286,8 +286,8 @@ int svb200_set_graph(svb200_ctx* ctx, int32_t nNo, int32_t nnz, const int32_t* r
   }
   std::sort(ctx->neigh.begin(), ctx->neigh.end(), [](const Neighbor& a, const Neighbor& b) { return a.rank < b.rank; });
   // state arrays depend on nNo
-  cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf);
-  ctx->d_x = ctx->d_Ag = ctx->d_Yg = ctx->d_Dg = ctx->d_Bf = nullptr;
+  cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf); cudaFree(ctx->d_Do);
+  ctx->d_x = ctx->d_Ag = ctx->d_Yg = ctx->d_Dg = ctx->d_Bf = ctx->d_Do = nullptr;
   ctx->tDof = 0;
   return SVB200_OK;
 }
@@ -415,8 +415,8 @@ int svb200_set_state(svb200_ctx* ctx, int32_t tDof, const double* Ag, const doub
   SVB_REQUIRE(ctx->d_rowPtr, "svb200_set_state: call svb200_set_graph first");
   SVB_REQUIRE(tDof >= 1 && tDof <= 16, "svb200_set_state: bad tDof");
   if (tDof != ctx->tDof) {
-    cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg);
-    ctx->d_Ag = ctx->d_Yg = ctx->d_Dg = nullptr;
+    cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Do);
+    ctx->d_Ag = ctx->d_Yg = ctx->d_Dg = ctx->d_Do = nullptr;
     ctx->tDof = tDof;
   }
   const size_t n = (size_t)tDof * ctx->nNo;
@@ -500,6 +500,14 @@ static int run_assemble(svb200_ctx* ctx, const Mesh& m, FluidArgs& A)
   return SVB200_OK;
 }
 
+int svb200_set_old_disp(svb200_ctx* ctx, int32_t tDof, const double* Do)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(ctx->d_rowPtr && Do, "svb200_set_old_disp: call svb200_set_graph first");
+  SVB_REQUIRE(tDof == ctx->tDof, "svb200_set_old_disp: tDof differs from svb200_set_state");
+  return upload_nodal(ctx, tDof, Do, &ctx->d_Do);
+}
+
 int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int32_t nDmn)
 {
   CTX_GUARD(ctx);
@@ -532,6 +540,9 @@ int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, cons
       }
       if (anySolid) TRY(run_assemble_struct(ctx, m, eq, dmn, nDmn));
     } break;
+    case SVB200_PHYS_MESH:
+      TRY(run_assemble_mesh(ctx, m, eq, dmn, nDmn));
+      break;
     default:
       set_error("svb200_assemble: this physics is not implemented in this build");
       return SVB200_ERR_UNSUPPORTED;

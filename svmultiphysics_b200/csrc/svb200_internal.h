@@ -108,6 +108,7 @@ struct svb200_ctx {
   double* d_Ag = nullptr;
   double* d_Yg = nullptr;
   double* d_Dg = nullptr;
+  double* d_Do = nullptr;        // old displacement (mesh-motion equation)
   double* d_Bf = nullptr;
   double* d_stage = nullptr;     // staging buffer for permuted uploads/downloads
   size_t stage_bytes = 0;
@@ -167,6 +168,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 int launch_assemble_fluid(svb200_ctx* ctx, const Mesh& m, const FluidArgs& args);
 // assemble_struct.cu
 int run_assemble_struct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);
+int run_assemble_mesh(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);
 // graph_kernels.cu
 int launch_build_slot_map(svb200_ctx* ctx, Mesh& m);
 int launch_find_diag(svb200_ctx* ctx);

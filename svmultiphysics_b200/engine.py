@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "svb200_comm_unique_id", "svb200_comm_init",
     "svb200_set_graph", "svb200_lhsa_begin", "svb200_lhsa_add_mesh", "svb200_lhsa_finish", "svb200_lhsa_get",
     "svb200_set_mesh", "svb200_set_coords", "svb200_set_num_faces", "svb200_set_face",
-    "svb200_alloc", "svb200_set_state", "svb200_assemble", "svb200_add_host_contrib", "svb200_commu_R",
+    "svb200_alloc", "svb200_set_state", "svb200_set_old_disp", "svb200_assemble", "svb200_add_host_contrib", "svb200_commu_R",
     "svb200_solve", "svb200_download", "svb200_upload", "svb200_spmv", "svb200_last_timing",
     "svb200_host_register", "svb200_host_unregister", "svb200_timer_mark", "svb200_timer_elapsed",
     "svb200_bench_assemble", "svb200_bench_spmv", "svb200_measure_fp64_peak", "svb200_launch_count",
@@ -195,6 +195,10 @@ class Engine:
         Ag, Yg, Dg, Bf = _f64(Ag), _f64(Yg), _f64(Dg), _f64(Bf)
         tDof = (Ag if Ag is not None else Yg).shape[0]
         self._call("svb200_set_state", C.c_int32(tDof), _d(Ag), _d(Yg), _d(Dg), _d(Bf))
+
+    def set_old_disp(self, Do):
+        Do = _f64(Do)
+        self._call("svb200_set_old_disp", C.c_int32(Do.shape[0]), _d(Do))
 
     def assemble(self, iM, eq: abi.EqParams, dmns):
         arr = (abi.DmnParams * len(dmns))(*dmns)

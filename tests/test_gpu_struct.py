@@ -106,3 +106,42 @@ def test_fsi_assembly_parity(scatter):
     fl_rows = np.unique(m.IEN[:, m.eId == 1])
     assert common.rel_err(R1[:, fl_rows], R0[:, fl_rows]) < 1e-11
     eng.close()
+
+
+@pytest.mark.parametrize("kind", ["tet4", "hex8"])
+def test_mesh_equation_parity(kind):
+    """Mesh-motion equation of an FSI run (mesh::construct_mesh + l_elas_3d): dof 3, state dofs 4..6."""
+    cls = _oracle()
+    if kind == "tet4":
+        m, Ag, Yg, Dg, Bf = common.fsi_case()
+        m.eId = None
+    else:
+        from svmultiphysics_b200 import meshgen
+        m = meshgen.box_hex8(3, 3, 2, (1.0, 2.0, 1.0))
+        rng = np.random.default_rng(5)
+        Ag = np.asfortranarray(rng.standard_normal((7, m.nNo))); Yg = np.asfortranarray(rng.standard_normal((7, m.nNo)))
+        Dg = np.asfortranarray(1e-2 * rng.standard_normal((7, m.nNo))); Bf = None
+    Do = np.asfortranarray(Dg + 3e-3 * np.random.default_rng(9).standard_normal(Dg.shape))
+    orc = cls(); orc.set_coords(m.x); orc.add_mesh(m.IEN)
+    rowPtr, colPtr = orc.build_graph(0)
+    eq, dmn = abi.mesh_eq(1e-3), [abi.mesh_domain(E=1.0, nu=0.3)]
+    orc.alloc(3); orc.set_state(Ag, Yg, Dg, Bf); orc.set_old_disp(Do); orc.assemble(0, eq, dmn)
+    R0, V0 = orc.get_R(), orc.get_Val()
+    eng = _engine(m, rowPtr, colPtr)
+    eng.alloc(3); eng.set_state(Ag, Yg, Dg, Bf); eng.set_old_disp(Do); eng.assemble(0, eq, dmn)
+    assert common.rel_err(eng.get_R(), R0) < ASM_TOL
+    assert common.rel_err(eng.get_Val(), V0) < ASM_TOL
+    # CG as in tests/cases/fsi/pipe_3d/solver.xml (mesh equation: LS type CG, tolerance 1e-12)
+    faces = [(abi.BC_DIR, m.faces[k], np.zeros((3, len(m.faces[k])), order="F")) for k in (("wall",) if kind == "tet4" else ("X0", "X1"))]
+    orc2 = cls(); orc2.set_coords(m.x); orc2.add_mesh(m.IEN); orc2.build_graph(len(faces))
+    eng.set_num_faces(len(faces))
+    for i, (g, nodes, val) in enumerate(faces):
+        orc2.set_face(i, g, nodes, val); eng.set_face(i, g, nodes, val)
+    orc2.alloc(3); orc2.set_state(Ag, Yg, Dg, Bf); orc2.set_old_disp(Do); orc2.assemble(0, eq, dmn)
+    ls = abi.ls_params(abi.LS_CG, mItr=1000, relTol=1e-12)
+    incL, res = np.ones(len(faces), np.int32), np.zeros(len(faces))
+    X0, o0, _ = orc2.solve(3, abi.LS_CG, ls, incL, res)
+    X1, o1, _ = eng.solve(3, abi.LS_CG, ls, incL, res)
+    assert o1.RI.success == o0.RI.success and abs(o1.RI.itr - o0.RI.itr) <= max(2, o0.RI.itr // 20)
+    assert common.rel_err(X1, X0) < 1e-8
+    eng.close()
