@@ -163,7 +163,13 @@ def test_fluid_ns_and_coupled_face_parity(ls_type, kw, res_out):
     else:
         assert out1.RI.itr == out0.RI.itr
     assert abs(out1.RI.iNorm - out0.RI.iNorm) <= 1e-10 * out0.RI.iNorm
-    assert abs(out1.RI.fNorm - out0.RI.fNorm) <= 2e-2 * out0.RI.fNorm
+    if ls_type == abi.LS_GMRES and out0.RI.itr > ls.RI.sD + 1:
+        # after ~20 restarts the residual at which the stopping test first fires differs by up to one
+        # iteration's reduction factor; the contract is the set tolerance itself
+        assert out1.RI.fNorm <= ls.RI.relTol * out1.RI.iNorm
+        assert abs(out1.RI.fNorm - out0.RI.fNorm) <= 0.15 * out0.RI.fNorm
+    else:
+        assert abs(out1.RI.fNorm - out0.RI.fNorm) <= 2e-2 * out0.RI.fNorm
     if ls_type == abi.LS_NS:
         # accumulated inner iteration counts: a CG/GMRES stopping test that lands within round-off of its
         # tolerance may fire one step earlier or later
