@@ -136,6 +136,165 @@ assemble_fluid_tet4_kernel(const __grid_constant__ FluidArgs P)
   }
 }
 
+// =====================================================================================================
+// Grouped scatter (default ATOMIC path).  One CTA owns ASM_GROUP consecutive elements:
+//   phase 1  one thread per element: gather, gnn, Gauss loop -> the element's ~60 moments go to shared memory;
+//   phase 2  one thread per DISTINCT CSR block the group touches (plan: group_sched.cu): it re-emits the 4x4
+//            blocks of all the group's contributions to that slot from the moments (tet4_block algebra), sums
+//            them in registers in a fixed order and adds the block through a per-warp transposition tile with ONE
+//            coalesced 128-byte RED per half-warp — 5.4 block reductions per element instead of 16.  (A TMA
+//            bulk reduce per block, cp.reduce.async.bulk...add.f64, was measured slower here: UBLKRED is a
+//            uniform-datapath instruction and serialises over the lanes of a warp.)
+//   (between the two) the same for the residual rows (distinct nodes of the group, 4 REDs each).
+// Phase 1 uses tet4_element_staged (fluid_elem.cuh): 168 registers, so three CTAs are resident per SM.
+// Only blocks shared between groups still meet in the L2 atomic units, so the result is bitwise reproducible
+// up to the order of those few cross-group additions.
+constexpr int ENT_CACHE = 768;              // plan entries of the group kept in shared memory (the rest: global)
+constexpr int ASM_WARPS = ASM_GROUP / 32;
+
+template <bool NN>
+__global__ void __launch_bounds__(ASM_GROUP, NN ? 2 : 3)
+assemble_fluid_tet4_grouped_kernel(const __grid_constant__ FluidArgs P)
+{
+  constexpr int RS = NN ? REC_NN : REC_NEWT;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* tiles = reinterpret_cast<double*>(smem_raw);                             // [warps][32*TILE_LD]
+  double* rec = tiles + ASM_WARPS * 32 * TILE_LD;                                  // [ASM_GROUP][RS]
+  int2* entc = reinterpret_cast<int2*>(rec + ASM_GROUP * RS);                      // [ENT_CACHE]
+  unsigned short* ctr = reinterpret_cast<unsigned short*>(entc + ENT_CACHE);       // [ASM_GROUP*16]
+  unsigned short* ctrR = ctr + ASM_GROUP * 16;                                     // [ASM_GROUP*4]
+  unsigned char* act = reinterpret_cast<unsigned char*>(ctrR + ASM_GROUP * 4);     // [ASM_GROUP]
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int g = blockIdx.x;
+  double* T = tiles + (tid >> 5) * 32 * TILE_LD;
+  {
+    const uint4* srcK = reinterpret_cast<const uint4*>(P.kContrib + (size_t)g * ASM_GROUP * 16);
+    uint4* dstK = reinterpret_cast<uint4*>(ctr);
+    dstK[tid] = __ldg(srcK + tid);
+    dstK[tid + ASM_GROUP] = __ldg(srcK + tid + ASM_GROUP);
+    if (tid < ASM_GROUP * 4 * 2 / 16)
+      reinterpret_cast<uint4*>(ctrR)[tid] = __ldg(reinterpret_cast<const uint4*>(P.rContrib + (size_t)g * ASM_GROUP * 4) + tid);
+  }
+  const int ub = __ldg(P.kU_ptr + g);
+  const int G = __ldg(P.kU_ptr + g + 1) - ub;
+  for (int k = tid; k < min(G, ENT_CACHE); k += ASM_GROUP) entc[k] = __ldg(P.kU_ent + ub + k);
+
+  // ---- phase 1: element record -> shared memory, element residual -> this lane's tile row ------------------
+  const int e = g * ASM_GROUP + tid;
+  bool active = e < P.e1;
+  if (active) {
+    const int iD = pick_domain(P, e);
+    if (!P.dmn[iD].isFluid) {
+      active = false;
+    } else {
+      const int4 n4 = *reinterpret_cast<const int4*>(P.IEN + 4 * (size_t)e);
+      const int node[4] = {n4.x, n4.y, n4.z, n4.w};
+      double xl[4][3], yl[4][4], uc[4][3], ab[4][3];
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const size_t n = (size_t)node[a];
+        const double* xp = P.x + 3 * n;
+        const double* bp = P.Bf + 3 * n;
+        const double* ap = P.Ag + (size_t)P.tDof * n;
+        const double* yp = P.Yg + (size_t)P.tDof * n;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          xl[a][i] = __ldg(xp + i) + (P.ale ? __ldg(P.Dg + (size_t)P.tDof * n + 4 + i) : 0.0);
+          ab[a][i] = __ldg(ap + i) - __ldg(bp + i);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) yl[a][i] = __ldg(yp + i);
+#pragma unroll
+        for (int i = 0; i < 3; i++) uc[a][i] = yl[a][i] - (P.mvMsh ? __ldg(yp + 4 + i) : 0.0);
+      }
+      tet4_element_staged(P, P.dmn[iD], xl, yl, uc, ab, NN, rec + tid * RS, T + lane * TILE_LD);
+    }
+  }
+  act[tid] = active ? 1 : 0;
+  __syncthreads();
+
+  // ---- phase 2: residual rows of the group's distinct nodes (element residuals sit in the tiles) ------------
+  {
+    const int rb = __ldg(P.rU_ptr + g);
+    const int GR = __ldg(P.rU_ptr + g + 1) - rb;
+    for (int k = tid; k < GR; k += ASM_GROUP) {
+      const int2 ent = __ldg(P.rU_ent + rb + k);
+      const int start = ent.y & 0xFFFF, end = start + (ent.y >> 16);
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      bool any = false;
+      for (int c = start; c < end; c++) {
+        const int id = ctrR[c];
+        const int el = id >> 2, a = id & 3;
+        if (!act[el]) continue;
+        any = true;
+        const double* r = tiles + el * TILE_LD + 4 * a;   // tile rows of consecutive warps are contiguous
+        s0 += r[0]; s1 += r[1]; s2 += r[2]; s3 += r[3];
+      }
+      if (any) {
+        double* dst = P.R + 4 * (size_t)ent.x;
+        add_f64<true>(dst, s0); add_f64<true>(dst + 1, s1); add_f64<true>(dst + 2, s2); add_f64<true>(dst + 3, s3);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 3: one thread per distinct CSR block ------------------------------------------------------------
+  {
+    const int half = lane >> 4, j = lane & 15;
+    for (int k0 = (tid & ~31); k0 < G; k0 += ASM_GROUP) {   // warp-uniform trip count
+      const int k = k0 + lane;
+      int myslot = -1;
+      if (k < G) {
+        const int2 ent = k < ENT_CACHE ? entc[k] : __ldg(P.kU_ent + ub + k);
+        const int start = ent.y & 0xFFFF, end = start + (ent.y >> 16);
+        double K[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) K[i] = 0.0;
+        for (int c = start; c < end; c++) {
+          const int id = ctr[c];
+          const int el = id >> 4;
+          if (!act[el]) continue;
+          myslot = ent.x;
+          tet4_block_rec_add(rec + el * RS, NN, (id >> 2) & 3, id & 3, K);
+        }
+        if (myslot >= 0) {
+#pragma unroll
+          for (int i = 0; i < 16; i++) T[lane * TILE_LD + i] = K[i];
+        }
+      }
+      __syncwarp();
+      // a half-warp adds the 16 contiguous doubles of one block with one coalesced RED
+#pragma unroll 4
+      for (int r = 0; r < 16; r++) {
+        const int src = 2 * r + half;
+        const int sl = __shfl_sync(0xffffffffu, myslot, src);
+        if (sl >= 0) add_f64<true>(P.Val + 16 * (size_t)sl + j, T[src * TILE_LD + j]);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <bool NN>
+static int launch_grouped(svb200_ctx* ctx, const FluidArgs& args)
+{
+  constexpr int RS = NN ? REC_NN : REC_NEWT;
+  constexpr size_t smem = sizeof(double) * ASM_GROUP * (TILE_LD + RS) + sizeof(int2) * ENT_CACHE + 2 * ASM_GROUP * 20 + ASM_GROUP;
+  static bool configured = false;
+  if (!configured) {
+    SVB_CUDA(cudaFuncSetAttribute(assemble_fluid_tet4_grouped_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    configured = true;
+  }
+  const int nGrp = (args.e1 + ASM_GROUP - 1) / ASM_GROUP;
+  assemble_fluid_tet4_grouped_kernel<NN><<<nGrp, ASM_GROUP, smem, ctx->stream>>>(args);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
 int launch_assemble_fluid(svb200_ctx* ctx, const Mesh& m, const FluidArgs& args)
 {
   if (m.eNoN != 4) {
@@ -146,6 +305,12 @@ int launch_assemble_fluid(svb200_ctx* ctx, const Mesh& m, const FluidArgs& args)
   if (n <= 0) return SVB200_OK;
   const int blocks = (n + ASM_THREADS - 1) / ASM_THREADS;
   static const int variant = getenv("SVB200_ASM_MINB") ? atoi(getenv("SVB200_ASM_MINB")) : 2;   // tuning knob
+  static const bool legacy = getenv("SVB200_ASM_LEGACY") != nullptr;   // A/B knob: per-entry RED scatter
+  if (args.atomic && !legacy && args.kU_ptr && args.e0 == 0) {
+    bool nn = false;
+    for (int d = 0; d < args.nDmn; d++) nn |= (args.dmn[d].viscType != SVB200_VISC_CONST);
+    return nn ? launch_grouped<true>(ctx, args) : launch_grouped<false>(ctx, args);
+  }
   if (args.atomic) {
     if (variant == 4) assemble_fluid_tet4_kernel<true, 4><<<blocks, ASM_THREADS, 0, ctx->stream>>>(args);
     else if (variant == 3) assemble_fluid_tet4_kernel<true, 3><<<blocks, ASM_THREADS, 0, ctx->stream>>>(args);

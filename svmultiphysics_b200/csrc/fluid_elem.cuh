@@ -317,4 +317,303 @@ SVB_HD void tet4_block(const Tet4Elem& E, int a, int b, double K[16])
   }
 }
 
+
+// =====================================================================================================
+// Staged variant used by the grouped scatter (assemble_fluid.cu).  Same algebra as tet4_element, but
+// organised for a small register footprint (3 CTAs of 128 threads per SM instead of 2):
+//   * the element "record" (what tet4_block needs) is written to `rec` (shared memory on the device) as
+//     soon as a field is final;
+//   * the not-yet-final part of the record doubles as per-thread scratch for Gauss-point values
+//     (u_g, ud_g, p_g -> up_g, tauM_g, tauB_g), so the nodal inputs die before the Gauss loops;
+//   * the Gauss loop is split in two: loop 1 accumulates the residual moments, loop 2 the tangent
+//     moments D, S2, S3 from the stored Gauss-point values.
+// Record layout (doubles): Nx[4][3] | Sb[4] | S2[4] | S3[4] | D[4][4] | A1 A2 Spp | pad pad | (A3 | esNx[4][3]).
+constexpr int REC_NEWT = 45, REC_NN = 59;   // odd strides: conflict-free lane-strided shared-memory access
+constexpr int O_NX = 0, O_SB = 12, O_S2 = 16, O_S3 = 20, O_D = 24, O_A1 = 40, O_A2 = 41, O_SPP = 42, O_A3 = 45, O_ES = 46;
+
+SVB_HD void tet4_element_staged(const FluidArgs& P, const FluidDmn& dm, const double xl[4][3], const double yl[4][4],
+                                const double uc[4][3], const double ab[4][3], const bool NN, double* rec, double* lRout)
+{
+  double nx[4][3];
+  double k00, k01, k02, k11, k12, k22, Jac;
+  {
+    double xXi[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < 4; a++) s += xl[a][i] * P.Nxi[0][a][k];
+        xXi[i][k] = s;
+      }
+    Jac = xXi[0][0] * xXi[1][1] * xXi[2][2] + xXi[0][1] * xXi[1][2] * xXi[2][0] + xXi[0][2] * xXi[1][0] * xXi[2][1] -
+          xXi[0][0] * xXi[1][2] * xXi[2][1] - xXi[0][1] * xXi[1][0] * xXi[2][2] - xXi[0][2] * xXi[1][1] * xXi[2][0];
+    const double iJ = 1.0 / Jac;
+    double xiX[3][3];
+    xiX[0][0] = (xXi[1][1] * xXi[2][2] - xXi[1][2] * xXi[2][1]) * iJ;
+    xiX[0][1] = (xXi[2][1] * xXi[0][2] - xXi[2][2] * xXi[0][1]) * iJ;
+    xiX[0][2] = (xXi[0][1] * xXi[1][2] - xXi[0][2] * xXi[1][1]) * iJ;
+    xiX[1][0] = (xXi[1][2] * xXi[2][0] - xXi[1][0] * xXi[2][2]) * iJ;
+    xiX[1][1] = (xXi[2][2] * xXi[0][0] - xXi[2][0] * xXi[0][2]) * iJ;
+    xiX[1][2] = (xXi[0][2] * xXi[1][0] - xXi[0][0] * xXi[1][2]) * iJ;
+    xiX[2][0] = (xXi[1][0] * xXi[2][1] - xXi[1][1] * xXi[2][0]) * iJ;
+    xiX[2][1] = (xXi[2][0] * xXi[0][1] - xXi[2][1] * xXi[0][0]) * iJ;
+    xiX[2][2] = (xXi[0][0] * xXi[1][1] - xXi[0][1] * xXi[1][0]) * iJ;
+    k00 = xiX[0][0] * xiX[0][0] + xiX[1][0] * xiX[1][0] + xiX[2][0] * xiX[2][0];
+    k01 = xiX[0][1] * xiX[0][0] + xiX[1][1] * xiX[1][0] + xiX[2][1] * xiX[2][0];
+    k02 = xiX[0][2] * xiX[0][0] + xiX[1][2] * xiX[1][0] + xiX[2][2] * xiX[2][0];
+    k11 = xiX[0][1] * xiX[0][1] + xiX[1][1] * xiX[1][1] + xiX[2][1] * xiX[2][1];
+    k12 = xiX[0][1] * xiX[0][2] + xiX[1][1] * xiX[1][2] + xiX[2][1] * xiX[2][2];
+    k22 = xiX[0][2] * xiX[0][2] + xiX[1][2] * xiX[1][2] + xiX[2][2] * xiX[2][2];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        nx[a][i] = P.Nxi[0][a][0] * xiX[0][i] + P.Nxi[0][a][1] * xiX[1][i] + P.Nxi[0][a][2] * xiX[2][i];
+        rec[O_NX + 3 * a + i] = nx[a][i];
+      }
+  }
+
+  // ---- element-constant kinematics ---------------------------------------------------------------------
+  double ux[3][3], px[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < 4; a++) s += nx[a][i] * yl[a][j];
+      ux[i][j] = s;
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; a++) s += nx[a][i] * yl[a][3];
+    px[i] = s;
+  }
+  const double divU = ux[0][0] + ux[1][1] + ux[2][2];
+  double gam = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const double es = ux[i][j] + ux[j][i];
+      gam += es * es;
+    }
+  gam = sqrt(0.5 * gam);
+  double mu, mu_g;
+  viscosity(dm, gam, mu, mu_g);
+  mu_g = is_zero(gam) ? 0.0 : mu_g / gam;
+  if (NN) {
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+        rec[O_ES + 3 * a + j] = (mu_g != 0.0) ? (ux[0][j] + ux[j][0]) * nx[a][0] + (ux[1][j] + ux[j][1]) * nx[a][1] +
+                                                    (ux[2][j] + ux[j][2]) * nx[a][2]
+                                              : 0.0;
+  }
+
+  // ---- Gauss-point interpolations go to scratch; the nodal inputs die here --------------------------------
+  double* S = rec + O_SB;   // 33 scratch doubles: S[8g+q]
+#pragma unroll
+  for (int g = 0; g < 4; g++) {
+    double u[3] = {0.0, 0.0, 0.0}, ud[3] = {-dm.f[0], -dm.f[1], -dm.f[2]}, p = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const double Na = P.N[g][a];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        u[i] += Na * uc[a][i];
+        ud[i] += Na * ab[a][i];
+      }
+      p += Na * yl[a][3];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      S[8 * g + i] = u[i];
+      S[8 * g + 3 + i] = ud[i];
+    }
+    S[8 * g + 6] = p;
+  }
+
+  const double rho = dm.rho;
+  const double T = P.af * P.gam * P.dt;
+  const double amd = P.am / T;
+  const double muKd = mu * dm.Kd;
+  const double nu = mu / rho;
+  const double kT = 4.0 / (P.dt * P.dt) + (dm.Kd * nu) * (dm.Kd * nu);
+  const double kS = 36.0 * (k00 * k00 + k11 * k11 + k22 * k22 + 2.0 * (k01 * k01 + k02 * k02 + k12 * k12)) * nu * nu;
+  const double kTS = kT + kS;
+  const double trK = k00 + k11 + k22;
+
+  // ---- loop 1: residual moments ---------------------------------------------------------------------------
+  double RM[3][3], UP[3] = {0.0, 0.0, 0.0}, lR[4][3];
+  double sPa = 0.0, sW = 0.0, sA2 = 0.0, sPP = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) RM[i][j] = 0.0;
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) lR[a][j] = 0.0;
+
+#pragma unroll 1
+  for (int g = 0; g < 4; g++) {
+    const double wJ = P.w[g] * Jac;
+    const double wl = wJ * T;
+    const double u[3] = {S[8 * g], S[8 * g + 1], S[8 * g + 2]};
+    const double ud[3] = {S[8 * g + 3], S[8 * g + 4], S[8 * g + 5]};
+    const double p = S[8 * g + 6];
+    const double kU = u[0] * u[0] * k00 + u[1] * u[1] * k11 + u[2] * u[2] * k22 +
+                      2.0 * (u[0] * u[1] * k01 + u[0] * u[2] * k02 + u[1] * u[2] * k12);
+    const double tauM = 1.0 / (rho * sqrt(kTS + kU));
+    double up[3], ua[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const double rV = ud[j] + u[0] * ux[0][j] + u[1] * ux[1][j] + u[2] * ux[2][j];
+      up[j] = -tauM * (rho * rV + px[j] + muKd * u[j]);
+    }
+    const double tauC = 1.0 / (tauM * trK);
+    double tauB = up[0] * up[0] * k00 + up[1] * up[1] * k11 + up[2] * up[2] * k22 +
+                  2.0 * (up[0] * up[1] * k01 + up[0] * up[2] * k02 + up[1] * up[2] * k12);
+    if (is_zero(tauB)) tauB = 2.220446049250313e-16;
+    tauB = rho / sqrt(tauB);
+#pragma unroll
+    for (int i = 0; i < 3; i++) ua[i] = u[i] + up[i];
+    const double pa = p - tauC * divU;
+    sPa += wJ * pa;
+    sW += wJ;
+    sA2 += wl * tauC;
+    sPP += wl * tauM;
+    double Aj[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const double rVb = tauB * (up[0] * ux[0][j] + up[1] * ux[1][j] + up[2] * ux[2][j]);
+      const double rV2 = ud[j] + ua[0] * ux[0][j] + ua[1] * ux[1][j] + ua[2] * ux[2][j];
+      Aj[j] = rho * rV2 + muKd * ua[j];
+#pragma unroll
+      for (int i = 0; i < 3; i++) RM[i][j] += wJ * (rVb * up[i] - rho * up[j] * ua[i]);
+      UP[j] += wJ * up[j];
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const double wN = wJ * P.N[g][a];
+#pragma unroll
+      for (int j = 0; j < 3; j++) lR[a][j] += wN * Aj[j];
+    }
+    S[8 * g + 3] = up[0]; S[8 * g + 4] = up[1]; S[8 * g + 5] = up[2];
+    S[8 * g + 6] = tauM;
+    S[8 * g + 7] = tauB;
+  }
+
+  // ---- finish the residual -----------------------------------------------------------------------------
+  double Sb[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int g = 0; g < 4; g++) {
+    const double wl = P.w[g] * Jac * T;
+#pragma unroll
+    for (int a = 0; a < 4; a++) Sb[a] += wl * P.N[g][a];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) RM[i][j] += mu * (ux[i][j] + ux[j][i]) * sW;
+    RM[i][i] -= sPa;
+  }
+  const double iT = 1.0 / T;
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+      lRout[4 * a + j] = lR[a][j] + (nx[a][0] * RM[0][j] + nx[a][1] * RM[1][j] + nx[a][2] * RM[2][j]);
+    lRout[4 * a + 3] = divU * (Sb[a] * iT) - (UP[0] * nx[a][0] + UP[1] * nx[a][1] + UP[2] * nx[a][2]);
+  }
+  const double sWl = sW * T;
+  const double A1 = mu * sWl, A3 = mu_g * sWl;
+
+  // ---- loop 2: tangent moments ---------------------------------------------------------------------------
+  const double q1c = rho * amd + muKd;
+  double D[4][4], S2[4] = {0.0, 0.0, 0.0, 0.0}, S3[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) D[a][b] = 0.0;
+#pragma unroll 1
+  for (int g = 0; g < 4; g++) {
+    const double wl = P.w[g] * Jac * T;
+    const double u[3] = {S[8 * g], S[8 * g + 1], S[8 * g + 2]};
+    const double up[3] = {S[8 * g + 3], S[8 * g + 4], S[8 * g + 5]};
+    const double tauM = S[8 * g + 6], tauB = S[8 * g + 7];
+    double Q1[4], Q2[4], Q3[4], Q4[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const double uNx = u[0] * nx[a][0] + u[1] * nx[a][1] + u[2] * nx[a][2];
+      const double upNx = up[0] * nx[a][0] + up[1] * nx[a][1] + up[2] * nx[a][2];
+      Q1[a] = q1c * P.N[g][a];
+      Q2[a] = uNx + upNx;
+      Q3[a] = upNx;
+      Q4[a] = rho * uNx;
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const double Na = P.N[g][a];
+      const double c = rho * tauM * Q2[a];
+      const double P1 = wl * (Na + c), P2 = wl * rho * Na, P3 = wl * tauB * Q3[a], P4 = wl * c;
+      S2[a] += P4;
+      S3[a] -= wl * tauM * (Q4[a] + Q1[a]);
+#pragma unroll
+      for (int b = 0; b < 4; b++) D[a][b] += P1 * Q1[b] + P2 * Q2[b] + P3 * Q3[b] + P4 * Q4[b];
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    rec[O_SB + a] = Sb[a];
+    rec[O_S2 + a] = S2[a];
+    rec[O_S3 + a] = S3[a];
+#pragma unroll
+    for (int b = 0; b < 4; b++) rec[O_D + 4 * a + b] = D[a][b];
+  }
+  rec[O_A1] = A1;
+  rec[O_A2] = sA2;
+  rec[O_SPP] = sPP;
+  if (NN) rec[O_A3] = A3;
+}
+
+// K += lK(:,a,b) of the element whose record is r (tet4_block from the record).
+SVB_HD void tet4_block_rec_add(const double* r, const bool NN, const int a, const int b, double K[16])
+{
+  const double xa[3] = {r[O_NX + 3 * a], r[O_NX + 3 * a + 1], r[O_NX + 3 * a + 2]};
+  const double xb[3] = {r[O_NX + 3 * b], r[O_NX + 3 * b + 1], r[O_NX + 3 * b + 2]};
+  const double A1 = r[O_A1], A2 = r[O_A2];
+  const double nn = xa[0] * xb[0] + xa[1] * xb[1] + xa[2] * xb[2];
+  const double dd = r[O_D + 4 * a + b] + A1 * nn;
+  const double Sba = r[O_SB + a], Sbb = r[O_SB + b], S2a = r[O_S2 + a], S3b = r[O_S3 + b];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const double q1 = A1 * xb[i];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      double v = xa[j] * q1 + xa[i] * (A2 * xb[j]);
+      if (i == j) v += dd;
+      K[4 * i + j] += v;
+    }
+    K[4 * i + 3] += xb[i] * S2a - xa[i] * Sbb;
+    K[12 + i] += xb[i] * Sba - xa[i] * S3b;
+  }
+  K[15] += r[O_SPP] * nn;
+  if (NN) {
+    const double A3 = r[O_A3];
+    if (A3 != 0.0) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const double t = A3 * r[O_ES + 3 * a + i];
+#pragma unroll
+        for (int j = 0; j < 3; j++) K[4 * i + j] += t * r[O_ES + 3 * b + j];
+      }
+    }
+  }
+}
+
 }  // namespace svb

@@ -87,6 +87,7 @@ static int download_nodal(svb200_ctx* ctx, int rows, const double* d, double* h)
 static void free_mesh(Mesh& m)
 {
   cudaFree(m.d_IEN); cudaFree(m.d_eId); cudaFree(m.d_fN); cudaFree(m.d_slot); cudaFree(m.d_color_perm);
+  free_group_sched(m.schedK); free_group_sched(m.schedR);
   m = Mesh();
 }
 
@@ -316,6 +317,7 @@ int svb200_set_mesh(svb200_ctx* ctx, int32_t iM, int32_t eNoN, int32_t nEl, cons
   m.N.assign(N, N + (size_t)eNoN * nG);
   m.Nx.assign(Nx, Nx + (size_t)3 * eNoN * nG);
   TRY(launch_build_slot_map(ctx, m));
+  TRY(build_group_schedules(ctx, m));
   TRY(build_coloring(ctx, m, ien));
   m.set = true;
   return SVB200_OK;
@@ -450,6 +452,8 @@ static int fill_fluid_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams
   SVB_REQUIRE(ctx->d_x, "svb200_assemble: coordinates not set");
   memset(&A, 0, sizeof(A));
   A.IEN = m.d_IEN; A.eId = m.d_eId; A.slot = m.d_slot; A.perm = nullptr;
+  A.kU_ptr = m.schedK.d_uptr; A.kU_ent = m.schedK.d_uent; A.kContrib = m.schedK.d_contrib;
+  A.rU_ptr = m.schedR.d_uptr; A.rU_ent = m.schedR.d_uent; A.rContrib = m.schedR.d_contrib;
   A.x = ctx->d_x; A.Ag = ctx->d_Ag; A.Yg = ctx->d_Yg; A.Bf = ctx->d_Bf; A.Dg = ctx->d_Dg;
   A.R = ctx->d_R; A.Val = ctx->d_Val;
   A.e0 = 0; A.e1 = m.nEl;

@@ -20,6 +20,17 @@ namespace svb {
 constexpr int MAX_DMN = 8;
 constexpr int MAX_ENON = 8;
 constexpr int MAX_NG = 8;
+constexpr int ASM_GROUP = 128;   // elements per CTA of the grouped (pre-reduced) scatter, group_sched.cu
+
+// Pre-reduction plan of one mesh for the grouped scatter (group_sched.cu).
+struct GroupSched {
+  int nGrp = 0;
+  long long total = 0;               // sum of nuniq
+  int* d_nuniq = nullptr;            // (nGrp) distinct targets of the group
+  int* d_uptr = nullptr;             // (nGrp+1) offsets into d_uent
+  int2* d_uent = nullptr;            // {target, start | count << 16}
+  unsigned short* d_contrib = nullptr;   // (nGrp, ASM_GROUP*PER_EL) contribution ids, sorted by target
+};
 
 struct Mesh {
   int eNoN = 0, nEl = 0, nG = 0, nFn = 0;
@@ -28,6 +39,7 @@ struct Mesh {
   double* d_fN = nullptr;    // (3*nFn, nEl) or null
   int* d_slot = nullptr;     // (eNoN*eNoN, nEl): CSR slot of pair (a,b) = entry a*eNoN+b
   int* d_color_perm = nullptr;   // element ids sorted by colour (coloured scatter)
+  GroupSched schedK, schedR;     // grouped scatter plans: tangent blocks / residual rows (TET4 meshes)
   std::vector<int> color_off;    // offsets into d_color_perm per colour
   std::vector<double> w, N, Nx;  // host copies of the reference-element tables
   bool set = false;
@@ -64,6 +76,9 @@ struct FluidArgs {
   const int* eId;
   const int* slot;
   const int* perm;      // optional element permutation (coloured scatter) or null
+  // grouped scatter (group_sched.cu): tangent (K) and residual (R) plans
+  const int* kU_ptr; const int2* kU_ent; const unsigned short* kContrib;
+  const int* rU_ptr; const int2* rU_ent; const unsigned short* rContrib;
   const double* x;
   const double* Ag;
   const double* Yg;
@@ -169,6 +184,9 @@ int launch_assemble_fluid(svb200_ctx* ctx, const Mesh& m, const FluidArgs& args)
 // assemble_struct.cu
 int run_assemble_struct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);
 int run_assemble_mesh(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);
+// group_sched.cu
+int build_group_schedules(svb200_ctx* ctx, Mesh& m);
+void free_group_sched(GroupSched& S);
 // graph_kernels.cu
 int launch_build_slot_map(svb200_ctx* ctx, Mesh& m);
 int launch_find_diag(svb200_ctx* ctx);

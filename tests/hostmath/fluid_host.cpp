@@ -43,4 +43,44 @@ extern "C" int hostmath_fluid_tet4(const svb::FluidArgs* P, int nNo, const int* 
   }
   return 0;
 }
+// Same loop through the staged element routine + record-based block emitter used by the grouped scatter.
+extern "C" int hostmath_fluid_tet4_staged(const svb::FluidArgs* P, int nNo, const int* rowPtr, const int* colPtr,
+                                          double* R, double* Val)
+{
+  using namespace svb;
+  bool NN = false;
+  for (int d = 0; d < P->nDmn; d++) NN |= (P->dmn[d].viscType != SVB200_VISC_CONST);
+  for (int e = P->e0; e < P->e1; e++) {
+    int n[4];
+    double xl[4][3], yl[4][4], uc[4][3], ab[4][3];
+    for (int a = 0; a < 4; a++) {
+      n[a] = P->IEN[4*e + a];
+      for (int i = 0; i < 3; i++) {
+        xl[a][i] = P->x[3*n[a] + i] + (P->ale ? P->Dg[P->tDof*n[a] + 4 + i] : 0.0);
+        ab[a][i] = P->Ag[P->tDof*n[a] + i] - P->Bf[3*n[a] + i];
+        uc[a][i] = P->Yg[P->tDof*n[a] + i] - (P->mvMsh ? P->Yg[P->tDof*n[a] + 4 + i] : 0.0);
+      }
+      for (int i = 0; i < 4; i++) yl[a][i] = P->Yg[P->tDof*n[a] + i];
+    }
+    int iD = 0;
+    for (int d = 0; d < P->nDmn; d++) { iD = d; if (P->dmn[d].Id == -1) break; if (P->eId && ((P->eId[e] >> P->dmn[d].Id) & 1)) break; }
+    if (!P->dmn[iD].isFluid) continue;
+    double rec[REC_NN], lR[16];
+    for (int i = 0; i < REC_NN; i++) rec[i] = 1e300;   // poison: every field read must have been written
+    tet4_element_staged(*P, P->dmn[iD], xl, yl, uc, ab, NN, rec, lR);
+    for (int a = 0; a < 4; a++) {
+      for (int i = 0; i < 4; i++) R[4*n[a] + i] += lR[4*a + i];
+      for (int b = 0; b < 4; b++) {
+        double K[16];
+        for (int i = 0; i < 16; i++) K[i] = 0.0;
+        tet4_block_rec_add(rec, NN, a, b, K);
+        int s = -1;
+        for (int k = rowPtr[n[a]]; k < rowPtr[n[a]+1]; k++) if (colPtr[k] == n[b]) { s = k; break; }
+        if (s < 0) return 1;
+        for (int i = 0; i < 16; i++) Val[16*(size_t)s + i] += K[i];
+      }
+    }
+  }
+  return 0;
+}
 extern "C" int hostmath_sizeof_fluidargs() { return (int)sizeof(svb::FluidArgs); }

@@ -20,7 +20,7 @@ class FluidDmn(C.Structure):
 
 
 class FluidArgs(C.Structure):
-    _fields_ = [(k, C.c_void_p) for k in ("IEN", "eId", "slot", "perm", "x", "Ag", "Yg", "Bf", "Dg", "R", "Val")] + \
+    _fields_ = [(k, C.c_void_p) for k in ("IEN", "eId", "slot", "perm", "kU_ptr", "kU_ent", "kContrib", "rU_ptr", "rU_ent", "rContrib", "x", "Ag", "Yg", "Bf", "Dg", "R", "Val")] + \
                [(k, C.c_int) for k in ("e0", "e1", "tDof", "mvMsh", "nDmn", "atomic", "ale", "pad0")] + \
                [(k, C.c_double) for k in ("dt", "af", "am", "gam")] + \
                [("w", C.c_double * 8), ("N", (C.c_double * 8) * 8), ("Nxi", ((C.c_double * 3) * 8) * 8), ("dmn", FluidDmn * 8)]
@@ -35,8 +35,9 @@ def hostmath():
     return lib
 
 
+@pytest.mark.parametrize("variant", ["hostmath_fluid_tet4", "hostmath_fluid_tet4_staged"], ids=["hoisted", "staged"])
 @pytest.mark.parametrize("case", common.FLUID_CASES, ids=[c[0] for c in common.FLUID_CASES])
-def test_device_element_algebra_matches_golden(hostmath, case):
+def test_device_element_algebra_matches_golden(hostmath, case, variant):
     golden = common.load_golden()
     name, visc, Kd, f, tDof, mv = case
     m, Ag, Yg, Dg, Bf = common.fluid_case(n=common.GOLDEN_N, nz=common.GOLDEN_NZ, tDof=tDof)
@@ -63,7 +64,7 @@ def test_device_element_algebra_matches_golden(hostmath, case):
     rowPtr, colPtr = golden["rowPtr"], golden["colPtr"]
     R = np.zeros((m.nNo, 4))
     V = np.zeros((len(colPtr), 16))
-    rc = hostmath.hostmath_fluid_tet4(C.byref(A), m.nNo, rowPtr.ctypes.data_as(C.c_void_p), colPtr.ctypes.data_as(C.c_void_p),
+    rc = getattr(hostmath, variant)(C.byref(A), m.nNo, rowPtr.ctypes.data_as(C.c_void_p), colPtr.ctypes.data_as(C.c_void_p),
                                       R.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p))
     assert rc == 0
     assert common.rel_err(R.T, golden[f"{name}/R"]) < 1e-12
