@@ -149,6 +149,15 @@ assemble_fluid_tet4_kernel(const __grid_constant__ FluidArgs P)
 // Phase 1 uses tet4_element_staged (fluid_elem.cuh): 168 registers, so three CTAs are resident per SM.
 // Only blocks shared between groups still meet in the L2 atomic units, so the result is bitwise reproducible
 // up to the order of those few cross-group additions.
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+
 constexpr int ENT_CACHE = 768;              // plan entries of the group kept in shared memory (the rest: global)
 constexpr int ASM_WARPS = ASM_GROUP / 32;
 
@@ -169,17 +178,17 @@ assemble_fluid_tet4_grouped_kernel(const __grid_constant__ FluidArgs P)
   const int lane = tid & 31;
   const int g = blockIdx.x;
   double* T = tiles + (tid >> 5) * 32 * TILE_LD;
+  // the group's plan goes to shared memory with cp.async (lands while phase 1 computes)
   {
-    const uint4* srcK = reinterpret_cast<const uint4*>(P.kContrib + (size_t)g * ASM_GROUP * 16);
-    uint4* dstK = reinterpret_cast<uint4*>(ctr);
-    dstK[tid] = __ldg(srcK + tid);
-    dstK[tid + ASM_GROUP] = __ldg(srcK + tid + ASM_GROUP);
-    if (tid < ASM_GROUP * 4 * 2 / 16)
-      reinterpret_cast<uint4*>(ctrR)[tid] = __ldg(reinterpret_cast<const uint4*>(P.rContrib + (size_t)g * ASM_GROUP * 4) + tid);
+    const unsigned short* srcK = P.kContrib + (size_t)g * ASM_GROUP * 16;
+    cp_async16(ctr + 8 * tid, srcK + 8 * tid);
+    cp_async16(ctr + 8 * (tid + ASM_GROUP), srcK + 8 * (tid + ASM_GROUP));
+    if (tid < ASM_GROUP * 4 * 2 / 16) cp_async16(ctrR + 8 * tid, P.rContrib + (size_t)g * ASM_GROUP * 4 + 8 * tid);
   }
   const int ub = __ldg(P.kU_ptr + g);
   const int G = __ldg(P.kU_ptr + g + 1) - ub;
-  for (int k = tid; k < min(G, ENT_CACHE); k += ASM_GROUP) entc[k] = __ldg(P.kU_ent + ub + k);
+  for (int k = tid; k < min(G, ENT_CACHE); k += ASM_GROUP) cp_async8(entc + k, P.kU_ent + ub + k);
+  asm volatile("cp.async.commit_group;" ::: "memory");
 
   // ---- phase 1: element record -> shared memory, element residual -> this lane's tile row ------------------
   const int e = g * ASM_GROUP + tid;
@@ -213,7 +222,8 @@ assemble_fluid_tet4_grouped_kernel(const __grid_constant__ FluidArgs P)
     }
   }
   act[tid] = active ? 1 : 0;
-  __syncthreads();
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  const bool allActive = __syncthreads_and(active);
 
   // ---- phase 2: residual rows of the group's distinct nodes (element residuals sit in the tiles) ------------
   {
@@ -252,12 +262,22 @@ assemble_fluid_tet4_grouped_kernel(const __grid_constant__ FluidArgs P)
         double K[16];
 #pragma unroll
         for (int i = 0; i < 16; i++) K[i] = 0.0;
-        for (int c = start; c < end; c++) {
-          const int id = ctr[c];
-          const int el = id >> 4;
-          if (!act[el]) continue;
+        if (allActive) {
           myslot = ent.x;
-          tet4_block_rec_add(rec + el * RS, NN, (id >> 2) & 3, id & 3, K);
+          int id = ctr[start];
+          for (int c = start; c < end; c++) {
+            const int idn = ctr[min(c + 1, ASM_GROUP * 16 - 1)];   // prefetch the next contribution id
+            tet4_block_rec_add(rec + (id >> 4) * RS, NN, (id >> 2) & 3, id & 3, K);
+            id = idn;
+          }
+        } else {
+          for (int c = start; c < end; c++) {
+            const int id = ctr[c];
+            const int el = id >> 4;
+            if (!act[el]) continue;
+            myslot = ent.x;
+            tet4_block_rec_add(rec + el * RS, NN, (id >> 2) & 3, id & 3, K);
+          }
         }
         if (myslot >= 0) {
 #pragma unroll
@@ -265,12 +285,20 @@ assemble_fluid_tet4_grouped_kernel(const __grid_constant__ FluidArgs P)
         }
       }
       __syncwarp();
-      // a half-warp adds the 16 contiguous doubles of one block with one coalesced RED
-#pragma unroll 4
-      for (int r = 0; r < 16; r++) {
-        const int src = 2 * r + half;
-        const int sl = __shfl_sync(0xffffffffu, myslot, src);
-        if (sl >= 0) add_f64<true>(P.Val + 16 * (size_t)sl + j, T[src * TILE_LD + j]);
+      // a half-warp adds the 16 contiguous doubles of one block with one coalesced RED; 4 blocks in flight
+#pragma unroll
+      for (int r0 = 0; r0 < 16; r0 += 4) {
+        int sl[4];
+        double v[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int src = 2 * (r0 + q) + half;
+          sl[q] = __shfl_sync(0xffffffffu, myslot, src);
+          v[q] = T[src * TILE_LD + j];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (sl[q] >= 0) add_f64<true>(P.Val + 16 * (size_t)sl[q] + j, v[q]);
       }
       __syncwarp();
     }
