@@ -139,8 +139,9 @@ assemble_fluid_tet4_kernel(const __grid_constant__ FluidArgs P)
 // =====================================================================================================
 // Grouped scatter (default ATOMIC path).  One CTA owns ASM_GROUP consecutive elements:
 //   phase 1  one thread per element: gather, gnn, Gauss loop -> the element's ~60 moments go to shared memory;
-//   phase 2  one thread per DISTINCT CSR block the group touches (plan: group_sched.cu): it re-emits the 4x4
-//            blocks of all the group's contributions to that slot from the moments (tet4_block algebra), sums
+//   phase 2  one thread per DISTINCT diagonal block / mesh edge the group touches (plan: group_sched.cu): it
+//            re-emits the 4x4 blocks of all the group's contributions from the moments (an edge yields both
+//            blocks (a,b) and (b,a) from one set of loads; their velocity parts are transposes), sums
 //            them in registers in a fixed order and adds the block through a per-warp transposition tile with ONE
 //            coalesced 128-byte RED per half-warp — 5.4 block reductions per element instead of 16.  (A TMA
 //            bulk reduce per block, cp.reduce.async.bulk...add.f64, was measured slower here: UBLKRED is a
@@ -158,7 +159,12 @@ __device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc)
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
 }
 
-constexpr int ENT_CACHE = 768;              // plan entries of the group kept in shared memory (the rest: global)
+__device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+
+constexpr int ENT_CACHE = 512;              // plan entries of the group kept in shared memory (the rest: global)
 constexpr int ASM_WARPS = ASM_GROUP / 32;
 
 template <bool NN>
@@ -170,8 +176,9 @@ assemble_fluid_tet4_grouped_kernel(const __grid_constant__ FluidArgs P)
   double* tiles = reinterpret_cast<double*>(smem_raw);                             // [warps][32*TILE_LD]
   double* rec = tiles + ASM_WARPS * 32 * TILE_LD;                                  // [ASM_GROUP][RS]
   int2* entc = reinterpret_cast<int2*>(rec + ASM_GROUP * RS);                      // [ENT_CACHE]
-  unsigned short* ctr = reinterpret_cast<unsigned short*>(entc + ENT_CACHE);       // [ASM_GROUP*16]
-  unsigned short* ctrR = ctr + ASM_GROUP * 16;                                     // [ASM_GROUP*4]
+  int* entp = reinterpret_cast<int*>(entc + ENT_CACHE);                            // [ENT_CACHE]
+  unsigned short* ctr = reinterpret_cast<unsigned short*>(entp + ENT_CACHE);       // [ASM_GROUP*10]
+  unsigned short* ctrR = ctr + ASM_GROUP * 10;                                     // [ASM_GROUP*4]
   unsigned char* act = reinterpret_cast<unsigned char*>(ctrR + ASM_GROUP * 4);     // [ASM_GROUP]
 
   const int tid = threadIdx.x;
@@ -180,14 +187,17 @@ assemble_fluid_tet4_grouped_kernel(const __grid_constant__ FluidArgs P)
   double* T = tiles + (tid >> 5) * 32 * TILE_LD;
   // the group's plan goes to shared memory with cp.async (lands while phase 1 computes)
   {
-    const unsigned short* srcK = P.kContrib + (size_t)g * ASM_GROUP * 16;
+    const unsigned short* srcK = P.kContrib + (size_t)g * ASM_GROUP * 10;   // 2560 bytes = 160 x 16
     cp_async16(ctr + 8 * tid, srcK + 8 * tid);
-    cp_async16(ctr + 8 * (tid + ASM_GROUP), srcK + 8 * (tid + ASM_GROUP));
+    if (tid < ASM_GROUP * 10 * 2 / 16 - ASM_GROUP) cp_async16(ctr + 8 * (tid + ASM_GROUP), srcK + 8 * (tid + ASM_GROUP));
     if (tid < ASM_GROUP * 4 * 2 / 16) cp_async16(ctrR + 8 * tid, P.rContrib + (size_t)g * ASM_GROUP * 4 + 8 * tid);
   }
   const int ub = __ldg(P.kU_ptr + g);
   const int G = __ldg(P.kU_ptr + g + 1) - ub;
-  for (int k = tid; k < min(G, ENT_CACHE); k += ASM_GROUP) cp_async8(entc + k, P.kU_ent + ub + k);
+  for (int k = tid; k < min(G, ENT_CACHE); k += ASM_GROUP) {
+    cp_async8(entc + k, P.kU_ent + ub + k);
+    cp_async4(entp + k, P.kU_partner + ub + k);
+  }
   asm volatile("cp.async.commit_group;" ::: "memory");
 
   // ---- phase 1: element record -> shared memory, element residual -> this lane's tile row ------------------
@@ -250,57 +260,64 @@ assemble_fluid_tet4_grouped_kernel(const __grid_constant__ FluidArgs P)
   }
   __syncthreads();
 
-  // ---- phase 3: one thread per distinct CSR block ------------------------------------------------------------
+  // ---- phase 3: one thread per distinct diagonal block / edge (both blocks of the edge) ----------------------
   {
     const int half = lane >> 4, j = lane & 15;
     for (int k0 = (tid & ~31); k0 < G; k0 += ASM_GROUP) {   // warp-uniform trip count
       const int k = k0 + lane;
-      int myslot = -1;
+      int slot1 = -1, slot2 = -1;
+      double K1[16], K2[16];
       if (k < G) {
         const int2 ent = k < ENT_CACHE ? entc[k] : __ldg(P.kU_ent + ub + k);
+        const int partner = k < ENT_CACHE ? entp[k] : __ldg(P.kU_partner + ub + k);
         const int start = ent.y & 0xFFFF, end = start + (ent.y >> 16);
-        double K[16];
 #pragma unroll
-        for (int i = 0; i < 16; i++) K[i] = 0.0;
-        if (allActive) {
-          myslot = ent.x;
-          int id = ctr[start];
+        for (int i = 0; i < 16; i++) { K1[i] = 0.0; K2[i] = 0.0; }
+        if (partner >= 0) {
           for (int c = start; c < end; c++) {
-            const int idn = ctr[min(c + 1, ASM_GROUP * 16 - 1)];   // prefetch the next contribution id
-            tet4_block_rec_add(rec + (id >> 4) * RS, NN, (id >> 2) & 3, id & 3, K);
-            id = idn;
+            const int id = ctr[c];
+            const int el = id >> 4;
+            if (!allActive && !act[el]) continue;
+            slot1 = ent.x;
+            slot2 = partner;
+            tet4_edge_rec_add(rec + el * RS, NN, (id >> 2) & 3, id & 3, K1, K2);
           }
         } else {
           for (int c = start; c < end; c++) {
             const int id = ctr[c];
             const int el = id >> 4;
-            if (!act[el]) continue;
-            myslot = ent.x;
-            tet4_block_rec_add(rec + el * RS, NN, (id >> 2) & 3, id & 3, K);
+            if (!allActive && !act[el]) continue;
+            slot1 = ent.x;
+            tet4_block_rec_add(rec + el * RS, NN, id & 3, id & 3, K1);
           }
         }
+      }
+      // a half-warp adds the 16 contiguous doubles of one block with one coalesced RED; 4 blocks in flight
+#pragma unroll 1
+      for (int pass = 0; pass < 2; pass++) {
+        const int myslot = pass == 0 ? slot1 : slot2;
+        if (pass == 1 && !__any_sync(0xffffffffu, myslot >= 0)) break;
         if (myslot >= 0) {
 #pragma unroll
-          for (int i = 0; i < 16; i++) T[lane * TILE_LD + i] = K[i];
+          for (int i = 0; i < 16; i++) T[lane * TILE_LD + i] = pass == 0 ? K1[i] : K2[i];
         }
-      }
-      __syncwarp();
-      // a half-warp adds the 16 contiguous doubles of one block with one coalesced RED; 4 blocks in flight
+        __syncwarp();
 #pragma unroll
-      for (int r0 = 0; r0 < 16; r0 += 4) {
-        int sl[4];
-        double v[4];
+        for (int r0 = 0; r0 < 16; r0 += 4) {
+          int sl[4];
+          double v[4];
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int src = 2 * (r0 + q) + half;
-          sl[q] = __shfl_sync(0xffffffffu, myslot, src);
-          v[q] = T[src * TILE_LD + j];
+          for (int q = 0; q < 4; q++) {
+            const int src = 2 * (r0 + q) + half;
+            sl[q] = __shfl_sync(0xffffffffu, myslot, src);
+            v[q] = T[src * TILE_LD + j];
+          }
+#pragma unroll
+          for (int q = 0; q < 4; q++)
+            if (sl[q] >= 0) add_f64<true>(P.Val + 16 * (size_t)sl[q] + j, v[q]);
         }
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-          if (sl[q] >= 0) add_f64<true>(P.Val + 16 * (size_t)sl[q] + j, v[q]);
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
 }
@@ -309,7 +326,7 @@ template <bool NN>
 static int launch_grouped(svb200_ctx* ctx, const FluidArgs& args)
 {
   constexpr int RS = NN ? REC_NN : REC_NEWT;
-  constexpr size_t smem = sizeof(double) * ASM_GROUP * (TILE_LD + RS) + sizeof(int2) * ENT_CACHE + 2 * ASM_GROUP * 20 + ASM_GROUP;
+  constexpr size_t smem = sizeof(double) * ASM_GROUP * (TILE_LD + RS) + sizeof(int2) * ENT_CACHE + sizeof(int) * ENT_CACHE + 2 * ASM_GROUP * 14 + ASM_GROUP;
   static bool configured = false;
   if (!configured) {
     SVB_CUDA(cudaFuncSetAttribute(assemble_fluid_tet4_grouped_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -616,4 +616,55 @@ SVB_HD void tet4_block_rec_add(const double* r, const bool NN, const int a, cons
   }
 }
 
+// Both blocks of an edge from one set of loads: K1 += lK(:,a,b), K2 += lK(:,b,a).  The velocity-velocity
+// parts are transposes of each other up to the diagonal term: W(i,j) = A1 xa_j xb_i + A2 xa_i xb_j.
+SVB_HD void tet4_edge_rec_add(const double* r, const bool NN, const int a, const int b, double K1[16], double K2[16])
+{
+  const double xa[3] = {r[O_NX + 3 * a], r[O_NX + 3 * a + 1], r[O_NX + 3 * a + 2]};
+  const double xb[3] = {r[O_NX + 3 * b], r[O_NX + 3 * b + 1], r[O_NX + 3 * b + 2]};
+  const double A1 = r[O_A1], A2 = r[O_A2];
+  double m[3][3];
+#pragma unroll
+  for (int p = 0; p < 3; p++)
+#pragma unroll
+    for (int q = 0; q < 3; q++) m[p][q] = xa[p] * xb[q];
+  const double nn = m[0][0] + m[1][1] + m[2][2];
+  const double dd1 = r[O_D + 4 * a + b] + A1 * nn;
+  const double dd2 = r[O_D + 4 * b + a] + A1 * nn;
+  const double Sba = r[O_SB + a], Sbb = r[O_SB + b];
+  const double S2a = r[O_S2 + a], S2b = r[O_S2 + b], S3a = r[O_S3 + a], S3b = r[O_S3 + b];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const double W = A1 * m[j][i] + A2 * m[i][j];
+      K1[4 * i + j] += W;
+      K2[4 * j + i] += W;
+    }
+    K1[4 * i + i] += dd1;
+    K2[4 * i + i] += dd2;
+    K1[4 * i + 3] += xb[i] * S2a - xa[i] * Sbb;
+    K2[4 * i + 3] += xa[i] * S2b - xb[i] * Sba;
+    K1[12 + i] += xb[i] * Sba - xa[i] * S3b;
+    K2[12 + i] += xa[i] * Sbb - xb[i] * S3a;
+  }
+  const double pp = r[O_SPP] * nn;
+  K1[15] += pp;
+  K2[15] += pp;
+  if (NN) {
+    const double A3 = r[O_A3];
+    if (A3 != 0.0) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const double ta = A3 * r[O_ES + 3 * a + i], tb = A3 * r[O_ES + 3 * b + i];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          K1[4 * i + j] += ta * r[O_ES + 3 * b + j];
+          K2[4 * i + j] += tb * r[O_ES + 3 * a + j];
+        }
+      }
+    }
+  }
+}
+
 }  // namespace svb

@@ -9,9 +9,10 @@
 //
 // For every group g (elements [g*GROUP, (g+1)*GROUP)) this file builds, on the device:
 //   uent[uptr[g] .. uptr[g]+nuniq[g])  : {target, start | count << 16}; target = CSR slot (tangent
-//                                        schedule) or node id (residual schedule), ordered by
-//                                        count descending so that the lanes of a warp see equal trip counts;
-//   contrib[g*GROUP*PER_EL + start ..]  : 16-bit ids  e_local*PER_EL + pair  of the contributions to that
+//                                        plan) or node id (residual plan), ordered by count
+//                                        descending so that the lanes of a warp see equal trip counts;
+//   upartner[...]                       : tangent plan only: the transposed slot of an edge, -1 for a diagonal block;
+//   contrib[g*GROUP*PER_EL + start ..]  : 16-bit ids (e_local, local nodes) of the contributions to that
 //                                        target, ascending (=> a fixed summation order).
 // Built by one CTA per group: bitonic sort of (target, id) keys in shared memory, run twice
 // (count, host prefix sum over groups, fill).
@@ -39,14 +40,29 @@ __device__ __forceinline__ void bitonic_sort(unsigned long long* s)
   }
 }
 
-// PER_EL targets per element (16 slots or 4 nodes); IDXBITS = log2(GROUP*PER_EL).
-template <int PER_EL, int IDXBITS>
+// MODE 0: residual plan — 4 targets per element (its nodes), id = e_local << 2 | a.
+// MODE 1: tangent plan — 10 targets per element: the 4 diagonal blocks (a,a) and the 6 edges {a,b}.  An edge
+//         is keyed by the CSR slot (lo,hi) with lo = the local node with the smaller global id, so that every
+//         element sharing the edge produces the same key; the thread that owns it emits BOTH blocks (lo,hi) and
+//         (hi,lo) from one set of loads (partner = slot (hi,lo), -1 for a diagonal).  id = e_local << 4 | lo << 2 | hi.
+template <int MODE>
+struct SchedTraits;
+template <>
+struct SchedTraits<0> { static constexpr int PER_EL = 4, NSORT = 512; };
+template <>
+struct SchedTraits<1> { static constexpr int PER_EL = 10, NSORT = 2048; };
+constexpr int IDBITS = 11;
+
+template <int MODE>
 __global__ void __launch_bounds__(SCHED_THREADS)
-build_sched_kernel(const int* __restrict__ src, int nEl, int fill, int* __restrict__ nuniq,
-                   const int* __restrict__ uptr, int2* __restrict__ uent, unsigned short* __restrict__ contrib)
+build_sched_kernel(const int* __restrict__ IEN, const int* __restrict__ slot, int nEl, int fill, int* __restrict__ nuniq,
+                   const int* __restrict__ uptr, int2* __restrict__ uent, int* __restrict__ upartner,
+                   unsigned short* __restrict__ contrib)
 {
-  constexpr int N = ASM_GROUP * PER_EL;
-  static_assert(N == (1 << IDXBITS), "group size");
+  constexpr int PER_EL = SchedTraits<MODE>::PER_EL;
+  constexpr int N = SchedTraits<MODE>::NSORT;
+  constexpr int NC = ASM_GROUP * PER_EL;
+  static_assert(NC <= N, "sort size");
   __shared__ unsigned long long keys[N];
   __shared__ unsigned long long keys2[N];
   __shared__ int scan[SCHED_THREADS];
@@ -55,11 +71,25 @@ build_sched_kernel(const int* __restrict__ src, int nEl, int fill, int* __restri
   const unsigned long long BAD = ~0ull;
 
   for (int i = threadIdx.x; i < N; i += SCHED_THREADS) {
-    const long long e = (long long)g * ASM_GROUP + i / PER_EL;
     unsigned long long key = BAD;
-    if (e < nEl) {
-      const int t = src[e * PER_EL + i % PER_EL];
-      if (t >= 0) key = ((unsigned long long)(unsigned)t << IDXBITS) | (unsigned)i;
+    const int el = i / PER_EL, q = i % PER_EL;
+    const long long e = (long long)g * ASM_GROUP + el;
+    if (i < NC && e < nEl) {
+      int t, id;
+      if (MODE == 0) {
+        t = IEN[e * 4 + q];
+        id = el << 2 | q;
+      } else {
+        int a, b;
+        if (q < 4) { a = q; b = q; }
+        else if (q < 7) { a = 0; b = q - 3; }
+        else if (q < 9) { a = 1; b = q - 5; }
+        else { a = 2; b = 3; }
+        if (IEN[e * 4 + a] > IEN[e * 4 + b]) { const int tmp = a; a = b; b = tmp; }
+        t = slot[e * 16 + a * 4 + b];
+        id = el << 4 | a << 2 | b;
+      }
+      if (t >= 0) key = ((unsigned long long)(unsigned)t << IDBITS) | (unsigned)id;
     }
     keys[i] = key;
   }
@@ -69,11 +99,12 @@ build_sched_kernel(const int* __restrict__ src, int nEl, int fill, int* __restri
   // heads of runs of equal targets; each thread owns N/SCHED_THREADS consecutive positions
   constexpr int PER_T = N / SCHED_THREADS;
   const int p0 = threadIdx.x * PER_T;
-  int nh = 0;
+  int nh = 0, nv = 0;
   for (int i = p0; i < p0 + PER_T; i++) {
     const bool valid = keys[i] != BAD;
-    const bool head = valid && (i == 0 || (keys[i] >> IDXBITS) != (keys[i - 1] >> IDXBITS));
+    const bool head = valid && (i == 0 || (keys[i] >> IDBITS) != (keys[i - 1] >> IDBITS));
     nh += head;
+    nv += valid;
   }
   scan[threadIdx.x] = nh;
   __syncthreads();
@@ -95,19 +126,16 @@ build_sched_kernel(const int* __restrict__ src, int nEl, int fill, int* __restri
   int u = scan[threadIdx.x] - nh;
   for (int i = p0; i < p0 + PER_T; i++) {
     const bool valid = keys[i] != BAD;
-    const bool head = valid && (i == 0 || (keys[i] >> IDXBITS) != (keys[i - 1] >> IDXBITS));
+    const bool head = valid && (i == 0 || (keys[i] >> IDBITS) != (keys[i - 1] >> IDBITS));
     if (head) keys2[u++] = (unsigned long long)i;
   }
   __syncthreads();
-  // number of valid keys = position of the first BAD (all BAD keys sort last)
-  int nValidLocal = 0;
-  for (int i = p0; i < p0 + PER_T; i++) nValidLocal += keys[i] != BAD;
-  scan[threadIdx.x] = nValidLocal;
+  scan[threadIdx.x] = nv;   // number of valid keys = position of the first BAD (BAD keys sort last)
   __syncthreads();
   if (threadIdx.x == 0) {
-    int s = 0;
-    for (int t = 0; t < SCHED_THREADS; t++) s += scan[t];
-    total = s;
+    int sum = 0;
+    for (int t = 0; t < SCHED_THREADS; t++) sum += scan[t];
+    total = sum;
   }
   __syncthreads();
   const int nValid = total;
@@ -116,7 +144,11 @@ build_sched_kernel(const int* __restrict__ src, int nEl, int fill, int* __restri
   for (int k = threadIdx.x; k < nU; k += SCHED_THREADS) {
     const int start = (int)keys2[k];
     const int end = (k + 1 < nU) ? (int)keys2[k + 1] : nValid;
-    const int count = end - start;
+    int count = end - start;   // <= ASM_GROUP
+    if (MODE == 1) {           // diagonal blocks first: a warp then runs one kind of target (one code path)
+      const int id = (int)(keys[start] & ((1 << IDBITS) - 1));
+      if (((id >> 2) & 3) == (id & 3)) count += 256;
+    }
     mine[cnt_i++] = ((unsigned long long)(0xFFFF - count) << 16) | (unsigned)start;
   }
   __syncthreads();
@@ -128,24 +160,31 @@ build_sched_kernel(const int* __restrict__ src, int nEl, int fill, int* __restri
   for (int k = threadIdx.x; k < nU; k += SCHED_THREADS) {
     const unsigned long long q = keys2[k];
     const int start = (int)(q & 0xFFFF);
-    const int count = 0xFFFF - (int)(q >> 16);
-    const int target = (int)(keys[start] >> IDXBITS);
+    const int count = (0xFFFF - (int)(q >> 16)) & 255;
+    const int target = (int)(keys[start] >> IDBITS);
     uent[base + k] = make_int2(target, start | (count << 16));
+    if (MODE == 1) {
+      const int id = (int)(keys[start] & ((1 << IDBITS) - 1));
+      const int el = id >> 4, lo = (id >> 2) & 3, hi = id & 3;
+      upartner[base + k] = (lo != hi) ? slot[((long long)g * ASM_GROUP + el) * 16 + hi * 4 + lo] : -1;
+    }
   }
-  for (int i = threadIdx.x; i < N; i += SCHED_THREADS)
-    contrib[(size_t)g * N + i] = keys[i] == BAD ? (unsigned short)0xFFFF : (unsigned short)(keys[i] & (N - 1));
+  for (int i = threadIdx.x; i < NC; i += SCHED_THREADS)
+    contrib[(size_t)g * NC + i] = keys[i] == BAD ? (unsigned short)0xFFFF : (unsigned short)(keys[i] & ((1 << IDBITS) - 1));
 }
 
-template <int PER_EL, int IDXBITS>
-static int build_one(svb200_ctx* ctx, const int* d_src, int nEl, GroupSched& S)
+template <int MODE>
+static int build_one(svb200_ctx* ctx, const Mesh& m, GroupSched& S)
 {
+  constexpr int NC = ASM_GROUP * SchedTraits<MODE>::PER_EL;
+  const int nEl = m.nEl;
   const int nGrp = (nEl + ASM_GROUP - 1) / ASM_GROUP;
   S.nGrp = nGrp;
   if (nGrp == 0) return SVB200_OK;
   SVB_CUDA(cudaMalloc(&S.d_nuniq, sizeof(int) * nGrp));
   SVB_CUDA(cudaMalloc(&S.d_uptr, sizeof(int) * (nGrp + 1)));
-  build_sched_kernel<PER_EL, IDXBITS><<<nGrp, SCHED_THREADS, 0, ctx->stream>>>(d_src, nEl, 0, S.d_nuniq, nullptr, nullptr,
-                                                                              nullptr);
+  build_sched_kernel<MODE><<<nGrp, SCHED_THREADS, 0, ctx->stream>>>(m.d_IEN, m.d_slot, nEl, 0, S.d_nuniq, nullptr, nullptr,
+                                                                   nullptr, nullptr);
   ctx->launches++;
   SVB_CUDA(cudaGetLastError());
   std::vector<int> nu(nGrp), ptr(nGrp + 1, 0);
@@ -164,9 +203,10 @@ static int build_one(svb200_ctx* ctx, const int* d_src, int nEl, GroupSched& S)
   S.total = tot;
   SVB_CUDA(cudaMemcpyAsync(S.d_uptr, ptr.data(), sizeof(int) * (nGrp + 1), cudaMemcpyHostToDevice, ctx->stream));
   SVB_CUDA(cudaMalloc(&S.d_uent, sizeof(int2) * std::max<long long>(tot, 1)));
-  SVB_CUDA(cudaMalloc(&S.d_contrib, sizeof(unsigned short) * (size_t)nGrp * ASM_GROUP * PER_EL));
-  build_sched_kernel<PER_EL, IDXBITS><<<nGrp, SCHED_THREADS, 0, ctx->stream>>>(d_src, nEl, 1, S.d_nuniq, S.d_uptr,
-                                                                              S.d_uent, S.d_contrib);
+  if (MODE == 1) SVB_CUDA(cudaMalloc(&S.d_upartner, sizeof(int) * std::max<long long>(tot, 1)));
+  SVB_CUDA(cudaMalloc(&S.d_contrib, sizeof(unsigned short) * (size_t)nGrp * NC));
+  build_sched_kernel<MODE><<<nGrp, SCHED_THREADS, 0, ctx->stream>>>(m.d_IEN, m.d_slot, nEl, 1, S.d_nuniq, S.d_uptr, S.d_uent,
+                                                                   S.d_upartner, S.d_contrib);
   ctx->launches++;
   SVB_CUDA(cudaGetLastError());
   SVB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -175,19 +215,19 @@ static int build_one(svb200_ctx* ctx, const int* d_src, int nEl, GroupSched& S)
 
 void free_group_sched(GroupSched& S)
 {
-  cudaFree(S.d_nuniq); cudaFree(S.d_uptr); cudaFree(S.d_uent); cudaFree(S.d_contrib);
+  cudaFree(S.d_nuniq); cudaFree(S.d_uptr); cudaFree(S.d_uent); cudaFree(S.d_upartner); cudaFree(S.d_contrib);
   S = GroupSched();
 }
 
-// Tangent schedule from the element->slot map (16 per tet4), residual schedule from IEN (4 per tet4).
+// Tangent plan (diagonal blocks + edges, 10 per tet4) and residual plan (nodes, 4 per tet4).
 int build_group_schedules(svb200_ctx* ctx, Mesh& m)
 {
   free_group_sched(m.schedK);
   free_group_sched(m.schedR);
   if (m.eNoN != 4 || m.nEl == 0) return SVB200_OK;
-  int rc = build_one<16, 11>(ctx, m.d_slot, m.nEl, m.schedK);
+  int rc = build_one<1>(ctx, m, m.schedK);
   if (rc) return rc;
-  return build_one<4, 9>(ctx, m.d_IEN, m.nEl, m.schedR);
+  return build_one<0>(ctx, m, m.schedR);
 }
 
 }  // namespace svb

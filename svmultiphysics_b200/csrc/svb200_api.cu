@@ -452,7 +452,7 @@ static int fill_fluid_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams
   SVB_REQUIRE(ctx->d_x, "svb200_assemble: coordinates not set");
   memset(&A, 0, sizeof(A));
   A.IEN = m.d_IEN; A.eId = m.d_eId; A.slot = m.d_slot; A.perm = nullptr;
-  A.kU_ptr = m.schedK.d_uptr; A.kU_ent = m.schedK.d_uent; A.kContrib = m.schedK.d_contrib;
+  A.kU_ptr = m.schedK.d_uptr; A.kU_ent = m.schedK.d_uent; A.kU_partner = m.schedK.d_upartner; A.kContrib = m.schedK.d_contrib;
   A.rU_ptr = m.schedR.d_uptr; A.rU_ent = m.schedR.d_uent; A.rContrib = m.schedR.d_contrib;
   A.x = ctx->d_x; A.Ag = ctx->d_Ag; A.Yg = ctx->d_Yg; A.Bf = ctx->d_Bf; A.Dg = ctx->d_Dg;
   A.R = ctx->d_R; A.Val = ctx->d_Val;

@@ -29,6 +29,7 @@ struct GroupSched {
   int* d_nuniq = nullptr;            // (nGrp) distinct targets of the group
   int* d_uptr = nullptr;             // (nGrp+1) offsets into d_uent
   int2* d_uent = nullptr;            // {target, start | count << 16}
+  int* d_upartner = nullptr;         // tangent plan: transposed slot of an edge, -1 for a diagonal block
   unsigned short* d_contrib = nullptr;   // (nGrp, ASM_GROUP*PER_EL) contribution ids, sorted by target
 };
 
@@ -77,7 +78,7 @@ struct FluidArgs {
   const int* slot;
   const int* perm;      // optional element permutation (coloured scatter) or null
   // grouped scatter (group_sched.cu): tangent (K) and residual (R) plans
-  const int* kU_ptr; const int2* kU_ent; const unsigned short* kContrib;
+  const int* kU_ptr; const int2* kU_ent; const int* kU_partner; const unsigned short* kContrib;
   const int* rU_ptr; const int2* rU_ent; const unsigned short* rContrib;
   const double* x;
   const double* Ag;

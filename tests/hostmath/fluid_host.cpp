@@ -68,16 +68,18 @@ extern "C" int hostmath_fluid_tet4_staged(const svb::FluidArgs* P, int nNo, cons
     double rec[REC_NN], lR[16];
     for (int i = 0; i < REC_NN; i++) rec[i] = 1e300;   // poison: every field read must have been written
     tet4_element_staged(*P, P->dmn[iD], xl, yl, uc, ab, NN, rec, lR);
+    auto find = [&](int row, int col) { for (int k = rowPtr[row]; k < rowPtr[row+1]; k++) if (colPtr[k] == col) return k; return -1; };
     for (int a = 0; a < 4; a++) {
       for (int i = 0; i < 4; i++) R[4*n[a] + i] += lR[4*a + i];
-      for (int b = 0; b < 4; b++) {
-        double K[16];
-        for (int i = 0; i < 16; i++) K[i] = 0.0;
-        tet4_block_rec_add(rec, NN, a, b, K);
-        int s = -1;
-        for (int k = rowPtr[n[a]]; k < rowPtr[n[a]+1]; k++) if (colPtr[k] == n[b]) { s = k; break; }
-        if (s < 0) return 1;
-        for (int i = 0; i < 16; i++) Val[16*(size_t)s + i] += K[i];
+      for (int b = a; b < 4; b++) {
+        double K1[16], K2[16];
+        for (int i = 0; i < 16; i++) K1[i] = K2[i] = 0.0;
+        if (a == b) tet4_block_rec_add(rec, NN, a, a, K1);
+        else tet4_edge_rec_add(rec, NN, a, b, K1, K2);   // both blocks of the edge, as the grouped kernel does
+        const int s1 = find(n[a], n[b]), s2 = find(n[b], n[a]);
+        if (s1 < 0 || s2 < 0) return 1;
+        for (int i = 0; i < 16; i++) Val[16*(size_t)s1 + i] += K1[i];
+        if (a != b) for (int i = 0; i < 16; i++) Val[16*(size_t)s2 + i] += K2[i];
       }
     }
   }
