@@ -335,6 +335,15 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     asm_tf = m.nEl * FLOP_PER_ELEMENT / (kern_ms * 1e-3) * 1e-12
+    # DRAM traffic per launch of the two kernels from the committed `ncu --set full` captures (profiles/), valid
+    # for the default C2 size only
+    traffic = {}
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if t.get("elements") == m.nEl:
+            traffic = t
+    except Exception:
+        pass
     spmv_gbs = SPMV_BYTES(len(colPtr), m.nNo) / (spmv_ms * 1e-3) * 1e-9
 
     if rank == 0:
@@ -346,11 +355,15 @@ def main():
             "newton_step_ms": step_ms, "assembly_stage_ms": asm_ms, "assembly_kernel_ms": kern_ms, "solve_ms": solve_ms,
             "gmres": {"itr": stats[-1][3], "success": int(stats[-1][4]), "iNorm": stats[-1][5], "fNorm": stats[-1][6]},
             "roofline": {"bound": "fp64", "achieved": asm_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": asm_tf / fp64_peak,
-                         "traffic": None, "kernel": "assemble_fluid_tet4_kernel",
+                         "traffic": traffic.get("assemble_bytes"), "traffic_unit": "bytes/launch (ncu dram read+write)",
+                         "kernel": "assemble_fluid_tet4_grouped_kernel" if args.scatter == "atomic" else "assemble_fluid_tet4_kernel",
+                         "hbm_check": {"algorithmic_bytes_per_element": 730, "note": "compulsory DRAM bytes (Val RMW + plan + gather) "
+                                       "x elements / kernel time vs HBM peak", "GB/s": m.nEl * 730 / (kern_ms * 1e-3) * 1e-9,
+                                       "frac_of_hbm_peak": m.nEl * 730 / (kern_ms * 1e-3) * 1e-9 / hbm_peak},
                          "peak_source": "FP64 FMA peak measured in this run by svb200_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 figure)",
                          "algorithmic": f"{FLOP_PER_ELEMENT:.0f} flop/element x {m.nEl} elements per launch"},
             "roofline_spmv": {"bound": "hbm", "achieved": spmv_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": spmv_gbs / hbm_peak,
-                              "traffic": None, "kernel": "bsr_spmv4_kernel", "peak_source": hbm_src,
+                              "traffic": traffic.get("spmv_bytes"), "kernel": "bsr_spmv4_kernel", "peak_source": hbm_src,
                               "algorithmic": "nnz*132 + nNo*72 bytes per launch", "ms": spmv_ms},
             "e2e": {"value": nEl_total / (e2e_ms * 1e-3), "unit": "element assemblies/s",
                     "h2d_bytes_per_step": int(Ah.nbytes + Yh.nbytes), "d2h_bytes_per_step": int(Rh.nbytes), "ms_per_step": e2e_ms},

@@ -167,6 +167,35 @@ __device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc)
 constexpr int ENT_CACHE = 512;              // plan entries of the group kept in shared memory (the rest: global)
 constexpr int ASM_WARPS = ASM_GROUP / 32;
 
+// Warp-wide scatter of one 4x4 block per lane (slot < 0: none): the blocks are transposed through the warp's
+// tile so that a half-warp adds the 16 contiguous doubles of one block with ONE coalesced RED; 4 in flight.
+__device__ __forceinline__ void red_blocks(double* __restrict__ Val, double* T, const int lane, const int myslot,
+                                           const double (&K)[16])
+{
+  const int half = lane >> 4, j = lane & 15;
+  if (myslot >= 0) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) T[lane * TILE_LD + i] = K[i];
+  }
+  __syncwarp();
+  double* base = Val + j;
+#pragma unroll
+  for (int r0 = 0; r0 < 16; r0 += 4) {
+    int sl[4];
+    double v[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int src = 2 * (r0 + q) + half;
+      sl[q] = __shfl_sync(0xffffffffu, myslot, src);
+      v[q] = T[src * TILE_LD + j];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      if (sl[q] >= 0) add_f64<true>(base + 16 * (size_t)sl[q], v[q]);
+  }
+  __syncwarp();
+}
+
 template <bool NN>
 __global__ void __launch_bounds__(ASM_GROUP, NN ? 2 : 3)
 assemble_fluid_tet4_grouped_kernel(const __grid_constant__ FluidArgs P)
@@ -262,7 +291,6 @@ assemble_fluid_tet4_grouped_kernel(const __grid_constant__ FluidArgs P)
 
   // ---- phase 3: one thread per distinct diagonal block / edge (both blocks of the edge) ----------------------
   {
-    const int half = lane >> 4, j = lane & 15;
     for (int k0 = (tid & ~31); k0 < G; k0 += ASM_GROUP) {   // warp-uniform trip count
       const int k = k0 + lane;
       int slot1 = -1, slot2 = -1;
@@ -292,32 +320,8 @@ assemble_fluid_tet4_grouped_kernel(const __grid_constant__ FluidArgs P)
           }
         }
       }
-      // a half-warp adds the 16 contiguous doubles of one block with one coalesced RED; 4 blocks in flight
-#pragma unroll 1
-      for (int pass = 0; pass < 2; pass++) {
-        const int myslot = pass == 0 ? slot1 : slot2;
-        if (pass == 1 && !__any_sync(0xffffffffu, myslot >= 0)) break;
-        if (myslot >= 0) {
-#pragma unroll
-          for (int i = 0; i < 16; i++) T[lane * TILE_LD + i] = pass == 0 ? K1[i] : K2[i];
-        }
-        __syncwarp();
-#pragma unroll
-        for (int r0 = 0; r0 < 16; r0 += 4) {
-          int sl[4];
-          double v[4];
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const int src = 2 * (r0 + q) + half;
-            sl[q] = __shfl_sync(0xffffffffu, myslot, src);
-            v[q] = T[src * TILE_LD + j];
-          }
-#pragma unroll
-          for (int q = 0; q < 4; q++)
-            if (sl[q] >= 0) add_f64<true>(P.Val + 16 * (size_t)sl[q] + j, v[q]);
-        }
-        __syncwarp();
-      }
+      red_blocks(P.Val, T, lane, slot1, K1);
+      if (__any_sync(0xffffffffu, slot2 >= 0)) red_blocks(P.Val, T, lane, slot2, K2);
     }
   }
 }
