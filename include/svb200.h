@@ -231,6 +231,37 @@ SVB200_API int svb200_solve(svb200_ctx* ctx, int32_t dof, int32_t ls_type, int32
                  int32_t nFaces, const int32_t* incL, const double* res,
                  double* R_out, svb200_lsresult* result);
 
+/* ---- generalised-alpha time integration on the device (optional) ----------------
+ * With these the Newton loop is device-resident: svb200_predictor once per time step, then per Newton
+ * iteration svb200_initiator -> svb200_alloc/assemble/solve -> svb200_corrector; only norms cross PCIe.
+ * The time-integration state is solutions.old (Ao,Yo,Do) and solutions.current (An,Yn,Dn), each (tDof,nNo)
+ * (Code/Source/solver/SolutionStates.h:15-43); the intermediate state is the one svb200_set_state uploads. */
+typedef enum { SVB200_SOL_OLD = 0, SVB200_SOL_CURRENT = 1, SVB200_SOL_INTERMEDIATE = 2 } svb200_sol;
+typedef struct {
+  int32_t s, e;      /* eq.s, eq.e: first and last state row of the equation (inclusive) */
+  int32_t phys;      /* svb200_phys */
+  int32_t reserved;
+  double af, am, gam, beta;
+} svb200_eqtime;
+/* Upload / download one solution triple; NULL pointers are skipped. */
+SVB200_API int svb200_set_solution(svb200_ctx* ctx, int32_t tDof, int32_t which, const double* A, const double* Y, const double* D);
+SVB200_API int svb200_get_solution(svb200_ctx* ctx, int32_t which, double* A, double* Y, double* D);
+/* Integrator::predictor (solver/Integrator.cpp:393-643), state part: An = Ao (gam-1)/gam, Yn = Yo,
+ * Dn = Do + Yn dt + An dt^2 (gam/2 - beta)/(gam-1) when dFlag (struct / mesh / FSI), else Dn = Do. */
+SVB200_API int svb200_predictor(svb200_ctx* ctx, int32_t nEq, const svb200_eqtime* eqs, double dt, int32_t dFlag);
+/* Integrator::initiator (solver/Integrator.cpp:662-750): Ag, Yg, Dg from old and current. */
+SVB200_API int svb200_initiator(svb200_ctx* ctx, int32_t nEq, const svb200_eqtime* eqs);
+/* Integrator::corrector (solver/Integrator.cpp:774-867): current -= increment left in R by svb200_solve.
+ * mesh_s >= 0 with solid-node flags set (svb200_set_node_flags) also applies the FSI copy of :887-912. */
+SVB200_API int svb200_corrector(svb200_ctx* ctx, const svb200_eqtime* eq, double dt, int32_t mesh_s);
+SVB200_API int svb200_set_node_flags(svb200_ctx* ctx, const int32_t* is_solid_node);
+/* set_bc::set_bc_dir (solver/set_bc.cpp:901-1067), the write: X(row0+i, nodes[k]) = val(i,k) for X = A, Y and/or D of
+ * the CURRENT solution (NULL = leave).  The prescribed values are the host's (profiles, time functions). */
+SVB200_API int svb200_set_dirichlet_rows(svb200_ctx* ctx, int32_t row0, int32_t nrow, int32_t n, const int32_t* nodes,
+                              const double* valA, const double* valY, const double* valD);
+/* End of a time step: old = current (solver/main.cpp: solutions.old = solutions.current). */
+SVB200_API int svb200_advance_time_step(svb200_ctx* ctx);
+
 /* ---- debug / parity --------------------------------------------------------------------- */
 /* R(dof,nNo) and Val(dof*dof,nnz) are returned in INPUT node order / input CSR slot order. */
 SVB200_API int svb200_download(svb200_ctx* ctx, int32_t what, double* dst);

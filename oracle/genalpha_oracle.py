@@ -1,0 +1,46 @@
+"""TEST INFRASTRUCTURE ONLY — numpy restatement of the generalised-alpha state updates of the reference.
+Only tests/ and __graft_entry__.smoke() may import this; the product never does.
+
+Parity pinning: Integrator.cpp is not part of oracle/_ref/libsvref.so (it needs the Simulation object), so these
+four formulas are pinned by restatement only ("parity unpinned" by a compiled reference); each line cites
+the statement it follows in /root/reference/Code/Source/solver/Integrator.cpp.  Arrays are (tDof, nNo).
+"""
+import numpy as np
+
+
+def predictor(eqs, dt, dFlag, Ao, Yo, Do, An, Yn, Dn):
+    """Integrator::predictor, Integrator.cpp:540-643 (state part; sstEq false)."""
+    for q in eqs:
+        r = slice(q.s, q.e + 1)
+        coef = (q.gam - 1.0) / q.gam                      # :551
+        An[r] = Ao[r] * coef                              # :555  eqn 87 of Bazilevs 2007
+        Yn[r] = Yo[r]                                     # :616  eqn 86
+        if dFlag:                                         # :618-623
+            c = dt * dt * (0.5 * q.gam - q.beta) / (q.gam - 1.0)
+            Dn[r] = (Do[r] + Yn[r] * dt) + An[r] * c
+        else:
+            Dn[r] = Do[r]                                 # :640
+
+
+def initiator(eqs, Ao, Yo, Do, An, Yn, Dn, Ag, Yg, Dg):
+    """Integrator::initiator, Integrator.cpp:704-741."""
+    for q in eqs:
+        r = slice(q.s, q.e + 1)
+        c0, c1, c2, c3 = 1.0 - q.am, q.am, 1.0 - q.af, q.af      # :709-712
+        Ag[r] = Ao[r] * c0 + An[r] * c1                   # :735  eqn 89
+        Yg[r] = Yo[r] * c2 + Yn[r] * c3                   # :738  eqn 90
+        Dg[r] = Do[r] * c2 + Dn[r] * c3                   # :740
+
+
+def corrector(q, dt, R, An, Yn, Dn, mesh_s=-1, solid=None):
+    """Integrator::corrector, Integrator.cpp:812-815 (coefficients), :861-872 (update), :887-912 (FSI copy)."""
+    c0, c1 = q.gam * dt, q.beta * dt * dt
+    n = q.e - q.s + 1
+    r = slice(q.s, q.e + 1)
+    An[r] = An[r] - R[:n]                                 # :864  eqn 94
+    Yn[r] = Yn[r] - R[:n] * c0                            # :867  eqn 95
+    Dn[r] = Dn[r] - R[:n] * c1                            # :869
+    if mesh_s >= 0 and solid is not None:
+        m = np.asarray(solid, bool)
+        for X in (An, Yn, Dn):
+            X[mesh_s:mesh_s + 3, m] = X[0:3, m]           # :905-909

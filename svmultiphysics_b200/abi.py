@@ -29,6 +29,15 @@ class EqParams(C.Structure):
     ]
 
 
+class EqTime(C.Structure):
+    """svb200_eqtime: rows [s,e] and generalised-alpha coefficients of one equation."""
+    _fields_ = [("s", C.c_int32), ("e", C.c_int32), ("phys", C.c_int32), ("reserved", C.c_int32),
+                ("af", C.c_double), ("am", C.c_double), ("gam", C.c_double), ("beta", C.c_double)]
+
+
+SOL_OLD, SOL_CURRENT, SOL_INTERMEDIATE = 0, 1, 2
+
+
 class DmnParams(C.Structure):
     _fields_ = [
         ("Id", C.c_int32), ("phys", C.c_int32),
@@ -74,6 +83,11 @@ def gen_alpha(rho_inf: float):
     gam = 0.5 + am - af
     beta = 0.25 * (1.0 + am - af) ** 2
     return af, am, gam, beta
+
+
+def eq_time(s: int, e: int, phys: int, rho_inf: float = 0.5) -> EqTime:
+    am, af, gam, beta = gen_alpha(rho_inf)
+    return EqTime(s=s, e=e, phys=phys, af=af, am=am, gam=gam, beta=beta)
 
 
 def fluid_eq(dt: float, rho_inf: float = 0.5, tDof: int = 4, scatter: int = SCATTER_ATOMIC, mvMsh: int = 0) -> EqParams:

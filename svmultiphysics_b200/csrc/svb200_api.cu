@@ -199,6 +199,7 @@ int svb200_destroy(svb200_ctx* ctx)
   for (auto& nb : ctx->neigh) { cudaFree(nb.d_ptr); cudaFree(nb.d_send); cudaFree(nb.d_recv); }
   cudaFree(ctx->d_map); cudaFree(ctx->d_rowPtr); cudaFree(ctx->d_colPtr); cudaFree(ctx->d_diagPtr);
   cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf); cudaFree(ctx->d_Do);
+  cudaFree(ctx->d_Ao); cudaFree(ctx->d_Yo); cudaFree(ctx->d_An); cudaFree(ctx->d_Yn); cudaFree(ctx->d_Dn); cudaFree(ctx->d_nodeflag);
   cudaFree(ctx->d_stage); cudaFree(ctx->d_R); cudaFree(ctx->d_Val); cudaFree(ctx->d_W);
   cudaFree(ctx->d_work); cudaFree(ctx->d_red); cudaFree(ctx->d_tslot);
   cudaFreeHost(ctx->h_pinned);
@@ -288,6 +289,8 @@ int svb200_set_graph(svb200_ctx* ctx, int32_t nNo, int32_t nnz, const int32_t* r
   std::sort(ctx->neigh.begin(), ctx->neigh.end(), [](const Neighbor& a, const Neighbor& b) { return a.rank < b.rank; });
   // state arrays depend on nNo
   cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf); cudaFree(ctx->d_Do);
+  cudaFree(ctx->d_Ao); cudaFree(ctx->d_Yo); cudaFree(ctx->d_An); cudaFree(ctx->d_Yn); cudaFree(ctx->d_Dn); cudaFree(ctx->d_nodeflag);
+  ctx->d_Ao = ctx->d_Yo = ctx->d_An = ctx->d_Yn = ctx->d_Dn = nullptr; ctx->d_nodeflag = nullptr;
   ctx->d_x = ctx->d_Ag = ctx->d_Yg = ctx->d_Dg = ctx->d_Bf = ctx->d_Do = nullptr;
   ctx->tDof = 0;
   return SVB200_OK;
@@ -418,7 +421,8 @@ int svb200_set_state(svb200_ctx* ctx, int32_t tDof, const double* Ag, const doub
   SVB_REQUIRE(tDof >= 1 && tDof <= 16, "svb200_set_state: bad tDof");
   if (tDof != ctx->tDof) {
     cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Do);
-    ctx->d_Ag = ctx->d_Yg = ctx->d_Dg = ctx->d_Do = nullptr;
+    cudaFree(ctx->d_Ao); cudaFree(ctx->d_Yo); cudaFree(ctx->d_An); cudaFree(ctx->d_Yn); cudaFree(ctx->d_Dn);
+    ctx->d_Ag = ctx->d_Yg = ctx->d_Dg = ctx->d_Do = ctx->d_Ao = ctx->d_Yo = ctx->d_An = ctx->d_Yn = ctx->d_Dn = nullptr;
     ctx->tDof = tDof;
   }
   const size_t n = (size_t)tDof * ctx->nNo;
@@ -510,6 +514,130 @@ int svb200_set_old_disp(svb200_ctx* ctx, int32_t tDof, const double* Do)
   SVB_REQUIRE(ctx->d_rowPtr && Do, "svb200_set_old_disp: call svb200_set_graph first");
   SVB_REQUIRE(tDof == ctx->tDof, "svb200_set_old_disp: tDof differs from svb200_set_state");
   return upload_nodal(ctx, tDof, Do, &ctx->d_Do);
+}
+
+static double** sol_ptrs(svb200_ctx* ctx, int which, int k)
+{
+  double** tab[3][3] = {{&ctx->d_Ao, &ctx->d_Yo, &ctx->d_Do}, {&ctx->d_An, &ctx->d_Yn, &ctx->d_Dn}, {&ctx->d_Ag, &ctx->d_Yg, &ctx->d_Dg}};
+  return tab[which][k];
+}
+
+static int ensure_solution_arrays(svb200_ctx* ctx)
+{
+  const size_t n = (size_t)ctx->tDof * ctx->nNo;
+  for (int w = 0; w < 3; w++)
+    for (int k = 0; k < 3; k++) {
+      double** d = sol_ptrs(ctx, w, k);
+      if (!*d) {
+        SVB_CUDA(cudaMalloc(d, sizeof(double) * std::max<size_t>(n, 1)));
+        SVB_CUDA(cudaMemsetAsync(*d, 0, sizeof(double) * n, ctx->stream));
+      }
+    }
+  return SVB200_OK;
+}
+
+int svb200_set_solution(svb200_ctx* ctx, int32_t tDof, int32_t which, const double* A, const double* Y, const double* D)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(ctx->d_rowPtr, "svb200_set_solution: call svb200_set_graph first");
+  SVB_REQUIRE(which >= 0 && which <= 2, "svb200_set_solution: bad selector");
+  if (ctx->tDof == 0) TRY(svb200_set_state(ctx, tDof, nullptr, nullptr, nullptr, nullptr));
+  SVB_REQUIRE(tDof == ctx->tDof, "svb200_set_solution: tDof differs from svb200_set_state");
+  TRY(ensure_solution_arrays(ctx));
+  const double* h[3] = {A, Y, D};
+  for (int k = 0; k < 3; k++)
+    if (h[k]) TRY(upload_nodal(ctx, tDof, h[k], sol_ptrs(ctx, which, k)));
+  return SVB200_OK;
+}
+
+int svb200_get_solution(svb200_ctx* ctx, int32_t which, double* A, double* Y, double* D)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(which >= 0 && which <= 2 && ctx->tDof > 0, "svb200_get_solution: bad selector or no state");
+  TRY(ensure_solution_arrays(ctx));
+  double* h[3] = {A, Y, D};
+  for (int k = 0; k < 3; k++)
+    if (h[k]) TRY(download_nodal(ctx, ctx->tDof, *sol_ptrs(ctx, which, k), h[k]));
+  return SVB200_OK;
+}
+
+int svb200_predictor(svb200_ctx* ctx, int32_t nEq, const svb200_eqtime* eqs, double dt, int32_t dFlag)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(ctx->tDof > 0, "svb200_predictor: no state (svb200_set_solution)");
+  TRY(ensure_solution_arrays(ctx));
+  for (int i = 0; i < nEq && eqs; i++) SVB_REQUIRE(eqs[i].e < ctx->tDof, "svb200_predictor: equation rows exceed tDof");
+  return launch_predictor(ctx, nEq, eqs, dt, dFlag);
+}
+
+int svb200_initiator(svb200_ctx* ctx, int32_t nEq, const svb200_eqtime* eqs)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(ctx->tDof > 0, "svb200_initiator: no state (svb200_set_solution)");
+  TRY(ensure_solution_arrays(ctx));
+  for (int i = 0; i < nEq && eqs; i++) SVB_REQUIRE(eqs[i].e < ctx->tDof, "svb200_initiator: equation rows exceed tDof");
+  return launch_initiator(ctx, nEq, eqs);
+}
+
+int svb200_corrector(svb200_ctx* ctx, const svb200_eqtime* eq, double dt, int32_t mesh_s)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(eq && ctx->tDof > 0 && ctx->d_R, "svb200_corrector: no state or no linear system");
+  SVB_REQUIRE(eq->s >= 0 && eq->e >= eq->s && eq->e < ctx->tDof && eq->e - eq->s + 1 == ctx->dof,
+              "svb200_corrector: equation rows do not match the dof of the solved system");
+  SVB_REQUIRE(mesh_s < 0 || (mesh_s + 3 <= ctx->tDof && ctx->d_nodeflag), "svb200_corrector: FSI copy needs svb200_set_node_flags");
+  TRY(ensure_solution_arrays(ctx));
+  return launch_corrector(ctx, eq, dt, mesh_s, ctx->d_nodeflag);
+}
+
+int svb200_set_node_flags(svb200_ctx* ctx, const int32_t* is_solid_node)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(ctx->d_rowPtr && is_solid_node, "svb200_set_node_flags: call svb200_set_graph first");
+  std::vector<int> f(ctx->nNo);
+  for (int a = 0; a < ctx->nNo; a++) f[ctx->h_map[a]] = is_solid_node[a];
+  return upload(ctx, &ctx->d_nodeflag, f.data(), f.size());
+}
+
+int svb200_set_dirichlet_rows(svb200_ctx* ctx, int32_t row0, int32_t nrow, int32_t n, const int32_t* nodes, const double* valA,
+                              const double* valY, const double* valD)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(ctx->tDof > 0 && row0 >= 0 && nrow >= 1 && row0 + nrow <= ctx->tDof && n >= 0 && (nodes || n == 0),
+              "svb200_set_dirichlet_rows: bad arguments");
+  TRY(ensure_solution_arrays(ctx));
+  if (n == 0) return SVB200_OK;
+  std::vector<int> g(n);
+  for (int k = 0; k < n; k++) {
+    SVB_REQUIRE(nodes[k] >= 0 && nodes[k] < ctx->nNo, "svb200_set_dirichlet_rows: node id out of range");
+    g[k] = ctx->h_map[nodes[k]];
+  }
+  int* d_nodes = nullptr;
+  TRY(upload(ctx, &d_nodes, g.data(), g.size()));
+  const double* h[3] = {valA, valY, valD};
+  int rc = SVB200_OK;
+  for (int k = 0; k < 3 && rc == SVB200_OK; k++) {
+    if (!h[k]) continue;
+    double* d_val = nullptr;
+    rc = upload(ctx, &d_val, h[k], (size_t)n * nrow);
+    if (rc == SVB200_OK) rc = launch_set_rows(ctx, row0, nrow, n, d_nodes, d_val, *sol_ptrs(ctx, SVB200_SOL_CURRENT, k));
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_val);
+  }
+  cudaFree(d_nodes);
+  return rc;
+}
+
+int svb200_advance_time_step(svb200_ctx* ctx)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(ctx->tDof > 0, "svb200_advance_time_step: no state");
+  TRY(ensure_solution_arrays(ctx));
+  const size_t bytes = sizeof(double) * (size_t)ctx->tDof * ctx->nNo;
+  for (int k = 0; k < 3; k++)
+    SVB_CUDA(cudaMemcpyAsync(*sol_ptrs(ctx, SVB200_SOL_OLD, k), *sol_ptrs(ctx, SVB200_SOL_CURRENT, k), bytes,
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+  return SVB200_OK;
 }
 
 int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int32_t nDmn)

@@ -124,7 +124,10 @@ struct svb200_ctx {
   double* d_Ag = nullptr;
   double* d_Yg = nullptr;
   double* d_Dg = nullptr;
-  double* d_Do = nullptr;        // old displacement (mesh-motion equation)
+  double* d_Do = nullptr;        // old displacement (mesh-motion equation; solutions.old)
+  double* d_Ao = nullptr; double* d_Yo = nullptr;                          // solutions.old
+  double* d_An = nullptr; double* d_Yn = nullptr; double* d_Dn = nullptr;  // solutions.current
+  int* d_nodeflag = nullptr;     // per node: belongs to a solid domain (FSI corrector)
   double* d_Bf = nullptr;
   double* d_stage = nullptr;     // staging buffer for permuted uploads/downloads
   size_t stage_bytes = 0;
@@ -185,6 +188,11 @@ int launch_assemble_fluid(svb200_ctx* ctx, const Mesh& m, const FluidArgs& args)
 // assemble_struct.cu
 int run_assemble_struct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);
 int run_assemble_mesh(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);
+// genalpha.cu
+int launch_predictor(svb200_ctx* ctx, int nEq, const svb200_eqtime* eqs, double dt, int dFlag);
+int launch_initiator(svb200_ctx* ctx, int nEq, const svb200_eqtime* eqs);
+int launch_corrector(svb200_ctx* ctx, const svb200_eqtime* eq, double dt, int mesh_s, const int* d_flag);
+int launch_set_rows(svb200_ctx* ctx, int row0, int nrow, int n, const int* d_nodes, const double* d_val, double* dst);
 // group_sched.cu
 int build_group_schedules(svb200_ctx* ctx, Mesh& m);
 void free_group_sched(GroupSched& S);

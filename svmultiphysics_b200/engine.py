@@ -40,6 +40,8 @@ ABI_SYMBOLS = [
     "svb200_solve", "svb200_download", "svb200_upload", "svb200_spmv", "svb200_last_timing",
     "svb200_host_register", "svb200_host_unregister", "svb200_timer_mark", "svb200_timer_elapsed",
     "svb200_bench_assemble", "svb200_bench_spmv", "svb200_measure_fp64_peak", "svb200_launch_count",
+    "svb200_set_solution", "svb200_get_solution", "svb200_predictor", "svb200_initiator", "svb200_corrector",
+    "svb200_set_node_flags", "svb200_set_dirichlet_rows", "svb200_advance_time_step",
 ]
 
 _lib = None
@@ -199,6 +201,42 @@ class Engine:
     def set_old_disp(self, Do):
         Do = _f64(Do)
         self._call("svb200_set_old_disp", C.c_int32(Do.shape[0]), _d(Do))
+
+    # ---- generalised-alpha state on the device (Integrator::predictor / initiator / corrector) -----------
+    def set_solution(self, which, A=None, Y=None, D=None):
+        A, Y, D = _f64(A), _f64(Y), _f64(D)
+        tDof = next(a for a in (A, Y, D) if a is not None).shape[0]
+        self._call("svb200_set_solution", C.c_int32(tDof), C.c_int32(which), _d(A), _d(Y), _d(D))
+        self.tDof = tDof
+
+    def get_solution(self, which):
+        out = [np.zeros((self.tDof, self.nNo), order="F") for _ in range(3)]
+        self._call("svb200_get_solution", C.c_int32(which), _d(out[0]), _d(out[1]), _d(out[2]))
+        return out
+
+    def predictor(self, eqs, dt, dFlag):
+        arr = (abi.EqTime * len(eqs))(*eqs)
+        self._call("svb200_predictor", C.c_int32(len(eqs)), arr, C.c_double(dt), C.c_int32(int(dFlag)))
+
+    def initiator(self, eqs):
+        arr = (abi.EqTime * len(eqs))(*eqs)
+        self._call("svb200_initiator", C.c_int32(len(eqs)), arr)
+
+    def corrector(self, eq, dt, mesh_s=-1):
+        self._call("svb200_corrector", C.byref(eq), C.c_double(dt), C.c_int32(mesh_s))
+
+    def set_node_flags(self, flags):
+        self._call("svb200_set_node_flags", _i(_i32(flags)))
+
+    def set_dirichlet_rows(self, row0, nodes, valA=None, valY=None, valD=None):
+        nodes = _i32(nodes)
+        valA, valY, valD = _f64(valA), _f64(valY), _f64(valD)
+        nrow = next(v for v in (valA, valY, valD) if v is not None).shape[0]
+        self._call("svb200_set_dirichlet_rows", C.c_int32(row0), C.c_int32(nrow), C.c_int32(len(nodes)), _i(nodes),
+                   _d(valA), _d(valY), _d(valD))
+
+    def advance_time_step(self):
+        self._call("svb200_advance_time_step")
 
     def assemble(self, iM, eq: abi.EqParams, dmns):
         arr = (abi.DmnParams * len(dmns))(*dmns)
