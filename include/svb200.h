@@ -125,6 +125,7 @@ typedef struct {
   double dmp;               /* damping */
   double E, nu;             /* elasticity_modulus, poisson_ratio (mesh / linear elasticity) */
   double solid_visc_mu;     /* 0 = no solid viscosity */
+  double backflow_stab;     /* backflow stabilisation coefficient (fluid Neumann faces, solver/fluid.cpp:65) */
 } svb200_dmnparams;
 
 /* FSILS_subLsType inputs (linear_solver/fils_struct.hpp:198-242). */
@@ -216,6 +217,19 @@ SVB200_API int svb200_set_old_disp(svb200_ctx* ctx, int32_t tDof, const double* 
 /* global_eq_assem for mesh iM: element loop + scatter, R/Val stay on the device. */
 SVB200_API int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq,
                     const svb200_dmnparams* dmn, int32_t nDmn);
+
+/* Boundary face iFa of mesh iM (faceType): connectivity IENb(eNoNb,nElb) in input node ids, parent element
+ * gE(nElb) (index into the mesh's elements), and the face reference-element tables w(nGb), N(eNoNb,nGb),
+ * Nx(2,eNoNb,nGb).  eNoNb = 3 (TRI3 on TET4) or 4 (QUD4 on HEX8). */
+SVB200_API int svb200_set_bface(svb200_ctx* ctx, int32_t iFa, int32_t iM, int32_t eNoNb, int32_t nElb, const int32_t* IENb,
+                     const int32_t* gE, int32_t nGb, const double* w, const double* N, const double* Nx);
+/* eq_assem::b_assem_neu_bc (solver/eq_assem.cpp:31-149) on the device: Neumann / traction face integral with
+ * nn::gnnb normals (solver/nn.cpp:911-1117, reference configuration or x + Do(4..6) when mvMsh),
+ * fluid::b_fluid incl. backflow stabilisation and its tangent (solver/fluid.cpp:21-108) on fluid domains,
+ * l_elas::b_l_elas (solver/l_elas.cpp:21-32) otherwise.  hg(nNo) is the nodal traction magnitude set_bc_neu_l
+ * builds (solver/set_bc.cpp:1489-1606), input node order; it is added into the device R / Val. */
+SVB200_API int svb200_assemble_neu(svb200_ctx* ctx, int32_t iFa, const svb200_eqparams* eq, const svb200_dmnparams* dmn,
+                        int32_t nDmn, const double* hg);
 
 /* Host-assembled surface terms (Neumann/backflow faces): R(:,rows[k]) += R_add(:,k),
  * Val(:,slot(rows_k,cols_k)) += K_add(:,k). */

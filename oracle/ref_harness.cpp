@@ -14,6 +14,8 @@
 //   fsi::construct_fsi, mesh::construct_mesh    solver/fsi.cpp:24, solver/mesh.cpp:22
 //   fsi_linear_solver::fsils_solve              linear_solver/solve.cpp:23
 //   spar_mul::fsils_spar_mul_vv                 linear_solver/spar_mul.cpp:164
+//   nn::get_gip / get_gnn (faces), nn::gnnb     solver/nn.cpp:455,500,911
+//   fluid::b_fluid, l_elas::b_l_elas            solver/fluid.cpp:21, solver/l_elas.cpp:21
 //
 // Parameter structs are shared with the product ABI (include/svb200.h) so that parity tests feed
 // both sides the same bytes.  Nothing here is linked into libsvb200.so.
@@ -29,6 +31,9 @@
 #include "fs.h"
 #include "nn.h"
 #include "lhsa.h"
+#include "l_elas.h"
+#include "all_fun.h"
+#include "utils.h"
 #include "fsils_api.hpp"
 #include "commu.h"
 #include "lhs.h"
@@ -78,7 +83,7 @@ void fill_domain(dmnType& d, const svb200_dmnparams& p)
   d.prop[PhysicalProperyType::f_y] = p.f[1];
   d.prop[PhysicalProperyType::f_z] = p.f[2];
   d.prop[PhysicalProperyType::inverse_darcy_permeability] = p.K_darcy;
-  d.prop[PhysicalProperyType::backflow_stab] = 0.0;
+  d.prop[PhysicalProperyType::backflow_stab] = p.backflow_stab;
   d.prop[PhysicalProperyType::damping] = p.dmp;
   d.prop[PhysicalProperyType::elasticity_modulus] = p.E;
   d.prop[PhysicalProperyType::poisson_ratio] = p.nu;
@@ -405,6 +410,95 @@ int svref_solve(void* h, int dof, int ls_type, int prec, const svb200_lsparams* 
       co(out->RI, fls.RI); co(out->GM, fls.GM); co(out->CG, fls.CG);
       out->Resm = fls.Resm; out->Resc = fls.Resc;
       out->hist_n = 0;
+    }
+  });
+}
+
+/// A boundary face of mesh iM: connectivity IENb(eNoNb,nElb) in global node ids and the parent element gE(nElb).
+/// What nn::select_eleb does (solver/nn.cpp:1354-1402) with the reference's own Gauss/shape routines.
+int svref_add_face(void* h, int iM, int eNoNb, int nElb, const int* IENb, const int* gE)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    auto& m = c.com_mod.msh.at(iM);
+    m.fa.emplace_back();
+    m.nFa = (int)m.fa.size();
+    auto& fa = m.fa.back();
+    fa.iM = iM; fa.eNoN = eNoNb; fa.nEl = nElb; fa.gnEl = nElb; fa.name = "face" + std::to_string(m.nFa - 1);
+    if (eNoNb == 3) { fa.eType = consts::ElementType::TRI3; fa.nG = 3; }      // nn_elem_props.h (face props)
+    else if (eNoNb == 4) { fa.eType = consts::ElementType::QUD4; fa.nG = 4; }
+    else throw std::runtime_error("[ref_harness] face type not supported");
+    fa.IEN.resize(eNoNb, nElb);
+    std::memcpy(fa.IEN.data(), IENb, sizeof(int)*eNoNb*nElb);
+    fa.gE.resize(nElb);
+    std::memcpy(fa.gE.data(), gE, sizeof(int)*nElb);
+    fa.w = Vector<double>(fa.nG);
+    fa.xi = Array<double>(2, fa.nG);
+    nn::get_gip(nullptr, fa);
+    fa.N = Array<double>(fa.eNoN, fa.nG);
+    fa.Nx = Array3<double>(2, fa.eNoN, fa.nG);
+    for (int g = 0; g < fa.nG; g++) nn::get_gnn(nullptr, g, fa);
+  });
+}
+
+int svref_get_face_tables(void* h, int iM, int iFa, int* nG, double* w, double* N, double* Nx)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    auto& fa = c.com_mod.msh.at(iM).fa.at(iFa);
+    *nG = fa.nG;
+    if (w) std::memcpy(w, fa.w.data(), sizeof(double)*fa.nG);
+    if (N) std::memcpy(N, fa.N.data(), sizeof(double)*fa.eNoN*fa.nG);
+    if (Nx) std::memcpy(Nx, fa.Nx.data(), sizeof(double)*2*fa.eNoN*fa.nG);
+  });
+}
+
+/// The loop of eq_assem::b_assem_neu_bc (solver/eq_assem.cpp:31-149) around the reference's own nn::gnnb,
+/// fluid::b_fluid / l_elas::b_l_elas and FsilsLinearAlgebra::assemble; hg(tnNo) as set_bc_neu_l builds it.
+int svref_assemble_neu(void* h, int iM, int iFa, const svb200_eqparams* e, const svb200_dmnparams* dmn, int nDmn,
+    const double* hg)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    fill_eq(c, *e, dmn, nDmn);
+    auto& cm = c.com_mod;
+    auto& msh = cm.msh.at(iM);
+    auto& lFa = msh.fa.at(iFa);
+    auto& eq = cm.eq[0];
+    const int nsd = 3, dof = cm.dof, tDof = cm.tDof, eNoN = lFa.eNoN;
+    const auto& Yg = c.sol.intermediate.get_velocity();
+    for (int el = 0; el < lFa.nEl; el++) {
+      int Ec = lFa.gE(el);
+      cm.cDmn = all_fun::domain(cm, msh, cm.cEq, Ec);
+      auto cPhys = eq.dmn[cm.cDmn].phys;
+      Vector<int> ptr(eNoN);
+      Vector<double> N(eNoN), hl(eNoN);
+      Array<double> yl(tDof,eNoN), lR(dof,eNoN);
+      Array3<double> lK(dof*dof,eNoN,eNoN);
+      for (int a = 0; a < eNoN; a++) {
+        int Ac = lFa.IEN(a,el);
+        ptr(a) = Ac;
+        hl(a) = hg[Ac];
+        for (int i = 0; i < tDof; i++) yl(i,a) = Yg(i,Ac);
+      }
+      for (int g = 0; g < lFa.nG; g++) {
+        Vector<double> nV(nsd);
+        auto Nx = lFa.Nx.rslice(g);
+        nn::gnnb(cm, lFa, el, g, nsd, nsd-1, eNoN, Nx, nV, c.sol, consts::MechanicalConfigurationType::reference);
+        double Jac = utils::norm(nV);
+        nV = nV / Jac;
+        double w = lFa.w(g)*Jac;
+        N = lFa.N.col(g);
+        double hh = 0.0;
+        Vector<double> y(tDof);
+        for (int a = 0; a < eNoN; a++) {
+          hh = hh + N(a)*hl(a);
+          y = y + N(a)*yl.col(a);
+        }
+        if (cPhys == consts::EquationType::phys_fluid) fluid::b_fluid(cm, eNoN, w, N, y, hh, nV, lR, lK);
+        else l_elas::b_l_elas(cm, eNoN, w, N, hh, nV, lR);
+      }
+      eq.linear_algebra->assemble(cm, eNoN, ptr, lK, lR);
     }
   });
 }

@@ -138,6 +138,28 @@ class _FlatCase:
         arr = (abi.DmnParams * len(dmns))(*dmns)
         self._call("assemble", C.c_int(iM), C.byref(eq), arr, C.c_int(len(dmns)))
 
+    # ---- boundary faces (compiled reference only) -------------------------------------------------------
+    def add_face(self, iM, IENb, gE):
+        IENb, gE = _i32(np.asfortranarray(IENb)), _i32(gE)
+        self._call("add_face", C.c_int(iM), C.c_int(IENb.shape[0]), C.c_int(IENb.shape[1]), _i(IENb), _i(gE))
+        self.faces = getattr(self, "faces", []) + [IENb.shape[0]]
+        return len(self.faces) - 1
+
+    def face_tables(self, iM, iFa):
+        eNoNb = self.faces[iFa]
+        nG = C.c_int(0)
+        self._call("get_face_tables", C.c_int(iM), C.c_int(iFa), C.byref(nG), None, None, None)
+        w = np.zeros(nG.value)
+        N = np.zeros((eNoNb, nG.value), order="F")
+        Nx = np.zeros((2, eNoNb, nG.value), order="F")
+        self._call("get_face_tables", C.c_int(iM), C.c_int(iFa), C.byref(nG), _d(w), _d(N), _d(Nx))
+        return w, N, Nx
+
+    def assemble_neu(self, iM, iFa, eq: abi.EqParams, dmns, hg):
+        arr = (abi.DmnParams * len(dmns))(*dmns)
+        hg = _f64(hg)
+        self._call("assemble_neu", C.c_int(iM), C.c_int(iFa), C.byref(eq), arr, C.c_int(len(dmns)), _d(hg))
+
     def get_R(self):
         R = np.zeros((self.dof, self.nNo), order="F")
         self._call("get", C.c_int(abi.ARRAY_R), _d(R))

@@ -53,6 +53,7 @@ class DmnParams(C.Structure):
         ("dmp", C.c_double),
         ("E", C.c_double), ("nu", C.c_double),
         ("solid_visc_mu", C.c_double),
+        ("backflow_stab", C.c_double),
     ]
 
 
@@ -98,10 +99,11 @@ def fluid_eq(dt: float, rho_inf: float = 0.5, tDof: int = 4, scatter: int = SCAT
 
 def fluid_domain(rho: float = 1.06, mu: float = 0.04, f=(0.0, 0.0, 0.0), K_darcy: float = 0.0,
                  viscType: int = VISC_CONST, mu_o: float = 0.0, lam: float = 0.0, a: float = 0.0, n: float = 0.0,
-                 Id: int = -1) -> DmnParams:
+                 Id: int = -1, backflow_stab: float = 0.0) -> DmnParams:
     d = DmnParams()
     d.Id = Id
     d.phys = PHYS_FLUID
+    d.backflow_stab = backflow_stab
     d.rho = rho
     d.f[0], d.f[1], d.f[2] = f
     d.K_darcy = K_darcy

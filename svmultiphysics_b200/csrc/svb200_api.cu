@@ -196,6 +196,8 @@ int svb200_destroy(svb200_ctx* ctx)
   nccl_destroy(ctx);
   for (auto& m : ctx->mesh) free_mesh(m);
   for (auto& f : ctx->face) free_face(f);
+  for (auto& f : ctx->bface) { cudaFree(f.d_IENb); cudaFree(f.d_gE); }
+  cudaFree(ctx->d_hg);
   for (auto& nb : ctx->neigh) { cudaFree(nb.d_ptr); cudaFree(nb.d_send); cudaFree(nb.d_recv); }
   cudaFree(ctx->d_map); cudaFree(ctx->d_rowPtr); cudaFree(ctx->d_colPtr); cudaFree(ctx->d_diagPtr);
   cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf); cudaFree(ctx->d_Do);
@@ -514,6 +516,45 @@ int svb200_set_old_disp(svb200_ctx* ctx, int32_t tDof, const double* Do)
   SVB_REQUIRE(ctx->d_rowPtr && Do, "svb200_set_old_disp: call svb200_set_graph first");
   SVB_REQUIRE(tDof == ctx->tDof, "svb200_set_old_disp: tDof differs from svb200_set_state");
   return upload_nodal(ctx, tDof, Do, &ctx->d_Do);
+}
+
+int svb200_set_bface(svb200_ctx* ctx, int32_t iFa, int32_t iM, int32_t eNoNb, int32_t nElb, const int32_t* IENb,
+                     const int32_t* gE, int32_t nGb, const double* w, const double* N, const double* Nx)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(iFa >= 0 && iFa < 1024, "svb200_set_bface: bad face index");
+  SVB_REQUIRE(iM >= 0 && iM < (int)ctx->mesh.size() && ctx->mesh[iM].set, "svb200_set_bface: parent mesh not set");
+  SVB_REQUIRE((eNoNb == 3 || eNoNb == 4) && nGb >= 1 && nGb <= 4, "svb200_set_bface: TRI3 / QUD4 faces with at most 4 Gauss points");
+  SVB_REQUIRE(nElb >= 0 && (nElb == 0 || (IENb && gE)) && w && N && Nx, "svb200_set_bface: bad arguments");
+  if ((int)ctx->bface.size() <= iFa) ctx->bface.resize(iFa + 1);
+  BFace& f = ctx->bface[iFa];
+  cudaFree(f.d_IENb); cudaFree(f.d_gE);
+  f = BFace();
+  f.iM = iM; f.eNoNb = eNoNb; f.nElb = nElb; f.nGb = nGb;
+  std::vector<int> ien((size_t)eNoNb * nElb);
+  for (size_t k = 0; k < ien.size(); k++) {
+    SVB_REQUIRE(IENb[k] >= 0 && IENb[k] < ctx->nNo, "svb200_set_bface: face node id out of range");
+    ien[k] = ctx->h_map[IENb[k]];
+  }
+  for (int e = 0; e < nElb; e++) SVB_REQUIRE(gE[e] >= 0 && gE[e] < ctx->mesh[iM].nEl, "svb200_set_bface: parent element out of range");
+  TRY(upload(ctx, &f.d_IENb, ien.data(), ien.size()));
+  TRY(upload(ctx, &f.d_gE, gE, (size_t)nElb));
+  f.w.assign(w, w + nGb);
+  f.N.assign(N, N + (size_t)eNoNb * nGb);
+  f.Nx.assign(Nx, Nx + (size_t)2 * eNoNb * nGb);
+  f.set = true;
+  return SVB200_OK;
+}
+
+int svb200_assemble_neu(svb200_ctx* ctx, int32_t iFa, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int32_t nDmn,
+                        const double* hg)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(eq && dmn && hg, "svb200_assemble_neu: null parameters");
+  SVB_REQUIRE(iFa >= 0 && iFa < (int)ctx->bface.size() && ctx->bface[iFa].set, "svb200_assemble_neu: face not set");
+  SVB_REQUIRE(ctx->d_R && ctx->d_Val, "svb200_assemble_neu: call svb200_alloc first");
+  TRY(upload_nodal(ctx, 1, hg, &ctx->d_hg));
+  return run_assemble_neu(ctx, ctx->bface[iFa], eq, dmn, nDmn, ctx->d_hg);
 }
 
 static double** sol_ptrs(svb200_ctx* ctx, int which, int k)

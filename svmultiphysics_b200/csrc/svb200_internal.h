@@ -58,6 +58,15 @@ struct Face {
   double res = 0.0;
 };
 
+// Boundary face (faceType) for the surface integrals of assemble_bnd.cu.
+struct BFace {
+  int iM = -1, eNoNb = 0, nElb = 0, nGb = 0;
+  int* d_IENb = nullptr;     // (eNoNb, nElb) internal node ids
+  int* d_gE = nullptr;       // (nElb) parent element index in mesh iM
+  std::vector<double> w, N, Nx;
+  bool set = false;
+};
+
 struct Neighbor {
   int rank = 0, n = 0;
   int* d_ptr = nullptr;       // internal node ids shared with that rank (same order on both sides)
@@ -142,6 +151,8 @@ struct svb200_ctx {
 
   std::vector<svb::Mesh> mesh;
   std::vector<svb::Face> face;
+  std::vector<svb::BFace> bface;
+  double* d_hg = nullptr;          // (nNo) nodal traction of svb200_assemble_neu
 
   // Krylov workspace
   double* d_work = nullptr;
@@ -188,6 +199,9 @@ int launch_assemble_fluid(svb200_ctx* ctx, const Mesh& m, const FluidArgs& args)
 // assemble_struct.cu
 int run_assemble_struct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);
 int run_assemble_mesh(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);
+// assemble_bnd.cu
+int run_assemble_neu(svb200_ctx* ctx, const BFace& f, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn,
+                     const double* d_hg);
 // genalpha.cu
 int launch_predictor(svb200_ctx* ctx, int nEq, const svb200_eqtime* eqs, double dt, int dFlag);
 int launch_initiator(svb200_ctx* ctx, int nEq, const svb200_eqtime* eqs);

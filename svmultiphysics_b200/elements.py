@@ -48,6 +48,47 @@ def hex8_tables():
     return w, N, Nx
 
 
+def tri3_face_tables(qm: float = 2.0 / 3.0):
+    """TRI3 boundary face (of TET4): Code/Source/solver/nn_elem_gip.h:720-738 (points, qmTRI3 = 2/3), shape functions
+    N = (xi0, xi1, 1 - xi0 - xi1) as evaluate_face_basis_values_and_gradients leaves them (pinned by tests against the
+    compiled reference).  Returns w(3), N(3,3), Nx(2,3,3)."""
+    s, t = qm, -0.5 * qm + 0.5
+    xi = np.array([[t, s, t], [t, t, s]])
+    w = np.full(3, 1.0 / 6.0)
+    N = np.zeros((3, 3), order="F")
+    N[0], N[1], N[2] = xi[0], xi[1], 1.0 - xi[0] - xi[1]
+    Nx = np.zeros((2, 3, 3), order="F")
+    for g in range(3):
+        Nx[:, :, g] = np.array([[1.0, 0.0, -1.0], [0.0, 1.0, -1.0]])
+    return w, N, Nx
+
+
+def quad4_face_tables():
+    """QUD4 boundary face (of HEX8): 2x2 Gauss, bilinear shape functions in VTK order."""
+    s = 1.0 / np.sqrt(3.0)
+    gp = np.array([[-s, -s], [s, -s], [s, s], [-s, s]])
+    sign = np.array([[-1, -1], [1, -1], [1, 1], [-1, 1]], dtype=float)
+    w = np.ones(4)
+    N = np.zeros((4, 4), order="F")
+    Nx = np.zeros((2, 4, 4), order="F")
+    for g in range(4):
+        lx, ly = gp[g]
+        for a in range(4):
+            sx, sy = sign[a]
+            N[a, g] = (1.0 + sx * lx) * (1.0 + sy * ly) / 4.0
+            Nx[0, a, g] = sx * (1.0 + sy * ly) / 4.0
+            Nx[1, a, g] = (1.0 + sx * lx) * sy / 4.0
+    return w, N, Nx
+
+
+def face_tables(eNoNb: int):
+    if eNoNb == 3:
+        return tri3_face_tables()
+    if eNoNb == 4:
+        return quad4_face_tables()
+    raise ValueError(f"no face table for eNoNb={eNoNb}")
+
+
 def tables(eNoN: int):
     if eNoN == 4:
         return tet4_tables()

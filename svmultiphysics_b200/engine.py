@@ -42,6 +42,7 @@ ABI_SYMBOLS = [
     "svb200_bench_assemble", "svb200_bench_spmv", "svb200_measure_fp64_peak", "svb200_launch_count",
     "svb200_set_solution", "svb200_get_solution", "svb200_predictor", "svb200_initiator", "svb200_corrector",
     "svb200_set_node_flags", "svb200_set_dirichlet_rows", "svb200_advance_time_step",
+    "svb200_set_bface", "svb200_assemble_neu",
 ]
 
 _lib = None
@@ -241,6 +242,16 @@ class Engine:
     def assemble(self, iM, eq: abi.EqParams, dmns):
         arr = (abi.DmnParams * len(dmns))(*dmns)
         self._call("svb200_assemble", C.c_int32(iM), C.byref(eq), arr, C.c_int32(len(dmns)))
+
+    def set_bface(self, iFa, iM, IENb, gE, w, N, Nx):
+        IENb, gE = _i32(np.asfortranarray(IENb)), _i32(gE)
+        w, N, Nx = _f64(w), _f64(N), _f64(Nx)
+        self._call("svb200_set_bface", C.c_int32(iFa), C.c_int32(iM), C.c_int32(IENb.shape[0]), C.c_int32(IENb.shape[1]),
+                   _i(IENb), _i(gE), C.c_int32(len(w)), _d(w), _d(N), _d(Nx))
+
+    def assemble_neu(self, iFa, eq: abi.EqParams, dmns, hg):
+        arr = (abi.DmnParams * len(dmns))(*dmns)
+        self._call("svb200_assemble_neu", C.c_int32(iFa), C.byref(eq), arr, C.c_int32(len(dmns)), _d(_f64(hg)))
 
     def add_host_contrib(self, dof, rows=None, R_add=None, krows=None, kcols=None, K_add=None):
         rows, krows, kcols = _i32(rows), _i32(krows), _i32(kcols)

@@ -164,3 +164,27 @@ def cylinder_slab(n: int, nz: int, rank: int, nranks: int, R: float = 2.0, Lseg:
     if rank < nranks - 1:
         other[plane_hi] = rank + 1
     return m, other, plane_lo, plane_hi
+
+
+_TET_FACES = ((0, 1, 2), (0, 1, 3), (0, 2, 3), (1, 2, 3))
+_HEX_FACES = ((0, 1, 2, 3), (4, 5, 6, 7), (0, 1, 5, 4), (1, 2, 6, 5), (2, 3, 7, 6), (3, 0, 4, 7))   # VTK hexahedron
+
+
+def boundary_face_elements(mesh: Mesh, nodes):
+    """Face elements (faceType.IEN / gE of the reference) of the boundary patch spanned by `nodes`: every element face
+    whose nodes all lie in the set and that belongs to exactly one element.  Returns IENb(eNoNb, nElb), gE(nElb)."""
+    inset = np.zeros(mesh.nNo, bool)
+    inset[np.asarray(nodes)] = True
+    loc = _TET_FACES if mesh.eNoN == 4 else _HEX_FACES
+    cand_f, cand_e = [], []
+    for f in loc:
+        fn = mesh.IEN[list(f), :]                     # (eNoNb, nEl)
+        sel = np.nonzero(inset[fn].all(axis=0))[0]
+        cand_f.append(fn[:, sel]); cand_e.append(sel)
+    F = np.concatenate(cand_f, axis=1)
+    E = np.concatenate(cand_e)
+    key = np.sort(F, axis=0)
+    _, inv, cnt = np.unique(key, axis=1, return_inverse=True, return_counts=True)
+    keep = cnt[inv.ravel()] == 1
+    order = np.argsort(E[keep], kind="stable")
+    return np.asfortranarray(F[:, keep][:, order].astype(np.int32)), E[keep][order].astype(np.int32)

@@ -111,3 +111,51 @@ def test_oracle_error_paths(oracle_cls):
     c.alloc(4)
     X, o, _ = c.solve(4, abi.LS_GMRES, abi.ls_params(abi.LS_GMRES), np.ones(1, np.int32), np.zeros(1))
     assert o.RI.success == 1 and o.RI.itr == 0 and np.all(X == 0.0)
+
+
+def test_face_tables_and_face_extraction_match_reference():
+    """TRI3 / QUD4 boundary-face Gauss points and shape functions of svmultiphysics_b200.elements against the compiled
+    reference's nn::get_gip / nn::get_gnn (solver/nn.cpp:455,500), and the face-element extraction used by the tests."""
+    from oracle import refbind
+    if not refbind.have_ref():
+        pytest.skip("needs oracle/_ref/libsvref.so")
+    from svmultiphysics_b200 import elements, meshgen
+    m, *_ = common.fluid_case()
+    orc, _, _ = common.make_oracle(refbind.RefCase, m)
+    IENb, gE = meshgen.boundary_face_elements(m, m.faces["outlet_all"])
+    assert IENb.shape == (3, 2 * m.lattice[0] * m.lattice[1])
+    for a in range(3):      # every face node belongs to its parent element
+        assert (m.IEN[:, gE] == IENb[a]).any(axis=0).all()
+    i = orc.add_face(0, IENb, gE)
+    for got, want in zip(orc.face_tables(0, i), elements.face_tables(3)):
+        assert np.array_equal(got, want)
+    mh = common.STRUCT_CASES[0][1]()
+    o2 = refbind.RefCase(); o2.set_coords(mh.x); o2.add_mesh(mh.IEN); o2.build_graph(0)
+    Ib, gEb = meshgen.boundary_face_elements(mh, mh.faces["Z1"])
+    assert Ib.shape == (4, mh.lattice[0] * mh.lattice[1])
+    j = o2.add_face(0, Ib, gEb)
+    for got, want in zip(o2.face_tables(0, j), elements.face_tables(4)):
+        assert np.allclose(got, want, rtol=0, atol=1e-15)
+
+
+def test_genalpha_restatement_identities():
+    """Known answers of the generalised-alpha restatement (oracle/genalpha_oracle.py): with rho_inf = 1 the scheme is the
+    mid-point rule (am = af = 1/2, gam = 1/2 ... ), a constant-acceleration field is reproduced exactly by
+    predictor + corrector, and initiator(am = af = 1) returns the current state."""
+    from oracle import genalpha_oracle as go
+    from svmultiphysics_b200 import abi
+    rng = np.random.default_rng(0)
+    q = abi.eq_time(0, 2, abi.PHYS_STRUCT, 0.3)
+    dt = 0.01
+    Ao, Yo, Do = (rng.standard_normal((3, 5)) for _ in range(3))
+    An, Yn, Dn = (np.zeros((3, 5)) for _ in range(3))
+    go.predictor([q], dt, 1, Ao, Yo, Do, An, Yn, Dn)
+    assert np.array_equal(Yn, Yo) and np.allclose(An, Ao * (q.gam - 1) / q.gam)
+    # Newmark consistency: correct An back to Ao (R = An - Ao) => Yn = Yo + dt Ao, Dn = Do + dt Yo + dt^2/2 Ao
+    R = An - Ao
+    go.corrector(q, dt, R, An, Yn, Dn)
+    assert np.allclose(An, Ao) and np.allclose(Yn, Yo + dt * Ao) and np.allclose(Dn, Do + dt * Yo + 0.5 * dt * dt * Ao)
+    q1 = abi.EqTime(s=0, e=2, phys=0, af=1.0, am=1.0, gam=0.5, beta=0.25)
+    Ag, Yg, Dg = (np.zeros((3, 5)) for _ in range(3))
+    go.initiator([q1], Ao, Yo, Do, An, Yn, Dn, Ag, Yg, Dg)
+    assert np.array_equal(Ag, An) and np.array_equal(Yg, Yn) and np.array_equal(Dg, Dn)
