@@ -6,8 +6,9 @@
 // TET4 and HEX8 meshes, neo-Hookean / Mooney-Rivlin / Guccione / St.Venant-Kirchhoff with Quad/ST91/M94
 // penalties, as a struct equation (dof = 3) or as the solid part of an FSI equation (dof = 4).
 //
-// Mapping: ENON lanes per element (lane = element node a), 32/ENON elements per warp.  Per Gauss point every
-// lane computes its own grad N_a, Bm_a and DBm_a = Dm Bm_a and publishes them through shared memory; the
+// Mapping: ENON lanes per element, 32/ENON elements per warp, two phases.  Phase A: lane g evaluates Gauss point g
+// (nn::gnn, F, compute_pk2cc) ONCE per element and leaves xiX, w, F, S, Dm, ud in shared memory.  Phase B: lane a
+// = element node a; per Gauss point it computes its own grad N_a, Bm_a and DBm_a = Dm Bm_a and publishes them; the
 // element matrix is symmetric for a hyperelastic solid (K_ab = K_ba^T), so lane a only accumulates the blocks
 // (a, a+k mod ENON), k = 0..ENON/2, in registers (5 x 9 doubles for HEX8) and scatters each of them twice
 // (as is, and transposed) — 36 of 64 block products instead of 64.
@@ -48,22 +49,38 @@ __device__ __forceinline__ void add64(double* p, double v)
 
 constexpr int STRUCT_THREADS = 128;
 
+// Shared-memory layout per element (doubles): nodal inputs x,d,q (9 ENON) | Gauss-point data (GP_LD per point) |
+// per-node exchange of the current Gauss point: Nx (3) + DBm (18).
+constexpr int GP_LD = 64;   // xiX 9 | w 1 | F 9 | S 6 (11,22,33,12,23,31) | Dm 36 | ud 3
+
 template <int ENON, bool ATOMIC>
 __global__ void __launch_bounds__(STRUCT_THREADS)
 assemble_struct_kernel(const __grid_constant__ StructArgs P)
 {
   constexpr int EPW = 32 / ENON;            // elements per warp
   constexpr int KMAX = ENON / 2;            // lane a owns blocks (a, a+k), k = 0..KMAX (k = KMAX only for a < KMAX)
-  constexpr int PER_EL = ENON * (3 + 3 + 3 + 3 + 18);   // x, d, q, Nx, DBm
-  __shared__ double sm[(STRUCT_THREADS / 32) * EPW * PER_EL];
+  constexpr int PER_EL = ENON * (9 + GP_LD + 21);
+  constexpr int NTAB = ENON * ENON * 4 + ENON;   // Nxi[g][a][3], N[g][a], w[g]  (nG == ENON)
+  extern __shared__ double sm[];
+  double* tab = sm;                          // reference-element tables (lane-dependent Gauss point in phase A)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int a = lane % ENON, el = lane / ENON;
-  double* se = sm + (size_t)(warp * EPW + el) * PER_EL;
+  double* se = sm + NTAB + (size_t)(warp * EPW + el) * PER_EL;
   double(*sx)[3] = reinterpret_cast<double(*)[3]>(se);
   double(*sd)[3] = reinterpret_cast<double(*)[3]>(se + 3 * ENON);
   double(*sq)[3] = reinterpret_cast<double(*)[3]>(se + 6 * ENON);
-  double(*sNx)[3] = reinterpret_cast<double(*)[3]>(se + 9 * ENON);
-  double(*sDB)[18] = reinterpret_cast<double(*)[18]>(se + 12 * ENON);
+  double* sgp = se + 9 * ENON;
+  double(*sNx)[3] = reinterpret_cast<double(*)[3]>(se + 9 * ENON + ENON * GP_LD);
+  double(*sDB)[18] = reinterpret_cast<double(*)[18]>(se + 12 * ENON + ENON * GP_LD);
+  double(*tNxi)[ENON][3] = reinterpret_cast<double(*)[ENON][3]>(tab);
+  double(*tN)[ENON] = reinterpret_cast<double(*)[ENON]>(tab + ENON * ENON * 3);
+  double* tw = tab + ENON * ENON * 4;
+  for (int t = threadIdx.x; t < ENON * ENON; t += STRUCT_THREADS) {
+    const int g = t / ENON, b = t % ENON;
+    tNxi[g][b][0] = P.Nxi[g][b][0]; tNxi[g][b][1] = P.Nxi[g][b][1]; tNxi[g][b][2] = P.Nxi[g][b][2];
+    tN[g][b] = P.N[g][b];
+    if (b == 0) tw[g] = P.w[g];
+  }
 
   const long long idx = (long long)P.e0 + ((long long)blockIdx.x * (STRUCT_THREADS / 32) + warp) * EPW + el;
   bool active = idx < P.e1;
@@ -81,7 +98,6 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
   const StructDmn& dm = P.dmn[iD];
   const int DOF = P.dof;
   int node = 0;
-  double fN[2][3] = {{0, 0, 0}, {0, 0, 0}};
   if (active) {
     node = P.IEN[(size_t)e * ENON + a];
     const size_t n = (size_t)node;
@@ -92,13 +108,70 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
       sq[a][i] = dm.rho * (__ldg(P.Ag + (size_t)P.tDof * n + P.s + i) - __ldg(P.Bf + 3 * n + i)) +
                  dm.dmp * __ldg(P.Yg + (size_t)P.tDof * n + P.s + i);
     }
+  }
+  __syncthreads();
+
+  // ---- phase A: lane a of the element evaluates Gauss point g = a (nG == ENON): nn::gnn, F, compute_pk2cc -----
+  if (active) {
+    const int g = a;
+    double fN[2][3] = {{0, 0, 0}, {0, 0, 0}};
     if (P.fN != nullptr)
       for (int k = 0; k < P.nFn && k < 2; k++)
 #pragma unroll
         for (int i = 0; i < 3; i++) fN[k][i] = __ldg(P.fN + (size_t)3 * P.nFn * e + 3 * k + i);
+    double xXi[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+    for (int b = 0; b < ENON; b++)
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) xXi[i][k] += sx[b][i] * tNxi[g][b][k];
+    const double Jac = xXi[0][0] * xXi[1][1] * xXi[2][2] + xXi[0][1] * xXi[1][2] * xXi[2][0] + xXi[0][2] * xXi[1][0] * xXi[2][1] -
+                       xXi[0][0] * xXi[1][2] * xXi[2][1] - xXi[0][1] * xXi[1][0] * xXi[2][2] - xXi[0][2] * xXi[1][1] * xXi[2][0];
+    const double iJ = 1.0 / Jac;
+    double xiX[3][3];
+    xiX[0][0] = (xXi[1][1] * xXi[2][2] - xXi[1][2] * xXi[2][1]) * iJ;
+    xiX[0][1] = (xXi[2][1] * xXi[0][2] - xXi[2][2] * xXi[0][1]) * iJ;
+    xiX[0][2] = (xXi[0][1] * xXi[1][2] - xXi[0][2] * xXi[1][1]) * iJ;
+    xiX[1][0] = (xXi[1][2] * xXi[2][0] - xXi[1][0] * xXi[2][2]) * iJ;
+    xiX[1][1] = (xXi[2][2] * xXi[0][0] - xXi[2][0] * xXi[0][2]) * iJ;
+    xiX[1][2] = (xXi[0][2] * xXi[1][0] - xXi[0][0] * xXi[1][2]) * iJ;
+    xiX[2][0] = (xXi[1][0] * xXi[2][1] - xXi[1][1] * xXi[2][0]) * iJ;
+    xiX[2][1] = (xXi[2][0] * xXi[0][1] - xXi[2][1] * xXi[0][0]) * iJ;
+    xiX[2][2] = (xXi[0][0] * xXi[1][1] - xXi[0][1] * xXi[1][0]) * iJ;
+    double F[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    double ud[3] = {-dm.rho * dm.f[0], -dm.rho * dm.f[1], -dm.rho * dm.f[2]};
+#pragma unroll
+    for (int b = 0; b < ENON; b++) {
+      const double Nb = tN[g][b];
+      double Nxb[3];
+#pragma unroll
+      for (int j = 0; j < 3; j++) Nxb[j] = tNxi[g][b][0] * xiX[0][j] + tNxi[g][b][1] * xiX[1][j] + tNxi[g][b][2] * xiX[2][j];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        ud[i] += Nb * sq[b][i];
+#pragma unroll
+        for (int j = 0; j < 3; j++) F[i][j] += Nxb[j] * sd[b][i];
+      }
+    }
+    double S[3][3], Dm[6][6];
+    pk2cc_voigt(dm, F, fN, S, Dm);
+    double* q = sgp + g * GP_LD;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) { q[3 * i + j] = xiX[i][j]; q[10 + 3 * i + j] = F[i][j]; }
+    q[9] = tw[g] * Jac;
+    q[19] = S[0][0]; q[20] = S[1][1]; q[21] = S[2][2]; q[22] = S[0][1]; q[23] = S[1][2]; q[24] = S[2][0];
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+      for (int c = 0; c < 6; c++) q[25 + 6 * r + c] = Dm[r][c];
+    q[61] = ud[0]; q[62] = ud[1]; q[63] = ud[2];
   }
   __syncwarp();
 
+  // ---- phase B: lane a = element node a; per Gauss point Bm_a, DBm_a (published), residual row, owned blocks ----
   const double afu = P.af * P.beta * P.dt * P.dt;
   const double amd = P.am * dm.rho + P.af * P.gam * P.dt * dm.dmp;
   double acc[KMAX + 1][3][3];
@@ -111,73 +184,50 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
       for (int j = 0; j < 3; j++) acc[k][i][j] = 0.0;
 
 #pragma unroll 1
-  for (int g = 0; g < P.nG; g++) {
-    double F[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, S[3][3], Bm[6][3], SNx[3], Nxa[3];
+  for (int g = 0; g < ENON; g++) {
+    double Bm[6][3], SNx[3], Nxa[3];
     double w = 0.0;
     if (active) {
-      // nn::gnn at this Gauss point (all lanes of the element repeat the 3x3 Jacobian)
-      double xXi[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-#pragma unroll
-      for (int b = 0; b < ENON; b++)
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-          for (int k = 0; k < 3; k++) xXi[i][k] += sx[b][i] * P.Nxi[g][b][k];
-      const double Jac = xXi[0][0] * xXi[1][1] * xXi[2][2] + xXi[0][1] * xXi[1][2] * xXi[2][0] + xXi[0][2] * xXi[1][0] * xXi[2][1] -
-                         xXi[0][0] * xXi[1][2] * xXi[2][1] - xXi[0][1] * xXi[1][0] * xXi[2][2] - xXi[0][2] * xXi[1][1] * xXi[2][0];
-      const double iJ = 1.0 / Jac;
-      double xiX[3][3];
-      xiX[0][0] = (xXi[1][1] * xXi[2][2] - xXi[1][2] * xXi[2][1]) * iJ;
-      xiX[0][1] = (xXi[2][1] * xXi[0][2] - xXi[2][2] * xXi[0][1]) * iJ;
-      xiX[0][2] = (xXi[0][1] * xXi[1][2] - xXi[0][2] * xXi[1][1]) * iJ;
-      xiX[1][0] = (xXi[1][2] * xXi[2][0] - xXi[1][0] * xXi[2][2]) * iJ;
-      xiX[1][1] = (xXi[2][2] * xXi[0][0] - xXi[2][0] * xXi[0][2]) * iJ;
-      xiX[1][2] = (xXi[0][2] * xXi[1][0] - xXi[0][0] * xXi[1][2]) * iJ;
-      xiX[2][0] = (xXi[1][0] * xXi[2][1] - xXi[1][1] * xXi[2][0]) * iJ;
-      xiX[2][1] = (xXi[2][0] * xXi[0][1] - xXi[2][1] * xXi[0][0]) * iJ;
-      xiX[2][2] = (xXi[0][0] * xXi[1][1] - xXi[0][1] * xXi[1][0]) * iJ;
-      w = P.w[g] * Jac;
+      const double* q = sgp + g * GP_LD;
+      w = q[9];
+      double F[3][3];
 #pragma unroll
       for (int i = 0; i < 3; i++) {
-        Nxa[i] = P.Nxi[g][a][0] * xiX[0][i] + P.Nxi[g][a][1] * xiX[1][i] + P.Nxi[g][a][2] * xiX[2][i];
+        Nxa[i] = tNxi[g][a][0] * q[i] + tNxi[g][a][1] * q[3 + i] + tNxi[g][a][2] * q[6 + i];
         sNx[a][i] = Nxa[i];
+#pragma unroll
+        for (int j = 0; j < 3; j++) F[i][j] = q[10 + 3 * i + j];
       }
-    }
-    __syncwarp();
-    if (active) {
-      double ud[3] = {-dm.rho * dm.f[0], -dm.rho * dm.f[1], -dm.rho * dm.f[2]};
+      make_Bm(Nxa, F, Bm);
+      // DBm_a = Dm Bm_a, Dm read row by row from shared memory
 #pragma unroll
-      for (int b = 0; b < ENON; b++) {
-        const double Nb = P.N[g][b];
+      for (int r = 0; r < 6; r++) {
+        double d[6];
 #pragma unroll
-        for (int i = 0; i < 3; i++) {
-          ud[i] += Nb * sq[b][i];
+        for (int c = 0; c < 6; c++) d[c] = q[25 + 6 * r + c];
 #pragma unroll
-          for (int j = 0; j < 3; j++) F[i][j] += sNx[b][j] * sd[b][i];
+        for (int j = 0; j < 3; j++) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int c = 0; c < 6; c++) sacc += d[c] * Bm[c][j];
+          sDB[a][3 * r + j] = sacc;
         }
       }
-      double Dm[6][6];
-      pk2cc_voigt(dm, F, fN, S, Dm);
-      make_Bm(Nxa, F, Bm);
-      double DBm[6][3];
-      make_DBm(Dm, Bm, DBm);
-#pragma unroll
-      for (int r = 0; r < 6; r++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) sDB[a][3 * r + j] = DBm[r][j];
-      const double Na = P.N[g][a];
-#pragma unroll
-      for (int i = 0; i < 3; i++) SNx[i] = Nxa[0] * S[0][i] + Nxa[1] * S[1][i] + Nxa[2] * S[2][i];
+      const double S00 = q[19], S11 = q[20], S22 = q[21], S01 = q[22], S12 = q[23], S20 = q[24];
+      SNx[0] = Nxa[0] * S00 + Nxa[1] * S01 + Nxa[2] * S20;
+      SNx[1] = Nxa[0] * S01 + Nxa[1] * S11 + Nxa[2] * S12;
+      SNx[2] = Nxa[0] * S20 + Nxa[1] * S12 + Nxa[2] * S22;
+      const double Na = tN[g][a];
 #pragma unroll
       for (int i = 0; i < 3; i++) {
         // P = F S ; lR(i,a) += w (N_a ud_i + sum_j Nx(j,a) P(i,j))
         const double PNx = F[i][0] * SNx[0] + F[i][1] * SNx[1] + F[i][2] * SNx[2];
-        lR[i] += w * (Na * ud[i] + PNx);
+        lR[i] += w * (Na * q[61 + i] + PNx);
       }
     }
     __syncwarp();
     if (active) {
-      const double Na = P.N[g][a];
+      const double Na = tN[g][a];
 #pragma unroll
       for (int k = 0; k <= KMAX; k++) {
         if (k == KMAX && a >= KMAX) continue;
@@ -189,7 +239,7 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
           for (int j = 0; j < 3; j++) DB[r][j] = sDB[b][3 * r + j];
 #pragma unroll
         for (int i = 0; i < 3; i++) Nxb[i] = sNx[b][i];
-        struct_block(acc[k], w, amd * Na * P.N[g][b], afu, SNx, Nxb, Bm, DB);
+        struct_block(acc[k], w, amd * Na * tN[g][b], afu, SNx, Nxb, Bm, DB);
       }
     }
     __syncwarp();
@@ -378,8 +428,16 @@ static int launch_one(svb200_ctx* ctx, const StructArgs& A)
   const long long n = (long long)A.e1 - A.e0;
   if (n <= 0) return SVB200_OK;
   const unsigned blocks = (unsigned)((n + EPB - 1) / EPB);
-  if (A.atomic) assemble_struct_kernel<ENON, true><<<blocks, STRUCT_THREADS, 0, ctx->stream>>>(A);
-  else assemble_struct_kernel<ENON, false><<<blocks, STRUCT_THREADS, 0, ctx->stream>>>(A);
+  constexpr size_t smem = sizeof(double) * ((size_t)ENON * ENON * 4 + ENON + (size_t)EPB * ENON * (9 + GP_LD + 21));
+  static bool configured = false;
+  if (!configured) {
+    SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  if (A.nG != ENON) { set_error("svb200: the solid kernel expects nG == eNoN (TET4: 4, HEX8: 8 Gauss points)"); return SVB200_ERR_UNSUPPORTED; }
+  if (A.atomic) assemble_struct_kernel<ENON, true><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
+  else assemble_struct_kernel<ENON, false><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
   ctx->launches++;
   SVB_CUDA(cudaGetLastError());
   return SVB200_OK;
