@@ -197,7 +197,9 @@ SVB200_API int svb200_set_mesh(svb200_ctx* ctx, int32_t iM, int32_t eNoN, int32_
 /* Reference coordinates com_mod.x(3,nNo). */
 SVB200_API int svb200_set_coords(svb200_ctx* ctx, const double* x);
 
-/* Linear-solver faces (fsils_bc_create): glob are INPUT-order node ids, val(face_dof,nNo). */
+/* Linear-solver faces (fsils_bc_create): glob are INPUT-order node ids, val(face_dof,nNo).
+ * sharedFlag: 0 = face lives on this partition only; 1 = shared between partitions, the library sums val over the
+ * shared nodes (linear_solver/bc.cpp:70-102); 2 = shared and val is lhs.face[].val, already summed by the host. */
 SVB200_API int svb200_set_num_faces(svb200_ctx* ctx, int32_t nFaces);
 SVB200_API int svb200_set_face(svb200_ctx* ctx, int32_t faIn, int32_t bGrp, int32_t face_dof, int32_t nNo,
                     const int32_t* glob, const double* val, int32_t sharedFlag);

@@ -59,6 +59,11 @@ struct RefCase {
   bool graph_built = false;
   double last_assemble_s = 0.0;
   double last_solve_s = 0.0;
+  // Optional plug-in backend (svref_set_backend): a LinearAlgebra implementation other than FsilsLinearAlgebra plus
+  // the early-out hook a maintainer adds at the top of eq_assem::global_eq_assem (solver/eq_assem.cpp:397).
+  LinearAlgebra* backend = nullptr;
+  int (*assem_hook)(void*, void*, const void*, const void*) = nullptr;
+  void (*backend_download)(void*, int, double*) = nullptr;
 };
 
 consts::EquationType to_phys(int p)
@@ -133,7 +138,7 @@ void fill_eq(RefCase& c, const svb200_eqparams& e, const svb200_dmnparams* dmn, 
   eq.dmn.resize(nDmn);
   for (int i = 0; i < nDmn; i++) fill_domain(eq.dmn[i], dmn[i]);
   if (!c.la) c.la = new FsilsLinearAlgebra();
-  eq.linear_algebra = c.la;
+  eq.linear_algebra = c.backend ? c.backend : c.la;
   eq.linear_algebra_preconditioner = consts::PreconditionerType::PREC_FSILS;
 }
 
@@ -159,6 +164,17 @@ void* svref_create(void)
 }
 
 void svref_destroy(void* h) { delete static_cast<RefCase*>(h); }
+
+/// Run the same harness through another LinearAlgebra plug-in (the product's C++ host layer B200LinearAlgebra):
+/// `la` is a LinearAlgebra*, `hook` the early-out of global_eq_assem, `download` fetches R / Val from the backend.
+int svref_set_backend(void* h, void* la, void* hook, void* download)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  c.backend = static_cast<LinearAlgebra*>(la);
+  c.assem_hook = reinterpret_cast<int (*)(void*, void*, const void*, const void*)>(hook);
+  c.backend_download = reinterpret_cast<void (*)(void*, int, double*)>(download);
+  return 0;
+}
 
 /// com_mod.x(3,nNo); also sizes Bf to zero.
 int svref_set_coords(void* h, int nNo, const double* x)
@@ -287,6 +303,14 @@ int svref_alloc(void* h, int dof)
     auto& cm = c.com_mod;
     cm.dof = dof;
     cm.R.resize(dof, cm.tnNo);
+    if (c.backend) {
+      // ls_alloc (solver/ls.cpp:24-40) through the plug-in interface
+      if (cm.eq.size() == 0) { cm.eq = std::vector<eqType>(1); cm.nEq = 1; }
+      cm.cEq = 0;
+      cm.eq[0].linear_algebra = c.backend;
+      c.backend->alloc(cm, cm.eq[0]);
+      return;
+    }
     cm.Val.resize(dof*dof, cm.lhs.nnz);
     cm.R = 0.0;
     cm.Val = 0.0;
@@ -335,6 +359,10 @@ int svref_assemble(void* h, int iM, const svb200_eqparams* e, const svb200_dmnpa
     auto& cm = c.com_mod;
     auto& m = cm.msh.at(iM);
     auto t0 = std::chrono::steady_clock::now();
+    if (c.assem_hook && c.assem_hook(&cm, &c.cep_mod, &m, &c.sol)) {
+      c.last_assemble_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      return;
+    }
     switch (e->phys) {
       case SVB200_PHYS_FLUID: fluid::construct_fluid(cm, m, c.sol); break;
       case SVB200_PHYS_STRUCT: struct_ns::construct_dsolid(cm, c.cep_mod, m, c.sol); break;
@@ -351,6 +379,7 @@ int svref_get(void* h, int what, double* dst)
   auto& c = *static_cast<RefCase*>(h);
   return guarded([&] {
     auto& cm = c.com_mod;
+    if (c.backend && c.backend_download) { c.backend_download(c.backend, what, dst); return; }
     if (what == SVB200_ARRAY_R) std::memcpy(dst, cm.R.data(), sizeof(double)*cm.R.size());
     else if (what == SVB200_ARRAY_VAL) std::memcpy(dst, cm.Val.data(), sizeof(double)*cm.Val.size());
     else throw std::runtime_error("[ref_harness] bad array id");
@@ -400,7 +429,17 @@ int svref_solve(void* h, int dof, int ls_type, int prec, const svb200_lsparams* 
     for (int i = 0; i < nFaces; i++) { incLv(i) = incL ? incL[i] : 1; resv(i) = res ? res[i] : 0.0; }
     (void)prec;
     auto t0 = std::chrono::steady_clock::now();
-    fsils_solve(cm.lhs, fls, dof, cm.R, cm.Val, consts::PreconditionerType::PREC_FSILS, incLv, resv);
+    if (c.backend) {
+      // ls_solve (solver/ls.cpp:42-54): lEq.linear_algebra->solve(com_mod, lEq, incL, res)
+      auto& eq = cm.eq.at(0);
+      eq.FSILS = fls;
+      eq.linear_algebra = c.backend;
+      cm.dof = dof;
+      eq.linear_algebra->solve(cm, eq, incLv, resv);
+      fls = eq.FSILS;
+    } else {
+      fsils_solve(cm.lhs, fls, dof, cm.R, cm.Val, consts::PreconditionerType::PREC_FSILS, incLv, resv);
+    }
     c.last_solve_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (R_out) std::memcpy(R_out, cm.R.data(), sizeof(double)*cm.R.size());
     if (out) {

@@ -18,6 +18,7 @@ from svmultiphysics_b200 import abi
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(_HERE, "_ref", "libsvref.so")
 ORACLE_SO = os.path.join(_HERE, "libsvoracle.so")
+HOST_SO = os.path.join(os.path.dirname(_HERE), "svmultiphysics_b200", "lib", "libsvb200_host.so")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -41,6 +42,10 @@ def _i32(a):
 
 def have_ref() -> bool:
     return os.path.exists(REF_SO)
+
+
+def have_host() -> bool:
+    return os.path.exists(REF_SO) and os.path.exists(HOST_SO)
 
 
 class _FlatCase:
@@ -209,6 +214,32 @@ class RefCase(_FlatCase):
     prefix = "svref_"
     so_path = REF_SO
     _lib = None
+    _host = None
+
+    def use_b200_backend(self, device=0, scatter=0):
+        """Swap FsilsLinearAlgebra for the product's C++ host layer B200LinearAlgebra (svmultiphysics_b200/host/):
+        the reference's own objects (ComMod, eqType, mshType, FSILS_lhsType) then drive libsvb200.so through the
+        LinearAlgebra plug-in interface and the global_eq_assem early-out, exactly as in INTEGRATION.md."""
+        cls = type(self)
+        if cls._host is None:
+            C.CDLL(REF_SO, mode=C.RTLD_GLOBAL)          # the host application's symbols (ComMod, Array, LinearAlgebra ...)
+            host = C.CDLL(HOST_SO)
+            host.b200host_new.restype = C.c_void_p
+            host.b200host_launch_count.restype = C.c_longlong
+            cls._host = host
+        host = cls._host
+        self.backend = host.b200host_new(C.c_int(device), C.c_int(scatter))
+        self._call("set_backend", C.c_void_p(self.backend), C.cast(host.b200host_global_eq_assem, C.c_void_p),
+                   C.cast(host.b200host_download, C.c_void_p))
+
+    def backend_launch_count(self):
+        return int(type(self)._host.b200host_launch_count(C.c_void_p(self.backend)))
+
+    def close(self):
+        super().close()
+        if getattr(self, "backend", None):
+            type(self)._host.b200host_delete(C.c_void_p(self.backend))
+            self.backend = None
 
 
 class OracleCase(_FlatCase):

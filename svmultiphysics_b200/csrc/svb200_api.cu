@@ -358,7 +358,7 @@ int svb200_set_face(svb200_ctx* ctx, int32_t faIn, int32_t bGrp, int32_t face_do
   SVB_REQUIRE(face_dof >= 1 && face_dof <= 4 && nNo >= 0 && (glob || nNo == 0), "svb200_set_face: bad arguments");
   Face& f = ctx->face[faIn];
   free_face(f);
-  f.bGrp = bGrp; f.dof = face_dof; f.nNo = nNo; f.shared = sharedFlag;
+  f.bGrp = bGrp; f.dof = face_dof; f.nNo = nNo; f.shared = sharedFlag != 0;
   std::vector<int> g(nNo);
   for (int a = 0; a < nNo; a++) {
     SVB_REQUIRE(glob[a] >= 0 && glob[a] < ctx->nNo, "svb200_set_face: node id out of range");
@@ -372,7 +372,8 @@ int svb200_set_face(svb200_ctx* ctx, int32_t faIn, int32_t bGrp, int32_t face_do
     SVB_CUDA(cudaMalloc(&f.d_valM, sizeof(double) * v.size()));
     SVB_CUDA(cudaMemsetAsync(f.d_valM, 0, sizeof(double) * v.size(), ctx->stream));
   }
-  if (sharedFlag && ctx->nranks > 1 && val) {
+  if (sharedFlag == 1 && ctx->nranks > 1 && val) {
+    // sharedFlag 2 = lhs.face[].val as the host's fsils_bc_create left it (already summed).
     // fsils_bc_create sums the face values of shared nodes across partitions (bc.cpp:70-102).
     const size_t n = (size_t)face_dof * ctx->nNo;
     TRY(ensure_stage(ctx, sizeof(double) * n));

@@ -1,0 +1,338 @@
+// B200LinearAlgebra.cpp — see B200LinearAlgebra.h.  Host C++ over the C ABI of libsvb200.so; the only place where
+// the reference's ComMod / eqType / mshType / FSILS_lhsType objects are translated into plain arrays.
+#include "B200LinearAlgebra.h"
+
+#include "consts.h"
+#include "fils_struct.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+namespace {
+
+int to_phys(consts::EquationType p)
+{
+  using consts::EquationType;
+  switch (p) {
+    case EquationType::phys_fluid: return SVB200_PHYS_FLUID;
+    case EquationType::phys_struct: return SVB200_PHYS_STRUCT;
+    case EquationType::phys_FSI: return SVB200_PHYS_FSI;
+    case EquationType::phys_mesh: return SVB200_PHYS_MESH;
+    default: return -1;
+  }
+}
+
+double prop_or(const dmnType& d, consts::PhysicalProperyType k, double dflt = 0.0)
+{
+  auto it = d.prop.find(k);
+  return it == d.prop.end() ? dflt : it->second;
+}
+
+}  // namespace
+
+namespace b200 {
+
+svb200_eqparams eq_params(const ComMod& com_mod, const eqType& eq, const mshType& lM, int scatter)
+{
+  svb200_eqparams e{};
+  e.dt = com_mod.dt;
+  e.af = eq.af; e.am = eq.am; e.gam = eq.gam; e.beta = eq.beta;
+  e.phys = to_phys(eq.phys);
+  if (e.phys < 0) throw std::runtime_error("[B200LinearAlgebra] this equation's physics is not on the device path");
+  e.dof = com_mod.dof;
+  e.tDof = com_mod.tDof;
+  e.s = eq.s;
+  e.mvMsh = com_mod.mvMsh ? 1 : 0;
+  e.vmsStab = (lM.nFs == 1) ? 1 : 0;        // Code/Source/solver/fluid.cpp:496-500
+  e.scatter = scatter;
+  return e;
+}
+
+std::vector<svb200_dmnparams> domain_params(const eqType& eq)
+{
+  using namespace consts;
+  std::vector<svb200_dmnparams> out(eq.nDmn);
+  for (int i = 0; i < eq.nDmn; i++) {
+    const dmnType& d = eq.dmn[i];
+    svb200_dmnparams p{};
+    p.Id = d.Id;
+    p.phys = to_phys(d.phys);
+    if (p.phys < 0) throw std::runtime_error("[B200LinearAlgebra] domain physics is not on the device path");
+    const bool solid = (d.phys == EquationType::phys_struct);
+    p.rho = prop_or(d, solid ? PhysicalProperyType::solid_density : PhysicalProperyType::fluid_density);
+    p.f[0] = prop_or(d, PhysicalProperyType::f_x);
+    p.f[1] = prop_or(d, PhysicalProperyType::f_y);
+    p.f[2] = prop_or(d, PhysicalProperyType::f_z);
+    p.K_darcy = prop_or(d, PhysicalProperyType::inverse_darcy_permeability);
+    p.backflow_stab = prop_or(d, PhysicalProperyType::backflow_stab);
+    p.dmp = prop_or(d, PhysicalProperyType::damping);
+    p.E = prop_or(d, PhysicalProperyType::elasticity_modulus);
+    p.nu = prop_or(d, PhysicalProperyType::poisson_ratio);
+    switch (d.fluid_visc.viscType) {
+      case FluidViscosityModelType::viscType_CY: p.viscType = SVB200_VISC_CY; break;
+      case FluidViscosityModelType::viscType_Cass: p.viscType = SVB200_VISC_CASSON; break;
+      default: p.viscType = SVB200_VISC_CONST; break;
+    }
+    p.mu_i = d.fluid_visc.mu_i; p.mu_o = d.fluid_visc.mu_o; p.lam = d.fluid_visc.lam;
+    p.a = d.fluid_visc.a; p.n = d.fluid_visc.n;
+    if (solid) {
+      switch (d.stM.isoType) {
+        case ConstitutiveModelType::stIso_nHook: p.isoType = SVB200_ISO_NHK; break;
+        case ConstitutiveModelType::stIso_MR: p.isoType = SVB200_ISO_MR; break;
+        case ConstitutiveModelType::stIso_Gucci: p.isoType = SVB200_ISO_GUCCIONE; break;
+        case ConstitutiveModelType::stIso_StVK: p.isoType = SVB200_ISO_STVK; break;
+        default: throw std::runtime_error("[B200LinearAlgebra] isochoric constitutive model not implemented on the device");
+      }
+      switch (d.stM.volType) {
+        case ConstitutiveModelType::stVol_Quad: p.volType = SVB200_VOL_QUAD; break;
+        case ConstitutiveModelType::stVol_ST91: p.volType = SVB200_VOL_ST91; break;
+        case ConstitutiveModelType::stVol_M94: p.volType = SVB200_VOL_M94; break;
+        default: p.volType = SVB200_VOL_NONE; break;
+      }
+      p.Kpen = d.stM.Kpen; p.C10 = d.stM.C10; p.C01 = d.stM.C01;
+      p.bff = d.stM.bff; p.bss = d.stM.bss; p.bfs = d.stM.bfs;
+      if (d.solid_visc.viscType != SolidViscosityModelType::viscType_NA) p.solid_visc_mu = d.solid_visc.mu;
+    }
+    out[i] = p;
+  }
+  return out;
+}
+
+svb200_lsparams ls_params(const fsi_linear_solver::FSILS_lsType& ls)
+{
+  auto cp = [](const fsi_linear_solver::FSILS_subLsType& s) {
+    svb200_sublsparams d{};
+    d.mItr = s.mItr; d.sD = s.sD; d.relTol = s.relTol; d.absTol = s.absTol;
+    return d;
+  };
+  svb200_lsparams p{};
+  p.RI = cp(ls.RI); p.GM = cp(ls.GM); p.CG = cp(ls.CG);
+  return p;
+}
+
+bool global_eq_assem(ComMod& com_mod, CepMod& cep_mod, const mshType& lM, const SolutionStates& solutions)
+{
+  (void)cep_mod;
+  auto& eq = com_mod.eq[com_mod.cEq];
+  auto* la = dynamic_cast<B200LinearAlgebra*>(eq.linear_algebra);
+  if (!la) return false;
+  if (to_phys(eq.phys) < 0) return false;          // heat, stokes, ... stay on the host loop (and its assemble())
+  la->assemble_mesh(com_mod, lM, solutions);
+  return true;
+}
+
+}  // namespace b200
+
+// ---------------------------------------------------------------------------------------------------------
+
+B200LinearAlgebra::B200LinearAlgebra()
+{
+  // consts::LinearAlgebraType has no `b200` member in the unmodified reference (INTEGRATION.md adds it).
+  interface_type = consts::LinearAlgebraType::none;
+  assembly_type = consts::LinearAlgebraType::none;
+  preconditioner_type = consts::PreconditionerType::PREC_FSILS;
+}
+
+B200LinearAlgebra::~B200LinearAlgebra() { finalize(); }
+
+void B200LinearAlgebra::check(int rc) const
+{
+  // the reference signals every failure on this path with std::runtime_error (e.g. linear_solver/gmres.cpp:500-502)
+  if (rc != SVB200_OK) throw std::runtime_error(std::string("[B200LinearAlgebra] ") + svb200_last_error());
+}
+
+void B200LinearAlgebra::check_options(const consts::PreconditionerType prec_cond_type, const consts::LinearAlgebraType atype)
+{
+  if (prec_cond_type != consts::PreconditionerType::PREC_FSILS && prec_cond_type != consts::PreconditionerType::PREC_NONE) {
+    throw std::runtime_error("[svMultiPhysics] ERROR: b200 linear algebra can't use '" +
+        consts::preconditioner_type_to_name.at(prec_cond_type) + "' for a preconditioner.");
+  }
+  if (atype != consts::LinearAlgebraType::none) {
+    throw std::runtime_error("[svMultiPhysics] ERROR: b200 linear algebra assembles on the device; no other assembly type can be set.");
+  }
+}
+
+void B200LinearAlgebra::set_assembly(consts::LinearAlgebraType atype)
+{
+  if (atype == consts::LinearAlgebraType::none) return;
+  throw std::runtime_error("[B200LinearAlgebra] ERROR: Can't set b200 linear algebra to use '" +
+      LinearAlgebra::type_to_name.at(atype) + "' for assembly.");
+}
+
+void B200LinearAlgebra::set_preconditioner(consts::PreconditionerType prec_type)
+{
+  if (prec_type != consts::PreconditionerType::PREC_FSILS) {
+    throw std::runtime_error("[B200LinearAlgebra] ERROR: b200 linear algebra can't use '" +
+        consts::preconditioner_type_to_name.at(prec_type) + "' for a preconditioner.");
+  }
+  preconditioner_type = prec_type;
+}
+
+void B200LinearAlgebra::initialize(ComMod& com_mod, eqType& lEq)
+{
+  (void)lEq;
+  if (ctx) return;
+  // add_eq_linear_algebra (Code/Source/solver/main.cpp:44-53) runs before lhsa / fsils_lhs_create
+  // (initialize.cpp:620,641), so only the device context is created here; the structure goes up on the first alloc().
+  check(svb200_create(&ctx, device));
+  (void)com_mod;
+}
+
+void B200LinearAlgebra::finalize()
+{
+  if (ctx) { svb200_destroy(ctx); ctx = nullptr; }
+  structure_uploaded = false;
+}
+
+void B200LinearAlgebra::upload_structure(ComMod& com_mod)
+{
+  auto& lhs = com_mod.lhs;
+  const int tnNo = com_mod.tnNo;
+  if (com_mod.cm.np() > 1) {
+    // one MPI rank = one partition = one B200: fsils_commu_create's communicator becomes an NCCL communicator
+    char id[128] = {0};
+    if (com_mod.cm.idcm() == 0) check(svb200_comm_unique_id(id));
+    MPI_Bcast(id, 128, MPI_CHAR, 0, com_mod.cm.com());
+    check(svb200_comm_init(ctx, com_mod.cm.np(), com_mod.cm.idcm(), id));
+  }
+  std::vector<int> nrank, ncount, nptr;
+  for (int i = 0; i < lhs.nReq; i++) {
+    auto& c = lhs.cS[i];
+    nrank.push_back(c.iP);
+    ncount.push_back(c.n);
+    for (int k = 0; k < c.n; k++) nptr.push_back(c.ptr(k));
+  }
+  if ((int)com_mod.rowPtr.size() != tnNo + 1) throw std::runtime_error("[B200LinearAlgebra] com_mod.rowPtr is not built (lhsa)");
+  check(svb200_set_graph(ctx, tnNo, lhs.nnz, com_mod.rowPtr.data(), com_mod.colPtr.data(), lhs.mynNo, lhs.map.data(),
+                         lhs.nReq, nrank.data(), ncount.data(), nptr.data()));
+  inv_map.assign(tnNo, -1);
+  for (int a = 0; a < tnNo; a++) inv_map[lhs.map(a)] = a;
+
+  for (int iM = 0; iM < com_mod.nMsh; iM++) {
+    auto& m = com_mod.msh[iM];
+    check(svb200_set_mesh(ctx, iM, m.eNoN, m.nEl, m.IEN.data(), m.eId.size() ? m.eId.data() : nullptr,
+                          m.nFn, (m.nFn > 0 && m.fN.size()) ? m.fN.data() : nullptr, m.nG, m.w.data(), m.N.data(), m.Nx.data()));
+  }
+  check(svb200_set_coords(ctx, com_mod.x.data()));
+  structure_uploaded = true;
+}
+
+void B200LinearAlgebra::upload_faces(ComMod& com_mod)
+{
+  auto& lhs = com_mod.lhs;
+  check(svb200_set_num_faces(ctx, lhs.nFaces));
+  std::vector<int> glob;
+  for (int f = 0; f < lhs.nFaces; f++) {
+    auto& fa = lhs.face[f];
+    glob.resize(fa.nNo);
+    for (int a = 0; a < fa.nNo; a++) glob[a] = inv_map[fa.glob(a)];     // FSILS order -> host order (bc.cpp:55-58)
+    const int grp = (fa.bGrp == fsi_linear_solver::BcType::BC_TYPE_Dir) ? SVB200_BC_DIR : SVB200_BC_NEU;
+    const int dofF = fa.dof > 0 ? fa.dof : 1;
+    check(svb200_set_face(ctx, f, grp, dofF, fa.nNo, glob.data(), fa.nNo ? fa.val.data() : nullptr, fa.sharedFlag ? 2 : 0));
+  }
+}
+
+/// ls_alloc (Code/Source/solver/ls.cpp:24-40): R and Val are zeroed ON THE DEVICE; com_mod.Val is never allocated on the
+/// host (3.2 GB per rank at 10 M tets), com_mod.R keeps its size because the corrector reads the increment from it.
+void B200LinearAlgebra::alloc(ComMod& com_mod, eqType& lEq)
+{
+  if (!ctx) initialize(com_mod, lEq);
+  if (!structure_uploaded) upload_structure(com_mod);
+  alloc_dof = com_mod.dof;
+  stage_rows.clear(); stage_R.clear(); stage_krows.clear(); stage_kcols.clear(); stage_K.clear();
+  check(svb200_alloc(ctx, alloc_dof));
+}
+
+/// Per-element contributions the host still computes (surface integrals b_assem_neu_bc, coupled BCs ...) are staged as a
+/// COO list in the host's node numbering — what lhsa_ns::do_assem (Code/Source/solver/lhsa.cpp:70-114) would add — and
+/// flushed to the device R / Val before the solve.
+void B200LinearAlgebra::assemble(ComMod& com_mod, const int num_elem_nodes, const Vector<int>& eqN,
+    const Array3<double>& lK, const Array<double>& lR)
+{
+  const int dof = com_mod.dof;
+  const int d2 = dof * dof;
+  for (int a = 0; a < num_elem_nodes; a++) {
+    const int rowN = eqN(a);
+    if (rowN == -1) continue;
+    stage_rows.push_back(rowN);
+    for (int i = 0; i < dof; i++) stage_R.push_back(lR(i, a));
+    for (int b = 0; b < num_elem_nodes; b++) {
+      const int colN = eqN(b);
+      if (colN == -1) continue;
+      stage_krows.push_back(rowN);
+      stage_kcols.push_back(colN);
+      for (int i = 0; i < d2; i++) stage_K.push_back(lK(i, a, b));
+    }
+  }
+}
+
+void B200LinearAlgebra::flush_host_contrib(int dof)
+{
+  if (stage_rows.empty() && stage_krows.empty()) return;
+  check(svb200_add_host_contrib(ctx, dof, (int)stage_rows.size(), stage_rows.data(), stage_R.data(),
+                                (int)stage_krows.size(), stage_krows.data(), stage_kcols.data(), stage_K.data()));
+  stage_rows.clear(); stage_R.clear(); stage_krows.clear(); stage_kcols.clear(); stage_K.clear();
+}
+
+void B200LinearAlgebra::assemble_mesh(ComMod& com_mod, const mshType& lM, const SolutionStates& solutions)
+{
+  if (!ctx || !structure_uploaded || alloc_dof != com_mod.dof)
+    throw std::runtime_error("[B200LinearAlgebra] assemble_mesh before ls_alloc");
+  auto& eq = com_mod.eq[com_mod.cEq];
+  const int iM = (int)(&lM - com_mod.msh.data());
+  if (iM < 0 || iM >= com_mod.nMsh) throw std::runtime_error("[B200LinearAlgebra] mesh is not a member of com_mod.msh");
+  const auto& Ag = solutions.intermediate.get_acceleration();
+  const auto& Yg = solutions.intermediate.get_velocity();
+  const auto& Dg = solutions.intermediate.get_displacement();
+  const int tDof = com_mod.tDof;
+  check(svb200_set_state(ctx, tDof, Ag.data(), Yg.data(), Dg.size() ? Dg.data() : nullptr,
+                         com_mod.Bf.size() ? com_mod.Bf.data() : nullptr));
+  if (eq.phys == consts::EquationType::phys_mesh) {
+    const auto& Do = solutions.old.get_displacement();            // Code/Source/solver/mesh.cpp:60-75
+    check(svb200_set_old_disp(ctx, tDof, Do.data()));
+  }
+  svb200_eqparams e = b200::eq_params(com_mod, eq, lM, scatter);
+  std::vector<svb200_dmnparams> d = b200::domain_params(eq);
+  check(svb200_assemble(ctx, iM, &e, d.data(), (int)d.size()));
+}
+
+void B200LinearAlgebra::commu_R()
+{
+  flush_host_contrib(alloc_dof);
+  check(svb200_commu_R(ctx));
+}
+
+void B200LinearAlgebra::download(int what, double* dst)
+{
+  flush_host_contrib(alloc_dof);
+  check(svb200_download(ctx, what, dst));
+}
+
+/// ls_solve -> fsils_solve (Code/Source/linear_solver/solve.cpp:23-166): on return com_mod.R holds the increment and
+/// lEq.FSILS.{RI,GM,CG} the iteration counts / norms the Newton convergence test reads (Integrator.cpp:941-964).
+void B200LinearAlgebra::solve(ComMod& com_mod, eqType& lEq, const Vector<int>& incL, const Vector<double>& res)
+{
+  using fsi_linear_solver::LinearSolverType;
+  const int dof = com_mod.dof;
+  flush_host_contrib(dof);
+  upload_faces(com_mod);
+  int type;
+  switch (lEq.FSILS.LS_type) {
+    case LinearSolverType::LS_TYPE_NS: type = SVB200_LS_NS; break;
+    case LinearSolverType::LS_TYPE_GMRES: type = SVB200_LS_GMRES; break;
+    case LinearSolverType::LS_TYPE_CG: type = SVB200_LS_CG; break;
+    case LinearSolverType::LS_TYPE_BICGS: type = SVB200_LS_BICGS; break;
+    default: throw std::runtime_error("FSILS: LS_type not defined");     // linear_solver/solve.cpp:141
+  }
+  svb200_lsparams p = b200::ls_params(lEq.FSILS);
+  svb200_lsresult r{};
+  if (com_mod.R.nrows() != dof || com_mod.R.ncols() != com_mod.tnNo) com_mod.R.resize(dof, com_mod.tnNo);
+  check(svb200_solve(ctx, dof, type, SVB200_PREC_FSILS, &p, incL.size(), incL.data(), res.data(), com_mod.R.data(), &r));
+  auto back = [](fsi_linear_solver::FSILS_subLsType& d, const svb200_sublsresult& s) {
+    d.success = s.success != 0; d.itr = s.itr; d.iNorm = s.iNorm; d.fNorm = s.fNorm; d.dB = s.dB; d.callD = s.callD;
+  };
+  back(lEq.FSILS.RI, r.RI); back(lEq.FSILS.GM, r.GM); back(lEq.FSILS.CG, r.CG);
+  lEq.FSILS.Resm = r.Resm; lEq.FSILS.Resc = r.Resc;
+}

@@ -64,3 +64,23 @@ def test_gen_alpha_matches_reference_formula():
     # rho_inf = 0.5 (pipe_RCR_3d): am = 5/6, af = 2/3, gam = 2/3 (Code/Source/solver/initialize.cpp:484-486)
     af, am, gam, beta = abi.gen_alpha(0.5)
     assert abs(am - 5.0 / 6.0) < 1e-15 and abs(af - 2.0 / 3.0) < 1e-15 and abs(gam - 2.0 / 3.0) < 1e-15
+
+
+def test_cpp_host_plugin_loads_and_fails_loudly_without_gpu():
+    """svmultiphysics_b200/host/B200LinearAlgebra (the reference-side C++ plug-in) links against the C ABI and, like the
+    library itself, has no CPU path: on a box without a B200 ls_alloc through it raises instead of falling back."""
+    import numpy as np
+    from oracle import refbind
+    from svmultiphysics_b200 import meshgen
+    if not refbind.have_host():
+        pytest.skip("host plug-in is built only where the reference tree is present")
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by tests/test_gpu_hostshim.py")
+    m = meshgen.cylinder_tet4(3, 3)
+    c = refbind.RefCase()
+    c.set_coords(m.x); c.add_mesh(m.IEN); c.build_graph(0)
+    c.use_b200_backend(device=0)
+    with pytest.raises(RuntimeError):
+        c.alloc(4)
+    c.close()

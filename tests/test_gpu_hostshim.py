@@ -1,0 +1,124 @@
+"""The reference's own host objects driving the GPU through the C++ plug-in layer.
+
+`svmultiphysics_b200/host/B200LinearAlgebra.cpp` implements the reference's `class LinearAlgebra`
+(Code/Source/solver/LinearAlgebra.h:13-37) over the C ABI and carries the early-out of
+`eq_assem::global_eq_assem` (Code/Source/solver/eq_assem.cpp:397).  Here the compiled reference fills its ComMod /
+eqType / mshType / FSILS_lhsType exactly as for the CPU runs and then executes
+
+    ls_alloc -> global_eq_assem -> [b_assem_neu_bc on the host -> LinearAlgebra::assemble] -> ls_solve
+
+twice: with FsilsLinearAlgebra (CPU, the oracle) and with B200LinearAlgebra (device).  Same bytes in, the
+assembled R / Val must agree to 1e-12 and the solver results to the set tolerance.
+"""
+import numpy as np
+import pytest
+
+from svmultiphysics_b200 import abi, meshgen
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(m, nFaces=0, **mesh_kw):
+    from oracle import refbind
+    if not refbind.have_host():
+        pytest.skip("needs oracle/_ref/libsvref.so and svmultiphysics_b200/lib/libsvb200_host.so (built where the reference tree is present)")
+    out = []
+    for gpu in (False, True):
+        c = refbind.RefCase()
+        c.set_coords(m.x)
+        c.add_mesh(m.IEN, **mesh_kw)
+        c.build_graph(nFaces)
+        if gpu:
+            c.use_b200_backend(device=0)
+        out.append(c)
+    return out
+
+
+def _close(*cs):
+    for c in cs:
+        c.close()
+
+
+@pytest.mark.parametrize("ls_type,kw", [
+    (abi.LS_GMRES, dict(mItr=100, sD=50, relTol=1e-8)),
+    (abi.LS_NS, dict(mItr=15, sD=250, relTol=1e-3, absTol=1e-17, gm=(10, 250, 1e-3, 1e-17), cg=(300, 0, 1e-3, 1e-17))),
+], ids=["gmres", "ns_resistance"])
+def test_fluid_newton_iteration_through_cpp_plugin(ls_type, kw):
+    m, Ag, Yg, Dg, Bf = common.fluid_case()
+    faces = common.dirichlet_faces(m)
+    out = m.faces["outlet"]
+    val = np.zeros((3, len(out)), order="F"); val[2] = 4.0 * np.pi / len(out)
+    faces.append((abi.BC_NEU, out, val))
+    cpu, gpu = _pair(m, nFaces=len(faces), eId=m.eId)
+    eq, dmn = abi.fluid_eq(0.005), [abi.fluid_domain(backflow_stab=0.2)]
+    # a Neumann face integrated on the HOST by the reference's b_assem_neu_bc: reaches the device through the
+    # per-element LinearAlgebra::assemble() of the plug-in
+    IENb, gE = meshgen.boundary_face_elements(m, m.faces["outlet_all"])
+    hg = np.zeros(m.nNo); hg[m.faces["outlet_all"]] = -120.0
+    res = []
+    for c in (cpu, gpu):
+        for i, (g, nodes, v) in enumerate(faces):
+            c.set_face(i, g, nodes, v)
+        c.alloc(4); c.set_state(Ag, Yg, Dg, Bf); c.assemble(0, eq, dmn)
+        iFa = c.add_face(0, IENb, gE)
+        c.assemble_neu(0, iFa, eq, dmn, hg)
+        R, V = c.get_R(), c.get_Val()
+        ls = abi.ls_params(ls_type, **kw)
+        X, o, _ = c.solve(4, ls_type, ls, np.ones(len(faces), np.int32), np.array([0.0, 0.0, 0.8]))
+        res.append((R, V, X, o))
+    (R0, V0, X0, o0), (R1, V1, X1, o1) = res
+    assert gpu.backend_launch_count() > 10, "the plug-in did not launch device kernels"
+    assert common.rel_err(R1, R0) < 1e-12 and common.rel_err(V1, V0) < 1e-12
+    assert o1.RI.success == o0.RI.success
+    assert abs(o1.RI.iNorm - o0.RI.iNorm) <= 1e-10 * o0.RI.iNorm
+    if ls_type == abi.LS_GMRES and o0.RI.itr > ls.RI.sD + 1:
+        # dozens of restarts (same contract as tests/test_gpu_fluid.py): the stopping test may fire a few steps apart
+        assert abs(o1.RI.itr - o0.RI.itr) <= max(2, o0.RI.itr // 25)
+        assert o1.RI.fNorm <= ls.RI.relTol * o1.RI.iNorm
+    else:
+        assert o1.RI.itr == o0.RI.itr
+        assert abs(o1.RI.fNorm - o0.RI.fNorm) <= 2e-2 * o0.RI.fNorm
+    assert common.rel_err(X1, X0) < (50 * ls.RI.relTol if ls_type == abi.LS_NS else 1e-6)
+    _close(cpu, gpu)
+
+
+@pytest.mark.parametrize("case", [0, -1], ids=["hex8_nHK_block_compression", "hex8_Guccione_fibres"])
+def test_struct_newton_iteration_through_cpp_plugin(case):
+    name, mk, dkw, nFn = common.STRUCT_CASES[case]
+    m = mk()
+    Ag, Yg, Dg, Bf, fN = common.struct_state(m, nFn=nFn)
+    faces = []
+    for k, fname in enumerate(("X0", "Y0", "Z0")):          # symmetric Dirichlet planes, one direction each
+        val = np.ones((3, len(m.faces[fname])), order="F"); val[k] = 0.0
+        faces.append((abi.BC_DIR, m.faces[fname], val))
+    cpu, gpu = _pair(m, nFaces=3, nFn=nFn, fN=fN)
+    eq, dmn = abi.struct_eq(1e-4), [abi.struct_domain(**dkw)]
+    ls = abi.ls_params(abi.LS_GMRES, mItr=50, sD=60, relTol=1e-10)
+    res = []
+    for c in (cpu, gpu):
+        for i, (g, nodes, v) in enumerate(faces):
+            c.set_face(i, g, nodes, v)
+        c.alloc(3); c.set_state(Ag, Yg, Dg, Bf); c.assemble(0, eq, dmn)
+        R, V = c.get_R(), c.get_Val()
+        X, o, _ = c.solve(3, abi.LS_GMRES, ls, np.ones(3, np.int32), np.zeros(3))
+        res.append((R, V, X, o))
+    (R0, V0, X0, o0), (R1, V1, X1, o1) = res
+    assert common.rel_err(R1, R0) < 1e-12 and common.rel_err(V1, V0) < 1e-12
+    assert o1.RI.success == o0.RI.success
+    assert abs(o1.RI.iNorm - o0.RI.iNorm) <= 1e-10 * o0.RI.iNorm
+    assert abs(o1.RI.itr - o0.RI.itr) <= max(3, o0.RI.itr // 20)
+    if o0.RI.success:
+        assert common.rel_err(X1, X0) < 1e-6
+    _close(cpu, gpu)
+
+
+def test_plugin_error_behaviour():
+    """Failures surface as std::runtime_error like everywhere on the reference's path (the harness turns them into a
+    status + message): element assembly before ls_alloc is a call-order error, not a silent host fallback."""
+    m, Ag, Yg, Dg, Bf = common.fluid_case(n=3, nz=3)
+    cpu, gpu = _pair(m, nFaces=0, eId=m.eId)
+    gpu.set_state(Ag, Yg, Dg, Bf)
+    with pytest.raises(RuntimeError, match="before ls_alloc"):
+        gpu.assemble(0, abi.fluid_eq(0.005), [abi.fluid_domain()])
+    _close(cpu, gpu)
