@@ -16,12 +16,97 @@ from svmultiphysics_b200.engine import Engine  # noqa: E402
 from tests import common  # noqa: E402
 
 
+def _gather(a, ltg, nNo):
+    """Glue per-rank nodal arrays (dof, local) into the global numbering on every rank (shared nodes averaged:
+    they hold identical values after the halo sum)."""
+    idx = torch.from_numpy(ltg).cuda()
+    t = torch.zeros((a.shape[0], nNo), dtype=torch.float64, device="cuda")
+    t[:, idx] = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    owner = torch.zeros(nNo, dtype=torch.float64, device="cuda")
+    owner[idx] = 1.0
+    dist.all_reduce(t); dist.all_reduce(owner)
+    return (t / owner).cpu().numpy()
+
+
+def fsi_main(rank, world, lr):
+    """Config C5 (FSI pipe: fluid core + solid wall + mesh motion, tests/cases/fsi/pipe_3d) on `world` GPUs: the coupled
+    FSI equation (dof 4, GMRES) and the mesh equation (dof 3, CG) assembled and solved on a scattered element partition,
+    compared with the single-partition oracle."""
+    m, Ag, Yg, Dg, Bf = common.fsi_case()
+    part = (((np.arange(m.nEl) // 6) * 7919) % world).astype(np.int32)
+    parts = partition.partition_mesh(m.IEN, m.nNo, part, world)
+    p = parts[rank]
+    eng = Engine(lr)
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid = torch.tensor(list(Engine.unique_id()), dtype=torch.uint8, device="cuda")
+    dist.broadcast(uid, 0)
+    eng.comm_init(world, rank, bytes(uid.cpu().tolist()))
+    rowPtr, colPtr = eng.lhsa(p.nNo, [p.IEN])
+    eng.set_graph(rowPtr, colPtr, mynNo=p.mynNo, node_map=p.node_map, neighbours=p.neighbours)
+    w, N, Nx = elements.tables(4)
+    eId_loc = m.eId[part == rank]
+    eng.set_mesh(0, p.IEN, w, N, Nx, eId=eId_loc)
+    eng.set_coords(m.x[:, p.ltg])
+    gtl = -np.ones(m.nNo, dtype=np.int64); gtl[p.ltg] = np.arange(p.nNo)
+    wall = m.faces["wall"]
+    mine = gtl[wall] >= 0
+    Do = np.asfortranarray(Dg + 3e-3 * np.random.default_rng(9).standard_normal(Dg.shape))
+    af, am, gam, beta = abi.gen_alpha(0.5)
+    eq_fsi = abi.EqParams(dt=1e-3, af=af, am=am, gam=gam, beta=beta, phys=abi.PHYS_FSI, dof=4, tDof=7, s=0, mvMsh=1,
+                          vmsStab=1, scatter=abi.SCATTER_ATOMIC, reserved=0)
+    dmn_fsi = [abi.fluid_domain(rho=1.0, mu=0.04, Id=0),
+               abi.struct_domain(rho=1.0, volType=abi.VOL_M94, E=1e7, nu=0.3, Kpen=1e7 / (3 * (1 - 0.6)), Id=1)]
+    eq_msh, dmn_msh = abi.mesh_eq(1e-3), [abi.mesh_domain(E=1.0, nu=0.3)]
+    ls_fsi = abi.ls_params(abi.LS_GMRES, mItr=100, sD=50, relTol=1e-8)
+    ls_msh = abi.ls_params(abi.LS_CG, mItr=1000, relTol=1e-12)
+    incL, res = np.ones(1, np.int32), np.zeros(1)
+    out = {}
+    for name, dof, eq, dmn, ls_type, ls, nrow in (("fsi", 4, eq_fsi, dmn_fsi, abi.LS_GMRES, ls_fsi, 3),
+                                                  ("mesh", 3, eq_msh, dmn_msh, abi.LS_CG, ls_msh, 3)):
+        eng.set_num_faces(1)
+        eng.set_face(0, abi.BC_DIR, gtl[wall[mine]].astype(np.int32), np.zeros((nrow, int(mine.sum())), order="F"), shared=1)
+        eng.alloc(dof)
+        eng.set_state(Ag[:, p.ltg], Yg[:, p.ltg], Dg[:, p.ltg], Bf[:, p.ltg])
+        eng.set_old_disp(Do[:, p.ltg])
+        eng.assemble(0, eq, dmn)
+        eng.commu_R()
+        R_loc = eng.get_R()
+        X_loc, o, _ = eng.solve(dof, ls_type, ls, incL, res)
+        out[name] = (_gather(R_loc, p.ltg, m.nNo), _gather(X_loc, p.ltg, m.nNo), o)
+    ok = 1
+    if rank == 0:
+        from oracle import refbind
+        if not refbind.have_ref():
+            print("[mgpu fsi] libsvref.so absent: FSI has no C restatement; only self-consistency was run")
+        else:
+            for name, dof, eq, dmn, ls_type, ls in (("fsi", 4, eq_fsi, dmn_fsi, abi.LS_GMRES, ls_fsi), ("mesh", 3, eq_msh, dmn_msh, abi.LS_CG, ls_msh)):
+                orc = refbind.RefCase(); orc.set_coords(m.x); orc.add_mesh(m.IEN, eId=m.eId if name == "fsi" else None)
+                orc.build_graph(1)
+                orc.set_face(0, abi.BC_DIR, wall, np.zeros((3, len(wall)), order="F"))
+                orc.alloc(dof); orc.set_state(Ag, Yg, Dg, Bf); orc.set_old_disp(Do); orc.assemble(0, eq, dmn)
+                R0 = orc.get_R()
+                X0, o0, _ = orc.solve(dof, ls_type, ls, incL, res)
+                Rg, Xg, o = out[name]
+                eR, eX = common.rel_err(Rg, R0), common.rel_err(Xg, X0)
+                print(f"[mgpu fsi/{name} x{world}] relerr R {eR:.2e} X {eX:.2e}; itr {o.RI.itr} vs {o0.RI.itr}; iNorm {o.RI.iNorm:.6e} vs {o0.RI.iNorm:.6e}")
+                ok &= int(eR < 1e-12 and eX < 1e-6 and abs(o.RI.iNorm - o0.RI.iNorm) < 1e-10 * o0.RI.iNorm
+                          and abs(o.RI.itr - o0.RI.itr) <= max(2, o0.RI.itr // 20))
+    flag = torch.tensor([ok], device="cuda")
+    dist.broadcast(flag, 0)
+    eng.close()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1 else 1)
+
+
 def main():
     mode = sys.argv[1] if len(sys.argv) > 1 else "slab"
     ls_name = sys.argv[2] if len(sys.argv) > 2 else "gmres"
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    if mode == "fsi":
+        return fsi_main(rank, world, lr)
     n, nz = 6, 8
     m, Ag, Yg, Dg, Bf = common.fluid_case(n=n, nz=nz)
     if mode == "slab":

@@ -15,11 +15,11 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("mode,ls", [("slab", "gmres"), ("scattered", "gmres"), ("slab", "ns")])
+@pytest.mark.parametrize("mode,ls", [("slab", "gmres"), ("scattered", "gmres"), ("slab", "ns"), ("fsi", "gmres+cg")])
 def test_two_gpu_parity(mode, ls):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
-    n = min(_ngpu(), 4) if mode == "scattered" else 2
+    n = min(_ngpu(), 4) if mode in ("scattered", "fsi") else 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", "29541", os.path.join(ROOT, "tests", "mgpu_worker.py"), mode, ls]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
