@@ -8,10 +8,10 @@
 //
 // Mapping: ENON lanes per element, 32/ENON elements per warp, two phases.  Phase A: lane g evaluates Gauss point g
 // (nn::gnn, F, compute_pk2cc) ONCE per element and leaves xiX, w, F, S, Dm, ud in shared memory.  Phase B: lane a
-// = element node a; per Gauss point it computes its own grad N_a, Bm_a and DBm_a = Dm Bm_a and publishes them; the
-// element matrix is symmetric for a hyperelastic solid (K_ab = K_ba^T), so lane a only accumulates the blocks
-// (a, a+k mod ENON), k = 0..ENON/2, in registers (5 x 9 doubles for HEX8) and scatters each of them twice
-// (as is, and transposed) — 36 of 64 block products instead of 64.
+// = element node a; per Gauss point it contracts its Bm_a with Dm and F into H_a(3,3,3) so that a block needs only
+// grad N_b of the other node (see phase B); the element matrix is symmetric for a hyperelastic solid
+// (K_ab = K_ba^T), so lane a only accumulates the blocks (a, a+k mod ENON), k = 0..ENON/2, in registers (5 x 9
+// doubles for HEX8) and scatters each of them twice (as is, and transposed) — 36 of 64 block products instead of 64.
 #include <cstdlib>
 #include <vector>
 #include "struct_elem.cuh"
@@ -50,8 +50,15 @@ __device__ __forceinline__ void add64(double* p, double v)
 constexpr int STRUCT_THREADS = 128;
 
 // Shared-memory layout per element (doubles): nodal inputs x,d,q (9 ENON) | Gauss-point data (GP_LD per point) |
-// per-node exchange of the current Gauss point: Nx (3) + DBm (18).
+// per-node exchange of grad N_a of the current Gauss point (double-buffered).
 constexpr int GP_LD = 64;   // xiX 9 | w 1 | F 9 | S 6 (11,22,33,12,23,31) | Dm 36 | ud 3
+// nodal inputs 9 ENON | Gauss data GP_LD ENON | grad N exchange, double-buffered, 6 ENON; the stride is padded to
+// 8 mod 16 doubles so that the elements of a half-warp read the same offset from different banks
+__host__ __device__ constexpr int struct_per_el(int enon)
+{
+  const int n = enon * (9 + GP_LD + 6);
+  return n + ((8 - (n % 16)) + 16) % 16;
+}
 
 template <int ENON, bool ATOMIC>
 __global__ void __launch_bounds__(STRUCT_THREADS)
@@ -59,7 +66,7 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
 {
   constexpr int EPW = 32 / ENON;            // elements per warp
   constexpr int KMAX = ENON / 2;            // lane a owns blocks (a, a+k), k = 0..KMAX (k = KMAX only for a < KMAX)
-  constexpr int PER_EL = ENON * (9 + GP_LD + 21);
+  constexpr int PER_EL = struct_per_el(ENON);
   constexpr int NTAB = ENON * ENON * 4 + ENON;   // Nxi[g][a][3], N[g][a], w[g]  (nG == ENON)
   extern __shared__ double sm[];
   double* tab = sm;                          // reference-element tables (lane-dependent Gauss point in phase A)
@@ -71,7 +78,6 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
   double(*sq)[3] = reinterpret_cast<double(*)[3]>(se + 6 * ENON);
   double* sgp = se + 9 * ENON;
   double(*sNx)[3] = reinterpret_cast<double(*)[3]>(se + 9 * ENON + ENON * GP_LD);
-  double(*sDB)[18] = reinterpret_cast<double(*)[18]>(se + 12 * ENON + ENON * GP_LD);
   double(*tNxi)[ENON][3] = reinterpret_cast<double(*)[ENON][3]>(tab);
   double(*tN)[ENON] = reinterpret_cast<double(*)[ENON]>(tab + ENON * ENON * 3);
   double* tw = tab + ENON * ENON * 4;
@@ -171,7 +177,11 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
   }
   __syncwarp();
 
-  // ---- phase B: lane a = element node a; per Gauss point Bm_a, DBm_a (published), residual row, owned blocks ----
+  // ---- phase B: lane a = element node a.  Material tangent in contracted form: with G_a = Bm_a^T Dm (3x6) arranged as
+  // three symmetric 3x3 matrices Gs_i, Bm_b(r,j) being linear in grad N_b gives
+  //     Bm_a(:,i) . Dm Bm_b(:,j) = sum_L H_a(i,j,L) dN_b/dx_L ,   H_a(i,j,L) = sum_M Gs_i(L,M) F(j,M),
+  // so only grad N_b (3 doubles per node and Gauss point) is exchanged between lanes and a block costs 27 + 8 FMAs
+  // (sv_struct.cpp:736-825 evaluates the same sums as Bm_a^T (Dm Bm_b): 54 FMAs and an 18-double DBm_b per block). -----
   const double afu = P.af * P.beta * P.dt * P.dt;
   const double amd = P.am * dm.rho + P.af * P.gam * P.dt * dm.dmp;
   double acc[KMAX + 1][3][3];
@@ -185,32 +195,50 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
 
 #pragma unroll 1
   for (int g = 0; g < ENON; g++) {
-    double Bm[6][3], SNx[3], Nxa[3];
-    double w = 0.0;
+    double H[3][3][3], SNx[3];
+    double wamdNa = 0.0;
+    double(*pNx)[3] = sNx + (g & 1) * ENON;       // double-buffered exchange: one __syncwarp per Gauss point
     if (active) {
       const double* q = sgp + g * GP_LD;
-      w = q[9];
-      double F[3][3];
+      const double w = q[9];
+      const double wafu = w * afu;
+      double F[3][3], Nxa[3];
 #pragma unroll
       for (int i = 0; i < 3; i++) {
         Nxa[i] = tNxi[g][a][0] * q[i] + tNxi[g][a][1] * q[3 + i] + tNxi[g][a][2] * q[6 + i];
-        sNx[a][i] = Nxa[i];
+        pNx[a][i] = Nxa[i];
 #pragma unroll
         for (int j = 0; j < 3; j++) F[i][j] = q[10 + 3 * i + j];
       }
-      make_Bm(Nxa, F, Bm);
-      // DBm_a = Dm Bm_a, Dm read row by row from shared memory
+      {
+        double Bm[6][3], G[3][6];
+        make_Bm(Nxa, F, Bm);
 #pragma unroll
-      for (int r = 0; r < 6; r++) {
-        double d[6];
+        for (int i = 0; i < 3; i++)
 #pragma unroll
-        for (int c = 0; c < 6; c++) d[c] = q[25 + 6 * r + c];
+          for (int c = 0; c < 6; c++) G[i][c] = 0.0;
+        // G(i,c) = sum_r Bm_a(r,i) Dm(r,c), Dm read row by row from shared memory (broadcast within the element)
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
-          double sacc = 0.0;
+        for (int r = 0; r < 6; r++) {
+          double d[6];
 #pragma unroll
-          for (int c = 0; c < 6; c++) sacc += d[c] * Bm[c][j];
-          sDB[a][3 * r + j] = sacc;
+          for (int c = 0; c < 6; c++) d[c] = q[25 + 6 * r + c];
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int c = 0; c < 6; c++) G[i][c] += Bm[r][i] * d[c];
+        }
+        // Voigt order 11,22,33,12,23,31 -> symmetric matrix Gs_i(L,M); H(i,j,L) = w afu sum_M Gs_i(L,M) F(j,M)
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          const double g00 = wafu * G[i][0], g11 = wafu * G[i][1], g22 = wafu * G[i][2];
+          const double g01 = wafu * G[i][3], g12 = wafu * G[i][4], g20 = wafu * G[i][5];
+#pragma unroll
+          for (int j = 0; j < 3; j++) {
+            H[i][j][0] = g00 * F[j][0] + g01 * F[j][1] + g20 * F[j][2];
+            H[i][j][1] = g01 * F[j][0] + g11 * F[j][1] + g12 * F[j][2];
+            H[i][j][2] = g20 * F[j][0] + g12 * F[j][1] + g22 * F[j][2];
+          }
         }
       }
       const double S00 = q[19], S11 = q[20], S22 = q[21], S01 = q[22], S12 = q[23], S20 = q[24];
@@ -224,25 +252,26 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
         const double PNx = F[i][0] * SNx[0] + F[i][1] * SNx[1] + F[i][2] * SNx[2];
         lR[i] += w * (Na * q[61 + i] + PNx);
       }
+      wamdNa = w * amd * Na;
+#pragma unroll
+      for (int i = 0; i < 3; i++) SNx[i] *= wafu;
     }
     __syncwarp();
     if (active) {
-      const double Na = tN[g][a];
 #pragma unroll
       for (int k = 0; k <= KMAX; k++) {
         if (k == KMAX && a >= KMAX) continue;
         const int b = (a + k) % ENON;
-        double DB[6][3], Nxb[3];
+        const double n0 = pNx[b][0], n1 = pNx[b][1], n2 = pNx[b][2];
+        // delta_ij w (amd Na Nb + afu gradNa.S.gradNb)
+        const double T1 = wamdNa * tN[g][b] + (SNx[0] * n0 + SNx[1] * n1 + SNx[2] * n2);
 #pragma unroll
-        for (int r = 0; r < 6; r++)
+        for (int i = 0; i < 3; i++)
 #pragma unroll
-          for (int j = 0; j < 3; j++) DB[r][j] = sDB[b][3 * r + j];
-#pragma unroll
-        for (int i = 0; i < 3; i++) Nxb[i] = sNx[b][i];
-        struct_block(acc[k], w, amd * Na * tN[g][b], afu, SNx, Nxb, Bm, DB);
+          for (int j = 0; j < 3; j++)
+            acc[k][i][j] += (H[i][j][0] * n0 + H[i][j][1] * n1 + H[i][j][2] * n2) + (i == j ? T1 : 0.0);
       }
     }
-    __syncwarp();
   }
 
   if (!active) return;
@@ -428,7 +457,7 @@ static int launch_one(svb200_ctx* ctx, const StructArgs& A)
   const long long n = (long long)A.e1 - A.e0;
   if (n <= 0) return SVB200_OK;
   const unsigned blocks = (unsigned)((n + EPB - 1) / EPB);
-  constexpr size_t smem = sizeof(double) * ((size_t)ENON * ENON * 4 + ENON + (size_t)EPB * ENON * (9 + GP_LD + 21));
+  constexpr size_t smem = sizeof(double) * ((size_t)ENON * ENON * 4 + ENON + (size_t)EPB * struct_per_el(ENON));
   static bool configured = false;
   if (!configured) {
     SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
