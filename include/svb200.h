@@ -79,8 +79,9 @@ typedef enum { SVB200_VOL_NONE = 0, SVB200_VOL_QUAD = 1, SVB200_VOL_ST91 = 2, SV
 
 /* fsi_linear_solver::LinearSolverType (linear_solver/fils_struct.hpp). */
 typedef enum { SVB200_LS_NS = 0, SVB200_LS_GMRES = 1, SVB200_LS_CG = 2, SVB200_LS_BICGS = 3 } svb200_ls_type;
-/* consts::PreconditionerType: only the FSILS diagonal (Jacobi) preconditioner is on the path. */
-typedef enum { SVB200_PREC_FSILS = 0 } svb200_prec;
+/* consts::PreconditionerType, the two FSILS ones (consts.h:421-432): the diagonal (Jacobi) preconditioner
+ * precond_diag (linear_solver/precond.cpp:95-242) and the row-and-column max-norm scaling precond_rcs (:251-523). */
+typedef enum { SVB200_PREC_FSILS = 0, SVB200_PREC_RCS = 1 } svb200_prec;
 /* fsi_linear_solver::BcType. */
 typedef enum { SVB200_BC_DIR = 0, SVB200_BC_NEU = 1 } svb200_bc_type;
 /* Scatter mode of the element assembly. */

@@ -427,18 +427,20 @@ int svref_solve(void* h, int dof, int ls_type, int prec, const svb200_lsparams* 
     Vector<int> incLv(nFaces);
     Vector<double> resv(nFaces);
     for (int i = 0; i < nFaces; i++) { incLv(i) = incL ? incL[i] : 1; resv(i) = res ? res[i] : 0.0; }
-    (void)prec;
+    const auto ptype = (prec == SVB200_PREC_RCS) ? consts::PreconditionerType::PREC_RCS : consts::PreconditionerType::PREC_FSILS;
     auto t0 = std::chrono::steady_clock::now();
     if (c.backend) {
       // ls_solve (solver/ls.cpp:42-54): lEq.linear_algebra->solve(com_mod, lEq, incL, res)
       auto& eq = cm.eq.at(0);
       eq.FSILS = fls;
       eq.linear_algebra = c.backend;
+      eq.linear_algebra_preconditioner = ptype;
+      eq.linear_algebra->set_preconditioner(ptype);
       cm.dof = dof;
       eq.linear_algebra->solve(cm, eq, incLv, resv);
       fls = eq.FSILS;
     } else {
-      fsils_solve(cm.lhs, fls, dof, cm.R, cm.Val, consts::PreconditionerType::PREC_FSILS, incLv, resv);
+      fsils_solve(cm.lhs, fls, dof, cm.R, cm.Val, ptype, incLv, resv);
     }
     c.last_solve_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (R_out) std::memcpy(R_out, cm.R.data(), sizeof(double)*cm.R.size());

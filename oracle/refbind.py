@@ -185,7 +185,7 @@ class _FlatCase:
         self.dof = dof
         self._call("put", C.c_int(abi.ARRAY_VAL), C.c_int(dof), _d(V))
 
-    def solve(self, dof, ls_type, ls: abi.LsParams, incL=None, res=None, hist_cap=0):
+    def solve(self, dof, ls_type, ls: abi.LsParams, incL=None, res=None, hist_cap=0, prec=abi.PREC_FSILS):
         nFaces = 0 if incL is None else len(incL)
         incL = _i32(incL)
         res = _f64(res)
@@ -194,7 +194,7 @@ class _FlatCase:
         out.hist = hist.ctypes.data_as(_dp)
         out.hist_cap = hist_cap
         X = np.zeros((dof, self.nNo), order="F")
-        self._call("solve", C.c_int(dof), C.c_int(ls_type), C.c_int(abi.PREC_FSILS), C.byref(ls), C.c_int(nFaces),
+        self._call("solve", C.c_int(dof), C.c_int(ls_type), C.c_int(prec), C.byref(ls), C.c_int(nFaces),
                    _i(incL), _d(res), _d(X), C.byref(out))
         return X, out, hist[:out.hist_n].copy()
 

@@ -15,6 +15,7 @@ VOL_NONE, VOL_QUAD, VOL_ST91, VOL_M94 = 0, 1, 2, 3
 # svb200_ls_type
 LS_NS, LS_GMRES, LS_CG, LS_BICGS = 0, 1, 2, 3
 PREC_FSILS = 0
+PREC_RCS = 1
 BC_DIR, BC_NEU = 0, 1
 SCATTER_ATOMIC, SCATTER_COLORED = 0, 1
 ARRAY_R, ARRAY_VAL, ARRAY_W = 0, 1, 2

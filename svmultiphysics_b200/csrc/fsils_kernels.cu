@@ -10,6 +10,7 @@
 // All of them are HBM-bandwidth bound; vectors are (dof,nNo) node-major, the matrix is block-CSR
 // with dof*dof contiguous doubles per block.  Reductions are two-stage and run in a fixed order, so
 // results are bitwise reproducible from run to run.
+#include <algorithm>
 #include "svb200_internal.h"
 #include "fsils_kernels.h"
 
@@ -340,13 +341,12 @@ __global__ void face_valm_kernel(int fnNo, int fdof, int nd, int dof, const int*
   valM[t] = (i < nd) ? val[t] * W[(size_t)glob[a] * dof + i] : 0.0;
 }
 
-// Val(dof*i+j, k) = (Val * W(i,row)) * W(j,col(k)) — pre_mul then pos_mul in ONE pass (same rounding
-// sequence as the reference's two passes); one thread per matrix entry, coalesced over Val.
+// Val(dof*i+j, k) = (Val * Wr(i,row)) * Wc(j,col(k)) — pre_mul then pos_mul in ONE pass (same rounding
+// sequence as the reference's two passes, precond.cpp:534-611 / 19-94); one warp per row, coalesced over Val.
 __global__ void __launch_bounds__(256)
 scale_matrix_kernel(int nNo, int dof, const int* __restrict__ rowPtr, const int* __restrict__ colPtr,
-                    const double* __restrict__ W, double* __restrict__ Val)
+                    const double* __restrict__ Wr, const double* __restrict__ Wc, double* __restrict__ Val)
 {
-  // one warp per row
   const int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= nNo) return;
@@ -355,10 +355,189 @@ scale_matrix_kernel(int nNo, int dof, const int* __restrict__ rowPtr, const int*
   for (long long e = e0 + lane; e < e1; e += 32) {
     const int k = (int)(e / d2), r = (int)(e % d2);
     const int i = r / dof, j = r % dof;
-    const double wi = W[(size_t)row * dof + i];
-    const double wj = W[(size_t)colPtr[k] * dof + j];
+    const double wi = Wr[(size_t)row * dof + i];
+    const double wj = Wc[(size_t)colPtr[k] * dof + j];
     Val[e] = (Val[e] * wi) * wj;
   }
+}
+
+// dof = 4: 8 lanes per row, lane l owns the double2 (i = l/2, j0 = 2(l&1)) of every block, 4 blocks in flight;
+// a lane group moves whole 128-byte blocks, Wr(i,row) stays in a register.
+__global__ void __launch_bounds__(256)
+scale_matrix4_kernel(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ colPtr,
+                     const double* __restrict__ Wr, const double* __restrict__ Wc, double* __restrict__ Val)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = t >> 3;
+  if (row >= nNo) return;
+  const int l = t & 7, i = l >> 1, j0 = (l & 1) << 1;
+  const double wi = Wr[4 * (size_t)row + i];
+  const int k0 = rowPtr[row], k1 = rowPtr[row + 1];
+  double2* V2 = reinterpret_cast<double2*>(Val) + l;
+  int k = k0;
+  for (; k + 4 <= k1; k += 4) {
+    double2 v[4], w[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int c = __ldg(colPtr + k + q);
+      v[q] = __ldcs(V2 + 8 * (size_t)(k + q));
+      w[q] = *reinterpret_cast<const double2*>(Wc + 4 * (size_t)c + j0);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      v[q].x = (v[q].x * wi) * w[q].x;
+      v[q].y = (v[q].y * wi) * w[q].y;
+      __stcs(V2 + 8 * (size_t)(k + q), v[q]);
+    }
+  }
+  for (; k < k1; k++) {
+    const int c = __ldg(colPtr + k);
+    double2 v = __ldcs(V2 + 8 * (size_t)k);
+    const double2 w = *reinterpret_cast<const double2*>(Wc + 4 * (size_t)c + j0);
+    v.x = (v.x * wi) * w.x;
+    v.y = (v.y * wi) * w.y;
+    __stcs(V2 + 8 * (size_t)k, v);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// precond_rcs pieces (row-and-column max-norm equilibration, precond.cpp:251-523).
+// ----------------------------------------------------------------------------------------------
+__global__ void fill_kernel(long long n, double* __restrict__ W, double v)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) W[t] = v;
+}
+
+// The renormalisation of the summed Dirichlet mask (precond.cpp:289-291): Wr-0.5 -> sign -> {0,1}.
+__global__ void rcs_renorm_kernel(long long n, double* __restrict__ W)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  double w = W[t] - 0.5;
+  w = w / fabs(w);
+  W[t] = (w + fabs(w)) * 0.5;
+}
+
+// Val(ii,diag) = Wr(i)*(Val(ii,diag)-1)+1 (precond.cpp:305-349).
+__global__ void rcs_diag_one_kernel(int nNo, int dof, const int* __restrict__ diagPtr, const double* __restrict__ Wr,
+                                    double* __restrict__ Val)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)nNo * dof) return;
+  const int r = (int)(t / dof), i = (int)(t % dof);
+  double* v = Val + (size_t)diagPtr[r] * dof * dof + i * dof + i;
+  *v = Wr[t] * (*v - 1.0) + 1.0;
+}
+
+// Max norms along rows (warp reduction) and columns (atomic max on the bit pattern of a non-negative double, which
+// is order preserving; max is exact, so the result does not depend on the order).  Wr, Wc zeroed by the caller.
+__global__ void __launch_bounds__(256)
+rcs_rowcol_max_kernel(int nNo, int dof, const int* __restrict__ rowPtr, const int* __restrict__ colPtr,
+                      const double* __restrict__ Val, double* __restrict__ Wr, double* __restrict__ Wc)
+{
+  const int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= nNo) return;
+  const int d2 = dof * dof;
+  const long long e0 = (long long)rowPtr[row] * d2, e1 = (long long)rowPtr[row + 1] * d2;
+  double rmax[4] = {0.0, 0.0, 0.0, 0.0};    // dof <= 4
+  for (long long e = e0 + lane; e < e1; e += 32) {
+    const int k = (int)(e / d2), r = (int)(e % d2);
+    const int i = r / dof, j = r % dof;
+    const double v = fabs(Val[e]);
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      if (q == i) rmax[q] = fmax(rmax[q], v);
+    double* wc = Wc + (size_t)colPtr[k] * dof + j;
+    if (v > *wc) atomicMax(reinterpret_cast<unsigned long long*>(wc), (unsigned long long)__double_as_longlong(v));
+  }
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    for (int o = 16; o > 0; o >>= 1) rmax[q] = fmax(rmax[q], __shfl_xor_sync(0xffffffffu, rmax[q], o));
+    if (lane == 0 && q < dof) Wr[(size_t)row * dof + q] = rmax[q];
+  }
+}
+
+// out[which] = max |1 - W| (bit-pattern atomic max; out zeroed by the caller).
+__global__ void __launch_bounds__(256)
+rcs_dev_from_one_kernel(long long n, const double* __restrict__ W, double* __restrict__ out)
+{
+  __shared__ double red[256];
+  double m = 0.0;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+    m = fmax(m, fabs(1.0 - W[t]));
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(red[0]));
+}
+
+// W = 1/sqrt(W); Wacc *= W (precond.cpp:496-505).
+__global__ void rcs_invsqrt_acc_kernel(long long n, double* __restrict__ W, double* __restrict__ Wacc)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const double w = 1.0 / sqrt(W[t]);
+  W[t] = w;
+  Wacc[t] = Wacc[t] * w;
+}
+
+#define SVB_LAUNCH_1D(kernel, n, ...)                                                        \
+  do {                                                                                       \
+    if ((n) > 0) {                                                                           \
+      kernel<<<(unsigned)(((n) + 255) / 256), 256, 0, ctx->stream>>>(__VA_ARGS__);           \
+      ctx->launches++;                                                                       \
+      SVB_CUDA(cudaGetLastError());                                                          \
+    }                                                                                        \
+  } while (0)
+
+int fill(svb200_ctx* ctx, long long n, double* W, double v)
+{
+  SVB_LAUNCH_1D(fill_kernel, n, n, W, v);
+  return SVB200_OK;
+}
+
+int rcs_renorm(svb200_ctx* ctx, long long n, double* W)
+{
+  SVB_LAUNCH_1D(rcs_renorm_kernel, n, n, W);
+  return SVB200_OK;
+}
+
+int rcs_diag_one(svb200_ctx* ctx, int dof, const double* Wr, double* Val)
+{
+  const long long n = (long long)ctx->nNo * dof;
+  SVB_LAUNCH_1D(rcs_diag_one_kernel, n, ctx->nNo, dof, ctx->d_diagPtr, Wr, Val);
+  return SVB200_OK;
+}
+
+int rcs_rowcol_max(svb200_ctx* ctx, int dof, const double* Val, double* Wr, double* Wc)
+{
+  const long long threads = (long long)ctx->nNo * 32;
+  SVB_LAUNCH_1D(rcs_rowcol_max_kernel, threads, ctx->nNo, dof, ctx->d_rowPtr, ctx->d_colPtr, Val, Wr, Wc);
+  return SVB200_OK;
+}
+
+// d_out[0] = max|1-Wr|, d_out[1] = max|1-Wc|
+int rcs_dev_from_one(svb200_ctx* ctx, long long n, const double* Wr, const double* Wc, double* d_out)
+{
+  SVB_CUDA(cudaMemsetAsync(d_out, 0, 2 * sizeof(double), ctx->stream));
+  if (n == 0) return SVB200_OK;
+  const unsigned blocks = (unsigned)std::min<long long>((n + 255) / 256, 148 * 8);
+  rcs_dev_from_one_kernel<<<blocks, 256, 0, ctx->stream>>>(n, Wr, d_out);
+  rcs_dev_from_one_kernel<<<blocks, 256, 0, ctx->stream>>>(n, Wc, d_out + 1);
+  ctx->launches += 2;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
+int rcs_invsqrt_acc(svb200_ctx* ctx, long long n, double* W, double* Wacc)
+{
+  SVB_LAUNCH_1D(rcs_invsqrt_acc_kernel, n, n, W, Wacc);
+  return SVB200_OK;
 }
 
 int precond_extract_diag(svb200_ctx* ctx, int dof, const double* Val, double* W)
@@ -403,11 +582,16 @@ int precond_face_valm(svb200_ctx* ctx, const Face& f, int dof, const double* W)
   return SVB200_OK;
 }
 
-int precond_scale_matrix(svb200_ctx* ctx, int dof, const double* W, double* Val)
+int precond_scale_matrix(svb200_ctx* ctx, int dof, const double* Wr, const double* Wc, double* Val)
 {
   if (ctx->nNo == 0) return SVB200_OK;
-  const long long threads = (long long)ctx->nNo * 32;
-  scale_matrix_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(ctx->nNo, dof, ctx->d_rowPtr, ctx->d_colPtr, W, Val);
+  if (dof == 4) {
+    const long long threads = (long long)ctx->nNo * 8;
+    scale_matrix4_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(ctx->nNo, ctx->d_rowPtr, ctx->d_colPtr, Wr, Wc, Val);
+  } else {
+    const long long threads = (long long)ctx->nNo * 32;
+    scale_matrix_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(ctx->nNo, dof, ctx->d_rowPtr, ctx->d_colPtr, Wr, Wc, Val);
+  }
   ctx->launches++;
   SVB_CUDA(cudaGetLastError());
   return SVB200_OK;

@@ -15,7 +15,13 @@ int precond_extract_diag(svb200_ctx* ctx, int dof, const double* Val, double* W)
 int precond_invsqrt(svb200_ctx* ctx, int dof, double* W);
 int precond_face_scale(svb200_ctx* ctx, const Face& f, int dof, double* W);
 int precond_face_valm(svb200_ctx* ctx, const Face& f, int dof, const double* W);
-int precond_scale_matrix(svb200_ctx* ctx, int dof, const double* W, double* Val);
+int precond_scale_matrix(svb200_ctx* ctx, int dof, const double* Wr, const double* Wc, double* Val);
+int fill(svb200_ctx* ctx, long long n, double* W, double v);
+int rcs_renorm(svb200_ctx* ctx, long long n, double* W);
+int rcs_diag_one(svb200_ctx* ctx, int dof, const double* Wr, double* Val);
+int rcs_rowcol_max(svb200_ctx* ctx, int dof, const double* Val, double* Wr, double* Wc);
+int rcs_dev_from_one(svb200_ctx* ctx, long long n, const double* Wr, const double* Wc, double* d_out);
+int rcs_invsqrt_acc(svb200_ctx* ctx, long long n, double* W, double* Wacc);
 
 int spmv_rc(svb200_ctx* ctx, int R, int C, const double* K, const double* U, double* KU);
 int build_transpose_slots(svb200_ctx* ctx, int* d_tslot);

@@ -173,12 +173,69 @@ static int precond_diag_device(svb200_ctx* ctx, int dof, double* Val, double* R,
     if (!f.set || !f.incFlag) continue;
     if (f.bGrp == SVB200_BC_DIR) SVB_TRY(precond_face_scale(ctx, f, dof, W));
   }
-  SVB_TRY(precond_scale_matrix(ctx, dof, W, Val));
+  SVB_TRY(precond_scale_matrix(ctx, dof, W, W, Val));
   SVB_TRY(hadamard(ctx, n, W, R, R));
   for (auto& f : ctx->face) {
     if (!f.set || !f.coupledFlag) continue;
     SVB_TRY(precond_face_valm(ctx, f, dof, W));
   }
+  return SVB200_OK;
+}
+
+// ---- precond_rcs (precond.cpp:251-523) ---------------------------------------------------------------
+// Row-and-column max-norm equilibration, at most 10 sweeps.  W2 (column scaling) is what fsils_solve multiplies the
+// solution with afterwards (solve.cpp:157-159); W1 (row scaling) is applied to R here.  Reference behaviour kept:
+// the shared-node exchange of the max norms is a SUM (fsils_commuv), the Dirichlet mask is renormalised through
+// sign(Wr - 0.5), and face.valM of coupled Neumann faces is NOT recomputed by this preconditioner.
+static int precond_rcs_device(svb200_ctx* ctx, int dof, double* Val, double* R, double* W1, double* W2, double* Wr,
+                              double* Wc, double* d_scal)
+{
+  const long long n = (long long)ctx->nNo * dof;
+  if (dof > 4) {
+    set_error("precond_rcs: dof > 4 is not supported");
+    return SVB200_ERR_UNSUPPORTED;
+  }
+  const int maxiter = 10;
+  const double tol = 2.0;
+  SVB_TRY(fill(ctx, n, W1, 1.0));
+  SVB_TRY(fill(ctx, n, W2, 1.0));
+  SVB_TRY(fill(ctx, n, Wr, 1.0));
+  for (auto& f : ctx->face) {
+    if (!f.set || !f.incFlag) continue;
+    if (f.bGrp == SVB200_BC_DIR) SVB_TRY(precond_face_scale(ctx, f, dof, Wr));
+  }
+  SVB_TRY(halo_sum(ctx, dof, Wr));
+  SVB_TRY(rcs_renorm(ctx, n, Wr));
+  // kill the Dirichlet rows and columns, unit diagonal
+  SVB_TRY(precond_scale_matrix(ctx, dof, Wr, Wr, Val));
+  SVB_TRY(hadamard(ctx, n, Wr, R, R));
+  SVB_TRY(rcs_diag_one(ctx, dof, Wr, Val));
+  bool flag = true;
+  int iter = 0;
+  while (flag) {
+    SVB_CUDA(cudaMemsetAsync(Wr, 0, sizeof(double) * n, ctx->stream));
+    SVB_CUDA(cudaMemsetAsync(Wc, 0, sizeof(double) * n, ctx->stream));
+    iter++;
+    if (iter >= maxiter) flag = false;
+    SVB_TRY(rcs_rowcol_max(ctx, dof, Val, Wr, Wc));
+    SVB_TRY(halo_sum(ctx, dof, Wr));
+    SVB_TRY(halo_sum(ctx, dof, Wc));
+    SVB_TRY(rcs_dev_from_one(ctx, n, Wr, Wc, d_scal));
+    SVB_TRY(fetch(ctx, d_scal, 2, ctx->h_pinned));
+    if (ctx->h_pinned[0] < tol && ctx->h_pinned[1] < tol) flag = false;
+    SVB_TRY(rcs_invsqrt_acc(ctx, n, Wr, W1));
+    SVB_TRY(rcs_invsqrt_acc(ctx, n, Wc, W2));
+    SVB_TRY(precond_scale_matrix(ctx, dof, Wr, Wc, Val));
+    if (ctx->nranks > 1) {
+      // MPI_Allgather of the flags + any() (precond.cpp:507-512)
+      ctx->h_pinned[0] = flag ? 1.0 : 0.0;
+      SVB_CUDA(cudaMemcpyAsync(d_scal, ctx->h_pinned, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      SVB_TRY(allreduce_sum(ctx, d_scal, 1));
+      SVB_TRY(fetch(ctx, d_scal, 1, ctx->h_pinned));
+      flag = ctx->h_pinned[0] > 0.0;
+    }
+  }
+  SVB_TRY(hadamard(ctx, n, W1, R, R));
   return SVB200_OK;
 }
 
@@ -459,8 +516,8 @@ static int bicgs_device(svb200_ctx* ctx, int dof, const svb200_sublsparams& p, s
 int ns_solver_device(svb200_ctx* ctx, int dof, const svb200_lsparams* ls, svb200_lsresult* res, double* Val, double* R);
 
 // ---- fsils_solve ---------------------------------------------------------------------------------
-int fsils_solve_device(svb200_ctx* ctx, int dof, int ls_type, const svb200_lsparams* ls, int nFaces, const int* incL,
-                       const double* res, svb200_lsresult* result)
+int fsils_solve_device(svb200_ctx* ctx, int dof, int ls_type, int prec, const svb200_lsparams* ls, int nFaces,
+                       const int* incL, const double* res, svb200_lsresult* result)
 {
   SVB_TRY(ensure_scalars(ctx));
   // face flags (solve.cpp:45-85)
@@ -485,11 +542,15 @@ int fsils_solve_device(svb200_ctx* ctx, int dof, int ls_type, const svb200_lspar
     }
   }
   const size_t nW = (size_t)ctx->nNo * dof;
-  if (nW > ctx->W_cap) {
+  // d_W = [Wc | W1 | Wr | Wc_sweep | 8 scalars]; the diagonal preconditioner only uses the first slice
+  const size_t nWs = (nW + 1) & ~(size_t)1;
+  const size_t needW = (prec == SVB200_PREC_RCS) ? 4 * nWs + 8 : nW;
+  if (needW > ctx->W_cap) {
     if (ctx->d_W) cudaFree(ctx->d_W);
     ctx->d_W = nullptr;
-    SVB_CUDA(cudaMalloc(&ctx->d_W, sizeof(double) * std::max<size_t>(nW, 1)));
-    ctx->W_cap = nW;
+    ctx->W_cap = 0;
+    SVB_CUDA(cudaMalloc(&ctx->d_W, sizeof(double) * std::max<size_t>(needW, 1)));
+    ctx->W_cap = needW;
   }
   svb200_lsresult local{};
   svb200_lsresult* out = result ? result : &local;
@@ -499,7 +560,12 @@ int fsils_solve_device(svb200_ctx* ctx, int dof, int ls_type, const svb200_lspar
   out->hist = hist;
   out->hist_cap = hist ? hist_cap : 0;
 
-  SVB_TRY(precond_diag_device(ctx, dof, ctx->d_Val, ctx->d_R, ctx->d_W));
+  if (prec == SVB200_PREC_RCS) {
+    double* W = ctx->d_W;
+    SVB_TRY(precond_rcs_device(ctx, dof, ctx->d_Val, ctx->d_R, W + nWs, W, W + 2 * nWs, W + 3 * nWs, W + 4 * nWs));
+  } else {
+    SVB_TRY(precond_diag_device(ctx, dof, ctx->d_Val, ctx->d_R, ctx->d_W));
+  }
 
   switch (ls_type) {
     case SVB200_LS_NS:

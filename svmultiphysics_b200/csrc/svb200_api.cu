@@ -796,10 +796,10 @@ int svb200_solve(svb200_ctx* ctx, int32_t dof, int32_t ls_type, int32_t prec, co
   CTX_GUARD(ctx);
   SVB_REQUIRE(ls, "svb200_solve: null solver parameters");
   SVB_REQUIRE(dof == ctx->dof && ctx->d_R && ctx->d_Val, "svb200_solve: call svb200_alloc(dof) and assemble first");
-  SVB_REQUIRE(prec == SVB200_PREC_FSILS, "svb200_solve: only the FSILS diagonal preconditioner is implemented");
+  SVB_REQUIRE(prec == SVB200_PREC_FSILS || prec == SVB200_PREC_RCS, "svb200_solve: preconditioner must be SVB200_PREC_FSILS or SVB200_PREC_RCS");
   SVB_REQUIRE(nFaces <= (int)ctx->face.size(), "svb200_solve: nFaces exceeds svb200_set_num_faces");
   SVB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-  TRY(fsils_solve_device(ctx, dof, ls_type, ls, nFaces, incL, res, result));
+  TRY(fsils_solve_device(ctx, dof, ls_type, prec, ls, nFaces, incL, res, result));
   SVB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
   SVB_CUDA(cudaEventSynchronize(ctx->ev1));
   float ms = 0.f;

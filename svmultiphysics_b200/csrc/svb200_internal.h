@@ -219,8 +219,8 @@ int launch_spmv(svb200_ctx* ctx, int dof, const double* Val, const double* U, do
 int launch_dots(svb200_ctx* ctx, int n, int nvec, const double* const* d_vec_list, const double* base, size_t stride,
                 const double* v, double* d_out);
 // fsils_solvers.cu
-int fsils_solve_device(svb200_ctx* ctx, int dof, int ls_type, const svb200_lsparams* ls, int nFaces, const int* incL,
-                       const double* res, svb200_lsresult* result);
+int fsils_solve_device(svb200_ctx* ctx, int dof, int ls_type, int prec, const svb200_lsparams* ls, int nFaces,
+                       const int* incL, const double* res, svb200_lsresult* result);
 int fp64_peak(svb200_ctx* ctx, double* tflops);
 
 }  // namespace svb

@@ -262,7 +262,8 @@ class Engine:
     def commu_R(self):
         self._call("svb200_commu_R")
 
-    def solve(self, dof, ls_type, ls: abi.LsParams, incL=None, res=None, hist_cap=0, want_solution=True):
+    def solve(self, dof, ls_type, ls: abi.LsParams, incL=None, res=None, hist_cap=0, want_solution=True,
+              prec=abi.PREC_FSILS):
         nFaces = 0 if incL is None else len(incL)
         incL, res = _i32(incL), _f64(res)
         out = abi.LsResult()
@@ -270,7 +271,7 @@ class Engine:
         out.hist = hist.ctypes.data_as(_dp)
         out.hist_cap = hist_cap
         X = np.zeros((dof, self.nNo), order="F") if want_solution else None
-        self._call("svb200_solve", C.c_int32(dof), C.c_int32(ls_type), C.c_int32(abi.PREC_FSILS), C.byref(ls),
+        self._call("svb200_solve", C.c_int32(dof), C.c_int32(ls_type), C.c_int32(prec), C.byref(ls),
                    C.c_int32(nFaces), _i(incL), _d(res), _d(X), C.byref(out))
         return X, out, hist[:out.hist_n].copy()
 

@@ -145,7 +145,9 @@ void B200LinearAlgebra::check(int rc) const
 
 void B200LinearAlgebra::check_options(const consts::PreconditionerType prec_cond_type, const consts::LinearAlgebraType atype)
 {
-  if (prec_cond_type != consts::PreconditionerType::PREC_FSILS && prec_cond_type != consts::PreconditionerType::PREC_NONE) {
+  // the two FSILS preconditioners (consts::fsils_preconditioners), as FsilsLinearAlgebra::check_options
+  if (prec_cond_type != consts::PreconditionerType::PREC_FSILS && prec_cond_type != consts::PreconditionerType::PREC_RCS &&
+      prec_cond_type != consts::PreconditionerType::PREC_NONE) {
     throw std::runtime_error("[svMultiPhysics] ERROR: b200 linear algebra can't use '" +
         consts::preconditioner_type_to_name.at(prec_cond_type) + "' for a preconditioner.");
   }
@@ -163,7 +165,7 @@ void B200LinearAlgebra::set_assembly(consts::LinearAlgebraType atype)
 
 void B200LinearAlgebra::set_preconditioner(consts::PreconditionerType prec_type)
 {
-  if (prec_type != consts::PreconditionerType::PREC_FSILS) {
+  if (consts::fsils_preconditioners.count(prec_type) == 0) {
     throw std::runtime_error("[B200LinearAlgebra] ERROR: b200 linear algebra can't use '" +
         consts::preconditioner_type_to_name.at(prec_type) + "' for a preconditioner.");
   }
@@ -329,7 +331,8 @@ void B200LinearAlgebra::solve(ComMod& com_mod, eqType& lEq, const Vector<int>& i
   svb200_lsparams p = b200::ls_params(lEq.FSILS);
   svb200_lsresult r{};
   if (com_mod.R.nrows() != dof || com_mod.R.ncols() != com_mod.tnNo) com_mod.R.resize(dof, com_mod.tnNo);
-  check(svb200_solve(ctx, dof, type, SVB200_PREC_FSILS, &p, incL.size(), incL.data(), res.data(), com_mod.R.data(), &r));
+  const int prec = (lEq.linear_algebra_preconditioner == consts::PreconditionerType::PREC_RCS) ? SVB200_PREC_RCS : SVB200_PREC_FSILS;
+  check(svb200_solve(ctx, dof, type, prec, &p, incL.size(), incL.data(), res.data(), com_mod.R.data(), &r));
   auto back = [](fsi_linear_solver::FSILS_subLsType& d, const svb200_sublsresult& s) {
     d.success = s.success != 0; d.itr = s.itr; d.iNorm = s.iNorm; d.fNorm = s.fNorm; d.dB = s.dB; d.callD = s.callD;
   };

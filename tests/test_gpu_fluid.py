@@ -180,3 +180,48 @@ def test_fluid_ns_and_coupled_face_parity(ls_type, kw, res_out):
     tol = 50 * ls.RI.relTol if ls_type == abi.LS_NS else 1e-6
     assert common.rel_err(X1, X0) < tol
     eng.close()
+
+
+@pytest.mark.parametrize("ls_type,kw", [
+    (abi.LS_GMRES, dict(mItr=100, sD=50, relTol=1e-8)),
+    (abi.LS_BICGS, dict(mItr=400, relTol=1e-8)),
+], ids=["rcs_gmres", "rcs_bicgs"])
+def test_precond_rcs_parity(ls_type, kw):
+    """precond_rcs (linear_solver/precond.cpp:251-523) on the device against the compiled reference: the equilibrated
+    matrix fsils_solve leaves in Val, the preconditioned initial norm, the iteration count and the solution."""
+    from oracle import refbind
+    if not refbind.have_ref():
+        pytest.skip("precond_rcs is checked against libsvref.so only")
+    m, Ag, Yg, Dg, Bf = common.fluid_case()
+    faces = common.dirichlet_faces(m)
+    orc, rowPtr, colPtr = common.make_oracle(refbind.RefCase, m, nFaces=len(faces))
+    eq, dmn = abi.fluid_eq(0.005), [abi.fluid_domain()]
+    for i, (g, nodes, val) in enumerate(faces):
+        orc.set_face(i, g, nodes, val)
+    orc.alloc(4); orc.set_state(Ag, Yg, Dg, Bf); orc.assemble(0, eq, dmn)
+    R0, V0 = orc.get_R(), orc.get_Val()
+    ls = abi.ls_params(ls_type, **kw)
+    incL, res = np.ones(len(faces), dtype=np.int32), np.zeros(len(faces))
+    X0, out0, _ = orc.solve(4, ls_type, ls, incL, res, prec=abi.PREC_RCS)
+    Vs0 = orc.get_Val()
+
+    eng = common.make_engine(m, rowPtr, colPtr)
+    eng.set_num_faces(len(faces))
+    for i, (g, nodes, val) in enumerate(faces):
+        eng.set_face(i, g, nodes, val)
+    eng.alloc(4)
+    eng.put_Val(V0, 4); eng.put_R(R0)        # identical input bits: the comparison isolates the preconditioner + solver
+    X1, out1, _ = eng.solve(4, ls_type, ls, incL, res, prec=abi.PREC_RCS)
+    Vs1 = eng.get_Val()
+    assert common.rel_err(Vs1, Vs0) < 1e-14
+    assert abs(np.abs(Vs1).max() - 1.0) < 1.0            # equilibrated: max norms O(1)
+    assert abs(out1.RI.iNorm - out0.RI.iNorm) <= 1e-12 * out0.RI.iNorm
+    assert out1.RI.success == out0.RI.success
+    if ls_type == abi.LS_BICGS:
+        assert abs(out1.RI.itr - out0.RI.itr) <= max(3, out0.RI.itr // 20)
+    else:
+        # ~90 restarts: summation-order differences of the dots may move the stopping test by a few steps
+        assert abs(out1.RI.itr - out0.RI.itr) <= max(2, out0.RI.itr // 25)
+        assert out1.RI.fNorm <= ls.RI.relTol * out1.RI.iNorm
+    assert common.rel_err(X1, X0) < 1e-6
+    eng.close()
