@@ -77,6 +77,9 @@ typedef enum { SVB200_ISO_NHK = 0, SVB200_ISO_MR = 1, SVB200_ISO_GUCCIONE = 2, S
 /* volumetric part (solver/mat_models.cpp:1441-1464). */
 typedef enum { SVB200_VOL_NONE = 0, SVB200_VOL_QUAD = 1, SVB200_VOL_ST91 = 2, SVB200_VOL_M94 = 3 } svb200_vol;
 
+/* consts::SolidViscosityModelType (solver/consts.h:466-471, solver/mat_models.cpp:1583-1762). */
+typedef enum { SVB200_SOLID_VISC_NONE = 0, SVB200_SOLID_VISC_NEWTONIAN = 1, SVB200_SOLID_VISC_POTENTIAL = 2 } svb200_solid_visc;
+
 /* fsi_linear_solver::LinearSolverType (linear_solver/fils_struct.hpp). */
 typedef enum { SVB200_LS_NS = 0, SVB200_LS_GMRES = 1, SVB200_LS_CG = 2, SVB200_LS_BICGS = 3 } svb200_ls_type;
 /* consts::PreconditionerType, the two FSILS ones (consts.h:421-432): the diagonal (Jacobi) preconditioner
@@ -119,13 +122,13 @@ typedef struct {
   double mu_i, mu_o, lam, a, n;
   /* solid */
   int32_t volType;   /* svb200_vol */
-  int32_t reserved;
+  int32_t solidViscType;   /* svb200_solid_visc; used only when solid_visc_mu != 0 (0 is read as Newtonian then) */
   double Kpen;
   double C10, C01;
   double bff, bss, bfs;     /* Guccione exponents (stModelType bff/bss/bfs) */
   double dmp;               /* damping */
   double E, nu;             /* elasticity_modulus, poisson_ratio (mesh / linear elasticity) */
-  double solid_visc_mu;     /* 0 = no solid viscosity */
+  double solid_visc_mu;     /* solid_visc.mu; 0 = no solid viscosity */
   double backflow_stab;     /* backflow stabilisation coefficient (fluid Neumann faces, solver/fluid.cpp:65) */
 } svb200_dmnparams;
 

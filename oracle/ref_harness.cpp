@@ -114,7 +114,8 @@ void fill_domain(dmnType& d, const svb200_dmnparams& p)
   d.stM.Kpen = p.Kpen; d.stM.C10 = p.C10; d.stM.C01 = p.C01;
   d.stM.bff = p.bff; d.stM.bss = p.bss; d.stM.bfs = p.bfs;
   if (p.solid_visc_mu != 0.0) {
-    d.solid_visc.viscType = SolidViscosityModelType::viscType_Newtonian;
+    d.solid_visc.viscType = (p.solidViscType == SVB200_SOLID_VISC_POTENTIAL) ? SolidViscosityModelType::viscType_Potential
+                                                                              : SolidViscosityModelType::viscType_Newtonian;
     d.solid_visc.mu = p.solid_visc_mu;
   } else {
     d.solid_visc.viscType = SolidViscosityModelType::viscType_NA;

@@ -16,6 +16,7 @@ VOL_NONE, VOL_QUAD, VOL_ST91, VOL_M94 = 0, 1, 2, 3
 LS_NS, LS_GMRES, LS_CG, LS_BICGS = 0, 1, 2, 3
 PREC_FSILS = 0
 PREC_RCS = 1
+SOLID_VISC_NONE, SOLID_VISC_NEWTONIAN, SOLID_VISC_POTENTIAL = 0, 1, 2
 BC_DIR, BC_NEU = 0, 1
 SCATTER_ATOMIC, SCATTER_COLORED = 0, 1
 ARRAY_R, ARRAY_VAL, ARRAY_W = 0, 1, 2
@@ -47,7 +48,7 @@ class DmnParams(C.Structure):
         ("K_darcy", C.c_double),
         ("viscType", C.c_int32), ("isoType", C.c_int32),
         ("mu_i", C.c_double), ("mu_o", C.c_double), ("lam", C.c_double), ("a", C.c_double), ("n", C.c_double),
-        ("volType", C.c_int32), ("reserved", C.c_int32),
+        ("volType", C.c_int32), ("solidViscType", C.c_int32),
         ("Kpen", C.c_double),
         ("C10", C.c_double), ("C01", C.c_double),
         ("bff", C.c_double), ("bss", C.c_double), ("bfs", C.c_double),
@@ -121,7 +122,7 @@ def struct_eq(dt: float, rho_inf: float = 0.5, tDof: int = 3, dof: int = 3, s: i
 
 def struct_domain(rho: float = 1000.0, isoType: int = ISO_NHK, volType: int = VOL_ST91, E: float = 240.56596e6, nu: float = 0.5,
                   Kpen: float = 4.0e9, C10=None, C01: float = 0.0, bff: float = 0.0, bss: float = 0.0, bfs: float = 0.0,
-                  dmp: float = 0.0, f=(0.0, 0.0, 0.0), Id: int = -1) -> DmnParams:
+                  dmp: float = 0.0, f=(0.0, 0.0, 0.0), Id: int = -1, solid_visc: int = 0, solid_visc_mu: float = 0.0) -> DmnParams:
     """Solid domain; C10 defaults to mu/2 with mu = E/(2(1+nu)) as set_material_props does for nHK
     (Code/Source/solver/set_material_props.h)."""
     d = DmnParams()
@@ -137,6 +138,7 @@ def struct_domain(rho: float = 1000.0, isoType: int = ISO_NHK, volType: int = VO
     d.bff, d.bss, d.bfs = bff, bss, bfs
     d.dmp = dmp
     d.E, d.nu = E, nu
+    d.solidViscType, d.solid_visc_mu = solid_visc, solid_visc_mu
     return d
 
 

@@ -60,7 +60,7 @@ __host__ __device__ constexpr int struct_per_el(int enon)
   return n + ((8 - (n % 16)) + 16) % 16;
 }
 
-template <int ENON, bool ATOMIC>
+template <int ENON, bool ATOMIC, bool VISC>
 __global__ void __launch_bounds__(STRUCT_THREADS)
 assemble_struct_kernel(const __grid_constant__ StructArgs P)
 {
@@ -162,6 +162,29 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
     }
     double S[3][3], Dm[6][6];
     pk2cc_voigt(dm, F, fN, S, Dm);
+    if (VISC && dm.viscType != SVB200_SOLID_VISC_NONE) {
+      // S += Svis (sv_struct.cpp:666-669); the viscous tangent is added by assemble_struct_visc_kernel
+      double vx[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, Svis[3][3];
+#pragma unroll
+      for (int b = 0; b < ENON; b++) {
+        const size_t nb = (size_t)P.IEN[(size_t)e * ENON + b];
+        double Nxb[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) Nxb[j] = tNxi[g][b][0] * xiX[0][j] + tNxi[g][b][1] * xiX[1][j] + tNxi[g][b][2] * xiX[2][j];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          const double y = __ldg(P.Yg + (size_t)P.tDof * nb + P.s + i);
+#pragma unroll
+          for (int j = 0; j < 3; j++) vx[i][j] += Nxb[j] * y;
+        }
+      }
+      ViscGP vgp;
+      visc_gauss_point(dm.viscType, dm.visc_mu, 0.0, 0.0, F, vx, Svis, vgp);
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) S[i][j] += Svis[i][j];
+    }
     double* q = sgp + g * GP_LD;
 #pragma unroll
     for (int i = 0; i < 3; i++)
@@ -298,6 +321,109 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
   }
 }
 
+// ---- viscous tangent of the solid (mat_models.cpp:1583-1762, sv_struct.cpp:759-823) ---------------------
+// Launched after assemble_struct_kernel<.., VISC = true> for the domains with a solid viscosity model; adds
+// w (afu Kvis_u + afv Kvis_v) for ALL ENON x ENON node pairs (this part of the element matrix is not symmetric).
+// Same lane mapping: in phase A lane g evaluates Gauss point g (nn::gnn, F, vx, visc_gauss_point) and leaves the
+// three vectors V1..V3 of every element node plus M and w c in shared memory; in phase B lane a accumulates block
+// (a, b) over the Gauss points for one b at a time and scatters it.
+constexpr int VISC_THREADS = 128;
+__host__ __device__ constexpr int visc_per_el(int enon)
+{
+  const int n = enon * (enon * 9 + 10);
+  return n + ((8 - (n % 16)) + 16) % 16;
+}
+
+template <int ENON, bool ATOMIC>
+__global__ void __launch_bounds__(VISC_THREADS)
+assemble_struct_visc_kernel(const __grid_constant__ StructArgs P)
+{
+  constexpr int EPW = 32 / ENON;
+  constexpr int PER_EL = visc_per_el(ENON);
+  extern __shared__ double sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int a = lane % ENON, el = lane / ENON;
+  double* se = sm + (size_t)(warp * EPW + el) * PER_EL;
+  double* sV = se;                           // [g][b][9]
+  double* sM = se + ENON * ENON * 9;         // [g][10]: M (9), w c
+  const long long idx = (long long)P.e0 + ((long long)blockIdx.x * (VISC_THREADS / 32) + warp) * EPW + el;
+  bool active = idx < P.e1;
+  int e = 0;
+  if (active) e = P.perm ? P.perm[idx] : (int)idx;
+  int iD = 0;
+  if (active) {
+    for (int d = 0; d < P.nDmn; d++) {
+      iD = d;
+      if (P.dmn[d].Id == -1) break;
+      if (P.eId != nullptr && ((P.eId[e] >> P.dmn[d].Id) & 1)) break;
+    }
+    if (!P.dmn[iD].isStruct || P.dmn[iD].viscType == SVB200_SOLID_VISC_NONE) active = false;
+  }
+  const StructDmn& dm = P.dmn[iD];
+  const int DOF = P.dof;
+  const double afu = P.af * P.beta * P.dt * P.dt, afv = P.af * P.gam * P.dt;
+  if (active) {
+    const int g = a;
+    double xl[ENON][3], Nx[ENON][3];
+    double F[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, vx[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+    for (int b = 0; b < ENON; b++) {
+      const size_t n = (size_t)P.IEN[(size_t)e * ENON + b];
+#pragma unroll
+      for (int i = 0; i < 3; i++) xl[b][i] = __ldg(P.x + 3 * n + i);
+    }
+    const double Jac = gnn3<ENON>(P.Nxi[g], xl, Nx);
+#pragma unroll
+    for (int b = 0; b < ENON; b++) {
+      const size_t n = (size_t)P.IEN[(size_t)e * ENON + b];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const double d = __ldg(P.Dg + (size_t)P.tDof * n + P.s + i), y = __ldg(P.Yg + (size_t)P.tDof * n + P.s + i);
+#pragma unroll
+        for (int j = 0; j < 3; j++) { F[i][j] += Nx[b][j] * d; vx[i][j] += Nx[b][j] * y; }
+      }
+    }
+    ViscGP vgp;
+    double Svis[3][3];
+    visc_gauss_point(dm.viscType, dm.visc_mu, afu, afv, F, vx, Svis, vgp);
+#pragma unroll
+    for (int b = 0; b < ENON; b++) {
+      double V[9];
+      visc_node(vgp, Nx[b], V);
+#pragma unroll
+      for (int k = 0; k < 9; k++) sV[(g * ENON + b) * 9 + k] = V[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) sM[g * 10 + k] = vgp.M[k / 3][k % 3];
+    sM[g * 10 + 9] = P.w[g] * Jac * vgp.c;
+  }
+  __syncwarp();
+  if (!active) return;
+  const int node = P.IEN[(size_t)e * ENON + a];
+  (void)node;
+  const int* sl = P.slot + (size_t)e * ENON * ENON;
+#pragma unroll 1
+  for (int b = 0; b < ENON; b++) {
+    double K[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll 1
+    for (int g = 0; g < ENON; g++) {
+      double Va[9], Vb[9], M[9];
+#pragma unroll
+      for (int k = 0; k < 9; k++) {
+        Va[k] = sV[(g * ENON + a) * 9 + k];
+        Vb[k] = sV[(g * ENON + b) * 9 + k];
+        M[k] = sM[g * 10 + k];
+      }
+      visc_block(dm.viscType, sM[g * 10 + 9], afu, afv, M, Va, Vb, K);
+    }
+    double* v = P.Val + (size_t)DOF * DOF * sl[a * ENON + b];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) add64<ATOMIC>(v + DOF * i + j, K[i][j]);
+  }
+}
+
 // ---- mesh-motion equation: linear elasticity on the configuration at t_n --------------------------------
 // mesh::construct_mesh (Code/Source/solver/mesh.cpp:22-135) + l_elas::l_elas_3d (Code/Source/solver/l_elas.cpp:249-365):
 // geometry x + Do(is..), displacement Dg(is..) - Do(is..), and the Gauss weight WITHOUT the Jacobian
@@ -431,11 +557,14 @@ int fill_struct_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, 
     o.Kpen = dmn[d].Kpen; o.C10 = dmn[d].C10; o.C01 = dmn[d].C01;
     o.bff = dmn[d].bff; o.bss = dmn[d].bss; o.bfs = dmn[d].bfs;
     o.isoType = dmn[d].isoType; o.volType = dmn[d].volType;
+    o.visc_mu = dmn[d].solid_visc_mu;
+    o.viscType = SVB200_SOLID_VISC_NONE;
+    if (dmn[d].phys == SVB200_PHYS_STRUCT && dmn[d].solid_visc_mu != 0.0)
+      o.viscType = (dmn[d].solidViscType == SVB200_SOLID_VISC_POTENTIAL) ? SVB200_SOLID_VISC_POTENTIAL : SVB200_SOLID_VISC_NEWTONIAN;
     o.Id = dmn[d].Id;
     o.isStruct = (dmn[d].phys == SVB200_PHYS_STRUCT);
     SVB_REQUIRE(o.Id >= -1 && o.Id < 31, "svb200_assemble: domain Id out of range");
     if (o.isStruct) {
-      SVB_REQUIRE(dmn[d].solid_visc_mu == 0.0, "svb200_assemble: solid viscosity is not implemented");
       SVB_REQUIRE(o.isoType == SVB200_ISO_NHK || o.isoType == SVB200_ISO_MR || o.isoType == SVB200_ISO_GUCCIONE ||
                       o.isoType == SVB200_ISO_STVK, "svb200_assemble: constitutive model not implemented");
       // compute_pk2cc throws for Guccione without two fibre families (mat_models.cpp:514-516)
@@ -458,16 +587,36 @@ static int launch_one(svb200_ctx* ctx, const StructArgs& A)
   if (n <= 0) return SVB200_OK;
   const unsigned blocks = (unsigned)((n + EPB - 1) / EPB);
   constexpr size_t smem = sizeof(double) * ((size_t)ENON * ENON * 4 + ENON + (size_t)EPB * struct_per_el(ENON));
+  constexpr int EPBV = (VISC_THREADS / 32) * (32 / ENON);
+  constexpr size_t smemV = sizeof(double) * (size_t)EPBV * visc_per_el(ENON);
   static bool configured = false;
   if (!configured) {
-    SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVB_CUDA(cudaFuncSetAttribute(assemble_struct_visc_kernel<ENON, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemV));
+    SVB_CUDA(cudaFuncSetAttribute(assemble_struct_visc_kernel<ENON, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemV));
     configured = true;
   }
   if (A.nG != ENON) { set_error("svb200: the solid kernel expects nG == eNoN (TET4: 4, HEX8: 8 Gauss points)"); return SVB200_ERR_UNSUPPORTED; }
-  if (A.atomic) assemble_struct_kernel<ENON, true><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
-  else assemble_struct_kernel<ENON, false><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
-  ctx->launches++;
+  bool visc = false;
+  for (int d = 0; d < A.nDmn; d++) visc |= (A.dmn[d].isStruct && A.dmn[d].viscType != SVB200_SOLID_VISC_NONE);
+  if (!visc) {
+    if (A.atomic) assemble_struct_kernel<ENON, true, false><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
+    else assemble_struct_kernel<ENON, false, false><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
+    ctx->launches++;
+  } else {
+    const unsigned blocksV = (unsigned)((n + EPBV - 1) / EPBV);
+    if (A.atomic) {
+      assemble_struct_kernel<ENON, true, true><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
+      assemble_struct_visc_kernel<ENON, true><<<blocksV, VISC_THREADS, smemV, ctx->stream>>>(A);
+    } else {
+      assemble_struct_kernel<ENON, false, true><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
+      assemble_struct_visc_kernel<ENON, false><<<blocksV, VISC_THREADS, smemV, ctx->stream>>>(A);
+    }
+    ctx->launches += 2;
+  }
   SVB_CUDA(cudaGetLastError());
   return SVB200_OK;
 }

@@ -22,7 +22,9 @@ namespace svb {
 struct StructDmn {
   double rho, f[3], dmp;
   double Kpen, C10, C01, bff, bss, bfs;
+  double visc_mu;
   int isoType, volType, Id, isStruct;
+  int viscType, pad;      // svb200_solid_visc
 };
 
 #define SVB_VI(a) ((a) < 3 ? (a) : ((a) == 3 ? 0 : ((a) == 4 ? 1 : 2)))
@@ -293,6 +295,120 @@ SVB_HD void struct_block(double K[3][3], double w, double amdNaNb, double afu, c
 #pragma unroll
       for (int r = 0; r < 6; r++) s += Bma[r][i] * DBmb[r][j];
       K[i][j] += w * ((i == j ? T1 : 0.0) + afu * s);
+    }
+}
+
+// ---- solid viscosity (mat_models.cpp:1583-1762) ----------------------------------------------------------
+// Both models of compute_visc_stress_and_tangent have the same structure: three vectors per element node,
+//     V1_a = T grad N_a,  V2_a = A V1_a,  V3_a = B V1_a,
+// one 3x3 matrix M and one scalar c per Gauss point, and a tangent block that is bilinear in (V_a, V_b):
+//   Potential  (:1583-1637)  T = I, A = F, B = afu vx + afv F, M = afu F vx^T + afv F F^T, c = mu/2
+//       afu Kvis_u + afv Kvis_v = c [ V2_b(i) V3_a(j) + (V1_a.V1_b) M(i,j) ]
+//   Newtonian  (:1660-1733)  T = F^-T, A = dev sym(vx F^-1), B = M = vx F^-1, c = mu J
+//       Kvis_u = c [ 2 (V2_a(i) V1_b(j) - V2_b(i) V1_a(j)) - ((V1_a.V1_b) M(i,j) + V1_b(i) V3_a(j) - 2/3 V1_a(i) V3_b(j)) ]
+//       Kvis_v = c [ (V1_a.V1_b) delta_ij + V1_b(i) V1_a(j) - 2/3 V1_a(i) V1_b(j) ]
+// (the reference's own comment notes that the Newtonian tangent is probably not the exact derivative; it is
+// reproduced as written).
+struct ViscGP {
+  double T[3][3], A[3][3], B[3][3], M[3][3];
+  double c;
+};
+
+// Svis (added to S before the prestress / P = F S, sv_struct.cpp:666-669) and the Gauss-point terms above.
+SVB_HD void visc_gauss_point(int viscType, double mu, double afu, double afv, const double F[3][3], const double vx[3][3],
+                             double Svis[3][3], ViscGP& gp)
+{
+  if (viscType == SVB200_SOLID_VISC_POTENTIAL) {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const double Ftvx_ij = F[0][i] * vx[0][j] + F[1][i] * vx[1][j] + F[2][i] * vx[2][j];
+        const double Ftvx_ji = F[0][j] * vx[0][i] + F[1][j] * vx[1][i] + F[2][j] * vx[2][i];
+        Svis[i][j] = mu * 0.5 * (Ftvx_ij + Ftvx_ji);
+        gp.T[i][j] = (i == j) ? 1.0 : 0.0;
+        gp.A[i][j] = F[i][j];
+        gp.B[i][j] = afu * vx[i][j] + afv * F[i][j];
+        const double FFt = F[i][0] * F[j][0] + F[i][1] * F[j][1] + F[i][2] * F[j][2];
+        const double Fvxt = F[i][0] * vx[j][0] + F[i][1] * vx[j][1] + F[i][2] * vx[j][2];
+        gp.M[i][j] = afu * Fvxt + afv * FFt;
+      }
+    gp.c = 0.5 * mu;
+    return;
+  }
+  // Newtonian
+  const double J = F[0][0] * (F[1][1] * F[2][2] - F[1][2] * F[2][1]) - F[0][1] * (F[1][0] * F[2][2] - F[1][2] * F[2][0]) +
+                   F[0][2] * (F[1][0] * F[2][1] - F[1][1] * F[2][0]);
+  double Fi[3][3];
+  Fi[0][0] = (F[1][1] * F[2][2] - F[1][2] * F[2][1]) / J;
+  Fi[0][1] = (F[0][2] * F[2][1] - F[0][1] * F[2][2]) / J;
+  Fi[0][2] = (F[0][1] * F[1][2] - F[0][2] * F[1][1]) / J;
+  Fi[1][0] = (F[1][2] * F[2][0] - F[1][0] * F[2][2]) / J;
+  Fi[1][1] = (F[0][0] * F[2][2] - F[0][2] * F[2][0]) / J;
+  Fi[1][2] = (F[0][2] * F[1][0] - F[0][0] * F[1][2]) / J;
+  Fi[2][0] = (F[1][0] * F[2][1] - F[1][1] * F[2][0]) / J;
+  Fi[2][1] = (F[0][1] * F[2][0] - F[0][0] * F[2][1]) / J;
+  Fi[2][2] = (F[0][0] * F[1][1] - F[0][1] * F[1][0]) / J;
+  double vF[3][3], dd[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) vF[i][j] = vx[i][0] * Fi[0][j] + vx[i][1] * Fi[1][j] + vx[i][2] * Fi[2][j];
+  const double tr3 = (vF[0][0] + vF[1][1] + vF[2][2]) / 3.0;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) dd[i][j] = 0.5 * (vF[i][j] + vF[j][i]) - (i == j ? tr3 : 0.0);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int l = 0; l < 3; l++) s += Fi[i][k] * dd[k][l] * Fi[j][l];
+      Svis[i][j] = 2.0 * mu * J * s;
+      gp.T[i][j] = Fi[j][i];
+      gp.A[i][j] = dd[i][j];
+      gp.B[i][j] = vF[i][j];
+      gp.M[i][j] = vF[i][j];
+    }
+  gp.c = mu * J;
+}
+
+// V[0..2] = V1, V[3..5] = V2, V[6..8] = V3 of one node.
+SVB_HD void visc_node(const ViscGP& gp, const double Nx[3], double V[9])
+{
+#pragma unroll
+  for (int i = 0; i < 3; i++) V[i] = gp.T[i][0] * Nx[0] + gp.T[i][1] * Nx[1] + gp.T[i][2] * Nx[2];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    V[3 + i] = gp.A[i][0] * V[0] + gp.A[i][1] * V[1] + gp.A[i][2] * V[2];
+    V[6 + i] = gp.B[i][0] * V[0] + gp.B[i][1] * V[1] + gp.B[i][2] * V[2];
+  }
+}
+
+// K(i,j) += wc (afu Kvis_u(i,j;a,b) + afv Kvis_v(i,j;a,b)) / c, wc = Gauss weight * gp.c  (sv_struct.cpp:759-823)
+SVB_HD void visc_block(int viscType, double wc, double afu, double afv, const double M[9], const double Va[9], const double Vb[9],
+                       double K[3][3])
+{
+  const double dot = Va[0] * Vb[0] + Va[1] * Vb[1] + Va[2] * Vb[2];
+  if (viscType == SVB200_SOLID_VISC_POTENTIAL) {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) K[i][j] += wc * (Vb[3 + i] * Va[6 + j] + dot * M[3 * i + j]);
+    return;
+  }
+  const double r2d = 2.0 / 3.0;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const double ku = 2.0 * (Va[3 + i] * Vb[j] - Vb[3 + i] * Va[j]) - (dot * M[3 * i + j] + Vb[i] * Va[6 + j] - r2d * Va[i] * Vb[6 + j]);
+      const double kv = (i == j ? dot : 0.0) + Vb[i] * Va[j] - r2d * Va[i] * Vb[j];
+      K[i][j] += wc * (afu * ku + afv * kv);
     }
 }
 

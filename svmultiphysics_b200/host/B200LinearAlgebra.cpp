@@ -93,7 +93,11 @@ std::vector<svb200_dmnparams> domain_params(const eqType& eq)
       }
       p.Kpen = d.stM.Kpen; p.C10 = d.stM.C10; p.C01 = d.stM.C01;
       p.bff = d.stM.bff; p.bss = d.stM.bss; p.bfs = d.stM.bfs;
-      if (d.solid_visc.viscType != SolidViscosityModelType::viscType_NA) p.solid_visc_mu = d.solid_visc.mu;
+      if (d.solid_visc.viscType != SolidViscosityModelType::viscType_NA) {
+        p.solid_visc_mu = d.solid_visc.mu;
+        p.solidViscType = (d.solid_visc.viscType == SolidViscosityModelType::viscType_Potential) ? SVB200_SOLID_VISC_POTENTIAL
+                                                                                                 : SVB200_SOLID_VISC_NEWTONIAN;
+      }
     }
     out[i] = p;
   }

@@ -91,6 +91,12 @@ STRUCT_CASES = [
     ("tet4_nHK_Quad", _tet, dict(volType=abi.VOL_QUAD, E=1e6, nu=0.4, Kpen=1e6, rho=1.0), 0),
     ("hex8_MR", _hex, dict(isoType=abi.ISO_MR, C10=1e5, C01=3e4, Kpen=1e7, rho=1.0), 0),
     ("hex8_StVK", _hex, dict(isoType=abi.ISO_STVK, C10=2e5, C01=1e5, Kpen=0.0, rho=1.0), 0),
+    # solid viscosity (mat_models.cpp:1583-1762): pseudo-potential and Newtonian models, element matrix no longer symmetric
+    ("hex8_nHK_visc_potential", _hex, dict(solid_visc=abi.SOLID_VISC_POTENTIAL, solid_visc_mu=2.0e4, dmp=3.0), 0),
+    ("tet4_nHK_visc_newtonian", _tet, dict(volType=abi.VOL_QUAD, E=1e6, nu=0.4, Kpen=1e6, rho=1.0, solid_visc=abi.SOLID_VISC_NEWTONIAN,
+                                           solid_visc_mu=3.0e5), 0),
+    ("hex8_MR_visc_newtonian", _hex, dict(isoType=abi.ISO_MR, C10=1e5, C01=3e4, Kpen=1e7, rho=1.0, solid_visc=abi.SOLID_VISC_NEWTONIAN,
+                                          solid_visc_mu=50.0), 0),
     ("hex8_Guccione", _hex, dict(isoType=abi.ISO_GUCCIONE, C10=440.0, bff=8.0, bss=6.0, bfs=12.0, Kpen=1e6, rho=1e-3), 2),   # struct/LV_Guccione_passive
 ]
 

@@ -50,7 +50,23 @@ def fluid_golden():
     print("wrote fluid_tet4.npz with", len(out), "arrays")
 
 
+def struct_golden():
+    """Assembled R / Val of every solid case of tests/common.py (struct_3d + compute_pk2cc + solid viscosity)."""
+    out = {}
+    for name, mk, dkw, nFn in common.STRUCT_CASES:
+        m = mk()
+        Ag, Yg, Dg, Bf, fN = common.struct_state(m, nFn)
+        c = RefCase(); c.set_coords(m.x); c.add_mesh(m.IEN, nFn=nFn, fN=fN)
+        rowPtr, colPtr = c.build_graph(0)
+        c.alloc(3); c.set_state(Ag, Yg, Dg, Bf); c.assemble(0, abi.struct_eq(1e-4), [abi.struct_domain(**dkw)])
+        out[f"{name}/R"], out[f"{name}/Val"] = c.get_R(), c.get_Val()
+        out[f"{name}/rowPtr"], out[f"{name}/colPtr"] = rowPtr, colPtr
+    np.savez_compressed(os.path.join(HERE, "struct.npz"), **out)
+    print("wrote struct.npz with", len(out), "arrays")
+
+
 if __name__ == "__main__":
     if not have_ref():
         raise SystemExit("oracle/_ref/libsvref.so is missing: run `make -C oracle ref` first")
     fluid_golden()
+    struct_golden()

@@ -23,12 +23,13 @@ static int run(const HostStructArgs* P, const int* rowPtr, const int* colPtr, do
   const double amd = P->am * P->dm.rho + P->af * P->gam * P->dt * P->dm.dmp;
   for (int e = 0; e < P->nEl; e++) {
     int n[ENON];
-    double xl[ENON][3], q[ENON][3], dl[ENON][3], fN[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    double xl[ENON][3], q[ENON][3], dl[ENON][3], yl[ENON][3], fN[2][3] = {{0, 0, 0}, {0, 0, 0}};
     for (int a = 0; a < ENON; a++) {
       n[a] = P->IEN[ENON * e + a];
       for (int i = 0; i < 3; i++) {
         xl[a][i] = P->x[3 * n[a] + i];
         dl[a][i] = P->Dg[P->tDof * n[a] + s0 + i];
+        yl[a][i] = P->Yg[P->tDof * n[a] + s0 + i];
         q[a][i] = P->dm.rho * (P->Ag[P->tDof * n[a] + s0 + i] - P->Bf[3 * n[a] + i]) + P->dm.dmp * P->Yg[P->tDof * n[a] + s0 + i];
       }
     }
@@ -46,6 +47,19 @@ static int run(const HostStructArgs* P, const int* rowPtr, const int* colPtr, do
         }
       double S[3][3], Dm[6][6];
       if (pk2cc_voigt(P->dm, F, fN, S, Dm)) return 2;
+      const bool visc = P->dm.viscType != 0 && P->dm.visc_mu != 0.0;
+      const double afv = P->af * P->gam * P->dt;
+      ViscGP vgp;
+      double V[ENON][9];
+      if (visc) {
+        double vx[3][3] = {}, Svis[3][3];
+        for (int a = 0; a < ENON; a++)
+          for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) vx[i][j] += Nx[a][j] * yl[a][i];
+        visc_gauss_point(P->dm.viscType, P->dm.visc_mu, afu, afv, F, vx, Svis, vgp);
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) S[i][j] += Svis[i][j];
+        for (int a = 0; a < ENON; a++) visc_node(vgp, Nx[a], V[a]);
+      }
       double Pk[3][3];
       for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Pk[i][j] = F[i][0] * S[0][j] + F[i][1] * S[1][j] + F[i][2] * S[2][j];
       double Bm[ENON][6][3], DBm[ENON][6][3], SNx[ENON][3];
@@ -56,7 +70,10 @@ static int run(const HostStructArgs* P, const int* rowPtr, const int* colPtr, do
         for (int i = 0; i < 3; i++) SNx[a][i] = Nx[a][0] * S[0][i] + Nx[a][1] * S[1][i] + Nx[a][2] * S[2][i];
       }
       for (int a = 0; a < ENON; a++)
-        for (int b = 0; b < ENON; b++) struct_block(lK[a][b], w, amd * P->N[g][a] * P->N[g][b], afu, SNx[a], Nx[b], Bm[a], DBm[b]);
+        for (int b = 0; b < ENON; b++) {
+          struct_block(lK[a][b], w, amd * P->N[g][a] * P->N[g][b], afu, SNx[a], Nx[b], Bm[a], DBm[b]);
+          if (visc) visc_block(P->dm.viscType, w * vgp.c, afu, afv, &vgp.M[0][0], V[a], V[b], lK[a][b]);
+        }
     }
     for (int a = 0; a < ENON; a++) {
       for (int i = 0; i < 3; i++) R[dof * n[a] + i] += lR[a][i];

@@ -69,3 +69,58 @@ def test_device_element_algebra_matches_golden(hostmath, case, variant):
     assert rc == 0
     assert common.rel_err(R.T, golden[f"{name}/R"]) < 1e-12
     assert common.rel_err(V.T, golden[f"{name}/Val"]) < 1e-12
+
+
+class StructDmn(C.Structure):
+    _fields_ = [("rho", C.c_double), ("f", C.c_double * 3), ("dmp", C.c_double),
+                ("Kpen", C.c_double), ("C10", C.c_double), ("C01", C.c_double), ("bff", C.c_double), ("bss", C.c_double),
+                ("bfs", C.c_double), ("visc_mu", C.c_double),
+                ("isoType", C.c_int), ("volType", C.c_int), ("Id", C.c_int), ("isStruct", C.c_int), ("viscType", C.c_int), ("pad", C.c_int)]
+
+
+class HostStructArgs(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("IEN", "fN", "x", "Ag", "Yg", "Dg", "Bf")] + \
+               [(k, C.c_int) for k in ("eNoN", "nEl", "nG", "tDof", "dof", "s", "nFn")] + \
+               [(k, C.c_double) for k in ("dt", "af", "am", "gam", "beta")] + \
+               [("w", C.c_double * 8), ("N", (C.c_double * 8) * 8), ("Nxi", ((C.c_double * 3) * 8) * 8), ("dm", StructDmn)]
+
+
+@pytest.mark.parametrize("name,mk,dkw,nFn", common.STRUCT_CASES, ids=[c[0] for c in common.STRUCT_CASES])
+def test_device_solid_algebra_matches_golden(hostmath, name, mk, dkw, nFn):
+    """svmultiphysics_b200/csrc/struct_elem.cuh (pk2cc_voigt, solid viscosity, Bm/DBm blocks) compiled for the host
+    against the R / Val the unmodified reference assembled (tests/golden/struct.npz), tolerance 1e-12."""
+    golden = common.load_golden("struct.npz")
+    assert hostmath.hostmath_sizeof_structargs() == C.sizeof(HostStructArgs)
+    m = mk()
+    Ag, Yg, Dg, Bf, fN = common.struct_state(m, nFn)
+    eq, d = abi.struct_eq(1e-4), abi.struct_domain(**dkw)
+    w, N, Nx = elements.tables(m.eNoN)
+    A = HostStructArgs()
+    keep = [np.ascontiguousarray(m.IEN.T.astype(np.int32)), np.ascontiguousarray(m.x.T), np.ascontiguousarray(Ag.T),
+            np.ascontiguousarray(Yg.T), np.ascontiguousarray(Dg.T), np.ascontiguousarray(Bf.T)]
+    A.IEN, A.x, A.Ag, A.Yg, A.Dg, A.Bf = (k.ctypes.data for k in keep)
+    if nFn:
+        fk = np.ascontiguousarray(fN.T)
+        A.fN = fk.ctypes.data
+    A.eNoN, A.nEl, A.nG, A.tDof, A.dof, A.s, A.nFn = m.eNoN, m.nEl, len(w), 3, 3, 0, nFn
+    A.dt, A.af, A.am, A.gam, A.beta = eq.dt, eq.af, eq.am, eq.gam, eq.beta
+    for g in range(len(w)):
+        A.w[g] = w[g]
+        for a in range(m.eNoN):
+            A.N[g][a] = N[a, g]
+            for k in range(3):
+                A.Nxi[g][a][k] = Nx[k, a, g]
+    dm = A.dm
+    dm.rho, dm.dmp, dm.Kpen, dm.C10, dm.C01, dm.bff, dm.bss, dm.bfs = d.rho, d.dmp, d.Kpen, d.C10, d.C01, d.bff, d.bss, d.bfs
+    for i in range(3):
+        dm.f[i] = d.f[i]
+    dm.visc_mu, dm.viscType = d.solid_visc_mu, d.solidViscType
+    dm.isoType, dm.volType, dm.Id, dm.isStruct = d.isoType, d.volType, -1, 1
+    rowPtr, colPtr = golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"]
+    R = np.zeros((m.nNo, 3))
+    V = np.zeros((len(colPtr), 9))
+    rc = hostmath.hostmath_struct(C.byref(A), rowPtr.ctypes.data_as(C.c_void_p), colPtr.ctypes.data_as(C.c_void_p),
+                                  R.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    assert common.rel_err(R.T, golden[f"{name}/R"]) < 1e-12
+    assert common.rel_err(V.T, golden[f"{name}/Val"]) < 1e-12
