@@ -224,6 +224,19 @@ int svref_get_mesh_tables(void* h, int iM, int* nG, double* w, double* N, double
   });
 }
 
+/// Second derivatives of the shape functions on the reference element, fs[0].Nxx(6,eNoN,nG) (fs::init_fs_msh):
+/// what construct_fluid hands to nn::gn_nxx (solver/fluid.cpp:648-650).
+int svref_get_mesh_nxx(void* h, int iM, double* Nxx)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    auto& m = c.com_mod.msh.at(iM);
+    auto& f = m.fs.at(0);
+    if (f.Nxx.size() != 6*m.eNoN*m.nG) throw std::runtime_error("[ref_harness] fs[0].Nxx has an unexpected size");
+    std::memcpy(Nxx, f.Nxx.data(), sizeof(double)*6*m.eNoN*m.nG);
+  });
+}
+
 /// The element loop of lhsa_ns::lhsa (solver/lhsa.cpp:155-166) through the reference's own add_col,
 /// then its compaction (:352-380), then fsils_commu_create + fsils_lhs_create as initialize() does.
 int svref_build_graph(void* h, int nFaces, int* nnz_out)

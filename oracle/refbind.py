@@ -113,6 +113,14 @@ class _FlatCase:
         self._call("get_mesh_tables", C.c_int(iM), C.byref(nG), _d(w), _d(N), _d(Nx))
         return w, N, Nx
 
+    def mesh_nxx(self, iM):
+        """fs[0].Nxx(6,eNoN,nG) of the reference (compiled reference only)."""
+        eNoN = self.meshes[iM][0]
+        w, _, _ = self.mesh_tables(iM)
+        Nxx = np.zeros((6, eNoN, len(w)), order="F")
+        self._call("get_mesh_nxx", C.c_int(iM), _d(Nxx))
+        return Nxx
+
     def build_graph(self, nFaces=0):
         nnz = C.c_int(0)
         self._call("build_graph", C.c_int(nFaces), C.byref(nnz))

@@ -1,0 +1,306 @@
+// fluid_gen.cuh — Gauss-point algebra of the VMS Navier-Stokes element for ANY 3-D Lagrange element with equal-order
+// velocity/pressure (HEX8 today; TET4 runs through it in the tests as a cross-check of the specialised kernel).
+//
+// Reference: fluid::construct_fluid (Code/Source/solver/fluid.cpp:480-762) with nn::gnn per Gauss point
+// (solver/nn.cpp:862-899), nn::gn_nxx (solver/nn.cpp:1172-1283), fluid_3d_m (fluid.cpp:1768-2237) and
+// fluid_3d_c (fluid.cpp:1443-1760).  Unlike fluid_elem.cuh (linear tetrahedra) nothing is constant over the element
+// and the second derivatives of the shape functions do not vanish: they enter through the viscous part of the
+// strong momentum residual (rS), the viscosity gradient mu_x and the fine-scale velocity tangent updu.
+//
+// Layout of the work: everything that does not depend on the node pair (a,b) is evaluated ONCE per Gauss point
+// (FluidGP, ~45 doubles) together with 11 numbers per element node (FluidNode); a tangent block is then a short
+// bilinear expression in (FluidNode_a, FluidNode_b) — see fluid_gen_block.
+//
+// Two reference behaviours that parity needs and that are easy to miss:
+//  * gn_nxx solves a 6x6 system K X = B with LAPACK dgesv, K built from the Jacobian dx/dxi.  K is the Voigt form of
+//    the transformation of a symmetric second-order tensor, so K^-1 is the same matrix built from dxi/dx, which gnn
+//    has already computed: the solve becomes a 6x6 product (agreement with dgesv to round-off).
+//  * the continuity loop (second Gauss loop of construct_fluid, fluid.cpp:697-745) recomputes gnn per Gauss point but
+//    NOT gn_nxx: fluid_3d_c sees the Nwxx of the LAST Gauss point of the momentum loop at every Gauss point.  The
+//    continuity rows therefore use their own d2u2 / mu_x / up / updu (the *_c members below).
+#pragma once
+#include "fluid_elem.cuh"
+
+namespace svb {
+
+struct FluidGP {
+  double w, wl, wr, rho, amd, mu, mu_g, muKd, tauM, tauC, tauB, divU;
+  double u[3], up[3], rV[3], rM[3][3];
+  double mu_x[3], d2u2[3];
+  double up_c[3], mu_x_c[3], d2u2_c[3];
+};
+constexpr int FLUID_GP_DOUBLES = sizeof(FluidGP) / sizeof(double);
+
+struct FluidNode {
+  double N, Nx[3], esNx[3], uNx, upNx, T1b, T1b_c;
+};
+constexpr int FLUID_NODE_DOUBLES = sizeof(FluidNode) / sizeof(double);
+
+// nn::gnn, insd = 3: Nx[a][i], xiX[k][i] = d xi_k / d x_i, ks = xiX^T xiX, returns Jac.
+template <int ENON>
+SVB_HD double gnn3_full(const double Nxi[][3], const double xl[][3], double Nx[][3], double xiX[3][3], double ks[3][3])
+{
+  double xXi[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+  for (int a = 0; a < ENON; a++)
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) xXi[i][k] += xl[a][i] * Nxi[a][k];
+  const double Jac = xXi[0][0] * xXi[1][1] * xXi[2][2] + xXi[0][1] * xXi[1][2] * xXi[2][0] + xXi[0][2] * xXi[1][0] * xXi[2][1] -
+                     xXi[0][0] * xXi[1][2] * xXi[2][1] - xXi[0][1] * xXi[1][0] * xXi[2][2] - xXi[0][2] * xXi[1][1] * xXi[2][0];
+  xiX[0][0] = (xXi[1][1] * xXi[2][2] - xXi[1][2] * xXi[2][1]) / Jac;
+  xiX[0][1] = (xXi[2][1] * xXi[0][2] - xXi[2][2] * xXi[0][1]) / Jac;
+  xiX[0][2] = (xXi[0][1] * xXi[1][2] - xXi[0][2] * xXi[1][1]) / Jac;
+  xiX[1][0] = (xXi[1][2] * xXi[2][0] - xXi[1][0] * xXi[2][2]) / Jac;
+  xiX[1][1] = (xXi[2][2] * xXi[0][0] - xXi[2][0] * xXi[0][2]) / Jac;
+  xiX[1][2] = (xXi[0][2] * xXi[1][0] - xXi[0][0] * xXi[1][2]) / Jac;
+  xiX[2][0] = (xXi[1][0] * xXi[2][1] - xXi[1][1] * xXi[2][0]) / Jac;
+  xiX[2][1] = (xXi[2][0] * xXi[0][1] - xXi[2][1] * xXi[0][0]) / Jac;
+  xiX[2][2] = (xXi[0][0] * xXi[1][1] - xXi[0][1] * xXi[1][0]) / Jac;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) ks[i][j] = xiX[0][i] * xiX[0][j] + xiX[1][i] * xiX[1][j] + xiX[2][i] * xiX[2][j];
+#pragma unroll
+  for (int a = 0; a < ENON; a++)
+#pragma unroll
+    for (int i = 0; i < 3; i++) Nx[a][i] = Nxi[a][0] * xiX[0][i] + Nxi[a][1] * xiX[1][i] + Nxi[a][2] * xiX[2][i];
+  return Jac;
+}
+
+// nn::gn_nxx, insd = 3.  Voigt order (00, 11, 22, 01, 12, 02) in both the parametric and the physical frame.
+template <int ENON>
+SVB_HD void gn_nxx3(const double Nxi2[][6], const double xl[][3], const double xiX[3][3], const double Nx[][3], double Nxx[][6])
+{
+  const int vi[6] = {0, 1, 2, 0, 1, 0}, vj[6] = {0, 1, 2, 1, 2, 2};
+  double xXi2[3][6];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int v = 0; v < 6; v++) xXi2[i][v] = 0.0;
+#pragma unroll
+  for (int a = 0; a < ENON; a++)
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int v = 0; v < 6; v++) xXi2[i][v] += xl[a][i] * Nxi2[a][v];
+  // Kinv(v_phys, v_par): N_,kl = sum_ij xiX(i,k) xiX(j,l) B_ij with B symmetric
+  double Kinv[6][6];
+#pragma unroll
+  for (int p = 0; p < 6; p++) {
+    const int k = vi[p], l = vj[p];
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+      const int i = vi[q], j = vj[q];
+      Kinv[p][q] = (i == j) ? xiX[i][k] * xiX[i][l] : xiX[i][k] * xiX[j][l] + xiX[j][k] * xiX[i][l];
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < ENON; a++) {
+    double B[6];
+#pragma unroll
+    for (int v = 0; v < 6; v++) B[v] = Nxi2[a][v] - Nx[a][0] * xXi2[0][v] - Nx[a][1] * xXi2[1][v] - Nx[a][2] * xXi2[2][v];
+#pragma unroll
+    for (int p = 0; p < 6; p++) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < 6; q++) s += Kinv[p][q] * B[q];
+      Nxx[a][p] = s;
+    }
+  }
+}
+
+// d2u2 (Laplacian of the velocity) and mu_x / mu_g (gradient of the shear rate, before the mu_g factor) from the
+// physical second derivatives Nxx (fluid.cpp:1846-1886, 1944-1973).
+template <int ENON>
+SVB_HD void second_derivative_terms(const double Nxx[][6], const double yl[][3], const double es[3][3], double d2u2[3], double gx[3])
+{
+  // H[i][v] = sum_a Nxx[a][v] u_i(a): Hessian of velocity component i in Voigt form
+  double H[3][6];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int v = 0; v < 6; v++) H[i][v] = 0.0;
+#pragma unroll
+  for (int a = 0; a < ENON; a++)
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int v = 0; v < 6; v++) H[i][v] += Nxx[a][v] * yl[a][i];
+  const int vv[3][3] = {{0, 3, 5}, {3, 1, 4}, {5, 4, 2}};      // Voigt index of the pair (k,l)
+#pragma unroll
+  for (int i = 0; i < 3; i++) d2u2[i] = H[i][0] + H[i][1] + H[i][2];
+  // gx[k] = 1/2 sum_ij es_x[i][j][k] es[i][j],  es_x[i][j][k] = d/dx_k (u_j,i + u_i,j) = H[j][(i,k)] + H[i][(j,k)]
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) s += (H[j][vv[i][k]] + H[i][vv[j][k]]) * es[i][j];
+    gx[k] = 0.5 * s;
+  }
+}
+
+// Everything of fluid_3d_m / fluid_3d_c at one Gauss point that does not depend on the node pair.
+//   al/yl: nodal acceleration / velocity+pressure (al[a][0..2], yl[a][0..3]); ym: nodal mesh velocity or null;
+//   Nxx: physical second derivatives at THIS Gauss point, NxxL: those of the LAST Gauss point (continuity quirk).
+template <int ENON>
+SVB_HD void fluid_gen_gauss_point(const FluidDmn& dm, double dt, double af, double am, double gam_t, double w, const double ks[3][3],
+                                  const double N[], const double Nx[][3], const double Nxx[][6], const double NxxL[][6],
+                                  const double al[][3], const double yl[][4], const double bfl[][3], const double (*ym)[3],
+                                  FluidGP& q, FluidNode nd[])
+{
+  const double ctM = 1.0, ctC = 36.0;
+  const double rho = dm.rho, Kd = dm.Kd;
+  const double T1 = af * gam_t * dt;
+  q.w = w; q.rho = rho; q.amd = am / T1; q.wl = w * T1; q.wr = w * rho;
+  double ud[3] = {-dm.f[0], -dm.f[1], -dm.f[2]}, u[3] = {0, 0, 0}, ux[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, p = 0.0, px[3] = {0, 0, 0};
+  double yv[ENON][3];
+#pragma unroll
+  for (int a = 0; a < ENON; a++) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      yv[a][i] = yl[a][i];
+      ud[i] += N[a] * (al[a][i] - bfl[a][i]);
+      u[i] += N[a] * yl[a][i];
+#pragma unroll
+      for (int k = 0; k < 3; k++) ux[k][i] += Nx[a][k] * yl[a][i];      // ux[k][i] = d u_i / d x_k
+    }
+    p += N[a] * yl[a][3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) px[k] += Nx[a][k] * yl[a][3];
+  }
+  q.divU = ux[0][0] + ux[1][1] + ux[2][2];
+  if (ym != nullptr)
+#pragma unroll
+    for (int a = 0; a < ENON; a++)
+#pragma unroll
+      for (int i = 0; i < 3; i++) u[i] -= N[a] * ym[a][i];
+  double es[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) es[i][j] = ux[i][j] + ux[j][i];
+  double gam = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) gam += es[i][j] * es[i][j];
+  gam = sqrt(0.5 * gam);
+  double mu, mu_g;
+  viscosity(dm, gam, mu, mu_g);
+  mu_g = is_zero(gam) ? 0.0 : mu_g / gam;
+  q.mu = mu; q.mu_g = mu_g; q.muKd = mu * Kd;
+
+  double gx[3], gxc[3];
+  second_derivative_terms<ENON>(Nxx, yv, es, q.d2u2, gx);
+  second_derivative_terms<ENON>(NxxL, yv, es, q.d2u2_c, gxc);
+#pragma unroll
+  for (int k = 0; k < 3; k++) { q.mu_x[k] = mu_g * gx[k]; q.mu_x_c[k] = mu_g * gxc[k]; }
+
+  double kT = 4.0 * (ctM / dt) * (ctM / dt);
+  kT += (Kd * mu / rho) * (Kd * mu / rho);
+  double kU = 0.0, kS = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) { kU += u[i] * u[j] * ks[i][j]; kS += ks[i][j] * ks[i][j]; }
+  kS = ctC * kS * (mu / rho) * (mu / rho);
+  const double tauM = 1.0 / (rho * sqrt(kT + kU + kS));
+  q.tauM = tauM;
+  double up[3];
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const double rVj = ud[j] + u[0] * ux[0][j] + u[1] * ux[1][j] + u[2] * ux[2][j];
+    const double rS = q.mu_x[0] * es[0][j] + q.mu_x[1] * es[1][j] + q.mu_x[2] * es[2][j] + mu * q.d2u2[j];
+    const double rSc = q.mu_x_c[0] * es[0][j] + q.mu_x_c[1] * es[1][j] + q.mu_x_c[2] * es[2][j] + mu * q.d2u2_c[j];
+    up[j] = -tauM * (rho * rVj + px[j] - rS + mu * Kd * u[j]);
+    q.up_c[j] = -tauM * (rho * rVj + px[j] - rSc + mu * Kd * u[j]);
+    q.up[j] = up[j];
+    q.u[j] = u[j];
+  }
+  const double eps = 2.220446049250313e-16;
+  q.tauC = 1.0 / (tauM * (ks[0][0] + ks[1][1] + ks[2][2]));
+  double tauB = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) tauB += up[i] * up[j] * ks[i][j];
+  if (is_zero(tauB)) tauB = eps;
+  tauB = rho / sqrt(tauB);
+  q.tauB = tauB;
+  const double ua[3] = {u[0] + up[0], u[1] + up[1], u[2] + up[2]};
+  const double pa = p - q.tauC * q.divU;
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const double rVb = tauB * (up[0] * ux[0][j] + up[1] * ux[1][j] + up[2] * ux[2][j]);
+#pragma unroll
+    for (int i = 0; i < 3; i++) q.rM[i][j] = mu * es[i][j] - rho * up[j] * ua[i] + rVb * up[i] - (i == j ? pa : 0.0);
+    q.rV[j] = ud[j] + ua[0] * ux[0][j] + ua[1] * ux[1][j] + ua[2] * ux[2][j];
+  }
+#pragma unroll
+  for (int a = 0; a < ENON; a++) {
+    FluidNode& n = nd[a];
+    n.N = N[a];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      n.Nx[i] = Nx[a][i];
+      n.esNx[i] = es[0][i] * Nx[a][0] + es[1][i] * Nx[a][1] + es[2][i] * Nx[a][2];
+    }
+    n.uNx = u[0] * Nx[a][0] + u[1] * Nx[a][1] + u[2] * Nx[a][2];
+    n.upNx = up[0] * Nx[a][0] + up[1] * Nx[a][1] + up[2] * Nx[a][2];
+    const double base = -rho * n.uNx - mu * Kd * N[a];
+    n.T1b = base + mu * (Nxx[a][0] + Nxx[a][1] + Nxx[a][2]) + q.mu_x[0] * Nx[a][0] + q.mu_x[1] * Nx[a][1] + q.mu_x[2] * Nx[a][2];
+    n.T1b_c = base + mu * (NxxL[a][0] + NxxL[a][1] + NxxL[a][2]) + q.mu_x_c[0] * Nx[a][0] + q.mu_x_c[1] * Nx[a][1] + q.mu_x_c[2] * Nx[a][2];
+  }
+}
+
+// lR(0..3, a) += ... (fluid.cpp:2108-2111, 2228-2235, 1726-1729)
+SVB_HD void fluid_gen_residual(const FluidGP& q, const FluidNode& a, double lR[4])
+{
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+    lR[j] += q.wr * a.N * q.rV[j] + q.w * (a.Nx[0] * q.rM[0][j] + a.Nx[1] * q.rM[1][j] + a.Nx[2] * q.rM[2][j]) +
+             q.muKd * q.w * a.N * (q.u[j] + q.up[j]);
+  lR[3] += q.w * (a.N * q.divU - (q.up_c[0] * a.Nx[0] + q.up_c[1] * a.Nx[1] + q.up_c[2] * a.Nx[2]));
+}
+
+// K(4 i + j) += block (a,b) at one Gauss point (fluid.cpp:2146-2224, 1733-1759); K is row-major 4x4.
+SVB_HD void fluid_gen_block(const FluidGP& q, const FluidNode& a, const FluidNode& b, double K[16])
+{
+  const double rho = q.rho, mu = q.mu, wl = q.wl;
+  const double NxNx = a.Nx[0] * b.Nx[0] + a.Nx[1] * b.Nx[1] + a.Nx[2] * b.Nx[2];
+  const double uaNxa = a.uNx + a.upNx;
+  const double rtu = rho * q.tauM * uaNxa;
+  const double T1 = mu * NxNx + rho * q.amd * b.N * (a.N + rtu) + rho * a.N * (b.uNx + b.upNx) + q.tauB * a.upNx * b.upNx;
+  const double dk = q.muKd * b.N * a.N;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      // updu[j][i][b] = mu_x[j] Nx(i,b) + d2u2[j] mu_g esNx(i,b) + delta_ij T1b
+      const double updu = q.mu_x[j] * b.Nx[i] + q.d2u2[j] * q.mu_g * b.esNx[i] + (i == j ? b.T1b : 0.0);
+      double T2;
+      if (i == j) T2 = (mu + q.tauC) * a.Nx[i] * b.Nx[i] + a.esNx[i] * q.mu_g * b.esNx[i] - rtu * updu + T1 + dk;
+      else T2 = mu * a.Nx[j] * b.Nx[i] + q.tauC * a.Nx[i] * b.Nx[j] + a.esNx[i] * q.mu_g * b.esNx[j] - rtu * updu;
+      K[4 * i + j] += wl * T2;
+    }
+    K[4 * i + 3] -= wl * (a.Nx[i] * b.N - b.Nx[i] * rtu);
+  }
+  const double T1c = rho * q.amd * b.N;
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    double T2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const double updu_c = q.mu_x_c[j] * b.Nx[i] + q.d2u2_c[j] * q.mu_g * b.esNx[i] + (i == j ? b.T1b_c - T1c : 0.0);
+      T2 += a.Nx[i] * updu_c;
+    }
+    K[12 + j] += wl * (a.N * b.Nx[j] - q.tauM * T2);
+  }
+  K[15] += wl * q.tauM * NxNx;
+}
+
+}  // namespace svb

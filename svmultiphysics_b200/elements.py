@@ -48,6 +48,29 @@ def hex8_tables():
     return w, N, Nx
 
 
+def nxx_tables(eNoN: int):
+    """Second parametric derivatives Nxx(6,eNoN,nG) of the shape functions (fs[0].Nxx of the reference, handed to
+    nn::gn_nxx, Code/Source/solver/nn.cpp:1172-1283), Voigt order (00, 11, 22, 01, 12, 02).  TET4: identically zero."""
+    if eNoN == 4:
+        return np.zeros((6, 4, 4), order="F")
+    if eNoN != 8:
+        raise ValueError(f"no second-derivative table for eNoN={eNoN}")
+    s = 1.0 / np.sqrt(3.0)
+    gp = np.array([[-s, -s, -s], [s, -s, -s], [s, s, -s], [-s, s, -s],
+                   [-s, -s, s], [s, -s, s], [s, s, s], [-s, s, s]])
+    sign = np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1],
+                     [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]], dtype=float)
+    Nxx = np.zeros((6, 8, 8), order="F")
+    for g in range(8):
+        lx, ly, lz = gp[g]
+        for a in range(8):
+            sx, sy, sz = sign[a]
+            Nxx[3, a, g] = sx * sy * (1.0 + sz * lz) / 8.0
+            Nxx[4, a, g] = sy * sz * (1.0 + sx * lx) / 8.0
+            Nxx[5, a, g] = sx * sz * (1.0 + sy * ly) / 8.0
+    return Nxx
+
+
 def tri3_face_tables(qm: float = 2.0 / 3.0):
     """TRI3 boundary face (of TET4): Code/Source/solver/nn_elem_gip.h:720-738 (points, qmTRI3 = 2/3), shape functions
     N = (xi0, xi1, 1 - xi0 - xi1) as evaluate_face_basis_values_and_gradients leaves them (pinned by tests against the

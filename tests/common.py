@@ -132,3 +132,41 @@ def fsi_case(n=4, nz=6):
     Dg[4:7] = 5e-3 * rng.standard_normal((3, m.nNo))
     Bf = np.asfortranarray(0.1 * rng.standard_normal((3, m.nNo)))
     return m, Ag, Yg, Dg, Bf
+
+
+# ---- general (non-TET4) fluid elements: gnn + gn_nxx per Gauss point -----------------------------------------------
+def _hex_skewed():
+    """HEX8 box whose nodes are displaced pseudo-randomly: no element is a parallelepiped, so the second derivatives
+    of the isoparametric map (xXi2 in nn::gn_nxx) do not vanish."""
+    m = meshgen.box_hex8(3, 3, 2, (1.0, 1.2, 0.8))
+    rng = np.random.default_rng(17)
+    m.x = np.asfortranarray(m.x + 0.035 * rng.standard_normal(m.x.shape))
+    return m
+
+
+def _tet_cyl():
+    return meshgen.cylinder_tet4(GOLDEN_N, GOLDEN_NZ)
+
+
+# (name, mesh factory, viscosity kwargs, K_darcy, body force, tDof, mvMsh)
+FLUID_GEN_CASES = [
+    ("hex8_newtonian", _hex_skewed, {}, 0.0, (0.0, 0.0, 0.0), 4, 0),
+    ("hex8_carreau_yasuda_darcy", _hex_skewed, dict(viscType=abi.VISC_CY, mu=0.035, mu_o=0.16, lam=8.2, a=0.64, n=0.2128), 2.0,
+     (0.1, -0.2, 0.3), 4, 0),
+    ("hex8_casson_moving_mesh", _hex_skewed, dict(viscType=abi.VISC_CASSON, mu=0.3, mu_o=0.1, lam=0.5), 0.0, (0.0, 0.0, 1.0), 7, 1),
+    ("tet4_newtonian_general_path", _tet_cyl, {}, 0.5, (0.0, 0.1, 0.0), 4, 0),
+]
+
+
+def fluid_gen_state(m, tDof, seed=31):
+    rng = np.random.default_rng(seed)
+    Yg = np.zeros((tDof, m.nNo), order="F")
+    Yg[0] = 1.0 + 0.5 * np.sin(2.0 * m.x[1]) + 0.1 * rng.standard_normal(m.nNo)
+    Yg[1] = 0.3 * np.cos(1.5 * m.x[0] + m.x[2]) + 0.1 * rng.standard_normal(m.nNo)
+    Yg[2] = 0.7 * m.x[0] * m.x[1] + 0.1 * rng.standard_normal(m.nNo)
+    Yg[3] = 2.0 - m.x[2] + 0.05 * rng.standard_normal(m.nNo)
+    if tDof >= 7:
+        Yg[4:7] = 0.2 * rng.standard_normal((3, m.nNo))
+    Ag = np.asfortranarray(0.5 * rng.standard_normal((tDof, m.nNo)))
+    Bf = np.asfortranarray(0.1 * rng.standard_normal((3, m.nNo)))
+    return Ag, Yg, None, Bf

@@ -65,8 +65,26 @@ def struct_golden():
     print("wrote struct.npz with", len(out), "arrays")
 
 
+def fluid_gen_golden():
+    """HEX8 (and TET4 through the same general path) VMS fluid: gnn + gn_nxx per Gauss point, fluid_3d_m / fluid_3d_c."""
+    out = {}
+    for name, mk, visc, Kd, f, tDof, mv in common.FLUID_GEN_CASES:
+        m = mk()
+        Ag, Yg, Dg, Bf = common.fluid_gen_state(m, tDof)
+        c = RefCase(); c.set_coords(m.x); c.add_mesh(m.IEN)
+        rowPtr, colPtr = c.build_graph(0)
+        c.alloc(4); c.set_state(Ag, Yg, Dg, Bf)
+        c.assemble(0, abi.fluid_eq(0.005, tDof=tDof, mvMsh=mv), [abi.fluid_domain(K_darcy=Kd, f=f, **visc)])
+        out[f"{name}/R"], out[f"{name}/Val"] = c.get_R(), c.get_Val()
+        out[f"{name}/rowPtr"], out[f"{name}/colPtr"] = rowPtr, colPtr
+        out[f"{name}/Nxx"] = c.mesh_nxx(0)
+    np.savez_compressed(os.path.join(HERE, "fluid_gen.npz"), **out)
+    print("wrote fluid_gen.npz with", len(out), "arrays")
+
+
 if __name__ == "__main__":
     if not have_ref():
         raise SystemExit("oracle/_ref/libsvref.so is missing: run `make -C oracle ref` first")
     fluid_golden()
     struct_golden()
+    fluid_gen_golden()

@@ -124,3 +124,53 @@ def test_device_solid_algebra_matches_golden(hostmath, name, mk, dkw, nFn):
     assert rc == 0
     assert common.rel_err(R.T, golden[f"{name}/R"]) < 1e-12
     assert common.rel_err(V.T, golden[f"{name}/Val"]) < 1e-12
+
+
+class HostFluidGenArgs(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("IEN", "x", "Ag", "Yg", "Bf")] + \
+               [(k, C.c_int) for k in ("eNoN", "nEl", "nG", "tDof", "mvMsh", "pad")] + \
+               [(k, C.c_double) for k in ("dt", "af", "am", "gam")] + \
+               [("w", C.c_double * 8), ("N", (C.c_double * 8) * 8), ("Nxi", ((C.c_double * 3) * 8) * 8),
+                ("Nxi2", ((C.c_double * 6) * 8) * 8), ("dm", FluidDmn)]
+
+
+@pytest.mark.parametrize("case", common.FLUID_GEN_CASES, ids=[c[0] for c in common.FLUID_GEN_CASES])
+def test_device_general_fluid_algebra_matches_golden(hostmath, case):
+    """svmultiphysics_b200/csrc/fluid_gen.cuh (gnn + gn_nxx per Gauss point, fluid_3d_m/c for any element) compiled for
+    the host against what the unmodified reference assembled for skewed HEX8 meshes (tests/golden/fluid_gen.npz)."""
+    golden = common.load_golden("fluid_gen.npz")
+    assert hostmath.hostmath_sizeof_fluidgenargs() == C.sizeof(HostFluidGenArgs)
+    name, mk, visc, Kd, f, tDof, mv = case
+    m = mk()
+    Ag, Yg, _, Bf = common.fluid_gen_state(m, tDof)
+    eq, d = abi.fluid_eq(0.005, tDof=tDof, mvMsh=mv), abi.fluid_domain(K_darcy=Kd, f=f, **visc)
+    w, N, Nx = elements.tables(m.eNoN)
+    Nxx = elements.nxx_tables(m.eNoN)
+    assert np.array_equal(Nxx, golden[f"{name}/Nxx"])
+    A = HostFluidGenArgs()
+    keep = [np.ascontiguousarray(m.IEN.T.astype(np.int32)), np.ascontiguousarray(m.x.T), np.ascontiguousarray(Ag.T),
+            np.ascontiguousarray(Yg.T), np.ascontiguousarray(Bf.T)]
+    A.IEN, A.x, A.Ag, A.Yg, A.Bf = (k.ctypes.data for k in keep)
+    A.eNoN, A.nEl, A.nG, A.tDof, A.mvMsh = m.eNoN, m.nEl, len(w), tDof, mv
+    A.dt, A.af, A.am, A.gam = eq.dt, eq.af, eq.am, eq.gam
+    for g in range(len(w)):
+        A.w[g] = w[g]
+        for a in range(m.eNoN):
+            A.N[g][a] = N[a, g]
+            for k in range(3):
+                A.Nxi[g][a][k] = Nx[k, a, g]
+            for k in range(6):
+                A.Nxi2[g][a][k] = Nxx[k, a, g]
+    A.dm.rho, A.dm.Kd = d.rho, d.K_darcy
+    for i in range(3):
+        A.dm.f[i] = d.f[i]
+    A.dm.mu_i, A.dm.mu_o, A.dm.lam, A.dm.a, A.dm.n = d.mu_i, d.mu_o, d.lam, d.a, d.n
+    A.dm.viscType, A.dm.Id, A.dm.isFluid = d.viscType, -1, 1
+    rowPtr, colPtr = golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"]
+    R = np.zeros((m.nNo, 4))
+    V = np.zeros((len(colPtr), 16))
+    rc = hostmath.hostmath_fluid_gen(C.byref(A), rowPtr.ctypes.data_as(C.c_void_p), colPtr.ctypes.data_as(C.c_void_p),
+                                     R.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    assert common.rel_err(R.T, golden[f"{name}/R"]) < 1e-12
+    assert common.rel_err(V.T, golden[f"{name}/Val"]) < 1e-12
