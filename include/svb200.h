@@ -106,8 +106,10 @@ typedef struct {
   int32_t mvMsh;     /* com_mod.mvMsh: ALE convective velocity (solver/fluid.cpp:1909-1915) */
   int32_t vmsStab;   /* lM.nFs == 1 (solver/fluid.cpp:496-500); only 1 is supported */
   int32_t scatter;   /* svb200_scatter */
-  int32_t reserved;
+  int32_t reserved;  /* bit flags, 0 by default; SVB200_EQ_GENERAL_KERNEL: run a TET4 fluid mesh through the
+                        per-Gauss-point kernel that serves HEX8 (cross-check of the specialised TET4 kernel) */
 } svb200_eqparams;
+#define SVB200_EQ_GENERAL_KERNEL 1
 
 /* Per-domain material parameters (dmnType, stModelType, fluidViscModelType). */
 typedef struct {
@@ -197,6 +199,11 @@ SVB200_API int svb200_lhsa_get(svb200_ctx* ctx, int32_t* rowPtr, int32_t* colPtr
 SVB200_API int svb200_set_mesh(svb200_ctx* ctx, int32_t iM, int32_t eNoN, int32_t nEl, const int32_t* IEN,
                     const int32_t* eId, int32_t nFn, const double* fN,
                     int32_t nG, const double* w, const double* N, const double* Nx);
+
+/* Second parametric derivatives of the shape functions, fs[0].Nxx(6,eNoN,nG), Voigt order (00,11,22,01,12,02): what
+ * construct_fluid hands to nn::gn_nxx (solver/fluid.cpp:648-650, solver/nn.cpp:1172-1283).  Needed for the fluid on
+ * HEX8 meshes; identically zero (and optional) for TET4.  Call after svb200_set_mesh. */
+SVB200_API int svb200_set_mesh_nxx(svb200_ctx* ctx, int32_t iM, const double* Nxx);
 
 /* Reference coordinates com_mod.x(3,nNo). */
 SVB200_API int svb200_set_coords(svb200_ctx* ctx, const double* x);

@@ -93,10 +93,14 @@ def eq_time(s: int, e: int, phys: int, rho_inf: float = 0.5) -> EqTime:
     return EqTime(s=s, e=e, phys=phys, af=af, am=am, gam=gam, beta=beta)
 
 
-def fluid_eq(dt: float, rho_inf: float = 0.5, tDof: int = 4, scatter: int = SCATTER_ATOMIC, mvMsh: int = 0) -> EqParams:
+EQ_GENERAL_KERNEL = 1
+
+
+def fluid_eq(dt: float, rho_inf: float = 0.5, tDof: int = 4, scatter: int = SCATTER_ATOMIC, mvMsh: int = 0,
+             general: bool = False) -> EqParams:
     af, am, gam, beta = gen_alpha(rho_inf)
     return EqParams(dt=dt, af=af, am=am, gam=gam, beta=beta, phys=PHYS_FLUID, dof=4, tDof=tDof, s=0,
-                    mvMsh=mvMsh, vmsStab=1, scatter=scatter, reserved=0)
+                    mvMsh=mvMsh, vmsStab=1, scatter=scatter, reserved=EQ_GENERAL_KERNEL if general else 0)
 
 
 def fluid_domain(rho: float = 1.06, mu: float = 0.04, f=(0.0, 0.0, 0.0), K_darcy: float = 0.0,

@@ -1,0 +1,227 @@
+// assemble_fluid_gen.cu — fused element loop + scatter of the VMS fluid for elements that are not linear
+// tetrahedra (HEX8; TET4 also runs through it as a cross-check of the specialised kernel of assemble_fluid.cu).
+//
+// Replaces fluid::construct_fluid (Code/Source/solver/fluid.cpp:480-762) with nn::gnn + nn::gn_nxx PER GAUSS POINT
+// (solver/nn.cpp:862-899, 1172-1283), fluid_3d_m / fluid_3d_c (fluid.cpp:1768-2237 / 1443-1760) and the do_assem
+// scatter (solver/lhsa.cpp:70-114).  The algebra is fluid_gen.cuh.
+//
+// Mapping (same idea as the solid kernel): ENON lanes per element, 32/ENON elements per warp, nG == ENON.
+//   phase A  lane g evaluates Gauss point g once: Jacobian, physical first and second derivatives, the interpolated
+//            state, viscosity, tau_M/C/B, the fine-scale velocity — and leaves a FluidGP (45 doubles) plus one
+//            FluidNode (11 doubles) per element node in shared memory.  The lane of the LAST Gauss point publishes its
+//            second derivatives first, because the reference's continuity loop uses them at every Gauss point.
+//   phase B  lane a = element node a = one block row of the element matrix: residual row, then for one b at a time the
+//            4x4 block summed over the Gauss points in registers and scattered (16 contiguous doubles = one CSR block).
+#include <cstdlib>
+#include <vector>
+#include "fluid_gen.cuh"
+
+namespace svb {
+
+struct FluidGenArgs {
+  const int* IEN;
+  const int* eId;
+  const int* slot;
+  const int* perm;
+  const double* x;
+  const double* Ag;
+  const double* Yg;
+  const double* Bf;
+  const double* Dg;
+  const double* tab;    // per Gauss point: w | N[ENON] | Nxi[ENON][3] | Nxi2[ENON][6]
+  double* R;
+  double* Val;
+  int e0, e1;
+  int tDof, mvMsh, nDmn, atomic, ale, pad;
+  double dt, af, am, gam;
+  FluidDmn dmn[MAX_DMN];
+};
+
+template <bool ATOMIC>
+__device__ __forceinline__ void fg_add(double* p, double v)
+{
+  if (ATOMIC) asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+  else *p += v;
+}
+
+constexpr int FG_THREADS = 64;
+__host__ __device__ constexpr int fg_tab_ld(int enon) { return 1 + enon * 10; }
+// per element: nodal inputs (x 3, a-b... kept separate: al 3, yl 4, bfl 3, ym 3 = 16) | NxxL 6 | FluidGP | FluidNode[ENON]
+__host__ __device__ constexpr int fg_per_el(int enon)
+{
+  const int n = enon * 16 + enon * 6 + enon * FLUID_GP_DOUBLES + enon * enon * FLUID_NODE_DOUBLES;
+  return n + ((8 - (n % 16)) + 16) % 16;
+}
+
+template <int ENON, bool ATOMIC>
+__global__ void __launch_bounds__(FG_THREADS)
+assemble_fluid_gen_kernel(const __grid_constant__ FluidGenArgs P)
+{
+  constexpr int EPW = 32 / ENON;
+  constexpr int PER_EL = fg_per_el(ENON);
+  constexpr int TLD = fg_tab_ld(ENON);
+  extern __shared__ double sm[];
+  double* stab = sm;
+  for (int t = threadIdx.x; t < ENON * TLD; t += FG_THREADS) stab[t] = __ldg(P.tab + t);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int a = lane % ENON, el = lane / ENON;
+  double* se = sm + ENON * TLD + (size_t)(warp * EPW + el) * PER_EL;
+  double(*sx)[3] = reinterpret_cast<double(*)[3]>(se);
+  double(*sal)[3] = reinterpret_cast<double(*)[3]>(se + 3 * ENON);
+  double(*syl)[4] = reinterpret_cast<double(*)[4]>(se + 6 * ENON);
+  double(*sbf)[3] = reinterpret_cast<double(*)[3]>(se + 10 * ENON);
+  double(*sym)[3] = reinterpret_cast<double(*)[3]>(se + 13 * ENON);
+  double(*sNxxL)[6] = reinterpret_cast<double(*)[6]>(se + 16 * ENON);
+  FluidGP* sgp = reinterpret_cast<FluidGP*>(se + 22 * ENON);
+  FluidNode* snd = reinterpret_cast<FluidNode*>(se + 22 * ENON + ENON * FLUID_GP_DOUBLES);   // [g][node]
+
+  const long long idx = (long long)P.e0 + ((long long)blockIdx.x * (FG_THREADS / 32) + warp) * EPW + el;
+  bool active = (lane < EPW * ENON) && idx < P.e1;
+  int e = 0;
+  if (active) e = P.perm ? P.perm[idx] : (int)idx;
+  int iD = 0;
+  if (active) {
+    for (int d = 0; d < P.nDmn; d++) {
+      iD = d;
+      if (P.dmn[d].Id == -1) break;
+      if (P.eId != nullptr && ((P.eId[e] >> P.dmn[d].Id) & 1)) break;
+    }
+    if (!P.dmn[iD].isFluid) active = false;
+  }
+  const FluidDmn& dm = P.dmn[iD];
+  int node = 0;
+  if (active) {
+    node = P.IEN[(size_t)e * ENON + a];
+    const size_t n = (size_t)node;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      sx[a][i] = __ldg(P.x + 3 * n + i) + (P.ale ? __ldg(P.Dg + (size_t)P.tDof * n + 4 + i) : 0.0);
+      sal[a][i] = __ldg(P.Ag + (size_t)P.tDof * n + i);
+      sbf[a][i] = __ldg(P.Bf + 3 * n + i);
+      sym[a][i] = P.mvMsh ? __ldg(P.Yg + (size_t)P.tDof * n + 4 + i) : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) syl[a][i] = __ldg(P.Yg + (size_t)P.tDof * n + i);
+  }
+  __syncthreads();      // tables + nodal inputs
+
+  // ---- phase A ------------------------------------------------------------------------------------------------
+  {
+    const int g = a;
+    const double* tg = stab + g * TLD;
+    const double(*Nxi)[3] = reinterpret_cast<const double(*)[3]>(tg + 1 + ENON);
+    const double(*Nxi2)[6] = reinterpret_cast<const double(*)[6]>(tg + 1 + 4 * ENON);
+    double Nx[ENON][3], Nxx[ENON][6], xiX[3][3], ks[3][3];
+    double Jac = 1.0;
+    if (active) {
+      Jac = gnn3_full<ENON>(Nxi, sx, Nx, xiX, ks);
+      gn_nxx3<ENON>(Nxi2, sx, xiX, Nx, Nxx);
+      if (g == ENON - 1) {
+#pragma unroll
+        for (int b = 0; b < ENON; b++)
+#pragma unroll
+          for (int v = 0; v < 6; v++) sNxxL[b][v] = Nxx[b][v];
+      }
+    }
+    __syncwarp();
+    if (active)
+      fluid_gen_gauss_point<ENON>(dm, P.dt, P.af, P.am, P.gam, tg[0] * Jac, ks, tg + 1, Nx, Nxx, sNxxL, sal, syl, sbf,
+                                  P.mvMsh ? sym : nullptr, sgp[g], snd + g * ENON);
+  }
+  __syncwarp();
+  if (!active) return;
+
+  // ---- phase B ------------------------------------------------------------------------------------------------
+  double lR[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+  for (int g = 0; g < ENON; g++) fluid_gen_residual(sgp[g], snd[g * ENON + a], lR);
+#pragma unroll
+  for (int i = 0; i < 4; i++) fg_add<ATOMIC>(P.R + 4 * (size_t)node + i, lR[i]);
+  const int* sl = P.slot + (size_t)e * ENON * ENON;
+#pragma unroll 1
+  for (int b = 0; b < ENON; b++) {
+    double K[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) K[i] = 0.0;
+#pragma unroll 1
+    for (int g = 0; g < ENON; g++) fluid_gen_block(sgp[g], snd[g * ENON + a], snd[g * ENON + b], K);
+    double* v = P.Val + 16 * (size_t)sl[a * ENON + b];
+#pragma unroll
+    for (int i = 0; i < 16; i++) fg_add<ATOMIC>(v + i, K[i]);
+  }
+}
+
+template <int ENON>
+static int launch_gen(svb200_ctx* ctx, const FluidGenArgs& A)
+{
+  constexpr int EPB = (FG_THREADS / 32) * (32 / ENON);
+  const long long n = (long long)A.e1 - A.e0;
+  if (n <= 0) return SVB200_OK;
+  const unsigned blocks = (unsigned)((n + EPB - 1) / EPB);
+  constexpr size_t smem = sizeof(double) * ((size_t)ENON * fg_tab_ld(ENON) + (size_t)EPB * fg_per_el(ENON));
+  static bool configured = false;
+  if (!configured) {
+    SVB_CUDA(cudaFuncSetAttribute(assemble_fluid_gen_kernel<ENON, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVB_CUDA(cudaFuncSetAttribute(assemble_fluid_gen_kernel<ENON, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  if (A.atomic) assemble_fluid_gen_kernel<ENON, true><<<blocks, FG_THREADS, smem, ctx->stream>>>(A);
+  else assemble_fluid_gen_kernel<ENON, false><<<blocks, FG_THREADS, smem, ctx->stream>>>(A);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
+// Device copy of the reference-element tables in the layout the kernel stages into shared memory.
+int upload_fluid_gen_tables(svb200_ctx* ctx, Mesh& m)
+{
+  const int E = m.eNoN, G = m.nG, LD = fg_tab_ld(E);
+  if (G != E) return SVB200_OK;    // only nG == eNoN elements run through this kernel
+  std::vector<double> t((size_t)G * LD, 0.0);
+  for (int g = 0; g < G; g++) {
+    double* p = t.data() + (size_t)g * LD;
+    p[0] = m.w[g];
+    for (int a = 0; a < E; a++) {
+      p[1 + a] = m.N[(size_t)g * E + a];
+      for (int k = 0; k < 3; k++) p[1 + E + 3 * a + k] = m.Nx[((size_t)g * E + a) * 3 + k];
+      for (int k = 0; k < 6; k++) p[1 + 4 * E + 6 * a + k] = m.Nxx.empty() ? 0.0 : m.Nxx[((size_t)g * E + a) * 6 + k];
+    }
+  }
+  if (m.d_gtab) cudaFree(m.d_gtab);
+  m.d_gtab = nullptr;
+  SVB_CUDA(cudaMalloc(&m.d_gtab, sizeof(double) * t.size()));
+  SVB_CUDA(cudaMemcpyAsync(m.d_gtab, t.data(), sizeof(double) * t.size(), cudaMemcpyHostToDevice, ctx->stream));
+  SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SVB200_OK;
+}
+
+int run_assemble_fluid_gen(svb200_ctx* ctx, const Mesh& m, const FluidArgs& F)
+{
+  SVB_REQUIRE(m.eNoN == 8 || m.eNoN == 4, "svb200_assemble: the general fluid kernel covers HEX8 and TET4 meshes");
+  SVB_REQUIRE(m.nG == m.eNoN, "svb200_assemble: the general fluid kernel expects nG == eNoN");
+  SVB_REQUIRE(m.d_gtab, "svb200_assemble: element tables missing");
+  if (m.eNoN == 8 && m.Nxx.empty()) {
+    set_error("svb200_assemble: a HEX8 fluid mesh needs the second-derivative table (svb200_set_mesh_nxx)");
+    return SVB200_ERR_INVALID;
+  }
+  FluidGenArgs A;
+  memset(&A, 0, sizeof(A));
+  A.IEN = F.IEN; A.eId = F.eId; A.slot = F.slot; A.perm = nullptr;
+  A.x = F.x; A.Ag = F.Ag; A.Yg = F.Yg; A.Bf = F.Bf; A.Dg = F.Dg; A.tab = m.d_gtab; A.R = F.R; A.Val = F.Val;
+  A.e0 = 0; A.e1 = m.nEl;
+  A.tDof = F.tDof; A.mvMsh = F.mvMsh; A.nDmn = F.nDmn; A.atomic = F.atomic; A.ale = F.ale;
+  A.dt = F.dt; A.af = F.af; A.am = F.am; A.gam = F.gam;
+  for (int d = 0; d < MAX_DMN; d++) A.dmn[d] = F.dmn[d];
+  auto launch = [&](const FluidGenArgs& B) { return m.eNoN == 8 ? launch_gen<8>(ctx, B) : launch_gen<4>(ctx, B); };
+  if (A.atomic) return launch(A);
+  A.perm = m.d_color_perm;
+  for (size_t c = 0; c + 1 < m.color_off.size(); c++) {
+    A.e0 = m.color_off[c];
+    A.e1 = m.color_off[c + 1];
+    int rc = launch(A);
+    if (rc) return rc;
+  }
+  return SVB200_OK;
+}
+
+}  // namespace svb

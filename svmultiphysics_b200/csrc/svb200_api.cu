@@ -86,7 +86,7 @@ static int download_nodal(svb200_ctx* ctx, int rows, const double* d, double* h)
 
 static void free_mesh(Mesh& m)
 {
-  cudaFree(m.d_IEN); cudaFree(m.d_eId); cudaFree(m.d_fN); cudaFree(m.d_slot); cudaFree(m.d_color_perm);
+  cudaFree(m.d_IEN); cudaFree(m.d_eId); cudaFree(m.d_fN); cudaFree(m.d_slot); cudaFree(m.d_color_perm); cudaFree(m.d_gtab);
   free_group_sched(m.schedK); free_group_sched(m.schedR);
   m = Mesh();
 }
@@ -324,8 +324,18 @@ int svb200_set_mesh(svb200_ctx* ctx, int32_t iM, int32_t eNoN, int32_t nEl, cons
   TRY(launch_build_slot_map(ctx, m));
   TRY(build_group_schedules(ctx, m));
   TRY(build_coloring(ctx, m, ien));
+  TRY(upload_fluid_gen_tables(ctx, m));
   m.set = true;
   return SVB200_OK;
+}
+
+int svb200_set_mesh_nxx(svb200_ctx* ctx, int32_t iM, const double* Nxx)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(iM >= 0 && iM < (int)ctx->mesh.size() && ctx->mesh[iM].set && Nxx, "svb200_set_mesh_nxx: mesh not set");
+  Mesh& m = ctx->mesh[iM];
+  m.Nxx.assign(Nxx, Nxx + (size_t)6 * m.eNoN * m.nG);
+  return upload_fluid_gen_tables(ctx, m);
 }
 
 int svb200_set_coords(svb200_ctx* ctx, const double* x)
@@ -452,7 +462,7 @@ static int fill_fluid_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams
 {
   SVB_REQUIRE(nDmn >= 1 && nDmn <= MAX_DMN, "svb200_assemble: between 1 and 8 domains are supported");
   SVB_REQUIRE(eq->dof == 4 && ctx->dof == 4, "svb200_assemble: the fluid equation has dof = 4 (call svb200_alloc(4))");
-  SVB_REQUIRE(m.eNoN == 4, "svb200_assemble: fluid assembly is implemented for TET4 meshes");
+  SVB_REQUIRE(m.eNoN == 4 || m.eNoN == 8, "svb200_assemble: fluid assembly is implemented for TET4 and HEX8 meshes");
   SVB_REQUIRE(eq->vmsStab == 1, "svb200_assemble: only VMS-stabilised equal-order elements are supported");
   SVB_REQUIRE(eq->tDof == ctx->tDof && ctx->d_Yg, "svb200_assemble: state not set (svb200_set_state) or tDof mismatch");
   SVB_REQUIRE(!eq->mvMsh || eq->tDof >= 7, "svb200_assemble: mvMsh needs the mesh velocity in state dofs 4..6");
@@ -499,8 +509,11 @@ static int fill_fluid_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams
   return SVB200_OK;
 }
 
-static int run_assemble(svb200_ctx* ctx, const Mesh& m, FluidArgs& A)
+static int run_assemble(svb200_ctx* ctx, const Mesh& m, FluidArgs& A, bool general = false)
 {
+  // linear tetrahedra have their own kernel (constant gradients, no second derivatives); everything else, or
+  // SVB200_EQ_GENERAL_KERNEL, goes through the per-Gauss-point kernel of assemble_fluid_gen.cu
+  if (m.eNoN != 4 || general) return run_assemble_fluid_gen(ctx, m, A);
   if (A.atomic) return launch_assemble_fluid(ctx, m, A);
   A.perm = m.d_color_perm;
   for (size_t c = 0; c + 1 < m.color_off.size(); c++) {
@@ -694,7 +707,7 @@ int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, cons
     case SVB200_PHYS_FLUID: {
       FluidArgs A;
       TRY(fill_fluid_args(ctx, m, eq, dmn, nDmn, A));
-      TRY(run_assemble(ctx, m, A));
+      TRY(run_assemble(ctx, m, A, (eq->reserved & SVB200_EQ_GENERAL_KERNEL) != 0));
     } break;
     case SVB200_PHYS_STRUCT:
       TRY(run_assemble_struct(ctx, m, eq, dmn, nDmn));
@@ -710,7 +723,7 @@ int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, cons
       if (anyFluid) {
         FluidArgs A;
         TRY(fill_fluid_args(ctx, m, eq, dmn, nDmn, A));
-        TRY(run_assemble(ctx, m, A));
+        TRY(run_assemble(ctx, m, A, (eq->reserved & SVB200_EQ_GENERAL_KERNEL) != 0));
       }
       if (anySolid) TRY(run_assemble_struct(ctx, m, eq, dmn, nDmn));
     } break;

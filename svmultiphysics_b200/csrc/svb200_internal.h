@@ -43,6 +43,8 @@ struct Mesh {
   GroupSched schedK, schedR;     // grouped scatter plans: tangent blocks / residual rows (TET4 meshes)
   std::vector<int> color_off;    // offsets into d_color_perm per colour
   std::vector<double> w, N, Nx;  // host copies of the reference-element tables
+  std::vector<double> Nxx;       // (6,eNoN,nG) second parametric derivatives (svb200_set_mesh_nxx), empty = all zero
+  double* d_gtab = nullptr;      // tables in the layout of assemble_fluid_gen.cu
   bool set = false;
 };
 
@@ -197,6 +199,8 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 // assemble_fluid.cu
 int launch_assemble_fluid(svb200_ctx* ctx, const Mesh& m, const FluidArgs& args);
 // assemble_struct.cu
+int upload_fluid_gen_tables(svb200_ctx* ctx, Mesh& m);
+int run_assemble_fluid_gen(svb200_ctx* ctx, const Mesh& m, const FluidArgs& F);
 int run_assemble_struct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);
 int run_assemble_mesh(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);
 // assemble_bnd.cu

@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "svb200_abi_version", "svb200_last_error", "svb200_create", "svb200_destroy",
     "svb200_comm_unique_id", "svb200_comm_init",
     "svb200_set_graph", "svb200_lhsa_begin", "svb200_lhsa_add_mesh", "svb200_lhsa_finish", "svb200_lhsa_get",
-    "svb200_set_mesh", "svb200_set_coords", "svb200_set_num_faces", "svb200_set_face",
+    "svb200_set_mesh", "svb200_set_mesh_nxx", "svb200_set_coords", "svb200_set_num_faces", "svb200_set_face",
     "svb200_alloc", "svb200_set_state", "svb200_set_old_disp", "svb200_assemble", "svb200_add_host_contrib", "svb200_commu_R",
     "svb200_solve", "svb200_download", "svb200_upload", "svb200_spmv", "svb200_last_timing",
     "svb200_host_register", "svb200_host_unregister", "svb200_timer_mark", "svb200_timer_elapsed",
@@ -167,11 +167,15 @@ class Engine:
                    C.c_int32(self.nNo if mynNo is None else mynNo), _i(node_map),
                    C.c_int32(len(neighbours)), _i(ranks), _i(counts), _i(np.ascontiguousarray(ptrs)))
 
-    def set_mesh(self, iM, IEN, w, N, Nx, eId=None, nFn=0, fN=None):
+    def set_mesh(self, iM, IEN, w, N, Nx, eId=None, nFn=0, fN=None, Nxx=None):
         IEN, eId, fN = _i32(IEN), _i32(eId), _f64(fN)
         w, N, Nx = _f64(w), _f64(N), _f64(Nx)
         self._call("svb200_set_mesh", C.c_int32(iM), C.c_int32(IEN.shape[0]), C.c_int32(IEN.shape[1]), _i(IEN), _i(eId),
                    C.c_int32(nFn), _d(fN), C.c_int32(len(w)), _d(w), _d(N), _d(Nx))
+        if Nxx is not None:      # fs[0].Nxx(6,eNoN,nG): second derivatives for nn::gn_nxx (fluid on non-linear elements)
+            Nxx = _f64(Nxx)
+            assert Nxx.shape == (6, IEN.shape[0], len(w))
+            self._call("svb200_set_mesh_nxx", C.c_int32(iM), _d(Nxx))
         while len(self.meshes) <= iM:
             self.meshes.append(None)
         self.meshes[iM] = (IEN.shape[0], IEN.shape[1])

@@ -60,7 +60,7 @@ def make_engine(m, rowPtr, colPtr, device=0, **graph_kw):
     e = Engine(device)
     e.set_graph(rowPtr, colPtr, **graph_kw)
     w, N, Nx = elements.tables(m.eNoN)
-    e.set_mesh(0, m.IEN, w, N, Nx, eId=m.eId)
+    e.set_mesh(0, m.IEN, w, N, Nx, eId=m.eId, Nxx=elements.nxx_tables(m.eNoN) if m.eNoN == 8 else None)
     e.set_coords(m.x)
     return e
 

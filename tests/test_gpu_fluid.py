@@ -253,3 +253,60 @@ def test_precond_rcs_parity(ls_type, kw):
         assert abs(out1.RI.fNorm - out0.RI.fNorm) <= 0.05 * out0.RI.fNorm
     assert common.rel_err(X1, X0) < max(1e-6, 20 * ls.RI.relTol)
     eng.close()
+
+
+@pytest.mark.parametrize("scatter", [abi.SCATTER_ATOMIC, abi.SCATTER_COLORED], ids=["atomic", "colored"])
+@pytest.mark.parametrize("case", common.FLUID_GEN_CASES, ids=[c[0] for c in common.FLUID_GEN_CASES])
+def test_general_element_fluid_assembly_parity(case, scatter):
+    """HEX8 fluid (gnn + gn_nxx per Gauss point, second-derivative terms, stale-Nwxx continuity loop) and TET4 through
+    the same general kernel, against what the unmodified reference assembled (tests/golden/fluid_gen.npz)."""
+    golden = common.load_golden("fluid_gen.npz")
+    name, mk, visc, Kd, f, tDof, mv = case
+    m = mk()
+    Ag, Yg, Dg, Bf = common.fluid_gen_state(m, tDof)
+    rowPtr, colPtr = golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"]
+    eq = abi.fluid_eq(0.005, tDof=tDof, mvMsh=mv, scatter=scatter, general=True)
+    dmn = [abi.fluid_domain(K_darcy=Kd, f=f, **visc)]
+    eng = common.make_engine(m, rowPtr, colPtr)
+    eng.alloc(4); eng.set_state(Ag, Yg, Dg, Bf); eng.assemble(0, eq, dmn)
+    R1, V1 = eng.get_R(), eng.get_Val()
+    assert common.rel_err(R1, golden[f"{name}/R"]) < ASM_TOL
+    assert common.rel_err(V1, golden[f"{name}/Val"]) < ASM_TOL
+    if m.eNoN == 4:
+        # the specialised TET4 kernel and the general kernel are two independent derivations of the same element
+        eng.alloc(4); eng.assemble(0, abi.fluid_eq(0.005, tDof=tDof, mvMsh=mv, scatter=scatter), dmn)
+        assert common.rel_err(eng.get_Val(), V1) < ASM_TOL and common.rel_err(eng.get_R(), R1) < ASM_TOL
+    if scatter == abi.SCATTER_COLORED:
+        eng.alloc(4); eng.assemble(0, eq, dmn)
+        assert np.array_equal(eng.get_Val(), V1) and np.array_equal(eng.get_R(), R1)
+    eng.close()
+
+
+def test_hex8_fluid_newton_iteration_parity():
+    """Assembly + GMRES on a HEX8 fluid mesh against the compiled reference."""
+    from oracle import refbind
+    if not refbind.have_ref():
+        pytest.skip("needs libsvref.so")
+    name, mk, visc, Kd, f, tDof, mv = common.FLUID_GEN_CASES[0]
+    m = mk()
+    Ag, Yg, Dg, Bf = common.fluid_gen_state(m, tDof)
+    faces = [(abi.BC_DIR, m.faces[k], np.zeros((3, len(m.faces[k])), order="F")) for k in ("X0", "Y0", "Y1", "Z0", "Z1")]
+    orc = refbind.RefCase(); orc.set_coords(m.x); orc.add_mesh(m.IEN)
+    rowPtr, colPtr = orc.build_graph(len(faces))
+    eq, dmn = abi.fluid_eq(0.005), [abi.fluid_domain()]
+    eng = common.make_engine(m, rowPtr, colPtr)
+    eng.set_num_faces(len(faces))
+    for i, (g, nodes, val) in enumerate(faces):
+        orc.set_face(i, g, nodes, val); eng.set_face(i, g, nodes, val)
+    ls = abi.ls_params(abi.LS_GMRES, mItr=10, sD=100, relTol=1e-8)
+    incL, res = np.ones(len(faces), np.int32), np.zeros(len(faces))
+    orc.alloc(4); orc.set_state(Ag, Yg, Dg, Bf); orc.assemble(0, eq, dmn)
+    R0 = orc.get_R()
+    X0, o0, _ = orc.solve(4, abi.LS_GMRES, ls, incL, res)
+    eng.alloc(4); eng.set_state(Ag, Yg, Dg, Bf); eng.assemble(0, eq, dmn)
+    assert common.rel_err(eng.get_R(), R0) < ASM_TOL
+    X1, o1, _ = eng.solve(4, abi.LS_GMRES, ls, incL, res)
+    assert o1.RI.success == o0.RI.success and abs(o1.RI.itr - o0.RI.itr) <= 1
+    assert abs(o1.RI.iNorm - o0.RI.iNorm) <= 1e-10 * o0.RI.iNorm
+    assert common.rel_err(X1, X0) < 1e-6
+    eng.close()
