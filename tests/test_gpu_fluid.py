@@ -298,7 +298,10 @@ def test_hex8_fluid_newton_iteration_parity():
     eng.set_num_faces(len(faces))
     for i, (g, nodes, val) in enumerate(faces):
         orc.set_face(i, g, nodes, val); eng.set_face(i, g, nodes, val)
-    ls = abi.ls_params(abi.LS_GMRES, mItr=10, sD=100, relTol=1e-8)
+    # relTol 1e-6: on this 48-node mesh the GMRES residual stagnates at 1.6e-8 |r0| from iteration 23 on, so a tighter
+    # tolerance sits on the plateau and the iteration count then depends on the last bits of the atomically scattered Val
+    # (tools/stress_hex8.py: 23 iterations in 200/200 runs with the coloured scatter, 24 / 85 / 115 with atomics)
+    ls = abi.ls_params(abi.LS_GMRES, mItr=10, sD=100, relTol=1e-6)
     incL, res = np.ones(len(faces), np.int32), np.zeros(len(faces))
     orc.alloc(4); orc.set_state(Ag, Yg, Dg, Bf); orc.assemble(0, eq, dmn)
     R0 = orc.get_R()
