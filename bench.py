@@ -257,6 +257,7 @@ def main():
         eng.set_graph(rowPtr, colPtr, mynNo=mynNo, node_map=node_map, neighbours=neigh)
     else:
         eng.set_graph(rowPtr, colPtr)
+    cfg["transport"] = eng.comm_transport()     # "p2p": halo sums / scalar all-reduces by the library's own peer-memory kernels
     w, N, Nx = elements.tables(4)
     eng.set_mesh(0, m.IEN, w, N, Nx)
     eng.set_coords(m.x)

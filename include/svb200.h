@@ -174,6 +174,10 @@ SVB200_API int svb200_destroy(svb200_ctx* ctx);
  * Replaces fsils_commu_create (linear_solver/commu.cpp:17-46). */
 SVB200_API int svb200_comm_unique_id(void* id128);
 SVB200_API int svb200_comm_init(svb200_ctx* ctx, int nranks, int rank, const void* id128);
+/* Transport of the shared-node sums and scalar all-reduces: "p2p" = the library's own kernels storing into the peers'
+ * HBM over NVLink / NVSwitch (CUDA IPC mailboxes; default), "nccl" = ncclSend/Recv + ncclAllReduce (SVB200_COMM=nccl or
+ * when IPC is unavailable), "none" = single partition.  Valid after svb200_set_graph. */
+SVB200_API const char* svb200_comm_transport(svb200_ctx* ctx);
 
 /* ---- structure (once) ------------------------------------------------------------------- */
 /* CSR graph in INPUT node order exactly as lhsa_ns::lhsa builds it (columns ascending per row).

@@ -11,10 +11,27 @@
 // order of additions) everywhere.  Pack -> grouped ncclSend/ncclRecv -> unpack-add all run on the
 // context's stream: no host round trip, no CPU fallback.
 //
+// Two transports, same semantics:
+//   * "p2p" (default when CUDA IPC works between the ranks of the box): every rank owns a MAILBOX in its HBM that its
+//     peers map through cudaIpcOpenMemHandle.  A halo sum is then ONE push kernel per neighbour that gathers the shared
+//     rows of V and stores them straight into the neighbour's mailbox over NVLink / NVSwitch, followed by a release
+//     flag; the receiving side's unpack kernel spins on that flag and adds.  The scalar all-reduce of a GMRES / CG
+//     iteration is ONE single-CTA kernel: store my partial results into every peer's slot, signal, wait for all
+//     peers, then sum the nranks slots in rank order — so every rank computes bit-identical sums, and there is no
+//     NCCL launch (3 proxied kernels + host-side group bookkeeping per iteration before).  Mailboxes are double-buffered
+//     by the parity of a sequence number: a rank cannot run more than one exchange ahead of a peer because it needs
+//     that peer's data to get past its own wait.
+//   * "nccl": grouped ncclSend/ncclRecv + ncclAllReduce (SVB200_COMM=nccl, or when IPC is unavailable).
+//
 // NCCL is resolved with dlopen at svb200_comm_init time so that single-GPU users of libsvb200.so do
 // not need libnccl at all.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
 #include "svb200_internal.h"
 #include "fsils_kernels.h"
 
@@ -27,6 +44,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
@@ -70,6 +88,7 @@ int nccl_load()
   LOAD(CommInitRank, "ncclCommInitRank")
   LOAD(CommDestroy, "ncclCommDestroy")
   LOAD(AllReduce, "ncclAllReduce")
+  LOAD(AllGather, "ncclAllGather")
   LOAD(Send, "ncclSend")
   LOAD(Recv, "ncclRecv")
   LOAD(GroupStart, "ncclGroupStart")
@@ -109,6 +128,282 @@ void nccl_destroy(svb200_ctx* ctx)
   ctx->nccl_comm = nullptr;
 }
 
+// ---- peer-memory transport ---------------------------------------------------------------------------------
+constexpr int AR_MAX = 512;                       // doubles per scalar all-reduce
+constexpr unsigned long long SPIN_LIMIT_NS = 20ull * 1000 * 1000 * 1000;   // give up (error flag) after 20 s
+
+struct P2PNeighbor {
+  size_t my_off = 0;       // offset (doubles) in MY mailbox of the two receive buffers for this neighbour
+  size_t peer_off = 0;     // offset (doubles) in the NEIGHBOUR's mailbox of its receive buffers for me
+  unsigned* d_count = nullptr;   // block counter of the push kernel
+};
+
+struct P2P {
+  bool ready = false;
+  int nranks = 0, rank = 0;
+  double* base = nullptr;                 // my mailbox
+  size_t doubles = 0;
+  std::vector<double*> peer;              // mapped mailboxes, peer[rank] = base
+  double** d_peer = nullptr;              // device copy of peer[]
+  std::vector<P2PNeighbor> nb;            // same order as ctx->neigh
+  unsigned long long halo_seq = 0, ar_seq = 0;
+  // fixed layout at the start of every mailbox (in doubles / 8-byte words):
+  //   [0, 2R)            halo flags  [parity][src rank]
+  //   [2R, 4R)           all-reduce flags [parity][src rank]
+  //   [4R, 4R + 1)       error word
+  //   [hdr, hdr + 2 R AR_MAX)   all-reduce slots [parity][src rank][AR_MAX]
+  size_t off_arflag() const { return 2 * (size_t)nranks; }
+  size_t off_err() const { return 4 * (size_t)nranks; }
+  size_t off_slots() const { return 4 * (size_t)nranks + 8; }
+  size_t off_data() const { return off_slots() + 2 * (size_t)nranks * AR_MAX; }
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// Spin until *flag >= seq; on time-out raise the error word and return false.
+__device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsigned long long seq, unsigned long long* err)
+{
+  const unsigned long long t0 = global_ns();
+  while (ld_acquire_sys(flag) < seq) {
+    __nanosleep(64);
+    if (global_ns() - t0 > SPIN_LIMIT_NS) { *err = 1ull; return false; }
+  }
+  return true;
+}
+
+// Gather the shared rows of V and store them into the neighbour's mailbox; the last block to finish publishes the flag.
+__global__ void __launch_bounds__(256)
+halo_push_kernel(int n, int dof, const int* __restrict__ ptr, const double* __restrict__ V, double* __restrict__ remote_buf,
+                 unsigned long long* remote_flag, unsigned long long seq, unsigned* __restrict__ count)
+{
+  const int total = n * dof;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x)
+    remote_buf[t] = V[(size_t)ptr[t / dof] * dof + t % dof];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(count, 1u);
+    if (done == gridDim.x - 1) {
+      *count = 0u;
+      __threadfence_system();
+      st_release_sys(remote_flag, seq);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+halo_wait_add_kernel(int n, int dof, const int* __restrict__ ptr, const double* __restrict__ buf, double* __restrict__ V,
+                     const unsigned long long* flag, unsigned long long seq, unsigned long long* err)
+{
+  __shared__ int ok;
+  if (threadIdx.x == 0) ok = wait_flag(flag, seq, err) ? 1 : 0;
+  __syncthreads();
+  if (!ok) return;
+  const int total = n * dof;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x)
+    V[(size_t)ptr[t / dof] * dof + t % dof] += __ldcg(buf + t);
+}
+
+// Scalar all-reduce (sum) of n <= AR_MAX doubles in one CTA: push to every mailbox, signal, wait, sum in rank order.
+__global__ void __launch_bounds__(512)
+allreduce_p2p_kernel(int n, int nranks, int rank, double* __restrict__ buf, double* const* __restrict__ peer, size_t off_arflag,
+                     size_t off_slots, size_t off_err, unsigned long long seq)
+{
+  const int b = (int)(seq & 1ull);
+  const int t = threadIdx.x;
+  if (t < n) {
+    const double v = buf[t];
+    for (int r = 0; r < nranks; r++) peer[r][off_slots + ((size_t)b * nranks + rank) * AR_MAX + t] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t < nranks)
+    st_release_sys(reinterpret_cast<unsigned long long*>(peer[t]) + off_arflag + (size_t)b * nranks + rank, seq);
+  double* mine = peer[rank];
+  __shared__ int ok;
+  if (t == 0) ok = 1;
+  __syncthreads();
+  if (t < nranks) {
+    if (!wait_flag(reinterpret_cast<const unsigned long long*>(mine) + off_arflag + (size_t)b * nranks + t, seq,
+                   reinterpret_cast<unsigned long long*>(mine) + off_err))
+      ok = 0;
+  }
+  __syncthreads();
+  if (!ok || t >= n) return;
+  double s = 0.0;
+  for (int r = 0; r < nranks; r++) s += __ldcg(mine + off_slots + ((size_t)b * nranks + r) * AR_MAX + t);
+  buf[t] = s;
+}
+
+static P2P* p2p_of(svb200_ctx* ctx) { return static_cast<P2P*>(ctx->p2p); }
+
+void p2p_destroy(svb200_ctx* ctx)
+{
+  P2P* p = p2p_of(ctx);
+  if (!p) return;
+  for (int r = 0; r < (int)p->peer.size(); r++)
+    if (r != p->rank && p->peer[r]) cudaIpcCloseMemHandle(p->peer[r]);
+  for (auto& nb : p->nb) cudaFree(nb.d_count);
+  cudaFree(p->d_peer);
+  cudaFree(p->base);
+  delete p;
+  ctx->p2p = nullptr;
+}
+
+// Collective over all ranks (call from svb200_set_graph / svb200_comm_init on every rank).  Any failure on any rank
+// makes ALL ranks fall back to the NCCL transport.
+int p2p_setup(svb200_ctx* ctx)
+{
+  p2p_destroy(ctx);
+  if (ctx->nranks <= 1 || !ctx->nccl_comm) return SVB200_OK;
+  const char* mode = getenv("SVB200_COMM");
+  const bool want = !(mode && std::string(mode) == "nccl");
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  const int R = ctx->nranks;
+  P2P* p = new P2P();
+  p->nranks = R; p->rank = ctx->rank;
+  p->nb.resize(ctx->neigh.size());
+  size_t off = p->off_data();
+  for (size_t j = 0; j < ctx->neigh.size(); j++) {
+    p->nb[j].my_off = off;
+    off += 2 * (size_t)4 * std::max(ctx->neigh[j].n, 1);
+  }
+  p->doubles = off;
+  bool ok = want;
+  cudaIpcMemHandle_t handle;
+  memset(&handle, 0, sizeof(handle));
+  if (ok) ok = cudaMalloc(&p->base, sizeof(double) * p->doubles) == cudaSuccess;
+  if (ok) ok = cudaMemset(p->base, 0, sizeof(double) * p->doubles) == cudaSuccess;
+  if (ok) ok = cudaIpcGetMemHandle(&handle, p->base) == cudaSuccess;
+  cudaGetLastError();
+  // record per rank: ok flag | IPC handle (64 B) | offset of my receive buffer for every source rank (-1 = none)
+  const size_t rec = 8 + sizeof(handle) + sizeof(long long) * R;
+  std::vector<unsigned char> mine(rec, 0), all(rec * R, 0);
+  long long okw = ok ? 1 : 0;
+  memcpy(mine.data(), &okw, 8);
+  memcpy(mine.data() + 8, &handle, sizeof(handle));
+  std::vector<long long> offs(R, -1);
+  for (size_t j = 0; j < ctx->neigh.size(); j++) offs[ctx->neigh[j].rank] = (long long)p->nb[j].my_off;
+  memcpy(mine.data() + 8 + sizeof(handle), offs.data(), sizeof(long long) * R);
+  unsigned char *d_mine = nullptr, *d_all = nullptr;
+  SVB_CUDA(cudaMalloc(&d_mine, rec));
+  SVB_CUDA(cudaMalloc(&d_all, rec * R));
+  SVB_CUDA(cudaMemcpyAsync(d_mine, mine.data(), rec, cudaMemcpyHostToDevice, ctx->stream));
+  SVB_NCCL(g_nccl.AllGather(d_mine, d_all, rec, ncclChar, comm, ctx->stream));
+  SVB_CUDA(cudaMemcpyAsync(all.data(), d_all, rec * R, cudaMemcpyDeviceToHost, ctx->stream));
+  SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int r = 0; r < R; r++) {
+    long long f;
+    memcpy(&f, all.data() + rec * r, 8);
+    ok = ok && f == 1;
+  }
+  p->peer.assign(R, nullptr);
+  if (ok) {
+    for (int r = 0; r < R && ok; r++) {
+      if (r == ctx->rank) { p->peer[r] = p->base; continue; }
+      cudaIpcMemHandle_t h;
+      memcpy(&h, all.data() + rec * r + 8, sizeof(h));
+      void* q = nullptr;
+      ok = cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+      p->peer[r] = static_cast<double*>(q);
+    }
+    cudaGetLastError();
+  }
+  // second agreement round: every rank must have mapped every mailbox
+  double* d_flag = reinterpret_cast<double*>(d_mine);
+  double okd = ok ? 1.0 : 0.0;
+  SVB_CUDA(cudaMemcpyAsync(d_flag, &okd, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  SVB_NCCL(g_nccl.AllReduce(d_flag, d_flag, 1, ncclDouble, ncclMin, comm, ctx->stream));
+  SVB_CUDA(cudaMemcpyAsync(&okd, d_flag, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_mine); cudaFree(d_all);
+  ctx->p2p = p;
+  if (okd != 1.0) {
+    p2p_destroy(ctx);
+    return SVB200_OK;     // NCCL transport
+  }
+  for (size_t j = 0; j < ctx->neigh.size(); j++) {
+    long long o;
+    memcpy(&o, all.data() + rec * ctx->neigh[j].rank + 8 + sizeof(handle) + sizeof(long long) * ctx->rank, sizeof(o));
+    if (o < 0) {
+      set_error("svb200: neighbour lists are not symmetric between partitions");
+      p2p_destroy(ctx);
+      return SVB200_ERR_INVALID;
+    }
+    p->nb[j].peer_off = (size_t)o;
+    SVB_CUDA(cudaMalloc(&p->nb[j].d_count, sizeof(unsigned)));
+    SVB_CUDA(cudaMemset(p->nb[j].d_count, 0, sizeof(unsigned)));
+  }
+  SVB_CUDA(cudaMalloc(&p->d_peer, sizeof(double*) * R));
+  SVB_CUDA(cudaMemcpy(p->d_peer, p->peer.data(), sizeof(double*) * R, cudaMemcpyHostToDevice));
+  p->ready = true;
+  return SVB200_OK;
+}
+
+const char* comm_transport(svb200_ctx* ctx)
+{
+  if (ctx->nranks <= 1) return "none";
+  return (p2p_of(ctx) && p2p_of(ctx)->ready) ? "p2p" : "nccl";
+}
+
+// Raise an error if a spin-wait of the peer-memory transport timed out since the last check.
+int p2p_check(svb200_ctx* ctx)
+{
+  P2P* p = p2p_of(ctx);
+  if (!p || !p->ready) return SVB200_OK;
+  unsigned long long e = 0;
+  SVB_CUDA(cudaMemcpyAsync(&e, reinterpret_cast<unsigned long long*>(p->base) + p->off_err(), sizeof(e), cudaMemcpyDeviceToHost, ctx->stream));
+  SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (e != 0) {
+    set_error("svb200: a peer-memory exchange timed out (a partner rank did not arrive within 20 s)");
+    return SVB200_ERR_NCCL;
+  }
+  return SVB200_OK;
+}
+
+static int halo_sum_p2p(svb200_ctx* ctx, int dof, double* V)
+{
+  P2P* p = p2p_of(ctx);
+  const unsigned long long seq = ++p->halo_seq;
+  const int b = (int)(seq & 1ull);
+  unsigned long long* myflags = reinterpret_cast<unsigned long long*>(p->base);
+  for (size_t j = 0; j < ctx->neigh.size(); j++) {
+    auto& nb = ctx->neigh[j];
+    const int n = nb.n * dof;
+    double* rbase = p->peer[nb.rank];
+    double* rbuf = rbase + p->nb[j].peer_off + (size_t)b * 4 * std::max(nb.n, 1);
+    unsigned long long* rflag = reinterpret_cast<unsigned long long*>(rbase) + (size_t)b * p->nranks + p->rank;
+    const int blocks = std::max(1, std::min((n + 255) / 256, 148));
+    halo_push_kernel<<<blocks, 256, 0, ctx->stream>>>(nb.n, dof, nb.d_ptr, V, rbuf, rflag, seq, p->nb[j].d_count);
+    ctx->launches++;
+  }
+  for (size_t j = 0; j < ctx->neigh.size(); j++) {   // ascending rank order, like in_commu.cpp:128-135
+    auto& nb = ctx->neigh[j];
+    const int n = nb.n * dof;
+    const double* buf = p->base + p->nb[j].my_off + (size_t)b * 4 * std::max(nb.n, 1);
+    const int blocks = std::max(1, std::min((n + 255) / 256, 148));
+    halo_wait_add_kernel<<<blocks, 256, 0, ctx->stream>>>(nb.n, dof, nb.d_ptr, buf, V, myflags + (size_t)b * p->nranks + nb.rank, seq,
+                                                         myflags + p->off_err());
+    ctx->launches++;
+  }
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
 __global__ void halo_pack_kernel(int n, int dof, const int* __restrict__ ptr, const double* __restrict__ V,
                                  double* __restrict__ buf)
 {
@@ -132,6 +427,7 @@ int halo_sum(svb200_ctx* ctx, int dof, double* V)
     set_error("svb200: graph has neighbour partitions but svb200_comm_init was not called");
     return SVB200_ERR_INVALID;
   }
+  if (p2p_of(ctx) && p2p_of(ctx)->ready) return halo_sum_p2p(ctx, dof, V);
   ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
   for (auto& nb : ctx->neigh) {
     const int n = nb.n * dof;
@@ -163,6 +459,15 @@ int allreduce_sum(svb200_ctx* ctx, double* d_buf, int n)
   if (!ctx->nccl_comm) {
     set_error("svb200: multi-rank context without a communicator");
     return SVB200_ERR_INVALID;
+  }
+  P2P* p = p2p_of(ctx);
+  if (p && p->ready && n <= AR_MAX) {
+    const unsigned long long seq = ++p->ar_seq;
+    allreduce_p2p_kernel<<<1, 512, 0, ctx->stream>>>(n, p->nranks, p->rank, d_buf, p->d_peer, p->off_arflag(), p->off_slots(),
+                                                    p->off_err(), seq);
+    ctx->launches++;
+    SVB_CUDA(cudaGetLastError());
+    return SVB200_OK;
   }
   SVB_NCCL(g_nccl.AllReduce(d_buf, d_buf, (size_t)n, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
   return SVB200_OK;

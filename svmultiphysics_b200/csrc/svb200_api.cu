@@ -23,6 +23,10 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
 int nccl_unique_id(void* id128);
 int nccl_init(svb200_ctx* ctx, int nranks, int rank, const void* id128);
 void nccl_destroy(svb200_ctx* ctx);
+int p2p_setup(svb200_ctx* ctx);
+void p2p_destroy(svb200_ctx* ctx);
+int p2p_check(svb200_ctx* ctx);
+const char* comm_transport(svb200_ctx* ctx);
 int add_bc_mul_device(svb200_ctx* ctx, int op, int dof, const double* X, double* Y, double* d_scal);
 
 template <class T>
@@ -193,6 +197,7 @@ int svb200_destroy(svb200_ctx* ctx)
   if (!ctx) return SVB200_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  p2p_destroy(ctx);
   nccl_destroy(ctx);
   for (auto& m : ctx->mesh) free_mesh(m);
   for (auto& f : ctx->face) free_face(f);
@@ -221,7 +226,15 @@ int svb200_comm_init(svb200_ctx* ctx, int nranks, int rank, const void* id128)
 {
   CTX_GUARD(ctx);
   SVB_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks && id128, "svb200_comm_init: bad arguments");
-  return nccl_init(ctx, nranks, rank, id128);
+  TRY(nccl_init(ctx, nranks, rank, id128));
+  if (ctx->d_rowPtr) TRY(p2p_setup(ctx));     // graph already set: map the peers' mailboxes now
+  return SVB200_OK;
+}
+
+const char* svb200_comm_transport(svb200_ctx* ctx)
+{
+  if (!ctx) return "none";
+  return comm_transport(ctx);
 }
 
 int svb200_set_graph(svb200_ctx* ctx, int32_t nNo, int32_t nnz, const int32_t* rowPtr, const int32_t* colPtr,
@@ -289,6 +302,7 @@ int svb200_set_graph(svb200_ctx* ctx, int32_t nNo, int32_t nnz, const int32_t* r
     ctx->neigh.push_back(nb);
   }
   std::sort(ctx->neigh.begin(), ctx->neigh.end(), [](const Neighbor& a, const Neighbor& b) { return a.rank < b.rank; });
+  TRY(p2p_setup(ctx));      // collective: every rank calls svb200_set_graph
   // state arrays depend on nNo
   cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf); cudaFree(ctx->d_Do);
   cudaFree(ctx->d_Ao); cudaFree(ctx->d_Yo); cudaFree(ctx->d_An); cudaFree(ctx->d_Yn); cudaFree(ctx->d_Dn); cudaFree(ctx->d_nodeflag);
@@ -800,7 +814,8 @@ int svb200_commu_R(svb200_ctx* ctx)
 {
   CTX_GUARD(ctx);
   SVB_REQUIRE(ctx->d_R, "svb200_commu_R: call svb200_alloc first");
-  return halo_sum(ctx, ctx->dof, ctx->d_R);
+  TRY(halo_sum(ctx, ctx->dof, ctx->d_R));
+  return SVB200_OK;
 }
 
 int svb200_solve(svb200_ctx* ctx, int32_t dof, int32_t ls_type, int32_t prec, const svb200_lsparams* ls,
@@ -818,6 +833,7 @@ int svb200_solve(svb200_ctx* ctx, int32_t dof, int32_t ls_type, int32_t prec, co
   float ms = 0.f;
   SVB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   ctx->last_solve_ms = ms;
+  TRY(p2p_check(ctx));
   if (R_out) TRY(download_nodal(ctx, dof, ctx->d_R, R_out));
   return SVB200_OK;
 }

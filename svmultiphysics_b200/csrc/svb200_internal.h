@@ -166,6 +166,7 @@ struct svb200_ctx {
   // multi-GPU
   int nranks = 1, rank = 0;
   void* nccl_comm = nullptr;
+  void* p2p = nullptr;             // peer-memory transport state (comm.cu), null = NCCL transport
   std::vector<svb::Neighbor> neigh;
 
   double last_assemble_ms = 0.0, last_solve_ms = 0.0;

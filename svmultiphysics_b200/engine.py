@@ -33,7 +33,7 @@ _ip = C.POINTER(C.c_int32)
 # every symbol include/svb200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "svb200_abi_version", "svb200_last_error", "svb200_create", "svb200_destroy",
-    "svb200_comm_unique_id", "svb200_comm_init",
+    "svb200_comm_unique_id", "svb200_comm_init", "svb200_comm_transport",
     "svb200_set_graph", "svb200_lhsa_begin", "svb200_lhsa_add_mesh", "svb200_lhsa_finish", "svb200_lhsa_get",
     "svb200_set_mesh", "svb200_set_mesh_nxx", "svb200_set_coords", "svb200_set_num_faces", "svb200_set_face",
     "svb200_alloc", "svb200_set_state", "svb200_set_old_disp", "svb200_assemble", "svb200_add_host_contrib", "svb200_commu_R",
@@ -64,6 +64,7 @@ def load_library():
         lib = C.CDLL(LIB_PATH)
         lib.svb200_last_error.restype = C.c_char_p
         lib.svb200_launch_count.restype = C.c_int64
+        lib.svb200_comm_transport.restype = C.c_char_p
         lib.svb200_launch_count.argtypes = [C.c_void_p]
         _lib = lib
     return _lib
@@ -138,6 +139,10 @@ class Engine:
 
     def comm_init(self, nranks: int, rank: int, uid: bytes):
         self._call("svb200_comm_init", C.c_int(nranks), C.c_int(rank), C.c_char_p(uid))
+
+    def comm_transport(self) -> str:
+        """"p2p" (own kernels over peer memory), "nccl" or "none"; valid after set_graph."""
+        return self.lib.svb200_comm_transport(self.h).decode()
 
     # ---- structure -----------------------------------------------------------------------------
     def lhsa(self, nNo: int, IENs):

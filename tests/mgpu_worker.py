@@ -89,7 +89,7 @@ def fsi_main(rank, world, lr):
                 X0, o0, _ = orc.solve(dof, ls_type, ls, incL, res)
                 Rg, Xg, o = out[name]
                 eR, eX = common.rel_err(Rg, R0), common.rel_err(Xg, X0)
-                print(f"[mgpu fsi/{name} x{world}] relerr R {eR:.2e} X {eX:.2e}; itr {o.RI.itr} vs {o0.RI.itr}; iNorm {o.RI.iNorm:.6e} vs {o0.RI.iNorm:.6e}")
+                print(f"[mgpu fsi/{name} x{world}, transport {eng.comm_transport()}] relerr R {eR:.2e} X {eX:.2e}; itr {o.RI.itr} vs {o0.RI.itr}; iNorm {o.RI.iNorm:.6e} vs {o0.RI.iNorm:.6e}")
                 # The FSI system is so ill-conditioned (solid blocks 1e7 x the fluid ones) that classical Gram-Schmidt loses
                 # orthogonality after ~20 iterations: the reference then stagnates until its restart at 50 (53 iterations)
                 # while another summation order gets under the tolerance at 33 (tests/test_gpu_struct.py::
@@ -182,7 +182,7 @@ def main():
         X0, o0, _ = orc.solve(4, ls_type, ls, incL, res)
         eR, eX = common.rel_err(Rg, R0), common.rel_err(Xg, X0)
         tolX = 0.05 if ls_type == abi.LS_NS else 1e-6
-        print(f"[mgpu {mode}/{ls_name} x{world}] relerr R {eR:.2e} X {eX:.2e}; itr {o.RI.itr} vs {o0.RI.itr}; iNorm {o.RI.iNorm:.6e} vs {o0.RI.iNorm:.6e}")
+        print(f"[mgpu {mode}/{ls_name} x{world}, transport {eng.comm_transport()}] relerr R {eR:.2e} X {eX:.2e}; itr {o.RI.itr} vs {o0.RI.itr}; iNorm {o.RI.iNorm:.6e} vs {o0.RI.iNorm:.6e}")
         ok = int(eR < 1e-12 and eX < tolX and abs(o.RI.iNorm - o0.RI.iNorm) < 1e-10 * o0.RI.iNorm
                  and abs(o.RI.itr - o0.RI.itr) <= max(2, o0.RI.itr // 25))
     flag = torch.tensor([ok], device="cuda")

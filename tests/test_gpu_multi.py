@@ -20,13 +20,19 @@ def _ngpu():
     return sum(1 for line in out.splitlines() if line.startswith("GPU "))
 
 
+@pytest.mark.parametrize("transport", ["p2p", "nccl"])
 @pytest.mark.parametrize("mode,ls", [("slab", "gmres"), ("scattered", "gmres"), ("slab", "ns"), ("fsi", "gmres+cg")])
-def test_two_gpu_parity(mode, ls):
+def test_two_gpu_parity(mode, ls, transport):
+    """transport p2p: shared-node sums and scalar all-reduces by the library's own kernels over peer memory (CUDA IPC
+    mailboxes, NVLink); nccl: ncclSend/Recv + ncclAllReduce.  Same parity bar for both."""
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     n = min(_ngpu(), 4) if mode in ("scattered", "fsi") else 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", "29541", os.path.join(ROOT, "tests", "mgpu_worker.py"), mode, ls]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    env = dict(os.environ)
+    env["SVB200_COMM"] = transport
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900, env=env)
     print(r.stdout[-2000:])
     assert r.returncode == 0, r.stdout[-4000:]
+    assert f"transport {transport}" in r.stdout, "the requested transport was not the one used:\n" + r.stdout[-2000:]
