@@ -183,8 +183,10 @@ def main():
         eR, eX = common.rel_err(Rg, R0), common.rel_err(Xg, X0)
         tolX = 0.05 if ls_type == abi.LS_NS else 1e-6
         print(f"[mgpu {mode}/{ls_name} x{world}, transport {eng.comm_transport()}] relerr R {eR:.2e} X {eX:.2e}; itr {o.RI.itr} vs {o0.RI.itr}; iNorm {o.RI.iNorm:.6e} vs {o0.RI.iNorm:.6e}")
+        # dozens of GMRES(50) restarts: the count moves by a few per cent with the summation order of the dots (partition
+        # sums, transport); the answer and the set tolerance are what is compared
         ok = int(eR < 1e-12 and eX < tolX and abs(o.RI.iNorm - o0.RI.iNorm) < 1e-10 * o0.RI.iNorm
-                 and abs(o.RI.itr - o0.RI.itr) <= max(2, o0.RI.itr // 25))
+                 and abs(o.RI.itr - o0.RI.itr) <= max(2, o0.RI.itr // 10) and bool(o.RI.success) == bool(o0.RI.success))
     flag = torch.tensor([ok], device="cuda")
     dist.broadcast(flag, 0)
     eng.close()
