@@ -29,6 +29,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL prints its version banner on STDOUT when NCCL_DEBUG=VERSION; stdout of this script is exactly one JSON line
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 from svmultiphysics_b200 import abi, elements, meshgen, partition  # noqa: E402
 
