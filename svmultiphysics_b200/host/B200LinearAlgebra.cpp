@@ -220,6 +220,8 @@ void B200LinearAlgebra::upload_structure(ComMod& com_mod)
     auto& m = com_mod.msh[iM];
     check(svb200_set_mesh(ctx, iM, m.eNoN, m.nEl, m.IEN.data(), m.eId.size() ? m.eId.data() : nullptr,
                           m.nFn, (m.nFn > 0 && m.fN.size()) ? m.fN.data() : nullptr, m.nG, m.w.data(), m.N.data(), m.Nx.data()));
+    // second derivatives of the shape functions for nn::gn_nxx (fluid on non-linear elements, fluid.cpp:648-650)
+    if (!m.fs.empty() && m.fs[0].Nxx.size() == 6 * m.eNoN * m.nG) check(svb200_set_mesh_nxx(ctx, iM, m.fs[0].Nxx.data()));
   }
   check(svb200_set_coords(ctx, com_mod.x.data()));
   structure_uploaded = true;

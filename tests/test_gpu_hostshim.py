@@ -122,3 +122,31 @@ def test_plugin_error_behaviour():
     with pytest.raises(RuntimeError, match="before ls_alloc"):
         gpu.assemble(0, abi.fluid_eq(0.005), [abi.fluid_domain()])
     _close(cpu, gpu)
+
+
+def test_hex8_fluid_through_cpp_plugin():
+    """HEX8 fluid: the plug-in hands fs[0].Nxx of the reference's own mshType to svb200_set_mesh_nxx; the general-element
+    kernel must reproduce construct_fluid (gnn + gn_nxx per Gauss point) to 1e-12, and the RCS preconditioner selected
+    through eq.linear_algebra_preconditioner must reach the device."""
+    name, mk, visc, Kd, f, tDof, mv = common.FLUID_GEN_CASES[1]
+    m = mk()
+    Ag, Yg, Dg, Bf = common.fluid_gen_state(m, tDof)
+    faces = [(abi.BC_DIR, m.faces[k], np.zeros((3, len(m.faces[k])), order="F")) for k in ("X0", "Y0", "Y1", "Z0", "Z1")]
+    cpu, gpu = _pair(m, nFaces=len(faces))
+    eq, dmn = abi.fluid_eq(0.005), [abi.fluid_domain(K_darcy=Kd, f=f, **visc)]
+    ls = abi.ls_params(abi.LS_GMRES, mItr=10, sD=100, relTol=1e-6)
+    res = []
+    for c in (cpu, gpu):
+        for i, (g, nodes, v) in enumerate(faces):
+            c.set_face(i, g, nodes, v)
+        c.alloc(4); c.set_state(Ag, Yg, Dg, Bf); c.assemble(0, eq, dmn)
+        R, V = c.get_R(), c.get_Val()
+        X, o, _ = c.solve(4, abi.LS_GMRES, ls, np.ones(len(faces), np.int32), np.zeros(len(faces)), prec=abi.PREC_RCS)
+        res.append((R, V, X, o))
+    (R0, V0, X0, o0), (R1, V1, X1, o1) = res
+    assert gpu.backend_launch_count() > 10
+    assert common.rel_err(R1, R0) < 1e-12 and common.rel_err(V1, V0) < 1e-12
+    assert o1.RI.success == o0.RI.success and abs(o1.RI.itr - o0.RI.itr) <= 2
+    assert abs(o1.RI.iNorm - o0.RI.iNorm) <= 1e-10 * o0.RI.iNorm
+    assert common.rel_err(X1, X0) < 2e-5
+    _close(cpu, gpu)
