@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define SVB200_ABI_VERSION 1
+#define SVB200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SVB200_API __attribute__((visibility("default")))
@@ -73,7 +73,12 @@ typedef enum {
 typedef enum { SVB200_VISC_CONST = 0, SVB200_VISC_CY = 1, SVB200_VISC_CASSON = 2 } svb200_visc;
 
 /* consts::ConstitutiveModelType, isochoric part (solver/mat_models.cpp:435-581). */
-typedef enum { SVB200_ISO_NHK = 0, SVB200_ISO_MR = 1, SVB200_ISO_GUCCIONE = 2, SVB200_ISO_STVK = 3 } svb200_iso;
+typedef enum {
+  SVB200_ISO_NHK = 0, SVB200_ISO_MR = 1, SVB200_ISO_GUCCIONE = 2, SVB200_ISO_STVK = 3,
+  SVB200_ISO_HGO = 4,      /* Holzapfel-Gasser-Ogden, additive split (mat_models.cpp:469-511): C10, aff, bff, ass, bss, kap */
+  SVB200_ISO_HO = 5,       /* Holzapfel-Ogden myocardium (:582-687): st_a, st_b, aff, bff, ass, bss, afs, bfs, khs */
+  SVB200_ISO_HO_MA = 6     /* Holzapfel-Ogden, modified anisotropy / full invariants (:689-773) */
+} svb200_iso;
 /* volumetric part (solver/mat_models.cpp:1441-1464). */
 typedef enum { SVB200_VOL_NONE = 0, SVB200_VOL_QUAD = 1, SVB200_VOL_ST91 = 2, SVB200_VOL_M94 = 3 } svb200_vol;
 
@@ -132,6 +137,8 @@ typedef struct {
   double E, nu;             /* elasticity_modulus, poisson_ratio (mesh / linear elasticity) */
   double solid_visc_mu;     /* solid_visc.mu; 0 = no solid viscosity */
   double backflow_stab;     /* backflow stabilisation coefficient (fluid Neumann faces, solver/fluid.cpp:65) */
+  /* stModelType a, b, aff, ass, afs, kap, khs (HGO / Holzapfel-Ogden; bff, bss, bfs above) — appended in ABI version 2 */
+  double st_a, st_b, aff, ass, afs, kap, khs;
 } svb200_dmnparams;
 
 /* FSILS_subLsType inputs (linear_solver/fils_struct.hpp:198-242). */

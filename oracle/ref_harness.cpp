@@ -104,6 +104,9 @@ void fill_domain(dmnType& d, const svb200_dmnparams& p)
     case SVB200_ISO_MR: d.stM.isoType = ConstitutiveModelType::stIso_MR; break;
     case SVB200_ISO_GUCCIONE: d.stM.isoType = ConstitutiveModelType::stIso_Gucci; break;
     case SVB200_ISO_STVK: d.stM.isoType = ConstitutiveModelType::stIso_StVK; break;
+    case SVB200_ISO_HGO: d.stM.isoType = ConstitutiveModelType::stIso_HGO; break;
+    case SVB200_ISO_HO: d.stM.isoType = ConstitutiveModelType::stIso_HO; break;
+    case SVB200_ISO_HO_MA: d.stM.isoType = ConstitutiveModelType::stIso_HO_ma; break;
   }
   switch (p.volType) {
     case SVB200_VOL_NONE: d.stM.volType = ConstitutiveModelType::stVol_NA; break;
@@ -113,6 +116,7 @@ void fill_domain(dmnType& d, const svb200_dmnparams& p)
   }
   d.stM.Kpen = p.Kpen; d.stM.C10 = p.C10; d.stM.C01 = p.C01;
   d.stM.bff = p.bff; d.stM.bss = p.bss; d.stM.bfs = p.bfs;
+  d.stM.a = p.st_a; d.stM.b = p.st_b; d.stM.aff = p.aff; d.stM.ass = p.ass; d.stM.afs = p.afs; d.stM.kap = p.kap; d.stM.khs = p.khs;
   if (p.solid_visc_mu != 0.0) {
     d.solid_visc.viscType = (p.solidViscType == SVB200_SOLID_VISC_POTENTIAL) ? SolidViscosityModelType::viscType_Potential
                                                                               : SolidViscosityModelType::viscType_Newtonian;

@@ -3,14 +3,14 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # svb200_phys
 PHYS_FLUID, PHYS_STRUCT, PHYS_FSI, PHYS_MESH = 0, 1, 2, 3
 # svb200_visc
 VISC_CONST, VISC_CY, VISC_CASSON = 0, 1, 2
 # svb200_iso / svb200_vol
-ISO_NHK, ISO_MR, ISO_GUCCIONE, ISO_STVK = 0, 1, 2, 3
+ISO_NHK, ISO_MR, ISO_GUCCIONE, ISO_STVK, ISO_HGO, ISO_HO, ISO_HO_MA = 0, 1, 2, 3, 4, 5, 6
 VOL_NONE, VOL_QUAD, VOL_ST91, VOL_M94 = 0, 1, 2, 3
 # svb200_ls_type
 LS_NS, LS_GMRES, LS_CG, LS_BICGS = 0, 1, 2, 3
@@ -56,6 +56,8 @@ class DmnParams(C.Structure):
         ("E", C.c_double), ("nu", C.c_double),
         ("solid_visc_mu", C.c_double),
         ("backflow_stab", C.c_double),
+        ("st_a", C.c_double), ("st_b", C.c_double), ("aff", C.c_double), ("ass", C.c_double), ("afs", C.c_double),
+        ("kap", C.c_double), ("khs", C.c_double),
     ]
 
 
@@ -126,7 +128,9 @@ def struct_eq(dt: float, rho_inf: float = 0.5, tDof: int = 3, dof: int = 3, s: i
 
 def struct_domain(rho: float = 1000.0, isoType: int = ISO_NHK, volType: int = VOL_ST91, E: float = 240.56596e6, nu: float = 0.5,
                   Kpen: float = 4.0e9, C10=None, C01: float = 0.0, bff: float = 0.0, bss: float = 0.0, bfs: float = 0.0,
-                  dmp: float = 0.0, f=(0.0, 0.0, 0.0), Id: int = -1, solid_visc: int = 0, solid_visc_mu: float = 0.0) -> DmnParams:
+                  dmp: float = 0.0, f=(0.0, 0.0, 0.0), Id: int = -1, solid_visc: int = 0, solid_visc_mu: float = 0.0,
+                  st_a: float = 0.0, st_b: float = 0.0, aff: float = 0.0, ass: float = 0.0, afs: float = 0.0, kap: float = 0.0,
+                  khs: float = 100.0) -> DmnParams:
     """Solid domain; C10 defaults to mu/2 with mu = E/(2(1+nu)) as set_material_props does for nHK
     (Code/Source/solver/set_material_props.h)."""
     d = DmnParams()
@@ -143,6 +147,7 @@ def struct_domain(rho: float = 1000.0, isoType: int = ISO_NHK, volType: int = VO
     d.dmp = dmp
     d.E, d.nu = E, nu
     d.solidViscType, d.solid_visc_mu = solid_visc, solid_visc_mu
+    d.st_a, d.st_b, d.aff, d.ass, d.afs, d.kap, d.khs = st_a, st_b, aff, ass, afs, kap, khs
     return d
 
 

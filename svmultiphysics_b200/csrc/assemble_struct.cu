@@ -556,6 +556,8 @@ int fill_struct_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, 
     o.dmp = dmn[d].dmp;
     o.Kpen = dmn[d].Kpen; o.C10 = dmn[d].C10; o.C01 = dmn[d].C01;
     o.bff = dmn[d].bff; o.bss = dmn[d].bss; o.bfs = dmn[d].bfs;
+    o.st_a = dmn[d].st_a; o.st_b = dmn[d].st_b; o.aff = dmn[d].aff; o.ass = dmn[d].ass; o.afs = dmn[d].afs;
+    o.kap = dmn[d].kap; o.khs = dmn[d].khs;
     o.isoType = dmn[d].isoType; o.volType = dmn[d].volType;
     o.visc_mu = dmn[d].solid_visc_mu;
     o.viscType = SVB200_SOLID_VISC_NONE;
@@ -565,11 +567,19 @@ int fill_struct_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, 
     o.isStruct = (dmn[d].phys == SVB200_PHYS_STRUCT);
     SVB_REQUIRE(o.Id >= -1 && o.Id < 31, "svb200_assemble: domain Id out of range");
     if (o.isStruct) {
-      SVB_REQUIRE(o.isoType == SVB200_ISO_NHK || o.isoType == SVB200_ISO_MR || o.isoType == SVB200_ISO_GUCCIONE ||
-                      o.isoType == SVB200_ISO_STVK, "svb200_assemble: constitutive model not implemented");
-      // compute_pk2cc throws for Guccione without two fibre families (mat_models.cpp:514-516)
-      if (o.isoType == SVB200_ISO_GUCCIONE && (m.nFn != 2 || !m.d_fN)) {
+      SVB_REQUIRE(o.isoType >= SVB200_ISO_NHK && o.isoType <= SVB200_ISO_HO_MA, "svb200_assemble: constitutive model not implemented");
+      // compute_pk2cc throws for the fibre models without two fibre families (mat_models.cpp:472-474, 514-516, 584-586)
+      const bool fibres = (m.nFn == 2 && m.d_fN);
+      if (o.isoType == SVB200_ISO_GUCCIONE && !fibres) {
         set_error("[compute_pk2cc] Min fiber directions not defined for Guccione material model.");
+        return SVB200_ERR_INVALID;
+      }
+      if (o.isoType == SVB200_ISO_HGO && !fibres) {
+        set_error("[compute_pk2cc] Min fiber directions not defined for HGO material model.");
+        return SVB200_ERR_INVALID;
+      }
+      if ((o.isoType == SVB200_ISO_HO || o.isoType == SVB200_ISO_HO_MA) && !fibres) {
+        set_error("[compute_pk2cc] Min fiber directions not defined for Holzapfel material model.");
         return SVB200_ERR_INVALID;
       }
     }

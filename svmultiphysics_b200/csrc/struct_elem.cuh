@@ -12,7 +12,9 @@
 //                     Dm += sum_k c_k (A~_k x A~_k)            with CC_bar = sum_k c_k A_k x A_k,
 //                                                              A~ = A - (C:A)/3 Ci   (= P : A)
 //                           - 2/3 (Ci x S_iso + S_iso x Ci) + 2 r1 (Ci (.) Ci) - 2 r1/3 (Ci x Ci)
-//   nHK: CC_bar = 0; Guccione: 7 dyads; Mooney-Rivlin: I x I and the symmetric identity handled in closed form.
+//   nHK: CC_bar = 0; Guccione: 7 dyads; Mooney-Rivlin: I x I and the symmetric identity handled in closed form;
+//   HGO: 2 dyads (dispersed structure tensors); Holzapfel-Ogden: 4 dyads (I, fibre-sheet, fibre, sheet) with the smoothed
+//   Heaviside switch; HO-ma: the isotropic dyad through bar_to_iso, the three anisotropic ones added un-projected.
 // (x = dyadic product, (.) = symmetric dyadic product 1/2(A_ik B_jl + A_il B_jk), mat_fun.h:201-223).
 #pragma once
 #include "fluid_elem.cuh"   // SVB_HD, is_zero
@@ -22,6 +24,7 @@ namespace svb {
 struct StructDmn {
   double rho, f[3], dmp;
   double Kpen, C10, C01, bff, bss, bfs;
+  double st_a, st_b, aff, ass, afs, kap, khs;   // stModelType a, b, aff, ass, afs, kap, khs (HGO / Holzapfel-Ogden)
   double visc_mu;
   int isoType, volType, Id, isStruct;
   int viscType, pad;      // svb200_solid_visc
@@ -203,6 +206,98 @@ SVB_HD int pk2cc_voigt(const StructDmn& dm, const double F[3][3], const double f
 #pragma unroll
         for (int j = 0; j < 3; j++) { St[i][j] = Sh[i][j] - cS * Ci[i][j]; Sb[i][j] = r2 * Sh[i][j]; }
       dm_add_dyad(Dm, 2.0 * cbar, St, St);
+    }
+  } else if (dm.isoType == SVB200_ISO_HGO || dm.isoType == SVB200_ISO_HO || dm.isoType == SVB200_ISO_HO_MA) {
+    // mat_models.cpp:469-511 (HGO), 582-687 (HO), 689-773 (HO-ma); active stresses Tfa/Tsa/Tna = 0 (no CEP coupling)
+    double Hff[3][3], Hss[3][3], Hfs[3][3];
+    double Cf1[3], Cf2[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      Cf1[i] = C[i][0] * fN[0][0] + C[i][1] * fN[0][1] + C[i][2] * fN[0][2];
+      Cf2[i] = C[i][0] * fN[1][0] + C[i][1] * fN[1][1] + C[i][2] * fN[1][2];
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        Hff[i][j] = fN[0][i] * fN[0][j];
+        Hss[i][j] = fN[1][i] * fN[1][j];
+        Hfs[i][j] = 0.5 * (fN[0][i] * fN[1][j] + fN[1][i] * fN[0][j]);
+      }
+    }
+    const double I4 = fN[0][0] * Cf1[0] + fN[0][1] * Cf1[1] + fN[0][2] * Cf1[2];
+    const double I6 = fN[1][0] * Cf2[0] + fN[1][1] * Cf2[1] + fN[1][2] * Cf2[2];
+    const double I8 = fN[0][0] * Cf2[0] + fN[0][1] * Cf2[1] + fN[0][2] * Cf2[2];
+    const double Inv1 = J2d * trC;
+    // S_bar = sum_k sw[k] A_k, CC_bar = sum_k cw[k] A_k x A_k (projected); un-projected extras for HO-ma
+    double A[4][3][3], sw[4] = {0, 0, 0, 0}, cw[4] = {0, 0, 0, 0};
+    int nA = 0;
+    if (dm.isoType == SVB200_ISO_HGO) {
+      const double kap = dm.kap;
+      const double Eff = kap * Inv1 + (1.0 - 3.0 * kap) * J2d * I4 - 1.0;
+      const double Ess = kap * Inv1 + (1.0 - 3.0 * kap) * J2d * I6 - 1.0;
+      const double ef = exp(dm.bff * Eff * Eff), es = exp(dm.bss * Ess * Ess);
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          A[0][i][j] = Idm[i][j];
+          A[1][i][j] = kap * Idm[i][j] + (1.0 - 3.0 * kap) * Hff[i][j];
+          A[2][i][j] = kap * Idm[i][j] + (1.0 - 3.0 * kap) * Hss[i][j];
+        }
+      nA = 3;
+      sw[0] = 2.0 * dm.C10; sw[1] = 2.0 * dm.aff * Eff * ef; sw[2] = 2.0 * dm.ass * Ess * es;
+      cw[1] = 4.0 * J4d * dm.aff * (1.0 + 2.0 * dm.bff * Eff * Eff) * ef;
+      cw[2] = 4.0 * J4d * dm.ass * (1.0 + 2.0 * dm.bss * Ess * Ess) * es;
+    } else {
+      const bool ma = (dm.isoType == SVB200_ISO_HO_MA);
+      const double jf = ma ? 1.0 : J2d;             // HO: isochoric invariants; HO-ma: full invariants
+      const double Eff = jf * I4 - 1.0, Ess = jf * I6 - 1.0, Efs = jf * I8;
+      const double k = dm.khs;
+      const double of = 1.0 / (exp(k * Eff) + 1.0), os = 1.0 / (exp(k * Ess) + 1.0);
+      const double c4f = 1.0 - of, c4s = 1.0 - os;
+      const double dc4f = k * (of - of * of), dc4s = k * (os - os * os);
+      const double ddc4f = k * k * (-of + 3.0 * of * of - 2.0 * of * of * of);
+      const double ddc4s = k * k * (-os + 3.0 * os * os - 2.0 * os * os * os);
+      const double giso = dm.st_a * exp(dm.st_b * (Inv1 - 3.0));
+      const double efs = exp(dm.bfs * Efs * Efs), rf = exp(dm.bff * Eff * Eff), rs = exp(dm.bss * Ess * Ess);
+      const double s_fs = 2.0 * dm.afs * Efs * efs;
+      const double c_fs = 4.0 * dm.afs * (1.0 + 2.0 * dm.bfs * Efs * Efs) * efs;
+      const double s_ff = 2.0 * dm.aff * (c4f * Eff * rf + (0.5 * dc4f / dm.bff) * (rf - 1.0));
+      const double c_ff = 4.0 * dm.aff * ((c4f * (1.0 + 2.0 * dm.bff * Eff * Eff) + 2.0 * dc4f * Eff) * rf + (0.5 * ddc4f / dm.bff) * (rf - 1.0));
+      const double s_ss = 2.0 * dm.ass * (c4s * Ess * rs + (0.5 * dc4s / dm.bss) * (rs - 1.0));
+      const double c_ss = 4.0 * dm.ass * ((c4s * (1.0 + 2.0 * dm.bss * Ess * Ess) + 2.0 * dc4s * Ess) * rs + (0.5 * ddc4s / dm.bss) * (rs - 1.0));
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) { A[0][i][j] = Idm[i][j]; A[1][i][j] = Hfs[i][j]; A[2][i][j] = Hff[i][j]; A[3][i][j] = Hss[i][j]; }
+      sw[0] = giso; cw[0] = 2.0 * J4d * dm.st_b * giso;
+      if (!ma) {
+        nA = 4;
+        sw[1] = s_fs; cw[1] = J4d * c_fs;
+        sw[2] = s_ff; cw[2] = J4d * c_ff;
+        sw[3] = s_ss; cw[3] = J4d * c_ss;
+      } else {
+        nA = 1;
+        // anisotropic terms enter S and CC directly, without the deviatoric projection (mat_models.cpp:737-767)
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = 0; j < 3; j++) S[i][j] += s_fs * Hfs[i][j] + s_ff * Hff[i][j] + s_ss * Hss[i][j];
+        dm_add_dyad(Dm, c_fs, Hfs, Hfs);
+        dm_add_dyad(Dm, c_ff, Hff, Hff);
+        dm_add_dyad(Dm, c_ss, Hss, Hss);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) Sb[i][j] = 0.0;
+    for (int k = 0; k < nA; k++) {
+      double At[3][3];
+      const double cA = ddot(C, A[k]) / 3.0;
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) { Sb[i][j] += sw[k] * A[k][i][j]; At[i][j] = A[k][i][j] - cA * Ci[i][j]; }
+      if (cw[k] != 0.0) dm_add_dyad(Dm, cw[k], At, At);
     }
   } else {
     return 1;

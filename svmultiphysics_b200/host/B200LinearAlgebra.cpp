@@ -83,6 +83,9 @@ std::vector<svb200_dmnparams> domain_params(const eqType& eq)
         case ConstitutiveModelType::stIso_MR: p.isoType = SVB200_ISO_MR; break;
         case ConstitutiveModelType::stIso_Gucci: p.isoType = SVB200_ISO_GUCCIONE; break;
         case ConstitutiveModelType::stIso_StVK: p.isoType = SVB200_ISO_STVK; break;
+        case ConstitutiveModelType::stIso_HGO: p.isoType = SVB200_ISO_HGO; break;
+        case ConstitutiveModelType::stIso_HO: p.isoType = SVB200_ISO_HO; break;
+        case ConstitutiveModelType::stIso_HO_ma: p.isoType = SVB200_ISO_HO_MA; break;
         default: throw std::runtime_error("[B200LinearAlgebra] isochoric constitutive model not implemented on the device");
       }
       switch (d.stM.volType) {
@@ -93,6 +96,7 @@ std::vector<svb200_dmnparams> domain_params(const eqType& eq)
       }
       p.Kpen = d.stM.Kpen; p.C10 = d.stM.C10; p.C01 = d.stM.C01;
       p.bff = d.stM.bff; p.bss = d.stM.bss; p.bfs = d.stM.bfs;
+      p.st_a = d.stM.a; p.st_b = d.stM.b; p.aff = d.stM.aff; p.ass = d.stM.ass; p.afs = d.stM.afs; p.kap = d.stM.kap; p.khs = d.stM.khs;
       if (d.solid_visc.viscType != SolidViscosityModelType::viscType_NA) {
         p.solid_visc_mu = d.solid_visc.mu;
         p.solidViscType = (d.solid_visc.viscType == SolidViscosityModelType::viscType_Potential) ? SVB200_SOLID_VISC_POTENTIAL

@@ -97,6 +97,12 @@ STRUCT_CASES = [
                                            solid_visc_mu=3.0e5), 0),
     ("hex8_MR_visc_newtonian", _hex, dict(isoType=abi.ISO_MR, C10=1e5, C01=3e4, Kpen=1e7, rho=1.0, solid_visc=abi.SOLID_VISC_NEWTONIAN,
                                           solid_visc_mu=50.0), 0),
+    # fibre-reinforced models with the parameters of tests/cases/struct (LV_Holzapfel*, HGO arteries), cgs-like units
+    ("hex8_HGO", _hex, dict(isoType=abi.ISO_HGO, C10=3.0e4, aff=2.4e4, bff=0.84, ass=2.4e4, bss=0.84, kap=0.226, Kpen=1e7, rho=1.0), 2),
+    ("hex8_HO", _hex, dict(isoType=abi.ISO_HO, st_a=590.0, st_b=8.023, aff=184720.0, bff=16.026, ass=24810.0, bss=11.12, afs=2160.0,
+                           bfs=11.436, khs=100.0, Kpen=1e7, rho=1.0), 2),
+    ("tet4_HO_ma", _tet, dict(isoType=abi.ISO_HO_MA, st_a=590.0, st_b=8.023, aff=184720.0, bff=16.026, ass=24810.0, bss=11.12,
+                              afs=2160.0, bfs=11.436, khs=100.0, volType=abi.VOL_QUAD, Kpen=1e6, rho=1.0), 2),
     ("hex8_Guccione", _hex, dict(isoType=abi.ISO_GUCCIONE, C10=440.0, bff=8.0, bss=6.0, bfs=12.0, Kpen=1e6, rho=1e-3), 2),   # struct/LV_Guccione_passive
 ]
 

@@ -74,7 +74,8 @@ def test_device_element_algebra_matches_golden(hostmath, case, variant):
 class StructDmn(C.Structure):
     _fields_ = [("rho", C.c_double), ("f", C.c_double * 3), ("dmp", C.c_double),
                 ("Kpen", C.c_double), ("C10", C.c_double), ("C01", C.c_double), ("bff", C.c_double), ("bss", C.c_double),
-                ("bfs", C.c_double), ("visc_mu", C.c_double),
+                ("bfs", C.c_double), ("st_a", C.c_double), ("st_b", C.c_double), ("aff", C.c_double), ("ass", C.c_double),
+                ("afs", C.c_double), ("kap", C.c_double), ("khs", C.c_double), ("visc_mu", C.c_double),
                 ("isoType", C.c_int), ("volType", C.c_int), ("Id", C.c_int), ("isStruct", C.c_int), ("viscType", C.c_int), ("pad", C.c_int)]
 
 
@@ -115,6 +116,7 @@ def test_device_solid_algebra_matches_golden(hostmath, name, mk, dkw, nFn):
     for i in range(3):
         dm.f[i] = d.f[i]
     dm.visc_mu, dm.viscType = d.solid_visc_mu, d.solidViscType
+    dm.st_a, dm.st_b, dm.aff, dm.ass, dm.afs, dm.kap, dm.khs = d.st_a, d.st_b, d.aff, d.ass, d.afs, d.kap, d.khs
     dm.isoType, dm.volType, dm.Id, dm.isStruct = d.isoType, d.volType, -1, 1
     rowPtr, colPtr = golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"]
     R = np.zeros((m.nNo, 3))
