@@ -10,8 +10,10 @@
 //            state, viscosity, tau_M/C/B, the fine-scale velocity — and leaves a FluidGP (45 doubles) plus one
 //            FluidNode (11 doubles) per element node in shared memory.  The lane of the LAST Gauss point publishes its
 //            second derivatives first, because the reference's continuity loop uses them at every Gauss point.
-//   phase B  lane a = element node a = one block row of the element matrix: residual row, then for one b at a time the
-//            4x4 block summed over the Gauss points in registers and scattered (16 contiguous doubles = one CSR block).
+//   phase B  lane a = element node a = one block row of the element matrix: residual row, then FG_NB column nodes at a
+//            time: per Gauss point the (g, a) part of the tangent is folded into a FluidRow once (fluid_gen_row) and the
+//            FG_NB 4x4 blocks accumulate in registers (~80 FMAs and 11 shared loads per block and Gauss point), then each
+//            is scattered as 16 contiguous doubles = one CSR block.
 #include <cstdlib>
 #include <vector>
 #include "fluid_gen.cuh"
@@ -45,11 +47,16 @@ __device__ __forceinline__ void fg_add(double* p, double v)
 }
 
 constexpr int FG_THREADS = 64;
+constexpr int FG_NB = 4;      // column nodes per pass of phase B
 __host__ __device__ constexpr int fg_tab_ld(int enon) { return 1 + enon * 10; }
-// per element: nodal inputs (x 3, a-b... kept separate: al 3, yl 4, bfl 3, ym 3 = 16) | NxxL 6 | FluidGP | FluidNode[ENON]
+// stride between the FluidNode tables of consecutive Gauss points: odd, so that the phase-A stores of the lanes of an
+// element (lane = Gauss point) fall into different banks
+__host__ __device__ constexpr int fg_nd_ld(int enon) { return enon * FLUID_NODE_DOUBLES + 1; }
+// per element: nodal inputs (x 3, al 3, yl 4, bfl 3, ym 3 = 16) | NxxL 6 | FluidGP per Gauss point | FluidNode tables;
+// padded to 8 mod 16 doubles (the two elements of a half-warp then use disjoint banks)
 __host__ __device__ constexpr int fg_per_el(int enon)
 {
-  const int n = enon * 16 + enon * 6 + enon * FLUID_GP_DOUBLES + enon * enon * FLUID_NODE_DOUBLES;
+  const int n = enon * 16 + enon * 6 + enon * FLUID_GP_DOUBLES + enon * fg_nd_ld(enon);
   return n + ((8 - (n % 16)) + 16) % 16;
 }
 
@@ -73,7 +80,9 @@ assemble_fluid_gen_kernel(const __grid_constant__ FluidGenArgs P)
   double(*sym)[3] = reinterpret_cast<double(*)[3]>(se + 13 * ENON);
   double(*sNxxL)[6] = reinterpret_cast<double(*)[6]>(se + 16 * ENON);
   FluidGP* sgp = reinterpret_cast<FluidGP*>(se + 22 * ENON);
-  FluidNode* snd = reinterpret_cast<FluidNode*>(se + 22 * ENON + ENON * FLUID_GP_DOUBLES);   // [g][node]
+  constexpr int NLD = fg_nd_ld(ENON);
+  double* sndd = se + 22 * ENON + ENON * FLUID_GP_DOUBLES;      // FluidNode tables, one per Gauss point, stride NLD
+  auto snd = [&](int g) { return reinterpret_cast<FluidNode*>(sndd + g * NLD); };
 
   const long long idx = (long long)P.e0 + ((long long)blockIdx.x * (FG_THREADS / 32) + warp) * EPW + el;
   bool active = (lane < EPW * ENON) && idx < P.e1;
@@ -126,7 +135,7 @@ assemble_fluid_gen_kernel(const __grid_constant__ FluidGenArgs P)
     __syncwarp();
     if (active)
       fluid_gen_gauss_point<ENON>(dm, P.dt, P.af, P.am, P.gam, tg[0] * Jac, ks, tg + 1, Nx, Nxx, sNxxL, sal, syl, sbf,
-                                  P.mvMsh ? sym : nullptr, sgp[g], snd + g * ENON);
+                                  P.mvMsh ? sym : nullptr, sgp[g], snd(g));
   }
   __syncwarp();
   if (!active) return;
@@ -134,20 +143,36 @@ assemble_fluid_gen_kernel(const __grid_constant__ FluidGenArgs P)
   // ---- phase B ------------------------------------------------------------------------------------------------
   double lR[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
-  for (int g = 0; g < ENON; g++) fluid_gen_residual(sgp[g], snd[g * ENON + a], lR);
+  for (int g = 0; g < ENON; g++) fluid_gen_residual(sgp[g], snd(g)[a], lR);
 #pragma unroll
   for (int i = 0; i < 4; i++) fg_add<ATOMIC>(P.R + 4 * (size_t)node + i, lR[i]);
   const int* sl = P.slot + (size_t)e * ENON * ENON;
+  constexpr int NB = (ENON % FG_NB == 0) ? FG_NB : 1;
 #pragma unroll 1
-  for (int b = 0; b < ENON; b++) {
-    double K[16];
+  for (int b0 = 0; b0 < ENON; b0 += NB) {
+    // CSR slots of the NB blocks, requested before the Gauss loop so that the load latency hides behind the FMAs
+    int slots[NB];
 #pragma unroll
-    for (int i = 0; i < 16; i++) K[i] = 0.0;
+    for (int bb = 0; bb < NB; bb++) slots[bb] = __ldg(sl + a * ENON + b0 + bb);
+    double K[NB][16];
+#pragma unroll
+    for (int bb = 0; bb < NB; bb++)
+#pragma unroll
+      for (int i = 0; i < 16; i++) K[bb][i] = 0.0;
 #pragma unroll 1
-    for (int g = 0; g < ENON; g++) fluid_gen_block(sgp[g], snd[g * ENON + a], snd[g * ENON + b], K);
-    double* v = P.Val + 16 * (size_t)sl[a * ENON + b];
+    for (int g = 0; g < ENON; g++) {
+      const FluidNode* nd = snd(g);
+      FluidRow row;
+      fluid_gen_row(sgp[g], nd[a], row);
 #pragma unroll
-    for (int i = 0; i < 16; i++) fg_add<ATOMIC>(v + i, K[i]);
+      for (int bb = 0; bb < NB; bb++) fluid_gen_block_row(row, nd[b0 + bb], K[bb]);
+    }
+#pragma unroll
+    for (int bb = 0; bb < NB; bb++) {
+      double* v = P.Val + 16 * (size_t)slots[bb];
+#pragma unroll
+      for (int i = 0; i < 16; i++) fg_add<ATOMIC>(v + i, K[bb][i]);
+    }
   }
 }
 

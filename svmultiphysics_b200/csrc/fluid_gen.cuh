@@ -303,4 +303,63 @@ SVB_HD void fluid_gen_block(const FluidGP& q, const FluidNode& a, const FluidNod
   K[15] += wl * q.tauM * NxNx;
 }
 
+// ---- factored form of fluid_gen_block -----------------------------------------------------------------------------
+// Everything of a tangent block that depends on (Gauss point, row node a) only is folded into a FluidRow once and reused
+// for all column nodes b; a block then costs ~80 FMAs and reads 11 doubles (FluidNode_b):
+//   K(i,j)  += U_j Nx_i,b + tC Nx_i,a Nx_j,b + mg esNx_i,a esNx_j,b + V_j esNx_i,b + delta_ij D
+//      U_j = wl (mu Nx_j,a - rtu mu_x_j),  V_j = -wl rtu mu_g d2u2_j,  tC = wl tauC,  mg = wl mu_g,
+//      D   = wl mu (Nx_a.Nx_b) + c0 N_b + c1 (uNx_b + upNx_b) + c2 upNx_b - wl rtu T1b_b
+//      c0  = wl (rho amd (N_a + rtu) + muKd N_a),  c1 = wl rho N_a,  c2 = wl tauB upNx_a
+//   K(i,3)  += -wl Nx_i,a N_b + wl rtu Nx_i,b
+//   K(3,j)  += wl N_a Nx_j,b - wl tauM [ mu_x_c_j (Nx_a.Nx_b) + mu_g d2u2_c_j (Nx_a.esNx_b) + Nx_j,a (T1b_c_b - rho amd N_b) ]
+//   K(3,3)  += wl tauM (Nx_a.Nx_b)
+struct FluidRow {
+  double U[3], V[3], tCNx[3], mgEs[3], wlNx[3], Nx[3];
+  double wlmu, c0, c1, c2, wlrtu, wlNa, wltM, ramd;
+  double Pc[3], Qc[3];       // wl tauM mu_x_c_j, wl tauM mu_g d2u2_c_j
+};
+
+SVB_HD void fluid_gen_row(const FluidGP& q, const FluidNode& a, FluidRow& r)
+{
+  const double wl = q.wl;
+  const double rtu = q.rho * q.tauM * (a.uNx + a.upNx);
+  r.wlrtu = wl * rtu;
+  r.wlmu = wl * q.mu;
+  r.c0 = wl * (q.rho * q.amd * (a.N + rtu) + q.muKd * a.N);
+  r.c1 = wl * q.rho * a.N;
+  r.c2 = wl * q.tauB * a.upNx;
+  r.wlNa = wl * a.N;
+  r.wltM = wl * q.tauM;
+  r.ramd = q.rho * q.amd;
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    r.U[j] = wl * (q.mu * a.Nx[j] - rtu * q.mu_x[j]);
+    r.V[j] = -wl * rtu * q.mu_g * q.d2u2[j];
+    r.tCNx[j] = wl * q.tauC * a.Nx[j];
+    r.mgEs[j] = wl * q.mu_g * a.esNx[j];
+    r.wlNx[j] = wl * a.Nx[j];
+    r.Nx[j] = a.Nx[j];
+    r.Pc[j] = r.wltM * q.mu_x_c[j];
+    r.Qc[j] = r.wltM * q.mu_g * q.d2u2_c[j];
+  }
+}
+
+SVB_HD void fluid_gen_block_row(const FluidRow& r, const FluidNode& b, double K[16])
+{
+  const double NxNx = r.Nx[0] * b.Nx[0] + r.Nx[1] * b.Nx[1] + r.Nx[2] * b.Nx[2];
+  const double NxEs = r.Nx[0] * b.esNx[0] + r.Nx[1] * b.esNx[1] + r.Nx[2] * b.esNx[2];
+  const double D = r.wlmu * NxNx + r.c0 * b.N + r.c1 * (b.uNx + b.upNx) + r.c2 * b.upNx - r.wlrtu * b.T1b;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+      K[4 * i + j] += r.U[j] * b.Nx[i] + r.tCNx[i] * b.Nx[j] + r.mgEs[i] * b.esNx[j] + r.V[j] * b.esNx[i] + (i == j ? D : 0.0);
+    K[4 * i + 3] += r.wlrtu * b.Nx[i] - r.wlNx[i] * b.N;
+  }
+  const double tc = r.wltM * (b.T1b_c - r.ramd * b.N);
+#pragma unroll
+  for (int j = 0; j < 3; j++) K[12 + j] += r.wlNa * b.Nx[j] - (r.Pc[j] * NxNx + r.Qc[j] * NxEs + r.Nx[j] * tc);
+  K[15] += r.wltM * NxNx;
+}
+
 }  // namespace svb

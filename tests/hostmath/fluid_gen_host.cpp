@@ -8,7 +8,7 @@ using std::fabs; using std::sqrt; using std::pow; using std::exp;
 
 struct HostFluidGenArgs {
   const int* IEN; const double *x, *Ag, *Yg, *Bf;
-  int eNoN, nEl, nG, tDof, mvMsh, pad;
+  int eNoN, nEl, nG, tDof, mvMsh, factored;   // factored: tangent through fluid_gen_row / fluid_gen_block_row
   double dt, af, am, gam;
   double w[8], N[8][8], Nxi[8][8][3], Nxi2[8][8][6];
   svb::FluidDmn dm;
@@ -51,7 +51,13 @@ static int run(const HostFluidGenArgs* P, const int* rowPtr, const int* colPtr, 
                                   P->mvMsh ? ym : nullptr, q, nd);
       for (int a = 0; a < ENON; a++) {
         fluid_gen_residual(q, nd[a], lR[a]);
-        for (int b = 0; b < ENON; b++) fluid_gen_block(q, nd[a], nd[b], lK[a][b]);
+        if (P->factored) {
+          FluidRow row;
+          fluid_gen_row(q, nd[a], row);
+          for (int b = 0; b < ENON; b++) fluid_gen_block_row(row, nd[b], lK[a][b]);
+        } else {
+          for (int b = 0; b < ENON; b++) fluid_gen_block(q, nd[a], nd[b], lK[a][b]);
+        }
       }
     }
     for (int a = 0; a < ENON; a++) {

@@ -130,14 +130,15 @@ def test_device_solid_algebra_matches_golden(hostmath, name, mk, dkw, nFn):
 
 class HostFluidGenArgs(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("IEN", "x", "Ag", "Yg", "Bf")] + \
-               [(k, C.c_int) for k in ("eNoN", "nEl", "nG", "tDof", "mvMsh", "pad")] + \
+               [(k, C.c_int) for k in ("eNoN", "nEl", "nG", "tDof", "mvMsh", "factored")] + \
                [(k, C.c_double) for k in ("dt", "af", "am", "gam")] + \
                [("w", C.c_double * 8), ("N", (C.c_double * 8) * 8), ("Nxi", ((C.c_double * 3) * 8) * 8),
                 ("Nxi2", ((C.c_double * 6) * 8) * 8), ("dm", FluidDmn)]
 
 
+@pytest.mark.parametrize("factored", [0, 1], ids=["reference_form", "factored_rows"])
 @pytest.mark.parametrize("case", common.FLUID_GEN_CASES, ids=[c[0] for c in common.FLUID_GEN_CASES])
-def test_device_general_fluid_algebra_matches_golden(hostmath, case):
+def test_device_general_fluid_algebra_matches_golden(hostmath, case, factored):
     """svmultiphysics_b200/csrc/fluid_gen.cuh (gnn + gn_nxx per Gauss point, fluid_3d_m/c for any element) compiled for
     the host against what the unmodified reference assembled for skewed HEX8 meshes (tests/golden/fluid_gen.npz)."""
     golden = common.load_golden("fluid_gen.npz")
@@ -153,7 +154,7 @@ def test_device_general_fluid_algebra_matches_golden(hostmath, case):
     keep = [np.ascontiguousarray(m.IEN.T.astype(np.int32)), np.ascontiguousarray(m.x.T), np.ascontiguousarray(Ag.T),
             np.ascontiguousarray(Yg.T), np.ascontiguousarray(Bf.T)]
     A.IEN, A.x, A.Ag, A.Yg, A.Bf = (k.ctypes.data for k in keep)
-    A.eNoN, A.nEl, A.nG, A.tDof, A.mvMsh = m.eNoN, m.nEl, len(w), tDof, mv
+    A.eNoN, A.nEl, A.nG, A.tDof, A.mvMsh, A.factored = m.eNoN, m.nEl, len(w), tDof, mv, factored
     A.dt, A.af, A.am, A.gam = eq.dt, eq.af, eq.am, eq.gam
     for g in range(len(w)):
         A.w[g] = w[g]
