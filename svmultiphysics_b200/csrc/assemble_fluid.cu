@@ -326,6 +326,45 @@ assemble_fluid_tet4_grouped_kernel(const __grid_constant__ FluidArgs P)
   }
 }
 
+// nn::gnn of a linear tetrahedron is constant over the element: Jac = det[x0-x3, x1-x3, x2-x3].  construct_fluid /
+// construct_fsi throw when utils::is_zero(Jac) (fluid.cpp:637-639, fsi.cpp:185); the assembly kernels are register-tuned,
+// so the test runs here, once per set of coordinates (every assembly when the geometry moves, ALE).
+__global__ void __launch_bounds__(256) tet4_jacobian_check_kernel(const __grid_constant__ FluidArgs P)
+{
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P.e1) return;
+  if (!P.dmn[pick_domain(P, e)].isFluid) return;
+  const int4 n4 = *reinterpret_cast<const int4*>(P.IEN + 4 * (size_t)e);
+  const int node[4] = {n4.x, n4.y, n4.z, n4.w};
+  double xl[4][3];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+      xl[a][i] = __ldg(P.x + 3 * (size_t)node[a] + i) + (P.ale ? __ldg(P.Dg + (size_t)P.tDof * node[a] + 4 + i) : 0.0);
+  double xXi[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) xXi[i][k] += xl[a][i] * P.Nxi[0][a][k];
+  const double Jac = xXi[0][0] * xXi[1][1] * xXi[2][2] + xXi[0][1] * xXi[1][2] * xXi[2][0] + xXi[0][2] * xXi[1][0] * xXi[2][1] -
+                     xXi[0][0] * xXi[1][2] * xXi[2][1] - xXi[0][1] * xXi[1][0] * xXi[2][2] - xXi[0][2] * xXi[1][1] * xXi[2][0];
+  if (is_zero(Jac)) atomicMax(P.err, e + 1);
+}
+
+int launch_tet4_jacobian_check(svb200_ctx* ctx, const Mesh& m, const FluidArgs& args)
+{
+  if (m.eNoN != 4 || m.nEl == 0) return SVB200_OK;
+  FluidArgs A = args;
+  A.e0 = 0; A.e1 = m.nEl; A.perm = nullptr;
+  tet4_jacobian_check_kernel<<<(m.nEl + 255) / 256, 256, 0, ctx->stream>>>(A);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
 template <bool NN>
 static int launch_grouped(svb200_ctx* ctx, const FluidArgs& args)
 {

@@ -31,6 +31,7 @@ struct FluidGenArgs {
   const double* Bf;
   const double* Dg;
   const double* tab;    // per Gauss point: w | N[ENON] | Nxi[ENON][3] | Nxi2[ENON][6]
+  int* err;             // 1 + index of an element with a zero Jacobian (construct_fluid throws, fluid.cpp:645-647)
   double* R;
   double* Val;
   int e0, e1;
@@ -124,6 +125,7 @@ assemble_fluid_gen_kernel(const __grid_constant__ FluidGenArgs P)
     double Jac = 1.0;
     if (active) {
       Jac = gnn3_full<ENON>(Nxi, sx, Nx, xiX, ks);
+      if (is_zero(Jac)) atomicMax(P.err, e + 1);
       gn_nxx3<ENON>(Nxi2, sx, xiX, Nx, Nxx);
       if (g == ENON - 1) {
 #pragma unroll
@@ -232,7 +234,7 @@ int run_assemble_fluid_gen(svb200_ctx* ctx, const Mesh& m, const FluidArgs& F)
   FluidGenArgs A;
   memset(&A, 0, sizeof(A));
   A.IEN = F.IEN; A.eId = F.eId; A.slot = F.slot; A.perm = nullptr;
-  A.x = F.x; A.Ag = F.Ag; A.Yg = F.Yg; A.Bf = F.Bf; A.Dg = F.Dg; A.tab = m.d_gtab; A.R = F.R; A.Val = F.Val;
+  A.x = F.x; A.Ag = F.Ag; A.Yg = F.Yg; A.Bf = F.Bf; A.Dg = F.Dg; A.tab = m.d_gtab; A.R = F.R; A.Val = F.Val; A.err = F.err;
   A.e0 = 0; A.e1 = m.nEl;
   A.tDof = F.tDof; A.mvMsh = F.mvMsh; A.nDmn = F.nDmn; A.atomic = F.atomic; A.ale = F.ale;
   A.dt = F.dt; A.af = F.af; A.am = F.am; A.gam = F.gam;

@@ -207,6 +207,7 @@ int svb200_destroy(svb200_ctx* ctx)
   cudaFree(ctx->d_map); cudaFree(ctx->d_rowPtr); cudaFree(ctx->d_colPtr); cudaFree(ctx->d_diagPtr);
   cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf); cudaFree(ctx->d_Do);
   cudaFree(ctx->d_Ao); cudaFree(ctx->d_Yo); cudaFree(ctx->d_An); cudaFree(ctx->d_Yn); cudaFree(ctx->d_Dn); cudaFree(ctx->d_nodeflag);
+  cudaFree(ctx->d_err);
   cudaFree(ctx->d_stage); cudaFree(ctx->d_R); cudaFree(ctx->d_Val); cudaFree(ctx->d_W);
   cudaFree(ctx->d_work); cudaFree(ctx->d_red); cudaFree(ctx->d_tslot);
   cudaFreeHost(ctx->h_pinned);
@@ -356,6 +357,7 @@ int svb200_set_coords(svb200_ctx* ctx, const double* x)
 {
   CTX_GUARD(ctx);
   SVB_REQUIRE(ctx->d_rowPtr && x, "svb200_set_coords: call svb200_set_graph first");
+  for (auto& m : ctx->mesh) m.jac_checked = false;
   return upload_nodal(ctx, 3, x, &ctx->d_x);
 }
 
@@ -487,6 +489,11 @@ static int fill_fluid_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams
   A.rU_ptr = m.schedR.d_uptr; A.rU_ent = m.schedR.d_uent; A.rContrib = m.schedR.d_contrib;
   A.x = ctx->d_x; A.Ag = ctx->d_Ag; A.Yg = ctx->d_Yg; A.Bf = ctx->d_Bf; A.Dg = ctx->d_Dg;
   A.R = ctx->d_R; A.Val = ctx->d_Val;
+  if (!ctx->d_err) {
+    SVB_CUDA(cudaMalloc(&ctx->d_err, sizeof(int)));
+    SVB_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+  }
+  A.err = ctx->d_err;
   A.e0 = 0; A.e1 = m.nEl;
   A.tDof = eq->tDof; A.mvMsh = eq->mvMsh; A.nDmn = nDmn;
   A.ale = (eq->phys == SVB200_PHYS_FSI);
@@ -523,11 +530,32 @@ static int fill_fluid_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams
   return SVB200_OK;
 }
 
+// construct_fluid / construct_fsi throw "Jacobian for element e is < 0." when utils::is_zero(Jac) (fluid.cpp:637-647,
+// fsi.cpp:185-193); the kernels leave 1 + e in the device error word.
+static int check_jacobian_word(svb200_ctx* ctx, bool fsi)
+{
+  int e = 0;
+  SVB_CUDA(cudaMemcpyAsync(&e, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (e == 0) return SVB200_OK;
+  SVB_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+  set_error(std::string(fsi ? "[construct_fsi]" : "[construct_fluid]") + " Jacobian for element " + std::to_string(e - 1) + " is < 0.");
+  return SVB200_ERR_NUMERIC;
+}
+
 static int run_assemble(svb200_ctx* ctx, const Mesh& m, FluidArgs& A, bool general = false)
 {
   // linear tetrahedra have their own kernel (constant gradients, no second derivatives); everything else, or
   // SVB200_EQ_GENERAL_KERNEL, goes through the per-Gauss-point kernel of assemble_fluid_gen.cu
-  if (m.eNoN != 4 || general) return run_assemble_fluid_gen(ctx, m, A);
+  if (m.eNoN != 4 || general) {
+    TRY(run_assemble_fluid_gen(ctx, m, A));
+    return check_jacobian_word(ctx, A.ale != 0);
+  }
+  if (A.ale || !m.jac_checked) {
+    TRY(launch_tet4_jacobian_check(ctx, m, A));
+    TRY(check_jacobian_word(ctx, A.ale != 0));
+    m.jac_checked = true;
+  }
   if (A.atomic) return launch_assemble_fluid(ctx, m, A);
   A.perm = m.d_color_perm;
   for (size_t c = 0; c + 1 < m.color_off.size(); c++) {

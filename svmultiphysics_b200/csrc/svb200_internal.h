@@ -45,6 +45,7 @@ struct Mesh {
   std::vector<double> w, N, Nx;  // host copies of the reference-element tables
   std::vector<double> Nxx;       // (6,eNoN,nG) second parametric derivatives (svb200_set_mesh_nxx), empty = all zero
   double* d_gtab = nullptr;      // tables in the layout of assemble_fluid_gen.cu
+  mutable bool jac_checked = false;   // element Jacobians verified for the current reference coordinates (fluid, fixed mesh)
   bool set = false;
 };
 
@@ -101,6 +102,7 @@ struct FluidArgs {
   int e0, e1;           // element range [e0,e1) (indices into perm when perm != null)
   int tDof, mvMsh, nDmn, atomic;
   int ale, pad0;        // ale: element geometry is x + Dg(4..6) (fsi::construct_fsi, fsi.cpp:140-146)
+  int* err;             // device error word: 1 + index of an element with a zero Jacobian (0 = none)
   double dt, af, am, gam;
   double w[MAX_NG];
   double N[MAX_NG][MAX_ENON];        // N[g][a]
@@ -139,6 +141,7 @@ struct svb200_ctx {
   double* d_Ao = nullptr; double* d_Yo = nullptr;                          // solutions.old
   double* d_An = nullptr; double* d_Yn = nullptr; double* d_Dn = nullptr;  // solutions.current
   int* d_nodeflag = nullptr;     // per node: belongs to a solid domain (FSI corrector)
+  int* d_err = nullptr;          // element-loop error word (zero Jacobian), see FluidArgs::err
   double* d_Bf = nullptr;
   double* d_stage = nullptr;     // staging buffer for permuted uploads/downloads
   size_t stage_bytes = 0;
@@ -199,6 +202,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 // assemble_fluid.cu
 int launch_assemble_fluid(svb200_ctx* ctx, const Mesh& m, const FluidArgs& args);
+int launch_tet4_jacobian_check(svb200_ctx* ctx, const Mesh& m, const FluidArgs& args);
 // assemble_struct.cu
 int upload_fluid_gen_tables(svb200_ctx* ctx, Mesh& m);
 int run_assemble_fluid_gen(svb200_ctx* ctx, const Mesh& m, const FluidArgs& F);

@@ -1,8 +1,10 @@
 """GPU parity tests (run on a B200 with -m gpu): CUDA path through the C ABI vs the oracle."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
-from svmultiphysics_b200 import abi
+from svmultiphysics_b200 import abi, elements
 from tests import common
 
 pytestmark = pytest.mark.gpu
@@ -313,3 +315,55 @@ def test_hex8_fluid_newton_iteration_parity():
     assert abs(o1.RI.iNorm - o0.RI.iNorm) <= 1e-10 * o0.RI.iNorm
     assert common.rel_err(X1, X0) < 1e-6
     eng.close()
+
+
+def test_edge_cases_and_error_behaviour():
+    """Edge cases of the reference path: a degenerate element makes construct_fluid throw "Jacobian for element e is < 0."
+    (fluid.cpp:637-639) -> SVB200_ERR_NUMERIC with the same text; a zero right-hand side returns immediately with R
+    untouched (gmres.cpp:470-475); a zero-node face and a domain without elements are accepted; a missing res for a
+    Neumann face is the reference's "res is required" error (solve.cpp:69-71)."""
+    from svmultiphysics_b200.engine import Svb200Error
+    m, Ag, Yg, Dg, Bf = common.fluid_case(n=3, nz=3)
+    orc, rowPtr, colPtr = common.make_oracle(_oracle(), m)
+    eq, dmn = abi.fluid_eq(0.005), [abi.fluid_domain()]
+    # (1) degenerate element: nodes 0 and 1 of element 5 moved onto node 3, so that a column of dx/dxi is exactly zero
+    # (utils::is_zero only fires for |Jac| < 10 eps^2: a merely flat element leaves round-off in the determinant)
+    x = m.x.copy()
+    e_bad = 5
+    x[:, m.IEN[0, e_bad]] = x[:, m.IEN[3, e_bad]]
+    x[:, m.IEN[1, e_bad]] = x[:, m.IEN[3, e_bad]]
+    eng = common.make_engine(m, rowPtr, colPtr)
+    eng.set_coords(np.asfortranarray(x))
+    eng.alloc(4); eng.set_state(Ag, Yg, Dg, Bf)
+    with pytest.raises(Svb200Error, match=r"\[construct_fluid\] Jacobian for element \d+ is < 0\."):
+        eng.assemble(0, eq, dmn)
+    with pytest.raises(Svb200Error, match=r"\[construct_fluid\] Jacobian for element \d+ is < 0\."):
+        eng.alloc(4); eng.assemble(0, abi.fluid_eq(0.005, general=True), dmn)
+    # the context stays usable: good coordinates assemble and match the oracle
+    eng.set_coords(m.x)
+    eng.alloc(4); eng.assemble(0, eq, dmn)
+    orc.alloc(4); orc.set_state(Ag, Yg, Dg, Bf); orc.assemble(0, eq, dmn)
+    assert common.rel_err(eng.get_Val(), orc.get_Val()) < ASM_TOL
+    # (2) zero right-hand side: success, zero iterations, R untouched
+    eng.put_R(np.zeros((4, m.nNo), order="F"))
+    ls = abi.ls_params(abi.LS_GMRES, mItr=10, sD=20, relTol=1e-8, absTol=1e-10)
+    X, o, _ = eng.solve(4, abi.LS_GMRES, ls)
+    assert o.RI.success == 1 and o.RI.itr == 0 and o.RI.iNorm == 0.0 and not X.any()
+    # (3) faces: an empty Dirichlet face is legal; a Neumann face without res is the reference's error
+    eng.set_num_faces(2)
+    eng.set_face(0, abi.BC_DIR, np.zeros(0, np.int32), np.zeros((3, 0), order="F"))
+    out = m.faces["outlet"]
+    eng.set_face(1, abi.BC_NEU, out, np.ones((3, len(out)), order="F"))
+    eng.alloc(4); eng.assemble(0, eq, dmn)
+    with pytest.raises(Svb200Error, match="res is required for Neu surfaces"):
+        eng._call("svb200_solve", C.c_int32(4), C.c_int32(abi.LS_GMRES), C.c_int32(abi.PREC_FSILS), C.byref(ls), C.c_int32(2),
+                  None, None, None, None)
+    # (4) a domain list whose fluid domain owns no element: nothing is assembled, nothing fails
+    eId = np.full(m.nEl, 2, np.int32)                       # every element in domain bit 1
+    eng2 = common.make_engine(m, rowPtr, colPtr)
+    w, N, Nx = elements.tables(4)
+    eng2.set_mesh(0, m.IEN, w, N, Nx, eId=eId)
+    eng2.alloc(4); eng2.set_state(Ag, Yg, Dg, Bf)
+    eng2.assemble(0, eq, [abi.fluid_domain(Id=0), abi.struct_domain(Id=1)])   # fluid equation: struct elements are skipped
+    assert not eng2.get_Val().any() and not eng2.get_R().any()
+    eng.close(); eng2.close()
