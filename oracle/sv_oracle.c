@@ -276,241 +276,9 @@ int svorc_set_old_disp(void* h, int tDof, const double* Do)
   return 0;
 }
 
-/* utils::is_zero(value, 0) */
-static int is_zero(double v)
-{
-  const double eps = 2.220446049250313e-16;
-  double a = fabs(v), b = 0.0;
-  double nrm = fmax(a, eps);
-  return (a - b) / nrm < 10.0 * eps;
-}
-
-/* nn::gnn, insd = nsd = 3.  Nxi(3,eNoN), x(3,eNoN) -> Nx(3,eNoN), Jac, ks(3,3) (column-major). */
-static void gnn3(int eNoN, const double* Nxi, const double* x, double* Nx, double* Jac, double* ks)
-{
-  double xXi[9] = {0}, xiX[9];
-#define XXI(i, j) xXi[(i) + 3 * (j)]
-#define XIX(i, j) xiX[(i) + 3 * (j)]
-#define KS(i, j) ks[(i) + 3 * (j)]
-  for (int a = 0; a < eNoN; a++)
-    for (int i = 0; i < 3; i++) {
-      XXI(i, 0) = XXI(i, 0) + x[i + 3 * a] * Nxi[0 + 3 * a];
-      XXI(i, 1) = XXI(i, 1) + x[i + 3 * a] * Nxi[1 + 3 * a];
-      XXI(i, 2) = XXI(i, 2) + x[i + 3 * a] * Nxi[2 + 3 * a];
-    }
-  const double J = XXI(0, 0) * XXI(1, 1) * XXI(2, 2) + XXI(0, 1) * XXI(1, 2) * XXI(2, 0) + XXI(0, 2) * XXI(1, 0) * XXI(2, 1) -
-                   XXI(0, 0) * XXI(1, 2) * XXI(2, 1) - XXI(0, 1) * XXI(1, 0) * XXI(2, 2) - XXI(0, 2) * XXI(1, 1) * XXI(2, 0);
-  XIX(0, 0) = (XXI(1, 1) * XXI(2, 2) - XXI(1, 2) * XXI(2, 1)) / J;
-  XIX(0, 1) = (XXI(2, 1) * XXI(0, 2) - XXI(2, 2) * XXI(0, 1)) / J;
-  XIX(0, 2) = (XXI(0, 1) * XXI(1, 2) - XXI(0, 2) * XXI(1, 1)) / J;
-  XIX(1, 0) = (XXI(1, 2) * XXI(2, 0) - XXI(1, 0) * XXI(2, 2)) / J;
-  XIX(1, 1) = (XXI(2, 2) * XXI(0, 0) - XXI(2, 0) * XXI(0, 2)) / J;
-  XIX(1, 2) = (XXI(0, 2) * XXI(1, 0) - XXI(0, 0) * XXI(1, 2)) / J;
-  XIX(2, 0) = (XXI(1, 0) * XXI(2, 1) - XXI(1, 1) * XXI(2, 0)) / J;
-  XIX(2, 1) = (XXI(2, 0) * XXI(0, 1) - XXI(2, 1) * XXI(0, 0)) / J;
-  XIX(2, 2) = (XXI(0, 0) * XXI(1, 1) - XXI(0, 1) * XXI(1, 0)) / J;
-  KS(0, 0) = XIX(0, 0) * XIX(0, 0) + XIX(1, 0) * XIX(1, 0) + XIX(2, 0) * XIX(2, 0);
-  KS(0, 1) = XIX(0, 1) * XIX(0, 0) + XIX(1, 1) * XIX(1, 0) + XIX(2, 1) * XIX(2, 0);
-  KS(0, 2) = XIX(0, 2) * XIX(0, 0) + XIX(1, 2) * XIX(1, 0) + XIX(2, 2) * XIX(2, 0);
-  KS(1, 1) = XIX(0, 1) * XIX(0, 1) + XIX(1, 1) * XIX(1, 1) + XIX(2, 1) * XIX(2, 1);
-  KS(1, 2) = XIX(0, 1) * XIX(0, 2) + XIX(1, 1) * XIX(1, 2) + XIX(2, 1) * XIX(2, 2);
-  KS(2, 2) = XIX(0, 2) * XIX(0, 2) + XIX(1, 2) * XIX(1, 2) + XIX(2, 2) * XIX(2, 2);
-  KS(1, 0) = KS(0, 1); KS(2, 0) = KS(0, 2); KS(2, 1) = KS(1, 2);
-  for (int a = 0; a < eNoN; a++) {
-    Nx[0 + 3 * a] = Nxi[0 + 3 * a] * XIX(0, 0) + Nxi[1 + 3 * a] * XIX(1, 0) + Nxi[2 + 3 * a] * XIX(2, 0);
-    Nx[1 + 3 * a] = Nxi[0 + 3 * a] * XIX(0, 1) + Nxi[1 + 3 * a] * XIX(1, 1) + Nxi[2 + 3 * a] * XIX(2, 1);
-    Nx[2 + 3 * a] = Nxi[0 + 3 * a] * XIX(0, 2) + Nxi[1 + 3 * a] * XIX(1, 2) + Nxi[2 + 3 * a] * XIX(2, 2);
-  }
-  *Jac = J;
-#undef XXI
-#undef XIX
-#undef KS
-}
-
-/* fluid::get_viscosity; gamma is in/out like the reference's by-reference argument. */
-static void get_viscosity(const svb200_dmnparams* d, double* gamma, double* mu, double* mu_x)
-{
-  *mu = 0.0; *mu_x = 0.0;
-  if (d->viscType == SVB200_VISC_CONST) {
-    *mu = d->mu_i;
-  } else if (d->viscType == SVB200_VISC_CY) {
-    double T1 = 1.0 + pow(d->lam * (*gamma), d->a);
-    double T2 = pow(T1, (d->n - 1.0) / d->a);
-    *mu = d->mu_i + (d->mu_o - d->mu_i) * T2;
-    T1 = T2 / T1;
-    T2 = pow(d->lam, d->a) * pow(*gamma, d->a - 1.0) * T1;
-    *mu_x = (d->mu_o - d->mu_i) * (d->n - 1.0) * T2;
-  } else {
-    double mu_o;
-    if (*gamma < d->lam) { mu_o = d->mu_o / sqrt(d->lam); *gamma = d->lam; }
-    else mu_o = d->mu_o / sqrt(*gamma);
-    *mu = (d->mu_i + mu_o) * (d->mu_i + mu_o);
-    *mu_x = 2.0 * mu_o * (mu_o + d->mu_i) / (*gamma);
-  }
-}
-
-/* Shared front part of fluid_3d_m and fluid_3d_c (the reference recomputes it in both):
- * interpolation, strain rate, viscosity, tauM, up, updu.  Linear elements: Nwxx = 0. */
-typedef struct {
-  double ud[3], u[3], ux[3][3], p, px[3], divU, es[3][3], esNx[3][MAXE], mu, mu_g, tauM, up[3], updu[3][3][MAXE];
-  double rho, T1, amd, wl, wr;
-} GP;
-
-static void gauss_point_common(const svb200_eqparams* eq, const svb200_dmnparams* dm, int eNoN, double w, const double* Kxi,
-                               const double* N, const double* Nx, const double* al, const double* yl, const double* bfl, int tDof,
-                               GP* q)
-{
-#define KXI(i, j) Kxi[(i) + 3 * (j)]
-  const double ctM = 1.0, ctC = 36.0;
-  const double rho = dm->rho, Kd = dm->K_darcy;
-  q->rho = rho;
-  q->T1 = eq->af * eq->gam * eq->dt;
-  q->amd = eq->am / q->T1;
-  q->wl = w * q->T1;
-  q->wr = w * rho;
-  for (int i = 0; i < 3; i++) { q->ud[i] = -dm->f[i]; q->u[i] = 0.0; q->px[i] = 0.0; for (int j = 0; j < 3; j++) q->ux[i][j] = 0.0; }
-  q->p = 0.0;
-  for (int a = 0; a < eNoN; a++) {
-    for (int i = 0; i < 3; i++) {
-      q->ud[i] = q->ud[i] + N[a] * (al[i + tDof * a] - bfl[i + 3 * a]);
-      q->u[i] = q->u[i] + N[a] * yl[i + tDof * a];
-    }
-    for (int j = 0; j < 3; j++)
-      for (int i = 0; i < 3; i++) q->ux[i][j] += Nx[i + 3 * a] * yl[j + tDof * a];
-  }
-  q->divU = q->ux[0][0] + q->ux[1][1] + q->ux[2][2];
-  for (int a = 0; a < eNoN; a++) {
-    q->p = q->p + N[a] * yl[3 + tDof * a];
-    for (int i = 0; i < 3; i++) q->px[i] = q->px[i] + Nx[i + 3 * a] * yl[3 + tDof * a];
-  }
-  if (eq->mvMsh)
-    for (int a = 0; a < eNoN; a++)
-      for (int i = 0; i < 3; i++) q->u[i] = q->u[i] - N[a] * yl[4 + i + tDof * a];
-  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) q->es[i][j] = q->ux[i][j] + q->ux[j][i];
-  for (int a = 0; a < eNoN; a++)
-    for (int j = 0; j < 3; j++)
-      q->esNx[j][a] = q->es[0][j] * Nx[0 + 3 * a] + q->es[1][j] * Nx[1 + 3 * a] + q->es[2][j] * Nx[2 + 3 * a];
-  double gam = 0.0;
-  for (int j = 0; j < 3; j++) for (int i = 0; i < 3; i++) gam += q->es[i][j] * q->es[i][j];
-  gam = sqrt(0.5 * gam);
-  double mu, mu_g;
-  get_viscosity(dm, &gam, &mu, &mu_g);
-  mu_g = is_zero(gam) ? 0.0 : mu_g / gam;
-  q->mu = mu; q->mu_g = mu_g;
-  /* second derivatives vanish for linear elements: mu_x = 0, d2u2 = 0, rS = 0 */
-  double kT = 4.0 * pow(ctM / eq->dt, 2.0);
-  kT = kT + pow(Kd * mu / rho, 2.0);
-  const double* u = q->u;
-  double kU = u[0] * u[0] * KXI(0, 0) + u[1] * u[0] * KXI(1, 0) + u[2] * u[0] * KXI(2, 0) + u[0] * u[1] * KXI(0, 1) +
-              u[1] * u[1] * KXI(1, 1) + u[2] * u[1] * KXI(2, 1) + u[0] * u[2] * KXI(0, 2) + u[1] * u[2] * KXI(1, 2) +
-              u[2] * u[2] * KXI(2, 2);
-  double kS = 0.0;
-  for (int j = 0; j < 3; j++) for (int i = 0; i < 3; i++) kS += KXI(i, j) * KXI(i, j);
-  kS = ctC * kS * pow(mu / rho, 2.0);
-  q->tauM = 1.0 / (rho * sqrt(kT + kU + kS));
-  for (int j = 0; j < 3; j++) {
-    const double rV = q->ud[j] + u[0] * q->ux[0][j] + u[1] * q->ux[1][j] + u[2] * q->ux[2][j];
-    q->up[j] = -q->tauM * (rho * rV + q->px[j] - 0.0 + mu * Kd * u[j]);
-  }
-  for (int a = 0; a < eNoN; a++) {
-    const double uNx = u[0] * Nx[0 + 3 * a] + u[1] * Nx[1 + 3 * a] + u[2] * Nx[2 + 3 * a];
-    const double T1 = -rho * uNx - mu * Kd * N[a];
-    for (int j = 0; j < 3; j++) for (int i = 0; i < 3; i++) q->updu[j][i][a] = (i == j) ? T1 : 0.0;
-  }
-#undef KXI
-}
-
-/* fluid_3d_m: momentum residual and tangent blocks 0-11 at one Gauss point (vmsFlag = true). */
-static void fluid_3d_m(const svb200_eqparams* eq, const svb200_dmnparams* dm, int eNoN, double w, const double* Kxi, const double* N,
-                       const double* Nx, const double* al, const double* yl, const double* bfl, int tDof, double* lR, double* lK)
-{
-#define KXI(i, j) Kxi[(i) + 3 * (j)]
-#define LR(i, a) lR[(i) + 4 * (a)]
-#define LK(i, a, b) lK[(i) + 16 * ((a) + eNoN * (b))]
-  GP q;
-  gauss_point_common(eq, dm, eNoN, w, Kxi, N, Nx, al, yl, bfl, tDof, &q);
-  const double rho = q.rho, mu = q.mu, mu_g = q.mu_g, tauM = q.tauM, wl = q.wl, wr = q.wr, amd = q.amd, Kd = dm->K_darcy;
-  const double eps = 2.220446049250313e-16;
-  double* up = q.up;
-  double tauC = 1.0 / (tauM * (KXI(0, 0) + KXI(1, 1) + KXI(2, 2)));
-  double tauB = up[0] * up[0] * KXI(0, 0) + up[1] * up[0] * KXI(1, 0) + up[2] * up[0] * KXI(2, 0) + up[0] * up[1] * KXI(0, 1) +
-                up[1] * up[1] * KXI(1, 1) + up[2] * up[1] * KXI(2, 1) + up[0] * up[2] * KXI(0, 2) + up[1] * up[2] * KXI(1, 2) +
-                up[2] * up[2] * KXI(2, 2);
-  if (is_zero(tauB)) tauB = eps;
-  tauB = rho / sqrt(tauB);
-  double ua[3] = {q.u[0] + up[0], q.u[1] + up[1], q.u[2] + up[2]};
-  const double pa = q.p - tauC * q.divU;
-  double rV[3], rM[3][3];
-  for (int j = 0; j < 3; j++) rV[j] = tauB * (up[0] * q.ux[0][j] + up[1] * q.ux[1][j] + up[2] * q.ux[2][j]);
-  for (int j = 0; j < 3; j++)
-    for (int i = 0; i < 3; i++) rM[i][j] = mu * q.es[i][j] - rho * up[j] * ua[i] + rV[j] * up[i] - ((i == j) ? pa : 0.0);
-  for (int j = 0; j < 3; j++) rV[j] = q.ud[j] + ua[0] * q.ux[0][j] + ua[1] * q.ux[1][j] + ua[2] * q.ux[2][j];
-  double uNx[MAXE], upNx[MAXE], uaNx[MAXE];
-  for (int a = 0; a < eNoN; a++) {
-    for (int j = 0; j < 3; j++)
-      LR(j, a) = LR(j, a) + wr * N[a] * rV[j] + w * (Nx[0 + 3 * a] * rM[0][j] + Nx[1 + 3 * a] * rM[1][j] + Nx[2 + 3 * a] * rM[2][j]);
-    uNx[a] = q.u[0] * Nx[0 + 3 * a] + q.u[1] * Nx[1 + 3 * a] + q.u[2] * Nx[2 + 3 * a];
-    upNx[a] = up[0] * Nx[0 + 3 * a] + up[1] * Nx[1 + 3 * a] + up[2] * Nx[2 + 3 * a];
-    uaNx[a] = uNx[a] + upNx[a];
-  }
-  for (int b = 0; b < eNoN; b++)
-    for (int a = 0; a < eNoN; a++) {
-      double nn[3][3];   /* nn[k][l] = Nx(k,a) * Nx(l,b) */
-      for (int k = 0; k < 3; k++) for (int l = 0; l < 3; l++) nn[k][l] = Nx[k + 3 * a] * Nx[l + 3 * b];
-      const double NxNx = nn[0][0] + nn[1][1] + nn[2][2];
-      const double T1 = mu * NxNx + rho * amd * N[b] * (N[a] + rho * tauM * uaNx[a]) + rho * N[a] * (uNx[b] + upNx[b]) +
-                        tauB * upNx[a] * upNx[b];
-      for (int i = 0; i < 3; i++)
-        for (int j = 0; j < 3; j++) {
-          double T2;
-          if (i == j) {
-            T2 = (mu + tauC) * nn[i][i] + q.esNx[i][a] * mu_g * q.esNx[i][b] - rho * tauM * uaNx[a] * q.updu[i][i][b];
-            LK(4 * i + j, a, b) = LK(4 * i + j, a, b) + wl * (T2 + T1);
-            LK(4 * i + j, a, b) = LK(4 * i + j, a, b) + mu * Kd * wl * N[b] * N[a];
-          } else {
-            T2 = mu * nn[j][i] + tauC * nn[i][j] + q.esNx[i][a] * mu_g * q.esNx[j][b] - rho * tauM * uaNx[a] * q.updu[j][i][b];
-            LK(4 * i + j, a, b) = LK(4 * i + j, a, b) + wl * T2;
-          }
-        }
-    }
-  for (int b = 0; b < eNoN; b++)
-    for (int a = 0; a < eNoN; a++) {
-      const double T1 = rho * tauM * uaNx[a];
-      for (int i = 0; i < 3; i++) LK(4 * i + 3, a, b) = LK(4 * i + 3, a, b) - wl * (Nx[i + 3 * a] * N[b] - Nx[i + 3 * b] * T1);
-    }
-  for (int a = 0; a < eNoN; a++)
-    for (int j = 0; j < 3; j++) LR(j, a) = LR(j, a) + mu * Kd * w * N[a] * (q.u[j] + up[j]);
-#undef KXI
-}
-
-/* fluid_3d_c: continuity residual and tangent blocks 12-15 at one Gauss point. */
-static void fluid_3d_c(const svb200_eqparams* eq, const svb200_dmnparams* dm, int eNoN, double w, const double* Kxi, const double* N,
-                       const double* Nx, const double* al, const double* yl, const double* bfl, int tDof, double* lR, double* lK)
-{
-  GP q;
-  gauss_point_common(eq, dm, eNoN, w, Kxi, N, Nx, al, yl, bfl, tDof, &q);
-  const double wl = q.wl, tauM = q.tauM;
-  for (int a = 0; a < eNoN; a++) {
-    const double upNx = q.up[0] * Nx[0 + 3 * a] + q.up[1] * Nx[1 + 3 * a] + q.up[2] * Nx[2 + 3 * a];
-    LR(3, a) = LR(3, a) + w * (N[a] * q.divU - upNx);
-  }
-  for (int b = 0; b < eNoN; b++) {
-    const double T1 = q.rho * q.amd * N[b];
-    for (int a = 0; a < eNoN; a++)
-      for (int j = 0; j < 3; j++) {
-        double T2 = 0.0;
-        for (int i = 0; i < 3; i++) T2 += Nx[i + 3 * a] * (q.updu[j][i][b] - ((i == j) ? T1 : 0.0));
-        LK(12 + j, a, b) = LK(12 + j, a, b) + wl * (N[a] * Nx[j + 3 * b] - tauM * T2);
-      }
-  }
-  for (int b = 0; b < eNoN; b++)
-    for (int a = 0; a < eNoN; a++) {
-      const double NxNx = Nx[0 + 3 * a] * Nx[0 + 3 * b] + Nx[1 + 3 * a] * Nx[1 + 3 * b] + Nx[2 + 3 * a] * Nx[2 + 3 * b];
-      LK(15, a, b) = LK(15, a, b) + wl * tauM * NxNx;
-    }
-#undef LR
-#undef LK
-}
+#define REAL double
+#include "fluid_gp.inc"
+#undef REAL
 
 /* all_fun::domain */
 static int domain_of(const OMesh* m, const svb200_dmnparams* dmn, int nDmn, int e, int* err)

@@ -159,3 +159,19 @@ def test_genalpha_restatement_identities():
     Ag, Yg, Dg = (np.zeros((3, 5)) for _ in range(3))
     go.initiator([q1], Ao, Yo, Do, An, Yn, Dn, Ag, Yg, Dg)
     assert np.array_equal(Ag, An) and np.array_equal(Yg, Yn) and np.array_equal(Dg, Dn)
+
+
+def test_algorithmic_flop_count_pins_the_roofline_numerator():
+    """oracle/flop_count.cpp instantiates the restatement's Gauss-point arithmetic (oracle/fluid_gp.inc, the text that
+    reproduces the reference bit for bit) over a counting scalar.  bench.py's FP64 roofline uses SURVEY.md 8(d)'s hand count
+    of 11.6 kflop per TET4 element; it must not exceed the counted figure (structural zeros removed, shared front part
+    evaluated once) and must agree with it within the SURVEY's +-10 %."""
+    import json
+    out = subprocess.check_output(["make", "-s", "flops"], cwd=os.path.join(ROOT, "oracle"), text=True)
+    d = json.loads(out)
+    counted = d["structural_zeros_removed"]["per_element_front_part_evaluated_once"]
+    executed = d["executed_by_restatement"]["per_element_2gnn_plus_nG_times_m_plus_c"]
+    import bench
+    assert bench.FLOP_PER_ELEMENT <= counted <= executed
+    assert abs(counted - bench.FLOP_PER_ELEMENT) <= 0.10 * bench.FLOP_PER_ELEMENT
+    assert d["survey_hand_count"]["per_element"] == bench.FLOP_PER_ELEMENT
