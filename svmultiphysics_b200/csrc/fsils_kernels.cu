@@ -11,6 +11,7 @@
 // with dof*dof contiguous doubles per block.  Reductions are two-stage and run in a fixed order, so
 // results are bitwise reproducible from run to run.
 #include <algorithm>
+#include <cstdlib>
 #include "svb200_internal.h"
 #include "fsils_kernels.h"
 
@@ -620,6 +621,108 @@ bsr_spmv_rc_kernel(int nNo, const int* __restrict__ rowPtr, const int* __restric
     for (int j = 0; j < C; j++) acc += v[j] * u[j];
   }
   KU[t] = acc;
+}
+
+// ---- device-resident Schur-complement CG (cgrad::schur, linear_solver/cgrad.cpp:23-133) ----------------------------
+// Scalars of the iteration live in a small device array `cg` so that no kernel waits for the host:
+//   cg[0] errO (|r|^2 entering the iteration)   cg[1] err (|r|^2 after the update)   cg[2] <p, S p>   cg[3] eps
+//   cg[4] done flag   cg[5] iterations executed   cg[6] errO of the last executed iteration
+// The kernels that change X, R, P or the scalars return at once when `done` is set, so iterations the host enqueued
+// ahead of the device's stopping test are no-ops.
+// SP = L p - D (G p): one pass over the row, two accumulators so that both sums keep the reference's order
+// (spar_mul_ss on L, spar_mul_vs on D, then SP = -DGP + SP; cgrad.cpp:77-84).
+template <int NSD>
+__global__ void __launch_bounds__(256)
+schur_sp_kernel(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ colPtr, const double* __restrict__ L,
+                const double* __restrict__ D, const double* __restrict__ P, const double* __restrict__ GP, double* __restrict__ SP)
+{
+  // 4 threads per row, one 8-byte stream each: q = 0 walks L (times P), q = 1..NSD walk component q-1 of the 1 x NSD
+  // blocks of D (times GP) — the interleaving of bsr_spmv_rc_kernel<3,1>, which reaches 4.7 TB/s where a thread reading a
+  // whole 24-byte D block per step reaches 2.7 (profiles/r1j_ns_launches.csv).  The NSD partial sums of D are added
+  // component by component instead of block by block (round-off level difference to cgrad.cpp:77-84).
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = (int)(t >> 2), q = (int)(t & 3);
+  double acc = 0.0;
+  if (row < nNo && q <= NSD) {
+    const int k1 = rowPtr[row + 1];
+    if (q == 0) {
+      for (int k = rowPtr[row]; k < k1; k++) acc += L[k] * P[colPtr[k]];
+    } else {
+      const double* d = D + (q - 1);
+      const double* g = GP + (q - 1);
+      for (int k = rowPtr[row]; k < k1; k++) acc += d[(size_t)k * NSD] * g[(size_t)colPtr[k] * NSD];
+    }
+  }
+  const double a1 = __shfl_down_sync(0xffffffffu, acc, 1), a2 = __shfl_down_sync(0xffffffffu, acc, 2),
+               a3 = __shfl_down_sync(0xffffffffu, acc, 3);
+  if (row < nNo && q == 0) {
+    const double accD = (NSD == 3) ? (a1 + a2) + a3 : a1 + a2;
+    SP[row] = -1.0 * accD + acc;
+  }
+}
+
+// X = alpha P + X, R = -alpha SP + R with alpha = errO / <p, S p> taken from the device scalars.
+__global__ void __launch_bounds__(256)
+cg_xr_kernel(long long n, const double* __restrict__ cg, const double* __restrict__ P, const double* __restrict__ SP,
+             double* __restrict__ X, double* __restrict__ R)
+{
+  if (cg[4] != 0.0) return;
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const double alpha = cg[0] / cg[2];
+  X[k] = alpha * P[k] + X[k];
+  R[k] = -alpha * SP[k] + R[k];
+}
+
+// P = (errO/err) R + P, then P = (err/errO) P  (the two omp_sum_s / omp_mul_s calls of cgrad.cpp:95-96).
+__global__ void __launch_bounds__(256)
+cg_p_kernel(long long n, const double* __restrict__ cg, const double* __restrict__ R, double* __restrict__ P)
+{
+  if (cg[4] != 0.0) return;
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const double errO = cg[0];
+  double err = sqrt(cg[1]);      // err = norm(R); err = err*err as in cgrad.cpp:92-93 (cg[1] holds the raw dot product)
+  err = err * err;
+  double p = (errO / err) * R[k] + P[k];
+  P[k] = (err / errO) * p;
+}
+
+// End of an iteration: count it, shift err -> errO, raise `done` when the NEXT iteration's test `err < eps` would fire.
+__global__ void cg_advance_kernel(double* cg)
+{
+  if (cg[4] != 0.0) return;
+  double err = sqrt(cg[1]);
+  err = err * err;
+  cg[6] = cg[0];
+  cg[0] = err;
+  cg[5] += 1.0;
+  if (err < cg[3]) cg[4] = 1.0;
+}
+
+int schur_sp(svb200_ctx* ctx, int nsd, const double* L, const double* D, const double* P, const double* GP, double* SP)
+{
+  const int nNo = ctx->nNo;
+  if (nNo == 0) return SVB200_OK;
+  const unsigned blocks = (unsigned)(((long long)nNo * 4 + 255) / 256);
+  if (nsd == 3) schur_sp_kernel<3><<<blocks, 256, 0, ctx->stream>>>(nNo, ctx->d_rowPtr, ctx->d_colPtr, L, D, P, GP, SP);
+  else schur_sp_kernel<2><<<blocks, 256, 0, ctx->stream>>>(nNo, ctx->d_rowPtr, ctx->d_colPtr, L, D, P, GP, SP);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
+int cg_step_kernels(svb200_ctx* ctx, int which, long long n, double* cg, const double* P, const double* SP, double* X, double* R,
+                    double* Pw)
+{
+  if (n == 0) return SVB200_OK;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (which == 0) cg_xr_kernel<<<blocks, 256, 0, ctx->stream>>>(n, cg, P, SP, X, R);
+  else if (which == 1) cg_p_kernel<<<blocks, 256, 0, ctx->stream>>>(n, cg, R, Pw);
+  else cg_advance_kernel<<<1, 1, 0, ctx->stream>>>(cg);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
 }
 
 int spmv_rc(svb200_ctx* ctx, int R, int C, const double* K, const double* U, double* KU)

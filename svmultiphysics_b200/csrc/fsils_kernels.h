@@ -24,6 +24,9 @@ int rcs_dev_from_one(svb200_ctx* ctx, long long n, const double* Wr, const doubl
 int rcs_invsqrt_acc(svb200_ctx* ctx, long long n, double* W, double* Wacc);
 
 int spmv_rc(svb200_ctx* ctx, int R, int C, const double* K, const double* U, double* KU);
+int schur_sp(svb200_ctx* ctx, int nsd, const double* L, const double* D, const double* P, const double* GP, double* SP);
+int cg_step_kernels(svb200_ctx* ctx, int which, long long n, double* cg, const double* P, const double* SP, double* X, double* R,
+                    double* Pw);
 int build_transpose_slots(svb200_ctx* ctx, int* d_tslot);
 int ns_depart(svb200_ctx* ctx, int nsd, const double* Val, const int* d_tslot, double* mK, double* mG, double* mD, double* mL, double* Gt);
 int ns_split(svb200_ctx* ctx, int dof, const double* Ri, double* Rm, double* Rc);

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <limits>
 #include "svb200_internal.h"
 #include "fsils_kernels.h"
@@ -49,6 +50,10 @@ constexpr int SCAL_N = 1024;
 static int ensure_scalars(svb200_ctx* ctx)
 {
   if (!ctx->h_pinned) SVB_CUDA(cudaMallocHost(&ctx->h_pinned, sizeof(double) * SCAL_N));
+  if (!ctx->h_cg) SVB_CUDA(cudaMallocHost(&ctx->h_cg, sizeof(double) * 24));
+  if (!ctx->d_cg) SVB_CUDA(cudaMalloc(&ctx->d_cg, sizeof(double) * 8));
+  for (int k = 0; k < 2; k++)
+    if (!ctx->ev_cg[k]) SVB_CUDA(cudaEventCreateWithFlags(&ctx->ev_cg[k], cudaEventDisableTiming));
   return SVB200_OK;
 }
 
@@ -78,12 +83,17 @@ static int norm_owned(svb200_ctx* ctx, int dof, const double* a, double* d_scal,
 }
 
 // ---- coupled Neumann faces: Y += coef * valM (valM . X) ------------------------------------------
-__global__ void face_dot_kernel(int fnNo, int fdof, int nd, int dof, int mynNo, int shared, const int* __restrict__ glob,
-                                const double* __restrict__ valM, const double* __restrict__ X, double* __restrict__ out)
+// Two-stage, fixed-order reduction (bitwise reproducible): FACE_DOT_BLOCKS partial sums, then one block adds them.
+// (A single CTA walking the whole face took 154 us per call on the 14 k-node outlet of C2 — a quarter of the NS solve.)
+constexpr int FACE_DOT_BLOCKS = 64;
+__global__ void __launch_bounds__(256)
+face_dot_kernel(int fnNo, int fdof, int nd, int dof, int mynNo, int shared, const int* __restrict__ glob,
+                const double* __restrict__ valM, const double* __restrict__ X, double* __restrict__ part)
 {
   __shared__ double red[256];
   double s = 0.0;
-  for (int t = threadIdx.x; t < fnNo * nd; t += blockDim.x) {
+  const int total = fnNo * nd;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
     const int a = t / nd, i = t % nd;
     const int Ac = glob[a];
     if (!shared || Ac < mynNo) s += valM[(size_t)a * fdof + i] * X[(size_t)Ac * dof + i];
@@ -91,6 +101,18 @@ __global__ void face_dot_kernel(int fnNo, int fdof, int nd, int dof, int mynNo, 
   red[threadIdx.x] = s;
   __syncthreads();
   for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+
+__global__ void face_dot_stage2_kernel(int nblocks, const double* __restrict__ part, double* __restrict__ out)
+{
+  __shared__ double red[FACE_DOT_BLOCKS];
+  red[threadIdx.x] = threadIdx.x < nblocks ? part[threadIdx.x] : 0.0;
+  __syncthreads();
+  for (int o = FACE_DOT_BLOCKS / 2; o > 0; o >>= 1) {
     if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
@@ -113,8 +135,11 @@ int add_bc_mul_device(svb200_ctx* ctx, int op, int dof, const double* X, double*
     if (!f.set || !f.coupledFlag) continue;
     const int nd = std::min(f.dof, dof);
     const double coef = (op == 0) ? f.res : -f.res / (1.0 + f.res * f.nS);
-    face_dot_kernel<<<1, 256, 0, ctx->stream>>>(f.nNo, f.dof, nd, dof, ctx->mynNo, f.shared, f.d_glob, f.d_valM, X, d_scal);
-    ctx->launches++;
+    // partial sums go to the top of the scalar scratch (consumed at once by stage 2), the result to d_scal[0]
+    double* part = d_scal + SCAL_N - FACE_DOT_BLOCKS;
+    face_dot_kernel<<<FACE_DOT_BLOCKS, 256, 0, ctx->stream>>>(f.nNo, f.dof, nd, dof, ctx->mynNo, f.shared, f.d_glob, f.d_valM, X, part);
+    face_dot_stage2_kernel<<<1, FACE_DOT_BLOCKS, 0, ctx->stream>>>(FACE_DOT_BLOCKS, part, d_scal);
+    ctx->launches += 2;
     if (f.shared) SVB_TRY(allreduce_sum(ctx, d_scal, 1));
     const int n = f.nNo * nd;
     if (n > 0) {
@@ -669,6 +694,51 @@ static int schur_device(svb200_ctx* ctx, int nsd, const svb200_sublsparams& p, s
   SVB_CUDA(cudaMemsetAsync(X, 0, sizeof(double) * nNo, ctx->stream));
   SVB_CUDA(cudaMemcpyAsync(P, R, sizeof(double) * nNo, cudaMemcpyDeviceToDevice, ctx->stream));
   int last_i = 0;
+  static const bool host_loop = getenv("SVB200_SCHUR_HOST_LOOP") != nullptr;     // A/B knob: the round-1 host-driven loop
+  if (!host_loop) {
+    // Device-resident loop: alpha, beta and the stopping test are evaluated on the device (fsils_kernels.cu, `cg` scalars);
+    // the host enqueues iteration i+1 while iteration i runs and reads the status one iteration late, so the GPU never
+    // waits for a host round trip (two per iteration in the host-driven loop, with ~13 small launches between them).
+    if (err < eps) {
+      r.success = 1;          // cgrad.cpp:72-75 at i = 0
+    } else if (p.mItr > 0) {
+      double* cg = ctx->d_cg;
+      double* h0 = ctx->h_cg + 16;
+      h0[0] = err; h0[1] = err; h0[2] = 0.0; h0[3] = eps; h0[4] = 0.0; h0[5] = 0.0; h0[6] = err; h0[7] = 0.0;
+      SVB_CUDA(cudaMemcpyAsync(cg, h0, sizeof(double) * 8, cudaMemcpyHostToDevice, ctx->stream));
+      bool done = false;
+      for (int i = 0; i < p.mItr && !done; i++) {
+        SVB_TRY(spmv_rc(ctx, nsd, 1, mG, P, GP));
+        SVB_TRY(halo_sum(ctx, nsd, GP));
+        if (anyCoupled) SVB_TRY(add_bc_mul_device(ctx, 1, nsd, GP, GP, d_scal));
+        SVB_TRY(schur_sp(ctx, nsd, mL, Gt, P, GP, SP));
+        SVB_TRY(halo_sum(ctx, 1, SP));
+        SVB_TRY(multi_dot(ctx, (long long)ctx->mynNo, 1, P, 0, SP, cg + 2));
+        SVB_TRY(allreduce_sum(ctx, cg + 2, 1));
+        SVB_TRY(cg_step_kernels(ctx, 0, nNo, cg, P, SP, X, R, nullptr));
+        SVB_TRY(multi_dot(ctx, (long long)ctx->mynNo, 1, R, 0, R, cg + 1));
+        SVB_TRY(allreduce_sum(ctx, cg + 1, 1));
+        SVB_TRY(cg_step_kernels(ctx, 1, nNo, cg, nullptr, nullptr, nullptr, R, P));
+        SVB_TRY(cg_step_kernels(ctx, 2, 1, cg, nullptr, nullptr, nullptr, nullptr, nullptr));
+        SVB_CUDA(cudaMemcpyAsync(ctx->h_cg + 8 * (i & 1), cg, sizeof(double) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        SVB_CUDA(cudaEventRecord(ctx->ev_cg[i & 1], ctx->stream));
+        if (i >= 1) {
+          SVB_CUDA(cudaEventSynchronize(ctx->ev_cg[(i - 1) & 1]));
+          done = ctx->h_cg[8 * ((i - 1) & 1) + 4] != 0.0;
+        }
+      }
+      SVB_CUDA(cudaMemcpyAsync(h0, cg, sizeof(double) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+      const int executed = (int)h0[5];
+      // the reference tests err < eps at the TOP of the next iteration: converging in the very last allowed iteration
+      // is not reported as success, and last_i stays mItr-1 (cgrad.cpp:70-76, 128)
+      r.success = (h0[4] != 0.0 && executed < p.mItr) ? 1 : 0;
+      last_i = r.success ? executed : p.mItr - 1;
+      err = std::sqrt(h0[1]);      // cg[1] is the raw <r,r>; the reference squares the norm (cgrad.cpp:92-93)
+      err = err * err;
+      errO = h0[6];
+    }
+  } else
   for (int i = 0; i < p.mItr; i++) {
     last_i = i;
     if (err < eps) {

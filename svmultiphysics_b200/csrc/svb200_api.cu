@@ -210,7 +210,8 @@ int svb200_destroy(svb200_ctx* ctx)
   cudaFree(ctx->d_err);
   cudaFree(ctx->d_stage); cudaFree(ctx->d_R); cudaFree(ctx->d_Val); cudaFree(ctx->d_W);
   cudaFree(ctx->d_work); cudaFree(ctx->d_red); cudaFree(ctx->d_tslot);
-  cudaFreeHost(ctx->h_pinned);
+  cudaFreeHost(ctx->h_pinned); cudaFreeHost(ctx->h_cg); cudaFree(ctx->d_cg);
+  for (int k = 0; k < 2; k++) if (ctx->ev_cg[k]) cudaEventDestroy(ctx->ev_cg[k]);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
   delete ctx;

@@ -164,6 +164,9 @@ struct svb200_ctx {
   size_t work_cap = 0;
   double* d_red = nullptr;         // partial-reduction scratch
   double* h_pinned = nullptr;      // pinned host scratch for scalar read-back
+  double* d_cg = nullptr;          // device scalars of the Schur-complement CG (8 doubles)
+  double* h_cg = nullptr;          // pinned: 2 status slots x 8 doubles + 8 for the initial values
+  cudaEvent_t ev_cg[2] = {nullptr, nullptr};
   size_t red_cap = 0;
 
   // multi-GPU
