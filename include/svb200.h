@@ -66,7 +66,8 @@ typedef enum {
   SVB200_PHYS_FLUID = 0,
   SVB200_PHYS_STRUCT = 1,
   SVB200_PHYS_FSI = 2,
-  SVB200_PHYS_MESH = 3
+  SVB200_PHYS_MESH = 3,
+  SVB200_PHYS_LELAS = 4     /* linear elasticity: l_elas::construct_l_elas + l_elas_3d (solver/l_elas.cpp:36-145, 249-365) */
 } svb200_phys;
 
 /* consts::FluidViscosityModelType (solver/fluid.cpp:2254-2297). */

@@ -73,6 +73,7 @@ consts::EquationType to_phys(int p)
     case SVB200_PHYS_STRUCT: return consts::EquationType::phys_struct;
     case SVB200_PHYS_FSI: return consts::EquationType::phys_FSI;
     case SVB200_PHYS_MESH: return consts::EquationType::phys_mesh;
+    case SVB200_PHYS_LELAS: return consts::EquationType::phys_lElas;
   }
   throw std::runtime_error("[ref_harness] unknown physics");
 }
@@ -386,6 +387,7 @@ int svref_assemble(void* h, int iM, const svb200_eqparams* e, const svb200_dmnpa
       case SVB200_PHYS_STRUCT: struct_ns::construct_dsolid(cm, c.cep_mod, m, c.sol); break;
       case SVB200_PHYS_FSI: fsi::construct_fsi(cm, c.cep_mod, m, c.sol); break;
       case SVB200_PHYS_MESH: mesh::construct_mesh(cm, c.cep_mod, m, c.sol); break;
+      case SVB200_PHYS_LELAS: l_elas::construct_l_elas(cm, m, c.sol); break;
       default: throw std::runtime_error("[ref_harness] physics not supported");
     }
     c.last_assemble_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

@@ -6,7 +6,7 @@ import ctypes as C
 ABI_VERSION = 2
 
 # svb200_phys
-PHYS_FLUID, PHYS_STRUCT, PHYS_FSI, PHYS_MESH = 0, 1, 2, 3
+PHYS_FLUID, PHYS_STRUCT, PHYS_FSI, PHYS_MESH, PHYS_LELAS = 0, 1, 2, 3, 4
 # svb200_visc
 VISC_CONST, VISC_CY, VISC_CASSON = 0, 1, 2
 # svb200_iso / svb200_vol
@@ -165,6 +165,19 @@ def mesh_domain(E: float = 1.0, nu: float = 0.3, rho: float = 0.0, f=(0.0, 0.0, 
     d.rho = rho
     d.f[0], d.f[1], d.f[2] = f
     d.E, d.nu = E, nu
+    return d
+
+
+def lelas_eq(dt: float, rho_inf: float = 0.5, tDof: int = 3, scatter: int = SCATTER_ATOMIC) -> EqParams:
+    """Linear-elasticity equation (tests/cases/linear-elasticity): dof = 3, displacement-based."""
+    af, am, gam, beta = gen_alpha(rho_inf)
+    return EqParams(dt=dt, af=af, am=am, gam=gam, beta=beta, phys=PHYS_LELAS, dof=3, tDof=tDof, s=0,
+                    mvMsh=0, vmsStab=1, scatter=scatter, reserved=0)
+
+
+def lelas_domain(E: float = 1.0e6, nu: float = 0.3, rho: float = 1.0, f=(0.0, 0.0, 0.0), Id: int = -1) -> DmnParams:
+    d = mesh_domain(E=E, nu=nu, rho=rho, f=f, Id=Id)
+    d.phys = PHYS_LELAS
     return d
 
 

@@ -440,7 +440,9 @@ assemble_struct_visc_kernel(const __grid_constant__ StructArgs P)
 // mesh::construct_mesh (Code/Source/solver/mesh.cpp:22-135) + l_elas::l_elas_3d (Code/Source/solver/l_elas.cpp:249-365):
 // geometry x + Do(is..), displacement Dg(is..) - Do(is..), and the Gauss weight WITHOUT the Jacobian
 // (w = lM.w(g), mesh.cpp:122: Jacobian-based stiffening).  ENON lanes per element, lane a owns row a.
-template <int ENON, bool ATOMIC>
+// LELAS = true: the linear-elasticity EQUATION, l_elas::construct_l_elas (l_elas.cpp:36-145): reference geometry, the
+// displacement itself, w = lM.w(g) * Jac and the nodal body force Bf in the inertia term.
+template <int ENON, bool ATOMIC, bool LELAS>
 __global__ void __launch_bounds__(128)
 assemble_mesh_kernel(const __grid_constant__ StructArgs P, const double* __restrict__ Do)
 {
@@ -467,7 +469,7 @@ assemble_mesh_kernel(const __grid_constant__ StructArgs P, const double* __restr
     const size_t n = (size_t)node[b];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-      const double dol = __ldg(Do + (size_t)P.tDof * n + is + i);
+      const double dol = LELAS ? 0.0 : __ldg(Do + (size_t)P.tDof * n + is + i);
       xl[b][i] = __ldg(P.x + 3 * n + i) + dol;
       dl[b][i] = __ldg(P.Dg + (size_t)P.tDof * n + is + i) - dol;
     }
@@ -487,10 +489,11 @@ assemble_mesh_kernel(const __grid_constant__ StructArgs P, const double* __restr
 #pragma unroll
       for (int j = 0; j < 3; j++) K[b][i][j] = 0.0;
   double Nx[ENON][3];
+  double Jac = 1.0;
 #pragma unroll 1
   for (int g = 0; g < P.nG; g++) {
-    if (g == 0 || ENON != 4) gnn3<ENON>(P.Nxi[g], xl, Nx);     // TET4: lShpF, gradients constant
-    const double w = P.w[g];
+    if (g == 0 || ENON != 4) Jac = gnn3<ENON>(P.Nxi[g], xl, Nx);     // TET4: lShpF, gradients constant
+    const double w = LELAS ? P.w[g] * Jac : P.w[g];
     const double wl = w * T1c * mu;
     double ud[3] = {-dm.f[0], -dm.f[1], -dm.f[2]}, ed[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
@@ -498,7 +501,8 @@ assemble_mesh_kernel(const __grid_constant__ StructArgs P, const double* __restr
       const double Nb = P.N[g][b];
       const size_t n = (size_t)node[b];
 #pragma unroll
-      for (int i = 0; i < 3; i++) ud[i] += Nb * __ldg(P.Ag + (size_t)P.tDof * n + is + i);
+      for (int i = 0; i < 3; i++)
+        ud[i] += Nb * (__ldg(P.Ag + (size_t)P.tDof * n + is + i) - (LELAS ? __ldg(P.Bf + 3 * n + i) : 0.0));
       ed[0] += Nx[b][0] * dl[b][0];
       ed[1] += Nx[b][1] * dl[b][1];
       ed[2] += Nx[b][2] * dl[b][2];
@@ -667,8 +671,13 @@ static int launch_mesh(svb200_ctx* ctx, const StructArgs& A, const double* Do)
   const long long n = (long long)A.e1 - A.e0;
   if (n <= 0) return SVB200_OK;
   const unsigned blocks = (unsigned)((n + EPB - 1) / EPB);
-  if (A.atomic) assemble_mesh_kernel<ENON, true><<<blocks, 128, 0, ctx->stream>>>(A, Do);
-  else assemble_mesh_kernel<ENON, false><<<blocks, 128, 0, ctx->stream>>>(A, Do);
+  if (Do == nullptr) {      // linear-elasticity equation
+    if (A.atomic) assemble_mesh_kernel<ENON, true, true><<<blocks, 128, 0, ctx->stream>>>(A, nullptr);
+    else assemble_mesh_kernel<ENON, false, true><<<blocks, 128, 0, ctx->stream>>>(A, nullptr);
+  } else {
+    if (A.atomic) assemble_mesh_kernel<ENON, true, false><<<blocks, 128, 0, ctx->stream>>>(A, Do);
+    else assemble_mesh_kernel<ENON, false, false><<<blocks, 128, 0, ctx->stream>>>(A, Do);
+  }
   ctx->launches++;
   SVB_CUDA(cudaGetLastError());
   return SVB200_OK;
@@ -676,12 +685,13 @@ static int launch_mesh(svb200_ctx* ctx, const StructArgs& A, const double* Do)
 
 int run_assemble_mesh(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn)
 {
-  SVB_REQUIRE(ctx->d_Do, "svb200_assemble: the mesh equation needs the old displacement (svb200_set_old_disp)");
-  SVB_REQUIRE(eq->dof == 3 && ctx->dof == 3, "svb200_assemble: the mesh equation has dof = 3");
+  const bool lelas = (eq->phys == SVB200_PHYS_LELAS);
+  SVB_REQUIRE(lelas || ctx->d_Do, "svb200_assemble: the mesh equation needs the old displacement (svb200_set_old_disp)");
+  SVB_REQUIRE(eq->dof == 3 && ctx->dof == 3, "svb200_assemble: the mesh / linear-elasticity equation has dof = 3");
   // reuse the solid argument block: mark mesh domains as the ones to assemble, E / nu travel in C10 / C01
   std::vector<svb200_dmnparams> d(dmn, dmn + nDmn);
   for (auto& q : d) {
-    const bool isMesh = (q.phys == SVB200_PHYS_MESH);
+    const bool isMesh = (q.phys == (lelas ? SVB200_PHYS_LELAS : SVB200_PHYS_MESH));
     q.phys = isMesh ? SVB200_PHYS_STRUCT : SVB200_PHYS_FLUID;
     q.isoType = SVB200_ISO_NHK;
     q.solid_visc_mu = 0.0;
@@ -691,7 +701,8 @@ int run_assemble_mesh(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq,
   StructArgs A;
   int rc = fill_struct_args(ctx, m, eq, d.data(), nDmn, A);
   if (rc) return rc;
-  auto launch = [&](const StructArgs& B) { return m.eNoN == 8 ? launch_mesh<8>(ctx, B, ctx->d_Do) : launch_mesh<4>(ctx, B, ctx->d_Do); };
+  const double* Do = lelas ? nullptr : ctx->d_Do;
+  auto launch = [&](const StructArgs& B) { return m.eNoN == 8 ? launch_mesh<8>(ctx, B, Do) : launch_mesh<4>(ctx, B, Do); };
   if (A.atomic) return launch(A);
   A.perm = m.d_color_perm;
   for (size_t c = 0; c + 1 < m.color_off.size(); c++) {

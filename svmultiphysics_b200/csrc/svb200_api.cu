@@ -771,6 +771,7 @@ int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, cons
       if (anySolid) TRY(run_assemble_struct(ctx, m, eq, dmn, nDmn));
     } break;
     case SVB200_PHYS_MESH:
+    case SVB200_PHYS_LELAS:
       TRY(run_assemble_mesh(ctx, m, eq, dmn, nDmn));
       break;
     default:

@@ -20,6 +20,7 @@ int to_phys(consts::EquationType p)
     case EquationType::phys_struct: return SVB200_PHYS_STRUCT;
     case EquationType::phys_FSI: return SVB200_PHYS_FSI;
     case EquationType::phys_mesh: return SVB200_PHYS_MESH;
+    case EquationType::phys_lElas: return SVB200_PHYS_LELAS;
     default: return -1;
   }
 }
@@ -61,7 +62,9 @@ std::vector<svb200_dmnparams> domain_params(const eqType& eq)
     p.phys = to_phys(d.phys);
     if (p.phys < 0) throw std::runtime_error("[B200LinearAlgebra] domain physics is not on the device path");
     const bool solid = (d.phys == EquationType::phys_struct);
-    p.rho = prop_or(d, solid ? PhysicalProperyType::solid_density : PhysicalProperyType::fluid_density);
+    // l_elas_3d (mesh and linear-elasticity equations) reads solid_density like struct_3d (l_elas.cpp:275)
+    const bool solid_rho = solid || d.phys == EquationType::phys_mesh || d.phys == EquationType::phys_lElas;
+    p.rho = prop_or(d, solid_rho ? PhysicalProperyType::solid_density : PhysicalProperyType::fluid_density);
     p.f[0] = prop_or(d, PhysicalProperyType::f_x);
     p.f[1] = prop_or(d, PhysicalProperyType::f_y);
     p.f[2] = prop_or(d, PhysicalProperyType::f_z);

@@ -186,3 +186,34 @@ def test_mesh_equation_parity(kind):
     assert o1.RI.success == o0.RI.success and abs(o1.RI.itr - o0.RI.itr) <= max(2, o0.RI.itr // 20)
     assert common.rel_err(X1, X0) < 1e-8
     eng.close()
+
+
+@pytest.mark.parametrize("scatter", [abi.SCATTER_ATOMIC, abi.SCATTER_COLORED])
+@pytest.mark.parametrize("kind", ["tet4", "hex8"])
+def test_linear_elasticity_parity(kind, scatter):
+    """Linear-elasticity equation (l_elas::construct_l_elas + l_elas_3d, tests/cases/linear-elasticity): assembly to 1e-12
+    and a CG solve against the compiled reference."""
+    cls = _oracle()
+    from svmultiphysics_b200 import meshgen
+    m = meshgen.box_tet4(3, 3, 2, (1.0, 1.0, 1.0)) if kind == "tet4" else meshgen.box_hex8(4, 3, 3, (1.0, 2.0, 1.0))
+    Ag, Yg, Dg, Bf, _ = common.struct_state(m, 0)
+    eq, dmn = abi.lelas_eq(1e-3, scatter=scatter), [abi.lelas_domain(E=1.0e6, nu=0.3, rho=2.0, f=(0.1, -0.2, 0.3))]
+    faces = [(abi.BC_DIR, m.faces["X0"], np.zeros((3, len(m.faces["X0"])), order="F"))]
+    orc = cls(); orc.set_coords(m.x); orc.add_mesh(m.IEN)
+    rowPtr, colPtr = orc.build_graph(len(faces))
+    eng = _engine(m, rowPtr, colPtr)
+    eng.set_num_faces(len(faces))
+    for i, (g, nodes, val) in enumerate(faces):
+        orc.set_face(i, g, nodes, val); eng.set_face(i, g, nodes, val)
+    orc.alloc(3); orc.set_state(Ag, Yg, Dg, Bf); orc.assemble(0, eq, dmn)
+    R0, V0 = orc.get_R(), orc.get_Val()
+    eng.alloc(3); eng.set_state(Ag, Yg, Dg, Bf); eng.assemble(0, eq, dmn)
+    assert common.rel_err(eng.get_R(), R0) < ASM_TOL
+    assert common.rel_err(eng.get_Val(), V0) < ASM_TOL
+    ls = abi.ls_params(abi.LS_CG, mItr=1000, relTol=1e-10)
+    incL, res = np.ones(len(faces), np.int32), np.zeros(len(faces))
+    X0, o0, _ = orc.solve(3, abi.LS_CG, ls, incL, res)
+    X1, o1, _ = eng.solve(3, abi.LS_CG, ls, incL, res)
+    assert o1.RI.success == o0.RI.success and abs(o1.RI.itr - o0.RI.itr) <= max(2, o0.RI.itr // 20)
+    assert common.rel_err(X1, X0) < 1e-7
+    eng.close()
