@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define SVB200_ABI_VERSION 2
+#define SVB200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define SVB200_API __attribute__((visibility("default")))
@@ -67,7 +67,11 @@ typedef enum {
   SVB200_PHYS_STRUCT = 1,
   SVB200_PHYS_FSI = 2,
   SVB200_PHYS_MESH = 3,
-  SVB200_PHYS_LELAS = 4     /* linear elasticity: l_elas::construct_l_elas + l_elas_3d (solver/l_elas.cpp:36-145, 249-365) */
+  SVB200_PHYS_LELAS = 4,    /* linear elasticity: l_elas::construct_l_elas + l_elas_3d (solver/l_elas.cpp:36-145, 249-365) */
+  SVB200_PHYS_HEATS = 5,    /* heat conduction in a solid: heats::construct_heats + heats_3d (solver/heats.cpp:30-119, 186-233), dof = 1 */
+  SVB200_PHYS_HEATF = 6,    /* advection-diffusion in a fluid: heatf::construct_heatf + heatf_3d (solver/heatf.cpp:52-139, 238-331), dof = 1 */
+  SVB200_PHYS_USTRUCT = 7   /* mixed velocity-pressure solid: ustruct::construct_usolid + ustruct_3d_m/c + ustruct_do_assem
+                               (solver/ustruct.cpp:203-400, 1165-1591, 629-871, 1595-1737), dof = 4 */
 } svb200_phys;
 
 /* consts::FluidViscosityModelType (solver/fluid.cpp:2254-2297). */
@@ -99,7 +103,9 @@ typedef enum {
   SVB200_SCATTER_COLORED = 1  /* graph-coloured, conflict-free, bitwise reproducible */
 } svb200_scatter;
 /* What svb200_download / svb200_upload move. */
-typedef enum { SVB200_ARRAY_R = 0, SVB200_ARRAY_VAL = 1, SVB200_ARRAY_W = 2 } svb200_array;
+typedef enum { SVB200_ARRAY_R = 0, SVB200_ARRAY_VAL = 1, SVB200_ARRAY_W = 2,
+               SVB200_ARRAY_KD = 3   /* com_mod.Kd((nsd+1)*nsd, nnz), the displacement tangent of ustruct (solver/ustruct.cpp:1621) */
+} svb200_array;
 
 /* Per-equation time-integration parameters (eqType af/am/gam/beta, ComMod dt/tDof/dof/mvMsh). */
 typedef struct {
@@ -140,6 +146,9 @@ typedef struct {
   double backflow_stab;     /* backflow stabilisation coefficient (fluid Neumann faces, solver/fluid.cpp:65) */
   /* stModelType a, b, aff, ass, afs, kap, khs (HGO / Holzapfel-Ogden; bff, bss, bfs above) — appended in ABI version 2 */
   double st_a, st_b, aff, ass, afs, kap, khs;
+  /* appended in ABI version 3 */
+  double conductivity, source_term;   /* heatS / heatF (solver/heats.cpp:202-204, heatf.cpp:259-260) */
+  double ctau_M, ctau_C;              /* ustruct VMS constants (mat_models.cpp:1478-1479) */
 } svb200_dmnparams;
 
 /* FSILS_subLsType inputs (linear_solver/fils_struct.hpp:198-242). */

@@ -16,6 +16,8 @@
 //   spar_mul::fsils_spar_mul_vv                 linear_solver/spar_mul.cpp:164
 //   nn::get_gip / get_gnn (faces), nn::gnnb     solver/nn.cpp:455,500,911
 //   fluid::b_fluid, l_elas::b_l_elas            solver/fluid.cpp:21, solver/l_elas.cpp:21
+//   heats::construct_heats, heatf::construct_heatf   solver/heats.cpp:30, solver/heatf.cpp:52
+//   ustruct::construct_usolid, ustruct::ustruct_r     solver/ustruct.cpp:203, 1742
 //
 // Parameter structs are shared with the product ABI (include/svb200.h) so that parity tests feed
 // both sides the same bytes.  Nothing here is linked into libsvb200.so.
@@ -32,6 +34,9 @@
 #include "nn.h"
 #include "lhsa.h"
 #include "l_elas.h"
+#include "heats.h"
+#include "heatf.h"
+#include "ustruct.h"
 #include "all_fun.h"
 #include "utils.h"
 #include "fsils_api.hpp"
@@ -74,6 +79,9 @@ consts::EquationType to_phys(int p)
     case SVB200_PHYS_FSI: return consts::EquationType::phys_FSI;
     case SVB200_PHYS_MESH: return consts::EquationType::phys_mesh;
     case SVB200_PHYS_LELAS: return consts::EquationType::phys_lElas;
+    case SVB200_PHYS_HEATS: return consts::EquationType::phys_heatS;
+    case SVB200_PHYS_HEATF: return consts::EquationType::phys_heatF;
+    case SVB200_PHYS_USTRUCT: return consts::EquationType::phys_ustruct;
   }
   throw std::runtime_error("[ref_harness] unknown physics");
 }
@@ -93,6 +101,10 @@ void fill_domain(dmnType& d, const svb200_dmnparams& p)
   d.prop[PhysicalProperyType::damping] = p.dmp;
   d.prop[PhysicalProperyType::elasticity_modulus] = p.E;
   d.prop[PhysicalProperyType::poisson_ratio] = p.nu;
+  d.prop[PhysicalProperyType::conductivity] = p.conductivity;
+  d.prop[PhysicalProperyType::source_term] = p.source_term;
+  d.prop[PhysicalProperyType::ctau_M] = p.ctau_M;
+  d.prop[PhysicalProperyType::ctau_C] = p.ctau_C;
   switch (p.viscType) {
     case SVB200_VISC_CONST: d.fluid_visc.viscType = FluidViscosityModelType::viscType_Const; break;
     case SVB200_VISC_CY: d.fluid_visc.viscType = FluidViscosityModelType::viscType_CY; break;
@@ -388,6 +400,16 @@ int svref_assemble(void* h, int iM, const svb200_eqparams* e, const svb200_dmnpa
       case SVB200_PHYS_FSI: fsi::construct_fsi(cm, c.cep_mod, m, c.sol); break;
       case SVB200_PHYS_MESH: mesh::construct_mesh(cm, c.cep_mod, m, c.sol); break;
       case SVB200_PHYS_LELAS: l_elas::construct_l_elas(cm, m, c.sol); break;
+      case SVB200_PHYS_HEATS: heats::construct_heats(cm, m, c.sol); break;
+      case SVB200_PHYS_HEATF: heatf::construct_heatf(cm, m, c.sol); break;
+      case SVB200_PHYS_USTRUCT: {
+        // what Integrator::step does around the assembly of a ustruct equation (solver/Integrator.cpp:106-109,
+        // initialize.cpp:668-670): Kd((nsd+1)*nsd, nnz) zeroed; idMap is the identity without Taylor-Hood elements
+        if (cm.Kd.nrows() != 12 || cm.Kd.ncols() != cm.lhs.nnz) cm.Kd.resize(12, cm.lhs.nnz);
+        cm.Kd = 0.0;
+        if (cm.idMap.size() != cm.tnNo) { cm.idMap.resize(cm.tnNo); for (int a = 0; a < cm.tnNo; a++) cm.idMap(a) = a; }
+        ustruct::construct_usolid(cm, c.cep_mod, m, c.sol);
+      } break;
       default: throw std::runtime_error("[ref_harness] physics not supported");
     }
     c.last_assemble_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -402,6 +424,7 @@ int svref_get(void* h, int what, double* dst)
     if (c.backend && c.backend_download) { c.backend_download(c.backend, what, dst); return; }
     if (what == SVB200_ARRAY_R) std::memcpy(dst, cm.R.data(), sizeof(double)*cm.R.size());
     else if (what == SVB200_ARRAY_VAL) std::memcpy(dst, cm.Val.data(), sizeof(double)*cm.Val.size());
+    else if (what == SVB200_ARRAY_KD) std::memcpy(dst, cm.Kd.data(), sizeof(double)*cm.Kd.size());
     else throw std::runtime_error("[ref_harness] bad array id");
   });
 }
@@ -574,6 +597,25 @@ int svref_spmv(void* h, int dof, const double* U, double* KU)
     std::memcpy(u.data(), U, sizeof(double)*dof*cm.tnNo);
     spar_mul::fsils_spar_mul_vv(cm.lhs, cm.lhs.rowPtr, cm.lhs.colPtr, dof, cm.Val, u, ku);
     std::memcpy(KU, ku.data(), sizeof(double)*dof*cm.tnNo);
+  });
+}
+
+/// ustruct::ustruct_r (solver/ustruct.cpp:1742-1845) for Newton iteration `itr` (1-based like eq.itr): R -= Kd Rd / am with
+/// Rd = amg Ad - Yg; eq and domain parameters are those of the last svref_assemble.
+int svref_ustruct_r(void* h, int itr, const double* Ad)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    auto& cm = c.com_mod;
+    const int n = cm.tnNo;
+    cm.Ad.resize(3, n);
+    std::memcpy(cm.Ad.data(), Ad, sizeof(double)*3*n);
+    cm.Rd.resize(3, n);
+    cm.Rd = 0.0;
+    cm.eq[0].itr = itr;
+    // all_fun::is_domain (solver/all_fun.cpp) with a single domain needs nothing else; rowPtr/colPtr were set by
+    // svref_build_graph
+    ustruct::ustruct_r(cm, c.sol);
   });
 }
 

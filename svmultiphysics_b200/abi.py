@@ -3,10 +3,10 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # svb200_phys
-PHYS_FLUID, PHYS_STRUCT, PHYS_FSI, PHYS_MESH, PHYS_LELAS = 0, 1, 2, 3, 4
+PHYS_FLUID, PHYS_STRUCT, PHYS_FSI, PHYS_MESH, PHYS_LELAS, PHYS_HEATS, PHYS_HEATF, PHYS_USTRUCT = 0, 1, 2, 3, 4, 5, 6, 7
 # svb200_visc
 VISC_CONST, VISC_CY, VISC_CASSON = 0, 1, 2
 # svb200_iso / svb200_vol
@@ -58,6 +58,8 @@ class DmnParams(C.Structure):
         ("backflow_stab", C.c_double),
         ("st_a", C.c_double), ("st_b", C.c_double), ("aff", C.c_double), ("ass", C.c_double), ("afs", C.c_double),
         ("kap", C.c_double), ("khs", C.c_double),
+        ("conductivity", C.c_double), ("source_term", C.c_double),
+        ("ctau_M", C.c_double), ("ctau_C", C.c_double),
     ]
 
 
@@ -178,6 +180,42 @@ def lelas_eq(dt: float, rho_inf: float = 0.5, tDof: int = 3, scatter: int = SCAT
 def lelas_domain(E: float = 1.0e6, nu: float = 0.3, rho: float = 1.0, f=(0.0, 0.0, 0.0), Id: int = -1) -> DmnParams:
     d = mesh_domain(E=E, nu=nu, rho=rho, f=f, Id=Id)
     d.phys = PHYS_LELAS
+    return d
+
+
+def heat_eq(dt: float, fluid: bool, rho_inf: float = 0.5, tDof: int = 1, s: int = 0, mvMsh: int = 0,
+            scatter: int = SCATTER_ATOMIC) -> EqParams:
+    """Heat equation in a solid (heatS) or advection-diffusion in a fluid (heatF): dof = 1, temperature in state dof s
+    (Code/Source/solver/heats.cpp:196, heatf.cpp:253)."""
+    af, am, gam, beta = gen_alpha(rho_inf)
+    return EqParams(dt=dt, af=af, am=am, gam=gam, beta=beta, phys=PHYS_HEATF if fluid else PHYS_HEATS, dof=1, tDof=tDof,
+                    s=s, mvMsh=mvMsh, vmsStab=1, scatter=scatter, reserved=0)
+
+
+def heat_domain(fluid: bool, conductivity: float = 1.0, source: float = 0.0, rho: float = 1.0, Id: int = -1) -> DmnParams:
+    d = DmnParams()
+    d.Id = Id
+    d.phys = PHYS_HEATF if fluid else PHYS_HEATS
+    d.rho = rho
+    d.conductivity, d.source_term = conductivity, source
+    return d
+
+
+def ustruct_eq(dt: float, rho_inf: float = 0.5, tDof: int = 4, scatter: int = SCATTER_ATOMIC) -> EqParams:
+    """Mixed velocity-pressure solid (ustruct): dof = 4 = (v, p), equal-order VMS (Code/Source/solver/ustruct.cpp:203-400)."""
+    af, am, gam, beta = gen_alpha(rho_inf)
+    return EqParams(dt=dt, af=af, am=am, gam=gam, beta=beta, phys=PHYS_USTRUCT, dof=4, tDof=tDof, s=0,
+                    mvMsh=0, vmsStab=1, scatter=scatter, reserved=0)
+
+
+def ustruct_domain(isoType: int = ISO_NHK, volType: int = VOL_ST91, E: float = 1.0e6, nu: float = 0.45, rho: float = 1.0,
+                   ctau_M: float = 1.0e-3, ctau_C: float = 1.0e-3, **kw) -> DmnParams:
+    """Like struct_domain, with the VMS constants ctau_M / ctau_C and E / nu kept for compute_tau
+    (Code/Source/solver/mat_models.cpp:1470-1493)."""
+    d = struct_domain(isoType=isoType, volType=volType, E=E, nu=nu, rho=rho, **kw)
+    d.phys = PHYS_USTRUCT
+    d.E, d.nu = E, nu
+    d.ctau_M, d.ctau_C = ctau_M, ctau_C
     return d
 
 

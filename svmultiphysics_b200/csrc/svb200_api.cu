@@ -774,6 +774,10 @@ int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, cons
     case SVB200_PHYS_LELAS:
       TRY(run_assemble_mesh(ctx, m, eq, dmn, nDmn));
       break;
+    case SVB200_PHYS_HEATS:
+    case SVB200_PHYS_HEATF:
+      TRY(run_assemble_heat(ctx, m, eq, dmn, nDmn));
+      break;
     default:
       set_error("svb200_assemble: this physics is not implemented in this build");
       return SVB200_ERR_UNSUPPORTED;

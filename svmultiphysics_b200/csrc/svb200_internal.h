@@ -211,6 +211,8 @@ int upload_fluid_gen_tables(svb200_ctx* ctx, Mesh& m);
 int run_assemble_fluid_gen(svb200_ctx* ctx, const Mesh& m, const FluidArgs& F);
 int run_assemble_struct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);
 int run_assemble_mesh(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);
+// assemble_heat.cu
+int run_assemble_heat(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);
 // assemble_bnd.cu
 int run_assemble_neu(svb200_ctx* ctx, const BFace& f, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn,
                      const double* d_hg);

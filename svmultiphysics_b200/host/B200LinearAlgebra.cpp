@@ -21,6 +21,8 @@ int to_phys(consts::EquationType p)
     case EquationType::phys_FSI: return SVB200_PHYS_FSI;
     case EquationType::phys_mesh: return SVB200_PHYS_MESH;
     case EquationType::phys_lElas: return SVB200_PHYS_LELAS;
+    case EquationType::phys_heatS: return SVB200_PHYS_HEATS;
+    case EquationType::phys_heatF: return SVB200_PHYS_HEATF;
     default: return -1;
   }
 }
@@ -63,7 +65,9 @@ std::vector<svb200_dmnparams> domain_params(const eqType& eq)
     if (p.phys < 0) throw std::runtime_error("[B200LinearAlgebra] domain physics is not on the device path");
     const bool solid = (d.phys == EquationType::phys_struct);
     // l_elas_3d (mesh and linear-elasticity equations) reads solid_density like struct_3d (l_elas.cpp:275)
-    const bool solid_rho = solid || d.phys == EquationType::phys_mesh || d.phys == EquationType::phys_lElas;
+    // heats_3d reads solid_density as well (heats.cpp:204); heatf_3d uses no density
+    const bool solid_rho = solid || d.phys == EquationType::phys_mesh || d.phys == EquationType::phys_lElas ||
+                           d.phys == EquationType::phys_heatS;
     p.rho = prop_or(d, solid_rho ? PhysicalProperyType::solid_density : PhysicalProperyType::fluid_density);
     p.f[0] = prop_or(d, PhysicalProperyType::f_x);
     p.f[1] = prop_or(d, PhysicalProperyType::f_y);
@@ -73,6 +77,10 @@ std::vector<svb200_dmnparams> domain_params(const eqType& eq)
     p.dmp = prop_or(d, PhysicalProperyType::damping);
     p.E = prop_or(d, PhysicalProperyType::elasticity_modulus);
     p.nu = prop_or(d, PhysicalProperyType::poisson_ratio);
+    p.conductivity = prop_or(d, PhysicalProperyType::conductivity);
+    p.source_term = prop_or(d, PhysicalProperyType::source_term);
+    p.ctau_M = prop_or(d, PhysicalProperyType::ctau_M);
+    p.ctau_C = prop_or(d, PhysicalProperyType::ctau_C);
     switch (d.fluid_visc.viscType) {
       case FluidViscosityModelType::viscType_CY: p.viscType = SVB200_VISC_CY; break;
       case FluidViscosityModelType::viscType_Cass: p.viscType = SVB200_VISC_CASSON; break;
@@ -129,7 +137,7 @@ bool global_eq_assem(ComMod& com_mod, CepMod& cep_mod, const mshType& lM, const 
   auto& eq = com_mod.eq[com_mod.cEq];
   auto* la = dynamic_cast<B200LinearAlgebra*>(eq.linear_algebra);
   if (!la) return false;
-  if (to_phys(eq.phys) < 0) return false;          // heat, stokes, ... stay on the host loop (and its assemble())
+  if (to_phys(eq.phys) < 0) return false;          // stokes, shells, CEP, ... stay on the host loop (and its assemble())
   la->assemble_mesh(com_mod, lM, solutions);
   return true;
 }

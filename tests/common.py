@@ -176,3 +176,27 @@ def fluid_gen_state(m, tDof, seed=31):
     Ag = np.asfortranarray(0.5 * rng.standard_normal((tDof, m.nNo)))
     Bf = np.asfortranarray(0.1 * rng.standard_normal((3, m.nNo)))
     return Ag, Yg, None, Bf
+
+
+# ---- scalar heat equations (heatS / heatF) -------------------------------------------------------
+# (name, mesh factory, fluid?, tDof, eq.s, mvMsh, heat_domain kwargs)
+HEAT_CASES = [
+    ("heats_tet4", _tet, False, 1, 0, 0, dict(conductivity=0.7, source=0.3, rho=2.5)),
+    ("heats_hex8", _hex_skewed, False, 3, 2, 0, dict(conductivity=12.0, source=-1.5, rho=0.8)),
+    ("heatf_tet4", _tet_cyl, True, 5, 4, 0, dict(conductivity=0.01, source=0.2)),
+    ("heatf_hex8_moving_mesh", _hex_skewed, True, 8, 7, 1, dict(conductivity=0.05, source=0.0)),
+]
+
+
+def heat_state(m, tDof, s, seed=47):
+    """Velocity-like fields in dofs 0..2 (and 4..6), a smooth temperature + noise in dof s."""
+    rng = np.random.default_rng(seed)
+    Yg = np.asfortranarray(0.3 * rng.standard_normal((tDof, m.nNo)))
+    if tDof >= 4:
+        Yg[0] += 1.0 + 0.5 * np.sin(2.0 * m.x[1])
+        Yg[2] += 0.7 * m.x[0]
+    Yg[s] = 300.0 + 20.0 * np.sin(m.x[0] + 0.5 * m.x[2]) + 5.0 * m.x[1] + 0.5 * rng.standard_normal(m.nNo)
+    Ag = np.asfortranarray(rng.standard_normal((tDof, m.nNo)))
+    Dg = np.zeros((tDof, m.nNo), order="F")
+    Bf = np.zeros((3, m.nNo), order="F")
+    return Ag, Yg, Dg, Bf

@@ -82,9 +82,26 @@ def fluid_gen_golden():
     print("wrote fluid_gen.npz with", len(out), "arrays")
 
 
+def heat_golden():
+    """Assembled R / Val of the scalar heat equations (heats_3d / heatf_3d) for tests/common.py:HEAT_CASES."""
+    out = {}
+    for name, mk, fluid, tDof, s, mv, dkw in common.HEAT_CASES:
+        m = mk()
+        Ag, Yg, Dg, Bf = common.heat_state(m, tDof, s)
+        c = RefCase(); c.set_coords(m.x); c.add_mesh(m.IEN)
+        rowPtr, colPtr = c.build_graph(0)
+        eq, dmn = abi.heat_eq(0.01, fluid, tDof=tDof, s=s, mvMsh=mv), [abi.heat_domain(fluid, **dkw)]
+        c.alloc(1); c.set_state(Ag, Yg, Dg, Bf); c.assemble(0, eq, dmn)
+        out[f"{name}/R"], out[f"{name}/Val"] = c.get_R(), c.get_Val()
+        out[f"{name}/rowPtr"], out[f"{name}/colPtr"] = rowPtr, colPtr
+    np.savez_compressed(os.path.join(HERE, "heat.npz"), **out)
+    print("wrote heat.npz with", len(out), "arrays")
+
+
 if __name__ == "__main__":
     if not have_ref():
         raise SystemExit("oracle/_ref/libsvref.so is missing: run `make -C oracle ref` first")
-    fluid_golden()
-    struct_golden()
-    fluid_gen_golden()
+    only = sys.argv[1:]
+    for fn in (fluid_golden, struct_golden, fluid_gen_golden, heat_golden):
+        if not only or fn.__name__.replace("_golden", "") in only:
+            fn()

@@ -46,7 +46,7 @@ def test_header_and_library_agree(lib):
 def test_struct_layouts_match_header():
     # sizes implied by include/svb200.h (natural alignment, LP64)
     assert C.sizeof(abi.EqParams) == 5 * 8 + 8 * 4
-    assert C.sizeof(abi.DmnParams) == 8 + 8 * 5 + 8 + 8 * 5 + 8 + 8 * 11 + 8 * 7
+    assert C.sizeof(abi.DmnParams) == 8 + 8 * 5 + 8 + 8 * 5 + 8 + 8 * 11 + 8 * 7 + 8 * 4
     assert C.sizeof(abi.SubLsParams) == 24 and C.sizeof(abi.LsParams) == 72
     assert C.sizeof(abi.SubLsResult) == 40 and C.sizeof(abi.LsResult) == 3 * 40 + 8 + 8 + 8
 

@@ -1,0 +1,93 @@
+"""GPU parity tests for the scalar heat equations (heatS / heatF): assembly against the golden
+vectors of the compiled reference and against the reference itself, and the dof = 1 Krylov solvers."""
+import numpy as np
+import pytest
+
+from svmultiphysics_b200 import abi, elements
+from tests import common
+
+pytestmark = pytest.mark.gpu
+ASM_TOL = 1e-12
+
+
+def _engine(m, rowPtr, colPtr):
+    from svmultiphysics_b200.engine import Engine
+    e = Engine(0)
+    e.set_graph(rowPtr, colPtr)
+    w, N, Nx = elements.tables(m.eNoN)
+    e.set_mesh(0, m.IEN, w, N, Nx, eId=m.eId)
+    e.set_coords(m.x)
+    return e
+
+
+@pytest.mark.parametrize("scatter", [abi.SCATTER_ATOMIC, abi.SCATTER_COLORED])
+@pytest.mark.parametrize("name,mk,fluid,tDof,s,mv,dkw", common.HEAT_CASES, ids=[c[0] for c in common.HEAT_CASES])
+def test_heat_assembly_matches_golden(name, mk, fluid, tDof, s, mv, dkw, scatter):
+    golden = common.load_golden("heat.npz")
+    m = mk()
+    Ag, Yg, Dg, Bf = common.heat_state(m, tDof, s)
+    eq, dmn = abi.heat_eq(0.01, fluid, tDof=tDof, s=s, mvMsh=mv, scatter=scatter), [abi.heat_domain(fluid, **dkw)]
+    eng = _engine(m, golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"])
+    eng.alloc(1); eng.set_state(Ag, Yg, Dg, Bf); eng.assemble(0, eq, dmn)
+    R1, V1 = eng.get_R(), eng.get_Val()
+    assert common.rel_err(R1, golden[f"{name}/R"]) < ASM_TOL
+    assert common.rel_err(V1, golden[f"{name}/Val"]) < ASM_TOL
+    if scatter == abi.SCATTER_COLORED:
+        eng.alloc(1); eng.assemble(0, eq, dmn)
+        assert np.array_equal(eng.get_Val(), V1) and np.array_equal(eng.get_R(), R1)
+    eng.close()
+
+
+@pytest.mark.parametrize("ls_type,kw", [(abi.LS_GMRES, dict(mItr=20, sD=80, relTol=1e-10)), (abi.LS_CG, dict(mItr=2000, relTol=1e-10)),
+                                        (abi.LS_BICGS, dict(mItr=600, relTol=1e-10))], ids=["gmres", "cg", "bicgs"])
+@pytest.mark.parametrize("fluid", [False, True], ids=["heatS", "heatF"])
+def test_heat_solve_parity(fluid, ls_type, kw):
+    """dof = 1 (gmres_s / cgrad_s / bicgss, linear_solver/gmres.cpp:257-412, cgrad.cpp:225, bicgs.cpp:123) with a Dirichlet
+    face, against the compiled reference."""
+    from oracle import refbind
+    if not refbind.have_ref():
+        pytest.skip("needs oracle/_ref/libsvref.so")
+    if fluid and ls_type == abi.LS_CG:
+        pytest.skip("the heatF matrix is not symmetric")
+    from svmultiphysics_b200 import meshgen
+    m = meshgen.box_hex8(5, 4, 4, (1.0, 1.0, 1.0))
+    tDof, s = (5, 4) if fluid else (1, 0)
+    Ag, Yg, Dg, Bf = common.heat_state(m, tDof, s)
+    eq, dmn = abi.heat_eq(0.01, fluid, tDof=tDof, s=s), [abi.heat_domain(fluid, conductivity=0.5, source=1.0, rho=2.0)]
+    faces = [(abi.BC_DIR, m.faces["X0"], np.zeros((1, len(m.faces["X0"])), order="F"))]
+    orc = refbind.RefCase(); orc.set_coords(m.x); orc.add_mesh(m.IEN)
+    rowPtr, colPtr = orc.build_graph(len(faces))
+    eng = _engine(m, rowPtr, colPtr)
+    eng.set_num_faces(len(faces))
+    for i, (g, nodes, val) in enumerate(faces):
+        orc.set_face(i, g, nodes, val); eng.set_face(i, g, nodes, val)
+    orc.alloc(1); orc.set_state(Ag, Yg, Dg, Bf); orc.assemble(0, eq, dmn)
+    eng.alloc(1); eng.set_state(Ag, Yg, Dg, Bf); eng.assemble(0, eq, dmn)
+    assert common.rel_err(eng.get_R(), orc.get_R()) < ASM_TOL
+    assert common.rel_err(eng.get_Val(), orc.get_Val()) < ASM_TOL
+    ls = abi.ls_params(ls_type, **kw)
+    incL, res = np.ones(len(faces), np.int32), np.zeros(len(faces))
+    X0, o0, _ = orc.solve(1, ls_type, ls, incL, res)
+    X1, o1, _ = eng.solve(1, ls_type, ls, incL, res)
+    assert o1.RI.success == o0.RI.success and abs(o1.RI.itr - o0.RI.itr) <= max(2, o0.RI.itr // 20)
+    assert abs(o1.RI.iNorm - o0.RI.iNorm) <= 1e-10 * o0.RI.iNorm
+    assert common.rel_err(X1, X0) < 1e-7
+    eng.close()
+
+
+def test_heat_zero_jacobian_error():
+    """construct_heats throws "Jacobian for element e is < 0." when utils::is_zero(Jac) (heats.cpp:96-98)."""
+    from svmultiphysics_b200 import meshgen
+    from svmultiphysics_b200.engine import Svb200Error
+    m = meshgen.box_tet4(2, 2, 2, (1.0, 1.0, 1.0))
+    x = m.x.copy(order="F")
+    x[:, m.IEN[:, 5]] = x[:, [m.IEN[0, 5]]]            # collapse element 5
+    from oracle import refbind
+    _, rowPtr, colPtr = common.make_oracle(refbind.OracleCase, m)
+    eng = _engine(m, rowPtr, colPtr)
+    eng.set_coords(x)
+    Ag, Yg, Dg, Bf = common.heat_state(m, 1, 0)
+    eng.alloc(1); eng.set_state(Ag, Yg, Dg, Bf)
+    with pytest.raises(Svb200Error, match=r"\[construct_heats\] Jacobian for element"):
+        eng.assemble(0, abi.heat_eq(0.01, False), [abi.heat_domain(False)])
+    eng.close()

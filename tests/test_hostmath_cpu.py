@@ -177,3 +177,54 @@ def test_device_general_fluid_algebra_matches_golden(hostmath, case, factored):
     assert rc == 0
     assert common.rel_err(R.T, golden[f"{name}/R"]) < 1e-12
     assert common.rel_err(V.T, golden[f"{name}/Val"]) < 1e-12
+
+
+class HeatDmn(C.Structure):
+    _fields_ = [("rho", C.c_double), ("nu", C.c_double), ("s", C.c_double),
+                ("Id", C.c_int), ("active", C.c_int), ("pad0", C.c_int), ("pad1", C.c_int)]
+
+
+class HostHeatArgs(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("IEN", "x", "Ag", "Yg")] + \
+               [(k, C.c_int) for k in ("eNoN", "nEl", "nG", "tDof", "s", "mvMsh", "fluid", "pad")] + \
+               [(k, C.c_double) for k in ("dt", "af", "am", "gam")] + \
+               [("w", C.c_double * 8), ("N", (C.c_double * 8) * 8), ("Nxi", ((C.c_double * 3) * 8) * 8), ("dm", HeatDmn)]
+
+
+def _fill_tables(A, eNoN):
+    w, N, Nx = elements.tables(eNoN)
+    for g in range(len(w)):
+        A.w[g] = w[g]
+        for a in range(eNoN):
+            A.N[g][a] = N[a, g]
+            for k in range(3):
+                A.Nxi[g][a][k] = Nx[k, a, g]
+    return len(w)
+
+
+@pytest.mark.parametrize("name,mk,fluid,tDof,s,mv,dkw", common.HEAT_CASES, ids=[c[0] for c in common.HEAT_CASES])
+def test_device_heat_algebra_matches_golden(hostmath, name, mk, fluid, tDof, s, mv, dkw):
+    """svmultiphysics_b200/csrc/heat_elem.cuh compiled for the host against the R / Val that the unmodified reference
+    (heats_3d / heatf_3d) assembled (tests/golden/heat.npz), tolerance 1e-12."""
+    golden = common.load_golden("heat.npz")
+    assert hostmath.hostmath_sizeof_heatargs() == C.sizeof(HostHeatArgs)
+    m = mk()
+    Ag, Yg, _, _ = common.heat_state(m, tDof, s)
+    eq, d = abi.heat_eq(0.01, fluid, tDof=tDof, s=s, mvMsh=mv), abi.heat_domain(fluid, **dkw)
+    A = HostHeatArgs()
+    keep = [np.ascontiguousarray(m.IEN.T.astype(np.int32)), np.ascontiguousarray(m.x.T), np.ascontiguousarray(Ag.T),
+            np.ascontiguousarray(Yg.T)]
+    A.IEN, A.x, A.Ag, A.Yg = (k.ctypes.data for k in keep)
+    A.eNoN, A.nEl, A.tDof, A.s, A.mvMsh, A.fluid = m.eNoN, m.nEl, tDof, s, mv, int(fluid)
+    A.nG = _fill_tables(A, m.eNoN)
+    A.dt, A.af, A.am, A.gam = eq.dt, eq.af, eq.am, eq.gam
+    A.dm.rho, A.dm.nu, A.dm.s, A.dm.Id, A.dm.active = d.rho, d.conductivity, d.source_term, -1, 1
+    rowPtr, colPtr = golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"]
+    R = np.zeros(m.nNo)
+    V = np.zeros(len(colPtr))
+    rc = hostmath.hostmath_heat(C.byref(A), rowPtr.ctypes.data_as(C.c_void_p), colPtr.ctypes.data_as(C.c_void_p),
+                                R.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    assert np.abs(golden[f"{name}/R"]).max() > 0
+    assert common.rel_err(R, golden[f"{name}/R"].ravel()) < 1e-12
+    assert common.rel_err(V, golden[f"{name}/Val"].ravel()) < 1e-12
