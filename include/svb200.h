@@ -273,6 +273,12 @@ SVB200_API int svb200_add_host_contrib(svb200_ctx* ctx, int32_t dof, int32_t nR,
 /* all_fun::commu(R): shared-node sum of the residual across partitions (no-op for one rank). */
 SVB200_API int svb200_commu_R(svb200_ctx* ctx);
 
+/* ustruct::ustruct_r (solver/ustruct.cpp:1742-1845, called from Integrator::step after commu(R), Integrator.cpp:135-137):
+ * in the first Newton iteration of a time step (itr == 1, 1-based like eq.itr) R -= Kd (amg Ad - Yg(s..s+2)) / am with
+ * amg = (gam - am)/(gam - 1); later iterations leave R unchanged.  Ad(3,nNo) is com_mod.Ad in INPUT node order; Kd is what the
+ * last svb200_assemble(phys = USTRUCT) left on the device (download: SVB200_ARRAY_KD). */
+SVB200_API int svb200_ustruct_r(svb200_ctx* ctx, const svb200_eqparams* eq, int32_t itr, const double* Ad);
+
 /* fsils_solve: preconditions in place, runs the Krylov solver, writes the increment to R_out
  * (dof,nNo, INPUT node order; may be NULL to keep it on the device only). */
 SVB200_API int svb200_solve(svb200_ctx* ctx, int32_t dof, int32_t ls_type, int32_t prec, const svb200_lsparams* ls,

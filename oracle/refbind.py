@@ -240,6 +240,16 @@ class RefCase(_FlatCase):
         self._call("set_backend", C.c_void_p(self.backend), C.cast(host.b200host_global_eq_assem, C.c_void_p),
                    C.cast(host.b200host_download, C.c_void_p))
 
+    def get_Kd(self):
+        """com_mod.Kd(12, nnz): displacement tangent of the ustruct equation (solver/ustruct.cpp:1621)."""
+        K = np.zeros((12, self.nnz), order="F")
+        self._call("get", C.c_int(abi.ARRAY_KD), _d(K))
+        return K
+
+    def ustruct_r(self, itr, Ad):
+        """ustruct::ustruct_r (solver/ustruct.cpp:1742-1845) on the assembled R / Kd."""
+        self._call("ustruct_r", C.c_int(itr), _d(_f64(Ad)))
+
     def backend_launch_count(self):
         return int(type(self)._host.b200host_launch_count(C.c_void_p(self.backend)))
 

@@ -19,7 +19,7 @@ PREC_RCS = 1
 SOLID_VISC_NONE, SOLID_VISC_NEWTONIAN, SOLID_VISC_POTENTIAL = 0, 1, 2
 BC_DIR, BC_NEU = 0, 1
 SCATTER_ATOMIC, SCATTER_COLORED = 0, 1
-ARRAY_R, ARRAY_VAL, ARRAY_W = 0, 1, 2
+ARRAY_R, ARRAY_VAL, ARRAY_W, ARRAY_KD = 0, 1, 2, 3
 
 
 class EqParams(C.Structure):

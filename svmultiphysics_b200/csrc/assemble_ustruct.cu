@@ -1,0 +1,354 @@
+// assemble_ustruct.cu — element loop + scatter of the mixed velocity-pressure solid.
+//
+// Replaces ustruct::construct_usolid, ustruct_3d_m, ustruct_3d_c and ustruct_do_assem
+// (Code/Source/solver/ustruct.cpp:203-400, 1165-1591, 629-871, 1595-1737) for equal-order (VMS) TET4 and HEX8 meshes,
+// and ustruct::ustruct_r (:1742-1845).  Outputs: R(4,nNo), Val(16,nnz) and the displacement tangent Kd(12,nnz).
+//
+// Mapping (like assemble_struct.cu): ENON lanes per element, two phases.  Phase A: lane g evaluates Gauss point g ONCE
+// per element (gnn, F, F^-1, compute_pk2cc without the volumetric part, g_vol_pen, compute_tau, the strong residuals)
+// and leaves a UGP (110 doubles) in shared memory.  Phase B: lane a owns row a of the element matrices; column nodes
+// are taken NB at a time so that the 28 NB accumulators (16 of lK + 12 of lKd per block) stay in registers, the Gauss
+// loop is inside, and each finished block goes out as 16 + 12 contiguous doubles.
+#include <vector>
+#include "svb200_internal.h"
+#include "ustruct_elem.cuh"
+#include "fsils_kernels.h"
+
+namespace svb {
+
+struct UstructArgs {
+  const int* IEN;
+  const int* eId;
+  const int* slot;
+  const int* perm;
+  const double* fN;
+  const double* x;
+  const double* Ag;
+  const double* Yg;
+  const double* Dg;
+  const double* Bf;
+  double* R;
+  double* Val;
+  double* Kd;
+  int* err;
+  int e0, e1;
+  int tDof, s, nFn, nDmn, nG, pad;
+  double dt, af, am, gam;
+  double w[MAX_NG];
+  double N[MAX_NG][MAX_ENON];
+  double Nxi[MAX_NG][MAX_ENON][3];
+  UstructDmn dmn[MAX_DMN];
+  int active[MAX_DMN];
+};
+
+constexpr int USTRUCT_THREADS = 64;
+constexpr int UGP_LD = (int)(sizeof(UGP) / sizeof(double));
+// per-element stride in doubles: the elements of a warp (4 for HEX8, 8 for TET4) read the same UGP field at the same
+// time, so the stride is padded to 4 (HEX8) / 2 (TET4) mod 16 to spread them over the banks
+__host__ __device__ constexpr int ustruct_per_el(int enon)
+{
+  const int n = enon * UGP_LD, want = (enon == 8) ? 4 : 2;
+  return n + ((want - (n % 16)) + 16) % 16;
+}
+
+template <bool ATOMIC>
+__device__ __forceinline__ void uadd(double* p, double v)
+{
+  if (ATOMIC) asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+  else *p += v;
+}
+
+template <int ENON, bool ATOMIC>
+__global__ void __launch_bounds__(USTRUCT_THREADS)
+assemble_ustruct_kernel(const __grid_constant__ UstructArgs P)
+{
+  constexpr int EPW = 32 / ENON;
+  constexpr int NB = 2;
+  constexpr int PER_EL = ustruct_per_el(ENON);
+  extern __shared__ double sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int a = lane % ENON, el = lane / ENON;
+  UGP* gp = reinterpret_cast<UGP*>(sm + (size_t)(warp * EPW + el) * PER_EL);
+
+  const long long idx = (long long)P.e0 + ((long long)blockIdx.x * (USTRUCT_THREADS / 32) + warp) * EPW + el;
+  bool active = idx < P.e1;
+  int e = 0;
+  if (active) e = P.perm ? P.perm[idx] : (int)idx;
+  int iD = 0;
+  if (active) {
+    for (int d = 0; d < P.nDmn; d++) {
+      iD = d;
+      if (P.dmn[d].st.Id == -1) break;
+      if (P.eId != nullptr && ((P.eId[e] >> P.dmn[d].st.Id) & 1)) break;
+    }
+    if (!P.active[iD]) active = false;
+  }
+  const UstructDmn& dm = P.dmn[iD];
+  const double af = P.af * P.gam * P.dt, am = P.am;
+
+  // ---- phase A: lane g = a evaluates Gauss point g (nG == ENON) ------------------------------------------------
+  int node[ENON];
+  if (active) {
+    double xl[ENON][3], ql[ENON][3], vl[ENON][3], dl[ENON][3], pl[ENON], pdl[ENON];
+#pragma unroll
+    for (int b = 0; b < ENON; b++) {
+      node[b] = P.IEN[(size_t)e * ENON + b];
+      const size_t n = (size_t)node[b];
+      const double* A = P.Ag + (size_t)P.tDof * n + P.s;
+      const double* Y = P.Yg + (size_t)P.tDof * n + P.s;
+      const double* D = P.Dg + (size_t)P.tDof * n + P.s;
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        xl[b][i] = __ldg(P.x + 3 * n + i);
+        ql[b][i] = __ldg(A + i) - __ldg(P.Bf + 3 * n + i);
+        vl[b][i] = __ldg(Y + i);
+        dl[b][i] = __ldg(D + i);
+      }
+      pl[b] = __ldg(Y + 3);
+      pdl[b] = __ldg(A + 3);
+    }
+    double fN[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    if (P.fN != nullptr)
+      for (int k = 0; k < P.nFn && k < 2; k++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) fN[k][i] = __ldg(P.fN + (size_t)3 * P.nFn * e + 3 * k + i);
+    const int g = a;
+    UGP& q = gp[g];                       // written in place: a local copy would cost 880 B of stack per thread
+    ustruct_gauss_point<ENON>(dm, P.dt, P.af, P.am, P.gam, P.w[g], P.N[g], P.Nxi[g], xl, ql, vl, dl, pl, pdl, fN, q);
+    // construct_usolid throws when utils::is_zero(Jac) (ustruct.cpp:312-314); q.w = w_g * Jac
+    if (fabs(q.w) < fabs(P.w[g]) * 10.0 * 2.220446049250313e-16 * 2.220446049250313e-16) atomicMax(P.err, e + 1);
+  }
+  __syncwarp();
+  if (!active) return;
+
+  // ---- phase B: lane a owns row a ------------------------------------------------------------------------------
+  int na = 0;
+#pragma unroll
+  for (int b = 0; b < ENON; b++)
+    if (b == a) na = node[b];
+  {
+    double lR[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+    for (int g = 0; g < ENON; g++) {
+      UNode A;
+      ustruct_node(gp[g], P.N[g][a], P.Nxi[g][a], A);
+      ustruct_resid(gp[g], A, lR);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) uadd<ATOMIC>(P.R + (size_t)4 * na + i, lR[i]);
+  }
+  const int* sl = P.slot + (size_t)e * ENON * ENON + a * ENON;
+#pragma unroll 1
+  for (int b0 = 0; b0 < ENON; b0 += NB) {
+    double K[NB][16], Kd[NB][12];
+#pragma unroll
+    for (int k = 0; k < NB; k++) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) K[k][i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < 12; i++) Kd[k][i] = 0.0;
+    }
+#pragma unroll 1
+    for (int g = 0; g < ENON; g++) {
+      const UGP& q = gp[g];
+      UNode A;
+      double Bma[6][3];
+      ustruct_node(q, P.N[g][a], P.Nxi[g][a], A);
+      make_Bm(A.Nx, q.F, Bma);
+#pragma unroll
+      for (int k = 0; k < NB; k++) {
+        UNode B;
+        double Bmb[6][3], DBmb[6][3];
+        ustruct_node(q, P.N[g][b0 + k], P.Nxi[g][b0 + k], B);
+        make_Bm(B.Nx, q.F, Bmb);
+        make_DBm(q.Dm, Bmb, DBmb);
+        ustruct_block(q, af, am, A, B, Bma, DBmb, K[k], Kd[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NB; k++) {
+      const size_t s = (size_t)sl[b0 + k];
+      double* v = P.Val + 16 * s;
+      double* d = P.Kd + 12 * s;
+#pragma unroll
+      for (int i = 0; i < 16; i++) uadd<ATOMIC>(v + i, K[k][i]);
+#pragma unroll
+      for (int i = 0; i < 12; i++) uadd<ATOMIC>(d + i, Kd[k][i]);
+    }
+  }
+}
+
+template <int ENON>
+static int launch_ustruct(svb200_ctx* ctx, const UstructArgs& A, bool atomic)
+{
+  constexpr int EPB = (USTRUCT_THREADS / 32) * (32 / ENON);
+  constexpr size_t smem = sizeof(double) * (size_t)EPB * ustruct_per_el(ENON);
+  static bool configured = false;
+  if (!configured) {
+    SVB_CUDA(cudaFuncSetAttribute(assemble_ustruct_kernel<ENON, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVB_CUDA(cudaFuncSetAttribute(assemble_ustruct_kernel<ENON, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const long long n = (long long)A.e1 - A.e0;
+  if (n <= 0) return SVB200_OK;
+  const unsigned blocks = (unsigned)((n + EPB - 1) / EPB);
+  if (atomic) assemble_ustruct_kernel<ENON, true><<<blocks, USTRUCT_THREADS, smem, ctx->stream>>>(A);
+  else assemble_ustruct_kernel<ENON, false><<<blocks, USTRUCT_THREADS, smem, ctx->stream>>>(A);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
+int run_assemble_ustruct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn)
+{
+  SVB_REQUIRE(nDmn >= 1 && nDmn <= MAX_DMN, "svb200_assemble: between 1 and 8 domains are supported");
+  SVB_REQUIRE(eq->dof == 4 && ctx->dof == 4, "svb200_assemble: the ustruct equation has dof = 4 (call svb200_alloc(4))");
+  SVB_REQUIRE(eq->tDof == ctx->tDof && ctx->d_Dg && ctx->d_Yg && ctx->d_Ag, "svb200_assemble: state not set or tDof mismatch");
+  SVB_REQUIRE(eq->s >= 0 && eq->s + 4 <= eq->tDof, "svb200_assemble: eq.s out of range");
+  SVB_REQUIRE(eq->vmsStab == 1, "svb200_assemble: only equal-order (VMS-stabilised) ustruct elements are supported");
+  SVB_REQUIRE(ctx->d_x, "svb200_assemble: coordinates not set");
+  SVB_REQUIRE(m.eNoN == 4 || m.eNoN == 8, "svb200_assemble: ustruct is implemented for TET4 and HEX8 meshes");
+  SVB_REQUIRE(m.nG == m.eNoN, "svb200_assemble: the ustruct kernel expects nG == eNoN (TET4: 4, HEX8: 8 Gauss points)");
+  // Kd((nsd+1)*nsd, nnz): allocated with the first ustruct assembly, zeroed there and by every later svb200_alloc
+  // (Integrator::step zeroes it together with R and Val, solver/Integrator.cpp:106-109)
+  if (!ctx->d_Kd) {
+    SVB_CUDA(cudaMalloc(&ctx->d_Kd, sizeof(double) * 12 * std::max<size_t>((size_t)ctx->nnz, 1)));
+    SVB_CUDA(cudaMemsetAsync(ctx->d_Kd, 0, sizeof(double) * 12 * (size_t)ctx->nnz, ctx->stream));
+  }
+  UstructArgs A;
+  memset(&A, 0, sizeof(A));
+  A.IEN = m.d_IEN; A.eId = m.d_eId; A.slot = m.d_slot; A.perm = nullptr; A.fN = m.d_fN;
+  A.x = ctx->d_x; A.Ag = ctx->d_Ag; A.Yg = ctx->d_Yg; A.Dg = ctx->d_Dg; A.Bf = ctx->d_Bf;
+  A.R = ctx->d_R; A.Val = ctx->d_Val; A.Kd = ctx->d_Kd;
+  if (!ctx->d_err) {
+    SVB_CUDA(cudaMalloc(&ctx->d_err, sizeof(int)));
+    SVB_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+  }
+  A.err = ctx->d_err;
+  A.e0 = 0; A.e1 = m.nEl;
+  A.tDof = eq->tDof; A.s = eq->s; A.nFn = m.nFn; A.nDmn = nDmn; A.nG = m.nG;
+  A.dt = eq->dt; A.af = eq->af; A.am = eq->am; A.gam = eq->gam;
+  for (int g = 0; g < m.nG; g++) {
+    A.w[g] = m.w[g];
+    for (int a = 0; a < m.eNoN; a++) {
+      A.N[g][a] = m.N[(size_t)g * m.eNoN + a];
+      for (int k = 0; k < 3; k++) A.Nxi[g][a][k] = m.Nx[((size_t)g * m.eNoN + a) * 3 + k];
+    }
+  }
+  bool whole = false;
+  for (int d = 0; d < nDmn; d++) {
+    StructDmn& o = A.dmn[d].st;
+    o.rho = dmn[d].rho;
+    for (int k = 0; k < 3; k++) o.f[k] = dmn[d].f[k];
+    o.dmp = dmn[d].dmp;
+    o.Kpen = dmn[d].Kpen; o.C10 = dmn[d].C10; o.C01 = dmn[d].C01;
+    o.bff = dmn[d].bff; o.bss = dmn[d].bss; o.bfs = dmn[d].bfs;
+    o.st_a = dmn[d].st_a; o.st_b = dmn[d].st_b; o.aff = dmn[d].aff; o.ass = dmn[d].ass; o.afs = dmn[d].afs;
+    o.kap = dmn[d].kap; o.khs = dmn[d].khs;
+    o.isoType = dmn[d].isoType; o.volType = dmn[d].volType;
+    o.visc_mu = 0.0; o.viscType = SVB200_SOLID_VISC_NONE;
+    o.Id = dmn[d].Id;
+    o.isStruct = A.active[d] = (dmn[d].phys == SVB200_PHYS_USTRUCT);
+    A.dmn[d].E = dmn[d].E; A.dmn[d].nu = dmn[d].nu; A.dmn[d].ctM = dmn[d].ctau_M; A.dmn[d].ctC = dmn[d].ctau_C;
+    SVB_REQUIRE(o.Id >= -1 && o.Id < 31, "svb200_assemble: domain Id out of range");
+    if (A.active[d]) {
+      SVB_REQUIRE(o.isoType >= SVB200_ISO_NHK && o.isoType <= SVB200_ISO_HO_MA, "svb200_assemble: constitutive model not implemented");
+      if (dmn[d].solid_visc_mu != 0.0) {
+        set_error("svb200_assemble: solid viscosity is not implemented for the ustruct equation in this build");
+        return SVB200_ERR_UNSUPPORTED;
+      }
+      const bool fibres = (m.nFn == 2 && m.d_fN);
+      if ((o.isoType == SVB200_ISO_GUCCIONE || o.isoType == SVB200_ISO_HGO || o.isoType == SVB200_ISO_HO || o.isoType == SVB200_ISO_HO_MA) && !fibres) {
+        set_error("[compute_pk2cc] Min fiber directions not defined for this material model.");
+        return SVB200_ERR_INVALID;
+      }
+    }
+    whole |= (o.Id == -1);
+  }
+  if (!whole && !m.d_eId) { set_error("eId is not allocated"); return SVB200_ERR_INVALID; }
+  const bool atomic = (eq->scatter == SVB200_SCATTER_ATOMIC);
+  auto launch = [&](const UstructArgs& B) { return m.eNoN == 8 ? launch_ustruct<8>(ctx, B, atomic) : launch_ustruct<4>(ctx, B, atomic); };
+  int rc = SVB200_OK;
+  if (atomic) rc = launch(A);
+  else {
+    A.perm = m.d_color_perm;
+    for (size_t c = 0; c + 1 < m.color_off.size() && rc == SVB200_OK; c++) {
+      A.e0 = m.color_off[c];
+      A.e1 = m.color_off[c + 1];
+      rc = launch(A);
+    }
+  }
+  if (rc) return rc;
+  int e = 0;
+  SVB_CUDA(cudaMemcpyAsync(&e, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (e != 0) {
+    SVB_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+    set_error("[construct_usolid] Jacobian for element " + std::to_string(e - 1) + " is < 0.");
+    return SVB200_ERR_NUMERIC;
+  }
+  return SVB200_OK;
+}
+
+// ---- ustruct::ustruct_r (ustruct.cpp:1742-1845) -----------------------------------------------------------------
+// Rd = amg Ad - Yg(s..s+2);  KU = Kd Rd (4x3 blocks);  halo sum;  R -= KU / am.   Only in the first Newton iteration.
+__global__ void __launch_bounds__(256)
+ustruct_rd_kernel(int nNo, int tDof, int s, double amg, const double* __restrict__ Ad, const double* __restrict__ Yg,
+                  double* __restrict__ Rd)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 3 * nNo) return;
+  const int n = t / 3, i = t % 3;
+  Rd[t] = amg * Ad[t] - Yg[(size_t)tDof * n + s + i];
+}
+
+__global__ void __launch_bounds__(256)
+ustruct_kd_spmv_kernel(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ colPtr, const double* __restrict__ Kd,
+                       const double* __restrict__ Rd, double* __restrict__ KU)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)nNo * 4) return;
+  const int row = (int)(t >> 2), i = (int)(t & 3);
+  double acc = 0.0;
+  for (int k = rowPtr[row]; k < rowPtr[row + 1]; k++) {
+    const double* v = Kd + (size_t)k * 12 + 3 * i;
+    const double* u = Rd + (size_t)colPtr[k] * 3;
+    acc += v[0] * u[0] + v[1] * u[1] + v[2] * u[2];
+  }
+  KU[t] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+ustruct_r_update_kernel(size_t n, double ami, const double* __restrict__ KU, double* __restrict__ R)
+{
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) R[t] -= ami * KU[t];
+}
+
+int run_ustruct_r(svb200_ctx* ctx, const svb200_eqparams* eq, int itr, const double* d_Ad)
+{
+  if (itr > 1) return SVB200_OK;            // Rd = 0: nothing to add (ustruct.cpp:1773-1775)
+  const int n = ctx->nNo;
+  if (n == 0) return SVB200_OK;
+  double* buf = nullptr;
+  SVB_CUDA(cudaMalloc(&buf, sizeof(double) * 7 * (size_t)n));
+  double* Rd = buf;
+  double* KU = buf + 3 * (size_t)n;
+  const double amg = (eq->gam - eq->am) / (eq->gam - 1.0), ami = 1.0 / eq->am;
+  ustruct_rd_kernel<<<(3 * n + 255) / 256, 256, 0, ctx->stream>>>(n, ctx->tDof, eq->s, amg, d_Ad, ctx->d_Yg, Rd);
+  ustruct_kd_spmv_kernel<<<(unsigned)(((long long)n * 4 + 255) / 256), 256, 0, ctx->stream>>>(n, ctx->d_rowPtr, ctx->d_colPtr, ctx->d_Kd, Rd, KU);
+  ctx->launches += 2;
+  int rc = halo_sum(ctx, 4, KU);
+  if (!rc) {
+    ustruct_r_update_kernel<<<(unsigned)(((size_t)n * 4 + 255) / 256), 256, 0, ctx->stream>>>((size_t)n * 4, ami, KU, ctx->d_R);
+    ctx->launches++;
+  }
+  cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+  cudaFree(buf);
+  if (rc) return rc;
+  SVB_CUDA(ce);
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
+}  // namespace svb

@@ -207,7 +207,7 @@ int svb200_destroy(svb200_ctx* ctx)
   cudaFree(ctx->d_map); cudaFree(ctx->d_rowPtr); cudaFree(ctx->d_colPtr); cudaFree(ctx->d_diagPtr);
   cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf); cudaFree(ctx->d_Do);
   cudaFree(ctx->d_Ao); cudaFree(ctx->d_Yo); cudaFree(ctx->d_An); cudaFree(ctx->d_Yn); cudaFree(ctx->d_Dn); cudaFree(ctx->d_nodeflag);
-  cudaFree(ctx->d_err);
+  cudaFree(ctx->d_err); cudaFree(ctx->d_Kd); cudaFree(ctx->d_Ad);
   cudaFree(ctx->d_stage); cudaFree(ctx->d_R); cudaFree(ctx->d_Val); cudaFree(ctx->d_W);
   cudaFree(ctx->d_work); cudaFree(ctx->d_red); cudaFree(ctx->d_tslot);
   cudaFreeHost(ctx->h_pinned); cudaFreeHost(ctx->h_cg); cudaFree(ctx->d_cg);
@@ -440,6 +440,8 @@ int svb200_alloc(svb200_ctx* ctx, int32_t dof)
   ctx->dof = dof;
   if (nR) SVB_CUDA(cudaMemsetAsync(ctx->d_R, 0, sizeof(double) * nR, ctx->stream));
   if (nV) SVB_CUDA(cudaMemsetAsync(ctx->d_Val, 0, sizeof(double) * nV, ctx->stream));
+  // com_mod.Kd is zeroed with the linear system (solver/Integrator.cpp:106-109)
+  if (ctx->d_Kd && ctx->nnz) SVB_CUDA(cudaMemsetAsync(ctx->d_Kd, 0, sizeof(double) * 12 * (size_t)ctx->nnz, ctx->stream));
   return SVB200_OK;
 }
 
@@ -774,6 +776,9 @@ int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, cons
     case SVB200_PHYS_LELAS:
       TRY(run_assemble_mesh(ctx, m, eq, dmn, nDmn));
       break;
+    case SVB200_PHYS_USTRUCT:
+      TRY(run_assemble_ustruct(ctx, m, eq, dmn, nDmn));
+      break;
     case SVB200_PHYS_HEATS:
     case SVB200_PHYS_HEATF:
       TRY(run_assemble_heat(ctx, m, eq, dmn, nDmn));
@@ -852,6 +857,18 @@ int svb200_commu_R(svb200_ctx* ctx)
   return SVB200_OK;
 }
 
+int svb200_ustruct_r(svb200_ctx* ctx, const svb200_eqparams* eq, int32_t itr, const double* Ad)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(eq && Ad, "svb200_ustruct_r: null parameters");
+  SVB_REQUIRE(eq->phys == SVB200_PHYS_USTRUCT, "svb200_ustruct_r: the equation is not ustruct");
+  SVB_REQUIRE(ctx->dof == 4 && ctx->d_R && ctx->d_Kd && ctx->d_Yg, "svb200_ustruct_r: assemble the ustruct equation first");
+  SVB_REQUIRE(eq->tDof == ctx->tDof && eq->s >= 0 && eq->s + 4 <= eq->tDof, "svb200_ustruct_r: tDof / eq.s mismatch");
+  TRY(upload_nodal(ctx, 3, Ad, &ctx->d_Ad));
+  TRY(run_ustruct_r(ctx, eq, itr, ctx->d_Ad));
+  return SVB200_OK;
+}
+
 int svb200_solve(svb200_ctx* ctx, int32_t dof, int32_t ls_type, int32_t prec, const svb200_lsparams* ls,
                  int32_t nFaces, const int32_t* incL, const double* res, double* R_out, svb200_lsresult* result)
 {
@@ -873,26 +890,31 @@ int svb200_solve(svb200_ctx* ctx, int32_t dof, int32_t ls_type, int32_t prec, co
 }
 
 // Val is returned in the caller's CSR slot order: caller row a occupies internal row map[a].
-static int copy_val(svb200_ctx* ctx, int dof, double* host, bool to_host)
+// Per-CSR-entry blocks of d2 doubles (Val: dof*dof, Kd: 12) between the caller's and the internal row order.
+static int copy_blocks(svb200_ctx* ctx, double* d_blocks, size_t d2, double* host, bool to_host)
 {
-  const size_t d2 = (size_t)dof * dof;
   if (!ctx->has_map) {
     if (to_host)
-      SVB_CUDA(cudaMemcpyAsync(host, ctx->d_Val, sizeof(double) * d2 * ctx->nnz, cudaMemcpyDeviceToHost, ctx->stream));
+      SVB_CUDA(cudaMemcpyAsync(host, d_blocks, sizeof(double) * d2 * ctx->nnz, cudaMemcpyDeviceToHost, ctx->stream));
     else
-      SVB_CUDA(cudaMemcpyAsync(ctx->d_Val, host, sizeof(double) * d2 * ctx->nnz, cudaMemcpyHostToDevice, ctx->stream));
+      SVB_CUDA(cudaMemcpyAsync(d_blocks, host, sizeof(double) * d2 * ctx->nnz, cudaMemcpyHostToDevice, ctx->stream));
     SVB_CUDA(cudaStreamSynchronize(ctx->stream));
     return SVB200_OK;
   }
   for (int a = 0; a < ctx->nNo; a++) {
     const size_t len = (size_t)(ctx->h_rowPtr_in[a + 1] - ctx->h_rowPtr_in[a]) * d2;
     double* h = host + (size_t)ctx->h_rowPtr_in[a] * d2;
-    double* d = ctx->d_Val + (size_t)ctx->h_rowPtr[ctx->h_map[a]] * d2;
+    double* d = d_blocks + (size_t)ctx->h_rowPtr[ctx->h_map[a]] * d2;
     if (to_host) SVB_CUDA(cudaMemcpyAsync(h, d, sizeof(double) * len, cudaMemcpyDeviceToHost, ctx->stream));
     else SVB_CUDA(cudaMemcpyAsync(d, h, sizeof(double) * len, cudaMemcpyHostToDevice, ctx->stream));
   }
   SVB_CUDA(cudaStreamSynchronize(ctx->stream));
   return SVB200_OK;
+}
+
+static int copy_val(svb200_ctx* ctx, int dof, double* host, bool to_host)
+{
+  return copy_blocks(ctx, ctx->d_Val, (size_t)dof * dof, host, to_host);
 }
 
 int svb200_download(svb200_ctx* ctx, int32_t what, double* dst)
@@ -909,6 +931,9 @@ int svb200_download(svb200_ctx* ctx, int32_t what, double* dst)
     case SVB200_ARRAY_W:
       SVB_REQUIRE(ctx->d_W, "svb200_download: W not computed yet");
       return download_nodal(ctx, ctx->dof, ctx->d_W, dst);
+    case SVB200_ARRAY_KD:
+      SVB_REQUIRE(ctx->d_Kd, "svb200_download: Kd exists only after a ustruct assembly");
+      return copy_blocks(ctx, ctx->d_Kd, 12, dst, true);
   }
   set_error("svb200_download: unknown array id");
   return SVB200_ERR_INVALID;

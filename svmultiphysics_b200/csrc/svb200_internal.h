@@ -152,6 +152,8 @@ struct svb200_ctx {
   double* d_Val = nullptr;
   size_t R_cap = 0, Val_cap = 0;   // capacities in doubles
   double* d_W = nullptr;           // (dof,nNo) preconditioner scaling
+  double* d_Kd = nullptr;          // (12,nnz) displacement tangent of the ustruct equation (com_mod.Kd), assemble_ustruct.cu
+  double* d_Ad = nullptr;          // (3,nNo) com_mod.Ad of the last svb200_ustruct_r
   size_t W_cap = 0;
 
   std::vector<svb::Mesh> mesh;
@@ -211,6 +213,9 @@ int upload_fluid_gen_tables(svb200_ctx* ctx, Mesh& m);
 int run_assemble_fluid_gen(svb200_ctx* ctx, const Mesh& m, const FluidArgs& F);
 int run_assemble_struct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);
 int run_assemble_mesh(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);
+// assemble_ustruct.cu
+int run_assemble_ustruct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);
+int run_ustruct_r(svb200_ctx* ctx, const svb200_eqparams* eq, int itr, const double* d_Ad);
 // assemble_heat.cu
 int run_assemble_heat(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);
 // assemble_bnd.cu

@@ -200,3 +200,40 @@ def heat_state(m, tDof, s, seed=47):
     Dg = np.zeros((tDof, m.nNo), order="F")
     Bf = np.zeros((3, m.nNo), order="F")
     return Ag, Yg, Dg, Bf
+
+
+# ---- mixed velocity-pressure solid (ustruct) ------------------------------------------------------
+# (name, mesh factory, ustruct_domain kwargs, number of fibre families)
+USTRUCT_CASES = [
+    ("tet4_nHK_ST91", _tet, dict(E=1.0e6, nu=0.45, Kpen=1.0e6 / (3 * (1 - 0.9)), rho=1.2, ctau_M=1e-3, ctau_C=1e-3, f=(0.1, -0.2, 0.3)), 0),  # ustruct/block_compression
+    ("hex8_nHK_M94", _hex_skewed, dict(volType=abi.VOL_M94, E=2.0e5, nu=0.3, Kpen=1.0e6, rho=1.0, ctau_M=1e-2, ctau_C=1e-2), 0),
+    ("hex8_MR_Quad_incompressible", _hex_skewed, dict(isoType=abi.ISO_MR, volType=abi.VOL_QUAD, C10=1e5, C01=3e4, E=8e5, nu=0.5, Kpen=5.0e6,
+                                                      rho=1.0, ctau_M=1e-3, ctau_C=1e-5), 0),
+    ("tet4_HO_ma_fibres", _tet, dict(isoType=abi.ISO_HO_MA, st_a=590.0, st_b=8.023, aff=184720.0, bff=16.026, ass=24810.0, bss=11.12,
+                                     afs=2160.0, bfs=11.436, khs=100.0, E=1.0e5, nu=0.483333, Kpen=1e6, rho=1.0, ctau_M=1e-5, ctau_C=1e-5), 2),
+    ("hex8_nHK_no_penalty", _hex_skewed, dict(E=1.0e6, nu=0.4, Kpen=0.0, rho=2.0, ctau_M=1e-3, ctau_C=1e-3), 0),
+]
+
+
+def ustruct_state(m, nFn=0, seed=23):
+    """tDof = 4: velocity + pressure in Yg, their rates in Ag, displacement in Dg(0..2)."""
+    rng = np.random.default_rng(seed)
+    L = m.x.max()
+    Dg = np.zeros((4, m.nNo), order="F")
+    Dg[:3] = 0.02 * L * (m.x / L) * np.array([[1.0], [-0.5], [0.3]]) + 2e-3 * L * rng.standard_normal((3, m.nNo))
+    Yg = np.asfortranarray(0.1 * rng.standard_normal((4, m.nNo)))
+    Yg[3] = 1.0e3 * (1.0 + 0.3 * rng.standard_normal(m.nNo))
+    Ag = np.asfortranarray(rng.standard_normal((4, m.nNo)))
+    Ag[3] *= 50.0
+    Bf = np.asfortranarray(0.1 * rng.standard_normal((3, m.nNo)))
+    fN = None
+    if nFn:
+        f = rng.standard_normal((3, m.nEl)); f /= np.linalg.norm(f, axis=0)
+        s = rng.standard_normal((3, m.nEl)); s -= (s * f).sum(0) * f; s /= np.linalg.norm(s, axis=0)
+        fN = np.asfortranarray(np.vstack([f, s]))
+    return Ag, Yg, Dg, Bf, fN
+
+
+def ustruct_Ad(m, seed=29):
+    """com_mod.Ad(3, tnNo): time derivative of the displacement (Integrator.cpp:412, ustruct_r)."""
+    return np.asfortranarray(0.05 * np.random.default_rng(seed).standard_normal((3, m.nNo)))

@@ -98,10 +98,29 @@ def heat_golden():
     print("wrote heat.npz with", len(out), "arrays")
 
 
+def ustruct_golden():
+    """Assembled R / Val / Kd of the mixed solid (ustruct_3d_m/c + ustruct_do_assem) and R after ustruct_r."""
+    out = {}
+    for name, mk, dkw, nFn in common.USTRUCT_CASES:
+        m = mk()
+        Ag, Yg, Dg, Bf, fN = common.ustruct_state(m, nFn)
+        c = RefCase(); c.set_coords(m.x); c.add_mesh(m.IEN, nFn=nFn, fN=fN)
+        rowPtr, colPtr = c.build_graph(0)
+        eq, dmn = abi.ustruct_eq(1e-3), [abi.ustruct_domain(**dkw)]
+        c.alloc(4); c.set_state(Ag, Yg, Dg, Bf); c.assemble(0, eq, dmn)
+        out[f"{name}/R"], out[f"{name}/Val"], out[f"{name}/Kd"] = c.get_R(), c.get_Val(), c.get_Kd()
+        out[f"{name}/rowPtr"], out[f"{name}/colPtr"] = rowPtr, colPtr
+        Ad = common.ustruct_Ad(m)
+        c.ustruct_r(1, Ad)
+        out[f"{name}/R_after_ustruct_r"] = c.get_R()
+    np.savez_compressed(os.path.join(HERE, "ustruct.npz"), **out)
+    print("wrote ustruct.npz with", len(out), "arrays")
+
+
 if __name__ == "__main__":
     if not have_ref():
         raise SystemExit("oracle/_ref/libsvref.so is missing: run `make -C oracle ref` first")
     only = sys.argv[1:]
-    for fn in (fluid_golden, struct_golden, fluid_gen_golden, heat_golden):
+    for fn in (fluid_golden, struct_golden, fluid_gen_golden, heat_golden, ustruct_golden):
         if not only or fn.__name__.replace("_golden", "") in only:
             fn()

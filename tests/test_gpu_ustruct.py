@@ -1,0 +1,100 @@
+"""GPU parity tests for the mixed velocity-pressure solid (ustruct): R / Val / Kd against the golden
+vectors of the compiled reference (ustruct_3d_m/c + ustruct_do_assem), ustruct_r, and a GMRES solve."""
+import numpy as np
+import pytest
+
+from svmultiphysics_b200 import abi, elements
+from tests import common
+
+pytestmark = pytest.mark.gpu
+ASM_TOL = 1e-12
+VAL_GROUPS = ([0, 1, 2, 4, 5, 6, 8, 9, 10], [3, 7, 11], [12, 13, 14], [15])   # (v,v) (v,p) (p,v) (p,p): orders of magnitude apart
+
+
+def _engine(m, rowPtr, colPtr, nFn=0, fN=None):
+    from svmultiphysics_b200.engine import Engine
+    e = Engine(0)
+    e.set_graph(rowPtr, colPtr)
+    w, N, Nx = elements.tables(m.eNoN)
+    e.set_mesh(0, m.IEN, w, N, Nx, eId=m.eId, nFn=nFn, fN=fN)
+    e.set_coords(m.x)
+    return e
+
+
+@pytest.mark.parametrize("scatter", [abi.SCATTER_ATOMIC, abi.SCATTER_COLORED])
+@pytest.mark.parametrize("name,mk,dkw,nFn", common.USTRUCT_CASES, ids=[c[0] for c in common.USTRUCT_CASES])
+def test_ustruct_assembly_matches_golden(name, mk, dkw, nFn, scatter):
+    golden = common.load_golden("ustruct.npz")
+    m = mk()
+    Ag, Yg, Dg, Bf, fN = common.ustruct_state(m, nFn)
+    eq, dmn = abi.ustruct_eq(1e-3, scatter=scatter), [abi.ustruct_domain(**dkw)]
+    eng = _engine(m, golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"], nFn, fN)
+    eng.alloc(4); eng.set_state(Ag, Yg, Dg, Bf); eng.assemble(0, eq, dmn)
+    R1, V1, K1 = eng.get_R(), eng.get_Val(), eng.get_Kd()
+    assert common.rel_err(R1, golden[f"{name}/R"]) < ASM_TOL
+    assert common.rel_err(K1, golden[f"{name}/Kd"]) < ASM_TOL
+    for rows in VAL_GROUPS:
+        assert common.rel_err(V1[rows], golden[f"{name}/Val"][rows]) < ASM_TOL
+    # ustruct_r, first Newton iteration: R -= Kd (amg Ad - Yg) / am; later iterations: unchanged
+    eng.ustruct_r(eq, 1, common.ustruct_Ad(m))
+    R2 = eng.get_R()
+    assert common.rel_err(R2, golden[f"{name}/R_after_ustruct_r"]) < ASM_TOL
+    eng.ustruct_r(eq, 2, common.ustruct_Ad(m))
+    assert np.array_equal(eng.get_R(), R2)
+    if scatter == abi.SCATTER_COLORED:
+        eng.alloc(4); eng.assemble(0, eq, dmn)            # alloc zeroes Kd together with R and Val
+        assert np.array_equal(eng.get_Val(), V1) and np.array_equal(eng.get_R(), R1) and np.array_equal(eng.get_Kd(), K1)
+    eng.close()
+
+
+def test_ustruct_solve_parity():
+    """ustruct/block_compression-like Newton iteration: assembly, ustruct_r, GMRES (dof = 4) against the compiled reference."""
+    from oracle import refbind
+    if not refbind.have_ref():
+        pytest.skip("needs oracle/_ref/libsvref.so")
+    from svmultiphysics_b200 import meshgen
+    m = meshgen.box_hex8(5, 4, 4, (1.0, 1.0, 1.0))
+    Ag, Yg, Dg, Bf, _ = common.ustruct_state(m)
+    eq, dmn = abi.ustruct_eq(1e-3), [abi.ustruct_domain(E=1.0e6, nu=0.45, Kpen=1.0e6 / (3 * (1 - 0.9)), rho=1.2)]
+    faces = []
+    for k, name in enumerate(("X0", "Y0", "Z0")):
+        val = np.ones((4, len(m.faces[name])), order="F"); val[k] = 0.0
+        faces.append((abi.BC_DIR, m.faces[name], val))
+    orc = refbind.RefCase(); orc.set_coords(m.x); orc.add_mesh(m.IEN)
+    rowPtr, colPtr = orc.build_graph(len(faces))
+    eng = _engine(m, rowPtr, colPtr)
+    eng.set_num_faces(len(faces))
+    for i, (g, nodes, val) in enumerate(faces):
+        orc.set_face(i, g, nodes, val); eng.set_face(i, g, nodes, val)
+    Ad = common.ustruct_Ad(m)
+    orc.alloc(4); orc.set_state(Ag, Yg, Dg, Bf); orc.assemble(0, eq, dmn); orc.ustruct_r(1, Ad)
+    eng.alloc(4); eng.set_state(Ag, Yg, Dg, Bf); eng.assemble(0, eq, dmn); eng.ustruct_r(eq, 1, Ad)
+    assert common.rel_err(eng.get_R(), orc.get_R()) < ASM_TOL
+    V0, V1 = orc.get_Val(), eng.get_Val()
+    for rows in VAL_GROUPS:
+        assert common.rel_err(V1[rows], V0[rows]) < ASM_TOL
+    ls = abi.ls_params(abi.LS_GMRES, mItr=4, sD=200, relTol=1e-6)      # 117 iterations inside one Krylov cycle in the reference
+    incL, res = np.ones(len(faces), np.int32), np.zeros(len(faces))
+    X0, o0, _ = orc.solve(4, abi.LS_GMRES, ls, incL, res)
+    X1, o1, _ = eng.solve(4, abi.LS_GMRES, ls, incL, res)
+    assert o1.RI.success == o0.RI.success and abs(o1.RI.itr - o0.RI.itr) <= max(2, o0.RI.itr // 20)
+    assert abs(o1.RI.iNorm - o0.RI.iNorm) <= 1e-10 * o0.RI.iNorm
+    assert common.rel_err(X1, X0) < 1e-4                                 # solver tolerance 1e-6 on an ill-conditioned saddle-point system
+    eng.close()
+
+
+def test_ustruct_unsupported_options_fail_loudly():
+    from svmultiphysics_b200 import meshgen
+    from svmultiphysics_b200.engine import Svb200Error
+    from oracle import refbind
+    m = meshgen.box_tet4(2, 2, 2, (1.0, 1.0, 1.0))
+    _, rowPtr, colPtr = common.make_oracle(refbind.OracleCase, m)
+    eng = _engine(m, rowPtr, colPtr)
+    Ag, Yg, Dg, Bf, _ = common.ustruct_state(m)
+    eng.alloc(4); eng.set_state(Ag, Yg, Dg, Bf)
+    d = abi.ustruct_domain(solid_visc=abi.SOLID_VISC_NEWTONIAN, solid_visc_mu=10.0)
+    with pytest.raises(Svb200Error, match="solid viscosity is not implemented for the ustruct"):
+        eng.assemble(0, abi.ustruct_eq(1e-3), [d])
+    with pytest.raises(Svb200Error, match="Min fiber directions"):
+        eng.assemble(0, abi.ustruct_eq(1e-3), [abi.ustruct_domain(isoType=abi.ISO_HGO)])
+    eng.close()

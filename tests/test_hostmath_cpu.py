@@ -228,3 +228,55 @@ def test_device_heat_algebra_matches_golden(hostmath, name, mk, fluid, tDof, s, 
     assert np.abs(golden[f"{name}/R"]).max() > 0
     assert common.rel_err(R, golden[f"{name}/R"].ravel()) < 1e-12
     assert common.rel_err(V, golden[f"{name}/Val"].ravel()) < 1e-12
+
+
+class UstructDmn(C.Structure):
+    _fields_ = [("st", StructDmn), ("E", C.c_double), ("nu", C.c_double), ("ctM", C.c_double), ("ctC", C.c_double)]
+
+
+class HostUstructArgs(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("IEN", "fN", "x", "Ag", "Yg", "Dg", "Bf")] + \
+               [(k, C.c_int) for k in ("eNoN", "nEl", "nG", "tDof", "s", "nFn")] + \
+               [(k, C.c_double) for k in ("dt", "af", "am", "gam")] + \
+               [("w", C.c_double * 8), ("N", (C.c_double * 8) * 8), ("Nxi", ((C.c_double * 3) * 8) * 8), ("dm", UstructDmn)]
+
+
+@pytest.mark.parametrize("name,mk,dkw,nFn", common.USTRUCT_CASES, ids=[c[0] for c in common.USTRUCT_CASES])
+def test_device_ustruct_algebra_matches_golden(hostmath, name, mk, dkw, nFn):
+    """svmultiphysics_b200/csrc/ustruct_elem.cuh compiled for the host against R / Val / Kd of the unmodified reference
+    (ustruct_3d_m, ustruct_3d_c, ustruct_do_assem; tests/golden/ustruct.npz), tolerance 1e-12."""
+    golden = common.load_golden("ustruct.npz")
+    assert hostmath.hostmath_sizeof_ustructargs() == C.sizeof(HostUstructArgs)
+    m = mk()
+    Ag, Yg, Dg, Bf, fN = common.ustruct_state(m, nFn)
+    eq, d = abi.ustruct_eq(1e-3), abi.ustruct_domain(**dkw)
+    A = HostUstructArgs()
+    keep = [np.ascontiguousarray(m.IEN.T.astype(np.int32)), np.ascontiguousarray(m.x.T), np.ascontiguousarray(Ag.T),
+            np.ascontiguousarray(Yg.T), np.ascontiguousarray(Dg.T), np.ascontiguousarray(Bf.T)]
+    A.IEN, A.x, A.Ag, A.Yg, A.Dg, A.Bf = (k.ctypes.data for k in keep)
+    if nFn:
+        fk = np.ascontiguousarray(fN.T)
+        A.fN = fk.ctypes.data
+    A.eNoN, A.nEl, A.tDof, A.s, A.nFn = m.eNoN, m.nEl, 4, 0, nFn
+    A.nG = _fill_tables(A, m.eNoN)
+    A.dt, A.af, A.am, A.gam = eq.dt, eq.af, eq.am, eq.gam
+    dm = A.dm.st
+    dm.rho, dm.dmp, dm.Kpen, dm.C10, dm.C01, dm.bff, dm.bss, dm.bfs = d.rho, d.dmp, d.Kpen, d.C10, d.C01, d.bff, d.bss, d.bfs
+    for i in range(3):
+        dm.f[i] = d.f[i]
+    dm.st_a, dm.st_b, dm.aff, dm.ass, dm.afs, dm.kap, dm.khs = d.st_a, d.st_b, d.aff, d.ass, d.afs, d.kap, d.khs
+    dm.isoType, dm.volType, dm.Id, dm.isStruct = d.isoType, d.volType, -1, 1
+    A.dm.E, A.dm.nu, A.dm.ctM, A.dm.ctC = d.E, d.nu, d.ctau_M, d.ctau_C
+    rowPtr, colPtr = golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"]
+    R = np.zeros((m.nNo, 4))
+    V = np.zeros((len(colPtr), 16))
+    Kd = np.zeros((len(colPtr), 12))
+    rc = hostmath.hostmath_ustruct(C.byref(A), rowPtr.ctypes.data_as(C.c_void_p), colPtr.ctypes.data_as(C.c_void_p),
+                                   R.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p), Kd.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    assert common.rel_err(R.T, golden[f"{name}/R"]) < 1e-12
+    assert common.rel_err(Kd.T, golden[f"{name}/Kd"]) < 1e-12
+    # entry-type-wise: the (v,v), (v,p), (p,v) and (p,p) blocks differ by orders of magnitude
+    G = golden[f"{name}/Val"]
+    for rows in ([0, 1, 2, 4, 5, 6, 8, 9, 10], [3, 7, 11], [12, 13, 14], [15]):
+        assert common.rel_err(V.T[rows], G[rows]) < 1e-12
