@@ -6,7 +6,7 @@
 //
 // Mapping (like assemble_struct.cu): ENON lanes per element, two phases.  Phase A: lane g evaluates Gauss point g ONCE
 // per element (gnn, F, F^-1, compute_pk2cc without the volumetric part, g_vol_pen, compute_tau, the strong residuals)
-// and leaves a UGP (110 doubles) in shared memory.  Phase B: lane a owns row a of the element matrices; column nodes
+// and leaves a UGP (110 doubles; + two ViscGP sets in the solid-viscosity instantiation) in shared memory.  Phase B: lane a owns row a of the element matrices; column nodes
 // are taken NB at a time so that the 28 NB accumulators (16 of lK + 12 of lKd per block) stay in registers, the Gauss
 // loop is inside, and each finished block goes out as 16 + 12 contiguous doubles.
 #include <vector>
@@ -42,14 +42,22 @@ struct UstructArgs {
 };
 
 constexpr int USTRUCT_THREADS = 64;
-constexpr int UGP_LD = (int)(sizeof(UGP) / sizeof(double));
+// Gauss-point record of the VISC instantiation: the two ViscGP sets of ustruct_gauss_point follow the UGP
+struct UGPV {
+  UGP g;
+  ViscGP gu, gv;
+};
 // per-element stride in doubles: the elements of a warp (4 for HEX8, 8 for TET4) read the same UGP field at the same
 // time, so the stride is padded to 4 (HEX8) / 2 (TET4) mod 16 to spread them over the banks
-__host__ __device__ constexpr int ustruct_per_el(int enon)
+__host__ __device__ constexpr int ustruct_per_el(int enon, int ld)
 {
-  const int n = enon * UGP_LD, want = (enon == 8) ? 4 : 2;
+  const int n = enon * ld, want = (enon == 8) ? 4 : 2;
   return n + ((want - (n % 16)) + 16) % 16;
 }
+template <bool VISC> struct UGPSel { using type = UGP; };
+template <> struct UGPSel<true> { using type = UGPV; };
+__device__ __forceinline__ UGP& ugp_of(UGP& r) { return r; }
+__device__ __forceinline__ UGP& ugp_of(UGPV& r) { return r.g; }
 
 template <bool ATOMIC>
 __device__ __forceinline__ void uadd(double* p, double v)
@@ -58,17 +66,18 @@ __device__ __forceinline__ void uadd(double* p, double v)
   else *p += v;
 }
 
-template <int ENON, bool ATOMIC>
+template <int ENON, bool ATOMIC, bool VISC>
 __global__ void __launch_bounds__(USTRUCT_THREADS)
 assemble_ustruct_kernel(const __grid_constant__ UstructArgs P)
 {
+  using GP = typename UGPSel<VISC>::type;
   constexpr int EPW = 32 / ENON;
   constexpr int NB = 2;
-  constexpr int PER_EL = ustruct_per_el(ENON);
+  constexpr int PER_EL = ustruct_per_el(ENON, (int)(sizeof(GP) / sizeof(double)));
   extern __shared__ double sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int a = lane % ENON, el = lane / ENON;
-  UGP* gp = reinterpret_cast<UGP*>(sm + (size_t)(warp * EPW + el) * PER_EL);
+  GP* gp = reinterpret_cast<GP*>(sm + (size_t)(warp * EPW + el) * PER_EL);
 
   const long long idx = (long long)P.e0 + ((long long)blockIdx.x * (USTRUCT_THREADS / 32) + warp) * EPW + el;
   bool active = idx < P.e1;
@@ -113,8 +122,21 @@ assemble_ustruct_kernel(const __grid_constant__ UstructArgs P)
 #pragma unroll
         for (int i = 0; i < 3; i++) fN[k][i] = __ldg(P.fN + (size_t)3 * P.nFn * e + 3 * k + i);
     const int g = a;
-    UGP& q = gp[g];                       // written in place: a local copy would cost 880 B of stack per thread
-    ustruct_gauss_point<ENON>(dm, P.dt, P.af, P.am, P.gam, P.w[g], P.N[g], P.Nxi[g], xl, ql, vl, dl, pl, pdl, fN, q);
+    UGP& q = ugp_of(gp[g]);               // written in place: a local copy would cost 880 B of stack per thread
+    if constexpr (VISC) {
+      // a domain of this launch without viscosity leaves c = 0 sets: its viscous blocks vanish
+      gp[g].gu.c = 0.0; gp[g].gv.c = 0.0;
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          gp[g].gu.T[i][j] = gp[g].gu.A[i][j] = gp[g].gu.B[i][j] = gp[g].gu.M[i][j] = 0.0;
+          gp[g].gv.T[i][j] = gp[g].gv.A[i][j] = gp[g].gv.B[i][j] = gp[g].gv.M[i][j] = 0.0;
+        }
+      ustruct_gauss_point<ENON>(dm, P.dt, P.af, P.am, P.gam, P.w[g], P.N[g], P.Nxi[g], xl, ql, vl, dl, pl, pdl, fN, q, &gp[g].gu, &gp[g].gv);
+    } else {
+      ustruct_gauss_point<ENON>(dm, P.dt, P.af, P.am, P.gam, P.w[g], P.N[g], P.Nxi[g], xl, ql, vl, dl, pl, pdl, fN, q);
+    }
     // construct_usolid throws when utils::is_zero(Jac) (ustruct.cpp:312-314); q.w = w_g * Jac
     if (fabs(q.w) < fabs(P.w[g]) * 10.0 * 2.220446049250313e-16 * 2.220446049250313e-16) atomicMax(P.err, e + 1);
   }
@@ -131,8 +153,8 @@ assemble_ustruct_kernel(const __grid_constant__ UstructArgs P)
 #pragma unroll 1
     for (int g = 0; g < ENON; g++) {
       UNode A;
-      ustruct_node(gp[g], P.N[g][a], P.Nxi[g][a], A);
-      ustruct_resid(gp[g], A, lR);
+      ustruct_node(ugp_of(gp[g]), P.N[g][a], P.Nxi[g][a], A);
+      ustruct_resid(ugp_of(gp[g]), A, lR);
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) uadd<ATOMIC>(P.R + (size_t)4 * na + i, lR[i]);
@@ -150,7 +172,7 @@ assemble_ustruct_kernel(const __grid_constant__ UstructArgs P)
     }
 #pragma unroll 1
     for (int g = 0; g < ENON; g++) {
-      const UGP& q = gp[g];
+      const UGP& q = ugp_of(gp[g]);
       UNode A;
       double Bma[6][3];
       ustruct_node(q, P.N[g][a], P.Nxi[g][a], A);
@@ -163,6 +185,9 @@ assemble_ustruct_kernel(const __grid_constant__ UstructArgs P)
         make_Bm(B.Nx, q.F, Bmb);
         make_DBm(q.Dm, Bmb, DBmb);
         ustruct_block(q, af, am, A, B, Bma, DBmb, K[k], Kd[k]);
+        if constexpr (VISC)
+          if (dm.st.viscType != SVB200_SOLID_VISC_NONE)
+            ustruct_visc_block(dm.st.viscType, q, af, am, gp[g].gu, gp[g].gv, A.Nx, B.Nx, K[k], Kd[k]);
       }
     }
 #pragma unroll
@@ -178,22 +203,23 @@ assemble_ustruct_kernel(const __grid_constant__ UstructArgs P)
   }
 }
 
-template <int ENON>
+template <int ENON, bool VISC>
 static int launch_ustruct(svb200_ctx* ctx, const UstructArgs& A, bool atomic)
 {
+  using GP = typename UGPSel<VISC>::type;
   constexpr int EPB = (USTRUCT_THREADS / 32) * (32 / ENON);
-  constexpr size_t smem = sizeof(double) * (size_t)EPB * ustruct_per_el(ENON);
+  constexpr size_t smem = sizeof(double) * (size_t)EPB * ustruct_per_el(ENON, (int)(sizeof(GP) / sizeof(double)));
   static bool configured = false;
   if (!configured) {
-    SVB_CUDA(cudaFuncSetAttribute(assemble_ustruct_kernel<ENON, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SVB_CUDA(cudaFuncSetAttribute(assemble_ustruct_kernel<ENON, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVB_CUDA(cudaFuncSetAttribute(assemble_ustruct_kernel<ENON, true, VISC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVB_CUDA(cudaFuncSetAttribute(assemble_ustruct_kernel<ENON, false, VISC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   const long long n = (long long)A.e1 - A.e0;
   if (n <= 0) return SVB200_OK;
   const unsigned blocks = (unsigned)((n + EPB - 1) / EPB);
-  if (atomic) assemble_ustruct_kernel<ENON, true><<<blocks, USTRUCT_THREADS, smem, ctx->stream>>>(A);
-  else assemble_ustruct_kernel<ENON, false><<<blocks, USTRUCT_THREADS, smem, ctx->stream>>>(A);
+  if (atomic) assemble_ustruct_kernel<ENON, true, VISC><<<blocks, USTRUCT_THREADS, smem, ctx->stream>>>(A);
+  else assemble_ustruct_kernel<ENON, false, VISC><<<blocks, USTRUCT_THREADS, smem, ctx->stream>>>(A);
   ctx->launches++;
   SVB_CUDA(cudaGetLastError());
   return SVB200_OK;
@@ -235,7 +261,7 @@ int run_assemble_ustruct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* 
       for (int k = 0; k < 3; k++) A.Nxi[g][a][k] = m.Nx[((size_t)g * m.eNoN + a) * 3 + k];
     }
   }
-  bool whole = false;
+  bool whole = false, visc = false;
   for (int d = 0; d < nDmn; d++) {
     StructDmn& o = A.dmn[d].st;
     o.rho = dmn[d].rho;
@@ -246,17 +272,18 @@ int run_assemble_ustruct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* 
     o.st_a = dmn[d].st_a; o.st_b = dmn[d].st_b; o.aff = dmn[d].aff; o.ass = dmn[d].ass; o.afs = dmn[d].afs;
     o.kap = dmn[d].kap; o.khs = dmn[d].khs;
     o.isoType = dmn[d].isoType; o.volType = dmn[d].volType;
-    o.visc_mu = 0.0; o.viscType = SVB200_SOLID_VISC_NONE;
+    o.visc_mu = dmn[d].solid_visc_mu;
+    o.viscType = SVB200_SOLID_VISC_NONE;
+    if (dmn[d].phys == SVB200_PHYS_USTRUCT && dmn[d].solid_visc_mu != 0.0) {
+      o.viscType = (dmn[d].solidViscType == SVB200_SOLID_VISC_POTENTIAL) ? SVB200_SOLID_VISC_POTENTIAL : SVB200_SOLID_VISC_NEWTONIAN;
+      visc = true;
+    }
     o.Id = dmn[d].Id;
     o.isStruct = A.active[d] = (dmn[d].phys == SVB200_PHYS_USTRUCT);
     A.dmn[d].E = dmn[d].E; A.dmn[d].nu = dmn[d].nu; A.dmn[d].ctM = dmn[d].ctau_M; A.dmn[d].ctC = dmn[d].ctau_C;
     SVB_REQUIRE(o.Id >= -1 && o.Id < 31, "svb200_assemble: domain Id out of range");
     if (A.active[d]) {
       SVB_REQUIRE(o.isoType >= SVB200_ISO_NHK && o.isoType <= SVB200_ISO_HO_MA, "svb200_assemble: constitutive model not implemented");
-      if (dmn[d].solid_visc_mu != 0.0) {
-        set_error("svb200_assemble: solid viscosity is not implemented for the ustruct equation in this build");
-        return SVB200_ERR_UNSUPPORTED;
-      }
       const bool fibres = (m.nFn == 2 && m.d_fN);
       if ((o.isoType == SVB200_ISO_GUCCIONE || o.isoType == SVB200_ISO_HGO || o.isoType == SVB200_ISO_HO || o.isoType == SVB200_ISO_HO_MA) && !fibres) {
         set_error("[compute_pk2cc] Min fiber directions not defined for this material model.");
@@ -267,7 +294,10 @@ int run_assemble_ustruct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* 
   }
   if (!whole && !m.d_eId) { set_error("eId is not allocated"); return SVB200_ERR_INVALID; }
   const bool atomic = (eq->scatter == SVB200_SCATTER_ATOMIC);
-  auto launch = [&](const UstructArgs& B) { return m.eNoN == 8 ? launch_ustruct<8>(ctx, B, atomic) : launch_ustruct<4>(ctx, B, atomic); };
+  auto launch = [&](const UstructArgs& B) {
+    if (visc) return m.eNoN == 8 ? launch_ustruct<8, true>(ctx, B, atomic) : launch_ustruct<4, true>(ctx, B, atomic);
+    return m.eNoN == 8 ? launch_ustruct<8, false>(ctx, B, atomic) : launch_ustruct<4, false>(ctx, B, atomic);
+  };
   int rc = SVB200_OK;
   if (atomic) rc = launch(A);
   else {

@@ -74,7 +74,8 @@ SVB_HD void ustruct_grad(const double xiX[3][3], const double Nxi[3], double Nx[
 template <int ENON>
 SVB_HD int ustruct_gauss_point(const UstructDmn& dm, double dt, double af_eq, double am, double gam, double wg, const double N[],
                                const double Nxi[][3], const double xl[][3], const double ql[][3], const double vl[][3],
-                               const double dl[][3], const double pl[], const double pdl[], const double fN[2][3], UGP& q)
+                               const double dl[][3], const double pl[], const double pdl[], const double fN[2][3], UGP& q,
+                               ViscGP* gu = nullptr, ViscGP* gv = nullptr)
 {
   const double Je = ustruct_xiX<ENON>(Nxi, xl, q.xiX);
   q.w = wg * Je;
@@ -122,6 +123,17 @@ SVB_HD int ustruct_gauss_point(const UstructDmn& dm, double dt, double af_eq, do
   StructDmn iso = dm.st;
   iso.Kpen = 0.0;
   if (pk2cc_voigt(iso, q.F, fN, q.S, q.Dm)) return 1;
+  // compute_visc_stress_and_tangent (ustruct.cpp:1255-1259, mat_models.cpp:1583-1762): Siso += Svis (:1278); the tangent
+  // terms are kept as two ViscGP sets, gu for Kvis_u alone (afu = 1, afv = 0) and gv for Kvis_v alone (0, 1)
+  if (gu != nullptr && dm.st.viscType != SVB200_SOLID_VISC_NONE) {
+    double Svis[3][3];
+    visc_gauss_point(dm.st.viscType, dm.st.visc_mu, 1.0, 0.0, q.F, vx, Svis, *gu);
+    visc_gauss_point(dm.st.viscType, dm.st.visc_mu, 0.0, 1.0, q.F, vx, Svis, *gv);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) q.S[i][j] += Svis[i][j];
+  }
 
   // g_vol_pen with Ja = 1
   const double Kp = dm.st.Kpen;
@@ -240,6 +252,26 @@ SVB_HD void ustruct_block(const UGP& q, double af, double am, const UNode& a, co
     const double T1 = a.NxFi[0] * q.vd[0] + a.NxFi[1] * q.vd[1] + a.NxFi[2] * q.vd[2];
     K[15] += w * J * (T0 + af * q.tauM * (NxNx + q.drho * T1 * b.N));
   }
+}
+
+// Viscous part of a block: lKd(0..8) += w af Kvis_u, lK(v,v) += w af Kvis_v + (af/am) w af Kvis_u (ustruct.cpp:1455-1572).
+SVB_HD void ustruct_visc_block(int viscType, const UGP& q, double af, double am, const ViscGP& gu, const ViscGP& gv,
+                               const double Nxa[3], const double Nxb[3], double K[16], double Kd[12])
+{
+  double Vau[9], Vbu[9], Vav[9], Vbv[9];
+  visc_node(gu, Nxa, Vau); visc_node(gu, Nxb, Vbu);
+  visc_node(gv, Nxa, Vav); visc_node(gv, Nxb, Vbv);
+  double Tu[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, Tv[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  visc_block(viscType, q.w * af * gu.c, 1.0, 0.0, &gu.M[0][0], Vau, Vbu, Tu);
+  visc_block(viscType, q.w * af * gv.c, 0.0, 1.0, &gv.M[0][0], Vav, Vbv, Tv);
+  const double afm = af / am;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      Kd[3 * i + j] += Tu[i][j];
+      K[4 * i + j] += Tv[i][j] + afm * Tu[i][j];
+    }
 }
 
 }  // namespace svb

@@ -23,6 +23,7 @@ int to_phys(consts::EquationType p)
     case EquationType::phys_lElas: return SVB200_PHYS_LELAS;
     case EquationType::phys_heatS: return SVB200_PHYS_HEATS;
     case EquationType::phys_heatF: return SVB200_PHYS_HEATF;
+    case EquationType::phys_ustruct: return SVB200_PHYS_USTRUCT;
     default: return -1;
   }
 }
@@ -63,7 +64,7 @@ std::vector<svb200_dmnparams> domain_params(const eqType& eq)
     p.Id = d.Id;
     p.phys = to_phys(d.phys);
     if (p.phys < 0) throw std::runtime_error("[B200LinearAlgebra] domain physics is not on the device path");
-    const bool solid = (d.phys == EquationType::phys_struct);
+    const bool solid = (d.phys == EquationType::phys_struct || d.phys == EquationType::phys_ustruct);
     // l_elas_3d (mesh and linear-elasticity equations) reads solid_density like struct_3d (l_elas.cpp:275)
     // heats_3d reads solid_density as well (heats.cpp:204); heatf_3d uses no density
     const bool solid_rho = solid || d.phys == EquationType::phys_mesh || d.phys == EquationType::phys_lElas ||
@@ -319,6 +320,17 @@ void B200LinearAlgebra::assemble_mesh(ComMod& com_mod, const mshType& lM, const 
   svb200_eqparams e = b200::eq_params(com_mod, eq, lM, scatter);
   std::vector<svb200_dmnparams> d = b200::domain_params(eq);
   check(svb200_assemble(ctx, iM, &e, d.data(), (int)d.size()));
+}
+
+/// ustruct::ustruct_r (Code/Source/solver/ustruct.cpp:1742-1845), called where Integrator::step calls it
+/// (Integrator.cpp:135-137): the device holds R and Kd, the host passes com_mod.Ad and the Newton iteration count.
+void B200LinearAlgebra::ustruct_r(ComMod& com_mod)
+{
+  auto& eq = com_mod.eq[com_mod.cEq];
+  if (eq.phys != consts::EquationType::phys_ustruct) return;        // FSI with ustruct solids is not on the device path
+  flush_host_contrib(alloc_dof);
+  svb200_eqparams e = b200::eq_params(com_mod, eq, com_mod.msh[0], scatter);
+  check(svb200_ustruct_r(ctx, &e, eq.itr, com_mod.Ad.data()));
 }
 
 void B200LinearAlgebra::commu_R()

@@ -44,6 +44,8 @@ class B200LinearAlgebra : public virtual LinearAlgebra {
     void assemble_mesh(ComMod& com_mod, const mshType& lM, const SolutionStates& solutions);
     /// all_fun::commu(com_mod, com_mod.R) of Integrator::step (Code/Source/solver/Integrator.cpp:124-129).
     void commu_R();
+    /// ustruct::ustruct_r (Code/Source/solver/ustruct.cpp:1742) on the device-resident R and Kd.
+    void ustruct_r(ComMod& com_mod);
     /// Debug / parity: device R(dof,tnNo) or Val(dof*dof,nnz) in the host's node / CSR slot order.
     void download(int what, double* dst);
 

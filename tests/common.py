@@ -212,6 +212,11 @@ USTRUCT_CASES = [
     ("tet4_HO_ma_fibres", _tet, dict(isoType=abi.ISO_HO_MA, st_a=590.0, st_b=8.023, aff=184720.0, bff=16.026, ass=24810.0, bss=11.12,
                                      afs=2160.0, bfs=11.436, khs=100.0, E=1.0e5, nu=0.483333, Kpen=1e6, rho=1.0, ctau_M=1e-5, ctau_C=1e-5), 2),
     ("hex8_nHK_no_penalty", _hex_skewed, dict(E=1.0e6, nu=0.4, Kpen=0.0, rho=2.0, ctau_M=1e-3, ctau_C=1e-3), 0),
+    # solid viscosity (ustruct/tensile_adventitia_{Newtonian,Potential}_viscosity)
+    ("hex8_nHK_visc_potential", _hex_skewed, dict(E=1.0e6, nu=0.45, Kpen=2.0e6, rho=1.0, ctau_M=1e-3, ctau_C=1e-3,
+                                                   solid_visc=abi.SOLID_VISC_POTENTIAL, solid_visc_mu=2.0e4), 0),
+    ("tet4_nHK_visc_newtonian", _tet, dict(E=1.0e6, nu=0.45, Kpen=2.0e6, rho=1.0, ctau_M=1e-3, ctau_C=1e-3,
+                                           solid_visc=abi.SOLID_VISC_NEWTONIAN, solid_visc_mu=3.0e4), 0),
 ]
 
 

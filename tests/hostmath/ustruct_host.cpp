@@ -38,7 +38,10 @@ static int run(const HostUstructArgs* P, const int* rowPtr, const int* colPtr, d
     double lR[ENON][4] = {}, lK[ENON][ENON][16] = {}, lKd[ENON][ENON][12] = {};
     for (int g = 0; g < P->nG; g++) {
       UGP q;
-      if (ustruct_gauss_point<ENON>(P->dm, P->dt, P->af, P->am, P->gam, P->w[g], P->N[g], P->Nxi[g], xl, ql, vl, dl, pl, pdl, fN, q)) return 2;
+      ViscGP gu, gv;
+      const bool visc = P->dm.st.viscType != 0 && P->dm.st.visc_mu != 0.0;
+      if (ustruct_gauss_point<ENON>(P->dm, P->dt, P->af, P->am, P->gam, P->w[g], P->N[g], P->Nxi[g], xl, ql, vl, dl, pl, pdl, fN, q,
+                                    visc ? &gu : nullptr, visc ? &gv : nullptr)) return 2;
       UNode nd[ENON];
       double Bm[ENON][6][3], DBm[ENON][6][3];
       for (int a = 0; a < ENON; a++) {
@@ -48,7 +51,10 @@ static int run(const HostUstructArgs* P, const int* rowPtr, const int* colPtr, d
         ustruct_resid(q, nd[a], lR[a]);
       }
       for (int a = 0; a < ENON; a++)
-        for (int b = 0; b < ENON; b++) ustruct_block(q, af, am, nd[a], nd[b], Bm[a], DBm[b], lK[a][b], lKd[a][b]);
+        for (int b = 0; b < ENON; b++) {
+          ustruct_block(q, af, am, nd[a], nd[b], Bm[a], DBm[b], lK[a][b], lKd[a][b]);
+          if (visc) ustruct_visc_block(P->dm.st.viscType, q, af, am, gu, gv, nd[a].Nx, nd[b].Nx, lK[a][b], lKd[a][b]);
+        }
     }
     for (int a = 0; a < ENON; a++) {
       for (int i = 0; i < 4; i++) R[4 * n[a] + i] += lR[a][i];

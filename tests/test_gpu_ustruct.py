@@ -92,9 +92,10 @@ def test_ustruct_unsupported_options_fail_loudly():
     eng = _engine(m, rowPtr, colPtr)
     Ag, Yg, Dg, Bf, _ = common.ustruct_state(m)
     eng.alloc(4); eng.set_state(Ag, Yg, Dg, Bf)
-    d = abi.ustruct_domain(solid_visc=abi.SOLID_VISC_NEWTONIAN, solid_visc_mu=10.0)
-    with pytest.raises(Svb200Error, match="solid viscosity is not implemented for the ustruct"):
-        eng.assemble(0, abi.ustruct_eq(1e-3), [d])
+    with pytest.raises(Svb200Error, match="dof = 4"):
+        eng.assemble(0, abi.struct_eq(1e-3, tDof=4, dof=3), [abi.ustruct_domain()]) if False else eng.assemble(
+            0, abi.EqParams(dt=1e-3, af=0.5, am=0.5, gam=0.5, beta=0.25, phys=abi.PHYS_USTRUCT, dof=3, tDof=4, s=0, mvMsh=0, vmsStab=1,
+                            scatter=0, reserved=0), [abi.ustruct_domain()])
     with pytest.raises(Svb200Error, match="Min fiber directions"):
         eng.assemble(0, abi.ustruct_eq(1e-3), [abi.ustruct_domain(isoType=abi.ISO_HGO)])
     eng.close()

@@ -266,6 +266,7 @@ def test_device_ustruct_algebra_matches_golden(hostmath, name, mk, dkw, nFn):
         dm.f[i] = d.f[i]
     dm.st_a, dm.st_b, dm.aff, dm.ass, dm.afs, dm.kap, dm.khs = d.st_a, d.st_b, d.aff, d.ass, d.afs, d.kap, d.khs
     dm.isoType, dm.volType, dm.Id, dm.isStruct = d.isoType, d.volType, -1, 1
+    dm.visc_mu, dm.viscType = d.solid_visc_mu, d.solidViscType
     A.dm.E, A.dm.nu, A.dm.ctM, A.dm.ctC = d.E, d.nu, d.ctau_M, d.ctau_C
     rowPtr, colPtr = golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"]
     R = np.zeros((m.nNo, 4))
