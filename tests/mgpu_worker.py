@@ -117,6 +117,9 @@ def main():
     m, Ag, Yg, Dg, Bf = common.fluid_case(n=n, nz=nz)
     if mode == "slab":
         part = (((np.arange(m.nEl) // 6) // (n * n)) * world // nz).astype(np.int32)
+    elif mode == "metis":   # k-way partition of the dual graph by the METIS the reference vendors (oracle/metis_shim.c)
+        from oracle import metis_part
+        part, _ = metis_part.part_mesh_dual(m.IEN, m.nNo, world)
     else:   # scattered blocks: many neighbours, nodes shared by more than two ranks
         part = (((np.arange(m.nEl) // 6) * 7919) % world).astype(np.int32)
     parts = partition.partition_mesh(m.IEN, m.nNo, part, world)

@@ -21,13 +21,15 @@ def _ngpu():
 
 
 @pytest.mark.parametrize("transport", ["p2p", "nccl"])
-@pytest.mark.parametrize("mode,ls", [("slab", "gmres"), ("scattered", "gmres"), ("slab", "ns"), ("fsi", "gmres+cg")])
+@pytest.mark.parametrize("mode,ls", [("slab", "gmres"), ("scattered", "gmres"), ("slab", "ns"), ("fsi", "gmres+cg"), ("metis", "gmres")])
 def test_two_gpu_parity(mode, ls, transport):
     """transport p2p: shared-node sums and scalar all-reduces by the library's own kernels over peer memory (CUDA IPC
     mailboxes, NVLink); nccl: ncclSend/Recv + ncclAllReduce.  Same parity bar for both."""
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
-    n = min(_ngpu(), 4) if mode in ("scattered", "fsi") else 2
+    if mode == "metis" and not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libsvmetis.so")):
+        pytest.skip("needs oracle/_ref/libsvmetis.so (make -C oracle metis)")
+    n = min(_ngpu(), 4) if mode in ("scattered", "fsi") else (_ngpu() if mode == "metis" else 2)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", "29541", os.path.join(ROOT, "tests", "mgpu_worker.py"), mode, ls]
     env = dict(os.environ)

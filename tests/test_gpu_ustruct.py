@@ -93,9 +93,9 @@ def test_ustruct_unsupported_options_fail_loudly():
     Ag, Yg, Dg, Bf, _ = common.ustruct_state(m)
     eng.alloc(4); eng.set_state(Ag, Yg, Dg, Bf)
     with pytest.raises(Svb200Error, match="dof = 4"):
-        eng.assemble(0, abi.struct_eq(1e-3, tDof=4, dof=3), [abi.ustruct_domain()]) if False else eng.assemble(
-            0, abi.EqParams(dt=1e-3, af=0.5, am=0.5, gam=0.5, beta=0.25, phys=abi.PHYS_USTRUCT, dof=3, tDof=4, s=0, mvMsh=0, vmsStab=1,
-                            scatter=0, reserved=0), [abi.ustruct_domain()])
+        bad = abi.ustruct_eq(1e-3)
+        bad.dof = 3
+        eng.assemble(0, bad, [abi.ustruct_domain()])
     with pytest.raises(Svb200Error, match="Min fiber directions"):
         eng.assemble(0, abi.ustruct_eq(1e-3), [abi.ustruct_domain(isoType=abi.ISO_HGO)])
     eng.close()

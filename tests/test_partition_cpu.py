@@ -17,12 +17,19 @@ def _parts(nranks, n=4, nz=6, mode="slab"):
         hexid = np.arange(m.nEl) // 6
         k = hexid // (n * n)
         part = (k * nranks // nz).astype(np.int32)
+    elif mode == "metis":
+        from oracle import metis_part
+        if not metis_part.have_metis():
+            pytest.skip("needs oracle/_ref/libsvmetis.so (make -C oracle metis)")
+        part, cut = metis_part.part_mesh_dual(m.IEN, m.nNo, nranks)
+        counts = np.bincount(part, minlength=nranks)
+        assert cut > 0 and counts.min() > 0 and counts.max() <= 1.10 * m.nEl / nranks     # balanced k-way partition
     else:
         part = np.random.default_rng(7).integers(0, nranks, m.nEl).astype(np.int32)
     return m, part, partition.partition_mesh(m.IEN, m.nNo, part, nranks)
 
 
-@pytest.mark.parametrize("nranks,mode", [(2, "slab"), (3, "slab"), (4, "random")])
+@pytest.mark.parametrize("nranks,mode", [(2, "slab"), (3, "slab"), (4, "random"), (2, "metis"), (8, "metis")])
 def test_partition_invariants(nranks, mode):
     m, part, parts = _parts(nranks, mode=mode)
     owned = np.zeros(m.nNo, dtype=np.int32)
