@@ -311,24 +311,45 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
     }
   }
 
-  if (!active) return;
   // ---- scatter ------------------------------------------------------------------------------------------
+  if (active) {
 #pragma unroll
-  for (int i = 0; i < 3; i++) add64<ATOMIC>(P.R + (size_t)DOF * node + i, lR[i]);
+    for (int i = 0; i < 3; i++) add64<ATOMIC>(P.R + (size_t)DOF * node + i, lR[i]);
+  }
+  // Blocks go out through a per-warp transposition tile (the warp's own Gauss-point area, dead by now): every lane deposits
+  // a finished 3x3 block, then the warp adds the 32 blocks with consecutive lanes on consecutive doubles, first as they
+  // are, then transposed into the mirrored slots.  Lane-strided REDs (each lane walking its own block) reach a third of
+  // the coalesced rate at best (profiles/r1_microbench_fp64_red.txt: 174 vs 554 G adds/s, 42 vs 285 when Val streams
+  // from DRAM) and were what bounded this kernel.
+  double* tile = sm + NTAB + (size_t)warp * EPW * PER_EL;
+  int* tsl = reinterpret_cast<int*>(tile + 32 * 9);
+  const int DD = DOF * DOF;
 #pragma unroll
   for (int k = 0; k <= KMAX; k++) {
-    if (k == KMAX && a >= KMAX) continue;
-    double* v = P.Val + (size_t)DOF * DOF * slotA[k];
+    const bool mine = active && !(k == KMAX && a >= KMAX);
+    __syncwarp();
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
-      for (int j = 0; j < 3; j++) add64<ATOMIC>(v + DOF * i + j, acc[k][i][j]);
+      for (int j = 0; j < 3; j++) tile[lane * 9 + 3 * i + j] = acc[k][i][j];
+    tsl[lane] = mine ? slotA[k] : -1;
+    tsl[32 + lane] = (mine && k > 0) ? slotT[k] : -1;
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 9; it++) {
+      const int p = it * 32 + lane, src = p / 9, idx = p - 9 * src, i = idx / 3, j = idx - 3 * i;
+      const double v = tile[p];
+      const int s0 = tsl[src];
+      if (s0 >= 0) add64<ATOMIC>(P.Val + (size_t)DD * s0 + DOF * i + j, v);
+    }
     if (k > 0) {
-      double* vt = P.Val + (size_t)DOF * DOF * slotT[k];
 #pragma unroll
-      for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) add64<ATOMIC>(vt + DOF * j + i, acc[k][i][j]);
+      for (int it = 0; it < 9; it++) {
+        // walk the TRANSPOSED block in its own memory order so that the adds stay on consecutive doubles
+        const int p = it * 32 + lane, src = p / 9, idx = p - 9 * src, i = idx / 3, j = idx - 3 * i;
+        const int s1 = tsl[32 + src];
+        if (s1 >= 0) add64<ATOMIC>(P.Val + (size_t)DD * s1 + DOF * i + j, tile[src * 9 + 3 * j + i]);
+      }
     }
   }
 }

@@ -8,7 +8,8 @@
 // per element (gnn, F, F^-1, compute_pk2cc without the volumetric part, g_vol_pen, compute_tau, the strong residuals)
 // and leaves a UGP (110 doubles; + two ViscGP sets in the solid-viscosity instantiation) in shared memory.  Phase B: lane a owns row a of the element matrices; column nodes
 // are taken NB at a time so that the 28 NB accumulators (16 of lK + 12 of lKd per block) stay in registers, the Gauss
-// loop is inside, and each finished block goes out as 16 + 12 contiguous doubles.
+// loop is inside (the column-node terms of a pass are published once per (g, b) through shared memory), and the finished
+// blocks go out through a per-warp transposition tile as coalesced adds.
 #include <vector>
 #include "svb200_internal.h"
 #include "ustruct_elem.cuh"
@@ -49,9 +50,17 @@ struct UGPV {
 };
 // per-element stride in doubles: the elements of a warp (4 for HEX8, 8 for TET4) read the same UGP field at the same
 // time, so the stride is padded to 4 (HEX8) / 2 (TET4) mod 16 to spread them over the banks
+// What phase B needs of a column node b at one Gauss point: published once per (g, b) by lane g instead of being
+// recomputed by every row lane a (DBm_b alone is 108 FMAs).
+struct UCol {
+  UNode n;
+  double DBm[6][3];
+};
+constexpr int USTRUCT_NB = 2;           // column nodes per pass of phase B
+constexpr int UCOL_LD = (int)(sizeof(UCol) / sizeof(double));
 __host__ __device__ constexpr int ustruct_per_el(int enon, int ld)
 {
-  const int n = enon * ld, want = (enon == 8) ? 4 : 2;
+  const int n = enon * ld + enon * USTRUCT_NB * UCOL_LD, want = (enon == 8) ? 4 : 2;
   return n + ((want - (n % 16)) + 16) % 16;
 }
 template <bool VISC> struct UGPSel { using type = UGP; };
@@ -72,12 +81,13 @@ assemble_ustruct_kernel(const __grid_constant__ UstructArgs P)
 {
   using GP = typename UGPSel<VISC>::type;
   constexpr int EPW = 32 / ENON;
-  constexpr int NB = 2;
+  constexpr int NB = USTRUCT_NB;
   constexpr int PER_EL = ustruct_per_el(ENON, (int)(sizeof(GP) / sizeof(double)));
   extern __shared__ double sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int a = lane % ENON, el = lane / ENON;
   GP* gp = reinterpret_cast<GP*>(sm + (size_t)(warp * EPW + el) * PER_EL);
+  UCol (*col)[NB] = reinterpret_cast<UCol (*)[NB]>(reinterpret_cast<double*>(gp) + ENON * (sizeof(GP) / sizeof(double)));
 
   const long long idx = (long long)P.e0 + ((long long)blockIdx.x * (USTRUCT_THREADS / 32) + warp) * EPW + el;
   bool active = idx < P.e1;
@@ -141,14 +151,14 @@ assemble_ustruct_kernel(const __grid_constant__ UstructArgs P)
     if (fabs(q.w) < fabs(P.w[g]) * 10.0 * 2.220446049250313e-16 * 2.220446049250313e-16) atomicMax(P.err, e + 1);
   }
   __syncwarp();
-  if (!active) return;
 
   // ---- phase B: lane a owns row a ------------------------------------------------------------------------------
-  int na = 0;
+  // Lanes without an element stay in the loops: the scatter below is a whole-warp operation.
+  if (active) {
+    int na = 0;
 #pragma unroll
-  for (int b = 0; b < ENON; b++)
-    if (b == a) na = node[b];
-  {
+    for (int b = 0; b < ENON; b++)
+      if (b == a) na = node[b];
     double lR[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
     for (int g = 0; g < ENON; g++) {
@@ -159,9 +169,29 @@ assemble_ustruct_kernel(const __grid_constant__ UstructArgs P)
 #pragma unroll
     for (int i = 0; i < 4; i++) uadd<ATOMIC>(P.R + (size_t)4 * na + i, lR[i]);
   }
+  // Per-warp transposition tile of the scatter: every lane deposits its finished 16 + 12 doubles, then the warp adds them
+  // with consecutive lanes on consecutive doubles (a half-warp = one 128-byte Val block) — lane-strided REDs run at a
+  // third of the coalesced rate or worse (profiles/r1_microbench_fp64_red.txt: 174 vs 554 G adds/s, 42 vs 285 from DRAM).
+  constexpr int TILE_LD = 29;
+  double* tile = sm + (size_t)(USTRUCT_THREADS / 32) * EPW * PER_EL + (size_t)warp * (32 * TILE_LD + 16);
+  int* tslot = reinterpret_cast<int*>(tile + 32 * TILE_LD);
   const int* sl = P.slot + (size_t)e * ENON * ENON + a * ENON;
 #pragma unroll 1
   for (int b0 = 0; b0 < ENON; b0 += NB) {
+    // lane g = a publishes the column-node data of b0 .. b0+NB-1 at Gauss point g
+    __syncwarp();
+    if (active) {
+      const UGP& q = ugp_of(gp[a]);
+#pragma unroll
+      for (int k = 0; k < NB; k++) {
+        UCol& c = col[a][k];
+        double Bmb[6][3];
+        ustruct_node(q, P.N[a][b0 + k], P.Nxi[a][b0 + k], c.n);
+        make_Bm(c.n.Nx, q.F, Bmb);
+        make_DBm(q.Dm, Bmb, c.DBm);
+      }
+    }
+    __syncwarp();
     double K[NB][16], Kd[NB][12];
 #pragma unroll
     for (int k = 0; k < NB; k++) {
@@ -170,35 +200,45 @@ assemble_ustruct_kernel(const __grid_constant__ UstructArgs P)
 #pragma unroll
       for (int i = 0; i < 12; i++) Kd[k][i] = 0.0;
     }
+    if (active) {
 #pragma unroll 1
-    for (int g = 0; g < ENON; g++) {
-      const UGP& q = ugp_of(gp[g]);
-      UNode A;
-      double Bma[6][3];
-      ustruct_node(q, P.N[g][a], P.Nxi[g][a], A);
-      make_Bm(A.Nx, q.F, Bma);
+      for (int g = 0; g < ENON; g++) {
+        const UGP& q = ugp_of(gp[g]);
+        UNode A;
+        double Bma[6][3];
+        ustruct_node(q, P.N[g][a], P.Nxi[g][a], A);
+        make_Bm(A.Nx, q.F, Bma);
 #pragma unroll
-      for (int k = 0; k < NB; k++) {
-        UNode B;
-        double Bmb[6][3], DBmb[6][3];
-        ustruct_node(q, P.N[g][b0 + k], P.Nxi[g][b0 + k], B);
-        make_Bm(B.Nx, q.F, Bmb);
-        make_DBm(q.Dm, Bmb, DBmb);
-        ustruct_block(q, af, am, A, B, Bma, DBmb, K[k], Kd[k]);
-        if constexpr (VISC)
-          if (dm.st.viscType != SVB200_SOLID_VISC_NONE)
-            ustruct_visc_block(dm.st.viscType, q, af, am, gp[g].gu, gp[g].gv, A.Nx, B.Nx, K[k], Kd[k]);
+        for (int k = 0; k < NB; k++) {
+          const UCol& c = col[g][k];
+          ustruct_block(q, af, am, A, c.n, Bma, c.DBm, K[k], Kd[k]);
+          if constexpr (VISC)
+            if (dm.st.viscType != SVB200_SOLID_VISC_NONE)
+              ustruct_visc_block(dm.st.viscType, q, af, am, gp[g].gu, gp[g].gv, A.Nx, c.n.Nx, K[k], Kd[k]);
+        }
       }
     }
 #pragma unroll
     for (int k = 0; k < NB; k++) {
-      const size_t s = (size_t)sl[b0 + k];
-      double* v = P.Val + 16 * s;
-      double* d = P.Kd + 12 * s;
+      __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 16; i++) uadd<ATOMIC>(v + i, K[k][i]);
+      for (int i = 0; i < 16; i++) tile[lane * TILE_LD + i] = K[k][i];
 #pragma unroll
-      for (int i = 0; i < 12; i++) uadd<ATOMIC>(d + i, Kd[k][i]);
+      for (int i = 0; i < 12; i++) tile[lane * TILE_LD + 16 + i] = Kd[k][i];
+      tslot[lane] = active ? sl[b0 + k] : -1;
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 16; it++) {             // 32 Val blocks x 16 doubles
+        const int p = it * 32 + lane, src = p >> 4, i = p & 15;
+        const int s_ = tslot[src];
+        if (s_ >= 0) uadd<ATOMIC>(P.Val + (size_t)16 * s_ + i, tile[src * TILE_LD + i]);
+      }
+#pragma unroll
+      for (int it = 0; it < 12; it++) {             // 32 Kd blocks x 12 doubles
+        const int p = it * 32 + lane, src = p / 12, i = p - 12 * src;
+        const int s_ = tslot[src];
+        if (s_ >= 0) uadd<ATOMIC>(P.Kd + (size_t)12 * s_ + i, tile[src * TILE_LD + 16 + i]);
+      }
     }
   }
 }
@@ -208,7 +248,8 @@ static int launch_ustruct(svb200_ctx* ctx, const UstructArgs& A, bool atomic)
 {
   using GP = typename UGPSel<VISC>::type;
   constexpr int EPB = (USTRUCT_THREADS / 32) * (32 / ENON);
-  constexpr size_t smem = sizeof(double) * (size_t)EPB * ustruct_per_el(ENON, (int)(sizeof(GP) / sizeof(double)));
+  constexpr size_t smem = sizeof(double) * ((size_t)EPB * ustruct_per_el(ENON, (int)(sizeof(GP) / sizeof(double))) +
+                                            (size_t)(USTRUCT_THREADS / 32) * (32 * 29 + 16));
   static bool configured = false;
   if (!configured) {
     SVB_CUDA(cudaFuncSetAttribute(assemble_ustruct_kernel<ENON, true, VISC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,5 +1,5 @@
 """Assembly time of the SURVEY 8f rank-4 physics on one B200: heatS / heatF on a TET4 cylinder and a HEX8 block, ustruct on
-TET4 and HEX8 blocks.  Usage: python tools/bench_phys.py [n_tet=80] [n_hex=100] [reps=3]
+TET4 and HEX8 blocks.  Usage: python tools/bench_phys.py [n_tet=80] [n_hex=100] [reps=3] [heat|ustruct]
 Prints elements/s and the compulsory-traffic figure (RMW of the CSR values + nodal gather) next to the HBM peak."""
 import sys, time
 import numpy as np
@@ -11,6 +11,7 @@ from tests import common
 n_tet = int(sys.argv[1]) if len(sys.argv) > 1 else 80
 n_hex = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+only = sys.argv[4] if len(sys.argv) > 4 else ""      # "heat" or "ustruct"
 
 
 def run(label, m, dof, state, eq, dm, val_bytes_per_blk, extra=None):
@@ -32,15 +33,15 @@ def run(label, m, dof, state, eq, dm, val_bytes_per_blk, extra=None):
     e.close()
 
 
-mt = meshgen.cylinder_tet4(n_tet, n_tet)
+mt = meshgen.cylinder_tet4(n_tet, n_tet) if only in ("", "heat") else None
 mh = meshgen.box_hex8(n_hex, n_hex, n_hex, (1.0, 1.0, 1.0))
-for fluid, tDof, s in ((False, 1, 0), (True, 5, 4)):
+for fluid, tDof, s in (((False, 1, 0), (True, 5, 4)) if only in ("", "heat") else ()):
     name = "heatF" if fluid else "heatS"
     for m in (mt, mh):
         Ag, Yg, Dg, Bf = common.heat_state(m, tDof, s)
         run(f"{name} {'tet4' if m.eNoN == 4 else 'hex8'}", m, 1, (Ag, Yg, Dg, Bf), abi.heat_eq(0.01, fluid, tDof=tDof, s=s),
             [abi.heat_domain(fluid, conductivity=0.5, source=1.0, rho=2.0)], 8)
-for m in (meshgen.box_tet4(n_hex // 2, n_hex // 2, n_hex // 2, (1.0, 1.0, 1.0)), mh):
+for m in ((meshgen.box_tet4(n_hex // 2, n_hex // 2, n_hex // 2, (1.0, 1.0, 1.0)), mh) if only in ("", "ustruct") else ()):
     Ag, Yg, Dg, Bf, _ = common.ustruct_state(m)
     Dg *= 0.05
     run(f"ustruct {'tet4' if m.eNoN == 4 else 'hex8'}", m, 4, (Ag, Yg, Dg, Bf), abi.ustruct_eq(1e-3),
