@@ -278,6 +278,11 @@ SVB200_API int svb200_commu_R(svb200_ctx* ctx);
  * amg = (gam - am)/(gam - 1); later iterations leave R unchanged.  Ad(3,nNo) is com_mod.Ad in INPUT node order; Kd is what the
  * last svb200_assemble(phys = USTRUCT) left on the device (download: SVB200_ARRAY_KD). */
 SVB200_API int svb200_ustruct_r(svb200_ctx* ctx, const svb200_eqparams* eq, int32_t itr, const double* Ad);
+/* com_mod.Ad(3,nNo) for the device-resident ustruct loop: uploaded once, then svb200_predictor scales it by (gam-1)/gam
+ * (Integrator.cpp:627-628), svb200_ustruct_r(..., Ad = NULL) reads it and svb200_corrector(phys = USTRUCT) updates it together
+ * with An, Yn, Dn (Integrator.cpp:826-846: dUl = Rd/am + R af gam dt/am, Ad -= dUl, Dn -= dUl gam dt). */
+SVB200_API int svb200_set_ad(svb200_ctx* ctx, const double* Ad);
+SVB200_API int svb200_get_ad(svb200_ctx* ctx, double* Ad);
 
 /* fsils_solve: preconditions in place, runs the Krylov solver, writes the increment to R_out
  * (dof,nNo, INPUT node order; may be NULL to keep it on the device only). */
@@ -301,7 +306,8 @@ typedef struct {
 SVB200_API int svb200_set_solution(svb200_ctx* ctx, int32_t tDof, int32_t which, const double* A, const double* Y, const double* D);
 SVB200_API int svb200_get_solution(svb200_ctx* ctx, int32_t which, double* A, double* Y, double* D);
 /* Integrator::predictor (solver/Integrator.cpp:393-643), state part: An = Ao (gam-1)/gam, Yn = Yo,
- * Dn = Do + Yn dt + An dt^2 (gam/2 - beta)/(gam-1) when dFlag (struct / mesh / FSI), else Dn = Do. */
+ * Dn = Do + Yn dt + An dt^2 (gam/2 - beta)/(gam-1) when dFlag (struct / mesh / FSI), else Dn = Do; for a ustruct equation
+ * (phys = SVB200_PHYS_USTRUCT) Dn = Do and Ad is scaled instead (:626-630). */
 SVB200_API int svb200_predictor(svb200_ctx* ctx, int32_t nEq, const svb200_eqtime* eqs, double dt, int32_t dFlag);
 /* Integrator::initiator (solver/Integrator.cpp:662-750): Ag, Yg, Dg from old and current. */
 SVB200_API int svb200_initiator(svb200_ctx* ctx, int32_t nEq, const svb200_eqtime* eqs);

@@ -8,14 +8,20 @@ the statement it follows in /root/reference/Code/Source/solver/Integrator.cpp.  
 import numpy as np
 
 
-def predictor(eqs, dt, dFlag, Ao, Yo, Do, An, Yn, Dn):
-    """Integrator::predictor, Integrator.cpp:540-643 (state part; sstEq false)."""
+USTRUCT = 7   # svb200_phys
+
+
+def predictor(eqs, dt, dFlag, Ao, Yo, Do, An, Yn, Dn, Ad=None):
+    """Integrator::predictor, Integrator.cpp:540-643 (state part); a ustruct equation takes the sstEq branch :626-630."""
     for q in eqs:
         r = slice(q.s, q.e + 1)
         coef = (q.gam - 1.0) / q.gam                      # :551
         An[r] = Ao[r] * coef                              # :555  eqn 87 of Bazilevs 2007
         Yn[r] = Yo[r]                                     # :616  eqn 86
-        if dFlag:                                         # :618-623
+        if dFlag and q.phys == USTRUCT:
+            Ad *= (q.gam - 1.0) / q.gam                   # :627-628
+            Dn[r] = Do[r]                                 # :629
+        elif dFlag:                                       # :618-623
             c = dt * dt * (0.5 * q.gam - q.beta) / (q.gam - 1.0)
             Dn[r] = (Do[r] + Yn[r] * dt) + An[r] * c
         else:
@@ -44,3 +50,15 @@ def corrector(q, dt, R, An, Yn, Dn, mesh_s=-1, solid=None):
         m = np.asarray(solid, bool)
         for X in (An, Yn, Dn):
             X[mesh_s:mesh_s + 3, m] = X[0:3, m]           # :905-909
+
+
+def corrector_ustruct(q, dt, R, Rd, An, Yn, Dn, Ad):
+    """Integrator::corrector for a ustruct equation (sstEq), Integrator.cpp:812-815 (coefficients), :826-846."""
+    c0, c2 = q.gam * dt, 1.0 / q.am
+    c3 = q.af * c0 * c2
+    r = slice(q.s, q.e + 1)
+    An[r] = An[r] - R[:4]                                 # :832
+    Yn[r] = Yn[r] - R[:4] * c0                            # :833
+    dUl = Rd * c2 + R[:3] * c3                            # :837
+    Ad -= dUl                                             # :838
+    Dn[q.s:q.s + 3] = Dn[q.s:q.s + 3] - dUl * c0          # :839

@@ -93,7 +93,7 @@ def gen_alpha(rho_inf: float):
 
 
 def eq_time(s: int, e: int, phys: int, rho_inf: float = 0.5) -> EqTime:
-    am, af, gam, beta = gen_alpha(rho_inf)
+    af, am, gam, beta = gen_alpha(rho_inf)
     return EqTime(s=s, e=e, phys=phys, af=af, am=am, gam=gam, beta=beta)
 
 

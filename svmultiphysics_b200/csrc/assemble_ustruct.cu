@@ -398,13 +398,16 @@ ustruct_r_update_kernel(size_t n, double ami, const double* __restrict__ KU, dou
 
 int run_ustruct_r(svb200_ctx* ctx, const svb200_eqparams* eq, int itr, const double* d_Ad)
 {
-  if (itr > 1) return SVB200_OK;            // Rd = 0: nothing to add (ustruct.cpp:1773-1775)
   const int n = ctx->nNo;
   if (n == 0) return SVB200_OK;
-  double* buf = nullptr;
-  SVB_CUDA(cudaMalloc(&buf, sizeof(double) * 7 * (size_t)n));
-  double* Rd = buf;
-  double* KU = buf + 3 * (size_t)n;
+  if (!ctx->d_Rd) SVB_CUDA(cudaMalloc(&ctx->d_Rd, sizeof(double) * 3 * (size_t)n));
+  if (itr > 1) {                            // Rd = 0: nothing to add (ustruct.cpp:1773-1775)
+    SVB_CUDA(cudaMemsetAsync(ctx->d_Rd, 0, sizeof(double) * 3 * (size_t)n, ctx->stream));
+    return SVB200_OK;
+  }
+  double* KU = nullptr;
+  SVB_CUDA(cudaMalloc(&KU, sizeof(double) * 4 * (size_t)n));
+  double* Rd = ctx->d_Rd;
   const double amg = (eq->gam - eq->am) / (eq->gam - 1.0), ami = 1.0 / eq->am;
   ustruct_rd_kernel<<<(3 * n + 255) / 256, 256, 0, ctx->stream>>>(n, ctx->tDof, eq->s, amg, d_Ad, ctx->d_Yg, Rd);
   ustruct_kd_spmv_kernel<<<(unsigned)(((long long)n * 4 + 255) / 256), 256, 0, ctx->stream>>>(n, ctx->d_rowPtr, ctx->d_colPtr, ctx->d_Kd, Rd, KU);
@@ -415,7 +418,7 @@ int run_ustruct_r(svb200_ctx* ctx, const svb200_eqparams* eq, int itr, const dou
     ctx->launches++;
   }
   cudaError_t ce = cudaStreamSynchronize(ctx->stream);
-  cudaFree(buf);
+  cudaFree(KU);
   if (rc) return rc;
   SVB_CUDA(ce);
   SVB_CUDA(cudaGetLastError());

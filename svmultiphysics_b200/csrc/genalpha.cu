@@ -37,7 +37,8 @@ __global__ void predictor_kernel(int tDof, long long n, const __grid_constant__ 
   const double yn = Yo[t];
   An[t] = an;
   Yn[t] = yn;
-  if (dFlag) {
+  // ustruct (sstEq, Integrator.cpp:626-630): the displacement rows are integrated through Ad by the corrector, Dn = Do here
+  if (dFlag && Q.phys[q] != SVB200_PHYS_USTRUCT) {
     const double cD = dt * dt * (0.5 * Q.gam[q] - Q.beta[q]) / (Q.gam[q] - 1.0);
     Dn[t] = __dadd_rn(__dadd_rn(Do[t], __dmul_rn(yn, dt)), __dmul_rn(an, cD));
   } else {
@@ -75,6 +76,33 @@ __global__ void corrector_kernel(int tDof, int dof, int s, int nrow, long long n
   An[k] = __dadd_rn(An[k], -r);
   Yn[k] = __dadd_rn(Yn[k], -__dmul_rn(r, c0));
   Dn[k] = __dadd_rn(Dn[k], -__dmul_rn(r, c1));
+}
+
+// ustruct (Integrator.cpp:826-846): An(s+i) -= R(i), Yn(s+i) -= R(i) gam dt for the 4 rows; for the 3 velocity rows
+// dUl = Rd(i)/am + R(i) af gam dt / am, Ad(i) -= dUl, Dn(s+i) -= dUl gam dt.
+__global__ void corrector_ustruct_kernel(int tDof, int s, long long nNo, double c0, double c2, double c3, const double* __restrict__ R,
+                                         const double* __restrict__ Rd, double* __restrict__ An, double* __restrict__ Yn,
+                                         double* __restrict__ Dn, double* __restrict__ Ad)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nNo * 4) return;
+  const long long a = t >> 2;
+  const int i = (int)(t & 3);
+  const double r = R[t];
+  const long long k = a * tDof + s + i;
+  An[k] = __dadd_rn(An[k], -r);
+  Yn[k] = __dadd_rn(Yn[k], -__dmul_rn(r, c0));
+  if (i < 3) {
+    const double dUl = __dadd_rn(__dmul_rn(Rd[a * 3 + i], c2), __dmul_rn(r, c3));
+    Ad[a * 3 + i] = __dadd_rn(Ad[a * 3 + i], -dUl);
+    Dn[k] = __dadd_rn(Dn[k], -__dmul_rn(dUl, c0));
+  }
+}
+
+__global__ void scale_kernel(long long n, double c, double* __restrict__ x)
+{
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) x[t] = __dmul_rn(x[t], c);
 }
 
 // FSI without explicit geometric coupling (Integrator.cpp:887-912): on solid nodes the mesh-equation rows
@@ -126,6 +154,13 @@ int launch_predictor(svb200_ctx* ctx, int nEq, const svb200_eqtime* eqs, double 
   predictor_kernel<<<nblk(n), 256, 0, ctx->stream>>>(ctx->tDof, n, Q, dt, dFlag, ctx->d_Ao, ctx->d_Yo, ctx->d_Do, ctx->d_An,
                                                      ctx->d_Yn, ctx->d_Dn);
   ctx->launches++;
+  if (dFlag && ctx->d_Ad)
+    for (int i = 0; i < nEq; i++)
+      if (eqs[i].phys == SVB200_PHYS_USTRUCT) {          // Ad = Ad (gam-1)/gam, Integrator.cpp:627-628
+        const long long m = 3LL * ctx->nNo;
+        scale_kernel<<<nblk(m), 256, 0, ctx->stream>>>(m, (eqs[i].gam - 1.0) / eqs[i].gam, ctx->d_Ad);
+        ctx->launches++;
+      }
   SVB_CUDA(cudaGetLastError());
   return SVB200_OK;
 }
@@ -150,6 +185,14 @@ int launch_corrector(svb200_ctx* ctx, const svb200_eqtime* eq, double dt, int me
   const long long n = (long long)ctx->nNo * nrow;
   if (n == 0) return SVB200_OK;
   const double c0 = eq->gam * dt, c1 = eq->beta * dt * dt;
+  if (eq->phys == SVB200_PHYS_USTRUCT) {
+    const double c2 = 1.0 / eq->am, c3 = eq->af * c0 * c2;
+    corrector_ustruct_kernel<<<nblk((long long)ctx->nNo * 4), 256, 0, ctx->stream>>>(ctx->tDof, eq->s, ctx->nNo, c0, c2, c3, ctx->d_R,
+                                                                                      ctx->d_Rd, ctx->d_An, ctx->d_Yn, ctx->d_Dn, ctx->d_Ad);
+    ctx->launches++;
+    SVB_CUDA(cudaGetLastError());
+    return SVB200_OK;
+  }
   corrector_kernel<<<nblk(n), 256, 0, ctx->stream>>>(ctx->tDof, ctx->dof, eq->s, nrow, ctx->nNo, c0, c1, ctx->d_R, ctx->d_An,
                                                      ctx->d_Yn, ctx->d_Dn);
   ctx->launches++;

@@ -207,7 +207,7 @@ int svb200_destroy(svb200_ctx* ctx)
   cudaFree(ctx->d_map); cudaFree(ctx->d_rowPtr); cudaFree(ctx->d_colPtr); cudaFree(ctx->d_diagPtr);
   cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf); cudaFree(ctx->d_Do);
   cudaFree(ctx->d_Ao); cudaFree(ctx->d_Yo); cudaFree(ctx->d_An); cudaFree(ctx->d_Yn); cudaFree(ctx->d_Dn); cudaFree(ctx->d_nodeflag);
-  cudaFree(ctx->d_err); cudaFree(ctx->d_Kd); cudaFree(ctx->d_Ad);
+  cudaFree(ctx->d_err); cudaFree(ctx->d_Kd); cudaFree(ctx->d_Ad); cudaFree(ctx->d_Rd);
   cudaFree(ctx->d_stage); cudaFree(ctx->d_R); cudaFree(ctx->d_Val); cudaFree(ctx->d_W);
   cudaFree(ctx->d_work); cudaFree(ctx->d_red); cudaFree(ctx->d_tslot);
   cudaFreeHost(ctx->h_pinned); cudaFreeHost(ctx->h_cg); cudaFree(ctx->d_cg);
@@ -442,6 +442,7 @@ int svb200_alloc(svb200_ctx* ctx, int32_t dof)
   if (nV) SVB_CUDA(cudaMemsetAsync(ctx->d_Val, 0, sizeof(double) * nV, ctx->stream));
   // com_mod.Kd is zeroed with the linear system (solver/Integrator.cpp:106-109)
   if (ctx->d_Kd && ctx->nnz) SVB_CUDA(cudaMemsetAsync(ctx->d_Kd, 0, sizeof(double) * 12 * (size_t)ctx->nnz, ctx->stream));
+  if (ctx->d_Rd && ctx->nNo) SVB_CUDA(cudaMemsetAsync(ctx->d_Rd, 0, sizeof(double) * 3 * (size_t)ctx->nNo, ctx->stream));
   return SVB200_OK;
 }
 
@@ -687,6 +688,13 @@ int svb200_corrector(svb200_ctx* ctx, const svb200_eqtime* eq, double dt, int32_
               "svb200_corrector: equation rows do not match the dof of the solved system");
   SVB_REQUIRE(mesh_s < 0 || (mesh_s + 3 <= ctx->tDof && ctx->d_nodeflag), "svb200_corrector: FSI copy needs svb200_set_node_flags");
   TRY(ensure_solution_arrays(ctx));
+  if (eq->phys == SVB200_PHYS_USTRUCT) {
+    SVB_REQUIRE(ctx->dof == 4 && ctx->d_Ad, "svb200_corrector: the ustruct update needs Ad (svb200_set_ad)");
+    if (!ctx->d_Rd) {                       // ustruct_r was not called: Rd = 0 like Integrator.cpp:106-108
+      SVB_CUDA(cudaMalloc(&ctx->d_Rd, sizeof(double) * 3 * std::max<size_t>((size_t)ctx->nNo, 1)));
+      SVB_CUDA(cudaMemsetAsync(ctx->d_Rd, 0, sizeof(double) * 3 * (size_t)ctx->nNo, ctx->stream));
+    }
+  }
   return launch_corrector(ctx, eq, dt, mesh_s, ctx->d_nodeflag);
 }
 
@@ -860,13 +868,28 @@ int svb200_commu_R(svb200_ctx* ctx)
 int svb200_ustruct_r(svb200_ctx* ctx, const svb200_eqparams* eq, int32_t itr, const double* Ad)
 {
   CTX_GUARD(ctx);
-  SVB_REQUIRE(eq && Ad, "svb200_ustruct_r: null parameters");
+  SVB_REQUIRE(eq, "svb200_ustruct_r: null parameters");
+  SVB_REQUIRE(Ad || ctx->d_Ad, "svb200_ustruct_r: no Ad (pass it, or svb200_set_ad once for the device-resident loop)");
   SVB_REQUIRE(eq->phys == SVB200_PHYS_USTRUCT, "svb200_ustruct_r: the equation is not ustruct");
   SVB_REQUIRE(ctx->dof == 4 && ctx->d_R && ctx->d_Kd && ctx->d_Yg, "svb200_ustruct_r: assemble the ustruct equation first");
   SVB_REQUIRE(eq->tDof == ctx->tDof && eq->s >= 0 && eq->s + 4 <= eq->tDof, "svb200_ustruct_r: tDof / eq.s mismatch");
-  TRY(upload_nodal(ctx, 3, Ad, &ctx->d_Ad));
+  if (Ad) TRY(upload_nodal(ctx, 3, Ad, &ctx->d_Ad));
   TRY(run_ustruct_r(ctx, eq, itr, ctx->d_Ad));
   return SVB200_OK;
+}
+
+int svb200_set_ad(svb200_ctx* ctx, const double* Ad)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(ctx->d_rowPtr && Ad, "svb200_set_ad: call svb200_set_graph first");
+  return upload_nodal(ctx, 3, Ad, &ctx->d_Ad);
+}
+
+int svb200_get_ad(svb200_ctx* ctx, double* Ad)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(ctx->d_Ad && Ad, "svb200_get_ad: Ad was never set");
+  return download_nodal(ctx, 3, ctx->d_Ad, Ad);
 }
 
 int svb200_solve(svb200_ctx* ctx, int32_t dof, int32_t ls_type, int32_t prec, const svb200_lsparams* ls,

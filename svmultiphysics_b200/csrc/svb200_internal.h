@@ -153,7 +153,8 @@ struct svb200_ctx {
   size_t R_cap = 0, Val_cap = 0;   // capacities in doubles
   double* d_W = nullptr;           // (dof,nNo) preconditioner scaling
   double* d_Kd = nullptr;          // (12,nnz) displacement tangent of the ustruct equation (com_mod.Kd), assemble_ustruct.cu
-  double* d_Ad = nullptr;          // (3,nNo) com_mod.Ad of the last svb200_ustruct_r
+  double* d_Ad = nullptr;          // (3,nNo) com_mod.Ad: time derivative of the displacement (ustruct)
+  double* d_Rd = nullptr;          // (3,nNo) com_mod.Rd as svb200_ustruct_r left it (read by the ustruct corrector)
   size_t W_cap = 0;
 
   std::vector<svb::Mesh> mesh;

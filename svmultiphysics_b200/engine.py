@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "svb200_comm_unique_id", "svb200_comm_init", "svb200_comm_transport",
     "svb200_set_graph", "svb200_lhsa_begin", "svb200_lhsa_add_mesh", "svb200_lhsa_finish", "svb200_lhsa_get",
     "svb200_set_mesh", "svb200_set_mesh_nxx", "svb200_set_coords", "svb200_set_num_faces", "svb200_set_face",
-    "svb200_alloc", "svb200_set_state", "svb200_set_old_disp", "svb200_assemble", "svb200_add_host_contrib", "svb200_commu_R", "svb200_ustruct_r",
+    "svb200_alloc", "svb200_set_state", "svb200_set_old_disp", "svb200_assemble", "svb200_add_host_contrib", "svb200_commu_R", "svb200_ustruct_r", "svb200_set_ad", "svb200_get_ad",
     "svb200_solve", "svb200_download", "svb200_upload", "svb200_spmv", "svb200_last_timing",
     "svb200_host_register", "svb200_host_unregister", "svb200_timer_mark", "svb200_timer_elapsed",
     "svb200_bench_assemble", "svb200_bench_spmv", "svb200_measure_fp64_peak", "svb200_launch_count",
@@ -301,8 +301,17 @@ class Engine:
         self._call("svb200_download", C.c_int32(abi.ARRAY_KD), _d(K))
         return K
 
-    def ustruct_r(self, eq: abi.EqParams, itr, Ad):
-        self._call("svb200_ustruct_r", C.byref(eq), C.c_int32(itr), _d(_f64(Ad)))
+    def ustruct_r(self, eq: abi.EqParams, itr, Ad=None):
+        """Ad = None: use the device-resident Ad (set_ad / predictor / corrector keep it)."""
+        self._call("svb200_ustruct_r", C.byref(eq), C.c_int32(itr), _d(_f64(Ad)) if Ad is not None else None)
+
+    def set_ad(self, Ad):
+        self._call("svb200_set_ad", _d(_f64(Ad)))
+
+    def get_ad(self):
+        Ad = np.zeros((3, self.nNo), order="F")
+        self._call("svb200_get_ad", _d(Ad))
+        return Ad
 
     def get_W(self):
         W = np.zeros((self.dof, self.nNo), order="F")

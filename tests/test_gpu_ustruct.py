@@ -99,3 +99,69 @@ def test_ustruct_unsupported_options_fail_loudly():
     with pytest.raises(Svb200Error, match="Min fiber directions"):
         eng.assemble(0, abi.ustruct_eq(1e-3), [abi.ustruct_domain(isoType=abi.ISO_HGO)])
     eng.close()
+
+
+def test_ustruct_device_resident_newton_loop():
+    """Two time steps x three Newton iterations of a ustruct equation: (a) everything on the device (predictor incl. the Ad
+    scaling, initiator, assemble, ustruct_r on the device-resident Ad, GMRES, the ustruct corrector that updates An, Yn, Dn
+    and Ad) against (b) the same loop with the compiled reference's assembly + ustruct_r + GMRES and the numpy restatement
+    of Integrator::predictor / initiator / corrector (sstEq branches, Integrator.cpp:626-630, 826-846)."""
+    from oracle import genalpha_oracle as go, refbind
+    if not refbind.have_ref():
+        pytest.skip("needs oracle/_ref/libsvref.so")
+    from svmultiphysics_b200 import meshgen
+    m = meshgen.box_hex8(4, 4, 3, (1.0, 1.0, 1.0))
+    rng = np.random.default_rng(5)
+    dt = 1e-3
+    eq, dmn = abi.ustruct_eq(dt), [abi.ustruct_domain(E=1.0e6, nu=0.45, Kpen=1.0e6 / (3 * (1 - 0.9)), rho=1.2, f=(0.0, 0.0, -50.0))]
+    qt = [abi.eq_time(0, 3, abi.PHYS_USTRUCT, 0.5)]
+    assert abs(qt[0].af - eq.af) < 1e-15 and abs(qt[0].am - eq.am) < 1e-15
+    faces = []
+    for k, name in enumerate(("X0", "Y0", "Z0")):
+        val = np.ones((4, len(m.faces[name])), order="F"); val[k] = 0.0
+        faces.append((abi.BC_DIR, m.faces[name], val))
+    orc = refbind.RefCase(); orc.set_coords(m.x); orc.add_mesh(m.IEN)
+    rowPtr, colPtr = orc.build_graph(len(faces))
+    eng = _engine(m, rowPtr, colPtr)
+    eng.set_num_faces(len(faces))
+    for i, (g, nodes, val) in enumerate(faces):
+        orc.set_face(i, g, nodes, val); eng.set_face(i, g, nodes, val)
+    ls = abi.ls_params(abi.LS_GMRES, mItr=4, sD=200, relTol=1e-6)
+    incL, res = np.ones(len(faces), np.int32), np.zeros(len(faces))
+    Ao = np.zeros((4, m.nNo), order="F")
+    Yo = np.asfortranarray(np.vstack([1e-2 * rng.standard_normal((3, m.nNo)), np.zeros((1, m.nNo))]))
+    Do = np.zeros((4, m.nNo), order="F"); Do[:3] = 1e-3 * rng.standard_normal((3, m.nNo))
+    Ad = np.asfortranarray(1e-2 * rng.standard_normal((3, m.nNo)))
+    An, Yn, Dn = Ao.copy(order="F"), Yo.copy(order="F"), Do.copy(order="F")
+    Ag, Yg, Dg = (np.zeros_like(Ao) for _ in range(3))
+    Bf = np.zeros((3, m.nNo), order="F")
+    eng.set_state(Ag, Yg, Dg, Bf)
+    eng.set_solution(abi.SOL_OLD, Ao, Yo, Do)
+    eng.set_solution(abi.SOL_CURRENT, An, Yn, Dn)
+    eng.set_ad(Ad)
+    amg = (eq.gam - eq.am) / (eq.gam - 1.0)
+    norms_dev, norms_ref = [], []
+    for step in range(2):
+        eng.predictor(qt, dt, 1)
+        go.predictor(qt, dt, 1, Ao, Yo, Do, An, Yn, Dn, Ad)
+        for it in range(3):
+            eng.initiator(qt)
+            eng.alloc(4); eng.assemble(0, eq, dmn); eng.ustruct_r(eq, it + 1)
+            _, out1, _ = eng.solve(4, abi.LS_GMRES, ls, incL, res, want_solution=False)
+            eng.corrector(qt[0], dt)
+            go.initiator(qt, Ao, Yo, Do, An, Yn, Dn, Ag, Yg, Dg)
+            orc.alloc(4); orc.set_state(Ag, Yg, Dg, Bf); orc.assemble(0, eq, dmn); orc.ustruct_r(it + 1, Ad)
+            Rd = (amg * Ad - Yg[0:3]) if it == 0 else np.zeros_like(Ad)          # ustruct.cpp:1773-1783
+            X0, out0, _ = orc.solve(4, abi.LS_GMRES, ls, incL, res)
+            go.corrector_ustruct(qt[0], dt, X0, Rd, An, Yn, Dn, Ad)
+            norms_dev.append(out1.RI.iNorm); norms_ref.append(out0.RI.iNorm)
+        eng.advance_time_step()
+        Ao, Yo, Do = An.copy(order="F"), Yn.copy(order="F"), Dn.copy(order="F")
+    # Newton history: 1.3e4 -> 98 -> 6e-3 in the reference.  The first two norms of a step are determined by the state to
+    # ~1e-6 (the linear-solver tolerance); the third one IS the linear-solver error of the first two and only has to be as small.
+    nd, nr = np.array(norms_dev).reshape(2, 3), np.array(norms_ref).reshape(2, 3)
+    assert np.allclose(nd[:, 0], nr[:, 0], rtol=1e-5) and np.allclose(nd[:, 1], nr[:, 1], rtol=2e-3)
+    assert np.all(nr[:, 2] < 1e-5 * nr[:, 0]) and np.all(nd[:, 2] < 1e-5 * nd[:, 0])
+    A1, Y1, D1 = eng.get_solution(abi.SOL_CURRENT)
+    assert common.rel_err(Y1[:3], Yn[:3]) < 1e-4 and common.rel_err(D1[:3], Dn[:3]) < 1e-4 and common.rel_err(eng.get_ad(), Ad) < 1e-4
+    eng.close()
