@@ -69,6 +69,7 @@ struct RefCase {
   LinearAlgebra* backend = nullptr;
   int (*assem_hook)(void*, void*, const void*, const void*) = nullptr;
   void (*backend_download)(void*, int, double*) = nullptr;
+  void (*backend_ustruct_r)(void*, void*) = nullptr;       // B200LinearAlgebra::ustruct_r(ComMod&), INTEGRATION.md
 };
 
 consts::EquationType to_phys(int p)
@@ -191,6 +192,12 @@ int svref_set_backend(void* h, void* la, void* hook, void* download)
   c.backend = static_cast<LinearAlgebra*>(la);
   c.assem_hook = reinterpret_cast<int (*)(void*, void*, const void*, const void*)>(hook);
   c.backend_download = reinterpret_cast<void (*)(void*, int, double*)>(download);
+  return 0;
+}
+
+int svref_set_backend_ustruct_r(void* h, void* fn)
+{
+  static_cast<RefCase*>(h)->backend_ustruct_r = reinterpret_cast<void (*)(void*, void*)>(fn);
   return 0;
 }
 
@@ -613,6 +620,12 @@ int svref_ustruct_r(void* h, int itr, const double* Ad)
     cm.Rd.resize(3, n);
     cm.Rd = 0.0;
     cm.eq[0].itr = itr;
+    if (c.backend) {
+      // the patch of Integrator::step: the plug-in runs ustruct_r on the device-resident R and Kd
+      if (!c.backend_ustruct_r) throw std::runtime_error("[ref_harness] backend without ustruct_r hook");
+      c.backend_ustruct_r(c.backend, &cm);
+      return;
+    }
     // all_fun::is_domain (solver/all_fun.cpp) with a single domain needs nothing else; rowPtr/colPtr were set by
     // svref_build_graph
     ustruct::ustruct_r(cm, c.sol);

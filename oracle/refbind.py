@@ -239,6 +239,7 @@ class RefCase(_FlatCase):
         self.backend = host.b200host_new(C.c_int(device), C.c_int(scatter))
         self._call("set_backend", C.c_void_p(self.backend), C.cast(host.b200host_global_eq_assem, C.c_void_p),
                    C.cast(host.b200host_download, C.c_void_p))
+        self._call("set_backend_ustruct_r", C.cast(host.b200host_ustruct_r, C.c_void_p))
 
     def get_Kd(self):
         """com_mod.Kd(12, nnz): displacement tangent of the ustruct equation (solver/ustruct.cpp:1621)."""

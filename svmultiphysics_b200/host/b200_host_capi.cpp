@@ -36,6 +36,15 @@ void b200host_download(void* p, int what, double* dst)
   la->download(what, dst);
 }
 
+/// Where Integrator::step calls ustruct::ustruct_r (Integrator.cpp:135-137).
+__attribute__((visibility("default")))
+void b200host_ustruct_r(void* p, void* com_mod)
+{
+  auto* la = dynamic_cast<B200LinearAlgebra*>(static_cast<LinearAlgebra*>(p));
+  if (!la) throw std::runtime_error("b200host_ustruct_r: not a B200LinearAlgebra");
+  la->ustruct_r(*static_cast<ComMod*>(com_mod));
+}
+
 __attribute__((visibility("default")))
 long long b200host_launch_count(void* p)
 {

@@ -150,3 +150,64 @@ def test_hex8_fluid_through_cpp_plugin():
     assert abs(o1.RI.iNorm - o0.RI.iNorm) <= 1e-10 * o0.RI.iNorm
     assert common.rel_err(X1, X0) < 2e-5
     _close(cpu, gpu)
+
+
+@pytest.mark.parametrize("case", [1, 2], ids=["heatS_hex8", "heatF_tet4"])
+def test_heat_through_cpp_plugin(case):
+    """heatS / heatF (dof = 1): conductivity, source term and solid density travel from dmnType.prop through
+    b200::domain_params; assembly to 1e-12 and a BiCGStab solve against the reference's own run."""
+    name, mk, fluid, tDof, s, mv, dkw = common.HEAT_CASES[case]
+    m = mk()
+    Ag, Yg, Dg, Bf = common.heat_state(m, tDof, s)
+    fname = "X0" if "X0" in m.faces else "inlet"
+    faces = [(abi.BC_DIR, m.faces[fname], np.zeros((1, len(m.faces[fname])), order="F"))]
+    cpu, gpu = _pair(m, nFaces=1)
+    eq, dmn = abi.heat_eq(0.01, fluid, tDof=tDof, s=s, mvMsh=mv), [abi.heat_domain(fluid, **dkw)]
+    ls = abi.ls_params(abi.LS_BICGS, mItr=400, relTol=1e-10)
+    res = []
+    for c in (cpu, gpu):
+        for i, (g, nodes, v) in enumerate(faces):
+            c.set_face(i, g, nodes, v)
+        c.alloc(1); c.set_state(Ag, Yg, Dg, Bf); c.assemble(0, eq, dmn)
+        R, V = c.get_R(), c.get_Val()
+        X, o, _ = c.solve(1, abi.LS_BICGS, ls, np.ones(1, np.int32), np.zeros(1))
+        res.append((R, V, X, o))
+    (R0, V0, X0, o0), (R1, V1, X1, o1) = res
+    assert gpu.backend_launch_count() > 0
+    assert common.rel_err(R1, R0) < 1e-12 and common.rel_err(V1, V0) < 1e-12
+    assert o1.RI.success == o0.RI.success and abs(o1.RI.iNorm - o0.RI.iNorm) <= 1e-10 * o0.RI.iNorm
+    assert common.rel_err(X1, X0) < 1e-6
+    _close(cpu, gpu)
+
+
+def test_ustruct_through_cpp_plugin():
+    """ustruct: stM + ctau_M / ctau_C / E / nu through b200::domain_params, Kd stays on the device, and the Integrator::step patch
+    calls B200LinearAlgebra::ustruct_r where the reference calls ustruct::ustruct_r."""
+    name, mk, dkw, nFn = common.USTRUCT_CASES[1]
+    m = mk()
+    Ag, Yg, Dg, Bf, fN = common.ustruct_state(m, nFn)
+    faces = []
+    for k, fname in enumerate(("X0", "Y0", "Z0")):
+        val = np.ones((4, len(m.faces[fname])), order="F"); val[k] = 0.0
+        faces.append((abi.BC_DIR, m.faces[fname], val))
+    cpu, gpu = _pair(m, nFaces=3)
+    eq, dmn = abi.ustruct_eq(1e-3), [abi.ustruct_domain(**dkw)]
+    Ad = common.ustruct_Ad(m)
+    ls = abi.ls_params(abi.LS_GMRES, mItr=4, sD=200, relTol=1e-6)
+    res = []
+    for c in (cpu, gpu):
+        for i, (g, nodes, v) in enumerate(faces):
+            c.set_face(i, g, nodes, v)
+        c.alloc(4); c.set_state(Ag, Yg, Dg, Bf); c.assemble(0, eq, dmn)
+        R, V, K = c.get_R(), c.get_Val(), c.get_Kd()
+        c.ustruct_r(1, Ad)
+        R2 = c.get_R()
+        X, o, _ = c.solve(4, abi.LS_GMRES, ls, np.ones(3, np.int32), np.zeros(3))
+        res.append((R, V, K, R2, X, o))
+    (R0, V0, K0, R20, X0, o0), (R1, V1, K1, R21, X1, o1) = res
+    assert common.rel_err(R1, R0) < 1e-12 and common.rel_err(K1, K0) < 1e-12 and common.rel_err(R21, R20) < 1e-12
+    for rows in ([0, 1, 2, 4, 5, 6, 8, 9, 10], [3, 7, 11], [12, 13, 14], [15]):
+        assert common.rel_err(V1[rows], V0[rows]) < 1e-12
+    assert o1.RI.success == o0.RI.success and abs(o1.RI.iNorm - o0.RI.iNorm) <= 1e-10 * o0.RI.iNorm
+    assert common.rel_err(X1, X0) < 1e-4
+    _close(cpu, gpu)
