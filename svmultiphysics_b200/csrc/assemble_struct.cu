@@ -366,12 +366,45 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
 // the general kernel).  FSI pipe C5: 4.4 M solid tets 5.85 ms with the general kernel.
 constexpr int STET_THREADS = 128;
 
+// Whole-warp scatter of one 3x3 block per lane: every lane deposits its block in the warp's tile, then the 32 blocks are
+// added with consecutive lanes on consecutive doubles — into slot `s_ab` as they are and, when `mirrored` (uniform over the
+// warp), transposed into `s_ba`.  Lanes with nothing to add pass slot -1.  Must be called by all 32 lanes.
+template <bool ATOMIC>
+__device__ __forceinline__ void warp_scatter_block_pair(double* tile, int* tsl, int lane, const double K[3][3], int s_ab, int s_ba,
+                                                        bool mirrored, double* Val, int DD, int DOF)
+{
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) tile[lane * 9 + 3 * i + j] = K[i][j];
+  tsl[lane] = s_ab;
+  tsl[32 + lane] = s_ba;
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 9; it++) {
+    const int p = it * 32 + lane, src = p / 9, idx9 = p - 9 * src, i = idx9 / 3, j = idx9 - 3 * i;
+    const int s0 = tsl[src];
+    if (s0 >= 0) add64<ATOMIC>(Val + (size_t)DD * s0 + DOF * i + j, tile[p]);
+  }
+  if (mirrored) {
+#pragma unroll
+    for (int it = 0; it < 9; it++) {
+      const int p = it * 32 + lane, src = p / 9, idx9 = p - 9 * src, i = idx9 / 3, j = idx9 - 3 * i;
+      const int s1 = tsl[32 + src];
+      if (s1 >= 0) add64<ATOMIC>(Val + (size_t)DD * s1 + DOF * i + j, tile[src * 9 + 3 * j + i]);
+    }
+  }
+}
+
+
 template <bool ATOMIC>
 __global__ void __launch_bounds__(STET_THREADS)
 assemble_struct_tet4_kernel(const __grid_constant__ StructArgs P)
 {
   __shared__ double s_tile[STET_THREADS / 32][32 * 9];
   __shared__ int s_slot[STET_THREADS / 32][64];
+  __shared__ double s_Dm[36][STET_THREADS];      // the element's Dm, one column per thread: 36 registers less in the block loop
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* tile = s_tile[warp];
   int* tsl = s_slot[warp];
@@ -397,7 +430,7 @@ assemble_struct_tet4_kernel(const __grid_constant__ StructArgs P)
   int sl[16];
 #pragma unroll
   for (int k = 0; k < 16; k++) sl[k] = -1;
-  double Nx[4][3], F[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, S[3][3], Dm[6][6], M2[4][4];
+  double Nx[4][3], F[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, S[3][3], M2[4][4];
   double W = 0.0, Jac = 0.0;
 #pragma unroll
   for (int a = 0; a < 4; a++) {
@@ -409,10 +442,7 @@ assemble_struct_tet4_kernel(const __grid_constant__ StructArgs P)
   for (int i = 0; i < 3; i++)
 #pragma unroll
     for (int j = 0; j < 3; j++) S[i][j] = 0.0;
-#pragma unroll
-  for (int i = 0; i < 6; i++)
-#pragma unroll
-    for (int j = 0; j < 6; j++) Dm[i][j] = 0.0;
+
   if (active) {
     const int4 nn = __ldg(reinterpret_cast<const int4*>(P.IEN) + e);
     node[0] = nn.x; node[1] = nn.y; node[2] = nn.z; node[3] = nn.w;
@@ -446,7 +476,12 @@ assemble_struct_tet4_kernel(const __grid_constant__ StructArgs P)
       for (int k = 0; k < P.nFn && k < 2; k++)
 #pragma unroll
         for (int i = 0; i < 3; i++) fN[k][i] = __ldg(P.fN + (size_t)3 * P.nFn * e + 3 * k + i);
+    double Dm[6][6];
     pk2cc_voigt(dm, F, fN, S, Dm);
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+      for (int c = 0; c < 6; c++) s_Dm[6 * r + c][threadIdx.x] = Dm[r][c];
     // reference-element moments of the quadrature rule (4 points): sum w, sum w N_a, sum w N_a N_b
     double m1[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -491,7 +526,15 @@ assemble_struct_tet4_kernel(const __grid_constant__ StructArgs P)
     {
       double Bmb[6][3];
       make_Bm(Nx[b], F, Bmb);
-      make_DBm(Dm, Bmb, DBmb);
+#pragma unroll
+      for (int r = 0; r < 6; r++) {
+        double d[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++) d[c] = active ? s_Dm[6 * r + c][threadIdx.x] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+          DBmb[r][j] = d[0] * Bmb[0][j] + d[1] * Bmb[1][j] + d[2] * Bmb[2][j] + d[3] * Bmb[3][j] + d[4] * Bmb[4][j] + d[5] * Bmb[5][j];
+      }
     }
 #pragma unroll
     for (int i = 0; i < 3; i++) SNb[i] = S[i][0] * Nx[b][0] + S[i][1] * Nx[b][1] + S[i][2] * Nx[b][2];
@@ -509,29 +552,7 @@ assemble_struct_tet4_kernel(const __grid_constant__ StructArgs P)
           for (int r = 0; r < 6; r++) t += Bma[r][i] * DBmb[r][j];
           K[i][j] = wafu * t + (i == j ? T1 : 0.0);
         }
-      // deposit and add: block (a,b) as is, block (b,a) transposed
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) tile[lane * 9 + 3 * i + j] = K[i][j];
-      tsl[lane] = sl[4 * a + b];
-      tsl[32 + lane] = (a != b) ? sl[4 * b + a] : -1;
-      __syncwarp();
-#pragma unroll
-      for (int it = 0; it < 9; it++) {
-        const int p = it * 32 + lane, src = p / 9, idx9 = p - 9 * src, i = idx9 / 3, j = idx9 - 3 * i;
-        const int s0 = tsl[src];
-        if (s0 >= 0) add64<ATOMIC>(P.Val + (size_t)DD * s0 + DOF * i + j, tile[p]);
-      }
-      if (a != b) {
-#pragma unroll
-        for (int it = 0; it < 9; it++) {
-          const int p = it * 32 + lane, src = p / 9, idx9 = p - 9 * src, i = idx9 / 3, j = idx9 - 3 * i;
-          const int s1 = tsl[32 + src];
-          if (s1 >= 0) add64<ATOMIC>(P.Val + (size_t)DD * s1 + DOF * i + j, tile[src * 9 + 3 * j + i]);
-        }
-      }
+      warp_scatter_block_pair<ATOMIC>(tile, tsl, lane, K, sl[4 * a + b], (a != b) ? sl[4 * b + a] : -1, a != b, P.Val, DD, DOF);
     }
   }
 }
@@ -744,6 +765,132 @@ assemble_mesh_kernel(const __grid_constant__ StructArgs P, const double* __restr
   }
 }
 
+// ---- mesh-motion / linear-elasticity equation on linear tetrahedra: one thread per element ------------------------
+// l_elas_3d with constant gradients (l_elas.cpp:249-365): the strain and stress are constant over the element, only the
+// inertia term sees N_a(g).  With the weights w = w_g (mesh equation: Jacobian-free, mesh.cpp:122) or w_g Jac (lElas),
+// W = sum w, m_a = sum w N_a, M_ab = sum w N_a N_b:
+//     lR(i,a)   = rho (-f_i m_a + sum_b M_ab q_b(i)) + W (S grad N_a)_i
+//     lK(ij,ab) = T1c [ delta_ij (amd M_ab + mu W grad N_a . grad N_b) + mu W (lDm Nx_a(i) Nx_b(j) + Nx_a(j) Nx_b(i)) ]
+// (for i = j the last bracket is (1 + lDm) Nx_a(i) Nx_b(i), the same expression).  K_ba = K_ab^T: 10 blocks, scattered like
+// the solid's.
+template <bool ATOMIC, bool LELAS>
+__global__ void __launch_bounds__(STET_THREADS)
+assemble_mesh_tet4_kernel(const __grid_constant__ StructArgs P, const double* __restrict__ Do)
+{
+  __shared__ double s_tile[STET_THREADS / 32][32 * 9];
+  __shared__ int s_slot[STET_THREADS / 32][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* tile = s_tile[warp];
+  int* tsl = s_slot[warp];
+  const long long idx = (long long)P.e0 + (long long)blockIdx.x * STET_THREADS + threadIdx.x;
+  bool active = idx < P.e1;
+  int e = 0;
+  if (active) e = P.perm ? P.perm[idx] : (int)idx;
+  int iD = 0;
+  if (active) {
+    for (int d = 0; d < P.nDmn; d++) {
+      iD = d;
+      if (P.dmn[d].Id == -1) break;
+      if (P.eId != nullptr && ((P.eId[e] >> P.dmn[d].Id) & 1)) break;
+    }
+    if (!P.dmn[iD].isStruct) active = false;
+  }
+  const StructDmn& dm = P.dmn[iD];
+  const int DOF = P.dof, DD = DOF * DOF, is = P.s;
+  const double elM = dm.C10, nu = dm.C01, rho = dm.rho;        // elasticity_modulus / poisson_ratio travel in C10 / C01
+  const double lambda = elM * nu / (1.0 + nu) / (1.0 - 2.0 * nu);
+  const double mu = elM * 0.5 / (1.0 + nu);
+  const double lDm = lambda / mu;
+  const double T1c = P.af * P.beta * P.dt * P.dt;
+  const double amd = P.am / T1c * rho;
+  int sl[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) sl[k] = -1;
+  double Nx[4][3], M2[4][4], W = 0.0;
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    Nx[a][0] = Nx[a][1] = Nx[a][2] = 0.0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) M2[a][b] = 0.0;
+  }
+  if (active) {
+    int node[4];
+    const int4 nn = __ldg(reinterpret_cast<const int4*>(P.IEN) + e);
+    node[0] = nn.x; node[1] = nn.y; node[2] = nn.z; node[3] = nn.w;
+    const int4* sp = reinterpret_cast<const int4*>(P.slot) + (size_t)e * 4;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int4 v = __ldg(sp + k);
+      sl[4 * k] = v.x; sl[4 * k + 1] = v.y; sl[4 * k + 2] = v.z; sl[4 * k + 3] = v.w;
+    }
+    double xl[4][3], dl[4][3], ql[4][3];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const size_t n = (size_t)node[a];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const double dol = LELAS ? 0.0 : __ldg(Do + (size_t)P.tDof * n + is + i);
+        xl[a][i] = __ldg(P.x + 3 * n + i) + dol;
+        dl[a][i] = __ldg(P.Dg + (size_t)P.tDof * n + is + i) - dol;
+        ql[a][i] = __ldg(P.Ag + (size_t)P.tDof * n + is + i) - (LELAS ? __ldg(P.Bf + 3 * n + i) : 0.0);
+      }
+    }
+    const double Jac = gnn3<4>(P.Nxi[0], xl, Nx);
+    double m1[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      const double wg = LELAS ? P.w[g] * Jac : P.w[g];
+      W += wg;
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        m1[a] += wg * P.N[g][a];
+#pragma unroll
+        for (int b = 0; b < 4; b++) M2[a][b] += wg * P.N[g][a] * P.N[g][b];
+      }
+    }
+    double ed[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      ed[0] += Nx[b][0] * dl[b][0];
+      ed[1] += Nx[b][1] * dl[b][1];
+      ed[2] += Nx[b][2] * dl[b][2];
+      ed[3] += Nx[b][1] * dl[b][0] + Nx[b][0] * dl[b][1];
+      ed[4] += Nx[b][2] * dl[b][1] + Nx[b][1] * dl[b][2];
+      ed[5] += Nx[b][0] * dl[b][2] + Nx[b][2] * dl[b][0];
+    }
+    const double divD = lambda * (ed[0] + ed[1] + ed[2]);
+    const double S0 = divD + 2.0 * mu * ed[0], S1 = divD + 2.0 * mu * ed[1], S2 = divD + 2.0 * mu * ed[2];
+    const double S3 = mu * ed[3], S4 = mu * ed[4], S5 = mu * ed[5];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      double r[3];
+      r[0] = W * (Nx[a][0] * S0 + Nx[a][1] * S3 + Nx[a][2] * S5);
+      r[1] = W * (Nx[a][0] * S3 + Nx[a][1] * S1 + Nx[a][2] * S4);
+      r[2] = W * (Nx[a][0] * S5 + Nx[a][1] * S4 + Nx[a][2] * S2);
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        double t = -dm.f[i] * m1[a];
+#pragma unroll
+        for (int b = 0; b < 4; b++) t += M2[a][b] * ql[b][i];
+        add64<ATOMIC>(P.R + (size_t)DOF * node[a] + i, r[i] + rho * t);
+      }
+    }
+  }
+  const double c0 = T1c * amd, c1 = T1c * mu * W;
+#pragma unroll
+  for (int b = 0; b < 4; b++)
+#pragma unroll
+    for (int a = 0; a <= b; a++) {
+      double K[3][3];
+      const double T1 = c0 * M2[a][b] + c1 * (Nx[a][0] * Nx[b][0] + Nx[a][1] * Nx[b][1] + Nx[a][2] * Nx[b][2]);
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) K[i][j] = c1 * (lDm * Nx[a][i] * Nx[b][j] + Nx[a][j] * Nx[b][i]) + (i == j ? T1 : 0.0);
+      warp_scatter_block_pair<ATOMIC>(tile, tsl, lane, K, sl[4 * a + b], (a != b) ? sl[4 * b + a] : -1, a != b, P.Val, DD, DOF);
+    }
+}
+
 int fill_struct_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn, StructArgs& A)
 {
   SVB_REQUIRE(nDmn >= 1 && nDmn <= MAX_DMN, "svb200_assemble: between 1 and 8 domains are supported");
@@ -927,7 +1074,26 @@ int run_assemble_mesh(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq,
   int rc = fill_struct_args(ctx, m, eq, d.data(), nDmn, A);
   if (rc) return rc;
   const double* Do = lelas ? nullptr : ctx->d_Do;
-  auto launch = [&](const StructArgs& B) { return m.eNoN == 8 ? launch_mesh<8>(ctx, B, Do) : launch_mesh<4>(ctx, B, Do); };
+  static const bool force_general = (getenv("SVB200_STRUCT_GENERAL") != nullptr && atoi(getenv("SVB200_STRUCT_GENERAL")) != 0);
+  auto launch_t4 = [&](const StructArgs& B) {
+    const long long n = (long long)B.e1 - B.e0;
+    if (n <= 0) return (int)SVB200_OK;
+    const unsigned blocks = (unsigned)((n + STET_THREADS - 1) / STET_THREADS);
+    if (Do == nullptr) {
+      if (B.atomic) assemble_mesh_tet4_kernel<true, true><<<blocks, STET_THREADS, 0, ctx->stream>>>(B, nullptr);
+      else assemble_mesh_tet4_kernel<false, true><<<blocks, STET_THREADS, 0, ctx->stream>>>(B, nullptr);
+    } else {
+      if (B.atomic) assemble_mesh_tet4_kernel<true, false><<<blocks, STET_THREADS, 0, ctx->stream>>>(B, Do);
+      else assemble_mesh_tet4_kernel<false, false><<<blocks, STET_THREADS, 0, ctx->stream>>>(B, Do);
+    }
+    ctx->launches++;
+    if (cudaGetLastError() != cudaSuccess) { set_error("assemble_mesh_tet4_kernel launch failed"); return (int)SVB200_ERR_CUDA; }
+    return (int)SVB200_OK;
+  };
+  auto launch = [&](const StructArgs& B) {
+    if (m.eNoN == 4 && m.nG == 4 && !force_general) return launch_t4(B);
+    return m.eNoN == 8 ? launch_mesh<8>(ctx, B, Do) : launch_mesh<4>(ctx, B, Do);
+  };
   if (A.atomic) return launch(A);
   A.perm = m.d_color_perm;
   for (size_t c = 0; c + 1 < m.color_off.size(); c++) {
