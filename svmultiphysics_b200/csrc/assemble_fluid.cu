@@ -212,7 +212,7 @@ assemble_fluid_tet4_grouped_kernel(const __grid_constant__ FluidArgs P)
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  const int g = blockIdx.x;
+  const int g = P.gperm ? __ldg(P.gperm + P.g0 + blockIdx.x) : (int)blockIdx.x;
   double* T = tiles + (tid >> 5) * 32 * TILE_LD;
   // the group's plan goes to shared memory with cp.async (lands while phase 1 computes)
   {
@@ -376,7 +376,8 @@ static int launch_grouped(svb200_ctx* ctx, const FluidArgs& args)
                                   (int)smem));
     configured = true;
   }
-  const int nGrp = (args.e1 + ASM_GROUP - 1) / ASM_GROUP;
+  const int nGrp = args.gperm ? args.nGrpLaunch : (args.e1 + ASM_GROUP - 1) / ASM_GROUP;
+  if (nGrp <= 0) return SVB200_OK;
   assemble_fluid_tet4_grouped_kernel<NN><<<nGrp, ASM_GROUP, smem, ctx->stream>>>(args);
   ctx->launches++;
   SVB_CUDA(cudaGetLastError());
@@ -394,7 +395,7 @@ int launch_assemble_fluid(svb200_ctx* ctx, const Mesh& m, const FluidArgs& args)
   const int blocks = (n + ASM_THREADS - 1) / ASM_THREADS;
   static const int variant = getenv("SVB200_ASM_MINB") ? atoi(getenv("SVB200_ASM_MINB")) : 2;   // tuning knob
   static const bool legacy = getenv("SVB200_ASM_LEGACY") != nullptr;   // A/B knob: per-entry RED scatter
-  if (args.atomic && !legacy && args.kU_ptr && args.e0 == 0) {
+  if ((args.atomic || args.gperm) && !legacy && args.kU_ptr && args.e0 == 0) {
     bool nn = false;
     for (int d = 0; d < args.nDmn; d++) nn |= (args.dmn[d].viscType != SVB200_VISC_CONST);
     return nn ? launch_grouped<true>(ctx, args) : launch_grouped<false>(ctx, args);

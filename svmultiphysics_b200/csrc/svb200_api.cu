@@ -90,7 +90,7 @@ static int download_nodal(svb200_ctx* ctx, int rows, const double* d, double* h)
 
 static void free_mesh(Mesh& m)
 {
-  cudaFree(m.d_IEN); cudaFree(m.d_eId); cudaFree(m.d_fN); cudaFree(m.d_slot); cudaFree(m.d_color_perm); cudaFree(m.d_gtab);
+  cudaFree(m.d_IEN); cudaFree(m.d_eId); cudaFree(m.d_fN); cudaFree(m.d_slot); cudaFree(m.d_color_perm); cudaFree(m.d_gcolor_perm); cudaFree(m.d_gtab);
   free_group_sched(m.schedK); free_group_sched(m.schedR);
   m = Mesh();
 }
@@ -135,7 +135,37 @@ static int build_coloring(svb200_ctx* ctx, Mesh& m, const std::vector<int>& ien)
   for (int c = 0; c < ncol; c++) m.color_off[c + 1] += m.color_off[c];
   std::vector<int> pos(m.color_off.begin(), m.color_off.end() - 1), perm(m.nEl);
   for (int e = 0; e < m.nEl; e++) perm[pos[color[e]]++] = e;
-  return upload(ctx, &m.d_color_perm, perm.data(), perm.size());
+  { int rc = upload(ctx, &m.d_color_perm, perm.data(), perm.size()); if (rc) return rc; }
+  m.gcolor_off.clear();
+  if (m.eNoN != 4) return SVB200_OK;
+  // TET4: colour the 128-element GROUPS of the grouped scatter (group_sched.cu) the same way.  Groups of one colour share
+  // no node, hence no R row and no CSR block: launched colour by colour, the grouped kernel adds every value in a fixed
+  // order — the deterministic mode keeps the pre-reduction and the locality of the default path.
+  const int nGrp = (m.nEl + ASM_GROUP - 1) / ASM_GROUP;
+  std::fill(mask.begin(), mask.end(), 0); std::fill(mask2.begin(), mask2.end(), 0);
+  std::vector<int> gcolor(nGrp);
+  int ngc = 0;
+  for (int g = 0; g < nGrp; g++) {
+    const size_t b = (size_t)g * ASM_GROUP * 4, eend = std::min<size_t>((size_t)(g + 1) * ASM_GROUP, (size_t)m.nEl) * 4;
+    uint64_t u0 = 0, u1 = 0;
+    for (size_t k = b; k < eend; k++) { u0 |= mask[ien[k]]; u1 |= mask2[ien[k]]; }
+    int c;
+    if (~u0) c = __builtin_ctzll(~u0);
+    else if (~u1) c = 64 + __builtin_ctzll(~u1);
+    else return SVB200_OK;                    // more than 128 group colours: keep the per-element colouring only
+    gcolor[g] = c;
+    ngc = std::max(ngc, c + 1);
+    for (size_t k = b; k < eend; k++) {
+      if (c < 64) mask[ien[k]] |= (1ull << c);
+      else mask2[ien[k]] |= (1ull << (c - 64));
+    }
+  }
+  m.gcolor_off.assign(ngc + 1, 0);
+  for (int g = 0; g < nGrp; g++) m.gcolor_off[gcolor[g] + 1]++;
+  for (int c = 0; c < ngc; c++) m.gcolor_off[c + 1] += m.gcolor_off[c];
+  std::vector<int> gpos(m.gcolor_off.begin(), m.gcolor_off.end() - 1), gperm(nGrp);
+  for (int g = 0; g < nGrp; g++) gperm[gpos[gcolor[g]]++] = g;
+  return upload(ctx, &m.d_gcolor_perm, gperm.data(), gperm.size());
 }
 
 }  // namespace svb
@@ -561,6 +591,17 @@ static int run_assemble(svb200_ctx* ctx, const Mesh& m, FluidArgs& A, bool gener
     m.jac_checked = true;
   }
   if (A.atomic) return launch_assemble_fluid(ctx, m, A);
+  // deterministic mode: the grouped kernel, one launch per GROUP colour (SVB200_ASM_LEGACY=1: per-element colours, plain RMW)
+  static const bool legacy_colored = getenv("SVB200_ASM_LEGACY") != nullptr;
+  if (!legacy_colored && A.kU_ptr && m.d_gcolor_perm && !m.gcolor_off.empty()) {
+    A.gperm = m.d_gcolor_perm;
+    for (size_t c = 0; c + 1 < m.gcolor_off.size(); c++) {
+      A.g0 = m.gcolor_off[c];
+      A.nGrpLaunch = m.gcolor_off[c + 1] - m.gcolor_off[c];
+      TRY(launch_assemble_fluid(ctx, m, A));
+    }
+    return SVB200_OK;
+  }
   A.perm = m.d_color_perm;
   for (size_t c = 0; c + 1 < m.color_off.size(); c++) {
     A.e0 = m.color_off[c];

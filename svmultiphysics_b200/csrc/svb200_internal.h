@@ -42,6 +42,8 @@ struct Mesh {
   int* d_color_perm = nullptr;   // element ids sorted by colour (coloured scatter)
   GroupSched schedK, schedR;     // grouped scatter plans: tangent blocks / residual rows (TET4 meshes)
   std::vector<int> color_off;    // offsets into d_color_perm per colour
+  int* d_gcolor_perm = nullptr;  // TET4: ids of the 128-element groups of the grouped scatter, sorted by GROUP colour
+  std::vector<int> gcolor_off;   // offsets into d_gcolor_perm per group colour (groups of one colour share no node)
   std::vector<double> w, N, Nx;  // host copies of the reference-element tables
   std::vector<double> Nxx;       // (6,eNoN,nG) second parametric derivatives (svb200_set_mesh_nxx), empty = all zero
   double* d_gtab = nullptr;      // tables in the layout of assemble_fluid_gen.cu
@@ -103,6 +105,8 @@ struct FluidArgs {
   int tDof, mvMsh, nDmn, atomic;
   int ale, pad0;        // ale: element geometry is x + Dg(4..6) (fsi::construct_fsi, fsi.cpp:140-146)
   int* err;             // device error word: 1 + index of an element with a zero Jacobian (0 = none)
+  const int* gperm;     // grouped kernel: CTA blockIdx.x works on group gperm[g0 + blockIdx.x] (null: group blockIdx.x)
+  int g0, nGrpLaunch;   // first entry / number of entries of gperm in this launch (deterministic mode: one group colour)
   double dt, af, am, gam;
   double w[MAX_NG];
   double N[MAX_NG][MAX_ENON];        // N[g][a]

@@ -21,7 +21,7 @@ class FluidDmn(C.Structure):
 
 class FluidArgs(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("IEN", "eId", "slot", "perm", "kU_ptr", "kU_ent", "kU_partner", "kContrib", "rU_ptr", "rU_ent", "rContrib", "x", "Ag", "Yg", "Bf", "Dg", "R", "Val")] + \
-               [(k, C.c_int) for k in ("e0", "e1", "tDof", "mvMsh", "nDmn", "atomic", "ale", "pad0")] + [("err", C.c_void_p)] + \
+               [(k, C.c_int) for k in ("e0", "e1", "tDof", "mvMsh", "nDmn", "atomic", "ale", "pad0")] + [("err", C.c_void_p), ("gperm", C.c_void_p), ("g0", C.c_int), ("nGrpLaunch", C.c_int)] + \
                [(k, C.c_double) for k in ("dt", "af", "am", "gam")] + \
                [("w", C.c_double * 8), ("N", (C.c_double * 8) * 8), ("Nxi", ((C.c_double * 3) * 8) * 8), ("dmn", FluidDmn * 8)]
 
