@@ -56,12 +56,21 @@ struct UCol {
   UNode n;
   double DBm[6][3];
 };
-constexpr int USTRUCT_NB = 2;           // column nodes per pass of phase B
+constexpr int USTRUCT_NB = 1;           // column nodes per pass of phase B (2: 56 accumulators, spills)
 constexpr int UCOL_LD = (int)(sizeof(UCol) / sizeof(double));
-__host__ __device__ constexpr int ustruct_per_el(int enon, int ld)
+// Shared memory of one warp: the Gauss-point records of its 32/ENON elements (element stride padded to 4 (HEX8) / 2 (TET4)
+// mod 16 doubles: the elements of a warp read the same field at the same time), then ONE area that holds the column-node
+// records of the current pass and, once the pass has consumed them, the 32 x 29 transposition tile of the scatter.
+__host__ __device__ constexpr int ustruct_el_ld(int enon, int ld)
 {
-  const int n = enon * ld + enon * USTRUCT_NB * UCOL_LD, want = (enon == 8) ? 4 : 2;
+  const int n = enon * ld, want = (enon == 8) ? 4 : 2;
   return n + ((want - (n % 16)) + 16) % 16;
+}
+__host__ __device__ constexpr int ustruct_warp_ld(int enon, int ld)
+{
+  const int epw = 32 / enon;
+  const int cols = epw * enon * USTRUCT_NB * UCOL_LD, tile = 32 * 29;
+  return epw * ustruct_el_ld(enon, ld) + (cols > tile ? cols : tile);
 }
 template <bool VISC> struct UGPSel { using type = UGP; };
 template <> struct UGPSel<true> { using type = UGPV; };
@@ -82,12 +91,16 @@ assemble_ustruct_kernel(const __grid_constant__ UstructArgs P)
   using GP = typename UGPSel<VISC>::type;
   constexpr int EPW = 32 / ENON;
   constexpr int NB = USTRUCT_NB;
-  constexpr int PER_EL = ustruct_per_el(ENON, (int)(sizeof(GP) / sizeof(double)));
+  constexpr int GP_LDD = (int)(sizeof(GP) / sizeof(double));
+  constexpr int EL_LD = ustruct_el_ld(ENON, GP_LDD);
+  constexpr int WARP_LD = ustruct_warp_ld(ENON, GP_LDD);
   extern __shared__ double sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int a = lane % ENON, el = lane / ENON;
-  GP* gp = reinterpret_cast<GP*>(sm + (size_t)(warp * EPW + el) * PER_EL);
-  UCol (*col)[NB] = reinterpret_cast<UCol (*)[NB]>(reinterpret_cast<double*>(gp) + ENON * (sizeof(GP) / sizeof(double)));
+  double* wbase = sm + (size_t)warp * WARP_LD;
+  GP* gp = reinterpret_cast<GP*>(wbase + (size_t)el * EL_LD);
+  double* tile = wbase + (size_t)EPW * EL_LD;                 // aliases the column-node records (see above)
+  UCol (*col)[NB] = reinterpret_cast<UCol (*)[NB]>(tile + (size_t)el * ENON * NB * UCOL_LD);
 
   const long long idx = (long long)P.e0 + ((long long)blockIdx.x * (USTRUCT_THREADS / 32) + warp) * EPW + el;
   bool active = idx < P.e1;
@@ -173,8 +186,6 @@ assemble_ustruct_kernel(const __grid_constant__ UstructArgs P)
   // with consecutive lanes on consecutive doubles (a half-warp = one 128-byte Val block) — lane-strided REDs run at a
   // third of the coalesced rate or worse (profiles/r1_microbench_fp64_red.txt: 174 vs 554 G adds/s, 42 vs 285 from DRAM).
   constexpr int TILE_LD = 29;
-  double* tile = sm + (size_t)(USTRUCT_THREADS / 32) * EPW * PER_EL + (size_t)warp * (32 * TILE_LD + 16);
-  int* tslot = reinterpret_cast<int*>(tile + 32 * TILE_LD);
   const int* sl = P.slot + (size_t)e * ENON * ENON + a * ENON;
 #pragma unroll 1
   for (int b0 = 0; b0 < ENON; b0 += NB) {
@@ -225,18 +236,18 @@ assemble_ustruct_kernel(const __grid_constant__ UstructArgs P)
       for (int i = 0; i < 16; i++) tile[lane * TILE_LD + i] = K[k][i];
 #pragma unroll
       for (int i = 0; i < 12; i++) tile[lane * TILE_LD + 16 + i] = Kd[k][i];
-      tslot[lane] = active ? sl[b0 + k] : -1;
+      const int myslot = active ? sl[b0 + k] : -1;
       __syncwarp();
 #pragma unroll
       for (int it = 0; it < 16; it++) {             // 32 Val blocks x 16 doubles
         const int p = it * 32 + lane, src = p >> 4, i = p & 15;
-        const int s_ = tslot[src];
+        const int s_ = __shfl_sync(0xffffffffu, myslot, src);
         if (s_ >= 0) uadd<ATOMIC>(P.Val + (size_t)16 * s_ + i, tile[src * TILE_LD + i]);
       }
 #pragma unroll
       for (int it = 0; it < 12; it++) {             // 32 Kd blocks x 12 doubles
         const int p = it * 32 + lane, src = p / 12, i = p - 12 * src;
-        const int s_ = tslot[src];
+        const int s_ = __shfl_sync(0xffffffffu, myslot, src);
         if (s_ >= 0) uadd<ATOMIC>(P.Kd + (size_t)12 * s_ + i, tile[src * TILE_LD + 16 + i]);
       }
     }
@@ -248,8 +259,7 @@ static int launch_ustruct(svb200_ctx* ctx, const UstructArgs& A, bool atomic)
 {
   using GP = typename UGPSel<VISC>::type;
   constexpr int EPB = (USTRUCT_THREADS / 32) * (32 / ENON);
-  constexpr size_t smem = sizeof(double) * ((size_t)EPB * ustruct_per_el(ENON, (int)(sizeof(GP) / sizeof(double))) +
-                                            (size_t)(USTRUCT_THREADS / 32) * (32 * 29 + 16));
+  constexpr size_t smem = sizeof(double) * (size_t)(USTRUCT_THREADS / 32) * ustruct_warp_ld(ENON, (int)(sizeof(GP) / sizeof(double)));
   static bool configured = false;
   if (!configured) {
     SVB_CUDA(cudaFuncSetAttribute(assemble_ustruct_kernel<ENON, true, VISC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
