@@ -108,6 +108,43 @@ def test_fsi_assembly_parity(scatter):
     eng.close()
 
 
+def test_fsi_two_meshes_parity():
+    """The layout of tests/cases/fsi/pipe_3d: TWO meshes over one node set (lumen = fluid domain, wall = solid domain), assembled
+    mesh by mesh into the same R / Val like the loop over msh[] around global_eq_assem (eq_assem.cpp:377).  Each launch then
+    sees only elements of its own physics (the all-active fast path of the grouped fluid kernel, the TET4 solid kernel)."""
+    cls = _oracle()
+    from svmultiphysics_b200.engine import Engine
+    m, Ag, Yg, Dg, Bf = common.fsi_case()
+    fl, so = np.where(m.eId == 1)[0], np.where(m.eId == 2)[0]
+    af, am, gam, beta = abi.gen_alpha(0.5)
+    eq = abi.EqParams(dt=1e-3, af=af, am=am, gam=gam, beta=beta, phys=abi.PHYS_FSI, dof=4, tDof=7, s=0, mvMsh=1, vmsStab=1,
+                      scatter=abi.SCATTER_ATOMIC, reserved=0)
+    dmn = [abi.fluid_domain(rho=1.0, mu=0.04, Id=0), abi.struct_domain(rho=1.0, volType=abi.VOL_M94, E=1e7, nu=0.3, Kpen=1e7 / (3 * (1 - 0.6)), Id=1)]
+    orc = cls(); orc.set_coords(m.x)
+    orc.add_mesh(np.asfortranarray(m.IEN[:, fl]), eId=m.eId[fl]); orc.add_mesh(np.asfortranarray(m.IEN[:, so]), eId=m.eId[so])
+    rowPtr, colPtr = orc.build_graph(0)
+    orc.alloc(4); orc.set_state(Ag, Yg, Dg, Bf); orc.assemble(0, eq, dmn); orc.assemble(1, eq, dmn)
+    R0, V0 = orc.get_R(), orc.get_Val()
+    # the one-mesh layout of the other tests gives the same system (the CSR columns are sorted, lhsa.cpp:13-54)
+    one = cls(); one.set_coords(m.x); one.add_mesh(m.IEN, eId=m.eId)
+    rp1, cp1 = one.build_graph(0)
+    assert np.array_equal(rp1, rowPtr) and np.array_equal(cp1, colPtr)
+    one.alloc(4); one.set_state(Ag, Yg, Dg, Bf); one.assemble(0, eq, dmn)
+    assert common.rel_err(one.get_R(), R0) < 1e-13
+    eng = Engine(0)
+    eng.set_graph(rowPtr, colPtr)
+    w, N, Nx = elements.tables(4)
+    eng.set_mesh(0, np.asfortranarray(m.IEN[:, fl]), w, N, Nx, eId=m.eId[fl])
+    eng.set_mesh(1, np.asfortranarray(m.IEN[:, so]), w, N, Nx, eId=m.eId[so])
+    eng.set_coords(m.x)
+    eng.alloc(4); eng.set_state(Ag, Yg, Dg, Bf); eng.assemble(0, eq, dmn); eng.assemble(1, eq, dmn)
+    R1, V1 = eng.get_R(), eng.get_Val()
+    assert common.rel_err(R1, R0) < ASM_TOL and common.rel_err(V1, V0) < ASM_TOL
+    fl_rows = np.unique(m.IEN[:, fl])
+    assert common.rel_err(R1[:, fl_rows], R0[:, fl_rows]) < 1e-11
+    eng.close()
+
+
 def test_fsi_solve_history():
     """GMRES(50) on the coupled FSI system (config C5).  The system is ill-conditioned (solid blocks ~1e7 x the fluid
     ones): the residual histories of the device and of the reference agree to round-off over the first iterations and

@@ -29,6 +29,19 @@ for _ in range(reps):
     e.timer_mark(0); e.assemble(0, eq, dmn); e.timer_mark(1)
     ms = e.timer_elapsed()
     print(f"FSI assemble (construct_fsi) {ms:.3f} ms  {m.nEl/ms*1e-6:.3f} G el/s")
+# the layout of tests/cases/fsi/pipe_3d: lumen and wall as two meshes over the same nodes, assembled mesh by mesh
+fl, so = np.where(m.eId == 1)[0], np.where(m.eId == 2)[0]
+e2 = Engine(0)
+e2.set_graph(rp, cp)
+e2.set_mesh(0, np.asfortranarray(m.IEN[:, fl]), w, N, Nx, eId=m.eId[fl]); e2.set_mesh(1, np.asfortranarray(m.IEN[:, so]), w, N, Nx, eId=m.eId[so])
+e2.set_coords(m.x)
+e2.alloc(4); e2.set_state(Ag, Yg, Dg, Bf); e2.assemble(0, eq, dmn); e2.assemble(1, eq, dmn)
+for _ in range(reps):
+    e2.alloc(4)
+    e2.timer_mark(0); e2.assemble(0, eq, dmn); e2.assemble(1, eq, dmn); e2.timer_mark(1)
+    ms = e2.timer_elapsed()
+    print(f"FSI assemble, lumen + wall as two meshes {ms:.3f} ms  {m.nEl/ms*1e-6:.3f} G el/s")
+e2.close()
 wall = m.faces["wall"]
 e.set_num_faces(1); e.set_face(0, abi.BC_DIR, wall, np.zeros((3, len(wall)), order="F"))
 ls = abi.ls_params(abi.LS_GMRES, mItr=2, sD=50, relTol=1e-8)
