@@ -78,6 +78,42 @@ bsr_spmv_kernel(int nNo, const int* __restrict__ rowPtr, const int* __restrict__
   KU[t] = acc;
 }
 
+// dof = 3, long rows (HEX8 meshes: 27 blocks = 1944 contiguous bytes per row): one warp streams the row's Val segment with
+// consecutive lanes on consecutive doubles, every lane multiplies its doubles with the matching U entries and adds them to
+// the accumulator of their block row; three butterfly reductions finish the row.  MEASURED AND REJECTED as the default (B200, C4,
+// 9.8 GB matrix, gpurun_out/r1n_spmv3_ab.log): 4.50 ms = 2.36 TB/s against 2.06 ms = 5.15 TB/s of the thread-per-(row, i) kernel
+// above, whose three threads of a row keep the row's lines in L1 across the k loop and carry no index arithmetic or shuffles per
+// double.  Kept behind SVB200_SPMV3=warp as the A/B reference.
+__global__ void __launch_bounds__(256)
+bsr_spmv3_warp_kernel(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ colPtr,
+                      const double* __restrict__ Val, const double* __restrict__ U, double* __restrict__ KU)
+{
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= nNo) return;
+  const int row = (int)w;
+  const int k0 = __ldg(rowPtr + row), k1 = __ldg(rowPtr + row + 1);
+  const int nd = (k1 - k0) * 9;
+  const double* v = Val + (size_t)k0 * 9;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  for (int p = lane; p < nd; p += 32) {
+    const double x = __ldcs(v + p);
+    const int kb = p / 9, r = p - 9 * kb, i = r / 3, j = r - 3 * i;
+    const int c = __ldg(colPtr + k0 + kb);
+    const double t = x * __ldg(U + (size_t)c * 3 + j);
+    if (i == 0) a0 += t;
+    else if (i == 1) a1 += t;
+    else a2 += t;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+  }
+  if (lane < 3) KU[(size_t)row * 3 + lane] = (lane == 0) ? a0 : (lane == 1 ? a1 : a2);
+}
+
 int launch_spmv(svb200_ctx* ctx, int dof, const double* Val, const double* U, double* KU)
 {
   const int nNo = ctx->nNo;
@@ -91,7 +127,17 @@ int launch_spmv(svb200_ctx* ctx, int dof, const double* Val, const double* U, do
     switch (dof) {
       case 1: bsr_spmv_kernel<1><<<blocks, 256, 0, ctx->stream>>>(nNo, ctx->d_rowPtr, ctx->d_colPtr, Val, U, KU); break;
       case 2: bsr_spmv_kernel<2><<<blocks, 256, 0, ctx->stream>>>(nNo, ctx->d_rowPtr, ctx->d_colPtr, Val, U, KU); break;
-      case 3: bsr_spmv_kernel<3><<<blocks, 256, 0, ctx->stream>>>(nNo, ctx->d_rowPtr, ctx->d_colPtr, Val, U, KU); break;
+      case 3: {
+        // SVB200_SPMV3=warp selects the warp-per-row form (A/B knob; measured slower, see the kernel's comment)
+        static const char* mode = getenv("SVB200_SPMV3");
+        const bool warp_form = mode && mode[0] == 'w';
+        if (warp_form) {
+          const long long th = (long long)nNo * 32;
+          bsr_spmv3_warp_kernel<<<(unsigned)((th + 255) / 256), 256, 0, ctx->stream>>>(nNo, ctx->d_rowPtr, ctx->d_colPtr, Val, U, KU);
+        } else {
+          bsr_spmv_kernel<3><<<blocks, 256, 0, ctx->stream>>>(nNo, ctx->d_rowPtr, ctx->d_colPtr, Val, U, KU);
+        }
+      } break;
       default:
         set_error("svb200: SpMV supports dof 1..4");
         return SVB200_ERR_UNSUPPORTED;
