@@ -72,7 +72,11 @@ rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo")
 n, nz = 3, 4
 m = meshgen.cylinder_tet4(n, nz)
-part = ((np.arange(m.nEl) // 6) // (n * n) * world // nz).astype(np.int32)
+if len(sys.argv) > 2 and sys.argv[2] == "metis":
+    from oracle import metis_part
+    part, _ = metis_part.part_mesh_dual(m.IEN, m.nNo, world)
+else:
+    part = ((np.arange(m.nEl) // 6) // (n * n) * world // nz).astype(np.int32)
 parts = partition.partition_mesh(m.IEN, m.nNo, part, world)
 p = parts[rank]
 # a nodal field that is a partial sum on every rank: value = number of local elements touching the node
@@ -101,11 +105,16 @@ sys.exit(0 if flag.item() == 1 else 1)
 '''
 
 
-def test_halo_sum_pattern_gloo_world2(tmp_path):
+@pytest.mark.parametrize("world,mode", [(2, "slab"), (3, "metis")])
+def test_halo_sum_pattern_gloo_world2(tmp_path, world, mode):
     import subprocess
+    if mode == "metis":
+        from oracle import metis_part
+        if not metis_part.have_metis():
+            pytest.skip("needs oracle/_ref/libsvmetis.so (make -C oracle metis)")
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", str(script), ROOT]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29533" if world == 2 else "29534", str(script), ROOT, mode]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:]
