@@ -482,39 +482,27 @@ assemble_struct_tet4_kernel(const __grid_constant__ StructArgs P)
     for (int r = 0; r < 6; r++)
 #pragma unroll
       for (int c = 0; c < 6; c++) s_Dm[6 * r + c][threadIdx.x] = Dm[r][c];
-    // reference-element moments of the quadrature rule (4 points): sum w, sum w N_a, sum w N_a N_b
-    double m1[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int g = 0; g < 4; g++) {
-      const double wg = P.w[g] * Jac;
-      W += wg;
-#pragma unroll
-      for (int a = 0; a < 4; a++) {
-        m1[a] += wg * P.N[g][a];
-#pragma unroll
-        for (int b = 0; b < 4; b++) M2[a][b] += wg * P.N[g][a] * P.N[g][b];
-      }
-    }
-    // residual
+    // moments of the quadrature rule, residual (struct_elem.cuh: the same routines the CPU suite checks against the reference)
+    Tet4Mom q;
+    tet4_moments(P.w, &P.N[0][0], MAX_ENON, Jac, q);
+    W = q.W;
     double Pk[3][3];
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
       for (int j = 0; j < 3; j++) Pk[i][j] = F[i][0] * S[0][j] + F[i][1] * S[1][j] + F[i][2] * S[2][j];
 #pragma unroll
-    for (int a = 0; a < 4; a++)
+    for (int a = 0; a < 4; a++) {
+      double r[3];
+      struct_tet4_residual(dm, q, a, Nx[a], Pk, ql, r);
 #pragma unroll
-      for (int i = 0; i < 3; i++) {
-        double r = -dm.rho * dm.f[i] * m1[a] + W * (Pk[i][0] * Nx[a][0] + Pk[i][1] * Nx[a][1] + Pk[i][2] * Nx[a][2]);
-#pragma unroll
-        for (int b = 0; b < 4; b++) r += M2[a][b] * ql[b][i];
-        add64<ATOMIC>(P.R + (size_t)DOF * node[a] + i, r);
-      }
+      for (int i = 0; i < 3; i++) add64<ATOMIC>(P.R + (size_t)DOF * node[a] + i, r[i]);
+    }
     // from here on only amd M_ab is needed
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
-      for (int b = 0; b < 4; b++) M2[a][b] *= amd;
+      for (int b = 0; b < 4; b++) M2[a][b] = amd * q.M2[a][b];
   }
 
   // tangent blocks a <= b; every lane of the warp takes part in the deposit / add steps (lanes without an element carry
@@ -542,16 +530,7 @@ assemble_struct_tet4_kernel(const __grid_constant__ StructArgs P)
     for (int a = 0; a <= b; a++) {
       double Bma[6][3], K[3][3];
       make_Bm(Nx[a], F, Bma);
-      const double T1 = M2[a][b] + wafu * (Nx[a][0] * SNb[0] + Nx[a][1] * SNb[1] + Nx[a][2] * SNb[2]);
-#pragma unroll
-      for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-          double t = 0.0;
-#pragma unroll
-          for (int r = 0; r < 6; r++) t += Bma[r][i] * DBmb[r][j];
-          K[i][j] = wafu * t + (i == j ? T1 : 0.0);
-        }
+      struct_tet4_block(wafu, M2[a][b], Nx[a], SNb, Bma, DBmb, K);
       warp_scatter_block_pair<ATOMIC>(tile, tsl, lane, K, sl[4 * a + b], (a != b) ? sl[4 * b + a] : -1, a != b, P.Val, DD, DOF);
     }
   }
@@ -836,45 +815,22 @@ assemble_mesh_tet4_kernel(const __grid_constant__ StructArgs P, const double* __
       }
     }
     const double Jac = gnn3<4>(P.Nxi[0], xl, Nx);
-    double m1[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int g = 0; g < 4; g++) {
-      const double wg = LELAS ? P.w[g] * Jac : P.w[g];
-      W += wg;
-#pragma unroll
-      for (int a = 0; a < 4; a++) {
-        m1[a] += wg * P.N[g][a];
-#pragma unroll
-        for (int b = 0; b < 4; b++) M2[a][b] += wg * P.N[g][a] * P.N[g][b];
-      }
-    }
-    double ed[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-      ed[0] += Nx[b][0] * dl[b][0];
-      ed[1] += Nx[b][1] * dl[b][1];
-      ed[2] += Nx[b][2] * dl[b][2];
-      ed[3] += Nx[b][1] * dl[b][0] + Nx[b][0] * dl[b][1];
-      ed[4] += Nx[b][2] * dl[b][1] + Nx[b][1] * dl[b][2];
-      ed[5] += Nx[b][0] * dl[b][2] + Nx[b][2] * dl[b][0];
-    }
-    const double divD = lambda * (ed[0] + ed[1] + ed[2]);
-    const double S0 = divD + 2.0 * mu * ed[0], S1 = divD + 2.0 * mu * ed[1], S2 = divD + 2.0 * mu * ed[2];
-    const double S3 = mu * ed[3], S4 = mu * ed[4], S5 = mu * ed[5];
+    Tet4Mom q;
+    tet4_moments(P.w, &P.N[0][0], MAX_ENON, LELAS ? Jac : 1.0, q);
+    W = q.W;
+    double S[6];
+    lelas_tet4_stress(lambda, mu, Nx, dl, S);
 #pragma unroll
     for (int a = 0; a < 4; a++) {
       double r[3];
-      r[0] = W * (Nx[a][0] * S0 + Nx[a][1] * S3 + Nx[a][2] * S5);
-      r[1] = W * (Nx[a][0] * S3 + Nx[a][1] * S1 + Nx[a][2] * S4);
-      r[2] = W * (Nx[a][0] * S5 + Nx[a][1] * S4 + Nx[a][2] * S2);
+      lelas_tet4_residual(rho, dm.f, q, a, Nx[a], S, ql, r);
 #pragma unroll
-      for (int i = 0; i < 3; i++) {
-        double t = -dm.f[i] * m1[a];
-#pragma unroll
-        for (int b = 0; b < 4; b++) t += M2[a][b] * ql[b][i];
-        add64<ATOMIC>(P.R + (size_t)DOF * node[a] + i, r[i] + rho * t);
-      }
+      for (int i = 0; i < 3; i++) add64<ATOMIC>(P.R + (size_t)DOF * node[a] + i, r[i]);
     }
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) M2[a][b] = q.M2[a][b];
   }
   const double c0 = T1c * amd, c1 = T1c * mu * W;
 #pragma unroll
@@ -882,11 +838,7 @@ assemble_mesh_tet4_kernel(const __grid_constant__ StructArgs P, const double* __
 #pragma unroll
     for (int a = 0; a <= b; a++) {
       double K[3][3];
-      const double T1 = c0 * M2[a][b] + c1 * (Nx[a][0] * Nx[b][0] + Nx[a][1] * Nx[b][1] + Nx[a][2] * Nx[b][2]);
-#pragma unroll
-      for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) K[i][j] = c1 * (lDm * Nx[a][i] * Nx[b][j] + Nx[a][j] * Nx[b][i]) + (i == j ? T1 : 0.0);
+      lelas_tet4_block(c0 * M2[a][b], c1, lDm, Nx[a], Nx[b], K);
       warp_scatter_block_pair<ATOMIC>(tile, tsl, lane, K, sl[4 * a + b], (a != b) ? sl[4 * b + a] : -1, a != b, P.Val, DD, DOF);
     }
 }

@@ -393,6 +393,111 @@ SVB_HD void struct_block(double K[3][3], double w, double amdNaNb, double afu, c
     }
 }
 
+
+// ---- linear tetrahedra in closed form (assemble_struct_tet4_kernel, assemble_mesh_tet4_kernel) -------------------------
+// Moments of the quadrature rule: W = sum_g w_g, m1_a = sum_g w_g N_a(g), M2_ab = sum_g w_g N_a(g) N_b(g); `scale` is the
+// element Jacobian (struct, lElas) or 1 (mesh equation: Jacobian-free weight, mesh.cpp:122).  N is indexed [g][a] with row
+// stride ldN.
+struct Tet4Mom {
+  double W, m1[4], M2[4][4];
+};
+
+SVB_HD void tet4_moments(const double* w, const double* N, int ldN, double scale, Tet4Mom& q)
+{
+  q.W = 0.0;
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    q.m1[a] = 0.0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) q.M2[a][b] = 0.0;
+  }
+#pragma unroll
+  for (int g = 0; g < 4; g++) {
+    const double wg = w[g] * scale;
+    q.W += wg;
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      q.m1[a] += wg * N[g * ldN + a];
+#pragma unroll
+      for (int b = 0; b < 4; b++) q.M2[a][b] += wg * N[g * ldN + a] * N[g * ldN + b];
+    }
+  }
+}
+
+// struct_3d residual of node a: lR(i) = -rho f_i m1_a + sum_b M2_ab q_b(i) + W (F S grad N_a)_i, q_b = rho (a_b - bf_b) + dmp v_b.
+SVB_HD void struct_tet4_residual(const StructDmn& dm, const Tet4Mom& q, int a, const double Nxa[3], const double Pk[3][3],
+                                 const double ql[4][3], double lR[3])
+{
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    double r = -dm.rho * dm.f[i] * q.m1[a] + q.W * (Pk[i][0] * Nxa[0] + Pk[i][1] * Nxa[1] + Pk[i][2] * Nxa[2]);
+#pragma unroll
+    for (int b = 0; b < 4; b++) r += q.M2[a][b] * ql[b][i];
+    lR[i] = r;
+  }
+}
+
+// struct_3d block (a,b): K(i,j) = delta_ij (amd M2_ab + afu W grad N_a . S grad N_b) + afu W Bm_a(:,i) . DBm_b(:,j).
+SVB_HD void struct_tet4_block(double wafu, double amdMab, const double Nxa[3], const double SNb[3], const double Bma[6][3],
+                              const double DBmb[6][3], double K[3][3])
+{
+  const double T1 = amdMab + wafu * (Nxa[0] * SNb[0] + Nxa[1] * SNb[1] + Nxa[2] * SNb[2]);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      double t = 0.0;
+#pragma unroll
+      for (int r = 0; r < 6; r++) t += Bma[r][i] * DBmb[r][j];
+      K[i][j] = wafu * t + (i == j ? T1 : 0.0);
+    }
+}
+
+// l_elas_3d (mesh / lElas equation) on a linear tet: Voigt stress of the constant strain, residual of node a, block (a,b).
+SVB_HD void lelas_tet4_stress(double lambda, double mu, const double Nx[4][3], const double dl[4][3], double S[6])
+{
+  double ed[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    ed[0] += Nx[b][0] * dl[b][0];
+    ed[1] += Nx[b][1] * dl[b][1];
+    ed[2] += Nx[b][2] * dl[b][2];
+    ed[3] += Nx[b][1] * dl[b][0] + Nx[b][0] * dl[b][1];
+    ed[4] += Nx[b][2] * dl[b][1] + Nx[b][1] * dl[b][2];
+    ed[5] += Nx[b][0] * dl[b][2] + Nx[b][2] * dl[b][0];
+  }
+  const double divD = lambda * (ed[0] + ed[1] + ed[2]);
+  S[0] = divD + 2.0 * mu * ed[0]; S[1] = divD + 2.0 * mu * ed[1]; S[2] = divD + 2.0 * mu * ed[2];
+  S[3] = mu * ed[3]; S[4] = mu * ed[4]; S[5] = mu * ed[5];
+}
+
+SVB_HD void lelas_tet4_residual(double rho, const double f[3], const Tet4Mom& q, int a, const double Nxa[3], const double S[6],
+                                const double ql[4][3], double lR[3])
+{
+  double r[3];
+  r[0] = q.W * (Nxa[0] * S[0] + Nxa[1] * S[3] + Nxa[2] * S[5]);
+  r[1] = q.W * (Nxa[0] * S[3] + Nxa[1] * S[1] + Nxa[2] * S[4]);
+  r[2] = q.W * (Nxa[0] * S[5] + Nxa[1] * S[4] + Nxa[2] * S[2]);
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    double t = -f[i] * q.m1[a];
+#pragma unroll
+    for (int b = 0; b < 4; b++) t += q.M2[a][b] * ql[b][i];
+    lR[i] = r[i] + rho * t;
+  }
+}
+
+// K(i,j) = T1c [ delta_ij (amd M2_ab + mu W grad N_a . grad N_b) + mu W (lDm Nx_a(i) Nx_b(j) + Nx_a(j) Nx_b(i)) ]; c0 = T1c amd,
+// c1 = T1c mu W.
+SVB_HD void lelas_tet4_block(double c0Mab, double c1, double lDm, const double Nxa[3], const double Nxb[3], double K[3][3])
+{
+  const double T1 = c0Mab + c1 * (Nxa[0] * Nxb[0] + Nxa[1] * Nxb[1] + Nxa[2] * Nxb[2]);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) K[i][j] = c1 * (lDm * Nxa[i] * Nxb[j] + Nxa[j] * Nxb[i]) + (i == j ? T1 : 0.0);
+}
+
 // ---- solid viscosity (mat_models.cpp:1583-1762) ----------------------------------------------------------
 // Both models of compute_visc_stress_and_tangent have the same structure: three vectors per element node,
 //     V1_a = T grad N_a,  V2_a = A V1_a,  V3_a = B V1_a,

@@ -242,3 +242,19 @@ def ustruct_state(m, nFn=0, seed=23):
 def ustruct_Ad(m, seed=29):
     """com_mod.Ad(3, tnNo): time derivative of the displacement (Integrator.cpp:412, ustruct_r)."""
     return np.asfortranarray(0.05 * np.random.default_rng(seed).standard_normal((3, m.nNo)))
+
+
+# ---- l_elas_3d on TET4: linear-elasticity equation and mesh-motion equation ------------------------------------------
+LELAS_CASES = ["lelas_tet4", "mesh_tet4"]
+
+
+def lelas_case(name):
+    """(mesh, Ag, Yg, Dg, Bf, Do or None, eq, domains)"""
+    if name == "lelas_tet4":
+        m = _tet()
+        Ag, Yg, Dg, Bf, _ = struct_state(m, 0)
+        return m, Ag, Yg, Dg, Bf, None, abi.lelas_eq(1e-3), [abi.lelas_domain(E=1.0e6, nu=0.3, rho=2.0, f=(0.1, -0.2, 0.3))]
+    m, Ag, Yg, Dg, Bf = fsi_case()
+    m.eId = None
+    Do = np.asfortranarray(0.9 * Dg)
+    return m, Ag, Yg, Dg, Bf, Do, abi.mesh_eq(1e-3), [abi.mesh_domain(E=1.0, nu=0.3)]

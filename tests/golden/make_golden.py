@@ -117,10 +117,27 @@ def ustruct_golden():
     print("wrote ustruct.npz with", len(out), "arrays")
 
 
+def lelas_golden():
+    """R / Val of l_elas_3d on TET4: the linear-elasticity equation and the mesh-motion equation (tDof = 7, old displacement)."""
+    out = {}
+    for name in common.LELAS_CASES:
+        m, Ag, Yg, Dg, Bf, Do, eq, dmn = common.lelas_case(name)
+        c = RefCase(); c.set_coords(m.x); c.add_mesh(m.IEN)
+        rowPtr, colPtr = c.build_graph(0)
+        c.alloc(3); c.set_state(Ag, Yg, Dg, Bf)
+        if Do is not None:
+            c.set_old_disp(Do)
+        c.assemble(0, eq, dmn)
+        out[f"{name}/R"], out[f"{name}/Val"] = c.get_R(), c.get_Val()
+        out[f"{name}/rowPtr"], out[f"{name}/colPtr"] = rowPtr, colPtr
+    np.savez_compressed(os.path.join(HERE, "lelas.npz"), **out)
+    print("wrote lelas.npz with", len(out), "arrays")
+
+
 if __name__ == "__main__":
     if not have_ref():
         raise SystemExit("oracle/_ref/libsvref.so is missing: run `make -C oracle ref` first")
     only = sys.argv[1:]
-    for fn in (fluid_golden, struct_golden, fluid_gen_golden, heat_golden, ustruct_golden):
+    for fn in (fluid_golden, struct_golden, fluid_gen_golden, heat_golden, ustruct_golden, lelas_golden):
         if not only or fn.__name__.replace("_golden", "") in only:
             fn()

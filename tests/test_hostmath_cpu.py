@@ -281,3 +281,75 @@ def test_device_ustruct_algebra_matches_golden(hostmath, name, mk, dkw, nFn):
     G = golden[f"{name}/Val"]
     for rows in ([0, 1, 2, 4, 5, 6, 8, 9, 10], [3, 7, 11], [12, 13, 14], [15]):
         assert common.rel_err(V.T[rows], G[rows]) < 1e-12
+
+
+class HostTet4Args(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("IEN", "fN", "x", "Ag", "Yg", "Dg", "Bf", "Do")] + \
+               [(k, C.c_int) for k in ("nEl", "tDof", "dof", "s", "nFn", "kind")] + \
+               [(k, C.c_double) for k in ("dt", "af", "am", "gam", "beta")] + \
+               [("w", C.c_double * 8), ("N", (C.c_double * 8) * 8), ("Nxi", ((C.c_double * 3) * 8) * 8), ("dm", StructDmn)]
+
+
+def _run_tet4(hostmath, m, Ag, Yg, Dg, Bf, Do, eq, kind, fill_dm, nFn, fN, rowPtr, colPtr):
+    assert hostmath.hostmath_sizeof_tet4args() == C.sizeof(HostTet4Args)
+    A = HostTet4Args()
+    keep = [np.ascontiguousarray(m.IEN.T.astype(np.int32)), np.ascontiguousarray(m.x.T), np.ascontiguousarray(Ag.T),
+            np.ascontiguousarray(Yg.T), np.ascontiguousarray(Dg.T), np.ascontiguousarray(Bf.T)]
+    A.IEN, A.x, A.Ag, A.Yg, A.Dg, A.Bf = (k.ctypes.data for k in keep)
+    if Do is not None:
+        dk = np.ascontiguousarray(Do.T); keep.append(dk)
+        A.Do = dk.ctypes.data
+    if nFn:
+        fk = np.ascontiguousarray(fN.T); keep.append(fk)
+        A.fN = fk.ctypes.data
+    A.nEl, A.tDof, A.dof, A.s, A.nFn, A.kind = m.nEl, eq.tDof, eq.dof, eq.s, nFn, kind
+    assert _fill_tables(A, 4) == 4
+    A.dt, A.af, A.am, A.gam, A.beta = eq.dt, eq.af, eq.am, eq.gam, eq.beta
+    fill_dm(A.dm)
+    R = np.zeros((m.nNo, eq.dof))
+    V = np.zeros((len(colPtr), eq.dof * eq.dof))
+    rc = hostmath.hostmath_tet4(C.byref(A), rowPtr.ctypes.data_as(C.c_void_p), colPtr.ctypes.data_as(C.c_void_p),
+                                R.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return R.T, V.T
+
+
+@pytest.mark.parametrize("name,mk,dkw,nFn", [c for c in common.STRUCT_CASES if c[0].startswith("tet4") and "visc" not in c[0]],
+                         ids=[c[0] for c in common.STRUCT_CASES if c[0].startswith("tet4") and "visc" not in c[0]])
+def test_tet4_closed_form_solid_matches_golden(hostmath, name, mk, dkw, nFn):
+    """The closed-form Gauss sums of assemble_struct_tet4_kernel (tet4_moments, struct_tet4_residual, struct_tet4_block) against
+    the R / Val that struct_3d produced with its four-point Gauss loop in the compiled reference."""
+    golden = common.load_golden("struct.npz")
+    m = mk()
+    Ag, Yg, Dg, Bf, fN = common.struct_state(m, nFn)
+    eq, d = abi.struct_eq(1e-4), abi.struct_domain(**dkw)
+
+    def fill(dm):
+        dm.rho, dm.dmp, dm.Kpen, dm.C10, dm.C01, dm.bff, dm.bss, dm.bfs = d.rho, d.dmp, d.Kpen, d.C10, d.C01, d.bff, d.bss, d.bfs
+        for i in range(3):
+            dm.f[i] = d.f[i]
+        dm.st_a, dm.st_b, dm.aff, dm.ass, dm.afs, dm.kap, dm.khs = d.st_a, d.st_b, d.aff, d.ass, d.afs, d.kap, d.khs
+        dm.isoType, dm.volType, dm.Id, dm.isStruct = d.isoType, d.volType, -1, 1
+    R, V = _run_tet4(hostmath, m, Ag, Yg, Dg, Bf, None, eq, 0, fill, nFn, fN, golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"])
+    assert common.rel_err(R, golden[f"{name}/R"]) < 1e-12
+    assert common.rel_err(V, golden[f"{name}/Val"]) < 1e-12
+
+
+@pytest.mark.parametrize("name", common.LELAS_CASES)
+def test_tet4_closed_form_lelas_matches_golden(hostmath, name):
+    """lelas_tet4_stress / _residual / _block (assemble_mesh_tet4_kernel) against l_elas_3d of the compiled reference: the
+    linear-elasticity equation and the mesh-motion equation with its Jacobian-free weight and old displacement."""
+    golden = common.load_golden("lelas.npz")
+    m, Ag, Yg, Dg, Bf, Do, eq, dmn = common.lelas_case(name)
+    d = dmn[0]
+
+    def fill(dm):
+        dm.rho, dm.C10, dm.C01 = d.rho, d.E, d.nu
+        for i in range(3):
+            dm.f[i] = d.f[i]
+        dm.Id, dm.isStruct = -1, 1
+    R, V = _run_tet4(hostmath, m, Ag, Yg, Dg, Bf, Do, eq, 1 if Do is None else 2, fill, 0, None,
+                     golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"])
+    assert np.abs(golden[f"{name}/R"]).max() > 0
+    assert common.rel_err(R, golden[f"{name}/R"]) < 1e-12
+    assert common.rel_err(V, golden[f"{name}/Val"]) < 1e-12
