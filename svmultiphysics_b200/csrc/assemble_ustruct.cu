@@ -10,6 +10,7 @@
 // are taken NB at a time so that the 28 NB accumulators (16 of lK + 12 of lKd per block) stay in registers, the Gauss
 // loop is inside (the column-node terms of a pass are published once per (g, b) through shared memory), and the finished
 // blocks go out through a per-warp transposition tile as coalesced adds.
+#include <cstdlib>
 #include <vector>
 #include "svb200_internal.h"
 #include "ustruct_elem.cuh"
@@ -254,6 +255,158 @@ assemble_ustruct_kernel(const __grid_constant__ UstructArgs P)
   }
 }
 
+// ---- linear tetrahedra: one thread per element, Gauss sums in closed form (ustruct_elem.cuh: ustruct_tet4_*) ---------------
+// One compute_pk2cc, four Dm Bm_b and the scalars of the four Gauss points per element; the 16 blocks are assembled one at a
+// time from them and leave through the per-warp transposition tile.  Dm lives in shared memory (one column per thread).  Without solid viscosity.
+constexpr int UTET_THREADS = 128;
+constexpr size_t UTET_SMEM = sizeof(double) * ((size_t)(UTET_THREADS / 32) * 32 * 29 + 36 * UTET_THREADS);
+
+template <bool ATOMIC>
+__global__ void __launch_bounds__(UTET_THREADS)
+assemble_ustruct_tet4_kernel(const __grid_constant__ UstructArgs P)
+{
+  extern __shared__ double sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* tile = sm + (size_t)warp * 32 * 29;
+  double* sDm = sm + (size_t)(UTET_THREADS / 32) * 32 * 29 + threadIdx.x;      // element r*6+c at sDm[(6 r + c) * UTET_THREADS]
+  const long long idx = (long long)P.e0 + (long long)blockIdx.x * UTET_THREADS + threadIdx.x;
+  bool active = idx < P.e1;
+  int e = 0;
+  if (active) e = P.perm ? P.perm[idx] : (int)idx;
+  int iD = 0;
+  if (active) {
+    for (int d = 0; d < P.nDmn; d++) {
+      iD = d;
+      if (P.dmn[d].st.Id == -1) break;
+      if (P.eId != nullptr && ((P.eId[e] >> P.dmn[d].st.Id) & 1)) break;
+    }
+    if (!P.active[iD]) active = false;
+  }
+  const UstructDmn& dm = P.dmn[iD];
+  const double af = P.af * P.gam * P.dt, am = P.am;
+  int sl[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) sl[k] = -1;
+  UTet4Const C;
+  UTet4Mom M;
+  if (active) {
+    int node[4];
+    const int4 nn = __ldg(reinterpret_cast<const int4*>(P.IEN) + e);
+    node[0] = nn.x; node[1] = nn.y; node[2] = nn.z; node[3] = nn.w;
+    const int4* sp = reinterpret_cast<const int4*>(P.slot) + (size_t)e * 4;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int4 v = __ldg(sp + k);
+      sl[4 * k] = v.x; sl[4 * k + 1] = v.y; sl[4 * k + 2] = v.z; sl[4 * k + 3] = v.w;
+    }
+    double xl[4][3], ql[4][3], vl[4][3], dl[4][3], pl[4], pdl[4];
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const size_t n = (size_t)node[b];
+      const double* A = P.Ag + (size_t)P.tDof * n + P.s;
+      const double* Y = P.Yg + (size_t)P.tDof * n + P.s;
+      const double* D = P.Dg + (size_t)P.tDof * n + P.s;
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        xl[b][i] = __ldg(P.x + 3 * n + i);
+        ql[b][i] = __ldg(A + i) - __ldg(P.Bf + 3 * n + i);
+        vl[b][i] = __ldg(Y + i);
+        dl[b][i] = __ldg(D + i);
+      }
+      pl[b] = __ldg(Y + 3);
+      pdl[b] = __ldg(A + 3);
+    }
+    double fN[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    if (P.fN != nullptr)
+      for (int k = 0; k < P.nFn && k < 2; k++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) fN[k][i] = __ldg(P.fN + (size_t)3 * P.nFn * e + 3 * k + i);
+    double Dm[6][6], Je;
+    ustruct_tet4_setup(dm, af, am, P.w, &P.N[0][0], MAX_ENON, P.Nxi[0], xl, ql, vl, dl, pl, pdl, fN, C, M, Dm, &Je);
+    if (fabs(Je) < 10.0 * 2.220446049250313e-16 * 2.220446049250313e-16) atomicMax(P.err, e + 1);
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+      for (int c = 0; c < 6; c++) sDm[(6 * r + c) * UTET_THREADS] = Dm[r][c];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      double r[4];
+      ustruct_tet4_resid(C, M, &P.N[0][0], MAX_ENON, a, r);
+#pragma unroll
+      for (int i = 0; i < 4; i++) uadd<ATOMIC>(P.R + (size_t)4 * node[a] + i, r[i]);
+    }
+  }
+  constexpr int TILE_LD = 29;
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    double DBmb[6][3];
+    if (active) {
+      double Bmb[6][3];
+      make_Bm(C.Nx[b], C.F, Bmb);
+#pragma unroll
+      for (int r = 0; r < 6; r++) {
+        double d[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++) d[c] = sDm[(6 * r + c) * UTET_THREADS];
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+          DBmb[r][j] = d[0] * Bmb[0][j] + d[1] * Bmb[1][j] + d[2] * Bmb[2][j] + d[3] * Bmb[3][j] + d[4] * Bmb[4][j] + d[5] * Bmb[5][j];
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      double K[16], Kd[12];
+      if (active) {
+        double Bma[6][3];
+        make_Bm(C.Nx[a], C.F, Bma);
+        ustruct_tet4_block(C, M, &P.N[0][0], MAX_ENON, af, am, a, b, Bma, DBmb, K, Kd);
+      }
+      __syncwarp();
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) tile[lane * TILE_LD + i] = K[i];
+#pragma unroll
+        for (int i = 0; i < 12; i++) tile[lane * TILE_LD + 16 + i] = Kd[i];
+      }
+      int myslot = -1;
+#pragma unroll
+      for (int k = 0; k < 16; k++)
+        if (k == 4 * a + b) myslot = sl[k];
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 16; it++) {
+        const int p = it * 32 + lane, src = p >> 4, i = p & 15;
+        const int s_ = __shfl_sync(0xffffffffu, myslot, src);
+        if (s_ >= 0) uadd<ATOMIC>(P.Val + (size_t)16 * s_ + i, tile[src * TILE_LD + i]);
+      }
+#pragma unroll
+      for (int it = 0; it < 12; it++) {
+        const int p = it * 32 + lane, src = p / 12, i = p - 12 * src;
+        const int s_ = __shfl_sync(0xffffffffu, myslot, src);
+        if (s_ >= 0) uadd<ATOMIC>(P.Kd + (size_t)12 * s_ + i, tile[src * TILE_LD + 16 + i]);
+      }
+    }
+  }
+}
+
+static int launch_ustruct_tet4(svb200_ctx* ctx, const UstructArgs& A, bool atomic)
+{
+  static bool configured = false;
+  if (!configured) {
+    SVB_CUDA(cudaFuncSetAttribute(assemble_ustruct_tet4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UTET_SMEM));
+    SVB_CUDA(cudaFuncSetAttribute(assemble_ustruct_tet4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UTET_SMEM));
+    configured = true;
+  }
+  const long long n = (long long)A.e1 - A.e0;
+  if (n <= 0) return SVB200_OK;
+  const unsigned blocks = (unsigned)((n + UTET_THREADS - 1) / UTET_THREADS);
+  if (atomic) assemble_ustruct_tet4_kernel<true><<<blocks, UTET_THREADS, UTET_SMEM, ctx->stream>>>(A);
+  else assemble_ustruct_tet4_kernel<false><<<blocks, UTET_THREADS, UTET_SMEM, ctx->stream>>>(A);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
 template <int ENON, bool VISC>
 static int launch_ustruct(svb200_ctx* ctx, const UstructArgs& A, bool atomic)
 {
@@ -345,7 +498,10 @@ int run_assemble_ustruct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* 
   }
   if (!whole && !m.d_eId) { set_error("eId is not allocated"); return SVB200_ERR_INVALID; }
   const bool atomic = (eq->scatter == SVB200_SCATTER_ATOMIC);
+  // linear tets without solid viscosity: closed-form kernel (SVB200_STRUCT_GENERAL=1 keeps the general one: cross-check)
+  static const bool force_general = (getenv("SVB200_STRUCT_GENERAL") != nullptr && atoi(getenv("SVB200_STRUCT_GENERAL")) != 0);
   auto launch = [&](const UstructArgs& B) {
+    if (m.eNoN == 4 && !visc && !force_general) return launch_ustruct_tet4(ctx, B, atomic);
     if (visc) return m.eNoN == 8 ? launch_ustruct<8, true>(ctx, B, atomic) : launch_ustruct<4, true>(ctx, B, atomic);
     return m.eNoN == 8 ? launch_ustruct<8, false>(ctx, B, atomic) : launch_ustruct<4, false>(ctx, B, atomic);
   };

@@ -70,6 +70,59 @@ static int run(const HostUstructArgs* P, const int* rowPtr, const int* colPtr, d
   return 0;
 }
 
+// The closed-form TET4 path (ustruct_tet4_setup / _resid / _block) as a plain element loop.
+static int run_tet4(const HostUstructArgs* P, const int* rowPtr, const int* colPtr, double* R, double* Val, double* Kd)
+{
+  using namespace svb;
+  const int s0 = P->s, tD = P->tDof;
+  const double af = P->af * P->gam * P->dt, am = P->am;
+  for (int e = 0; e < P->nEl; e++) {
+    int n[4];
+    double xl[4][3], ql[4][3], vl[4][3], dl[4][3], pl[4], pdl[4], fN[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    for (int a = 0; a < 4; a++) {
+      n[a] = P->IEN[4 * e + a];
+      for (int i = 0; i < 3; i++) {
+        xl[a][i] = P->x[3 * n[a] + i];
+        ql[a][i] = P->Ag[(size_t)tD * n[a] + s0 + i] - P->Bf[3 * n[a] + i];
+        vl[a][i] = P->Yg[(size_t)tD * n[a] + s0 + i];
+        dl[a][i] = P->Dg[(size_t)tD * n[a] + s0 + i];
+      }
+      pl[a] = P->Yg[(size_t)tD * n[a] + s0 + 3];
+      pdl[a] = P->Ag[(size_t)tD * n[a] + s0 + 3];
+    }
+    for (int k = 0; k < P->nFn && k < 2; k++) for (int i = 0; i < 3; i++) fN[k][i] = P->fN[(size_t)3 * P->nFn * e + 3 * k + i];
+    UTet4Const C; UTet4Mom M; double Dm[6][6], Je;
+    if (ustruct_tet4_setup(P->dm, af, am, P->w, &P->N[0][0], 8, P->Nxi[0], xl, ql, vl, dl, pl, pdl, fN, C, M, Dm, &Je)) return 2;
+    for (int a = 0; a < 4; a++) {
+      double r[4];
+      ustruct_tet4_resid(C, M, &P->N[0][0], 8, a, r);
+      for (int i = 0; i < 4; i++) R[4 * n[a] + i] += r[i];
+    }
+    for (int b = 0; b < 4; b++) {
+      double Bmb[6][3], DBmb[6][3];
+      make_Bm(C.Nx[b], C.F, Bmb);
+      make_DBm(Dm, Bmb, DBmb);
+      for (int a = 0; a < 4; a++) {
+        double Bma[6][3], K[16], Kdd[12];
+        make_Bm(C.Nx[a], C.F, Bma);
+        ustruct_tet4_block(C, M, &P->N[0][0], 8, af, am, a, b, Bma, DBmb, K, Kdd);
+        int sl = -1;
+        for (int k = rowPtr[n[a]]; k < rowPtr[n[a] + 1]; k++) if (colPtr[k] == n[b]) { sl = k; break; }
+        if (sl < 0) return 1;
+        for (int i = 0; i < 16; i++) Val[(size_t)16 * sl + i] += K[i];
+        for (int i = 0; i < 12; i++) Kd[(size_t)12 * sl + i] += Kdd[i];
+      }
+    }
+  }
+  return 0;
+}
+
+extern "C" int hostmath_ustruct_tet4(const HostUstructArgs* P, const int* rowPtr, const int* colPtr, double* R, double* Val, double* Kd)
+{
+  if (P->eNoN != 4 || P->nG != 4) return 3;
+  return run_tet4(P, rowPtr, colPtr, R, Val, Kd);
+}
+
 extern "C" int hostmath_ustruct(const HostUstructArgs* P, const int* rowPtr, const int* colPtr, double* R, double* Val, double* Kd)
 {
   if (P->eNoN == 4) return run<4>(P, rowPtr, colPtr, R, Val, Kd);

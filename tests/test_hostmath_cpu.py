@@ -241,10 +241,15 @@ class HostUstructArgs(C.Structure):
                [("w", C.c_double * 8), ("N", (C.c_double * 8) * 8), ("Nxi", ((C.c_double * 3) * 8) * 8), ("dm", UstructDmn)]
 
 
-@pytest.mark.parametrize("name,mk,dkw,nFn", common.USTRUCT_CASES, ids=[c[0] for c in common.USTRUCT_CASES])
-def test_device_ustruct_algebra_matches_golden(hostmath, name, mk, dkw, nFn):
+USTRUCT_VARIANTS = [(c, "hostmath_ustruct") for c in common.USTRUCT_CASES] + \
+                   [(c, "hostmath_ustruct_tet4") for c in common.USTRUCT_CASES if c[0].startswith("tet4") and "visc" not in c[0]]
+
+
+@pytest.mark.parametrize("case,entry", USTRUCT_VARIANTS, ids=[c[0] + ("_closed_form" if e.endswith("tet4") else "") for c, e in USTRUCT_VARIANTS])
+def test_device_ustruct_algebra_matches_golden(hostmath, case, entry):
     """svmultiphysics_b200/csrc/ustruct_elem.cuh compiled for the host against R / Val / Kd of the unmodified reference
     (ustruct_3d_m, ustruct_3d_c, ustruct_do_assem; tests/golden/ustruct.npz), tolerance 1e-12."""
+    name, mk, dkw, nFn = case
     golden = common.load_golden("ustruct.npz")
     assert hostmath.hostmath_sizeof_ustructargs() == C.sizeof(HostUstructArgs)
     m = mk()
@@ -272,8 +277,8 @@ def test_device_ustruct_algebra_matches_golden(hostmath, name, mk, dkw, nFn):
     R = np.zeros((m.nNo, 4))
     V = np.zeros((len(colPtr), 16))
     Kd = np.zeros((len(colPtr), 12))
-    rc = hostmath.hostmath_ustruct(C.byref(A), rowPtr.ctypes.data_as(C.c_void_p), colPtr.ctypes.data_as(C.c_void_p),
-                                   R.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p), Kd.ctypes.data_as(C.c_void_p))
+    rc = getattr(hostmath, entry)(C.byref(A), rowPtr.ctypes.data_as(C.c_void_p), colPtr.ctypes.data_as(C.c_void_p),
+                                  R.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p), Kd.ctypes.data_as(C.c_void_p))
     assert rc == 0
     assert common.rel_err(R.T, golden[f"{name}/R"]) < 1e-12
     assert common.rel_err(Kd.T, golden[f"{name}/Kd"]) < 1e-12
