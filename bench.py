@@ -29,9 +29,17 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# NCCL prints its version banner on STDOUT when NCCL_DEBUG=VERSION; stdout of this script is exactly one JSON line
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout of this script is exactly ONE JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints
+# "NCCL version ..." there at every NCCL_DEBUG level from VERSION up, WARN included), so descriptor 1 is pointed at stderr
+# for the whole run and the JSON line goes to a private duplicate of the original stdout.
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit_line(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
 
 from svmultiphysics_b200 import abi, elements, meshgen, partition  # noqa: E402
 
@@ -213,7 +221,7 @@ def main():
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": "element assemblies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "newton_step_1core": r.get("newton_step_1core")}
-        print(json.dumps(line))
+        emit_line(line)
         return
 
     import torch
@@ -405,7 +413,7 @@ def main():
                 line["cpu_baseline"]["newton_step_1core"] = r.get("newton_step_1core")
             except Exception as ex:   # the baseline is a reported extra; never hide the GPU result
                 line["cpu_baseline"] = {"error": repr(ex)}
-        print(json.dumps(line))
+        emit_line(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
