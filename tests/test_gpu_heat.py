@@ -98,3 +98,61 @@ def test_heat_zero_jacobian_error():
     with pytest.raises(Svb200Error, match=r"\[construct_heats\] Jacobian for element"):
         eng.assemble(0, abi.heat_eq(0.01, False), [abi.heat_domain(False)])
     eng.close()
+
+
+@pytest.mark.parametrize("fluid", [False, True], ids=["heatS", "heatF"])
+def test_heat_device_resident_time_steps(fluid):
+    """Three time steps x two Newton iterations of a heat equation with the generalised-alpha updates on the device (predictor,
+    initiator, assemble, BiCGStab, corrector) against the same loop with the compiled reference's assembly + solve and the numpy
+    restatement of Integrator::predictor / initiator / corrector."""
+    from oracle import genalpha_oracle as go, refbind
+    if not refbind.have_ref():
+        pytest.skip("needs oracle/_ref/libsvref.so")
+    from svmultiphysics_b200 import meshgen
+    m = meshgen.box_hex8(5, 4, 4, (1.0, 1.0, 1.0))
+    tDof, s = (5, 4) if fluid else (1, 0)
+    dt = 0.01
+    eq, dmn = abi.heat_eq(dt, fluid, tDof=tDof, s=s), [abi.heat_domain(fluid, conductivity=0.5, source=1.0, rho=2.0)]
+    qt = [abi.eq_time(s, s, eq.phys, 0.5)]
+    faces = [(abi.BC_DIR, m.faces["X0"], np.zeros((1, len(m.faces["X0"])), order="F"))]
+    orc = refbind.RefCase(); orc.set_coords(m.x); orc.add_mesh(m.IEN)
+    rowPtr, colPtr = orc.build_graph(len(faces))
+    eng = _engine(m, rowPtr, colPtr)
+    eng.set_num_faces(len(faces))
+    for i, (g, nodes, val) in enumerate(faces):
+        orc.set_face(i, g, nodes, val); eng.set_face(i, g, nodes, val)
+    ls = abi.ls_params(abi.LS_BICGS, mItr=400, relTol=1e-10)
+    incL, res = np.ones(1, np.int32), np.zeros(1)
+    _, Y0, _, Bf = common.heat_state(m, tDof, s)
+    Y0[s, m.faces["X0"]] = 0.0                               # consistent with the homogeneous Dirichlet face
+    Ao, Yo, Do = np.zeros_like(Y0), Y0.copy(order="F"), np.zeros_like(Y0)
+    An, Yn, Dn = Ao.copy(order="F"), Yo.copy(order="F"), Do.copy(order="F")
+    Ag, Yg, Dg = (np.zeros_like(Ao) for _ in range(3))
+    if fluid:                                                # the velocity rows 0..2 are data for heatF: keep them in all states
+        Yg[:4] = Y0[:4]
+    eng.set_state(Ag, Yg, Dg, Bf)
+    eng.set_solution(abi.SOL_OLD, Ao, Yo, Do)
+    eng.set_solution(abi.SOL_CURRENT, An, Yn, Dn)
+    norms_dev, norms_ref = [], []
+    for step in range(3):
+        eng.predictor(qt, dt, 0)
+        go.predictor(qt, dt, 0, Ao, Yo, Do, An, Yn, Dn)
+        for it in range(2):
+            eng.initiator(qt)
+            eng.alloc(1); eng.assemble(0, eq, dmn)
+            _, out1, _ = eng.solve(1, abi.LS_BICGS, ls, incL, res, want_solution=False)
+            eng.corrector(qt[0], dt)
+            go.initiator(qt, Ao, Yo, Do, An, Yn, Dn, Ag, Yg, Dg)
+            orc.alloc(1); orc.set_state(Ag, Yg, Dg, Bf); orc.assemble(0, eq, dmn)
+            X0, out0, _ = orc.solve(1, abi.LS_BICGS, ls, incL, res)
+            go.corrector(qt[0], dt, X0, An, Yn, Dn)
+            norms_dev.append(out1.RI.iNorm); norms_ref.append(out0.RI.iNorm)
+        eng.advance_time_step()
+        Ao, Yo, Do = An.copy(order="F"), Yn.copy(order="F"), Dn.copy(order="F")
+    nd, nr = np.array(norms_dev).reshape(3, 2), np.array(norms_ref).reshape(3, 2)
+    assert np.allclose(nd[:, 0], nr[:, 0], rtol=1e-7)       # first residual of every step: set by the state
+    if not fluid:
+        assert np.all(nr[:, 1] < 1e-6 * nr[:, 0]) and np.all(nd[:, 1] < 1e-6 * nd[:, 0])    # heatS is linear: one Newton iteration
+    A1, Y1, D1 = eng.get_solution(abi.SOL_CURRENT)
+    assert common.rel_err(Y1[s], Yn[s]) < 1e-7 and common.rel_err(A1[s], An[s]) < 1e-6
+    eng.close()
