@@ -95,3 +95,15 @@ extern "C" int hostmath_struct(const HostStructArgs* P, const int* rowPtr, const
   return 3;
 }
 extern "C" int hostmath_sizeof_structargs() { return (int)sizeof(HostStructArgs); }
+
+// compute_pk2cc of the device algebra for one deformation gradient: F(3,3) row-major, fN = fibre | sheet -> S(3,3), Dm(6,6).
+extern "C" int hostmath_pk2cc(const svb::StructDmn* dm, const double* F, const double* fN, double* S, double* Dm)
+{
+  double Fm[3][3], f[2][3], Sm[3][3], D[6][6];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Fm[i][j] = F[3 * i + j];
+  for (int k = 0; k < 2; k++) for (int i = 0; i < 3; i++) f[k][i] = fN ? fN[3 * k + i] : 0.0;
+  const int rc = svb::pk2cc_voigt(*dm, Fm, f, Sm, D);
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) S[3 * i + j] = Sm[i][j];
+  for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) Dm[6 * i + j] = D[i][j];
+  return rc;
+}

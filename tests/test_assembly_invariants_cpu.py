@@ -1,0 +1,138 @@
+"""Assembly invariants (SURVEY.md 8(c) iii) for the DEVICE element algebra compiled for the host — no oracle involved:
+  * a uniform velocity field with zero pressure, acceleration and body force leaves no residual (VMS fluid, TET4);
+  * a linear pressure with the matching body force (hydrostatic state) leaves no momentum residual;
+  * the continuity residual sums to the integral of div u over the mesh (the shape functions sum to one);
+  * a rigid translation of a solid leaves no internal force, and its tangent annihilates translations;
+  * the heat residual vanishes for a uniform temperature without source, and its tangent rows sum to the mass term."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from svmultiphysics_b200 import abi, elements, meshgen
+from tests import common
+from tests.test_hostmath_cpu import FluidArgs, HostStructArgs, HostHeatArgs, hostmath, _fill_tables  # noqa: F401
+
+
+def _csr(m):
+    from oracle import refbind
+    c = refbind.OracleCase(); c.set_coords(m.x); c.add_mesh(m.IEN)
+    return c.build_graph(0)
+
+
+def _fluid(hostmath, m, Ag, Yg, Bf, d, rowPtr, colPtr, dt=0.005):
+    eq = abi.fluid_eq(dt)
+    w, N, Nx = elements.tables(4)
+    A = FluidArgs()
+    keep = [np.ascontiguousarray(m.IEN.T.astype(np.int32)), np.ascontiguousarray(m.x.T), np.ascontiguousarray(Ag.T),
+            np.ascontiguousarray(Yg.T), np.ascontiguousarray(Bf.T)]
+    A.IEN, A.x, A.Ag, A.Yg, A.Bf = (k.ctypes.data for k in keep)
+    A.e0, A.e1, A.tDof, A.mvMsh, A.nDmn = 0, m.nEl, 4, 0, 1
+    A.dt, A.af, A.am, A.gam = eq.dt, eq.af, eq.am, eq.gam
+    for g in range(4):
+        A.w[g] = w[g]
+        for a in range(4):
+            A.N[g][a] = N[a, g]
+            for k in range(3):
+                A.Nxi[g][a][k] = Nx[k, a, g]
+    A.dmn[0].rho, A.dmn[0].Kd = d.rho, d.K_darcy
+    for i in range(3):
+        A.dmn[0].f[i] = d.f[i]
+    A.dmn[0].mu_i, A.dmn[0].viscType, A.dmn[0].Id, A.dmn[0].isFluid = d.mu_i, d.viscType, -1, 1
+    R = np.zeros((m.nNo, 4))
+    V = np.zeros((len(colPtr), 16))
+    rc = hostmath.hostmath_fluid_tet4(C.byref(A), m.nNo, rowPtr.ctypes.data_as(C.c_void_p), colPtr.ctypes.data_as(C.c_void_p),
+                                      R.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return R.T, V.T
+
+
+def test_fluid_uniform_flow_and_hydrostatic_state_leave_no_residual(hostmath):
+    m = meshgen.cylinder_tet4(3, 4)
+    rowPtr, colPtr = _csr(m)
+    z = np.zeros((4, m.nNo), order="F")
+    Y = z.copy(order="F"); Y[0], Y[1], Y[2] = 1.5, -0.7, 3.0                        # uniform velocity, p = 0
+    R, _ = _fluid(hostmath, m, z, Y, np.zeros((3, m.nNo), order="F"), abi.fluid_domain(), rowPtr, colPtr)
+    interior = np.ones(m.nNo, bool)
+    for k in ("wall", "inlet", "outlet_all"):
+        interior[m.faces[k]] = False
+    # boundary nodes keep the flux terms of the weak form; interior rows vanish
+    assert np.abs(R[:, interior]).max() < 1e-11
+    # hydrostatic: u = 0, p = rho g . x, body force g  ->  momentum residual zero in the interior
+    d = abi.fluid_domain(rho=1.06, f=(0.3, -0.2, 0.5))
+    Y = z.copy(order="F"); Y[3] = d.rho * (0.3 * m.x[0] - 0.2 * m.x[1] + 0.5 * m.x[2])
+    R, _ = _fluid(hostmath, m, z, Y, np.zeros((3, m.nNo), order="F"), d, rowPtr, colPtr)
+    assert np.abs(R[:, interior]).max() < 1e-10
+
+
+def test_continuity_residual_sums_to_the_divergence_integral(hostmath):
+    """sum_a lR_c(a) = int div u: the stabilisation term int tau_M r_M . grad N_a sums to zero over a because sum_a N_a = 1."""
+    m = meshgen.cylinder_tet4(3, 4)
+    rowPtr, colPtr = _csr(m)
+    z = np.zeros((4, m.nNo), order="F")
+    Y = z.copy(order="F")
+    Y[0], Y[1], Y[2] = 0.3 * m.x[0], -0.1 * m.x[1] + 0.2 * m.x[2], 0.5 * m.x[2]     # div u = 0.3 - 0.1 + 0.5
+    R, _ = _fluid(hostmath, m, z, Y, np.zeros((3, m.nNo), order="F"), abi.fluid_domain(), rowPtr, colPtr)
+    w, N, Nx = elements.tables(4)
+    vol = 0.0
+    for e in range(m.nEl):
+        x = m.x[:, m.IEN[:, e]]
+        vol += abs(np.linalg.det(x[:, :3] - x[:, [3]])) / 6.0
+    assert abs(R[3].sum() - 0.7 * vol) < 1e-10 * vol
+
+
+def _struct(hostmath, m, Ag, Yg, Dg, Bf, d, rowPtr, colPtr):
+    eq = abi.struct_eq(1e-4)
+    A = HostStructArgs()
+    keep = [np.ascontiguousarray(m.IEN.T.astype(np.int32)), np.ascontiguousarray(m.x.T), np.ascontiguousarray(Ag.T),
+            np.ascontiguousarray(Yg.T), np.ascontiguousarray(Dg.T), np.ascontiguousarray(Bf.T)]
+    A.IEN, A.x, A.Ag, A.Yg, A.Dg, A.Bf = (k.ctypes.data for k in keep)
+    A.eNoN, A.nEl, A.tDof, A.dof, A.s, A.nFn = m.eNoN, m.nEl, 3, 3, 0, 0
+    A.nG = _fill_tables(A, m.eNoN)
+    A.dt, A.af, A.am, A.gam, A.beta = eq.dt, eq.af, eq.am, eq.gam, eq.beta
+    dm = A.dm
+    dm.rho, dm.Kpen, dm.C10, dm.C01 = d.rho, d.Kpen, d.C10, d.C01
+    dm.isoType, dm.volType, dm.Id, dm.isStruct = d.isoType, d.volType, -1, 1
+    R = np.zeros((m.nNo, 3))
+    V = np.zeros((len(colPtr), 9))
+    rc = hostmath.hostmath_struct(C.byref(A), rowPtr.ctypes.data_as(C.c_void_p), colPtr.ctypes.data_as(C.c_void_p),
+                                  R.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return R.T, V.T, eq
+
+
+@pytest.mark.parametrize("kind", ["hex8", "tet4"])
+def test_solid_rigid_translation(hostmath, kind):
+    m = meshgen.box_hex8(3, 2, 2, (1.0, 1.0, 1.0)) if kind == "hex8" else meshgen.box_tet4(2, 2, 2, (1.0, 1.0, 1.0))
+    rowPtr, colPtr = _csr(m)
+    z = np.zeros((3, m.nNo), order="F")
+    D = z.copy(order="F"); D[0], D[1], D[2] = 0.3, -0.2, 0.1                     # rigid translation: F = I, S = 0
+    d = abi.struct_domain(E=1e6, nu=0.4, Kpen=1e6, rho=0.0)                          # rho = 0: no inertia in the tangent
+    R, V, eq = _struct(hostmath, m, z, z, D, z, d, rowPtr, colPtr)
+    assert np.abs(R).max() < 1e-9
+    # K t = 0 for a translation t: the 3x3 blocks of every row sum to zero over the columns
+    rows = np.repeat(np.arange(m.nNo), np.diff(rowPtr))
+    S = np.zeros((m.nNo, 9))
+    np.add.at(S, rows, V.T)
+    assert np.abs(S).max() < 1e-9 * np.abs(V).max()
+
+
+def test_heat_uniform_temperature(hostmath):
+    m = meshgen.box_hex8(3, 2, 2, (1.0, 1.0, 1.0))
+    rowPtr, colPtr = _csr(m)
+    eq, d = abi.heat_eq(0.01, False), abi.heat_domain(False, conductivity=0.7, source=0.0, rho=2.5)
+    A = HostHeatArgs()
+    Ag = np.zeros((1, m.nNo), order="F"); Yg = np.full((1, m.nNo), 300.0, order="F")
+    keep = [np.ascontiguousarray(m.IEN.T.astype(np.int32)), np.ascontiguousarray(m.x.T), np.ascontiguousarray(Ag.T), np.ascontiguousarray(Yg.T)]
+    A.IEN, A.x, A.Ag, A.Yg = (k.ctypes.data for k in keep)
+    A.eNoN, A.nEl, A.tDof, A.s, A.mvMsh, A.fluid = 8, m.nEl, 1, 0, 0, 0
+    A.nG = _fill_tables(A, 8)
+    A.dt, A.af, A.am, A.gam = eq.dt, eq.af, eq.am, eq.gam
+    A.dm.rho, A.dm.nu, A.dm.s, A.dm.Id, A.dm.active = d.rho, d.conductivity, 0.0, -1, 1
+    R = np.zeros(m.nNo); V = np.zeros(len(colPtr))
+    assert hostmath.hostmath_heat(C.byref(A), rowPtr.ctypes.data_as(C.c_void_p), colPtr.ctypes.data_as(C.c_void_p),
+                                  R.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p)) == 0
+    assert np.abs(R).max() < 1e-12
+    # the conductivity part of a row sums to zero (constants are in its kernel); what is left is the lumped mass term:
+    # sum over all entries = am rho |Omega|
+    assert abs(V.sum() - eq.am * d.rho * 1.0) < 1e-12

@@ -1,0 +1,129 @@
+"""Known-answer identities for the DEVICE constitutive routine (struct_elem.cuh: pk2cc_voigt, compiled for the host), the ones the
+reference's own unit tests hold for mat_models::compute_pk2cc (tests/unitTests/material_model_tests/test_material_common.h:
+S(F = I) = 0, S = 2 dpsi/dC and CC = 2 dS/dC by finite differences; psi_nHK = C10 (I1bar - 3), test_material_neohookean.h:95-104).
+No oracle involved: these pin the algebra independently of the compiled reference."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from svmultiphysics_b200 import abi
+from tests.test_hostmath_cpu import StructDmn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+VOIGT = [(0, 0), (1, 1), (2, 2), (0, 1), (1, 2), (2, 0)]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    subprocess.check_call(["make"], cwd=os.path.join(HERE, "hostmath"))
+    return C.CDLL(os.path.join(HERE, "hostmath", "libhostmath.so"))
+
+
+def _dm(**kw):
+    d = abi.struct_domain(**kw)
+    dm = StructDmn()
+    dm.rho, dm.dmp, dm.Kpen, dm.C10, dm.C01, dm.bff, dm.bss, dm.bfs = d.rho, d.dmp, d.Kpen, d.C10, d.C01, d.bff, d.bss, d.bfs
+    dm.st_a, dm.st_b, dm.aff, dm.ass, dm.afs, dm.kap, dm.khs = d.st_a, d.st_b, d.aff, d.ass, d.afs, d.kap, d.khs
+    dm.isoType, dm.volType, dm.Id, dm.isStruct = d.isoType, d.volType, -1, 1
+    return dm
+
+
+def _pk2cc(lib, dm, F, fN=None):
+    F = np.ascontiguousarray(F, dtype=np.float64)
+    S, Dm = np.zeros((3, 3)), np.zeros((6, 6))
+    f = np.ascontiguousarray(fN, dtype=np.float64) if fN is not None else None
+    rc = lib.hostmath_pk2cc(C.byref(dm), F.ctypes.data_as(C.c_void_p), f.ctypes.data_as(C.c_void_p) if f is not None else None,
+                            S.ctypes.data_as(C.c_void_p), Dm.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return S, Dm
+
+
+FIBRES = np.array([[1.0, 0.0, 0.0], [0.0, 1.0, 0.0]])
+MODELS = [
+    ("nHK_ST91", dict(E=1e6, nu=0.45, Kpen=2e6, volType=abi.VOL_ST91), None),
+    ("nHK_Quad", dict(E=1e6, nu=0.45, Kpen=2e6, volType=abi.VOL_QUAD), None),
+    ("nHK_M94", dict(E=1e6, nu=0.45, Kpen=2e6, volType=abi.VOL_M94), None),
+    ("MR", dict(isoType=abi.ISO_MR, C10=1e5, C01=3e4, Kpen=1e6), None),
+    ("StVK", dict(isoType=abi.ISO_STVK, C10=2e5, C01=1e5, Kpen=0.0), None),
+    ("Guccione", dict(isoType=abi.ISO_GUCCIONE, C10=440.0, bff=8.0, bss=6.0, bfs=12.0, Kpen=1e5), FIBRES),
+    ("HGO", dict(isoType=abi.ISO_HGO, C10=3.0e4, aff=2.4e4, bff=0.84, ass=2.4e4, bss=0.84, kap=0.226, Kpen=1e6), FIBRES),
+    ("HO", dict(isoType=abi.ISO_HO, st_a=590.0, st_b=8.023, aff=184720.0, bff=16.026, ass=24810.0, bss=11.12, afs=2160.0, bfs=11.436,
+                khs=100.0, Kpen=1e6), FIBRES),
+    ("HO_ma", dict(isoType=abi.ISO_HO_MA, st_a=590.0, st_b=8.023, aff=184720.0, bff=16.026, ass=24810.0, bss=11.12, afs=2160.0,
+                   bfs=11.436, khs=100.0, Kpen=1e6), FIBRES),
+]
+
+
+def _F(seed, amp=0.08):
+    rng = np.random.default_rng(seed)
+    return np.eye(3) + amp * rng.standard_normal((3, 3))
+
+
+@pytest.mark.parametrize("name,kw,fN", MODELS, ids=[m[0] for m in MODELS])
+def test_stress_vanishes_in_the_reference_configuration(lib, name, kw, fN):
+    S, _ = _pk2cc(lib, _dm(**kw), np.eye(3), fN)
+    scale = max(abs(v) for v in (kw.get("E", 0.0), kw.get("C10", 0.0), kw.get("st_a", 0.0), kw.get("aff", 0.0), 1.0))
+    assert np.abs(S).max() < 1e-10 * scale
+
+
+@pytest.mark.parametrize("name,kw,fN", MODELS, ids=[m[0] for m in MODELS])
+def test_stress_is_symmetric_and_tangent_has_the_symmetries(lib, name, kw, fN):
+    S, Dm = _pk2cc(lib, _dm(**kw), _F(1), fN)
+    assert np.allclose(S, S.T, rtol=0, atol=1e-12 * np.abs(S).max())
+    assert np.allclose(Dm, Dm.T, rtol=0, atol=1e-10 * np.abs(Dm).max())          # major symmetry (hyperelastic)
+
+
+@pytest.mark.parametrize("name,kw,fN", MODELS, ids=[m[0] for m in MODELS])
+def test_tangent_is_twice_the_derivative_of_the_stress(lib, name, kw, fN):
+    """CC = 2 dS/dC: S(F + e dF) - S(F - e dF) = 2 e Dm : dE + O(e^3), dE = sym(F^T dF), Voigt with engineering shears."""
+    dm = _dm(**kw)
+    F = _F(2)
+    _, Dm = _pk2cc(lib, dm, F, fN)
+    rng = np.random.default_rng(3)
+    for _ in range(3):
+        dF = rng.standard_normal((3, 3))
+        e = 1e-6
+        Sp, _ = _pk2cc(lib, dm, F + e * dF, fN)
+        Sm, _ = _pk2cc(lib, dm, F - e * dF, fN)
+        dE = 0.5 * (F.T @ dF + dF.T @ F)
+        dEv = np.array([dE[0, 0], dE[1, 1], dE[2, 2], 2 * dE[0, 1], 2 * dE[1, 2], 2 * dE[2, 0]])
+        dS_fd = np.array([(Sp - Sm)[i, j] for i, j in VOIGT]) / (2 * e)
+        dS = Dm @ dEv
+        assert np.abs(dS - dS_fd).max() < 2e-6 * np.abs(dS).max()
+
+
+def _psi(name, kw, F):
+    """Strain energies with a closed form here: psi_iso(nHK) = C10 (I1bar - 3), MR adds C01 (I2bar - 3); volumetric parts whose
+    derivative is the pressure compute_svol_p uses (mat_models.cpp:1441-1464)."""
+    J = np.linalg.det(F)
+    Cm = F.T @ F
+    I1b = J ** (-2.0 / 3.0) * np.trace(Cm)
+    I2b = 0.5 * J ** (-4.0 / 3.0) * (np.trace(Cm) ** 2 - np.trace(Cm @ Cm))
+    d = abi.struct_domain(**kw)
+    psi = d.C10 * (I1b - 3.0) + (d.C01 * (I2b - 3.0) if kw.get("isoType") == abi.ISO_MR else 0.0)
+    Kp, vt = d.Kpen, d.volType
+    if vt == abi.VOL_QUAD:
+        psi += 0.5 * Kp * (J - 1.0) ** 2
+    elif vt == abi.VOL_ST91:
+        psi += 0.25 * Kp * (J * J - 1.0 - 2.0 * np.log(J))
+    elif vt == abi.VOL_M94:
+        psi += Kp * (J - np.log(J) - 1.0)
+    return psi
+
+
+@pytest.mark.parametrize("name,kw,fN", MODELS[:4], ids=[m[0] for m in MODELS[:4]])
+def test_stress_is_twice_the_derivative_of_the_strain_energy(lib, name, kw, fN):
+    """S = 2 dpsi/dC: psi(F + e dF) - psi(F - e dF) = 2 e S : dE + O(e^3)."""
+    dm = _dm(**kw)
+    F = _F(4)
+    S, _ = _pk2cc(lib, dm, F, fN)
+    rng = np.random.default_rng(5)
+    for _ in range(3):
+        dF = rng.standard_normal((3, 3))
+        e = 1e-5
+        dpsi = (_psi(name, kw, F + e * dF) - _psi(name, kw, F - e * dF)) / (2 * e)
+        dE = 0.5 * (F.T @ dF + dF.T @ F)
+        assert abs(dpsi - np.sum(S * dE)) < 1e-6 * abs(np.sum(np.abs(S) * np.abs(dE)))
