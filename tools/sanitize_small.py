@@ -10,6 +10,9 @@ from svmultiphysics_b200.engine import Engine
 from tests import common
 
 
+only = sys.argv[1] if len(sys.argv) > 1 else ""     # "", "heat", "ustruct", "struct", "fluid"
+
+
 def engine(m, nFn=0, fN=None):
     e = Engine(0)
     rp, cp = e.lhsa(m.nNo, [m.IEN]); e.set_graph(rp, cp)
@@ -18,24 +21,26 @@ def engine(m, nFn=0, fN=None):
 
 
 for sc in (abi.SCATTER_ATOMIC, abi.SCATTER_COLORED):
-    for name, mk, fluid, tDof, s, mv, dkw in common.HEAT_CASES:
+    for name, mk, fluid, tDof, s, mv, dkw in (common.HEAT_CASES if only in ("", "heat") else []):
         m = mk(); e = engine(m)
         Ag, Yg, Dg, Bf = common.heat_state(m, tDof, s)
         e.alloc(1); e.set_state(Ag, Yg, Dg, Bf); e.assemble(0, abi.heat_eq(0.01, fluid, tDof=tDof, s=s, mvMsh=mv, scatter=sc), [abi.heat_domain(fluid, **dkw)])
         e.get_R(); e.close()
-    for name, mk, dkw, nFn in common.USTRUCT_CASES:
+    for name, mk, dkw, nFn in (common.USTRUCT_CASES if only in ("", "ustruct") else []):
         m = mk()
         Ag, Yg, Dg, Bf, fN = common.ustruct_state(m, nFn)
         e = engine(m, nFn, fN)
         eq = abi.ustruct_eq(1e-3, scatter=sc)
         e.alloc(4); e.set_state(Ag, Yg, Dg, Bf); e.assemble(0, eq, [abi.ustruct_domain(**dkw)]); e.ustruct_r(eq, 1, common.ustruct_Ad(m))
         e.get_Kd(); e.close()
-    for name, mk, dkw, nFn in common.STRUCT_CASES:
+    for name, mk, dkw, nFn in (common.STRUCT_CASES if only in ("", "struct") else []):
         m = mk()
         Ag, Yg, Dg, Bf, fN = common.struct_state(m, nFn)
         e = engine(m, nFn, fN)
         e.alloc(3); e.set_state(Ag, Yg, Dg, Bf); e.assemble(0, abi.struct_eq(1e-4, scatter=sc), [abi.struct_domain(**dkw)])
         e.get_Val(); e.close()
+    if only not in ("", "struct", "fluid"):
+        continue
     m = meshgen.box_tet4(3, 3, 2, (1.0, 1.0, 1.0)); e = engine(m)
     Ag, Yg, Dg, Bf, _ = common.struct_state(m, 0)
     e.alloc(3); e.set_state(Ag, Yg, Dg, Bf); e.assemble(0, abi.lelas_eq(1e-3, scatter=sc), [abi.lelas_domain()]); e.get_Val(); e.close()
