@@ -70,6 +70,9 @@ struct RefCase {
   int (*assem_hook)(void*, void*, const void*, const void*) = nullptr;
   void (*backend_download)(void*, int, double*) = nullptr;
   void (*backend_ustruct_r)(void*, void*) = nullptr;       // B200LinearAlgebra::ustruct_r(ComMod&), INTEGRATION.md
+  // Multi-rank runs (oracle/ref_build/mpi_stub.cpp with SVREF_MPI_SIZE > 1): this rank's local -> global node map
+  int gnNo = -1;
+  std::vector<int> ltg;
 };
 
 consts::EquationType to_phys(int p)
@@ -300,14 +303,55 @@ int svref_build_graph(void* h, int nFaces, int* nnz_out)
     cm.idMap.resize(tnNo);
     for (int a = 0; a < tnNo; a++) cm.idMap[a] = a;
     cm.ltg.resize(tnNo);
-    for (int a = 0; a < tnNo; a++) cm.ltg[a] = a;
+    for (int a = 0; a < tnNo; a++) cm.ltg[a] = c.ltg.empty() ? a : c.ltg.at(a);
+    const int gnNo = c.ltg.empty() ? tnNo : c.gnNo;
+    cm.cm.new_cm(MPI_COMM_WORLD);                 // np() > 1 makes all_fun::commu exchange (all_fun.cpp:96)
 
     fsi_linear_solver::FSILS_commuType communicator;
     fsi_linear_solver::fsils_commu_create(communicator, MPI_COMM_WORLD);
-    fsi_linear_solver::fsils_lhs_create(cm.lhs, communicator, tnNo, tnNo, nnz, cm.ltg, cm.rowPtr, cm.colPtr, nFaces);
+    fsi_linear_solver::fsils_lhs_create(cm.lhs, communicator, gnNo, tnNo, nnz, cm.ltg, cm.rowPtr, cm.colPtr, nFaces);
     c.graph_built = true;
     *nnz_out = nnz;
   });
+}
+
+/// Multi-rank: the local -> global node map of this rank's partition (com_mod.ltg) and the global node count; call before
+/// svref_build_graph.  fsils_lhs_create then derives lhs.map, mynNo and the shared-node lists cS[] itself (lhs.cpp:30-348).
+int svref_set_partition(void* h, int gnNo, int nNo, const int* ltg)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  c.gnNo = gnNo;
+  c.ltg.assign(ltg, ltg + nNo);
+  return 0;
+}
+
+/// What fsils_lhs_create built: mynNo, nReq and map(nNo) (host node -> FSILS position).
+int svref_get_lhs(void* h, int* mynNo, int* nReq, int* map)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    auto& lhs = c.com_mod.lhs;
+    *mynNo = lhs.mynNo; *nReq = lhs.nReq;
+    if (map) for (int a = 0; a < lhs.nNo; a++) map[a] = lhs.map(a);
+  });
+}
+
+/// Shared-node list i: neighbour rank, length and (if ptr != NULL) the FSILS positions, lhs.cS[i].{iP,n,ptr}.
+int svref_get_lhs_req(void* h, int i, int* iP, int* n, int* ptr)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    auto& cs = c.com_mod.lhs.cS.at(i);
+    *iP = cs.iP; *n = cs.n;
+    if (ptr) for (int k = 0; k < cs.n; k++) ptr[k] = cs.ptr(k);
+  });
+}
+
+/// all_fun::commu(com_mod, com_mod.R) of Integrator::step (Integrator.cpp:124-129).
+int svref_commu_R(void* h)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] { all_fun::commu(c.com_mod, c.com_mod.R); });
 }
 
 int svref_get_graph(void* h, int* rowPtr, int* colPtr)

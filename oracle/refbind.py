@@ -241,6 +241,29 @@ class RefCase(_FlatCase):
                    C.cast(host.b200host_download, C.c_void_p))
         self._call("set_backend_ustruct_r", C.cast(host.b200host_ustruct_r, C.c_void_p))
 
+    def set_partition(self, gnNo, ltg):
+        """Multi-rank runs (SVREF_MPI_SIZE > 1 in the environment before this library is loaded): local -> global node map."""
+        ltg = _i32(ltg)
+        self._call("set_partition", C.c_int(gnNo), C.c_int(len(ltg)), _i(ltg))
+
+    def get_lhs(self):
+        """mynNo, lhs.map(nNo) and [(iP, ptr)] as fsils_lhs_create built them (linear_solver/lhs.cpp:30-348)."""
+        mynNo, nReq = C.c_int(0), C.c_int(0)
+        mp = np.zeros(self.nNo, dtype=np.int32)
+        self._call("get_lhs", C.byref(mynNo), C.byref(nReq), _i(mp))
+        reqs = []
+        for i in range(nReq.value):
+            iP, n = C.c_int(0), C.c_int(0)
+            self._call("get_lhs_req", C.c_int(i), C.byref(iP), C.byref(n), None)
+            ptr = np.zeros(n.value, dtype=np.int32)
+            self._call("get_lhs_req", C.c_int(i), C.byref(iP), C.byref(n), _i(ptr))
+            reqs.append((iP.value, ptr))
+        return mynNo.value, mp, reqs
+
+    def commu_R(self):
+        """all_fun::commu(com_mod, R): shared-node sum of the residual (solver/Integrator.cpp:124-129)."""
+        self._call("commu_R")
+
     def get_Kd(self):
         """com_mod.Kd(12, nnz): displacement tangent of the ustruct equation (solver/ustruct.cpp:1621)."""
         K = np.zeros((12, self.nnz), order="F")

@@ -47,6 +47,33 @@ def fsils_order(max_other_rank: np.ndarray, rank: int):
     return node_map, mynNo
 
 
+def fsils_order_exact(node_sets, rank: int):
+    """lhs.map and mynNo for one rank in EXACTLY the order fsils_lhs_create produces (linear_solver/lhs.cpp:118-175): the
+    other ranks are visited from the highest to the lowest, each one's nodes in that rank's local order (ascending global
+    id here); a node this rank also holds and that is not placed yet goes, for a LOWER rank, to the next free position at
+    the front, for a HIGHER rank to the last free position at the back (so the back group is in reverse order of encounter);
+    the interior nodes fill the middle in local order.  ``node_sets[r]`` = sorted global ids of rank r's nodes."""
+    mine = node_sets[rank]
+    n = len(mine)
+    placed = np.zeros(n, dtype=bool)
+    low, high = [], []
+    for i in range(len(node_sets) - 1, -1, -1):
+        if i == rank:
+            continue
+        common = np.intersect1d(node_sets[i], mine, assume_unique=True)      # ascending global id = rank i's local order
+        loc = np.searchsorted(mine, common)
+        sel = loc[~placed[loc]]
+        (low if i < rank else high).append(sel)
+        placed[sel] = True
+    low = np.concatenate(low) if low else np.zeros(0, dtype=np.int64)
+    high = np.concatenate(high) if high else np.zeros(0, dtype=np.int64)
+    interior = np.flatnonzero(~placed)
+    order = np.concatenate([low, interior, high[::-1]]).astype(np.int64)          # FSILS position -> local id
+    node_map = np.empty(n, dtype=np.int32)
+    node_map[order] = np.arange(n, dtype=np.int32)
+    return node_map, int(len(low) + len(interior))
+
+
 def partition_mesh(IEN: np.ndarray, nNo: int, part: np.ndarray, nranks: int):
     """Split a global mesh by the element partition ``part`` (values in [0,nranks))."""
     node_sets = []
@@ -68,7 +95,8 @@ def partition_mesh(IEN: np.ndarray, nNo: int, part: np.ndarray, nranks: int):
         lIEN = np.asfortranarray(gtl[IEN[:, el]].astype(np.int32))
         other = np.where(max1[nodes] != r, max1[nodes], max2[nodes])
         # a node held by lower ranks only besides r: max1 == r and max2 = highest lower rank (or -1)
-        node_map, mynNo = fsils_order(other, r)
+        node_map, mynNo = fsils_order_exact(node_sets, r)
+        assert mynNo == fsils_order(other, r)[1]          # same three groups as the closed-form rule above
         parts.append(LocalPart(rank=r, ltg=nodes.astype(np.int64), IEN=lIEN, elems=el, node_map=node_map, mynNo=mynNo))
     # neighbour lists: shared nodes of (lo,hi) in the order of hi's FSILS numbering
     for hi in range(nranks):

@@ -1,0 +1,60 @@
+"""One rank of the multi-rank REFERENCE run (TEST INFRASTRUCTURE): the compiled reference (oracle/_ref/libsvref.so) with the
+shared-memory MPI shim of oracle/ref_build/mpi_stub.cpp, SVREF_MPI_{SIZE,RANK,SHM} set by the parent test.  The rank builds its
+local mesh with the product's host logic (svmultiphysics_b200/partition.py), lets the reference's own fsils_lhs_create derive
+lhs.map / mynNo / cS[] from the local -> global map, compares them with partition.py's, then assembles, sums shared nodes and
+solves with the reference's multi-rank FSILS; results go to <outdir>/rank<r>.npz."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import refbind  # noqa: E402
+from svmultiphysics_b200 import abi, partition  # noqa: E402
+from tests import common  # noqa: E402
+
+
+def main():
+    outdir, mode = sys.argv[1], sys.argv[2]
+    rank, world = int(os.environ["SVREF_MPI_RANK"]), int(os.environ["SVREF_MPI_SIZE"])
+    n, nz = 4, 6
+    m, Ag, Yg, Dg, Bf = common.fluid_case(n=n, nz=nz)
+    if mode == "metis":
+        from oracle import metis_part
+        part, _ = metis_part.part_mesh_dual(m.IEN, m.nNo, world)
+    else:
+        part = (((np.arange(m.nEl) // 6) // (n * n)) * world // nz).astype(np.int32)
+    p = partition.partition_mesh(m.IEN, m.nNo, part, world)[rank]
+    faces = []
+    for (g, nodes, val) in common.dirichlet_faces(m):
+        loc = np.searchsorted(p.ltg, nodes)
+        ok = (loc < p.nNo) & (p.ltg[np.minimum(loc, p.nNo - 1)] == nodes)
+        faces.append((g, loc[ok].astype(np.int32), np.asfortranarray(val[:, ok])))
+    c = refbind.RefCase()
+    c.set_coords(m.x[:, p.ltg])
+    c.set_partition(m.nNo, p.ltg)
+    c.add_mesh(p.IEN)
+    c.build_graph(len(faces))
+    mynNo, lmap, reqs = c.get_lhs()
+    # ---- the product's host logic against fsils_lhs_create ------------------------------------------------------
+    same_map = bool(np.array_equal(lmap, p.node_map)) and mynNo == p.mynNo
+    same_nb = [q for q, _ in reqs] == [q for q, _ in p.neighbours]
+    same_ptr = same_nb and all(np.array_equal(a[1], b[1]) for a, b in zip(reqs, p.neighbours))
+    same_sets = same_nb and all(np.array_equal(np.sort(a[1]), np.sort(b[1])) for a, b in zip(reqs, p.neighbours))
+    for i, (g, nodes, val) in enumerate(faces):
+        c.set_face(i, g, nodes, val)
+    eq, dmn = abi.fluid_eq(0.005), [abi.fluid_domain()]
+    c.alloc(4)
+    c.set_state(Ag[:, p.ltg], Yg[:, p.ltg], Dg[:, p.ltg], Bf[:, p.ltg])
+    c.assemble(0, eq, dmn)
+    c.commu_R()
+    R = c.get_R()
+    ls = abi.ls_params(abi.LS_GMRES, mItr=10, sD=80, relTol=1e-9)
+    X, o, _ = c.solve(4, abi.LS_GMRES, ls, np.ones(len(faces), np.int32), np.zeros(len(faces)))
+    np.savez(os.path.join(outdir, f"rank{rank}.npz"), ltg=p.ltg, R=R, X=X, itr=o.RI.itr, iNorm=o.RI.iNorm, fNorm=o.RI.fNorm,
+             success=o.RI.success, same_map=same_map, same_nb=same_nb, same_ptr=same_ptr, same_sets=same_sets, mynNo=mynNo)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,71 @@
+"""Multi-rank REFERENCE runs on the CPU: N processes of the compiled reference (oracle/_ref/libsvref.so) talk through the
+shared-memory MPI shim (oracle/ref_build/mpi_stub.cpp), so that
+  * the product's partition logic (svmultiphysics_b200/partition.py: FSILS node order lhs.map, mynNo, shared-node lists) is
+    compared with what the reference's own fsils_lhs_create derives for the same partition, rank by rank;
+  * the reference's multi-rank assembly + fsils_commuv + GMRES is compared with its single-rank run (the ground truth the
+    multi-GPU tests use), which validates both the shim and that single-partition equivalence."""
+import os
+import subprocess
+import sys
+import uuid
+
+import numpy as np
+import pytest
+
+from svmultiphysics_b200 import abi
+from tests import common
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("world,mode", [(2, "slab"), (3, "slab"), (4, "metis")])
+def test_reference_multirank_matches_single_rank_and_partition_logic(tmp_path, world, mode):
+    from oracle import refbind, metis_part
+    if not refbind.have_ref():
+        pytest.skip("needs oracle/_ref/libsvref.so")
+    if mode == "metis" and not metis_part.have_metis():
+        pytest.skip("needs oracle/_ref/libsvmetis.so")
+    shm = "/svref_" + uuid.uuid4().hex[:12]
+    procs = []
+    try:
+        for r in range(world):
+            env = dict(os.environ, SVREF_MPI_SIZE=str(world), SVREF_MPI_RANK=str(r), SVREF_MPI_SHM=shm)
+            procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "mrank_ref_worker.py"), str(tmp_path), mode],
+                                          env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+        outs = [p.communicate(timeout=600)[0] for p in procs]
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+        try:
+            os.unlink("/dev/shm" + shm)
+        except OSError:
+            pass
+    for r, p in enumerate(procs):
+        assert p.returncode == 0, f"rank {r}:\n{outs[r][-3000:]}"
+    ranks = [np.load(os.path.join(tmp_path, f"rank{r}.npz")) for r in range(world)]
+    # ---- partition.py against fsils_lhs_create ---------------------------------------------------------------
+    for r, d in enumerate(ranks):
+        assert bool(d["same_map"]), f"rank {r}: lhs.map / mynNo differ from fsils_lhs_create"
+        assert bool(d["same_nb"]), f"rank {r}: neighbour ranks differ"
+        assert bool(d["same_sets"]), f"rank {r}: shared-node sets differ"
+        assert bool(d["same_ptr"]), f"rank {r}: order of the shared-node lists differs"
+    # ---- multi-rank reference against its single-rank run ----------------------------------------------------
+    m, Ag, Yg, Dg, Bf = common.fluid_case(n=4, nz=6)
+    faces = common.dirichlet_faces(m)
+    c, _, _ = common.make_oracle(refbind.RefCase, m, nFaces=len(faces))
+    for i, (g, nodes, val) in enumerate(faces):
+        c.set_face(i, g, nodes, val)
+    c.alloc(4); c.set_state(Ag, Yg, Dg, Bf); c.assemble(0, abi.fluid_eq(0.005), [abi.fluid_domain()])
+    R0 = c.get_R()
+    ls = abi.ls_params(abi.LS_GMRES, mItr=10, sD=80, relTol=1e-9)
+    X0, o0, _ = c.solve(4, abi.LS_GMRES, ls, np.ones(len(faces), np.int32), np.zeros(len(faces)))
+    Rg, Xg = np.zeros_like(R0), np.zeros_like(X0)
+    for d in ranks:
+        Rg[:, d["ltg"]] = d["R"]
+        Xg[:, d["ltg"]] = d["X"]
+    assert common.rel_err(Rg, R0) < 1e-12
+    assert all(int(d["success"]) == int(o0.RI.success) for d in ranks)
+    assert all(abs(float(d["iNorm"]) - o0.RI.iNorm) <= 1e-10 * o0.RI.iNorm for d in ranks)
+    assert all(abs(int(d["itr"]) - o0.RI.itr) <= max(2, o0.RI.itr // 20) for d in ranks)
+    assert common.rel_err(Xg, X0) < 1e-6
