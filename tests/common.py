@@ -258,3 +258,23 @@ def lelas_case(name):
     m.eId = None
     Do = np.asfortranarray(0.9 * Dg)
     return m, Ag, Yg, Dg, Bf, Do, abi.mesh_eq(1e-3), [abi.mesh_domain(E=1.0, nu=0.3)]
+
+
+# ---- multi-rank reference runs (tests/test_multirank_reference_cpu.py, tests/mrank_ref_worker.py) -------------------------
+def mrank_faces(m, ls_name):
+    """Global face list and resistances: Dirichlet wall + inlet; for "ns" also the coupled resistance outlet of pipe_RCR_3d."""
+    faces = dirichlet_faces(m)
+    res = np.zeros(len(faces))
+    if ls_name == "ns":
+        out = m.faces["outlet"]
+        val = np.zeros((3, len(out)), order="F"); val[2] = 4.0 * np.pi / len(out)
+        faces.append((abi.BC_NEU, out, val))
+        res = np.append(res, 0.8)
+    return faces, res
+
+
+def mrank_ls(ls_name):
+    if ls_name == "ns":
+        return abi.LS_NS, abi.ls_params(abi.LS_NS, mItr=15, sD=250, relTol=1e-3, absTol=1e-17, gm=(10, 250, 1e-3, 1e-17),
+                                        cg=(300, 0, 1e-3, 1e-17))
+    return abi.LS_GMRES, abi.ls_params(abi.LS_GMRES, mItr=10, sD=80, relTol=1e-9)

@@ -17,6 +17,7 @@ from tests import common  # noqa: E402
 
 def main():
     outdir, mode = sys.argv[1], sys.argv[2]
+    ls_name = sys.argv[3] if len(sys.argv) > 3 else "gmres"
     rank, world = int(os.environ["SVREF_MPI_RANK"]), int(os.environ["SVREF_MPI_SIZE"])
     n, nz = 4, 6
     m, Ag, Yg, Dg, Bf = common.fluid_case(n=n, nz=nz)
@@ -25,12 +26,18 @@ def main():
         part, _ = metis_part.part_mesh_dual(m.IEN, m.nNo, world)
     else:
         part = (((np.arange(m.nEl) // 6) // (n * n)) * world // nz).astype(np.int32)
-    p = partition.partition_mesh(m.IEN, m.nNo, part, world)[rank]
+    parts = partition.partition_mesh(m.IEN, m.nNo, part, world)
+    p = parts[rank]
+    gfaces, res = common.mrank_faces(m, ls_name)
+    count = np.zeros(m.nNo, dtype=np.int32)
+    for q in parts:
+        count[q.ltg] += 1
     faces = []
-    for (g, nodes, val) in common.dirichlet_faces(m):
+    for (g, nodes, val) in gfaces:
         loc = np.searchsorted(p.ltg, nodes)
         ok = (loc < p.nNo) & (p.ltg[np.minimum(loc, p.nNo - 1)] == nodes)
-        faces.append((g, loc[ok].astype(np.int32), np.asfortranarray(val[:, ok])))
+        # nodal normal integrals of a shared face node are PARTIAL on each rank (fsils_bc_create sums them, bc.cpp:60-90)
+        faces.append((g, loc[ok].astype(np.int32), np.asfortranarray(val[:, ok] / count[nodes[ok]])))
     c = refbind.RefCase()
     c.set_coords(m.x[:, p.ltg])
     c.set_partition(m.nNo, p.ltg)
@@ -50,8 +57,8 @@ def main():
     c.assemble(0, eq, dmn)
     c.commu_R()
     R = c.get_R()
-    ls = abi.ls_params(abi.LS_GMRES, mItr=10, sD=80, relTol=1e-9)
-    X, o, _ = c.solve(4, abi.LS_GMRES, ls, np.ones(len(faces), np.int32), np.zeros(len(faces)))
+    ls_type, ls = common.mrank_ls(ls_name)
+    X, o, _ = c.solve(4, ls_type, ls, np.ones(len(faces), np.int32), res)
     np.savez(os.path.join(outdir, f"rank{rank}.npz"), ltg=p.ltg, R=R, X=X, itr=o.RI.itr, iNorm=o.RI.iNorm, fNorm=o.RI.fNorm,
              success=o.RI.success, same_map=same_map, same_nb=same_nb, same_ptr=same_ptr, same_sets=same_sets, mynNo=mynNo)
 

@@ -18,8 +18,9 @@ from tests import common
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("world,mode", [(2, "slab"), (3, "slab"), (4, "metis")])
-def test_reference_multirank_matches_single_rank_and_partition_logic(tmp_path, world, mode):
+@pytest.mark.parametrize("world,mode,ls_name", [(2, "slab", "gmres"), (3, "slab", "gmres"), (4, "metis", "gmres"), (2, "slab", "ns"),
+                                                (3, "metis", "ns")])
+def test_reference_multirank_matches_single_rank_and_partition_logic(tmp_path, world, mode, ls_name):
     from oracle import refbind, metis_part
     if not refbind.have_ref():
         pytest.skip("needs oracle/_ref/libsvref.so")
@@ -30,7 +31,7 @@ def test_reference_multirank_matches_single_rank_and_partition_logic(tmp_path, w
     try:
         for r in range(world):
             env = dict(os.environ, SVREF_MPI_SIZE=str(world), SVREF_MPI_RANK=str(r), SVREF_MPI_SHM=shm)
-            procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "mrank_ref_worker.py"), str(tmp_path), mode],
+            procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "mrank_ref_worker.py"), str(tmp_path), mode, ls_name],
                                           env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
         outs = [p.communicate(timeout=600)[0] for p in procs]
     finally:
@@ -52,14 +53,14 @@ def test_reference_multirank_matches_single_rank_and_partition_logic(tmp_path, w
         assert bool(d["same_ptr"]), f"rank {r}: order of the shared-node lists differs"
     # ---- multi-rank reference against its single-rank run ----------------------------------------------------
     m, Ag, Yg, Dg, Bf = common.fluid_case(n=4, nz=6)
-    faces = common.dirichlet_faces(m)
+    faces, res = common.mrank_faces(m, ls_name)
     c, _, _ = common.make_oracle(refbind.RefCase, m, nFaces=len(faces))
     for i, (g, nodes, val) in enumerate(faces):
         c.set_face(i, g, nodes, val)
     c.alloc(4); c.set_state(Ag, Yg, Dg, Bf); c.assemble(0, abi.fluid_eq(0.005), [abi.fluid_domain()])
     R0 = c.get_R()
-    ls = abi.ls_params(abi.LS_GMRES, mItr=10, sD=80, relTol=1e-9)
-    X0, o0, _ = c.solve(4, abi.LS_GMRES, ls, np.ones(len(faces), np.int32), np.zeros(len(faces)))
+    ls_type, ls = common.mrank_ls(ls_name)
+    X0, o0, _ = c.solve(4, ls_type, ls, np.ones(len(faces), np.int32), res)
     Rg, Xg = np.zeros_like(R0), np.zeros_like(X0)
     for d in ranks:
         Rg[:, d["ltg"]] = d["R"]
@@ -68,4 +69,5 @@ def test_reference_multirank_matches_single_rank_and_partition_logic(tmp_path, w
     assert all(int(d["success"]) == int(o0.RI.success) for d in ranks)
     assert all(abs(float(d["iNorm"]) - o0.RI.iNorm) <= 1e-10 * o0.RI.iNorm for d in ranks)
     assert all(abs(int(d["itr"]) - o0.RI.itr) <= max(2, o0.RI.itr // 20) for d in ranks)
-    assert common.rel_err(Xg, X0) < 1e-6
+    # NS: the outer iteration stops at relTol 1e-3, so two runs agree to a few per cent of that only (same bar as test_gpu_multi)
+    assert common.rel_err(Xg, X0) < (0.05 if ls_name == "ns" else 1e-6)
