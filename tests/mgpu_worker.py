@@ -105,9 +105,56 @@ def fsi_main(rank, world, lr):
     sys.exit(0 if flag.item() == 1 else 1)
 
 
+def ranklocal_check(rank, world, m, p, parts, gfaces, gtl, count, rowPtr, colPtr, state, eq, dmn, ls_type, ls, incL, res,
+                    Val_loc, R_loc, X_loc, o, eng):
+    """Rank-local parity: this process also becomes rank `rank` of a `world`-rank run of the compiled reference (shared-memory
+    MPI shim, oracle/ref_build/mpi_stub.cpp) on the SAME partition, and compares its own local CSR, Val, R (after the
+    shared-node sum) and solution with that rank's reference arrays — no gluing, no single-partition stand-in."""
+    from oracle import refbind
+    name = [None]
+    if rank == 0:
+        import uuid
+        name[0] = "/svref_mgpu_" + uuid.uuid4().hex[:10]
+    dist.broadcast_object_list(name, 0)
+    os.environ.update(SVREF_MPI_SIZE=str(world), SVREF_MPI_RANK=str(rank), SVREF_MPI_SHM=name[0])
+    Ag, Yg, Dg, Bf = state
+    c = refbind.RefCase()
+    c.set_coords(m.x[:, p.ltg]); c.set_partition(m.nNo, p.ltg); c.add_mesh(p.IEN)
+    rp, cp = c.build_graph(len(gfaces))
+    same_graph = bool(np.array_equal(rp, rowPtr) and np.array_equal(cp, colPtr))
+    mynNo, lmap, reqs = c.get_lhs()
+    same_lhs = bool(np.array_equal(lmap, p.node_map) and mynNo == p.mynNo and
+                    all(a[0] == b[0] and np.array_equal(a[1], b[1]) for a, b in zip(reqs, p.neighbours)) and len(reqs) == len(p.neighbours))
+    for i, (g, nodes, v) in enumerate(gfaces):
+        mine = gtl[nodes] >= 0
+        c.set_face(i, g, gtl[nodes[mine]].astype(np.int32), np.asfortranarray(v[:, mine] / count[nodes[mine]]))
+    c.alloc(4); c.set_state(Ag[:, p.ltg], Yg[:, p.ltg], Dg[:, p.ltg], Bf[:, p.ltg]); c.assemble(0, eq, dmn)
+    V0 = c.get_Val()
+    c.commu_R()
+    R0 = c.get_R()
+    X0, o0, _ = c.solve(4, ls_type, ls, incL, res)
+    eV, eR, eX = common.rel_err(Val_loc, V0), common.rel_err(R_loc, R0), common.rel_err(X_loc, X0)
+    print(f"[mgpu ranklocal rank {rank}/{world}, transport {eng.comm_transport()}] graph {same_graph} lhs {same_lhs} relerr Val {eV:.2e} "
+          f"R {eR:.2e} X {eX:.2e}; itr {o.RI.itr} vs {o0.RI.itr}; iNorm {o.RI.iNorm:.6e} vs {o0.RI.iNorm:.6e}", flush=True)
+    ok = int(same_graph and same_lhs and eV < 1e-12 and eR < 1e-12 and eX < 1e-6 and abs(o.RI.iNorm - o0.RI.iNorm) < 1e-10 * o0.RI.iNorm
+             and abs(o.RI.itr - o0.RI.itr) <= max(2, o0.RI.itr // 10) and bool(o.RI.success) == bool(o0.RI.success))
+    flag = torch.tensor([ok], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    if rank == 0:
+        try:
+            os.unlink("/dev/shm" + name[0])
+        except OSError:
+            pass
+    eng.close()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1 else 1)
+
+
 def main():
     mode = sys.argv[1] if len(sys.argv) > 1 else "slab"
     ls_name = sys.argv[2] if len(sys.argv) > 2 else "gmres"
+    ranklocal = len(sys.argv) > 3 and sys.argv[3] == "ranklocal"
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
@@ -154,6 +201,7 @@ def main():
     eng.set_state(Ag[:, p.ltg], Yg[:, p.ltg], None, Bf[:, p.ltg])
     eq, dmn = abi.fluid_eq(0.005), [abi.fluid_domain()]
     eng.assemble(0, eq, dmn)
+    Val_loc = eng.get_Val() if ranklocal else None       # before the solve preconditions it in place
     eng.commu_R()
     R_loc = eng.get_R()
     if ls_name == "ns":
@@ -164,6 +212,9 @@ def main():
         ls = abi.ls_params(abi.LS_GMRES, mItr=100, sD=50, relTol=1e-8)
     incL, res = np.ones(3, np.int32), np.array([0.0, 0.0, 0.8])
     X_loc, o, _ = eng.solve(4, ls_type, ls, incL, res)
+    if ranklocal:
+        return ranklocal_check(rank, world, m, p, parts, gfaces, gtl, count, rowPtr, colPtr, (Ag, Yg, Dg, Bf), eq, dmn, ls_type, ls,
+                               incL, res, Val_loc, R_loc, X_loc, o, eng)
     # gather on rank 0
     def gather(a):
         t = torch.zeros((4, m.nNo), dtype=torch.float64, device="cuda")
