@@ -32,13 +32,23 @@ sys.path.insert(0, ROOT)
 # stdout of this script is exactly ONE JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints
 # "NCCL version ..." there at every NCCL_DEBUG level from VERSION up, WARN included), so descriptor 1 is pointed at stderr
 # for the whole run and the JSON line goes to a private duplicate of the original stdout.
-sys.stdout.flush()
-_REAL_STDOUT = os.dup(1)
-os.dup2(2, 1)
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Called by main() only (importing this module, as tests/test_gpu_fullsize.py does, must not touch the descriptors)."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
 
 
 def emit_line(obj):
-    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+    if _REAL_STDOUT is None:
+        print(json.dumps(obj), flush=True)
+    else:
+        os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
 
 
 from svmultiphysics_b200 import abi, elements, meshgen, partition  # noqa: E402
@@ -182,6 +192,7 @@ def run_reference_arm(args, sample_n=36, sample_nz=24, procs=None, with_solve=Tr
 
 # ------------------------------------------------------------------------------------------------
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
