@@ -136,3 +136,78 @@ def test_heat_uniform_temperature(hostmath):
     # the conductivity part of a row sums to zero (constants are in its kernel); what is left is the lumped mass term:
     # sum over all entries = am rho |Omega|
     assert abs(V.sum() - eq.am * d.rho * 1.0) < 1e-12
+
+
+def _csr_matvec(rowPtr, colPtr, V, x, dof=3):
+    """y = K x for the block-CSR Val (dof*dof, nnz) with blocks row-major; x, y are (dof, nNo)."""
+    y = np.zeros_like(x)
+    rows = np.repeat(np.arange(len(rowPtr) - 1), np.diff(rowPtr))
+    B = V.T.reshape(-1, dof, dof)
+    np.add.at(y.T, rows, np.einsum("kij,kj->ki", B, x.T[colPtr]))
+    return y
+
+
+@pytest.mark.parametrize("kind,iso", [("hex8", abi.ISO_NHK), ("hex8", abi.ISO_MR), ("tet4", abi.ISO_NHK), ("tet4_closed_form", abi.ISO_NHK),
+                                      ("tet4_closed_form", abi.ISO_STVK)])
+def test_solid_tangent_is_the_derivative_of_the_residual(hostmath, kind, iso):
+    """For a hyperelastic solid without inertia the assembled tangent is exact: Val = af beta dt^2 dR/dd (sv_struct.cpp:736-825), so
+    Val . delta = afu (R(d + e delta) - R(d - e delta)) / (2 e) + O(e^2) for any nodal field delta — the general two-phase algebra
+    (hostmath_struct) and the closed-form TET4 algebra (hostmath_tet4) both have to satisfy it."""
+    from tests.test_hostmath_cpu import _run_tet4
+    m = meshgen.box_hex8(3, 2, 2, (1.0, 1.0, 1.0)) if kind == "hex8" else meshgen.box_tet4(2, 2, 2, (1.0, 1.0, 1.0))
+    rowPtr, colPtr = _csr(m)
+    rng = np.random.default_rng(8)
+    z = np.zeros((3, m.nNo), order="F")
+    D = np.asfortranarray(0.02 * rng.standard_normal((3, m.nNo)))
+    delta = np.asfortranarray(rng.standard_normal((3, m.nNo)))
+    kw = dict(E=1e6, nu=0.4, Kpen=1e6, rho=0.0)
+    if iso == abi.ISO_MR:
+        kw.update(isoType=iso, C10=1e5, C01=3e4)
+    if iso == abi.ISO_STVK:
+        kw.update(isoType=iso, C10=2e5, C01=1e5, Kpen=0.0)
+    d = abi.struct_domain(**kw)
+
+    def run(Dg):
+        if kind == "tet4_closed_form":
+            eq = abi.struct_eq(1e-4)
+
+            def fill(dm):
+                dm.rho, dm.Kpen, dm.C10, dm.C01 = d.rho, d.Kpen, d.C10, d.C01
+                dm.isoType, dm.volType, dm.Id, dm.isStruct = d.isoType, d.volType, -1, 1
+            R, V = _run_tet4(hostmath, m, z, z, Dg, z, None, eq, 0, fill, 0, None, rowPtr, colPtr)
+            return R, V, eq
+        return _struct(hostmath, m, z, z, Dg, z, d, rowPtr, colPtr)
+
+    R0, V, eq = run(D)
+    e = 1e-6
+    Rp, _, _ = run(np.asfortranarray(D + e * delta))
+    Rm, _, _ = run(np.asfortranarray(D - e * delta))
+    afu = eq.af * eq.beta * eq.dt * eq.dt
+    lhs = _csr_matvec(rowPtr, colPtr, V, delta)
+    rhs = afu * (Rp - Rm) / (2 * e)
+    assert np.abs(lhs - rhs).max() < 1e-6 * np.abs(rhs).max()
+
+
+def test_linear_elasticity_tangent_is_the_derivative_of_the_residual(hostmath):
+    """Same identity for the closed-form TET4 routines of the mesh / lElas equation (l_elas_3d is linear in d: the difference
+    quotient is exact up to round-off)."""
+    from tests.test_hostmath_cpu import _run_tet4
+    m = meshgen.box_tet4(2, 2, 2, (1.0, 1.0, 1.0))
+    rowPtr, colPtr = _csr(m)
+    rng = np.random.default_rng(9)
+    z = np.zeros((3, m.nNo), order="F")
+    D = np.asfortranarray(0.02 * rng.standard_normal((3, m.nNo)))
+    delta = np.asfortranarray(rng.standard_normal((3, m.nNo)))
+    eq = abi.lelas_eq(1e-3)
+
+    def fill(dm):
+        dm.rho, dm.C10, dm.C01 = 0.0, 1.0e6, 0.3
+        dm.Id, dm.isStruct = -1, 1
+    run = lambda Dg: _run_tet4(hostmath, m, z, z, Dg, z, None, eq, 1, fill, 0, None, rowPtr, colPtr)   # noqa: E731
+    _, V = run(D)
+    Rp, _ = run(np.asfortranarray(D + delta))
+    Rm, _ = run(np.asfortranarray(D - delta))
+    afu = eq.af * eq.beta * eq.dt * eq.dt
+    lhs = _csr_matvec(rowPtr, colPtr, V, delta)
+    rhs = afu * (Rp - Rm) / 2.0
+    assert np.abs(lhs - rhs).max() < 1e-11 * np.abs(rhs).max()
