@@ -211,3 +211,54 @@ def test_linear_elasticity_tangent_is_the_derivative_of_the_residual(hostmath):
     lhs = _csr_matvec(rowPtr, colPtr, V, delta)
     rhs = afu * (Rp - Rm) / 2.0
     assert np.abs(lhs - rhs).max() < 1e-11 * np.abs(rhs).max()
+
+
+@pytest.mark.parametrize("kind,entry", [("hex8", "hostmath_ustruct"), ("tet4", "hostmath_ustruct"), ("tet4", "hostmath_ustruct_tet4")],
+                         ids=["hex8", "tet4", "tet4_closed_form"])
+def test_ustruct_displacement_tangent_is_the_derivative_of_the_residual(hostmath, kind, entry):
+    """com_mod.Kd of the mixed solid: with the VMS constants switched off (ctau_M = ctau_C = 0) lKd = af dR/dd EXACTLY, momentum and
+    continuity rows alike (ustruct.cpp:1455-1572, 820-856): Kd . delta = af (R(d + e delta) - R(d - e delta)) / (2 e).  With the
+    stabilisation on, the reference does not linearise tauM(J), tauC(J) (compute_tau is evaluated at the current J), so only the
+    momentum rows, where those terms are small, still agree to 1e-5 — measured, and asserted as such."""
+    from tests.test_hostmath_cpu import HostUstructArgs
+    m = meshgen.box_hex8(3, 2, 2, (1.0, 1.0, 1.0)) if kind == "hex8" else meshgen.box_tet4(2, 2, 2, (1.0, 1.0, 1.0))
+    rowPtr, colPtr = _csr(m)
+    Ag, Yg, Dg, Bf, _ = common.ustruct_state(m)
+    eq = abi.ustruct_eq(1e-3)
+    rng = np.random.default_rng(1)
+    delta = np.zeros((4, m.nNo), order="F"); delta[:3] = rng.standard_normal((3, m.nNo))
+
+    def run(d, D):
+        A = HostUstructArgs()
+        keep = [np.ascontiguousarray(m.IEN.T.astype(np.int32)), np.ascontiguousarray(m.x.T), np.ascontiguousarray(Ag.T),
+                np.ascontiguousarray(Yg.T), np.ascontiguousarray(D.T), np.ascontiguousarray(Bf.T)]
+        A.IEN, A.x, A.Ag, A.Yg, A.Dg, A.Bf = (k.ctypes.data for k in keep)
+        A.eNoN, A.nEl, A.tDof, A.s, A.nFn = m.eNoN, m.nEl, 4, 0, 0
+        A.nG = _fill_tables(A, m.eNoN)
+        A.dt, A.af, A.am, A.gam = eq.dt, eq.af, eq.am, eq.gam
+        dm = A.dm.st
+        dm.rho, dm.Kpen, dm.C10, dm.C01 = d.rho, d.Kpen, d.C10, d.C01
+        for i in range(3):
+            dm.f[i] = d.f[i]
+        dm.isoType, dm.volType, dm.Id, dm.isStruct = d.isoType, d.volType, -1, 1
+        A.dm.E, A.dm.nu, A.dm.ctM, A.dm.ctC = d.E, d.nu, d.ctau_M, d.ctau_C
+        R = np.zeros((m.nNo, 4)); V = np.zeros((len(colPtr), 16)); Kd = np.zeros((len(colPtr), 12))
+        rc = getattr(hostmath, entry)(C.byref(A), rowPtr.ctypes.data_as(C.c_void_p), colPtr.ctypes.data_as(C.c_void_p),
+                                      R.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p), Kd.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        return R.T, Kd.T
+
+    af = eq.af * eq.gam * eq.dt
+    rows = np.repeat(np.arange(m.nNo), np.diff(rowPtr))
+    for ct, tol_m, tol_c in ((0.0, 1e-8, 1e-8), (1e-3, 1e-5, None)):
+        d = abi.ustruct_domain(E=1e6, nu=0.45, Kpen=2e6, rho=1.2, ctau_M=ct, ctau_C=ct, f=(0.1, -0.2, 0.3))
+        _, Kd = run(d, Dg)
+        e = 1e-6
+        Rp, _ = run(d, np.asfortranarray(Dg + e * delta))
+        Rm, _ = run(d, np.asfortranarray(Dg - e * delta))
+        y = np.zeros((m.nNo, 4))
+        np.add.at(y, rows, np.einsum("kij,kj->ki", Kd.T.reshape(-1, 4, 3), delta[:3].T[colPtr]))
+        rhs = af * (Rp - Rm) / (2 * e)
+        assert np.abs(y.T[:3] - rhs[:3]).max() < tol_m * np.abs(rhs[:3]).max()
+        if tol_c is not None:
+            assert np.abs(y.T[3] - rhs[3]).max() < tol_c * np.abs(rhs[3]).max()
