@@ -278,3 +278,14 @@ def mrank_ls(ls_name):
         return abi.LS_NS, abi.ls_params(abi.LS_NS, mItr=15, sD=250, relTol=1e-3, absTol=1e-17, gm=(10, 250, 1e-3, 1e-17),
                                         cg=(300, 0, 1e-3, 1e-17))
     return abi.LS_GMRES, abi.ls_params(abi.LS_GMRES, mItr=10, sD=80, relTol=1e-9)
+
+
+def mrank_struct_case():
+    """HEX8 nHK/ST91 block with the symmetric Dirichlet planes of struct/block_compression; Dirichlet values are not partial sums."""
+    m = meshgen.box_hex8(5, 4, 6, (1e-3, 1e-3, 1e-3))
+    Ag, Yg, Dg, Bf, _ = struct_state(m, 0)
+    faces = []
+    for k, name in enumerate(("X0", "Y0", "Z0")):
+        val = np.ones((3, len(m.faces[name])), order="F"); val[k] = 0.0
+        faces.append((abi.BC_DIR, m.faces[name], val))
+    return m, Ag, Yg, Dg, Bf, faces, abi.struct_eq(1e-4), [abi.struct_domain()], abi.ls_params(abi.LS_BICGS, mItr=600, relTol=1e-10)

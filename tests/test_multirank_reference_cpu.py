@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("world,mode,ls_name", [(2, "slab", "gmres"), (3, "slab", "gmres"), (4, "metis", "gmres"), (2, "slab", "ns"),
-                                                (3, "metis", "ns")])
+                                                (3, "metis", "ns"), (3, "slab", "struct"), (4, "metis", "struct")])
 def test_reference_multirank_matches_single_rank_and_partition_logic(tmp_path, world, mode, ls_name):
     from oracle import refbind, metis_part
     if not refbind.have_ref():
@@ -52,15 +52,20 @@ def test_reference_multirank_matches_single_rank_and_partition_logic(tmp_path, w
         assert bool(d["same_sets"]), f"rank {r}: shared-node sets differ"
         assert bool(d["same_ptr"]), f"rank {r}: order of the shared-node lists differs"
     # ---- multi-rank reference against its single-rank run ----------------------------------------------------
-    m, Ag, Yg, Dg, Bf = common.fluid_case(n=4, nz=6)
-    faces, res = common.mrank_faces(m, ls_name)
+    if ls_name == "struct":
+        m, Ag, Yg, Dg, Bf, faces, eq, dmn, ls = common.mrank_struct_case()
+        dof, ls_type, res = 3, abi.LS_BICGS, np.zeros(len(faces))
+    else:
+        m, Ag, Yg, Dg, Bf = common.fluid_case(n=4, nz=6)
+        faces, res = common.mrank_faces(m, ls_name)
+        eq, dmn, dof = abi.fluid_eq(0.005), [abi.fluid_domain()], 4
+        ls_type, ls = common.mrank_ls(ls_name)
     c, _, _ = common.make_oracle(refbind.RefCase, m, nFaces=len(faces))
     for i, (g, nodes, val) in enumerate(faces):
         c.set_face(i, g, nodes, val)
-    c.alloc(4); c.set_state(Ag, Yg, Dg, Bf); c.assemble(0, abi.fluid_eq(0.005), [abi.fluid_domain()])
+    c.alloc(dof); c.set_state(Ag, Yg, Dg, Bf); c.assemble(0, eq, dmn)
     R0 = c.get_R()
-    ls_type, ls = common.mrank_ls(ls_name)
-    X0, o0, _ = c.solve(4, ls_type, ls, np.ones(len(faces), np.int32), res)
+    X0, o0, _ = c.solve(dof, ls_type, ls, np.ones(len(faces), np.int32), res)
     Rg, Xg = np.zeros_like(R0), np.zeros_like(X0)
     for d in ranks:
         Rg[:, d["ltg"]] = d["R"]
@@ -68,6 +73,6 @@ def test_reference_multirank_matches_single_rank_and_partition_logic(tmp_path, w
     assert common.rel_err(Rg, R0) < 1e-12
     assert all(int(d["success"]) == int(o0.RI.success) for d in ranks)
     assert all(abs(float(d["iNorm"]) - o0.RI.iNorm) <= 1e-10 * o0.RI.iNorm for d in ranks)
-    assert all(abs(int(d["itr"]) - o0.RI.itr) <= max(2, o0.RI.itr // 20) for d in ranks)
+    assert all(abs(int(d["itr"]) - o0.RI.itr) <= max(2, o0.RI.itr // 10) for d in ranks)
     # NS: the outer iteration stops at relTol 1e-3, so two runs agree to a few per cent of that only (same bar as test_gpu_multi)
     assert common.rel_err(Xg, X0) < (0.05 if ls_name == "ns" else 1e-6)
