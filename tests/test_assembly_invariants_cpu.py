@@ -287,3 +287,67 @@ def test_fluid_tangent_against_the_derivative_of_the_residual(hostmath):
         lhs, rhs = _csr_matvec(rowPtr, colPtr, V, delta, dof=4), (Rp - Rm) / (2 * e)
         assert np.abs(lhs[:3] - rhs[:3]).max() < tol * np.abs(rhs[:3]).max()
         assert np.abs(lhs[3] - rhs[3]).max() < tol * np.abs(rhs[3]).max()
+
+
+def _fluid_gen(hostmath, m, Ag, Yg, Bf, d, rowPtr, colPtr, dt=0.005):
+    from tests.test_hostmath_cpu import HostFluidGenArgs
+    eq = abi.fluid_eq(dt)
+    w, N, Nx = elements.tables(m.eNoN)
+    Nxx = elements.nxx_tables(m.eNoN)
+    A = HostFluidGenArgs()
+    keep = [np.ascontiguousarray(m.IEN.T.astype(np.int32)), np.ascontiguousarray(m.x.T), np.ascontiguousarray(Ag.T),
+            np.ascontiguousarray(Yg.T), np.ascontiguousarray(Bf.T)]
+    A.IEN, A.x, A.Ag, A.Yg, A.Bf = (k.ctypes.data for k in keep)
+    A.eNoN, A.nEl, A.nG, A.tDof, A.mvMsh, A.factored = m.eNoN, m.nEl, len(w), 4, 0, 1
+    A.dt, A.af, A.am, A.gam = eq.dt, eq.af, eq.am, eq.gam
+    for g in range(len(w)):
+        A.w[g] = w[g]
+        for a in range(m.eNoN):
+            A.N[g][a] = N[a, g]
+            for k in range(3):
+                A.Nxi[g][a][k] = Nx[k, a, g]
+            for k in range(6):
+                A.Nxi2[g][a][k] = Nxx[k, a, g]
+    A.dm.rho, A.dm.Kd = d.rho, d.K_darcy
+    for i in range(3):
+        A.dm.f[i] = d.f[i]
+    A.dm.mu_i, A.dm.viscType, A.dm.Id, A.dm.isFluid = d.mu_i, d.viscType, -1, 1
+    R = np.zeros((m.nNo, 4))
+    V = np.zeros((len(colPtr), 16))
+    rc = hostmath.hostmath_fluid_gen(C.byref(A), rowPtr.ctypes.data_as(C.c_void_p), colPtr.ctypes.data_as(C.c_void_p),
+                                     R.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return R.T, V.T, eq
+
+
+def test_general_fluid_kernel_algebra_on_skewed_hex8(hostmath):
+    """The per-Gauss-point VMS algebra (gnn + gn_nxx, second-derivative terms) on non-parallelepiped HEX8: uniform flow and the
+    hydrostatic state leave no interior residual; at rest the tangent is the derivative of the residual."""
+    m = common._hex_skewed()
+    rowPtr, colPtr = _csr(m)
+    z = np.zeros((4, m.nNo), order="F")
+    Bf = np.zeros((3, m.nNo), order="F")
+    interior = np.ones(m.nNo, bool)
+    for k in ("X0", "X1", "Y0", "Y1", "Z0", "Z1"):
+        interior[m.faces[k]] = False
+    assert interior.any()
+    Y = z.copy(order="F"); Y[0], Y[1], Y[2] = 1.5, -0.7, 3.0
+    R, _, _ = _fluid_gen(hostmath, m, z, Y, Bf, abi.fluid_domain(), rowPtr, colPtr)
+    assert np.abs(R[:, interior]).max() < 1e-11
+    d = abi.fluid_domain(rho=1.06, f=(0.3, -0.2, 0.5))
+    Y = z.copy(order="F"); Y[3] = d.rho * (0.3 * m.x[0] - 0.2 * m.x[1] + 0.5 * m.x[2])
+    R, _, _ = _fluid_gen(hostmath, m, z, Y, Bf, d, rowPtr, colPtr)
+    assert np.abs(R[:, interior]).max() < 1e-10
+    # tangent at rest
+    rng = np.random.default_rng(6)
+    A0 = np.asfortranarray(0.1 * rng.standard_normal((4, m.nNo)))
+    Y0 = z.copy(order="F"); Y0[3] = rng.standard_normal(m.nNo)
+    delta = np.asfortranarray(rng.standard_normal((4, m.nNo)))
+    _, V, eq = _fluid_gen(hostmath, m, A0, Y0, Bf, abi.fluid_domain(), rowPtr, colPtr)
+    e, c_a, c_y = 1e-6, eq.am, eq.af * eq.gam * eq.dt
+    Rp, _, _ = _fluid_gen(hostmath, m, np.asfortranarray(A0 + e * c_a * delta), np.asfortranarray(Y0 + e * c_y * delta), Bf, abi.fluid_domain(), rowPtr, colPtr)
+    Rm, _, _ = _fluid_gen(hostmath, m, np.asfortranarray(A0 - e * c_a * delta), np.asfortranarray(Y0 - e * c_y * delta), Bf, abi.fluid_domain(), rowPtr, colPtr)
+    lhs, rhs = _csr_matvec(rowPtr, colPtr, V, delta, dof=4), (Rp - Rm) / (2 * e)
+    print("hex8 tangent-vs-FD at rest:", np.abs(lhs[:3] - rhs[:3]).max() / np.abs(rhs[:3]).max(), np.abs(lhs[3] - rhs[3]).max() / np.abs(rhs[3]).max())
+    assert np.abs(lhs[:3] - rhs[:3]).max() < 1e-4 * np.abs(rhs[:3]).max()
+    assert np.abs(lhs[3] - rhs[3]).max() < 1e-4 * np.abs(rhs[3]).max()
