@@ -66,6 +66,10 @@ def main():
     if mode == "metis":
         from oracle import metis_part
         part, _ = metis_part.part_mesh_dual(m.IEN, m.nNo, world)
+    elif mode == "scattered":      # hexes dealt round-robin: many neighbours, nodes shared by three and more ranks
+        part = (((np.arange(m.nEl) // 6) * 7919) % world).astype(np.int32)
+    elif mode == "random":
+        part = np.random.default_rng(77).integers(0, world, m.nEl).astype(np.int32)
     else:
         part = (((np.arange(m.nEl) // 6) // (n * n)) * world // nz).astype(np.int32)
     parts = partition.partition_mesh(m.IEN, m.nNo, part, world)

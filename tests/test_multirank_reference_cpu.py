@@ -19,7 +19,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("world,mode,ls_name", [(2, "slab", "gmres"), (3, "slab", "gmres"), (4, "metis", "gmres"), (2, "slab", "ns"),
-                                                (3, "metis", "ns"), (3, "slab", "struct"), (4, "metis", "struct")])
+                                                (3, "metis", "ns"), (3, "slab", "struct"), (4, "metis", "struct"), (4, "scattered", "gmres"),
+                                                (5, "random", "gmres")])
 def test_reference_multirank_matches_single_rank_and_partition_logic(tmp_path, world, mode, ls_name):
     from oracle import refbind, metis_part
     if not refbind.have_ref():
