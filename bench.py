@@ -6,13 +6,20 @@ Contract:
   python bench.py --impl reference --gpus N ...            the reference's own CPU code on the host cores
 
 One "step" is one Newton iteration of the hot path on the synthetic 10 M-tet4 cylinder (config C2 of
-SURVEY.md §8d), one such cylinder slab per GPU (weak scaling):
+SURVEY.md §8d), one 10 M-element partition per GPU (weak scaling; the global mesh is the N-times longer cylinder):
     predictor/initiator -> ls_alloc (zero R, Val) -> element assembly + scatter -> shared-node sum of R ->
     fsils_solve (GMRES) -> corrector, all on the device (no nodal array crosses PCIe inside the step).
 `value` is elements assembled per second over the ASSEMBLY stage of the timed steps (zero + kernel +
 halo, device-resident inputs, CUDA events on the library's stream, max over ranks); `ms_per_step` is
 the whole Newton step; `e2e` is the assembly stage driven with HOST buffers through the C ABI (H2D
 of Ag/Yg from pinned memory and D2H of the residual inside the timed region).
+
+After the timed region every rank runs the PARITY GATE (never timed): its assembled R / Val against an oracle
+assembly (oracle/_ref/libsvref.so = the compiled reference, else the C restatement) of sub-blocks of the same mesh and
+state — one inside the partition and one straddling the partition interface where the most ranks meet (rows completed
+by the shared-node sum against the single-partition oracle) — and the TRUE preconditioned residual of the GMRES
+answer, ||W (R - K x)|| <= relTol ||W R||, reduced over the ranks.  The line carries "parity": {...}; a failed gate
+makes the process exit non-zero.
 """
 from __future__ import annotations
 
@@ -24,6 +31,7 @@ import subprocess
 import sys
 import threading
 import time
+import uuid
 
 import numpy as np
 
@@ -55,14 +63,20 @@ from svmultiphysics_b200 import abi, elements, meshgen, partition  # noqa: E402
 
 FLOP_PER_ELEMENT = 11.6e3     # algorithmic FP64 flop per tet4 VMS element (Newtonian)
 SPMV_BYTES = lambda nnz, nNo: nnz * 132 + nNo * 72   # noqa: E731  SURVEY.md §8(d), dof = 4
+LSEG = 30.0                   # cylinder length per GPU share
 
 
-def lattice_state(m, rank, nz, U=10.0, R=2.0, tDof=4, noise=0.01):
-    """Poiseuille flow + 1 % deterministic pseudo-noise keyed on the GLOBAL lattice index, so that the
-    nodes two slabs share carry identical state on both ranks (seeds replaced by a hash)."""
-    n1 = m.lattice[0] + 1
-    ids = np.arange(m.nNo, dtype=np.int64)
-    i, j, k = ids % n1, (ids // n1) % n1, ids // (n1 * n1) + rank * nz
+def lattice_state(m, rank=0, nz=0, U=10.0, R=2.0, tDof=4, noise=0.01):
+    """Poiseuille flow + 1 % deterministic pseudo-noise keyed on the GLOBAL lattice index, so that the nodes two
+    partitions share carry identical state on both ranks and any sub-block of the mesh can be regenerated on its own
+    (seeds replaced by a hash).  Meshes of meshgen.cylinder_box carry their global indices (m.gijk); for
+    the slabs of meshgen.cylinder_slab the index is rebuilt from (rank, nz)."""
+    if m.gijk is not None:
+        i, j, k = m.gijk
+    else:
+        n1 = m.lattice[0] + 1
+        ids = np.arange(m.nNo, dtype=np.int64)
+        i, j, k = ids % n1, (ids // n1) % n1, ids // (n1 * n1) + rank * nz
     def h(c):
         v = (i * 73856093) ^ (j * 19349663) ^ (k * 83492791) ^ (c * 2654435761)
         v = (v ^ (v >> 13)) * 1274126177 & 0xFFFFFFFF
@@ -81,6 +95,17 @@ def lattice_state(m, rank, nz, U=10.0, R=2.0, tDof=4, noise=0.01):
 
 def ls_config(args):
     return abi.ls_params(abi.LS_GMRES, mItr=args.ls_mitr, sD=args.ls_sd, relTol=args.ls_reltol)
+
+
+def workload_config(args):
+    """The workload both arms are run on (identical in the two JSON lines); everything arm-specific (partition,
+    transport, scatter mode, cores) lives under "run" / "cpu_baseline"."""
+    nel = 6 * args.n * args.n * args.nz
+    return {"workload": f"C2 synthetic cylinder, 6*{args.n}^2*{args.nz} = {nel} tet4 per GPU, Newtonian VMS fluid",
+            "elements_per_gpu": nel, "dt": 1e-3,
+            "linear_solver": f"GMRES sD={args.ls_sd} mItr={args.ls_mitr} relTol={args.ls_reltol} + FSILS diagonal preconditioner",
+            "newton_step": "ls_alloc -> construct_fluid (+ do_assem) -> commu(R) -> fsils_solve",
+            "l2": "inputs larger than L2 (Val = 3.2 GB/GPU is rewritten every step)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -107,9 +132,7 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.samples.append((time.perf_counter(), line.strip()))
 
-    def stop(self, t0, t1):
-        if self.proc:
-            self.proc.terminate()
+    def window(self, t0, t1):
         sm, mx, reasons = [], 0.0, set()
         for t, line in self.samples:
             if t < t0 or t > t1:
@@ -125,68 +148,260 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
                 "samples": len(sm)}
 
+    def stop(self, t0=None, t1=None):
+        if self.proc:
+            self.proc.terminate()
+        return self.window(t0, t1) if t0 is not None else None
+
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the UNMODIFIED reference (oracle/_ref/libsvref.so) on the host cores
+# reference arm / CPU baseline: the UNMODIFIED reference (oracle/_ref/libsvref.so) as an MPI run on the host cores
 # ------------------------------------------------------------------------------------------------
-def _ref_worker(q, n, nz, rank, nranks, steps, warmup, ls_tuple, with_solve):
+def best_blocks(ncells, P):
+    """(bx, by, bz) with bx*by*bz = P minimising the largest block, then the interface area — what a graph partitioner
+    balances (ParMETIS_V3_PartMeshKway, Code/Source/solver/SPLIT.c:76-89)."""
+    best = None
+    for bx in range(1, P + 1):
+        if P % bx:
+            continue
+        for by in range(1, P // bx + 1):
+            if (P // bx) % by:
+                continue
+            bz = P // (bx * by)
+            if bx > ncells[0] or by > ncells[1] or bz > ncells[2]:
+                continue
+            big = [-(-ncells[d] // b) for d, b in enumerate((bx, by, bz))]
+            vol = big[0] * big[1] * big[2]
+            cut = (bx - 1) * ncells[1] * ncells[2] + (by - 1) * ncells[0] * ncells[2] + (bz - 1) * ncells[0] * ncells[1]
+            key = (vol, cut)
+            if best is None or key < best[0]:
+                best = (key, (bx, by, bz))
+    return best[1]
+
+
+def _ref_rank_worker(q, n, nzg, L, blocks, r, P, shm, steps, warmup, solve_steps, ls_tuple):
+    """Rank r of a P-rank run of the compiled reference over the shared-memory MPI shim (oracle/ref_build/mpi_stub.cpp):
+    the reference's own partition set-up (fsils_lhs_create), then per step ls_alloc -> construct_fluid -> commu(R) ->
+    fsils_solve (Code/Source/solver/Integrator.cpp:104-160)."""
+    try:
+        os.environ.update(SVREF_MPI_SIZE=str(P), SVREF_MPI_RANK=str(r), SVREF_MPI_SHM=shm)
+        from oracle import refbind
+        m = meshgen.cylinder_block(n, nzg, blocks, r, L=L)
+        Ag, Yg = lattice_state(m)
+        gid = (m.gijk[0] + (n + 1) * (m.gijk[1] + (n + 1) * m.gijk[2])).astype(np.int32)
+        c = refbind.RefCase()
+        c.set_coords(m.x)
+        if P > 1:
+            c.set_partition((n + 1) * (n + 1) * (nzg + 1), gid)
+        c.add_mesh(m.IEN)
+        c.build_graph(1)
+        wall = m.faces["wall"]
+        c.set_face(0, abi.BC_DIR, wall, np.zeros((3, len(wall)), order="F"))
+        eq, dmn = abi.fluid_eq(1e-3), [abi.fluid_domain()]
+        ls = abi.ls_params(abi.LS_GMRES, mItr=ls_tuple[0], sD=ls_tuple[1], relTol=ls_tuple[2])
+        c.set_state(Ag, Yg)
+        t_asm, t_solve, info = [], [], None
+        for s in range(warmup + steps):
+            c.barrier()
+            t0 = time.perf_counter()
+            c.alloc(4)
+            c.assemble(0, eq, dmn)
+            c.commu_R()
+            t1 = time.perf_counter()
+            timed = s >= warmup
+            if timed:
+                t_asm.append(t1 - t0)
+            if timed and len(t_solve) < solve_steps:
+                c.barrier()
+                t2 = time.perf_counter()
+                _, out, _ = c.solve(4, abi.LS_GMRES, ls, np.ones(1, np.int32), np.zeros(1))
+                t_solve.append(time.perf_counter() - t2)
+                info = (out.RI.itr, int(out.RI.success), out.RI.iNorm, out.RI.fNorm)
+        q.put(("ok", r, m.nEl, t_asm, t_solve, info))
+    except Exception as ex:      # a dead rank would leave the others in a barrier: report, the parent tears the run down
+        q.put(("error", r, repr(ex)))
+
+
+def reference_newton(args, steps, warmup, solve_steps, procs=None, timeout_s=1500):
+    """The reference arm / CPU baseline: the C2 mesh (one GPU's share of the workload: 6*n^2*nz tet4) on all host cores as
+    an MPI-style run of the unmodified reference, element-partitioned into balanced blocks.  Returns a dict."""
     from oracle import refbind
-    cls, kind = (refbind.RefCase, "reference") if refbind.have_ref() else (refbind.OracleCase, "port")
-    m, other, plo, phi = meshgen.cylinder_slab(n, nz, rank, nranks)
-    Ag, Yg = lattice_state(m, rank, nz)
-    c = cls()
-    c.set_coords(m.x)
-    c.add_mesh(m.IEN)
-    wall = m.faces["wall"]
-    c.build_graph(1)
-    c.set_face(0, abi.BC_DIR, wall, np.zeros((3, len(wall)), order="F"))
-    eq, dmn = abi.fluid_eq(1e-3), [abi.fluid_domain()]
-    ts, tsolve, itr = [], [], 0
-    for s in range(warmup + steps):
-        t0 = time.perf_counter()
-        c.alloc(4)
-        c.set_state(Ag, Yg) if s == 0 else None
-        c.assemble(0, eq, dmn)
-        t1 = time.perf_counter()
-        if s >= warmup:
-            ts.append(t1 - t0)
-        if with_solve and s >= warmup:
-            ls = abi.ls_params(abi.LS_GMRES, mItr=ls_tuple[0], sD=ls_tuple[1], relTol=ls_tuple[2])
-            t2 = time.perf_counter()
-            _, out, _ = c.solve(4, abi.LS_GMRES, ls, np.ones(1, np.int32), np.zeros(1))
-            tsolve.append(time.perf_counter() - t2)
-            itr = out.RI.itr
-    q.put((m.nEl, ts, tsolve, itr, kind))
-
-
-def run_reference_arm(args, sample_n=36, sample_nz=24, procs=None, with_solve=True):
-    """All host cores, one independent mesh partition per process (what the reference's MPI ranks do in
-    construct_fluid, which has no inter-rank communication).  Bounded sample: 6*n*n*nz tets per core."""
-    procs = procs or os.cpu_count() or 1
-    ctx = mp.get_context("fork")
+    if not refbind.have_ref():
+        return reference_port_sample(args)
+    procs = int(procs or os.environ.get("SVB200_REF_PROCS", 0) or os.cpu_count() or 1)
+    procs = max(1, min(procs, 64))
+    blocks = best_blocks((args.n, args.n, args.nz), procs)
+    shm = "/svref_bench_" + uuid.uuid4().hex[:10]
+    ctx = mp.get_context("spawn")     # fresh interpreters: the MPI shim reads its environment once per process
     q = ctx.Queue()
     ls_tuple = (args.ls_mitr, args.ls_sd, args.ls_reltol)
-    steps = getattr(args, "ref_steps_eff", args.steps_ref)
-    warm = getattr(args, "ref_warmup_eff", 1)
-    ps = [ctx.Process(target=_ref_worker, args=(q, sample_n, sample_nz, r, procs, steps, warm, ls_tuple, with_solve and r == 0))
-          for r in range(procs)]
+    ps = [ctx.Process(target=_ref_rank_worker, args=(q, args.n, args.nz, LSEG, blocks, r, procs, shm, steps, warmup,
+                                                     solve_steps, ls_tuple)) for r in range(procs)]
     for p in ps:
         p.start()
-    res = [q.get() for _ in ps]
-    for p in ps:
-        p.join()
-    nEl = sum(r[0] for r in res)
-    steps = len(res[0][1])
-    t_step = [max(r[1][s] for r in res) for s in range(steps)]        # max over "ranks" per step
-    t_asm = float(np.mean(t_step))
-    solve = [r for r in res if r[2]]
-    out = {"value": nEl / t_asm, "unit": "element assemblies/s", "cores": procs, "kind": res[0][4],
-           "sample": f"{procs} independent cylinder slabs of {res[0][0]} tet4 each (6*{sample_n}^2*{sample_nz}), "
-                     f"ls_alloc + construct_fluid per step, mean of {steps} steps, max over processes",
-           "ms_per_step": t_asm * 1e3, "elements": nEl}
-    if solve:
-        out["newton_step_1core"] = {"elements": solve[0][0], "assemble_ms": float(np.mean(solve[0][1])) * 1e3,
-                                    "fsils_solve_ms": float(np.mean(solve[0][2])) * 1e3, "gmres_itr": solve[0][3]}
+    res, err = [], None
+    deadline = time.time() + timeout_s
+    try:
+        while len(res) < procs and err is None:
+            try:
+                item = q.get(timeout=max(1.0, min(5.0, deadline - time.time())))
+            except Exception:
+                if time.time() > deadline:
+                    err = "timeout"
+                elif any(p.exitcode not in (None, 0) for p in ps):
+                    err = "a reference rank died"
+                continue
+            if item[0] == "error":
+                err = f"rank {item[1]}: {item[2]}"
+            else:
+                res.append(item)
+    finally:
+        for p in ps:
+            if err is not None and p.is_alive():
+                p.terminate()
+            p.join(timeout=30)
+        try:
+            os.unlink("/dev/shm" + shm)
+        except OSError:
+            pass
+    if err is not None:
+        raise RuntimeError("reference run failed: " + err)
+    nEl = sum(r[2] for r in res)
+    nst = len(res[0][3])
+    asm = [max(r[3][s] for r in res) for s in range(nst)]                 # max over ranks per step
+    nso = len(res[0][4])
+    sol = [max(r[4][s] for r in res) for s in range(nso)]
+    t_asm, t_sol = float(np.mean(asm)), (float(np.mean(sol)) if sol else None)
+    info = res[0][5]
+    out = {"value": nEl / t_asm, "unit": "element assemblies/s", "cores": procs, "kind": "reference", "elements": nEl,
+           "sample": f"the C2 mesh itself (6*{args.n}^2*{args.nz} = {nEl} tet4, one GPU's share of the workload), element-partitioned "
+                     f"into {blocks[0]}x{blocks[1]}x{blocks[2]} blocks over {procs} MPI ranks of the compiled reference (shared-memory MPI shim); "
+                     f"ls_alloc + construct_fluid + commu(R) in each of {nst} timed steps, fsils_solve in the first {nso}; max over ranks",
+           "assemble_ms": t_asm * 1e3, "solve_ms": None if t_sol is None else t_sol * 1e3,
+           "newton_step_ms": None if t_sol is None else (t_asm + t_sol) * 1e3, "partition_blocks": list(blocks)}
+    if info:
+        out["gmres"] = {"itr": info[0], "success": info[1], "iNorm": info[2], "fNorm": info[3]}
+    return out
+
+
+def reference_port_sample(args, n=24, nz=12):
+    """No compiled reference on this box: the C restatement (oracle/libsvoracle.so) on one core, bounded sample."""
+    from oracle import refbind
+    m = meshgen.cylinder_box(n, nz, [(0, n), (0, n), (0, nz)])
+    Ag, Yg = lattice_state(m)
+    c = refbind.OracleCase()
+    c.set_coords(m.x); c.add_mesh(m.IEN); c.build_graph(1)
+    wall = m.faces["wall"]
+    c.set_face(0, abi.BC_DIR, wall, np.zeros((3, len(wall)), order="F"))
+    eq, dmn = abi.fluid_eq(1e-3), [abi.fluid_domain()]
+    c.set_state(Ag, Yg)
+    ts = []
+    for s in range(3):
+        t0 = time.perf_counter(); c.alloc(4); c.assemble(0, eq, dmn); ts.append(time.perf_counter() - t0)
+    t2 = time.perf_counter()
+    _, o, _ = c.solve(4, abi.LS_GMRES, ls_config(args), np.ones(1, np.int32), np.zeros(1))
+    ts_sol = time.perf_counter() - t2
+    t = float(np.mean(ts[1:]))
+    return {"value": m.nEl / t, "unit": "element assemblies/s", "cores": 1, "kind": "port", "elements": m.nEl,
+            "sample": f"6*{n}^2*{nz} = {m.nEl} tet4 cylinder, C restatement on one core (oracle/_ref/libsvref.so absent)",
+            "assemble_ms": t * 1e3, "solve_ms": ts_sol * 1e3, "newton_step_ms": (t + ts_sol) * 1e3,
+            "gmres": {"itr": o.RI.itr, "success": int(o.RI.success), "iNorm": o.RI.iNorm, "fNorm": o.RI.fNorm}}
+
+
+# ------------------------------------------------------------------------------------------------
+# parity gate
+# ------------------------------------------------------------------------------------------------
+def _oracle_cls():
+    from oracle import refbind
+    return (refbind.RefCase, "reference") if refbind.have_ref() else (refbind.OracleCase, "port")
+
+
+def _clip_box(centre, half, lo3, hi3):
+    return [(max(lo3[d], centre[d] - half[d]), min(hi3[d], centre[d] + half[d])) for d in range(3)]
+
+
+def parity_boxes(lb, rank, half=(4, 4, 4)):
+    """Two sub-boxes of GLOBAL cells per rank: one centred inside the rank's block, one centred on the corner of the block
+    where the most partitions meet (straddling the interfaces; at the global boundary when there is no neighbour)."""
+    nc = lb.nc
+    rng = lb.cell_ranges(rank)
+    centre = [(lo + hi) // 2 for lo, hi in rng]
+    inner = _clip_box(centre, half, [lo for lo, _ in rng], [hi for _, hi in rng])
+    corner = []
+    for d in range(3):
+        lo, hi = rng[d]
+        if hi < nc[d]:
+            corner.append(hi)              # interface with a higher block
+        elif lo > 0:
+            corner.append(lo)              # interface with a lower block
+        else:
+            corner.append(0 if d < 2 else nc[d])   # no neighbour: the lateral wall / the outlet plane
+    iface = _clip_box(corner, half, [0, 0, 0], list(nc))
+    return {"interior": inner, "interface": iface}
+
+
+def parity_assembly(eng, m, lb, rank, rowPtr, colPtr, eq, dmn, n, nzg, L):
+    """max relative error of this rank's R rows (after the shared-node sum) and Val rows against oracle assemblies of
+    sub-boxes of the same mesh and state.  R is compared with the oracle on ALL cells of the box (the single-partition
+    answer); Val, which is never communicated, with the oracle on the cells of the box this rank owns."""
+    cls, kind = _oracle_cls()
+    rng = lb.cell_ranges(rank)
+    gid_mine = m.gijk[0] + (n + 1) * (m.gijk[1] + (n + 1) * m.gijk[2])
+    out = {"oracle": kind, "boxes": {}}
+    worst = 0.0
+    for name, F in parity_boxes(lb, rank).items():
+        M = [(max(F[d][0], rng[d][0]), min(F[d][1], rng[d][1])) for d in range(3)]     # cells of the box this rank owns
+        if any(lo >= hi for lo, hi in M):
+            continue
+        res = {}
+        for which, box in (("full", F), ("mine", M)):
+            if which == "mine" and box == F:
+                res["mine"] = res["full"]
+                continue
+            b = meshgen.cylinder_box(n, nzg, box, L=L)
+            Ab, Yb = lattice_state(b)
+            c = cls()
+            c.set_coords(b.x); c.add_mesh(b.IEN)
+            rp, cp = c.build_graph(0)
+            c.alloc(4); c.set_state(Ab, Yb); c.assemble(0, eq, dmn)
+            res[which] = (b, rp, cp, c.get_R(), c.get_Val())
+            c.close()
+        # rows that see all of their elements inside F: strictly inside the box or on the global lattice boundary
+        bM = res["mine"][0]
+        gi, gj, gk = bM.gijk
+        nc = lb.nc
+        comp = np.ones(bM.nNo, bool)
+        for d, g in enumerate((gi, gj, gk)):
+            comp &= ((g > F[d][0]) | (g == 0)) & ((g < F[d][1]) | (g == nc[d]))
+        rowsM = np.flatnonzero(comp)
+        gidM = (gi + (n + 1) * (gj + (n + 1) * gk))[rowsM]
+        loc = lb.local_of(rank, gidM).astype(np.int32)
+        assert np.array_equal(gid_mine[loc], gidM)
+        # R: the full-box oracle (all ranks' elements) against this rank's summed rows
+        bF, _, _, RF, _ = res["full"]
+        gidF = bF.gijk[0] + (n + 1) * (bF.gijk[1] + (n + 1) * bF.gijk[2])
+        posF = np.searchsorted(gidF, gidM)
+        assert np.array_equal(gidF[posF], gidM)
+        R_loc = eng.get_rows(abi.ARRAY_R, loc)
+        scaleR = max(np.abs(RF).max(), 1e-300)
+        eR = float(np.abs(R_loc - RF[:, posF]).max() / scaleR)
+        # Val: this rank's own elements only
+        _, rpM, cpM, _, VM = res["mine"]
+        V_loc = eng.get_rows(abi.ARRAY_VAL, loc, rowPtr)
+        cols_loc = np.concatenate([colPtr[rowPtr[a]:rowPtr[a + 1]] for a in loc])
+        cols_or = np.concatenate([cpM[rpM[a]:rpM[a + 1]] for a in rowsM])
+        gidMall = gi + (n + 1) * (gj + (n + 1) * gk)
+        same_graph = len(cols_loc) == len(cols_or) and bool(np.array_equal(gid_mine[cols_loc], gidMall[cols_or]))
+        eV = float("inf")
+        if same_graph:
+            V_or = np.concatenate([VM[:, rpM[a]:rpM[a + 1]] for a in rowsM], axis=1)
+            eV = float(np.abs(V_loc - V_or).max() / max(np.abs(VM).max(), 1e-300))
+        nshared = int((lb.multiplicity(rank)[loc] > 1).sum())
+        out["boxes"][name] = {"cells": [list(x) for x in F], "rows": int(len(rowsM)), "rows_shared": nshared,
+                              "max_ranks_on_a_row": int(lb.multiplicity(rank)[loc].max()), "R_max_rel": eR, "Val_max_rel": eV,
+                              "same_graph": same_graph}
+        worst = max(worst, eR, eV)
+    out["max_rel"] = worst
     return out
 
 
@@ -199,39 +414,42 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=118, help="cross-section lattice (hexes per side)")
-    ap.add_argument("--nz", type=int, default=120, help="cell layers per GPU slab")
+    ap.add_argument("--nz", type=int, default=120, help="cell layers per GPU share")
     ap.add_argument("--ls-reltol", type=float, default=1e-3)
     ap.add_argument("--ls-sd", type=int, default=50)
     ap.add_argument("--ls-mitr", type=int, default=4)
-    ap.add_argument("--steps-ref", type=int, default=3)
+    ap.add_argument("--partition", default="auto", choices=["auto", "slab", "blocks"],
+                    help="element partition over the GPUs: z-slabs, or x/y/z blocks (2 -> 2x1x1, 4 -> 2x2x1, 8 -> 2x2x2: up to 7 "
+                         "neighbours per rank, nodes shared by up to 8 ranks); auto = blocks from 4 GPUs on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true")
     ap.add_argument("--scatter", default="atomic", choices=["atomic", "colored"])
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = f"C2 synthetic cylinder, 6*{args.n}^2*{args.nz} = {6*args.n*args.n*args.nz} tet4 per GPU, Newtonian VMS fluid"
-    cfg = {"workload": workload, "elements_per_gpu": 6 * args.n * args.n * args.nz, "dt": 1e-3,
-           "linear_solver": f"GMRES sD={args.ls_sd} mItr={args.ls_mitr} relTol={args.ls_reltol} + FSILS diagonal preconditioner",
-           "partition": "z-slabs, one per GPU, shared interface planes (stand-in for ParMETIS, which needs MPI)",
-           "scatter": args.scatter,
-           "l2": "inputs larger than L2 (Val = 3.2 GB/GPU is rewritten every step)"}
+    cfg = workload_config(args)
+    metric = "element assemblies/s (FP64 tet4 fluid)"
 
     if args.impl == "reference":
         if rank != 0:
             return
-        # the driver's --steps K --warmup W are honoured; each step is a bounded sample (186,624 tet4 per core,
-        # about 1 s of construct_fluid), so K + W steps end within a few minutes
-        args.ref_steps_eff, args.ref_warmup_eff = max(1, min(args.steps, 50)), max(0, min(args.warmup, 10))
-        r = run_reference_arm(args)
-        line = {"impl": "reference", "metric": "element assemblies/s (FP64 tet4 fluid)", "value": r["value"],
-                "unit": "element assemblies/s", "n_gpus": args.gpus, "steps": args.ref_steps_eff, "warmup": args.ref_warmup_eff,
-                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        # the driver's --steps K --warmup W are honoured: every step runs ls_alloc + construct_fluid + commu(R) on the whole
+        # C2 mesh over all host cores (about 3 s); the fsils_solve (about 5-10 s) only in the first few, so K + W steps end
+        # within a few minutes
+        steps, warm = max(1, min(args.steps, 50)), max(0, min(args.warmup, 10))
+        r = reference_newton(args, steps, warm, solve_steps=min(steps, 3))
+        line = {"impl": "reference", "metric": metric, "value": r["value"],
+                "unit": "element assemblies/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+                "ms_per_step": r["newton_step_ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": cfg,
-                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-                "e2e": {"value": r["value"], "unit": "element assemblies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "newton_step_1core": r.get("newton_step_1core")}
+                "newton_step_ms": r["newton_step_ms"], "assembly_stage_ms": r["assemble_ms"], "solve_ms": r["solve_ms"],
+                "gmres": r.get("gmres"),
+                "cpu_baseline": {k: r.get(k) for k in ("value", "unit", "cores", "kind", "sample", "assemble_ms", "solve_ms",
+                                                       "newton_step_ms", "gmres", "partition_blocks")},
+                "e2e": {"value": r["value"], "unit": "element assemblies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit_line(line)
         return
 
@@ -251,16 +469,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(v):
+    def reduce_ranks(v, op="max"):
         if world == 1:
             return v
         t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op={"max": dist.ReduceOp.MAX, "min": dist.ReduceOp.MIN, "sum": dist.ReduceOp.SUM}[op])
         return float(t.item())
 
+    max_over_ranks = reduce_ranks
+
     # ---- build this rank's partition ------------------------------------------------------------
-    m, other, plane_lo, plane_hi = meshgen.cylinder_slab(args.n, args.nz, rank, world)
-    Ag, Yg = lattice_state(m, rank, args.nz)
+    pmode = args.partition if args.partition != "auto" else ("blocks" if world >= 4 else "slab")
+    blocks = meshgen.default_blocks(world, pmode)
+    n, nzg, L = args.n, args.nz * world, LSEG * world
+    lb = partition.LatticeBlocks((n, n, nzg), blocks)
+    m = meshgen.cylinder_block(n, nzg, blocks, rank, L=L)
+    Ag, Yg = lattice_state(m)
     eng = Engine(local_rank)
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -269,17 +493,19 @@ def main():
         dist.broadcast(uid, 0)
         eng.comm_init(world, rank, bytes(uid.cpu().tolist()))
     rowPtr, colPtr = eng.lhsa(m.nNo, [m.IEN])
+    node_map, mynNo = lb.order(rank)
+    neigh = lb.neighbours(rank)
     if world > 1:
-        node_map, mynNo = partition.fsils_order(other, rank)
-        neigh = []
-        if rank > 0:
-            neigh.append((rank - 1, node_map[plane_lo]))
-        if rank < world - 1:
-            neigh.append((rank + 1, node_map[plane_hi]))
         eng.set_graph(rowPtr, colPtr, mynNo=mynNo, node_map=node_map, neighbours=neigh)
     else:
         eng.set_graph(rowPtr, colPtr)
-    cfg["transport"] = eng.comm_transport()     # "p2p": halo sums / scalar all-reduces by the library's own peer-memory kernels
+    mult = lb.multiplicity(rank)
+    run = {"partition": {"slab": "z-slabs", "blocks": "x/y/z blocks"}[pmode] + f" {blocks[0]}x{blocks[1]}x{blocks[2]}, one per GPU "
+                        "(element partition with duplicated interface nodes, FSILS node order; stand-in for ParMETIS, which needs MPI)",
+           "blocks": list(blocks), "transport": eng.comm_transport(), "scatter": args.scatter,
+           "neighbours_per_rank": int(reduce_ranks(float(len(neigh)), "max")),
+           "shared_nodes_per_rank": int(reduce_ranks(float((mult > 1).sum()), "max")),
+           "max_ranks_sharing_a_node": int(reduce_ranks(float(mult.max()), "max"))}
     w, N, Nx = elements.tables(4)
     eng.set_mesh(0, m.IEN, w, N, Nx)
     eng.set_coords(m.x)
@@ -292,7 +518,7 @@ def main():
     dmn = [abi.fluid_domain()]
     ls = ls_config(args)
     incL, res = np.ones(1, np.int32), np.zeros(1)
-    nEl_total = m.nEl * world
+    nEl_total = int(reduce_ranks(float(m.nEl), "sum"))
 
     # device-resident generalised-alpha state: old = (Ao, Yo) chosen so that predictor + initiator reproduce exactly
     # the (Ag, Yg) the reference arm assembles with; every bench step is then the first Newton iteration of a time
@@ -331,7 +557,7 @@ def main():
     barrier()
     t1 = time.perf_counter()
     launches = eng.launch_count - launches0
-    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    clocks = sampler.window(t0, t1) if rank == 0 else None
     step_ms = max_over_ranks((t1 - t0) * 1e3 / args.steps)
     asm_ms = max_over_ranks(float(np.mean([s[0] for s in stats])))
     kern_ms = max_over_ranks(float(np.mean([s[1] for s in stats])))
@@ -391,14 +617,48 @@ def main():
     eng.bench_assemble(0, eq_other, dmn, 1)
     other_ms = max_over_ranks(eng.bench_assemble(0, eq_other, dmn, 5))
 
+    # ---- parity gate (never timed) ------------------------------------------------------------------
+    parity = None
+    if not args.no_parity:
+        eng.set_state(Ag, Yg)
+        eng.alloc(4)
+        eng.assemble(0, eq, dmn)
+        eng.commu_R()
+        pa = parity_assembly(eng, m, lb, rank, rowPtr, colPtr, eq, dmn, n, nzg, L)
+        R_loc = eng.get_R()
+        X_loc, o, _ = eng.solve(4, abi.LS_GMRES, ls, incL, res)
+        W_loc = eng.get_W()
+        eng.alloc(4)
+        eng.assemble(0, eq, dmn)                     # the solve preconditioned Val in place: the unscaled matrix again
+        KX = eng.spmv(4, X_loc)                      # K x incl. the shared-node sum
+        owned = node_map < mynNo
+        rr = (W_loc * (R_loc - KX))[:, owned]
+        r0 = (W_loc * R_loc)[:, owned]
+        nr = float(np.sqrt(reduce_ranks(float((rr * rr).sum()), "sum")))
+        n0 = float(np.sqrt(reduce_ranks(float((r0 * r0).sum()), "sum")))
+        asm_err = reduce_ranks(pa["max_rel"], "max")
+        ratio = nr / (args.ls_reltol * n0)
+        # per-box detail of the rank with the largest number of ranks on a compared row (rank 0 otherwise)
+        solve_ok = bool(o.RI.success) and ratio <= 1.05 and abs(n0 - o.RI.iNorm) <= 1e-10 * n0 and abs(nr - o.RI.fNorm) <= 0.05 * nr
+        ok_local = float(pa["max_rel"] < 1e-12 and all(b["same_graph"] for b in pa["boxes"].values()) and solve_ok)
+        ok = reduce_ranks(ok_local, "min") == 1.0
+        parity = {"ok": ok, "assembly_max_rel": asm_err, "assembly_tol": 1e-12, "oracle": pa["oracle"],
+                  "solve_true_res_ratio": ratio, "solve_true_res": nr, "solve_reported_fNorm": o.RI.fNorm,
+                  "solve_iNorm_rel_diff": abs(n0 - o.RI.iNorm) / n0, "gmres_itr": o.RI.itr,
+                  "what": "R (after the shared-node sum) and Val rows of two sub-boxes per rank vs the oracle on the same mesh/state, "
+                          "max over ranks; ||W(R-Kx)|| / (relTol ||WR||) over all ranks",
+                  "rank0_boxes": pa["boxes"]}
+
     if rank == 0:
         line = {
-            "metric": "element assemblies/s (FP64 tet4 fluid)", "value": nEl_total / (asm_ms * 1e-3),
+            "metric": metric, "value": nEl_total / (asm_ms * 1e-3),
             "unit": "element assemblies/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": cfg,
+            "dtype": "f64", "data": "synthetic", "config": cfg, "run": run,
             "newton_step_ms": step_ms, "assembly_stage_ms": asm_ms, "assembly_kernel_ms": kern_ms, "solve_ms": solve_ms,
-            "gmres": {"itr": stats[-1][3], "success": int(stats[-1][4]), "iNorm": stats[-1][5], "fNorm": stats[-1][6]},
+            "gmres": {"itr": stats[-1][3], "success": int(stats[-1][4]), "iNorm": stats[-1][5], "fNorm": stats[-1][6],
+                      "ms_per_iteration": solve_ms / max(stats[-1][3], 1)},
+            "parity": parity,
             "roofline": {"bound": "fp64", "achieved": asm_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": asm_tf / fp64_peak,
                          "traffic": traffic.get("assemble_bytes"), "traffic_unit": "bytes/launch (ncu dram read+write)",
                          "kernel": "assemble_fluid_tet4_grouped_kernel" if args.scatter == "atomic" else "assemble_fluid_tet4_kernel",
@@ -417,17 +677,22 @@ def main():
                                    "assembly_kernel_ms": other_ms, "value": nEl_total / (other_ms * 1e-3),
                                    "unit": "element assemblies/s (kernel only, outside the timed steps)"},
         }
+    eng.close()
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:
-                r = run_reference_arm(args, sample_n=30, sample_nz=16, procs=1)
-                line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-                line["cpu_baseline"]["newton_step_1core"] = r.get("newton_step_1core")
+                r = reference_newton(args, steps=2, warmup=1, solve_steps=1)
+                line["cpu_baseline"] = {k: r.get(k) for k in ("value", "unit", "cores", "kind", "sample", "assemble_ms", "solve_ms",
+                                                              "newton_step_ms", "gmres", "partition_blocks")}
             except Exception as ex:   # the baseline is a reported extra; never hide the GPU result
                 line["cpu_baseline"] = {"error": repr(ex)}
+        sampler.stop()
         emit_line(line)
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        sys.stderr.write("bench.py: PARITY GATE FAILED: " + json.dumps(parity) + "\n")
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -326,6 +326,10 @@ SVB200_API int svb200_advance_time_step(svb200_ctx* ctx);
 /* R(dof,nNo) and Val(dof*dof,nnz) are returned in INPUT node order / input CSR slot order. */
 SVB200_API int svb200_download(svb200_ctx* ctx, int32_t what, double* dst);
 SVB200_API int svb200_upload(svb200_ctx* ctx, int32_t what, int32_t dof, const double* src);
+/* The rows of R / W (dst(dof, n)) or the CSR rows of Val / Kd (dst(dof*dof | 12, sum of the row lengths), the rows of the
+ * listed nodes one after the other, columns in the caller's order) of n INPUT-order nodes: what the parity gate of bench.py
+ * compares with an oracle assembly of a sub-block of a 10 M-element partition without moving the 3 GB matrix. */
+SVB200_API int svb200_download_rows(svb200_ctx* ctx, int32_t what, int32_t n, const int32_t* nodes, double* dst);
 
 /* Stand-alone operators on the current device Val, for tests and the bench:
  * KU = K*U (+ halo sum), both (dof,nNo) host arrays in INPUT order. */

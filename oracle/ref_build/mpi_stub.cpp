@@ -1,6 +1,6 @@
 // MPI subset the reference hot path links against.  Test infrastructure only (see mpi.h in this directory).
 //
-// Default: a single rank (collectives are copies).  With SVREF_MPI_SIZE=N (2..8), SVREF_MPI_RANK=r and SVREF_MPI_SHM=/name in
+// Default: a single rank (collectives are copies).  With SVREF_MPI_SIZE=N (2..64), SVREF_MPI_RANK=r and SVREF_MPI_SHM=/name in
 // the environment of N cooperating PROCESSES, the calls FSILS makes (Comm_rank/size, Allreduce, Allgather(v), Bcast, Reduce,
 // Send/Recv, Isend/Irecv/Wait, Barrier) run over one POSIX shared-memory segment: per-rank collective slots read in rank
 // order between two barriers, and a one-message mailbox per ordered rank pair.  This is the multi-rank reference of
@@ -19,8 +19,8 @@
 #include <sys/mman.h>
 
 namespace {
-constexpr int MAXR = 8;
-constexpr size_t COLL_BYTES = 8u << 20, BOX_BYTES = 2u << 20;
+constexpr int MAXR = 64;      // the segment is sparse: only the slots and mailboxes a run touches are ever backed by memory
+constexpr size_t COLL_BYTES = 8u << 20, BOX_BYTES = 1u << 20;
 struct Box { std::atomic<int> full; int bytes; char data[BOX_BYTES]; };
 struct Shm {
   std::atomic<int> bar_count, bar_gen;
@@ -42,7 +42,9 @@ void mp_init()
   const char* nm = std::getenv("SVREF_MPI_SHM");
   if (!rk || !nm || g_size > MAXR) { std::fprintf(stderr, "[mpi_stub] bad SVREF_MPI_* environment\n"); std::abort(); }
   g_rank = std::atoi(rk);
-  int fd = shm_open(nm, O_CREAT | O_RDWR, 0600);
+  // "/name" = POSIX shared memory; a name with a directory part ("/tmp/x") = an ordinary file mapped MAP_SHARED
+  const bool plain_file = std::strchr(nm + 1, '/') != nullptr;
+  int fd = plain_file ? open(nm, O_CREAT | O_RDWR, 0600) : shm_open(nm, O_CREAT | O_RDWR, 0600);
   if (fd < 0 || ftruncate(fd, sizeof(Shm)) != 0) { std::perror("[mpi_stub] shm_open/ftruncate"); std::abort(); }
   void* p = mmap(nullptr, sizeof(Shm), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
   close(fd);

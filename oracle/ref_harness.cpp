@@ -354,6 +354,12 @@ int svref_commu_R(void* h)
   return guarded([&] { all_fun::commu(c.com_mod, c.com_mod.R); });
 }
 
+/// MPI_Barrier over the ranks of a multi-rank run (no-op for one rank): bench.py brackets its timed steps with it.
+int svref_barrier(void*)
+{
+  return guarded([&] { MPI_Barrier(MPI_COMM_WORLD); });
+}
+
 int svref_get_graph(void* h, int* rowPtr, int* colPtr)
 {
   auto& c = *static_cast<RefCase*>(h);

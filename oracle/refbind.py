@@ -260,6 +260,10 @@ class RefCase(_FlatCase):
             reqs.append((iP.value, ptr))
         return mynNo.value, mp, reqs
 
+    def barrier(self):
+        """MPI_Barrier of the multi-rank shim (no-op for one rank)."""
+        self._call("barrier")
+
     def commu_R(self):
         """all_fun::commu(com_mod, R): shared-node sum of the residual (solver/Integrator.cpp:124-129)."""
         self._call("commu_R")

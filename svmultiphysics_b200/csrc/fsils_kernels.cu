@@ -22,11 +22,12 @@ namespace svb {
 // 4x4 block of that row, so that a lane group reads one whole 128-byte block per load instruction.
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-bsr_spmv4_kernel(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ colPtr,
+bsr_spmv4_kernel(int row0, int nNo, const int* __restrict__ rowPtr, const int* __restrict__ colPtr,
                  const double* __restrict__ Val, const double* __restrict__ U, double* __restrict__ KU)
 {
+  // rows [row0, nNo)
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int row = t >> 3;
+  const int row = row0 + (t >> 3);
   const int l = t & 7;
   const int i = l >> 1, j0 = (l & 1) << 1;
   double acc = 0.0;
@@ -120,7 +121,7 @@ int launch_spmv(svb200_ctx* ctx, int dof, const double* Val, const double* U, do
   if (nNo == 0) return SVB200_OK;
   if (dof == 4) {
     const long long threads = (long long)nNo * 8;
-    bsr_spmv4_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(nNo, ctx->d_rowPtr, ctx->d_colPtr, Val, U, KU);
+    bsr_spmv4_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(0, nNo, ctx->d_rowPtr, ctx->d_colPtr, Val, U, KU);
   } else {
     const long long threads = (long long)nNo * dof;
     const unsigned blocks = (unsigned)((threads + 255) / 256);
@@ -143,6 +144,17 @@ int launch_spmv(svb200_ctx* ctx, int dof, const double* Val, const double* U, do
         return SVB200_ERR_UNSUPPORTED;
     }
   }
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
+// dof = 4, rows [row0, row0 + nrows) only (the interior rows of the overlapped multi-GPU SpMV, comm.cu).
+int launch_spmv4_rows(svb200_ctx* ctx, int row0, int nrows, const double* Val, const double* U, double* KU)
+{
+  if (nrows <= 0) return SVB200_OK;
+  const long long threads = (long long)nrows * 8;
+  bsr_spmv4_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(row0, row0 + nrows, ctx->d_rowPtr, ctx->d_colPtr, Val, U, KU);
   ctx->launches++;
   SVB_CUDA(cudaGetLastError());
   return SVB200_OK;
@@ -211,7 +223,8 @@ __global__ void multi_dot_stage2(int nblocks, int nvec, const double* __restrict
   if (lane == 0) out[j] = s;
 }
 
-int multi_dot(svb200_ctx* ctx, long long n, int nvec, const double* ubase, long long stride, const double* v, double* d_out)
+int multi_dot(svb200_ctx* ctx, long long n, int nvec, const double* ubase, long long stride, const double* v, double* d_out,
+              bool reduce_ranks)
 {
   if (nvec <= 0) return SVB200_OK;
   const long long ntiles = (n + DOT_TILE - 1) / DOT_TILE;
@@ -224,9 +237,18 @@ int multi_dot(svb200_ctx* ctx, long long n, int nvec, const double* ubase, long 
   }
   const size_t smem = sizeof(double) * (DOT_THREADS / 32) * nvec;
   multi_dot_stage1<<<blocks, DOT_THREADS, smem, ctx->stream>>>(n, nvec, ubase, stride, v, ctx->d_red);
+  ctx->launches++;
+  if (reduce_ranks && ctx->nranks > 1) {
+    // the cross-rank sum as the tail of the second stage (one launch, comm.cu); same local summation order
+    bool handled = false;
+    int rc = dot_stage2_allreduce(ctx, blocks, nvec, ctx->d_red, d_out, &handled);
+    if (rc) return rc;
+    if (handled) return SVB200_OK;
+  }
   multi_dot_stage2<<<(nvec * 32 + 127) / 128, 128, 0, ctx->stream>>>(blocks, nvec, ctx->d_red, d_out);
-  ctx->launches += 2;
+  ctx->launches++;
   SVB_CUDA(cudaGetLastError());
+  if (reduce_ranks && ctx->nranks > 1) return allreduce_sum(ctx, d_out, nvec);
   return SVB200_OK;
 }
 

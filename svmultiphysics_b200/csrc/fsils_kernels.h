@@ -6,7 +6,9 @@ namespace svb {
 
 struct Coefs { double c[256]; };
 
-int multi_dot(svb200_ctx* ctx, long long n, int nvec, const double* ubase, long long stride, const double* v, double* d_out);
+// reduce_ranks: d_out is summed over the ranks as well (fused into the second stage on the p2p transport)
+int multi_dot(svb200_ctx* ctx, long long n, int nvec, const double* ubase, long long stride, const double* v, double* d_out,
+              bool reduce_ranks = false);
 int cgs_update(svb200_ctx* ctx, long long n, int nprev, const double* ubase, long long stride, double* v, double* d_h, double* d_hn);
 int lincomb(svb200_ctx* ctx, long long n, int ny, const Coefs& y, const double* ubase, long long stride, double* X);
 int axpby(svb200_ctx* ctx, long long n, double a, const double* x, double b, const double* y, double* z);
@@ -35,5 +37,8 @@ int ns_merge(svb200_ctx* ctx, int dof, const double* Rm, const double* Rc, doubl
 // comm.cu: shared-node sums and scalar all-reduces (no-ops for a single partition)
 int halo_sum(svb200_ctx* ctx, int dof, double* V);
 int allreduce_sum(svb200_ctx* ctx, double* d_buf, int n);
+int spmv4_halo_fused(svb200_ctx* ctx, const double* Val, const double* U, double* KU, bool* handled);
+int dot_stage2_allreduce(svb200_ctx* ctx, int nblocks, int nvec, const double* d_part, double* d_out, bool* handled);
+int launch_spmv4_rows(svb200_ctx* ctx, int row0, int nrows, const double* Val, const double* U, double* KU);
 
 }  // namespace svb

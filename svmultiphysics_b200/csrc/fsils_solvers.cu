@@ -68,8 +68,7 @@ static int fetch(svb200_ctx* ctx, const double* d_src, int n, double* h_dst)
 // Global dot over owned nodes (dot::fsils_dot_v) and norm (norm::fsi_ls_normv).
 static int dot_owned(svb200_ctx* ctx, int dof, const double* a, const double* b, double* d_scal, double* out)
 {
-  SVB_TRY(multi_dot(ctx, (long long)ctx->mynNo * dof, 1, a, 0, b, d_scal));
-  SVB_TRY(allreduce_sum(ctx, d_scal, 1));
+  SVB_TRY(multi_dot(ctx, (long long)ctx->mynNo * dof, 1, a, 0, b, d_scal, true));
   SVB_TRY(fetch(ctx, d_scal, 1, ctx->h_pinned));
   *out = ctx->h_pinned[0];
   return SVB200_OK;
@@ -182,6 +181,12 @@ static int bc_pre_device(svb200_ctx* ctx, int dof, double* d_scal)
 // K*U + halo sum (every fsils_spar_mul_* ends in fsils_commuv, spar_mul.cpp:230).
 static int spmv_halo(svb200_ctx* ctx, int dof, const double* Val, const double* U, double* KU)
 {
+  if (dof == 4 && ctx->nranks > 1) {
+    // interface rows + push, interior rows, wait-add: the exchange travels behind the interior rows (comm.cu)
+    bool handled = false;
+    SVB_TRY(spmv4_halo_fused(ctx, Val, U, KU, &handled));
+    if (handled) return SVB200_OK;
+  }
   SVB_TRY(launch_spmv(ctx, dof, Val, U, KU));
   SVB_TRY(halo_sum(ctx, dof, KU));
   return SVB200_OK;
@@ -350,8 +355,7 @@ static int gmres_core(svb200_ctx* ctx, int dof, const svb200_sublsparams& p, svb
         r.itr++;
         if (anyCoupled) SVB_TRY(add_bc_mul_device(ctx, 1, dof, ui1, ui1, d_scal));
       }
-      SVB_TRY(multi_dot(ctx, (long long)ctx->mynNo * dof, i + 2, u, us, ui1, d_h));
-      SVB_TRY(allreduce_sum(ctx, d_h, i + 2));
+      SVB_TRY(multi_dot(ctx, (long long)ctx->mynNo * dof, i + 2, u, us, ui1, d_h, true));
       SVB_CUDA(cudaMemcpyAsync(hp, d_h, sizeof(double) * (i + 2), cudaMemcpyDeviceToHost, ctx->stream));
       SVB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
       SVB_TRY(cgs_update(ctx, n, i + 1, u, us, ui1, d_h, d_hn));
@@ -713,11 +717,9 @@ static int schur_device(svb200_ctx* ctx, int nsd, const svb200_sublsparams& p, s
         if (anyCoupled) SVB_TRY(add_bc_mul_device(ctx, 1, nsd, GP, GP, d_scal));
         SVB_TRY(schur_sp(ctx, nsd, mL, Gt, P, GP, SP));
         SVB_TRY(halo_sum(ctx, 1, SP));
-        SVB_TRY(multi_dot(ctx, (long long)ctx->mynNo, 1, P, 0, SP, cg + 2));
-        SVB_TRY(allreduce_sum(ctx, cg + 2, 1));
+        SVB_TRY(multi_dot(ctx, (long long)ctx->mynNo, 1, P, 0, SP, cg + 2, true));
         SVB_TRY(cg_step_kernels(ctx, 0, nNo, cg, P, SP, X, R, nullptr));
-        SVB_TRY(multi_dot(ctx, (long long)ctx->mynNo, 1, R, 0, R, cg + 1));
-        SVB_TRY(allreduce_sum(ctx, cg + 1, 1));
+        SVB_TRY(multi_dot(ctx, (long long)ctx->mynNo, 1, R, 0, R, cg + 1, true));
         SVB_TRY(cg_step_kernels(ctx, 1, nNo, cg, nullptr, nullptr, nullptr, R, P));
         SVB_TRY(cg_step_kernels(ctx, 2, 1, cg, nullptr, nullptr, nullptr, nullptr, nullptr));
         SVB_CUDA(cudaMemcpyAsync(ctx->h_cg + 8 * (i & 1), cg, sizeof(double) * 8, cudaMemcpyDeviceToHost, ctx->stream));

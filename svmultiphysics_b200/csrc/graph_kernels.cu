@@ -57,6 +57,63 @@ __global__ void permute_cols_kernel(int rows, int n, const int* __restrict__ map
     dst[(size_t)m * rows + i] = src[t];
 }
 
+// CSR blocks between the caller's row order and the internal (FSILS) row order: caller row a is internal row map[a], the
+// columns of a row keep the caller's order.  One warp per caller row of the chunk [a0,a1); `staged` holds the chunk's caller
+// entries starting at rowPtr_in[a0].
+__global__ void __launch_bounds__(256)
+permute_row_blocks_kernel(int a0, int a1, int d2, const int* __restrict__ rowPtr_in, const int* __restrict__ rowPtr,
+                          const int* __restrict__ map, double* __restrict__ internal, double* __restrict__ staged, int to_caller)
+{
+  const int a = a0 + (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (a >= a1) return;
+  const long long len = (long long)(rowPtr_in[a + 1] - rowPtr_in[a]) * d2;
+  double* h = staged + (long long)(rowPtr_in[a] - rowPtr_in[a0]) * d2;
+  double* d = internal + (long long)rowPtr[map ? map[a] : a] * d2;
+  if (to_caller) for (long long k = lane; k < len; k += 32) h[k] = d[k];
+  else for (long long k = lane; k < len; k += 32) d[k] = h[k];
+}
+
+// dst[off[k] ...) = the d2-blocks of internal row rows[k] (one warp per listed row); rowPtr == null: a nodal (d2, nNo) array,
+// one block per row.
+__global__ void __launch_bounds__(256)
+gather_row_blocks_kernel(int n, int d2, const int* __restrict__ rows, const int* __restrict__ rowPtr,
+                         const long long* __restrict__ off, const double* __restrict__ src, double* __restrict__ dst)
+{
+  const int k = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (k >= n) return;
+  const int r = rows[k];
+  const long long len = rowPtr ? (long long)(rowPtr[r + 1] - rowPtr[r]) * d2 : d2;
+  const double* s = src + (long long)(rowPtr ? rowPtr[r] : r) * d2;
+  double* d = dst + off[k] * d2;
+  for (long long q = lane; q < len; q += 32) d[q] = s[q];
+}
+
+int launch_permute_row_blocks(svb200_ctx* ctx, int a0, int a1, int d2, const int* d_rowPtr_in, double* internal, double* staged,
+                              bool to_caller)
+{
+  if (a1 <= a0) return SVB200_OK;
+  const long long threads = (long long)(a1 - a0) * 32;
+  permute_row_blocks_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(
+      a0, a1, d2, d_rowPtr_in, ctx->d_rowPtr, ctx->has_map ? ctx->d_map : nullptr, internal, staged, to_caller ? 1 : 0);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
+int launch_gather_row_blocks(svb200_ctx* ctx, int n, int d2, const int* d_rows, bool csr, const long long* d_off, const double* src,
+                             double* dst)
+{
+  if (n <= 0) return SVB200_OK;
+  const long long threads = (long long)n * 32;
+  gather_row_blocks_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(n, d2, d_rows, csr ? ctx->d_rowPtr : nullptr, d_off, src,
+                                                                                       dst);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
 static int check_flag(svb200_ctx* ctx, int* d_err, const char* what)
 {
   int h = 0;

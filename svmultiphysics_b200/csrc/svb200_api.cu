@@ -234,7 +234,7 @@ int svb200_destroy(svb200_ctx* ctx)
   for (auto& f : ctx->bface) { cudaFree(f.d_IENb); cudaFree(f.d_gE); }
   cudaFree(ctx->d_hg);
   for (auto& nb : ctx->neigh) { cudaFree(nb.d_ptr); cudaFree(nb.d_send); cudaFree(nb.d_recv); }
-  cudaFree(ctx->d_map); cudaFree(ctx->d_rowPtr); cudaFree(ctx->d_colPtr); cudaFree(ctx->d_diagPtr);
+  cudaFree(ctx->d_map); cudaFree(ctx->d_rowPtr_in); cudaFree(ctx->d_rowPtr); cudaFree(ctx->d_colPtr); cudaFree(ctx->d_diagPtr);
   cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf); cudaFree(ctx->d_Do);
   cudaFree(ctx->d_Ao); cudaFree(ctx->d_Yo); cudaFree(ctx->d_An); cudaFree(ctx->d_Yn); cudaFree(ctx->d_Dn); cudaFree(ctx->d_nodeflag);
   cudaFree(ctx->d_err); cudaFree(ctx->d_Kd); cudaFree(ctx->d_Ad); cudaFree(ctx->d_Rd);
@@ -312,6 +312,7 @@ int svb200_set_graph(svb200_ctx* ctx, int32_t nNo, int32_t nnz, const int32_t* r
   TRY(upload(ctx, &ctx->d_rowPtr, ctx->h_rowPtr.data(), (size_t)nNo + 1));
   TRY(upload(ctx, &ctx->d_colPtr, col.data(), (size_t)nnz));
   TRY(upload(ctx, &ctx->d_map, ctx->h_map.data(), (size_t)nNo));
+  TRY(upload(ctx, &ctx->d_rowPtr_in, ctx->h_rowPtr_in.data(), (size_t)nNo + 1));
   if (ctx->d_diagPtr) { cudaFree(ctx->d_diagPtr); ctx->d_diagPtr = nullptr; }
   if (ctx->d_tslot) { cudaFree(ctx->d_tslot); ctx->d_tslot = nullptr; }
   SVB_CUDA(cudaMalloc(&ctx->d_diagPtr, sizeof(int) * std::max(nNo, 1)));
@@ -328,6 +329,7 @@ int svb200_set_graph(svb200_ctx* ctx, int32_t nNo, int32_t nnz, const int32_t* r
     for (int k = 0; k < nb.n; k++)
       SVB_REQUIRE(neigh_ptr[off + k] >= 0 && neigh_ptr[off + k] < nNo, "svb200_set_graph: shared node id out of range");
     TRY(upload(ctx, &nb.d_ptr, neigh_ptr + off, (size_t)nb.n));
+    nb.h_ptr.assign(neigh_ptr + off, neigh_ptr + off + nb.n);
     SVB_CUDA(cudaMalloc(&nb.d_send, sizeof(double) * 4 * std::max(nb.n, 1)));
     SVB_CUDA(cudaMalloc(&nb.d_recv, sizeof(double) * 4 * std::max(nb.n, 1)));
     off += nb.n;
@@ -965,14 +967,30 @@ static int copy_blocks(svb200_ctx* ctx, double* d_blocks, size_t d2, double* hos
     SVB_CUDA(cudaStreamSynchronize(ctx->stream));
     return SVB200_OK;
   }
-  for (int a = 0; a < ctx->nNo; a++) {
-    const size_t len = (size_t)(ctx->h_rowPtr_in[a + 1] - ctx->h_rowPtr_in[a]) * d2;
-    double* h = host + (size_t)ctx->h_rowPtr_in[a] * d2;
-    double* d = d_blocks + (size_t)ctx->h_rowPtr[ctx->h_map[a]] * d2;
-    if (to_host) SVB_CUDA(cudaMemcpyAsync(h, d, sizeof(double) * len, cudaMemcpyDeviceToHost, ctx->stream));
-    else SVB_CUDA(cudaMemcpyAsync(d, h, sizeof(double) * len, cudaMemcpyHostToDevice, ctx->stream));
+  // permuted rows: a device kernel moves whole chunks of caller rows through the staging buffer (one memcpy per chunk)
+  const size_t chunk_doubles = (size_t)32 << 20;      // 256 MB of staging
+  int a0 = 0;
+  while (a0 < ctx->nNo) {
+    int a1 = a0;
+    size_t cnt = 0;
+    while (a1 < ctx->nNo) {
+      const size_t len = (size_t)(ctx->h_rowPtr_in[a1 + 1] - ctx->h_rowPtr_in[a1]) * d2;
+      if (cnt + len > chunk_doubles && a1 > a0) break;
+      cnt += len;
+      a1++;
+    }
+    TRY(ensure_stage(ctx, sizeof(double) * std::max<size_t>(cnt, 1)));
+    double* h = host + (size_t)ctx->h_rowPtr_in[a0] * d2;
+    if (to_host) {
+      TRY(launch_permute_row_blocks(ctx, a0, a1, (int)d2, ctx->d_rowPtr_in, d_blocks, ctx->d_stage, true));
+      SVB_CUDA(cudaMemcpyAsync(h, ctx->d_stage, sizeof(double) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+      SVB_CUDA(cudaMemcpyAsync(ctx->d_stage, h, sizeof(double) * cnt, cudaMemcpyHostToDevice, ctx->stream));
+      TRY(launch_permute_row_blocks(ctx, a0, a1, (int)d2, ctx->d_rowPtr_in, d_blocks, ctx->d_stage, false));
+    }
+    SVB_CUDA(cudaStreamSynchronize(ctx->stream));     // the staging buffer is reused by the next chunk
+    a0 = a1;
   }
-  SVB_CUDA(cudaStreamSynchronize(ctx->stream));
   return SVB200_OK;
 }
 
@@ -1001,6 +1019,44 @@ int svb200_download(svb200_ctx* ctx, int32_t what, double* dst)
   }
   set_error("svb200_download: unknown array id");
   return SVB200_ERR_INVALID;
+}
+
+int svb200_download_rows(svb200_ctx* ctx, int32_t what, int32_t n, const int32_t* nodes, double* dst)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(n >= 0 && (n == 0 || (nodes && dst)), "svb200_download_rows: bad arguments");
+  if (n == 0) return SVB200_OK;
+  const double* src = nullptr;
+  int d2 = 0;
+  bool blocks = false;
+  switch (what) {
+    case SVB200_ARRAY_R: src = ctx->d_R; d2 = ctx->dof; break;
+    case SVB200_ARRAY_W: src = ctx->d_W; d2 = ctx->dof; break;
+    case SVB200_ARRAY_VAL: src = ctx->d_Val; d2 = ctx->dof * ctx->dof; blocks = true; break;
+    case SVB200_ARRAY_KD: src = ctx->d_Kd; d2 = 12; blocks = true; break;
+    default: set_error("svb200_download_rows: unknown array id"); return SVB200_ERR_INVALID;
+  }
+  SVB_REQUIRE(src && d2 > 0, "svb200_download_rows: the array does not exist yet");
+  std::vector<int> rows(n);
+  std::vector<long long> off(n + 1, 0);
+  for (int k = 0; k < n; k++) {
+    SVB_REQUIRE(nodes[k] >= 0 && nodes[k] < ctx->nNo, "svb200_download_rows: node id out of range");
+    rows[k] = ctx->h_map[nodes[k]];
+    off[k + 1] = off[k] + (blocks ? ctx->h_rowPtr[rows[k] + 1] - ctx->h_rowPtr[rows[k]] : 1);
+  }
+  int* d_rows = nullptr; long long* d_off = nullptr;
+  const size_t total = (size_t)off[n] * d2;
+  TRY(ensure_stage(ctx, sizeof(double) * std::max<size_t>(total, 1)));
+  int rc = upload(ctx, &d_rows, rows.data(), rows.size());
+  if (!rc) rc = upload(ctx, &d_off, off.data(), off.size());
+  if (!rc) rc = launch_gather_row_blocks(ctx, n, d2, d_rows, blocks, d_off, src, ctx->d_stage);
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(dst, ctx->d_stage, sizeof(double) * total, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = cuda_fail(e, "svb200_download_rows copy", __FILE__, __LINE__);
+  }
+  cudaFree(d_rows); cudaFree(d_off);
+  return rc;
 }
 
 int svb200_upload(svb200_ctx* ctx, int32_t what, int32_t dof, const double* src)

@@ -75,6 +75,7 @@ struct BFace {
 struct Neighbor {
   int rank = 0, n = 0;
   int* d_ptr = nullptr;       // internal node ids shared with that rank (same order on both sides)
+  std::vector<int> h_ptr;     // host copy (the fused exchange tables of comm.cu are built from it)
   double* d_send = nullptr;   // (maxdof, n)
   double* d_recv = nullptr;
 };
@@ -130,6 +131,7 @@ struct svb200_ctx {
   std::vector<int> h_rowPtr_in;  // input CSR (kept for slot translation on download)
   std::vector<int> h_rowPtr;     // internal CSR row pointer
   int* d_map = nullptr;
+  int* d_rowPtr_in = nullptr;    // (nNo+1) caller-order row pointer (block up/downloads when a node map is active)
   int* d_rowPtr = nullptr;       // (nNo+1) internal
   int* d_colPtr = nullptr;       // (nnz) internal column ids
   int* d_diagPtr = nullptr;      // (nNo)
@@ -238,6 +240,10 @@ void free_group_sched(GroupSched& S);
 int launch_build_slot_map(svb200_ctx* ctx, Mesh& m);
 int launch_find_diag(svb200_ctx* ctx);
 int launch_permute_cols(svb200_ctx* ctx, int rows, int n, const int* d_map, const double* src, double* dst, bool inverse);
+int launch_permute_row_blocks(svb200_ctx* ctx, int a0, int a1, int d2, const int* d_rowPtr_in, double* internal, double* staged,
+                              bool to_caller);
+int launch_gather_row_blocks(svb200_ctx* ctx, int n, int d2, const int* d_rows, bool csr, const long long* d_off, const double* src,
+                             double* dst);
 // fsils_kernels.cu
 int launch_spmv(svb200_ctx* ctx, int dof, const double* Val, const double* U, double* KU);
 int launch_dots(svb200_ctx* ctx, int n, int nvec, const double* const* d_vec_list, const double* base, size_t stride,

@@ -37,7 +37,7 @@ ABI_SYMBOLS = [
     "svb200_set_graph", "svb200_lhsa_begin", "svb200_lhsa_add_mesh", "svb200_lhsa_finish", "svb200_lhsa_get",
     "svb200_set_mesh", "svb200_set_mesh_nxx", "svb200_set_coords", "svb200_set_num_faces", "svb200_set_face",
     "svb200_alloc", "svb200_set_state", "svb200_set_old_disp", "svb200_assemble", "svb200_add_host_contrib", "svb200_commu_R", "svb200_ustruct_r", "svb200_set_ad", "svb200_get_ad",
-    "svb200_solve", "svb200_download", "svb200_upload", "svb200_spmv", "svb200_last_timing",
+    "svb200_solve", "svb200_download", "svb200_download_rows", "svb200_upload", "svb200_spmv", "svb200_last_timing",
     "svb200_host_register", "svb200_host_unregister", "svb200_timer_mark", "svb200_timer_elapsed",
     "svb200_bench_assemble", "svb200_bench_spmv", "svb200_measure_fp64_peak", "svb200_launch_count",
     "svb200_set_solution", "svb200_get_solution", "svb200_predictor", "svb200_initiator", "svb200_corrector",
@@ -312,6 +312,19 @@ class Engine:
         Ad = np.zeros((3, self.nNo), order="F")
         self._call("svb200_get_ad", _d(Ad))
         return Ad
+
+    def get_rows(self, what, nodes, rowPtr=None):
+        """Rows of R / W (-> (dof, n)) or CSR rows of Val (-> (dof*dof, sum of row lengths); needs the caller's rowPtr) of the
+        listed input-order nodes."""
+        nodes = _i32(nodes)
+        if what in (abi.ARRAY_VAL, abi.ARRAY_KD):
+            d2 = self.dof * self.dof if what == abi.ARRAY_VAL else 12
+            cnt = int((np.asarray(rowPtr)[nodes + 1] - np.asarray(rowPtr)[nodes]).sum())
+        else:
+            d2, cnt = self.dof, len(nodes)
+        out = np.zeros((d2, cnt), order="F")
+        self._call("svb200_download_rows", C.c_int32(what), C.c_int32(len(nodes)), _i(nodes), _d(out))
+        return out
 
     def get_W(self):
         W = np.zeros((self.dof, self.nNo), order="F")

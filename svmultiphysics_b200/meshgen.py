@@ -29,6 +29,9 @@ class Mesh:
     faces: dict = field(default_factory=dict)   # name -> int32 node ids
     eId: np.ndarray | None = None               # (nEl,) int32 domain bitmask
     lattice: tuple | None = None                # (nx, ny, nz) cells
+    gijk: tuple | None = None                   # lattice blocks: GLOBAL lattice indices (i, j, k) of the local nodes
+    glattice: tuple | None = None               # lattice blocks: cells of the GLOBAL lattice
+    origin: tuple | None = None                 # lattice blocks: first global cell (i0, j0, k0) of this block
 
     @property
     def nNo(self) -> int:
@@ -164,6 +167,59 @@ def cylinder_slab(n: int, nz: int, rank: int, nranks: int, R: float = 2.0, Lseg:
     if rank < nranks - 1:
         other[plane_hi] = rank + 1
     return m, other, plane_lo, plane_hi
+
+
+def block_ranges(ncells, blocks, rank):
+    """Cell ranges [(lo, hi)] x 3 of block `rank` of a (bx, by, bz) split of an (nx, ny, nz)-cell lattice; rank = ri + bx (rj + by rk)."""
+    bx, by, bz = blocks
+    r3 = (rank % bx, (rank // bx) % by, rank // (bx * by))
+    return [((ncells[d] * r3[d]) // blocks[d], (ncells[d] * (r3[d] + 1)) // blocks[d]) for d in range(3)]
+
+
+def cylinder_box(n: int, nzg: int, ranges, R: float = 2.0, L: float = 30.0) -> Mesh:
+    """The cells [i0,i1) x [j0,j1) x [k0,k1) (``ranges``) of the (n x n x nzg)-hex cylinder lattice of ``cylinder_tet4(n, nzg, R, L)``
+    as a mesh of its own in local node ids (local lattice order, i fastest = ascending global node id); elements keep the global
+    order.  faces / gijk refer to the GLOBAL lattice (wall = lateral surface, inlet k = 0, outlet k = nzg)."""
+    (i0, i1), (j0, j1), (k0, k1) = ranges
+    nx, ny, nz = i1 - i0, j1 - j0, k1 - k0
+    i, j, k = _lattice_nodes(nx, ny, nz)
+    gi, gj, gk = i + i0, j + j0, k + k0
+    u = 2.0 * gi / n - 1.0
+    v = 2.0 * gj / n - 1.0
+    xs = R * u * np.sqrt(1.0 - 0.5 * v * v)
+    ys = R * v * np.sqrt(1.0 - 0.5 * u * u)
+    zs = L * gk / nzg
+    x = np.asfortranarray(np.stack([xs, ys, zs]).astype(np.float64))
+    IEN = _fix_orientation(x, _kuhn_tets(_hex_cells(nx, ny, nz)))
+    ids = np.arange(x.shape[1], dtype=np.int32)
+    wall = (gi == 0) | (gi == n) | (gj == 0) | (gj == n)
+    faces = {"wall": ids[wall], "inlet": ids[(gk == 0) & ~wall], "outlet": ids[(gk == nzg) & ~wall], "outlet_all": ids[gk == nzg]}
+    return Mesh(x=x, IEN=np.asfortranarray(IEN.astype(np.int32)), eNoN=4, faces=faces, lattice=(nx, ny, nz),
+                gijk=(gi.astype(np.int64), gj.astype(np.int64), gk.astype(np.int64)), glattice=(n, n, nzg), origin=(i0, j0, k0))
+
+
+def cylinder_block(n: int, nzg: int, blocks, rank: int, R: float = 2.0, L: float = 30.0) -> Mesh:
+    """Block `rank` of a (bx, by, bz) split of the cylinder lattice as a local mesh.  Nodes on block interfaces are
+    duplicated on every block that touches them, exactly what an ELEMENT partition does (Code/Source/solver/distribute.cpp:1972);
+    the local mesh equals ``partition.partition_mesh`` applied to the global mesh with the block ``part[]`` array
+    (tests/test_partition_cpu.py).  ``blocks = (1, 1, N)`` is the z-slab partition; (2, 2, 2) gives every rank 7 neighbours and
+    nodes shared by up to 8 ranks."""
+    return cylinder_box(n, nzg, block_ranges((n, n, nzg), blocks, rank), R=R, L=L)
+
+
+def default_blocks(nranks: int, mode: str = "blocks"):
+    """(bx, by, bz) for `nranks` partitions: "slab" = (1, 1, N); "blocks" = split x, then y, then z by powers of two
+    (2 -> (2,1,1), 4 -> (2,2,1), 8 -> (2,2,2)); other counts fall back to slabs."""
+    if mode == "slab" or nranks & (nranks - 1):
+        return (1, 1, nranks)
+    b = [1, 1, 1]
+    d = 0
+    r = nranks
+    while r > 1:
+        b[d % 3] *= 2
+        r //= 2
+        d += 1
+    return tuple(b)
 
 
 _TET_FACES = ((0, 1, 2), (0, 1, 3), (0, 2, 3), (1, 2, 3))

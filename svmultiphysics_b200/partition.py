@@ -125,3 +125,117 @@ def glue_nodal(parts, arrays, nNo_global):
     for p, a in zip(parts, arrays):
         out[:, p.ltg] = a
     return out
+
+
+class LatticeBlocks:
+    """The element partition of a structured (nx, ny, nz)-cell lattice into (bx, by, bz) blocks, rank = ri + bx (rj + by rk), with
+    the FSILS node order and shared-node lists of every rank computed from index arithmetic instead of from global node sets:
+    the same numbers ``partition_mesh`` produces for the block ``part[]`` array (and hence the reference's ``fsils_lhs_create``,
+    linear_solver/lhs.cpp:30-348; tests/test_partition_cpu.py checks the identity), without ever holding the global mesh —
+    bench.py builds one 10 M-element block per GPU.  A rank's local node order is its local lattice order (i fastest), which is
+    the ascending-global-id order ``partition_mesh`` uses."""
+
+    def __init__(self, ncells, blocks):
+        self.nc = tuple(int(c) for c in ncells)
+        self.blocks = tuple(int(b) for b in blocks)
+        self.nranks = self.blocks[0] * self.blocks[1] * self.blocks[2]
+        self._order = {}
+
+    def cell_ranges(self, r):
+        bx, by, _ = self.blocks
+        r3 = (r % bx, (r // bx) % by, r // (bx * by))
+        return [((self.nc[d] * r3[d]) // self.blocks[d], (self.nc[d] * (r3[d] + 1)) // self.blocks[d]) for d in range(3)]
+
+    def nNo(self, r):
+        return int(np.prod([hi - lo + 1 for lo, hi in self.cell_ranges(r)]))
+
+    def _gids_box(self, box):
+        """Ascending global node ids of the closed index box [(lo, hi)] x 3."""
+        n1x, n1y = self.nc[0] + 1, self.nc[1] + 1
+        i = np.arange(box[0][0], box[0][1] + 1, dtype=np.int64)
+        j = np.arange(box[1][0], box[1][1] + 1, dtype=np.int64)
+        k = np.arange(box[2][0], box[2][1] + 1, dtype=np.int64)
+        return (i[None, None, :] + n1x * (j[None, :, None] + n1y * k[:, None, None])).reshape(-1)
+
+    def common(self, r, s):
+        """Global ids (ascending) of the nodes ranks r and s both hold."""
+        a, b = self.cell_ranges(r), self.cell_ranges(s)
+        box = [(max(a[d][0], b[d][0]), min(a[d][1], b[d][1])) for d in range(3)]
+        if any(lo > hi for lo, hi in box):
+            return np.zeros(0, dtype=np.int64)
+        return self._gids_box(box)
+
+    def local_of(self, r, gids):
+        """Local (input-order) node ids on rank r of global node ids that lie in its box."""
+        n1x, n1y = self.nc[0] + 1, self.nc[1] + 1
+        (i0, i1), (j0, j1), (k0, _) = self.cell_ranges(r)
+        i, j, k = gids % n1x, (gids // n1x) % n1y, gids // (n1x * n1y)
+        return (i - i0) + (i1 - i0 + 1) * ((j - j0) + (j1 - j0 + 1) * (k - k0))
+
+    def order(self, r):
+        """(lhs.map, mynNo) of rank r, visit by visit like lhs.cpp:118-175 (see fsils_order_exact)."""
+        if r in self._order:
+            return self._order[r]
+        n = self.nNo(r)
+        placed = np.zeros(n, dtype=bool)
+        low, high = [], []
+        for s in range(self.nranks - 1, -1, -1):
+            if s == r:
+                continue
+            c = self.common(r, s)
+            if len(c) == 0:
+                continue
+            loc = self.local_of(r, c)
+            sel = loc[~placed[loc]]
+            (low if s < r else high).append(sel)
+            placed[sel] = True
+        low = np.concatenate(low) if low else np.zeros(0, dtype=np.int64)
+        high = np.concatenate(high) if high else np.zeros(0, dtype=np.int64)
+        interior = np.flatnonzero(~placed)
+        order = np.concatenate([low, interior, high[::-1]]).astype(np.int64)
+        node_map = np.empty(n, dtype=np.int32)
+        node_map[order] = np.arange(n, dtype=np.int32)
+        self._order[r] = (node_map, int(len(low) + len(interior)))
+        return self._order[r]
+
+    def neighbours(self, r):
+        """[(rank, ptr)] ascending in rank; ptr = FSILS-order local ids in the order of the HIGHER rank's numbering (lhs.cpp:281-347)."""
+        out = []
+        for s in range(self.nranks):
+            if s == r:
+                continue
+            c = self.common(r, s)
+            if len(c) == 0:
+                continue
+            hi, lo = max(r, s), min(r, s)
+            fs_hi = self.order(hi)[0][self.local_of(hi, c)]
+            o = np.argsort(fs_hi, kind="stable")
+            if r == hi:
+                ptr = fs_hi[o].astype(np.int32)
+            else:
+                ptr = self.order(lo)[0][self.local_of(lo, c[o])].astype(np.int32)
+            out.append((s, ptr))
+        return out
+
+    def multiplicity(self, r):
+        """Number of ranks holding each local node of rank r (1 = interior)."""
+        cnt = np.ones(self.nNo(r), dtype=np.int32)
+        for s in range(self.nranks):
+            if s != r:
+                c = self.common(r, s)
+                if len(c):
+                    cnt[self.local_of(r, c)] += 1
+        return cnt
+
+    def part_array(self):
+        """part[e] of the GLOBAL tet mesh (6 tets per cell, cells i fastest) — small lattices / tests only."""
+        nx, ny, nz = self.nc
+        ci, cj, ck = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+        cid = (ci + nx * (cj + ny * ck)).ravel()
+        o = np.argsort(cid, kind="stable")
+        ci, cj, ck = ci.ravel()[o], cj.ravel()[o], ck.ravel()[o]
+        part = np.zeros(len(ci), dtype=np.int32)
+        for r in range(self.nranks):
+            (i0, i1), (j0, j1), (k0, k1) = self.cell_ranges(r)
+            part[(ci >= i0) & (ci < i1) & (cj >= j0) & (cj < j1) & (ck >= k0) & (ck < k1)] = r
+        return part

@@ -118,3 +118,36 @@ def test_halo_sum_pattern_gloo_world2(tmp_path, world, mode):
            "--master-port", "29533" if world == 2 else "29534", str(script), ROOT, mode]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:]
+
+
+@pytest.mark.parametrize("n,nzg,blocks", [(4, 6, (1, 1, 3)), (4, 4, (2, 1, 1)), (4, 6, (2, 2, 1)), (4, 4, (2, 2, 2)), (6, 5, (3, 2, 2))])
+def test_lattice_blocks_equal_general_partition(n, nzg, blocks):
+    """The index-arithmetic block partitioner bench.py uses at 10 M elements per GPU produces exactly what partition_mesh
+    (itself identical to the reference's fsils_lhs_create, test_multirank_reference_cpu.py) gives for the block part[] array:
+    local meshes, lhs.map, mynNo, neighbour ranks and the order of every shared-node list."""
+    m = meshgen.cylinder_tet4(n, nzg)
+    lb = partition.LatticeBlocks((n, n, nzg), blocks)
+    part = np.repeat(lb.part_array(), 6)
+    parts = partition.partition_mesh(m.IEN, m.nNo, part, lb.nranks)
+    maxshare = 0
+    for r, p in enumerate(parts):
+        mb = meshgen.cylinder_block(n, nzg, blocks, r)
+        gid = mb.gijk[0] + (n + 1) * (mb.gijk[1] + (n + 1) * mb.gijk[2])
+        assert np.array_equal(gid, p.ltg)
+        assert np.array_equal(mb.IEN, p.IEN)
+        assert np.array_equal(mb.x, m.x[:, p.ltg])
+        node_map, mynNo = lb.order(r)
+        assert mynNo == p.mynNo and np.array_equal(node_map, p.node_map)
+        nb = lb.neighbours(r)
+        assert [q for q, _ in nb] == [q for q, _ in p.neighbours]
+        for (q, ptr), (_, ptr0) in zip(nb, p.neighbours):
+            assert np.array_equal(ptr, ptr0)
+        for name in ("wall", "inlet", "outlet"):
+            assert np.array_equal(np.sort(p.ltg[mb.faces[name]]), np.intersect1d(m.faces[name], p.ltg))
+        maxshare = max(maxshare, int(lb.multiplicity(r).max()))
+    assert maxshare == min(lb.nranks, 2 ** sum(b > 1 for b in blocks))
+
+
+def test_default_blocks():
+    assert meshgen.default_blocks(8) == (2, 2, 2) and meshgen.default_blocks(4) == (2, 2, 1) and meshgen.default_blocks(2) == (2, 1, 1)
+    assert meshgen.default_blocks(8, "slab") == (1, 1, 8) and meshgen.default_blocks(6) == (1, 1, 6) and meshgen.default_blocks(1) == (1, 1, 1)
