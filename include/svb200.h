@@ -236,6 +236,13 @@ SVB200_API int svb200_set_num_faces(svb200_ctx* ctx, int32_t nFaces);
 SVB200_API int svb200_set_face(svb200_ctx* ctx, int32_t faIn, int32_t bGrp, int32_t face_dof, int32_t nNo,
                     const int32_t* glob, const double* val, int32_t sharedFlag);
 
+/* Capping surface of a coupled Neumann face (FSILS_faceType::has_cap / cap_glob / cap_val, linear_solver/fils_struct.hpp:131-143):
+ * cap_glob are INPUT-order node ids (negative = the cap node is not on this partition, add_bc_mul.cpp:70), cap_val(face_dof,
+ * cap_nNo) the cap's nodal normal integrals.  The cap adds coef * (cap_val W . X) to the face's flow-rate sum in add_bc_mul
+ * (add_bc_mul.cpp:62-81, 102-111); precond_diag scales it with W like face.val (precond.cpp:229-237).  Call after svb200_set_face,
+ * on every partition (cap_nNo = 0 where the partition holds no cap node). */
+SVB200_API int svb200_set_face_cap(svb200_ctx* ctx, int32_t faIn, int32_t cap_nNo, const int32_t* cap_glob, const double* cap_val);
+
 /* ---- per Newton iteration --------------------------------------------------------------- */
 /* ls_alloc (solver/ls.cpp:24-40): R(dof,nNo) and Val(dof*dof,nnz) are (re)zeroed on the device. */
 SVB200_API int svb200_alloc(svb200_ctx* ctx, int32_t dof);

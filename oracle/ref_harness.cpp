@@ -383,6 +383,25 @@ int svref_set_face(void* h, int faIn, int bGrp, int face_dof, int nNo, const int
   });
 }
 
+/// Capping surface of a coupled face: what CoupledBoundaryCondition leaves in lhs.face[faIn].{has_cap, cap_glob, cap_val, cap_valM}
+/// (linear_solver/fils_struct.hpp:131-143); glob are host node ids (negative = not on this rank), mapped like bc.cpp:55-58.
+int svref_set_face_cap(void* h, int faIn, int n, const int* glob, const double* val)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    auto& lhs = c.com_mod.lhs;
+    auto& fa = lhs.face.at(faIn);
+    fa.has_cap = true;
+    fa.cap_glob.resize(n);
+    fa.cap_val.resize(fa.dof, n);
+    fa.cap_valM.resize(fa.dof, n);
+    for (int a = 0; a < n; a++) {
+      fa.cap_glob(a) = glob[a] < 0 ? -1 : lhs.map(glob[a]);
+      for (int i = 0; i < fa.dof; i++) { fa.cap_val(i,a) = val[(size_t)a*fa.dof + i]; fa.cap_valM(i,a) = 0.0; }
+    }
+  });
+}
+
 /// ls_alloc (solver/ls.cpp:24-40): fresh zero R(dof,tnNo), Val(dof*dof,nnz).
 int svref_alloc(void* h, int dof)
 {

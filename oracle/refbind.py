@@ -260,6 +260,11 @@ class RefCase(_FlatCase):
             reqs.append((iP.value, ptr))
         return mynNo.value, mp, reqs
 
+    def set_face_cap(self, faIn, cap_glob, cap_val):
+        """lhs.face[faIn].{has_cap, cap_glob, cap_val}: the capping surface of a coupled face (fils_struct.hpp:131-143)."""
+        cap_glob, cap_val = _i32(cap_glob), _f64(cap_val)
+        self._call("set_face_cap", C.c_int(faIn), C.c_int(len(cap_glob)), _i(cap_glob), _d(cap_val))
+
     def barrier(self):
         """MPI_Barrier of the multi-rank shim (no-op for one rank)."""
         self._call("barrier")

@@ -553,8 +553,10 @@ done:
 #undef H
 }
 
-static int cgrad_v(OCase* c, int dof, const svb200_sublsparams* p, svb200_sublsresult* r, const double* K, double* R)
+static int cgrad_v(OCase* c, int dof, const svb200_sublsparams* p, svb200_sublsresult* r, const double* K, double* R,
+                   svb200_lsresult* full)
 {
+  if (full) full->hist_n = 0;
   const size_t n = (size_t)dof * c->nNo;
   double *P = malloc(sizeof(double) * n), *KP = malloc(sizeof(double) * n), *X = calloc(n, sizeof(double));
   const double t0 = now_s();
@@ -574,6 +576,7 @@ static int cgrad_v(OCase* c, int dof, const svb200_sublsparams* p, svb200_sublsr
     for (size_t k = 0; k < n; k++) R[k] = R[k] + (-alpha) * KP[k];
     err = normv((int)n, R);
     err = err * err;
+    if (full && full->hist && full->hist_n < full->hist_cap) full->hist[full->hist_n++] = sqrt(err);
     { const double q = errO / err; for (size_t k = 0; k < n; k++) P[k] = P[k] + q * R[k]; }
     { const double q = err / errO; for (size_t k = 0; k < n; k++) P[k] = q * P[k]; }
   }
@@ -586,8 +589,10 @@ static int cgrad_v(OCase* c, int dof, const svb200_sublsparams* p, svb200_sublsr
   return 0;
 }
 
-static int bicgsv(OCase* c, int dof, const svb200_sublsparams* p, svb200_sublsresult* r, const double* K, double* R)
+static int bicgsv(OCase* c, int dof, const svb200_sublsparams* p, svb200_sublsresult* r, const double* K, double* R,
+                  svb200_lsresult* full)
 {
+  if (full) full->hist_n = 0;
   const size_t n = (size_t)dof * c->nNo;
   double *P = malloc(sizeof(double) * n), *Rh = malloc(sizeof(double) * n), *X = calloc(n, sizeof(double)),
          *V = malloc(sizeof(double) * n), *S = malloc(sizeof(double) * n), *T = malloc(sizeof(double) * n);
@@ -612,6 +617,7 @@ static int bicgsv(OCase* c, int dof, const svb200_sublsparams* p, svb200_sublsre
     for (size_t k = 0; k < n; k++) R[k] = S[k] - omega * T[k];
     errO = err;
     err = normv((int)n, R);
+    if (full && full->hist && full->hist_n < full->hist_cap) full->hist[full->hist_n++] = err;
     const double rhoO = rho;
     rho = nc_dot((int)n, R, Rh);
     const double beta = rho * alpha / (rhoO * omega);
@@ -659,8 +665,8 @@ int svorc_solve(void* h, int dof, int ls_type, int prec, const svb200_lsparams* 
   int rc = 0;
   switch (ls_type) {
     case SVB200_LS_GMRES: rc = gmres_v(c, dof, &ls->RI, &o->RI, c->Val, c->R, o); break;
-    case SVB200_LS_CG: rc = cgrad_v(c, dof, &ls->RI, &o->RI, c->Val, c->R); break;
-    case SVB200_LS_BICGS: rc = bicgsv(c, dof, &ls->RI, &o->RI, c->Val, c->R); break;
+    case SVB200_LS_CG: rc = cgrad_v(c, dof, &ls->RI, &o->RI, c->Val, c->R, o); break;
+    case SVB200_LS_BICGS: rc = bicgsv(c, dof, &ls->RI, &o->RI, c->Val, c->R, o); break;
     default: rc = fail("[sv_oracle] LS type not restated yet");
   }
   if (!rc) {

@@ -322,7 +322,21 @@ bsr_spmv4_bnd_push_kernel(int nB, int nnb, const int* __restrict__ brow, const i
     row = brow[b];
     const int k0 = rowPtr[row], k1 = rowPtr[row + 1];
     const double2* V2 = reinterpret_cast<const double2*>(Val) + l;
-    for (int k = k0; k < k1; k++) {
+    int k = k0;
+    for (; k + 4 <= k1; k += 4) {          // 4 blocks in flight per lane, same summation order as bsr_spmv4_kernel
+      const int c0 = __ldg(colPtr + k), c1 = __ldg(colPtr + k + 1), c2 = __ldg(colPtr + k + 2), c3 = __ldg(colPtr + k + 3);
+      const double2 v0 = __ldcs(V2 + 8 * (size_t)k), v1 = __ldcs(V2 + 8 * (size_t)(k + 1));
+      const double2 v2 = __ldcs(V2 + 8 * (size_t)(k + 2)), v3 = __ldcs(V2 + 8 * (size_t)(k + 3));
+      const double2 u0 = *reinterpret_cast<const double2*>(U + 4 * (size_t)c0 + j0);
+      const double2 u1 = *reinterpret_cast<const double2*>(U + 4 * (size_t)c1 + j0);
+      const double2 u2 = *reinterpret_cast<const double2*>(U + 4 * (size_t)c2 + j0);
+      const double2 u3 = *reinterpret_cast<const double2*>(U + 4 * (size_t)c3 + j0);
+      acc += v0.x * u0.x + v0.y * u0.y;
+      acc += v1.x * u1.x + v1.y * u1.y;
+      acc += v2.x * u2.x + v2.y * u2.y;
+      acc += v3.x * u3.x + v3.y * u3.y;
+    }
+    for (; k < k1; k++) {
       const int c0 = __ldg(colPtr + k);
       const double2 v0 = __ldcs(V2 + 8 * (size_t)k);
       const double2 u0 = *reinterpret_cast<const double2*>(U + 4 * (size_t)c0 + j0);

@@ -644,9 +644,14 @@ int precond_face_valm(svb200_ctx* ctx, const Face& f, int dof, const double* W)
 {
   const int nd = f.dof < dof ? f.dof : dof;
   const int n = f.nNo * f.dof;
-  if (n == 0) return SVB200_OK;
-  face_valm_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(f.nNo, f.dof, nd, dof, f.d_glob, f.d_val, W, f.d_valM);
+  if (n == 0 && !(f.has_cap && f.cap_n > 0)) return SVB200_OK;
+  if (n > 0) face_valm_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(f.nNo, f.dof, nd, dof, f.d_glob, f.d_val, W, f.d_valM);
   ctx->launches++;
+  if (f.has_cap && f.cap_n > 0) {     // cap_valM = cap_val * W (precond.cpp:229-237)
+    const int nc = f.cap_n * f.dof;
+    face_valm_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(f.cap_n, f.dof, nd, dof, f.d_cap_glob, f.d_cap_val, W, f.d_cap_valM);
+    ctx->launches++;
+  }
   SVB_CUDA(cudaGetLastError());
   return SVB200_OK;
 }

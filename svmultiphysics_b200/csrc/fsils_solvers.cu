@@ -118,13 +118,16 @@ __global__ void face_dot_stage2_kernel(int nblocks, const double* __restrict__ p
   if (threadIdx.x == 0) *out = red[0];
 }
 
-__global__ void face_axpy_kernel(int fnNo, int fdof, int nd, int dof, double coef, const double* __restrict__ S,
+// Y += valM * S with S = coef * (valM . X) (+ coef * (cap_valM . X) when the face has a cap, add_bc_mul.cpp:62-81)
+__global__ void face_axpy_kernel(int fnNo, int fdof, int nd, int dof, double coef, const double* __restrict__ S, int has_cap,
                                  const int* __restrict__ glob, const double* __restrict__ valM, double* __restrict__ Y)
 {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= fnNo * nd) return;
   const int a = t / nd, i = t % nd;
-  Y[(size_t)glob[a] * dof + i] += valM[(size_t)a * fdof + i] * (coef * (*S));
+  double s = coef * S[0];
+  if (has_cap) s = s + coef * S[1];
+  Y[(size_t)glob[a] * dof + i] += valM[(size_t)a * fdof + i] * s;
 }
 
 // op: 0 = BCOP_TYPE_ADD (coef = res), 1 = BCOP_TYPE_PRE (coef = -res/(1+res*nS)).
@@ -139,10 +142,16 @@ int add_bc_mul_device(svb200_ctx* ctx, int op, int dof, const double* X, double*
     face_dot_kernel<<<FACE_DOT_BLOCKS, 256, 0, ctx->stream>>>(f.nNo, f.dof, nd, dof, ctx->mynNo, f.shared, f.d_glob, f.d_valM, X, part);
     face_dot_stage2_kernel<<<1, FACE_DOT_BLOCKS, 0, ctx->stream>>>(FACE_DOT_BLOCKS, part, d_scal);
     ctx->launches += 2;
-    if (f.shared) SVB_TRY(allreduce_sum(ctx, d_scal, 1));
+    if (f.has_cap) {
+      // the cap's flow-rate contribution: ALL cap nodes of this partition, not only the owned ones (add_bc_mul.cpp:67-79)
+      face_dot_kernel<<<FACE_DOT_BLOCKS, 256, 0, ctx->stream>>>(f.cap_n, f.dof, nd, dof, ctx->mynNo, 0, f.d_cap_glob, f.d_cap_valM, X, part);
+      face_dot_stage2_kernel<<<1, FACE_DOT_BLOCKS, 0, ctx->stream>>>(FACE_DOT_BLOCKS, part, d_scal + 1);
+      ctx->launches += 2;
+    }
+    if (f.shared) SVB_TRY(allreduce_sum(ctx, d_scal, f.has_cap ? 2 : 1));
     const int n = f.nNo * nd;
     if (n > 0) {
-      face_axpy_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(f.nNo, f.dof, nd, dof, coef, d_scal, f.d_glob, f.d_valM, Y);
+      face_axpy_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(f.nNo, f.dof, nd, dof, coef, d_scal, f.has_cap ? 1 : 0, f.d_glob, f.d_valM, Y);
       ctx->launches++;
     }
     SVB_CUDA(cudaGetLastError());
@@ -800,12 +809,14 @@ int ns_solver_device(svb200_ctx* ctx, int dof, const svb200_lsparams* ls, svb200
   const size_t oU = take((size_t)nvs * iBmax), oMU = take((size_t)nvs * nB), oP = take((size_t)nns * iBmax), oMP = take((size_t)nns * nB);
   const size_t oK = take((size_t)nnz * nsd * nsd), oG = take((size_t)nnz * nsd), oD = take((size_t)nnz * nsd), oL = take(nnz),
                oGt = take((size_t)nnz * nsd);
-  const size_t oGm = take((size_t)nvs * (sD + 1)), oSch = take((size_t)nns * 4 + nvs), oScal = take(SCAL_N);
+  // scalar scratch: SCAL_N for the solvers + the Gram-matrix partial results, 2 (4 i + 5) doubles in outer iteration i
+  const size_t nGram = (size_t)2 * (4 * iBmax + 5);
+  const size_t oGm = take((size_t)nvs * (sD + 1)), oSch = take((size_t)nns * 4 + nvs), oScal = take(SCAL_N + nGram);
   SVB_TRY(ensure_work(ctx, need));
   double* W = ctx->d_work;
   double *Rm = W + oRm, *Rmi = W + oRmi, *Rc = W + oRc, *Rci = W + oRci, *U = W + oU, *MU = W + oMU, *P = W + oP, *MP = W + oMP;
   double *mK = W + oK, *mG = W + oG, *mD = W + oD, *mL = W + oL, *Gt = W + oGt, *gm_u = W + oGm, *sch = W + oSch, *d_scal = W + oScal;
-  double* d_gram = d_scal + 300;     // Gram-matrix partial results (<= 2*(nB+1) + ... doubles)
+  double* d_gram = d_scal + SCAL_N;  // Gram-matrix partial results, sized from Max_iterations above
   if (!ctx->d_tslot) {
     SVB_CUDA(cudaMalloc(&ctx->d_tslot, sizeof(int) * std::max<long long>(nnz, 1)));
     SVB_TRY(build_transpose_slots(ctx, ctx->d_tslot));
@@ -875,7 +886,7 @@ int ns_solver_device(svb200_ctx* ctx, int dof, const svb200_lsparams* ls, svb200
       SVB_TRY(multi_dot(ctx, (long long)ctx->mynNo, 1, Rci, 0, MP + (size_t)nns * k, d_gram + cnt + k + 1));
       cnt += k + 2;
     }
-    if (cnt > SCAL_N - 300) {
+    if ((size_t)cnt > nGram || cnt > SCAL_N) {      // h_pinned holds SCAL_N doubles; 8 i + 10 <= 802 for i < 100
       set_error("svb200: NS Gram buffer overflow");
       return SVB200_ERR_INVALID;
     }

@@ -98,74 +98,70 @@ static void free_mesh(Mesh& m)
 static void free_face(Face& f)
 {
   cudaFree(f.d_glob); cudaFree(f.d_val); cudaFree(f.d_valM);
+  cudaFree(f.d_cap_glob); cudaFree(f.d_cap_val); cudaFree(f.d_cap_valM);
   f = Face();
 }
 
-// Greedy element colouring: two elements of one colour never share a node, so a colour can be
-// scattered with plain read-modify-write (deterministic mode).
+// Greedy colouring of items (elements, or 128-element groups) that conflict when they share a node: item k takes the
+// smallest colour none of its nodes carries yet.  The per-node colour sets are bitsets that grow on demand, so meshes with
+// high-valence nodes (more than 128 conflicting colours) are coloured as well instead of being rejected.
+static int greedy_color(int nNo, int nItems, const std::vector<int>& ien, size_t nodes_per_item, size_t total_nodes,
+                        std::vector<int>& color)
+{
+  int nw = 2;                                   // 64-bit words per node
+  std::vector<uint64_t> mask((size_t)nNo * nw, 0);
+  color.assign(nItems, 0);
+  int ncol = 0;
+  std::vector<uint64_t> used;
+  for (int k = 0; k < nItems; k++) {
+    const size_t b = (size_t)k * nodes_per_item, e = std::min(b + nodes_per_item, total_nodes);
+    used.assign(nw, 0);
+    for (size_t q = b; q < e; q++)
+      for (int w = 0; w < nw; w++) used[w] |= mask[(size_t)ien[q] * nw + w];
+    int c = -1;
+    for (int w = 0; w < nw && c < 0; w++)
+      if (~used[w]) c = 64 * w + __builtin_ctzll(~used[w]);
+    if (c < 0) {                                // every colour of the current width is taken: widen the bitsets
+      c = 64 * nw;
+      const int nw2 = nw * 2;
+      std::vector<uint64_t> wide((size_t)nNo * nw2, 0);
+      for (int n = 0; n < nNo; n++)
+        for (int w = 0; w < nw; w++) wide[(size_t)n * nw2 + w] = mask[(size_t)n * nw + w];
+      mask.swap(wide);
+      nw = nw2;
+    }
+    color[k] = c;
+    ncol = std::max(ncol, c + 1);
+    for (size_t q = b; q < e; q++) mask[(size_t)ien[q] * nw + (c >> 6)] |= (1ull << (c & 63));
+  }
+  return ncol;
+}
+
+static int upload_color_perm(svb200_ctx* ctx, int nItems, int ncol, const std::vector<int>& color, std::vector<int>& off, int** d_perm)
+{
+  off.assign(ncol + 1, 0);
+  for (int k = 0; k < nItems; k++) off[color[k] + 1]++;
+  for (int c = 0; c < ncol; c++) off[c + 1] += off[c];
+  std::vector<int> pos(off.begin(), off.end() - 1), perm(nItems);
+  for (int k = 0; k < nItems; k++) perm[pos[color[k]]++] = k;
+  return upload(ctx, d_perm, perm.data(), perm.size());
+}
+
+// Element colouring (two elements of one colour never share a node: a colour can be scattered with plain
+// read-modify-write, the deterministic mode) and, for TET4, the colouring of the 128-element GROUPS of the grouped scatter
+// (group_sched.cu): groups of one colour share no node, hence no R row and no CSR block — launched colour by colour, the
+// grouped kernel adds every value in a fixed order, so the deterministic mode keeps the pre-reduction and the locality of
+// the default path.
 static int build_coloring(svb200_ctx* ctx, Mesh& m, const std::vector<int>& ien)
 {
-  std::vector<uint64_t> mask(ctx->nNo, 0), mask2(ctx->nNo, 0);   // 128 colours max
-  std::vector<int> color(m.nEl);
-  int ncol = 0;
-  for (int e = 0; e < m.nEl; e++) {
-    uint64_t u0 = 0, u1 = 0;
-    for (int a = 0; a < m.eNoN; a++) {
-      const int n = ien[(size_t)e * m.eNoN + a];
-      u0 |= mask[n];
-      u1 |= mask2[n];
-    }
-    int c;
-    if (~u0) c = __builtin_ctzll(~u0);
-    else if (~u1) c = 64 + __builtin_ctzll(~u1);
-    else {
-      set_error("svb200: more than 128 colours needed for the coloured scatter");
-      return SVB200_ERR_UNSUPPORTED;
-    }
-    color[e] = c;
-    ncol = std::max(ncol, c + 1);
-    for (int a = 0; a < m.eNoN; a++) {
-      const int n = ien[(size_t)e * m.eNoN + a];
-      if (c < 64) mask[n] |= (1ull << c);
-      else mask2[n] |= (1ull << (c - 64));
-    }
-  }
-  m.color_off.assign(ncol + 1, 0);
-  for (int e = 0; e < m.nEl; e++) m.color_off[color[e] + 1]++;
-  for (int c = 0; c < ncol; c++) m.color_off[c + 1] += m.color_off[c];
-  std::vector<int> pos(m.color_off.begin(), m.color_off.end() - 1), perm(m.nEl);
-  for (int e = 0; e < m.nEl; e++) perm[pos[color[e]]++] = e;
-  { int rc = upload(ctx, &m.d_color_perm, perm.data(), perm.size()); if (rc) return rc; }
+  std::vector<int> color;
+  int ncol = greedy_color(ctx->nNo, m.nEl, ien, (size_t)m.eNoN, ien.size(), color);
+  { int rc = upload_color_perm(ctx, m.nEl, ncol, color, m.color_off, &m.d_color_perm); if (rc) return rc; }
   m.gcolor_off.clear();
   if (m.eNoN != 4) return SVB200_OK;
-  // TET4: colour the 128-element GROUPS of the grouped scatter (group_sched.cu) the same way.  Groups of one colour share
-  // no node, hence no R row and no CSR block: launched colour by colour, the grouped kernel adds every value in a fixed
-  // order — the deterministic mode keeps the pre-reduction and the locality of the default path.
   const int nGrp = (m.nEl + ASM_GROUP - 1) / ASM_GROUP;
-  std::fill(mask.begin(), mask.end(), 0); std::fill(mask2.begin(), mask2.end(), 0);
-  std::vector<int> gcolor(nGrp);
-  int ngc = 0;
-  for (int g = 0; g < nGrp; g++) {
-    const size_t b = (size_t)g * ASM_GROUP * 4, eend = std::min<size_t>((size_t)(g + 1) * ASM_GROUP, (size_t)m.nEl) * 4;
-    uint64_t u0 = 0, u1 = 0;
-    for (size_t k = b; k < eend; k++) { u0 |= mask[ien[k]]; u1 |= mask2[ien[k]]; }
-    int c;
-    if (~u0) c = __builtin_ctzll(~u0);
-    else if (~u1) c = 64 + __builtin_ctzll(~u1);
-    else return SVB200_OK;                    // more than 128 group colours: keep the per-element colouring only
-    gcolor[g] = c;
-    ngc = std::max(ngc, c + 1);
-    for (size_t k = b; k < eend; k++) {
-      if (c < 64) mask[ien[k]] |= (1ull << c);
-      else mask2[ien[k]] |= (1ull << (c - 64));
-    }
-  }
-  m.gcolor_off.assign(ngc + 1, 0);
-  for (int g = 0; g < nGrp; g++) m.gcolor_off[gcolor[g] + 1]++;
-  for (int c = 0; c < ngc; c++) m.gcolor_off[c + 1] += m.gcolor_off[c];
-  std::vector<int> gpos(m.gcolor_off.begin(), m.gcolor_off.end() - 1), gperm(nGrp);
-  for (int g = 0; g < nGrp; g++) gperm[gpos[gcolor[g]]++] = g;
-  return upload(ctx, &m.d_gcolor_perm, gperm.data(), gperm.size());
+  ncol = greedy_color(ctx->nNo, nGrp, ien, (size_t)ASM_GROUP * 4, ien.size(), color);
+  return upload_color_perm(ctx, nGrp, ncol, color, m.gcolor_off, &m.d_gcolor_perm);
 }
 
 }  // namespace svb
@@ -311,6 +307,7 @@ int svb200_set_graph(svb200_ctx* ctx, int32_t nNo, int32_t nnz, const int32_t* r
   }
   TRY(upload(ctx, &ctx->d_rowPtr, ctx->h_rowPtr.data(), (size_t)nNo + 1));
   TRY(upload(ctx, &ctx->d_colPtr, col.data(), (size_t)nnz));
+  ctx->h_colPtr.swap(col);
   TRY(upload(ctx, &ctx->d_map, ctx->h_map.data(), (size_t)nNo));
   TRY(upload(ctx, &ctx->d_rowPtr_in, ctx->h_rowPtr_in.data(), (size_t)nNo + 1));
   if (ctx->d_diagPtr) { cudaFree(ctx->d_diagPtr); ctx->d_diagPtr = nullptr; }
@@ -450,6 +447,34 @@ int svb200_set_face(svb200_ctx* ctx, int32_t faIn, int32_t bGrp, int32_t face_do
   }
   SVB_CUDA(cudaStreamSynchronize(ctx->stream));
   f.set = true;
+  return SVB200_OK;
+}
+
+int svb200_set_face_cap(svb200_ctx* ctx, int32_t faIn, int32_t cap_nNo, const int32_t* cap_glob, const double* cap_val)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(faIn >= 0 && faIn < (int)ctx->face.size() && ctx->face[faIn].set, "svb200_set_face_cap: call svb200_set_face first");
+  SVB_REQUIRE(cap_nNo >= 0 && (cap_nNo == 0 || (cap_glob && cap_val)), "svb200_set_face_cap: bad arguments");
+  Face& f = ctx->face[faIn];
+  cudaFree(f.d_cap_glob); cudaFree(f.d_cap_val); cudaFree(f.d_cap_valM);
+  f.d_cap_glob = nullptr; f.d_cap_val = f.d_cap_valM = nullptr; f.cap_n = 0;
+  // cap nodes that are not on this partition carry a negative id (add_bc_mul.cpp:70) and are dropped here
+  std::vector<int> g;
+  std::vector<double> v;
+  for (int a = 0; a < cap_nNo; a++) {
+    if (cap_glob[a] < 0) continue;
+    SVB_REQUIRE(cap_glob[a] < ctx->nNo, "svb200_set_face_cap: node id out of range");
+    g.push_back(ctx->h_map[cap_glob[a]]);
+    for (int i = 0; i < f.dof; i++) v.push_back(cap_val[(size_t)a * f.dof + i]);
+  }
+  f.cap_n = (int)g.size();
+  f.has_cap = true;           // all ranks agree on the flag even when a rank holds no cap node (collective sums)
+  if (f.cap_n == 0) return SVB200_OK;
+  TRY(upload(ctx, &f.d_cap_glob, g.data(), g.size()));
+  TRY(upload(ctx, &f.d_cap_val, v.data(), v.size()));
+  SVB_CUDA(cudaMalloc(&f.d_cap_valM, sizeof(double) * v.size()));
+  SVB_CUDA(cudaMemsetAsync(f.d_cap_valM, 0, sizeof(double) * v.size(), ctx->stream));
+  SVB_CUDA(cudaStreamSynchronize(ctx->stream));
   return SVB200_OK;
 }
 
@@ -815,6 +840,14 @@ int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, cons
       for (int d = 0; d < nDmn; d++) {
         anyFluid |= (dmn[d].phys == SVB200_PHYS_FLUID);
         anySolid |= (dmn[d].phys == SVB200_PHYS_STRUCT);
+        // construct_fsi sends ustruct solids through ustruct_3d_m/c (fsi.cpp:243-262) and has no branch for anything else
+        // (a lElas domain assembles nothing there): neither is built here, so such a domain must not be skipped silently
+        if (dmn[d].phys != SVB200_PHYS_FLUID && dmn[d].phys != SVB200_PHYS_STRUCT) {
+          set_error("svb200_assemble: an FSI equation with a domain that is neither fluid nor struct (e.g. a ustruct solid) is not "
+                    "implemented on the device");
+          return SVB200_ERR_UNSUPPORTED;
+        }
+        if (dmn[d].Id == -1) break;
       }
       if (anyFluid) {
         FluidArgs A;
@@ -846,12 +879,49 @@ int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, cons
   return SVB200_OK;
 }
 
+// dst(:, rows[k]) += add(:, k); the targets are distinct (duplicates were summed on the host), so plain adds suffice.
 __global__ void add_rows_kernel(int n, int dof, const int* __restrict__ rows, const double* __restrict__ add,
                                 double* __restrict__ dst)
 {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n * dof) return;
-  atomicAdd(dst + (size_t)rows[t / dof] * dof + t % dof, add[t]);
+  dst[(size_t)rows[t / dof] * dof + t % dof] += add[t];
+}
+
+// Sum the d-double entries of `vals` that share a target, in the order they were staged (the order of the host's
+// element loop, i.e. the reference's own do_assem order), and add the result to the device array: one deterministic add
+// per distinct target instead of an atomic per staged entry.
+static int add_reduced(svb200_ctx* ctx, const std::vector<int>& target, const double* vals, int d, double* d_dst)
+{
+  const size_t n = target.size();
+  if (n == 0) return SVB200_OK;
+  std::vector<size_t> order(n);
+  std::iota(order.begin(), order.end(), (size_t)0);
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return target[a] < target[b]; });
+  std::vector<int> uniq;
+  std::vector<double> sum;
+  for (size_t q = 0; q < n; q++) {
+    const size_t k = order[q];
+    if (q == 0 || target[k] != uniq.back()) {
+      uniq.push_back(target[k]);
+      sum.insert(sum.end(), vals + k * d, vals + (k + 1) * d);
+    } else {
+      double* s = sum.data() + sum.size() - d;
+      for (int i = 0; i < d; i++) s[i] += vals[k * d + i];
+    }
+  }
+  int* d_t = nullptr; double* d_a = nullptr;
+  int rc = upload(ctx, &d_t, uniq.data(), uniq.size());
+  if (!rc) rc = upload(ctx, &d_a, sum.data(), sum.size());
+  if (!rc) {
+    const int nu = (int)uniq.size();
+    add_rows_kernel<<<(nu * d + 255) / 256, 256, 0, ctx->stream>>>(nu, d, d_t, d_a, d_dst);
+    ctx->launches++;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = cuda_fail(e, "svb200_add_host_contrib", __FILE__, __LINE__);
+  }
+  cudaFree(d_t); cudaFree(d_a);
+  return rc;
 }
 
 int svb200_add_host_contrib(svb200_ctx* ctx, int32_t dof, int32_t nR, const int32_t* rows, const double* R_add,
@@ -866,18 +936,11 @@ int svb200_add_host_contrib(svb200_ctx* ctx, int32_t dof, int32_t nR, const int3
       SVB_REQUIRE(rows[k] >= 0 && rows[k] < ctx->nNo, "svb200_add_host_contrib: row out of range");
       r[k] = ctx->h_map[rows[k]];
     }
-    int* d_r = nullptr; double* d_a = nullptr;
-    TRY(upload(ctx, &d_r, r.data(), r.size()));
-    TRY(upload(ctx, &d_a, R_add, (size_t)nR * dof));
-    add_rows_kernel<<<(nR * dof + 255) / 256, 256, 0, ctx->stream>>>(nR, dof, d_r, d_a, ctx->d_R);
-    ctx->launches++;
-    SVB_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_r); cudaFree(d_a);
+    TRY(add_reduced(ctx, r, R_add, dof, ctx->d_R));
   }
   if (nK > 0) {
     SVB_REQUIRE(krows && kcols && K_add, "svb200_add_host_contrib: null tangent arrays");
-    std::vector<int> col(ctx->nnz);
-    SVB_CUDA(cudaMemcpy(col.data(), ctx->d_colPtr, sizeof(int) * ctx->nnz, cudaMemcpyDeviceToHost));
+    const std::vector<int>& col = ctx->h_colPtr;
     std::vector<int> s(nK);
     for (int k = 0; k < nK; k++) {
       SVB_REQUIRE(krows[k] >= 0 && krows[k] < ctx->nNo && kcols[k] >= 0 && kcols[k] < ctx->nNo,
@@ -889,13 +952,7 @@ int svb200_add_host_contrib(svb200_ctx* ctx, int32_t dof, int32_t nR, const int3
       SVB_REQUIRE(slot >= 0, "svb200_add_host_contrib: (row,col) pair is not in the CSR graph");
       s[k] = slot;
     }
-    int* d_s = nullptr; double* d_a = nullptr;
-    TRY(upload(ctx, &d_s, s.data(), s.size()));
-    TRY(upload(ctx, &d_a, K_add, (size_t)nK * dof * dof));
-    add_rows_kernel<<<(nK * dof * dof + 255) / 256, 256, 0, ctx->stream>>>(nK, dof * dof, d_s, d_a, ctx->d_Val);
-    ctx->launches++;
-    SVB_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_s); cudaFree(d_a);
+    TRY(add_reduced(ctx, s, K_add, dof * dof, ctx->d_Val));
   }
   return SVB200_OK;
 }

@@ -58,6 +58,12 @@ struct Face {
   double* d_val = nullptr;   // (dof, nNo)
   double* d_valM = nullptr;  // (dof, nNo): val * W (precond_diag)
   double nS = 0.0;           // sum of val^2 over owned nodes (fsils_bc_create)
+  // capping surface of a coupled face (fils_struct.hpp:131-143): cap nodes on this partition, their normal integrals
+  int cap_n = 0;
+  bool has_cap = false;
+  int* d_cap_glob = nullptr;     // internal node ids
+  double* d_cap_val = nullptr;   // (dof, cap_n)
+  double* d_cap_valM = nullptr;  // (dof, cap_n): cap_val * W (precond.cpp:229-237)
   // per-solve flags (fsils_solve)
   bool incFlag = true, coupledFlag = false;
   double res = 0.0;
@@ -130,6 +136,7 @@ struct svb200_ctx {
   std::vector<int> h_map;        // input -> internal node id
   std::vector<int> h_rowPtr_in;  // input CSR (kept for slot translation on download)
   std::vector<int> h_rowPtr;     // internal CSR row pointer
+  std::vector<int> h_colPtr;     // internal CSR column ids (host copy: slot look-up of svb200_add_host_contrib)
   int* d_map = nullptr;
   int* d_rowPtr_in = nullptr;    // (nNo+1) caller-order row pointer (block up/downloads when a node map is active)
   int* d_rowPtr = nullptr;       // (nNo+1) internal

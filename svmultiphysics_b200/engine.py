@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "svb200_abi_version", "svb200_last_error", "svb200_create", "svb200_destroy",
     "svb200_comm_unique_id", "svb200_comm_init", "svb200_comm_transport",
     "svb200_set_graph", "svb200_lhsa_begin", "svb200_lhsa_add_mesh", "svb200_lhsa_finish", "svb200_lhsa_get",
-    "svb200_set_mesh", "svb200_set_mesh_nxx", "svb200_set_coords", "svb200_set_num_faces", "svb200_set_face",
+    "svb200_set_mesh", "svb200_set_mesh_nxx", "svb200_set_coords", "svb200_set_num_faces", "svb200_set_face", "svb200_set_face_cap",
     "svb200_alloc", "svb200_set_state", "svb200_set_old_disp", "svb200_assemble", "svb200_add_host_contrib", "svb200_commu_R", "svb200_ustruct_r", "svb200_set_ad", "svb200_get_ad",
     "svb200_solve", "svb200_download", "svb200_download_rows", "svb200_upload", "svb200_spmv", "svb200_last_timing",
     "svb200_host_register", "svb200_host_unregister", "svb200_timer_mark", "svb200_timer_elapsed",
@@ -197,6 +197,11 @@ class Engine:
         glob, val = _i32(glob), _f64(val)
         self._call("svb200_set_face", C.c_int32(faIn), C.c_int32(bGrp), C.c_int32(val.shape[0]), C.c_int32(len(glob)),
                    _i(glob), _d(val), C.c_int32(shared))
+
+    def set_face_cap(self, faIn, cap_glob, cap_val):
+        """Capping surface of a coupled face: cap node ids (input order, negative = not on this partition), cap_val(face_dof, n)."""
+        cap_glob, cap_val = _i32(cap_glob), _f64(cap_val)
+        self._call("svb200_set_face_cap", C.c_int32(faIn), C.c_int32(len(cap_glob)), _i(cap_glob), _d(cap_val))
 
     # ---- per Newton iteration ------------------------------------------------------------------
     def alloc(self, dof):

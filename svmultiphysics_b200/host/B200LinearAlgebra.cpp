@@ -139,6 +139,16 @@ bool global_eq_assem(ComMod& com_mod, CepMod& cep_mod, const mshType& lM, const 
   auto* la = dynamic_cast<B200LinearAlgebra*>(eq.linear_algebra);
   if (!la) return false;
   if (to_phys(eq.phys) < 0) return false;          // stokes, shells, CEP, ... stay on the host loop (and its assemble())
+  if (eq.phys == consts::EquationType::phys_FSI) {
+    // construct_fsi with ustruct solids (fsi.cpp:243-262) is not built on the device: fail loudly instead of assembling
+    // a system without the solid's stiffness and residual
+    for (int d = 0; d < eq.nDmn; d++) {
+      const auto ph = eq.dmn[d].phys;
+      if (ph != consts::EquationType::phys_fluid && ph != consts::EquationType::phys_struct)
+        throw std::runtime_error("[B200LinearAlgebra] FSI with a solid domain that is not 'struct' (ustruct / lElas) is not "
+                                 "implemented on the device; use the fsils linear algebra for this equation");
+    }
+  }
   la->assemble_mesh(com_mod, lM, solutions);
   return true;
 }
@@ -255,6 +265,13 @@ void B200LinearAlgebra::upload_faces(ComMod& com_mod)
     const int grp = (fa.bGrp == fsi_linear_solver::BcType::BC_TYPE_Dir) ? SVB200_BC_DIR : SVB200_BC_NEU;
     const int dofF = fa.dof > 0 ? fa.dof : 1;
     check(svb200_set_face(ctx, f, grp, dofF, fa.nNo, glob.data(), fa.nNo ? fa.val.data() : nullptr, fa.sharedFlag ? 2 : 0));
+    if (fa.has_cap) {
+      // capping surface of a coupled BC (fils_struct.hpp:131-143): cap_glob is in FSILS order, negative = not on this rank
+      const int nc = fa.cap_glob.size();
+      std::vector<int> cg(nc);
+      for (int a = 0; a < nc; a++) cg[a] = fa.cap_glob(a) < 0 ? -1 : inv_map[fa.cap_glob(a)];
+      check(svb200_set_face_cap(ctx, f, nc, cg.data(), nc ? fa.cap_val.data() : nullptr));
+    }
   }
 }
 

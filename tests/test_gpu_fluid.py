@@ -207,6 +207,64 @@ def test_fluid_ns_and_coupled_face_parity(ls_type, kw, res_out):
 
 
 @pytest.mark.parametrize("ls_type,kw", [
+    (abi.LS_GMRES, dict(mItr=100, sD=50, relTol=1e-8)),
+    (abi.LS_NS, dict(mItr=15, sD=250, relTol=1e-3, absTol=1e-17, gm=(10, 250, 1e-3, 1e-17), cg=(300, 0, 1e-3, 1e-17))),
+], ids=["gmres_cap", "ns_cap"])
+def test_capped_coupled_face_parity(ls_type, kw):
+    """A coupled (resistance) outlet WITH a capping surface (FSILS_faceType::has_cap, fils_struct.hpp:131-143): the cap's normal
+    integrals enter the flow-rate sum of add_bc_mul (add_bc_mul.cpp:62-81, 102-111) and are scaled by precond_diag
+    (precond.cpp:229-237).  The cap here is the free interior nodes of the plane one layer upstream of the outlet."""
+    from oracle import refbind
+    if not refbind.have_ref():
+        pytest.skip("needs oracle/_ref/libsvref.so (the restatement has no coupled faces)")
+    m, Ag, Yg, Dg, Bf = common.fluid_case()
+    n, _, nz = m.lattice
+    faces = _pipe_faces(m)
+    plane = np.arange((n + 1) ** 2) + (n + 1) ** 2 * (nz - 1)
+    cap = np.setdiff1d(plane, m.faces["wall"]).astype(np.int32)
+    cap_val = np.zeros((3, len(cap)), order="F")
+    cap_val[2] = 2.0 * np.pi / len(cap)
+    cap_val[0] = 0.1 * np.pi / len(cap)
+    orc, rowPtr, colPtr = common.make_oracle(refbind.RefCase, m, nFaces=len(faces))
+    eq, dmn = abi.fluid_eq(0.005), [abi.fluid_domain()]
+    for i, (g, nodes, val) in enumerate(faces):
+        orc.set_face(i, g, nodes, val)
+    orc.set_face_cap(2, cap, cap_val)
+    orc.alloc(4); orc.set_state(Ag, Yg, Dg, Bf); orc.assemble(0, eq, dmn)
+    ls = abi.ls_params(ls_type, **kw)
+    incL, res = np.ones(len(faces), dtype=np.int32), np.array([0.0, 0.0, 0.8])
+    X0, out0, _ = orc.solve(4, ls_type, ls, incL, res)
+    # the same system WITHOUT the cap: the cap must change the answer, or the test proves nothing
+    orc2, _, _ = common.make_oracle(refbind.RefCase, m, nFaces=len(faces))
+    for i, (g, nodes, val) in enumerate(faces):
+        orc2.set_face(i, g, nodes, val)
+    orc2.alloc(4); orc2.set_state(Ag, Yg, Dg, Bf); orc2.assemble(0, eq, dmn)
+    Xn, _, _ = orc2.solve(4, ls_type, ls, incL, res)
+    assert common.rel_err(Xn, X0) > 1e-3
+
+    eng = common.make_engine(m, rowPtr, colPtr)
+    eng.set_num_faces(len(faces))
+    for i, (g, nodes, val) in enumerate(faces):
+        eng.set_face(i, g, nodes, val)
+    eng.set_face_cap(2, cap, cap_val)
+    eng.alloc(4); eng.set_state(Ag, Yg, Dg, Bf); eng.assemble(0, eq, dmn)
+    X1, out1, _ = eng.solve(4, ls_type, ls, incL, res)
+    eng.close()
+    print(f"cap: itr {out1.RI.itr} vs {out0.RI.itr}, fNorm {out1.RI.fNorm:.6e} vs {out0.RI.fNorm:.6e}, relerr X {common.rel_err(X1, X0):.2e}; "
+          f"without the cap the answer differs by {common.rel_err(Xn, X0):.2e}")
+    assert out1.RI.success == out0.RI.success
+    assert abs(out1.RI.iNorm - out0.RI.iNorm) <= 1e-10 * out0.RI.iNorm
+    if ls_type == abi.LS_NS:
+        assert out1.RI.itr == out0.RI.itr
+        assert abs(out1.RI.fNorm - out0.RI.fNorm) <= 2e-2 * out0.RI.fNorm
+        assert common.rel_err(X1, X0) < 50 * ls.RI.relTol
+    else:
+        assert abs(out1.RI.itr - out0.RI.itr) <= max(2, out0.RI.itr // 25)
+        assert out1.RI.fNorm <= ls.RI.relTol * out1.RI.iNorm
+        assert common.rel_err(X1, X0) < 1e-6
+
+
+@pytest.mark.parametrize("ls_type,kw", [
     (abi.LS_GMRES, dict(mItr=10, sD=250, relTol=1e-4)),     # converges inside one cycle (241 iterations in the reference)
     (abi.LS_GMRES, dict(mItr=100, sD=50, relTol=1e-8)),     # stagnating restarts (4328 iterations in the reference)
     (abi.LS_BICGS, dict(mItr=400, relTol=1e-8)),
