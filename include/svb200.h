@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define SVB200_ABI_VERSION 3
+#define SVB200_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define SVB200_API __attribute__((visibility("default")))
@@ -104,7 +104,8 @@ typedef enum {
 } svb200_scatter;
 /* What svb200_download / svb200_upload move. */
 typedef enum { SVB200_ARRAY_R = 0, SVB200_ARRAY_VAL = 1, SVB200_ARRAY_W = 2,
-               SVB200_ARRAY_KD = 3   /* com_mod.Kd((nsd+1)*nsd, nnz), the displacement tangent of ustruct (solver/ustruct.cpp:1621) */
+               SVB200_ARRAY_KD = 3,  /* com_mod.Kd((nsd+1)*nsd, nnz), the displacement tangent of ustruct (solver/ustruct.cpp:1621) */
+               SVB200_ARRAY_RD = 4   /* com_mod.Rd(nsd, nNo), the displacement residual svb200_ustruct_r leaves for the ustruct corrector */
 } svb200_array;
 
 /* Per-equation time-integration parameters (eqType af/am/gam/beta, ComMod dt/tDof/dof/mvMsh). */
@@ -326,6 +327,13 @@ SVB200_API int svb200_set_node_flags(svb200_ctx* ctx, const int32_t* is_solid_no
  * the CURRENT solution (NULL = leave).  The prescribed values are the host's (profiles, time functions). */
 SVB200_API int svb200_set_dirichlet_rows(svb200_ctx* ctx, int32_t row0, int32_t nrow, int32_t n, const int32_t* nodes,
                               const double* valA, const double* valY, const double* valD);
+/* set_bc::set_bc_dir, the part that follows the write for a velocity-pressure solid (ustruct; solver/set_bc.cpp:1046-1117), for
+ * the listed nodes and the directions i of dir_mask (bit i; 7 = all, the "no eDrn set" case), j = eq.s + i:
+ *   impD == 0:  Dn(j) = gam dt Yn(j) - (gam-1) dt Ad(i) + Do(j),  Ad(i) = Yn(j)
+ *   impD != 0:  An(j) = (Yn(j) - Yo(j) + (gam-1) dt Ao(j)) / (gam dt),  Ad(i) = (Dn(j) - Do(j) + (gam-1) dt Ad(i)) / (gam dt)
+ * Call after svb200_set_dirichlet_rows; Ad is the device-resident com_mod.Ad (svb200_set_ad). */
+SVB200_API int svb200_dirichlet_ustruct(svb200_ctx* ctx, const svb200_eqtime* eq, double dt, int32_t n, const int32_t* nodes,
+                             int32_t dir_mask, int32_t impD);
 /* End of a time step: old = current (solver/main.cpp: solutions.old = solutions.current). */
 SVB200_API int svb200_advance_time_step(svb200_ctx* ctx);
 

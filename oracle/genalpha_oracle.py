@@ -1,9 +1,11 @@
 """TEST INFRASTRUCTURE ONLY — numpy restatement of the generalised-alpha state updates of the reference.
 Only tests/ and __graft_entry__.smoke() may import this; the product never does.
 
-Parity pinning: Integrator.cpp is not part of oracle/_ref/libsvref.so (it needs the Simulation object), so these
-four formulas are pinned by restatement only ("parity unpinned" by a compiled reference); each line cites
-the statement it follows in /root/reference/Code/Source/solver/Integrator.cpp.  Arrays are (tDof, nNo).
+Parity pinning: since round 2 oracle/_ref/libsvref.so contains the reference's Integrator.cpp and set_bc.cpp (unmodified; harness
+oracle/ref_harness_genalpha.cpp, binding oracle.refbind.GenAlphaRef).  tests/golden/genalpha.npz is generated from that compiled
+reference and tests/test_genalpha_cpu.py checks that this restatement reproduces it BIT FOR BIT; the device kernels are compared
+with the same fixtures in tests/test_gpu_genalpha.py.  Each line cites the statement it follows in
+/root/reference/Code/Source/solver/Integrator.cpp.  Arrays are (tDof, nNo).
 """
 import numpy as np
 

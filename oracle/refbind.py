@@ -297,3 +297,75 @@ class OracleCase(_FlatCase):
     prefix = "svorc_"
     so_path = ORACLE_SO
     _lib = None
+
+
+class GenAlphaRef:
+    """The reference's own Integrator (predictor / initiator / corrector) and set_bc::set_bc_dir on a hand-filled Simulation
+    (oracle/ref_harness_genalpha.cpp; Code/Source/solver/Integrator.cpp:393-1070, set_bc.cpp:901-1182).  Arrays are (tDof, nNo)."""
+
+    def __init__(self, eqs, dt, dFlag, sstEq, Ao, Yo, Do, maxBc=8):
+        lib = RefCase.lib()
+        lib.svref_ga_create.restype = C.c_void_p
+        lib.svref_ga_last_error.restype = C.c_char_p
+        self.lib = lib
+        Ao, Yo, Do = _f64(Ao), _f64(Yo), _f64(Do)
+        self.tDof, self.nNo = Ao.shape
+        self.eqs = list(eqs)
+        arr = (abi.EqTime * len(eqs))(*eqs)
+        self.h = lib.svref_ga_create(C.c_int(self.tDof), C.c_int(self.nNo), C.c_int(len(eqs)), arr, C.c_double(dt), C.c_int(int(dFlag)),
+                                     C.c_int(int(sstEq)), _d(Ao), _d(Yo), _d(Do), C.c_int(maxBc))
+        if not self.h:
+            raise RuntimeError("svref_ga_create: " + lib.svref_ga_last_error().decode())
+
+    def _call(self, name, *args):
+        rc = getattr(self.lib, "svref_ga_" + name)(C.c_void_p(self.h), *args)
+        if rc != 0:
+            raise RuntimeError(f"svref_ga_{name}: {self.lib.svref_ga_last_error().decode()}")
+
+    def close(self):
+        if self.h:
+            self.lib.svref_ga_destroy(C.c_void_p(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set(self, which, A=None, Y=None, D=None):
+        self._call("set", C.c_int(which), _d(_f64(A)), _d(_f64(Y)), _d(_f64(D)))
+
+    def get(self, which):
+        out = [np.zeros((self.tDof, self.nNo), order="F") for _ in range(3)]
+        self._call("get", C.c_int(which), _d(out[0]), _d(out[1]), _d(out[2]))
+        return out
+
+    def set_ad(self, Ad):
+        self._call("set_ad", _d(_f64(Ad)))
+
+    def get_ad(self):
+        Ad = np.zeros((3, self.nNo), order="F")
+        self._call("get_ad", _d(Ad))
+        return Ad
+
+    def set_solid_nodes(self, iEq, solid_phys, flags):
+        self._call("set_solid_nodes", C.c_int(iEq), C.c_int(solid_phys), _i(_i32(flags)))
+
+    def predictor(self):
+        self._call("predictor")
+
+    def initiator(self, cEq=0):
+        self._call("initiator", C.c_int(cEq))
+
+    def corrector(self, cEq, R, Rd=None):
+        self._call("corrector", C.c_int(cEq), _d(_f64(R)), _d(_f64(Rd)))
+
+    def add_dir_bc(self, iEq, nodes, eDrn=(0, 0, 0), impD=False, g=1.0, gx=None, nV=None):
+        nodes = _i32(nodes)
+        e = _i32(np.asarray(eDrn, dtype=np.int32))
+        self._call("add_dir_bc", C.c_int(iEq), C.c_int(len(nodes)), _i(nodes), _i(e), C.c_int(int(impD)), C.c_double(g),
+                   _d(_f64(gx)), _d(_f64(nV)))
+
+    def set_bc_dir(self):
+        self._call("set_bc_dir")

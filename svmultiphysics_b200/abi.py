@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # svb200_phys
 PHYS_FLUID, PHYS_STRUCT, PHYS_FSI, PHYS_MESH, PHYS_LELAS, PHYS_HEATS, PHYS_HEATF, PHYS_USTRUCT = 0, 1, 2, 3, 4, 5, 6, 7
@@ -19,7 +19,7 @@ PREC_RCS = 1
 SOLID_VISC_NONE, SOLID_VISC_NEWTONIAN, SOLID_VISC_POTENTIAL = 0, 1, 2
 BC_DIR, BC_NEU = 0, 1
 SCATTER_ATOMIC, SCATTER_COLORED = 0, 1
-ARRAY_R, ARRAY_VAL, ARRAY_W, ARRAY_KD = 0, 1, 2, 3
+ARRAY_R, ARRAY_VAL, ARRAY_W, ARRAY_KD, ARRAY_RD = 0, 1, 2, 3, 4
 
 
 class EqParams(C.Structure):

@@ -130,6 +130,43 @@ __global__ void set_rows_kernel(int tDof, int row0, int nrow, int n, const int* 
   dst[(size_t)nodes[k] * tDof + row0 + i] = val[t];
 }
 
+// set_bc::set_bc_dir for a velocity-pressure solid (ustruct; set_bc.cpp:1046-1117), after the prescribed values were written:
+//   impD == 0:  Dn(j) = c1 Yn(j) - c2 Ad(i) + Do(j) ;  Ad(i) = Yn(j)
+//   impD != 0:  An(j) = c1i (Yn(j) - Yo(j) + c2 Ao(j)) ;  Ad(i) = c1i (Dn(j) - Do(j) + c2 Ad(i))
+// with j = s + i, c1 = gam dt, c1i = 1 / c1, c2 = (gam - 1) dt, for the directions i of dir_mask.
+__global__ void dirichlet_ustruct_kernel(int tDof, int s, int n, const int* __restrict__ nodes, int dir_mask, int impD, double c1,
+                                         double c1i, double c2, const double* __restrict__ Ao, const double* __restrict__ Yo,
+                                         const double* __restrict__ Do, double* __restrict__ An, const double* __restrict__ Yn,
+                                         double* __restrict__ Dn, double* __restrict__ Ad)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * 3) return;
+  const int k = t / 3, i = t % 3;
+  if (!((dir_mask >> i) & 1)) return;
+  const size_t a = (size_t)nodes[k];
+  const size_t j = a * tDof + s + i;
+  double* ad = Ad + a * 3 + i;
+  if (impD) {
+    An[j] = __dmul_rn(c1i, __dadd_rn(__dadd_rn(Yn[j], -Yo[j]), __dmul_rn(c2, Ao[j])));
+    *ad = __dmul_rn(c1i, __dadd_rn(__dadd_rn(Dn[j], -Do[j]), __dmul_rn(c2, *ad)));
+  } else {
+    Dn[j] = __dadd_rn(__dadd_rn(__dmul_rn(c1, Yn[j]), -__dmul_rn(c2, *ad)), Do[j]);
+    *ad = Yn[j];
+  }
+}
+
+int launch_dirichlet_ustruct(svb200_ctx* ctx, const svb200_eqtime* eq, double dt, int n, const int* d_nodes, int dir_mask, int impD)
+{
+  if (n == 0) return SVB200_OK;
+  const double c1 = eq->gam * dt, c1i = 1.0 / c1, c2 = (eq->gam - 1.0) * dt;
+  dirichlet_ustruct_kernel<<<(n * 3 + 255) / 256, 256, 0, ctx->stream>>>(ctx->tDof, eq->s, n, d_nodes, dir_mask, impD, c1, c1i, c2,
+                                                                        ctx->d_Ao, ctx->d_Yo, ctx->d_Do, ctx->d_An, ctx->d_Yn,
+                                                                        ctx->d_Dn, ctx->d_Ad);
+  ctx->launches++;
+  SVB_CUDA(cudaGetLastError());
+  return SVB200_OK;
+}
+
 static int fill(const svb200_eqtime* eqs, int nEq, TimeEqs& Q)
 {
   SVB_REQUIRE(eqs && nEq >= 1 && nEq <= 8, "gen-alpha: between 1 and 8 equations");

@@ -804,6 +804,28 @@ int svb200_set_dirichlet_rows(svb200_ctx* ctx, int32_t row0, int32_t nrow, int32
   return rc;
 }
 
+int svb200_dirichlet_ustruct(svb200_ctx* ctx, const svb200_eqtime* eq, double dt, int32_t n, const int32_t* nodes, int32_t dir_mask,
+                             int32_t impD)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(eq && ctx->tDof > 0 && n >= 0 && (nodes || n == 0), "svb200_dirichlet_ustruct: bad arguments");
+  SVB_REQUIRE(eq->s >= 0 && eq->s + 3 <= ctx->tDof, "svb200_dirichlet_ustruct: equation rows exceed tDof");
+  SVB_REQUIRE(ctx->d_Ad, "svb200_dirichlet_ustruct: Ad was never set (svb200_set_ad)");
+  TRY(ensure_solution_arrays(ctx));
+  if (n == 0) return SVB200_OK;
+  std::vector<int> g(n);
+  for (int k = 0; k < n; k++) {
+    SVB_REQUIRE(nodes[k] >= 0 && nodes[k] < ctx->nNo, "svb200_dirichlet_ustruct: node id out of range");
+    g[k] = ctx->h_map[nodes[k]];
+  }
+  int* d_nodes = nullptr;
+  TRY(upload(ctx, &d_nodes, g.data(), g.size()));
+  int rc = launch_dirichlet_ustruct(ctx, eq, dt, n, d_nodes, dir_mask & 7, impD);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_nodes);
+  return rc;
+}
+
 int svb200_advance_time_step(svb200_ctx* ctx)
 {
   CTX_GUARD(ctx);
@@ -1073,6 +1095,9 @@ int svb200_download(svb200_ctx* ctx, int32_t what, double* dst)
     case SVB200_ARRAY_KD:
       SVB_REQUIRE(ctx->d_Kd, "svb200_download: Kd exists only after a ustruct assembly");
       return copy_blocks(ctx, ctx->d_Kd, 12, dst, true);
+    case SVB200_ARRAY_RD:
+      SVB_REQUIRE(ctx->d_Rd, "svb200_download: Rd exists only after svb200_ustruct_r");
+      return download_nodal(ctx, 3, ctx->d_Rd, dst);
   }
   set_error("svb200_download: unknown array id");
   return SVB200_ERR_INVALID;
@@ -1124,6 +1149,7 @@ int svb200_upload(svb200_ctx* ctx, int32_t what, int32_t dof, const double* src)
   switch (what) {
     case SVB200_ARRAY_R: return upload_nodal(ctx, dof, src, &ctx->d_R);
     case SVB200_ARRAY_VAL: return copy_val(ctx, dof, const_cast<double*>(src), false);
+    case SVB200_ARRAY_RD: return upload_nodal(ctx, 3, src, &ctx->d_Rd);
   }
   set_error("svb200_upload: unknown array id");
   return SVB200_ERR_INVALID;

@@ -240,6 +240,7 @@ int launch_predictor(svb200_ctx* ctx, int nEq, const svb200_eqtime* eqs, double 
 int launch_initiator(svb200_ctx* ctx, int nEq, const svb200_eqtime* eqs);
 int launch_corrector(svb200_ctx* ctx, const svb200_eqtime* eq, double dt, int mesh_s, const int* d_flag);
 int launch_set_rows(svb200_ctx* ctx, int row0, int nrow, int n, const int* d_nodes, const double* d_val, double* dst);
+int launch_dirichlet_ustruct(svb200_ctx* ctx, const svb200_eqtime* eq, double dt, int n, const int* d_nodes, int dir_mask, int impD);
 // group_sched.cu
 int build_group_schedules(svb200_ctx* ctx, Mesh& m);
 void free_group_sched(GroupSched& S);

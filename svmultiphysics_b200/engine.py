@@ -41,7 +41,7 @@ ABI_SYMBOLS = [
     "svb200_host_register", "svb200_host_unregister", "svb200_timer_mark", "svb200_timer_elapsed",
     "svb200_bench_assemble", "svb200_bench_spmv", "svb200_measure_fp64_peak", "svb200_launch_count",
     "svb200_set_solution", "svb200_get_solution", "svb200_predictor", "svb200_initiator", "svb200_corrector",
-    "svb200_set_node_flags", "svb200_set_dirichlet_rows", "svb200_advance_time_step",
+    "svb200_set_node_flags", "svb200_set_dirichlet_rows", "svb200_dirichlet_ustruct", "svb200_advance_time_step",
     "svb200_set_bface", "svb200_assemble_neu",
 ]
 
@@ -250,6 +250,12 @@ class Engine:
         self._call("svb200_set_dirichlet_rows", C.c_int32(row0), C.c_int32(nrow), C.c_int32(len(nodes)), _i(nodes),
                    _d(valA), _d(valY), _d(valD))
 
+    def dirichlet_ustruct(self, eq, dt, nodes, dir_mask=7, impD=False):
+        """set_bc_dir's update of (Dn, Ad) / (An, Ad) on the Dirichlet nodes of a ustruct equation (set_bc.cpp:1046-1117)."""
+        nodes = _i32(nodes)
+        self._call("svb200_dirichlet_ustruct", C.byref(eq), C.c_double(dt), C.c_int32(len(nodes)), _i(nodes), C.c_int32(dir_mask),
+                   C.c_int32(int(impD)))
+
     def advance_time_step(self):
         self._call("svb200_advance_time_step")
 
@@ -339,6 +345,10 @@ class Engine:
     def put_R(self, R):
         R = _f64(R)
         self._call("svb200_upload", C.c_int32(abi.ARRAY_R), C.c_int32(R.shape[0]), _d(R))
+
+    def put_Rd(self, Rd):
+        """com_mod.Rd(3, nNo) (normally left on the device by ustruct_r)."""
+        self._call("svb200_upload", C.c_int32(abi.ARRAY_RD), C.c_int32(self.dof), _d(_f64(Rd)))
 
     def put_Val(self, V, dof):
         V = _f64(V)
