@@ -481,10 +481,12 @@ def config_c4_struct(device, fp64_peak, hbm_peak, n=171):
         for i, (g, nodes, val) in enumerate(faces):
             e.set_face(i, g, nodes, val)
         ls = abi.ls_params(abi.LS_BICGS, mItr=50, relTol=1e-12)
-        e.timer_mark(0)
-        _, o, _ = e.solve(3, abi.LS_BICGS, ls, np.ones(3, np.int32), np.zeros(3), want_solution=False)
-        e.timer_mark(1)
-        sol = e.timer_elapsed()
+        for rep in range(2):      # the first solve allocates the Krylov workspace (host-side cudaMalloc inside the timed window)
+            e.alloc(3); e.assemble(0, eq, dm)
+            e.timer_mark(0)
+            _, o, _ = e.solve(3, abi.LS_BICGS, ls, np.ones(3, np.int32), np.zeros(3), want_solution=False)
+            e.timer_mark(1)
+            sol = e.timer_elapsed()
     finally:
         e.close()
     tf = m.nEl * 130e3 / (kern * 1e-3) * 1e-12
@@ -533,18 +535,22 @@ def config_c5_fsi(device, hbm_peak, n=90, nz=120):
         wall = m.faces["wall"]
         e.set_num_faces(1); e.set_face(0, abi.BC_DIR, wall, np.zeros((3, len(wall)), order="F"))
         ls = abi.ls_params(abi.LS_GMRES, mItr=2, sD=50, relTol=1e-8)
-        e.timer_mark(0)
-        _, o, _ = e.solve(4, abi.LS_GMRES, ls, np.ones(1, np.int32), np.zeros(1), want_solution=False)
-        e.timer_mark(1)
-        gm_ms = e.timer_elapsed() / max(o.RI.itr, 1)
+        for rep in range(2):      # first solve = workspace allocation
+            e.alloc(4); e.assemble(0, eq, dmn); e.assemble(1, eq, dmn)
+            e.timer_mark(0)
+            _, o, _ = e.solve(4, abi.LS_GMRES, ls, np.ones(1, np.int32), np.zeros(1), want_solution=False)
+            e.timer_mark(1)
+            gm_ms = e.timer_elapsed() / max(o.RI.itr, 1)
         eqm, dmm = abi.mesh_eq(1e-3), [abi.mesh_domain(E=1.0, nu=0.3)]
         e.alloc(3); e.set_old_disp(np.asfortranarray(0.9 * Dg)); e.assemble(2, eqm, dmm)
         msh_ms = _timed(e, lambda: (e.alloc(3), e.assemble(2, eqm, dmm)), 3)
         lsc = abi.ls_params(abi.LS_CG, mItr=100, relTol=1e-10)
-        e.timer_mark(0)
-        _, oc, _ = e.solve(3, abi.LS_CG, lsc, np.ones(1, np.int32), np.zeros(1), want_solution=False)
-        e.timer_mark(1)
-        cg_ms = e.timer_elapsed() / max(oc.RI.itr, 1)
+        for rep in range(2):
+            e.alloc(3); e.assemble(2, eqm, dmm)
+            e.timer_mark(0)
+            _, oc, _ = e.solve(3, abi.LS_CG, lsc, np.ones(1, np.int32), np.zeros(1), want_solution=False)
+            e.timer_mark(1)
+            cg_ms = e.timer_elapsed() / max(oc.RI.itr, 1)
     finally:
         e.close()
     nnz = len(cp)
