@@ -212,7 +212,7 @@ assemble_fluid_tet4_grouped_kernel(const __grid_constant__ FluidArgs P)
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  const int g = P.gperm ? __ldg(P.gperm + P.g0 + blockIdx.x) : (int)blockIdx.x;
+  const int g = P.gperm ? __ldg(P.gperm + P.g0 + blockIdx.x) : P.g0 + (int)blockIdx.x;
   double* T = tiles + (tid >> 5) * 32 * TILE_LD;
   // the group's plan goes to shared memory with cp.async (lands while phase 1 computes)
   {
@@ -376,7 +376,9 @@ static int launch_grouped(svb200_ctx* ctx, const FluidArgs& args)
                                   (int)smem));
     configured = true;
   }
-  const int nGrp = args.gperm ? args.nGrpLaunch : (args.e1 + ASM_GROUP - 1) / ASM_GROUP;
+  // gperm: the groups gperm[g0 .. g0 + nGrpLaunch) (one group colour); else nGrpLaunch > 0: the group range [g0, g0 + nGrpLaunch)
+  // (chunked launches behind the overlapped zeroing of Val); else all groups
+  const int nGrp = (args.gperm || args.nGrpLaunch > 0) ? args.nGrpLaunch : (args.e1 + ASM_GROUP - 1) / ASM_GROUP;
   if (nGrp <= 0) return SVB200_OK;
   assemble_fluid_tet4_grouped_kernel<NN><<<nGrp, ASM_GROUP, smem, ctx->stream>>>(args);
   ctx->launches++;

@@ -16,6 +16,7 @@
 //                                        target, ascending (=> a fixed summation order).
 // Built by one CTA per group: bitonic sort of (target, id) keys in shared memory, run twice
 // (count, host prefix sum over groups, fill).
+#include <algorithm>
 #include "svb200_internal.h"
 
 namespace svb {
@@ -210,6 +211,49 @@ static int build_one(svb200_ctx* ctx, const Mesh& m, GroupSched& S)
   ctx->launches++;
   SVB_CUDA(cudaGetLastError());
   SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SVB200_OK;
+}
+
+// Highest CSR slot each 128-element group adds to (one CTA per group, max over its elements' 16 slots).
+__global__ void __launch_bounds__(ASM_GROUP) group_max_slot_kernel(const int* __restrict__ slot, int nEl, int* __restrict__ gmax)
+{
+  __shared__ int red[ASM_GROUP];
+  const long long e = (long long)blockIdx.x * ASM_GROUP + threadIdx.x;
+  int mx = -1;
+  if (e < nEl)
+    for (int k = 0; k < 16; k++) mx = max(mx, slot[e * 16 + k]);
+  red[threadIdx.x] = mx;
+  __syncthreads();
+  for (int o = ASM_GROUP / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] = max(red[threadIdx.x], red[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) gmax[blockIdx.x] = red[0];
+}
+
+// grp_need[g] = 1 + the highest slot any of the groups 0..g adds to: Val[0, grp_need[g]) must be zero before group g runs.
+// On a mesh whose numbering has locality this grows with g, so the zeroing of Val can run AHEAD of the element kernel on a
+// second stream instead of in front of it (run_assemble, svb200_api.cu).
+int build_group_slot_need(svb200_ctx* ctx, Mesh& m)
+{
+  m.grp_need.clear();
+  if (m.eNoN != 4 || m.nEl == 0 || !m.d_slot) return SVB200_OK;
+  const int nGrp = (m.nEl + ASM_GROUP - 1) / ASM_GROUP;
+  int* d_gmax = nullptr;
+  SVB_CUDA(cudaMalloc(&d_gmax, sizeof(int) * nGrp));
+  group_max_slot_kernel<<<nGrp, ASM_GROUP, 0, ctx->stream>>>(m.d_slot, m.nEl, d_gmax);
+  ctx->launches++;
+  std::vector<int> gmax(nGrp);
+  cudaError_t e = cudaMemcpyAsync(gmax.data(), d_gmax, sizeof(int) * nGrp, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_gmax);
+  if (e != cudaSuccess) return cuda_fail(e, "build_group_slot_need", __FILE__, __LINE__);
+  m.grp_need.resize(nGrp);
+  long long run = 0;
+  for (int g = 0; g < nGrp; g++) {
+    run = std::max(run, (long long)gmax[g] + 1);
+    m.grp_need[g] = run;
+  }
   return SVB200_OK;
 }
 

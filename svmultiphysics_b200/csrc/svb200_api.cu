@@ -213,6 +213,8 @@ int svb200_create(svb200_ctx** out, int device)
   SVB_CUDA(cudaEventCreate(&ctx->ev1));
   SVB_CUDA(cudaEventCreate(&ctx->tm0));
   SVB_CUDA(cudaEventCreate(&ctx->tm1));
+  SVB_CUDA(cudaStreamCreateWithFlags(&ctx->zstream, cudaStreamNonBlocking));
+  for (auto& e : ctx->zev) SVB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   SVB_CUDA(cudaMallocHost(&ctx->h_pinned, sizeof(double) * 1024));
   *out = ctx;
   return SVB200_OK;
@@ -239,10 +241,28 @@ int svb200_destroy(svb200_ctx* ctx)
   cudaFreeHost(ctx->h_pinned); cudaFreeHost(ctx->h_cg); cudaFree(ctx->d_cg);
   for (int k = 0; k < 2; k++) if (ctx->ev_cg[k]) cudaEventDestroy(ctx->ev_cg[k]);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+  for (auto& e : ctx->zev) if (e) cudaEventDestroy(e);
+  if (ctx->zstream) { cudaStreamSynchronize(ctx->zstream); cudaStreamDestroy(ctx->zstream); }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return SVB200_OK;
 }
+
+}  // extern "C"
+
+namespace svb {
+// svb200_alloc may defer the zeroing of Val (val_zero_pending): whoever touches Val next zeroes it first.
+int flush_val_zero(svb200_ctx* ctx)
+{
+  if (!ctx->val_zero_pending) return SVB200_OK;
+  ctx->val_zero_pending = false;
+  const size_t nV = (size_t)ctx->dof * ctx->dof * ctx->nnz;
+  if (nV) SVB_CUDA(cudaMemsetAsync(ctx->d_Val, 0, sizeof(double) * nV, ctx->stream));
+  return SVB200_OK;
+}
+}  // namespace svb
+
+extern "C" {
 
 int svb200_comm_unique_id(void* id128)
 {
@@ -368,6 +388,7 @@ int svb200_set_mesh(svb200_ctx* ctx, int32_t iM, int32_t eNoN, int32_t nEl, cons
   m.Nx.assign(Nx, Nx + (size_t)3 * eNoN * nG);
   TRY(launch_build_slot_map(ctx, m));
   TRY(build_group_schedules(ctx, m));
+  TRY(build_group_slot_need(ctx, m));
   TRY(build_coloring(ctx, m, ien));
   TRY(upload_fluid_gen_tables(ctx, m));
   m.set = true;
@@ -496,7 +517,14 @@ int svb200_alloc(svb200_ctx* ctx, int32_t dof)
   }
   ctx->dof = dof;
   if (nR) SVB_CUDA(cudaMemsetAsync(ctx->d_R, 0, sizeof(double) * nR, ctx->stream));
-  if (nV) SVB_CUDA(cudaMemsetAsync(ctx->d_Val, 0, sizeof(double) * nV, ctx->stream));
+  // Val (3.3 GB at 10 M tets) is zeroed lazily: the TET4 fluid assembly overlaps the zeroing with its first chunk of elements
+  // (run_assemble); every other consumer of Val zeroes it in full first (flush_val_zero).  SVB200_EAGER_ZERO=1: zero here.
+  static const bool eager_zero = getenv("SVB200_EAGER_ZERO") != nullptr;
+  ctx->val_zero_pending = false;
+  if (nV) {
+    if (eager_zero) SVB_CUDA(cudaMemsetAsync(ctx->d_Val, 0, sizeof(double) * nV, ctx->stream));
+    else ctx->val_zero_pending = true;
+  }
   // com_mod.Kd is zeroed with the linear system (solver/Integrator.cpp:106-109)
   if (ctx->d_Kd && ctx->nnz) SVB_CUDA(cudaMemsetAsync(ctx->d_Kd, 0, sizeof(double) * 12 * (size_t)ctx->nnz, ctx->stream));
   if (ctx->d_Rd && ctx->nNo) SVB_CUDA(cudaMemsetAsync(ctx->d_Rd, 0, sizeof(double) * 3 * (size_t)ctx->nNo, ctx->stream));
@@ -609,6 +637,7 @@ static int run_assemble(svb200_ctx* ctx, const Mesh& m, FluidArgs& A, bool gener
   // linear tetrahedra have their own kernel (constant gradients, no second derivatives); everything else, or
   // SVB200_EQ_GENERAL_KERNEL, goes through the per-Gauss-point kernel of assemble_fluid_gen.cu
   if (m.eNoN != 4 || general) {
+    TRY(flush_val_zero(ctx));
     TRY(run_assemble_fluid_gen(ctx, m, A));
     return check_jacobian_word(ctx, A.ale != 0);
   }
@@ -617,7 +646,37 @@ static int run_assemble(svb200_ctx* ctx, const Mesh& m, FluidArgs& A, bool gener
     TRY(check_jacobian_word(ctx, A.ale != 0));
     m.jac_checked = true;
   }
-  if (A.atomic) return launch_assemble_fluid(ctx, m, A);
+  if (A.atomic) {
+    static const bool legacy = getenv("SVB200_ASM_LEGACY") != nullptr;
+    const int nGrp = (m.nEl + ASM_GROUP - 1) / ASM_GROUP;
+    if (ctx->val_zero_pending && !legacy && A.kU_ptr && (int)m.grp_need.size() == nGrp && nGrp >= 64) {
+      // Overlapped zeroing: Val is zeroed on a second stream while the first chunk of element groups runs.  Chunk 0 = the
+      // first ~1/7 of the groups (its kernel time covers the rest of the memset); it waits only for the part of Val its groups
+      // add to (grp_need), chunk 1 for all of it.
+      ctx->val_zero_pending = false;
+      const long long nnz = ctx->nnz;
+      const size_t blk = sizeof(double) * 16;
+      const int g1 = std::max(1, nGrp / 7);
+      const long long need0 = std::min(nnz, m.grp_need[g1 - 1]);
+      SVB_CUDA(cudaEventRecord(ctx->zev[0], ctx->stream));               // Val's previous readers (the last solve) are done
+      SVB_CUDA(cudaStreamWaitEvent(ctx->zstream, ctx->zev[0], 0));
+      if (need0 > 0) SVB_CUDA(cudaMemsetAsync(ctx->d_Val, 0, blk * need0, ctx->zstream));
+      SVB_CUDA(cudaEventRecord(ctx->zev[1], ctx->zstream));
+      if (nnz > need0) SVB_CUDA(cudaMemsetAsync(ctx->d_Val + 16 * need0, 0, blk * (nnz - need0), ctx->zstream));
+      SVB_CUDA(cudaEventRecord(ctx->zev[2], ctx->zstream));
+      SVB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->zev[1], 0));
+      A.g0 = 0; A.nGrpLaunch = g1;
+      TRY(launch_assemble_fluid(ctx, m, A));
+      SVB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->zev[2], 0));
+      A.g0 = g1; A.nGrpLaunch = nGrp - g1;
+      if (A.nGrpLaunch > 0) TRY(launch_assemble_fluid(ctx, m, A));
+      A.g0 = 0; A.nGrpLaunch = 0;
+      return SVB200_OK;
+    }
+    TRY(flush_val_zero(ctx));
+    return launch_assemble_fluid(ctx, m, A);
+  }
+  TRY(flush_val_zero(ctx));
   // deterministic mode: the grouped kernel, one launch per GROUP colour (SVB200_ASM_LEGACY=1: per-element colours, plain RMW)
   static const bool legacy_colored = getenv("SVB200_ASM_LEGACY") != nullptr;
   if (!legacy_colored && A.kU_ptr && m.d_gcolor_perm && !m.gcolor_off.empty()) {
@@ -682,6 +741,7 @@ int svb200_assemble_neu(svb200_ctx* ctx, int32_t iFa, const svb200_eqparams* eq,
   SVB_REQUIRE(iFa >= 0 && iFa < (int)ctx->bface.size() && ctx->bface[iFa].set, "svb200_assemble_neu: face not set");
   SVB_REQUIRE(ctx->d_R && ctx->d_Val, "svb200_assemble_neu: call svb200_alloc first");
   TRY(upload_nodal(ctx, 1, hg, &ctx->d_hg));
+  TRY(flush_val_zero(ctx));
   return run_assemble_neu(ctx, ctx->bface[iFa], eq, dmn, nDmn, ctx->d_hg);
 }
 
@@ -846,6 +906,8 @@ int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, cons
   SVB_REQUIRE(ctx->d_R && ctx->d_Val, "svb200_assemble: call svb200_alloc first");
   const Mesh& m = ctx->mesh[iM];
   SVB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  // a deferred zeroing of Val (svb200_alloc) is consumed by the TET4 fluid path; every other kernel needs Val zeroed first
+  if (eq->phys != SVB200_PHYS_FLUID && eq->phys != SVB200_PHYS_FSI) TRY(flush_val_zero(ctx));
   switch (eq->phys) {
     case SVB200_PHYS_FLUID: {
       FluidArgs A;
@@ -876,6 +938,7 @@ int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, cons
         TRY(fill_fluid_args(ctx, m, eq, dmn, nDmn, A));
         TRY(run_assemble(ctx, m, A, (eq->reserved & SVB200_EQ_GENERAL_KERNEL) != 0));
       }
+      TRY(flush_val_zero(ctx));
       if (anySolid) TRY(run_assemble_struct(ctx, m, eq, dmn, nDmn));
     } break;
     case SVB200_PHYS_MESH:
@@ -951,6 +1014,7 @@ int svb200_add_host_contrib(svb200_ctx* ctx, int32_t dof, int32_t nR, const int3
 {
   CTX_GUARD(ctx);
   SVB_REQUIRE(dof == ctx->dof && ctx->d_R && ctx->d_Val, "svb200_add_host_contrib: call svb200_alloc(dof) first");
+  TRY(flush_val_zero(ctx));
   if (nR > 0) {
     SVB_REQUIRE(rows && R_add, "svb200_add_host_contrib: null residual arrays");
     std::vector<int> r(nR);
@@ -1022,6 +1086,7 @@ int svb200_solve(svb200_ctx* ctx, int32_t dof, int32_t ls_type, int32_t prec, co
   SVB_REQUIRE(dof == ctx->dof && ctx->d_R && ctx->d_Val, "svb200_solve: call svb200_alloc(dof) and assemble first");
   SVB_REQUIRE(prec == SVB200_PREC_FSILS || prec == SVB200_PREC_RCS, "svb200_solve: preconditioner must be SVB200_PREC_FSILS or SVB200_PREC_RCS");
   SVB_REQUIRE(nFaces <= (int)ctx->face.size(), "svb200_solve: nFaces exceeds svb200_set_num_faces");
+  TRY(flush_val_zero(ctx));
   SVB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
   TRY(fsils_solve_device(ctx, dof, ls_type, prec, ls, nFaces, incL, res, result));
   SVB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -1088,6 +1153,7 @@ int svb200_download(svb200_ctx* ctx, int32_t what, double* dst)
       return download_nodal(ctx, ctx->dof, ctx->d_R, dst);
     case SVB200_ARRAY_VAL:
       SVB_REQUIRE(ctx->d_Val, "svb200_download: Val not allocated");
+      TRY(flush_val_zero(ctx));
       return copy_val(ctx, ctx->dof, dst, true);
     case SVB200_ARRAY_W:
       SVB_REQUIRE(ctx->d_W, "svb200_download: W not computed yet");
@@ -1114,7 +1180,7 @@ int svb200_download_rows(svb200_ctx* ctx, int32_t what, int32_t n, const int32_t
   switch (what) {
     case SVB200_ARRAY_R: src = ctx->d_R; d2 = ctx->dof; break;
     case SVB200_ARRAY_W: src = ctx->d_W; d2 = ctx->dof; break;
-    case SVB200_ARRAY_VAL: src = ctx->d_Val; d2 = ctx->dof * ctx->dof; blocks = true; break;
+    case SVB200_ARRAY_VAL: TRY(flush_val_zero(ctx)); src = ctx->d_Val; d2 = ctx->dof * ctx->dof; blocks = true; break;
     case SVB200_ARRAY_KD: src = ctx->d_Kd; d2 = 12; blocks = true; break;
     default: set_error("svb200_download_rows: unknown array id"); return SVB200_ERR_INVALID;
   }
@@ -1148,7 +1214,7 @@ int svb200_upload(svb200_ctx* ctx, int32_t what, int32_t dof, const double* src)
   SVB_REQUIRE(dof == ctx->dof && ctx->d_R && ctx->d_Val, "svb200_upload: call svb200_alloc(dof) first");
   switch (what) {
     case SVB200_ARRAY_R: return upload_nodal(ctx, dof, src, &ctx->d_R);
-    case SVB200_ARRAY_VAL: return copy_val(ctx, dof, const_cast<double*>(src), false);
+    case SVB200_ARRAY_VAL: ctx->val_zero_pending = false; return copy_val(ctx, dof, const_cast<double*>(src), false);
     case SVB200_ARRAY_RD: return upload_nodal(ctx, 3, src, &ctx->d_Rd);
   }
   set_error("svb200_upload: unknown array id");
@@ -1160,6 +1226,7 @@ int svb200_spmv(svb200_ctx* ctx, int32_t dof, const double* U, double* KU)
   CTX_GUARD(ctx);
   SVB_REQUIRE(U && KU, "svb200_spmv: null vectors");
   SVB_REQUIRE(dof == ctx->dof && ctx->d_Val, "svb200_spmv: call svb200_alloc(dof) first");
+  TRY(flush_val_zero(ctx));
   const size_t n = (size_t)dof * ctx->nNo;
   double* d_u = nullptr; double* d_ku = nullptr;
   SVB_CUDA(cudaMalloc(&d_u, sizeof(double) * std::max<size_t>(n, 1)));
@@ -1208,6 +1275,7 @@ int svb200_bench_spmv(svb200_ctx* ctx, int32_t dof, int32_t reps, double* ms_per
   CTX_GUARD(ctx);
   SVB_REQUIRE(ms_per_launch && reps >= 1, "svb200_bench_spmv: bad arguments");
   SVB_REQUIRE(dof == ctx->dof && ctx->d_Val, "svb200_bench_spmv: call svb200_alloc(dof) first");
+  TRY(flush_val_zero(ctx));
   const size_t n = (size_t)dof * ctx->nNo;
   double* d_u = nullptr; double* d_ku = nullptr;
   SVB_CUDA(cudaMalloc(&d_u, sizeof(double) * std::max<size_t>(n, 1)));

@@ -44,6 +44,8 @@ struct Mesh {
   std::vector<int> color_off;    // offsets into d_color_perm per colour
   int* d_gcolor_perm = nullptr;  // TET4: ids of the 128-element groups of the grouped scatter, sorted by GROUP colour
   std::vector<int> gcolor_off;   // offsets into d_gcolor_perm per group colour (groups of one colour share no node)
+  std::vector<long long> grp_need;   // TET4: running max over groups 0..g of (highest CSR slot the group adds to) + 1 — how far Val
+                                     // must be zeroed before group g may run (overlapped zeroing, svb200_api.cu run_assemble)
   std::vector<double> w, N, Nx;  // host copies of the reference-element tables
   std::vector<double> Nxx;       // (6,eNoN,nG) second parametric derivatives (svb200_set_mesh_nxx), empty = all zero
   double* d_gtab = nullptr;      // tables in the layout of assemble_fluid_gen.cu
@@ -164,6 +166,10 @@ struct svb200_ctx {
   double* d_R = nullptr;
   double* d_Val = nullptr;
   size_t R_cap = 0, Val_cap = 0;   // capacities in doubles
+  bool val_zero_pending = false;   // svb200_alloc deferred the zeroing of Val: the next consumer zeroes it (overlapped with the first
+                                   // chunk of the TET4 fluid kernel, or in full before anything else touches Val)
+  cudaStream_t zstream = nullptr;  // stream of the overlapped zeroing
+  cudaEvent_t zev[4] = {nullptr, nullptr, nullptr, nullptr};
   double* d_W = nullptr;           // (dof,nNo) preconditioner scaling
   double* d_Kd = nullptr;          // (12,nnz) displacement tangent of the ustruct equation (com_mod.Kd), assemble_ustruct.cu
   double* d_Ad = nullptr;          // (3,nNo) com_mod.Ad: time derivative of the displacement (ustruct)
@@ -204,6 +210,7 @@ namespace svb {
 
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+int flush_val_zero(svb200_ctx* ctx);     // svb200_api.cu: zero Val now if svb200_alloc deferred it
 
 #define SVB_CUDA(call)                                                             \
   do {                                                                             \
@@ -243,6 +250,7 @@ int launch_set_rows(svb200_ctx* ctx, int row0, int nrow, int n, const int* d_nod
 int launch_dirichlet_ustruct(svb200_ctx* ctx, const svb200_eqtime* eq, double dt, int n, const int* d_nodes, int dir_mask, int impD);
 // group_sched.cu
 int build_group_schedules(svb200_ctx* ctx, Mesh& m);
+int build_group_slot_need(svb200_ctx* ctx, Mesh& m);
 void free_group_sched(GroupSched& S);
 // graph_kernels.cu
 int launch_build_slot_map(svb200_ctx* ctx, Mesh& m);
