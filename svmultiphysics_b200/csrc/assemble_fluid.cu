@@ -290,38 +290,50 @@ assemble_fluid_tet4_grouped_kernel(const __grid_constant__ FluidArgs P)
   __syncthreads();
 
   // ---- phase 3: one thread per distinct diagonal block / edge (both blocks of the edge) ----------------------
+  // The contributions of the group's elements are accumulated in the bilinear form of fluid_elem.cuh (EdgeAcc / DiagAcc)
+  // and the 4x4 blocks are assembled once per target (SVB200_ASM_BLOCKWISE=1 at build time restores the per-contribution
+  // block form).
   {
     for (int k0 = (tid & ~31); k0 < G; k0 += ASM_GROUP) {   // warp-uniform trip count
       const int k = k0 + lane;
       int slot1 = -1, slot2 = -1;
-      double K1[16], K2[16];
+      double K1[16];
+      bool isEdge = false;
+      EdgeAcc EA;
       if (k < G) {
         const int2 ent = k < ENT_CACHE ? entc[k] : __ldg(P.kU_ent + ub + k);
         const int partner = k < ENT_CACHE ? entp[k] : __ldg(P.kU_partner + ub + k);
         const int start = ent.y & 0xFFFF, end = start + (ent.y >> 16);
-#pragma unroll
-        for (int i = 0; i < 16; i++) { K1[i] = 0.0; K2[i] = 0.0; }
         if (partner >= 0) {
+          isEdge = true;
+          edge_acc_zero(EA, NN);
           for (int c = start; c < end; c++) {
             const int id = ctr[c];
             const int el = id >> 4;
             if (!allActive && !act[el]) continue;
             slot1 = ent.x;
             slot2 = partner;
-            tet4_edge_rec_add(rec + el * RS, NN, (id >> 2) & 3, id & 3, K1, K2);
+            tet4_edge_rec_acc(rec + el * RS, NN, (id >> 2) & 3, id & 3, EA);
           }
+          edge_acc_block(EA, NN, 0, K1);
         } else {
+          DiagAcc DA;
+          diag_acc_zero(DA, NN);
           for (int c = start; c < end; c++) {
             const int id = ctr[c];
             const int el = id >> 4;
             if (!allActive && !act[el]) continue;
             slot1 = ent.x;
-            tet4_block_rec_add(rec + el * RS, NN, id & 3, id & 3, K1);
+            tet4_diag_rec_acc(rec + el * RS, NN, id & 3, DA);
           }
+          diag_acc_block(DA, NN, K1);
         }
       }
       red_blocks(P.Val, T, lane, slot1, K1);
-      if (__any_sync(0xffffffffu, slot2 >= 0)) red_blocks(P.Val, T, lane, slot2, K2);
+      if (__any_sync(0xffffffffu, slot2 >= 0)) {
+        if (isEdge) edge_acc_block(EA, NN, 1, K1);
+        red_blocks(P.Val, T, lane, slot2, K1);
+      }
     }
   }
 }

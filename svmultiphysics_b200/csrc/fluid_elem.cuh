@@ -667,4 +667,162 @@ SVB_HD void tet4_edge_rec_add(const double* r, const bool NN, const int a, const
   }
 }
 
+// =====================================================================================================
+// Accumulator form of the two routines above, used by the grouped scatter since round 2.  A thread that owns an
+// edge sums the contributions of ~5 elements; instead of forming both 4x4 blocks per element (about 90 flops each way)
+// it accumulates the BILINEAR pieces the blocks are made of and assembles the two blocks once at the end:
+//   P(p,q) += A1 xa_p xb_q,  Q(p,q) += A2 xa_p xb_q     =>  K1_uu(i,j) = P(j,i) + Q(i,j),  K2_uu = K1_uu^T,
+//   sum A1 (grad Na . grad Nb) = tr P                    (the diagonal term needs no extra work),
+//   T1 += xb Sb_a, T2 += xa Sb_b, T3 += xb S2_a, T4 += xa S3_b, T5 += xa S2_b, T6 += xb S3_a
+//                                                        =>  K1_up = T3 - T2, K1_pu = T1 - T4, K2_up = T5 - T1, K2_pu = T2 - T6,
+// 48 flops per contribution instead of ~90; same terms, different association (agreement with the reference stays at 1e-15).
+struct EdgeAcc {
+  double P[9], Q[9], T[18], E[9];
+  double dd1, dd2, pp;
+};
+
+SVB_HD void edge_acc_zero(EdgeAcc& A, const bool NN)
+{
+#pragma unroll
+  for (int k = 0; k < 9; k++) { A.P[k] = 0.0; A.Q[k] = 0.0; }
+#pragma unroll
+  for (int k = 0; k < 18; k++) A.T[k] = 0.0;
+  if (NN) {
+#pragma unroll
+    for (int k = 0; k < 9; k++) A.E[k] = 0.0;
+  }
+  A.dd1 = 0.0; A.dd2 = 0.0; A.pp = 0.0;
+}
+
+SVB_HD void tet4_edge_rec_acc(const double* r, const bool NN, const int a, const int b, EdgeAcc& A)
+{
+  const double xa[3] = {r[O_NX + 3 * a], r[O_NX + 3 * a + 1], r[O_NX + 3 * a + 2]};
+  const double xb[3] = {r[O_NX + 3 * b], r[O_NX + 3 * b + 1], r[O_NX + 3 * b + 2]};
+  const double A1 = r[O_A1], A2 = r[O_A2];
+#pragma unroll
+  for (int p = 0; p < 3; p++) {
+    const double a1 = A1 * xa[p], a2 = A2 * xa[p];
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      A.P[3 * p + q] += a1 * xb[q];
+      A.Q[3 * p + q] += a2 * xb[q];
+    }
+  }
+  A.dd1 += r[O_D + 4 * a + b];
+  A.dd2 += r[O_D + 4 * b + a];
+  A.pp += r[O_SPP] * (xa[0] * xb[0] + xa[1] * xb[1] + xa[2] * xb[2]);
+  const double Sba = r[O_SB + a], Sbb = r[O_SB + b];
+  const double S2a = r[O_S2 + a], S2b = r[O_S2 + b], S3a = r[O_S3 + a], S3b = r[O_S3 + b];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    A.T[i] += xb[i] * Sba;
+    A.T[3 + i] += xa[i] * Sbb;
+    A.T[6 + i] += xb[i] * S2a;
+    A.T[9 + i] += xa[i] * S3b;
+    A.T[12 + i] += xa[i] * S2b;
+    A.T[15 + i] += xb[i] * S3a;
+  }
+  if (NN) {
+    const double A3 = r[O_A3];
+    if (A3 != 0.0) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const double t = A3 * r[O_ES + 3 * a + i];
+#pragma unroll
+        for (int j = 0; j < 3; j++) A.E[3 * i + j] += t * r[O_ES + 3 * b + j];
+      }
+    }
+  }
+}
+
+// which = 0: lK(:,a,b); which = 1: lK(:,b,a) of the accumulated edge.
+SVB_HD void edge_acc_block(const EdgeAcc& A, const bool NN, const int which, double K[16])
+{
+  const double trP = A.P[0] + A.P[4] + A.P[8];
+  const double dd = (which == 0 ? A.dd1 : A.dd2) + trP;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      // K1(i,j) = P(j,i) + Q(i,j);  K2(i,j) = K1(j,i)
+      double v = (which == 0) ? A.P[3 * j + i] + A.Q[3 * i + j] : A.P[3 * i + j] + A.Q[3 * j + i];
+      if (NN) v += (which == 0) ? A.E[3 * i + j] : A.E[3 * j + i];
+      if (i == j) v += dd;
+      K[4 * i + j] = v;
+    }
+    K[4 * i + 3] = (which == 0) ? A.T[6 + i] - A.T[3 + i] : A.T[12 + i] - A.T[i];
+    K[12 + i] = (which == 0) ? A.T[i] - A.T[9 + i] : A.T[3 + i] - A.T[15 + i];
+  }
+  K[15] = A.pp;
+}
+
+// Diagonal block (a, a): W = (A1 + A2) xa xa^T is symmetric.
+struct DiagAcc {
+  double S[6];       // (00, 01, 02, 11, 12, 22) of sum (A1 + A2) xa xa^T
+  double up[3], pu[3], E[9];
+  double dd, pp;
+};
+
+SVB_HD void diag_acc_zero(DiagAcc& A, const bool NN)
+{
+#pragma unroll
+  for (int k = 0; k < 6; k++) A.S[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { A.up[k] = 0.0; A.pu[k] = 0.0; }
+  if (NN) {
+#pragma unroll
+    for (int k = 0; k < 9; k++) A.E[k] = 0.0;
+  }
+  A.dd = 0.0; A.pp = 0.0;
+}
+
+SVB_HD void tet4_diag_rec_acc(const double* r, const bool NN, const int a, DiagAcc& A)
+{
+  const double xa[3] = {r[O_NX + 3 * a], r[O_NX + 3 * a + 1], r[O_NX + 3 * a + 2]};
+  const double A1 = r[O_A1], A2 = r[O_A2];
+  const double c = A1 + A2;
+  const double c0 = c * xa[0], c1 = c * xa[1], c2 = c * xa[2];
+  A.S[0] += c0 * xa[0]; A.S[1] += c0 * xa[1]; A.S[2] += c0 * xa[2];
+  A.S[3] += c1 * xa[1]; A.S[4] += c1 * xa[2]; A.S[5] += c2 * xa[2];
+  const double nn = xa[0] * xa[0] + xa[1] * xa[1] + xa[2] * xa[2];
+  A.dd += r[O_D + 5 * a] + A1 * nn;
+  A.pp += r[O_SPP] * nn;
+  const double Sba = r[O_SB + a];
+  const double du = r[O_S2 + a] - Sba, dp = Sba - r[O_S3 + a];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    A.up[i] += xa[i] * du;
+    A.pu[i] += xa[i] * dp;
+  }
+  if (NN) {
+    const double A3 = r[O_A3];
+    if (A3 != 0.0) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const double t = A3 * r[O_ES + 3 * a + i];
+#pragma unroll
+        for (int j = 0; j < 3; j++) A.E[3 * i + j] += t * r[O_ES + 3 * a + j];
+      }
+    }
+  }
+}
+
+SVB_HD void diag_acc_block(const DiagAcc& A, const bool NN, double K[16])
+{
+  const double S[3][3] = {{A.S[0], A.S[1], A.S[2]}, {A.S[1], A.S[3], A.S[4]}, {A.S[2], A.S[4], A.S[5]}};
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      double v = S[i][j];
+      if (NN) v += A.E[3 * i + j];
+      if (i == j) v += A.dd;
+      K[4 * i + j] = v;
+    }
+    K[4 * i + 3] = A.up[i];
+    K[12 + i] = A.pu[i];
+  }
+  K[15] = A.pp;
+}
+
 }  // namespace svb

@@ -251,6 +251,23 @@ int svb200_destroy(svb200_ctx* ctx)
 }  // extern "C"
 
 namespace svb {
+// Zeroing with a footprint of ONE warp per SM (148 CTAs x 32 threads, <= 32 registers): cudaMemsetAsync launches a grid
+// that fills the machine, so a kernel on another stream cannot start until it has drained; this kernel leaves room
+// (1024 registers are exactly what three resident CTAs of the 168-register assembly kernel leave free on an SM) for the
+// element kernel to run beside it.  Stores are fire-and-forget, so one warp per SM saturates the HBM write bandwidth.
+__global__ void __launch_bounds__(128, 1) zero_small_footprint_kernel(double2* __restrict__ p, long long n2)
+{
+  const double2 z = make_double2(0.0, 0.0);
+  const int nt = blockDim.x;
+  const long long stride = (long long)gridDim.x * nt * 4;
+  for (long long k = (long long)blockIdx.x * nt * 4 + threadIdx.x; k < n2; k += stride) {
+    p[k] = z;
+    if (k + nt < n2) p[k + nt] = z;
+    if (k + 2 * nt < n2) p[k + 2 * nt] = z;
+    if (k + 3 * nt < n2) p[k + 3 * nt] = z;
+  }
+}
+
 // svb200_alloc may defer the zeroing of Val (val_zero_pending): whoever touches Val next zeroes it first.
 int flush_val_zero(svb200_ctx* ctx)
 {
@@ -517,12 +534,15 @@ int svb200_alloc(svb200_ctx* ctx, int32_t dof)
   }
   ctx->dof = dof;
   if (nR) SVB_CUDA(cudaMemsetAsync(ctx->d_R, 0, sizeof(double) * nR, ctx->stream));
-  // Val (3.3 GB at 10 M tets) is zeroed lazily: the TET4 fluid assembly overlaps the zeroing with its first chunk of elements
-  // (run_assemble); every other consumer of Val zeroes it in full first (flush_val_zero).  SVB200_EAGER_ZERO=1: zero here.
-  static const bool eager_zero = getenv("SVB200_EAGER_ZERO") != nullptr;
+  // Val (3.3 GB at 10 M tets) is zeroed here.  SVB200_LAZY_ZERO=1 defers it so that the TET4 fluid assembly overlaps the zeroing
+  // with its first chunk of elements (run_assemble; every other consumer of Val then zeroes it in full first, flush_val_zero).
+  // Measured on B200 (profiles/r2k_zero_overlap_ab.txt): the one-warp-per-SM zeroing kernel does reach 6.4 TB/s beside the element
+  // kernel, but the assembly stage does not get shorter (4.87-4.94 ms against 4.86-4.93 ms): the chip sits at its power cap during
+  // this FP64-heavy stage, so the stage is bound by the energy of the work, which overlapping does not change.  Kept as an option.
+  static const bool lazy_zero = getenv("SVB200_LAZY_ZERO") != nullptr;
   ctx->val_zero_pending = false;
   if (nV) {
-    if (eager_zero) SVB_CUDA(cudaMemsetAsync(ctx->d_Val, 0, sizeof(double) * nV, ctx->stream));
+    if (!lazy_zero) SVB_CUDA(cudaMemsetAsync(ctx->d_Val, 0, sizeof(double) * nV, ctx->stream));
     else ctx->val_zero_pending = true;
   }
   // com_mod.Kd is zeroed with the linear system (solver/Integrator.cpp:106-109)
@@ -656,13 +676,27 @@ static int run_assemble(svb200_ctx* ctx, const Mesh& m, FluidArgs& A, bool gener
       ctx->val_zero_pending = false;
       const long long nnz = ctx->nnz;
       const size_t blk = sizeof(double) * 16;
-      const int g1 = std::max(1, nGrp / 7);
+      static const int zfrac = getenv("SVB200_ZERO_CHUNK0_DIV") ? atoi(getenv("SVB200_ZERO_CHUNK0_DIV")) : 7;
+      const int g1 = std::max(1, nGrp / std::max(zfrac, 2));
       const long long need0 = std::min(nnz, m.grp_need[g1 - 1]);
       SVB_CUDA(cudaEventRecord(ctx->zev[0], ctx->stream));               // Val's previous readers (the last solve) are done
       SVB_CUDA(cudaStreamWaitEvent(ctx->zstream, ctx->zev[0], 0));
       if (need0 > 0) SVB_CUDA(cudaMemsetAsync(ctx->d_Val, 0, blk * need0, ctx->zstream));
       SVB_CUDA(cudaEventRecord(ctx->zev[1], ctx->zstream));
-      if (nnz > need0) SVB_CUDA(cudaMemsetAsync(ctx->d_Val + 16 * need0, 0, blk * (nnz - need0), ctx->zstream));
+      if (nnz > need0) {
+        static const bool plain_memset = getenv("SVB200_ZERO_MEMSET") != nullptr;      // A/B knob
+        if (plain_memset) {
+          SVB_CUDA(cudaMemsetAsync(ctx->d_Val + 16 * need0, 0, blk * (nnz - need0), ctx->zstream));
+        } else {
+          int nsm = 148;
+          cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+          static const int zthreads = getenv("SVB200_ZERO_THREADS") ? atoi(getenv("SVB200_ZERO_THREADS")) : 32;   // tuning knobs
+          static const int zmult = getenv("SVB200_ZERO_CTAS_PER_SM") ? atoi(getenv("SVB200_ZERO_CTAS_PER_SM")) : 1;
+          zero_small_footprint_kernel<<<nsm * zmult, zthreads, 0, ctx->zstream>>>(reinterpret_cast<double2*>(ctx->d_Val + 16 * need0),
+                                                                                   8 * (nnz - need0));
+          ctx->launches++;
+        }
+      }
       SVB_CUDA(cudaEventRecord(ctx->zev[2], ctx->zstream));
       SVB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->zev[1], 0));
       A.g0 = 0; A.nGrpLaunch = g1;

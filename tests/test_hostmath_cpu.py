@@ -35,7 +35,8 @@ def hostmath():
     return lib
 
 
-@pytest.mark.parametrize("variant", ["hostmath_fluid_tet4", "hostmath_fluid_tet4_staged"], ids=["hoisted", "staged"])
+@pytest.mark.parametrize("variant", ["hostmath_fluid_tet4", "hostmath_fluid_tet4_staged", "hostmath_fluid_tet4_acc"],
+                         ids=["hoisted", "staged", "accumulator_form"])
 @pytest.mark.parametrize("case", common.FLUID_CASES, ids=[c[0] for c in common.FLUID_CASES])
 def test_device_element_algebra_matches_golden(hostmath, case, variant):
     golden = common.load_golden()
