@@ -260,6 +260,16 @@ SVB200_API int svb200_set_old_disp(svb200_ctx* ctx, int32_t tDof, const double* 
 SVB200_API int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq,
                     const svb200_dmnparams* dmn, int32_t nDmn);
 
+/* The assembly stage for HOST-resident state in one pipelined call: what svb200_set_state(Ag, Yg) + svb200_alloc(dof) +
+ * svb200_assemble + svb200_commu_R + svb200_download(R) do one after the other (the sequence B200LinearAlgebra runs per Newton
+ * iteration), with the transfers hidden behind the element kernel: the nodal state goes up in node chunks on a
+ * copy stream and every chunk of element groups starts as soon as the nodes it reads have arrived; on a single partition the
+ * finished residual rows come back on a third stream while later groups are assembled.  Ag, Yg are (tDof, nNo), R_out (dof, nNo)
+ * or NULL, all in INPUT node order; page-lock them (svb200_host_register) for the copies to be asynchronous.  Pipelined for the
+ * TET4 fluid equation with the atomic scatter; any other equation runs the plain sequence.  Call svb200_alloc(dof) once before. */
+SVB200_API int svb200_assemble_host(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int32_t nDmn,
+                         const double* Ag, const double* Yg, double* R_out);
+
 /* Boundary face iFa of mesh iM (faceType): connectivity IENb(eNoNb,nElb) in input node ids, parent element
  * gE(nElb) (index into the mesh's elements), and the face reference-element tables w(nGb), N(eNoNb,nGb),
  * Nx(2,eNoNb,nGb).  eNoNb = 3 (TRI3 on TET4) or 4 (QUD4 on HEX8). */

@@ -158,13 +158,14 @@ int launch_find_diag(svb200_ctx* ctx)
   return check_flag(ctx, d_err, "CSR graph has a row without a diagonal entry");
 }
 
-int launch_permute_cols(svb200_ctx* ctx, int rows, int n, const int* d_map, const double* src, double* dst, bool inverse)
+int launch_permute_cols(svb200_ctx* ctx, int rows, int n, const int* d_map, const double* src, double* dst, bool inverse,
+                        cudaStream_t stream)
 {
   const long long total = (long long)rows * n;
   if (total == 0) return SVB200_OK;
   const int threads = 256;
-  permute_cols_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, ctx->stream>>>(rows, n, d_map, src, dst,
-                                                                                              inverse ? 1 : 0);
+  permute_cols_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream ? stream : ctx->stream>>>(rows, n, d_map, src, dst,
+                                                                                                                inverse ? 1 : 0);
   ctx->launches++;
   SVB_CUDA(cudaGetLastError());
   return SVB200_OK;

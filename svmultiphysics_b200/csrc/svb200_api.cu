@@ -214,6 +214,8 @@ int svb200_create(svb200_ctx** out, int device)
   SVB_CUDA(cudaEventCreate(&ctx->tm0));
   SVB_CUDA(cudaEventCreate(&ctx->tm1));
   SVB_CUDA(cudaStreamCreateWithFlags(&ctx->zstream, cudaStreamNonBlocking));
+  SVB_CUDA(cudaStreamCreateWithFlags(&ctx->dstream, cudaStreamNonBlocking));
+  for (auto& row : ctx->pev) for (auto& e : row) SVB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : ctx->zev) SVB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   SVB_CUDA(cudaMallocHost(&ctx->h_pinned, sizeof(double) * 1024));
   *out = ctx;
@@ -243,6 +245,8 @@ int svb200_destroy(svb200_ctx* ctx)
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   for (auto& e : ctx->zev) if (e) cudaEventDestroy(e);
   if (ctx->zstream) { cudaStreamSynchronize(ctx->zstream); cudaStreamDestroy(ctx->zstream); }
+  if (ctx->dstream) { cudaStreamSynchronize(ctx->dstream); cudaStreamDestroy(ctx->dstream); }
+  for (auto& row : ctx->pev) for (auto& e : row) if (e) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return SVB200_OK;
@@ -398,6 +402,21 @@ int svb200_set_mesh(svb200_ctx* ctx, int32_t iM, int32_t eNoN, int32_t nEl, cons
     ien[k] = ctx->h_map[IEN[k]];
   }
   TRY(upload(ctx, &m.d_IEN, ien.data(), ien.size()));
+  if (eNoN == 4 && nEl > 0) {
+    // caller-order node window of every 128-element group (svb200_assemble_host pipelines uploads / downloads on it)
+    const int nGrp = (nEl + ASM_GROUP - 1) / ASM_GROUP;
+    std::vector<int> gmax(nGrp, -1), gmin(nGrp, ctx->nNo);
+    for (int e = 0; e < nEl; e++)
+      for (int a = 0; a < 4; a++) {
+        const int n = IEN[(size_t)e * 4 + a], g = e / ASM_GROUP;
+        gmax[g] = std::max(gmax[g], n); gmin[g] = std::min(gmin[g], n);
+      }
+    m.grp_node_need.resize(nGrp); m.grp_node_done.resize(nGrp);
+    int run = 0;
+    for (int g = 0; g < nGrp; g++) { run = std::max(run, gmax[g] + 1); m.grp_node_need[g] = run; }
+    run = ctx->nNo;
+    for (int g = nGrp - 1; g >= 0; g--) { run = std::min(run, gmin[g]); m.grp_node_done[g] = run; }
+  }
   if (eId) TRY(upload(ctx, &m.d_eId, eId, (size_t)nEl));
   if (fN && nFn > 0) TRY(upload(ctx, &m.d_fN, fN, (size_t)3 * nFn * nEl));
   m.w.assign(w, w + nG);
@@ -992,6 +1011,99 @@ int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, cons
   }
   SVB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
   SVB_CUDA(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f;
+  SVB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  ctx->last_assemble_ms = ms;
+  return SVB200_OK;
+}
+
+// The host-resident assembly stage in one pipelined call (see include/svb200.h).
+int svb200_assemble_host(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int32_t nDmn,
+                         const double* Ag, const double* Yg, double* R_out)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(eq && dmn && Ag && Yg, "svb200_assemble_host: null parameters");
+  SVB_REQUIRE(iM >= 0 && iM < (int)ctx->mesh.size() && ctx->mesh[iM].set, "svb200_assemble_host: mesh not set");
+  const Mesh& m = ctx->mesh[iM];
+  const int nGrp = (m.nEl + ASM_GROUP - 1) / ASM_GROUP;
+  static const bool no_pipe = getenv("SVB200_HOST_NO_PIPELINE") != nullptr;       // A/B knob
+  const bool fast = !no_pipe && eq->phys == SVB200_PHYS_FLUID && m.eNoN == 4 && eq->scatter == SVB200_SCATTER_ATOMIC &&
+                    !(eq->reserved & SVB200_EQ_GENERAL_KERNEL) && m.schedK.d_uptr && (int)m.grp_node_need.size() == nGrp && nGrp >= 256 &&
+                    m.jac_checked && ctx->tDof == eq->tDof && ctx->d_Ag && ctx->d_Yg && getenv("SVB200_ASM_LEGACY") == nullptr;
+  if (!fast) {
+    // any other case: the plain sequence (also the first call on a mesh, which runs the Jacobian check)
+    TRY(svb200_set_state(ctx, eq->tDof, Ag, Yg, nullptr, nullptr));
+    TRY(svb200_alloc(ctx, eq->dof));
+    TRY(svb200_assemble(ctx, iM, eq, dmn, nDmn));
+    TRY(svb200_commu_R(ctx));
+    if (R_out) TRY(svb200_download(ctx, SVB200_ARRAY_R, R_out));
+    return SVB200_OK;
+  }
+  const int tDof = eq->tDof, dof = eq->dof;
+  const size_t nV = (size_t)dof * dof * ctx->nnz, nR = (size_t)dof * ctx->nNo;
+  SVB_REQUIRE(ctx->d_R && ctx->d_Val && ctx->dof == dof && nR <= ctx->R_cap && nV <= ctx->Val_cap,
+              "svb200_assemble_host: call svb200_alloc(dof) once before the first pipelined assembly");
+  SVB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  ctx->val_zero_pending = false;
+  SVB_CUDA(cudaMemsetAsync(ctx->d_R, 0, sizeof(double) * nR, ctx->stream));
+  SVB_CUDA(cudaMemsetAsync(ctx->d_Val, 0, sizeof(double) * nV, ctx->stream));
+  if (ctx->d_Kd && ctx->nnz) SVB_CUDA(cudaMemsetAsync(ctx->d_Kd, 0, sizeof(double) * 12 * (size_t)ctx->nnz, ctx->stream));
+  FluidArgs A;
+  TRY(fill_fluid_args(ctx, m, eq, dmn, nDmn, A));
+  // the copy streams start after whatever the main stream was doing with the state arrays
+  SVB_CUDA(cudaEventRecord(ctx->zev[0], ctx->stream));
+  SVB_CUDA(cudaStreamWaitEvent(ctx->zstream, ctx->zev[0], 0));
+  SVB_CUDA(cudaStreamWaitEvent(ctx->dstream, ctx->zev[0], 0));
+  constexpr int K = 8;
+  const bool direct = !ctx->has_map;
+  if (!direct) TRY(ensure_stage(ctx, sizeof(double) * 2 * (size_t)tDof * ctx->nNo));
+  double* stageA = ctx->d_stage;
+  double* stageY = ctx->d_stage + (size_t)tDof * ctx->nNo;
+  const bool stream_down = R_out && direct && ctx->nranks == 1;
+  int up = 0, down = 0;
+  for (int c = 0; c < K; c++) {
+    const int g0 = (int)((long long)nGrp * c / K), g1 = (int)((long long)nGrp * (c + 1) / K);
+    if (g1 <= g0) continue;
+    const int need = (c == K - 1) ? ctx->nNo : m.grp_node_need[g1 - 1];
+    if (need > up) {
+      const size_t off = (size_t)tDof * up, cnt = (size_t)tDof * (need - up);
+      if (direct) {
+        SVB_CUDA(cudaMemcpyAsync(ctx->d_Ag + off, Ag + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, ctx->zstream));
+        SVB_CUDA(cudaMemcpyAsync(ctx->d_Yg + off, Yg + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, ctx->zstream));
+      } else {
+        SVB_CUDA(cudaMemcpyAsync(stageA + off, Ag + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, ctx->zstream));
+        SVB_CUDA(cudaMemcpyAsync(stageY + off, Yg + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, ctx->zstream));
+        TRY(launch_permute_cols(ctx, tDof, need - up, ctx->d_map + up, stageA + off, ctx->d_Ag, false, ctx->zstream));
+        TRY(launch_permute_cols(ctx, tDof, need - up, ctx->d_map + up, stageY + off, ctx->d_Yg, false, ctx->zstream));
+      }
+      up = need;
+    }
+    SVB_CUDA(cudaEventRecord(ctx->pev[0][c], ctx->zstream));
+    SVB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pev[0][c], 0));
+    A.g0 = g0; A.nGrpLaunch = g1 - g0; A.gperm = nullptr;
+    TRY(launch_assemble_fluid(ctx, m, A));
+    if (stream_down) {
+      // residual rows no later group touches are final: bring them back while the next chunk runs
+      const int fin = (c == K - 1) ? ctx->nNo : m.grp_node_done[g1];
+      if (fin > down) {
+        SVB_CUDA(cudaEventRecord(ctx->pev[1][c], ctx->stream));
+        SVB_CUDA(cudaStreamWaitEvent(ctx->dstream, ctx->pev[1][c], 0));
+        SVB_CUDA(cudaMemcpyAsync(R_out + (size_t)dof * down, ctx->d_R + (size_t)dof * down, sizeof(double) * dof * (fin - down),
+                                 cudaMemcpyDeviceToHost, ctx->dstream));
+        down = fin;
+      }
+    }
+  }
+  SVB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (stream_down) {
+    SVB_CUDA(cudaStreamSynchronize(ctx->dstream));
+    SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  } else {
+    TRY(halo_sum(ctx, dof, ctx->d_R));
+    if (R_out) TRY(download_nodal(ctx, dof, ctx->d_R, R_out));
+    else SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  SVB_CUDA(cudaStreamSynchronize(ctx->zstream));
   float ms = 0.f;
   SVB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   ctx->last_assemble_ms = ms;

@@ -44,6 +44,10 @@ struct Mesh {
   std::vector<int> color_off;    // offsets into d_color_perm per colour
   int* d_gcolor_perm = nullptr;  // TET4: ids of the 128-element groups of the grouped scatter, sorted by GROUP colour
   std::vector<int> gcolor_off;   // offsets into d_gcolor_perm per group colour (groups of one colour share no node)
+  std::vector<int> grp_node_need;    // TET4: running max over groups 0..g of (highest CALLER node id of the group) + 1: the nodal state
+                                     // of the caller's nodes [0, grp_node_need[g]) must be on the device before group g runs
+  std::vector<int> grp_node_done;    // suffix min over groups g.. of the lowest caller node id: the residual rows of the caller's nodes
+                                     // [0, grp_node_done[g]) are final once the groups before g have run (svb200_assemble_host)
   std::vector<long long> grp_need;   // TET4: running max over groups 0..g of (highest CSR slot the group adds to) + 1 — how far Val
                                      // must be zeroed before group g may run (overlapped zeroing, svb200_api.cu run_assemble)
   std::vector<double> w, N, Nx;  // host copies of the reference-element tables
@@ -168,8 +172,10 @@ struct svb200_ctx {
   size_t R_cap = 0, Val_cap = 0;   // capacities in doubles
   bool val_zero_pending = false;   // svb200_alloc deferred the zeroing of Val: the next consumer zeroes it (overlapped with the first
                                    // chunk of the TET4 fluid kernel, or in full before anything else touches Val)
-  cudaStream_t zstream = nullptr;  // stream of the overlapped zeroing
+  cudaStream_t zstream = nullptr;  // stream of the overlapped zeroing / of the H2D copies of svb200_assemble_host
+  cudaStream_t dstream = nullptr;  // stream of the D2H copies of svb200_assemble_host
   cudaEvent_t zev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t pev[2][16] = {};     // svb200_assemble_host: [0][c] chunk c uploaded, [1][c] chunk c assembled
   double* d_W = nullptr;           // (dof,nNo) preconditioner scaling
   double* d_Kd = nullptr;          // (12,nnz) displacement tangent of the ustruct equation (com_mod.Kd), assemble_ustruct.cu
   double* d_Ad = nullptr;          // (3,nNo) com_mod.Ad: time derivative of the displacement (ustruct)
@@ -255,7 +261,8 @@ void free_group_sched(GroupSched& S);
 // graph_kernels.cu
 int launch_build_slot_map(svb200_ctx* ctx, Mesh& m);
 int launch_find_diag(svb200_ctx* ctx);
-int launch_permute_cols(svb200_ctx* ctx, int rows, int n, const int* d_map, const double* src, double* dst, bool inverse);
+int launch_permute_cols(svb200_ctx* ctx, int rows, int n, const int* d_map, const double* src, double* dst, bool inverse,
+                        cudaStream_t stream = nullptr);
 int launch_permute_row_blocks(svb200_ctx* ctx, int a0, int a1, int d2, const int* d_rowPtr_in, double* internal, double* staged,
                               bool to_caller);
 int launch_gather_row_blocks(svb200_ctx* ctx, int n, int d2, const int* d_rows, bool csr, const long long* d_off, const double* src,

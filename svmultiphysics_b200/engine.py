@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "svb200_comm_unique_id", "svb200_comm_init", "svb200_comm_transport",
     "svb200_set_graph", "svb200_lhsa_begin", "svb200_lhsa_add_mesh", "svb200_lhsa_finish", "svb200_lhsa_get",
     "svb200_set_mesh", "svb200_set_mesh_nxx", "svb200_set_coords", "svb200_set_num_faces", "svb200_set_face", "svb200_set_face_cap",
-    "svb200_alloc", "svb200_set_state", "svb200_set_old_disp", "svb200_assemble", "svb200_add_host_contrib", "svb200_commu_R", "svb200_ustruct_r", "svb200_set_ad", "svb200_get_ad",
+    "svb200_alloc", "svb200_set_state", "svb200_set_old_disp", "svb200_assemble", "svb200_assemble_host", "svb200_add_host_contrib", "svb200_commu_R", "svb200_ustruct_r", "svb200_set_ad", "svb200_get_ad",
     "svb200_solve", "svb200_download", "svb200_download_rows", "svb200_upload", "svb200_spmv", "svb200_last_timing",
     "svb200_host_register", "svb200_host_unregister", "svb200_timer_mark", "svb200_timer_elapsed",
     "svb200_bench_assemble", "svb200_bench_spmv", "svb200_measure_fp64_peak", "svb200_launch_count",
@@ -262,6 +262,12 @@ class Engine:
     def assemble(self, iM, eq: abi.EqParams, dmns):
         arr = (abi.DmnParams * len(dmns))(*dmns)
         self._call("svb200_assemble", C.c_int32(iM), C.byref(eq), arr, C.c_int32(len(dmns)))
+
+    def assemble_host(self, iM, eq: abi.EqParams, dmns, Ag, Yg, R_out=None):
+        """set_state + alloc + assemble + commu_R + download(R) in one pipelined call (host-resident state)."""
+        arr = (abi.DmnParams * len(dmns))(*dmns)
+        assert Ag.flags.f_contiguous and Yg.flags.f_contiguous and (R_out is None or R_out.flags.f_contiguous)
+        self._call("svb200_assemble_host", C.c_int32(iM), C.byref(eq), arr, C.c_int32(len(dmns)), _d(Ag), _d(Yg), _d(R_out))
 
     def set_bface(self, iFa, iM, IENb, gE, w, N, Nx):
         IENb, gE = _i32(np.asfortranarray(IENb)), _i32(gE)
