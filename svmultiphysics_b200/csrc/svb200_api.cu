@@ -241,6 +241,7 @@ int svb200_destroy(svb200_ctx* ctx)
   cudaFree(ctx->d_stage); cudaFree(ctx->d_R); cudaFree(ctx->d_Val); cudaFree(ctx->d_W);
   cudaFree(ctx->d_work); cudaFree(ctx->d_red); cudaFree(ctx->d_tslot);
   cudaFreeHost(ctx->h_pinned); cudaFreeHost(ctx->h_cg); cudaFree(ctx->d_cg);
+  cudaFree(ctx->d_shared_rows); cudaFree(ctx->d_shared_off); cudaFreeHost(ctx->h_shared_buf);
   for (int k = 0; k < 2; k++) if (ctx->ev_cg[k]) cudaEventDestroy(ctx->ev_cg[k]);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   for (auto& e : ctx->zev) if (e) cudaEventDestroy(e);
@@ -374,6 +375,7 @@ int svb200_set_graph(svb200_ctx* ctx, int32_t nNo, int32_t nnz, const int32_t* r
     ctx->neigh.push_back(nb);
   }
   std::sort(ctx->neigh.begin(), ctx->neigh.end(), [](const Neighbor& a, const Neighbor& b) { return a.rank < b.rank; });
+  ctx->shared_built = false;
   TRY(p2p_setup(ctx));      // collective: every rank calls svb200_set_graph
   // state arrays depend on nNo
   cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf); cudaFree(ctx->d_Do);
@@ -1056,10 +1058,31 @@ int svb200_assemble_host(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq,
   SVB_CUDA(cudaStreamWaitEvent(ctx->dstream, ctx->zev[0], 0));
   constexpr int K = 8;
   const bool direct = !ctx->has_map;
-  if (!direct) TRY(ensure_stage(ctx, sizeof(double) * 2 * (size_t)tDof * ctx->nNo));
+  // Residual rows come back while later chunks run.  On a partitioned mesh the interface rows are streamed with their partial
+  // sums and fetched again after the shared-node sum (a few 10^4 rows).
+  const bool stream_down = R_out != nullptr;
+  const bool multi = ctx->nranks > 1 && !ctx->neigh.empty();
+  if (stream_down && multi && !ctx->shared_built) {
+    std::vector<int> inv(ctx->nNo);
+    for (int a = 0; a < ctx->nNo; a++) inv[ctx->h_map[a]] = a;
+    std::vector<int> rows;
+    for (auto& nb : ctx->neigh) rows.insert(rows.end(), nb.h_ptr.begin(), nb.h_ptr.end());
+    std::sort(rows.begin(), rows.end());
+    rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+    ctx->h_shared_caller.resize(rows.size());
+    std::vector<long long> off(rows.size() + 1);
+    for (size_t k = 0; k < rows.size(); k++) { ctx->h_shared_caller[k] = inv[rows[k]]; off[k] = (long long)k; }
+    off[rows.size()] = (long long)rows.size();
+    TRY(upload(ctx, &ctx->d_shared_rows, rows.data(), rows.size()));
+    TRY(upload(ctx, &ctx->d_shared_off, off.data(), off.size()));
+    cudaFreeHost(ctx->h_shared_buf); ctx->h_shared_buf = nullptr;
+    SVB_CUDA(cudaMallocHost(&ctx->h_shared_buf, sizeof(double) * 4 * std::max<size_t>(rows.size(), 1)));
+    ctx->shared_built = true;
+  }
+  if (!direct) TRY(ensure_stage(ctx, sizeof(double) * (2 * (size_t)tDof + dof) * ctx->nNo));
   double* stageA = ctx->d_stage;
   double* stageY = ctx->d_stage + (size_t)tDof * ctx->nNo;
-  const bool stream_down = R_out && direct && ctx->nranks == 1;
+  double* stageR = ctx->d_stage + 2 * (size_t)tDof * ctx->nNo;
   int up = 0, down = 0;
   for (int c = 0; c < K; c++) {
     const int g0 = (int)((long long)nGrp * c / K), g1 = (int)((long long)nGrp * (c + 1) / K);
@@ -1083,25 +1106,39 @@ int svb200_assemble_host(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq,
     A.g0 = g0; A.nGrpLaunch = g1 - g0; A.gperm = nullptr;
     TRY(launch_assemble_fluid(ctx, m, A));
     if (stream_down) {
-      // residual rows no later group touches are final: bring them back while the next chunk runs
+      // residual rows no later group touches are final (up to the shared-node sum): bring them back while the next chunk runs
       const int fin = (c == K - 1) ? ctx->nNo : m.grp_node_done[g1];
       if (fin > down) {
         SVB_CUDA(cudaEventRecord(ctx->pev[1][c], ctx->stream));
         SVB_CUDA(cudaStreamWaitEvent(ctx->dstream, ctx->pev[1][c], 0));
-        SVB_CUDA(cudaMemcpyAsync(R_out + (size_t)dof * down, ctx->d_R + (size_t)dof * down, sizeof(double) * dof * (fin - down),
-                                 cudaMemcpyDeviceToHost, ctx->dstream));
+        const size_t off = (size_t)dof * down, cnt = (size_t)dof * (fin - down);
+        if (direct) {
+          SVB_CUDA(cudaMemcpyAsync(R_out + off, ctx->d_R + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost, ctx->dstream));
+        } else {
+          TRY(launch_permute_cols(ctx, dof, fin - down, ctx->d_map + down, ctx->d_R, stageR + off, true, ctx->dstream));
+          SVB_CUDA(cudaMemcpyAsync(R_out + off, stageR + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost, ctx->dstream));
+        }
         down = fin;
       }
     }
   }
-  SVB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-  if (stream_down) {
-    SVB_CUDA(cudaStreamSynchronize(ctx->dstream));
-    SVB_CUDA(cudaStreamSynchronize(ctx->stream));
-  } else {
+  if (multi) {
     TRY(halo_sum(ctx, dof, ctx->d_R));
-    if (R_out) TRY(download_nodal(ctx, dof, ctx->d_R, R_out));
-    else SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (stream_down && !ctx->h_shared_caller.empty()) {
+      // the interface rows again, now complete: gather -> pinned scratch -> patched into R_out by the host
+      const int ns = (int)ctx->h_shared_caller.size();
+      SVB_CUDA(cudaStreamSynchronize(ctx->dstream));          // stageR is free, the streamed rows are in R_out
+      TRY(launch_gather_row_blocks(ctx, ns, dof, ctx->d_shared_rows, false, ctx->d_shared_off, ctx->d_R, stageR));
+      SVB_CUDA(cudaMemcpyAsync(ctx->h_shared_buf, stageR, sizeof(double) * dof * ns, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  }
+  SVB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  SVB_CUDA(cudaStreamSynchronize(ctx->dstream));
+  SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (multi && stream_down) {
+    const int ns = (int)ctx->h_shared_caller.size();
+    for (int k = 0; k < ns; k++)
+      for (int i = 0; i < dof; i++) R_out[(size_t)dof * ctx->h_shared_caller[k] + i] = ctx->h_shared_buf[(size_t)dof * k + i];
   }
   SVB_CUDA(cudaStreamSynchronize(ctx->zstream));
   float ms = 0.f;

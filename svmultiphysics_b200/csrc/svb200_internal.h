@@ -176,6 +176,12 @@ struct svb200_ctx {
   cudaStream_t dstream = nullptr;  // stream of the D2H copies of svb200_assemble_host
   cudaEvent_t zev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t pev[2][16] = {};     // svb200_assemble_host: [0][c] chunk c uploaded, [1][c] chunk c assembled
+  // svb200_assemble_host on a partitioned mesh: the interface rows (changed by the shared-node sum after they were streamed back)
+  std::vector<int> h_shared_caller;   // caller node ids of the interface rows
+  int* d_shared_rows = nullptr;       // their internal ids
+  long long* d_shared_off = nullptr;  // 0, 1, 2, ... (offsets for the row gather)
+  double* h_shared_buf = nullptr;     // pinned (dof, nShared)
+  bool shared_built = false;
   double* d_W = nullptr;           // (dof,nNo) preconditioner scaling
   double* d_Kd = nullptr;          // (12,nnz) displacement tangent of the ustruct equation (com_mod.Kd), assemble_ustruct.cu
   double* d_Ad = nullptr;          // (3,nNo) com_mod.Ad: time derivative of the displacement (ustruct)
