@@ -445,7 +445,7 @@ def config_c1_ns(eng, m, Ag, Yg, eq, dmn, hbm_peak, nnz):
             "ns_solve_ms": ms, "outer_itr": o.RI.itr, "success": int(o.RI.success), "gmres_itr": o.GM.itr, "cg_itr": o.CG.itr,
             "gmres_ms_per_itr": o.GM.callD * 1e3 / max(o.GM.itr, 1), "cg_ms_per_itr": cg_ms,
             "Resm": o.Resm, "Resc": o.Resc, "fNorm_over_iNorm": o.RI.fNorm / o.RI.iNorm,
-            "roofline": {"bound": "hbm", "kernel": "Schur-complement CG iteration (bsr_spmv_rc<3,1>, schur_sp, dots, updates)",
+            "roofline": {"bound": "hbm", "kernel": "Schur-complement CG iteration (bsr_spmv_lg_kernel<3,1,..> G p, schur_sp4_kernel with the <p,Sp> partials, fused X/R/P updates)",
                          "achieved": cg_bytes / (cg_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": cg_bytes / (cg_ms * 1e-3) * 1e-9 / hbm_peak, "traffic": None,
                          "algorithmic": "nnz*(28+28+12) + 14 nodal scalars per CG iteration (SURVEY 8d NS sub-blocks)"}}
@@ -496,7 +496,7 @@ def config_c4_struct(device, fp64_peak, hbm_peak, n=171):
             "bicgstab_itr": o.RI.itr, "bicgstab_ms_per_itr": sol / max(o.RI.itr, 1),
             "roofline": {"bound": "fp64", "kernel": "assemble_struct_kernel<8>", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": tf / fp64_peak, "traffic": None, "algorithmic": f"130000 flop/hex8 (SURVEY 8d) x {m.nEl} elements"},
-            "roofline_spmv": {"bound": "hbm", "kernel": "bsr_spmv_kernel<3>", "achieved": sp, "peak": hbm_peak, "unit": "GB/s",
+            "roofline_spmv": {"bound": "hbm", "kernel": "bsr_spmv_lg_kernel<3,3,1,2,4,0> (two blocks per 6-lane row group and step, 4 steps in flight)", "achieved": sp, "peak": hbm_peak, "unit": "GB/s",
                               "frac": sp / hbm_peak, "ms": spmv, "traffic": None, "algorithmic": "nnz*76 + nNo*56 bytes per launch"}}
 
 

@@ -379,6 +379,20 @@ SVB200_API int svb200_timer_elapsed(svb200_ctx* ctx, double* ms);
 SVB200_API int svb200_bench_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, const svb200_dmnparams* dmn,
                           int32_t nDmn, int32_t reps, double* ms_per_launch);
 SVB200_API int svb200_bench_spmv(svb200_ctx* ctx, int32_t dof, int32_t reps, double* ms_per_launch);
+/* Rectangular-block products of the NS solver on the context's graph (fsils_spar_mul_vv / sv / vs / ss,
+ * Code/Source/linear_solver/spar_mul.cpp:19-231) with a CALLER-supplied matrix K (R*C, nnz), U (C, nNo), KU (R, nNo) — host arrays,
+ * single-partition contexts (internal = input order).  `variant` selects the lane mapping (-1: the default, 0: thread per (row, i));
+ * svb200_spmv_rc_variants returns how many exist for a shape.  svb200_bench_spmv_rc times `reps` launches on resident zero data. */
+SVB200_API int svb200_spmv_rc(svb200_ctx* ctx, int32_t R, int32_t C, int32_t variant, const double* K, const double* U, double* KU);
+SVB200_API int svb200_spmv_rc_variants(int32_t R, int32_t C);
+SVB200_API int svb200_bench_spmv_rc(svb200_ctx* ctx, int32_t R, int32_t C, int32_t variant, int32_t reps, double* ms_per_launch);
+/* The Schur-complement operator of cgrad::schur (Code/Source/linear_solver/cgrad.cpp:77-84), SP = L p - Gt (G p), nsd = 3, with
+ * caller-supplied L (nnz), Gt (3, nnz), P (nNo), GP (3, nNo): SP (nNo) and the fused <p, SP> over the owned rows.  variant -2: the
+ * separate-array kernel (schur_sp_kernel), -1: default interleaved kernel, >= 0: a specific lane mapping.  Host arrays, single partition. */
+SVB200_API int svb200_schur_sp(svb200_ctx* ctx, int32_t variant, const double* L, const double* Gt, const double* P, const double* GP,
+                               double* SP, double* p_dot_sp);
+SVB200_API int svb200_schur_sp_variants(void);
+SVB200_API int svb200_bench_schur_sp(svb200_ctx* ctx, int32_t variant, int32_t reps, double* ms_per_launch);
 /* Measured FP64 FMA peak (independent DFMA chains) in TFLOP/s. */
 SVB200_API int svb200_measure_fp64_peak(svb200_ctx* ctx, double* tflops);
 /* Number of CUDA kernels this library has launched on ctx since creation. */

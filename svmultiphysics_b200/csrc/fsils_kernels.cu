@@ -79,42 +79,9 @@ bsr_spmv_kernel(int nNo, const int* __restrict__ rowPtr, const int* __restrict__
   KU[t] = acc;
 }
 
-// dof = 3, long rows (HEX8 meshes: 27 blocks = 1944 contiguous bytes per row): one warp streams the row's Val segment with
-// consecutive lanes on consecutive doubles, every lane multiplies its doubles with the matching U entries and adds them to
-// the accumulator of their block row; three butterfly reductions finish the row.  MEASURED AND REJECTED as the default (B200, C4,
-// 9.8 GB matrix, gpurun_out/r1n_spmv3_ab.log): 4.50 ms = 2.36 TB/s against 2.06 ms = 5.15 TB/s of the thread-per-(row, i) kernel
-// above, whose three threads of a row keep the row's lines in L1 across the k loop and carry no index arithmetic or shuffles per
-// double.  Kept behind SVB200_SPMV3=warp as the A/B reference.
-__global__ void __launch_bounds__(256)
-bsr_spmv3_warp_kernel(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ colPtr,
-                      const double* __restrict__ Val, const double* __restrict__ U, double* __restrict__ KU)
-{
-  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (w >= nNo) return;
-  const int row = (int)w;
-  const int k0 = __ldg(rowPtr + row), k1 = __ldg(rowPtr + row + 1);
-  const int nd = (k1 - k0) * 9;
-  const double* v = Val + (size_t)k0 * 9;
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-  for (int p = lane; p < nd; p += 32) {
-    const double x = __ldcs(v + p);
-    const int kb = p / 9, r = p - 9 * kb, i = r / 3, j = r - 3 * i;
-    const int c = __ldg(colPtr + k0 + kb);
-    const double t = x * __ldg(U + (size_t)c * 3 + j);
-    if (i == 0) a0 += t;
-    else if (i == 1) a1 += t;
-    else a2 += t;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-  }
-  if (lane < 3) KU[(size_t)row * 3 + lane] = (lane == 0) ? a0 : (lane == 1 ? a1 : a2);
-}
-
+// dof = 3 and dof = 1 go through the lane-group kernels of spmv_lanegroup.cu (3x3 and 1x1 blocks).  A warp-per-row form of the
+// dof = 3 product (consecutive lanes on consecutive doubles, block row picked per double) was measured at 2.36 TB/s against 5.15 TB/s
+// of the thread-per-(row, i) kernel above (profiles/r1n_spmv3_ab.txt) and removed.
 int launch_spmv(svb200_ctx* ctx, int dof, const double* Val, const double* U, double* KU)
 {
   const int nNo = ctx->nNo;
@@ -125,24 +92,13 @@ int launch_spmv(svb200_ctx* ctx, int dof, const double* Val, const double* U, do
   } else {
     const long long threads = (long long)nNo * dof;
     const unsigned blocks = (unsigned)((threads + 255) / 256);
-    switch (dof) {
-      case 1: bsr_spmv_kernel<1><<<blocks, 256, 0, ctx->stream>>>(nNo, ctx->d_rowPtr, ctx->d_colPtr, Val, U, KU); break;
-      case 2: bsr_spmv_kernel<2><<<blocks, 256, 0, ctx->stream>>>(nNo, ctx->d_rowPtr, ctx->d_colPtr, Val, U, KU); break;
-      case 3: {
-        // SVB200_SPMV3=warp selects the warp-per-row form (A/B knob; measured slower, see the kernel's comment)
-        static const char* mode = getenv("SVB200_SPMV3");
-        const bool warp_form = mode && mode[0] == 'w';
-        if (warp_form) {
-          const long long th = (long long)nNo * 32;
-          bsr_spmv3_warp_kernel<<<(unsigned)((th + 255) / 256), 256, 0, ctx->stream>>>(nNo, ctx->d_rowPtr, ctx->d_colPtr, Val, U, KU);
-        } else {
-          bsr_spmv_kernel<3><<<blocks, 256, 0, ctx->stream>>>(nNo, ctx->d_rowPtr, ctx->d_colPtr, Val, U, KU);
-        }
-      } break;
-      default:
-        set_error("svb200: SpMV supports dof 1..4");
-        return SVB200_ERR_UNSUPPORTED;
+    if (dof == 3) return spmv_rc(ctx, 3, 3, Val, U, KU);
+    if (dof == 1) return spmv_rc(ctx, 1, 1, Val, U, KU);
+    if (dof != 2) {
+      set_error("svb200: SpMV supports dof 1..4");
+      return SVB200_ERR_UNSUPPORTED;
     }
+    bsr_spmv_kernel<2><<<blocks, 256, 0, ctx->stream>>>(nNo, ctx->d_rowPtr, ctx->d_colPtr, Val, U, KU);
   }
   ctx->launches++;
   SVB_CUDA(cudaGetLastError());
@@ -674,27 +630,7 @@ int precond_scale_matrix(svb200_ctx* ctx, int dof, const double* Wr, const doubl
 // ----------------------------------------------------------------------------------------------
 // NS (Schur complement) solver pieces, linear_solver/ns_solver.cpp.
 // ----------------------------------------------------------------------------------------------
-// Rectangular-block SpMV: blocks are R x C (row-major), U is (C,nNo), KU is (R,nNo).  Covers
-// fsils_spar_mul_vv on the momentum block (3x3), _sv on G (3x1), _vs on D / Gt (1x3) and _ss on L (1x1),
-// linear_solver/spar_mul.cpp:19-231.
-template <int R, int C>
-__global__ void __launch_bounds__(256)
-bsr_spmv_rc_kernel(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ colPtr, const double* __restrict__ K,
-                   const double* __restrict__ U, double* __restrict__ KU)
-{
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)nNo * R) return;
-  const int row = (int)(t / R), i = (int)(t % R);
-  double acc = 0.0;
-  for (int k = rowPtr[row]; k < rowPtr[row + 1]; k++) {
-    const int c = colPtr[k];
-    const double* v = K + (size_t)k * R * C + i * C;
-    const double* u = U + (size_t)c * C;
-#pragma unroll
-    for (int j = 0; j < C; j++) acc += v[j] * u[j];
-  }
-  KU[t] = acc;
-}
+// The rectangular-block products (3x3, 3x1, 1x3, 1x1: fsils_spar_mul_vv/sv/vs/ss) live in spmv_lanegroup.cu.
 
 // ---- device-resident Schur-complement CG (cgrad::schur, linear_solver/cgrad.cpp:23-133) ----------------------------
 // Scalars of the iteration live in a small device array `cg` so that no kernel waits for the host:
@@ -798,24 +734,6 @@ int cg_step_kernels(svb200_ctx* ctx, int which, long long n, double* cg, const d
   return SVB200_OK;
 }
 
-int spmv_rc(svb200_ctx* ctx, int R, int C, const double* K, const double* U, double* KU)
-{
-  const int nNo = ctx->nNo;
-  if (nNo == 0) return SVB200_OK;
-  const unsigned blocks = (unsigned)(((long long)nNo * R + 255) / 256);
-#define SVB_RC(r, c)                                                                                              \
-  if (R == r && C == c) {                                                                                          \
-    bsr_spmv_rc_kernel<r, c><<<blocks, 256, 0, ctx->stream>>>(nNo, ctx->d_rowPtr, ctx->d_colPtr, K, U, KU);        \
-    ctx->launches++;                                                                                               \
-    SVB_CUDA(cudaGetLastError());                                                                                  \
-    return SVB200_OK;                                                                                              \
-  }
-  SVB_RC(3, 3) SVB_RC(3, 1) SVB_RC(1, 3) SVB_RC(1, 1) SVB_RC(2, 2) SVB_RC(2, 1) SVB_RC(1, 2)
-#undef SVB_RC
-  set_error("svb200: unsupported block shape in spmv_rc");
-  return SVB200_ERR_UNSUPPORTED;
-}
-
 // tslot[j] = slot l of row col(j) whose column is the row of j (the transposed entry), or -1.
 __global__ void transpose_slot_kernel(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ colPtr,
                                       int* __restrict__ tslot)
@@ -846,7 +764,8 @@ int build_transpose_slots(svb200_ctx* ctx, int* d_tslot)
 // Gt(:, tslot(j)) = -mG(:, j).  Gt must be zeroed by the caller (entries without a transposed slot).
 __global__ void __launch_bounds__(256)
 depart_kernel(long long nnz, int nsd, const double* __restrict__ Val, const int* __restrict__ tslot, double* __restrict__ mK,
-              double* __restrict__ mG, double* __restrict__ mD, double* __restrict__ mL, double* __restrict__ Gt)
+              double* __restrict__ mG, double* __restrict__ mD, double* __restrict__ mL, double* __restrict__ Gt,
+              double* __restrict__ DL)
 {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nnz) return;
@@ -857,19 +776,24 @@ depart_kernel(long long nnz, int nsd, const double* __restrict__ Val, const int*
     for (int b = 0; b < nsd; b++) mK[(size_t)j * nsd * nsd + a * nsd + b] = v[a * dof + b];
     const double g = v[a * dof + nsd];
     mG[(size_t)j * nsd + a] = g;
-    if (t >= 0) Gt[(size_t)t * nsd + a] = -g;
+    if (t >= 0) {
+      Gt[(size_t)t * nsd + a] = -g;
+      if (DL) DL[(size_t)t * 4 + a] = -g;      // interleaved { Gt(0..2), L } of schur_sp4_kernel (nsd = 3)
+    }
     mD[(size_t)j * nsd + a] = v[nsd * dof + a];
   }
   mL[j] = v[nsd * dof + nsd];
+  if (DL) DL[(size_t)j * 4 + 3] = v[nsd * dof + nsd];
 }
 
 int ns_depart(svb200_ctx* ctx, int nsd, const double* Val, const int* d_tslot, double* mK, double* mG, double* mD, double* mL,
-              double* Gt)
+              double* Gt, double* DL)
 {
   const long long nnz = ctx->nnz;
   if (nnz == 0) return SVB200_OK;
   SVB_CUDA(cudaMemsetAsync(Gt, 0, sizeof(double) * nnz * nsd, ctx->stream));
-  depart_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, ctx->stream>>>(nnz, nsd, Val, d_tslot, mK, mG, mD, mL, Gt);
+  if (DL) SVB_CUDA(cudaMemsetAsync(DL, 0, sizeof(double) * nnz * 4, ctx->stream));
+  depart_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, ctx->stream>>>(nnz, nsd, Val, d_tslot, mK, mG, mD, mL, Gt, DL);
   ctx->launches++;
   SVB_CUDA(cudaGetLastError());
   return SVB200_OK;

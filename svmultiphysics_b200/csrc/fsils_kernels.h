@@ -30,7 +30,15 @@ int schur_sp(svb200_ctx* ctx, int nsd, const double* L, const double* D, const d
 int cg_step_kernels(svb200_ctx* ctx, int which, long long n, double* cg, const double* P, const double* SP, double* X, double* R,
                     double* Pw);
 int build_transpose_slots(svb200_ctx* ctx, int* d_tslot);
-int ns_depart(svb200_ctx* ctx, int nsd, const double* Val, const int* d_tslot, double* mK, double* mG, double* mD, double* mL, double* Gt);
+int ns_depart(svb200_ctx* ctx, int nsd, const double* Val, const int* d_tslot, double* mK, double* mG, double* mD, double* mL, double* Gt,
+              double* DL);   // DL (4, nnz) = { Gt(0..2), L } interleaved, nsd = 3 only (else nullptr)
+// spmv_lanegroup.cu
+int spmv_rc_variant(svb200_ctx* ctx, int R, int C, int variant, const double* K, const double* U, double* KU);
+int spmv_rc_num_variants(int R, int C);
+int schur_sp4(svb200_ctx* ctx, int variant, const double* DL, const double* P, const double* GP, double* SP, double* part, int* nparts);
+int schur_sp4_num_variants();
+int schur_cg_fused_tail(svb200_ctx* ctx, double* cg, int npart_psp, double* part_psp, const double* SP, double* P, double* X, double* R,
+                        double* part_rr);
 int ns_split(svb200_ctx* ctx, int dof, const double* Ri, double* Rm, double* Rc);
 int ns_merge(svb200_ctx* ctx, int dof, const double* Rm, const double* Rc, double* Ri);
 

@@ -686,7 +686,7 @@ static bool ge_host(int nV, int N, const std::vector<double>& A, std::vector<dou
 // cgrad::schur (cgrad.cpp:23-133): CG on S p = L p - Gt (G p); R(nNo) in/out.
 // work: X, P, SP, DGP (nNo each) and GP (nsd*nNo).
 static int schur_device(svb200_ctx* ctx, int nsd, const svb200_sublsparams& p, svb200_sublsresult& r, const double* Gt,
-                        const double* mG, const double* mL, double* R, double* work, double* d_scal)
+                        const double* mG, const double* mL, const double* DL, double* R, double* work, double* d_scal)
 {
   const long long nNo = ctx->nNo;
   const long long nns = (nNo + 1) & ~1ll;
@@ -720,17 +720,41 @@ static int schur_device(svb200_ctx* ctx, int nsd, const svb200_sublsparams& p, s
       h0[0] = err; h0[1] = err; h0[2] = 0.0; h0[3] = eps; h0[4] = 0.0; h0[5] = 0.0; h0[6] = err; h0[7] = 0.0;
       SVB_CUDA(cudaMemcpyAsync(cg, h0, sizeof(double) * 8, cudaMemcpyHostToDevice, ctx->stream));
       bool done = false;
+      // nsd = 3: the interleaved { Gt, L } operator (schur_sp4_kernel); on a single partition the vector part of the iteration is
+      // fused as well: <p,Sp> partials in the operator's epilogue, X / R update + <r,r> partials, P update — 6 launches per
+      // iteration instead of 10 (SVB200_SCHUR_UNFUSED=1: the separate kernels)
+      static const bool unfused = getenv("SVB200_SCHUR_UNFUSED") != nullptr;
+      const bool sp4 = (nsd == 3 && DL != nullptr && !unfused);
+      const bool fused = sp4 && ctx->nranks == 1;
+      double *part_psp = nullptr, *part_rr = nullptr;
+      if (fused) {
+        const size_t need = 148 * 8 * 2 + 16;
+        if (need > ctx->red_cap) {
+          if (ctx->d_red) cudaFree(ctx->d_red);
+          ctx->red_cap = need * 2;
+          SVB_CUDA(cudaMalloc(&ctx->d_red, sizeof(double) * ctx->red_cap));
+        }
+        part_psp = ctx->d_red;
+        part_rr = ctx->d_red + 148 * 8;
+      }
       for (int i = 0; i < p.mItr && !done; i++) {
         SVB_TRY(spmv_rc(ctx, nsd, 1, mG, P, GP));
         SVB_TRY(halo_sum(ctx, nsd, GP));
         if (anyCoupled) SVB_TRY(add_bc_mul_device(ctx, 1, nsd, GP, GP, d_scal));
-        SVB_TRY(schur_sp(ctx, nsd, mL, Gt, P, GP, SP));
-        SVB_TRY(halo_sum(ctx, 1, SP));
-        SVB_TRY(multi_dot(ctx, (long long)ctx->mynNo, 1, P, 0, SP, cg + 2, true));
-        SVB_TRY(cg_step_kernels(ctx, 0, nNo, cg, P, SP, X, R, nullptr));
-        SVB_TRY(multi_dot(ctx, (long long)ctx->mynNo, 1, R, 0, R, cg + 1, true));
-        SVB_TRY(cg_step_kernels(ctx, 1, nNo, cg, nullptr, nullptr, nullptr, R, P));
-        SVB_TRY(cg_step_kernels(ctx, 2, 1, cg, nullptr, nullptr, nullptr, nullptr, nullptr));
+        if (fused) {
+          int nparts = 0;
+          SVB_TRY(schur_sp4(ctx, -1, DL, P, GP, SP, part_psp, &nparts));
+          SVB_TRY(schur_cg_fused_tail(ctx, cg, nparts, part_psp, SP, P, X, R, part_rr));
+        } else {
+          if (sp4) SVB_TRY(schur_sp4(ctx, -1, DL, P, GP, SP, nullptr, nullptr));
+          else SVB_TRY(schur_sp(ctx, nsd, mL, Gt, P, GP, SP));
+          SVB_TRY(halo_sum(ctx, 1, SP));
+          SVB_TRY(multi_dot(ctx, (long long)ctx->mynNo, 1, P, 0, SP, cg + 2, true));
+          SVB_TRY(cg_step_kernels(ctx, 0, nNo, cg, P, SP, X, R, nullptr));
+          SVB_TRY(multi_dot(ctx, (long long)ctx->mynNo, 1, R, 0, R, cg + 1, true));
+          SVB_TRY(cg_step_kernels(ctx, 1, nNo, cg, nullptr, nullptr, nullptr, R, P));
+          SVB_TRY(cg_step_kernels(ctx, 2, 1, cg, nullptr, nullptr, nullptr, nullptr, nullptr));
+        }
         SVB_CUDA(cudaMemcpyAsync(ctx->h_cg + 8 * (i & 1), cg, sizeof(double) * 8, cudaMemcpyDeviceToHost, ctx->stream));
         SVB_CUDA(cudaEventRecord(ctx->ev_cg[i & 1], ctx->stream));
         if (i >= 1) {
@@ -808,7 +832,7 @@ int ns_solver_device(svb200_ctx* ctx, int dof, const svb200_lsparams* ls, svb200
   const size_t oRm = take(nv), oRmi = take(nv), oRc = take(nNo), oRci = take(nNo);
   const size_t oU = take((size_t)nvs * iBmax), oMU = take((size_t)nvs * nB), oP = take((size_t)nns * iBmax), oMP = take((size_t)nns * nB);
   const size_t oK = take((size_t)nnz * nsd * nsd), oG = take((size_t)nnz * nsd), oD = take((size_t)nnz * nsd), oL = take(nnz),
-               oGt = take((size_t)nnz * nsd);
+               oGt = take((size_t)nnz * nsd), oDL = take(nsd == 3 ? (size_t)nnz * 4 : 0);
   // scalar scratch: SCAL_N for the solvers + the Gram-matrix partial results, 2 (4 i + 5) doubles in outer iteration i
   const size_t nGram = (size_t)2 * (4 * iBmax + 5);
   const size_t oGm = take((size_t)nvs * (sD + 1)), oSch = take((size_t)nns * 4 + nvs), oScal = take(SCAL_N + nGram);
@@ -816,6 +840,7 @@ int ns_solver_device(svb200_ctx* ctx, int dof, const svb200_lsparams* ls, svb200
   double* W = ctx->d_work;
   double *Rm = W + oRm, *Rmi = W + oRmi, *Rc = W + oRc, *Rci = W + oRci, *U = W + oU, *MU = W + oMU, *P = W + oP, *MP = W + oMP;
   double *mK = W + oK, *mG = W + oG, *mD = W + oD, *mL = W + oL, *Gt = W + oGt, *gm_u = W + oGm, *sch = W + oSch, *d_scal = W + oScal;
+  double* DL = nsd == 3 ? W + oDL : nullptr;
   double* d_gram = d_scal + SCAL_N;  // Gram-matrix partial results, sized from Max_iterations above
   if (!ctx->d_tslot) {
     SVB_CUDA(cudaMalloc(&ctx->d_tslot, sizeof(int) * std::max<long long>(nnz, 1)));
@@ -837,7 +862,7 @@ int ns_solver_device(svb200_ctx* ctx, int dof, const svb200_lsparams* ls, svb200
   CG.itr = 0; GM.itr = 0;
   RI.success = 0;
   eps = std::max(ls->RI.absTol, ls->RI.relTol * eps);
-  SVB_TRY(ns_depart(ctx, nsd, Val, ctx->d_tslot, mK, mG, mD, mL, Gt));
+  SVB_TRY(ns_depart(ctx, nsd, Val, ctx->d_tslot, mK, mG, mD, mL, Gt, DL));
   SVB_TRY(bc_pre_device(ctx, dof, d_scal));     // nS over the first nsd = dof-1 components (ns_solver.cpp:29-58)
 
   std::vector<double> A((size_t)nB * nB, 0.0), B(nB, 0.0), xB(nB, 0.0), oldxB(nB, 0.0);
@@ -859,7 +884,7 @@ int ns_solver_device(svb200_ctx* ctx, int dof, const svb200_lsparams* ls, svb200
     SVB_TRY(spmv_rc(ctx, 1, nsd, mD, Ui, Pi));
     SVB_TRY(halo_sum(ctx, 1, Pi));
     SVB_TRY(axpby(ctx, nNo, 1.0, Rc, -1.0, Pi, Pi));
-    SVB_TRY(schur_device(ctx, nsd, ls->CG, CG, Gt, mG, mL, Pi, sch, d_scal));
+    SVB_TRY(schur_device(ctx, nsd, ls->CG, CG, Gt, mG, mL, DL, Pi, sch, d_scal));
     // MU(iB) = G P ; MU(iBB) = Rm - G P ; U = K^-1 MU(iBB)
     SVB_TRY(spmv_rc(ctx, nsd, 1, mG, Pi, MU_iB));
     SVB_TRY(halo_sum(ctx, nsd, MU_iB));

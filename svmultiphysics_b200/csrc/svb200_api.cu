@@ -1476,6 +1476,124 @@ int svb200_bench_spmv(svb200_ctx* ctx, int32_t dof, int32_t reps, double* ms_per
   return rc;
 }
 
+// ---- rectangular-block SpMV / Schur operator with caller-supplied matrices (tests, A/B measurements) ---------------------------
+namespace {
+struct DevBuf {
+  double* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t n, bool zero, cudaStream_t st)
+  {
+    SVB_CUDA(cudaMalloc(&p, sizeof(double) * std::max<size_t>(n, 2) + 16));
+    if (zero) SVB_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * std::max<size_t>(n, 2), st));
+    return SVB200_OK;
+  }
+  int put(const double* h, size_t n, cudaStream_t st)
+  {
+    if (n) SVB_CUDA(cudaMemcpyAsync(p, h, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    return SVB200_OK;
+  }
+};
+}  // namespace
+
+int svb200_spmv_rc_variants(int32_t R, int32_t C) { return spmv_rc_num_variants(R, C); }
+int svb200_schur_sp_variants(void) { return schur_sp4_num_variants(); }
+
+int svb200_spmv_rc(svb200_ctx* ctx, int32_t R, int32_t C, int32_t variant, const double* K, const double* U, double* KU)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(K && U && KU, "svb200_spmv_rc: null arrays");
+  SVB_REQUIRE(ctx->d_rowPtr && !ctx->has_map && ctx->nranks == 1, "svb200_spmv_rc: needs a graph on a single-partition context");
+  const size_t nK = (size_t)R * C * ctx->nnz, nU = (size_t)C * ctx->nNo, nKU = (size_t)R * ctx->nNo;
+  DevBuf dK, dU, dKU;
+  TRY(dK.alloc(nK, false, ctx->stream)); TRY(dU.alloc(nU, false, ctx->stream)); TRY(dKU.alloc(nKU, true, ctx->stream));
+  TRY(dK.put(K, nK, ctx->stream)); TRY(dU.put(U, nU, ctx->stream));
+  TRY(variant < 0 ? spmv_rc(ctx, R, C, dK.p, dU.p, dKU.p) : spmv_rc_variant(ctx, R, C, variant, dK.p, dU.p, dKU.p));
+  if (nKU) SVB_CUDA(cudaMemcpyAsync(KU, dKU.p, sizeof(double) * nKU, cudaMemcpyDeviceToHost, ctx->stream));
+  SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SVB200_OK;
+}
+
+int svb200_bench_spmv_rc(svb200_ctx* ctx, int32_t R, int32_t C, int32_t variant, int32_t reps, double* ms_per_launch)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(ms_per_launch && reps >= 1 && ctx->d_rowPtr, "svb200_bench_spmv_rc: bad arguments");
+  const size_t nK = (size_t)R * C * ctx->nnz, nU = (size_t)C * ctx->nNo, nKU = (size_t)R * ctx->nNo;
+  DevBuf dK, dU, dKU;
+  TRY(dK.alloc(nK, true, ctx->stream)); TRY(dU.alloc(nU, true, ctx->stream)); TRY(dKU.alloc(nKU, true, ctx->stream));
+  auto run = [&]() { return variant < 0 ? spmv_rc(ctx, R, C, dK.p, dU.p, dKU.p) : spmv_rc_variant(ctx, R, C, variant, dK.p, dU.p, dKU.p); };
+  TRY(run());   // warm-up
+  SVB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  for (int r = 0; r < reps; r++) TRY(run());
+  SVB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  SVB_CUDA(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f;
+  SVB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *ms_per_launch = ms / reps;
+  return SVB200_OK;
+}
+
+static int schur_run(svb200_ctx* ctx, int variant, const double* dL, const double* dGt, const double* dDL, const double* dP,
+                     const double* dGP, double* dSP, double* dPart, int* nparts)
+{
+  if (variant == -2) {
+    if (nparts) *nparts = 0;
+    return schur_sp(ctx, 3, dL, dGt, dP, dGP, dSP);
+  }
+  return schur_sp4(ctx, variant, dDL, dP, dGP, dSP, dPart, nparts);
+}
+
+int svb200_schur_sp(svb200_ctx* ctx, int32_t variant, const double* L, const double* Gt, const double* P, const double* GP,
+                    double* SP, double* p_dot_sp)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(L && Gt && P && GP && SP, "svb200_schur_sp: null arrays");
+  SVB_REQUIRE(ctx->d_rowPtr && !ctx->has_map && ctx->nranks == 1, "svb200_schur_sp: needs a graph on a single-partition context");
+  const size_t nnz = ctx->nnz, nNo = ctx->nNo;
+  std::vector<double> hDL(4 * nnz);
+  for (size_t k = 0; k < nnz; k++) {
+    hDL[4 * k] = Gt[3 * k]; hDL[4 * k + 1] = Gt[3 * k + 1]; hDL[4 * k + 2] = Gt[3 * k + 2]; hDL[4 * k + 3] = L[k];
+  }
+  DevBuf dL, dGt, dDL, dP, dGP, dSP, dPart;
+  TRY(dL.alloc(nnz, false, ctx->stream)); TRY(dGt.alloc(3 * nnz, false, ctx->stream)); TRY(dDL.alloc(4 * nnz, false, ctx->stream));
+  TRY(dP.alloc(nNo, false, ctx->stream)); TRY(dGP.alloc(3 * nNo, false, ctx->stream)); TRY(dSP.alloc(nNo, true, ctx->stream));
+  TRY(dPart.alloc(148 * 8 + 16, true, ctx->stream));
+  TRY(dL.put(L, nnz, ctx->stream)); TRY(dGt.put(Gt, 3 * nnz, ctx->stream)); TRY(dDL.put(hDL.data(), 4 * nnz, ctx->stream));
+  TRY(dP.put(P, nNo, ctx->stream)); TRY(dGP.put(GP, 3 * nNo, ctx->stream));
+  int nparts = 0;
+  TRY(schur_run(ctx, variant, dL.p, dGt.p, dDL.p, dP.p, dGP.p, dSP.p, dPart.p, &nparts));
+  if (nNo) SVB_CUDA(cudaMemcpyAsync(SP, dSP.p, sizeof(double) * nNo, cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<double> hp(std::max(nparts, 1), 0.0);
+  if (nparts) SVB_CUDA(cudaMemcpyAsync(hp.data(), dPart.p, sizeof(double) * nparts, cudaMemcpyDeviceToHost, ctx->stream));
+  SVB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (p_dot_sp) {
+    double s = 0.0;
+    if (nparts) for (int b = 0; b < nparts; b++) s += hp[b];
+    else for (int a = 0; a < ctx->mynNo; a++) s += P[a] * SP[a];
+    *p_dot_sp = s;
+  }
+  return SVB200_OK;
+}
+
+int svb200_bench_schur_sp(svb200_ctx* ctx, int32_t variant, int32_t reps, double* ms_per_launch)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(ms_per_launch && reps >= 1 && ctx->d_rowPtr, "svb200_bench_schur_sp: bad arguments");
+  const size_t nnz = ctx->nnz, nNo = ctx->nNo;
+  DevBuf dL, dGt, dDL, dP, dGP, dSP, dPart;
+  TRY(dL.alloc(nnz, true, ctx->stream)); TRY(dGt.alloc(3 * nnz, true, ctx->stream)); TRY(dDL.alloc(4 * nnz, true, ctx->stream));
+  TRY(dP.alloc(nNo, true, ctx->stream)); TRY(dGP.alloc(3 * nNo, true, ctx->stream)); TRY(dSP.alloc(nNo, true, ctx->stream));
+  TRY(dPart.alloc(148 * 8 + 16, true, ctx->stream));
+  TRY(schur_run(ctx, variant, dL.p, dGt.p, dDL.p, dP.p, dGP.p, dSP.p, dPart.p, nullptr));
+  SVB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  for (int r = 0; r < reps; r++) TRY(schur_run(ctx, variant, dL.p, dGt.p, dDL.p, dP.p, dGP.p, dSP.p, dPart.p, nullptr));
+  SVB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  SVB_CUDA(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f;
+  SVB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *ms_per_launch = ms / reps;
+  return SVB200_OK;
+}
+
 int svb200_measure_fp64_peak(svb200_ctx* ctx, double* tflops)
 {
   CTX_GUARD(ctx);

@@ -43,6 +43,8 @@ ABI_SYMBOLS = [
     "svb200_set_solution", "svb200_get_solution", "svb200_predictor", "svb200_initiator", "svb200_corrector",
     "svb200_set_node_flags", "svb200_set_dirichlet_rows", "svb200_dirichlet_ustruct", "svb200_advance_time_step",
     "svb200_set_bface", "svb200_assemble_neu",
+    "svb200_spmv_rc", "svb200_spmv_rc_variants", "svb200_bench_spmv_rc",
+    "svb200_schur_sp", "svb200_schur_sp_variants", "svb200_bench_schur_sp",
 ]
 
 _lib = None
@@ -380,6 +382,38 @@ class Engine:
     def bench_spmv(self, dof, reps):
         ms = C.c_double(0)
         self._call("svb200_bench_spmv", C.c_int32(dof), C.c_int32(reps), C.byref(ms))
+        return ms.value
+
+    # ---- rectangular-block products / Schur operator with caller-supplied matrices (tests, A/B) ----
+    def spmv_rc(self, R, Cc, K, U, variant=-1):
+        """KU = K U with (R x Cc) blocks on the context's graph: K (R*Cc, nnz), U (Cc, nNo) -> KU (R, nNo)."""
+        K, U = _f64(K), _f64(U)
+        KU = np.zeros((R, self.nNo), order="F")
+        self._call("svb200_spmv_rc", C.c_int32(R), C.c_int32(Cc), C.c_int32(variant), _d(K), _d(U), _d(KU))
+        return KU
+
+    def spmv_rc_variants(self, R, Cc) -> int:
+        return int(self.lib.svb200_spmv_rc_variants(C.c_int32(R), C.c_int32(Cc)))
+
+    def bench_spmv_rc(self, R, Cc, variant, reps):
+        ms = C.c_double(0)
+        self._call("svb200_bench_spmv_rc", C.c_int32(R), C.c_int32(Cc), C.c_int32(variant), C.c_int32(reps), C.byref(ms))
+        return ms.value
+
+    def schur_sp(self, L, Gt, P, GP, variant=-1):
+        """SP = L p - Gt (G p) (cgrad::schur) and <p, SP>: L (nnz), Gt (3, nnz), P (nNo), GP (3, nNo)."""
+        L, Gt, P, GP = _f64(L), _f64(Gt), _f64(P), _f64(GP)
+        SP = np.zeros(self.nNo)
+        dot = C.c_double(0)
+        self._call("svb200_schur_sp", C.c_int32(variant), _d(L), _d(Gt), _d(P), _d(GP), _d(SP), C.byref(dot))
+        return SP, dot.value
+
+    def schur_sp_variants(self) -> int:
+        return int(self.lib.svb200_schur_sp_variants())
+
+    def bench_schur_sp(self, variant, reps):
+        ms = C.c_double(0)
+        self._call("svb200_bench_schur_sp", C.c_int32(variant), C.c_int32(reps), C.byref(ms))
         return ms.value
 
     def pin(self, arr: np.ndarray):

@@ -290,7 +290,10 @@ def test_capped_coupled_face_parity(ls_type, kw):
         assert abs(out1.RI.fNorm - out0.RI.fNorm) <= 2e-2 * out0.RI.fNorm
         assert common.rel_err(X1, X0) < 50 * ls.RI.relTol
     else:
-        assert abs(out1.RI.itr - out0.RI.itr) <= max(2, out0.RI.itr // 25)
+        # 2100 iterations over 42 stagnating restarts: the atomically scattered Val changes the count from run to run
+        # (measured 2069 / 2091 / 2104 / 2175 on the same box, profiles/r2q: gpurun_out log), hence the wide band here; the
+        # equality-grade statement for GMRES lives in test_gpu_solver_equality.py
+        assert abs(out1.RI.itr - out0.RI.itr) <= out0.RI.itr // 12
         assert out1.RI.fNorm <= ls.RI.relTol * out1.RI.iNorm
         assert common.rel_err(X1, X0) < 1e-6
 
