@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define SVB200_ABI_VERSION 4
+#define SVB200_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define SVB200_API __attribute__((visibility("default")))
@@ -82,8 +82,10 @@ typedef enum {
   SVB200_ISO_NHK = 0, SVB200_ISO_MR = 1, SVB200_ISO_GUCCIONE = 2, SVB200_ISO_STVK = 3,
   SVB200_ISO_HGO = 4,      /* Holzapfel-Gasser-Ogden, additive split (mat_models.cpp:469-511): C10, aff, bff, ass, bss, kap */
   SVB200_ISO_HO = 5,       /* Holzapfel-Ogden myocardium (:582-687): st_a, st_b, aff, bff, ass, bss, afs, bfs, khs */
-  SVB200_ISO_HO_MA = 6     /* Holzapfel-Ogden, modified anisotropy / full invariants (:689-773) */
+  SVB200_ISO_HO_MA = 6,    /* Holzapfel-Ogden, modified anisotropy / full invariants (:689-773) */
+  SVB200_ISO_CANN = 7      /* constitutive artificial neural network (:776-800, ArtificialNeuralNetMaterial.cpp): cann_* table */
 } svb200_iso;
+#define SVB200_CANN_MAX_ROWS 16
 /* volumetric part (solver/mat_models.cpp:1441-1464). */
 typedef enum { SVB200_VOL_NONE = 0, SVB200_VOL_QUAD = 1, SVB200_VOL_ST91 = 2, SVB200_VOL_M94 = 3 } svb200_vol;
 
@@ -150,6 +152,13 @@ typedef struct {
   /* appended in ABI version 3 */
   double conductivity, source_term;   /* heatS / heatF (solver/heats.cpp:202-204, heatf.cpp:259-260) */
   double ctau_M, ctau_C;              /* ustruct VMS constants (mat_models.cpp:1478-1479) */
+  /* appended in ABI version 5 */
+  int32_t active_stress;              /* dmn.active_stress != nullptr: the nodal active tensions of svb200_set_active_tension enter
+                                         compute_pk2cc along the fibre / sheet / sheet-normal directions (sv_struct.cpp:277-281) */
+  int32_t cann_rows;                  /* SVB200_ISO_CANN: rows of stM.paramTable (ArtificialNeuralNetMaterial.h) */
+  int32_t cann_inv[SVB200_CANN_MAX_ROWS];      /* invariant_indices(row), 1..9 */
+  int32_t cann_act[SVB200_CANN_MAX_ROWS][3];   /* activation_functions(row, 0..2) */
+  double cann_w[SVB200_CANN_MAX_ROWS][3];      /* weights(row, 0..2) */
 } svb200_dmnparams;
 
 /* FSILS_subLsType inputs (linear_solver/fils_struct.hpp:198-242). */
@@ -255,6 +264,11 @@ SVB200_API int svb200_set_state(svb200_ctx* ctx, int32_t tDof, const double* Ag,
 
 /* Old displacement Do(tDof,nNo) (solutions.old), read by the mesh-motion equation (solver/mesh.cpp:22-135). */
 SVB200_API int svb200_set_old_disp(svb200_ctx* ctx, int32_t tDof, const double* Do);
+/* Nodal active tensions cep_mod.cem.Ya_f / Ya_s / Ya_n (solver/CepMod.h:205-217; filled once per time step by the active-stress
+ * model, solver/active_stress.cpp), nNo doubles each in INPUT node order; Ya_s / Ya_n may be NULL (zero).  Read by the struct,
+ * FSI-solid and ustruct kernels for domains with active_stress set (sv_struct.cpp:277-281, ustruct.cpp:294-298).  The reference
+ * throws when Ya_s or Ya_n is positive for a model other than Guccione / HO / HO-ma (mat_models.cpp:334-340): checked at assembly. */
+SVB200_API int svb200_set_active_tension(svb200_ctx* ctx, const double* Ya_f, const double* Ya_s, const double* Ya_n);
 
 /* global_eq_assem for mesh iM: element loop + scatter, R/Val stay on the device. */
 SVB200_API int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq,

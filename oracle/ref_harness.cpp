@@ -75,6 +75,18 @@ struct RefCase {
   std::vector<int> ltg;
 };
 
+// A do-nothing active-stress model: the hot path only tests the pointer (the model itself runs once per time step,
+// solver/active_stress.cpp:50-66, outside the path).
+struct HarnessActiveStress : public ActiveStress {
+  HarnessActiveStress() : ActiveStress(0) {}
+  std::unique_ptr<ActiveStressModelParameters> get_parameters() const override { return nullptr; }
+  void read_model_specific_parameters(const ActiveStressModelParameters&) override {}
+  void distribute_model_specific_parameters(const CmMod&, const cmType&) override {}
+  void init_local(Vector<double>&) const override {}
+  void advance_time_step_local(const double, const double, const double, const double, const double, Vector<double>&) const override {}
+  double compute_active_tension_local(const Vector<double>&) const override { return 0.0; }
+};
+
 consts::EquationType to_phys(int p)
 {
   switch (p) {
@@ -124,7 +136,24 @@ void fill_domain(dmnType& d, const svb200_dmnparams& p)
     case SVB200_ISO_HGO: d.stM.isoType = ConstitutiveModelType::stIso_HGO; break;
     case SVB200_ISO_HO: d.stM.isoType = ConstitutiveModelType::stIso_HO; break;
     case SVB200_ISO_HO_MA: d.stM.isoType = ConstitutiveModelType::stIso_HO_ma; break;
+    case SVB200_ISO_CANN: {
+      // what set_material_props.h:155-175 does with the <Add_row> entries of a Constitutive_model type="CANN"
+      d.stM.isoType = ConstitutiveModelType::stArtificialNeuralNet;
+      auto& t = d.stM.paramTable;
+      t.num_rows = p.cann_rows;
+      t.invariant_indices.resize(t.num_rows);
+      t.activation_functions.resize(t.num_rows, 3);
+      t.weights.resize(t.num_rows, 3);
+      for (int r = 0; r < t.num_rows; r++) {
+        t.invariant_indices(r) = p.cann_inv[r];
+        for (int k = 0; k < 3; k++) { t.activation_functions(r, k) = p.cann_act[r][k]; t.weights(r, k) = p.cann_w[r][k]; }
+      }
+    } break;
   }
+  // dmn.active_stress != nullptr is all struct_3d / ustruct_3d look at (sv_struct.cpp:277, ustruct.cpp:294); the nodal
+  // tensions themselves are cep_mod.cem.Ya_f / Ya_s / Ya_n (svref_set_active_tension)
+  if (p.active_stress) d.active_stress = std::make_shared<HarnessActiveStress>();
+  else d.active_stress.reset();
   switch (p.volType) {
     case SVB200_VOL_NONE: d.stM.volType = ConstitutiveModelType::stVol_NA; break;
     case SVB200_VOL_QUAD: d.stM.volType = ConstitutiveModelType::stVol_Quad; break;
@@ -443,6 +472,22 @@ int svref_set_state(void* h, int tDof, const double* Ag, const double* Yg, const
     auto& Do = c.sol.old.get_displacement();
     if (Do.nrows() != tDof || Do.ncols() != n) Do.resize(tDof, n);
     if (Dg) std::memcpy(Do.data(), Dg, sizeof(double)*tDof*n);
+  });
+}
+
+/// cep_mod.cem.Ya_f / Ya_s / Ya_n (solver/CepMod.h:205-217), nNo values each; Ya_s / Ya_n may be null (zero).
+int svref_set_active_tension(void* h, const double* Ya_f, const double* Ya_s, const double* Ya_n)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    const int n = c.com_mod.tnNo;
+    auto& cem = c.cep_mod.cem;
+    cem.Ya_f.resize(n); cem.Ya_s.resize(n); cem.Ya_n.resize(n);
+    for (int a = 0; a < n; a++) {
+      cem.Ya_f[a] = Ya_f[a];
+      cem.Ya_s[a] = Ya_s ? Ya_s[a] : 0.0;
+      cem.Ya_n[a] = Ya_n ? Ya_n[a] : 0.0;
+    }
   });
 }
 

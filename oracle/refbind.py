@@ -143,6 +143,12 @@ class _FlatCase:
         Ag, Yg, Dg, Bf = _f64(Ag), _f64(Yg), _f64(Dg), _f64(Bf)
         self._call("set_state", C.c_int(Ag.shape[0]), _d(Ag), _d(Yg), _d(Dg), _d(Bf))
 
+    def set_active_tension(self, Ya_f, Ya_s=None, Ya_n=None):
+        f = np.ascontiguousarray(Ya_f, dtype=np.float64)
+        s_ = None if Ya_s is None else np.ascontiguousarray(Ya_s, dtype=np.float64)
+        n_ = None if Ya_n is None else np.ascontiguousarray(Ya_n, dtype=np.float64)
+        self._call("set_active_tension", _d(f), _d(s_), _d(n_))
+
     def set_old_disp(self, Do):
         Do = _f64(Do)
         self._call("set_old_disp", C.c_int(Do.shape[0]), _d(Do))

@@ -3,14 +3,15 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # svb200_phys
 PHYS_FLUID, PHYS_STRUCT, PHYS_FSI, PHYS_MESH, PHYS_LELAS, PHYS_HEATS, PHYS_HEATF, PHYS_USTRUCT = 0, 1, 2, 3, 4, 5, 6, 7
 # svb200_visc
 VISC_CONST, VISC_CY, VISC_CASSON = 0, 1, 2
 # svb200_iso / svb200_vol
-ISO_NHK, ISO_MR, ISO_GUCCIONE, ISO_STVK, ISO_HGO, ISO_HO, ISO_HO_MA = 0, 1, 2, 3, 4, 5, 6
+ISO_NHK, ISO_MR, ISO_GUCCIONE, ISO_STVK, ISO_HGO, ISO_HO, ISO_HO_MA, ISO_CANN = 0, 1, 2, 3, 4, 5, 6, 7
+CANN_MAX_ROWS = 16
 VOL_NONE, VOL_QUAD, VOL_ST91, VOL_M94 = 0, 1, 2, 3
 # svb200_ls_type
 LS_NS, LS_GMRES, LS_CG, LS_BICGS = 0, 1, 2, 3
@@ -60,6 +61,10 @@ class DmnParams(C.Structure):
         ("kap", C.c_double), ("khs", C.c_double),
         ("conductivity", C.c_double), ("source_term", C.c_double),
         ("ctau_M", C.c_double), ("ctau_C", C.c_double),
+        ("active_stress", C.c_int32), ("cann_rows", C.c_int32),
+        ("cann_inv", C.c_int32 * CANN_MAX_ROWS),
+        ("cann_act", (C.c_int32 * 3) * CANN_MAX_ROWS),
+        ("cann_w", (C.c_double * 3) * CANN_MAX_ROWS),
     ]
 
 
@@ -132,9 +137,10 @@ def struct_domain(rho: float = 1000.0, isoType: int = ISO_NHK, volType: int = VO
                   Kpen: float = 4.0e9, C10=None, C01: float = 0.0, bff: float = 0.0, bss: float = 0.0, bfs: float = 0.0,
                   dmp: float = 0.0, f=(0.0, 0.0, 0.0), Id: int = -1, solid_visc: int = 0, solid_visc_mu: float = 0.0,
                   st_a: float = 0.0, st_b: float = 0.0, aff: float = 0.0, ass: float = 0.0, afs: float = 0.0, kap: float = 0.0,
-                  khs: float = 100.0) -> DmnParams:
+                  khs: float = 100.0, active_stress: bool = False, cann=None) -> DmnParams:
     """Solid domain; C10 defaults to mu/2 with mu = E/(2(1+nu)) as set_material_props does for nHK
-    (Code/Source/solver/set_material_props.h)."""
+    (Code/Source/solver/set_material_props.h).  cann: rows (invariant, (kf0, kf1, kf2), (W0, W1, W2)) of the CANN parameter
+    table (the <Add_row> entries of a Constitutive_model type="CANN", ArtificialNeuralNetMaterial.h); sets isoType."""
     d = DmnParams()
     d.Id = Id
     d.phys = PHYS_STRUCT
@@ -150,6 +156,16 @@ def struct_domain(rho: float = 1000.0, isoType: int = ISO_NHK, volType: int = VO
     d.E, d.nu = E, nu
     d.solidViscType, d.solid_visc_mu = solid_visc, solid_visc_mu
     d.st_a, d.st_b, d.aff, d.ass, d.afs, d.kap, d.khs = st_a, st_b, aff, ass, afs, kap, khs
+    d.active_stress = 1 if active_stress else 0
+    if cann is not None:
+        assert 1 <= len(cann) <= CANN_MAX_ROWS
+        d.isoType = ISO_CANN
+        d.cann_rows = len(cann)
+        for r, (inv, act, w) in enumerate(cann):
+            d.cann_inv[r] = inv
+            for k in range(3):
+                d.cann_act[r][k] = act[k]
+                d.cann_w[r][k] = w[k]
     return d
 
 

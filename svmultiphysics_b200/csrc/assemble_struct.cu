@@ -29,6 +29,7 @@ struct StructArgs {
   const double* Yg;
   const double* Dg;
   const double* Bf;
+  const double* Ya;      // nodal active tensions (3, nNo): Ya_f, Ya_s, Ya_n (cep_mod.cem), or nullptr
   double* R;
   double* Val;
   int e0, e1;
@@ -38,6 +39,7 @@ struct StructArgs {
   double N[MAX_NG][MAX_ENON];
   double Nxi[MAX_NG][MAX_ENON][3];
   StructDmn dmn[MAX_DMN];
+  CannRow cann[MAX_CANN_ROWS];
 };
 
 template <bool ATOMIC>
@@ -160,8 +162,20 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
         for (int j = 0; j < 3; j++) F[i][j] += Nxb[j] * sd[b][i];
       }
     }
+    // active tensions at the Gauss point: ya_g = sum_b N_b Ya(:, node_b)  (sv_struct.cpp:640-642)
+    double ya[3] = {0.0, 0.0, 0.0};
+    const bool act = (P.Ya != nullptr) && dm.active;
+    if (act) {
+#pragma unroll
+      for (int b = 0; b < ENON; b++) {
+        const size_t nb = (size_t)P.IEN[(size_t)e * ENON + b];
+        const double Nb = tN[g][b];
+#pragma unroll
+        for (int i = 0; i < 3; i++) ya[i] += Nb * __ldg(P.Ya + 3 * nb + i);
+      }
+    }
     double S[3][3], Dm[6][6];
-    pk2cc_voigt(dm, F, fN, S, Dm);
+    pk2cc_voigt(dm, F, fN, act ? ya : nullptr, P.cann, P.nFn, S, Dm);
     if (VISC && dm.viscType != SVB200_SOLID_VISC_NONE) {
       // S += Svis (sv_struct.cpp:666-669); the viscous tangent is added by assemble_struct_visc_kernel
       double vx[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, Svis[3][3];
@@ -476,16 +490,28 @@ assemble_struct_tet4_kernel(const __grid_constant__ StructArgs P)
       for (int k = 0; k < P.nFn && k < 2; k++)
 #pragma unroll
         for (int i = 0; i < 3; i++) fN[k][i] = __ldg(P.fN + (size_t)3 * P.nFn * e + 3 * k + i);
+    // moments of the quadrature rule (struct_elem.cuh: the same routines the CPU suite checks against the reference)
+    Tet4Mom q;
+    tet4_moments(P.w, &P.N[0][0], MAX_ENON, Jac, q);
+    W = q.W;
+    // active tensions: S and Dm are affine in (Tfa, Tsa, Tna), so the Gauss sum of struct_3d equals one evaluation at the
+    // weighted mean sum_g w_g ya_g / W = sum_a m1_a Ya_a / W
+    double ya[3] = {0.0, 0.0, 0.0};
+    const bool act = (P.Ya != nullptr) && dm.active;
+    if (act) {
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) ya[i] += q.m1[a] * __ldg(P.Ya + 3 * (size_t)node[a] + i);
+#pragma unroll
+      for (int i = 0; i < 3; i++) ya[i] /= q.W;
+    }
     double Dm[6][6];
-    pk2cc_voigt(dm, F, fN, S, Dm);
+    pk2cc_voigt(dm, F, fN, act ? ya : nullptr, P.cann, P.nFn, S, Dm);
 #pragma unroll
     for (int r = 0; r < 6; r++)
 #pragma unroll
       for (int c = 0; c < 6; c++) s_Dm[6 * r + c][threadIdx.x] = Dm[r][c];
-    // moments of the quadrature rule, residual (struct_elem.cuh: the same routines the CPU suite checks against the reference)
-    Tet4Mom q;
-    tet4_moments(P.w, &P.N[0][0], MAX_ENON, Jac, q);
-    W = q.W;
     double Pk[3][3];
 #pragma unroll
     for (int i = 0; i < 3; i++)
@@ -843,6 +869,45 @@ assemble_mesh_tet4_kernel(const __grid_constant__ StructArgs P, const double* __
     }
 }
 
+// Active stress flag and CANN table of one solid domain (shared by the struct and the ustruct argument blocks).
+int fill_solid_extras(svb200_ctx* ctx, const svb200_dmnparams& p, StructDmn& o, CannRow* table, int* used)
+{
+  o.active = (p.active_stress != 0 && ctx->d_Ya != nullptr) ? 1 : 0;
+  if (p.active_stress != 0 && ctx->d_Ya == nullptr) {
+    set_error("svb200_assemble: the domain has an active-stress model but svb200_set_active_tension was not called");
+    return SVB200_ERR_INVALID;
+  }
+  const bool dirs = (o.isoType == SVB200_ISO_GUCCIONE || o.isoType == SVB200_ISO_HO || o.isoType == SVB200_ISO_HO_MA);
+  if (o.active && !dirs && ctx->ya_sn_positive) {
+    // mat_models.cpp:334-340
+    set_error("Directional distribution of active stress (eta_s > 0 or eta_n > 0) is only supported for Guccione, "
+              "Holzapfel-Ogden (HO), and Holzapfel-Ogden Modified Anisotropy (HO-ma) models.");
+    return SVB200_ERR_INVALID;
+  }
+  o.cann_off = 0;
+  o.cann_rows = 0;
+  if (o.isoType == SVB200_ISO_CANN) {
+    const int n = p.cann_rows;
+    if (n < 1 || n > SVB200_CANN_MAX_ROWS || *used + n > MAX_CANN_ROWS) {
+      set_error("svb200_assemble: CANN parameter table must have 1..16 rows (32 over all domains)");
+      return SVB200_ERR_INVALID;
+    }
+    o.cann_off = *used;
+    o.cann_rows = n;
+    for (int r = 0; r < n; r++) {
+      CannRow& q = table[*used + r];
+      q.inv = p.cann_inv[r]; q.a0 = p.cann_act[r][0]; q.a1 = p.cann_act[r][1]; q.a2 = p.cann_act[r][2];
+      q.w0 = p.cann_w[r][0]; q.w1 = p.cann_w[r][1]; q.w2 = p.cann_w[r][2];
+      if (q.inv < 1 || q.inv > 9 || q.a0 < 1 || q.a0 > 3 || q.a1 < 1 || q.a1 > 2 || q.a2 < 1 || q.a2 > 3) {
+        set_error("svb200_assemble: CANN row out of range (invariant 1..9, activation functions (1..3, 1..2, 1..3))");
+        return SVB200_ERR_INVALID;
+      }
+    }
+    *used += n;
+  }
+  return SVB200_OK;
+}
+
 int fill_struct_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn, StructArgs& A)
 {
   SVB_REQUIRE(nDmn >= 1 && nDmn <= MAX_DMN, "svb200_assemble: between 1 and 8 domains are supported");
@@ -854,9 +919,11 @@ int fill_struct_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, 
   memset(&A, 0, sizeof(A));
   A.IEN = m.d_IEN; A.eId = m.d_eId; A.slot = m.d_slot; A.perm = nullptr; A.fN = m.d_fN;
   A.x = ctx->d_x; A.Ag = ctx->d_Ag; A.Yg = ctx->d_Yg; A.Dg = ctx->d_Dg; A.Bf = ctx->d_Bf;
+  A.Ya = ctx->d_Ya;
   A.R = ctx->d_R; A.Val = ctx->d_Val;
   A.e0 = 0; A.e1 = m.nEl;
   A.tDof = eq->tDof; A.dof = eq->dof; A.s = eq->s; A.nFn = m.nFn; A.nDmn = nDmn; A.nG = m.nG;
+  int cann_used = 0;
   A.atomic = (eq->scatter == SVB200_SCATTER_ATOMIC);
   A.dt = eq->dt; A.af = eq->af; A.am = eq->am; A.gam = eq->gam; A.beta = eq->beta;
   for (int g = 0; g < m.nG; g++) {
@@ -885,7 +952,9 @@ int fill_struct_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, 
     o.isStruct = (dmn[d].phys == SVB200_PHYS_STRUCT);
     SVB_REQUIRE(o.Id >= -1 && o.Id < 31, "svb200_assemble: domain Id out of range");
     if (o.isStruct) {
-      SVB_REQUIRE(o.isoType >= SVB200_ISO_NHK && o.isoType <= SVB200_ISO_HO_MA, "svb200_assemble: constitutive model not implemented");
+      SVB_REQUIRE(o.isoType >= SVB200_ISO_NHK && o.isoType <= SVB200_ISO_CANN, "svb200_assemble: constitutive model not implemented");
+      int rc = fill_solid_extras(ctx, dmn[d], o, A.cann, &cann_used);
+      if (rc) return rc;
       // compute_pk2cc throws for the fibre models without two fibre families (mat_models.cpp:472-474, 514-516, 584-586)
       const bool fibres = (m.nFn == 2 && m.d_fN);
       if (o.isoType == SVB200_ISO_GUCCIONE && !fibres) {

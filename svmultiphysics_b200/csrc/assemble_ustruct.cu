@@ -18,6 +18,8 @@
 
 namespace svb {
 
+int fill_solid_extras(svb200_ctx* ctx, const svb200_dmnparams& p, StructDmn& o, CannRow* table, int* used);   // assemble_struct.cu
+
 struct UstructArgs {
   const int* IEN;
   const int* eId;
@@ -29,6 +31,7 @@ struct UstructArgs {
   const double* Yg;
   const double* Dg;
   const double* Bf;
+  const double* Ya;      // nodal active tensions (3, nNo) or nullptr (ustruct.cpp:294-298)
   double* R;
   double* Val;
   double* Kd;
@@ -41,6 +44,7 @@ struct UstructArgs {
   double Nxi[MAX_NG][MAX_ENON][3];
   UstructDmn dmn[MAX_DMN];
   int active[MAX_DMN];
+  CannRow cann[MAX_CANN_ROWS];
 };
 
 constexpr int USTRUCT_THREADS = 64;
@@ -146,6 +150,16 @@ assemble_ustruct_kernel(const __grid_constant__ UstructArgs P)
 #pragma unroll
         for (int i = 0; i < 3; i++) fN[k][i] = __ldg(P.fN + (size_t)3 * P.nFn * e + 3 * k + i);
     const int g = a;
+    // active tensions at the Gauss point (ustruct.cpp:955-957, 1265-1267)
+    double ya[3] = {0.0, 0.0, 0.0};
+    const bool act = (P.Ya != nullptr) && dm.st.active;
+    if (act) {
+#pragma unroll
+      for (int b = 0; b < ENON; b++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) ya[i] += P.N[g][b] * __ldg(P.Ya + 3 * (size_t)node[b] + i);
+    }
+    const double* yap = act ? ya : nullptr;
     UGP& q = ugp_of(gp[g]);               // written in place: a local copy would cost 880 B of stack per thread
     if constexpr (VISC) {
       // a domain of this launch without viscosity leaves c = 0 sets: its viscous blocks vanish
@@ -157,9 +171,9 @@ assemble_ustruct_kernel(const __grid_constant__ UstructArgs P)
           gp[g].gu.T[i][j] = gp[g].gu.A[i][j] = gp[g].gu.B[i][j] = gp[g].gu.M[i][j] = 0.0;
           gp[g].gv.T[i][j] = gp[g].gv.A[i][j] = gp[g].gv.B[i][j] = gp[g].gv.M[i][j] = 0.0;
         }
-      ustruct_gauss_point<ENON>(dm, P.dt, P.af, P.am, P.gam, P.w[g], P.N[g], P.Nxi[g], xl, ql, vl, dl, pl, pdl, fN, q, &gp[g].gu, &gp[g].gv);
+      ustruct_gauss_point<ENON>(dm, P.dt, P.af, P.am, P.gam, P.w[g], P.N[g], P.Nxi[g], xl, ql, vl, dl, pl, pdl, fN, q, &gp[g].gu, &gp[g].gv, yap, P.cann, P.nFn);
     } else {
-      ustruct_gauss_point<ENON>(dm, P.dt, P.af, P.am, P.gam, P.w[g], P.N[g], P.Nxi[g], xl, ql, vl, dl, pl, pdl, fN, q);
+      ustruct_gauss_point<ENON>(dm, P.dt, P.af, P.am, P.gam, P.w[g], P.N[g], P.Nxi[g], xl, ql, vl, dl, pl, pdl, fN, q, nullptr, nullptr, yap, P.cann, P.nFn);
     }
     // construct_usolid throws when utils::is_zero(Jac) (ustruct.cpp:312-314); q.w = w_g * Jac
     if (fabs(q.w) < fabs(P.w[g]) * 10.0 * 2.220446049250313e-16 * 2.220446049250313e-16) atomicMax(P.err, e + 1);
@@ -321,8 +335,26 @@ assemble_ustruct_tet4_kernel(const __grid_constant__ UstructArgs P)
       for (int k = 0; k < P.nFn && k < 2; k++)
 #pragma unroll
         for (int i = 0; i < 3; i++) fN[k][i] = __ldg(P.fN + (size_t)3 * P.nFn * e + 3 * k + i);
+    // active tensions: Siso and Dm are affine in them and enter the Gauss sums with the weight alone, so one evaluation at
+    // the weighted mean sum_g w_g ya_g / sum_g w_g reproduces the sum
+    double ya[3] = {0.0, 0.0, 0.0};
+    const bool act = (P.Ya != nullptr) && dm.st.active;
+    if (act) {
+      double wsum = 0.0;
+#pragma unroll
+      for (int g = 0; g < 4; g++) {
+        wsum += P.w[g];
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+#pragma unroll
+          for (int i = 0; i < 3; i++) ya[i] += P.w[g] * P.N[g][b] * __ldg(P.Ya + 3 * (size_t)node[b] + i);
+      }
+#pragma unroll
+      for (int i = 0; i < 3; i++) ya[i] /= wsum;
+    }
     double Dm[6][6], Je;
-    ustruct_tet4_setup(dm, af, am, P.w, &P.N[0][0], MAX_ENON, P.Nxi[0], xl, ql, vl, dl, pl, pdl, fN, C, M, Dm, &Je);
+    ustruct_tet4_setup(dm, af, am, P.w, &P.N[0][0], MAX_ENON, P.Nxi[0], xl, ql, vl, dl, pl, pdl, fN, C, M, Dm, &Je,
+                       act ? ya : nullptr, P.cann, P.nFn);
     if (fabs(Je) < 10.0 * 2.220446049250313e-16 * 2.220446049250313e-16) atomicMax(P.err, e + 1);
 #pragma unroll
     for (int r = 0; r < 6; r++)
@@ -450,6 +482,8 @@ int run_assemble_ustruct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* 
   A.IEN = m.d_IEN; A.eId = m.d_eId; A.slot = m.d_slot; A.perm = nullptr; A.fN = m.d_fN;
   A.x = ctx->d_x; A.Ag = ctx->d_Ag; A.Yg = ctx->d_Yg; A.Dg = ctx->d_Dg; A.Bf = ctx->d_Bf;
   A.R = ctx->d_R; A.Val = ctx->d_Val; A.Kd = ctx->d_Kd;
+  A.Ya = ctx->d_Ya;
+  int cann_used = 0;
   if (!ctx->d_err) {
     SVB_CUDA(cudaMalloc(&ctx->d_err, sizeof(int)));
     SVB_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
@@ -487,7 +521,9 @@ int run_assemble_ustruct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* 
     A.dmn[d].E = dmn[d].E; A.dmn[d].nu = dmn[d].nu; A.dmn[d].ctM = dmn[d].ctau_M; A.dmn[d].ctC = dmn[d].ctau_C;
     SVB_REQUIRE(o.Id >= -1 && o.Id < 31, "svb200_assemble: domain Id out of range");
     if (A.active[d]) {
-      SVB_REQUIRE(o.isoType >= SVB200_ISO_NHK && o.isoType <= SVB200_ISO_HO_MA, "svb200_assemble: constitutive model not implemented");
+      SVB_REQUIRE(o.isoType >= SVB200_ISO_NHK && o.isoType <= SVB200_ISO_CANN, "svb200_assemble: constitutive model not implemented");
+      int rce = fill_solid_extras(ctx, dmn[d], o, A.cann, &cann_used);
+      if (rce) return rce;
       const bool fibres = (m.nFn == 2 && m.d_fN);
       if ((o.isoType == SVB200_ISO_GUCCIONE || o.isoType == SVB200_ISO_HGO || o.isoType == SVB200_ISO_HO || o.isoType == SVB200_ISO_HO_MA) && !fibres) {
         set_error("[compute_pk2cc] Min fiber directions not defined for this material model.");

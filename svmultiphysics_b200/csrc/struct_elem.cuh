@@ -27,8 +27,17 @@ struct StructDmn {
   double st_a, st_b, aff, ass, afs, kap, khs;   // stModelType a, b, aff, ass, afs, kap, khs (HGO / Holzapfel-Ogden)
   double visc_mu;
   int isoType, volType, Id, isStruct;
-  int viscType, pad;      // svb200_solid_visc
+  int viscType, active;   // svb200_solid_visc; active = dmn.active_stress != nullptr (nodal Ya_f / Ya_s / Ya_n are used)
+  int cann_off, cann_rows;   // rows [cann_off, cann_off + cann_rows) of the argument block's CANN table (SVB200_ISO_CANN)
 };
+
+// One row of ArtificialNeuralNetMaterial's parameter table (ArtificialNeuralNetMaterial.h: invariant_indices,
+// activation_functions(:,0..2), weights(:,0..2)).
+struct CannRow {
+  int inv, a0, a1, a2;
+  double w0, w1, w2;
+};
+constexpr int MAX_CANN_ROWS = 32;   // all domains of one assembly call together
 
 #define SVB_VI(a) ((a) < 3 ? (a) : ((a) == 3 ? 0 : ((a) == 4 ? 1 : 2)))
 #define SVB_VJ(a) ((a) < 3 ? (a) : ((a) == 3 ? 1 : ((a) == 4 ? 2 : 0)))
@@ -53,6 +62,18 @@ SVB_HD void dm_add_symdyad(double Dm[6][6], double c, const double A[3][3])
     }
 }
 
+// Dm += c * symmetric_dyadic_product(A, B): 1/2 (A_ik B_jl + A_il B_jk)  (mat_fun.h:203-223)
+SVB_HD void dm_add_symdyad2(double Dm[6][6], double c, const double A[3][3], const double B[3][3])
+{
+#pragma unroll
+  for (int a = 0; a < 6; a++)
+#pragma unroll
+    for (int b = 0; b < 6; b++) {
+      const int i = SVB_VI(a), j = SVB_VJ(a), k = SVB_VI(b), l = SVB_VJ(b);
+      Dm[a][b] += c * 0.5 * (A[i][k] * B[j][l] + A[i][l] * B[j][k]);
+    }
+}
+
 SVB_HD double ddot(const double A[3][3], const double B[3][3])
 {
   double s = 0.0;
@@ -63,9 +84,15 @@ SVB_HD double ddot(const double A[3][3], const double B[3][3])
   return s;
 }
 
-// compute_pk2cc<3> without active stress / prestress / viscosity: F -> S (3x3), Dm (6x6).
-// fN[0] = fibre, fN[1] = sheet direction (Guccione only).  Returns 0, or 1 for an unsupported model.
-SVB_HD int pk2cc_voigt(const StructDmn& dm, const double F[3][3], const double fN[2][3], double S[3][3], double Dm[6][6])
+// The CANN model (mat_models.cpp:776-800 with ArtificialNeuralNetMaterial.cpp:16-190) on the Voigt matrix; below.
+SVB_HD void cann_voigt(const CannRow* rows, int nrows, int nFn, const double fN[2][3], const double C[3][3], const double Ci[3][3],
+                       double J, double J2d, double J4d, double S[3][3], double Dm[6][6]);
+
+// compute_pk2cc<3> (without prestress / viscosity, which struct_3d adds): F -> S (3x3), Dm (6x6).
+// fN[0] = fibre, fN[1] = sheet direction.  ya = {Tfa, Tsa, Tna}: active stresses along the fibre, sheet and sheet-normal
+// directions (mat_models.cpp:321-326; nullptr = none).  Returns 0, or 1 for an unsupported model.
+SVB_HD int pk2cc_voigt(const StructDmn& dm, const double F[3][3], const double fN[2][3], const double* ya, const CannRow* cann,
+                       int nFn, double S[3][3], double Dm[6][6])
 {
 #pragma unroll
   for (int a = 0; a < 6; a++)
@@ -109,7 +136,44 @@ SVB_HD int pk2cc_voigt(const StructDmn& dm, const double F[3][3], const double f
     dm_add_dyad(Dm, pl * J, Ci, Ci);
   }
 
+  // Active stress Tfa f(x)f [+ Tsa s(x)s + Tna n(x)n for the Guccione / HO / HO-ma models; the reference throws for the
+  // others when Tsa or Tna > 0, which the host checks at svb200_set_active_tension] — added to S_bar before the deviatoric
+  // projection (mat_models.cpp:443, 461, 503, 570-575, 636, 650, 661-664) or, for HO-ma and CANN, to S directly (:745-772, 800).
+  double Sact[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  const bool act = (ya != nullptr) && dm.active;
+  if (act) {
+    const bool dirs = (dm.isoType == SVB200_ISO_GUCCIONE || dm.isoType == SVB200_ISO_HO || dm.isoType == SVB200_ISO_HO_MA);
+    double nrm[3] = {0, 0, 0};
+    const bool useN = dirs && ya[2] > 0.0;
+    if (useN) {
+      nrm[0] = fN[0][1] * fN[1][2] - fN[0][2] * fN[1][1];
+      nrm[1] = fN[0][2] * fN[1][0] - fN[0][0] * fN[1][2];
+      nrm[2] = fN[0][0] * fN[1][1] - fN[0][1] * fN[1][0];
+      const double nn = sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+      nrm[0] /= nn; nrm[1] /= nn; nrm[2] /= nn;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        double t = ya[0] * fN[0][i] * fN[0][j];
+        if (dirs) t += ya[1] * fN[1][i] * fN[1][j];
+        if (useN) t += ya[2] * nrm[i] * nrm[j];
+        Sact[i][j] = t;
+      }
+  }
+
   double Idm[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  if (dm.isoType == SVB200_ISO_CANN) {
+    cann_voigt(cann + dm.cann_off, dm.cann_rows, nFn, fN, C, Ci, J, J2d, J4d, S, Dm);
+    if (act) {
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) S[i][j] += ya[0] * fN[0][i] * fN[0][j];
+    }
+    return 0;
+  }
   if (dm.isoType == SVB200_ISO_STVK) {        // mat_models.cpp:415-421
     const double g1 = dm.C10, g2 = dm.C01 * 2.0;
     const double trE = 0.5 * (trC - 3.0);
@@ -284,6 +348,12 @@ SVB_HD int pk2cc_voigt(const StructDmn& dm, const double F[3][3], const double f
         dm_add_dyad(Dm, c_fs, Hfs, Hfs);
         dm_add_dyad(Dm, c_ff, Hff, Hff);
         dm_add_dyad(Dm, c_ss, Hss, Hss);
+        if (act) {
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) { S[i][j] += Sact[i][j]; Sact[i][j] = 0.0; }
+        }
       }
     }
 #pragma unroll
@@ -302,6 +372,12 @@ SVB_HD int pk2cc_voigt(const StructDmn& dm, const double F[3][3], const double f
   } else {
     return 1;
   }
+  if (act) {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) Sb[i][j] += Sact[i][j];
+  }
   // bar_to_iso (mat_models.cpp:232-255)
   const double r1 = J2d * ddot(C, Sb) / 3.0;
   double Siso[3][3];
@@ -317,6 +393,186 @@ SVB_HD int pk2cc_voigt(const StructDmn& dm, const double F[3][3], const double f
   dm_add_symdyad(Dm, 2.0 * r1, Ci);
   dm_add_dyad(Dm, -2.0 * r1 / 3.0, Ci, Ci);
   return 0;
+}
+
+// ---- CANN: constitutive artificial neural network (Peirlinck et al. 2025; ArtificialNeuralNetMaterial.cpp) ------------------
+// psi = sum_rows W2 f2(f1(f0(I_k - ref_k))), S = 2 sum_k dpsi_k dI_k/dC, CC = 4 sum_k (dpsi_k d2I_k/dC2 + ddpsi_k dI_k (x) dI_k).
+// The invariants and their first / second derivatives follow computeInvariantsAndDerivatives (:114-190) term by term; the
+// fourth-order tensors are accumulated directly on the Voigt matrix (cc_to_voigt_eigen picks CC(i,j,k,l) with (i,j), (k,l) the
+// Voigt pairs 00,11,22,01,12,20 of the upper triangle and mirrors it).
+SVB_HD void cann_act(const CannRow& r, double x, double& d1, double& d2)
+{
+  // uCANN_h0 / h1 / h2 (:16-70) and the chain rule of uCANN (:73-88); returns d psi_row / dI and d2 psi_row / dI2 (without W2)
+  double f0 = x, df0 = 1.0, ddf0 = 0.0;
+  if (r.a0 == 2) { f0 = 0.5 * (fabs(x) + x); df0 = (x == 0.0) ? 0.0 : 0.5 * (fabs(x) / x + 1.0); }
+  else if (r.a0 == 3) { f0 = fabs(x); df0 = fabs(x) / x; }
+  double f1 = r.w0 * f0, df1 = r.w0, ddf1 = 0.0;
+  if (r.a1 == 2) { f1 = r.w0 * r.w0 * f0 * f0; df1 = 2.0 * r.w0 * r.w0 * f0; ddf1 = 2.0 * r.w0 * r.w0; }
+  double df2 = r.w1, ddf2 = 0.0;
+  if (r.a2 == 2) { const double ex = exp(r.w1 * f1); df2 = r.w1 * ex; ddf2 = r.w1 * r.w1 * ex; }
+  else if (r.a2 == 3) { const double q = 1.0 - r.w1 * f1; df2 = r.w1 / q; ddf2 = -r.w1 * r.w1 / (q * q); }
+  d1 = df2 * df1 * df0;
+  d2 = (ddf2 * df1 * df1 + df2 * ddf1) * df0 * df0 + df2 * df1 * ddf0;
+}
+
+// Invariant pair (J2d n.C m, J4d n.C^2 m) of a structure tensor N = sym(n (x) m): first derivatives dA = -IA/3 Ci + J2d N,
+// dB = J4d (N C + C N) - IB/3 Ci and their second derivatives, weighted by (pA, ppA) and (pB, ppB) = (dpsi, ddpsi).
+SVB_HD void cann_fibre_pair(const double N[3][3], double IA, double IB, double pA, double ppA, double pB, double ppB,
+                            const double C[3][3], const double Ci[3][3], const double Idm[3][3], double J2d, double J4d,
+                            double S[3][3], double Dm[6][6])
+{
+  double dA[3][3], dB[3][3], NC[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; k++) t += N[i][k] * C[k][j] + C[i][k] * N[k][j];
+      NC[i][j] = t;
+    }
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      dA[i][j] = -IA / 3.0 * Ci[i][j] + J2d * N[i][j];
+      dB[i][j] = J4d * NC[i][j] - IB / 3.0 * Ci[i][j];
+      S[i][j] += 2.0 * (pA * dA[i][j] + pB * dB[i][j]);
+    }
+  if (pA != 0.0) {
+    // ddA = -1/3 (dA (x) Ci + J2d Ci (x) N + IA dCidC), dCidC = -sym(Ci, Ci)
+    const double c = 4.0 * pA * (-1.0 / 3.0);
+    dm_add_dyad(Dm, c, dA, Ci);
+    dm_add_dyad(Dm, c * J2d, Ci, N);
+    dm_add_symdyad(Dm, -c * IA, Ci);
+  }
+  if (ppA != 0.0) dm_add_dyad(Dm, 4.0 * ppA, dA, dA);
+  if (pB != 0.0) {
+    // ddB = -1/3 (dB (x) Ci + IB dCidC + 2 J4d Ci (x) (N C + C N)) + J4d (2 sym(N, I) - N (x) I + 2 sym(I, N) - I (x) N)
+    const double c = 4.0 * pB * (-1.0 / 3.0);
+    dm_add_dyad(Dm, c, dB, Ci);
+    dm_add_symdyad(Dm, -c * IB, Ci);
+    dm_add_dyad(Dm, c * 2.0 * J4d, Ci, NC);
+    const double d = 4.0 * pB * J4d;
+    dm_add_symdyad2(Dm, 2.0 * d, N, Idm);
+    dm_add_dyad(Dm, -d, N, Idm);
+    dm_add_symdyad2(Dm, 2.0 * d, Idm, N);
+    dm_add_dyad(Dm, -d, Idm, N);
+  }
+  if (ppB != 0.0) dm_add_dyad(Dm, 4.0 * ppB, dB, dB);
+}
+
+SVB_HD void cann_voigt(const CannRow* rows, int nrows, int nFn, const double fN[2][3], const double C[3][3], const double Ci[3][3],
+                       double J, double J2d, double J4d, double S[3][3], double Dm[6][6])
+{
+  const double Idm[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  double C2[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) C2[i][j] = C[i][0] * C[0][j] + C[i][1] * C[1][j] + C[i][2] * C[2][j];
+  const double trC = C[0][0] + C[1][1] + C[2][2], trC2 = C2[0][0] + C2[1][1] + C2[2][2];
+  double N1[3][3], N2[3][3], N12[3][3];
+  double Inv[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  Inv[0] = J2d * trC;
+  Inv[1] = 0.5 * (Inv[0] * Inv[0] - J4d * trC2);
+  Inv[2] = J * J;   // det C
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      N1[i][j] = fN[0][i] * fN[0][j];
+      N2[i][j] = fN[1][i] * fN[1][j];
+      N12[i][j] = 0.5 * (fN[0][i] * fN[1][j] + fN[1][i] * fN[0][j]);
+    }
+  auto quad = [](const double a[3], const double M[3][3], const double b[3]) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) s += a[i] * M[i][j] * b[j];
+    return s;
+  };
+  Inv[3] = J2d * quad(fN[0], C, fN[0]);
+  Inv[4] = J4d * quad(fN[0], C2, fN[0]);
+  if (nFn == 2) {
+    Inv[5] = J2d * quad(fN[0], C, fN[1]);
+    Inv[6] = J4d * quad(fN[0], C2, fN[1]);
+    Inv[7] = J2d * quad(fN[1], C, fN[1]);
+    Inv[8] = J4d * quad(fN[1], C2, fN[1]);
+  }
+  // evaluate (:90-112): dpsi / ddpsi per invariant
+  const double ref[9] = {3, 3, 1, 1, 1, 0, 0, 1, 1};
+  double dpsi[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ddpsi[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int r = 0; r < nrows; r++) {
+    const int k = rows[r].inv - 1;
+    double d1, d2;
+    cann_act(rows[r], Inv[k] - ref[k], d1, d2);
+    dpsi[k] += rows[r].w2 * d1;
+    ddpsi[k] += rows[r].w2 * d2;
+  }
+  // invariants 1-3
+  double d1[3][3], d2[3][3], d3[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      d1[i][j] = -Inv[0] / 3.0 * Ci[i][j] + J2d * Idm[i][j];
+      d3[i][j] = Inv[2] * Ci[i][j];
+    }
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      d2[i][j] = (trC2 / 3.0) * Ci[i][j] + Inv[0] * d1[i][j] + J4d * C[i][j];
+      S[i][j] += 2.0 * (dpsi[0] * d1[i][j] + dpsi[1] * d2[i][j] + dpsi[2] * d3[i][j]);
+    }
+  // ddInv1 = -1/3 (d1 (x) Ci - Inv0 sym(Ci,Ci) + J2d Ci (x) I); it also enters ddInv2 with the factor Inv0
+  {
+    const double c = (4.0 * dpsi[0] + 4.0 * dpsi[1] * Inv[0]) * (-1.0 / 3.0);
+    if (c != 0.0) {
+      dm_add_dyad(Dm, c, d1, Ci);
+      dm_add_symdyad(Dm, -c * Inv[0], Ci);
+      dm_add_dyad(Dm, c * J2d, Ci, Idm);
+    }
+  }
+  if (ddpsi[0] != 0.0) dm_add_dyad(Dm, 4.0 * ddpsi[0], d1, d1);
+  if (dpsi[1] != 0.0) {
+    // ddInv2 - Inv0 ddInv1 = d1 (x) d1 - trC2/3 sym(Ci,Ci) + 1/3 (trC2 dJ4ddC + 2 J4d C) (x) Ci + dJ4ddC (x) C - J4d Isym,
+    // dJ4ddC = -2/3 J4d Ci
+    const double c = 4.0 * dpsi[1];
+    double T[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) T[i][j] = trC2 * (-2.0 / 3.0 * J4d) * Ci[i][j] + 2.0 * J4d * C[i][j];
+    dm_add_dyad(Dm, c, d1, d1);
+    dm_add_symdyad(Dm, -c * trC2 / 3.0, Ci);
+    dm_add_dyad(Dm, c / 3.0, T, Ci);
+    dm_add_dyad(Dm, c * (-2.0 / 3.0 * J4d), Ci, C);
+    dm_add_symdyad(Dm, -c * J4d, Idm);
+  }
+  if (ddpsi[1] != 0.0) dm_add_dyad(Dm, 4.0 * ddpsi[1], d2, d2);
+  if (dpsi[2] != 0.0) {
+    // ddInv3 = d3 (x) Ci - Inv2 sym(Ci,Ci)
+    dm_add_dyad(Dm, 4.0 * dpsi[2], d3, Ci);
+    dm_add_symdyad(Dm, -4.0 * dpsi[2] * Inv[2], Ci);
+  }
+  if (ddpsi[2] != 0.0) dm_add_dyad(Dm, 4.0 * ddpsi[2], d3, d3);
+  // invariants 4-5 (fibre), 6-7 (fibre-sheet), 8-9 (sheet).  Without a second fibre family the reference leaves dInv6..9 = 0.
+  if (dpsi[3] != 0.0 || ddpsi[3] != 0.0 || dpsi[4] != 0.0 || ddpsi[4] != 0.0)
+    cann_fibre_pair(N1, Inv[3], Inv[4], dpsi[3], ddpsi[3], dpsi[4], ddpsi[4], C, Ci, Idm, J2d, J4d, S, Dm);
+  if (nFn == 2) {
+    if (dpsi[5] != 0.0 || ddpsi[5] != 0.0 || dpsi[6] != 0.0 || ddpsi[6] != 0.0)
+      cann_fibre_pair(N12, Inv[5], Inv[6], dpsi[5], ddpsi[5], dpsi[6], ddpsi[6], C, Ci, Idm, J2d, J4d, S, Dm);
+    if (dpsi[7] != 0.0 || ddpsi[7] != 0.0 || dpsi[8] != 0.0 || ddpsi[8] != 0.0)
+      cann_fibre_pair(N2, Inv[7], Inv[8], dpsi[7], ddpsi[7], dpsi[8], ddpsi[8], C, Ci, Idm, J2d, J4d, S, Dm);
+  }
+  // cc_to_voigt_eigen keeps the upper triangle and mirrors it
+#pragma unroll
+  for (int a = 1; a < 6; a++)
+#pragma unroll
+    for (int b = 0; b < a; b++) Dm[a][b] = Dm[b][a];
 }
 
 // nn::gnn for insd = 3 and any eNoN (Code/Source/solver/nn.cpp:862-899): Nxi[a][k] -> Nx[a][i], Jac.

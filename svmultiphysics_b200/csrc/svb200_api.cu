@@ -235,7 +235,7 @@ int svb200_destroy(svb200_ctx* ctx)
   cudaFree(ctx->d_hg);
   for (auto& nb : ctx->neigh) { cudaFree(nb.d_ptr); cudaFree(nb.d_send); cudaFree(nb.d_recv); }
   cudaFree(ctx->d_map); cudaFree(ctx->d_rowPtr_in); cudaFree(ctx->d_rowPtr); cudaFree(ctx->d_colPtr); cudaFree(ctx->d_diagPtr);
-  cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf); cudaFree(ctx->d_Do);
+  cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf); cudaFree(ctx->d_Do); cudaFree(ctx->d_Ya);
   cudaFree(ctx->d_Ao); cudaFree(ctx->d_Yo); cudaFree(ctx->d_An); cudaFree(ctx->d_Yn); cudaFree(ctx->d_Dn); cudaFree(ctx->d_nodeflag);
   cudaFree(ctx->d_err); cudaFree(ctx->d_Kd); cudaFree(ctx->d_Ad); cudaFree(ctx->d_Rd);
   cudaFree(ctx->d_stage); cudaFree(ctx->d_R); cudaFree(ctx->d_Val); cudaFree(ctx->d_W);
@@ -379,6 +379,7 @@ int svb200_set_graph(svb200_ctx* ctx, int32_t nNo, int32_t nnz, const int32_t* r
   TRY(p2p_setup(ctx));      // collective: every rank calls svb200_set_graph
   // state arrays depend on nNo
   cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf); cudaFree(ctx->d_Do);
+  cudaFree(ctx->d_Ya); ctx->d_Ya = nullptr; ctx->ya_sn_positive = false;
   cudaFree(ctx->d_Ao); cudaFree(ctx->d_Yo); cudaFree(ctx->d_An); cudaFree(ctx->d_Yn); cudaFree(ctx->d_Dn); cudaFree(ctx->d_nodeflag);
   ctx->d_Ao = ctx->d_Yo = ctx->d_An = ctx->d_Yn = ctx->d_Dn = nullptr; ctx->d_nodeflag = nullptr;
   ctx->d_x = ctx->d_Ag = ctx->d_Yg = ctx->d_Dg = ctx->d_Bf = ctx->d_Do = nullptr;
@@ -750,6 +751,24 @@ static int run_assemble(svb200_ctx* ctx, const Mesh& m, FluidArgs& A, bool gener
     TRY(launch_assemble_fluid(ctx, m, A));
   }
   return SVB200_OK;
+}
+
+int svb200_set_active_tension(svb200_ctx* ctx, const double* Ya_f, const double* Ya_s, const double* Ya_n)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(Ya_f, "svb200_set_active_tension: Ya_f is null");
+  SVB_REQUIRE(ctx->nNo > 0 || ctx->d_rowPtr, "svb200_set_active_tension: set the graph first");
+  const size_t n = (size_t)ctx->nNo;
+  std::vector<double> h(3 * n);
+  bool sn = false;
+  for (size_t a = 0; a < n; a++) {
+    h[3 * a] = Ya_f[a];
+    h[3 * a + 1] = Ya_s ? Ya_s[a] : 0.0;
+    h[3 * a + 2] = Ya_n ? Ya_n[a] : 0.0;
+    sn |= (h[3 * a + 1] > 0.0 || h[3 * a + 2] > 0.0);
+  }
+  ctx->ya_sn_positive = sn;
+  return upload_nodal(ctx, 3, h.data(), &ctx->d_Ya);
 }
 
 int svb200_set_old_disp(svb200_ctx* ctx, int32_t tDof, const double* Do)

@@ -157,6 +157,8 @@ struct svb200_ctx {
   double* d_Yg = nullptr;
   double* d_Dg = nullptr;
   double* d_Do = nullptr;        // old displacement (mesh-motion equation; solutions.old)
+  double* d_Ya = nullptr;        // nodal active tensions (3, nNo): Ya_f, Ya_s, Ya_n (svb200_set_active_tension)
+  bool ya_sn_positive = false;   // any Ya_s or Ya_n > 0 (only the Guccione / HO / HO-ma models accept that)
   double* d_Ao = nullptr; double* d_Yo = nullptr;                          // solutions.old
   double* d_An = nullptr; double* d_Yn = nullptr; double* d_Dn = nullptr;  // solutions.current
   int* d_nodeflag = nullptr;     // per node: belongs to a solid domain (FSI corrector)

@@ -105,7 +105,8 @@ template <int ENON>
 SVB_HD int ustruct_gauss_point(const UstructDmn& dm, double dt, double af_eq, double am, double gam, double wg, const double N[],
                                const double Nxi[][3], const double xl[][3], const double ql[][3], const double vl[][3],
                                const double dl[][3], const double pl[], const double pdl[], const double fN[2][3], UGP& q,
-                               ViscGP* gu = nullptr, ViscGP* gv = nullptr)
+                               ViscGP* gu = nullptr, ViscGP* gv = nullptr, const double* ya = nullptr, const CannRow* cann = nullptr,
+                               int nFn = 2)
 {
   const double Je = ustruct_xiX<ENON>(Nxi, xl, q.xiX);
   q.w = wg * Je;
@@ -152,7 +153,7 @@ SVB_HD int ustruct_gauss_point(const UstructDmn& dm, double dt, double af_eq, do
   // compute_pk2cc with the ustruct flag: isochoric part only (mat_models.cpp:311-312, 395-405)
   StructDmn iso = dm.st;
   iso.Kpen = 0.0;
-  if (pk2cc_voigt(iso, q.F, fN, q.S, q.Dm)) return 1;
+  if (pk2cc_voigt(iso, q.F, fN, ya, cann, nFn, q.S, q.Dm)) return 1;
   // compute_visc_stress_and_tangent (ustruct.cpp:1255-1259, mat_models.cpp:1583-1762): Siso += Svis (:1278); the tangent
   // terms are kept as two ViscGP sets, gu for Kvis_u alone (afu = 1, afv = 0) and gv for Kvis_v alone (0, 1)
   if (gu != nullptr && dm.st.viscType != SVB200_SOLID_VISC_NONE) {
@@ -289,7 +290,8 @@ using UTet4Mom = UTet4GP;
 SVB_HD int ustruct_tet4_setup(const UstructDmn& dm, double af, double am, const double* w, const double* N, int ldN,
                               const double Nxi[][3], const double xl[4][3], const double ql[4][3], const double vl[4][3],
                               const double dl[4][3], const double pl[4], const double pdl[4], const double fN[2][3],
-                              UTet4Const& C, UTet4GP& M, double Dm[6][6], double* Je_out)
+                              UTet4Const& C, UTet4GP& M, double Dm[6][6], double* Je_out, const double* ya = nullptr,
+                              const CannRow* cann = nullptr, int nFn = 2)
 {
   double xiX[3][3];
   const double Je = ustruct_xiX<4>(Nxi, xl, xiX);
@@ -327,7 +329,7 @@ SVB_HD int ustruct_tet4_setup(const UstructDmn& dm, double af, double am, const 
   Fi[2][2] = (F[0][0] * F[1][1] - F[0][1] * F[1][0]) * iJ;
   StructDmn iso = dm.st;
   iso.Kpen = 0.0;
-  if (pk2cc_voigt(iso, C.F, fN, C.S, Dm)) return 1;
+  if (pk2cc_voigt(iso, C.F, fN, ya, cann, nFn, C.S, Dm)) return 1;
   ustruct_tau(dm, Je, C.J, C.tauM, C.tauC);
   double VxFi[3][3], divV = 0.0;
 #pragma unroll

@@ -43,6 +43,7 @@ ABI_SYMBOLS = [
     "svb200_set_solution", "svb200_get_solution", "svb200_predictor", "svb200_initiator", "svb200_corrector",
     "svb200_set_node_flags", "svb200_set_dirichlet_rows", "svb200_dirichlet_ustruct", "svb200_advance_time_step",
     "svb200_set_bface", "svb200_assemble_neu",
+    "svb200_set_active_tension",
     "svb200_spmv_rc", "svb200_spmv_rc_variants", "svb200_bench_spmv_rc",
     "svb200_schur_sp", "svb200_schur_sp_variants", "svb200_bench_schur_sp",
 ]
@@ -214,6 +215,13 @@ class Engine:
         Ag, Yg, Dg, Bf = _f64(Ag), _f64(Yg), _f64(Dg), _f64(Bf)
         tDof = (Ag if Ag is not None else Yg).shape[0]
         self._call("svb200_set_state", C.c_int32(tDof), _d(Ag), _d(Yg), _d(Dg), _d(Bf))
+
+    def set_active_tension(self, Ya_f, Ya_s=None, Ya_n=None):
+        """Nodal active tensions cep_mod.cem.Ya_f / Ya_s / Ya_n (nNo each) for domains with an active-stress model."""
+        f = np.ascontiguousarray(Ya_f, dtype=np.float64)
+        s_ = None if Ya_s is None else np.ascontiguousarray(Ya_s, dtype=np.float64)
+        n_ = None if Ya_n is None else np.ascontiguousarray(Ya_n, dtype=np.float64)
+        self._call("svb200_set_active_tension", _d(f), _d(s_), _d(n_))
 
     def set_old_disp(self, Do):
         Do = _f64(Do)

@@ -98,8 +98,21 @@ std::vector<svb200_dmnparams> domain_params(const eqType& eq)
         case ConstitutiveModelType::stIso_HGO: p.isoType = SVB200_ISO_HGO; break;
         case ConstitutiveModelType::stIso_HO: p.isoType = SVB200_ISO_HO; break;
         case ConstitutiveModelType::stIso_HO_ma: p.isoType = SVB200_ISO_HO_MA; break;
+        case ConstitutiveModelType::stArtificialNeuralNet: {
+          // the CANN parameter table (set_material_props.h:155-175)
+          p.isoType = SVB200_ISO_CANN;
+          const auto& t = d.stM.paramTable;
+          if (t.num_rows < 1 || t.num_rows > SVB200_CANN_MAX_ROWS)
+            throw std::runtime_error("[B200LinearAlgebra] CANN parameter table with more than 16 rows");
+          p.cann_rows = t.num_rows;
+          for (int r = 0; r < t.num_rows; r++) {
+            p.cann_inv[r] = t.invariant_indices(r);
+            for (int k = 0; k < 3; k++) { p.cann_act[r][k] = t.activation_functions(r, k); p.cann_w[r][k] = t.weights(r, k); }
+          }
+        } break;
         default: throw std::runtime_error("[B200LinearAlgebra] isochoric constitutive model not implemented on the device");
       }
+      p.active_stress = (d.active_stress != nullptr) ? 1 : 0;
       switch (d.stM.volType) {
         case ConstitutiveModelType::stVol_Quad: p.volType = SVB200_VOL_QUAD; break;
         case ConstitutiveModelType::stVol_ST91: p.volType = SVB200_VOL_ST91; break;
@@ -134,7 +147,6 @@ svb200_lsparams ls_params(const fsi_linear_solver::FSILS_lsType& ls)
 
 bool global_eq_assem(ComMod& com_mod, CepMod& cep_mod, const mshType& lM, const SolutionStates& solutions)
 {
-  (void)cep_mod;
   auto& eq = com_mod.eq[com_mod.cEq];
   auto* la = dynamic_cast<B200LinearAlgebra*>(eq.linear_algebra);
   if (!la) return false;
@@ -149,6 +161,11 @@ bool global_eq_assem(ComMod& com_mod, CepMod& cep_mod, const mshType& lM, const 
                                  "implemented on the device; use the fsils linear algebra for this equation");
     }
   }
+  // nodal active tensions of the electromechanics coupling (sv_struct.cpp:277-281, ustruct.cpp:294-298): they change once per
+  // time step (active_stress.cpp:50-66), the copy is 3 doubles per node
+  bool active = false;
+  for (int d = 0; d < eq.nDmn; d++) active |= (eq.dmn[d].active_stress != nullptr);
+  if (active) la->set_active_tension(cep_mod);
   la->assemble_mesh(com_mod, lM, solutions);
   return true;
 }
@@ -337,6 +354,14 @@ void B200LinearAlgebra::assemble_mesh(ComMod& com_mod, const mshType& lM, const 
   svb200_eqparams e = b200::eq_params(com_mod, eq, lM, scatter);
   std::vector<svb200_dmnparams> d = b200::domain_params(eq);
   check(svb200_assemble(ctx, iM, &e, d.data(), (int)d.size()));
+}
+
+void B200LinearAlgebra::set_active_tension(const CepMod& cep_mod)
+{
+  const auto& cem = cep_mod.cem;
+  if (cem.Ya_f.size() == 0) throw std::runtime_error("[B200LinearAlgebra] active stress: cep_mod.cem.Ya_f is empty");
+  check(svb200_set_active_tension(ctx, cem.Ya_f.data(), cem.Ya_s.size() ? cem.Ya_s.data() : nullptr,
+                                  cem.Ya_n.size() ? cem.Ya_n.data() : nullptr));
 }
 
 /// ustruct::ustruct_r (Code/Source/solver/ustruct.cpp:1742-1845), called where Integrator::step calls it

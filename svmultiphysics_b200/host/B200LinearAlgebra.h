@@ -42,6 +42,8 @@ class B200LinearAlgebra : public virtual LinearAlgebra {
 
     // ---- whole-mesh element assembly on the device (called by b200::global_eq_assem) ---------------------
     void assemble_mesh(ComMod& com_mod, const mshType& lM, const SolutionStates& solutions);
+    /// cep_mod.cem.Ya_f / Ya_s / Ya_n -> device (domains with an active-stress model; sv_struct.cpp:277-281).
+    void set_active_tension(const CepMod& cep_mod);
     /// all_fun::commu(com_mod, com_mod.R) of Integrator::step (Code/Source/solver/Integrator.cpp:124-129).
     void commu_R();
     /// ustruct::ustruct_r (Code/Source/solver/ustruct.cpp:1742) on the device-resident R and Kd.

@@ -85,6 +85,16 @@ def _tet():
     return meshgen.box_tet4(3, 3, 2, (1.0, 1.0, 1.0))
 
 
+# CANN parameter tables: rows (invariant, (kf0, kf1, kf2), (W0, W1, W2)).
+CANN_HO = [(1, (1, 1, 2), (1.0, 8.023, 36.769)), (4, (1, 2, 2), (1.0, 16.026, 2881.6)), (8, (1, 2, 2), (1.0, 11.12, 557.7788)),
+           (6, (1, 2, 2), (1.0, 11.436, 94.438))]
+CANN_NHK = [(1, (1, 1, 1), (1.0, 1.0, 40.0942e4))]
+CANN_ARTERY = [(1, (1, 1, 1), (1.0, 1.0, 4.0e4)), (1, (1, 2, 2), (1.0, 1.2, 3.0e3)), (4, (2, 2, 2), (1.0, 2.5, 6.0e4)),
+               (8, (2, 2, 2), (1.0, 2.5, 6.0e4))]
+CANN_ALL = [(1, (1, 1, 2), (1.0, 2.0, 5.0e4)), (2, (1, 2, 1), (0.7, 1.3, 4.0e4)), (3, (3, 1, 3), (0.5, 0.4, 2.0e4)),
+            (4, (2, 2, 2), (1.0, 3.0, 3.0e4)), (5, (1, 1, 2), (1.0, 1.5, 1.0e4)), (6, (3, 2, 1), (1.0, 1.0, 2.0e4)),
+            (7, (1, 2, 2), (0.8, 1.1, 1.5e4)), (8, (2, 1, 3), (0.6, 0.5, 2.5e4)), (9, (1, 2, 1), (1.0, 1.0, 1.0e4))]
+
 STRUCT_CASES = [
     ("hex8_nHK_ST91", _hex, dict(), 0),                                         # struct/block_compression
     ("hex8_nHK_M94_damped", _hex, dict(volType=abi.VOL_M94, E=1e7, nu=0.3, Kpen=1e7 / (3 * (1 - 0.6)), dmp=5.0, f=(0.1, 0.2, 0.3)), 0),
@@ -104,7 +114,37 @@ STRUCT_CASES = [
     ("tet4_HO_ma", _tet, dict(isoType=abi.ISO_HO_MA, st_a=590.0, st_b=8.023, aff=184720.0, bff=16.026, ass=24810.0, bss=11.12,
                               afs=2160.0, bfs=11.436, khs=100.0, volType=abi.VOL_QUAD, Kpen=1e6, rho=1.0), 2),
     ("hex8_Guccione", _hex, dict(isoType=abi.ISO_GUCCIONE, C10=440.0, bff=8.0, bss=6.0, bfs=12.0, Kpen=1e6, rho=1e-3), 2),   # struct/LV_Guccione_passive
+    # active stress along the fibre / sheet / sheet-normal directions (sv_struct.cpp:277-281, mat_models.cpp:321-340;
+    # struct/LV_HolzapfelOgden_active, directionally_distributed_active_stress, tensile_adventitia_Guccione_active)
+    ("hex8_nHK_active", _hex, dict(active_stress=True), 2),
+    ("hex8_MR_active", _hex, dict(isoType=abi.ISO_MR, C10=1e5, C01=3e4, Kpen=1e7, rho=1.0, active_stress=True), 2),
+    ("hex8_HGO_active", _hex, dict(isoType=abi.ISO_HGO, C10=3.0e4, aff=2.4e4, bff=0.84, ass=2.4e4, bss=0.84, kap=0.226, Kpen=1e7, rho=1.0,
+                                   active_stress=True), 2),
+    ("tet4_Guccione_active_fsn", _tet, dict(isoType=abi.ISO_GUCCIONE, C10=440.0, bff=8.0, bss=6.0, bfs=12.0, Kpen=1e6, rho=1e-3,
+                                            volType=abi.VOL_QUAD, active_stress=True), 2),
+    ("hex8_HO_active_fsn", _hex, dict(isoType=abi.ISO_HO, st_a=590.0, st_b=8.023, aff=184720.0, bff=16.026, ass=24810.0, bss=11.12,
+                                      afs=2160.0, bfs=11.436, khs=100.0, Kpen=1e7, rho=1.0, active_stress=True), 2),
+    ("tet4_HO_ma_active_fsn", _tet, dict(isoType=abi.ISO_HO_MA, st_a=590.0, st_b=8.023, aff=184720.0, bff=16.026, ass=24810.0, bss=11.12,
+                                         afs=2160.0, bfs=11.436, khs=100.0, volType=abi.VOL_QUAD, Kpen=1e6, rho=1.0, active_stress=True), 2),
+    # CANN: the parameter tables of struct/LV_HolzapfelOgden_passive_CANN, block_compression_CANN and
+    # LV_CANN_artery_material_model (solver.xml <Add_row>), and a synthetic table touching every invariant and activation function
+    ("hex8_CANN_HO", _hex, dict(cann=CANN_HO, Kpen=1e7, rho=1.0), 2),
+    ("tet4_CANN_nHK", _tet, dict(cann=CANN_NHK, volType=abi.VOL_QUAD, Kpen=1e6, rho=1.0), 0),
+    ("hex8_CANN_artery", _hex, dict(cann=CANN_ARTERY, Kpen=1e6, rho=1.0), 2),
+    ("hex8_CANN_all_terms", _hex, dict(cann=CANN_ALL, Kpen=1e6, rho=1.0), 2),
+    ("tet4_CANN_HO_active", _tet, dict(cann=CANN_HO, volType=abi.VOL_QUAD, Kpen=1e6, rho=1.0, active_stress=True), 2),
 ]
+
+
+def active_tension(m, isoType, seed=31):
+    """Nodal active tensions (cep_mod.cem.Ya_f, Ya_s, Ya_n): sheet / sheet-normal parts only for the models that accept them."""
+    rng = np.random.default_rng(seed)
+    scale = 2.0e4
+    Ya_f = scale * (0.5 + rng.random(m.nNo))
+    dirs = isoType in (abi.ISO_GUCCIONE, abi.ISO_HO, abi.ISO_HO_MA)
+    Ya_s = 0.4 * scale * rng.random(m.nNo) if dirs else np.zeros(m.nNo)
+    Ya_n = 0.2 * scale * rng.random(m.nNo) if dirs else np.zeros(m.nNo)
+    return Ya_f, Ya_s, Ya_n
 
 
 def struct_state(m, nFn=0, seed=11, tDof=3):
@@ -217,6 +257,13 @@ USTRUCT_CASES = [
                                                    solid_visc=abi.SOLID_VISC_POTENTIAL, solid_visc_mu=2.0e4), 0),
     ("tet4_nHK_visc_newtonian", _tet, dict(E=1.0e6, nu=0.45, Kpen=2.0e6, rho=1.0, ctau_M=1e-3, ctau_C=1e-3,
                                            solid_visc=abi.SOLID_VISC_NEWTONIAN, solid_visc_mu=3.0e4), 0),
+    # active stress (ustruct/LV_Guccione_active, LV_HolzapfelOgden_active) and CANN
+    ("tet4_Guccione_active_fsn", _tet, dict(isoType=abi.ISO_GUCCIONE, C10=440.0, bff=8.0, bss=6.0, bfs=12.0, E=1.0e5, nu=0.45, Kpen=1e6,
+                                            rho=1.0, ctau_M=1e-4, ctau_C=1e-4, active_stress=True), 2),
+    ("hex8_HO_active_fsn", _hex_skewed, dict(isoType=abi.ISO_HO, st_a=590.0, st_b=8.023, aff=184720.0, bff=16.026, ass=24810.0, bss=11.12,
+                                             afs=2160.0, bfs=11.436, khs=100.0, E=1.0e5, nu=0.483333, Kpen=1e6, rho=1.0, ctau_M=1e-5,
+                                             ctau_C=1e-5, active_stress=True), 2),
+    ("tet4_CANN_HO", _tet, dict(cann=CANN_HO, E=1.0e5, nu=0.483333, Kpen=1e6, rho=1.0, ctau_M=1e-5, ctau_C=1e-5), 2),
 ]
 
 

@@ -58,7 +58,11 @@ def struct_golden():
         Ag, Yg, Dg, Bf, fN = common.struct_state(m, nFn)
         c = RefCase(); c.set_coords(m.x); c.add_mesh(m.IEN, nFn=nFn, fN=fN)
         rowPtr, colPtr = c.build_graph(0)
-        c.alloc(3); c.set_state(Ag, Yg, Dg, Bf); c.assemble(0, abi.struct_eq(1e-4), [abi.struct_domain(**dkw)])
+        d = abi.struct_domain(**dkw)
+        c.alloc(3); c.set_state(Ag, Yg, Dg, Bf)
+        if d.active_stress:
+            c.set_active_tension(*common.active_tension(m, d.isoType))
+        c.assemble(0, abi.struct_eq(1e-4), [d])
         out[f"{name}/R"], out[f"{name}/Val"] = c.get_R(), c.get_Val()
         out[f"{name}/rowPtr"], out[f"{name}/colPtr"] = rowPtr, colPtr
     np.savez_compressed(os.path.join(HERE, "struct.npz"), **out)
@@ -107,7 +111,10 @@ def ustruct_golden():
         c = RefCase(); c.set_coords(m.x); c.add_mesh(m.IEN, nFn=nFn, fN=fN)
         rowPtr, colPtr = c.build_graph(0)
         eq, dmn = abi.ustruct_eq(1e-3), [abi.ustruct_domain(**dkw)]
-        c.alloc(4); c.set_state(Ag, Yg, Dg, Bf); c.assemble(0, eq, dmn)
+        c.alloc(4); c.set_state(Ag, Yg, Dg, Bf)
+        if dmn[0].active_stress:
+            c.set_active_tension(*common.active_tension(m, dmn[0].isoType))
+        c.assemble(0, eq, dmn)
         out[f"{name}/R"], out[f"{name}/Val"], out[f"{name}/Kd"] = c.get_R(), c.get_Val(), c.get_Kd()
         out[f"{name}/rowPtr"], out[f"{name}/colPtr"] = rowPtr, colPtr
         Ad = common.ustruct_Ad(m)

@@ -12,6 +12,8 @@ struct HostStructArgs {
   double dt, af, am, gam, beta;
   double w[8], N[8][8], Nxi[8][8][3];
   svb::StructDmn dm;
+  const double* Ya;              // (nNo, 3) active tensions f, s, n or null
+  svb::CannRow cann[16];
 };
 
 template <int ENON>
@@ -45,8 +47,10 @@ static int run(const HostStructArgs* P, const int* rowPtr, const int* colPtr, do
           ud[i] += P->N[g][a] * q[a][i];
           for (int j = 0; j < 3; j++) F[i][j] += Nx[a][j] * dl[a][i];
         }
-      double S[3][3], Dm[6][6];
-      if (pk2cc_voigt(P->dm, F, fN, S, Dm)) return 2;
+      double S[3][3], Dm[6][6], ya[3] = {0, 0, 0};
+      const bool act = P->Ya && P->dm.active;
+      if (act) for (int a = 0; a < ENON; a++) for (int i = 0; i < 3; i++) ya[i] += P->N[g][a] * P->Ya[3 * n[a] + i];
+      if (pk2cc_voigt(P->dm, F, fN, act ? ya : nullptr, P->cann, P->nFn, S, Dm)) return 2;
       const bool visc = P->dm.viscType != 0 && P->dm.visc_mu != 0.0;
       const double afv = P->af * P->gam * P->dt;
       ViscGP vgp;
@@ -97,12 +101,13 @@ extern "C" int hostmath_struct(const HostStructArgs* P, const int* rowPtr, const
 extern "C" int hostmath_sizeof_structargs() { return (int)sizeof(HostStructArgs); }
 
 // compute_pk2cc of the device algebra for one deformation gradient: F(3,3) row-major, fN = fibre | sheet -> S(3,3), Dm(6,6).
-extern "C" int hostmath_pk2cc(const svb::StructDmn* dm, const double* F, const double* fN, double* S, double* Dm)
+extern "C" int hostmath_pk2cc(const svb::StructDmn* dm, const double* F, const double* fN, double* S, double* Dm, const double* ya,
+                              const svb::CannRow* cann, int nFn)
 {
   double Fm[3][3], f[2][3], Sm[3][3], D[6][6];
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Fm[i][j] = F[3 * i + j];
   for (int k = 0; k < 2; k++) for (int i = 0; i < 3; i++) f[k][i] = fN ? fN[3 * k + i] : 0.0;
-  const int rc = svb::pk2cc_voigt(*dm, Fm, f, Sm, D);
+  const int rc = svb::pk2cc_voigt(*dm, Fm, f, ya, cann, nFn, Sm, D);
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) S[3 * i + j] = Sm[i][j];
   for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) Dm[6 * i + j] = D[i][j];
   return rc;

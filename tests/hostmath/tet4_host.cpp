@@ -14,6 +14,8 @@ struct HostTet4Args {
   double dt, af, am, gam, beta;
   double w[8], N[8][8], Nxi[8][8][3];
   svb::StructDmn dm;                      // kind 1 / 2: elasticity modulus in C10, Poisson ratio in C01
+  const double* Ya;                       // (nNo, 3) active tensions or null
+  svb::CannRow cann[16];
 };
 
 static int scatter(const int* rowPtr, const int* colPtr, int dof, const int n[4], int a, int b, const double K[3][3], bool transposed, double* Val)
@@ -54,7 +56,14 @@ extern "C" int hostmath_tet4(const HostTet4Args* P, const int* rowPtr, const int
       const double amd = P->am * P->dm.rho + P->af * P->gam * P->dt * P->dm.dmp;
       double F[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, S[3][3], Dm[6][6], Pk[3][3];
       for (int a = 0; a < 4; a++) for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) F[i][j] += Nx[a][j] * dl[a][i];
-      if (pk2cc_voigt(P->dm, F, fN, S, Dm)) return 2;
+      // active tensions at the weighted mean of the Gauss points (S, Dm affine in them), as assemble_struct_tet4_kernel does
+      double ya[3] = {0, 0, 0};
+      const bool act = P->Ya && P->dm.active;
+      if (act) {
+        for (int a = 0; a < 4; a++) for (int i = 0; i < 3; i++) ya[i] += q.m1[a] * P->Ya[3 * n[a] + i];
+        for (int i = 0; i < 3; i++) ya[i] /= q.W;
+      }
+      if (pk2cc_voigt(P->dm, F, fN, act ? ya : nullptr, P->cann, P->nFn, S, Dm)) return 2;
       for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Pk[i][j] = F[i][0] * S[0][j] + F[i][1] * S[1][j] + F[i][2] * S[2][j];
       for (int a = 0; a < 4; a++) {
         double r[3];

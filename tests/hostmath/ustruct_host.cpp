@@ -12,6 +12,8 @@ struct HostUstructArgs {
   double dt, af, am, gam;
   double w[8], N[8][8], Nxi[8][8][3];
   svb::UstructDmn dm;
+  const double* Ya;              // (nNo, 3) active tensions or null
+  svb::CannRow cann[16];
 };
 
 template <int ENON>
@@ -40,8 +42,11 @@ static int run(const HostUstructArgs* P, const int* rowPtr, const int* colPtr, d
       UGP q;
       ViscGP gu, gv;
       const bool visc = P->dm.st.viscType != 0 && P->dm.st.visc_mu != 0.0;
+      double ya[3] = {0, 0, 0};
+      const bool act = P->Ya && P->dm.st.active;
+      if (act) for (int a = 0; a < ENON; a++) for (int i = 0; i < 3; i++) ya[i] += P->N[g][a] * P->Ya[3 * n[a] + i];
       if (ustruct_gauss_point<ENON>(P->dm, P->dt, P->af, P->am, P->gam, P->w[g], P->N[g], P->Nxi[g], xl, ql, vl, dl, pl, pdl, fN, q,
-                                    visc ? &gu : nullptr, visc ? &gv : nullptr)) return 2;
+                                    visc ? &gu : nullptr, visc ? &gv : nullptr, act ? ya : nullptr, P->cann, P->nFn)) return 2;
       UNode nd[ENON];
       double Bm[ENON][6][3], DBm[ENON][6][3];
       for (int a = 0; a < ENON; a++) {
@@ -92,7 +97,18 @@ static int run_tet4(const HostUstructArgs* P, const int* rowPtr, const int* colP
     }
     for (int k = 0; k < P->nFn && k < 2; k++) for (int i = 0; i < 3; i++) fN[k][i] = P->fN[(size_t)3 * P->nFn * e + 3 * k + i];
     UTet4Const C; UTet4Mom M; double Dm[6][6], Je;
-    if (ustruct_tet4_setup(P->dm, af, am, P->w, &P->N[0][0], 8, P->Nxi[0], xl, ql, vl, dl, pl, pdl, fN, C, M, Dm, &Je)) return 2;
+    double ya[3] = {0, 0, 0};
+    const bool act = P->Ya && P->dm.st.active;
+    if (act) {
+      double wsum = 0.0;
+      for (int g = 0; g < 4; g++) {
+        wsum += P->w[g];
+        for (int a = 0; a < 4; a++) for (int i = 0; i < 3; i++) ya[i] += P->w[g] * P->N[g][a] * P->Ya[3 * n[a] + i];
+      }
+      for (int i = 0; i < 3; i++) ya[i] /= wsum;
+    }
+    if (ustruct_tet4_setup(P->dm, af, am, P->w, &P->N[0][0], 8, P->Nxi[0], xl, ql, vl, dl, pl, pdl, fN, C, M, Dm, &Je,
+                           act ? ya : nullptr, P->cann, P->nFn)) return 2;
     for (int a = 0; a < 4; a++) {
       double r[4];
       ustruct_tet4_resid(C, M, &P->N[0][0], 8, a, r);

@@ -43,12 +43,32 @@ def test_header_and_library_agree(lib):
     assert lib.svb200_abi_version() == abi.ABI_VERSION
 
 
-def test_struct_layouts_match_header():
-    # sizes implied by include/svb200.h (natural alignment, LP64)
-    assert C.sizeof(abi.EqParams) == 5 * 8 + 8 * 4
-    assert C.sizeof(abi.DmnParams) == 8 + 8 * 5 + 8 + 8 * 5 + 8 + 8 * 11 + 8 * 7 + 8 * 4
-    assert C.sizeof(abi.SubLsParams) == 24 and C.sizeof(abi.LsParams) == 72
-    assert C.sizeof(abi.SubLsResult) == 40 and C.sizeof(abi.LsResult) == 3 * 40 + 8 + 8 + 8
+def test_struct_layouts_match_header(tmp_path):
+    """Sizes and field offsets of the ctypes mirrors against what a C compiler makes of include/svb200.h."""
+    src = tmp_path / "layout.c"
+    fields = {
+        "svb200_eqparams": (abi.EqParams, ["dt", "phys", "reserved"]),
+        "svb200_dmnparams": (abi.DmnParams, ["Id", "rho", "viscType", "volType", "Kpen", "st_a", "ctau_C", "active_stress",
+                                              "cann_rows", "cann_inv", "cann_act", "cann_w"]),
+        "svb200_sublsparams": (abi.SubLsParams, ["mItr", "absTol"]),
+        "svb200_lsparams": (abi.LsParams, ["CG"]),
+        "svb200_sublsresult": (abi.SubLsResult, ["success", "callD"]),
+        "svb200_lsresult": (abi.LsResult, ["Resm", "hist"]),
+    }
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "svb200.h"', 'int main(void) {']
+    for cname, (_, names) in fields.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for n in names:
+            lines.append(f'  printf("{cname}.{n} %zu\\n", offsetof({cname}, {n}));')
+    lines += ['  return 0;', '}']
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, (cls, names) in fields.items():
+        assert C.sizeof(cls) == int(out[cname]), cname
+        for n in names:
+            assert getattr(cls, n).offset == int(out[f"{cname}.{n}"]), f"{cname}.{n}"
 
 
 def test_no_cpu_fallback(lib):

@@ -83,9 +83,11 @@ def test_fluid_newton_iteration_through_cpp_plugin(ls_type, kw):
     _close(cpu, gpu)
 
 
-@pytest.mark.parametrize("case", [0, -1], ids=["hex8_nHK_block_compression", "hex8_Guccione_fibres"])
+@pytest.mark.parametrize("case", ["hex8_nHK_ST91", "hex8_Guccione", "hex8_HO_active_fsn", "hex8_CANN_HO"])
 def test_struct_newton_iteration_through_cpp_plugin(case):
-    name, mk, dkw, nFn = common.STRUCT_CASES[case]
+    """The last two cases also check that the plug-in hands cep_mod.cem.Ya_f / Ya_s / Ya_n and the CANN parameter table of
+    stM.paramTable to the device (B200LinearAlgebra.cpp: domain_params, set_active_tension)."""
+    name, mk, dkw, nFn = next(c for c in common.STRUCT_CASES if c[0] == case)
     m = mk()
     Ag, Yg, Dg, Bf, fN = common.struct_state(m, nFn=nFn)
     faces = []
@@ -99,7 +101,10 @@ def test_struct_newton_iteration_through_cpp_plugin(case):
     for c in (cpu, gpu):
         for i, (g, nodes, v) in enumerate(faces):
             c.set_face(i, g, nodes, v)
-        c.alloc(3); c.set_state(Ag, Yg, Dg, Bf); c.assemble(0, eq, dmn)
+        c.alloc(3); c.set_state(Ag, Yg, Dg, Bf)
+        if dmn[0].active_stress:
+            c.set_active_tension(*common.active_tension(m, dmn[0].isoType))      # fills cep_mod.cem of the reference
+        c.assemble(0, eq, dmn)
         R, V = c.get_R(), c.get_Val()
         X, o, _ = c.solve(3, abi.LS_GMRES, ls, np.ones(3, np.int32), np.zeros(3))
         res.append((R, V, X, o))

@@ -35,13 +35,22 @@ def test_struct_assembly_parity(name, mk, dkw, nFn, scatter):
     orc = cls(); orc.set_coords(m.x); orc.add_mesh(m.IEN, nFn=nFn, fN=fN)
     rowPtr, colPtr = orc.build_graph(0)
     eq, dmn = abi.struct_eq(1e-4, scatter=scatter), [abi.struct_domain(**dkw)]
-    orc.alloc(3); orc.set_state(Ag, Yg, Dg, Bf); orc.assemble(0, eq, dmn)
-    R0, V0 = orc.get_R(), orc.get_Val()
+    orc.alloc(3); orc.set_state(Ag, Yg, Dg, Bf)
     eng = _engine(m, rowPtr, colPtr, nFn, fN)
-    eng.alloc(3); eng.set_state(Ag, Yg, Dg, Bf); eng.assemble(0, eq, dmn)
+    eng.alloc(3); eng.set_state(Ag, Yg, Dg, Bf)
+    if dmn[0].active_stress:
+        ya = common.active_tension(m, dmn[0].isoType)
+        orc.set_active_tension(*ya)
+        eng.set_active_tension(*ya)
+    orc.assemble(0, eq, dmn)
+    R0, V0 = orc.get_R(), orc.get_Val()
+    eng.assemble(0, eq, dmn)
     R1, V1 = eng.get_R(), eng.get_Val()
     assert common.rel_err(R1, R0) < ASM_TOL
     assert common.rel_err(V1, V0) < ASM_TOL
+    golden = common.load_golden("struct.npz")          # and the committed vectors of the same cases
+    assert common.rel_err(R1, golden[f"{name}/R"]) < ASM_TOL
+    assert common.rel_err(V1, golden[f"{name}/Val"]) < ASM_TOL
     if scatter == abi.SCATTER_COLORED:
         eng.alloc(3); eng.assemble(0, eq, dmn)
         assert np.array_equal(eng.get_Val(), V1) and np.array_equal(eng.get_R(), R1)
@@ -253,4 +262,25 @@ def test_linear_elasticity_parity(kind, scatter):
     X1, o1, _ = eng.solve(3, abi.LS_CG, ls, incL, res)
     assert o1.RI.success == o0.RI.success and abs(o1.RI.itr - o0.RI.itr) <= max(2, o0.RI.itr // 20)
     assert common.rel_err(X1, X0) < 1e-7
+    eng.close()
+
+
+def test_active_stress_errors_like_the_reference():
+    """mat_models.cpp:334-340: sheet / sheet-normal active tensions are rejected for models without directional distribution;
+    an active-stress domain without nodal tensions is an error, not a silent passive run."""
+    m = common.STRUCT_CASES[0][1]()
+    Ag, Yg, Dg, Bf, fN = common.struct_state(m, 2)
+    from svmultiphysics_b200.engine import Engine, Svb200Error
+    e0 = Engine(0)
+    rowPtr, colPtr = e0.lhsa(m.nNo, [m.IEN]); e0.close()
+    eng = _engine(m, rowPtr, colPtr, 2, fN)
+    eq, dmn = abi.struct_eq(1e-4), [abi.struct_domain(active_stress=True)]
+    eng.alloc(3); eng.set_state(Ag, Yg, Dg, Bf)
+    with pytest.raises(Svb200Error, match="svb200_set_active_tension"):
+        eng.assemble(0, eq, dmn)
+    eng.set_active_tension(np.ones(m.nNo), 0.5 * np.ones(m.nNo), None)
+    with pytest.raises(Svb200Error, match="Directional distribution of active stress"):
+        eng.assemble(0, eq, dmn)
+    eng.set_active_tension(np.ones(m.nNo))
+    eng.assemble(0, eq, dmn)
     eng.close()

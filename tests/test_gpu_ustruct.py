@@ -29,7 +29,10 @@ def test_ustruct_assembly_matches_golden(name, mk, dkw, nFn, scatter):
     Ag, Yg, Dg, Bf, fN = common.ustruct_state(m, nFn)
     eq, dmn = abi.ustruct_eq(1e-3, scatter=scatter), [abi.ustruct_domain(**dkw)]
     eng = _engine(m, golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"], nFn, fN)
-    eng.alloc(4); eng.set_state(Ag, Yg, Dg, Bf); eng.assemble(0, eq, dmn)
+    eng.alloc(4); eng.set_state(Ag, Yg, Dg, Bf)
+    if dmn[0].active_stress:
+        eng.set_active_tension(*common.active_tension(m, dmn[0].isoType))
+    eng.assemble(0, eq, dmn)
     R1, V1, K1 = eng.get_R(), eng.get_Val(), eng.get_Kd()
     assert common.rel_err(R1, golden[f"{name}/R"]) < ASM_TOL
     assert common.rel_err(K1, golden[f"{name}/Kd"]) < ASM_TOL

@@ -77,14 +77,41 @@ class StructDmn(C.Structure):
                 ("Kpen", C.c_double), ("C10", C.c_double), ("C01", C.c_double), ("bff", C.c_double), ("bss", C.c_double),
                 ("bfs", C.c_double), ("st_a", C.c_double), ("st_b", C.c_double), ("aff", C.c_double), ("ass", C.c_double),
                 ("afs", C.c_double), ("kap", C.c_double), ("khs", C.c_double), ("visc_mu", C.c_double),
-                ("isoType", C.c_int), ("volType", C.c_int), ("Id", C.c_int), ("isStruct", C.c_int), ("viscType", C.c_int), ("pad", C.c_int)]
+                ("isoType", C.c_int), ("volType", C.c_int), ("Id", C.c_int), ("isStruct", C.c_int), ("viscType", C.c_int), ("active", C.c_int),
+                ("cann_off", C.c_int), ("cann_rows", C.c_int)]
+
+
+class CannRow(C.Structure):
+    _fields_ = [("inv", C.c_int), ("a0", C.c_int), ("a1", C.c_int), ("a2", C.c_int), ("w0", C.c_double), ("w1", C.c_double), ("w2", C.c_double)]
+
+
+_EXTRAS = [("Ya", C.c_void_p), ("cann", CannRow * 16)]
+
+
+def fill_cann(dm, table, d):
+    """CANN parameter table of the domain d -> the host argument block (rows 0.. of `table`)."""
+    dm.cann_off, dm.cann_rows = 0, d.cann_rows
+    for r in range(d.cann_rows):
+        table[r].inv = d.cann_inv[r]
+        table[r].a0, table[r].a1, table[r].a2 = d.cann_act[r][0], d.cann_act[r][1], d.cann_act[r][2]
+        table[r].w0, table[r].w1, table[r].w2 = d.cann_w[r][0], d.cann_w[r][1], d.cann_w[r][2]
+
+
+def _fill_extras(A, dm, d, m, keep):
+    """Active tensions and the CANN table of a solid case (tests/common.py: active_tension)."""
+    fill_cann(dm, A.cann, d)
+    dm.active = d.active_stress
+    if d.active_stress:
+        ya = np.ascontiguousarray(np.stack(common.active_tension(m, d.isoType), axis=1))
+        keep.append(ya)
+        A.Ya = ya.ctypes.data
 
 
 class HostStructArgs(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("IEN", "fN", "x", "Ag", "Yg", "Dg", "Bf")] + \
                [(k, C.c_int) for k in ("eNoN", "nEl", "nG", "tDof", "dof", "s", "nFn")] + \
                [(k, C.c_double) for k in ("dt", "af", "am", "gam", "beta")] + \
-               [("w", C.c_double * 8), ("N", (C.c_double * 8) * 8), ("Nxi", ((C.c_double * 3) * 8) * 8), ("dm", StructDmn)]
+               [("w", C.c_double * 8), ("N", (C.c_double * 8) * 8), ("Nxi", ((C.c_double * 3) * 8) * 8), ("dm", StructDmn)] + _EXTRAS
 
 
 @pytest.mark.parametrize("name,mk,dkw,nFn", common.STRUCT_CASES, ids=[c[0] for c in common.STRUCT_CASES])
@@ -119,6 +146,7 @@ def test_device_solid_algebra_matches_golden(hostmath, name, mk, dkw, nFn):
     dm.visc_mu, dm.viscType = d.solid_visc_mu, d.solidViscType
     dm.st_a, dm.st_b, dm.aff, dm.ass, dm.afs, dm.kap, dm.khs = d.st_a, d.st_b, d.aff, d.ass, d.afs, d.kap, d.khs
     dm.isoType, dm.volType, dm.Id, dm.isStruct = d.isoType, d.volType, -1, 1
+    _fill_extras(A, dm, d, m, keep)
     rowPtr, colPtr = golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"]
     R = np.zeros((m.nNo, 3))
     V = np.zeros((len(colPtr), 9))
@@ -239,7 +267,7 @@ class HostUstructArgs(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("IEN", "fN", "x", "Ag", "Yg", "Dg", "Bf")] + \
                [(k, C.c_int) for k in ("eNoN", "nEl", "nG", "tDof", "s", "nFn")] + \
                [(k, C.c_double) for k in ("dt", "af", "am", "gam")] + \
-               [("w", C.c_double * 8), ("N", (C.c_double * 8) * 8), ("Nxi", ((C.c_double * 3) * 8) * 8), ("dm", UstructDmn)]
+               [("w", C.c_double * 8), ("N", (C.c_double * 8) * 8), ("Nxi", ((C.c_double * 3) * 8) * 8), ("dm", UstructDmn)] + _EXTRAS
 
 
 USTRUCT_VARIANTS = [(c, "hostmath_ustruct") for c in common.USTRUCT_CASES] + \
@@ -273,6 +301,7 @@ def test_device_ustruct_algebra_matches_golden(hostmath, case, entry):
     dm.st_a, dm.st_b, dm.aff, dm.ass, dm.afs, dm.kap, dm.khs = d.st_a, d.st_b, d.aff, d.ass, d.afs, d.kap, d.khs
     dm.isoType, dm.volType, dm.Id, dm.isStruct = d.isoType, d.volType, -1, 1
     dm.visc_mu, dm.viscType = d.solid_visc_mu, d.solidViscType
+    _fill_extras(A, dm, d, m, keep)
     A.dm.E, A.dm.nu, A.dm.ctM, A.dm.ctC = d.E, d.nu, d.ctau_M, d.ctau_C
     rowPtr, colPtr = golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"]
     R = np.zeros((m.nNo, 4))
@@ -293,10 +322,10 @@ class HostTet4Args(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("IEN", "fN", "x", "Ag", "Yg", "Dg", "Bf", "Do")] + \
                [(k, C.c_int) for k in ("nEl", "tDof", "dof", "s", "nFn", "kind")] + \
                [(k, C.c_double) for k in ("dt", "af", "am", "gam", "beta")] + \
-               [("w", C.c_double * 8), ("N", (C.c_double * 8) * 8), ("Nxi", ((C.c_double * 3) * 8) * 8), ("dm", StructDmn)]
+               [("w", C.c_double * 8), ("N", (C.c_double * 8) * 8), ("Nxi", ((C.c_double * 3) * 8) * 8), ("dm", StructDmn)] + _EXTRAS
 
 
-def _run_tet4(hostmath, m, Ag, Yg, Dg, Bf, Do, eq, kind, fill_dm, nFn, fN, rowPtr, colPtr):
+def _run_tet4(hostmath, m, Ag, Yg, Dg, Bf, Do, eq, kind, fill_dm, nFn, fN, rowPtr, colPtr, d=None):
     assert hostmath.hostmath_sizeof_tet4args() == C.sizeof(HostTet4Args)
     A = HostTet4Args()
     keep = [np.ascontiguousarray(m.IEN.T.astype(np.int32)), np.ascontiguousarray(m.x.T), np.ascontiguousarray(Ag.T),
@@ -312,6 +341,8 @@ def _run_tet4(hostmath, m, Ag, Yg, Dg, Bf, Do, eq, kind, fill_dm, nFn, fN, rowPt
     assert _fill_tables(A, 4) == 4
     A.dt, A.af, A.am, A.gam, A.beta = eq.dt, eq.af, eq.am, eq.gam, eq.beta
     fill_dm(A.dm)
+    if d is not None:
+        _fill_extras(A, A.dm, d, m, keep)
     R = np.zeros((m.nNo, eq.dof))
     V = np.zeros((len(colPtr), eq.dof * eq.dof))
     rc = hostmath.hostmath_tet4(C.byref(A), rowPtr.ctypes.data_as(C.c_void_p), colPtr.ctypes.data_as(C.c_void_p),
@@ -336,7 +367,7 @@ def test_tet4_closed_form_solid_matches_golden(hostmath, name, mk, dkw, nFn):
             dm.f[i] = d.f[i]
         dm.st_a, dm.st_b, dm.aff, dm.ass, dm.afs, dm.kap, dm.khs = d.st_a, d.st_b, d.aff, d.ass, d.afs, d.kap, d.khs
         dm.isoType, dm.volType, dm.Id, dm.isStruct = d.isoType, d.volType, -1, 1
-    R, V = _run_tet4(hostmath, m, Ag, Yg, Dg, Bf, None, eq, 0, fill, nFn, fN, golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"])
+    R, V = _run_tet4(hostmath, m, Ag, Yg, Dg, Bf, None, eq, 0, fill, nFn, fN, golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"], d=d)
     assert common.rel_err(R, golden[f"{name}/R"]) < 1e-12
     assert common.rel_err(V, golden[f"{name}/Val"]) < 1e-12
 

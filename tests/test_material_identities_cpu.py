@@ -10,7 +10,8 @@ import numpy as np
 import pytest
 
 from svmultiphysics_b200 import abi
-from tests.test_hostmath_cpu import StructDmn
+from tests import common
+from tests.test_hostmath_cpu import CannRow, StructDmn, fill_cann
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 VOIGT = [(0, 0), (1, 1), (2, 2), (0, 1), (1, 2), (2, 0)]
@@ -28,15 +29,20 @@ def _dm(**kw):
     dm.rho, dm.dmp, dm.Kpen, dm.C10, dm.C01, dm.bff, dm.bss, dm.bfs = d.rho, d.dmp, d.Kpen, d.C10, d.C01, d.bff, d.bss, d.bfs
     dm.st_a, dm.st_b, dm.aff, dm.ass, dm.afs, dm.kap, dm.khs = d.st_a, d.st_b, d.aff, d.ass, d.afs, d.kap, d.khs
     dm.isoType, dm.volType, dm.Id, dm.isStruct = d.isoType, d.volType, -1, 1
+    dm.active = d.active_stress
+    dm.table = (CannRow * 16)()          # kept alive with the domain
+    fill_cann(dm, dm.table, d)
     return dm
 
 
-def _pk2cc(lib, dm, F, fN=None):
+def _pk2cc(lib, dm, F, fN=None, ya=None):
     F = np.ascontiguousarray(F, dtype=np.float64)
     S, Dm = np.zeros((3, 3)), np.zeros((6, 6))
     f = np.ascontiguousarray(fN, dtype=np.float64) if fN is not None else None
+    y = np.ascontiguousarray(ya, dtype=np.float64) if ya is not None else None
     rc = lib.hostmath_pk2cc(C.byref(dm), F.ctypes.data_as(C.c_void_p), f.ctypes.data_as(C.c_void_p) if f is not None else None,
-                            S.ctypes.data_as(C.c_void_p), Dm.ctypes.data_as(C.c_void_p))
+                            S.ctypes.data_as(C.c_void_p), Dm.ctypes.data_as(C.c_void_p),
+                            y.ctypes.data_as(C.c_void_p) if y is not None else None, dm.table, C.c_int(2 if f is not None else 0))
     assert rc == 0
     return S, Dm
 
@@ -54,6 +60,14 @@ MODELS = [
                 khs=100.0, Kpen=1e6), FIBRES),
     ("HO_ma", dict(isoType=abi.ISO_HO_MA, st_a=590.0, st_b=8.023, aff=184720.0, bff=16.026, ass=24810.0, bss=11.12, afs=2160.0,
                    bfs=11.436, khs=100.0, Kpen=1e6), FIBRES),
+    # CANN (Peirlinck et al. 2025): S(I) = 0 and CC = 2 dS/dC must hold for any parameter table
+    ("CANN_HO", dict(cann=common.CANN_HO, Kpen=1e6), FIBRES),
+    ("CANN_artery", dict(cann=common.CANN_ARTERY, Kpen=1e6), FIBRES),
+    # invariants 1 and 3.  (Invariant 2 is left out on purpose: the reference's dInv2 = tr(C^2)/3 Ci + I1 dInv1 + J4d C
+    # (ArtificialNeuralNetMaterial.cpp:131) is not the derivative of its own Inv[1] = (I1^2 - J4d tr C^2)/2, which is
+    # I1 dInv1 + J4d tr(C^2)/3 Ci - J4d C, so CC = 2 dS/dC cannot hold for it; the device routine reproduces the reference
+    # term by term — tests/golden/struct.npz: hex8_CANN_all_terms — and the finite-difference check below confirms the mismatch.)
+    ("CANN_isotropic", dict(cann=[(1, (1, 1, 2), (1.0, 2.0, 5.0e4)), (3, (1, 2, 1), (0.7, 1.3, 4.0e4))], Kpen=1e6, volType=abi.VOL_M94), None),
 ]
 
 
@@ -127,3 +141,52 @@ def test_stress_is_twice_the_derivative_of_the_strain_energy(lib, name, kw, fN):
         dpsi = (_psi(name, kw, F + e * dF) - _psi(name, kw, F - e * dF)) / (2 * e)
         dE = 0.5 * (F.T @ dF + dF.T @ F)
         assert abs(dpsi - np.sum(S * dE)) < 1e-6 * abs(np.sum(np.abs(S) * np.abs(dE)))
+
+
+@pytest.mark.parametrize("name,kw,fN", [m for m in MODELS if m[2] is not None], ids=[m[0] for m in MODELS if m[2] is not None])
+def test_active_stress_is_the_projected_fibre_tension(lib, name, kw, fN):
+    """Active tensions enter S_bar (or S for HO-ma / CANN) and are independent of C except through the deviatoric projection
+    (mat_models.cpp:443-800): S(active) - S(passive) must equal Dev-projected Tfa f(x)f [+ Tsa s(x)s + Tna n(x)n] in closed form, and
+    CC = 2 dS/dC must still hold with the tensions held fixed."""
+    dirs = kw.get("isoType") in (abi.ISO_GUCCIONE, abi.ISO_HO, abi.ISO_HO_MA)
+    ya = np.array([3.0e4, 1.2e4 if dirs else 0.0, 0.7e4 if dirs else 0.0])
+    F = _F(6)
+    dmp, dma = _dm(**kw), _dm(active_stress=True, **kw)
+    Sp, Dp = _pk2cc(lib, dmp, F, fN, ya)            # domain without an active-stress model: ya must be ignored
+    S0, D0 = _pk2cc(lib, dmp, F, fN)
+    assert np.array_equal(Sp, S0) and np.array_equal(Dp, D0)
+    Sa, Da = _pk2cc(lib, dma, F, fN, ya)
+    f, sh = fN[0], fN[1]
+    n = np.cross(f, sh); n /= np.linalg.norm(n)
+    T = ya[0] * np.outer(f, f) + ya[1] * np.outer(sh, sh) + ya[2] * np.outer(n, n)
+    if kw.get("isoType") == abi.ISO_HO_MA or "cann" in kw:
+        expect = T
+    else:
+        Cm = F.T @ F
+        J = np.linalg.det(F)
+        expect = J ** (-2.0 / 3.0) * (T - np.sum(Cm * T) / 3.0 * np.linalg.inv(Cm))
+    assert np.abs((Sa - S0) - expect).max() < 1e-11 * np.abs(expect).max()
+    rng = np.random.default_rng(7)
+    dF = rng.standard_normal((3, 3))
+    e = 1e-6
+    Sp2, _ = _pk2cc(lib, dma, F + e * dF, fN, ya)
+    Sm2, _ = _pk2cc(lib, dma, F - e * dF, fN, ya)
+    dE = 0.5 * (F.T @ dF + dF.T @ F)
+    dEv = np.array([dE[0, 0], dE[1, 1], dE[2, 2], 2 * dE[0, 1], 2 * dE[1, 2], 2 * dE[2, 0]])
+    dS_fd = np.array([(Sp2 - Sm2)[i, j] for i, j in VOIGT]) / (2 * e)
+    assert np.abs(Da @ dEv - dS_fd).max() < 2e-6 * np.abs(Da @ dEv).max()
+
+
+def test_cann_second_invariant_follows_the_reference_not_the_exact_derivative(lib):
+    """Documents a property of the reference this port reproduces: with a row on invariant 2 the CANN tangent is NOT 2 dS/dC."""
+    dm = _dm(cann=[(2, (1, 1, 1), (1.0, 1.0, 4.0e4))], Kpen=0.0)
+    F = _F(2)
+    _, Dm = _pk2cc(lib, dm, F)
+    dF = np.random.default_rng(3).standard_normal((3, 3))
+    e = 1e-6
+    Sp, _ = _pk2cc(lib, dm, F + e * dF)
+    Sm, _ = _pk2cc(lib, dm, F - e * dF)
+    dE = 0.5 * (F.T @ dF + dF.T @ F)
+    dEv = np.array([dE[0, 0], dE[1, 1], dE[2, 2], 2 * dE[0, 1], 2 * dE[1, 2], 2 * dE[2, 0]])
+    dS_fd = np.array([(Sp - Sm)[i, j] for i, j in VOIGT]) / (2 * e)
+    assert np.abs(Dm @ dEv - dS_fd).max() > 1e-2 * np.abs(Dm @ dEv).max()
