@@ -125,6 +125,7 @@ typedef struct {
                         per-Gauss-point kernel that serves HEX8 (cross-check of the specialised TET4 kernel) */
 } svb200_eqparams;
 #define SVB200_EQ_GENERAL_KERNEL 1
+#define SVB200_EQ_PRESTRESS 2        /* com_mod.pstEq: struct / lElas assembly accumulates pSn, pSa (svb200_get_prestress) */
 
 /* Per-domain material parameters (dmnType, stModelType, fluidViscModelType). */
 typedef struct {
@@ -268,6 +269,14 @@ SVB200_API int svb200_set_old_disp(svb200_ctx* ctx, int32_t tDof, const double* 
  * model, solver/active_stress.cpp), nNo doubles each in INPUT node order; Ya_s / Ya_n may be NULL (zero).  Read by the struct,
  * FSI-solid and ustruct kernels for domains with active_stress set (sv_struct.cpp:277-281, ustruct.cpp:294-298).  The reference
  * throws when Ya_s or Ya_n is positive for a model other than Guccione / HO / HO-ma (mat_models.cpp:334-340): checked at assembly. */
+/* Nodal prestress com_mod.pS0 (nsymd = 6, nNo), Voigt order 11,22,33,12,23,31, INPUT node order; NULL removes it.  Interpolated to
+ * the Gauss points and added to the 2nd Piola-Kirchhoff stress by the struct, FSI-solid and lElas kernels (sv_struct.cpp:635-680,
+ * l_elas.cpp:321-338).  With SVB200_EQ_PRESTRESS in eq.reserved (com_mod.pstEq) the struct / lElas assembly also accumulates
+ * pSn(:,A) += w N_a pSl and pSa(A) += w N_a (sv_struct.cpp:327-336); svb200_alloc zeroes the accumulators (Integrator::initiator,
+ * Integrator.cpp:745-748) and svb200_get_prestress returns this partition's raw sums — the corrector's commu and division
+ * (Integrator.cpp:912-924) stay with the caller. */
+SVB200_API int svb200_set_prestress(svb200_ctx* ctx, const double* pS0);
+SVB200_API int svb200_get_prestress(svb200_ctx* ctx, double* pSn, double* pSa);
 SVB200_API int svb200_set_active_tension(svb200_ctx* ctx, const double* Ya_f, const double* Ya_s, const double* Ya_n);
 
 /* global_eq_assem for mesh iM: element loop + scatter, R/Val stay on the device. */

@@ -182,6 +182,13 @@ void fill_eq(RefCase& c, const svb200_eqparams& e, const svb200_dmnparams* dmn, 
   cm.dof = e.dof;
   cm.tDof = e.tDof;
   cm.mvMsh = (e.mvMsh != 0);
+  // prestress equation (com_mod.pstEq): accumulators as initialize.cpp:674-679 sizes them
+  cm.pstEq = (e.reserved & SVB200_EQ_PRESTRESS) != 0;
+  cm.nsymd = 6;
+  if (cm.pstEq && cm.pSa.size() != cm.tnNo) {
+    cm.pSn.resize(6, cm.tnNo); cm.pSa.resize(cm.tnNo);
+    cm.pSn = 0.0; cm.pSa = 0.0;
+  }
   eq.phys = to_phys(e.phys);
   eq.af = e.af; eq.am = e.am; eq.gam = e.gam; eq.beta = e.beta;
   eq.dof = e.dof; eq.s = e.s; eq.e = e.s + e.dof - 1;
@@ -450,6 +457,8 @@ int svref_alloc(void* h, int dof)
     cm.Val.resize(dof*dof, cm.lhs.nnz);
     cm.R = 0.0;
     cm.Val = 0.0;
+    // Integrator::initiator zeroes the prestress accumulators once per Newton iteration (Integrator.cpp:745-748)
+    if (cm.pSa.size() != 0) { cm.pSn = 0.0; cm.pSa = 0.0; }
   });
 }
 
@@ -472,6 +481,30 @@ int svref_set_state(void* h, int tDof, const double* Ag, const double* Yg, const
     auto& Do = c.sol.old.get_displacement();
     if (Do.nrows() != tDof || Do.ncols() != n) Do.resize(tDof, n);
     if (Dg) std::memcpy(Do.data(), Dg, sizeof(double)*tDof*n);
+  });
+}
+
+/// com_mod.pS0(nsymd, tnNo); null clears it (pS0.size() == 0 switches the prestress terms off, sv_struct.cpp:273).
+int svref_set_prestress(void* h, const double* pS0)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    auto& cm = c.com_mod;
+    cm.nsymd = 6;
+    if (!pS0) { cm.pS0.resize(0, 0); return; }
+    cm.pS0.resize(6, cm.tnNo);
+    std::memcpy(cm.pS0.data(), pS0, sizeof(double) * 6 * cm.tnNo);
+  });
+}
+
+int svref_get_prestress(void* h, double* pSn, double* pSa)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    auto& cm = c.com_mod;
+    if (cm.pSa.size() != cm.tnNo) throw std::runtime_error("[ref_harness] no prestress equation assembled");
+    std::memcpy(pSn, cm.pSn.data(), sizeof(double) * 6 * cm.tnNo);
+    std::memcpy(pSa, cm.pSa.data(), sizeof(double) * cm.tnNo);
   });
 }
 

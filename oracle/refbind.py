@@ -143,6 +143,14 @@ class _FlatCase:
         Ag, Yg, Dg, Bf = _f64(Ag), _f64(Yg), _f64(Dg), _f64(Bf)
         self._call("set_state", C.c_int(Ag.shape[0]), _d(Ag), _d(Yg), _d(Dg), _d(Bf))
 
+    def set_prestress(self, pS0):
+        self._call("set_prestress", _d(_f64(pS0)))
+
+    def get_prestress(self):
+        pSn, pSa = np.zeros((6, self.nNo), order="F"), np.zeros(self.nNo)
+        self._call("get_prestress", _d(pSn), _d(pSa))
+        return pSn, pSa
+
     def set_active_tension(self, Ya_f, Ya_s=None, Ya_n=None):
         f = np.ascontiguousarray(Ya_f, dtype=np.float64)
         s_ = None if Ya_s is None else np.ascontiguousarray(Ya_s, dtype=np.float64)

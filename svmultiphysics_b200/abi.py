@@ -103,6 +103,7 @@ def eq_time(s: int, e: int, phys: int, rho_inf: float = 0.5) -> EqTime:
 
 
 EQ_GENERAL_KERNEL = 1
+EQ_PRESTRESS = 2     # com_mod.pstEq
 
 
 def fluid_eq(dt: float, rho_inf: float = 0.5, tDof: int = 4, scatter: int = SCATTER_ATOMIC, mvMsh: int = 0,

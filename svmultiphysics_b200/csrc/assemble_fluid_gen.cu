@@ -35,7 +35,9 @@ struct FluidGenArgs {
   double* R;
   double* Val;
   int e0, e1;
-  int tDof, mvMsh, nDmn, atomic, ale, pad;
+  int tDof, mvMsh, nDmn, atomic, ale;
+  int lShpF;            // mshType::lShpF (nn_elem_props.h): TET4 and WDG — nn::gnn / gn_nxx are evaluated at Gauss point 0 only
+                        // (fluid.cpp:641, 707), also for the wedge, whose gradients are NOT constant: reproduced as is
   double dt, af, am, gam;
   FluidDmn dmn[MAX_DMN];
 };
@@ -55,25 +57,32 @@ __host__ __device__ constexpr int fg_tab_ld(int enon) { return 1 + enon * 10; }
 __host__ __device__ constexpr int fg_nd_ld(int enon) { return enon * FLUID_NODE_DOUBLES + 1; }
 // per element: nodal inputs (x 3, al 3, yl 4, bfl 3, ym 3 = 16) | NxxL 6 | FluidGP per Gauss point | FluidNode tables;
 // padded to 8 mod 16 doubles (the two elements of a half-warp then use disjoint banks)
-__host__ __device__ constexpr int fg_per_el(int enon)
+__host__ __device__ constexpr int fg_per_el(int enon, int ng)
 {
-  const int n = enon * 16 + enon * 6 + enon * FLUID_GP_DOUBLES + enon * fg_nd_ld(enon);
+  const int n = enon * 16 + enon * 6 + ng * FLUID_GP_DOUBLES + ng * fg_nd_ld(enon);
   return n + ((8 - (n % 16)) + 16) % 16;
 }
+// lanes per element: one per element node in phase B and one per Gauss point in phase A
+__host__ __device__ constexpr int fg_lpe(int enon, int ng) { return enon > ng ? enon : ng; }
+// CTA size: two warps, one for the big quadratic elements (HEX20 / HEX27 need ~75 KB of shared memory per element)
+__host__ __device__ constexpr int fg_threads(int enon, int ng) { return fg_per_el(enon, ng) * (32 / fg_lpe(enon, ng)) > 6000 ? 32 : FG_THREADS; }
 
-template <int ENON, bool ATOMIC>
-__global__ void __launch_bounds__(FG_THREADS)
+// NG = number of Gauss points: NG == ENON for TET4 / HEX8 / WDG, 15 for TET10, 27 for HEX20 / HEX27 (nn_elem_props.h).
+template <int ENON, int NG, bool ATOMIC>
+__global__ void __launch_bounds__(fg_threads(ENON, NG))
 assemble_fluid_gen_kernel(const __grid_constant__ FluidGenArgs P)
 {
-  constexpr int EPW = 32 / ENON;
-  constexpr int PER_EL = fg_per_el(ENON);
+  constexpr int LPE = fg_lpe(ENON, NG);
+  constexpr int EPW = 32 / LPE;
+  constexpr int PER_EL = fg_per_el(ENON, NG);
   constexpr int TLD = fg_tab_ld(ENON);
+  constexpr int THREADS = fg_threads(ENON, NG);
   extern __shared__ double sm[];
   double* stab = sm;
-  for (int t = threadIdx.x; t < ENON * TLD; t += FG_THREADS) stab[t] = __ldg(P.tab + t);
+  for (int t = threadIdx.x; t < NG * TLD; t += THREADS) stab[t] = __ldg(P.tab + t);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int a = lane % ENON, el = lane / ENON;
-  double* se = sm + ENON * TLD + (size_t)(warp * EPW + el) * PER_EL;
+  const int a = lane % LPE, el = lane / LPE;
+  double* se = sm + NG * TLD + (size_t)(warp * EPW + el) * PER_EL;
   double(*sx)[3] = reinterpret_cast<double(*)[3]>(se);
   double(*sal)[3] = reinterpret_cast<double(*)[3]>(se + 3 * ENON);
   double(*syl)[4] = reinterpret_cast<double(*)[4]>(se + 6 * ENON);
@@ -82,11 +91,11 @@ assemble_fluid_gen_kernel(const __grid_constant__ FluidGenArgs P)
   double(*sNxxL)[6] = reinterpret_cast<double(*)[6]>(se + 16 * ENON);
   FluidGP* sgp = reinterpret_cast<FluidGP*>(se + 22 * ENON);
   constexpr int NLD = fg_nd_ld(ENON);
-  double* sndd = se + 22 * ENON + ENON * FLUID_GP_DOUBLES;      // FluidNode tables, one per Gauss point, stride NLD
+  double* sndd = se + 22 * ENON + NG * FLUID_GP_DOUBLES;        // FluidNode tables, one per Gauss point, stride NLD
   auto snd = [&](int g) { return reinterpret_cast<FluidNode*>(sndd + g * NLD); };
 
-  const long long idx = (long long)P.e0 + ((long long)blockIdx.x * (FG_THREADS / 32) + warp) * EPW + el;
-  bool active = (lane < EPW * ENON) && idx < P.e1;
+  const long long idx = (long long)P.e0 + ((long long)blockIdx.x * (THREADS / 32) + warp) * EPW + el;
+  bool active = (lane < EPW * LPE) && idx < P.e1;
   int e = 0;
   if (active) e = P.perm ? P.perm[idx] : (int)idx;
   int iD = 0;
@@ -100,7 +109,7 @@ assemble_fluid_gen_kernel(const __grid_constant__ FluidGenArgs P)
   }
   const FluidDmn& dm = P.dmn[iD];
   int node = 0;
-  if (active) {
+  if (active && a < ENON) {
     node = P.IEN[(size_t)e * ENON + a];
     const size_t n = (size_t)node;
 #pragma unroll
@@ -119,15 +128,17 @@ assemble_fluid_gen_kernel(const __grid_constant__ FluidGenArgs P)
   {
     const int g = a;
     const double* tg = stab + g * TLD;
-    const double(*Nxi)[3] = reinterpret_cast<const double(*)[3]>(tg + 1 + ENON);
-    const double(*Nxi2)[6] = reinterpret_cast<const double(*)[6]>(tg + 1 + 4 * ENON);
+    const double* tgd = P.lShpF ? stab : tg;       // derivative tables: Gauss point 0 for the lShpF elements
+    const double(*Nxi)[3] = reinterpret_cast<const double(*)[3]>(tgd + 1 + ENON);
+    const double(*Nxi2)[6] = reinterpret_cast<const double(*)[6]>(tgd + 1 + 4 * ENON);
     double Nx[ENON][3], Nxx[ENON][6], xiX[3][3], ks[3][3];
     double Jac = 1.0;
-    if (active) {
+    const bool gp = active && g < NG;
+    if (gp) {
       Jac = gnn3_full<ENON>(Nxi, sx, Nx, xiX, ks);
       if (is_zero(Jac)) atomicMax(P.err, e + 1);
       gn_nxx3<ENON>(Nxi2, sx, xiX, Nx, Nxx);
-      if (g == ENON - 1) {
+      if (g == NG - 1) {
 #pragma unroll
         for (int b = 0; b < ENON; b++)
 #pragma unroll
@@ -135,21 +146,21 @@ assemble_fluid_gen_kernel(const __grid_constant__ FluidGenArgs P)
       }
     }
     __syncwarp();
-    if (active)
+    if (gp)
       fluid_gen_gauss_point<ENON>(dm, P.dt, P.af, P.am, P.gam, tg[0] * Jac, ks, tg + 1, Nx, Nxx, sNxxL, sal, syl, sbf,
                                   P.mvMsh ? sym : nullptr, sgp[g], snd(g));
   }
   __syncwarp();
-  if (!active) return;
+  if (!active || a >= ENON) return;
 
   // ---- phase B ------------------------------------------------------------------------------------------------
   double lR[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
-  for (int g = 0; g < ENON; g++) fluid_gen_residual(sgp[g], snd(g)[a], lR);
+  for (int g = 0; g < NG; g++) fluid_gen_residual(sgp[g], snd(g)[a], lR);
 #pragma unroll
   for (int i = 0; i < 4; i++) fg_add<ATOMIC>(P.R + 4 * (size_t)node + i, lR[i]);
   const int* sl = P.slot + (size_t)e * ENON * ENON;
-  constexpr int NB = (ENON % FG_NB == 0) ? FG_NB : 1;
+  constexpr int NB = (ENON % FG_NB == 0) ? FG_NB : (ENON % 2 == 0 ? 2 : 1);
 #pragma unroll 1
   for (int b0 = 0; b0 < ENON; b0 += NB) {
     // CSR slots of the NB blocks, requested before the Gauss loop so that the load latency hides behind the FMAs
@@ -162,7 +173,7 @@ assemble_fluid_gen_kernel(const __grid_constant__ FluidGenArgs P)
 #pragma unroll
       for (int i = 0; i < 16; i++) K[bb][i] = 0.0;
 #pragma unroll 1
-    for (int g = 0; g < ENON; g++) {
+    for (int g = 0; g < NG; g++) {
       const FluidNode* nd = snd(g);
       FluidRow row;
       fluid_gen_row(sgp[g], nd[a], row);
@@ -178,22 +189,24 @@ assemble_fluid_gen_kernel(const __grid_constant__ FluidGenArgs P)
   }
 }
 
-template <int ENON>
+template <int ENON, int NG>
 static int launch_gen(svb200_ctx* ctx, const FluidGenArgs& A)
 {
-  constexpr int EPB = (FG_THREADS / 32) * (32 / ENON);
+  constexpr int THREADS = fg_threads(ENON, NG);
+  constexpr int EPB = (THREADS / 32) * (32 / fg_lpe(ENON, NG));
   const long long n = (long long)A.e1 - A.e0;
   if (n <= 0) return SVB200_OK;
   const unsigned blocks = (unsigned)((n + EPB - 1) / EPB);
-  constexpr size_t smem = sizeof(double) * ((size_t)ENON * fg_tab_ld(ENON) + (size_t)EPB * fg_per_el(ENON));
+  constexpr size_t smem = sizeof(double) * ((size_t)NG * fg_tab_ld(ENON) + (size_t)EPB * fg_per_el(ENON, NG));
+  static_assert(smem <= 227 * 1024, "element does not fit in shared memory");
   static bool configured = false;
   if (!configured) {
-    SVB_CUDA(cudaFuncSetAttribute(assemble_fluid_gen_kernel<ENON, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SVB_CUDA(cudaFuncSetAttribute(assemble_fluid_gen_kernel<ENON, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVB_CUDA(cudaFuncSetAttribute(assemble_fluid_gen_kernel<ENON, NG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVB_CUDA(cudaFuncSetAttribute(assemble_fluid_gen_kernel<ENON, NG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  if (A.atomic) assemble_fluid_gen_kernel<ENON, true><<<blocks, FG_THREADS, smem, ctx->stream>>>(A);
-  else assemble_fluid_gen_kernel<ENON, false><<<blocks, FG_THREADS, smem, ctx->stream>>>(A);
+  if (A.atomic) assemble_fluid_gen_kernel<ENON, NG, true><<<blocks, THREADS, smem, ctx->stream>>>(A);
+  else assemble_fluid_gen_kernel<ENON, NG, false><<<blocks, THREADS, smem, ctx->stream>>>(A);
   ctx->launches++;
   SVB_CUDA(cudaGetLastError());
   return SVB200_OK;
@@ -203,7 +216,6 @@ static int launch_gen(svb200_ctx* ctx, const FluidGenArgs& A)
 int upload_fluid_gen_tables(svb200_ctx* ctx, Mesh& m)
 {
   const int E = m.eNoN, G = m.nG, LD = fg_tab_ld(E);
-  if (G != E) return SVB200_OK;    // only nG == eNoN elements run through this kernel
   std::vector<double> t((size_t)G * LD, 0.0);
   for (int g = 0; g < G; g++) {
     double* p = t.data() + (size_t)g * LD;
@@ -224,11 +236,13 @@ int upload_fluid_gen_tables(svb200_ctx* ctx, Mesh& m)
 
 int run_assemble_fluid_gen(svb200_ctx* ctx, const Mesh& m, const FluidArgs& F)
 {
-  SVB_REQUIRE(m.eNoN == 8 || m.eNoN == 4, "svb200_assemble: the general fluid kernel covers HEX8 and TET4 meshes");
-  SVB_REQUIRE(m.nG == m.eNoN, "svb200_assemble: the general fluid kernel expects nG == eNoN");
+  // element types of nn_elem_props.h with their quadrature rules: TET4 (4), HEX8 (8), WDG (6), TET10 (15), HEX20 / HEX27 (27)
+  const int key = m.eNoN * 100 + m.nG;
+  SVB_REQUIRE(key == 404 || key == 808 || key == 606 || key == 1015 || key == 2027 || key == 2727,
+              "svb200_assemble: the general fluid kernel covers TET4, HEX8, WDG, TET10, HEX20 and HEX27 meshes with the reference's quadrature rules");
   SVB_REQUIRE(m.d_gtab, "svb200_assemble: element tables missing");
-  if (m.eNoN == 8 && m.Nxx.empty()) {
-    set_error("svb200_assemble: a HEX8 fluid mesh needs the second-derivative table (svb200_set_mesh_nxx)");
+  if (m.eNoN != 4 && m.Nxx.empty()) {
+    set_error("svb200_assemble: a fluid mesh of non-linear elements needs the second-derivative table (svb200_set_mesh_nxx)");
     return SVB200_ERR_INVALID;
   }
   FluidGenArgs A;
@@ -237,9 +251,19 @@ int run_assemble_fluid_gen(svb200_ctx* ctx, const Mesh& m, const FluidArgs& F)
   A.x = F.x; A.Ag = F.Ag; A.Yg = F.Yg; A.Bf = F.Bf; A.Dg = F.Dg; A.tab = m.d_gtab; A.R = F.R; A.Val = F.Val; A.err = F.err;
   A.e0 = 0; A.e1 = m.nEl;
   A.tDof = F.tDof; A.mvMsh = F.mvMsh; A.nDmn = F.nDmn; A.atomic = F.atomic; A.ale = F.ale;
+  A.lShpF = (m.eNoN == 4 || m.eNoN == 6) ? 1 : 0;
   A.dt = F.dt; A.af = F.af; A.am = F.am; A.gam = F.gam;
   for (int d = 0; d < MAX_DMN; d++) A.dmn[d] = F.dmn[d];
-  auto launch = [&](const FluidGenArgs& B) { return m.eNoN == 8 ? launch_gen<8>(ctx, B) : launch_gen<4>(ctx, B); };
+  auto launch = [&](const FluidGenArgs& B) {
+    switch (key) {
+      case 404: return launch_gen<4, 4>(ctx, B);
+      case 808: return launch_gen<8, 8>(ctx, B);
+      case 606: return launch_gen<6, 6>(ctx, B);
+      case 1015: return launch_gen<10, 15>(ctx, B);
+      case 2027: return launch_gen<20, 27>(ctx, B);
+      default: return launch_gen<27, 27>(ctx, B);
+    }
+  };
   if (A.atomic) return launch(A);
   A.perm = m.d_color_perm;
   for (size_t c = 0; c + 1 < m.color_off.size(); c++) {

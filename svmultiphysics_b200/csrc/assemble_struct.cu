@@ -30,6 +30,9 @@ struct StructArgs {
   const double* Dg;
   const double* Bf;
   const double* Ya;      // nodal active tensions (3, nNo): Ya_f, Ya_s, Ya_n (cep_mod.cem), or nullptr
+  const double* pS0;     // nodal prestress com_mod.pS0 (6, nNo), Voigt 11,22,33,12,23,31, or nullptr
+  double* pSn;           // pstEq: accumulators com_mod.pSn (6, nNo) and pSa (nNo) (sv_struct.cpp:327-336), else nullptr
+  double* pSa;
   double* R;
   double* Val;
   int e0, e1;
@@ -198,6 +201,32 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
       for (int i = 0; i < 3; i++)
 #pragma unroll
         for (int j = 0; j < 3; j++) S[i][j] += Svis[i][j];
+    }
+    // Prestress (sv_struct.cpp:671-680, 327-336): pSl = S before the nodal prestress S0 = sum_b N_b pS0(:, node_b) is added;
+    // a prestress equation accumulates w N_a pSl and w N_a per node (the corrector divides them, Integrator.cpp:912-924).
+    if (P.pSn != nullptr) {
+      const double wg = tw[g] * Jac;
+      const double pSl[6] = {S[0][0], S[1][1], S[2][2], S[0][1], S[1][2], S[2][0]};
+#pragma unroll
+      for (int b = 0; b < ENON; b++) {
+        const size_t nb = (size_t)P.IEN[(size_t)e * ENON + b];
+        const double wN = wg * tN[g][b];
+        add64<true>(P.pSa + nb, wN);
+#pragma unroll
+        for (int i = 0; i < 6; i++) add64<true>(P.pSn + 6 * nb + i, wN * pSl[i]);
+      }
+    }
+    if (P.pS0 != nullptr) {
+      double S0[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int b = 0; b < ENON; b++) {
+        const size_t nb = (size_t)P.IEN[(size_t)e * ENON + b];
+        const double Nb = tN[g][b];
+#pragma unroll
+        for (int i = 0; i < 6; i++) S0[i] += Nb * __ldg(P.pS0 + 6 * nb + i);
+      }
+      S[0][0] += S0[0]; S[1][1] += S0[1]; S[2][2] += S0[2];
+      S[0][1] += S0[3]; S[1][0] += S0[3]; S[1][2] += S0[4]; S[2][1] += S0[4]; S[2][0] += S0[5]; S[0][2] += S0[5];
     }
     double* q = sgp + g * GP_LD;
 #pragma unroll
@@ -740,9 +769,27 @@ assemble_mesh_kernel(const __grid_constant__ StructArgs P, const double* __restr
       ed[5] += Nx[b][0] * dl[b][2] + Nx[b][2] * dl[b][0];
     }
     const double divD = lambda * (ed[0] + ed[1] + ed[2]);
-    const double S0 = divD + 2.0 * mu * ed[0], S1 = divD + 2.0 * mu * ed[1], S2 = divD + 2.0 * mu * ed[2];
-    const double S3 = mu * ed[3], S4 = mu * ed[4], S5 = mu * ed[5];
+    double S0 = divD + 2.0 * mu * ed[0], S1 = divD + 2.0 * mu * ed[1], S2 = divD + 2.0 * mu * ed[2];
+    double S3 = mu * ed[3], S4 = mu * ed[4], S5 = mu * ed[5];
     const double Na = P.N[g][a];
+    if (LELAS) {
+      // prestress of the linear-elasticity equation (l_elas.cpp:321-338, 130-140): lane a accumulates its own node
+      if (P.pSn != nullptr) {
+        const double wN = w * Na;
+        add64<true>(P.pSa + node[a], wN);
+        add64<true>(P.pSn + 6 * (size_t)node[a] + 0, wN * S0); add64<true>(P.pSn + 6 * (size_t)node[a] + 1, wN * S1);
+        add64<true>(P.pSn + 6 * (size_t)node[a] + 2, wN * S2); add64<true>(P.pSn + 6 * (size_t)node[a] + 3, wN * S3);
+        add64<true>(P.pSn + 6 * (size_t)node[a] + 4, wN * S4); add64<true>(P.pSn + 6 * (size_t)node[a] + 5, wN * S5);
+      }
+      if (P.pS0 != nullptr) {
+        double p0[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int b = 0; b < ENON; b++)
+#pragma unroll
+          for (int i = 0; i < 6; i++) p0[i] += P.N[g][b] * __ldg(P.pS0 + 6 * (size_t)node[b] + i);
+        S0 += p0[0]; S1 += p0[1]; S2 += p0[2]; S3 += p0[3]; S4 += p0[4]; S5 += p0[5];
+      }
+    }
     lR[0] += w * (rho * Na * ud[0] + Nx[a][0] * S0 + Nx[a][1] * S3 + Nx[a][2] * S5);
     lR[1] += w * (rho * Na * ud[1] + Nx[a][0] * S3 + Nx[a][1] * S1 + Nx[a][2] * S4);
     lR[2] += w * (rho * Na * ud[2] + Nx[a][0] * S5 + Nx[a][1] * S4 + Nx[a][2] * S2);
@@ -920,6 +967,17 @@ int fill_struct_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, 
   A.IEN = m.d_IEN; A.eId = m.d_eId; A.slot = m.d_slot; A.perm = nullptr; A.fN = m.d_fN;
   A.x = ctx->d_x; A.Ag = ctx->d_Ag; A.Yg = ctx->d_Yg; A.Dg = ctx->d_Dg; A.Bf = ctx->d_Bf;
   A.Ya = ctx->d_Ya;
+  A.pS0 = ctx->d_pS0;
+  if (eq->reserved & SVB200_EQ_PRESTRESS) {
+    // pstEq: the accumulators live until the next svb200_alloc (which zeroes them like Integrator::initiator does)
+    const size_t n = std::max<size_t>((size_t)ctx->nNo, 1);
+    if (!ctx->d_pSn) {
+      SVB_CUDA(cudaMalloc(&ctx->d_pSn, sizeof(double) * 7 * n));
+      SVB_CUDA(cudaMemsetAsync(ctx->d_pSn, 0, sizeof(double) * 7 * n, ctx->stream));
+    }
+    A.pSn = ctx->d_pSn;
+    A.pSa = ctx->d_pSn + 6 * n;
+  }
   A.R = ctx->d_R; A.Val = ctx->d_Val;
   A.e0 = 0; A.e1 = m.nEl;
   A.tDof = eq->tDof; A.dof = eq->dof; A.s = eq->s; A.nFn = m.nFn; A.nDmn = nDmn; A.nG = m.nG;
@@ -1041,7 +1099,8 @@ int run_assemble_struct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* e
   bool visc = false;
   for (int d = 0; d < A.nDmn; d++) visc |= (A.dmn[d].isStruct && A.dmn[d].viscType != SVB200_SOLID_VISC_NONE);
   static const bool force_general = (getenv("SVB200_STRUCT_GENERAL") != nullptr && atoi(getenv("SVB200_STRUCT_GENERAL")) != 0);
-  const bool tet4 = (m.eNoN == 4 && !visc && !force_general);
+  // (the closed-form kernel has no prestress terms: S0 and pSl vary over the Gauss points with N_a)
+  const bool tet4 = (m.eNoN == 4 && !visc && !force_general && A.pS0 == nullptr && A.pSn == nullptr);
   auto launch = [&](const StructArgs& B) {
     if (tet4) return launch_tet4(ctx, B);
     return m.eNoN == 8 ? launch_one<8>(ctx, B) : launch_one<4>(ctx, B);
@@ -1094,6 +1153,7 @@ int run_assemble_mesh(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq,
   StructArgs A;
   int rc = fill_struct_args(ctx, m, eq, d.data(), nDmn, A);
   if (rc) return rc;
+  if (!lelas) { A.pS0 = nullptr; A.pSn = nullptr; A.pSa = nullptr; }     // construct_mesh passes a zero pS0l (mesh.cpp)
   const double* Do = lelas ? nullptr : ctx->d_Do;
   static const bool force_general = (getenv("SVB200_STRUCT_GENERAL") != nullptr && atoi(getenv("SVB200_STRUCT_GENERAL")) != 0);
   auto launch_t4 = [&](const StructArgs& B) {
@@ -1112,7 +1172,7 @@ int run_assemble_mesh(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq,
     return (int)SVB200_OK;
   };
   auto launch = [&](const StructArgs& B) {
-    if (m.eNoN == 4 && m.nG == 4 && !force_general) return launch_t4(B);
+    if (m.eNoN == 4 && m.nG == 4 && !force_general && !(lelas && (A.pS0 || A.pSn))) return launch_t4(B);
     return m.eNoN == 8 ? launch_mesh<8>(ctx, B, Do) : launch_mesh<4>(ctx, B, Do);
   };
   if (A.atomic) return launch(A);

@@ -235,7 +235,7 @@ int svb200_destroy(svb200_ctx* ctx)
   cudaFree(ctx->d_hg);
   for (auto& nb : ctx->neigh) { cudaFree(nb.d_ptr); cudaFree(nb.d_send); cudaFree(nb.d_recv); }
   cudaFree(ctx->d_map); cudaFree(ctx->d_rowPtr_in); cudaFree(ctx->d_rowPtr); cudaFree(ctx->d_colPtr); cudaFree(ctx->d_diagPtr);
-  cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf); cudaFree(ctx->d_Do); cudaFree(ctx->d_Ya);
+  cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf); cudaFree(ctx->d_Do); cudaFree(ctx->d_Ya); cudaFree(ctx->d_pS0); cudaFree(ctx->d_pSn);
   cudaFree(ctx->d_Ao); cudaFree(ctx->d_Yo); cudaFree(ctx->d_An); cudaFree(ctx->d_Yn); cudaFree(ctx->d_Dn); cudaFree(ctx->d_nodeflag);
   cudaFree(ctx->d_err); cudaFree(ctx->d_Kd); cudaFree(ctx->d_Ad); cudaFree(ctx->d_Rd);
   cudaFree(ctx->d_stage); cudaFree(ctx->d_R); cudaFree(ctx->d_Val); cudaFree(ctx->d_W);
@@ -380,6 +380,7 @@ int svb200_set_graph(svb200_ctx* ctx, int32_t nNo, int32_t nnz, const int32_t* r
   // state arrays depend on nNo
   cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf); cudaFree(ctx->d_Do);
   cudaFree(ctx->d_Ya); ctx->d_Ya = nullptr; ctx->ya_sn_positive = false;
+  cudaFree(ctx->d_pS0); cudaFree(ctx->d_pSn); ctx->d_pS0 = ctx->d_pSn = nullptr;
   cudaFree(ctx->d_Ao); cudaFree(ctx->d_Yo); cudaFree(ctx->d_An); cudaFree(ctx->d_Yn); cudaFree(ctx->d_Dn); cudaFree(ctx->d_nodeflag);
   ctx->d_Ao = ctx->d_Yo = ctx->d_An = ctx->d_Yn = ctx->d_Dn = nullptr; ctx->d_nodeflag = nullptr;
   ctx->d_x = ctx->d_Ag = ctx->d_Yg = ctx->d_Dg = ctx->d_Bf = ctx->d_Do = nullptr;
@@ -393,7 +394,7 @@ int svb200_set_mesh(svb200_ctx* ctx, int32_t iM, int32_t eNoN, int32_t nEl, cons
   CTX_GUARD(ctx);
   SVB_REQUIRE(ctx->d_rowPtr, "svb200_set_mesh: call svb200_set_graph first");
   SVB_REQUIRE(iM >= 0 && iM < 64, "svb200_set_mesh: bad mesh index");
-  SVB_REQUIRE(eNoN >= 1 && eNoN <= MAX_ENON && nG >= 1 && nG <= MAX_NG, "svb200_set_mesh: unsupported eNoN / nG");
+  SVB_REQUIRE(eNoN >= 1 && eNoN <= MAX_ENON_ANY && nG >= 1 && nG <= MAX_NG_ANY, "svb200_set_mesh: unsupported eNoN / nG");
   SVB_REQUIRE(nEl >= 0 && (IEN || nEl == 0) && w && N && Nx, "svb200_set_mesh: bad arguments");
   if ((int)ctx->mesh.size() <= iM) ctx->mesh.resize(iM + 1);
   Mesh& m = ctx->mesh[iM];
@@ -569,6 +570,8 @@ int svb200_alloc(svb200_ctx* ctx, int32_t dof)
   }
   // com_mod.Kd is zeroed with the linear system (solver/Integrator.cpp:106-109)
   if (ctx->d_Kd && ctx->nnz) SVB_CUDA(cudaMemsetAsync(ctx->d_Kd, 0, sizeof(double) * 12 * (size_t)ctx->nnz, ctx->stream));
+  // the prestress accumulators pSn / pSa are zeroed once per Newton iteration by Integrator::initiator (Integrator.cpp:745-748)
+  if (ctx->d_pSn && ctx->nNo) SVB_CUDA(cudaMemsetAsync(ctx->d_pSn, 0, sizeof(double) * 7 * (size_t)ctx->nNo, ctx->stream));
   if (ctx->d_Rd && ctx->nNo) SVB_CUDA(cudaMemsetAsync(ctx->d_Rd, 0, sizeof(double) * 3 * (size_t)ctx->nNo, ctx->stream));
   return SVB200_OK;
 }
@@ -609,7 +612,6 @@ static int fill_fluid_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams
 {
   SVB_REQUIRE(nDmn >= 1 && nDmn <= MAX_DMN, "svb200_assemble: between 1 and 8 domains are supported");
   SVB_REQUIRE(eq->dof == 4 && ctx->dof == 4, "svb200_assemble: the fluid equation has dof = 4 (call svb200_alloc(4))");
-  SVB_REQUIRE(m.eNoN == 4 || m.eNoN == 8, "svb200_assemble: fluid assembly is implemented for TET4 and HEX8 meshes");
   SVB_REQUIRE(eq->vmsStab == 1, "svb200_assemble: only VMS-stabilised equal-order elements are supported");
   SVB_REQUIRE(eq->tDof == ctx->tDof && ctx->d_Yg, "svb200_assemble: state not set (svb200_set_state) or tDof mismatch");
   SVB_REQUIRE(!eq->mvMsh || eq->tDof >= 7, "svb200_assemble: mvMsh needs the mesh velocity in state dofs 4..6");
@@ -631,13 +633,15 @@ static int fill_fluid_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams
   SVB_REQUIRE(!A.ale || (eq->tDof >= 7 && ctx->d_Dg), "svb200_assemble: FSI needs tDof >= 7 and the displacement state");
   A.atomic = (eq->scatter == SVB200_SCATTER_ATOMIC);
   A.dt = eq->dt; A.af = eq->af; A.am = eq->am; A.gam = eq->gam;
-  for (int g = 0; g < m.nG; g++) {
-    A.w[g] = m.w[g];
-    for (int a = 0; a < m.eNoN; a++) {
-      A.N[g][a] = m.N[(size_t)g * m.eNoN + a];
-      for (int k = 0; k < 3; k++) A.Nxi[g][a][k] = m.Nx[((size_t)g * m.eNoN + a) * 3 + k];
+  // (the general kernel reads the tables of the quadratic elements from m.d_gtab; the fixed-size copy serves TET4 / HEX8)
+  if (m.nG <= MAX_NG && m.eNoN <= MAX_ENON)
+    for (int g = 0; g < m.nG; g++) {
+      A.w[g] = m.w[g];
+      for (int a = 0; a < m.eNoN; a++) {
+        A.N[g][a] = m.N[(size_t)g * m.eNoN + a];
+        for (int k = 0; k < 3; k++) A.Nxi[g][a][k] = m.Nx[((size_t)g * m.eNoN + a) * 3 + k];
+      }
     }
-  }
   bool needEId = false;
   for (int d = 0; d < nDmn; d++) {
     FluidDmn& o = A.dmn[d];
@@ -751,6 +755,24 @@ static int run_assemble(svb200_ctx* ctx, const Mesh& m, FluidArgs& A, bool gener
     TRY(launch_assemble_fluid(ctx, m, A));
   }
   return SVB200_OK;
+}
+
+int svb200_set_prestress(svb200_ctx* ctx, const double* pS0)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(ctx->d_rowPtr, "svb200_set_prestress: set the graph first");
+  if (!pS0) { cudaFree(ctx->d_pS0); ctx->d_pS0 = nullptr; return SVB200_OK; }
+  return upload_nodal(ctx, 6, pS0, &ctx->d_pS0);
+}
+
+int svb200_get_prestress(svb200_ctx* ctx, double* pSn, double* pSa)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(pSn && pSa, "svb200_get_prestress: null output");
+  SVB_REQUIRE(ctx->d_pSn, "svb200_get_prestress: no prestress equation (SVB200_EQ_PRESTRESS) has been assembled");
+  const size_t n = std::max<size_t>((size_t)ctx->nNo, 1);
+  TRY(download_nodal(ctx, 6, ctx->d_pSn, pSn));
+  return download_nodal(ctx, 1, ctx->d_pSn + 6 * n, pSa);
 }
 
 int svb200_set_active_tension(svb200_ctx* ctx, const double* Ya_f, const double* Ya_s, const double* Ya_n)
@@ -1069,6 +1091,8 @@ int svb200_assemble_host(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq,
   SVB_CUDA(cudaMemsetAsync(ctx->d_R, 0, sizeof(double) * nR, ctx->stream));
   SVB_CUDA(cudaMemsetAsync(ctx->d_Val, 0, sizeof(double) * nV, ctx->stream));
   if (ctx->d_Kd && ctx->nnz) SVB_CUDA(cudaMemsetAsync(ctx->d_Kd, 0, sizeof(double) * 12 * (size_t)ctx->nnz, ctx->stream));
+  // the prestress accumulators pSn / pSa are zeroed once per Newton iteration by Integrator::initiator (Integrator.cpp:745-748)
+  if (ctx->d_pSn && ctx->nNo) SVB_CUDA(cudaMemsetAsync(ctx->d_pSn, 0, sizeof(double) * 7 * (size_t)ctx->nNo, ctx->stream));
   FluidArgs A;
   TRY(fill_fluid_args(ctx, m, eq, dmn, nDmn, A));
   // the copy streams start after whatever the main stream was doing with the state arrays

@@ -20,6 +20,9 @@ namespace svb {
 constexpr int MAX_DMN = 8;
 constexpr int MAX_ENON = 8;
 constexpr int MAX_NG = 8;
+// the general fluid kernel reads its tables from a device buffer and also takes the quadratic elements
+constexpr int MAX_ENON_ANY = 27;
+constexpr int MAX_NG_ANY = 27;
 constexpr int ASM_GROUP = 128;   // elements per CTA of the grouped (pre-reduced) scatter, group_sched.cu
 
 // Pre-reduction plan of one mesh for the grouped scatter (group_sched.cu).
@@ -158,7 +161,9 @@ struct svb200_ctx {
   double* d_Dg = nullptr;
   double* d_Do = nullptr;        // old displacement (mesh-motion equation; solutions.old)
   double* d_Ya = nullptr;        // nodal active tensions (3, nNo): Ya_f, Ya_s, Ya_n (svb200_set_active_tension)
-  bool ya_sn_positive = false;   // any Ya_s or Ya_n > 0 (only the Guccione / HO / HO-ma models accept that)
+  bool ya_sn_positive = false;
+  double* d_pS0 = nullptr;       // nodal prestress com_mod.pS0 (6, nNo) (svb200_set_prestress)
+  double* d_pSn = nullptr;       // pstEq accumulators: pSn (6, nNo) followed by pSa (nNo)   // any Ya_s or Ya_n > 0 (only the Guccione / HO / HO-ma models accept that)
   double* d_Ao = nullptr; double* d_Yo = nullptr;                          // solutions.old
   double* d_An = nullptr; double* d_Yn = nullptr; double* d_Dn = nullptr;  // solutions.current
   int* d_nodeflag = nullptr;     // per node: belongs to a solid domain (FSI corrector)

@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "svb200_set_solution", "svb200_get_solution", "svb200_predictor", "svb200_initiator", "svb200_corrector",
     "svb200_set_node_flags", "svb200_set_dirichlet_rows", "svb200_dirichlet_ustruct", "svb200_advance_time_step",
     "svb200_set_bface", "svb200_assemble_neu",
-    "svb200_set_active_tension",
+    "svb200_set_active_tension", "svb200_set_prestress", "svb200_get_prestress",
     "svb200_spmv_rc", "svb200_spmv_rc_variants", "svb200_bench_spmv_rc",
     "svb200_schur_sp", "svb200_schur_sp_variants", "svb200_bench_schur_sp",
 ]
@@ -215,6 +215,16 @@ class Engine:
         Ag, Yg, Dg, Bf = _f64(Ag), _f64(Yg), _f64(Dg), _f64(Bf)
         tDof = (Ag if Ag is not None else Yg).shape[0]
         self._call("svb200_set_state", C.c_int32(tDof), _d(Ag), _d(Yg), _d(Dg), _d(Bf))
+
+    def set_prestress(self, pS0):
+        """Nodal prestress com_mod.pS0 (6, nNo), Voigt 11,22,33,12,23,31; None removes it."""
+        self._call("svb200_set_prestress", _d(_f64(pS0)))
+
+    def get_prestress(self):
+        """(pSn (6, nNo), pSa (nNo)) accumulated by the last assembly of a prestress equation (abi.EQ_PRESTRESS)."""
+        pSn, pSa = np.zeros((6, self.nNo), order="F"), np.zeros(self.nNo)
+        self._call("svb200_get_prestress", _d(pSn), _d(pSa))
+        return pSn, pSa
 
     def set_active_tension(self, Ya_f, Ya_s=None, Ya_n=None):
         """Nodal active tensions cep_mod.cem.Ya_f / Ya_s / Ya_n (nNo each) for domains with an active-stress model."""

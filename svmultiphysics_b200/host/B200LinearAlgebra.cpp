@@ -51,6 +51,7 @@ svb200_eqparams eq_params(const ComMod& com_mod, const eqType& eq, const mshType
   e.mvMsh = com_mod.mvMsh ? 1 : 0;
   e.vmsStab = (lM.nFs == 1) ? 1 : 0;        // Code/Source/solver/fluid.cpp:496-500
   e.scatter = scatter;
+  if (com_mod.pstEq) e.reserved |= SVB200_EQ_PRESTRESS;     // prestress equation: pSn / pSa accumulated on the device
   return e;
 }
 
@@ -351,9 +352,21 @@ void B200LinearAlgebra::assemble_mesh(ComMod& com_mod, const mshType& lM, const 
     const auto& Do = solutions.old.get_displacement();            // Code/Source/solver/mesh.cpp:60-75
     check(svb200_set_old_disp(ctx, tDof, Do.data()));
   }
+  // nodal prestress (sv_struct.cpp:271-274, l_elas.cpp:90-92, fsi.cpp:127-129): pS0 changes once per time step
+  // (Integrator.cpp:422-424), 6 doubles per node
+  const bool solidEq = eq.phys == consts::EquationType::phys_struct || eq.phys == consts::EquationType::phys_lElas ||
+                       eq.phys == consts::EquationType::phys_FSI;
+  if (solidEq) check(svb200_set_prestress(ctx, com_mod.pS0.size() ? com_mod.pS0.data() : nullptr));
   svb200_eqparams e = b200::eq_params(com_mod, eq, lM, scatter);
   std::vector<svb200_dmnparams> d = b200::domain_params(eq);
   check(svb200_assemble(ctx, iM, &e, d.data(), (int)d.size()));
+  if (com_mod.pstEq && (eq.phys == consts::EquationType::phys_struct || eq.phys == consts::EquationType::phys_lElas)) {
+    // the running sums of this Newton iteration (zeroed by ls_alloc) back into com_mod for Integrator::corrector
+    // (Integrator.cpp:912-924: commu, division by pSa)
+    if (com_mod.pSn.nrows() != 6 || com_mod.pSn.ncols() != com_mod.tnNo) com_mod.pSn.resize(6, com_mod.tnNo);
+    if (com_mod.pSa.size() != com_mod.tnNo) com_mod.pSa.resize(com_mod.tnNo);
+    check(svb200_get_prestress(ctx, com_mod.pSn.data(), com_mod.pSa.data()));
+  }
 }
 
 void B200LinearAlgebra::set_active_tension(const CepMod& cep_mod)

@@ -244,3 +244,57 @@ def boundary_face_elements(mesh: Mesh, nodes):
     keep = cnt[inv.ravel()] == 1
     order = np.argsort(E[keep], kind="stable")
     return np.asfortranarray(F[:, keep][:, order].astype(np.int32)), E[keep][order].astype(np.int32)
+
+
+# ---- quadratic and wedge elements (nn_elem_props.h: TET10, HEX20, HEX27, WDG; VTK node order, checked against the reference's
+# shape-function tables in tests/test_quadratic_elements_cpu.py) ---------------------------------------------------------------
+_TET_EDGES = [(0, 1), (1, 2), (0, 2), (0, 3), (1, 3), (2, 3)]
+_HEX_EDGES = [(0, 1), (1, 2), (2, 3), (3, 0), (4, 5), (5, 6), (6, 7), (7, 4), (0, 4), (1, 5), (2, 6), (3, 7)]
+_HEX_FACES = [(0, 4, 7, 3), (1, 2, 6, 5), (0, 1, 5, 4), (3, 2, 6, 7), (0, 1, 2, 3), (4, 5, 6, 7)]
+
+
+def elevate(m: Mesh, kind: str, bend: float = 0.0) -> Mesh:
+    """TET4 -> "tet10", HEX8 -> "hex20" / "hex27": one new node per edge (and per face and cell for hex27), shared between the
+    elements, placed at the mean of its corners; `bend` then applies a smooth non-linear map to ALL nodes so that the elements are
+    curved (non-constant Jacobian, non-zero second derivatives of the geometry)."""
+    if kind == "tet10":
+        assert m.eNoN == 4
+        groups = _TET_EDGES
+    elif kind == "hex20":
+        assert m.eNoN == 8
+        groups = _HEX_EDGES
+    elif kind == "hex27":
+        assert m.eNoN == 8
+        groups = _HEX_EDGES + _HEX_FACES + [tuple(range(8))]
+    else:
+        raise ValueError(kind)
+    ids = {}
+    pts = [m.x[:, a] for a in range(m.nNo)]
+    IEN = np.zeros((m.eNoN + len(groups), m.nEl), dtype=np.int32, order="F")
+    IEN[:m.eNoN] = m.IEN
+    for e in range(m.nEl):
+        for k, grp in enumerate(groups):
+            key = tuple(sorted(int(m.IEN[c, e]) for c in grp))
+            if key not in ids:
+                ids[key] = len(pts)
+                pts.append(m.x[:, list(key)].mean(axis=1))
+            IEN[m.eNoN + k, e] = ids[key]
+    x = np.asfortranarray(np.stack(pts, axis=1))
+    if bend:
+        L = np.abs(x).max()
+        s = x / L
+        x = np.asfortranarray(x + bend * L * np.stack([np.sin(2.1 * s[1]) * s[2], s[0] * s[0] - 0.5 * s[2], np.cos(1.7 * s[0]) * s[1]]))
+    return Mesh(x=x, IEN=IEN, eNoN=IEN.shape[0], faces={}, lattice=m.lattice)
+
+
+def box_wdg6(nx: int, ny: int, nz: int, lengths=(1.0, 1.0, 1.0), bend: float = 0.0) -> Mesh:
+    """Every hex of the box split into two 6-node wedges (triangles in the x-y plane, "origin-last" like the solver's TRI3 / TET4)."""
+    h = box_hex8(nx, ny, nz, lengths)
+    H = h.IEN
+    IEN = np.concatenate([np.stack([H[1], H[3], H[0], H[5], H[7], H[4]]), np.stack([H[3], H[1], H[2], H[7], H[5], H[6]])], axis=1)
+    x = h.x
+    if bend:
+        L = np.abs(x).max()
+        s = x / L
+        x = np.asfortranarray(x + bend * L * np.stack([np.sin(2.1 * s[1]) * s[2], s[0] * s[0] - 0.5 * s[2], np.cos(1.7 * s[0]) * s[1]]))
+    return Mesh(x=x, IEN=np.asfortranarray(IEN.astype(np.int32)), eNoN=6, faces=h.faces, lattice=h.lattice)

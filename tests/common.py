@@ -204,6 +204,34 @@ FLUID_GEN_CASES = [
 ]
 
 
+# Quadratic and wedge elements of nn_elem_props.h through the same general path (nG != eNoN: TET10 15, HEX20 / HEX27 27 Gauss
+# points; tests/cases/fluid/quadratic_tet10 is a TET10 VMS case).  Curved elements: the geometry's second derivatives enter gn_nxx.
+def _tet10():
+    return meshgen.elevate(meshgen.box_tet4(2, 2, 2, (1.0, 1.2, 0.8)), "tet10", bend=0.05)
+
+
+def _hex20():
+    return meshgen.elevate(meshgen.box_hex8(2, 2, 2, (1.0, 1.2, 0.8)), "hex20", bend=0.05)
+
+
+def _hex27():
+    return meshgen.elevate(meshgen.box_hex8(2, 2, 2, (1.0, 1.2, 0.8)), "hex27", bend=0.05)
+
+
+def _wdg6():
+    return meshgen.box_wdg6(2, 2, 2, (1.0, 1.2, 0.8), bend=0.05)
+
+
+FLUID_HI_CASES = [
+    ("tet10_newtonian", _tet10, {}, 0.0, (0.0, 0.0, 0.0), 4, 0),
+    ("tet10_carreau_yasuda_moving_mesh", _tet10, dict(viscType=abi.VISC_CY, mu=0.035, mu_o=0.16, lam=8.2, a=0.64, n=0.2128), 2.0,
+     (0.1, -0.2, 0.3), 7, 1),
+    ("hex20_newtonian", _hex20, {}, 0.5, (0.0, 0.1, 0.0), 4, 0),
+    ("hex27_casson", _hex27, dict(viscType=abi.VISC_CASSON, mu=0.3, mu_o=0.1, lam=0.5), 0.0, (0.0, 0.0, 1.0), 4, 0),
+    ("wdg6_newtonian", _wdg6, {}, 0.0, (0.2, 0.0, 0.0), 4, 0),
+]
+
+
 def fluid_gen_state(m, tDof, seed=31):
     rng = np.random.default_rng(seed)
     Yg = np.zeros((tDof, m.nNo), order="F")
@@ -305,6 +333,34 @@ def lelas_case(name):
     m.eId = None
     Do = np.asfortranarray(0.9 * Dg)
     return m, Ag, Yg, Dg, Bf, Do, abi.mesh_eq(1e-3), [abi.mesh_domain(E=1.0, nu=0.3)]
+
+
+# ---- prestress (com_mod.pS0, pstEq: sv_struct.cpp:271-274, 635-680, 327-336; l_elas.cpp:321-338, 130-140) -----------------------
+# (name, mesh, physics, domain kwargs, pstEq)
+PRESTRESS_CASES = [
+    ("hex8_struct_pS0", _hex, "struct", dict(), False),
+    ("hex8_struct_pstEq", _hex, "struct", dict(isoType=abi.ISO_MR, C10=1e5, C01=3e4, Kpen=1e7, rho=1.0), True),
+    ("tet4_struct_pstEq_visc", _tet, "struct", dict(volType=abi.VOL_QUAD, E=1e6, nu=0.4, Kpen=1e6, rho=1.0,
+                                                   solid_visc=abi.SOLID_VISC_POTENTIAL, solid_visc_mu=2.0e4), True),
+    ("tet4_struct_pstEq", _tet, "struct", dict(volType=abi.VOL_QUAD, E=1e6, nu=0.4, Kpen=1e6, rho=1.0), True),
+    ("tet4_lelas_pstEq", _tet, "lelas", dict(E=1.0e6, nu=0.3, rho=2.0, f=(0.1, -0.2, 0.3)), True),
+    ("hex8_lelas_pS0", _hex, "lelas", dict(E=2.0e6, nu=0.25, rho=1.0), False),
+]
+
+
+def prestress_case(name):
+    """(mesh, Ag, Yg, Dg, Bf, pS0, eq, domains) of a PRESTRESS_CASES entry."""
+    _, mk, phys, dkw, pst = next(c for c in PRESTRESS_CASES if c[0] == name)
+    m = mk()
+    Ag, Yg, Dg, Bf, _ = struct_state(m, 0)
+    pS0 = np.asfortranarray(2.0e6 * np.random.default_rng(41).standard_normal((6, m.nNo)))
+    if phys == "struct":
+        eq, dmn = abi.struct_eq(1e-4), [abi.struct_domain(**dkw)]
+    else:
+        eq, dmn = abi.lelas_eq(1e-3), [abi.lelas_domain(**dkw)]
+    if pst:
+        eq.reserved |= abi.EQ_PRESTRESS
+    return m, Ag, Yg, Dg, Bf, pS0, eq, dmn
 
 
 # ---- multi-rank reference runs (tests/test_multirank_reference_cpu.py, tests/mrank_ref_worker.py) -------------------------

@@ -86,6 +86,26 @@ def fluid_gen_golden():
     print("wrote fluid_gen.npz with", len(out), "arrays")
 
 
+def fluid_hi_golden():
+    """VMS fluid on TET10 / HEX20 / HEX27 / WDG (curved elements), with the reference's own element tables: the tests feed them
+    to svb200_set_mesh / svb200_set_mesh_nxx, as the plug-in does from mshType."""
+    out = {}
+    for name, mk, visc, Kd, f, tDof, mv in common.FLUID_HI_CASES:
+        m = mk()
+        Ag, Yg, Dg, Bf = common.fluid_gen_state(m, tDof)
+        c = RefCase(); c.set_coords(m.x); c.add_mesh(m.IEN)
+        rowPtr, colPtr = c.build_graph(0)
+        c.alloc(4); c.set_state(Ag, Yg, Dg, Bf)
+        c.assemble(0, abi.fluid_eq(0.005, tDof=tDof, mvMsh=mv), [abi.fluid_domain(K_darcy=Kd, f=f, **visc)])
+        out[f"{name}/R"], out[f"{name}/Val"] = c.get_R(), c.get_Val()
+        out[f"{name}/rowPtr"], out[f"{name}/colPtr"] = rowPtr, colPtr
+        et = name.split("_")[0]
+        out[f"tables/{et}/w"], out[f"tables/{et}/N"], out[f"tables/{et}/Nx"] = c.mesh_tables(0)
+        out[f"tables/{et}/Nxx"] = c.mesh_nxx(0)
+    np.savez_compressed(os.path.join(HERE, "fluid_hi.npz"), **out)
+    print("wrote fluid_hi.npz with", len(out), "arrays")
+
+
 def heat_golden():
     """Assembled R / Val of the scalar heat equations (heats_3d / heatf_3d) for tests/common.py:HEAT_CASES."""
     out = {}
@@ -141,10 +161,31 @@ def lelas_golden():
     print("wrote lelas.npz with", len(out), "arrays")
 
 
+def prestress_golden():
+    """struct_3d / l_elas_3d with a nodal prestress pS0, and the pSn / pSa accumulators of a prestress equation (pstEq)."""
+    out = {}
+    for name, *_ in common.PRESTRESS_CASES:
+        m, Ag, Yg, Dg, Bf, pS0, eq, dmn = common.prestress_case(name)
+        c = RefCase(); c.set_coords(m.x); c.add_mesh(m.IEN)
+        rowPtr, colPtr = c.build_graph(0)
+        c.set_prestress(pS0)
+        c.alloc(3); c.set_state(Ag, Yg, Dg, Bf); c.assemble(0, eq, dmn)
+        out[f"{name}/R"], out[f"{name}/Val"] = c.get_R(), c.get_Val()
+        out[f"{name}/rowPtr"], out[f"{name}/colPtr"] = rowPtr, colPtr
+        if eq.reserved & abi.EQ_PRESTRESS:
+            out[f"{name}/pSn"], out[f"{name}/pSa"] = c.get_prestress()
+        # the same case without pS0: the prestress must change the residual, or the fixture proves nothing
+        c2 = RefCase(); c2.set_coords(m.x); c2.add_mesh(m.IEN); c2.build_graph(0)
+        c2.alloc(3); c2.set_state(Ag, Yg, Dg, Bf); c2.assemble(0, eq, dmn)
+        assert common.rel_err(c2.get_R(), out[f"{name}/R"]) > 1e-3, name
+    np.savez_compressed(os.path.join(HERE, "prestress.npz"), **out)
+    print("wrote prestress.npz with", len(out), "arrays")
+
+
 if __name__ == "__main__":
     if not have_ref():
         raise SystemExit("oracle/_ref/libsvref.so is missing: run `make -C oracle ref` first")
     only = sys.argv[1:]
-    for fn in (fluid_golden, struct_golden, fluid_gen_golden, heat_golden, ustruct_golden, lelas_golden):
+    for fn in (fluid_golden, struct_golden, fluid_gen_golden, fluid_hi_golden, heat_golden, ustruct_golden, lelas_golden, prestress_golden):
         if not only or fn.__name__.replace("_golden", "") in only:
             fn()

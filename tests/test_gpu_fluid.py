@@ -376,6 +376,43 @@ def test_general_element_fluid_assembly_parity(case, scatter):
     eng.close()
 
 
+@pytest.mark.parametrize("scatter", [abi.SCATTER_ATOMIC, abi.SCATTER_COLORED], ids=["atomic", "colored"])
+@pytest.mark.parametrize("case", common.FLUID_HI_CASES, ids=[c[0] for c in common.FLUID_HI_CASES])
+def test_quadratic_and_wedge_fluid_assembly_parity(case, scatter):
+    """VMS fluid on curved TET10 (15 Gauss points; tests/cases/fluid/quadratic_tet10), HEX20 / HEX27 (27) and WDG (6, with the
+    reference's lShpF behaviour) elements: the general kernel with nG != eNoN against the committed vectors of the compiled
+    reference (tests/golden/fluid_hi.npz) and, when it is present, a live run of it."""
+    from svmultiphysics_b200.engine import Engine
+    golden = common.load_golden("fluid_hi.npz")
+    name, mk, visc, Kd, f, tDof, mv = case
+    m = mk()
+    Ag, Yg, Dg, Bf = common.fluid_gen_state(m, tDof)
+    rowPtr, colPtr = golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"]
+    et = name.split("_")[0]
+    w, N, Nx, Nxx = (golden[f"tables/{et}/{k}"] for k in ("w", "N", "Nx", "Nxx"))
+    eq = abi.fluid_eq(0.005, tDof=tDof, mvMsh=mv, scatter=scatter)
+    dmn = [abi.fluid_domain(K_darcy=Kd, f=f, **visc)]
+    eng = Engine(0)
+    rp, cp = eng.lhsa(m.nNo, [m.IEN])                     # lhsa on the device for eNoN = 6 / 10 / 20 / 27 as well
+    assert np.array_equal(rp, rowPtr) and np.array_equal(cp, colPtr)
+    eng.set_graph(rowPtr, colPtr)
+    eng.set_mesh(0, m.IEN, w, N, Nx, Nxx=Nxx)
+    eng.set_coords(m.x)
+    eng.alloc(4); eng.set_state(Ag, Yg, Dg, Bf); eng.assemble(0, eq, dmn)
+    R1, V1 = eng.get_R(), eng.get_Val()
+    assert common.rel_err(R1, golden[f"{name}/R"]) < ASM_TOL
+    assert common.rel_err(V1, golden[f"{name}/Val"]) < ASM_TOL
+    from oracle import refbind
+    if refbind.have_ref():
+        orc = refbind.RefCase(); orc.set_coords(m.x); orc.add_mesh(m.IEN); orc.build_graph(0)
+        orc.alloc(4); orc.set_state(Ag, Yg, Dg, Bf); orc.assemble(0, eq, dmn)
+        assert common.rel_err(R1, orc.get_R()) < ASM_TOL and common.rel_err(V1, orc.get_Val()) < ASM_TOL
+    if scatter == abi.SCATTER_COLORED:
+        eng.alloc(4); eng.assemble(0, eq, dmn)
+        assert np.array_equal(eng.get_Val(), V1) and np.array_equal(eng.get_R(), R1)
+    eng.close()
+
+
 def test_hex8_fluid_newton_iteration_parity():
     """Assembly + GMRES on a HEX8 fluid mesh against the compiled reference."""
     from oracle import refbind

@@ -216,3 +216,37 @@ def test_ustruct_through_cpp_plugin():
     assert o1.RI.success == o0.RI.success and abs(o1.RI.iNorm - o0.RI.iNorm) <= 1e-10 * o0.RI.iNorm
     assert common.rel_err(X1, X0) < 1e-4
     _close(cpu, gpu)
+
+
+def test_prestress_equation_through_cpp_plugin():
+    """com_mod.pS0 and pstEq through B200LinearAlgebra: the plug-in uploads pS0, flags the prestress equation and writes the
+    device accumulators back into com_mod.pSn / pSa (what Integrator::corrector then communicates and divides)."""
+    m, Ag, Yg, Dg, Bf, pS0, eq, dmn = common.prestress_case("hex8_struct_pstEq")
+    cpu, gpu = _pair(m, nFaces=0)
+    res = []
+    for c in (cpu, gpu):
+        c.set_prestress(pS0)
+        c.alloc(3); c.set_state(Ag, Yg, Dg, Bf); c.assemble(0, eq, dmn)
+        res.append((c.get_R(), c.get_Val()) + c.get_prestress())
+    (R0, V0, pSn0, pSa0), (R1, V1, pSn1, pSa1) = res
+    assert common.rel_err(R1, R0) < 1e-12 and common.rel_err(V1, V0) < 1e-12
+    assert common.rel_err(pSn1, pSn0) < 1e-12 and common.rel_err(pSa1, pSa0) < 1e-12
+    _close(cpu, gpu)
+
+
+@pytest.mark.parametrize("case", ["tet10_newtonian", "hex27_casson", "wdg6_newtonian"])
+def test_quadratic_fluid_through_cpp_plugin(case):
+    """TET10 / HEX27 / WDG fluid meshes of the reference's own mshType (w, N, Nx, fs[0].Nxx, nG != eNoN) through the plug-in."""
+    name, mk, visc, Kd, f, tDof, mv = next(c for c in common.FLUID_HI_CASES if c[0] == case)
+    m = mk()
+    Ag, Yg, Dg, Bf = common.fluid_gen_state(m, tDof)
+    cpu, gpu = _pair(m, nFaces=0)
+    eq, dmn = abi.fluid_eq(0.005, tDof=tDof, mvMsh=mv), [abi.fluid_domain(K_darcy=Kd, f=f, **visc)]
+    res = []
+    for c in (cpu, gpu):
+        c.alloc(4); c.set_state(Ag, Yg, Dg, Bf); c.assemble(0, eq, dmn)
+        res.append((c.get_R(), c.get_Val()))
+    (R0, V0), (R1, V1) = res
+    assert gpu.backend_launch_count() > 3
+    assert common.rel_err(R1, R0) < 1e-12 and common.rel_err(V1, V0) < 1e-12
+    _close(cpu, gpu)

@@ -284,3 +284,63 @@ def test_active_stress_errors_like_the_reference():
     eng.set_active_tension(np.ones(m.nNo))
     eng.assemble(0, eq, dmn)
     eng.close()
+
+
+@pytest.mark.parametrize("name", [c[0] for c in common.PRESTRESS_CASES])
+def test_prestress_parity(name):
+    """Nodal prestress pS0 in struct_3d / l_elas_3d and the pSn / pSa accumulators of a prestress equation (com_mod.pstEq):
+    sv_struct.cpp:271-274, 635-680, 327-336; l_elas.cpp:321-338, 130-140 — against the committed vectors of the compiled
+    reference (tests/golden/prestress.npz) and a live run of it."""
+    cls = _oracle()
+    golden = common.load_golden("prestress.npz")
+    m, Ag, Yg, Dg, Bf, pS0, eq, dmn = common.prestress_case(name)
+    orc = cls(); orc.set_coords(m.x); orc.add_mesh(m.IEN)
+    rowPtr, colPtr = orc.build_graph(0)
+    orc.set_prestress(pS0)
+    orc.alloc(3); orc.set_state(Ag, Yg, Dg, Bf); orc.assemble(0, eq, dmn)
+    eng = _engine(m, rowPtr, colPtr)
+    eng.set_prestress(pS0)
+    for rep in range(2):          # twice: svb200_alloc must zero the accumulators like Integrator::initiator
+        eng.alloc(3); eng.set_state(Ag, Yg, Dg, Bf); eng.assemble(0, eq, dmn)
+    R1, V1 = eng.get_R(), eng.get_Val()
+    for R0, V0 in ((orc.get_R(), orc.get_Val()), (golden[f"{name}/R"], golden[f"{name}/Val"])):
+        assert common.rel_err(R1, R0) < ASM_TOL
+        assert common.rel_err(V1, V0) < ASM_TOL
+    if eq.reserved & abi.EQ_PRESTRESS:
+        pSn1, pSa1 = eng.get_prestress()
+        pSn0, pSa0 = orc.get_prestress()
+        assert common.rel_err(pSn1, pSn0) < ASM_TOL and common.rel_err(pSa1, pSa0) < ASM_TOL
+        assert common.rel_err(pSn1, golden[f"{name}/pSn"]) < ASM_TOL and common.rel_err(pSa1, golden[f"{name}/pSa"]) < ASM_TOL
+    # removing the prestress restores the plain equation
+    eng.set_prestress(None)
+    orc.set_prestress(None)
+    orc.alloc(3); orc.assemble(0, eq, dmn)
+    eng.alloc(3); eng.assemble(0, eq, dmn)
+    assert common.rel_err(eng.get_R(), orc.get_R()) < ASM_TOL
+    assert common.rel_err(eng.get_R(), R1) > 1e-3
+    eng.close()
+
+
+def test_fsi_solid_prestress_parity():
+    """construct_fsi hands pS0 to struct_3d for the solid elements (fsi.cpp:127-129, 222)."""
+    cls = _oracle()
+    m, Ag, Yg, Dg, Bf = common.fsi_case()
+    pS0 = np.asfortranarray(5.0e5 * np.random.default_rng(43).standard_normal((6, m.nNo)))
+    orc = cls(); orc.set_coords(m.x); orc.add_mesh(m.IEN, eId=m.eId)
+    rowPtr, colPtr = orc.build_graph(0)
+    af, am, gam, beta = abi.gen_alpha(0.5)
+    eq = abi.EqParams(dt=1e-3, af=af, am=am, gam=gam, beta=beta, phys=abi.PHYS_FSI, dof=4, tDof=7, s=0, mvMsh=1, vmsStab=1,
+                      scatter=abi.SCATTER_ATOMIC, reserved=0)
+    dmn = [abi.fluid_domain(rho=1.0, mu=0.04, Id=0), abi.struct_domain(rho=1.0, volType=abi.VOL_M94, E=1e7, nu=0.3, Kpen=1e7 / (3 * (1 - 0.6)), Id=1)]
+    orc.alloc(4); orc.set_state(Ag, Yg, Dg, Bf); orc.assemble(0, eq, dmn)
+    Rplain = orc.get_R()
+    orc.set_prestress(pS0)
+    orc.alloc(4); orc.assemble(0, eq, dmn)
+    R0, V0 = orc.get_R(), orc.get_Val()
+    assert common.rel_err(Rplain, R0) > 1e-3
+    eng = _engine(m, rowPtr, colPtr)
+    eng.set_prestress(pS0)
+    eng.alloc(4); eng.set_state(Ag, Yg, Dg, Bf); eng.assemble(0, eq, dmn)
+    assert common.rel_err(eng.get_R(), R0) < ASM_TOL
+    assert common.rel_err(eng.get_Val(), V0) < ASM_TOL
+    eng.close()

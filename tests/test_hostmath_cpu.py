@@ -208,6 +208,52 @@ def test_device_general_fluid_algebra_matches_golden(hostmath, case, factored):
     assert common.rel_err(V.T, golden[f"{name}/Val"]) < 1e-12
 
 
+class HostFluidAnyArgs(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("IEN", "x", "Ag", "Yg", "Bf", "w", "N", "Nxi", "Nxi2")] + \
+               [(k, C.c_int) for k in ("eNoN", "nEl", "nG", "tDof", "mvMsh", "lShpF")] + \
+               [(k, C.c_double) for k in ("dt", "af", "am", "gam")] + [("dm", FluidDmn)]
+
+
+@pytest.mark.parametrize("case", common.FLUID_HI_CASES, ids=[c[0] for c in common.FLUID_HI_CASES])
+def test_device_fluid_algebra_on_quadratic_and_wedge_elements(hostmath, case):
+    """fluid_gen.cuh on curved TET10 (15 Gauss points), HEX20 / HEX27 (27) and WDG (6) elements against what the unmodified reference
+    assembled (tests/golden/fluid_hi.npz), with the reference's own shape-function tables — the general path of
+    construct_fluid: nn::gnn + nn::gn_nxx per Gauss point, fluid_3d_m / fluid_3d_c (fluid.cpp:620-745)."""
+    golden = common.load_golden("fluid_hi.npz")
+    assert hostmath.hostmath_sizeof_fluidanyargs() == C.sizeof(HostFluidAnyArgs)
+    name, mk, visc, Kd, f, tDof, mv = case
+    m = mk()
+    Ag, Yg, _, Bf = common.fluid_gen_state(m, tDof)
+    eq, d = abi.fluid_eq(0.005, tDof=tDof, mvMsh=mv), abi.fluid_domain(K_darcy=Kd, f=f, **visc)
+    et = name.split("_")[0]
+    w, N, Nx, Nxx = (golden[f"tables/{et}/{k}"] for k in ("w", "N", "Nx", "Nxx"))
+    nG = len(w)
+    assert N.shape == (m.eNoN, nG) and Nx.shape == (3, m.eNoN, nG) and Nxx.shape == (6, m.eNoN, nG)
+    A = HostFluidAnyArgs()
+    keep = [np.ascontiguousarray(m.IEN.T.astype(np.int32)), np.ascontiguousarray(m.x.T), np.ascontiguousarray(Ag.T),
+            np.ascontiguousarray(Yg.T), np.ascontiguousarray(Bf.T), np.ascontiguousarray(w), np.ascontiguousarray(N.T),
+            np.ascontiguousarray(Nx.transpose(2, 1, 0)), np.ascontiguousarray(Nxx.transpose(2, 1, 0))]
+    A.IEN, A.x, A.Ag, A.Yg, A.Bf, A.w, A.N, A.Nxi, A.Nxi2 = (k.ctypes.data for k in keep)
+    A.eNoN, A.nEl, A.nG, A.tDof, A.mvMsh = m.eNoN, m.nEl, nG, tDof, mv
+    # mshType::lShpF is set for the wedge (nn_elem_props.h:23-30): construct_fluid evaluates gnn / gn_nxx at Gauss point 0 only,
+    # although the wedge's gradients vary — the device path reproduces that
+    A.lShpF = 1 if m.eNoN in (4, 6) else 0
+    A.dt, A.af, A.am, A.gam = eq.dt, eq.af, eq.am, eq.gam
+    A.dm.rho, A.dm.Kd = d.rho, d.K_darcy
+    for i in range(3):
+        A.dm.f[i] = d.f[i]
+    A.dm.mu_i, A.dm.mu_o, A.dm.lam, A.dm.a, A.dm.n = d.mu_i, d.mu_o, d.lam, d.a, d.n
+    A.dm.viscType, A.dm.Id, A.dm.isFluid = d.viscType, -1, 1
+    rowPtr, colPtr = golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"]
+    R = np.zeros((m.nNo, 4))
+    V = np.zeros((len(colPtr), 16))
+    rc = hostmath.hostmath_fluid_any(C.byref(A), rowPtr.ctypes.data_as(C.c_void_p), colPtr.ctypes.data_as(C.c_void_p),
+                                     R.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    assert common.rel_err(R.T, golden[f"{name}/R"]) < 1e-12
+    assert common.rel_err(V.T, golden[f"{name}/Val"]) < 1e-12
+
+
 class HeatDmn(C.Structure):
     _fields_ = [("rho", C.c_double), ("nu", C.c_double), ("s", C.c_double),
                 ("Id", C.c_int), ("active", C.c_int), ("pad0", C.c_int), ("pad1", C.c_int)]
