@@ -52,6 +52,30 @@ def claim_stdout():
         os.dup2(2, 1)
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Run this rank on the CPUs of the NUMA node its GPU hangs off (sysfs: numa_node / local_cpulist of the PCI device), so that
+    the page-locked host buffers of the e2e stage are first-touched next to the GPU's root complex.  What `mpirun --bind-to` /
+    `numactl` does for the reference's MPI ranks; a no-op on single-node virtual machines (numa_node = -1)."""
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(f"{base}/numa_node").read())
+        cpus = set()
+        for part in open(f"{base}/local_cpulist").read().strip().split(","):
+            if part:
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if node < 0 or not use or use == allowed:
+            return {"bound": False, "node": node, "pci": bdf, "cpus_allowed": len(allowed)}
+        os.sched_setaffinity(0, use)
+        return {"bound": True, "node": node, "pci": bdf, "cpus": len(use), "cpus_allowed": len(allowed)}
+    except Exception as ex:        # no sysfs entry, old torch: stay unbound
+        return {"bound": False, "why": str(ex)[:80]}
+
+
 def emit_line(obj):
     if _REAL_STDOUT is None:
         print(json.dumps(obj), flush=True)
@@ -598,6 +622,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-extra-configs", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not bind the rank to the CPUs / memory of its GPU's NUMA node")
     ap.add_argument("--scatter", default="atomic", choices=["atomic", "colored"])
     args = ap.parse_args()
 
@@ -634,6 +659,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device visible; the B200 arm has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if not args.no_numa_bind else {"bound": False, "why": "--no-numa-bind"}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -679,7 +705,7 @@ def main():
            "blocks": list(blocks), "transport": eng.comm_transport(), "scatter": args.scatter,
            "neighbours_per_rank": int(reduce_ranks(float(len(neigh)), "max")),
            "shared_nodes_per_rank": int(reduce_ranks(float((mult > 1).sum()), "max")),
-           "max_ranks_sharing_a_node": int(reduce_ranks(float(mult.max()), "max"))}
+           "max_ranks_sharing_a_node": int(reduce_ranks(float(mult.max()), "max")), "numa": numa}
     w, N, Nx = elements.tables(4)
     eng.set_mesh(0, m.IEN, w, N, Nx)
     eng.set_coords(m.x)
@@ -757,6 +783,21 @@ def main():
     barrier()
     te1 = time.perf_counter()
     e2e_ms = max_over_ranks((te1 - te0) * 1e3 / args.steps)
+    e2e_timeline = eng.last_host_stage()          # rank 0, last step
+    # the PCIe floor of the same call: only its copies (H2D of Ag, Yg; D2H of R), all ranks at once — H2D and D2H are full duplex,
+    # so the stage cannot be shorter than max(h2d, d2h, kernel)
+    def timed(fn, reps=3):
+        fn()
+        barrier()
+        t = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t) * 1e3 / reps
+        barrier()
+        return max_over_ranks(dt)
+    h2d_ms = timed(lambda: eng.set_state(Ah, Yh))
+    d2h_ms = timed(lambda: eng.download_into(abi.ARRAY_R, Rh))
     # what the pipelined call returned against the plain sequence of calls (device-resident R after the shared-node sum)
     eng.set_state(Ag, Yg); eng.alloc(4); eng.assemble(0, eq, dmn); eng.commu_R()
     R_plain = eng.get_R()
@@ -849,7 +890,11 @@ def main():
             "e2e": {"value": nEl_total / (e2e_ms * 1e-3), "unit": "element assemblies/s",
                     "h2d_bytes_per_step": int(Ah.nbytes + Yh.nbytes), "d2h_bytes_per_step": int(Rh.nbytes), "ms_per_step": e2e_ms,
                     "call": "svb200_assemble_host (pinned host Ag, Yg in; R out; copies pipelined behind the element kernel)",
-                    "R_max_rel_vs_plain_sequence": e2e_err},
+                    "R_max_rel_vs_plain_sequence": e2e_err, "device_timeline_ms_rank0": e2e_timeline,
+                    "copies_alone_ms": {"h2d": h2d_ms, "d2h": d2h_ms, "GB/s_h2d_per_gpu": (Ah.nbytes + Yh.nbytes) / h2d_ms * 1e-6,
+                                        "GB/s_d2h_per_gpu": Rh.nbytes / d2h_ms * 1e-6,
+                                        "note": "the same pinned buffers copied with no kernel running, all ranks at once (max over "
+                                                "ranks): the PCIe / host-memory floor of the host-buffer stage on this box"}},
             "gpu_launches": int(launches), "clocks": clocks,
             "other_scatter_mode": {"scatter": "colored (deterministic)" if args.scatter == "atomic" else "atomic",
                                    "assembly_kernel_ms": other_ms, "value": nEl_total / (other_ms * 1e-3),

@@ -296,6 +296,11 @@ SVB200_API int svb200_assemble_host(svb200_ctx* ctx, int32_t iM, const svb200_eq
 /* Boundary face iFa of mesh iM (faceType): connectivity IENb(eNoNb,nElb) in input node ids, parent element
  * gE(nElb) (index into the mesh's elements), and the face reference-element tables w(nGb), N(eNoNb,nGb),
  * Nx(2,eNoNb,nGb).  eNoNb = 3 (TRI3 on TET4) or 4 (QUD4 on HEX8). */
+/* Device timeline of the last pipelined svb200_assemble_host call, in ms after its start (CUDA events): [0] last upload chunk on the
+ * device, [1] last element group done, [2] shared-node sum done (0 on a single partition), [3] streamed residual rows on the host,
+ * [4] end of the call's device work; host wall clock after entry: [5] everything enqueued, [6] streams drained, [7] return.
+ * ms8 holds 8 doubles. */
+SVB200_API int svb200_last_host_stage(svb200_ctx* ctx, double* ms8);
 SVB200_API int svb200_set_bface(svb200_ctx* ctx, int32_t iFa, int32_t iM, int32_t eNoNb, int32_t nElb, const int32_t* IENb,
                      const int32_t* gE, int32_t nGb, const double* w, const double* N, const double* Nx);
 /* eq_assem::b_assem_neu_bc (solver/eq_assem.cpp:31-149) on the device: Neumann / traction face integral with

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <numeric>
 #include "svb200_internal.h"
+#include <chrono>
 #include "fsils_kernels.h"
 
 namespace svb {
@@ -217,6 +218,7 @@ int svb200_create(svb200_ctx** out, int device)
   SVB_CUDA(cudaStreamCreateWithFlags(&ctx->dstream, cudaStreamNonBlocking));
   for (auto& row : ctx->pev) for (auto& e : row) SVB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : ctx->zev) SVB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : ctx->hev) SVB_CUDA(cudaEventCreate(&e));
   SVB_CUDA(cudaMallocHost(&ctx->h_pinned, sizeof(double) * 1024));
   *out = ctx;
   return SVB200_OK;
@@ -241,7 +243,7 @@ int svb200_destroy(svb200_ctx* ctx)
   cudaFree(ctx->d_stage); cudaFree(ctx->d_R); cudaFree(ctx->d_Val); cudaFree(ctx->d_W);
   cudaFree(ctx->d_work); cudaFree(ctx->d_red); cudaFree(ctx->d_tslot);
   cudaFreeHost(ctx->h_pinned); cudaFreeHost(ctx->h_cg); cudaFree(ctx->d_cg);
-  cudaFree(ctx->d_shared_rows); cudaFree(ctx->d_shared_off); cudaFreeHost(ctx->h_shared_buf);
+  cudaFree(ctx->d_shared_rows); cudaFree(ctx->d_shared_off); cudaFree(ctx->d_shared_caller); cudaFreeHost(ctx->h_shared_buf);
   for (int k = 0; k < 2; k++) if (ctx->ev_cg[k]) cudaEventDestroy(ctx->ev_cg[k]);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   for (auto& e : ctx->zev) if (e) cudaEventDestroy(e);
@@ -1061,6 +1063,17 @@ int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, cons
 }
 
 // The host-resident assembly stage in one pipelined call (see include/svb200.h).
+// dst(:, caller[k]) = src(:, rows[k]): the completed interface rows written straight into the caller's page-locked residual
+// (mapped host memory, a few 10^4 rows of dof doubles over PCIe).
+__global__ void scatter_rows_to_host_kernel(int n, int dof, const int* __restrict__ rows, const int* __restrict__ caller,
+                                            const double* __restrict__ src, double* __restrict__ dst)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * dof) return;
+  const int k = t / dof, i = t - k * dof;
+  dst[(size_t)caller[k] * dof + i] = src[(size_t)rows[k] * dof + i];
+}
+
 int svb200_assemble_host(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int32_t nDmn,
                          const double* Ag, const double* Yg, double* R_out)
 {
@@ -1086,6 +1099,9 @@ int svb200_assemble_host(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq,
   const size_t nV = (size_t)dof * dof * ctx->nnz, nR = (size_t)dof * ctx->nNo;
   SVB_REQUIRE(ctx->d_R && ctx->d_Val && ctx->dof == dof && nR <= ctx->R_cap && nV <= ctx->Val_cap,
               "svb200_assemble_host: call svb200_alloc(dof) once before the first pipelined assembly");
+  auto wall_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = wall_ms();
+  bool patched_on_device = false;
   SVB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
   ctx->val_zero_pending = false;
   SVB_CUDA(cudaMemsetAsync(ctx->d_R, 0, sizeof(double) * nR, ctx->stream));
@@ -1118,6 +1134,7 @@ int svb200_assemble_host(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq,
     off[rows.size()] = (long long)rows.size();
     TRY(upload(ctx, &ctx->d_shared_rows, rows.data(), rows.size()));
     TRY(upload(ctx, &ctx->d_shared_off, off.data(), off.size()));
+    TRY(upload(ctx, &ctx->d_shared_caller, ctx->h_shared_caller.data(), ctx->h_shared_caller.size()));
     cudaFreeHost(ctx->h_shared_buf); ctx->h_shared_buf = nullptr;
     SVB_CUDA(cudaMallocHost(&ctx->h_shared_buf, sizeof(double) * 4 * std::max<size_t>(rows.size(), 1)));
     ctx->shared_built = true;
@@ -1165,28 +1182,64 @@ int svb200_assemble_host(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq,
       }
     }
   }
+  SVB_CUDA(cudaEventRecord(ctx->hev[0], ctx->zstream));     // all uploads done
+  SVB_CUDA(cudaEventRecord(ctx->hev[1], ctx->stream));      // all element groups done
+  SVB_CUDA(cudaEventRecord(ctx->hev[3], ctx->dstream));     // streamed residual rows on the host
   if (multi) {
     TRY(halo_sum(ctx, dof, ctx->d_R));
+    SVB_CUDA(cudaEventRecord(ctx->hev[2], ctx->stream));    // shared-node sum done
     if (stream_down && !ctx->h_shared_caller.empty()) {
-      // the interface rows again, now complete: gather -> pinned scratch -> patched into R_out by the host
+      // the interface rows again, now complete
       const int ns = (int)ctx->h_shared_caller.size();
-      SVB_CUDA(cudaStreamSynchronize(ctx->dstream));          // stageR is free, the streamed rows are in R_out
-      TRY(launch_gather_row_blocks(ctx, ns, dof, ctx->d_shared_rows, false, ctx->d_shared_off, ctx->d_R, stageR));
-      SVB_CUDA(cudaMemcpyAsync(ctx->h_shared_buf, stageR, sizeof(double) * dof * ns, cudaMemcpyDeviceToHost, ctx->stream));
+      static const bool no_zc = getenv("SVB200_HOST_NO_ZEROCOPY") != nullptr;      // A/B knob
+      double* dR = nullptr;
+      if (!no_zc && cudaHostGetDevicePointer(reinterpret_cast<void**>(&dR), R_out, 0) != cudaSuccess) { dR = nullptr; cudaGetLastError(); }
+      if (dR) {
+        // page-locked caller buffer: a kernel writes the rows in place (after the streamed copies of the same rows, which
+        // carried partial sums: the main stream waits for the download stream)
+        SVB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->hev[3], 0));
+        scatter_rows_to_host_kernel<<<(ns * dof + 255) / 256, 256, 0, ctx->stream>>>(ns, dof, ctx->d_shared_rows, ctx->d_shared_caller,
+                                                                                 ctx->d_R, dR);
+        ctx->launches++;
+        patched_on_device = true;
+      } else {
+        // pageable caller buffer: gather -> pinned scratch -> patched into R_out by the host
+        SVB_CUDA(cudaStreamSynchronize(ctx->dstream));          // stageR is free, the streamed rows are in R_out
+        TRY(launch_gather_row_blocks(ctx, ns, dof, ctx->d_shared_rows, false, ctx->d_shared_off, ctx->d_R, stageR));
+        SVB_CUDA(cudaMemcpyAsync(ctx->h_shared_buf, stageR, sizeof(double) * dof * ns, cudaMemcpyDeviceToHost, ctx->stream));
+      }
     }
   }
+  const double t_enq = wall_ms();
   SVB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
   SVB_CUDA(cudaStreamSynchronize(ctx->dstream));
   SVB_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (multi && stream_down) {
+  const double t_sync = wall_ms();
+  if (multi && stream_down && !patched_on_device) {
     const int ns = (int)ctx->h_shared_caller.size();
     for (int k = 0; k < ns; k++)
       for (int i = 0; i < dof; i++) R_out[(size_t)dof * ctx->h_shared_caller[k] + i] = ctx->h_shared_buf[(size_t)dof * k + i];
   }
   SVB_CUDA(cudaStreamSynchronize(ctx->zstream));
+  const double t_end = wall_ms();
+  ctx->host_stage_ms[5] = t_enq - t_begin; ctx->host_stage_ms[6] = t_sync - t_begin; ctx->host_stage_ms[7] = t_end - t_begin;
   float ms = 0.f;
   SVB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   ctx->last_assemble_ms = ms;
+  ctx->host_stage_ms[4] = ms;
+  for (int k = 0; k < 4; k++) {
+    float t = 0.f;
+    if ((k == 2 && !multi) || cudaEventElapsedTime(&t, ctx->ev0, ctx->hev[k]) != cudaSuccess) { t = 0.f; cudaGetLastError(); }
+    ctx->host_stage_ms[k] = t;
+  }
+  return SVB200_OK;
+}
+
+int svb200_last_host_stage(svb200_ctx* ctx, double* ms5)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(ms5, "svb200_last_host_stage: null output (8 doubles)");
+  for (int k = 0; k < 8; k++) ms5[k] = ctx->host_stage_ms[k];
   return SVB200_OK;
 }
 

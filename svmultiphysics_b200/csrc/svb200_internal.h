@@ -182,11 +182,14 @@ struct svb200_ctx {
   cudaStream_t zstream = nullptr;  // stream of the overlapped zeroing / of the H2D copies of svb200_assemble_host
   cudaStream_t dstream = nullptr;  // stream of the D2H copies of svb200_assemble_host
   cudaEvent_t zev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t hev[4] = {nullptr, nullptr, nullptr, nullptr};   // svb200_assemble_host timeline: upload, kernels, halo, streamed D2H done
+  double host_stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};                     // ... in ms after the start of the call, and the end of the call
   cudaEvent_t pev[2][16] = {};     // svb200_assemble_host: [0][c] chunk c uploaded, [1][c] chunk c assembled
   // svb200_assemble_host on a partitioned mesh: the interface rows (changed by the shared-node sum after they were streamed back)
   std::vector<int> h_shared_caller;   // caller node ids of the interface rows
   int* d_shared_rows = nullptr;       // their internal ids
   long long* d_shared_off = nullptr;  // 0, 1, 2, ... (offsets for the row gather)
+  int* d_shared_caller = nullptr;     // h_shared_caller on the device (zero-copy scatter into the caller's residual)
   double* h_shared_buf = nullptr;     // pinned (dof, nShared)
   bool shared_built = false;
   double* d_W = nullptr;           // (dof,nNo) preconditioner scaling

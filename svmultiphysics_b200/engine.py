@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "svb200_set_solution", "svb200_get_solution", "svb200_predictor", "svb200_initiator", "svb200_corrector",
     "svb200_set_node_flags", "svb200_set_dirichlet_rows", "svb200_dirichlet_ustruct", "svb200_advance_time_step",
     "svb200_set_bface", "svb200_assemble_neu",
-    "svb200_set_active_tension", "svb200_set_prestress", "svb200_get_prestress",
+    "svb200_last_host_stage", "svb200_set_active_tension", "svb200_set_prestress", "svb200_get_prestress",
     "svb200_spmv_rc", "svb200_spmv_rc_variants", "svb200_bench_spmv_rc",
     "svb200_schur_sp", "svb200_schur_sp_variants", "svb200_bench_schur_sp",
 ]
@@ -326,6 +326,17 @@ class Engine:
         R = np.zeros((self.dof, self.nNo), order="F")
         self._call("svb200_download", C.c_int32(abi.ARRAY_R), _d(R))
         return R
+
+    def last_host_stage(self):
+        """Timeline (ms) of the last pipelined assemble_host: uploads, kernels, shared-node sum, streamed D2H, end."""
+        t = (C.c_double * 8)()
+        self._call("svb200_last_host_stage", t)
+        return dict(zip(("uploads_done", "kernels_done", "halo_done", "streamed_rows_on_host", "end", "host_enqueued", "host_drained",
+                         "host_return"), (round(float(v), 4) for v in t)))
+
+    def download_into(self, what, dst):
+        """svb200_download into a caller-owned (e.g. page-locked) array."""
+        self._call("svb200_download", C.c_int32(what), _d(dst))
 
     def get_Val(self):
         V = np.zeros((self.dof * self.dof, self.nnz), order="F")
