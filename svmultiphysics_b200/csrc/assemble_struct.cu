@@ -36,7 +36,9 @@ struct StructArgs {
   double* R;
   double* Val;
   int e0, e1;
-  int tDof, dof, s, nFn, nDmn, atomic, nG, pad;
+  int tDof, dof, s, nFn, nDmn, atomic, nG;
+  int lShpF;             // mshType::lShpF (nn_elem_props.h): gnn at Gauss point 0 only (TET4, WDG)
+  const double* tab;     // per-mesh device copy of the element tables (quadratic elements)
   double dt, af, am, gam, beta;
   double w[MAX_NG];
   double N[MAX_NG][MAX_ENON];
@@ -59,42 +61,55 @@ constexpr int STRUCT_THREADS = 128;
 constexpr int GP_LD = 64;   // xiX 9 | w 1 | F 9 | S 6 (11,22,33,12,23,31) | Dm 36 | ud 3
 // nodal inputs 9 ENON | Gauss data GP_LD ENON | grad N exchange, double-buffered, 6 ENON; the stride is padded to
 // 8 mod 16 doubles so that the elements of a half-warp read the same offset from different banks
-__host__ __device__ constexpr int struct_per_el(int enon)
+__host__ __device__ constexpr int struct_per_el(int enon, int ng)
 {
-  const int n = enon * (9 + GP_LD + 6);
+  const int n = enon * (9 + 6) + ng * GP_LD;
   return n + ((8 - (n % 16)) + 16) % 16;
 }
 
-template <int ENON, bool ATOMIC, bool VISC>
+// NG = number of Gauss points: ENON for TET4 / HEX8 / WDG; 15 for TET10, 27 for HEX20 / HEX27 (tables then come from P.tab, the
+// per-mesh device copy of w | N | Nxi, because the fixed-size argument arrays stop at 8).
+template <int ENON, int NG, bool ATOMIC, bool VISC>
 __global__ void __launch_bounds__(STRUCT_THREADS)
 assemble_struct_kernel(const __grid_constant__ StructArgs P)
 {
-  constexpr int EPW = 32 / ENON;            // elements per warp
-  constexpr int KMAX = ENON / 2;            // lane a owns blocks (a, a+k), k = 0..KMAX (k = KMAX only for a < KMAX)
-  constexpr int PER_EL = struct_per_el(ENON);
-  constexpr int NTAB = ENON * ENON * 4 + ENON;   // Nxi[g][a][3], N[g][a], w[g]  (nG == ENON)
+  constexpr int LPE = ENON > NG ? ENON : NG; // lanes per element: Gauss points in phase A, element nodes in phase B
+  constexpr int EPW = 32 / LPE;             // elements per warp
+  constexpr bool ODD = (ENON & 1) != 0;
+  constexpr int KMAX = ENON / 2;            // lane a owns blocks (a, a+k), k = 0..KMAX (even ENON: k = KMAX only for a < KMAX;
+                                            // odd ENON: k = 1..KMAX for every a covers each unordered pair once)
+  constexpr int PER_EL = struct_per_el(ENON, NG);
+  constexpr int NTAB = NG * ENON * 4 + NG;  // Nxi[g][a][3], N[g][a], w[g]
   extern __shared__ double sm[];
   double* tab = sm;                          // reference-element tables (lane-dependent Gauss point in phase A)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int a = lane % ENON, el = lane / ENON;
+  const int a = lane % LPE, el = lane / LPE;
   double* se = sm + NTAB + (size_t)(warp * EPW + el) * PER_EL;
   double(*sx)[3] = reinterpret_cast<double(*)[3]>(se);
   double(*sd)[3] = reinterpret_cast<double(*)[3]>(se + 3 * ENON);
   double(*sq)[3] = reinterpret_cast<double(*)[3]>(se + 6 * ENON);
   double* sgp = se + 9 * ENON;
-  double(*sNx)[3] = reinterpret_cast<double(*)[3]>(se + 9 * ENON + ENON * GP_LD);
+  double(*sNx)[3] = reinterpret_cast<double(*)[3]>(se + 9 * ENON + NG * GP_LD);
   double(*tNxi)[ENON][3] = reinterpret_cast<double(*)[ENON][3]>(tab);
-  double(*tN)[ENON] = reinterpret_cast<double(*)[ENON]>(tab + ENON * ENON * 3);
-  double* tw = tab + ENON * ENON * 4;
-  for (int t = threadIdx.x; t < ENON * ENON; t += STRUCT_THREADS) {
+  double(*tN)[ENON] = reinterpret_cast<double(*)[ENON]>(tab + NG * ENON * 3);
+  double* tw = tab + NG * ENON * 4;
+  for (int t = threadIdx.x; t < NG * ENON; t += STRUCT_THREADS) {
     const int g = t / ENON, b = t % ENON;
-    tNxi[g][b][0] = P.Nxi[g][b][0]; tNxi[g][b][1] = P.Nxi[g][b][1]; tNxi[g][b][2] = P.Nxi[g][b][2];
-    tN[g][b] = P.N[g][b];
-    if (b == 0) tw[g] = P.w[g];
+    if (NG <= MAX_NG && ENON <= MAX_ENON) {
+      tNxi[g][b][0] = P.Nxi[g][b][0]; tNxi[g][b][1] = P.Nxi[g][b][1]; tNxi[g][b][2] = P.Nxi[g][b][2];
+      tN[g][b] = P.N[g][b];
+      if (b == 0) tw[g] = P.w[g];
+    } else {
+      // per Gauss point in P.tab: w | N[ENON] | Nxi[ENON][3] | Nxi2[ENON][6]  (fg_tab_ld = 1 + 10 ENON doubles)
+      const double* tg = P.tab + (size_t)g * (1 + 10 * ENON);
+      tNxi[g][b][0] = __ldg(tg + 1 + ENON + 3 * b); tNxi[g][b][1] = __ldg(tg + 2 + ENON + 3 * b); tNxi[g][b][2] = __ldg(tg + 3 + ENON + 3 * b);
+      tN[g][b] = __ldg(tg + 1 + b);
+      if (b == 0) tw[g] = __ldg(tg);
+    }
   }
 
   const long long idx = (long long)P.e0 + ((long long)blockIdx.x * (STRUCT_THREADS / 32) + warp) * EPW + el;
-  bool active = idx < P.e1;
+  bool active = (lane < EPW * LPE) && idx < P.e1;
   int e = 0;
   if (active) e = P.perm ? P.perm[idx] : (int)idx;
   int iD = 0;
@@ -108,8 +123,9 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
   }
   const StructDmn& dm = P.dmn[iD];
   const int DOF = P.dof;
+  const bool rowLane = active && a < ENON;      // phase B / nodal loads: one lane per element node
   int node = 0;
-  if (active) {
+  if (rowLane) {
     node = P.IEN[(size_t)e * ENON + a];
     const size_t n = (size_t)node;
 #pragma unroll
@@ -122,9 +138,11 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
   }
   __syncthreads();
 
-  // ---- phase A: lane a of the element evaluates Gauss point g = a (nG == ENON): nn::gnn, F, compute_pk2cc -----
-  if (active) {
+  // ---- phase A: lane a of the element evaluates Gauss point g = a: nn::gnn, F, compute_pk2cc -----
+  // (mshType::lShpF elements — TET4, WDG — take the derivatives of Gauss point 0 everywhere, sv_struct.cpp:297-303)
+  if (active && a < NG) {
     const int g = a;
+    const int gd = P.lShpF ? 0 : g;
     double fN[2][3] = {{0, 0, 0}, {0, 0, 0}};
     if (P.fN != nullptr)
       for (int k = 0; k < P.nFn && k < 2; k++)
@@ -136,7 +154,7 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
 #pragma unroll
       for (int i = 0; i < 3; i++)
 #pragma unroll
-        for (int k = 0; k < 3; k++) xXi[i][k] += sx[b][i] * tNxi[g][b][k];
+        for (int k = 0; k < 3; k++) xXi[i][k] += sx[b][i] * tNxi[gd][b][k];
     const double Jac = xXi[0][0] * xXi[1][1] * xXi[2][2] + xXi[0][1] * xXi[1][2] * xXi[2][0] + xXi[0][2] * xXi[1][0] * xXi[2][1] -
                        xXi[0][0] * xXi[1][2] * xXi[2][1] - xXi[0][1] * xXi[1][0] * xXi[2][2] - xXi[0][2] * xXi[1][1] * xXi[2][0];
     const double iJ = 1.0 / Jac;
@@ -157,7 +175,7 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
       const double Nb = tN[g][b];
       double Nxb[3];
 #pragma unroll
-      for (int j = 0; j < 3; j++) Nxb[j] = tNxi[g][b][0] * xiX[0][j] + tNxi[g][b][1] * xiX[1][j] + tNxi[g][b][2] * xiX[2][j];
+      for (int j = 0; j < 3; j++) Nxb[j] = tNxi[gd][b][0] * xiX[0][j] + tNxi[gd][b][1] * xiX[1][j] + tNxi[gd][b][2] * xiX[2][j];
 #pragma unroll
       for (int i = 0; i < 3; i++) {
         ud[i] += Nb * sq[b][i];
@@ -187,7 +205,7 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
         const size_t nb = (size_t)P.IEN[(size_t)e * ENON + b];
         double Nxb[3];
 #pragma unroll
-        for (int j = 0; j < 3; j++) Nxb[j] = tNxi[g][b][0] * xiX[0][j] + tNxi[g][b][1] * xiX[1][j] + tNxi[g][b][2] * xiX[2][j];
+        for (int j = 0; j < 3; j++) Nxb[j] = tNxi[gd][b][0] * xiX[0][j] + tNxi[gd][b][1] * xiX[1][j] + tNxi[gd][b][2] * xiX[2][j];
 #pragma unroll
         for (int i = 0; i < 3; i++) {
           const double y = __ldg(P.Yg + (size_t)P.tDof * nb + P.s + i);
@@ -264,7 +282,7 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
   int slotA[KMAX + 1], slotT[KMAX + 1];
 #pragma unroll
   for (int k = 0; k <= KMAX; k++) { slotA[k] = 0; slotT[k] = 0; }
-  if (active) {
+  if (rowLane) {
     const int* sl = P.slot + (size_t)e * ENON * ENON;
 #pragma unroll
     for (int k = 0; k <= KMAX; k++) {
@@ -274,18 +292,19 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
     }
   }
 #pragma unroll 1
-  for (int g = 0; g < ENON; g++) {
+  for (int g = 0; g < NG; g++) {
     double H[3][3][3], SNx[3];
     double wamdNa = 0.0;
     double(*pNx)[3] = sNx + (g & 1) * ENON;       // double-buffered exchange: one __syncwarp per Gauss point
-    if (active) {
+    const int gd = P.lShpF ? 0 : g;
+    if (rowLane) {
       const double* q = sgp + g * GP_LD;
       const double w = q[9];
       const double wafu = w * afu;
       double F[3][3], Nxa[3];
 #pragma unroll
       for (int i = 0; i < 3; i++) {
-        Nxa[i] = tNxi[g][a][0] * q[i] + tNxi[g][a][1] * q[3 + i] + tNxi[g][a][2] * q[6 + i];
+        Nxa[i] = tNxi[gd][a][0] * q[i] + tNxi[gd][a][1] * q[3 + i] + tNxi[gd][a][2] * q[6 + i];
         pNx[a][i] = Nxa[i];
 #pragma unroll
         for (int j = 0; j < 3; j++) F[i][j] = q[10 + 3 * i + j];
@@ -337,10 +356,10 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
       for (int i = 0; i < 3; i++) SNx[i] *= wafu;
     }
     __syncwarp();
-    if (active) {
+    if (rowLane) {
 #pragma unroll
       for (int k = 0; k <= KMAX; k++) {
-        if (k == KMAX && a >= KMAX) continue;
+        if (!ODD && k == KMAX && a >= KMAX) continue;
         const int b = (a + k) % ENON;
         const double n0 = pNx[b][0], n1 = pNx[b][1], n2 = pNx[b][2];
         // delta_ij w (amd Na Nb + afu gradNa.S.gradNb)
@@ -355,7 +374,7 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
   }
 
   // ---- scatter ------------------------------------------------------------------------------------------
-  if (active) {
+  if (rowLane) {
 #pragma unroll
     for (int i = 0; i < 3; i++) add64<ATOMIC>(P.R + (size_t)DOF * node + i, lR[i]);
   }
@@ -369,7 +388,7 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
   const int DD = DOF * DOF;
 #pragma unroll
   for (int k = 0; k <= KMAX; k++) {
-    const bool mine = active && !(k == KMAX && a >= KMAX);
+    const bool mine = rowLane && !(!ODD && k == KMAX && a >= KMAX);
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < 3; i++)
@@ -962,8 +981,9 @@ int fill_struct_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, 
   SVB_REQUIRE(eq->tDof == ctx->tDof && ctx->d_Dg && ctx->d_Yg && ctx->d_Ag, "svb200_assemble: state not set or tDof mismatch");
   SVB_REQUIRE(eq->s >= 0 && eq->s + 3 <= eq->tDof, "svb200_assemble: eq.s out of range");
   SVB_REQUIRE(ctx->d_x, "svb200_assemble: coordinates not set");
-  SVB_REQUIRE(m.eNoN == 4 || m.eNoN == 8, "svb200_assemble: the solid is implemented for TET4 and HEX8 meshes");
   memset(&A, 0, sizeof(A));
+  A.tab = m.d_gtab;
+  A.lShpF = (m.eNoN == 4 || m.eNoN == 6) ? 1 : 0;
   A.IEN = m.d_IEN; A.eId = m.d_eId; A.slot = m.d_slot; A.perm = nullptr; A.fN = m.d_fN;
   A.x = ctx->d_x; A.Ag = ctx->d_Ag; A.Yg = ctx->d_Yg; A.Dg = ctx->d_Dg; A.Bf = ctx->d_Bf;
   A.Ya = ctx->d_Ya;
@@ -984,13 +1004,14 @@ int fill_struct_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, 
   int cann_used = 0;
   A.atomic = (eq->scatter == SVB200_SCATTER_ATOMIC);
   A.dt = eq->dt; A.af = eq->af; A.am = eq->am; A.gam = eq->gam; A.beta = eq->beta;
-  for (int g = 0; g < m.nG; g++) {
-    A.w[g] = m.w[g];
-    for (int a = 0; a < m.eNoN; a++) {
-      A.N[g][a] = m.N[(size_t)g * m.eNoN + a];
-      for (int k = 0; k < 3; k++) A.Nxi[g][a][k] = m.Nx[((size_t)g * m.eNoN + a) * 3 + k];
+  if (m.nG <= MAX_NG && m.eNoN <= MAX_ENON)
+    for (int g = 0; g < m.nG; g++) {
+      A.w[g] = m.w[g];
+      for (int a = 0; a < m.eNoN; a++) {
+        A.N[g][a] = m.N[(size_t)g * m.eNoN + a];
+        for (int k = 0; k < 3; k++) A.Nxi[g][a][k] = m.Nx[((size_t)g * m.eNoN + a) * 3 + k];
+      }
     }
-  }
   bool whole = false;
   for (int d = 0; d < nDmn; d++) {
     StructDmn& o = A.dmn[d];
@@ -1034,43 +1055,54 @@ int fill_struct_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, 
   return SVB200_OK;
 }
 
-template <int ENON>
+template <int ENON, int NG>
 static int launch_one(svb200_ctx* ctx, const StructArgs& A)
 {
-  constexpr int EPB = (STRUCT_THREADS / 32) * (32 / ENON);   // elements per CTA
+  constexpr int LPE = ENON > NG ? ENON : NG;
+  constexpr int EPB = (STRUCT_THREADS / 32) * (32 / LPE);   // elements per CTA
   const long long n = (long long)A.e1 - A.e0;
   if (n <= 0) return SVB200_OK;
   const unsigned blocks = (unsigned)((n + EPB - 1) / EPB);
-  constexpr size_t smem = sizeof(double) * ((size_t)ENON * ENON * 4 + ENON + (size_t)EPB * struct_per_el(ENON));
-  constexpr int EPBV = (VISC_THREADS / 32) * (32 / ENON);
-  constexpr size_t smemV = sizeof(double) * (size_t)EPBV * visc_per_el(ENON);
+  constexpr size_t smem = sizeof(double) * ((size_t)NG * ENON * 4 + NG + (size_t)EPB * struct_per_el(ENON, NG));
+  static_assert(smem <= 227 * 1024, "element does not fit in shared memory");
+  constexpr bool LINEAR = (NG == ENON && (ENON == 4 || ENON == 8));     // TET4 / HEX8: the solid-viscosity kernels exist
+  constexpr int EV = LINEAR ? ENON : 8;
+  constexpr int EPBV = (VISC_THREADS / 32) * (32 / EV);
+  constexpr size_t smemV = sizeof(double) * (size_t)EPBV * visc_per_el(EV);
   static bool configured = false;
   if (!configured) {
-    SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SVB_CUDA(cudaFuncSetAttribute(assemble_struct_visc_kernel<ENON, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemV));
-    SVB_CUDA(cudaFuncSetAttribute(assemble_struct_visc_kernel<ENON, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemV));
+    SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, NG, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, NG, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if constexpr (LINEAR) {
+      SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, NG, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, NG, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SVB_CUDA(cudaFuncSetAttribute(assemble_struct_visc_kernel<EV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemV));
+      SVB_CUDA(cudaFuncSetAttribute(assemble_struct_visc_kernel<EV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemV));
+    }
     configured = true;
   }
-  if (A.nG != ENON) { set_error("svb200: the solid kernel expects nG == eNoN (TET4: 4, HEX8: 8 Gauss points)"); return SVB200_ERR_UNSUPPORTED; }
+  if (A.nG != NG) { set_error("svb200: the solid kernel expects the reference's quadrature rule for this element type"); return SVB200_ERR_UNSUPPORTED; }
   bool visc = false;
   for (int d = 0; d < A.nDmn; d++) visc |= (A.dmn[d].isStruct && A.dmn[d].viscType != SVB200_SOLID_VISC_NONE);
   if (!visc) {
-    if (A.atomic) assemble_struct_kernel<ENON, true, false><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
-    else assemble_struct_kernel<ENON, false, false><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
+    if (A.atomic) assemble_struct_kernel<ENON, NG, true, false><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
+    else assemble_struct_kernel<ENON, NG, false, false><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
     ctx->launches++;
   } else {
-    const unsigned blocksV = (unsigned)((n + EPBV - 1) / EPBV);
-    if (A.atomic) {
-      assemble_struct_kernel<ENON, true, true><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
-      assemble_struct_visc_kernel<ENON, true><<<blocksV, VISC_THREADS, smemV, ctx->stream>>>(A);
+    if constexpr (LINEAR) {
+      const unsigned blocksV = (unsigned)((n + EPBV - 1) / EPBV);
+      if (A.atomic) {
+        assemble_struct_kernel<ENON, NG, true, true><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
+        assemble_struct_visc_kernel<EV, true><<<blocksV, VISC_THREADS, smemV, ctx->stream>>>(A);
+      } else {
+        assemble_struct_kernel<ENON, NG, false, true><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
+        assemble_struct_visc_kernel<EV, false><<<blocksV, VISC_THREADS, smemV, ctx->stream>>>(A);
+      }
+      ctx->launches += 2;
     } else {
-      assemble_struct_kernel<ENON, false, true><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
-      assemble_struct_visc_kernel<ENON, false><<<blocksV, VISC_THREADS, smemV, ctx->stream>>>(A);
+      set_error("svb200_assemble: solid viscosity is implemented for TET4 and HEX8 meshes");
+      return SVB200_ERR_UNSUPPORTED;
     }
-    ctx->launches += 2;
   }
   SVB_CUDA(cudaGetLastError());
   return SVB200_OK;
@@ -1103,7 +1135,16 @@ int run_assemble_struct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* e
   const bool tet4 = (m.eNoN == 4 && !visc && !force_general && A.pS0 == nullptr && A.pSn == nullptr);
   auto launch = [&](const StructArgs& B) {
     if (tet4) return launch_tet4(ctx, B);
-    return m.eNoN == 8 ? launch_one<8>(ctx, B) : launch_one<4>(ctx, B);
+    switch (m.eNoN * 100 + m.nG) {
+      case 404: return launch_one<4, 4>(ctx, B);
+      case 808: return launch_one<8, 8>(ctx, B);
+      case 606: return launch_one<6, 6>(ctx, B);
+      case 1015: return launch_one<10, 15>(ctx, B);
+      case 2027: return launch_one<20, 27>(ctx, B);
+      case 2727: return launch_one<27, 27>(ctx, B);
+    }
+    set_error("svb200_assemble: the solid covers TET4, HEX8, WDG, TET10, HEX20 and HEX27 meshes with the reference's quadrature rules");
+    return (int)SVB200_ERR_UNSUPPORTED;
   };
   if (A.atomic) return launch(A);
   A.perm = m.d_color_perm;
@@ -1140,6 +1181,7 @@ int run_assemble_mesh(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq,
   const bool lelas = (eq->phys == SVB200_PHYS_LELAS);
   SVB_REQUIRE(lelas || ctx->d_Do, "svb200_assemble: the mesh equation needs the old displacement (svb200_set_old_disp)");
   SVB_REQUIRE(eq->dof == 3 && ctx->dof == 3, "svb200_assemble: the mesh / linear-elasticity equation has dof = 3");
+  SVB_REQUIRE(m.eNoN == 4 || m.eNoN == 8, "svb200_assemble: the mesh / linear-elasticity equation is implemented for TET4 and HEX8 meshes");
   // reuse the solid argument block: mark mesh domains as the ones to assemble, E / nu travel in C10 / C01
   std::vector<svb200_dmnparams> d(dmn, dmn + nDmn);
   for (auto& q : d) {

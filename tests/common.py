@@ -232,6 +232,17 @@ FLUID_HI_CASES = [
 ]
 
 
+# displacement-based solid on the same curved quadratic / wedge elements (struct_3d through the general kernel with nG != eNoN)
+STRUCT_HI_CASES = [
+    ("tet10_nHK_ST91", _tet10, dict(E=1e6, nu=0.4, Kpen=1e6, rho=1.0, dmp=2.0, f=(0.1, 0.2, 0.3)), 0),
+    ("hex20_MR", _hex20, dict(isoType=abi.ISO_MR, C10=1e5, C01=3e4, Kpen=1e6, rho=1.0), 0),
+    ("hex27_HO_active_fsn", _hex27, dict(isoType=abi.ISO_HO, st_a=590.0, st_b=8.023, aff=184720.0, bff=16.026, ass=24810.0, bss=11.12,
+                                        afs=2160.0, bfs=11.436, khs=100.0, Kpen=1e6, rho=1.0, active_stress=True), 2),
+    ("wdg6_nHK_M94", _wdg6, dict(volType=abi.VOL_M94, E=1e6, nu=0.3, Kpen=1e6, rho=1.0), 0),
+    ("tet10_CANN_HO", _tet10, dict(cann=CANN_HO, Kpen=1e6, rho=1.0), 2),
+]
+
+
 def fluid_gen_state(m, tDof, seed=31):
     rng = np.random.default_rng(seed)
     Yg = np.zeros((tDof, m.nNo), order="F")

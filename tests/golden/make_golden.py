@@ -106,6 +106,25 @@ def fluid_hi_golden():
     print("wrote fluid_hi.npz with", len(out), "arrays")
 
 
+def struct_hi_golden():
+    """struct_3d on curved TET10 / HEX20 / HEX27 / WDG elements (element tables: tests/golden/fluid_hi.npz)."""
+    out = {}
+    for name, mk, dkw, nFn in common.STRUCT_HI_CASES:
+        m = mk()
+        Ag, Yg, Dg, Bf, fN = common.struct_state(m, nFn)
+        c = RefCase(); c.set_coords(m.x); c.add_mesh(m.IEN, nFn=nFn, fN=fN)
+        rowPtr, colPtr = c.build_graph(0)
+        d = abi.struct_domain(**dkw)
+        c.alloc(3); c.set_state(Ag, Yg, Dg, Bf)
+        if d.active_stress:
+            c.set_active_tension(*common.active_tension(m, d.isoType))
+        c.assemble(0, abi.struct_eq(1e-4), [d])
+        out[f"{name}/R"], out[f"{name}/Val"] = c.get_R(), c.get_Val()
+        out[f"{name}/rowPtr"], out[f"{name}/colPtr"] = rowPtr, colPtr
+    np.savez_compressed(os.path.join(HERE, "struct_hi.npz"), **out)
+    print("wrote struct_hi.npz with", len(out), "arrays")
+
+
 def heat_golden():
     """Assembled R / Val of the scalar heat equations (heats_3d / heatf_3d) for tests/common.py:HEAT_CASES."""
     out = {}
@@ -186,6 +205,6 @@ if __name__ == "__main__":
     if not have_ref():
         raise SystemExit("oracle/_ref/libsvref.so is missing: run `make -C oracle ref` first")
     only = sys.argv[1:]
-    for fn in (fluid_golden, struct_golden, fluid_gen_golden, fluid_hi_golden, heat_golden, ustruct_golden, lelas_golden, prestress_golden):
+    for fn in (fluid_golden, struct_golden, fluid_gen_golden, fluid_hi_golden, struct_hi_golden, heat_golden, ustruct_golden, lelas_golden, prestress_golden):
         if not only or fn.__name__.replace("_golden", "") in only:
             fn()

@@ -344,3 +344,41 @@ def test_fsi_solid_prestress_parity():
     assert common.rel_err(eng.get_R(), R0) < ASM_TOL
     assert common.rel_err(eng.get_Val(), V0) < ASM_TOL
     eng.close()
+
+
+@pytest.mark.parametrize("scatter", [abi.SCATTER_ATOMIC, abi.SCATTER_COLORED])
+@pytest.mark.parametrize("name,mk,dkw,nFn", common.STRUCT_HI_CASES, ids=[c[0] for c in common.STRUCT_HI_CASES])
+def test_struct_on_quadratic_and_wedge_elements(name, mk, dkw, nFn, scatter):
+    """struct_3d on curved TET10 (15 Gauss points), HEX20 / HEX27 (27; odd node count: another half-block rule) and WDG (6, lShpF)
+    elements against the committed vectors of the compiled reference and a live run of it."""
+    from svmultiphysics_b200.engine import Engine
+    golden, tabs = common.load_golden("struct_hi.npz"), common.load_golden("fluid_hi.npz")
+    m = mk()
+    Ag, Yg, Dg, Bf, fN = common.struct_state(m, nFn)
+    et = name.split("_")[0]
+    w, N, Nx = (tabs[f"tables/{et}/{k}"] for k in ("w", "N", "Nx"))
+    eq, dmn = abi.struct_eq(1e-4, scatter=scatter), [abi.struct_domain(**dkw)]
+    eng = Engine(0)
+    eng.set_graph(golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"])
+    eng.set_mesh(0, m.IEN, w, N, Nx, nFn=nFn, fN=fN)
+    eng.set_coords(m.x)
+    eng.alloc(3); eng.set_state(Ag, Yg, Dg, Bf)
+    ya = common.active_tension(m, dmn[0].isoType) if dmn[0].active_stress else None
+    if ya is not None:
+        eng.set_active_tension(*ya)
+    eng.assemble(0, eq, dmn)
+    R1, V1 = eng.get_R(), eng.get_Val()
+    assert common.rel_err(R1, golden[f"{name}/R"]) < ASM_TOL
+    assert common.rel_err(V1, golden[f"{name}/Val"]) < ASM_TOL
+    from oracle import refbind
+    if refbind.have_ref():
+        orc = refbind.RefCase(); orc.set_coords(m.x); orc.add_mesh(m.IEN, nFn=nFn, fN=fN); orc.build_graph(0)
+        orc.alloc(3); orc.set_state(Ag, Yg, Dg, Bf)
+        if ya is not None:
+            orc.set_active_tension(*ya)
+        orc.assemble(0, eq, dmn)
+        assert common.rel_err(R1, orc.get_R()) < ASM_TOL and common.rel_err(V1, orc.get_Val()) < ASM_TOL
+    if scatter == abi.SCATTER_COLORED:
+        eng.alloc(3); eng.assemble(0, eq, dmn)
+        assert np.array_equal(eng.get_Val(), V1) and np.array_equal(eng.get_R(), R1)
+    eng.close()
