@@ -589,6 +589,105 @@ def config_c5_fsi(device, hbm_peak, n=90, nz=120):
                          "algorithmic": "nnz*128 (Val written once) + nNo*32 (R) + nEl*464 (nodal gather) bytes per assembly"}}
 
 
+def _lattice_hash(m, c):
+    """Deterministic pseudo-noise in [-1, 1) keyed on the GLOBAL lattice index of the nodes of a lattice block (m.gijk)."""
+    i, j, k = m.gijk
+    v = (i * 73856093) ^ (j * 19349663) ^ (k * 83492791) ^ (c * 2654435761)
+    v = (v ^ (v >> 13)) * 1274126177 & 0xFFFFFFFF
+    return (v / 2147483648.0) - 1.0
+
+
+def lattice_fsi_case(b, n, R=2.0):
+    """FSI set-up of a lattice block of the cylinder (any sub-box regenerates the same numbers): solid wall = elements whose
+    centroid lies outside 0.55 R (domain bit 1), lumen = fluid (bit 0); tDof = 7 state with mesh velocity / displacement."""
+    c = b.x[:, b.IEN].mean(axis=1)
+    eId = np.where(c[0] ** 2 + c[1] ** 2 > (0.55 * R) ** 2, 2, 1).astype(np.int32)
+    Ag, Yg = lattice_state(b, tDof=7)
+    h = 2.0 * R / n
+    Dg = np.zeros((7, b.nNo), order="F")
+    for k in range(3):
+        Yg[4 + k] = 0.2 * _lattice_hash(b, 20 + k)
+        Dg[k] = 1e-3 * h * _lattice_hash(b, 30 + k)
+        Dg[4 + k] = 2e-3 * h * _lattice_hash(b, 40 + k)
+        Ag[4 + k] = 1e-2 * _lattice_hash(b, 50 + k)
+    return eId, Ag, Yg, Dg
+
+
+def config_c5_fsi_multi(eng, m, lb, rank, world, rowPtr, colPtr, n, nzg, L, reduce_ranks, with_parity):
+    """C5 on N GPUs (BASELINE.json: "FSI pipe ... coupled assembly at 2/4/8 GPUs"): construct_fsi (ALE fluid lumen + nHK wall) and the
+    mesh-motion equation on this rank's block of the N-times-longer cylinder, shared-node sums included, on the engine and the
+    partition of the headline run; parity of the coupled residual on the block corner where the most ranks meet against a
+    single-partition oracle assembly of the same sub-box."""
+    eId, Ag, Yg, Dg = lattice_fsi_case(m, n)
+    fl, so = np.flatnonzero(eId == 1), np.flatnonzero(eId == 2)
+    af, am, gam, beta = abi.gen_alpha(0.5)
+    eq = abi.EqParams(dt=1e-3, af=af, am=am, gam=gam, beta=beta, phys=abi.PHYS_FSI, dof=4, tDof=7, s=0, mvMsh=1, vmsStab=1,
+                      scatter=abi.SCATTER_ATOMIC, reserved=0)
+    dmn = [abi.fluid_domain(rho=1.0, mu=0.04, Id=0), abi.struct_domain(rho=1.0, volType=abi.VOL_M94, E=1e7, nu=0.3, Kpen=1e7 / (3 * (1 - 0.6)), Id=1)]
+    w, N, Nx = elements.tables(4)
+    eng.set_mesh(1, np.asfortranarray(m.IEN[:, fl]), w, N, Nx, eId=eId[fl])
+    eng.set_mesh(2, np.asfortranarray(m.IEN[:, so]), w, N, Nx, eId=eId[so])
+    eng.set_mesh(3, m.IEN, w, N, Nx)
+    eng.alloc(4); eng.set_state(Ag, Yg, Dg)
+
+    def fsi():
+        eng.alloc(4); eng.assemble(1, eq, dmn); eng.assemble(2, eq, dmn); eng.commu_R()
+    fsi()
+    fsi_ms = reduce_ranks(_timed(eng, fsi, 3), "max")
+    out = {}
+    if with_parity:
+        cls, kind = _oracle_cls()
+        err, nrows, nwall, mult = 0.0, 0, 0, 0
+        gid_mine = m.gijk[0] + (n + 1) * (m.gijk[1] + (n + 1) * m.gijk[2])
+        for F in parity_boxes(lb, rank).values():      # the box inside the block and the one on its most-shared corner
+            b = meshgen.cylinder_box(n, nzg, F, L=L)
+            eIdb, Ab, Yb, Db = lattice_fsi_case(b, n)
+            c = cls(); c.set_coords(b.x); c.add_mesh(b.IEN, eId=eIdb); c.build_graph(0)
+            c.alloc(4); c.set_state(Ab, Yb, Db); c.assemble(0, eq, dmn)
+            RF = c.get_R(); c.close()
+            gi, gj, gk = b.gijk
+            comp = np.ones(b.nNo, bool)
+            for d, g in enumerate((gi, gj, gk)):
+                comp &= ((g > F[d][0]) | (g == 0)) & ((g < F[d][1]) | (g == lb.nc[d]))
+            gid = gi + (n + 1) * (gj + (n + 1) * gk)
+            rows = np.flatnonzero(comp & np.isin(gid, gid_mine))
+            if len(rows) == 0:
+                continue
+            loc = lb.local_of(rank, gid[rows]).astype(np.int32)
+            R_loc = eng.get_rows(abi.ARRAY_R, loc)
+            # momentum rows of the wall are ~10^7 x the fluid rows: compare every row against its own scale class
+            sol_nodes = np.isin(np.arange(b.nNo), np.unique(b.IEN[:, eIdb == 2]))[rows]
+            for sel in (sol_nodes, ~sol_nodes):
+                if sel.any():
+                    ref = RF[:, rows[sel]]
+                    err = max(err, float(np.abs(R_loc[:, sel] - ref).max() / max(np.abs(ref).max(), 1e-300)))
+            nrows += len(rows); nwall += int(sol_nodes.sum()); mult = max(mult, int(lb.multiplicity(rank)[loc].max()))
+        out["parity"] = {"oracle": kind, "rows_rank0": nrows, "rows_on_wall_rank0": nwall, "max_ranks_on_a_row_rank0": mult,
+                         "R_max_rel": reduce_ranks(err, "max"), "tol": 1e-12}
+        out["parity"]["ok"] = out["parity"]["R_max_rel"] < 1e-12
+    ls = abi.ls_params(abi.LS_GMRES, mItr=1, sD=50, relTol=1e-12)
+    gm_ms = 0.0
+    for rep in range(2):
+        fsi()
+        eng.timer_mark(0)
+        _, o, _ = eng.solve(4, abi.LS_GMRES, ls, np.ones(1, np.int32), np.zeros(1), want_solution=False)
+        eng.timer_mark(1)
+        gm_ms = reduce_ranks(eng.timer_elapsed() / max(o.RI.itr, 1), "max")
+    eqm, dmm = abi.mesh_eq(1e-3), [abi.mesh_domain(E=1.0, nu=0.3)]
+
+    def msh():
+        eng.alloc(3); eng.assemble(3, eqm, dmm); eng.commu_R()
+    eng.alloc(3); eng.set_old_disp(np.asfortranarray(0.9 * Dg)); msh()
+    msh_ms = reduce_ranks(_timed(eng, msh, 3), "max")
+    nEl = int(reduce_ranks(float(m.nEl), "sum"))
+    out.update({"workload": f"FSI pipe on {world} GPUs, {nEl} tet4 (lumen ALE VMS fluid + nHK M94 wall outside 0.55 R), tDof 7, on the "
+                            "partition of the headline run",
+                "value": nEl / (fsi_ms * 1e-3), "unit": "element assemblies/s (construct_fsi: zero + lumen + wall + shared-node sum)",
+                "construct_fsi_stage_ms": fsi_ms, "construct_mesh_stage_ms": msh_ms, "mesh_value": nEl / (msh_ms * 1e-3),
+                "fsi_gmres_ms_per_itr": gm_ms, "fluid_elements_rank0": int(len(fl)), "solid_elements_rank0": int(len(so))})
+    return out
+
+
 def extra_configs(args, device, sampler, fp64_peak, hbm_peak):
     out = {}
     for name, fn in (("C4_struct_hex8", lambda: config_c4_struct(device, fp64_peak, hbm_peak)),
@@ -909,6 +1008,17 @@ def main():
             configs["C1_ns_solver"] = {"error": repr(ex)}
         configs["C1_ns_solver"]["clocks"] = sampler.window(t0c, time.perf_counter())
         configs["C1_ns_solver"]["wall_s"] = time.perf_counter() - t0c
+    c5m = None
+    if world > 1 and not args.no_extra_configs:
+        t0c = time.perf_counter()
+        c5m = config_c5_fsi_multi(eng, m, lb, rank, world, rowPtr, colPtr, n, nzg, L, reduce_ranks, not args.no_parity)
+        c5m["wall_s"] = time.perf_counter() - t0c
+        if rank == 0:
+            c5m["clocks"] = sampler.window(t0c, time.perf_counter())
+            line["configs"] = {"C5_fsi_pipe_multi_gpu": c5m}
+        if parity is not None and "parity" in c5m:
+            parity["c5_fsi_R_max_rel"] = c5m["parity"]["R_max_rel"]
+            parity["ok"] = bool(parity["ok"] and c5m["parity"]["ok"])
     eng.close()
     if rank == 0:
         if world == 1 and not args.no_extra_configs:
