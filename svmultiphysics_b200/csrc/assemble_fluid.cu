@@ -75,7 +75,7 @@ assemble_fluid_tet4_kernel(const __grid_constant__ FluidArgs P)
 #pragma unroll
         for (int i = 0; i < 3; i++) {
           xl[a][i] = __ldg(xp + i) + (P.ale ? __ldg(P.Dg + (size_t)P.tDof * n + 4 + i) : 0.0);
-          ab[a][i] = __ldg(ap + i) - __ldg(bp + i);
+          ab[a][i] = P.bfZero ? __ldg(ap + i) : __ldg(ap + i) - __ldg(bp + i);
         }
 #pragma unroll
         for (int i = 0; i < 4; i++) yl[a][i] = __ldg(yp + i);
@@ -240,6 +240,23 @@ assemble_fluid_tet4_grouped_kernel(const __grid_constant__ FluidArgs P)
       const int4 n4 = *reinterpret_cast<const int4*>(P.IEN + 4 * (size_t)e);
       const int node[4] = {n4.x, n4.y, n4.z, n4.w};
       double xl[4][3], yl[4][4], uc[4][3], ab[4][3];
+      if (P.tDof == 4 && P.bfZero == 2 && !P.ale) {
+        // the common fluid case (tDof = 4: a node's state is one aligned 32-byte sector; no body-force array): 128-bit loads,
+        // 5 instead of 13 load instructions per node
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+          const size_t n = (size_t)node[a];
+          const double2 a01 = __ldg(reinterpret_cast<const double2*>(P.Ag + 4 * n));
+          const double a2 = __ldg(P.Ag + 4 * n + 2);
+          const double2 y01 = __ldg(reinterpret_cast<const double2*>(P.Yg + 4 * n));
+          const double2 y23 = __ldg(reinterpret_cast<const double2*>(P.Yg + 4 * n) + 1);
+          const double* xp = P.x + 3 * n;
+          xl[a][0] = __ldg(xp); xl[a][1] = __ldg(xp + 1); xl[a][2] = __ldg(xp + 2);
+          ab[a][0] = a01.x; ab[a][1] = a01.y; ab[a][2] = a2;
+          yl[a][0] = y01.x; yl[a][1] = y01.y; yl[a][2] = y23.x; yl[a][3] = y23.y;
+          uc[a][0] = y01.x; uc[a][1] = y01.y; uc[a][2] = y23.x;
+        }
+      } else {
 #pragma unroll
       for (int a = 0; a < 4; a++) {
         const size_t n = (size_t)node[a];
@@ -250,12 +267,13 @@ assemble_fluid_tet4_grouped_kernel(const __grid_constant__ FluidArgs P)
 #pragma unroll
         for (int i = 0; i < 3; i++) {
           xl[a][i] = __ldg(xp + i) + (P.ale ? __ldg(P.Dg + (size_t)P.tDof * n + 4 + i) : 0.0);
-          ab[a][i] = __ldg(ap + i) - __ldg(bp + i);
+          ab[a][i] = P.bfZero ? __ldg(ap + i) : __ldg(ap + i) - __ldg(bp + i);
         }
 #pragma unroll
         for (int i = 0; i < 4; i++) yl[a][i] = __ldg(yp + i);
 #pragma unroll
         for (int i = 0; i < 3; i++) uc[a][i] = yl[a][i] - (P.mvMsh ? __ldg(yp + 4 + i) : 0.0);
+      }
       }
       tet4_element_staged(P, P.dmn[iD], xl, yl, uc, ab, NN, rec + tid * RS, T + lane * TILE_LD);
     }
@@ -263,6 +281,19 @@ assemble_fluid_tet4_grouped_kernel(const __grid_constant__ FluidArgs P)
   act[tid] = active ? 1 : 0;
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   const bool allActive = __syncthreads_and(active);
+
+  // plan entries beyond the shared-memory cache (targets 512.. of the ~690 of a group, processed in the last passes of phase 3):
+  // requested now, so that their L2 latency hides behind phase 2 instead of stalling the start of those passes
+  constexpr int PF = 2;
+  int2 pfe[PF];
+  int pfp[PF];
+#pragma unroll
+  for (int q = 0; q < PF; q++) {
+    const int k = ENT_CACHE + q * ASM_GROUP + tid;
+    pfe[q] = make_int2(0, 0);
+    pfp[q] = -1;
+    if (k < G) { pfe[q] = __ldg(P.kU_ent + ub + k); pfp[q] = __ldg(P.kU_partner + ub + k); }
+  }
 
   // ---- phase 2: residual rows of the group's distinct nodes (element residuals sit in the tiles) ------------
   {
@@ -301,8 +332,15 @@ assemble_fluid_tet4_grouped_kernel(const __grid_constant__ FluidArgs P)
       bool isEdge = false;
       EdgeAcc EA;
       if (k < G) {
-        const int2 ent = k < ENT_CACHE ? entc[k] : __ldg(P.kU_ent + ub + k);
-        const int partner = k < ENT_CACHE ? entp[k] : __ldg(P.kU_partner + ub + k);
+        int2 ent;
+        int partner;
+        if (k < ENT_CACHE) { ent = entc[k]; partner = entp[k]; }
+        else if (k < ENT_CACHE + PF * ASM_GROUP) {
+          // k = ENT_CACHE + q ASM_GROUP + tid: this thread's own prefetched entry (ENT_CACHE is a multiple of ASM_GROUP)
+          const int q = (k - ENT_CACHE) / ASM_GROUP;
+          ent = q == 0 ? pfe[0] : pfe[1];
+          partner = q == 0 ? pfp[0] : pfp[1];
+        } else { ent = __ldg(P.kU_ent + ub + k); partner = __ldg(P.kU_partner + ub + k); }
         const int start = ent.y & 0xFFFF, end = start + (ent.y >> 16);
         if (partner >= 0) {
           isEdge = true;

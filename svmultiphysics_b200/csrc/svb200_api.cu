@@ -386,6 +386,7 @@ int svb200_set_graph(svb200_ctx* ctx, int32_t nNo, int32_t nnz, const int32_t* r
   cudaFree(ctx->d_Ao); cudaFree(ctx->d_Yo); cudaFree(ctx->d_An); cudaFree(ctx->d_Yn); cudaFree(ctx->d_Dn); cudaFree(ctx->d_nodeflag);
   ctx->d_Ao = ctx->d_Yo = ctx->d_An = ctx->d_Yn = ctx->d_Dn = nullptr; ctx->d_nodeflag = nullptr;
   ctx->d_x = ctx->d_Ag = ctx->d_Yg = ctx->d_Dg = ctx->d_Bf = ctx->d_Do = nullptr;
+  ctx->bf_set = false;
   ctx->tDof = 0;
   return SVB200_OK;
 }
@@ -605,7 +606,7 @@ int svb200_set_state(svb200_ctx* ctx, int32_t tDof, const double* Ag, const doub
   if (Ag) TRY(upload_nodal(ctx, tDof, Ag, &ctx->d_Ag));
   if (Yg) TRY(upload_nodal(ctx, tDof, Yg, &ctx->d_Yg));
   if (Dg) TRY(upload_nodal(ctx, tDof, Dg, &ctx->d_Dg));
-  if (Bf) TRY(upload_nodal(ctx, 3, Bf, &ctx->d_Bf));
+  if (Bf) { TRY(upload_nodal(ctx, 3, Bf, &ctx->d_Bf)); ctx->bf_set = true; }
   return SVB200_OK;
 }
 
@@ -623,6 +624,11 @@ static int fill_fluid_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams
   A.kU_ptr = m.schedK.d_uptr; A.kU_ent = m.schedK.d_uent; A.kU_partner = m.schedK.d_upartner; A.kContrib = m.schedK.d_contrib;
   A.rU_ptr = m.schedR.d_uptr; A.rU_ent = m.schedR.d_uent; A.rContrib = m.schedR.d_contrib;
   A.x = ctx->d_x; A.Ag = ctx->d_Ag; A.Yg = ctx->d_Yg; A.Bf = ctx->d_Bf; A.Dg = ctx->d_Dg;
+  // no body-force array was ever uploaded: com_mod.Bf is identically zero and the TET4 kernels skip the 12 loads per element
+  // (a - 0.0 == a bit for bit); SVB200_BF_ALWAYS=1 keeps the gather (A/B)
+  static const bool bf_always = getenv("SVB200_BF_ALWAYS") != nullptr;
+  static const bool gather_scalar = getenv("SVB200_GATHER_SCALAR") != nullptr;     // A/B: skip Bf but keep the 8-byte loads
+  A.bfZero = (!ctx->bf_set && !bf_always) ? (gather_scalar ? 1 : 2) : 0;
   A.R = ctx->d_R; A.Val = ctx->d_Val;
   if (!ctx->d_err) {
     SVB_CUDA(cudaMalloc(&ctx->d_err, sizeof(int)));

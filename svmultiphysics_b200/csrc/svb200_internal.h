@@ -119,7 +119,7 @@ struct FluidArgs {
   double* Val;
   int e0, e1;           // element range [e0,e1) (indices into perm when perm != null)
   int tDof, mvMsh, nDmn, atomic;
-  int ale, pad0;        // ale: element geometry is x + Dg(4..6) (fsi::construct_fsi, fsi.cpp:140-146)
+  int ale, bfZero;      // ale: element geometry is x + Dg(4..6) (fsi::construct_fsi, fsi.cpp:140-146); bfZero: Bf is all zeros
   int* err;             // device error word: 1 + index of an element with a zero Jacobian (0 = none)
   const int* gperm;     // grouped kernel: CTA blockIdx.x works on group gperm[g0 + blockIdx.x] (null: group blockIdx.x)
   int g0, nGrpLaunch;   // first entry / number of entries of gperm in this launch (deterministic mode: one group colour)
@@ -169,6 +169,7 @@ struct svb200_ctx {
   int* d_nodeflag = nullptr;     // per node: belongs to a solid domain (FSI corrector)
   int* d_err = nullptr;          // element-loop error word (zero Jacobian), see FluidArgs::err
   double* d_Bf = nullptr;
+  bool bf_set = false;           // a body-force array was uploaded (else d_Bf is all zeros and the TET4 fluid kernel skips its gather)
   double* d_stage = nullptr;     // staging buffer for permuted uploads/downloads
   size_t stage_bytes = 0;
 
