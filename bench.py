@@ -586,7 +586,13 @@ def config_c5_fsi(device, hbm_peak, n=90, nz=120):
             "roofline": {"bound": "hbm", "kernel": "construct_fsi (fluid TET4 grouped kernel + struct TET4 kernel)",
                          "achieved": bytes_fsi / (fsi_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": bytes_fsi / (fsi_ms * 1e-3) * 1e-9 / hbm_peak, "traffic": None,
-                         "algorithmic": "nnz*128 (Val written once) + nNo*32 (R) + nEl*464 (nodal gather) bytes per assembly"}}
+                         "algorithmic": "nnz*128 (Val written once) + nNo*32 (R) + nEl*464 (nodal gather) bytes per assembly",
+                         "note": "the stage is compute bound, not HBM bound: see fp64_model"},
+            "fp64_model": {"flop": len(fl) * FLOP_PER_ELEMENT + len(so) * 24000.0,
+                           "TFLOP/s": (len(fl) * FLOP_PER_ELEMENT + len(so) * 24000.0) / (fsi_ms * 1e-3) * 1e-12,
+                           "derivation": "fluid tets x 11.6 kflop (SURVEY 8d) + solid tets x 24 kflop = 4 Gauss points x (compute_pk2cc ~2 k + "
+                                         "4 nodes x 0.3 k Bm/DBm + 16 node pairs x 0.18 k), the SURVEY's 16 kflop per HEX8 Gauss point rescaled "
+                                         "from 8 nodes / 64 pairs to 4 / 16; the closed-form TET4 kernels execute about a quarter of it"}}
 
 
 def _lattice_hash(m, c):
