@@ -69,7 +69,7 @@ __host__ __device__ constexpr int struct_per_el(int enon, int ng)
 
 // NG = number of Gauss points: ENON for TET4 / HEX8 / WDG; 15 for TET10, 27 for HEX20 / HEX27 (tables then come from P.tab, the
 // per-mesh device copy of w | N | Nxi, because the fixed-size argument arrays stop at 8).
-template <int ENON, int NG, bool ATOMIC, bool VISC>
+template <int ENON, int NG, bool ATOMIC, bool VISC, bool CANN>
 __global__ void __launch_bounds__(STRUCT_THREADS)
 assemble_struct_kernel(const __grid_constant__ StructArgs P)
 {
@@ -185,7 +185,7 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
     }
     // active tensions at the Gauss point: ya_g = sum_b N_b Ya(:, node_b)  (sv_struct.cpp:640-642)
     double ya[3] = {0.0, 0.0, 0.0};
-    const bool act = (P.Ya != nullptr) && dm.active;
+    const bool act = CANN && (P.Ya != nullptr) && dm.active;
     if (act) {
 #pragma unroll
       for (int b = 0; b < ENON; b++) {
@@ -196,7 +196,7 @@ assemble_struct_kernel(const __grid_constant__ StructArgs P)
       }
     }
     double S[3][3], Dm[6][6];
-    pk2cc_voigt(dm, F, fN, act ? ya : nullptr, P.cann, P.nFn, S, Dm);
+    pk2cc_voigt<CANN>(dm, F, fN, act ? ya : nullptr, P.cann, P.nFn, S, Dm);
     if (VISC && dm.viscType != SVB200_SOLID_VISC_NONE) {
       // S += Svis (sv_struct.cpp:666-669); the viscous tangent is added by assemble_struct_visc_kernel
       double vx[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, Svis[3][3];
@@ -460,7 +460,7 @@ __device__ __forceinline__ void warp_scatter_block_pair(double* tile, int* tsl, 
 }
 
 
-template <bool ATOMIC>
+template <bool ATOMIC, bool CANN>
 __global__ void __launch_bounds__(STET_THREADS)
 assemble_struct_tet4_kernel(const __grid_constant__ StructArgs P)
 {
@@ -538,28 +538,34 @@ assemble_struct_tet4_kernel(const __grid_constant__ StructArgs P)
       for (int k = 0; k < P.nFn && k < 2; k++)
 #pragma unroll
         for (int i = 0; i < 3; i++) fN[k][i] = __ldg(P.fN + (size_t)3 * P.nFn * e + 3 * k + i);
-    // moments of the quadrature rule (struct_elem.cuh: the same routines the CPU suite checks against the reference)
-    Tet4Mom q;
-    tet4_moments(P.w, &P.N[0][0], MAX_ENON, Jac, q);
-    W = q.W;
-    // active tensions: S and Dm are affine in (Tfa, Tsa, Tna), so the Gauss sum of struct_3d equals one evaluation at the
-    // weighted mean sum_g w_g ya_g / W = sum_a m1_a Ya_a / W
+    // active tensions (full twin only): S and Dm are affine in (Tfa, Tsa, Tna), so the Gauss sum of struct_3d equals one
+    // evaluation at the weighted mean sum_g w_g ya_g / W = sum_a m1_a Ya_a / W (the weights' Jacobian cancels)
     double ya[3] = {0.0, 0.0, 0.0};
-    const bool act = (P.Ya != nullptr) && dm.active;
+    const bool act = CANN && (P.Ya != nullptr) && dm.active;
     if (act) {
+      double wsum = 0.0;
 #pragma unroll
-      for (int a = 0; a < 4; a++)
+      for (int g = 0; g < 4; g++) {
+        wsum += P.w[g];
 #pragma unroll
-        for (int i = 0; i < 3; i++) ya[i] += q.m1[a] * __ldg(P.Ya + 3 * (size_t)node[a] + i);
+        for (int a = 0; a < 4; a++)
 #pragma unroll
-      for (int i = 0; i < 3; i++) ya[i] /= q.W;
+          for (int i = 0; i < 3; i++) ya[i] += P.w[g] * P.N[g][a] * __ldg(P.Ya + 3 * (size_t)node[a] + i);
+      }
+#pragma unroll
+      for (int i = 0; i < 3; i++) ya[i] /= wsum;
     }
     double Dm[6][6];
-    pk2cc_voigt(dm, F, fN, act ? ya : nullptr, P.cann, P.nFn, S, Dm);
+    pk2cc_voigt<CANN>(dm, F, fN, act ? ya : nullptr, P.cann, P.nFn, S, Dm);
 #pragma unroll
     for (int r = 0; r < 6; r++)
 #pragma unroll
       for (int c = 0; c < 6; c++) s_Dm[6 * r + c][threadIdx.x] = Dm[r][c];
+    // moments of the quadrature rule, residual (struct_elem.cuh: the same routines the CPU suite checks against the reference);
+    // after compute_pk2cc, so that the 21 moments are not live across it
+    Tet4Mom q;
+    tet4_moments(P.w, &P.N[0][0], MAX_ENON, Jac, q);
+    W = q.W;
     double Pk[3][3];
 #pragma unroll
     for (int i = 0; i < 3; i++)
@@ -1069,13 +1075,20 @@ static int launch_one(svb200_ctx* ctx, const StructArgs& A)
   constexpr int EV = LINEAR ? ENON : 8;
   constexpr int EPBV = (VISC_THREADS / 32) * (32 / EV);
   constexpr size_t smemV = sizeof(double) * (size_t)EPBV * visc_per_el(EV);
+  // the hot instantiations (TET4 / HEX8 without viscosity) exist with and without the CANN branch (struct_elem.cuh: pk2cc_voigt<CANN>);
+  // everything else is built with it
+  constexpr bool NC = !LINEAR;                  // "no-CANN twin" collapses onto the CANN build for the quadratic elements
+  bool cannM = false;
+  for (int d = 0; d < A.nDmn; d++) cannM |= (A.dmn[d].isStruct && (A.dmn[d].isoType == SVB200_ISO_CANN || A.dmn[d].active));
   static bool configured = false;
   if (!configured) {
-    SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, NG, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, NG, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, NG, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, NG, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, NG, true, false, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, NG, false, false, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if constexpr (LINEAR) {
-      SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, NG, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, NG, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, NG, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SVB_CUDA(cudaFuncSetAttribute(assemble_struct_kernel<ENON, NG, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       SVB_CUDA(cudaFuncSetAttribute(assemble_struct_visc_kernel<EV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemV));
       SVB_CUDA(cudaFuncSetAttribute(assemble_struct_visc_kernel<EV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemV));
     }
@@ -1085,17 +1098,22 @@ static int launch_one(svb200_ctx* ctx, const StructArgs& A)
   bool visc = false;
   for (int d = 0; d < A.nDmn; d++) visc |= (A.dmn[d].isStruct && A.dmn[d].viscType != SVB200_SOLID_VISC_NONE);
   if (!visc) {
-    if (A.atomic) assemble_struct_kernel<ENON, NG, true, false><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
-    else assemble_struct_kernel<ENON, NG, false, false><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
+    if (cannM) {
+      if (A.atomic) assemble_struct_kernel<ENON, NG, true, false, true><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
+      else assemble_struct_kernel<ENON, NG, false, false, true><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
+    } else {
+      if (A.atomic) assemble_struct_kernel<ENON, NG, true, false, NC><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
+      else assemble_struct_kernel<ENON, NG, false, false, NC><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
+    }
     ctx->launches++;
   } else {
     if constexpr (LINEAR) {
       const unsigned blocksV = (unsigned)((n + EPBV - 1) / EPBV);
       if (A.atomic) {
-        assemble_struct_kernel<ENON, NG, true, true><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
+        assemble_struct_kernel<ENON, NG, true, true, true><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
         assemble_struct_visc_kernel<EV, true><<<blocksV, VISC_THREADS, smemV, ctx->stream>>>(A);
       } else {
-        assemble_struct_kernel<ENON, NG, false, true><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
+        assemble_struct_kernel<ENON, NG, false, true, true><<<blocks, STRUCT_THREADS, smem, ctx->stream>>>(A);
         assemble_struct_visc_kernel<EV, false><<<blocksV, VISC_THREADS, smemV, ctx->stream>>>(A);
       }
       ctx->launches += 2;
@@ -1114,8 +1132,15 @@ static int launch_tet4(svb200_ctx* ctx, const StructArgs& A)
   if (n <= 0) return SVB200_OK;
   if (A.nG != 4) { set_error("svb200: the TET4 solid kernel expects the 4-point rule"); return SVB200_ERR_UNSUPPORTED; }
   const unsigned blocks = (unsigned)((n + STET_THREADS - 1) / STET_THREADS);
-  if (A.atomic) assemble_struct_tet4_kernel<true><<<blocks, STET_THREADS, 0, ctx->stream>>>(A);
-  else assemble_struct_tet4_kernel<false><<<blocks, STET_THREADS, 0, ctx->stream>>>(A);
+  bool cannM = false;
+  for (int d = 0; d < A.nDmn; d++) cannM |= (A.dmn[d].isStruct && (A.dmn[d].isoType == SVB200_ISO_CANN || A.dmn[d].active));
+  if (cannM) {
+    if (A.atomic) assemble_struct_tet4_kernel<true, true><<<blocks, STET_THREADS, 0, ctx->stream>>>(A);
+    else assemble_struct_tet4_kernel<false, true><<<blocks, STET_THREADS, 0, ctx->stream>>>(A);
+  } else {
+    if (A.atomic) assemble_struct_tet4_kernel<true, false><<<blocks, STET_THREADS, 0, ctx->stream>>>(A);
+    else assemble_struct_tet4_kernel<false, false><<<blocks, STET_THREADS, 0, ctx->stream>>>(A);
+  }
   ctx->launches++;
   SVB_CUDA(cudaGetLastError());
   return SVB200_OK;

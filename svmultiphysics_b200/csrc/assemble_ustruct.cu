@@ -89,7 +89,7 @@ __device__ __forceinline__ void uadd(double* p, double v)
   else *p += v;
 }
 
-template <int ENON, bool ATOMIC, bool VISC>
+template <int ENON, bool ATOMIC, bool VISC, bool CANN>
 __global__ void __launch_bounds__(USTRUCT_THREADS)
 assemble_ustruct_kernel(const __grid_constant__ UstructArgs P)
 {
@@ -152,7 +152,7 @@ assemble_ustruct_kernel(const __grid_constant__ UstructArgs P)
     const int g = a;
     // active tensions at the Gauss point (ustruct.cpp:955-957, 1265-1267)
     double ya[3] = {0.0, 0.0, 0.0};
-    const bool act = (P.Ya != nullptr) && dm.st.active;
+    const bool act = CANN && (P.Ya != nullptr) && dm.st.active;
     if (act) {
 #pragma unroll
       for (int b = 0; b < ENON; b++)
@@ -171,9 +171,9 @@ assemble_ustruct_kernel(const __grid_constant__ UstructArgs P)
           gp[g].gu.T[i][j] = gp[g].gu.A[i][j] = gp[g].gu.B[i][j] = gp[g].gu.M[i][j] = 0.0;
           gp[g].gv.T[i][j] = gp[g].gv.A[i][j] = gp[g].gv.B[i][j] = gp[g].gv.M[i][j] = 0.0;
         }
-      ustruct_gauss_point<ENON>(dm, P.dt, P.af, P.am, P.gam, P.w[g], P.N[g], P.Nxi[g], xl, ql, vl, dl, pl, pdl, fN, q, &gp[g].gu, &gp[g].gv, yap, P.cann, P.nFn);
+      ustruct_gauss_point<ENON, CANN>(dm, P.dt, P.af, P.am, P.gam, P.w[g], P.N[g], P.Nxi[g], xl, ql, vl, dl, pl, pdl, fN, q, &gp[g].gu, &gp[g].gv, yap, P.cann, P.nFn);
     } else {
-      ustruct_gauss_point<ENON>(dm, P.dt, P.af, P.am, P.gam, P.w[g], P.N[g], P.Nxi[g], xl, ql, vl, dl, pl, pdl, fN, q, nullptr, nullptr, yap, P.cann, P.nFn);
+      ustruct_gauss_point<ENON, CANN>(dm, P.dt, P.af, P.am, P.gam, P.w[g], P.N[g], P.Nxi[g], xl, ql, vl, dl, pl, pdl, fN, q, nullptr, nullptr, yap, P.cann, P.nFn);
     }
     // construct_usolid throws when utils::is_zero(Jac) (ustruct.cpp:312-314); q.w = w_g * Jac
     if (fabs(q.w) < fabs(P.w[g]) * 10.0 * 2.220446049250313e-16 * 2.220446049250313e-16) atomicMax(P.err, e + 1);
@@ -275,7 +275,7 @@ assemble_ustruct_kernel(const __grid_constant__ UstructArgs P)
 constexpr int UTET_THREADS = 128;
 constexpr size_t UTET_SMEM = sizeof(double) * ((size_t)(UTET_THREADS / 32) * 32 * 29 + 36 * UTET_THREADS);
 
-template <bool ATOMIC>
+template <bool ATOMIC, bool CANN>
 __global__ void __launch_bounds__(UTET_THREADS)
 assemble_ustruct_tet4_kernel(const __grid_constant__ UstructArgs P)
 {
@@ -338,7 +338,7 @@ assemble_ustruct_tet4_kernel(const __grid_constant__ UstructArgs P)
     // active tensions: Siso and Dm are affine in them and enter the Gauss sums with the weight alone, so one evaluation at
     // the weighted mean sum_g w_g ya_g / sum_g w_g reproduces the sum
     double ya[3] = {0.0, 0.0, 0.0};
-    const bool act = (P.Ya != nullptr) && dm.st.active;
+    const bool act = CANN && (P.Ya != nullptr) && dm.st.active;
     if (act) {
       double wsum = 0.0;
 #pragma unroll
@@ -353,7 +353,7 @@ assemble_ustruct_tet4_kernel(const __grid_constant__ UstructArgs P)
       for (int i = 0; i < 3; i++) ya[i] /= wsum;
     }
     double Dm[6][6], Je;
-    ustruct_tet4_setup(dm, af, am, P.w, &P.N[0][0], MAX_ENON, P.Nxi[0], xl, ql, vl, dl, pl, pdl, fN, C, M, Dm, &Je,
+    ustruct_tet4_setup<CANN>(dm, af, am, P.w, &P.N[0][0], MAX_ENON, P.Nxi[0], xl, ql, vl, dl, pl, pdl, fN, C, M, Dm, &Je,
                        act ? ya : nullptr, P.cann, P.nFn);
     if (fabs(Je) < 10.0 * 2.220446049250313e-16 * 2.220446049250313e-16) atomicMax(P.err, e + 1);
 #pragma unroll
@@ -421,25 +421,27 @@ assemble_ustruct_tet4_kernel(const __grid_constant__ UstructArgs P)
   }
 }
 
+// CANN: a domain of the launch uses the CANN constitutive model (the twin of the kernel with that branch compiled in, struct_elem.cuh)
+template <bool CANN>
 static int launch_ustruct_tet4(svb200_ctx* ctx, const UstructArgs& A, bool atomic)
 {
   static bool configured = false;
   if (!configured) {
-    SVB_CUDA(cudaFuncSetAttribute(assemble_ustruct_tet4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UTET_SMEM));
-    SVB_CUDA(cudaFuncSetAttribute(assemble_ustruct_tet4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UTET_SMEM));
+    SVB_CUDA(cudaFuncSetAttribute(assemble_ustruct_tet4_kernel<true, CANN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UTET_SMEM));
+    SVB_CUDA(cudaFuncSetAttribute(assemble_ustruct_tet4_kernel<false, CANN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UTET_SMEM));
     configured = true;
   }
   const long long n = (long long)A.e1 - A.e0;
   if (n <= 0) return SVB200_OK;
   const unsigned blocks = (unsigned)((n + UTET_THREADS - 1) / UTET_THREADS);
-  if (atomic) assemble_ustruct_tet4_kernel<true><<<blocks, UTET_THREADS, UTET_SMEM, ctx->stream>>>(A);
-  else assemble_ustruct_tet4_kernel<false><<<blocks, UTET_THREADS, UTET_SMEM, ctx->stream>>>(A);
+  if (atomic) assemble_ustruct_tet4_kernel<true, CANN><<<blocks, UTET_THREADS, UTET_SMEM, ctx->stream>>>(A);
+  else assemble_ustruct_tet4_kernel<false, CANN><<<blocks, UTET_THREADS, UTET_SMEM, ctx->stream>>>(A);
   ctx->launches++;
   SVB_CUDA(cudaGetLastError());
   return SVB200_OK;
 }
 
-template <int ENON, bool VISC>
+template <int ENON, bool VISC, bool CANN>
 static int launch_ustruct(svb200_ctx* ctx, const UstructArgs& A, bool atomic)
 {
   using GP = typename UGPSel<VISC>::type;
@@ -447,15 +449,15 @@ static int launch_ustruct(svb200_ctx* ctx, const UstructArgs& A, bool atomic)
   constexpr size_t smem = sizeof(double) * (size_t)(USTRUCT_THREADS / 32) * ustruct_warp_ld(ENON, (int)(sizeof(GP) / sizeof(double)));
   static bool configured = false;
   if (!configured) {
-    SVB_CUDA(cudaFuncSetAttribute(assemble_ustruct_kernel<ENON, true, VISC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SVB_CUDA(cudaFuncSetAttribute(assemble_ustruct_kernel<ENON, false, VISC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVB_CUDA(cudaFuncSetAttribute(assemble_ustruct_kernel<ENON, true, VISC, CANN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVB_CUDA(cudaFuncSetAttribute(assemble_ustruct_kernel<ENON, false, VISC, CANN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   const long long n = (long long)A.e1 - A.e0;
   if (n <= 0) return SVB200_OK;
   const unsigned blocks = (unsigned)((n + EPB - 1) / EPB);
-  if (atomic) assemble_ustruct_kernel<ENON, true, VISC><<<blocks, USTRUCT_THREADS, smem, ctx->stream>>>(A);
-  else assemble_ustruct_kernel<ENON, false, VISC><<<blocks, USTRUCT_THREADS, smem, ctx->stream>>>(A);
+  if (atomic) assemble_ustruct_kernel<ENON, true, VISC, CANN><<<blocks, USTRUCT_THREADS, smem, ctx->stream>>>(A);
+  else assemble_ustruct_kernel<ENON, false, VISC, CANN><<<blocks, USTRUCT_THREADS, smem, ctx->stream>>>(A);
   ctx->launches++;
   SVB_CUDA(cudaGetLastError());
   return SVB200_OK;
@@ -536,10 +538,16 @@ int run_assemble_ustruct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* 
   const bool atomic = (eq->scatter == SVB200_SCATTER_ATOMIC);
   // linear tets without solid viscosity: closed-form kernel (SVB200_STRUCT_GENERAL=1 keeps the general one: cross-check)
   static const bool force_general = (getenv("SVB200_STRUCT_GENERAL") != nullptr && atoi(getenv("SVB200_STRUCT_GENERAL")) != 0);
+  bool cannM = cann_used > 0;       // the full-featured twin: CANN model or active stress in a domain of this launch
+  for (int d = 0; d < nDmn; d++) cannM |= (A.active[d] && A.dmn[d].st.active);
   auto launch = [&](const UstructArgs& B) {
-    if (m.eNoN == 4 && !visc && !force_general) return launch_ustruct_tet4(ctx, B, atomic);
-    if (visc) return m.eNoN == 8 ? launch_ustruct<8, true>(ctx, B, atomic) : launch_ustruct<4, true>(ctx, B, atomic);
-    return m.eNoN == 8 ? launch_ustruct<8, false>(ctx, B, atomic) : launch_ustruct<4, false>(ctx, B, atomic);
+    if (m.eNoN == 4 && !visc && !force_general) return cannM ? launch_ustruct_tet4<true>(ctx, B, atomic) : launch_ustruct_tet4<false>(ctx, B, atomic);
+    if (visc) {      // viscosity + CANN: the CANN twin exists for the plain kernels only; take it out of the hot build
+      if (m.eNoN == 8) return launch_ustruct<8, true, true>(ctx, B, atomic);
+      return launch_ustruct<4, true, true>(ctx, B, atomic);
+    }
+    if (m.eNoN == 8) return cannM ? launch_ustruct<8, false, true>(ctx, B, atomic) : launch_ustruct<8, false, false>(ctx, B, atomic);
+    return cannM ? launch_ustruct<4, false, true>(ctx, B, atomic) : launch_ustruct<4, false, false>(ctx, B, atomic);
   };
   int rc = SVB200_OK;
   if (atomic) rc = launch(A);

@@ -91,6 +91,11 @@ SVB_HD void cann_voigt(const CannRow* rows, int nrows, int nFn, const double fN[
 // compute_pk2cc<3> (without prestress / viscosity, which struct_3d adds): F -> S (3x3), Dm (6x6).
 // fN[0] = fibre, fN[1] = sheet direction.  ya = {Tfa, Tsa, Tna}: active stresses along the fibre, sheet and sheet-normal
 // directions (mat_models.cpp:321-326; nullptr = none).  Returns 0, or 1 for an unsupported model.
+// CANN = false compiles the CANN branch AND the active-stress terms out ("lean" twin: the closed-form TET4 kernels lost 8 % to the extra
+// live values when the terms were compiled in unconditionally; 2.13 -> 2.30 ms on 4.4 M tets): inlined, its ~60 live doubles and 3x3 temporaries land in the stack frame of every solid
+// kernel (HEX8 struct kernel 8 -> 568 bytes, TET4 216 -> 896), so the hot instantiations are built without it and a domain with a CANN
+// model selects the CANN = true twin of the kernel.
+template <bool CANN = true>
 SVB_HD int pk2cc_voigt(const StructDmn& dm, const double F[3][3], const double fN[2][3], const double* ya, const CannRow* cann,
                        int nFn, double S[3][3], double Dm[6][6])
 {
@@ -140,7 +145,7 @@ SVB_HD int pk2cc_voigt(const StructDmn& dm, const double F[3][3], const double f
   // others when Tsa or Tna > 0, which the host checks at svb200_set_active_tension] — added to S_bar before the deviatoric
   // projection (mat_models.cpp:443, 461, 503, 570-575, 636, 650, 661-664) or, for HO-ma and CANN, to S directly (:745-772, 800).
   double Sact[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-  const bool act = (ya != nullptr) && dm.active;
+  const bool act = CANN && (ya != nullptr) && dm.active;
   if (act) {
     const bool dirs = (dm.isoType == SVB200_ISO_GUCCIONE || dm.isoType == SVB200_ISO_HO || dm.isoType == SVB200_ISO_HO_MA);
     double nrm[3] = {0, 0, 0};
@@ -164,7 +169,7 @@ SVB_HD int pk2cc_voigt(const StructDmn& dm, const double F[3][3], const double f
   }
 
   double Idm[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-  if (dm.isoType == SVB200_ISO_CANN) {
+  if (CANN && dm.isoType == SVB200_ISO_CANN) {
     cann_voigt(cann + dm.cann_off, dm.cann_rows, nFn, fN, C, Ci, J, J2d, J4d, S, Dm);
     if (act) {
 #pragma unroll

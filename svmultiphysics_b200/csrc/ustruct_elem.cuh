@@ -101,7 +101,7 @@ SVB_HD void ustruct_tau(const UstructDmn& dm, double Je, double detF, double& ta
 // Everything ustruct_3d_m / ustruct_3d_c evaluate before their node loops.
 //   ql[a] = al(i..k,a) - bfl(:,a);  vl, dl: nodal velocity / displacement;  pl, pdl: nodal pressure and its rate.
 // Returns 0, 1 for an unsupported constitutive model.
-template <int ENON>
+template <int ENON, bool CANN = true>
 SVB_HD int ustruct_gauss_point(const UstructDmn& dm, double dt, double af_eq, double am, double gam, double wg, const double N[],
                                const double Nxi[][3], const double xl[][3], const double ql[][3], const double vl[][3],
                                const double dl[][3], const double pl[], const double pdl[], const double fN[2][3], UGP& q,
@@ -153,7 +153,7 @@ SVB_HD int ustruct_gauss_point(const UstructDmn& dm, double dt, double af_eq, do
   // compute_pk2cc with the ustruct flag: isochoric part only (mat_models.cpp:311-312, 395-405)
   StructDmn iso = dm.st;
   iso.Kpen = 0.0;
-  if (pk2cc_voigt(iso, q.F, fN, ya, cann, nFn, q.S, q.Dm)) return 1;
+  if (pk2cc_voigt<CANN>(iso, q.F, fN, ya, cann, nFn, q.S, q.Dm)) return 1;
   // compute_visc_stress_and_tangent (ustruct.cpp:1255-1259, mat_models.cpp:1583-1762): Siso += Svis (:1278); the tangent
   // terms are kept as two ViscGP sets, gu for Kvis_u alone (afu = 1, afv = 0) and gv for Kvis_v alone (0, 1)
   if (gu != nullptr && dm.st.viscType != SVB200_SOLID_VISC_NONE) {
@@ -287,6 +287,7 @@ using UTet4Mom = UTet4GP;
 
 // Element constants, Dm and the Gauss-point scalars.  w[g] are the reference weights, N is indexed [g][a] with row stride ldN.
 // Returns 0, 1 for an unsupported constitutive model; Je (Jacobian of the reference map) is returned through *Je_out.
+template <bool CANN = true>
 SVB_HD int ustruct_tet4_setup(const UstructDmn& dm, double af, double am, const double* w, const double* N, int ldN,
                               const double Nxi[][3], const double xl[4][3], const double ql[4][3], const double vl[4][3],
                               const double dl[4][3], const double pl[4], const double pdl[4], const double fN[2][3],
@@ -329,7 +330,7 @@ SVB_HD int ustruct_tet4_setup(const UstructDmn& dm, double af, double am, const 
   Fi[2][2] = (F[0][0] * F[1][1] - F[0][1] * F[1][0]) * iJ;
   StructDmn iso = dm.st;
   iso.Kpen = 0.0;
-  if (pk2cc_voigt(iso, C.F, fN, ya, cann, nFn, C.S, Dm)) return 1;
+  if (pk2cc_voigt<CANN>(iso, C.F, fN, ya, cann, nFn, C.S, Dm)) return 1;
   ustruct_tau(dm, Je, C.J, C.tauM, C.tauC);
   double VxFi[3][3], divV = 0.0;
 #pragma unroll
