@@ -10,7 +10,7 @@ from svmultiphysics_b200.engine import Engine
 from tests import common
 
 
-only = sys.argv[1] if len(sys.argv) > 1 else ""     # "", "heat", "ustruct", "struct", "fluid"
+only = sys.argv[1] if len(sys.argv) > 1 else ""     # "", "heat", "ustruct", "struct", "fluid", "new" (round-2 session-2 kernels only)
 
 
 def engine(m, nFn=0, fN=None):
@@ -20,7 +20,7 @@ def engine(m, nFn=0, fN=None):
     return e
 
 
-for sc in (abi.SCATTER_ATOMIC, abi.SCATTER_COLORED):
+for sc in ((abi.SCATTER_ATOMIC, abi.SCATTER_COLORED) if only != "new" else ()):
     for name, mk, fluid, tDof, s, mv, dkw in (common.HEAT_CASES if only in ("", "heat") else []):
         m = mk(); e = engine(m)
         Ag, Yg, Dg, Bf = common.heat_state(m, tDof, s)
@@ -31,13 +31,21 @@ for sc in (abi.SCATTER_ATOMIC, abi.SCATTER_COLORED):
         Ag, Yg, Dg, Bf, fN = common.ustruct_state(m, nFn)
         e = engine(m, nFn, fN)
         eq = abi.ustruct_eq(1e-3, scatter=sc)
-        e.alloc(4); e.set_state(Ag, Yg, Dg, Bf); e.assemble(0, eq, [abi.ustruct_domain(**dkw)]); e.ustruct_r(eq, 1, common.ustruct_Ad(m))
+        d = abi.ustruct_domain(**dkw)
+        e.alloc(4); e.set_state(Ag, Yg, Dg, Bf)
+        if d.active_stress:
+            e.set_active_tension(*common.active_tension(m, d.isoType))
+        e.assemble(0, eq, [d]); e.ustruct_r(eq, 1, common.ustruct_Ad(m))
         e.get_Kd(); e.close()
     for name, mk, dkw, nFn in (common.STRUCT_CASES if only in ("", "struct") else []):
         m = mk()
         Ag, Yg, Dg, Bf, fN = common.struct_state(m, nFn)
         e = engine(m, nFn, fN)
-        e.alloc(3); e.set_state(Ag, Yg, Dg, Bf); e.assemble(0, abi.struct_eq(1e-4, scatter=sc), [abi.struct_domain(**dkw)])
+        d = abi.struct_domain(**dkw)
+        e.alloc(3); e.set_state(Ag, Yg, Dg, Bf)
+        if d.active_stress:
+            e.set_active_tension(*common.active_tension(m, d.isoType))
+        e.assemble(0, abi.struct_eq(1e-4, scatter=sc), [d])
         e.get_Val(); e.close()
     if only not in ("", "struct", "fluid"):
         continue
@@ -46,4 +54,66 @@ for sc in (abi.SCATTER_ATOMIC, abi.SCATTER_COLORED):
     e.alloc(3); e.set_state(Ag, Yg, Dg, Bf); e.assemble(0, abi.lelas_eq(1e-3, scatter=sc), [abi.lelas_domain()]); e.get_Val(); e.close()
     m, Ag, Yg, Dg, Bf = common.fluid_case(n=4, nz=5); e = engine(m)
     e.alloc(4); e.set_state(Ag, Yg, Dg, Bf); e.assemble(0, abi.fluid_eq(0.005, scatter=sc), [abi.fluid_domain()]); e.get_Val(); e.close()
+
+
+def new_kernels():
+    """Round 2, session 2: lane-group SpMVs (every variant), the interleaved Schur operator, the fused CG tail inside an NS solve,
+    quadratic / wedge fluid and solid elements, prestress, active stress, CANN."""
+    golden = common.load_golden("fluid_hi.npz")
+    rng = np.random.default_rng(5)
+    m = meshgen.cylinder_tet4(4, 3)
+    e = Engine(0)
+    rp, cp = e.lhsa(m.nNo, [m.IEN]); e.set_graph(rp, cp)
+    for R, Cc in ((3, 3), (3, 1), (1, 3), (1, 1)):
+        K = np.asfortranarray(rng.standard_normal((R * Cc, len(cp)))); U = np.asfortranarray(rng.standard_normal((Cc, m.nNo)))
+        for v in range(e.spmv_rc_variants(R, Cc)):
+            e.spmv_rc(R, Cc, K, U, variant=v)
+    for v in [-2] + list(range(e.schur_sp_variants())):
+        e.schur_sp(rng.standard_normal(len(cp)), rng.standard_normal((3, len(cp))), rng.standard_normal(m.nNo),
+                   rng.standard_normal((3, m.nNo)), variant=v)
+    e.close()
+    # NS solve (depart with DL, schur_sp4 + fused tail, coupled resistance outlet)
+    m, Ag, Yg, Dg, Bf = common.fluid_case(n=4, nz=5)
+    e = engine(m)
+    faces = [(abi.BC_DIR, m.faces[k], np.zeros((3, len(m.faces[k])), order="F")) for k in ("wall", "inlet")]
+    out = m.faces["outlet"]; val = np.zeros((3, len(out)), order="F"); val[2] = 4.0 * np.pi / len(out)
+    faces.append((abi.BC_NEU, out, val))
+    e.set_num_faces(3)
+    for i, (g, nodes, v) in enumerate(faces):
+        e.set_face(i, g, nodes, v)
+    e.alloc(4); e.set_state(Ag, Yg, Dg, Bf); e.assemble(0, abi.fluid_eq(0.005), [abi.fluid_domain()])
+    ls = abi.ls_params(abi.LS_NS, mItr=5, sD=50, relTol=1e-3, absTol=1e-17, gm=(5, 50, 1e-3, 1e-17), cg=(50, 0, 1e-3, 1e-17))
+    e.solve(4, abi.LS_NS, ls, np.ones(3, np.int32), np.array([0.0, 0.0, 0.8]))
+    e.close()
+    for sc in (abi.SCATTER_ATOMIC, abi.SCATTER_COLORED):
+        for name, mk, visc, Kd, f, tDof, mv in common.FLUID_HI_CASES:
+            mm = mk(); et = name.split("_")[0]
+            w, N, Nx, Nxx = (golden[f"tables/{et}/{k}"] for k in ("w", "N", "Nx", "Nxx"))
+            A, Y, D, B = common.fluid_gen_state(mm, tDof)
+            e = Engine(0); rp, cp = e.lhsa(mm.nNo, [mm.IEN]); e.set_graph(rp, cp)
+            e.set_mesh(0, mm.IEN, w, N, Nx, Nxx=Nxx); e.set_coords(mm.x)
+            e.alloc(4); e.set_state(A, Y, D, B); e.assemble(0, abi.fluid_eq(0.005, tDof=tDof, mvMsh=mv, scatter=sc), [abi.fluid_domain(K_darcy=Kd, f=f, **visc)])
+            e.get_Val(); e.close()
+        for name, mk, dkw, nFn in common.STRUCT_HI_CASES:
+            mm = mk(); et = name.split("_")[0]
+            w, N, Nx = (golden[f"tables/{et}/{k}"] for k in ("w", "N", "Nx"))
+            A, Y, D, B, fN = common.struct_state(mm, nFn)
+            e = Engine(0); rp, cp = e.lhsa(mm.nNo, [mm.IEN]); e.set_graph(rp, cp)
+            e.set_mesh(0, mm.IEN, w, N, Nx, nFn=nFn, fN=fN); e.set_coords(mm.x)
+            d = abi.struct_domain(**dkw)
+            e.alloc(3); e.set_state(A, Y, D, B)
+            if d.active_stress:
+                e.set_active_tension(*common.active_tension(mm, d.isoType))
+            e.assemble(0, abi.struct_eq(1e-4, scatter=sc), [d]); e.get_Val(); e.close()
+    for name, *_ in common.PRESTRESS_CASES:
+        mm, A, Y, D, B, pS0, eq, dmn = common.prestress_case(name)
+        e = engine(mm); e.set_prestress(pS0)
+        e.alloc(3); e.set_state(A, Y, D, B); e.assemble(0, eq, dmn)
+        if eq.reserved & abi.EQ_PRESTRESS:
+            e.get_prestress()
+        e.close()
+
+
+if only in ("", "new"):
+    new_kernels()
 print("sanitize_small: done")
