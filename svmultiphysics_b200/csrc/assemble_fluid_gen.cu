@@ -54,14 +54,15 @@ constexpr int FG_NB = 4;      // column nodes per pass of phase B
 __host__ __device__ constexpr int fg_tab_ld(int enon) { return 1 + enon * 10; }
 // stride between the FluidNode tables of consecutive Gauss points: odd, so that the phase-A stores of the lanes of an
 // element (lane = Gauss point) fall into different banks
-__host__ __device__ constexpr int fg_nd_ld(int enon) { return enon * FLUID_NODE_DOUBLES + 1; }
-// per element: nodal inputs (x 3, al 3, yl 4, bfl 3, ym 3 = 16) | NxxL 6 | FluidGP per Gauss point | FluidNode tables;
+__host__ __device__ constexpr int fg_nd_ld(int enon) { return enon * FLUID_NODEC_DOUBLES + 1; }
+// per element: nodal inputs (x 3, al 3, yl 4, bfl 3, ym 3 = 16) | NxxL 6 | FluidGP per Gauss point | FluidNodeC tables;
 // padded to 8 mod 16 doubles (the two elements of a half-warp then use disjoint banks)
 __host__ __device__ constexpr int fg_per_el(int enon, int ng)
 {
   const int n = enon * 16 + enon * 6 + ng * FLUID_GP_DOUBLES + ng * fg_nd_ld(enon);
   return n + ((8 - (n % 16)) + 16) % 16;
 }
+__host__ __device__ constexpr bool fg_tab_in_smem(int enon, int ng) { return ng * fg_tab_ld(enon) <= 2048; }
 // lanes per element: one per element node in phase B and one per Gauss point in phase A
 __host__ __device__ constexpr int fg_lpe(int enon, int ng) { return enon > ng ? enon : ng; }
 // CTA size: two warps, one for the big quadratic elements (HEX20 / HEX27 need ~75 KB of shared memory per element)
@@ -77,12 +78,16 @@ assemble_fluid_gen_kernel(const __grid_constant__ FluidGenArgs P)
   constexpr int PER_EL = fg_per_el(ENON, NG);
   constexpr int TLD = fg_tab_ld(ENON);
   constexpr int THREADS = fg_threads(ENON, NG);
+  // reference-element tables: staged in shared memory when small (TET4 .. TET10), read in place (L2-resident, every CTA reads the
+  // same 58 KB) for the 27-point rules, where they would cost a resident CTA
+  constexpr bool TAB_SMEM = fg_tab_in_smem(ENON, NG);
   extern __shared__ double sm[];
-  double* stab = sm;
-  for (int t = threadIdx.x; t < NG * TLD; t += THREADS) stab[t] = __ldg(P.tab + t);
+  const double* stab = TAB_SMEM ? sm : P.tab;
+  if (TAB_SMEM)
+    for (int t = threadIdx.x; t < NG * TLD; t += THREADS) sm[t] = __ldg(P.tab + t);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int a = lane % LPE, el = lane / LPE;
-  double* se = sm + NG * TLD + (size_t)(warp * EPW + el) * PER_EL;
+  double* se = sm + (TAB_SMEM ? NG * TLD : 0) + (size_t)(warp * EPW + el) * PER_EL;
   double(*sx)[3] = reinterpret_cast<double(*)[3]>(se);
   double(*sal)[3] = reinterpret_cast<double(*)[3]>(se + 3 * ENON);
   double(*syl)[4] = reinterpret_cast<double(*)[4]>(se + 6 * ENON);
@@ -92,7 +97,7 @@ assemble_fluid_gen_kernel(const __grid_constant__ FluidGenArgs P)
   FluidGP* sgp = reinterpret_cast<FluidGP*>(se + 22 * ENON);
   constexpr int NLD = fg_nd_ld(ENON);
   double* sndd = se + 22 * ENON + NG * FLUID_GP_DOUBLES;        // FluidNode tables, one per Gauss point, stride NLD
-  auto snd = [&](int g) { return reinterpret_cast<FluidNode*>(sndd + g * NLD); };
+  auto snd = [&](int g) { return reinterpret_cast<FluidNodeC*>(sndd + g * NLD); };
 
   const long long idx = (long long)P.e0 + ((long long)blockIdx.x * (THREADS / 32) + warp) * EPW + el;
   bool active = (lane < EPW * LPE) && idx < P.e1;
@@ -156,7 +161,7 @@ assemble_fluid_gen_kernel(const __grid_constant__ FluidGenArgs P)
   // ---- phase B ------------------------------------------------------------------------------------------------
   double lR[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
-  for (int g = 0; g < NG; g++) fluid_gen_residual(sgp[g], snd(g)[a], lR);
+  for (int g = 0; g < NG; g++) fluid_gen_residual(sgp[g], fluid_node_expand(sgp[g], snd(g)[a]), lR);
 #pragma unroll
   for (int i = 0; i < 4; i++) fg_add<ATOMIC>(P.R + 4 * (size_t)node + i, lR[i]);
   const int* sl = P.slot + (size_t)e * ENON * ENON;
@@ -174,11 +179,11 @@ assemble_fluid_gen_kernel(const __grid_constant__ FluidGenArgs P)
       for (int i = 0; i < 16; i++) K[bb][i] = 0.0;
 #pragma unroll 1
     for (int g = 0; g < NG; g++) {
-      const FluidNode* nd = snd(g);
+      const FluidNodeC* nd = snd(g);
       FluidRow row;
-      fluid_gen_row(sgp[g], nd[a], row);
+      fluid_gen_row(sgp[g], fluid_node_expand(sgp[g], nd[a]), row);
 #pragma unroll
-      for (int bb = 0; bb < NB; bb++) fluid_gen_block_row(row, nd[b0 + bb], K[bb]);
+      for (int bb = 0; bb < NB; bb++) fluid_gen_block_row(row, fluid_node_expand(sgp[g], nd[b0 + bb]), K[bb]);
     }
 #pragma unroll
     for (int bb = 0; bb < NB; bb++) {
@@ -197,7 +202,7 @@ static int launch_gen(svb200_ctx* ctx, const FluidGenArgs& A)
   const long long n = (long long)A.e1 - A.e0;
   if (n <= 0) return SVB200_OK;
   const unsigned blocks = (unsigned)((n + EPB - 1) / EPB);
-  constexpr size_t smem = sizeof(double) * ((size_t)NG * fg_tab_ld(ENON) + (size_t)EPB * fg_per_el(ENON, NG));
+  constexpr size_t smem = sizeof(double) * ((fg_tab_in_smem(ENON, NG) ? (size_t)NG * fg_tab_ld(ENON) : 0) + (size_t)EPB * fg_per_el(ENON, NG));
   static_assert(smem <= 227 * 1024, "element does not fit in shared memory");
   static bool configured = false;
   if (!configured) {

@@ -28,6 +28,7 @@ struct FluidGP {
   double u[3], up[3], rV[3], rM[3][3];
   double mu_x[3], d2u2[3];
   double up_c[3], mu_x_c[3], d2u2_c[3];
+  double es[6];      // strain rate es = ux + ux^T: 00, 11, 22, 01, 12, 02 (for FluidNodeC::expand)
 };
 constexpr int FLUID_GP_DOUBLES = sizeof(FluidGP) / sizeof(double);
 
@@ -35,6 +36,20 @@ struct FluidNode {
   double N, Nx[3], esNx[3], uNx, upNx, T1b, T1b_c;
 };
 constexpr int FLUID_NODE_DOUBLES = sizeof(FluidNode) / sizeof(double);
+
+// What the kernel keeps per (Gauss point, node) in shared memory: the part of a FluidNode that cannot be rebuilt from the Gauss-point
+// record (T1b / T1b_c contain the node's second derivatives); esNx, uNx, upNx are 15 FMAs from Nx and q.es, q.u, q.up.
+// 6 instead of 11 doubles: one more CTA per SM for HEX8, and 6 instead of 11 shared loads per block in phase B.
+struct FluidNodeC {
+  double N, Nx[3], T1b, T1b_c;
+};
+constexpr int FLUID_NODEC_DOUBLES = sizeof(FluidNodeC) / sizeof(double);
+
+SVB_HD void fluid_node_store(FluidNode& d, const FluidNode& s) { d = s; }
+SVB_HD void fluid_node_store(FluidNodeC& d, const FluidNode& s)
+{
+  d.N = s.N; d.Nx[0] = s.Nx[0]; d.Nx[1] = s.Nx[1]; d.Nx[2] = s.Nx[2]; d.T1b = s.T1b; d.T1b_c = s.T1b_c;
+}
 
 // nn::gnn, insd = 3: Nx[a][i], xiX[k][i] = d xi_k / d x_i, ks = xiX^T xiX, returns Jac.
 template <int ENON>
@@ -146,11 +161,11 @@ SVB_HD void second_derivative_terms(const double Nxx[][6], const double yl[][3],
 // Everything of fluid_3d_m / fluid_3d_c at one Gauss point that does not depend on the node pair.
 //   al/yl: nodal acceleration / velocity+pressure (al[a][0..2], yl[a][0..3]); ym: nodal mesh velocity or null;
 //   Nxx: physical second derivatives at THIS Gauss point, NxxL: those of the LAST Gauss point (continuity quirk).
-template <int ENON>
+template <int ENON, class NodeT = FluidNode>
 SVB_HD void fluid_gen_gauss_point(const FluidDmn& dm, double dt, double af, double am, double gam_t, double w, const double ks[3][3],
                                   const double N[], const double Nx[][3], const double Nxx[][6], const double NxxL[][6],
                                   const double al[][3], const double yl[][4], const double bfl[][3], const double (*ym)[3],
-                                  FluidGP& q, FluidNode nd[])
+                                  FluidGP& q, NodeT nd[])
 {
   const double ctM = 1.0, ctC = 36.0;
   const double rho = dm.rho, Kd = dm.Kd;
@@ -183,6 +198,7 @@ SVB_HD void fluid_gen_gauss_point(const FluidDmn& dm, double dt, double af, doub
   for (int i = 0; i < 3; i++)
 #pragma unroll
     for (int j = 0; j < 3; j++) es[i][j] = ux[i][j] + ux[j][i];
+  q.es[0] = es[0][0]; q.es[1] = es[1][1]; q.es[2] = es[2][2]; q.es[3] = es[0][1]; q.es[4] = es[1][2]; q.es[5] = es[0][2];
   double gam = 0.0;
 #pragma unroll
   for (int i = 0; i < 3; i++)
@@ -242,7 +258,7 @@ SVB_HD void fluid_gen_gauss_point(const FluidDmn& dm, double dt, double af, doub
   }
 #pragma unroll
   for (int a = 0; a < ENON; a++) {
-    FluidNode& n = nd[a];
+    FluidNode n;
     n.N = N[a];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
@@ -254,7 +270,22 @@ SVB_HD void fluid_gen_gauss_point(const FluidDmn& dm, double dt, double af, doub
     const double base = -rho * n.uNx - mu * Kd * N[a];
     n.T1b = base + mu * (Nxx[a][0] + Nxx[a][1] + Nxx[a][2]) + q.mu_x[0] * Nx[a][0] + q.mu_x[1] * Nx[a][1] + q.mu_x[2] * Nx[a][2];
     n.T1b_c = base + mu * (NxxL[a][0] + NxxL[a][1] + NxxL[a][2]) + q.mu_x_c[0] * Nx[a][0] + q.mu_x_c[1] * Nx[a][1] + q.mu_x_c[2] * Nx[a][2];
+    fluid_node_store(nd[a], n);
   }
+}
+
+// FluidNodeC -> FluidNode with the terms of the Gauss-point record (same expressions as above, same order of operations).
+SVB_HD FluidNode fluid_node_expand(const FluidGP& q, const FluidNodeC& c)
+{
+  FluidNode n;
+  n.N = c.N; n.Nx[0] = c.Nx[0]; n.Nx[1] = c.Nx[1]; n.Nx[2] = c.Nx[2]; n.T1b = c.T1b; n.T1b_c = c.T1b_c;
+  const double e00 = q.es[0], e11 = q.es[1], e22 = q.es[2], e01 = q.es[3], e12 = q.es[4], e02 = q.es[5];
+  n.esNx[0] = e00 * c.Nx[0] + e01 * c.Nx[1] + e02 * c.Nx[2];
+  n.esNx[1] = e01 * c.Nx[0] + e11 * c.Nx[1] + e12 * c.Nx[2];
+  n.esNx[2] = e02 * c.Nx[0] + e12 * c.Nx[1] + e22 * c.Nx[2];
+  n.uNx = q.u[0] * c.Nx[0] + q.u[1] * c.Nx[1] + q.u[2] * c.Nx[2];
+  n.upNx = q.up[0] * c.Nx[0] + q.up[1] * c.Nx[1] + q.up[2] * c.Nx[2];
+  return n;
 }
 
 // lR(0..3, a) += ... (fluid.cpp:2108-2111, 2228-2235, 1726-1729)
