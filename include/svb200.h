@@ -322,7 +322,10 @@ SVB200_API int svb200_commu_R(svb200_ctx* ctx);
 /* ustruct::ustruct_r (solver/ustruct.cpp:1742-1845, called from Integrator::step after commu(R), Integrator.cpp:135-137):
  * in the first Newton iteration of a time step (itr == 1, 1-based like eq.itr) R -= Kd (amg Ad - Yg(s..s+2)) / am with
  * amg = (gam - am)/(gam - 1); later iterations leave R unchanged.  Ad(3,nNo) is com_mod.Ad in INPUT node order; Kd is what the
- * last svb200_assemble(phys = USTRUCT) left on the device (download: SVB200_ARRAY_KD). */
+ * last svb200_assemble(phys = USTRUCT) left on the device (download: SVB200_ARRAY_KD).
+ * For an FSI equation with ustruct solids (eq->phys = SVB200_PHYS_FSI; fsi.cpp:243-262 fills Kd) only the nodes flagged by
+ * svb200_set_node_flags take part, as all_fun::is_domain(..., phys_ustruct) decides in the reference (:1776-1793): pass the
+ * membership in the ustruct domains there. */
 SVB200_API int svb200_ustruct_r(svb200_ctx* ctx, const svb200_eqparams* eq, int32_t itr, const double* Ad);
 /* com_mod.Ad(3,nNo) for the device-resident ustruct loop: uploaded once, then svb200_predictor scales it by (gam-1)/gam
  * (Integrator.cpp:627-628), svb200_ustruct_r(..., Ad = NULL) reads it and svb200_corrector(phys = USTRUCT) updates it together
@@ -342,10 +345,14 @@ SVB200_API int svb200_solve(svb200_ctx* ctx, int32_t dof, int32_t ls_type, int32
  * The time-integration state is solutions.old (Ao,Yo,Do) and solutions.current (An,Yn,Dn), each (tDof,nNo)
  * (Code/Source/solver/SolutionStates.h:15-43); the intermediate state is the one svb200_set_state uploads. */
 typedef enum { SVB200_SOL_OLD = 0, SVB200_SOL_CURRENT = 1, SVB200_SOL_INTERMEDIATE = 2 } svb200_sol;
+/* svb200_eqtime.reserved bit: com_mod.sstEq (read_files.cpp:1486) for an FSI equation, i.e. its solids are ustruct domains: the
+ * predictor / corrector then take the velocity-pressure branches (Integrator.cpp:626-630, 828-846) for the FSI rows, followed by the
+ * usual copy to the mesh rows (:887-912).  A ustruct equation (phys = SVB200_PHYS_USTRUCT) always takes them. */
+#define SVB200_EQTIME_SSTEQ 1
 typedef struct {
   int32_t s, e;      /* eq.s, eq.e: first and last state row of the equation (inclusive) */
   int32_t phys;      /* svb200_phys */
-  int32_t reserved;
+  int32_t reserved;  /* SVB200_EQTIME_* bits */
   double af, am, gam, beta;
 } svb200_eqtime;
 /* Upload / download one solution triple; NULL pointers are skipped. */

@@ -10,7 +10,12 @@ with the same fixtures in tests/test_gpu_genalpha.py.  Each line cites the state
 import numpy as np
 
 
-USTRUCT = 7   # svb200_phys
+USTRUCT, FSI = 7, 2   # svb200_phys
+
+
+def is_sst(q):
+    """com_mod.sstEq for this equation's update: a ustruct equation, or an FSI equation flagged SVB200_EQTIME_SSTEQ (ustruct solids)."""
+    return q.phys == USTRUCT or (q.phys == FSI and (q.reserved & 1))
 
 
 def predictor(eqs, dt, dFlag, Ao, Yo, Do, An, Yn, Dn, Ad=None):
@@ -20,7 +25,7 @@ def predictor(eqs, dt, dFlag, Ao, Yo, Do, An, Yn, Dn, Ad=None):
         coef = (q.gam - 1.0) / q.gam                      # :551
         An[r] = Ao[r] * coef                              # :555  eqn 87 of Bazilevs 2007
         Yn[r] = Yo[r]                                     # :616  eqn 86
-        if dFlag and q.phys == USTRUCT:
+        if dFlag and is_sst(q):
             Ad *= (q.gam - 1.0) / q.gam                   # :627-628
             Dn[r] = Do[r]                                 # :629
         elif dFlag:                                       # :618-623
@@ -54,8 +59,9 @@ def corrector(q, dt, R, An, Yn, Dn, mesh_s=-1, solid=None):
             X[mesh_s:mesh_s + 3, m] = X[0:3, m]           # :905-909
 
 
-def corrector_ustruct(q, dt, R, Rd, An, Yn, Dn, Ad):
-    """Integrator::corrector for a ustruct equation (sstEq), Integrator.cpp:812-815 (coefficients), :826-846."""
+def corrector_ustruct(q, dt, R, Rd, An, Yn, Dn, Ad, mesh_s=-1, solid=None):
+    """Integrator::corrector for a ustruct equation or an FSI equation with ustruct solids (sstEq), Integrator.cpp:812-815
+    (coefficients), :826-846, and the FSI copy :887-912."""
     c0, c2 = q.gam * dt, 1.0 / q.am
     c3 = q.af * c0 * c2
     r = slice(q.s, q.e + 1)
@@ -64,3 +70,7 @@ def corrector_ustruct(q, dt, R, Rd, An, Yn, Dn, Ad):
     dUl = Rd * c2 + R[:3] * c3                            # :837
     Ad -= dUl                                             # :838
     Dn[q.s:q.s + 3] = Dn[q.s:q.s + 3] - dUl * c0          # :839
+    if mesh_s >= 0 and solid is not None:
+        m = np.asarray(solid, bool)
+        for X in (An, Yn, Dn):
+            X[mesh_s:mesh_s + 3, m] = X[0:3, m]           # :905-909

@@ -457,6 +457,7 @@ int svref_alloc(void* h, int dof)
     cm.Val.resize(dof*dof, cm.lhs.nnz);
     cm.R = 0.0;
     cm.Val = 0.0;
+    if (cm.Kd.size() != 0) cm.Kd = 0.0;          // Integrator.cpp:106-109
     // Integrator::initiator zeroes the prestress accumulators once per Newton iteration (Integrator.cpp:745-748)
     if (cm.pSa.size() != 0) { cm.pSn = 0.0; cm.pSa = 0.0; }
   });
@@ -551,7 +552,17 @@ int svref_assemble(void* h, int iM, const svb200_eqparams* e, const svb200_dmnpa
     switch (e->phys) {
       case SVB200_PHYS_FLUID: fluid::construct_fluid(cm, m, c.sol); break;
       case SVB200_PHYS_STRUCT: struct_ns::construct_dsolid(cm, c.cep_mod, m, c.sol); break;
-      case SVB200_PHYS_FSI: fsi::construct_fsi(cm, c.cep_mod, m, c.sol); break;
+      case SVB200_PHYS_FSI: {
+        // FSI with velocity-pressure solids (com_mod.sstEq, fsi.cpp:243-262): Kd as initialize.cpp:668-670 sizes it; it is zeroed
+        // once per Newton iteration (Integrator.cpp:106-109), here by svref_alloc, so that the meshes of one equation add up
+        bool ust = false;
+        for (int d = 0; d < nDmn; d++) ust |= (dmn[d].phys == SVB200_PHYS_USTRUCT);
+        if (ust) {
+          if (cm.Kd.nrows() != 12 || cm.Kd.ncols() != cm.lhs.nnz) { cm.Kd.resize(12, cm.lhs.nnz); cm.Kd = 0.0; }
+          if (cm.idMap.size() != cm.tnNo) { cm.idMap.resize(cm.tnNo); for (int a = 0; a < cm.tnNo; a++) cm.idMap(a) = a; }
+        }
+        fsi::construct_fsi(cm, c.cep_mod, m, c.sol);
+      } break;
       case SVB200_PHYS_MESH: mesh::construct_mesh(cm, c.cep_mod, m, c.sol); break;
       case SVB200_PHYS_LELAS: l_elas::construct_l_elas(cm, m, c.sol); break;
       case SVB200_PHYS_HEATS: heats::construct_heats(cm, m, c.sol); break;
@@ -767,14 +778,22 @@ int svref_ustruct_r(void* h, int itr, const double* Ad)
     cm.Rd.resize(3, n);
     cm.Rd = 0.0;
     cm.eq[0].itr = itr;
+    // all_fun::is_domain (solver/all_fun.cpp:1059-1089) with a single domain needs nothing else; with several (FSI) it reads
+    // com_mod.dmnId, built from the element domain ids as read_msh.cpp:1504-1519 does.  rowPtr/colPtr: svref_build_graph
+    if (cm.eq[0].nDmn > 1) {
+      cm.dmnId.resize(n);
+      for (int a = 0; a < n; a++) cm.dmnId(a) = 0;
+      for (auto& m : cm.msh)
+        if (m.eId.size() != 0)
+          for (int e = 0; e < m.nEl; e++)
+            for (int a = 0; a < m.eNoN; a++) cm.dmnId(m.IEN(a, e)) |= m.eId(e);
+    }
     if (c.backend) {
       // the patch of Integrator::step: the plug-in runs ustruct_r on the device-resident R and Kd
       if (!c.backend_ustruct_r) throw std::runtime_error("[ref_harness] backend without ustruct_r hook");
       c.backend_ustruct_r(c.backend, &cm);
       return;
     }
-    // all_fun::is_domain (solver/all_fun.cpp) with a single domain needs nothing else; rowPtr/colPtr were set by
-    // svref_build_graph
     ustruct::ustruct_r(cm, c.sol);
   });
 }

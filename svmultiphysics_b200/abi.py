@@ -97,9 +97,12 @@ def gen_alpha(rho_inf: float):
     return af, am, gam, beta
 
 
-def eq_time(s: int, e: int, phys: int, rho_inf: float = 0.5) -> EqTime:
+EQTIME_SSTEQ = 1     # com_mod.sstEq for an FSI equation (its solids are ustruct domains)
+
+
+def eq_time(s: int, e: int, phys: int, rho_inf: float = 0.5, sstEq: bool = False) -> EqTime:
     af, am, gam, beta = gen_alpha(rho_inf)
-    return EqTime(s=s, e=e, phys=phys, af=af, am=am, gam=gam, beta=beta)
+    return EqTime(s=s, e=e, phys=phys, reserved=EQTIME_SSTEQ if sstEq else 0, af=af, am=am, gam=gam, beta=beta)
 
 
 EQ_GENERAL_KERNEL = 1

@@ -575,22 +575,24 @@ int run_assemble_ustruct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* 
 // Rd = amg Ad - Yg(s..s+2);  KU = Kd Rd (4x3 blocks);  halo sum;  R -= KU / am.   Only in the first Newton iteration.
 __global__ void __launch_bounds__(256)
 ustruct_rd_kernel(int nNo, int tDof, int s, double amg, const double* __restrict__ Ad, const double* __restrict__ Yg,
-                  double* __restrict__ Rd)
+                  const int* __restrict__ flag, double* __restrict__ Rd)
 {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= 3 * nNo) return;
   const int n = t / 3, i = t % 3;
-  Rd[t] = amg * Ad[t] - Yg[(size_t)tDof * n + s + i];
+  // FSI: nodes outside the ustruct domains keep the zero Integrator::step wrote (Integrator.cpp:106-109)
+  Rd[t] = (flag && !flag[n]) ? 0.0 : amg * Ad[t] - Yg[(size_t)tDof * n + s + i];
 }
 
 __global__ void __launch_bounds__(256)
 ustruct_kd_spmv_kernel(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ colPtr, const double* __restrict__ Kd,
-                       const double* __restrict__ Rd, double* __restrict__ KU)
+                       const double* __restrict__ Rd, const int* __restrict__ flag, double* __restrict__ KU)
 {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)nNo * 4) return;
   const int row = (int)(t >> 2), i = (int)(t & 3);
   double acc = 0.0;
+  if (flag && !flag[row]) { KU[t] = 0.0; return; }
   for (int k = rowPtr[row]; k < rowPtr[row + 1]; k++) {
     const double* v = Kd + (size_t)k * 12 + 3 * i;
     const double* u = Rd + (size_t)colPtr[k] * 3;
@@ -619,8 +621,9 @@ int run_ustruct_r(svb200_ctx* ctx, const svb200_eqparams* eq, int itr, const dou
   SVB_CUDA(cudaMalloc(&KU, sizeof(double) * 4 * (size_t)n));
   double* Rd = ctx->d_Rd;
   const double amg = (eq->gam - eq->am) / (eq->gam - 1.0), ami = 1.0 / eq->am;
-  ustruct_rd_kernel<<<(3 * n + 255) / 256, 256, 0, ctx->stream>>>(n, ctx->tDof, eq->s, amg, d_Ad, ctx->d_Yg, Rd);
-  ustruct_kd_spmv_kernel<<<(unsigned)(((long long)n * 4 + 255) / 256), 256, 0, ctx->stream>>>(n, ctx->d_rowPtr, ctx->d_colPtr, ctx->d_Kd, Rd, KU);
+  const int* flag = (eq->phys == SVB200_PHYS_FSI) ? ctx->d_nodeflag : nullptr;     // is_domain(..., phys_ustruct) of an FSI equation
+  ustruct_rd_kernel<<<(3 * n + 255) / 256, 256, 0, ctx->stream>>>(n, ctx->tDof, eq->s, amg, d_Ad, ctx->d_Yg, flag, Rd);
+  ustruct_kd_spmv_kernel<<<(unsigned)(((long long)n * 4 + 255) / 256), 256, 0, ctx->stream>>>(n, ctx->d_rowPtr, ctx->d_colPtr, ctx->d_Kd, Rd, flag, KU);
   ctx->launches += 2;
   int rc = halo_sum(ctx, 4, KU);
   if (!rc) {

@@ -13,6 +13,7 @@ namespace svb {
 struct TimeEqs {
   int nEq;
   int s[8], e[8], phys[8];
+  int sst[8];        // velocity-pressure solid update (com_mod.sstEq): a ustruct equation, or an FSI equation with SVB200_EQTIME_SSTEQ
   double af[8], am[8], gam[8], beta[8];
 };
 
@@ -37,8 +38,9 @@ __global__ void predictor_kernel(int tDof, long long n, const __grid_constant__ 
   const double yn = Yo[t];
   An[t] = an;
   Yn[t] = yn;
-  // ustruct (sstEq, Integrator.cpp:626-630): the displacement rows are integrated through Ad by the corrector, Dn = Do here
-  if (dFlag && Q.phys[q] != SVB200_PHYS_USTRUCT) {
+  // ustruct / FSI with ustruct solids (sstEq, Integrator.cpp:626-630): the displacement rows are integrated through Ad by the
+  // corrector, Dn = Do here; the mesh equation of such an FSI case keeps the usual update (:632-635)
+  if (dFlag && !Q.sst[q]) {
     const double cD = dt * dt * (0.5 * Q.gam[q] - Q.beta[q]) / (Q.gam[q] - 1.0);
     Dn[t] = __dadd_rn(__dadd_rn(Do[t], __dmul_rn(yn, dt)), __dmul_rn(an, cD));
   } else {
@@ -173,6 +175,7 @@ static int fill(const svb200_eqtime* eqs, int nEq, TimeEqs& Q)
   Q.nEq = nEq;
   for (int i = 0; i < nEq; i++) {
     Q.s[i] = eqs[i].s; Q.e[i] = eqs[i].e; Q.phys[i] = eqs[i].phys;
+    Q.sst[i] = eqtime_is_sst(eqs[i]);
     Q.af[i] = eqs[i].af; Q.am[i] = eqs[i].am; Q.gam[i] = eqs[i].gam; Q.beta[i] = eqs[i].beta;
     SVB_REQUIRE(eqs[i].s >= 0 && eqs[i].e >= eqs[i].s, "gen-alpha: bad equation row range");
   }
@@ -193,7 +196,7 @@ int launch_predictor(svb200_ctx* ctx, int nEq, const svb200_eqtime* eqs, double 
   ctx->launches++;
   if (dFlag && ctx->d_Ad)
     for (int i = 0; i < nEq; i++)
-      if (eqs[i].phys == SVB200_PHYS_USTRUCT) {          // Ad = Ad (gam-1)/gam, Integrator.cpp:627-628
+      if (eqtime_is_sst(eqs[i])) {                       // Ad = Ad (gam-1)/gam, Integrator.cpp:627-628
         const long long m = 3LL * ctx->nNo;
         scale_kernel<<<nblk(m), 256, 0, ctx->stream>>>(m, (eqs[i].gam - 1.0) / eqs[i].gam, ctx->d_Ad);
         ctx->launches++;
@@ -222,16 +225,15 @@ int launch_corrector(svb200_ctx* ctx, const svb200_eqtime* eq, double dt, int me
   const long long n = (long long)ctx->nNo * nrow;
   if (n == 0) return SVB200_OK;
   const double c0 = eq->gam * dt, c1 = eq->beta * dt * dt;
-  if (eq->phys == SVB200_PHYS_USTRUCT) {
+  if (eqtime_is_sst(*eq)) {
+    // Integrator.cpp:828-846, the same update for a ustruct equation and for an FSI equation with ustruct solids (all nodes)
     const double c2 = 1.0 / eq->am, c3 = eq->af * c0 * c2;
     corrector_ustruct_kernel<<<nblk((long long)ctx->nNo * 4), 256, 0, ctx->stream>>>(ctx->tDof, eq->s, ctx->nNo, c0, c2, c3, ctx->d_R,
                                                                                       ctx->d_Rd, ctx->d_An, ctx->d_Yn, ctx->d_Dn, ctx->d_Ad);
-    ctx->launches++;
-    SVB_CUDA(cudaGetLastError());
-    return SVB200_OK;
+  } else {
+    corrector_kernel<<<nblk(n), 256, 0, ctx->stream>>>(ctx->tDof, ctx->dof, eq->s, nrow, ctx->nNo, c0, c1, ctx->d_R, ctx->d_An,
+                                                       ctx->d_Yn, ctx->d_Dn);
   }
-  corrector_kernel<<<nblk(n), 256, 0, ctx->stream>>>(ctx->tDof, ctx->dof, eq->s, nrow, ctx->nNo, c0, c1, ctx->d_R, ctx->d_An,
-                                                     ctx->d_Yn, ctx->d_Dn);
   ctx->launches++;
   if (mesh_s >= 0 && d_flag) {
     const long long m = (long long)ctx->nNo * 3;

@@ -920,7 +920,7 @@ int svb200_corrector(svb200_ctx* ctx, const svb200_eqtime* eq, double dt, int32_
               "svb200_corrector: equation rows do not match the dof of the solved system");
   SVB_REQUIRE(mesh_s < 0 || (mesh_s + 3 <= ctx->tDof && ctx->d_nodeflag), "svb200_corrector: FSI copy needs svb200_set_node_flags");
   TRY(ensure_solution_arrays(ctx));
-  if (eq->phys == SVB200_PHYS_USTRUCT) {
+  if (eqtime_is_sst(*eq)) {
     SVB_REQUIRE(ctx->dof == 4 && ctx->d_Ad, "svb200_corrector: the ustruct update needs Ad (svb200_set_ad)");
     if (!ctx->d_Rd) {                       // ustruct_r was not called: Rd = 0 like Integrator.cpp:106-108
       SVB_CUDA(cudaMalloc(&ctx->d_Rd, sizeof(double) * 3 * std::max<size_t>((size_t)ctx->nNo, 1)));
@@ -1024,15 +1024,16 @@ int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, cons
     case SVB200_PHYS_FSI: {
       // fsi::construct_fsi (fsi.cpp:24-362): per-element domain switch; fluid elements on the moved mesh
       // (ALE), solid elements through struct_3d writing the 3x3 part of the 4x4 blocks.
-      bool anyFluid = false, anySolid = false;
+      bool anyFluid = false, anySolid = false, anyUstruct = false;
       for (int d = 0; d < nDmn; d++) {
         anyFluid |= (dmn[d].phys == SVB200_PHYS_FLUID);
         anySolid |= (dmn[d].phys == SVB200_PHYS_STRUCT);
-        // construct_fsi sends ustruct solids through ustruct_3d_m/c (fsi.cpp:243-262) and has no branch for anything else
-        // (a lElas domain assembles nothing there): neither is built here, so such a domain must not be skipped silently
-        if (dmn[d].phys != SVB200_PHYS_FLUID && dmn[d].phys != SVB200_PHYS_STRUCT) {
-          set_error("svb200_assemble: an FSI equation with a domain that is neither fluid nor struct (e.g. a ustruct solid) is not "
-                    "implemented on the device");
+        anyUstruct |= (dmn[d].phys == SVB200_PHYS_USTRUCT);
+        // construct_fsi has branches for fluid, struct and ustruct domains (fsi.cpp:203-262) and throws for lElas (:236);
+        // any other domain would be skipped silently there, here it is an error
+        if (dmn[d].phys != SVB200_PHYS_FLUID && dmn[d].phys != SVB200_PHYS_STRUCT && dmn[d].phys != SVB200_PHYS_USTRUCT) {
+          set_error("svb200_assemble: an FSI equation with a domain that is neither fluid, struct nor ustruct "
+                    "([construct_fsi] LELAS3D not implemented)");
           return SVB200_ERR_UNSUPPORTED;
         }
         if (dmn[d].Id == -1) break;
@@ -1044,6 +1045,9 @@ int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, cons
       }
       TRY(flush_val_zero(ctx));
       if (anySolid) TRY(run_assemble_struct(ctx, m, eq, dmn, nDmn));
+      // velocity-pressure solid inside FSI (fsi.cpp:243-262, 318-322, 343-346): ustruct_3d_m / ustruct_3d_c / ustruct_do_assem
+      // on the reference configuration with the displacement rows eq.s..eq.s+2 of the tDof = 7 state; fills Kd as well
+      if (anyUstruct) TRY(run_assemble_ustruct(ctx, m, eq, dmn, nDmn));
     } break;
     case SVB200_PHYS_MESH:
     case SVB200_PHYS_LELAS:
@@ -1341,7 +1345,9 @@ int svb200_ustruct_r(svb200_ctx* ctx, const svb200_eqparams* eq, int32_t itr, co
   CTX_GUARD(ctx);
   SVB_REQUIRE(eq, "svb200_ustruct_r: null parameters");
   SVB_REQUIRE(Ad || ctx->d_Ad, "svb200_ustruct_r: no Ad (pass it, or svb200_set_ad once for the device-resident loop)");
-  SVB_REQUIRE(eq->phys == SVB200_PHYS_USTRUCT, "svb200_ustruct_r: the equation is not ustruct");
+  SVB_REQUIRE(eq->phys == SVB200_PHYS_USTRUCT || eq->phys == SVB200_PHYS_FSI, "svb200_ustruct_r: the equation is neither ustruct nor FSI");
+  // FSI (sstEq): only nodes of a ustruct domain take part (all_fun::is_domain, ustruct.cpp:1776-1779, 1791-1793)
+  SVB_REQUIRE(eq->phys != SVB200_PHYS_FSI || ctx->d_nodeflag, "svb200_ustruct_r: an FSI equation needs the solid-node flags (svb200_set_node_flags)");
   SVB_REQUIRE(ctx->dof == 4 && ctx->d_R && ctx->d_Kd && ctx->d_Yg, "svb200_ustruct_r: assemble the ustruct equation first");
   SVB_REQUIRE(eq->tDof == ctx->tDof && eq->s >= 0 && eq->s + 4 <= eq->tDof, "svb200_ustruct_r: tDof / eq.s mismatch");
   if (Ad) TRY(upload_nodal(ctx, 3, Ad, &ctx->d_Ad));

@@ -259,6 +259,11 @@ int run_assemble_struct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* e
 int run_assemble_mesh(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);
 // assemble_ustruct.cu
 int run_assemble_ustruct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);
+// com_mod.sstEq for this equation's gen-alpha update: a ustruct equation, or an FSI equation whose solids are ustruct
+static inline bool eqtime_is_sst(const svb200_eqtime& q)
+{
+  return q.phys == SVB200_PHYS_USTRUCT || (q.phys == SVB200_PHYS_FSI && (q.reserved & SVB200_EQTIME_SSTEQ));
+}
 int run_ustruct_r(svb200_ctx* ctx, const svb200_eqparams* eq, int itr, const double* d_Ad);
 // assemble_heat.cu
 int run_assemble_heat(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);

@@ -349,6 +349,12 @@ class Engine:
         self._call("svb200_download", C.c_int32(abi.ARRAY_KD), _d(K))
         return K
 
+    def get_Rd(self):
+        """com_mod.Rd(3, nNo) as the last ustruct_r left it."""
+        Rd = np.zeros((3, self.nNo), order="F")
+        self._call("svb200_download", C.c_int32(abi.ARRAY_RD), _d(Rd))
+        return Rd
+
     def ustruct_r(self, eq: abi.EqParams, itr, Ad=None):
         """Ad = None: use the device-resident Ad (set_ad / predictor / corrector keep it)."""
         self._call("svb200_ustruct_r", C.byref(eq), C.c_int32(itr), _d(_f64(Ad)) if Ad is not None else None)

@@ -153,12 +153,12 @@ bool global_eq_assem(ComMod& com_mod, CepMod& cep_mod, const mshType& lM, const 
   if (!la) return false;
   if (to_phys(eq.phys) < 0) return false;          // stokes, shells, CEP, ... stay on the host loop (and its assemble())
   if (eq.phys == consts::EquationType::phys_FSI) {
-    // construct_fsi with ustruct solids (fsi.cpp:243-262) is not built on the device: fail loudly instead of assembling
-    // a system without the solid's stiffness and residual
+    // construct_fsi assembles fluid, struct and ustruct domains (fsi.cpp:203-262) and throws for lElas (:236); any other domain is
+    // skipped there.  Fail loudly instead of assembling a system without such a domain's stiffness and residual.
     for (int d = 0; d < eq.nDmn; d++) {
       const auto ph = eq.dmn[d].phys;
-      if (ph != consts::EquationType::phys_fluid && ph != consts::EquationType::phys_struct)
-        throw std::runtime_error("[B200LinearAlgebra] FSI with a solid domain that is not 'struct' (ustruct / lElas) is not "
+      if (ph != consts::EquationType::phys_fluid && ph != consts::EquationType::phys_struct && ph != consts::EquationType::phys_ustruct)
+        throw std::runtime_error("[B200LinearAlgebra] FSI with a domain that is neither fluid, struct nor ustruct is not "
                                  "implemented on the device; use the fsils linear algebra for this equation");
     }
   }
@@ -382,8 +382,20 @@ void B200LinearAlgebra::set_active_tension(const CepMod& cep_mod)
 void B200LinearAlgebra::ustruct_r(ComMod& com_mod)
 {
   auto& eq = com_mod.eq[com_mod.cEq];
-  if (eq.phys != consts::EquationType::phys_ustruct) return;        // FSI with ustruct solids is not on the device path
+  if (eq.phys != consts::EquationType::phys_ustruct && eq.phys != consts::EquationType::phys_FSI) return;     // ustruct.cpp:1755-1757
   flush_host_contrib(alloc_dof);
+  if (eq.phys == consts::EquationType::phys_FSI) {
+    // only the nodes of a ustruct domain take part (all_fun::is_domain, ustruct.cpp:1776-1793)
+    // all_fun.cpp:1059-1089: one domain -> its physics decides; several -> bit dmn.Id of com_mod.dmnId(node)
+    std::vector<int32_t> flag(com_mod.tnNo, 0);
+    if (eq.nDmn > 1 && com_mod.dmnId.size() == 0) throw std::runtime_error("Domain partitioning info is not provided.");
+    for (int a = 0; a < com_mod.tnNo; a++)
+      for (int d = 0; d < eq.nDmn; d++) {
+        if (eq.dmn[d].phys != consts::EquationType::phys_ustruct) continue;
+        if (eq.nDmn == 1 || ((com_mod.dmnId(a) >> eq.dmn[d].Id) & 1)) { flag[a] = 1; break; }
+      }
+    check(svb200_set_node_flags(ctx, flag.data()));
+  }
   svb200_eqparams e = b200::eq_params(com_mod, eq, com_mod.msh[0], scatter);
   check(svb200_ustruct_r(ctx, &e, eq.itr, com_mod.Ad.data()));
 }

@@ -330,6 +330,36 @@ def ustruct_Ad(m, seed=29):
     return np.asfortranarray(0.05 * np.random.default_rng(seed).standard_normal((3, m.nNo)))
 
 
+# ---- FSI with velocity-pressure (ustruct) solids: construct_fsi's ustruct_3d_m/c branch (fsi.cpp:243-262, tests/cases/fsi_ustruct) ----
+FSI_USTRUCT_CASES = {
+    "nHK_ST91": (dict(E=1.0e6, nu=0.45, Kpen=1.0e6 / (3 * (1 - 0.9)), rho=1.2, ctau_M=1e-3, ctau_C=1e-3, f=(0.1, -0.2, 0.3)), 0),
+    "HO_ma_fibres_visc": (dict(isoType=abi.ISO_HO_MA, st_a=590.0, st_b=8.023, aff=184720.0, bff=16.026, ass=24810.0, bss=11.12,
+                               afs=2160.0, bfs=11.436, khs=100.0, E=1.0e5, nu=0.483333, Kpen=1e6, rho=1.0, ctau_M=1e-5, ctau_C=1e-5,
+                               solid_visc=abi.SOLID_VISC_NEWTONIAN, solid_visc_mu=3.0e4), 2),
+}
+
+
+def fsi_ustruct_case(name, scatter=abi.SCATTER_ATOMIC):
+    """(mesh, Ag, Yg, Dg, Bf, fN, nFn, eq, domains, Ad, ustruct-node flags): the pipe of fsi_case with a ustruct wall; the solid
+    nodes carry a pressure of the size the ustruct cases use."""
+    dkw, nFn = FSI_USTRUCT_CASES[name]
+    m, Ag, Yg, Dg, Bf = fsi_case()
+    rng = np.random.default_rng(37)
+    solid_nodes = np.unique(m.IEN[:, (m.eId & 2) != 0])
+    flags = np.zeros(m.nNo, np.int32); flags[solid_nodes] = 1
+    Yg[3, solid_nodes] = 1.0e3 * (1.0 + 0.3 * rng.standard_normal(len(solid_nodes)))
+    fN = None
+    if nFn:
+        f = rng.standard_normal((3, m.nEl)); f /= np.linalg.norm(f, axis=0)
+        t = rng.standard_normal((3, m.nEl)); t -= (t * f).sum(0) * f; t /= np.linalg.norm(t, axis=0)
+        fN = np.asfortranarray(np.vstack([f, t]))
+    af, am, gam, beta = abi.gen_alpha(0.5)
+    eq = abi.EqParams(dt=1e-3, af=af, am=am, gam=gam, beta=beta, phys=abi.PHYS_FSI, dof=4, tDof=7, s=0, mvMsh=1, vmsStab=1,
+                      scatter=scatter, reserved=0)
+    dmn = [abi.fluid_domain(rho=1.0, mu=0.04, Id=0), abi.ustruct_domain(Id=1, **dkw)]
+    return m, Ag, Yg, Dg, Bf, fN, nFn, eq, dmn, ustruct_Ad(m), flags
+
+
 # ---- l_elas_3d on TET4: linear-elasticity equation and mesh-motion equation ------------------------------------------
 LELAS_CASES = ["lelas_tet4", "mesh_tet4"]
 

@@ -54,6 +54,15 @@ def scenarios():
         bcs=[dict(iEq=0, nodes=wall, eDrn=(0, 0, 0), impD=False, g=0.8, gx=rng.standard_normal(len(wall)), nV=unit(len(wall))),
              dict(iEq=0, nodes=inlet, eDrn=(0, 1, 0), impD=True, g=-0.6, gx=rng.standard_normal(len(inlet)), nV=unit(len(inlet)))],
         R=np.asfortranarray(rng.standard_normal((4, nNo))), Rd=np.asfortranarray(rng.standard_normal((3, nNo))))
+    # FSI with ustruct solids (tests/cases/fsi_ustruct): com_mod.sstEq routes the FSI rows through the velocity-pressure branches of
+    # the predictor / set_bc_dir / corrector (Integrator.cpp:626-630, 828-846, set_bc.cpp:1062), the mesh equation keeps its own
+    out["fsi_ustruct"] = dict(
+        mesh=m, tDof=7, dFlag=1, sstEq=1, solid_phys=abi.PHYS_USTRUCT,
+        eqs=[abi.eq_time(0, 3, abi.PHYS_FSI, 0.5, sstEq=True), abi.eq_time(4, 6, abi.PHYS_MESH, 0.2)],
+        states=states(7), Ad=np.asfortranarray(rng.standard_normal((3, nNo))), solid=solid,
+        bcs=[dict(iEq=0, nodes=wall, eDrn=(0, 0, 0), impD=False, g=1.1, gx=rng.standard_normal(len(wall)), nV=unit(len(wall))),
+             dict(iEq=0, nodes=inlet, eDrn=(1, 1, 0), impD=True, g=-0.4, gx=rng.standard_normal(len(inlet)), nV=unit(len(inlet)))],
+        R=np.asfortranarray(rng.standard_normal((4, nNo))), Rd=np.asfortranarray(rng.standard_normal((3, nNo))))
     return out
 
 
@@ -79,7 +88,7 @@ def run_reference(s):
     g.set_bc_dir(); snap("set_bc_dir")
     g.initiator(0); snap("initiator", abi.SOL_INTERMEDIATE)
     if s["solid"] is not None:
-        g.set_solid_nodes(0, abi.PHYS_STRUCT, s["solid"])
+        g.set_solid_nodes(0, s.get("solid_phys", abi.PHYS_STRUCT), s["solid"])
     g.corrector(0, s["R"], s["Rd"]); snap("corrector")
     g.close()
     return out
@@ -120,7 +129,7 @@ def run_engine(s):
                 eng.set_dirichlet_rows(q.s + i, b["nodes"], valY=va, valD=vy)      # Yn = tmpA, Dn = tmpY (set_bc.cpp:1004-1016)
             else:
                 eng.set_dirichlet_rows(q.s + i, b["nodes"], valA=va, valY=vy)
-        if q.phys == abi.PHYS_USTRUCT:
+        if q.phys == abi.PHYS_USTRUCT or (q.phys == abi.PHYS_FSI and s["sstEq"]):      # set_bc.cpp:1062
             eng.dirichlet_ustruct(q, DT, b["nodes"], dir_mask=sum(1 << i for i in rows), impD=b["impD"])
     snap("set_bc_dir")
     eng.initiator(eqs); snap("initiator", abi.SOL_INTERMEDIATE)

@@ -163,6 +163,25 @@ def ustruct_golden():
     print("wrote ustruct.npz with", len(out), "arrays")
 
 
+def fsi_ustruct_golden():
+    """construct_fsi with a ustruct wall (fsi.cpp:243-262): R / Val / Kd, and R after ustruct_r (nodes of the ustruct domain only)."""
+    out = {}
+    for name in common.FSI_USTRUCT_CASES:
+        m, Ag, Yg, Dg, Bf, fN, nFn, eq, dmn, Ad, flags = common.fsi_ustruct_case(name)
+        c = RefCase(); c.set_coords(m.x); c.add_mesh(m.IEN, eId=m.eId, nFn=nFn, fN=fN)
+        rowPtr, colPtr = c.build_graph(0)
+        c.alloc(4); c.set_state(Ag, Yg, Dg, Bf); c.assemble(0, eq, dmn)
+        out[f"{name}/R"], out[f"{name}/Val"], out[f"{name}/Kd"] = c.get_R(), c.get_Val(), c.get_Kd()
+        out[f"{name}/rowPtr"], out[f"{name}/colPtr"] = rowPtr, colPtr
+        c.ustruct_r(1, Ad)
+        out[f"{name}/R_after_ustruct_r"] = c.get_R()
+        fl = np.where(flags == 0)[0]
+        assert np.abs(out[f"{name}/Kd"]).max() > 0 and common.rel_err(out[f"{name}/R_after_ustruct_r"], out[f"{name}/R"]) > 1e-6
+        assert np.array_equal(out[f"{name}/R_after_ustruct_r"][:, fl], out[f"{name}/R"][:, fl])     # fluid-only rows untouched
+    np.savez_compressed(os.path.join(HERE, "fsi_ustruct.npz"), **out)
+    print("wrote fsi_ustruct.npz with", len(out), "arrays")
+
+
 def lelas_golden():
     """R / Val of l_elas_3d on TET4: the linear-elasticity equation and the mesh-motion equation (tDof = 7, old displacement)."""
     out = {}
@@ -205,6 +224,6 @@ if __name__ == "__main__":
     if not have_ref():
         raise SystemExit("oracle/_ref/libsvref.so is missing: run `make -C oracle ref` first")
     only = sys.argv[1:]
-    for fn in (fluid_golden, struct_golden, fluid_gen_golden, fluid_hi_golden, struct_hi_golden, heat_golden, ustruct_golden, lelas_golden, prestress_golden):
+    for fn in (fluid_golden, struct_golden, fluid_gen_golden, fluid_hi_golden, struct_hi_golden, heat_golden, ustruct_golden, lelas_golden, prestress_golden, fsi_ustruct_golden):
         if not only or fn.__name__.replace("_golden", "") in only:
             fn()

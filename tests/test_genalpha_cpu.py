@@ -9,7 +9,7 @@ from tests import common
 from tests import genalpha_scenarios as gs
 
 
-@pytest.mark.parametrize("name", ["fsi_mesh", "fluid", "ustruct"])
+@pytest.mark.parametrize("name", ["fsi_mesh", "fluid", "ustruct", "fsi_ustruct"])
 def test_golden_is_the_compiled_reference(name):
     from oracle import refbind
     if not refbind.have_ref():
@@ -22,7 +22,7 @@ def test_golden_is_the_compiled_reference(name):
         assert np.array_equal(live[k[len(name) + 1:]], golden[k]), k
 
 
-@pytest.mark.parametrize("name", ["fsi_mesh", "fluid", "ustruct"])
+@pytest.mark.parametrize("name", ["fsi_mesh", "fluid", "ustruct", "fsi_ustruct"])
 def test_numpy_restatement_matches_golden(name):
     from oracle import genalpha_oracle as go
     golden = common.load_golden("genalpha.npz")
@@ -44,8 +44,8 @@ def test_numpy_restatement_matches_golden(name):
     for nm, a in zip("AYD", (Ag, Yg, Dg)):
         r = slice(eqs[0].s, eqs[-1].e + 1)
         assert np.array_equal(a[r], golden[f"{name}/initiator/{nm}"][r])
-    if eqs[0].phys == abi.PHYS_USTRUCT:
-        go.corrector_ustruct(eqs[0], gs.DT, s["R"], s["Rd"], An, Yn, Dn, Ad)
+    if go.is_sst(eqs[0]):
+        go.corrector_ustruct(eqs[0], gs.DT, s["R"], s["Rd"], An, Yn, Dn, Ad, mesh_s=4 if s["solid"] is not None else -1, solid=s["solid"])
         assert np.array_equal(Ad, golden[f"{name}/corrector/Ad"])
     else:
         go.corrector(eqs[0], gs.DT, s["R"], An, Yn, Dn, mesh_s=4 if s["solid"] is not None else -1, solid=s["solid"])

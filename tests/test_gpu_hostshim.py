@@ -218,6 +218,37 @@ def test_ustruct_through_cpp_plugin():
     _close(cpu, gpu)
 
 
+def test_fsi_ustruct_through_cpp_plugin():
+    """FSI with a ustruct wall (tests/cases/fsi_ustruct): b200::global_eq_assem hands construct_fsi's fluid + ustruct domains to the
+    device, and B200LinearAlgebra::ustruct_r restricts the displacement-residual update to the nodes all_fun::is_domain puts in the
+    ustruct domain (com_mod.dmnId)."""
+    name = "HO_ma_fibres_visc"
+    m, Ag, Yg, Dg, Bf, fN, nFn, eq, dmn, Ad, flags = common.fsi_ustruct_case(name)
+    faces = common.dirichlet_faces(m)
+    cpu, gpu = _pair(m, nFaces=len(faces), eId=m.eId, nFn=nFn, fN=fN)
+    ls = abi.ls_params(abi.LS_GMRES, mItr=4, sD=150, relTol=1e-6)
+    res = []
+    for c in (cpu, gpu):
+        for i, (g, nodes, v) in enumerate(faces):
+            c.set_face(i, g, nodes, v)
+        c.alloc(4); c.set_state(Ag, Yg, Dg, Bf); c.assemble(0, eq, dmn)
+        R, V, K = c.get_R(), c.get_Val(), c.get_Kd()
+        c.ustruct_r(1, Ad)
+        R2 = c.get_R()
+        X, o, _ = c.solve(4, abi.LS_GMRES, ls, np.ones(len(faces), np.int32), np.zeros(len(faces)))
+        res.append((R, V, K, R2, X, o))
+    (R0, V0, K0, R20, X0, o0), (R1, V1, K1, R21, X1, o1) = res
+    assert common.rel_err(K1, K0) < 1e-12
+    solid, fluid_only = np.where(flags != 0)[0], np.where(flags == 0)[0]
+    for nodes in (solid, fluid_only):
+        assert common.rel_err(R1[:, nodes], R0[:, nodes]) < 1e-12 and common.rel_err(R21[:, nodes], R20[:, nodes]) < 1e-12
+    assert np.array_equal(R21[:, fluid_only], R1[:, fluid_only]) and not np.array_equal(R21[:, solid], R1[:, solid])
+    assert common.rel_err(V1, V0) < 1e-12
+    assert o1.RI.success == o0.RI.success and abs(o1.RI.iNorm - o0.RI.iNorm) <= 1e-10 * o0.RI.iNorm
+    assert common.rel_err(X1, X0) < 1e-4
+    _close(cpu, gpu)
+
+
 def test_prestress_equation_through_cpp_plugin():
     """com_mod.pS0 and pstEq through B200LinearAlgebra: the plug-in uploads pS0, flags the prestress equation and writes the
     device accumulators back into com_mod.pSn / pSa (what Integrator::corrector then communicates and divides)."""

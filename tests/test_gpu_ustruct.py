@@ -168,3 +168,92 @@ def test_ustruct_device_resident_newton_loop():
     A1, Y1, D1 = eng.get_solution(abi.SOL_CURRENT)
     assert common.rel_err(Y1[:3], Yn[:3]) < 1e-4 and common.rel_err(D1[:3], Dn[:3]) < 1e-4 and common.rel_err(eng.get_ad(), Ad) < 1e-4
     eng.close()
+
+
+# ---- FSI with a ustruct wall: construct_fsi's ustruct_3d_m/c branch (fsi.cpp:243-262), tests/cases/fsi_ustruct ------------------
+@pytest.mark.parametrize("scatter", [abi.SCATTER_ATOMIC, abi.SCATTER_COLORED])
+@pytest.mark.parametrize("name", list(common.FSI_USTRUCT_CASES))
+def test_fsi_ustruct_assembly_matches_golden(name, scatter):
+    """One mesh with element domain ids: fluid elements through the ALE fluid kernel, solid elements through the ustruct kernel with
+    the tDof = 7 state; R / Val / Kd and R after ustruct_r (ustruct-domain nodes only) against the compiled reference."""
+    golden = common.load_golden("fsi_ustruct.npz")
+    m, Ag, Yg, Dg, Bf, fN, nFn, eq, dmn, Ad, flags = common.fsi_ustruct_case(name, scatter)
+    eng = _engine(m, golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"], nFn, fN)
+    eng.alloc(4); eng.set_state(Ag, Yg, Dg, Bf); eng.assemble(0, eq, dmn)
+    R1, V1, K1 = eng.get_R(), eng.get_Val(), eng.get_Kd()
+    G = golden[f"{name}/Val"]
+    assert common.rel_err(K1, golden[f"{name}/Kd"]) < ASM_TOL
+    # fluid and solid entries differ by many orders of magnitude: rows of fluid-only nodes, of solid-only nodes and of the interface
+    # are compared separately, and Val by entry type inside each set
+    fluid_nodes = np.unique(m.IEN[:, (m.eId & 2) == 0]); solid_nodes = np.where(flags != 0)[0]
+    rowPtr = golden[f"{name}/rowPtr"]
+    sets = (np.setdiff1d(fluid_nodes, solid_nodes), np.setdiff1d(solid_nodes, fluid_nodes), np.intersect1d(fluid_nodes, solid_nodes))
+    assert all(len(x) > 0 for x in sets)
+    for nodes in sets:
+        assert common.rel_err(R1[:, nodes], golden[f"{name}/R"][:, nodes]) < ASM_TOL
+        slots = np.concatenate([np.arange(rowPtr[a], rowPtr[a + 1]) for a in nodes])
+        for rows in VAL_GROUPS:
+            assert common.rel_err(V1[rows][:, slots], G[rows][:, slots]) < ASM_TOL
+    with pytest.raises(RuntimeError):
+        eng.ustruct_r(eq, 1, Ad)                  # an FSI equation needs the membership in the ustruct domains
+    eng.set_node_flags(flags)
+    eng.ustruct_r(eq, 1, Ad)
+    R2 = eng.get_R()
+    for nodes in sets:
+        assert common.rel_err(R2[:, nodes], golden[f"{name}/R_after_ustruct_r"][:, nodes]) < ASM_TOL
+    assert np.array_equal(R2[:, sets[0]], R1[:, sets[0]])          # fluid-only rows untouched
+    assert not np.array_equal(R2[:, sets[1]], R1[:, sets[1]])
+    Rd = eng.get_Rd()
+    assert np.all(Rd[:, flags == 0] == 0.0) and np.abs(Rd[:, flags != 0]).min() > 0
+    eng.ustruct_r(eq, 2, Ad)
+    assert np.array_equal(eng.get_R(), R2) and np.all(eng.get_Rd() == 0.0)
+    if scatter == abi.SCATTER_COLORED:
+        eng.alloc(4); eng.assemble(0, eq, dmn)
+        assert np.array_equal(eng.get_Val(), V1) and np.array_equal(eng.get_R(), R1) and np.array_equal(eng.get_Kd(), K1)
+    eng.close()
+
+
+def test_fsi_ustruct_two_meshes_and_solve_parity():
+    """The layout of tests/cases/fsi_ustruct/pipe_3d: lumen mesh (fluid domain) + wall mesh (ustruct domain) over one node set,
+    assembled mesh by mesh; then ustruct_r and a GMRES solve of the coupled system, against the compiled reference live."""
+    from oracle import refbind
+    if not refbind.have_ref():
+        pytest.skip("needs oracle/_ref/libsvref.so")
+    from svmultiphysics_b200.engine import Engine
+    name = "nHK_ST91"
+    m, Ag, Yg, Dg, Bf, fN, nFn, eq, dmn, Ad, flags = common.fsi_ustruct_case(name)
+    fl, so = np.where(m.eId == 1)[0], np.where(m.eId == 2)[0]
+    faces = common.dirichlet_faces(m)
+    orc = refbind.RefCase(); orc.set_coords(m.x)
+    orc.add_mesh(np.asfortranarray(m.IEN[:, fl]), eId=m.eId[fl]); orc.add_mesh(np.asfortranarray(m.IEN[:, so]), eId=m.eId[so])
+    rowPtr, colPtr = orc.build_graph(len(faces))
+    eng = Engine(0)
+    eng.set_graph(rowPtr, colPtr)
+    w, N, Nx = elements.tables(4)
+    eng.set_mesh(0, np.asfortranarray(m.IEN[:, fl]), w, N, Nx, eId=m.eId[fl])
+    eng.set_mesh(1, np.asfortranarray(m.IEN[:, so]), w, N, Nx, eId=m.eId[so])
+    eng.set_coords(m.x)
+    eng.set_num_faces(len(faces))
+    for i, (g, nodes, val) in enumerate(faces):
+        orc.set_face(i, g, nodes, val); eng.set_face(i, g, nodes, val)
+    orc.alloc(4); orc.set_state(Ag, Yg, Dg, Bf); orc.assemble(0, eq, dmn); orc.assemble(1, eq, dmn); orc.ustruct_r(1, Ad)
+    eng.alloc(4); eng.set_state(Ag, Yg, Dg, Bf); eng.assemble(0, eq, dmn); eng.assemble(1, eq, dmn)
+    eng.set_node_flags(flags); eng.ustruct_r(eq, 1, Ad)
+    golden = common.load_golden("fsi_ustruct.npz")
+    assert common.rel_err(orc.get_Kd(), golden[f"{name}/Kd"]) < 1e-13          # two meshes = one mesh with domain ids
+    assert common.rel_err(eng.get_Kd(), orc.get_Kd()) < ASM_TOL
+    R0, R1, V0, V1 = orc.get_R(), eng.get_R(), orc.get_Val(), eng.get_Val()
+    solid_nodes = np.where(flags != 0)[0]; fluid_only = np.where(flags == 0)[0]
+    for nodes in (solid_nodes, fluid_only):
+        assert common.rel_err(R1[:, nodes], R0[:, nodes]) < ASM_TOL
+        slots = np.concatenate([np.arange(rowPtr[a], rowPtr[a + 1]) for a in nodes])
+        for rows in VAL_GROUPS:
+            assert common.rel_err(V1[rows][:, slots], V0[rows][:, slots]) < 1e-11
+    ls = abi.ls_params(abi.LS_GMRES, mItr=4, sD=150, relTol=1e-6)
+    incL, res = np.ones(len(faces), np.int32), np.zeros(len(faces))
+    X0, o0, _ = orc.solve(4, abi.LS_GMRES, ls, incL, res)
+    X1, o1, _ = eng.solve(4, abi.LS_GMRES, ls, incL, res)
+    assert o1.RI.success == o0.RI.success and abs(o1.RI.iNorm - o0.RI.iNorm) <= 1e-10 * o0.RI.iNorm
+    assert abs(o1.RI.itr - o0.RI.itr) <= max(2, o0.RI.itr // 20)
+    assert common.rel_err(X1, X0) < 1e-4
+    eng.close()

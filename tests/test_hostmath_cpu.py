@@ -364,6 +364,63 @@ def test_device_ustruct_algebra_matches_golden(hostmath, case, entry):
         assert common.rel_err(V.T[rows], G[rows]) < 1e-12
 
 
+@pytest.mark.parametrize("entry", ["hostmath_ustruct", "hostmath_ustruct_tet4"])
+@pytest.mark.parametrize("name", list(common.FSI_USTRUCT_CASES))
+def test_device_ustruct_algebra_inside_fsi_matches_golden(hostmath, name, entry):
+    """construct_fsi with a ustruct wall (fsi.cpp:243-262; tests/golden/fsi_ustruct.npz from the compiled reference): the device
+    ustruct algebra run over the solid elements with the tDof = 7 state of the FSI equation reproduces Kd everywhere (only the
+    solid writes it) and R / Val on the rows of nodes no fluid element touches."""
+    dkw, nFn = common.FSI_USTRUCT_CASES[name]
+    if entry.endswith("tet4") and "visc" in name:
+        pytest.skip("the closed-form TET4 path has no solid viscosity (the kernel dispatch sends such domains to the general path)")
+    golden = common.load_golden("fsi_ustruct.npz")
+    m, Ag, Yg, Dg, Bf, fN, nFn, eq, dmn, Ad, flags = common.fsi_ustruct_case(name)
+    d = dmn[1]
+    so = np.where((m.eId & 2) != 0)[0]
+    A = HostUstructArgs()
+    keep = [np.ascontiguousarray(m.IEN[:, so].T.astype(np.int32)), np.ascontiguousarray(m.x.T), np.ascontiguousarray(Ag.T),
+            np.ascontiguousarray(Yg.T), np.ascontiguousarray(Dg.T), np.ascontiguousarray(Bf.T)]
+    A.IEN, A.x, A.Ag, A.Yg, A.Dg, A.Bf = (k.ctypes.data for k in keep)
+    if nFn:
+        fk = np.ascontiguousarray(fN[:, so].T); keep.append(fk)
+        A.fN = fk.ctypes.data
+    A.eNoN, A.nEl, A.tDof, A.s, A.nFn = 4, len(so), 7, 0, nFn
+    A.nG = _fill_tables(A, 4)
+    A.dt, A.af, A.am, A.gam = eq.dt, eq.af, eq.am, eq.gam
+    dm = A.dm.st
+    dm.rho, dm.dmp, dm.Kpen, dm.C10, dm.C01, dm.bff, dm.bss, dm.bfs = d.rho, d.dmp, d.Kpen, d.C10, d.C01, d.bff, d.bss, d.bfs
+    for i in range(3):
+        dm.f[i] = d.f[i]
+    dm.st_a, dm.st_b, dm.aff, dm.ass, dm.afs, dm.kap, dm.khs = d.st_a, d.st_b, d.aff, d.ass, d.afs, d.kap, d.khs
+    dm.isoType, dm.volType, dm.Id, dm.isStruct = d.isoType, d.volType, -1, 1
+    dm.visc_mu, dm.viscType = d.solid_visc_mu, d.solidViscType
+    _fill_extras(A, dm, d, m, keep)
+    A.dm.E, A.dm.nu, A.dm.ctM, A.dm.ctC = d.E, d.nu, d.ctau_M, d.ctau_C
+    rowPtr, colPtr = golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"]
+    R = np.zeros((m.nNo, 4)); V = np.zeros((len(colPtr), 16)); Kd = np.zeros((len(colPtr), 12))
+    rc = getattr(hostmath, entry)(C.byref(A), rowPtr.ctypes.data_as(C.c_void_p), colPtr.ctypes.data_as(C.c_void_p),
+                                  R.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p), Kd.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    assert common.rel_err(Kd.T, golden[f"{name}/Kd"]) < 1e-12
+    fluid_nodes = np.unique(m.IEN[:, (m.eId & 2) == 0])
+    pure = np.setdiff1d(np.arange(m.nNo), fluid_nodes)
+    assert len(pure) > 50
+    assert common.rel_err(R[pure].T, golden[f"{name}/R"][:, pure]) < 1e-12
+    slots = np.concatenate([np.arange(rowPtr[a], rowPtr[a + 1]) for a in pure])
+    G = golden[f"{name}/Val"]
+    for rows in ([0, 1, 2, 4, 5, 6, 8, 9, 10], [3, 7, 11], [12, 13, 14], [15]):
+        assert common.rel_err(V[slots].T[rows], G[rows][:, slots]) < 1e-12
+    # ustruct_r (ustruct.cpp:1742-1845) restated with numpy on the golden Kd: only the nodes of the ustruct domain take part
+    amg, ami = (eq.gam - eq.am) / (eq.gam - 1.0), 1.0 / eq.am
+    Rd = np.where(flags[None, :] != 0, amg * Ad - Yg[0:3], 0.0)
+    KU = np.zeros((4, m.nNo))
+    rows_of = np.repeat(np.arange(m.nNo), np.diff(rowPtr))
+    Kg = golden[f"{name}/Kd"].reshape(4, 3, -1)
+    np.add.at(KU.T, rows_of, np.einsum("ijk,jk->ki", Kg, Rd[:, colPtr]))
+    KU[:, flags == 0] = 0.0
+    assert common.rel_err(golden[f"{name}/R"] - ami * KU, golden[f"{name}/R_after_ustruct_r"]) < 1e-12
+
+
 class HostTet4Args(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("IEN", "fN", "x", "Ag", "Yg", "Dg", "Bf", "Do")] + \
                [(k, C.c_int) for k in ("nEl", "tDof", "dof", "s", "nFn", "kind")] + \
