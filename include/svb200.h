@@ -279,6 +279,29 @@ SVB200_API int svb200_set_prestress(svb200_ctx* ctx, const double* pS0);
 SVB200_API int svb200_get_prestress(svb200_ctx* ctx, double* pSn, double* pSa);
 SVB200_API int svb200_set_active_tension(svb200_ctx* ctx, const double* Ya_f, const double* Ya_s, const double* Ya_n);
 
+/* Unfitted resistive immersed surfaces (URIS valves): the penalty terms of fluid_3d_m / fluid_3d_c (solver/fluid.cpp:2006-2008,
+ * 2042-2047, 2126-2129, 2166-2204, 2228-2234 and :1660-1703) with the per-Gauss-point factor of
+ * uris::eval_uris_ris_factors_quadrature (solver/uris.cpp:1577-1673), used by construct_fluid (fluid.cpp:622-672) and the fluid
+ * elements of construct_fsi (fsi.cpp:170-216):
+ *   dist = sum_a N_a |sdf(A)|,  delta = (1 + cos(pi dist / deps)) / (2 deps^2) if dist < deps (and deps > 0), else 0
+ *   factor = sum_valves resistance (delta + delta_scaffold),  velocity term = sum_valves resistance delta sum_a N_a v_valve(A).
+ * One entry per valve (com_mod.uris[i]); sdf_deps is the half-thickness in effect at this step — the linear open/close ramp between
+ * sdf_deps and sdf_deps_close over DxOpen / DxClose (uris.cpp:1625-1649) is scalar host logic and stays with the caller. */
+#define SVB200_MAX_URIS 4
+typedef struct {
+  double resistance;          /* urisType::resistance */
+  double sdf_deps;            /* effective half-thickness of the valve surface at this step */
+  double scaffold_deps;       /* urisType::sdf_deps_close: thickness of the scaffold surface (read when scaffold != 0) */
+  int32_t scaffold;           /* urisType::scaffold_flag */
+  int32_t include_velocity;   /* urisType::include_uris_velocity */
+} svb200_uris;
+/* nUris = 0 removes the valves (com_mod.urisActFlag false).  sdf(nNo, nUris): urisType::sdf of valve i at sdf + i*nNo (signed or
+ * not: the absolute value is used); scaffold_udf likewise (NULL if no valve has a scaffold); valve_vel(3, nNo, nUris):
+ * urisType::valve_velocity_fluid (NULL if no valve includes its velocity).  INPUT node order.  While valves are set, the fluid
+ * elements run through the per-Gauss-point kernel (the closed-form TET4 kernel has no URIS terms). */
+SVB200_API int svb200_set_uris(svb200_ctx* ctx, int32_t nUris, const svb200_uris* valves, const double* sdf,
+                               const double* scaffold_udf, const double* valve_vel);
+
 /* global_eq_assem for mesh iM: element loop + scatter, R/Val stay on the device. */
 SVB200_API int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq,
                     const svb200_dmnparams* dmn, int32_t nDmn);

@@ -525,6 +525,37 @@ int svref_set_active_tension(void* h, const double* Ya_f, const double* Ya_s, co
   });
 }
 
+/// URIS valves: com_mod.urisFlag / urisActFlag / nUris / uris[] as uris::uris_read_msh and the time loop leave them for the
+/// element routines (only the members uris::eval_uris_ris_factors_quadrature reads).  scal(3, nUris) = resistance, sdf_deps,
+/// sdf_deps_close; flags(6, nUris) = clsFlg, cnt, DxOpen.nslices, DxClose.nslices, scaffold_flag, include_uris_velocity;
+/// sdf / udf: (nNo, nUris), vel: (3, nNo, nUris).  nUris = 0 switches the valves off.
+int svref_set_uris(void* h, int nUris, const double* scal, const int* flags, const double* sdf, const double* udf, const double* vel)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    auto& cm = c.com_mod;
+    const int n = cm.tnNo;
+    cm.nUris = nUris;
+    cm.urisFlag = cm.urisActFlag = (nUris > 0);
+    cm.uris.clear();
+    cm.uris.resize(nUris);
+    for (int v = 0; v < nUris; v++) {
+      auto& u = cm.uris[v];
+      u.resistance = scal[3*v]; u.sdf_deps = scal[3*v + 1]; u.sdf_deps_close = scal[3*v + 2];
+      u.clsFlg = flags[6*v] != 0; u.cnt = flags[6*v + 1];
+      u.DxOpen.resize(1, 1, flags[6*v + 2]); u.DxClose.resize(1, 1, flags[6*v + 3]);
+      u.scaffold_flag = flags[6*v + 4] != 0; u.include_uris_velocity = flags[6*v + 5] != 0;
+      u.sdf.resize(n);
+      for (int a = 0; a < n; a++) u.sdf(a) = sdf[(size_t)v*n + a];
+      if (u.scaffold_flag) { u.scaffold_udf.resize(n); for (int a = 0; a < n; a++) u.scaffold_udf(a) = udf[(size_t)v*n + a]; }
+      if (u.include_uris_velocity) {
+        u.valve_velocity_fluid.resize(3, n);
+        for (int a = 0; a < n; a++) for (int i = 0; i < 3; i++) u.valve_velocity_fluid(i, a) = vel[((size_t)v*n + a)*3 + i];
+      }
+    }
+  });
+}
+
 int svref_set_old_disp(void* h, int tDof, const double* Do_in)
 {
   auto& c = *static_cast<RefCase*>(h);

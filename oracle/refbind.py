@@ -157,6 +157,18 @@ class _FlatCase:
         n_ = None if Ya_n is None else np.ascontiguousarray(Ya_n, dtype=np.float64)
         self._call("set_active_tension", _d(f), _d(s_), _d(n_))
 
+    def set_uris(self, raw, sdf=None, scaffold_udf=None, valve_vel=None):
+        """com_mod.uris[] for uris::eval_uris_ris_factors_quadrature.  raw = list of dicts with resistance, sdf_deps, sdf_deps_close,
+        clsFlg, cnt, n_open, n_close, scaffold, include_velocity (the urisType members, not the effective thickness);
+        sdf / scaffold_udf: (nUris, nNo); valve_vel: (nUris, nNo, 3)."""
+        n = len(raw)
+        scal = np.array([[u["resistance"], u["sdf_deps"], u["sdf_deps_close"]] for u in raw], dtype=np.float64).reshape(-1)
+        flags = np.array([[int(u["clsFlg"]), u["cnt"], u["n_open"], u["n_close"], int(u["scaffold"]), int(u["include_velocity"])]
+                          for u in raw], dtype=np.int32).reshape(-1)
+        c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        self._call("set_uris", C.c_int(n), _d(c(scal)) if n else None, _i(flags) if n else None, _d(c(sdf)), _d(c(scaffold_udf)),
+                   _d(c(valve_vel)))
+
     def set_old_disp(self, Do):
         Do = _f64(Do)
         self._call("set_old_disp", C.c_int(Do.shape[0]), _d(Do))

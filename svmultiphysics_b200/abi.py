@@ -40,6 +40,25 @@ class EqTime(C.Structure):
 
 SOL_OLD, SOL_CURRENT, SOL_INTERMEDIATE = 0, 1, 2
 
+MAX_URIS = 4
+
+
+class Uris(C.Structure):
+    """svb200_uris: one unfitted-RIS valve (com_mod.uris[i]) as the element kernels need it."""
+    _fields_ = [("resistance", C.c_double), ("sdf_deps", C.c_double), ("scaffold_deps", C.c_double),
+                ("scaffold", C.c_int32), ("include_velocity", C.c_int32)]
+
+
+def uris_effective_deps(sdf_deps: float, sdf_deps_close: float, clsFlg: bool, cnt: int, n_open: int, n_close: int) -> float:
+    """Half-thickness of a valve surface at this step: the linear ramp between the open and the closed value over the DxOpen /
+    DxClose steps (Code/Source/solver/uris.cpp:1625-1649).  Scalar host logic: the device gets the result (svb200_uris.sdf_deps)."""
+    start, end, n = (sdf_deps, sdf_deps_close, n_close) if clsFlg else (sdf_deps_close, sdf_deps, n_open)
+    if n <= 0 or cnt >= n:
+        return end
+    if cnt <= 0:
+        return start
+    return start + (float(cnt) / float(n)) * (end - start)
+
 
 class DmnParams(C.Structure):
     _fields_ = [

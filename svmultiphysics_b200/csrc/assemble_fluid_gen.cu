@@ -40,6 +40,9 @@ struct FluidGenArgs {
                         // (fluid.cpp:641, 707), also for the wedge, whose gradients are NOT constant: reproduced as is
   double dt, af, am, gam;
   FluidDmn dmn[MAX_DMN];
+  const double* uris;   // URIS valves (svb200_set_uris) or null
+  int nUris;
+  svb200_uris urisP[SVB200_MAX_URIS];
 };
 
 template <bool ATOMIC>
@@ -151,9 +154,17 @@ assemble_fluid_gen_kernel(const __grid_constant__ FluidGenArgs P)
       }
     }
     __syncwarp();
+    // URIS valves: resistance factor and valve-velocity term at this Gauss point (fluid.cpp:622-672)
+    double uF = 0.0, uV[3] = {0.0, 0.0, 0.0};
+    if (gp && P.uris != nullptr) {
+      int nodes[ENON];
+#pragma unroll
+      for (int b = 0; b < ENON; b++) nodes[b] = __ldg(P.IEN + (size_t)e * ENON + b);
+      uris_factor<ENON>(P.uris, P.nUris, P.urisP, tg + 1, nodes, uF, uV);
+    }
     if (gp)
       fluid_gen_gauss_point<ENON>(dm, P.dt, P.af, P.am, P.gam, tg[0] * Jac, ks, tg + 1, Nx, Nxx, sNxxL, sal, syl, sbf,
-                                  P.mvMsh ? sym : nullptr, sgp[g], snd(g));
+                                  P.mvMsh ? sym : nullptr, sgp[g], snd(g), uF, uV);
   }
   __syncwarp();
   if (!active || a >= ENON) return;
@@ -259,6 +270,8 @@ int run_assemble_fluid_gen(svb200_ctx* ctx, const Mesh& m, const FluidArgs& F)
   A.lShpF = (m.eNoN == 4 || m.eNoN == 6) ? 1 : 0;
   A.dt = F.dt; A.af = F.af; A.am = F.am; A.gam = F.gam;
   for (int d = 0; d < MAX_DMN; d++) A.dmn[d] = F.dmn[d];
+  A.uris = F.uris; A.nUris = F.nUris;
+  for (int v = 0; v < F.nUris; v++) A.urisP[v] = F.urisP[v];
   auto launch = [&](const FluidGenArgs& B) {
     switch (key) {
       case 404: return launch_gen<4, 4>(ctx, B);

@@ -29,6 +29,10 @@ struct FluidGP {
   double mu_x[3], d2u2[3];
   double up_c[3], mu_x_c[3], d2u2_c[3];
   double es[6];      // strain rate es = ux + ux^T: 00, 11, 22, 01, 12, 02 (for FluidNodeC::expand)
+  // URIS valves (uris::eval_uris_ris_factors_quadrature): muKdT = mu Kd + urisFactorTotal is what the tangent and T1 see
+  // (fluid.cpp:2126-2129, 2166-2204); rB_j = urisFactorTotal u_j - urisValveVelTermTotal_j enters the residual (:2228-2234).
+  // Without valves muKdT = muKd and rB = 0: every sum below then gains an exact + 0.0.
+  double muKdT, rB[3];
 };
 constexpr int FLUID_GP_DOUBLES = sizeof(FluidGP) / sizeof(double);
 
@@ -158,6 +162,36 @@ SVB_HD void second_derivative_terms(const double Nxx[][6], const double yl[][3],
   }
 }
 
+// uris::eval_uris_ris_factors_quadrature (solver/uris.cpp:1577-1673) at one Gauss point: the total resistance factor and the valve
+// velocity term of the URIS valves.  `nodal` holds, per node and valve, |sdf|, |scaffold udf| and the valve velocity (5 doubles,
+// node-major: nodal[(node * nUris + v) * 5 + k]); N = shape functions at the Gauss point, nodes = the element's node ids.
+template <int ENON>
+SVB_HD void uris_factor(const double* nodal, int nUris, const svb200_uris* vp, const double N[], const int nodes[], double& uF, double uV[3])
+{
+  uF = 0.0; uV[0] = uV[1] = uV[2] = 0.0;
+  for (int v = 0; v < nUris; v++) {
+    double dist = 0.0, dsc = 0.0, vel[3] = {0.0, 0.0, 0.0};
+    for (int a = 0; a < ENON; a++) {
+      const double* r = nodal + ((size_t)nodes[a] * nUris + v) * 5;
+      dist += N[a] * r[0];
+      if (vp[v].scaffold) dsc += N[a] * r[1];
+      if (vp[v].include_velocity)
+        for (int i = 0; i < 3; i++) vel[i] += N[a] * r[2 + i];
+    }
+    const double pi = 3.141592653589793238462643383279502884;
+    double delta = 0.0, delta_sc = 0.0;
+    const double deps = vp[v].sdf_deps;
+    if (dist < deps && deps > 0.0) delta = (1 + cos(pi * dist / deps)) / (2 * deps * deps);
+    if (vp[v].scaffold) {
+      const double sd = vp[v].scaffold_deps;
+      if (dsc < sd && sd > 0.0) delta_sc = (1 + cos(pi * dsc / sd)) / (2 * sd * sd);
+    }
+    uF += vp[v].resistance * (delta + delta_sc);
+    if (vp[v].include_velocity)
+      for (int i = 0; i < 3; i++) uV[i] += vp[v].resistance * delta * vel[i];
+  }
+}
+
 // Everything of fluid_3d_m / fluid_3d_c at one Gauss point that does not depend on the node pair.
 //   al/yl: nodal acceleration / velocity+pressure (al[a][0..2], yl[a][0..3]); ym: nodal mesh velocity or null;
 //   Nxx: physical second derivatives at THIS Gauss point, NxxL: those of the LAST Gauss point (continuity quirk).
@@ -165,7 +199,7 @@ template <int ENON, class NodeT = FluidNode>
 SVB_HD void fluid_gen_gauss_point(const FluidDmn& dm, double dt, double af, double am, double gam_t, double w, const double ks[3][3],
                                   const double N[], const double Nx[][3], const double Nxx[][6], const double NxxL[][6],
                                   const double al[][3], const double yl[][4], const double bfl[][3], const double (*ym)[3],
-                                  FluidGP& q, NodeT nd[])
+                                  FluidGP& q, NodeT nd[], double uF = 0.0, const double* uV = nullptr)
 {
   const double ctM = 1.0, ctC = 36.0;
   const double rho = dm.rho, Kd = dm.Kd;
@@ -209,6 +243,8 @@ SVB_HD void fluid_gen_gauss_point(const FluidDmn& dm, double dt, double af, doub
   viscosity(dm, gam, mu, mu_g);
   mu_g = is_zero(gam) ? 0.0 : mu_g / gam;
   q.mu = mu; q.mu_g = mu_g; q.muKd = mu * Kd;
+  q.muKdT = q.muKd + uF;
+  const double uV0 = uV ? uV[0] : 0.0, uV1 = uV ? uV[1] : 0.0, uV2 = uV ? uV[2] : 0.0;
 
   double gx[3], gxc[3];
   second_derivative_terms<ENON>(Nxx, yv, es, q.d2u2, gx);
@@ -218,6 +254,7 @@ SVB_HD void fluid_gen_gauss_point(const FluidDmn& dm, double dt, double af, doub
 
   double kT = 4.0 * (ctM / dt) * (ctM / dt);
   kT += (Kd * mu / rho) * (Kd * mu / rho);
+  kT += uF * uF;                                  // fluid.cpp:2006-2008
   double kU = 0.0, kS = 0.0;
 #pragma unroll
   for (int i = 0; i < 3; i++)
@@ -232,8 +269,10 @@ SVB_HD void fluid_gen_gauss_point(const FluidDmn& dm, double dt, double af, doub
     const double rVj = ud[j] + u[0] * ux[0][j] + u[1] * ux[1][j] + u[2] * ux[2][j];
     const double rS = q.mu_x[0] * es[0][j] + q.mu_x[1] * es[1][j] + q.mu_x[2] * es[2][j] + mu * q.d2u2[j];
     const double rSc = q.mu_x_c[0] * es[0][j] + q.mu_x_c[1] * es[1][j] + q.mu_x_c[2] * es[2][j] + mu * q.d2u2_c[j];
-    up[j] = -tauM * (rho * rVj + px[j] - rS + mu * Kd * u[j]);
-    q.up_c[j] = -tauM * (rho * rVj + px[j] - rSc + mu * Kd * u[j]);
+    const double uVj = (j == 0) ? uV0 : (j == 1 ? uV1 : uV2);
+    q.rB[j] = uF * u[j] - uVj;
+    up[j] = -tauM * (rho * rVj + px[j] - rS + mu * Kd * u[j] + uF * u[j] - uVj);            // fluid.cpp:2042-2047
+    q.up_c[j] = -tauM * (rho * rVj + px[j] - rSc + mu * Kd * u[j] + uF * u[j] - uVj);        // fluid.cpp:1689-1694
     q.up[j] = up[j];
     q.u[j] = u[j];
   }
@@ -267,7 +306,7 @@ SVB_HD void fluid_gen_gauss_point(const FluidDmn& dm, double dt, double af, doub
     }
     n.uNx = u[0] * Nx[a][0] + u[1] * Nx[a][1] + u[2] * Nx[a][2];
     n.upNx = up[0] * Nx[a][0] + up[1] * Nx[a][1] + up[2] * Nx[a][2];
-    const double base = -rho * n.uNx - mu * Kd * N[a];
+    const double base = -rho * n.uNx - mu * Kd * N[a] - uF * N[a];                              // fluid.cpp:2126-2129, 1700-1703
     n.T1b = base + mu * (Nxx[a][0] + Nxx[a][1] + Nxx[a][2]) + q.mu_x[0] * Nx[a][0] + q.mu_x[1] * Nx[a][1] + q.mu_x[2] * Nx[a][2];
     n.T1b_c = base + mu * (NxxL[a][0] + NxxL[a][1] + NxxL[a][2]) + q.mu_x_c[0] * Nx[a][0] + q.mu_x_c[1] * Nx[a][1] + q.mu_x_c[2] * Nx[a][2];
     fluid_node_store(nd[a], n);
@@ -294,7 +333,7 @@ SVB_HD void fluid_gen_residual(const FluidGP& q, const FluidNode& a, double lR[4
 #pragma unroll
   for (int j = 0; j < 3; j++)
     lR[j] += q.wr * a.N * q.rV[j] + q.w * (a.Nx[0] * q.rM[0][j] + a.Nx[1] * q.rM[1][j] + a.Nx[2] * q.rM[2][j]) +
-             q.muKd * q.w * a.N * (q.u[j] + q.up[j]);
+             q.muKd * q.w * a.N * (q.u[j] + q.up[j]) + q.w * a.N * q.rB[j];
   lR[3] += q.w * (a.N * q.divU - (q.up_c[0] * a.Nx[0] + q.up_c[1] * a.Nx[1] + q.up_c[2] * a.Nx[2]));
 }
 
@@ -306,7 +345,7 @@ SVB_HD void fluid_gen_block(const FluidGP& q, const FluidNode& a, const FluidNod
   const double uaNxa = a.uNx + a.upNx;
   const double rtu = rho * q.tauM * uaNxa;
   const double T1 = mu * NxNx + rho * q.amd * b.N * (a.N + rtu) + rho * a.N * (b.uNx + b.upNx) + q.tauB * a.upNx * b.upNx;
-  const double dk = q.muKd * b.N * a.N;
+  const double dk = q.muKdT * b.N * a.N;
 #pragma unroll
   for (int i = 0; i < 3; i++) {
 #pragma unroll
@@ -356,7 +395,7 @@ SVB_HD void fluid_gen_row(const FluidGP& q, const FluidNode& a, FluidRow& r)
   const double rtu = q.rho * q.tauM * (a.uNx + a.upNx);
   r.wlrtu = wl * rtu;
   r.wlmu = wl * q.mu;
-  r.c0 = wl * (q.rho * q.amd * (a.N + rtu) + q.muKd * a.N);
+  r.c0 = wl * (q.rho * q.amd * (a.N + rtu) + q.muKdT * a.N);
   r.c1 = wl * q.rho * a.N;
   r.c2 = wl * q.tauB * a.upNx;
   r.wlNa = wl * a.N;

@@ -237,7 +237,7 @@ int svb200_destroy(svb200_ctx* ctx)
   cudaFree(ctx->d_hg);
   for (auto& nb : ctx->neigh) { cudaFree(nb.d_ptr); cudaFree(nb.d_send); cudaFree(nb.d_recv); }
   cudaFree(ctx->d_map); cudaFree(ctx->d_rowPtr_in); cudaFree(ctx->d_rowPtr); cudaFree(ctx->d_colPtr); cudaFree(ctx->d_diagPtr);
-  cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf); cudaFree(ctx->d_Do); cudaFree(ctx->d_Ya); cudaFree(ctx->d_pS0); cudaFree(ctx->d_pSn);
+  cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf); cudaFree(ctx->d_Do); cudaFree(ctx->d_Ya); cudaFree(ctx->d_uris); cudaFree(ctx->d_pS0); cudaFree(ctx->d_pSn);
   cudaFree(ctx->d_Ao); cudaFree(ctx->d_Yo); cudaFree(ctx->d_An); cudaFree(ctx->d_Yn); cudaFree(ctx->d_Dn); cudaFree(ctx->d_nodeflag);
   cudaFree(ctx->d_err); cudaFree(ctx->d_Kd); cudaFree(ctx->d_Ad); cudaFree(ctx->d_Rd);
   cudaFree(ctx->d_stage); cudaFree(ctx->d_R); cudaFree(ctx->d_Val); cudaFree(ctx->d_W);
@@ -382,6 +382,7 @@ int svb200_set_graph(svb200_ctx* ctx, int32_t nNo, int32_t nnz, const int32_t* r
   // state arrays depend on nNo
   cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf); cudaFree(ctx->d_Do);
   cudaFree(ctx->d_Ya); ctx->d_Ya = nullptr; ctx->ya_sn_positive = false;
+  cudaFree(ctx->d_uris); ctx->d_uris = nullptr; ctx->nUris = 0;
   cudaFree(ctx->d_pS0); cudaFree(ctx->d_pSn); ctx->d_pS0 = ctx->d_pSn = nullptr;
   cudaFree(ctx->d_Ao); cudaFree(ctx->d_Yo); cudaFree(ctx->d_An); cudaFree(ctx->d_Yn); cudaFree(ctx->d_Dn); cudaFree(ctx->d_nodeflag);
   ctx->d_Ao = ctx->d_Yo = ctx->d_An = ctx->d_Yn = ctx->d_Dn = nullptr; ctx->d_nodeflag = nullptr;
@@ -637,6 +638,9 @@ static int fill_fluid_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams
   A.err = ctx->d_err;
   A.e0 = 0; A.e1 = m.nEl;
   A.tDof = eq->tDof; A.mvMsh = eq->mvMsh; A.nDmn = nDmn;
+  A.uris = ctx->nUris ? ctx->d_uris : nullptr;
+  A.nUris = ctx->nUris;
+  for (int v = 0; v < ctx->nUris; v++) A.urisP[v] = ctx->urisP[v];
   A.ale = (eq->phys == SVB200_PHYS_FSI);
   SVB_REQUIRE(!A.ale || (eq->tDof >= 7 && ctx->d_Dg), "svb200_assemble: FSI needs tDof >= 7 and the displacement state");
   A.atomic = (eq->scatter == SVB200_SCATTER_ATOMIC);
@@ -690,7 +694,7 @@ static int run_assemble(svb200_ctx* ctx, const Mesh& m, FluidArgs& A, bool gener
 {
   // linear tetrahedra have their own kernel (constant gradients, no second derivatives); everything else, or
   // SVB200_EQ_GENERAL_KERNEL, goes through the per-Gauss-point kernel of assemble_fluid_gen.cu
-  if (m.eNoN != 4 || general) {
+  if (m.eNoN != 4 || general || A.nUris > 0) {        // the URIS terms exist in the per-Gauss-point kernel only
     TRY(flush_val_zero(ctx));
     TRY(run_assemble_fluid_gen(ctx, m, A));
     return check_jacobian_word(ctx, A.ale != 0);
@@ -799,6 +803,38 @@ int svb200_set_active_tension(svb200_ctx* ctx, const double* Ya_f, const double*
   }
   ctx->ya_sn_positive = sn;
   return upload_nodal(ctx, 3, h.data(), &ctx->d_Ya);
+}
+
+int svb200_set_uris(svb200_ctx* ctx, int32_t nUris, const svb200_uris* valves, const double* sdf, const double* scaffold_udf,
+                    const double* valve_vel)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(nUris >= 0 && nUris <= SVB200_MAX_URIS, "svb200_set_uris: between 0 and SVB200_MAX_URIS valves");
+  if (nUris == 0) {
+    cudaFree(ctx->d_uris); ctx->d_uris = nullptr; ctx->nUris = 0;
+    return SVB200_OK;
+  }
+  SVB_REQUIRE(valves && sdf, "svb200_set_uris: null valve parameters or signed distance function");
+  SVB_REQUIRE(ctx->d_rowPtr, "svb200_set_uris: set the graph first");
+  const size_t n = (size_t)ctx->nNo;
+  for (int v = 0; v < nUris; v++) {
+    SVB_REQUIRE(!valves[v].scaffold || scaffold_udf, "svb200_set_uris: a valve has a scaffold but scaffold_udf is null");
+    SVB_REQUIRE(!valves[v].include_velocity || valve_vel, "svb200_set_uris: a valve includes its velocity but valve_vel is null");
+  }
+  std::vector<double> h(5 * (size_t)nUris * n, 0.0);
+  for (int v = 0; v < nUris; v++)
+    for (size_t a = 0; a < n; a++) {
+      double* r = h.data() + (a * nUris + v) * 5;
+      r[0] = std::fabs(sdf[(size_t)v * n + a]);
+      if (valves[v].scaffold) r[1] = std::fabs(scaffold_udf[(size_t)v * n + a]);
+      if (valves[v].include_velocity)
+        for (int i = 0; i < 3; i++) r[2 + i] = valve_vel[((size_t)v * n + a) * 3 + i];
+    }
+  if (ctx->d_uris && ctx->nUris != nUris) { cudaFree(ctx->d_uris); ctx->d_uris = nullptr; }
+  TRY(upload_nodal(ctx, 5 * nUris, h.data(), &ctx->d_uris));
+  ctx->nUris = nUris;
+  for (int v = 0; v < nUris; v++) ctx->urisP[v] = valves[v];
+  return SVB200_OK;
 }
 
 int svb200_set_old_disp(svb200_ctx* ctx, int32_t tDof, const double* Do)
@@ -1095,7 +1131,7 @@ int svb200_assemble_host(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq,
   static const bool no_pipe = getenv("SVB200_HOST_NO_PIPELINE") != nullptr;       // A/B knob
   const bool fast = !no_pipe && eq->phys == SVB200_PHYS_FLUID && m.eNoN == 4 && eq->scatter == SVB200_SCATTER_ATOMIC &&
                     !(eq->reserved & SVB200_EQ_GENERAL_KERNEL) && m.schedK.d_uptr && (int)m.grp_node_need.size() == nGrp && nGrp >= 256 &&
-                    m.jac_checked && ctx->tDof == eq->tDof && ctx->d_Ag && ctx->d_Yg && getenv("SVB200_ASM_LEGACY") == nullptr;
+                    m.jac_checked && ctx->tDof == eq->tDof && ctx->d_Ag && ctx->d_Yg && ctx->nUris == 0 && getenv("SVB200_ASM_LEGACY") == nullptr;
   if (!fast) {
     // any other case: the plain sequence (also the first call on a mesh, which runs the Jacobian check)
     TRY(svb200_set_state(ctx, eq->tDof, Ag, Yg, nullptr, nullptr));

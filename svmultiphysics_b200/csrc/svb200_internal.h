@@ -128,6 +128,10 @@ struct FluidArgs {
   double N[MAX_NG][MAX_ENON];        // N[g][a]
   double Nxi[MAX_NG][MAX_ENON][3];   // Nxi[g][a][k] = d N_a / d xi_k at Gauss point g
   FluidDmn dmn[MAX_DMN];
+  // URIS valves (svb200_set_uris): per node and valve |sdf|, |scaffold udf|, valve velocity = 5 doubles, node-major
+  const double* uris;
+  int nUris;
+  svb200_uris urisP[SVB200_MAX_URIS];
 };
 
 }  // namespace svb
@@ -160,6 +164,9 @@ struct svb200_ctx {
   double* d_Yg = nullptr;
   double* d_Dg = nullptr;
   double* d_Do = nullptr;        // old displacement (mesh-motion equation; solutions.old)
+  double* d_uris = nullptr;      // URIS nodal fields (5 nUris, nNo): per valve |sdf|, |scaffold udf|, valve velocity (svb200_set_uris)
+  int nUris = 0;
+  svb200_uris urisP[SVB200_MAX_URIS] = {};
   double* d_Ya = nullptr;        // nodal active tensions (3, nNo): Ya_f, Ya_s, Ya_n (svb200_set_active_tension)
   bool ya_sn_positive = false;
   double* d_pS0 = nullptr;       // nodal prestress com_mod.pS0 (6, nNo) (svb200_set_prestress)

@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "svb200_set_solution", "svb200_get_solution", "svb200_predictor", "svb200_initiator", "svb200_corrector",
     "svb200_set_node_flags", "svb200_set_dirichlet_rows", "svb200_dirichlet_ustruct", "svb200_advance_time_step",
     "svb200_set_bface", "svb200_assemble_neu",
-    "svb200_last_host_stage", "svb200_set_active_tension", "svb200_set_prestress", "svb200_get_prestress",
+    "svb200_last_host_stage", "svb200_set_uris", "svb200_set_active_tension", "svb200_set_prestress", "svb200_get_prestress",
     "svb200_spmv_rc", "svb200_spmv_rc_variants", "svb200_bench_spmv_rc",
     "svb200_schur_sp", "svb200_schur_sp_variants", "svb200_bench_schur_sp",
 ]
@@ -232,6 +232,16 @@ class Engine:
         s_ = None if Ya_s is None else np.ascontiguousarray(Ya_s, dtype=np.float64)
         n_ = None if Ya_n is None else np.ascontiguousarray(Ya_n, dtype=np.float64)
         self._call("svb200_set_active_tension", _d(f), _d(s_), _d(n_))
+
+    def set_uris(self, valves, sdf=None, scaffold_udf=None, valve_vel=None):
+        """URIS valves (svb200_set_uris): valves = list of abi.Uris; sdf / scaffold_udf: (nUris, nNo); valve_vel: (nUris, nNo, 3).
+        An empty list removes them."""
+        n = len(valves)
+        arr = (abi.Uris * max(n, 1))(*valves)
+        c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        sdf, scaffold_udf, valve_vel = c(sdf), c(scaffold_udf), c(valve_vel)
+        self._keep_uris = (arr, sdf, scaffold_udf, valve_vel)
+        self._call("svb200_set_uris", C.c_int32(n), arr, _d(sdf), _d(scaffold_udf), _d(valve_vel))
 
     def set_old_disp(self, Do):
         Do = _f64(Do)

@@ -167,6 +167,10 @@ bool global_eq_assem(ComMod& com_mod, CepMod& cep_mod, const mshType& lM, const 
   bool active = false;
   for (int d = 0; d < eq.nDmn; d++) active |= (eq.dmn[d].active_stress != nullptr);
   if (active) la->set_active_tension(cep_mod);
+  // URIS valves (construct_fluid, fluid.cpp:622-672; the fluid elements of construct_fsi, fsi.cpp:170-216): the signed distance
+  // function and the valve velocity move with the valve, so they are handed over at every assembly
+  if (com_mod.urisFlag && (eq.phys == consts::EquationType::phys_fluid || eq.phys == consts::EquationType::phys_FSI))
+    la->set_uris(com_mod);
   la->assemble_mesh(com_mod, lM, solutions);
   return true;
 }
@@ -375,6 +379,40 @@ void B200LinearAlgebra::set_active_tension(const CepMod& cep_mod)
   if (cem.Ya_f.size() == 0) throw std::runtime_error("[B200LinearAlgebra] active stress: cep_mod.cem.Ya_f is empty");
   check(svb200_set_active_tension(ctx, cem.Ya_f.data(), cem.Ya_s.size() ? cem.Ya_s.data() : nullptr,
                                   cem.Ya_n.size() ? cem.Ya_n.data() : nullptr));
+}
+
+void B200LinearAlgebra::set_uris(const ComMod& com_mod)
+{
+  const int nU = (com_mod.urisFlag && com_mod.urisActFlag) ? com_mod.nUris : 0;      // uris.cpp:1592-1594
+  if (nU == 0) { check(svb200_set_uris(ctx, 0, nullptr, nullptr, nullptr, nullptr)); return; }
+  if (nU > SVB200_MAX_URIS) throw std::runtime_error("[B200LinearAlgebra] more URIS valves than SVB200_MAX_URIS");
+  const size_t n = (size_t)com_mod.tnNo;
+  std::vector<svb200_uris> v(nU);
+  std::vector<double> sdf(nU * n, 0.0), udf, vel;
+  for (int i = 0; i < nU; i++) {
+    const auto& u = com_mod.uris[i];
+    // half-thickness now: ramp from the previous state's value to the current one over the DxClose / DxOpen steps (uris.cpp:1625-1649)
+    const double d0 = u.clsFlg ? u.sdf_deps : u.sdf_deps_close, d1 = u.clsFlg ? u.sdf_deps_close : u.sdf_deps;
+    const int steps = u.clsFlg ? u.DxClose.nslices() : u.DxOpen.nslices();
+    double deps = d1;
+    if (steps > 0 && u.cnt < steps) deps = (u.cnt <= 0) ? d0 : d0 + (static_cast<double>(u.cnt) / static_cast<double>(steps)) * (d1 - d0);
+    v[i].resistance = u.resistance;
+    v[i].sdf_deps = deps;
+    v[i].scaffold_deps = u.sdf_deps_close;
+    v[i].scaffold = u.scaffold_flag ? 1 : 0;
+    v[i].include_velocity = u.include_uris_velocity ? 1 : 0;
+    if ((size_t)u.sdf.size() != n) throw std::runtime_error("[B200LinearAlgebra] URIS: sdf is not sized to the fluid mesh nodes");
+    std::memcpy(sdf.data() + i * n, u.sdf.data(), sizeof(double) * n);
+    if (u.scaffold_flag) {
+      if (udf.empty()) udf.assign(nU * n, 0.0);
+      std::memcpy(udf.data() + i * n, u.scaffold_udf.data(), sizeof(double) * n);
+    }
+    if (u.include_uris_velocity) {
+      if (vel.empty()) vel.assign(3 * nU * n, 0.0);
+      std::memcpy(vel.data() + 3 * i * n, u.valve_velocity_fluid.data(), sizeof(double) * 3 * n);      // (nsd, tnNo) column-major
+    }
+  }
+  check(svb200_set_uris(ctx, nU, v.data(), sdf.data(), udf.empty() ? nullptr : udf.data(), vel.empty() ? nullptr : vel.data()));
 }
 
 /// ustruct::ustruct_r (Code/Source/solver/ustruct.cpp:1742-1845), called where Integrator::step calls it

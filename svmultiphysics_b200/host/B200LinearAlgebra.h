@@ -44,6 +44,9 @@ class B200LinearAlgebra : public virtual LinearAlgebra {
     void assemble_mesh(ComMod& com_mod, const mshType& lM, const SolutionStates& solutions);
     /// cep_mod.cem.Ya_f / Ya_s / Ya_n -> device (domains with an active-stress model; sv_struct.cpp:277-281).
     void set_active_tension(const CepMod& cep_mod);
+    /// com_mod.uris[] (URIS valves) -> svb200_set_uris: nodal |sdf| / scaffold udf / valve velocity and, per valve, the resistance
+    /// and the half-thickness in effect (the open/close ramp of uris.cpp:1625-1649); removes them when urisActFlag is off.
+    void set_uris(const ComMod& com_mod);
     /// all_fun::commu(com_mod, com_mod.R) of Integrator::step (Code/Source/solver/Integrator.cpp:124-129).
     void commu_R();
     /// ustruct::ustruct_r (Code/Source/solver/ustruct.cpp:1742) on the device-resident R and Kd.

@@ -257,6 +257,74 @@ def fluid_gen_state(m, tDof, seed=31):
     return Ag, Yg, None, Bf
 
 
+# ---- URIS valves (unfitted resistive immersed surfaces; tests/cases/uris/pipe_uris_cfd, pipe_uris_fsi) ------------------------------
+# (name, mesh factory, tDof, mvMsh, FSI?)
+def _tet_pipe():
+    return meshgen.cylinder_tet4(4, 8, R=1.0, L=4.0)
+
+
+def _hex_skewed_fine():
+    m = meshgen.box_hex8(5, 5, 6, (1.0, 1.2, 1.5))
+    rng = np.random.default_rng(19)
+    m.x = np.asfortranarray(m.x + 0.02 * rng.standard_normal(m.x.shape))
+    return m
+
+
+URIS_CASES = [
+    ("tet4_two_valves", _tet_pipe, 4, 0, False),
+    ("hex8_two_valves_ale", _hex_skewed_fine, 7, 1, False),
+    ("tet4_fsi_pipe", None, 7, 1, True),
+]
+
+
+def uris_valves(m, seed=41):
+    """Two valves on mesh m: (raw urisType members for the reference harness, abi.Uris list for the device, sdf, scaffold_udf,
+    valve_vel).  Valve 0: a tilted plane through the middle of the mesh, closing (ramped thickness), with its velocity; valve 1: a
+    plane further downstream, fully open, with a cylindrical scaffold.  The thicknesses span a few elements, so that Gauss points
+    inside, at the edge of and outside the smeared surfaces all occur."""
+    rng = np.random.default_rng(seed)
+    lo, hi = m.x.min(axis=1), m.x.max(axis=1)
+    L = hi - lo
+    h = 0.1 * L[2]                                       # thickness unit: about one element layer along the axis
+    hs = 0.08 * min(L[0], L[1])                          # scaffold thickness unit
+    ctr = 0.5 * (lo + hi)
+    n0 = np.array([0.2, -0.1, 1.0]); n0 /= np.linalg.norm(n0)
+    sdf0 = n0 @ (m.x - (ctr - 0.15 * L * np.array([0, 0, 1.0]))[:, None])
+    sdf1 = m.x[2] - (ctr[2] + 0.25 * L[2])
+    r = np.hypot(m.x[0] - ctr[0], m.x[1] - ctr[1])
+    udf1 = np.abs(r - 0.3 * min(L[0], L[1]))
+    sdf = np.ascontiguousarray(np.stack([sdf0, sdf1]))
+    udf = np.ascontiguousarray(np.stack([np.zeros(m.nNo), udf1]))
+    vel = np.zeros((2, m.nNo, 3))
+    vel[0] = 0.5 * np.stack([np.sin(m.x[1]), np.cos(m.x[0]), 1.0 + 0.2 * m.x[2]], axis=1) + 0.05 * rng.standard_normal((m.nNo, 3))
+    raw = [dict(resistance=3.0e3, sdf_deps=1.2 * h, sdf_deps_close=2.4 * h, clsFlg=True, cnt=3, n_open=8, n_close=10, scaffold=False,
+                include_velocity=True),
+           dict(resistance=1.5e3, sdf_deps=1.6 * h, sdf_deps_close=2.0 * hs, clsFlg=False, cnt=50, n_open=8, n_close=10, scaffold=True,
+                include_velocity=False)]
+    dev = [abi.Uris(resistance=u["resistance"],
+                    sdf_deps=abi.uris_effective_deps(u["sdf_deps"], u["sdf_deps_close"], u["clsFlg"], u["cnt"], u["n_open"], u["n_close"]),
+                    scaffold_deps=u["sdf_deps_close"], scaffold=int(u["scaffold"]), include_velocity=int(u["include_velocity"]))
+           for u in raw]
+    return raw, dev, sdf, udf, vel
+
+
+def uris_case(name, scatter=abi.SCATTER_ATOMIC):
+    """(mesh, Ag, Yg, Dg, Bf, eq, domains)"""
+    _, mk, tDof, mv, fsi = next(c for c in URIS_CASES if c[0] == name)
+    if fsi:
+        m, Ag, Yg, Dg, Bf = fsi_case()
+        af, am, gam, beta = abi.gen_alpha(0.5)
+        eq = abi.EqParams(dt=1e-3, af=af, am=am, gam=gam, beta=beta, phys=abi.PHYS_FSI, dof=4, tDof=7, s=0, mvMsh=1, vmsStab=1,
+                          scatter=scatter, reserved=0)
+        dmn = [abi.fluid_domain(rho=1.0, mu=0.04, Id=0),
+               abi.struct_domain(rho=1.0, volType=abi.VOL_M94, E=1e7, nu=0.3, Kpen=1e7 / (3 * (1 - 0.6)), Id=1)]
+        return m, Ag, Yg, Dg, Bf, eq, dmn
+    m = mk()
+    Ag, Yg, Dg, Bf = fluid_gen_state(m, tDof)
+    eq = abi.fluid_eq(0.005, tDof=tDof, mvMsh=mv, scatter=scatter)
+    return m, Ag, Yg, Dg, Bf, eq, [abi.fluid_domain(K_darcy=1.5, f=(0.1, -0.2, 0.3))]
+
+
 # ---- scalar heat equations (heatS / heatF, SURVEY 8f rank 4) -------------------------------------------------------
 # (name, mesh factory, fluid?, tDof, eq.s, mvMsh, heat_domain kwargs)
 HEAT_CASES = [

@@ -182,6 +182,31 @@ def fsi_ustruct_golden():
     print("wrote fsi_ustruct.npz with", len(out), "arrays")
 
 
+def fluid_uris_golden():
+    """fluid_3d_m / fluid_3d_c with the URIS penalty terms (construct_fluid and the fluid elements of construct_fsi); the valve factor
+    itself comes from the restatement of uris::eval_uris_ris_factors_quadrature in oracle/ref_build/ref_stubs.cpp."""
+    out = {}
+    for name, *_ in common.URIS_CASES:
+        m, Ag, Yg, Dg, Bf, eq, dmn = common.uris_case(name)
+        raw, dev, sdf, udf, vel = common.uris_valves(m)
+        c = RefCase(); c.set_coords(m.x); c.add_mesh(m.IEN, eId=m.eId)
+        rowPtr, colPtr = c.build_graph(0)
+        c.alloc(4); c.set_state(Ag, Yg, Dg, Bf); c.assemble(0, eq, dmn)
+        R0, V0 = c.get_R(), c.get_Val()
+        c.set_uris(raw, sdf, udf, vel)
+        c.alloc(4); c.assemble(0, eq, dmn)
+        out[f"{name}/R"], out[f"{name}/Val"] = c.get_R(), c.get_Val()
+        out[f"{name}/rowPtr"], out[f"{name}/colPtr"] = rowPtr, colPtr
+        # the valves must matter, and not everywhere: the fixture proves nothing otherwise
+        assert common.rel_err(out[f"{name}/R"], R0) > 1e-3 and common.rel_err(out[f"{name}/Val"], V0) > 1e-6, name
+        for v in range(len(dev)):          # nodes inside and outside every smeared surface
+            assert 0.05 < (np.abs(sdf[v]) < dev[v].sdf_deps).mean() < 0.95, name
+        c.set_uris([]); c.alloc(4); c.assemble(0, eq, dmn)
+        assert np.array_equal(c.get_R(), R0)
+    np.savez_compressed(os.path.join(HERE, "fluid_uris.npz"), **out)
+    print("wrote fluid_uris.npz with", len(out), "arrays")
+
+
 def lelas_golden():
     """R / Val of l_elas_3d on TET4: the linear-elasticity equation and the mesh-motion equation (tDof = 7, old displacement)."""
     out = {}
@@ -224,6 +249,6 @@ if __name__ == "__main__":
     if not have_ref():
         raise SystemExit("oracle/_ref/libsvref.so is missing: run `make -C oracle ref` first")
     only = sys.argv[1:]
-    for fn in (fluid_golden, struct_golden, fluid_gen_golden, fluid_hi_golden, struct_hi_golden, heat_golden, ustruct_golden, lelas_golden, prestress_golden, fsi_ustruct_golden):
+    for fn in (fluid_golden, struct_golden, fluid_gen_golden, fluid_hi_golden, struct_hi_golden, heat_golden, ustruct_golden, lelas_golden, prestress_golden, fsi_ustruct_golden, fluid_uris_golden):
         if not only or fn.__name__.replace("_golden", "") in only:
             fn()

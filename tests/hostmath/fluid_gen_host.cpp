@@ -2,7 +2,7 @@
 // nG == eNoN Gauss points (HEX8, TET4) using the device Gauss-point routines, checked against the reference.
 #include <cmath>
 #include <cstring>
-using std::fabs; using std::sqrt; using std::pow; using std::exp;
+using std::fabs; using std::sqrt; using std::pow; using std::exp; using std::cos;
 #define SVB_HD inline
 #include "../../svmultiphysics_b200/csrc/fluid_gen.cuh"
 
@@ -12,6 +12,9 @@ struct HostFluidGenArgs {
   double dt, af, am, gam;
   double w[8], N[8][8], Nxi[8][8][3], Nxi2[8][8][6];
   svb::FluidDmn dm;
+  const double* uris;        // URIS valves: (nNo, nUris, 5) = |sdf|, |scaffold udf|, valve velocity; or null
+  int nUris;
+  svb200_uris urisP[SVB200_MAX_URIS];
 };
 
 template <int ENON>
@@ -47,8 +50,10 @@ static int run(const HostFluidGenArgs* P, const int* rowPtr, const int* colPtr, 
       gn_nxx3<ENON>(P->Nxi2[g], xl, xiX, Nx, Nxx);
       FluidGP q;
       FluidNode nd[ENON];
+      double uF = 0.0, uV[3] = {0.0, 0.0, 0.0};
+      if (P->uris) uris_factor<ENON>(P->uris, P->nUris, P->urisP, P->N[g], n, uF, uV);
       fluid_gen_gauss_point<ENON>(P->dm, P->dt, P->af, P->am, P->gam, P->w[g] * Jac, ks, P->N[g], Nx, Nxx, NxxL, al, yl, bfl,
-                                  P->mvMsh ? ym : nullptr, q, nd);
+                                  P->mvMsh ? ym : nullptr, q, nd, uF, uV);
       for (int a = 0; a < ENON; a++) {
         fluid_gen_residual(q, nd[a], lR[a]);
         if (P->factored) {

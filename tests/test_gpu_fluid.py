@@ -496,3 +496,41 @@ def test_edge_cases_and_error_behaviour():
     eng2.assemble(0, eq, [abi.fluid_domain(Id=0), abi.struct_domain(Id=1)])   # fluid equation: struct elements are skipped
     assert not eng2.get_Val().any() and not eng2.get_R().any()
     eng.close(); eng2.close()
+
+
+# ---- URIS valves: penalty terms of fluid_3d_m / fluid_3d_c with the per-Gauss-point valve factor (tests/cases/uris) --------------
+@pytest.mark.parametrize("scatter", [abi.SCATTER_ATOMIC, abi.SCATTER_COLORED])
+@pytest.mark.parametrize("name", [c[0] for c in common.URIS_CASES])
+def test_uris_valves_assembly_matches_golden(name, scatter):
+    """construct_fluid (TET4, HEX8 with a moving mesh) and the fluid elements of construct_fsi with two URIS valves (ramped thickness +
+    valve velocity; scaffold): R / Val against the compiled reference (tests/golden/fluid_uris.npz).  With valves set the TET4 mesh
+    runs through the per-Gauss-point kernel; removing them restores the closed-form kernel's result."""
+    from svmultiphysics_b200 import elements
+    from svmultiphysics_b200.engine import Engine
+    golden = common.load_golden("fluid_uris.npz")
+    m, Ag, Yg, Dg, Bf, eq, dmn = common.uris_case(name, scatter)
+    raw, dev, sdf, udf, vel = common.uris_valves(m)
+    eng = Engine(0)
+    eng.set_graph(golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"])
+    w, N, Nx = elements.tables(m.eNoN)
+    eng.set_mesh(0, m.IEN, w, N, Nx, eId=m.eId, Nxx=elements.nxx_tables(m.eNoN) if m.eNoN != 4 else None)
+    eng.set_coords(m.x)
+    eng.alloc(4); eng.set_state(Ag, Yg, Dg, Bf); eng.assemble(0, eq, dmn)
+    R0, V0 = eng.get_R(), eng.get_Val()
+    eng.set_uris(dev, sdf, udf, vel)
+    eng.alloc(4); eng.assemble(0, eq, dmn)
+    R1, V1 = eng.get_R(), eng.get_Val()
+    fl = np.arange(m.nNo) if m.eId is None else np.unique(m.IEN[:, (m.eId & 1) != 0])
+    rowPtr = golden[f"{name}/rowPtr"]
+    slots = np.concatenate([np.arange(rowPtr[a], rowPtr[a + 1]) for a in fl])
+    assert common.rel_err(R1[:, fl], golden[f"{name}/R"][:, fl]) < 1e-12
+    assert common.rel_err(V1[:, slots], golden[f"{name}/Val"][:, slots]) < 1e-12
+    assert common.rel_err(R1, golden[f"{name}/R"]) < 1e-12 and common.rel_err(V1, golden[f"{name}/Val"]) < 1e-12
+    assert common.rel_err(R1[:, fl], R0[:, fl]) > 1e-3                  # the valves matter
+    if scatter == abi.SCATTER_COLORED:
+        eng.alloc(4); eng.assemble(0, eq, dmn)
+        assert np.array_equal(eng.get_R(), R1) and np.array_equal(eng.get_Val(), V1)
+    eng.set_uris([])
+    eng.alloc(4); eng.assemble(0, eq, dmn)
+    assert common.rel_err(eng.get_R(), R0) < 1e-13 and common.rel_err(eng.get_Val(), V0) < 1e-13
+    eng.close()

@@ -249,6 +249,24 @@ def test_fsi_ustruct_through_cpp_plugin():
     _close(cpu, gpu)
 
 
+def test_uris_valves_through_cpp_plugin():
+    """com_mod.uris[] through B200LinearAlgebra::set_uris (the open/close thickness ramp is computed by the plug-in from clsFlg / cnt /
+    DxClose like uris.cpp:1625-1649) against the reference's own construct_fluid with the same valves."""
+    name = "tet4_two_valves"
+    m, Ag, Yg, Dg, Bf, eq, dmn = common.uris_case(name)
+    raw, dev, sdf, udf, vel = common.uris_valves(m)
+    cpu, gpu = _pair(m)
+    res = []
+    for c in (cpu, gpu):
+        c.set_uris(raw, sdf, udf, vel)
+        c.alloc(4); c.set_state(Ag, Yg, Dg, Bf); c.assemble(0, eq, dmn)
+        res.append((c.get_R(), c.get_Val()))
+    golden = common.load_golden("fluid_uris.npz")
+    assert np.array_equal(res[0][0], golden[f"{name}/R"])
+    assert common.rel_err(res[1][0], res[0][0]) < 1e-12 and common.rel_err(res[1][1], res[0][1]) < 1e-12
+    _close(cpu, gpu)
+
+
 def test_prestress_equation_through_cpp_plugin():
     """com_mod.pS0 and pstEq through B200LinearAlgebra: the plug-in uploads pS0, flags the prestress equation and writes the
     device accumulators back into com_mod.pSn / pSa (what Integrator::corrector then communicates and divides)."""

@@ -23,7 +23,8 @@ class FluidArgs(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("IEN", "eId", "slot", "perm", "kU_ptr", "kU_ent", "kU_partner", "kContrib", "rU_ptr", "rU_ent", "rContrib", "x", "Ag", "Yg", "Bf", "Dg", "R", "Val")] + \
                [(k, C.c_int) for k in ("e0", "e1", "tDof", "mvMsh", "nDmn", "atomic", "ale", "pad0")] + [("err", C.c_void_p), ("gperm", C.c_void_p), ("g0", C.c_int), ("nGrpLaunch", C.c_int)] + \
                [(k, C.c_double) for k in ("dt", "af", "am", "gam")] + \
-               [("w", C.c_double * 8), ("N", (C.c_double * 8) * 8), ("Nxi", ((C.c_double * 3) * 8) * 8), ("dmn", FluidDmn * 8)]
+               [("w", C.c_double * 8), ("N", (C.c_double * 8) * 8), ("Nxi", ((C.c_double * 3) * 8) * 8), ("dmn", FluidDmn * 8),
+                ("uris", C.c_void_p), ("nUris", C.c_int), ("urisP", abi.Uris * abi.MAX_URIS)]
 
 
 @pytest.fixture(scope="module")
@@ -162,7 +163,8 @@ class HostFluidGenArgs(C.Structure):
                [(k, C.c_int) for k in ("eNoN", "nEl", "nG", "tDof", "mvMsh", "factored")] + \
                [(k, C.c_double) for k in ("dt", "af", "am", "gam")] + \
                [("w", C.c_double * 8), ("N", (C.c_double * 8) * 8), ("Nxi", ((C.c_double * 3) * 8) * 8),
-                ("Nxi2", ((C.c_double * 6) * 8) * 8), ("dm", FluidDmn)]
+                ("Nxi2", ((C.c_double * 6) * 8) * 8), ("dm", FluidDmn),
+                ("uris", C.c_void_p), ("nUris", C.c_int), ("urisP", abi.Uris * abi.MAX_URIS)]
 
 
 @pytest.mark.parametrize("factored", [0, 1], ids=["reference_form", "factored_rows"])
@@ -201,6 +203,54 @@ def test_device_general_fluid_algebra_matches_golden(hostmath, case, factored):
     rowPtr, colPtr = golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"]
     R = np.zeros((m.nNo, 4))
     V = np.zeros((len(colPtr), 16))
+    rc = hostmath.hostmath_fluid_gen(C.byref(A), rowPtr.ctypes.data_as(C.c_void_p), colPtr.ctypes.data_as(C.c_void_p),
+                                     R.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    assert common.rel_err(R.T, golden[f"{name}/R"]) < 1e-12
+    assert common.rel_err(V.T, golden[f"{name}/Val"]) < 1e-12
+
+
+@pytest.mark.parametrize("factored", [0, 1], ids=["reference_form", "factored_rows"])
+@pytest.mark.parametrize("name", [c[0] for c in common.URIS_CASES if not c[4]])
+def test_device_fluid_algebra_with_uris_valves_matches_golden(hostmath, name, factored):
+    """URIS penalty terms of fluid_3d_m / fluid_3d_c (fluid.cpp:2006-2008, 2042-2047, 2126-2129, 2166-2204, 2228-2234, 1660-1703) and
+    the per-Gauss-point valve factor (uris.cpp:1577-1673) in fluid_gen.cuh, compiled for the host, against tests/golden/fluid_uris.npz
+    (compiled reference; two valves: ramped thickness + valve velocity, scaffold)."""
+    golden = common.load_golden("fluid_uris.npz")
+    assert hostmath.hostmath_sizeof_fluidgenargs() == C.sizeof(HostFluidGenArgs)
+    m, Ag, Yg, Dg, Bf, eq, dmn = common.uris_case(name)
+    raw, dev, sdf, udf, vel = common.uris_valves(m)
+    d = dmn[0]
+    w, N, Nx = elements.tables(m.eNoN)
+    Nxx = elements.nxx_tables(m.eNoN)
+    A = HostFluidGenArgs()
+    nodal = np.zeros((m.nNo, len(dev), 5))
+    nodal[:, :, 0] = np.abs(sdf).T
+    nodal[:, :, 1] = np.abs(udf).T * np.array([v.scaffold for v in dev])[None, :]
+    nodal[:, :, 2:5] = vel.transpose(1, 0, 2) * np.array([v.include_velocity for v in dev])[None, :, None]
+    keep = [np.ascontiguousarray(m.IEN.T.astype(np.int32)), np.ascontiguousarray(m.x.T), np.ascontiguousarray(Ag.T),
+            np.ascontiguousarray(Yg.T), np.ascontiguousarray(Bf.T), np.ascontiguousarray(nodal)]
+    A.IEN, A.x, A.Ag, A.Yg, A.Bf, A.uris = (k.ctypes.data for k in keep)
+    A.nUris = len(dev)
+    for v, u in enumerate(dev):
+        A.urisP[v] = u
+    A.eNoN, A.nEl, A.nG, A.tDof, A.mvMsh, A.factored = m.eNoN, m.nEl, len(w), eq.tDof, eq.mvMsh, factored
+    A.dt, A.af, A.am, A.gam = eq.dt, eq.af, eq.am, eq.gam
+    for g in range(len(w)):
+        A.w[g] = w[g]
+        for a in range(m.eNoN):
+            A.N[g][a] = N[a, g]
+            for k in range(3):
+                A.Nxi[g][a][k] = Nx[k, a, g]
+            for k in range(6):
+                A.Nxi2[g][a][k] = Nxx[k, a, g]
+    A.dm.rho, A.dm.Kd = d.rho, d.K_darcy
+    for i in range(3):
+        A.dm.f[i] = d.f[i]
+    A.dm.mu_i, A.dm.mu_o, A.dm.lam, A.dm.a, A.dm.n = d.mu_i, d.mu_o, d.lam, d.a, d.n
+    A.dm.viscType, A.dm.Id, A.dm.isFluid = d.viscType, -1, 1
+    rowPtr, colPtr = golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"]
+    R = np.zeros((m.nNo, 4)); V = np.zeros((len(colPtr), 16))
     rc = hostmath.hostmath_fluid_gen(C.byref(A), rowPtr.ctypes.data_as(C.c_void_p), colPtr.ctypes.data_as(C.c_void_p),
                                      R.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p))
     assert rc == 0
