@@ -86,8 +86,22 @@ assemble_fluid_gen_kernel(const __grid_constant__ FluidGenArgs P)
   constexpr bool TAB_SMEM = fg_tab_in_smem(ENON, NG);
   extern __shared__ double sm[];
   const double* stab = TAB_SMEM ? sm : P.tab;
-  if (TAB_SMEM)
-    for (int t = threadIdx.x; t < NG * TLD; t += THREADS) sm[t] = __ldg(P.tab + t);
+  if (TAB_SMEM) {
+    // all loads of a thread in flight at once (a plain copy loop waits for each L2 round trip before the next one: ten dependent
+    // round trips per thread at 6 warps per SM were 13 % of the HEX8 kernel's samples, profiles/r2al_ncu_fluid_hex8.txt)
+    constexpr int NT = (NG * TLD + THREADS - 1) / THREADS;
+    double tmp[NT];
+#pragma unroll
+    for (int k = 0; k < NT; k++) {
+      const int t = threadIdx.x + k * THREADS;
+      tmp[k] = (t < NG * TLD) ? __ldg(P.tab + t) : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < NT; k++) {
+      const int t = threadIdx.x + k * THREADS;
+      if (t < NG * TLD) sm[t] = tmp[k];
+    }
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int a = lane % LPE, el = lane / LPE;
   double* se = sm + (TAB_SMEM ? NG * TLD : 0) + (size_t)(warp * EPW + el) * PER_EL;

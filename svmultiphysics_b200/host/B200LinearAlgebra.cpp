@@ -167,6 +167,16 @@ bool global_eq_assem(ComMod& com_mod, CepMod& cep_mod, const mshType& lM, const 
   bool active = false;
   for (int d = 0; d < eq.nDmn; d++) active |= (eq.dmn[d].active_stress != nullptr);
   if (active) la->set_active_tension(cep_mod);
+  // fitted RIS: ris::doassem_ris (fluid.cpp:750-754, fsi.cpp:349-353) adds every element matrix a second time into the rows of the
+  // node across an open resistive surface, directly in com_mod.R / com_mod.Val — arrays this backend does not use.  Not on the
+  // device: fail loudly instead of solving without that coupling.
+  if (com_mod.risFlag && (eq.phys == consts::EquationType::phys_fluid || eq.phys == consts::EquationType::phys_FSI)) {
+    bool allClosed = true;
+    for (bool c : com_mod.ris.clsFlg) allClosed = allClosed && c;
+    if (!allClosed)
+      throw std::runtime_error("[B200LinearAlgebra] an open RIS surface (ris::doassem_ris) is not implemented on the device; "
+                               "use the fsils linear algebra for this equation");
+  }
   // URIS valves (construct_fluid, fluid.cpp:622-672; the fluid elements of construct_fsi, fsi.cpp:170-216): the signed distance
   // function and the valve velocity move with the valve, so they are handed over at every assembly
   if (com_mod.urisFlag && (eq.phys == consts::EquationType::phys_fluid || eq.phys == consts::EquationType::phys_FSI))
