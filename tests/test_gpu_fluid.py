@@ -48,6 +48,48 @@ def test_fluid_assembly_parity(name, visc, Kd, f, tDof, mv, scatter):
     eng.close()
 
 
+@pytest.mark.parametrize("scatter", [abi.SCATTER_ATOMIC, abi.SCATTER_COLORED])
+def test_grouped_scatter_on_a_mesh_without_numbering_locality(scatter):
+    """The grouped TET4 scatter pre-reduces the contributions of 128 CONSECUTIVE elements; its plan must stay correct when the element
+    and node numbering has no locality at all (a group then has ~1280 distinct tangent targets and ~510 distinct nodes instead of ~710
+    and ~90, the plan's worst case): elements and nodes of the cylinder randomly renumbered, R / Val against the oracle on the SAME
+    renumbered mesh and against the naturally numbered run mapped through the permutations."""
+    import copy
+    m0 = meshgen.cylinder_tet4(10, 12)                       # 7,200 tets = 57 groups
+    Ag0, Yg0, Dg0 = meshgen.poiseuille_state(m0)
+    rng = np.random.default_rng(5)
+    pn = rng.permutation(m0.nNo)                             # old node -> new node
+    pe = rng.permutation(m0.nEl)
+    m = copy.copy(m0)
+    m.x = np.asfortranarray(np.empty_like(m0.x)); m.x[:, pn] = m0.x
+    m.IEN = np.asfortranarray(pn[m0.IEN][:, pe].astype(np.int32))
+    m.faces = {k: pn[v].astype(np.int32) for k, v in m0.faces.items()}
+    Ag, Yg = np.asfortranarray(np.empty_like(Ag0)), np.asfortranarray(np.empty_like(Yg0))
+    Ag[:, pn], Yg[:, pn] = Ag0, Yg0
+    eq, dmn = abi.fluid_eq(0.005, scatter=scatter), [abi.fluid_domain(K_darcy=0.7, f=(0.1, 0.2, -0.3))]
+    res = []
+    for mm, A, Y in ((m0, Ag0, Yg0), (m, Ag, Yg)):
+        orc, rowPtr, colPtr = common.make_oracle(_oracle(), mm)
+        orc.alloc(4); orc.set_state(A, Y, None, None); orc.assemble(0, eq, dmn)
+        eng = common.make_engine(mm, rowPtr, colPtr)
+        eng.alloc(4); eng.set_state(A, Y, None, None); eng.assemble(0, eq, dmn)
+        R1, V1 = eng.get_R(), eng.get_Val()
+        assert common.rel_err(R1, orc.get_R()) < ASM_TOL and common.rel_err(V1, orc.get_Val()) < ASM_TOL
+        if scatter == abi.SCATTER_COLORED:
+            eng.alloc(4); eng.assemble(0, eq, dmn)
+            assert np.array_equal(eng.get_Val(), V1) and np.array_equal(eng.get_R(), R1)
+        res.append((R1, V1, rowPtr, colPtr))
+        eng.close()
+    (Rn, Vn, rp0, cp0), (Rs, Vs, rp1, cp1) = res
+    assert common.rel_err(Rs[:, pn], Rn) < ASM_TOL           # same physics, renumbered
+    # block (a, b) of the natural run = block (pn[a], pn[b]) of the shuffled run
+    rows0 = np.repeat(np.arange(m0.nNo), np.diff(rp0))
+    rows1 = np.repeat(np.arange(m.nNo), np.diff(rp1))
+    lut = dict(zip(zip(rows1.tolist(), cp1.tolist()), range(len(cp1))))
+    idx = np.array([lut[(int(pn[a]), int(pn[b]))] for a, b in zip(rows0, cp0)])
+    assert common.rel_err(Vs[:, idx], Vn) < ASM_TOL
+
+
 def test_assemble_host_pipelined_matches_plain_sequence():
     """svb200_assemble_host (state uploaded in node chunks on a copy stream, element groups launched chunk by chunk behind it,
     finished residual rows streamed back) leaves the same R and Val as set_state + alloc + assemble + download."""
