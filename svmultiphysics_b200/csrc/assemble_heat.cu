@@ -31,6 +31,7 @@ struct HeatArgs {
   double N[MAX_NG][MAX_ENON];
   double Nxi[MAX_NG][MAX_ENON][3];
   HeatDmn dmn[MAX_DMN];
+  const double* tab;     // per-mesh device copy of the element tables (w | N | Nxi | Nxi2 per Gauss point) for TET10 / HEX20 / HEX27
 };
 
 template <bool ATOMIC>
@@ -47,6 +48,9 @@ assemble_heat_kernel(const __grid_constant__ HeatArgs P)
   constexpr int EPW = 32 / ENON;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int a = lane % ENON, el = lane / ENON;
+  constexpr bool TAB = ENON > MAX_ENON;
+  constexpr int TLD = 1 + 10 * ENON;
+  if (el >= EPW) return;             // 32 is not a multiple of ENON (WDG, TET10, HEX20, HEX27): the last lanes of the warp idle
   const long long idx = (long long)P.e0 + ((long long)blockIdx.x * 4 + warp) * EPW + el;
   if (idx >= P.e1) return;
   const int e = P.perm ? P.perm[idx] : (int)idx;
@@ -81,18 +85,20 @@ assemble_heat_kernel(const __grid_constant__ HeatArgs P)
   double Nx[ENON][3], ks[3][3], Jac = 1.0;
 #pragma unroll 1
   for (int g = 0; g < P.nG; g++) {
-    if (g == 0 || ENON != 4) {                       // TET4: lShpF, one gnn per element (heats.cpp:93)
-      Jac = gnn3_metric<ENON>(P.Nxi[g], xl, Nx, ks);
+    const double* tg = TAB ? P.tab + (size_t)g * TLD : nullptr;
+    const double* Ng = TAB ? tg + 1 : P.N[g];
+    if (g == 0 || (ENON != 4 && ENON != 6)) {        // TET4 / WDG: lShpF, one gnn per element (heats.cpp:89, heatf.cpp:112)
+      Jac = gnn3_metric<ENON>(TAB ? reinterpret_cast<const double(*)[3]>(tg + 1 + ENON) : P.Nxi[g], xl, Nx, ks);
       if (fabs(Jac) < 10.0 * 2.220446049250313e-16 * 2.220446049250313e-16) { if (a == 0) atomicMax(P.err, e + 1); return; }
     }
-    const double w = P.w[g] * Jac;
+    const double w = (TAB ? tg[0] : P.w[g]) * Jac;
     HeatGP q;
-    heat_gauss_point<ENON, FLUID>(dm, P.dt, P.af, P.am, P.gam, P.N[g], Nx, ks, Tl, Tdl, ul, q);
+    heat_gauss_point<ENON, FLUID>(dm, P.dt, P.af, P.am, P.gam, Ng, Nx, ks, Tl, Tdl, ul, q);
     double Na = 0.0, Nxa[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int b = 0; b < ENON; b++)
-      if (b == a) { Na = P.N[g][b]; Nxa[0] = Nx[b][0]; Nxa[1] = Nx[b][1]; Nxa[2] = Nx[b][2]; }
-    heat_row<ENON>(q, w, w * T1, Na, Nxa, P.N[g], Nx, lR, lK);
+      if (b == a) { Na = Ng[b]; Nxa[0] = Nx[b][0]; Nxa[1] = Nx[b][1]; Nxa[2] = Nx[b][2]; }
+    heat_row<ENON>(q, w, w * T1, Na, Nxa, Ng, Nx, lR, lK);
   }
   int na = 0;
 #pragma unroll
@@ -128,7 +134,10 @@ int run_assemble_heat(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq,
   SVB_REQUIRE(!fluid || eq->tDof >= 4, "svb200_assemble: heatF reads the fluid velocity from state dofs 0..2 (tDof >= 4)");
   SVB_REQUIRE(!fluid || !eq->mvMsh || eq->tDof >= 7, "svb200_assemble: mvMsh needs the mesh velocity in state dofs 4..6");
   SVB_REQUIRE(ctx->d_x, "svb200_assemble: coordinates not set");
-  SVB_REQUIRE(m.eNoN == 4 || m.eNoN == 8, "svb200_assemble: the heat equations are implemented for TET4 and HEX8 meshes");
+  const int key = m.eNoN * 100 + m.nG;
+  SVB_REQUIRE(key == 404 || key == 808 || key == 606 || key == 1015 || key == 2027 || key == 2727,
+              "svb200_assemble: the heat equations cover TET4, HEX8, WDG, TET10, HEX20 and HEX27 meshes with the reference's quadrature rules");
+  SVB_REQUIRE(m.eNoN <= MAX_ENON || m.d_gtab, "svb200_assemble: element tables missing");
   HeatArgs A;
   memset(&A, 0, sizeof(A));
   A.IEN = m.d_IEN; A.eId = m.d_eId; A.slot = m.d_slot; A.perm = nullptr;
@@ -141,13 +150,15 @@ int run_assemble_heat(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq,
   A.e0 = 0; A.e1 = m.nEl;
   A.tDof = eq->tDof; A.s = eq->s; A.nDmn = nDmn; A.nG = m.nG; A.mvMsh = eq->mvMsh;
   A.dt = eq->dt; A.af = eq->af; A.am = eq->am; A.gam = eq->gam;
-  for (int g = 0; g < m.nG; g++) {
-    A.w[g] = m.w[g];
-    for (int a = 0; a < m.eNoN; a++) {
-      A.N[g][a] = m.N[(size_t)g * m.eNoN + a];
-      for (int k = 0; k < 3; k++) A.Nxi[g][a][k] = m.Nx[((size_t)g * m.eNoN + a) * 3 + k];
+  A.tab = m.d_gtab;
+  if (m.nG <= MAX_NG && m.eNoN <= MAX_ENON)
+    for (int g = 0; g < m.nG; g++) {
+      A.w[g] = m.w[g];
+      for (int a = 0; a < m.eNoN; a++) {
+        A.N[g][a] = m.N[(size_t)g * m.eNoN + a];
+        for (int k = 0; k < 3; k++) A.Nxi[g][a][k] = m.Nx[((size_t)g * m.eNoN + a) * 3 + k];
+      }
     }
-  }
   bool whole = false;
   for (int d = 0; d < nDmn; d++) {
     HeatDmn& o = A.dmn[d];
@@ -160,8 +171,14 @@ int run_assemble_heat(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq,
   if (!whole && !m.d_eId) { set_error("eId is not allocated"); return SVB200_ERR_INVALID; }
   const bool atomic = (eq->scatter == SVB200_SCATTER_ATOMIC);
   auto launch = [&](const HeatArgs& B) {
-    if (m.eNoN == 8) return fluid ? launch_heat<8, true>(ctx, B, atomic) : launch_heat<8, false>(ctx, B, atomic);
-    return fluid ? launch_heat<4, true>(ctx, B, atomic) : launch_heat<4, false>(ctx, B, atomic);
+    switch (m.eNoN) {
+      case 8: return fluid ? launch_heat<8, true>(ctx, B, atomic) : launch_heat<8, false>(ctx, B, atomic);
+      case 6: return fluid ? launch_heat<6, true>(ctx, B, atomic) : launch_heat<6, false>(ctx, B, atomic);
+      case 10: return fluid ? launch_heat<10, true>(ctx, B, atomic) : launch_heat<10, false>(ctx, B, atomic);
+      case 20: return fluid ? launch_heat<20, true>(ctx, B, atomic) : launch_heat<20, false>(ctx, B, atomic);
+      case 27: return fluid ? launch_heat<27, true>(ctx, B, atomic) : launch_heat<27, false>(ctx, B, atomic);
+      default: return fluid ? launch_heat<4, true>(ctx, B, atomic) : launch_heat<4, false>(ctx, B, atomic);
+    }
   };
   int rc = SVB200_OK;
   if (atomic) rc = launch(A);

@@ -732,6 +732,11 @@ assemble_mesh_kernel(const __grid_constant__ StructArgs P, const double* __restr
   constexpr int EPW = 32 / ENON;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int a = lane % ENON, el = lane / ENON;
+  // tables: the fixed-size argument arrays for TET4 / HEX8 / WDG, the per-mesh device copy (w | N | Nxi | Nxi2 per Gauss point,
+  // assemble_fluid_gen.cu) for TET10 / HEX20 / HEX27
+  constexpr bool TAB = ENON > MAX_ENON;
+  constexpr int TLD = 1 + 10 * ENON;
+  if (el >= EPW) return;             // 32 is not a multiple of ENON (WDG, TET10, HEX20, HEX27): the last lanes of the warp idle
   const long long idx = (long long)P.e0 + ((long long)blockIdx.x * 4 + warp) * EPW + el;
   if (idx >= P.e1) return;
   const int e = P.perm ? P.perm[idx] : (int)idx;
@@ -775,13 +780,18 @@ assemble_mesh_kernel(const __grid_constant__ StructArgs P, const double* __restr
   double Jac = 1.0;
 #pragma unroll 1
   for (int g = 0; g < P.nG; g++) {
-    if (g == 0 || ENON != 4) Jac = gnn3<ENON>(P.Nxi[g], xl, Nx);     // TET4: lShpF, gradients constant
-    const double w = LELAS ? P.w[g] * Jac : P.w[g];
+    const double* tg = TAB ? P.tab + (size_t)g * TLD : nullptr;
+    const double* Ng = TAB ? tg + 1 : P.N[g];
+    const double wg = TAB ? tg[0] : P.w[g];
+    // TET4 / WDG: lShpF, one gnn per element (l_elas.cpp:112, mesh.cpp:114) — for the wedge too, whose gradients are not constant
+    if (g == 0 || (ENON != 4 && ENON != 6))
+      Jac = gnn3<ENON>(TAB ? reinterpret_cast<const double(*)[3]>(tg + 1 + ENON) : P.Nxi[g], xl, Nx);
+    const double w = LELAS ? wg * Jac : wg;
     const double wl = w * T1c * mu;
     double ud[3] = {-dm.f[0], -dm.f[1], -dm.f[2]}, ed[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int b = 0; b < ENON; b++) {
-      const double Nb = P.N[g][b];
+      const double Nb = Ng[b];
       const size_t n = (size_t)node[b];
 #pragma unroll
       for (int i = 0; i < 3; i++)
@@ -796,7 +806,7 @@ assemble_mesh_kernel(const __grid_constant__ StructArgs P, const double* __restr
     const double divD = lambda * (ed[0] + ed[1] + ed[2]);
     double S0 = divD + 2.0 * mu * ed[0], S1 = divD + 2.0 * mu * ed[1], S2 = divD + 2.0 * mu * ed[2];
     double S3 = mu * ed[3], S4 = mu * ed[4], S5 = mu * ed[5];
-    const double Na = P.N[g][a];
+    const double Na = Ng[a];
     if (LELAS) {
       // prestress of the linear-elasticity equation (l_elas.cpp:321-338, 130-140): lane a accumulates its own node
       if (P.pSn != nullptr) {
@@ -811,7 +821,7 @@ assemble_mesh_kernel(const __grid_constant__ StructArgs P, const double* __restr
 #pragma unroll
         for (int b = 0; b < ENON; b++)
 #pragma unroll
-          for (int i = 0; i < 6; i++) p0[i] += P.N[g][b] * __ldg(P.pS0 + 6 * (size_t)node[b] + i);
+          for (int i = 0; i < 6; i++) p0[i] += Ng[b] * __ldg(P.pS0 + 6 * (size_t)node[b] + i);
         S0 += p0[0]; S1 += p0[1]; S2 += p0[2]; S3 += p0[3]; S4 += p0[4]; S5 += p0[5];
       }
     }
@@ -821,7 +831,7 @@ assemble_mesh_kernel(const __grid_constant__ StructArgs P, const double* __restr
 #pragma unroll
     for (int b = 0; b < ENON; b++) {
       const double NxdNx = Nx[a][0] * Nx[b][0] + Nx[a][1] * Nx[b][1] + Nx[a][2] * Nx[b][2];
-      const double T1 = amd * Na * P.N[g][b] / mu + NxdNx;
+      const double T1 = amd * Na * Ng[b] / mu + NxdNx;
 #pragma unroll
       for (int i = 0; i < 3; i++)
 #pragma unroll
@@ -1206,7 +1216,10 @@ int run_assemble_mesh(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq,
   const bool lelas = (eq->phys == SVB200_PHYS_LELAS);
   SVB_REQUIRE(lelas || ctx->d_Do, "svb200_assemble: the mesh equation needs the old displacement (svb200_set_old_disp)");
   SVB_REQUIRE(eq->dof == 3 && ctx->dof == 3, "svb200_assemble: the mesh / linear-elasticity equation has dof = 3");
-  SVB_REQUIRE(m.eNoN == 4 || m.eNoN == 8, "svb200_assemble: the mesh / linear-elasticity equation is implemented for TET4 and HEX8 meshes");
+  const int key = m.eNoN * 100 + m.nG;
+  SVB_REQUIRE(key == 404 || key == 808 || key == 606 || key == 1015 || key == 2027 || key == 2727,
+              "svb200_assemble: the mesh / linear-elasticity equation covers TET4, HEX8, WDG, TET10, HEX20 and HEX27 meshes with the reference's quadrature rules");
+  SVB_REQUIRE(m.eNoN <= MAX_ENON || m.d_gtab, "svb200_assemble: element tables missing");
   // reuse the solid argument block: mark mesh domains as the ones to assemble, E / nu travel in C10 / C01
   std::vector<svb200_dmnparams> d(dmn, dmn + nDmn);
   for (auto& q : d) {
@@ -1240,7 +1253,14 @@ int run_assemble_mesh(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq,
   };
   auto launch = [&](const StructArgs& B) {
     if (m.eNoN == 4 && m.nG == 4 && !force_general && !(lelas && (A.pS0 || A.pSn))) return launch_t4(B);
-    return m.eNoN == 8 ? launch_mesh<8>(ctx, B, Do) : launch_mesh<4>(ctx, B, Do);
+    switch (m.eNoN) {
+      case 8: return launch_mesh<8>(ctx, B, Do);
+      case 6: return launch_mesh<6>(ctx, B, Do);
+      case 10: return launch_mesh<10>(ctx, B, Do);
+      case 20: return launch_mesh<20>(ctx, B, Do);
+      case 27: return launch_mesh<27>(ctx, B, Do);
+      default: return launch_mesh<4>(ctx, B, Do);
+    }
   };
   if (A.atomic) return launch(A);
   A.perm = m.d_color_perm;

@@ -349,6 +349,39 @@ def heat_state(m, tDof, s, seed=47):
     return Ag, Yg, Dg, Bf
 
 
+# ---- heat / linear elasticity / mesh motion on curved TET10 / HEX20 / HEX27 / WDG elements (nG != eNoN; lShpF wedge behaviour) -------
+# (name, kind, mesh factory, parameters).  kind: heats | heatf | lelas | mesh
+OTHER_HI_CASES = [
+    ("tet10_heats", "heats", _tet10, dict(tDof=1, s=0, mv=0, dkw=dict(conductivity=0.7, source=0.3, rho=2.5))),
+    ("hex27_heatf_moving_mesh", "heatf", _hex27, dict(tDof=8, s=7, mv=1, dkw=dict(conductivity=0.05, source=0.1))),
+    ("hex20_heatf", "heatf", _hex20, dict(tDof=5, s=4, mv=0, dkw=dict(conductivity=0.01, source=0.2))),
+    ("wdg6_heats", "heats", _wdg6, dict(tDof=3, s=2, mv=0, dkw=dict(conductivity=12.0, source=-1.5, rho=0.8))),
+    ("tet10_lelas", "lelas", _tet10, dict(dkw=dict(E=1.0e6, nu=0.3, rho=2.0, f=(0.1, -0.2, 0.3)))),
+    ("hex27_lelas", "lelas", _hex27, dict(dkw=dict(E=2.0e6, nu=0.25, rho=1.0))),
+    ("wdg6_lelas", "lelas", _wdg6, dict(dkw=dict(E=1.0e6, nu=0.35, rho=1.5, f=(0.0, 0.0, -1.0)))),
+    ("hex20_mesh", "mesh", _hex20, dict(dkw=dict(E=1.0, nu=0.3))),
+    ("tet10_mesh", "mesh", _tet10, dict(dkw=dict(E=1.0, nu=0.3))),
+]
+
+
+def other_hi_case(name, scatter=abi.SCATTER_ATOMIC):
+    """(mesh, element type, dof, Ag, Yg, Dg, Bf, Do or None, eq, domains)"""
+    _, kind, mk, kw = next(c for c in OTHER_HI_CASES if c[0] == name)
+    m = mk()
+    et = name.split("_")[0]
+    if kind in ("heats", "heatf"):
+        Ag, Yg, Dg, Bf = heat_state(m, kw["tDof"], kw["s"])
+        eq = abi.heat_eq(0.01, kind == "heatf", tDof=kw["tDof"], s=kw["s"], mvMsh=kw["mv"], scatter=scatter)
+        return m, et, 1, Ag, Yg, Dg, Bf, None, eq, [abi.heat_domain(kind == "heatf", **kw["dkw"])]
+    if kind == "lelas":
+        Ag, Yg, Dg, Bf, _ = struct_state(m, 0)
+        return m, et, 3, Ag, Yg, Dg, Bf, None, abi.lelas_eq(1e-3, scatter=scatter), [abi.lelas_domain(**kw["dkw"])]
+    Ag, Yg, Dg, Bf, _ = struct_state(m, 0, tDof=7)
+    Dg[4:7] = Dg[0:3]; Ag[4:7] *= 0.5
+    Do = np.asfortranarray(0.9 * Dg)
+    return m, et, 3, Ag, Yg, Dg, Bf, Do, abi.mesh_eq(1e-3, scatter=scatter), [abi.mesh_domain(**kw["dkw"])]
+
+
 # ---- mixed velocity-pressure solid (ustruct, SURVEY 8f rank 4) ------------------------------------------------------
 # (name, mesh factory, ustruct_domain kwargs, number of fibre families)
 USTRUCT_CASES = [

@@ -207,6 +207,25 @@ def fluid_uris_golden():
     print("wrote fluid_uris.npz with", len(out), "arrays")
 
 
+def other_hi_golden():
+    """heats_3d / heatf_3d / l_elas_3d (linear-elasticity and mesh-motion equations) on curved TET10 / HEX20 / HEX27 / WDG elements
+    (element tables: tests/golden/fluid_hi.npz)."""
+    out = {}
+    for name, *_ in common.OTHER_HI_CASES:
+        m, et, dof, Ag, Yg, Dg, Bf, Do, eq, dmn = common.other_hi_case(name)
+        c = RefCase(); c.set_coords(m.x); c.add_mesh(m.IEN)
+        rowPtr, colPtr = c.build_graph(0)
+        c.alloc(dof); c.set_state(Ag, Yg, Dg, Bf)
+        if Do is not None:
+            c.set_old_disp(Do)
+        c.assemble(0, eq, dmn)
+        out[f"{name}/R"], out[f"{name}/Val"] = c.get_R(), c.get_Val()
+        out[f"{name}/rowPtr"], out[f"{name}/colPtr"] = rowPtr, colPtr
+        assert np.abs(out[f"{name}/R"]).max() > 0 and np.abs(out[f"{name}/Val"]).max() > 0
+    np.savez_compressed(os.path.join(HERE, "other_hi.npz"), **out)
+    print("wrote other_hi.npz with", len(out), "arrays")
+
+
 def lelas_golden():
     """R / Val of l_elas_3d on TET4: the linear-elasticity equation and the mesh-motion equation (tDof = 7, old displacement)."""
     out = {}
@@ -249,6 +268,6 @@ if __name__ == "__main__":
     if not have_ref():
         raise SystemExit("oracle/_ref/libsvref.so is missing: run `make -C oracle ref` first")
     only = sys.argv[1:]
-    for fn in (fluid_golden, struct_golden, fluid_gen_golden, fluid_hi_golden, struct_hi_golden, heat_golden, ustruct_golden, lelas_golden, prestress_golden, fsi_ustruct_golden, fluid_uris_golden):
+    for fn in (fluid_golden, struct_golden, fluid_gen_golden, fluid_hi_golden, struct_hi_golden, heat_golden, ustruct_golden, lelas_golden, prestress_golden, fsi_ustruct_golden, fluid_uris_golden, other_hi_golden):
         if not only or fn.__name__.replace("_golden", "") in only:
             fn()
