@@ -279,6 +279,17 @@ SVB200_API int svb200_set_prestress(svb200_ctx* ctx, const double* pS0);
 SVB200_API int svb200_get_prestress(svb200_ctx* ctx, double* pSn, double* pSa);
 SVB200_API int svb200_set_active_tension(svb200_ctx* ctx, const double* Ya_f, const double* Ya_s, const double* Ya_n);
 
+/* Fitted resistive immersed surfaces (RIS): the coupling an OPEN surface adds, ris::doassem_ris (solver/ris.cpp:269-349), called per
+ * element by construct_fluid (fluid.cpp:750-754) and construct_fsi (fsi.cpp:349-353): the residual row and the tangent row of every
+ * element node listed in grisMapList[iProj].map are added a second time into the row of its twin across the surface, mapped columns
+ * replaced by their twins.  On the device this is done on the ASSEMBLED rows of each mesh (csrc/ris.cu), inside svb200_assemble of a
+ * fluid / FSI equation.  nProj projections (RIS.nbrRIS); maps holds, for projection p, 2 * nMap[p] node ids in the order of the
+ * column-major grisMapList[p].map(2, n): map(0,0), map(1,0), map(0,1), ... (INPUT node order, every node with a twin: -1 is
+ * rejected); closed[p] = RIS.clsFlg[p] (closed surfaces add nothing).  The CSR graph must contain the extra connections lhsa adds
+ * when com_mod.risFlag is set (lhsa.cpp:168-193).  nProj = 0 removes the plan.  Call after svb200_set_graph and again whenever a
+ * surface opens or closes. */
+SVB200_API int svb200_set_ris(svb200_ctx* ctx, int32_t nProj, const int32_t* nMap, const int32_t* maps, const int32_t* closed);
+
 /* Unfitted resistive immersed surfaces (URIS valves): the penalty terms of fluid_3d_m / fluid_3d_c (solver/fluid.cpp:2006-2008,
  * 2042-2047, 2126-2129, 2166-2204, 2228-2234 and :1660-1703) with the per-Gauss-point factor of
  * uris::eval_uris_ris_factors_quadrature (solver/uris.cpp:1577-1673), used by construct_fluid (fluid.cpp:622-672) and the fluid

@@ -25,7 +25,6 @@ LinearAlgebra::LinearAlgebra() {}
 // uris::eval_uris_ris_factors_quadrature (uris.cpp:1577-1673).  RESTATEMENT of that routine (test infrastructure; parity of the
 // URIS factor itself is therefore against this restatement, while the URIS terms of fluid_3d_m / fluid_3d_c that consume it are the
 // compiled reference's).  It reads the same urisType members the reference reads; the harness fills them (svref_set_uris).
-#include "ris.h"
 #include "uris.h"
 #include <cmath>
 namespace uris {
@@ -67,8 +66,4 @@ void eval_uris_ris_factors_quadrature(const ComMod& cm, const mshType& lM, const
     }
   }
 }
-}
-namespace ris {
-void doassem_ris(ComMod&, const int, const Vector<int>&, const Array3<double>&, const Array<double>&)
-{ throw std::runtime_error("[oracle] ris is out of scope (SURVEY.md 2.3); the harness never sets com_mod.risFlag"); }
 }

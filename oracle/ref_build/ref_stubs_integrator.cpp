@@ -35,10 +35,7 @@
 
 namespace svZeroD { void calc_svZeroD(ComMod&, const CmMod&, char) { OUT_OF_SCOPE("svZeroD"); } }
 namespace svOneD { void calc_svOneD(ComMod&, const CmMod&, char) { OUT_OF_SCOPE("svOneD"); } }
-namespace ris {
-void ris_resbc(ComMod&, const SolutionStates&) { OUT_OF_SCOPE("ris"); }
-void ris0d_bc(ComMod&, CmMod&, const SolutionStates&) { OUT_OF_SCOPE("ris"); }
-}
+// (namespace ris: the reference's own ris.cpp is compiled since round 2 session 3)
 namespace post {
 void fib_stretch(const ComMod&, const int, const mshType&, const Array<double>&, Vector<double>&) { OUT_OF_SCOPE("post::fib_stretch"); }
 void fib_stretch_rate(const ComMod&, const int, const mshType&, const SolutionStates&, Vector<double>&) { OUT_OF_SCOPE("post::fib_stretch_rate"); }

@@ -313,12 +313,28 @@ int svref_build_graph(void* h, int nFaces, int* nnz_out)
     int mnnzeic = 10*max_enon;
     Array<int> uInd(mnnzeic, tnNo);
     uInd = -1;
-    for (auto& m : cm.msh) {
+    for (int iM = 0; iM < (int)cm.msh.size(); iM++) {
+      auto& m = cm.msh[iM];
       for (int e = 0; e < m.nEl; e++) {
         for (int a = 0; a < m.eNoN; a++) {
           int rowN = m.IEN(a,e);
           for (int b = 0; b < m.eNoN; b++) {
             lhsa_ns::add_col(tnNo, rowN, m.IEN(b,e), mnnzeic, uInd);
+          }
+          // extra connections of the twin node across a RIS surface (lhsa.cpp:168-193)
+          if (cm.risFlag) {
+            for (int iProj = 0; iProj < cm.ris.nbrRIS; iProj++) {
+              int jMRIS;
+              if (cm.ris.lst(0,0,iProj) == iM) jMRIS = 1;
+              else if (cm.ris.lst(1,0,iProj) == iM) jMRIS = 0;
+              else continue;
+              std::array<int, 2> mapIdx;
+              utils::find_loc(cm.grisMapList[iProj].map, rowN, mapIdx);
+              if (mapIdx[0] == -1) continue;
+              const int rowNR = cm.grisMapList[iProj].map(jMRIS, mapIdx[1]);
+              if (rowNR == -1) continue;
+              for (int b = 0; b < m.eNoN; b++) lhsa_ns::add_col(tnNo, rowNR, m.IEN(b,e), mnnzeic, uInd);
+            }
           }
         }
       }
@@ -521,6 +537,36 @@ int svref_set_active_tension(void* h, const double* Ya_f, const double* Ya_s, co
       cem.Ya_f[a] = Ya_f[a];
       cem.Ya_s[a] = Ya_s ? Ya_s[a] : 0.0;
       cem.Ya_n[a] = Ya_n ? Ya_n[a] : 0.0;
+    }
+  });
+}
+
+/// Fitted RIS: com_mod.risFlag, ris.nbrRIS / clsFlg / lst and grisMapList[] as ris::ris_read_msh leaves them for lhsa (extra CSR
+/// connections, lhsa.cpp:168-193 — call BEFORE svref_build_graph) and for ris::doassem_ris (ris.cpp:269-349; the reference's own
+/// ris.cpp is compiled into libsvref.so).  maps: for projection p, 2 * nMap[p] node ids, map(0,0), map(1,0), map(0,1), ...;
+/// meshes(2, nProj): the mesh index of face 0 and of face 1 of each projection (RIS.lst(0,0,p), RIS.lst(1,0,p)).
+int svref_set_ris(void* h, int nProj, const int* nMap, const int* maps, const int* closed, const int* meshes)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    auto& cm = c.com_mod;
+    cm.risFlag = nProj > 0;
+    cm.ris.nbrRIS = nProj;
+    cm.ris.clsFlg.assign(nProj, false);
+    cm.ris.lst.resize(2, 2, std::max(nProj, 1));
+    cm.grisMapList.clear();
+    cm.grisMapList.resize(nProj);
+    size_t off = 0;
+    for (int p = 0; p < nProj; p++) {
+      cm.ris.clsFlg[p] = closed[p] != 0;
+      cm.ris.lst(0, 0, p) = meshes[2*p]; cm.ris.lst(1, 0, p) = meshes[2*p + 1];
+      cm.ris.lst(0, 1, p) = 0; cm.ris.lst(1, 1, p) = 0;
+      cm.grisMapList[p].map.resize(2, nMap[p]);
+      for (int j = 0; j < nMap[p]; j++) {
+        cm.grisMapList[p].map(0, j) = maps[off + 2*j];
+        cm.grisMapList[p].map(1, j) = maps[off + 2*j + 1];
+      }
+      off += 2 * (size_t)nMap[p];
     }
   });
 }

@@ -157,6 +157,17 @@ class _FlatCase:
         n_ = None if Ya_n is None else np.ascontiguousarray(Ya_n, dtype=np.float64)
         self._call("set_active_tension", _d(f), _d(s_), _d(n_))
 
+    def set_ris(self, maps, closed, meshes):
+        """Fitted RIS (before build_graph): maps = list of (2, n) int arrays (grisMapList[p].map), closed = RIS.clsFlg, meshes = list of
+        (mesh of face 0, mesh of face 1)."""
+        n = len(maps)
+        nMap = np.array([mp.shape[1] for mp in maps], dtype=np.int32)
+        flat = np.concatenate([np.asfortranarray(mp, dtype=np.int32).ravel(order="F") for mp in maps]) if n else np.zeros(0, np.int32)
+        flat = np.ascontiguousarray(flat, dtype=np.int32)
+        cl = np.array([int(x) for x in closed], dtype=np.int32)
+        ms = np.ascontiguousarray(np.array(meshes, dtype=np.int32).reshape(-1))
+        self._call("set_ris", C.c_int(n), _i(nMap), _i(flat), _i(cl), _i(ms))
+
     def set_uris(self, raw, sdf=None, scaffold_udf=None, valve_vel=None):
         """com_mod.uris[] for uris::eval_uris_ris_factors_quadrature.  raw = list of dicts with resistance, sdf_deps, sdf_deps_close,
         clsFlg, cnt, n_open, n_close, scaffold, include_velocity (the urisType members, not the effective thickness);

@@ -238,6 +238,7 @@ int svb200_destroy(svb200_ctx* ctx)
   for (auto& nb : ctx->neigh) { cudaFree(nb.d_ptr); cudaFree(nb.d_send); cudaFree(nb.d_recv); }
   cudaFree(ctx->d_map); cudaFree(ctx->d_rowPtr_in); cudaFree(ctx->d_rowPtr); cudaFree(ctx->d_colPtr); cudaFree(ctx->d_diagPtr);
   cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf); cudaFree(ctx->d_Do); cudaFree(ctx->d_Ya); cudaFree(ctx->d_uris); cudaFree(ctx->d_pS0); cudaFree(ctx->d_pSn);
+  ris_build_plan(ctx, 0, nullptr, nullptr, nullptr);
   cudaFree(ctx->d_Ao); cudaFree(ctx->d_Yo); cudaFree(ctx->d_An); cudaFree(ctx->d_Yn); cudaFree(ctx->d_Dn); cudaFree(ctx->d_nodeflag);
   cudaFree(ctx->d_err); cudaFree(ctx->d_Kd); cudaFree(ctx->d_Ad); cudaFree(ctx->d_Rd);
   cudaFree(ctx->d_stage); cudaFree(ctx->d_R); cudaFree(ctx->d_Val); cudaFree(ctx->d_W);
@@ -383,6 +384,7 @@ int svb200_set_graph(svb200_ctx* ctx, int32_t nNo, int32_t nnz, const int32_t* r
   cudaFree(ctx->d_x); cudaFree(ctx->d_Ag); cudaFree(ctx->d_Yg); cudaFree(ctx->d_Dg); cudaFree(ctx->d_Bf); cudaFree(ctx->d_Do);
   cudaFree(ctx->d_Ya); ctx->d_Ya = nullptr; ctx->ya_sn_positive = false;
   cudaFree(ctx->d_uris); ctx->d_uris = nullptr; ctx->nUris = 0;
+  ris_build_plan(ctx, 0, nullptr, nullptr, nullptr);
   cudaFree(ctx->d_pS0); cudaFree(ctx->d_pSn); ctx->d_pS0 = ctx->d_pSn = nullptr;
   cudaFree(ctx->d_Ao); cudaFree(ctx->d_Yo); cudaFree(ctx->d_An); cudaFree(ctx->d_Yn); cudaFree(ctx->d_Dn); cudaFree(ctx->d_nodeflag);
   ctx->d_Ao = ctx->d_Yo = ctx->d_An = ctx->d_Yn = ctx->d_Dn = nullptr; ctx->d_nodeflag = nullptr;
@@ -837,6 +839,14 @@ int svb200_set_uris(svb200_ctx* ctx, int32_t nUris, const svb200_uris* valves, c
   return SVB200_OK;
 }
 
+int svb200_set_ris(svb200_ctx* ctx, int32_t nProj, const int32_t* nMap, const int32_t* maps, const int32_t* closed)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(nProj >= 0 && (nProj == 0 || (nMap && maps && closed)), "svb200_set_ris: bad arguments");
+  SVB_REQUIRE(nProj == 0 || !ctx->h_rowPtr.empty(), "svb200_set_ris: set the graph first");
+  return ris_build_plan(ctx, nProj, nMap, maps, closed);
+}
+
 int svb200_set_old_disp(svb200_ctx* ctx, int32_t tDof, const double* Do)
 {
   CTX_GUARD(ctx);
@@ -1048,6 +1058,13 @@ int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, cons
   SVB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
   // a deferred zeroing of Val (svb200_alloc) is consumed by the TET4 fluid path; every other kernel needs Val zeroed first
   if (eq->phys != SVB200_PHYS_FLUID && eq->phys != SVB200_PHYS_FSI) TRY(flush_val_zero(ctx));
+  // open fitted RIS surfaces (ris::doassem_ris, fluid.cpp:750-754, fsi.cpp:349-353): the rows of the mapped nodes are taken aside
+  // around the element kernels of this mesh and what the mesh contributed to them is added to the twin rows afterwards (ris.cu)
+  const bool ris = ris_active(ctx) && (eq->phys == SVB200_PHYS_FLUID || eq->phys == SVB200_PHYS_FSI);
+  if (ris) {
+    TRY(flush_val_zero(ctx));
+    TRY(ris_begin(ctx));
+  }
   switch (eq->phys) {
     case SVB200_PHYS_FLUID: {
       FluidArgs A;
@@ -1100,6 +1117,7 @@ int svb200_assemble(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq, cons
       set_error("svb200_assemble: this physics is not implemented in this build");
       return SVB200_ERR_UNSUPPORTED;
   }
+  if (ris) TRY(ris_end(ctx));
   SVB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
   SVB_CUDA(cudaEventSynchronize(ctx->ev1));
   float ms = 0.f;
@@ -1131,7 +1149,7 @@ int svb200_assemble_host(svb200_ctx* ctx, int32_t iM, const svb200_eqparams* eq,
   static const bool no_pipe = getenv("SVB200_HOST_NO_PIPELINE") != nullptr;       // A/B knob
   const bool fast = !no_pipe && eq->phys == SVB200_PHYS_FLUID && m.eNoN == 4 && eq->scatter == SVB200_SCATTER_ATOMIC &&
                     !(eq->reserved & SVB200_EQ_GENERAL_KERNEL) && m.schedK.d_uptr && (int)m.grp_node_need.size() == nGrp && nGrp >= 256 &&
-                    m.jac_checked && ctx->tDof == eq->tDof && ctx->d_Ag && ctx->d_Yg && ctx->nUris == 0 && getenv("SVB200_ASM_LEGACY") == nullptr;
+                    m.jac_checked && ctx->tDof == eq->tDof && ctx->d_Ag && ctx->d_Yg && ctx->nUris == 0 && !ris_active(ctx) && getenv("SVB200_ASM_LEGACY") == nullptr;
   if (!fast) {
     // any other case: the plain sequence (also the first call on a mesh, which runs the Jacobian check)
     TRY(svb200_set_state(ctx, eq->tDof, Ag, Yg, nullptr, nullptr));

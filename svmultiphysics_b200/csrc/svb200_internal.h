@@ -136,6 +136,16 @@ struct FluidArgs {
 
 }  // namespace svb
 
+namespace svb {
+// plan of the open resistive immersed surfaces (ris.cu)
+struct RisPlan {
+  int nNode = 0, nRApply = 0, buf_dof = 0;
+  long long nEnt = 0, nApply = 0;
+  int *d_ent = nullptr, *d_src = nullptr, *d_dst = nullptr, *d_node = nullptr, *d_rsrc = nullptr, *d_rdst = nullptr;
+  double *d_S = nullptr, *d_C = nullptr, *d_RS = nullptr, *d_RC = nullptr;
+};
+}  // namespace svb
+
 struct svb200_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -164,6 +174,7 @@ struct svb200_ctx {
   double* d_Yg = nullptr;
   double* d_Dg = nullptr;
   double* d_Do = nullptr;        // old displacement (mesh-motion equation; solutions.old)
+  svb::RisPlan ris;              // open fitted RIS surfaces (svb200_set_ris)
   double* d_uris = nullptr;      // URIS nodal fields (5 nUris, nNo): per valve |sdf|, |scaffold udf|, valve velocity (svb200_set_uris)
   int nUris = 0;
   svb200_uris urisP[SVB200_MAX_URIS] = {};
@@ -271,6 +282,10 @@ static inline bool eqtime_is_sst(const svb200_eqtime& q)
 {
   return q.phys == SVB200_PHYS_USTRUCT || (q.phys == SVB200_PHYS_FSI && (q.reserved & SVB200_EQTIME_SSTEQ));
 }
+bool ris_active(const svb200_ctx* ctx);
+int ris_build_plan(svb200_ctx* ctx, int nProj, const int* nMap, const int* maps, const int* closed);
+int ris_begin(svb200_ctx* ctx);
+int ris_end(svb200_ctx* ctx);
 int run_ustruct_r(svb200_ctx* ctx, const svb200_eqparams* eq, int itr, const double* d_Ad);
 // assemble_heat.cu
 int run_assemble_heat(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);

@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "svb200_set_solution", "svb200_get_solution", "svb200_predictor", "svb200_initiator", "svb200_corrector",
     "svb200_set_node_flags", "svb200_set_dirichlet_rows", "svb200_dirichlet_ustruct", "svb200_advance_time_step",
     "svb200_set_bface", "svb200_assemble_neu",
-    "svb200_last_host_stage", "svb200_set_uris", "svb200_set_active_tension", "svb200_set_prestress", "svb200_get_prestress",
+    "svb200_last_host_stage", "svb200_set_uris", "svb200_set_ris", "svb200_set_active_tension", "svb200_set_prestress", "svb200_get_prestress",
     "svb200_spmv_rc", "svb200_spmv_rc_variants", "svb200_bench_spmv_rc",
     "svb200_schur_sp", "svb200_schur_sp_variants", "svb200_bench_schur_sp",
 ]
@@ -232,6 +232,16 @@ class Engine:
         s_ = None if Ya_s is None else np.ascontiguousarray(Ya_s, dtype=np.float64)
         n_ = None if Ya_n is None else np.ascontiguousarray(Ya_n, dtype=np.float64)
         self._call("svb200_set_active_tension", _d(f), _d(s_), _d(n_))
+
+    def set_ris(self, maps, closed):
+        """Fitted RIS surfaces (svb200_set_ris): maps = list of (2, n) int arrays (grisMapList[p].map), closed = RIS.clsFlg.  An empty list
+        removes the plan."""
+        n = len(maps)
+        nMap = np.array([mp.shape[1] for mp in maps], dtype=np.int32)
+        flat = np.concatenate([np.asfortranarray(mp, dtype=np.int32).ravel(order="F") for mp in maps]) if n else np.zeros(0, np.int32)
+        flat = np.ascontiguousarray(flat, dtype=np.int32)
+        cl = np.array([int(x) for x in closed], dtype=np.int32)
+        self._call("svb200_set_ris", C.c_int32(n), _i(nMap) if n else None, _i(flat) if n else None, _i(cl) if n else None)
 
     def set_uris(self, valves, sdf=None, scaffold_udf=None, valve_vel=None):
         """URIS valves (svb200_set_uris): valves = list of abi.Uris; sdf / scaffold_udf: (nUris, nNo); valve_vel: (nUris, nNo, 3).

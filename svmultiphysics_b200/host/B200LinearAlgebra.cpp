@@ -167,16 +167,10 @@ bool global_eq_assem(ComMod& com_mod, CepMod& cep_mod, const mshType& lM, const 
   bool active = false;
   for (int d = 0; d < eq.nDmn; d++) active |= (eq.dmn[d].active_stress != nullptr);
   if (active) la->set_active_tension(cep_mod);
-  // fitted RIS: ris::doassem_ris (fluid.cpp:750-754, fsi.cpp:349-353) adds every element matrix a second time into the rows of the
-  // node across an open resistive surface, directly in com_mod.R / com_mod.Val — arrays this backend does not use.  Not on the
-  // device: fail loudly instead of solving without that coupling.
-  if (com_mod.risFlag && (eq.phys == consts::EquationType::phys_fluid || eq.phys == consts::EquationType::phys_FSI)) {
-    bool allClosed = true;
-    for (bool c : com_mod.ris.clsFlg) allClosed = allClosed && c;
-    if (!allClosed)
-      throw std::runtime_error("[B200LinearAlgebra] an open RIS surface (ris::doassem_ris) is not implemented on the device; "
-                               "use the fsils linear algebra for this equation");
-  }
+  // fitted RIS: ris::doassem_ris (fluid.cpp:750-754, fsi.cpp:349-353) — on the device as a row operation on the assembled rows of
+  // every mesh (csrc/ris.cu); the plan follows RIS.clsFlg
+  if (com_mod.risFlag && (eq.phys == consts::EquationType::phys_fluid || eq.phys == consts::EquationType::phys_FSI))
+    la->set_ris(com_mod);
   // URIS valves (construct_fluid, fluid.cpp:622-672; the fluid elements of construct_fsi, fsi.cpp:170-216): the signed distance
   // function and the valve velocity move with the valve, so they are handed over at every assembly
   if (com_mod.urisFlag && (eq.phys == consts::EquationType::phys_fluid || eq.phys == consts::EquationType::phys_FSI))
@@ -389,6 +383,22 @@ void B200LinearAlgebra::set_active_tension(const CepMod& cep_mod)
   if (cem.Ya_f.size() == 0) throw std::runtime_error("[B200LinearAlgebra] active stress: cep_mod.cem.Ya_f is empty");
   check(svb200_set_active_tension(ctx, cem.Ya_f.data(), cem.Ya_s.size() ? cem.Ya_s.data() : nullptr,
                                   cem.Ya_n.size() ? cem.Ya_n.data() : nullptr));
+}
+
+void B200LinearAlgebra::set_ris(const ComMod& com_mod)
+{
+  const int nP = com_mod.ris.nbrRIS;
+  std::vector<int> closed(nP);
+  for (int p = 0; p < nP; p++) closed[p] = com_mod.ris.clsFlg[p] ? 1 : 0;
+  if (closed == ris_state) return;                  // the surfaces did not change state since the plan was built
+  std::vector<int> nMap(nP), maps;
+  for (int p = 0; p < nP; p++) {
+    const auto& mp = com_mod.grisMapList[p].map;    // (2, n), column-major
+    nMap[p] = mp.ncols();
+    maps.insert(maps.end(), mp.data(), mp.data() + 2 * (size_t)mp.ncols());
+  }
+  check(svb200_set_ris(ctx, nP, nMap.data(), maps.data(), closed.data()));
+  ris_state = closed;
 }
 
 void B200LinearAlgebra::set_uris(const ComMod& com_mod)

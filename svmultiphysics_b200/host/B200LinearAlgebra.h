@@ -47,6 +47,8 @@ class B200LinearAlgebra : public virtual LinearAlgebra {
     /// com_mod.uris[] (URIS valves) -> svb200_set_uris: nodal |sdf| / scaffold udf / valve velocity and, per valve, the resistance
     /// and the half-thickness in effect (the open/close ramp of uris.cpp:1625-1649); removes them when urisActFlag is off.
     void set_uris(const ComMod& com_mod);
+    /// com_mod.ris / grisMapList -> svb200_set_ris whenever a surface opened or closed (ris::doassem_ris on the device, csrc/ris.cu).
+    void set_ris(const ComMod& com_mod);
     /// all_fun::commu(com_mod, com_mod.R) of Integrator::step (Code/Source/solver/Integrator.cpp:124-129).
     void commu_R();
     /// ustruct::ustruct_r (Code/Source/solver/ustruct.cpp:1742) on the device-resident R and Kd.
@@ -59,6 +61,7 @@ class B200LinearAlgebra : public virtual LinearAlgebra {
     svb200_ctx* ctx = nullptr;
 
   private:
+    std::vector<int> ris_state;                       // RIS.clsFlg the device plan was built for (empty: no plan)
     void upload_structure(ComMod& com_mod);           // graph, meshes, coordinates: once
     void upload_faces(ComMod& com_mod);               // lhs.face[]: before every solve (fsils_bc_update may change val)
     void flush_host_contrib(int dof);                 // surface terms the host assembled through assemble()

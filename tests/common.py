@@ -325,6 +325,36 @@ def uris_case(name, scatter=abi.SCATTER_ATOMIC):
     return m, Ag, Yg, Dg, Bf, eq, [abi.fluid_domain(K_darcy=1.5, f=(0.1, -0.2, 0.3))]
 
 
+# ---- fitted RIS: two lumen meshes separated by a resistive surface with node-to-node twins (tests/cases/ris/pipe_ris_3d) ------------
+def ris_case(scatter=abi.SCATTER_ATOMIC, seed=43):
+    """(x, [IEN upstream, IEN downstream], map(2, n), Ag, Yg, Bf, eq, domains): the cylinder cut at a cell layer; the nodes of the cut
+    plane exist twice (the upstream copy keeps its id, the downstream copy is appended), map(0, j) / map(1, j) are the twins."""
+    m = meshgen.cylinder_tet4(4, 8, R=1.0, L=4.0)
+    zc = m.x[2, m.IEN].mean(axis=0)
+    zcut = np.unique(np.round(m.x[2], 9))[4]                  # a node plane in the middle
+    up = zc < zcut
+    plane = np.where(np.abs(m.x[2] - zcut) < 1e-9)[0]
+    twin = np.full(m.nNo, -1, np.int64)
+    twin[plane] = m.nNo + np.arange(len(plane))
+    x = np.asfortranarray(np.hstack([m.x, m.x[:, plane]]))
+    IEN0 = np.asfortranarray(m.IEN[:, up].astype(np.int32))
+    I1 = m.IEN[:, ~up].astype(np.int64)
+    I1 = np.where(twin[I1] >= 0, twin[I1], I1)
+    IEN1 = np.asfortranarray(I1.astype(np.int32))
+    mp = np.asfortranarray(np.stack([plane, twin[plane]]).astype(np.int32))
+    nNo = x.shape[1]
+    rng = np.random.default_rng(seed)
+    Yg = np.zeros((4, nNo), order="F")
+    r2 = x[0] ** 2 + x[1] ** 2
+    Yg[2] = 5.0 * (1.0 - r2) + 0.2 * rng.standard_normal(nNo)
+    Yg[0:2] = 0.2 * rng.standard_normal((2, nNo))
+    Yg[3] = 10.0 - x[2] + 0.1 * rng.standard_normal(nNo)
+    Ag = np.asfortranarray(0.5 * rng.standard_normal((4, nNo)))
+    Bf = np.asfortranarray(0.1 * rng.standard_normal((3, nNo)))
+    eq = abi.fluid_eq(0.005, scatter=scatter)
+    return x, [IEN0, IEN1], mp, Ag, Yg, Bf, eq, [abi.fluid_domain(K_darcy=0.5, f=(0.1, 0.0, -0.2))]
+
+
 # ---- scalar heat equations (heatS / heatF, SURVEY 8f rank 4) -------------------------------------------------------
 # (name, mesh factory, fluid?, tDof, eq.s, mvMsh, heat_domain kwargs)
 HEAT_CASES = [

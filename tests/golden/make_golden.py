@@ -226,6 +226,35 @@ def other_hi_golden():
     print("wrote other_hi.npz with", len(out), "arrays")
 
 
+def ris_golden():
+    """construct_fluid on two lumen meshes separated by an OPEN resistive immersed surface: the reference's own ris::doassem_ris
+    (compiled ris.cpp) adds every element row of a mapped node into its twin's row; CSR graph with the RIS connections of lhsa."""
+    out = {}
+    x, IENs, mp, Ag, Yg, Bf, eq, dmn = common.ris_case()
+    res = {}
+    for label, closed in (("open", [0]), ("closed", [1])):
+        c = RefCase(); c.set_coords(x)
+        for I in IENs:
+            c.add_mesh(I)
+        c.set_ris([mp], closed, [(0, 1)])
+        rowPtr, colPtr = c.build_graph(0)
+        c.alloc(4); c.set_state(Ag, Yg, None, Bf)
+        for iM in range(len(IENs)):
+            c.assemble(iM, eq, dmn)
+        res[label] = (c.get_R(), c.get_Val())
+        out["rowPtr"], out["colPtr"] = rowPtr, colPtr
+    out["open/R"], out["open/Val"] = res["open"]
+    out["closed/R"], out["closed/Val"] = res["closed"]
+    out["map"] = mp
+    # open: rows of twins carry the sum of both sides; closed: the two lumens are uncoupled
+    Ro, Rc = res["open"][0], res["closed"][0]
+    assert common.rel_err(Ro[:, mp[0]], Rc[:, mp[0]] + Rc[:, mp[1]]) < 1e-13 and common.rel_err(Ro[:, mp[1]], Ro[:, mp[0]]) < 1e-13
+    rest = np.setdiff1d(np.arange(x.shape[1]), mp.ravel())
+    assert np.array_equal(Ro[:, rest], Rc[:, rest])
+    np.savez_compressed(os.path.join(HERE, "ris.npz"), **out)
+    print("wrote ris.npz with", len(out), "arrays")
+
+
 def lelas_golden():
     """R / Val of l_elas_3d on TET4: the linear-elasticity equation and the mesh-motion equation (tDof = 7, old displacement)."""
     out = {}
@@ -268,6 +297,6 @@ if __name__ == "__main__":
     if not have_ref():
         raise SystemExit("oracle/_ref/libsvref.so is missing: run `make -C oracle ref` first")
     only = sys.argv[1:]
-    for fn in (fluid_golden, struct_golden, fluid_gen_golden, fluid_hi_golden, struct_hi_golden, heat_golden, ustruct_golden, lelas_golden, prestress_golden, fsi_ustruct_golden, fluid_uris_golden, other_hi_golden):
+    for fn in (fluid_golden, struct_golden, fluid_gen_golden, fluid_hi_golden, struct_hi_golden, heat_golden, ustruct_golden, lelas_golden, prestress_golden, fsi_ustruct_golden, fluid_uris_golden, other_hi_golden, ris_golden):
         if not only or fn.__name__.replace("_golden", "") in only:
             fn()

@@ -576,3 +576,49 @@ def test_uris_valves_assembly_matches_golden(name, scatter):
     eng.alloc(4); eng.assemble(0, eq, dmn)
     assert common.rel_err(eng.get_R(), R0) < 1e-13 and common.rel_err(eng.get_Val(), V0) < 1e-13
     eng.close()
+
+
+# ---- fitted RIS: an open resistive immersed surface couples the twin nodes of two lumen meshes (tests/cases/ris) ---------------------
+@pytest.mark.parametrize("scatter", [abi.SCATTER_ATOMIC, abi.SCATTER_COLORED])
+def test_open_ris_surface_matches_the_reference(scatter):
+    """construct_fluid on two lumen meshes with ris::doassem_ris (the reference's own ris.cpp, tests/golden/ris.npz): surface open
+    (twin rows receive each other's element rows, mapped columns replaced by twins), closed (plain assembly), and opened again after a
+    closed step (svb200_set_ris is called whenever the surface changes state)."""
+    from svmultiphysics_b200 import elements
+    from svmultiphysics_b200.engine import Engine
+    g = common.load_golden("ris.npz")
+    x, IENs, mp, Ag, Yg, Bf, eq, dmn = common.ris_case(scatter)
+    eng = Engine(0)
+    eng.set_graph(g["rowPtr"], g["colPtr"])
+    w, N, Nx = elements.tables(4)
+    for iM, I in enumerate(IENs):
+        eng.set_mesh(iM, I, w, N, Nx)
+    eng.set_coords(x)
+
+    def run():
+        eng.alloc(4); eng.set_state(Ag, Yg, None, Bf)
+        for iM in range(len(IENs)):
+            eng.assemble(iM, eq, dmn)
+        return eng.get_R(), eng.get_Val()
+
+    R0, V0 = run()                                   # no plan: the two lumens uncoupled
+    assert common.rel_err(R0, g["closed/R"]) < 1e-12 and common.rel_err(V0, g["closed/Val"]) < 1e-12
+    eng.set_ris([mp], [0])
+    R1, V1 = run()
+    assert common.rel_err(R1, g["open/R"]) < 1e-12 and common.rel_err(V1, g["open/Val"]) < 1e-12
+    assert common.rel_err(R1[:, mp[0]], R1[:, mp[1]]) < 1e-13          # twins carry the same residual
+    eng.set_ris([mp], [1])
+    R2, V2 = run()
+    assert common.rel_err(R2, g["closed/R"]) < 1e-12 and common.rel_err(V2, g["closed/Val"]) < 1e-12
+    eng.set_ris([mp], [0])
+    R3, V3 = run()
+    assert common.rel_err(R3, g["open/R"]) < 1e-12 and common.rel_err(V3, g["open/Val"]) < 1e-12
+    if scatter == abi.SCATTER_COLORED:
+        assert np.array_equal(R3, R1) and np.array_equal(V3, V1)
+    bad = mp.copy(); bad[1, 0] = -1
+    with pytest.raises(RuntimeError):
+        eng.set_ris([bad], [0])                      # a mapped node without a twin (the reference would reuse a stale row)
+    eng.set_ris([], [])
+    R4, _ = run()
+    assert common.rel_err(R4, g["closed/R"]) < 1e-12
+    eng.close()

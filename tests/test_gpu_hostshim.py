@@ -267,6 +267,30 @@ def test_uris_valves_through_cpp_plugin():
     _close(cpu, gpu)
 
 
+def test_open_ris_surface_through_cpp_plugin():
+    """com_mod.risFlag / RIS.clsFlg / grisMapList through B200LinearAlgebra::set_ris: the reference's construct_fluid + doassem_ris on
+    the CPU against the device's row operation, surface open and then closed (the plug-in rebuilds the plan when clsFlg changes)."""
+    from oracle import refbind
+    if not refbind.have_host():
+        pytest.skip("needs oracle/_ref/libsvref.so and svmultiphysics_b200/lib/libsvb200_host.so")
+    x, IENs, mp, Ag, Yg, Bf, eq, dmn = common.ris_case()
+    golden = common.load_golden("ris.npz")
+    gpu = refbind.RefCase(); gpu.set_coords(x)
+    for I in IENs:
+        gpu.add_mesh(I)
+    gpu.set_ris([mp], [0], [(0, 1)])
+    gpu.build_graph(0)
+    gpu.use_b200_backend(device=0)
+    for label, closed in (("open", [0]), ("closed", [1]), ("open", [0])):
+        gpu.set_ris([mp], closed, [(0, 1)])
+        gpu.alloc(4); gpu.set_state(Ag, Yg, None, Bf)
+        for iM in range(len(IENs)):
+            gpu.assemble(iM, eq, dmn)
+        assert common.rel_err(gpu.get_R(), golden[f"{label}/R"]) < 1e-12
+        assert common.rel_err(gpu.get_Val(), golden[f"{label}/Val"]) < 1e-12
+    gpu.close()
+
+
 def test_prestress_equation_through_cpp_plugin():
     """com_mod.pS0 and pstEq through B200LinearAlgebra: the plug-in uploads pS0, flags the prestress equation and writes the
     device accumulators back into com_mod.pSn / pSa (what Integrator::corrector then communicates and divides)."""
