@@ -8,6 +8,7 @@
 // residual entry; the per-Gauss-point scalars (grad T, u, tauM, the discontinuity-capturing conductivity) are
 // evaluated by every lane of the element (a few hundred flops; the kernel is bound by the gather and the scatter:
 // 20 B/node of state in, ENON^2 + ENON adds out).
+#include <cstdlib>
 #include "svb200_internal.h"
 #include "heat_elem.cuh"
 
@@ -110,6 +111,88 @@ assemble_heat_kernel(const __grid_constant__ HeatArgs P)
   for (int b = 0; b < ENON; b++) heat_add<ATOMIC>(P.Val + sl[b], lK[b]);
 }
 
+// HEX8: one lane per Gauss point in phase A.  In the kernel above every lane of an element evaluates gnn and the Gauss-point scalars
+// of ALL Gauss points (8 x redundant for a hexahedron: 22 of the 30 kflop per element); here lane g evaluates Gauss point g once and
+// leaves its gradients Nx_g(8,3), the HeatGP record and the weight in shared memory (37 doubles, odd stride: conflict-free stores),
+// then lane a accumulates row a over the 8 records (broadcast reads: the lanes of an element read the same words).
+constexpr int HEAT_GP_LD = 37;
+template <bool ATOMIC, bool FLUID>
+__global__ void __launch_bounds__(128)
+assemble_heat_hex8_kernel(const __grid_constant__ HeatArgs P)
+{
+  constexpr int ENON = 8, EPW = 4;
+  __shared__ double sgp[4][EPW][ENON][HEAT_GP_LD];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int a = lane % ENON, el = lane / ENON;
+  const long long idx = (long long)P.e0 + ((long long)blockIdx.x * 4 + warp) * EPW + el;
+  bool active = idx < P.e1;
+  int e = 0, iD = 0;
+  if (active) {
+    e = P.perm ? P.perm[idx] : (int)idx;
+    for (int d = 0; d < P.nDmn; d++) {
+      iD = d;
+      if (P.dmn[d].Id == -1) break;
+      if (P.eId != nullptr && ((P.eId[e] >> P.dmn[d].Id) & 1)) break;
+    }
+    active = P.dmn[iD].active != 0;
+  }
+  const HeatDmn& dm = P.dmn[iD];
+  int na = 0;
+  if (active) {
+    // ---- phase A: lane g = a evaluates Gauss point g ----
+    const int g = a;
+    double xl[ENON][3], Tl[ENON], Tdl[ENON], ul[ENON][3];
+#pragma unroll
+    for (int b = 0; b < ENON; b++) {
+      const int nb = P.IEN[(size_t)e * ENON + b];
+      if (b == a) na = nb;
+      const size_t n = (size_t)nb;
+      const double* y = P.Yg + (size_t)P.tDof * n;
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        xl[b][i] = __ldg(P.x + 3 * n + i);
+        ul[b][i] = FLUID ? (__ldg(y + i) - (P.mvMsh ? __ldg(y + 4 + i) : 0.0)) : 0.0;
+      }
+      Tl[b] = __ldg(y + P.s);
+      Tdl[b] = __ldg(P.Ag + (size_t)P.tDof * n + P.s);
+    }
+    double Nx[ENON][3], ks[3][3];
+    const double Jac = gnn3_metric<ENON>(P.Nxi[g], xl, Nx, ks);
+    if (fabs(Jac) < 10.0 * 2.220446049250313e-16 * 2.220446049250313e-16) atomicMax(P.err, e + 1);
+    HeatGP q;
+    heat_gauss_point<ENON, FLUID>(dm, P.dt, P.af, P.am, P.gam, P.N[g], Nx, ks, Tl, Tdl, ul, q);
+    double* r = sgp[warp][el][g];
+#pragma unroll
+    for (int b = 0; b < ENON; b++)
+#pragma unroll
+      for (int i = 0; i < 3; i++) r[3 * b + i] = Nx[b][i];
+    r[24] = q.c0; r[25] = q.nu; r[26] = q.Tp; r[27] = q.tauM; r[28] = q.amd;
+    r[29] = q.Tx[0]; r[30] = q.Tx[1]; r[31] = q.Tx[2]; r[32] = q.u[0]; r[33] = q.u[1]; r[34] = q.u[2];
+    r[35] = P.w[g] * Jac;
+  }
+  __syncwarp();
+  if (!active) return;
+  // ---- phase B: lane a = row a ----
+  const double T1 = P.af * P.gam * P.dt;
+  double lK[ENON], lR = 0.0;
+#pragma unroll
+  for (int b = 0; b < ENON; b++) lK[b] = 0.0;
+#pragma unroll 1
+  for (int g = 0; g < ENON; g++) {
+    const double* r = sgp[warp][el][g];
+    HeatGP q;
+    q.c0 = r[24]; q.nu = r[25]; q.Tp = r[26]; q.tauM = r[27]; q.amd = r[28];
+    q.Tx[0] = r[29]; q.Tx[1] = r[30]; q.Tx[2] = r[31]; q.u[0] = r[32]; q.u[1] = r[33]; q.u[2] = r[34];
+    const double w = r[35];
+    const double Nxa[3] = {r[3 * a], r[3 * a + 1], r[3 * a + 2]};
+    heat_row<ENON>(q, w, w * T1, P.N[g][a], Nxa, P.N[g], reinterpret_cast<const double(*)[3]>(r), lR, lK);
+  }
+  heat_add<ATOMIC>(P.R + na, lR);
+  const int* sl = P.slot + (size_t)e * ENON * ENON + a * ENON;
+#pragma unroll
+  for (int b = 0; b < ENON; b++) heat_add<ATOMIC>(P.Val + sl[b], lK[b]);
+}
+
 template <int ENON, bool FLUID>
 static int launch_heat(svb200_ctx* ctx, const HeatArgs& A, bool atomic)
 {
@@ -117,7 +200,11 @@ static int launch_heat(svb200_ctx* ctx, const HeatArgs& A, bool atomic)
   const long long n = (long long)A.e1 - A.e0;
   if (n <= 0) return SVB200_OK;
   const unsigned blocks = (unsigned)((n + EPB - 1) / EPB);
-  if (atomic) assemble_heat_kernel<ENON, true, FLUID><<<blocks, 128, 0, ctx->stream>>>(A);
+  static const bool lane_rows = getenv("SVB200_HEAT_HEX8_LEGACY") != nullptr;      // A/B: the lane-per-row kernel for HEX8
+  if (ENON == 8 && !lane_rows) {
+    if (atomic) assemble_heat_hex8_kernel<true, FLUID><<<blocks, 128, 0, ctx->stream>>>(A);
+    else assemble_heat_hex8_kernel<false, FLUID><<<blocks, 128, 0, ctx->stream>>>(A);
+  } else if (atomic) assemble_heat_kernel<ENON, true, FLUID><<<blocks, 128, 0, ctx->stream>>>(A);
   else assemble_heat_kernel<ENON, false, FLUID><<<blocks, 128, 0, ctx->stream>>>(A);
   ctx->launches++;
   SVB_CUDA(cudaGetLastError());

@@ -852,6 +852,144 @@ assemble_mesh_kernel(const __grid_constant__ StructArgs P, const double* __restr
   }
 }
 
+// HEX8 variant with one lane per Gauss point in phase A (the kernel above lets every lane of an element evaluate gnn and the stress
+// at ALL 8 Gauss points): lane g leaves Nx_g(8,3), the stress S(6), the interpolated prestress p0(6), the inertia vector ud(3) and the
+// weight in shared memory (41 doubles, odd stride), lane a then accumulates row a over the 8 records.  Same expressions, same order
+// of the Gauss-point sums, so the results are those of the lane-per-row kernel.
+constexpr int MESH_GP_LD = 41;
+template <bool ATOMIC, bool LELAS>
+__global__ void __launch_bounds__(128)
+assemble_mesh_hex8_kernel(const __grid_constant__ StructArgs P, const double* __restrict__ Do)
+{
+  constexpr int ENON = 8, EPW = 4;
+  __shared__ double sgp[4][EPW][ENON][MESH_GP_LD];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int a = lane % ENON, el = lane / ENON;
+  const long long idx = (long long)P.e0 + ((long long)blockIdx.x * 4 + warp) * EPW + el;
+  bool active = idx < P.e1;
+  int e = 0, iD = 0;
+  if (active) {
+    e = P.perm ? P.perm[idx] : (int)idx;
+    for (int d = 0; d < P.nDmn; d++) {
+      iD = d;
+      if (P.dmn[d].Id == -1) break;
+      if (P.eId != nullptr && ((P.eId[e] >> P.dmn[d].Id) & 1)) break;
+    }
+    active = P.dmn[iD].isStruct != 0;
+  }
+  const StructDmn& dm = P.dmn[iD];
+  const int DOF = P.dof, is = P.s;
+  const double elM = dm.C10, nu = dm.C01, rho = dm.rho;
+  const double lambda = elM * nu / (1.0 + nu) / (1.0 - 2.0 * nu);
+  const double mu = elM * 0.5 / (1.0 + nu);
+  const double lDm = lambda / mu;
+  const double T1c = P.af * P.beta * P.dt * P.dt;
+  const double amd = P.am / T1c * rho;
+  int na = 0;
+  if (active) {
+    const int g = a;
+    int node[ENON];
+    double xl[ENON][3], dl[ENON][3];
+#pragma unroll
+    for (int b = 0; b < ENON; b++) {
+      node[b] = P.IEN[(size_t)e * ENON + b];
+      if (b == a) na = node[b];
+      const size_t n = (size_t)node[b];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const double dol = LELAS ? 0.0 : __ldg(Do + (size_t)P.tDof * n + is + i);
+        xl[b][i] = __ldg(P.x + 3 * n + i) + dol;
+        dl[b][i] = __ldg(P.Dg + (size_t)P.tDof * n + is + i) - dol;
+      }
+    }
+    double Nx[ENON][3];
+    const double Jac = gnn3<ENON>(P.Nxi[g], xl, Nx);
+    const double w = LELAS ? P.w[g] * Jac : P.w[g];
+    double ud[3] = {-dm.f[0], -dm.f[1], -dm.f[2]}, ed[6] = {0, 0, 0, 0, 0, 0}, p0[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int b = 0; b < ENON; b++) {
+      const double Nb = P.N[g][b];
+      const size_t n = (size_t)node[b];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+        ud[i] += Nb * (__ldg(P.Ag + (size_t)P.tDof * n + is + i) - (LELAS ? __ldg(P.Bf + 3 * n + i) : 0.0));
+      ed[0] += Nx[b][0] * dl[b][0];
+      ed[1] += Nx[b][1] * dl[b][1];
+      ed[2] += Nx[b][2] * dl[b][2];
+      ed[3] += Nx[b][1] * dl[b][0] + Nx[b][0] * dl[b][1];
+      ed[4] += Nx[b][2] * dl[b][1] + Nx[b][1] * dl[b][2];
+      ed[5] += Nx[b][0] * dl[b][2] + Nx[b][2] * dl[b][0];
+      if (LELAS && P.pS0 != nullptr)
+#pragma unroll
+        for (int i = 0; i < 6; i++) p0[i] += Nb * __ldg(P.pS0 + 6 * n + i);
+    }
+    const double divD = lambda * (ed[0] + ed[1] + ed[2]);
+    double* r = sgp[warp][el][g];
+#pragma unroll
+    for (int b = 0; b < ENON; b++)
+#pragma unroll
+      for (int i = 0; i < 3; i++) r[3 * b + i] = Nx[b][i];
+    r[24] = divD + 2.0 * mu * ed[0]; r[25] = divD + 2.0 * mu * ed[1]; r[26] = divD + 2.0 * mu * ed[2];
+    r[27] = mu * ed[3]; r[28] = mu * ed[4]; r[29] = mu * ed[5];
+#pragma unroll
+    for (int i = 0; i < 6; i++) r[30 + i] = p0[i];
+    r[36] = ud[0]; r[37] = ud[1]; r[38] = ud[2];
+    r[39] = w;
+  }
+  __syncwarp();
+  if (!active) return;
+  double K[ENON][3][3], lR[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int b = 0; b < ENON; b++)
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) K[b][i][j] = 0.0;
+#pragma unroll 1
+  for (int g = 0; g < ENON; g++) {
+    const double* r = sgp[warp][el][g];
+    const double w = r[39], wl = w * T1c * mu;
+    const double Na = P.N[g][a];
+    const double Nxa[3] = {r[3 * a], r[3 * a + 1], r[3 * a + 2]};
+    double S0 = r[24], S1 = r[25], S2 = r[26], S3 = r[27], S4 = r[28], S5 = r[29];
+    if (LELAS) {
+      if (P.pSn != nullptr) {           // l_elas.cpp:321-338, 130-140: the accumulators see the stress WITHOUT the prestress
+        const double wN = w * Na;
+        add64<true>(P.pSa + na, wN);
+        add64<true>(P.pSn + 6 * (size_t)na + 0, wN * S0); add64<true>(P.pSn + 6 * (size_t)na + 1, wN * S1);
+        add64<true>(P.pSn + 6 * (size_t)na + 2, wN * S2); add64<true>(P.pSn + 6 * (size_t)na + 3, wN * S3);
+        add64<true>(P.pSn + 6 * (size_t)na + 4, wN * S4); add64<true>(P.pSn + 6 * (size_t)na + 5, wN * S5);
+      }
+      if (P.pS0 != nullptr) { S0 += r[30]; S1 += r[31]; S2 += r[32]; S3 += r[33]; S4 += r[34]; S5 += r[35]; }
+    }
+    lR[0] += w * (rho * Na * r[36] + Nxa[0] * S0 + Nxa[1] * S3 + Nxa[2] * S5);
+    lR[1] += w * (rho * Na * r[37] + Nxa[0] * S3 + Nxa[1] * S1 + Nxa[2] * S4);
+    lR[2] += w * (rho * Na * r[38] + Nxa[0] * S5 + Nxa[1] * S4 + Nxa[2] * S2);
+#pragma unroll
+    for (int b = 0; b < ENON; b++) {
+      const double Nxb[3] = {r[3 * b], r[3 * b + 1], r[3 * b + 2]};
+      const double NxdNx = Nxa[0] * Nxb[0] + Nxa[1] * Nxb[1] + Nxa[2] * Nxb[2];
+      const double T1 = amd * Na * P.N[g][b] / mu + NxdNx;
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+          K[b][i][j] += wl * ((i == j ? T1 + (1.0 + lDm) * Nxa[i] * Nxb[i] : lDm * Nxa[i] * Nxb[j] + Nxa[j] * Nxb[i]));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++) add64<ATOMIC>(P.R + (size_t)DOF * na + i, lR[i]);
+  const int* sl = P.slot + (size_t)e * ENON * ENON + a * ENON;
+#pragma unroll
+  for (int b = 0; b < ENON; b++) {
+    double* v = P.Val + (size_t)DOF * DOF * sl[b];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) add64<ATOMIC>(v + DOF * i + j, K[b][i][j]);
+  }
+}
+
 // ---- mesh-motion / linear-elasticity equation on linear tetrahedra: one thread per element ------------------------
 // l_elas_3d with constant gradients (l_elas.cpp:249-365): the strain and stress are constant over the element, only the
 // inertia term sees N_a(g).  With the weights w = w_g (mesh equation: Jacobian-free, mesh.cpp:122) or w_g Jac (lElas),
@@ -1199,7 +1337,16 @@ static int launch_mesh(svb200_ctx* ctx, const StructArgs& A, const double* Do)
   const long long n = (long long)A.e1 - A.e0;
   if (n <= 0) return SVB200_OK;
   const unsigned blocks = (unsigned)((n + EPB - 1) / EPB);
-  if (Do == nullptr) {      // linear-elasticity equation
+  static const bool lane_rows = getenv("SVB200_MESH_HEX8_LEGACY") != nullptr;      // A/B: the lane-per-row kernel for HEX8
+  if (ENON == 8 && !lane_rows) {
+    if (Do == nullptr) {
+      if (A.atomic) assemble_mesh_hex8_kernel<true, true><<<blocks, 128, 0, ctx->stream>>>(A, nullptr);
+      else assemble_mesh_hex8_kernel<false, true><<<blocks, 128, 0, ctx->stream>>>(A, nullptr);
+    } else {
+      if (A.atomic) assemble_mesh_hex8_kernel<true, false><<<blocks, 128, 0, ctx->stream>>>(A, Do);
+      else assemble_mesh_hex8_kernel<false, false><<<blocks, 128, 0, ctx->stream>>>(A, Do);
+    }
+  } else if (Do == nullptr) {      // linear-elasticity equation
     if (A.atomic) assemble_mesh_kernel<ENON, true, true><<<blocks, 128, 0, ctx->stream>>>(A, nullptr);
     else assemble_mesh_kernel<ENON, false, true><<<blocks, 128, 0, ctx->stream>>>(A, nullptr);
   } else {
