@@ -59,7 +59,7 @@ assemble_fluid_tet4_kernel(const __grid_constant__ FluidArgs P)
   int node[4] = {0, 0, 0, 0};
   if (active) {
     const int iD = pick_domain(P, e);
-    if (!P.dmn[iD].isFluid) {
+    if (!P.dmn[iD].isFluid || (P.emask != nullptr && P.emask[e] != P.emask_val)) {
       active = false;
     } else {
       const int4 n4 = *reinterpret_cast<const int4*>(P.IEN + 4 * (size_t)e);
@@ -234,7 +234,7 @@ assemble_fluid_tet4_grouped_kernel(const __grid_constant__ FluidArgs P)
   bool active = e < P.e1;
   if (active) {
     const int iD = pick_domain(P, e);
-    if (!P.dmn[iD].isFluid) {
+    if (!P.dmn[iD].isFluid || (P.emask != nullptr && P.emask[e] != P.emask_val)) {
       active = false;
     } else {
       const int4 n4 = *reinterpret_cast<const int4*>(P.IEN + 4 * (size_t)e);

@@ -16,6 +16,7 @@
 //            is scattered as 16 contiguous doubles = one CSR block.
 #include <cstdlib>
 #include <vector>
+#include <cub/cub.cuh>
 #include "fluid_gen.cuh"
 
 namespace svb {
@@ -264,6 +265,56 @@ int upload_fluid_gen_tables(svb200_ctx* ctx, Mesh& m)
   return SVB200_OK;
 }
 
+// URIS split launch.  An element whose nodes all lie outside every valve's (and scaffold's) thickness has a zero valve factor at
+// every Gauss point (dist = sum_a N_a |sdf_a| >= min_a |sdf_a| >= deps for the non-negative shape functions of a linear element), so
+// the closed-form TET4 kernel is exact for it; the band around the valves goes through the per-Gauss-point kernel.
+__global__ void uris_element_mask_kernel(int nEl, int eNoN, const int* __restrict__ IEN, const double* __restrict__ nodal, int nUris,
+                                         const __grid_constant__ FluidGenArgs P, unsigned char* __restrict__ mask)
+{
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nEl) return;
+  bool near = false;
+  for (int a = 0; a < eNoN; a++) {
+    const double* r = nodal + (size_t)IEN[(size_t)e * eNoN + a] * nUris * 5;
+    for (int v = 0; v < nUris; v++) {
+      near |= r[5 * v] < P.urisP[v].sdf_deps;
+      if (P.urisP[v].scaffold) near |= r[5 * v + 1] < P.urisP[v].scaffold_deps;
+    }
+  }
+  mask[e] = near ? 1 : 0;
+}
+
+int build_uris_element_mask(svb200_ctx* ctx, const Mesh& m)
+{
+  if (m.uris_version == ctx->uris_version && m.d_uris_mask) return SVB200_OK;
+  if (!m.d_uris_mask) {
+    SVB_CUDA(cudaMalloc(&m.d_uris_mask, std::max(m.nEl, 1)));
+    SVB_CUDA(cudaMalloc(&m.d_uris_list, sizeof(int) * std::max(m.nEl, 1)));
+  }
+  FluidGenArgs A;
+  memset(&A, 0, sizeof(A));
+  for (int v = 0; v < ctx->nUris; v++) A.urisP[v] = ctx->urisP[v];
+  uris_element_mask_kernel<<<(m.nEl + 255) / 256, 256, 0, ctx->stream>>>(m.nEl, m.eNoN, m.d_IEN, ctx->d_uris, ctx->nUris, A, m.d_uris_mask);
+  // compact list in element order (deterministic): cub select over a counting iterator
+  int* d_n = nullptr;
+  SVB_CUDA(cudaMalloc(&d_n, sizeof(int)));
+  size_t tmp = 0;
+  cub::CountingInputIterator<int> it(0);
+  SVB_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp, it, m.d_uris_mask, m.d_uris_list, d_n, m.nEl, ctx->stream));
+  void* d_tmp = nullptr;
+  SVB_CUDA(cudaMalloc(&d_tmp, std::max<size_t>(tmp, 1)));
+  cudaError_t ce = cub::DeviceSelect::Flagged(d_tmp, tmp, it, m.d_uris_mask, m.d_uris_list, d_n, m.nEl, ctx->stream);
+  int n = 0;
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(&n, d_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_tmp); cudaFree(d_n);
+  SVB_CUDA(ce);
+  ctx->launches += 2;
+  m.n_uris_el = n;
+  m.uris_version = ctx->uris_version;
+  return SVB200_OK;
+}
+
 int run_assemble_fluid_gen(svb200_ctx* ctx, const Mesh& m, const FluidArgs& F)
 {
   // element types of nn_elem_props.h with their quadrature rules: TET4 (4), HEX8 (8), WDG (6), TET10 (15), HEX20 / HEX27 (27)
@@ -280,6 +331,9 @@ int run_assemble_fluid_gen(svb200_ctx* ctx, const Mesh& m, const FluidArgs& F)
   A.IEN = F.IEN; A.eId = F.eId; A.slot = F.slot; A.perm = nullptr;
   A.x = F.x; A.Ag = F.Ag; A.Yg = F.Yg; A.Bf = F.Bf; A.Dg = F.Dg; A.tab = m.d_gtab; A.R = F.R; A.Val = F.Val; A.err = F.err;
   A.e0 = 0; A.e1 = m.nEl;
+  if (F.emask != nullptr) {            // URIS split launch: only the band around the valves (compact list, atomic mode)
+    A.perm = m.d_uris_list; A.e1 = m.n_uris_el;
+  }
   A.tDof = F.tDof; A.mvMsh = F.mvMsh; A.nDmn = F.nDmn; A.atomic = F.atomic; A.ale = F.ale;
   A.lShpF = (m.eNoN == 4 || m.eNoN == 6) ? 1 : 0;
   A.dt = F.dt; A.af = F.af; A.am = F.am; A.gam = F.gam;

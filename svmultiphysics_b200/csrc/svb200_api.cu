@@ -92,6 +92,7 @@ static int download_nodal(svb200_ctx* ctx, int rows, const double* d, double* h)
 static void free_mesh(Mesh& m)
 {
   cudaFree(m.d_IEN); cudaFree(m.d_eId); cudaFree(m.d_fN); cudaFree(m.d_slot); cudaFree(m.d_color_perm); cudaFree(m.d_gcolor_perm); cudaFree(m.d_gtab);
+  cudaFree(m.d_uris_mask); cudaFree(m.d_uris_list);
   free_group_sched(m.schedK); free_group_sched(m.schedR);
   m = Mesh();
 }
@@ -696,7 +697,22 @@ static int run_assemble(svb200_ctx* ctx, const Mesh& m, FluidArgs& A, bool gener
 {
   // linear tetrahedra have their own kernel (constant gradients, no second derivatives); everything else, or
   // SVB200_EQ_GENERAL_KERNEL, goes through the per-Gauss-point kernel of assemble_fluid_gen.cu
-  if (m.eNoN != 4 || general || A.nUris > 0) {        // the URIS terms exist in the per-Gauss-point kernel only
+  // URIS valves on a TET4 mesh (atomic scatter): split launch — the band of elements around the valves through the per-Gauss-point
+  // kernel, which has the URIS terms, everything else through the closed-form kernel below (exact there: zero valve factor)
+  static const bool uris_no_split = getenv("SVB200_URIS_NO_SPLIT") != nullptr;       // A/B: all elements through the general kernel
+  const bool uris_split = A.nUris > 0 && m.eNoN == 4 && m.nG == 4 && !general && A.atomic && !uris_no_split;
+  if (uris_split) {
+    TRY(build_uris_element_mask(ctx, m));
+    TRY(flush_val_zero(ctx));
+    if (m.n_uris_el > 0) {
+      FluidArgs B = A;
+      B.emask = m.d_uris_mask; B.emask_val = 1;
+      TRY(run_assemble_fluid_gen(ctx, m, B));
+      TRY(check_jacobian_word(ctx, A.ale != 0));
+    }
+    A.emask = m.d_uris_mask; A.emask_val = 0;
+    A.uris = nullptr; A.nUris = 0;
+  } else if (m.eNoN != 4 || general || A.nUris > 0) {        // the URIS terms exist in the per-Gauss-point kernel only
     TRY(flush_val_zero(ctx));
     TRY(run_assemble_fluid_gen(ctx, m, A));
     return check_jacobian_word(ctx, A.ale != 0);
@@ -814,6 +830,7 @@ int svb200_set_uris(svb200_ctx* ctx, int32_t nUris, const svb200_uris* valves, c
   SVB_REQUIRE(nUris >= 0 && nUris <= SVB200_MAX_URIS, "svb200_set_uris: between 0 and SVB200_MAX_URIS valves");
   if (nUris == 0) {
     cudaFree(ctx->d_uris); ctx->d_uris = nullptr; ctx->nUris = 0;
+    ctx->uris_version++;
     return SVB200_OK;
   }
   SVB_REQUIRE(valves && sdf, "svb200_set_uris: null valve parameters or signed distance function");
@@ -835,6 +852,7 @@ int svb200_set_uris(svb200_ctx* ctx, int32_t nUris, const svb200_uris* valves, c
   if (ctx->d_uris && ctx->nUris != nUris) { cudaFree(ctx->d_uris); ctx->d_uris = nullptr; }
   TRY(upload_nodal(ctx, 5 * nUris, h.data(), &ctx->d_uris));
   ctx->nUris = nUris;
+  ctx->uris_version++;
   for (int v = 0; v < nUris; v++) ctx->urisP[v] = valves[v];
   return SVB200_OK;
 }

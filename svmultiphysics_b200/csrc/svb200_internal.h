@@ -56,6 +56,11 @@ struct Mesh {
   std::vector<double> w, N, Nx;  // host copies of the reference-element tables
   std::vector<double> Nxx;       // (6,eNoN,nG) second parametric derivatives (svb200_set_mesh_nxx), empty = all zero
   double* d_gtab = nullptr;      // tables in the layout of assemble_fluid_gen.cu
+  // URIS split launch (TET4): elements with a node inside a valve's or scaffold's thickness, as mask and as compact list
+  mutable unsigned char* d_uris_mask = nullptr;
+  mutable int* d_uris_list = nullptr;
+  mutable int n_uris_el = 0;
+  mutable long long uris_version = -1;
   mutable bool jac_checked = false;   // element Jacobians verified for the current reference coordinates (fluid, fixed mesh)
   bool set = false;
 };
@@ -132,6 +137,10 @@ struct FluidArgs {
   const double* uris;
   int nUris;
   svb200_uris urisP[SVB200_MAX_URIS];
+  // optional element mask: an element takes part iff emask == nullptr || emask[e] == emask_val (URIS split launch: the closed-form
+  // TET4 kernel runs the elements away from the valves, the per-Gauss-point kernel the band around them)
+  const unsigned char* emask;
+  int emask_val;
 };
 
 }  // namespace svb
@@ -177,6 +186,7 @@ struct svb200_ctx {
   svb::RisPlan ris;              // open fitted RIS surfaces (svb200_set_ris)
   double* d_uris = nullptr;      // URIS nodal fields (5 nUris, nNo): per valve |sdf|, |scaffold udf|, valve velocity (svb200_set_uris)
   int nUris = 0;
+  long long uris_version = 0;    // bumped by every svb200_set_uris: the per-mesh element masks follow it
   svb200_uris urisP[SVB200_MAX_URIS] = {};
   double* d_Ya = nullptr;        // nodal active tensions (3, nNo): Ya_f, Ya_s, Ya_n (svb200_set_active_tension)
   bool ya_sn_positive = false;
@@ -272,6 +282,7 @@ int launch_assemble_fluid(svb200_ctx* ctx, const Mesh& m, const FluidArgs& args)
 int launch_tet4_jacobian_check(svb200_ctx* ctx, const Mesh& m, const FluidArgs& args);
 // assemble_struct.cu
 int upload_fluid_gen_tables(svb200_ctx* ctx, Mesh& m);
+int build_uris_element_mask(svb200_ctx* ctx, const Mesh& m);
 int run_assemble_fluid_gen(svb200_ctx* ctx, const Mesh& m, const FluidArgs& F);
 int run_assemble_struct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);
 int run_assemble_mesh(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);

@@ -24,7 +24,7 @@ class FluidArgs(C.Structure):
                [(k, C.c_int) for k in ("e0", "e1", "tDof", "mvMsh", "nDmn", "atomic", "ale", "pad0")] + [("err", C.c_void_p), ("gperm", C.c_void_p), ("g0", C.c_int), ("nGrpLaunch", C.c_int)] + \
                [(k, C.c_double) for k in ("dt", "af", "am", "gam")] + \
                [("w", C.c_double * 8), ("N", (C.c_double * 8) * 8), ("Nxi", ((C.c_double * 3) * 8) * 8), ("dmn", FluidDmn * 8),
-                ("uris", C.c_void_p), ("nUris", C.c_int), ("urisP", abi.Uris * abi.MAX_URIS)]
+                ("uris", C.c_void_p), ("nUris", C.c_int), ("urisP", abi.Uris * abi.MAX_URIS), ("emask", C.c_void_p), ("emask_val", C.c_int)]
 
 
 @pytest.fixture(scope="module")
