@@ -291,6 +291,27 @@ def test_open_ris_surface_through_cpp_plugin():
     gpu.close()
 
 
+@pytest.mark.parametrize("name", ["lelas_tet4", "mesh_tet4", "hex27_lelas", "hex20_mesh"])
+def test_linear_elasticity_and_mesh_motion_through_cpp_plugin(name):
+    """phys_lElas and phys_mesh through b200::global_eq_assem: the plug-in passes solutions.old's displacement for the mesh equation
+    (mesh.cpp:60-75) and any mshType's tables (here also curved HEX27 / HEX20 elements)."""
+    if name in common.LELAS_CASES:
+        m, Ag, Yg, Dg, Bf, Do, eq, dmn = common.lelas_case(name)
+    else:
+        m, et, dof, Ag, Yg, Dg, Bf, Do, eq, dmn = common.other_hi_case(name)
+    cpu, gpu = _pair(m)
+    res = []
+    for c in (cpu, gpu):
+        c.alloc(3); c.set_state(Ag, Yg, Dg, Bf)
+        if Do is not None:
+            c.set_old_disp(Do)
+        c.assemble(0, eq, dmn)
+        res.append((c.get_R(), c.get_Val()))
+    assert np.abs(res[0][0]).max() > 0
+    assert common.rel_err(res[1][0], res[0][0]) < 1e-12 and common.rel_err(res[1][1], res[0][1]) < 1e-12
+    _close(cpu, gpu)
+
+
 def test_prestress_equation_through_cpp_plugin():
     """com_mod.pS0 and pstEq through B200LinearAlgebra: the plug-in uploads pS0, flags the prestress equation and writes the
     device accumulators back into com_mod.pSn / pSa (what Integrator::corrector then communicates and divides)."""
