@@ -12,6 +12,8 @@
 // blocks go out through a per-warp transposition tile as coalesced adds.
 #include <cstdlib>
 #include <vector>
+#define SVB_UTET_ROLL_B 1      // the (a, b) loops of the closed-form TET4 kernel stay rolled
+#define SVB_UTET_ROLL_A 1
 #include "svb200_internal.h"
 #include "ustruct_elem.cuh"
 #include "fsils_kernels.h"
@@ -369,7 +371,11 @@ assemble_ustruct_tet4_kernel(const __grid_constant__ UstructArgs P)
     }
   }
   constexpr int TILE_LD = 29;
+#ifdef SVB_UTET_ROLL_B
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
   for (int b = 0; b < 4; b++) {
     double DBmb[6][3];
     if (active) {
@@ -385,7 +391,11 @@ assemble_ustruct_tet4_kernel(const __grid_constant__ UstructArgs P)
           DBmb[r][j] = d[0] * Bmb[0][j] + d[1] * Bmb[1][j] + d[2] * Bmb[2][j] + d[3] * Bmb[3][j] + d[4] * Bmb[4][j] + d[5] * Bmb[5][j];
       }
     }
+#ifdef SVB_UTET_ROLL_A
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
     for (int a = 0; a < 4; a++) {
       double K[16], Kd[12];
       if (active) {
