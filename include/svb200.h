@@ -279,6 +279,22 @@ SVB200_API int svb200_set_prestress(svb200_ctx* ctx, const double* pS0);
 SVB200_API int svb200_get_prestress(svb200_ctx* ctx, double* pSn, double* pSa);
 SVB200_API int svb200_set_active_tension(svb200_ctx* ctx, const double* Ya_f, const double* Ya_s, const double* Ya_n);
 
+/* Taylor-Hood function spaces of a fluid mesh (mshType::nFs = 2, <Use_taylor_hood_type_basis>): velocity on the mesh's own quadratic
+ * element (svb200_set_mesh + svb200_set_mesh_nxx), pressure on its linear parent with eNoNq nodes = the first eNoNq nodes of every
+ * element (fs::set_thood_fs, solver/fs.cpp:336-390: TET10 -> TET4, HEX20 / HEX27 -> HEX8).  The tables are those of fs::get_thood_fs
+ * (fs.cpp:73-178), column-major like fsType holds them:
+ *   momentum loop (the mesh's own rule, nG points):   Nq1(eNoNq, nG), Nqxi1(3, eNoNq, nG)       pressure space at those points
+ *   continuity loop (the pressure space's rule, nG2): w2(nG2), Nw2(eNoN, nG2), Nwxi2(3, eNoN, nG2), Nq2(eNoNq, nG2), Nqxi2(3, eNoNq, nG2)
+ * lShpF_q: the pressure space is linear (TET4): its gnn runs at Gauss point 0 only (fluid.cpp:620-626, 709-716).  A fluid equation on such
+ * a mesh is assembled with eq.vmsStab = 0 (fluid.cpp:494-500): fluid_3d_m / fluid_3d_c with vmsFlag false.  eNoNq = 0 returns the mesh to
+ * equal-order spaces.  svb200_thood_val_rc is fs::thood_val_rc (fs.cpp:394-466; Integrator::step calls it after the assembly and the
+ * boundary terms): for every node that is not a pressure node of its elements R(3, a) = 0 and the pressure-pressure entries of its row
+ * become the identity. */
+SVB200_API int svb200_set_mesh_thood(svb200_ctx* ctx, int32_t iM, int32_t eNoNq, int32_t nG2, int32_t lShpF_q, const double* Nq1,
+                                     const double* Nqxi1, const double* w2, const double* Nw2, const double* Nwxi2, const double* Nq2,
+                                     const double* Nqxi2);
+SVB200_API int svb200_thood_val_rc(svb200_ctx* ctx);
+
 /* Fitted resistive immersed surfaces (RIS): the coupling an OPEN surface adds, ris::doassem_ris (solver/ris.cpp:269-349), called per
  * element by construct_fluid (fluid.cpp:750-754) and construct_fsi (fsi.cpp:349-353): the residual row and the tangent row of every
  * element node listed in grisMapList[iProj].map are added a second time into the row of its twin across the surface, mapped columns

@@ -69,6 +69,7 @@ struct RefCase {
   LinearAlgebra* backend = nullptr;
   int (*assem_hook)(void*, void*, const void*, const void*) = nullptr;
   void (*backend_download)(void*, int, double*) = nullptr;
+  void (*backend_thood_val_rc)(void*) = nullptr;            // B200LinearAlgebra::thood_val_rc(), INTEGRATION.md
   void (*backend_ustruct_r)(void*, void*) = nullptr;       // B200LinearAlgebra::ustruct_r(ComMod&), INTEGRATION.md
   // Multi-rank runs (oracle/ref_build/mpi_stub.cpp with SVREF_MPI_SIZE > 1): this rank's local -> global node map
   int gnNo = -1;
@@ -234,6 +235,12 @@ int svref_set_backend(void* h, void* la, void* hook, void* download)
   return 0;
 }
 
+int svref_set_backend_thood_val_rc(void* h, void* fn)
+{
+  static_cast<RefCase*>(h)->backend_thood_val_rc = reinterpret_cast<void (*)(void*)>(fn);
+  return 0;
+}
+
 int svref_set_backend_ustruct_r(void* h, void* fn)
 {
   static_cast<RefCase*>(h)->backend_ustruct_r = reinterpret_cast<void (*)(void*, void*)>(fn);
@@ -272,6 +279,58 @@ int svref_add_mesh(void* h, int eNoN, int nEl, const int* IEN, const int* eId, i
     if (nFn > 0 && fN) { m.fN.resize(3*nFn, nEl); std::memcpy(m.fN.data(), fN, sizeof(double)*3*nFn*nEl); }
     nn::select_ele(cm, m);
     fs::init_fs_msh(cm, m);
+  });
+}
+
+/// Switch mesh iM to Taylor-Hood function spaces (mshType::nFs = 2, what read_msh does for <Use_taylor_hood_type_basis>): velocity on
+/// the mesh's own (quadratic) element, pressure on its linear parent (fs::set_thood_fs, fs.cpp:336-390).
+int svref_set_mesh_thood(void* h, int iM)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    auto& m = c.com_mod.msh.at(iM);
+    m.nFs = 2;
+    fs::init_fs_msh(c.com_mod, m);
+  });
+}
+
+/// The four function-space tables construct_fluid uses for a Taylor-Hood mesh (fs::get_thood_fs, fs.cpp:73-178):
+///   loop 1 (momentum, the velocity space's Gauss rule, nG1 points): pressure shape functions Nq1(eNoNq, nG1), Nqxi1(3, eNoNq, nG1)
+///   loop 2 (continuity, the pressure space's rule, nG2 points): w2(nG2), Nw2(eNoN, nG2), Nwxi2(3, eNoN, nG2), Nq2(eNoNq, nG2), Nqxi2(3, eNoNq, nG2)
+/// dims = {eNoNq, nG1, nG2, lShpF of the velocity space, lShpF of the pressure space}; null pointers are skipped.
+int svref_get_thood_tables(void* h, int iM, int* dims, double* Nq1, double* Nqxi1, double* w2, double* Nw2, double* Nwxi2, double* Nq2,
+                           double* Nqxi2)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    auto& m = c.com_mod.msh.at(iM);
+    if (m.nFs != 2) throw std::runtime_error("[ref_harness] mesh has no Taylor-Hood function spaces");
+    std::array<fsType, 2> f1, f2;
+    fs::get_thood_fs(c.com_mod, f1, m, false, 1);
+    fs::get_thood_fs(c.com_mod, f2, m, false, 2);
+    dims[0] = f1[1].eNoN; dims[1] = f1[0].nG; dims[2] = f2[1].nG; dims[3] = f1[0].lShpF ? 1 : 0; dims[4] = f1[1].lShpF ? 1 : 0;
+    auto cp = [](double* dst, const double* src, size_t n) { if (dst) std::memcpy(dst, src, sizeof(double) * n); };
+    cp(Nq1, f1[1].N.data(), (size_t)f1[1].eNoN * f1[1].nG);
+    cp(Nqxi1, f1[1].Nx.data(), (size_t)3 * f1[1].eNoN * f1[1].nG);
+    cp(w2, f2[1].w.data(), (size_t)f2[1].nG);
+    cp(Nw2, f2[0].N.data(), (size_t)f2[0].eNoN * f2[0].nG);
+    cp(Nwxi2, f2[0].Nx.data(), (size_t)3 * f2[0].eNoN * f2[0].nG);
+    cp(Nq2, f2[1].N.data(), (size_t)f2[1].eNoN * f2[1].nG);
+    cp(Nqxi2, f2[1].Nx.data(), (size_t)3 * f2[1].eNoN * f2[1].nG);
+  });
+}
+
+/// fs::thood_val_rc (fs.cpp:394-466, called by Integrator::step after the assembly): pressure rows of the edge nodes.
+int svref_thood_val_rc(void* h)
+{
+  auto& c = *static_cast<RefCase*>(h);
+  return guarded([&] {
+    if (c.backend) {        // the patch of Integrator::step: R / Val live on the device
+      if (!c.backend_thood_val_rc) throw std::runtime_error("[ref_harness] backend without thood_val_rc hook");
+      c.backend_thood_val_rc(c.backend);
+      return;
+    }
+    fs::thood_val_rc(c.com_mod);
   });
 }
 

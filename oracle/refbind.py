@@ -157,6 +157,29 @@ class _FlatCase:
         n_ = None if Ya_n is None else np.ascontiguousarray(Ya_n, dtype=np.float64)
         self._call("set_active_tension", _d(f), _d(s_), _d(n_))
 
+    def set_mesh_thood(self, iM):
+        """Taylor-Hood function spaces for mesh iM (mshType::nFs = 2)."""
+        self._call("set_mesh_thood", C.c_int(iM))
+
+    def thood_tables(self, iM):
+        """dict with eNoNq, nG1, nG2, lShpF_w, lShpF_q and the tables Nq1(eNoNq,nG1), Nqxi1(3,eNoNq,nG1), w2, Nw2(eNoN,nG2), Nwxi2(3,eNoN,nG2),
+        Nq2(eNoNq,nG2), Nqxi2(3,eNoNq,nG2) of fs::get_thood_fs."""
+        dims = np.zeros(5, np.int32)
+        z = None
+        self._call("get_thood_tables", C.c_int(iM), _i(dims), z, z, z, z, z, z, z)
+        q, g1, g2 = int(dims[0]), int(dims[1]), int(dims[2])
+        eNoN = self.meshes[iM][0]
+        t = dict(eNoNq=q, nG1=g1, nG2=g2, lShpF_w=int(dims[3]), lShpF_q=int(dims[4]),
+                 Nq1=np.zeros((q, g1), order="F"), Nqxi1=np.zeros((3, q, g1), order="F"), w2=np.zeros(g2),
+                 Nw2=np.zeros((eNoN, g2), order="F"), Nwxi2=np.zeros((3, eNoN, g2), order="F"),
+                 Nq2=np.zeros((q, g2), order="F"), Nqxi2=np.zeros((3, q, g2), order="F"))
+        self._call("get_thood_tables", C.c_int(iM), _i(dims), _d(t["Nq1"]), _d(t["Nqxi1"]), _d(t["w2"]), _d(t["Nw2"]), _d(t["Nwxi2"]),
+                   _d(t["Nq2"]), _d(t["Nqxi2"]))
+        return t
+
+    def thood_val_rc(self):
+        self._call("thood_val_rc")
+
     def set_ris(self, maps, closed, meshes):
         """Fitted RIS (before build_graph): maps = list of (2, n) int arrays (grisMapList[p].map), closed = RIS.clsFlg, meshes = list of
         (mesh of face 0, mesh of face 1)."""
@@ -277,6 +300,7 @@ class RefCase(_FlatCase):
         self._call("set_backend", C.c_void_p(self.backend), C.cast(host.b200host_global_eq_assem, C.c_void_p),
                    C.cast(host.b200host_download, C.c_void_p))
         self._call("set_backend_ustruct_r", C.cast(host.b200host_ustruct_r, C.c_void_p))
+        self._call("set_backend_thood_val_rc", C.cast(host.b200host_thood_val_rc, C.c_void_p))
 
     def set_partition(self, gnNo, ltg):
         """Multi-rank runs (SVREF_MPI_SIZE > 1 in the environment before this library is loaded): local -> global node map."""

@@ -92,7 +92,7 @@ static int download_nodal(svb200_ctx* ctx, int rows, const double* d, double* h)
 static void free_mesh(Mesh& m)
 {
   cudaFree(m.d_IEN); cudaFree(m.d_eId); cudaFree(m.d_fN); cudaFree(m.d_slot); cudaFree(m.d_color_perm); cudaFree(m.d_gcolor_perm); cudaFree(m.d_gtab);
-  cudaFree(m.d_uris_mask); cudaFree(m.d_uris_list);
+  cudaFree(m.d_uris_mask); cudaFree(m.d_uris_list); cudaFree(m.d_thtab);
   free_group_sched(m.schedK); free_group_sched(m.schedR);
   m = Mesh();
 }
@@ -451,6 +451,29 @@ int svb200_set_mesh_nxx(svb200_ctx* ctx, int32_t iM, const double* Nxx)
   return upload_fluid_gen_tables(ctx, m);
 }
 
+int svb200_set_mesh_thood(svb200_ctx* ctx, int32_t iM, int32_t eNoNq, int32_t nG2, int32_t lShpF_q, const double* Nq1, const double* Nqxi1,
+                          const double* w2, const double* Nw2, const double* Nwxi2, const double* Nq2, const double* Nqxi2)
+{
+  CTX_GUARD(ctx);
+  SVB_REQUIRE(iM >= 0 && iM < (int)ctx->mesh.size() && ctx->mesh[iM].set, "svb200_set_mesh_thood: mesh not set");
+  Mesh& m = ctx->mesh[iM];
+  if (eNoNq <= 0) {                                  // back to equal-order function spaces
+    cudaFree(m.d_thtab); m.d_thtab = nullptr; m.th_eNoNq = m.th_nG2 = m.th_lShpFq = 0;
+    return SVB200_OK;
+  }
+  SVB_REQUIRE(eNoNq < m.eNoN && nG2 >= 1 && Nq1 && Nqxi1 && w2 && Nw2 && Nwxi2 && Nq2 && Nqxi2, "svb200_set_mesh_thood: bad arguments");
+  TRY(upload_thood_tables(ctx, m, eNoNq, nG2, Nq1, Nqxi1, w2, Nw2, Nwxi2, Nq2, Nqxi2));
+  m.th_eNoNq = eNoNq; m.th_nG2 = nG2; m.th_lShpFq = lShpF_q ? 1 : 0;
+  return SVB200_OK;
+}
+
+int svb200_thood_val_rc(svb200_ctx* ctx)
+{
+  CTX_GUARD(ctx);
+  TRY(flush_val_zero(ctx));
+  return run_thood_val_rc(ctx);
+}
+
 int svb200_set_coords(svb200_ctx* ctx, const double* x)
 {
   CTX_GUARD(ctx);
@@ -619,7 +642,8 @@ static int fill_fluid_args(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams
 {
   SVB_REQUIRE(nDmn >= 1 && nDmn <= MAX_DMN, "svb200_assemble: between 1 and 8 domains are supported");
   SVB_REQUIRE(eq->dof == 4 && ctx->dof == 4, "svb200_assemble: the fluid equation has dof = 4 (call svb200_alloc(4))");
-  SVB_REQUIRE(eq->vmsStab == 1, "svb200_assemble: only VMS-stabilised equal-order elements are supported");
+  SVB_REQUIRE((eq->vmsStab == 1) == (m.th_eNoNq == 0),
+              "svb200_assemble: vmsStab = 1 goes with equal-order function spaces, vmsStab = 0 with a Taylor-Hood mesh (svb200_set_mesh_thood)");
   SVB_REQUIRE(eq->tDof == ctx->tDof && ctx->d_Yg, "svb200_assemble: state not set (svb200_set_state) or tDof mismatch");
   SVB_REQUIRE(!eq->mvMsh || eq->tDof >= 7, "svb200_assemble: mvMsh needs the mesh velocity in state dofs 4..6");
   SVB_REQUIRE(ctx->d_x, "svb200_assemble: coordinates not set");
@@ -699,6 +723,12 @@ static int run_assemble(svb200_ctx* ctx, const Mesh& m, FluidArgs& A, bool gener
   // SVB200_EQ_GENERAL_KERNEL, goes through the per-Gauss-point kernel of assemble_fluid_gen.cu
   // URIS valves on a TET4 mesh (atomic scatter): split launch — the band of elements around the valves through the per-Gauss-point
   // kernel, which has the URIS terms, everything else through the closed-form kernel below (exact there: zero valve factor)
+  // Taylor-Hood function spaces (mshType::nFs = 2): construct_fluid's vmsStab = false branch has its own kernel
+  if (m.th_eNoNq > 0) {
+    TRY(flush_val_zero(ctx));
+    TRY(run_assemble_fluid_thood(ctx, m, A));
+    return check_jacobian_word(ctx, A.ale != 0);
+  }
   static const bool uris_no_split = getenv("SVB200_URIS_NO_SPLIT") != nullptr;       // A/B: all elements through the general kernel
   const bool uris_split = A.nUris > 0 && m.eNoN == 4 && m.nG == 4 && !general && A.atomic && !uris_no_split;
   if (uris_split) {

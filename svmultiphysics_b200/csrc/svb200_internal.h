@@ -56,6 +56,9 @@ struct Mesh {
   std::vector<double> w, N, Nx;  // host copies of the reference-element tables
   std::vector<double> Nxx;       // (6,eNoN,nG) second parametric derivatives (svb200_set_mesh_nxx), empty = all zero
   double* d_gtab = nullptr;      // tables in the layout of assemble_fluid_gen.cu
+  // Taylor-Hood function spaces (svb200_set_mesh_thood): pressure space with th_eNoNq nodes and its own rule of th_nG2 points
+  int th_eNoNq = 0, th_nG2 = 0, th_lShpFq = 0;
+  double* d_thtab = nullptr;     // tables in the layout of assemble_fluid_thood.cu
   // URIS split launch (TET4): elements with a node inside a valve's or scaffold's thickness, as mask and as compact list
   mutable unsigned char* d_uris_mask = nullptr;
   mutable int* d_uris_list = nullptr;
@@ -283,6 +286,10 @@ int launch_tet4_jacobian_check(svb200_ctx* ctx, const Mesh& m, const FluidArgs& 
 // assemble_struct.cu
 int upload_fluid_gen_tables(svb200_ctx* ctx, Mesh& m);
 int build_uris_element_mask(svb200_ctx* ctx, const Mesh& m);
+int upload_thood_tables(svb200_ctx* ctx, Mesh& m, int eNoNq, int nG2, const double* Nq1, const double* Nqxi1, const double* w2,
+                        const double* Nw2, const double* Nwxi2, const double* Nq2, const double* Nqxi2);
+int run_assemble_fluid_thood(svb200_ctx* ctx, const Mesh& m, const FluidArgs& F);
+int run_thood_val_rc(svb200_ctx* ctx);
 int run_assemble_fluid_gen(svb200_ctx* ctx, const Mesh& m, const FluidArgs& F);
 int run_assemble_struct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);
 int run_assemble_mesh(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* eq, const svb200_dmnparams* dmn, int nDmn);

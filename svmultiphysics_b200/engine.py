@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "svb200_set_solution", "svb200_get_solution", "svb200_predictor", "svb200_initiator", "svb200_corrector",
     "svb200_set_node_flags", "svb200_set_dirichlet_rows", "svb200_dirichlet_ustruct", "svb200_advance_time_step",
     "svb200_set_bface", "svb200_assemble_neu",
-    "svb200_last_host_stage", "svb200_set_uris", "svb200_set_ris", "svb200_set_active_tension", "svb200_set_prestress", "svb200_get_prestress",
+    "svb200_last_host_stage", "svb200_set_uris", "svb200_set_ris", "svb200_set_mesh_thood", "svb200_thood_val_rc", "svb200_set_active_tension", "svb200_set_prestress", "svb200_get_prestress",
     "svb200_spmv_rc", "svb200_spmv_rc_variants", "svb200_bench_spmv_rc",
     "svb200_schur_sp", "svb200_schur_sp_variants", "svb200_bench_schur_sp",
 ]
@@ -232,6 +232,20 @@ class Engine:
         s_ = None if Ya_s is None else np.ascontiguousarray(Ya_s, dtype=np.float64)
         n_ = None if Ya_n is None else np.ascontiguousarray(Ya_n, dtype=np.float64)
         self._call("svb200_set_active_tension", _d(f), _d(s_), _d(n_))
+
+    def set_mesh_thood(self, iM, t):
+        """Taylor-Hood function spaces for mesh iM (svb200_set_mesh_thood); t: the dict of fs::get_thood_fs tables (eNoNq, nG2, lShpF_q,
+        Nq1, Nqxi1, w2, Nw2, Nwxi2, Nq2, Nqxi2, column-major).  t = None returns the mesh to equal-order spaces."""
+        if t is None:
+            self._call("svb200_set_mesh_thood", C.c_int32(iM), C.c_int32(0), C.c_int32(0), C.c_int32(0), None, None, None, None, None, None, None)
+            return
+        a = {k: _f64(t[k]) for k in ("Nq1", "Nqxi1", "w2", "Nw2", "Nwxi2", "Nq2", "Nqxi2")}
+        self._call("svb200_set_mesh_thood", C.c_int32(iM), C.c_int32(int(t["eNoNq"])), C.c_int32(int(t["nG2"])), C.c_int32(int(t["lShpF_q"])),
+                   _d(a["Nq1"]), _d(a["Nqxi1"]), _d(a["w2"]), _d(a["Nw2"]), _d(a["Nwxi2"]), _d(a["Nq2"]), _d(a["Nqxi2"]))
+
+    def thood_val_rc(self):
+        """fs::thood_val_rc: pressure rows of the nodes that carry no pressure dof (call after the assembly and the boundary terms)."""
+        self._call("svb200_thood_val_rc")
 
     def set_ris(self, maps, closed):
         """Fitted RIS surfaces (svb200_set_ris): maps = list of (2, n) int arrays (grisMapList[p].map), closed = RIS.clsFlg.  An empty list

@@ -4,8 +4,10 @@
 
 #include "consts.h"
 #include "fils_struct.hpp"
+#include "fs.h"
 
 #include <algorithm>
+#include <array>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -274,6 +276,14 @@ void B200LinearAlgebra::upload_structure(ComMod& com_mod)
                           m.nFn, (m.nFn > 0 && m.fN.size()) ? m.fN.data() : nullptr, m.nG, m.w.data(), m.N.data(), m.Nx.data()));
     // second derivatives of the shape functions for nn::gn_nxx (fluid on non-linear elements, fluid.cpp:648-650)
     if (!m.fs.empty() && m.fs[0].Nxx.size() == 6 * m.eNoN * m.nG) check(svb200_set_mesh_nxx(ctx, iM, m.fs[0].Nxx.data()));
+    // Taylor-Hood function spaces (nFs = 2): the four tables construct_fluid builds with fs::get_thood_fs (fluid.cpp:567, 690)
+    if (m.nFs == 2) {
+      std::array<fsType, 2> f1, f2;
+      fs::get_thood_fs(com_mod, f1, m, false, 1);
+      fs::get_thood_fs(com_mod, f2, m, false, 2);
+      check(svb200_set_mesh_thood(ctx, iM, f1[1].eNoN, f2[1].nG, f1[1].lShpF ? 1 : 0, f1[1].N.data(), f1[1].Nx.data(), f2[1].w.data(),
+                                  f2[0].N.data(), f2[0].Nx.data(), f2[1].N.data(), f2[1].Nx.data()));
+    }
   }
   check(svb200_set_coords(ctx, com_mod.x.data()));
   structure_uploaded = true;
@@ -456,6 +466,13 @@ void B200LinearAlgebra::ustruct_r(ComMod& com_mod)
   }
   svb200_eqparams e = b200::eq_params(com_mod, eq, com_mod.msh[0], scatter);
   check(svb200_ustruct_r(ctx, &e, eq.itr, com_mod.Ad.data()));
+}
+
+/// fs::thood_val_rc (Code/Source/solver/fs.cpp:394-466), called where Integrator::step calls it (Integrator.cpp:140-147).
+void B200LinearAlgebra::thood_val_rc()
+{
+  flush_host_contrib(alloc_dof);
+  check(svb200_thood_val_rc(ctx));
 }
 
 void B200LinearAlgebra::commu_R()

@@ -49,6 +49,8 @@ class B200LinearAlgebra : public virtual LinearAlgebra {
     void set_uris(const ComMod& com_mod);
     /// com_mod.ris / grisMapList -> svb200_set_ris whenever a surface opened or closed (ris::doassem_ris on the device, csrc/ris.cu).
     void set_ris(const ComMod& com_mod);
+    /// fs::thood_val_rc on the device-resident R / Val (Taylor-Hood meshes; patch of Integrator::step like ustruct_r).
+    void thood_val_rc();
     /// all_fun::commu(com_mod, com_mod.R) of Integrator::step (Code/Source/solver/Integrator.cpp:124-129).
     void commu_R();
     /// ustruct::ustruct_r (Code/Source/solver/ustruct.cpp:1742) on the device-resident R and Kd.

@@ -45,6 +45,15 @@ void b200host_ustruct_r(void* p, void* com_mod)
   la->ustruct_r(*static_cast<ComMod*>(com_mod));
 }
 
+/// Where Integrator::step calls fs::thood_val_rc (Integrator.cpp:140-147).
+__attribute__((visibility("default")))
+void b200host_thood_val_rc(void* p)
+{
+  auto* la = dynamic_cast<B200LinearAlgebra*>(static_cast<LinearAlgebra*>(p));
+  if (!la) throw std::runtime_error("b200host_thood_val_rc: not a B200LinearAlgebra");
+  la->thood_val_rc();
+}
+
 __attribute__((visibility("default")))
 long long b200host_launch_count(void* p)
 {

@@ -355,6 +355,23 @@ def ris_case(scatter=abi.SCATTER_ATOMIC, seed=43):
     return x, [IEN0, IEN1], mp, Ag, Yg, Bf, eq, [abi.fluid_domain(K_darcy=0.5, f=(0.1, 0.0, -0.2))]
 
 
+# ---- Taylor-Hood fluid (mshType::nFs = 2: P2-P1 / Q2-Q1, vmsStab = false; fluid.cpp:494-500, fs.cpp:73-178) --------------------------
+# (name, mesh factory, viscosity kwargs, K_darcy, body force, tDof, mvMsh)
+FLUID_THOOD_CASES = [
+    ("tet10_newtonian", _tet10, {}, 0.0, (0.0, 0.0, 0.0), 4, 0),
+    ("tet10_carreau_yasuda_darcy_moving_mesh", _tet10, dict(viscType=abi.VISC_CY, mu=0.035, mu_o=0.16, lam=8.2, a=0.64, n=0.2128), 2.0,
+     (0.1, -0.2, 0.3), 7, 1),
+    ("hex27_casson", _hex27, dict(viscType=abi.VISC_CASSON, mu=0.3, mu_o=0.1, lam=0.5), 0.5, (0.0, 0.0, 1.0), 4, 0),
+    ("hex20_newtonian", _hex20, {}, 0.0, (0.0, 0.1, 0.0), 4, 0),
+]
+
+
+def fluid_thood_eq(dt, tDof=4, mvMsh=0, scatter=abi.SCATTER_ATOMIC):
+    eq = abi.fluid_eq(dt, tDof=tDof, mvMsh=mvMsh, scatter=scatter)
+    eq.vmsStab = 0
+    return eq
+
+
 # ---- scalar heat equations (heatS / heatF) -------------------------------------------------------
 # (name, mesh factory, fluid?, tDof, eq.s, mvMsh, heat_domain kwargs)
 HEAT_CASES = [

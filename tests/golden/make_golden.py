@@ -255,6 +255,29 @@ def ris_golden():
     print("wrote ris.npz with", len(out), "arrays")
 
 
+def fluid_thood_golden():
+    """Navier-Stokes on Taylor-Hood function spaces (construct_fluid with vmsStab = false): R / Val after the element loop and after
+    fs::thood_val_rc, and the four tables of fs::get_thood_fs per element type."""
+    out = {}
+    for name, mk, visc, Kd, f, tDof, mv in common.FLUID_THOOD_CASES:
+        m = mk()
+        Ag, Yg, Dg, Bf = common.fluid_gen_state(m, tDof)
+        c = RefCase(); c.set_coords(m.x); c.add_mesh(m.IEN); c.set_mesh_thood(0)
+        rowPtr, colPtr = c.build_graph(0)
+        c.alloc(4); c.set_state(Ag, Yg, Dg, Bf)
+        c.assemble(0, common.fluid_thood_eq(0.005, tDof=tDof, mvMsh=mv), [abi.fluid_domain(K_darcy=Kd, f=f, **visc)])
+        out[f"{name}/R"], out[f"{name}/Val"] = c.get_R(), c.get_Val()
+        c.thood_val_rc()
+        out[f"{name}/R_rc"], out[f"{name}/Val_rc"] = c.get_R(), c.get_Val()
+        out[f"{name}/rowPtr"], out[f"{name}/colPtr"] = rowPtr, colPtr
+        et = name.split("_")[0]
+        for k, v in c.thood_tables(0).items():
+            out[f"tables/{et}/{k}"] = np.asarray(v)
+        assert np.abs(out[f"{name}/Val"][12:15]).max() > 0 and not out[f"{name}/Val"][15].any()
+    np.savez_compressed(os.path.join(HERE, "fluid_thood.npz"), **out)
+    print("wrote fluid_thood.npz with", len(out), "arrays")
+
+
 def lelas_golden():
     """R / Val of l_elas_3d on TET4: the linear-elasticity equation and the mesh-motion equation (tDof = 7, old displacement)."""
     out = {}
@@ -297,6 +320,6 @@ if __name__ == "__main__":
     if not have_ref():
         raise SystemExit("oracle/_ref/libsvref.so is missing: run `make -C oracle ref` first")
     only = sys.argv[1:]
-    for fn in (fluid_golden, struct_golden, fluid_gen_golden, fluid_hi_golden, struct_hi_golden, heat_golden, ustruct_golden, lelas_golden, prestress_golden, fsi_ustruct_golden, fluid_uris_golden, other_hi_golden, ris_golden):
+    for fn in (fluid_golden, struct_golden, fluid_gen_golden, fluid_hi_golden, struct_hi_golden, heat_golden, ustruct_golden, lelas_golden, prestress_golden, fsi_ustruct_golden, fluid_uris_golden, other_hi_golden, ris_golden, fluid_thood_golden):
         if not only or fn.__name__.replace("_golden", "") in only:
             fn()

@@ -622,3 +622,54 @@ def test_open_ris_surface_matches_the_reference(scatter):
     R4, _ = run()
     assert common.rel_err(R4, g["closed/R"]) < 1e-12
     eng.close()
+
+
+# ---- Taylor-Hood function spaces (mshType::nFs = 2): construct_fluid with vmsStab = false ---------------------------------------
+@pytest.mark.parametrize("scatter", [abi.SCATTER_ATOMIC, abi.SCATTER_COLORED])
+@pytest.mark.parametrize("case", common.FLUID_THOOD_CASES, ids=[c[0] for c in common.FLUID_THOOD_CASES])
+def test_taylor_hood_fluid_matches_golden(case, scatter):
+    """P2-P1 tetrahedra (TET10 / TET4) and Q2-Q1 hexahedra (HEX27, HEX20 / HEX8): momentum loop on the velocity rule, continuity loop on
+    the pressure rule, then fs::thood_val_rc — R / Val against the compiled reference (tests/golden/fluid_thood.npz), entry type by
+    entry type; an equal-order assembly on the same mesh afterwards (svb200_set_mesh_thood(eNoNq = 0)) still matches fluid_hi.npz."""
+    from svmultiphysics_b200.engine import Engine
+    name, mk, visc, Kd, f, tDof, mv = case
+    golden, tabs = common.load_golden("fluid_thood.npz"), common.load_golden("fluid_hi.npz")
+    m = mk()
+    et = name.split("_")[0]
+    Ag, Yg, Dg, Bf = common.fluid_gen_state(m, tDof)
+    w, N, Nx, Nxx = (tabs[f"tables/{et}/{k}"] for k in ("w", "N", "Nx", "Nxx"))
+    t = {k: golden[f"tables/{et}/{k}"] for k in ("eNoNq", "nG1", "nG2", "lShpF_q", "Nq1", "Nqxi1", "w2", "Nw2", "Nwxi2", "Nq2", "Nqxi2")}
+    eq, dmn = common.fluid_thood_eq(0.005, tDof=tDof, mvMsh=mv, scatter=scatter), [abi.fluid_domain(K_darcy=Kd, f=f, **visc)]
+    eng = Engine(0)
+    eng.set_graph(golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"])
+    eng.set_mesh(0, m.IEN, w, N, Nx, Nxx=Nxx)
+    eng.set_coords(m.x)
+    eng.alloc(4); eng.set_state(Ag, Yg, Dg, Bf)
+    with pytest.raises(RuntimeError):
+        eng.assemble(0, eq, dmn)                        # vmsStab = 0 without Taylor-Hood tables
+    eng.set_mesh_thood(0, t)
+    eng.alloc(4); eng.assemble(0, eq, dmn)
+    R1, V1 = eng.get_R(), eng.get_Val()
+    GR, GV = golden[f"{name}/R"], golden[f"{name}/Val"]
+    assert common.rel_err(R1[:3], GR[:3]) < 1e-12 and common.rel_err(R1[3], GR[3]) < 1e-12
+    for rows in ([0, 1, 2, 4, 5, 6, 8, 9, 10], [3, 7, 11], [12, 13, 14]):
+        assert common.rel_err(V1[rows], GV[rows]) < 1e-12
+    assert not V1[15].any()
+    if scatter == abi.SCATTER_COLORED:
+        eng.alloc(4); eng.assemble(0, eq, dmn)
+        assert np.array_equal(eng.get_R(), R1) and np.array_equal(eng.get_Val(), V1)
+    eng.thood_val_rc()
+    R2, V2 = eng.get_R(), eng.get_Val()
+    assert common.rel_err(R2[:3], golden[f"{name}/R_rc"][:3]) < 1e-12 and common.rel_err(R2[3], golden[f"{name}/R_rc"][3]) < 1e-12
+    assert np.array_equal(V2[15], golden[f"{name}/Val_rc"][15])          # zeros and ones
+    assert (V2[15] == 1.0).sum() == (R2[3] == 0.0).sum() > 0
+    for rows in ([0, 1, 2, 4, 5, 6, 8, 9, 10], [3, 7, 11], [12, 13, 14]):
+        assert np.array_equal(V2[rows], V1[rows])
+    # back to equal-order VMS spaces on the same mesh object
+    eng.set_mesh_thood(0, None)
+    hi = next((c for c in common.FLUID_HI_CASES if c[0].startswith(et) and c[5] == tDof and c[6] == mv and c[3] == Kd and c[4] == f
+               and c[2] == visc), None)
+    if hi is not None:
+        eng.alloc(4); eng.assemble(0, abi.fluid_eq(0.005, tDof=tDof, mvMsh=mv, scatter=scatter), dmn)
+        assert common.rel_err(eng.get_R(), tabs[f"{hi[0]}/R"]) < 1e-12
+    eng.close()

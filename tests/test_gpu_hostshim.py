@@ -312,6 +312,33 @@ def test_linear_elasticity_and_mesh_motion_through_cpp_plugin(name):
     _close(cpu, gpu)
 
 
+@pytest.mark.parametrize("name", ["tet10_carreau_yasuda_darcy_moving_mesh", "hex27_casson"])
+def test_taylor_hood_fluid_through_cpp_plugin(name):
+    """A Taylor-Hood mesh (mshType::nFs = 2) through the plug-in: upload_structure hands the tables of fs::get_thood_fs to
+    svb200_set_mesh_thood, eq_params sets vmsStab = 0, and thood_val_rc runs on the device where Integrator::step calls fs::thood_val_rc."""
+    from oracle import refbind
+    if not refbind.have_host():
+        pytest.skip("needs oracle/_ref/libsvref.so and svmultiphysics_b200/lib/libsvb200_host.so")
+    _, mk, visc, Kd, f, tDof, mv = next(c for c in common.FLUID_THOOD_CASES if c[0] == name)
+    golden = common.load_golden("fluid_thood.npz")
+    m = mk()
+    Ag, Yg, Dg, Bf = common.fluid_gen_state(m, tDof)
+    gpu = refbind.RefCase(); gpu.set_coords(m.x); gpu.add_mesh(m.IEN); gpu.set_mesh_thood(0)
+    gpu.build_graph(0)
+    gpu.use_b200_backend(device=0)
+    gpu.alloc(4); gpu.set_state(Ag, Yg, Dg, Bf)
+    gpu.assemble(0, common.fluid_thood_eq(0.005, tDof=tDof, mvMsh=mv), [abi.fluid_domain(K_darcy=Kd, f=f, **visc)])
+    R1, V1 = gpu.get_R(), gpu.get_Val()
+    GR, GV = golden[f"{name}/R"], golden[f"{name}/Val"]
+    assert common.rel_err(R1[:3], GR[:3]) < 1e-12 and common.rel_err(R1[3], GR[3]) < 1e-12
+    for rows in ([0, 1, 2, 4, 5, 6, 8, 9, 10], [3, 7, 11], [12, 13, 14]):
+        assert common.rel_err(V1[rows], GV[rows]) < 1e-12
+    gpu.thood_val_rc()
+    assert np.array_equal(gpu.get_Val()[15], golden[f"{name}/Val_rc"][15])
+    assert common.rel_err(gpu.get_R()[3], golden[f"{name}/R_rc"][3]) < 1e-12
+    gpu.close()
+
+
 def test_prestress_equation_through_cpp_plugin():
     """com_mod.pS0 and pstEq through B200LinearAlgebra: the plug-in uploads pS0, flags the prestress equation and writes the
     device accumulators back into com_mod.pSn / pSa (what Integrator::corrector then communicates and divides)."""

@@ -258,6 +258,51 @@ def test_device_fluid_algebra_with_uris_valves_matches_golden(hostmath, name, fa
     assert common.rel_err(V.T, golden[f"{name}/Val"]) < 1e-12
 
 
+class HostThoodArgs(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("IEN", "x", "Ag", "Yg", "Bf", "w", "N", "Nxi", "Nxi2", "Nq1", "Nqxi1", "w2", "Nw2", "Nwxi2", "Nq2", "Nqxi2")] + \
+               [(k, C.c_int) for k in ("eNoN", "eNoNq", "nEl", "nG", "nG2", "tDof", "mvMsh", "lShpFq")] + \
+               [(k, C.c_double) for k in ("dt", "af", "am", "gam")] + [("dm", FluidDmn)]
+
+
+@pytest.mark.parametrize("case", common.FLUID_THOOD_CASES, ids=[c[0] for c in common.FLUID_THOOD_CASES])
+def test_device_taylor_hood_fluid_algebra_matches_golden(hostmath, case):
+    """svmultiphysics_b200/csrc/fluid_thood.cuh (fluid_3d_m / fluid_3d_c with vmsFlag false on P2-P1 / Q2-Q1 function spaces, the
+    momentum loop on the velocity rule and the continuity loop on the pressure rule with the reference's choice of Jacobian) compiled for
+    the host against what the unmodified reference assembled (tests/golden/fluid_thood.npz), entry type by entry type."""
+    name, mk, visc, Kd, f, tDof, mv = case
+    golden, tabs = common.load_golden("fluid_thood.npz"), common.load_golden("fluid_hi.npz")
+    assert hostmath.hostmath_sizeof_thoodargs() == C.sizeof(HostThoodArgs)
+    m = mk()
+    et = name.split("_")[0]
+    Ag, Yg, _, Bf = common.fluid_gen_state(m, tDof)
+    eq, d = common.fluid_thood_eq(0.005, tDof=tDof, mvMsh=mv), abi.fluid_domain(K_darcy=Kd, f=f, **visc)
+    w, N, Nx, Nxx = (tabs[f"tables/{et}/{k}"] for k in ("w", "N", "Nx", "Nxx"))
+    t = {k: golden[f"tables/{et}/{k}"] for k in ("eNoNq", "nG1", "nG2", "lShpF_q", "Nq1", "Nqxi1", "w2", "Nw2", "Nwxi2", "Nq2", "Nqxi2")}
+    tr = lambda a: np.ascontiguousarray(np.asarray(a).T)          # (k, a, g) column-major -> [g][a][k] row-major
+    keep = [np.ascontiguousarray(m.IEN.T.astype(np.int32)), tr(m.x), tr(Ag), tr(Yg), tr(Bf), np.ascontiguousarray(w), tr(N), tr(Nx), tr(Nxx),
+            tr(t["Nq1"]), tr(t["Nqxi1"]), np.ascontiguousarray(t["w2"]), tr(t["Nw2"]), tr(t["Nwxi2"]), tr(t["Nq2"]), tr(t["Nqxi2"])]
+    A = HostThoodArgs()
+    (A.IEN, A.x, A.Ag, A.Yg, A.Bf, A.w, A.N, A.Nxi, A.Nxi2, A.Nq1, A.Nqxi1, A.w2, A.Nw2, A.Nwxi2, A.Nq2, A.Nqxi2) = (k.ctypes.data for k in keep)
+    A.eNoN, A.eNoNq, A.nEl, A.nG, A.nG2, A.tDof, A.mvMsh, A.lShpFq = m.eNoN, int(t["eNoNq"]), m.nEl, len(w), int(t["nG2"]), tDof, mv, int(t["lShpF_q"])
+    assert int(t["nG1"]) == len(w)
+    A.dt, A.af, A.am, A.gam = eq.dt, eq.af, eq.am, eq.gam
+    A.dm.rho, A.dm.Kd = d.rho, d.K_darcy
+    for i in range(3):
+        A.dm.f[i] = d.f[i]
+    A.dm.mu_i, A.dm.mu_o, A.dm.lam, A.dm.a, A.dm.n = d.mu_i, d.mu_o, d.lam, d.a, d.n
+    A.dm.viscType, A.dm.Id, A.dm.isFluid = d.viscType, -1, 1
+    rowPtr, colPtr = golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"]
+    R = np.zeros((m.nNo, 4)); V = np.zeros((len(colPtr), 16))
+    rc = hostmath.hostmath_fluid_thood(C.byref(A), rowPtr.ctypes.data_as(C.c_void_p), colPtr.ctypes.data_as(C.c_void_p),
+                                       R.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    GR, GV = golden[f"{name}/R"], golden[f"{name}/Val"]
+    assert common.rel_err(R.T[:3], GR[:3]) < 1e-12 and common.rel_err(R.T[3], GR[3]) < 1e-12
+    for rows in ([0, 1, 2, 4, 5, 6, 8, 9, 10], [3, 7, 11], [12, 13, 14]):
+        assert common.rel_err(V.T[rows], GV[rows]) < 1e-12
+    assert not V.T[15].any() and not GV[15].any()
+
+
 class HostFluidAnyArgs(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("IEN", "x", "Ag", "Yg", "Bf", "w", "N", "Nxi", "Nxi2")] + \
                [(k, C.c_int) for k in ("eNoN", "nEl", "nG", "tDof", "mvMsh", "lShpF")] + \
