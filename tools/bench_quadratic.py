@@ -23,6 +23,17 @@ def run(name, m, et):
     for _ in range(3):
         e.alloc(4); e.timer_mark(0); e.assemble(0, eq, dm); e.timer_mark(1); ms.append(e.timer_elapsed())
     print(f"{name} fluid : {m.nEl} el, {m.nNo} nodes, nnz {len(cp)}: {min(ms):.3f} ms  {m.nEl / min(ms) * 1e-3:.2f} M el/s  {m.nNo / min(ms) * 1e-3:.2f} M nodes/s")
+    # the same mesh with Taylor-Hood function spaces (P2-P1 / Q2-Q1, vmsStab = false)
+    th = common.load_golden("fluid_thood.npz")
+    t = {k: th[f"tables/{et}/{k}"] for k in ("eNoNq", "nG1", "nG2", "lShpF_q", "Nq1", "Nqxi1", "w2", "Nw2", "Nwxi2", "Nq2", "Nqxi2")}
+    e.set_mesh_thood(0, t)
+    eqt = common.fluid_thood_eq(0.005)
+    e.alloc(4); e.assemble(0, eqt, dm)
+    ms = []
+    for _ in range(3):
+        e.alloc(4); e.timer_mark(0); e.assemble(0, eqt, dm); e.timer_mark(1); ms.append(e.timer_elapsed())
+    print(f"{name} Taylor-Hood fluid: {min(ms):.3f} ms  {m.nEl / min(ms) * 1e-3:.2f} M el/s  {m.nNo / min(ms) * 1e-3:.2f} M nodes/s")
+    e.set_mesh_thood(0, None)
     A, Y, D, B, _ = common.struct_state(m, 0)
     eqs, dms = abi.struct_eq(1e-4), [abi.struct_domain(E=1e6, nu=0.4, Kpen=1e6, rho=1.0)]
     e.alloc(3); e.set_state(A, Y, D, B); e.assemble(0, eqs, dms)
