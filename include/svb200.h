@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define SVB200_ABI_VERSION 5
+#define SVB200_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define SVB200_API __attribute__((visibility("default")))

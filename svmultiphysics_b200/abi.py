@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # svb200_phys
 PHYS_FLUID, PHYS_STRUCT, PHYS_FSI, PHYS_MESH, PHYS_LELAS, PHYS_HEATS, PHYS_HEATF, PHYS_USTRUCT = 0, 1, 2, 3, 4, 5, 6, 7
