@@ -114,6 +114,85 @@ def new_kernels():
         e.close()
 
 
+def session3_kernels():
+    """Round 2, session 3: FSI with a ustruct wall + masked ustruct_r, URIS valves (split launch and general kernel), fitted RIS
+    (take / put / apply), heat / lElas / mesh on quadratic and wedge elements, the HEX8 heat and lElas kernels with one lane per Gauss
+    point, the rolled ustruct TET4 kernel, Taylor-Hood fluid + thood_val_rc, degenerate sizes."""
+    tabs, th = common.load_golden("fluid_hi.npz"), common.load_golden("fluid_thood.npz")
+    for sc in (abi.SCATTER_ATOMIC, abi.SCATTER_COLORED):
+        for name in common.FSI_USTRUCT_CASES:
+            m, Ag, Yg, Dg, Bf, fN, nFn, eq, dmn, Ad, flags = common.fsi_ustruct_case(name, sc)
+            e = engine(m, nFn, fN)
+            e.alloc(4); e.set_state(Ag, Yg, Dg, Bf); e.assemble(0, eq, dmn)
+            e.set_node_flags(flags); e.ustruct_r(eq, 1, Ad); e.get_Kd(); e.get_Rd(); e.close()
+        for name, *_ in common.URIS_CASES:
+            m, Ag, Yg, Dg, Bf, eq, dmn = common.uris_case(name, sc)
+            raw, dev, sdf, udf, vel = common.uris_valves(m)
+            e = Engine(0); rp, cp = e.lhsa(m.nNo, [m.IEN]); e.set_graph(rp, cp)
+            w, N, Nx = elements.tables(m.eNoN)
+            e.set_mesh(0, m.IEN, w, N, Nx, eId=m.eId, Nxx=elements.nxx_tables(m.eNoN) if m.eNoN != 4 else None); e.set_coords(m.x)
+            e.set_uris(dev, sdf, udf, vel)
+            e.alloc(4); e.set_state(Ag, Yg, Dg, Bf); e.assemble(0, eq, dmn); e.get_Val()
+            e.set_uris([]); e.alloc(4); e.assemble(0, eq, dmn); e.close()
+        g = common.load_golden("ris.npz")
+        x, IENs, mp, Ag, Yg, Bf, eq, dmn = common.ris_case(sc)
+        e = Engine(0); e.set_graph(g["rowPtr"], g["colPtr"])
+        w, N, Nx = elements.tables(4)
+        for iM, I in enumerate(IENs):
+            e.set_mesh(iM, I, w, N, Nx)
+        e.set_coords(x); e.set_ris([mp], [0])
+        e.alloc(4); e.set_state(Ag, Yg, None, Bf)
+        for iM in range(len(IENs)):
+            e.assemble(iM, eq, dmn)
+        e.get_Val(); e.close()
+        for name, *_ in common.OTHER_HI_CASES:
+            m, et, dof, Ag, Yg, Dg, Bf, Do, eq, dmn = common.other_hi_case(name, sc)
+            w, N, Nx = (tabs[f"tables/{et}/{k}"] for k in ("w", "N", "Nx"))
+            e = Engine(0); rp, cp = e.lhsa(m.nNo, [m.IEN]); e.set_graph(rp, cp)
+            e.set_mesh(0, m.IEN, w, N, Nx); e.set_coords(m.x)
+            e.alloc(dof); e.set_state(Ag, Yg, Dg, Bf)
+            if Do is not None:
+                e.set_old_disp(Do)
+            e.assemble(0, eq, dmn); e.get_Val(); e.close()
+        for name, mk, fluid, tDof, s_, mv, dkw in common.HEAT_CASES:            # HEX8: the lane-per-Gauss-point kernel
+            m = mk(); e = engine(m)
+            Ag, Yg, Dg, Bf = common.heat_state(m, tDof, s_)
+            e.alloc(1); e.set_state(Ag, Yg, Dg, Bf)
+            e.assemble(0, abi.heat_eq(0.01, fluid, tDof=tDof, s=s_, mvMsh=mv, scatter=sc), [abi.heat_domain(fluid, **dkw)]); e.get_Val(); e.close()
+        m = meshgen.box_hex8(3, 2, 2, (1.0, 1.0, 1.0)); e = engine(m)
+        Ag, Yg, Dg, Bf, _ = common.struct_state(m, 0)
+        e.alloc(3); e.set_state(Ag, Yg, Dg, Bf); e.assemble(0, abi.lelas_eq(1e-3, scatter=sc), [abi.lelas_domain()]); e.get_Val(); e.close()
+        for name, mk, dkw, nFn in [c for c in common.USTRUCT_CASES if c[0].startswith("tet4")]:
+            m = mk(); Ag, Yg, Dg, Bf, fN = common.ustruct_state(m, nFn); e = engine(m, nFn, fN)
+            d = abi.ustruct_domain(**dkw)
+            e.alloc(4); e.set_state(Ag, Yg, Dg, Bf)
+            if d.active_stress:
+                e.set_active_tension(*common.active_tension(m, d.isoType))
+            e.assemble(0, abi.ustruct_eq(1e-3, scatter=sc), [d]); e.get_Kd(); e.close()
+        for name, mk, visc, Kd, f, tDof, mv in common.FLUID_THOOD_CASES:
+            m = mk(); et = name.split("_")[0]
+            w, N, Nx, Nxx = (tabs[f"tables/{et}/{k}"] for k in ("w", "N", "Nx", "Nxx"))
+            t = {k: th[f"tables/{et}/{k}"] for k in ("eNoNq", "nG1", "nG2", "lShpF_q", "Nq1", "Nqxi1", "w2", "Nw2", "Nwxi2", "Nq2", "Nqxi2")}
+            A, Y, D, B = common.fluid_gen_state(m, tDof)
+            e = Engine(0); rp, cp = e.lhsa(m.nNo, [m.IEN]); e.set_graph(rp, cp)
+            e.set_mesh(0, m.IEN, w, N, Nx, Nxx=Nxx); e.set_mesh_thood(0, t); e.set_coords(m.x)
+            e.alloc(4); e.set_state(A, Y, D, B)
+            e.assemble(0, common.fluid_thood_eq(0.005, tDof=tDof, mvMsh=mv, scatter=sc), [abi.fluid_domain(K_darcy=Kd, f=f, **visc)])
+            e.thood_val_rc(); e.get_Val(); e.close()
+    # degenerate sizes: one element, a partial group
+    big = meshgen.cylinder_tet4(4, 3)
+    for nEl in (1, 129):
+        import copy
+        I = big.IEN[:, :nEl]; nodes, inv = np.unique(I, return_inverse=True)
+        m = copy.copy(big); m.x = np.asfortranarray(big.x[:, nodes]); m.IEN = np.asfortranarray(inv.reshape(I.shape).astype(np.int32)); m.eId = None
+        e = engine(m)
+        rng = np.random.default_rng(1)
+        e.alloc(4); e.set_state(np.asfortranarray(rng.standard_normal((4, m.nNo))), np.asfortranarray(rng.standard_normal((4, m.nNo))), None, None)
+        e.assemble(0, abi.fluid_eq(0.005), [abi.fluid_domain()]); e.get_Val(); e.close()
+
+
 if only in ("", "new"):
     new_kernels()
+if only in ("", "s3"):
+    session3_kernels()
 print("sanitize_small: done")
