@@ -36,6 +36,9 @@ struct ThoodArgs {
   int tDof, mvMsh, nDmn, atomic, lShpFq;
   double dt, af, am, gam;
   FluidDmn dmn[MAX_DMN];
+  const double* uris;     // URIS valves (svb200_set_uris) or null: the momentum loop sees the factor at the velocity rule's points
+  int nUris;
+  svb200_uris urisP[SVB200_MAX_URIS];
 };
 
 template <bool ATOMIC>
@@ -132,8 +135,16 @@ assemble_fluid_thood_kernel(const __grid_constant__ ThoodArgs P)
 #pragma unroll
       for (int i = 0; i < 3; i++) rq[ENONQ + 3 * b + i] = Nqx[b][i];
     }
+    // URIS valves (fluid.cpp:622-672): with vmsFlag false the continuity loop has no URIS term left (tauM = 0, fluid.cpp:1711-1715)
+    double uF = 0.0, uV[3] = {0.0, 0.0, 0.0};
+    if (P.uris != nullptr) {
+      int nodes[ENON];
+#pragma unroll
+      for (int b = 0; b < ENON; b++) nodes[b] = __ldg(P.IEN + (size_t)e * ENON + b);
+      uris_factor<ENON>(P.uris, P.nUris, P.urisP, tg + 1, nodes, uF, uV);
+    }
     thood_gauss_point_m<ENON, ENONQ>(dm, P.dt, P.af, P.am, P.gam, tg[0] * Jac, ks, tg + 1, Nx, Nxx, tq, Nqx, sal, syl, sbf,
-                                     P.mvMsh ? sym : nullptr, *q, reinterpret_cast<FluidNodeC*>(rq + 4 * ENONQ));
+                                     P.mvMsh ? sym : nullptr, *q, reinterpret_cast<FluidNodeC*>(rq + 4 * ENONQ), uF, uV);
   }
   // ---- phase A2: pressure rule ----------------------------------------------------------------------------------
   if (active && a < NG2) {
@@ -290,7 +301,7 @@ int run_assemble_fluid_thood(svb200_ctx* ctx, const Mesh& m, const FluidArgs& F)
   SVB_REQUIRE(key == 10041504 || key == 27082708 || key == 20082708,
               "svb200_assemble: Taylor-Hood fluid elements: TET10 / TET4 (15 + 4 Gauss points), HEX27 / HEX8 and HEX20 / HEX8 (27 + 8)");
   SVB_REQUIRE(m.d_gtab && m.d_thtab && !m.Nxx.empty(), "svb200_assemble: Taylor-Hood mesh needs svb200_set_mesh_nxx and svb200_set_mesh_thood");
-  SVB_REQUIRE(!F.ale && F.nUris == 0, "svb200_assemble: Taylor-Hood fluid elements inside FSI or with URIS valves are not implemented");
+  SVB_REQUIRE(!F.ale, "svb200_assemble: Taylor-Hood fluid elements inside an FSI equation are not implemented");
   ThoodArgs A;
   memset(&A, 0, sizeof(A));
   A.IEN = F.IEN; A.eId = F.eId; A.slot = F.slot; A.perm = nullptr;
@@ -299,6 +310,8 @@ int run_assemble_fluid_thood(svb200_ctx* ctx, const Mesh& m, const FluidArgs& F)
   A.tDof = F.tDof; A.mvMsh = F.mvMsh; A.nDmn = F.nDmn; A.atomic = F.atomic; A.lShpFq = m.th_lShpFq;
   A.dt = F.dt; A.af = F.af; A.am = F.am; A.gam = F.gam;
   for (int d = 0; d < MAX_DMN; d++) A.dmn[d] = F.dmn[d];
+  A.uris = F.uris; A.nUris = F.nUris;
+  for (int v = 0; v < F.nUris; v++) A.urisP[v] = F.urisP[v];
   auto launch = [&](const ThoodArgs& B) {
     switch (key) {
       case 10041504: return launch_thood<10, 4, 15, 4>(ctx, B);

@@ -366,6 +366,10 @@ FLUID_THOOD_CASES = [
 ]
 
 
+# Taylor-Hood + two URIS valves (the momentum loop sees the valve factor at the velocity rule's Gauss points)
+FLUID_THOOD_URIS_CASE = ("tet10_uris", _tet10, {}, 0.5, (0.1, 0.0, -0.2), 4, 0)
+
+
 def fluid_thood_eq(dt, tDof=4, mvMsh=0, scatter=abi.SCATTER_ATOMIC):
     eq = abi.fluid_eq(dt, tDof=tDof, mvMsh=mvMsh, scatter=scatter)
     eq.vmsStab = 0

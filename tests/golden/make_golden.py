@@ -259,11 +259,14 @@ def fluid_thood_golden():
     """Navier-Stokes on Taylor-Hood function spaces (construct_fluid with vmsStab = false): R / Val after the element loop and after
     fs::thood_val_rc, and the four tables of fs::get_thood_fs per element type."""
     out = {}
-    for name, mk, visc, Kd, f, tDof, mv in common.FLUID_THOOD_CASES:
+    for name, mk, visc, Kd, f, tDof, mv in common.FLUID_THOOD_CASES + [common.FLUID_THOOD_URIS_CASE]:
         m = mk()
         Ag, Yg, Dg, Bf = common.fluid_gen_state(m, tDof)
         c = RefCase(); c.set_coords(m.x); c.add_mesh(m.IEN); c.set_mesh_thood(0)
         rowPtr, colPtr = c.build_graph(0)
+        if name.endswith("uris"):
+            raw, dev, sdf, udf, vel = common.uris_valves(m)
+            c.set_uris(raw, sdf, udf, vel)
         c.alloc(4); c.set_state(Ag, Yg, Dg, Bf)
         c.assemble(0, common.fluid_thood_eq(0.005, tDof=tDof, mvMsh=mv), [abi.fluid_domain(K_darcy=Kd, f=f, **visc)])
         out[f"{name}/R"], out[f"{name}/Val"] = c.get_R(), c.get_Val()

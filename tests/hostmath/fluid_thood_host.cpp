@@ -14,6 +14,9 @@ struct HostThoodArgs {
   int eNoN, eNoNq, nEl, nG, nG2, tDof, mvMsh, lShpFq;
   double dt, af, am, gam;
   svb::FluidDmn dm;
+  const double* uris;        // URIS valves: (nNo, nUris, 5) or null
+  int nUris;
+  svb200_uris urisP[SVB200_MAX_URIS];
 };
 
 template <int ENON, int ENONQ>
@@ -47,8 +50,10 @@ static int run(const HostThoodArgs* P, const int* rowPtr, const int* colPtr, dou
       const double* Nq = P->Nq1 + (size_t)g * ENONQ;
       FluidGP q;
       FluidNode nd[ENON];
+      double uF = 0.0, uV[3] = {0.0, 0.0, 0.0};
+      if (P->uris) uris_factor<ENON>(P->uris, P->nUris, P->urisP, P->N + (size_t)g * ENON, n, uF, uV);
       thood_gauss_point_m<ENON, ENONQ>(P->dm, P->dt, P->af, P->am, P->gam, P->w[g] * Jac, ks, P->N + (size_t)g * ENON, Nx, Nxx, Nq, Nqx,
-                                       al, yl, bfl, P->mvMsh ? ym : nullptr, q, nd);
+                                       al, yl, bfl, P->mvMsh ? ym : nullptr, q, nd, uF, uV);
       for (int a = 0; a < ENON; a++) {
         thood_residual_m(q, nd[a], lR[a]);
         FluidRow row;

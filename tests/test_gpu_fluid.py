@@ -626,7 +626,8 @@ def test_open_ris_surface_matches_the_reference(scatter):
 
 # ---- Taylor-Hood function spaces (mshType::nFs = 2): construct_fluid with vmsStab = false ---------------------------------------
 @pytest.mark.parametrize("scatter", [abi.SCATTER_ATOMIC, abi.SCATTER_COLORED])
-@pytest.mark.parametrize("case", common.FLUID_THOOD_CASES, ids=[c[0] for c in common.FLUID_THOOD_CASES])
+@pytest.mark.parametrize("case", common.FLUID_THOOD_CASES + [common.FLUID_THOOD_URIS_CASE],
+                         ids=[c[0] for c in common.FLUID_THOOD_CASES] + ["tet10_uris"])
 def test_taylor_hood_fluid_matches_golden(case, scatter):
     """P2-P1 tetrahedra (TET10 / TET4) and Q2-Q1 hexahedra (HEX27, HEX20 / HEX8): momentum loop on the velocity rule, continuity loop on
     the pressure rule, then fs::thood_val_rc — R / Val against the compiled reference (tests/golden/fluid_thood.npz), entry type by
@@ -648,6 +649,9 @@ def test_taylor_hood_fluid_matches_golden(case, scatter):
     with pytest.raises(RuntimeError):
         eng.assemble(0, eq, dmn)                        # vmsStab = 0 without Taylor-Hood tables
     eng.set_mesh_thood(0, t)
+    if name.endswith("uris"):                           # two URIS valves: the momentum loop sees the factor at the velocity rule's points
+        raw, dev, sdf, udf, vel = common.uris_valves(m)
+        eng.set_uris(dev, sdf, udf, vel)
     eng.alloc(4); eng.assemble(0, eq, dmn)
     R1, V1 = eng.get_R(), eng.get_Val()
     GR, GV = golden[f"{name}/R"], golden[f"{name}/Val"]
@@ -667,6 +671,7 @@ def test_taylor_hood_fluid_matches_golden(case, scatter):
         assert np.array_equal(V2[rows], V1[rows])
     # back to equal-order VMS spaces on the same mesh object
     eng.set_mesh_thood(0, None)
+    eng.set_uris([])
     hi = next((c for c in common.FLUID_HI_CASES if c[0].startswith(et) and c[5] == tDof and c[6] == mv and c[3] == Kd and c[4] == f
                and c[2] == visc), None)
     if hi is not None:

@@ -261,10 +261,11 @@ def test_device_fluid_algebra_with_uris_valves_matches_golden(hostmath, name, fa
 class HostThoodArgs(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("IEN", "x", "Ag", "Yg", "Bf", "w", "N", "Nxi", "Nxi2", "Nq1", "Nqxi1", "w2", "Nw2", "Nwxi2", "Nq2", "Nqxi2")] + \
                [(k, C.c_int) for k in ("eNoN", "eNoNq", "nEl", "nG", "nG2", "tDof", "mvMsh", "lShpFq")] + \
-               [(k, C.c_double) for k in ("dt", "af", "am", "gam")] + [("dm", FluidDmn)]
+               [(k, C.c_double) for k in ("dt", "af", "am", "gam")] + [("dm", FluidDmn)] + \
+               [("uris", C.c_void_p), ("nUris", C.c_int), ("urisP", abi.Uris * abi.MAX_URIS)]
 
 
-@pytest.mark.parametrize("case", common.FLUID_THOOD_CASES, ids=[c[0] for c in common.FLUID_THOOD_CASES])
+@pytest.mark.parametrize("case", common.FLUID_THOOD_CASES + [common.FLUID_THOOD_URIS_CASE], ids=[c[0] for c in common.FLUID_THOOD_CASES] + ["tet10_uris"])
 def test_device_taylor_hood_fluid_algebra_matches_golden(hostmath, case):
     """svmultiphysics_b200/csrc/fluid_thood.cuh (fluid_3d_m / fluid_3d_c with vmsFlag false on P2-P1 / Q2-Q1 function spaces, the
     momentum loop on the velocity rule and the continuity loop on the pressure rule with the reference's choice of Jacobian) compiled for
@@ -291,6 +292,16 @@ def test_device_taylor_hood_fluid_algebra_matches_golden(hostmath, case):
         A.dm.f[i] = d.f[i]
     A.dm.mu_i, A.dm.mu_o, A.dm.lam, A.dm.a, A.dm.n = d.mu_i, d.mu_o, d.lam, d.a, d.n
     A.dm.viscType, A.dm.Id, A.dm.isFluid = d.viscType, -1, 1
+    if name.endswith("uris"):
+        raw, dev, sdf, udf, vel = common.uris_valves(m)
+        nodal = np.zeros((m.nNo, len(dev), 5))
+        nodal[:, :, 0] = np.abs(sdf).T
+        nodal[:, :, 1] = np.abs(udf).T * np.array([v.scaffold for v in dev])[None, :]
+        nodal[:, :, 2:5] = vel.transpose(1, 0, 2) * np.array([v.include_velocity for v in dev])[None, :, None]
+        keep.append(np.ascontiguousarray(nodal))
+        A.uris, A.nUris = keep[-1].ctypes.data, len(dev)
+        for v, u in enumerate(dev):
+            A.urisP[v] = u
     rowPtr, colPtr = golden[f"{name}/rowPtr"], golden[f"{name}/colPtr"]
     R = np.zeros((m.nNo, 4)); V = np.zeros((len(colPtr), 16))
     rc = hostmath.hostmath_fluid_thood(C.byref(A), rowPtr.ctypes.data_as(C.c_void_p), colPtr.ctypes.data_as(C.c_void_p),
