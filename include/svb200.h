@@ -286,7 +286,8 @@ SVB200_API int svb200_set_active_tension(svb200_ctx* ctx, const double* Ya_f, co
  *   momentum loop (the mesh's own rule, nG points):   Nq1(eNoNq, nG), Nqxi1(3, eNoNq, nG)       pressure space at those points
  *   continuity loop (the pressure space's rule, nG2): w2(nG2), Nw2(eNoN, nG2), Nwxi2(3, eNoN, nG2), Nq2(eNoNq, nG2), Nqxi2(3, eNoNq, nG2)
  * lShpF_q: the pressure space is linear (TET4): its gnn runs at Gauss point 0 only (fluid.cpp:620-626, 709-716).  A fluid equation on such
- * a mesh is assembled with eq.vmsStab = 0 (fluid.cpp:494-500): fluid_3d_m / fluid_3d_c with vmsFlag false.  eNoNq = 0 returns the mesh to
+ * a mesh is assembled with eq.vmsStab = 0 (fluid.cpp:494-500): fluid_3d_m / fluid_3d_c with vmsFlag false; an FSI equation likewise
+ * (fsi.cpp:47-50: fluid elements on the moved geometry, struct elements on the velocity space).  eNoNq = 0 returns the mesh to
  * equal-order spaces.  svb200_thood_val_rc is fs::thood_val_rc (fs.cpp:394-466; Integrator::step calls it after the assembly and the
  * boundary terms): for every node that is not a pressure node of its elements R(3, a) = 0 and the pressure-pressure entries of its row
  * become the identity. */

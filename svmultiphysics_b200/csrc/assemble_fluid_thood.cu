@@ -2,6 +2,9 @@
 // Q2-Q1 hexahedra HEX27 / HEX8), the vmsStab = false branch of fluid::construct_fluid (Code/Source/solver/fluid.cpp:494-500, 596-748)
 // with the function spaces of fs::get_thood_fs (solver/fs.cpp:73-178), and fs::thood_val_rc (fs.cpp:394-466).  Algebra: fluid_thood.cuh.
 //
+// The fluid elements of fsi::construct_fsi on such a mesh (fsi.cpp:84-88, 170-216, 300-316) are the same loops on the moved geometry
+// x + Dg(4..6) with K_darcy = 0 (ale = 1).
+//
 // Mapping (that of assemble_fluid_gen.cu): LPE = max(eNoN, nG1) lanes per element.
 //   phase A1  lane g < nG1: Gauss point g of the VELOCITY rule — gnn + gn_nxx of the velocity space, gnn of the pressure space (at Gauss
 //             point 0 only when that space is linear, fluid.cpp:620-626), thood_gauss_point_m -> FluidGP + Nq, Nqx + node records;
@@ -27,13 +30,14 @@ struct ThoodArgs {
   const double* Ag;
   const double* Yg;
   const double* Bf;
+  const double* Dg;       // displacement state: dofs 4..6 = mesh displacement (FSI / ALE geometry, fsi.cpp:140-146)
   const double* tab;      // velocity space, velocity rule: w | N | Nxi | Nxi2 per Gauss point (assemble_fluid_gen.cu layout)
   const double* thtab;    // nG1 x [Nq1 | Nqxi1], then nG2 x [w2 | Nw2 | Nwxi2 | Nq2 | Nqxi2]
   int* err;
   double* R;
   double* Val;
   int e0, e1;
-  int tDof, mvMsh, nDmn, atomic, lShpFq;
+  int tDof, mvMsh, nDmn, atomic, lShpFq, ale;
   double dt, af, am, gam;
   FluidDmn dmn[MAX_DMN];
   const double* uris;     // URIS valves (svb200_set_uris) or null: the momentum loop sees the factor at the velocity rule's points
@@ -100,7 +104,7 @@ assemble_fluid_thood_kernel(const __grid_constant__ ThoodArgs P)
     const size_t n = (size_t)node;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-      sx[a][i] = __ldg(P.x + 3 * n + i);
+      sx[a][i] = __ldg(P.x + 3 * n + i) + (P.ale ? __ldg(P.Dg + (size_t)P.tDof * n + 4 + i) : 0.0);
       sal[a][i] = __ldg(P.Ag + (size_t)P.tDof * n + i);
       sbf[a][i] = __ldg(P.Bf + 3 * n + i);
       sym[a][i] = P.mvMsh ? __ldg(P.Yg + (size_t)P.tDof * n + 4 + i) : 0.0;
@@ -301,11 +305,10 @@ int run_assemble_fluid_thood(svb200_ctx* ctx, const Mesh& m, const FluidArgs& F)
   SVB_REQUIRE(key == 10041504 || key == 27082708 || key == 20082708,
               "svb200_assemble: Taylor-Hood fluid elements: TET10 / TET4 (15 + 4 Gauss points), HEX27 / HEX8 and HEX20 / HEX8 (27 + 8)");
   SVB_REQUIRE(m.d_gtab && m.d_thtab && !m.Nxx.empty(), "svb200_assemble: Taylor-Hood mesh needs svb200_set_mesh_nxx and svb200_set_mesh_thood");
-  SVB_REQUIRE(!F.ale, "svb200_assemble: Taylor-Hood fluid elements inside an FSI equation are not implemented");
   ThoodArgs A;
   memset(&A, 0, sizeof(A));
   A.IEN = F.IEN; A.eId = F.eId; A.slot = F.slot; A.perm = nullptr;
-  A.x = F.x; A.Ag = F.Ag; A.Yg = F.Yg; A.Bf = F.Bf; A.tab = m.d_gtab; A.thtab = m.d_thtab; A.R = F.R; A.Val = F.Val; A.err = F.err;
+  A.x = F.x; A.Ag = F.Ag; A.Yg = F.Yg; A.Bf = F.Bf; A.Dg = F.Dg; A.ale = F.ale; A.tab = m.d_gtab; A.thtab = m.d_thtab; A.R = F.R; A.Val = F.Val; A.err = F.err;
   A.e0 = 0; A.e1 = m.nEl;
   A.tDof = F.tDof; A.mvMsh = F.mvMsh; A.nDmn = F.nDmn; A.atomic = F.atomic; A.lShpFq = m.th_lShpFq;
   A.dt = F.dt; A.af = F.af; A.am = F.am; A.gam = F.gam;

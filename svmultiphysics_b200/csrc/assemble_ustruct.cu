@@ -479,7 +479,7 @@ int run_assemble_ustruct(svb200_ctx* ctx, const Mesh& m, const svb200_eqparams* 
   SVB_REQUIRE(eq->dof == 4 && ctx->dof == 4, "svb200_assemble: the ustruct equation has dof = 4 (call svb200_alloc(4))");
   SVB_REQUIRE(eq->tDof == ctx->tDof && ctx->d_Dg && ctx->d_Yg && ctx->d_Ag, "svb200_assemble: state not set or tDof mismatch");
   SVB_REQUIRE(eq->s >= 0 && eq->s + 4 <= eq->tDof, "svb200_assemble: eq.s out of range");
-  SVB_REQUIRE(eq->vmsStab == 1, "svb200_assemble: only equal-order (VMS-stabilised) ustruct elements are supported");
+  SVB_REQUIRE(eq->vmsStab == 1 && m.th_eNoNq == 0, "svb200_assemble: only equal-order (VMS-stabilised) ustruct elements are supported (no Taylor-Hood ustruct)");
   SVB_REQUIRE(ctx->d_x, "svb200_assemble: coordinates not set");
   SVB_REQUIRE(m.eNoN == 4 || m.eNoN == 8, "svb200_assemble: ustruct is implemented for TET4 and HEX8 meshes");
   SVB_REQUIRE(m.nG == m.eNoN, "svb200_assemble: the ustruct kernel expects nG == eNoN (TET4: 4, HEX8: 8 Gauss points)");

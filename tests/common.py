@@ -370,6 +370,25 @@ FLUID_THOOD_CASES = [
 FLUID_THOOD_URIS_CASE = ("tet10_uris", _tet10, {}, 0.5, (0.1, 0.0, -0.2), 4, 0)
 
 
+def fsi_thood_case(scatter=abi.SCATTER_ATOMIC, seed=53):
+    """(mesh, Ag, Yg, Dg, Bf, eq, domains): the FSI pipe of fsi_case elevated to curved TET10 elements — Taylor-Hood fluid core on the
+    moved (ALE) geometry, struct_3d wall on the velocity space (fsi.cpp:84-88, 170-262)."""
+    m0, *_ = fsi_case(n=3, nz=4)
+    m = meshgen.elevate(m0, "tet10", bend=0.01)
+    m.eId = m0.eId
+    rng = np.random.default_rng(seed)
+    Ag, Yg, _, Bf = fluid_gen_state(m, 7)
+    Dg = np.zeros((7, m.nNo), order="F")
+    Dg[:3] = 2e-3 * rng.standard_normal((3, m.nNo))
+    Dg[4:7] = 3e-3 * rng.standard_normal((3, m.nNo))
+    af, am, gam, beta = abi.gen_alpha(0.5)
+    eq = abi.EqParams(dt=1e-3, af=af, am=am, gam=gam, beta=beta, phys=abi.PHYS_FSI, dof=4, tDof=7, s=0, mvMsh=1, vmsStab=0,
+                      scatter=scatter, reserved=0)
+    dmn = [abi.fluid_domain(rho=1.0, mu=0.04, Id=0),
+           abi.struct_domain(rho=1.0, volType=abi.VOL_M94, E=1e7, nu=0.3, Kpen=1e7 / (3 * (1 - 0.6)), Id=1)]
+    return m, Ag, Yg, Dg, Bf, eq, dmn
+
+
 def fluid_thood_eq(dt, tDof=4, mvMsh=0, scatter=abi.SCATTER_ATOMIC):
     eq = abi.fluid_eq(dt, tDof=tDof, mvMsh=mvMsh, scatter=scatter)
     eq.vmsStab = 0

@@ -277,6 +277,15 @@ def fluid_thood_golden():
         for k, v in c.thood_tables(0).items():
             out[f"tables/{et}/{k}"] = np.asarray(v)
         assert np.abs(out[f"{name}/Val"][12:15]).max() > 0 and not out[f"{name}/Val"][15].any()
+    # construct_fsi on a Taylor-Hood mesh: fluid core (ALE geometry) + struct wall
+    m, Ag, Yg, Dg, Bf, eq, dmn = common.fsi_thood_case()
+    c = RefCase(); c.set_coords(m.x); c.add_mesh(m.IEN, eId=m.eId); c.set_mesh_thood(0)
+    rowPtr, colPtr = c.build_graph(0)
+    c.alloc(4); c.set_state(Ag, Yg, Dg, Bf); c.assemble(0, eq, dmn)
+    out["fsi_tet10/R"], out["fsi_tet10/Val"] = c.get_R(), c.get_Val()
+    c.thood_val_rc()
+    out["fsi_tet10/R_rc"], out["fsi_tet10/Val_rc"] = c.get_R(), c.get_Val()
+    out["fsi_tet10/rowPtr"], out["fsi_tet10/colPtr"] = rowPtr, colPtr
     np.savez_compressed(os.path.join(HERE, "fluid_thood.npz"), **out)
     print("wrote fluid_thood.npz with", len(out), "arrays")
 

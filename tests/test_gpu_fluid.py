@@ -725,3 +725,41 @@ def test_taylor_hood_newton_iteration_matches_the_reference():
     assert o0.RI.fNorm < 1e-2 * o0.RI.iNorm
     assert common.rel_err(X1, X0) < 1e-2, common.rel_err(X1, X0)
     eng.close()
+
+
+@pytest.mark.parametrize("scatter", [abi.SCATTER_ATOMIC, abi.SCATTER_COLORED])
+def test_fsi_on_a_taylor_hood_mesh_matches_golden(scatter):
+    """fsi::construct_fsi on a curved TET10 mesh with Taylor-Hood function spaces: the fluid core through the Taylor-Hood kernel on the
+    moved geometry (ale), the struct wall through the general solid kernel on the velocity space, then thood_val_rc — against the
+    compiled reference (tests/golden/fluid_thood.npz: fsi_tet10), rows compared per node class and Val per entry type."""
+    from svmultiphysics_b200.engine import Engine
+    golden, tabs = common.load_golden("fluid_thood.npz"), common.load_golden("fluid_hi.npz")
+    m, Ag, Yg, Dg, Bf, eq, dmn = common.fsi_thood_case(scatter)
+    w, N, Nx, Nxx = (tabs[f"tables/tet10/{k}"] for k in ("w", "N", "Nx", "Nxx"))
+    t = {k: golden[f"tables/tet10/{k}"] for k in ("eNoNq", "nG1", "nG2", "lShpF_q", "Nq1", "Nqxi1", "w2", "Nw2", "Nwxi2", "Nq2", "Nqxi2")}
+    eng = Engine(0)
+    rowPtr = golden["fsi_tet10/rowPtr"]
+    eng.set_graph(rowPtr, golden["fsi_tet10/colPtr"])
+    eng.set_mesh(0, m.IEN, w, N, Nx, eId=m.eId, Nxx=Nxx); eng.set_mesh_thood(0, t)
+    eng.set_coords(m.x)
+    eng.alloc(4); eng.set_state(Ag, Yg, Dg, Bf); eng.assemble(0, eq, dmn)
+    R1, V1 = eng.get_R(), eng.get_Val()
+    GR, GV = golden["fsi_tet10/R"], golden["fsi_tet10/Val"]
+    fluid_nodes = np.unique(m.IEN[:, (m.eId & 1) != 0]); solid_nodes = np.unique(m.IEN[:, (m.eId & 2) != 0])
+    sets = (np.setdiff1d(fluid_nodes, solid_nodes), np.setdiff1d(solid_nodes, fluid_nodes), np.intersect1d(fluid_nodes, solid_nodes))
+    assert all(len(x) > 0 for x in sets)
+    for nodes in sets:
+        assert common.rel_err(R1[:3, nodes], GR[:3, nodes]) < 1e-12
+        if np.abs(GR[3, nodes]).max() > 0:
+            assert common.rel_err(R1[3, nodes], GR[3, nodes]) < 1e-12
+        slots = np.concatenate([np.arange(rowPtr[a], rowPtr[a + 1]) for a in nodes])
+        for rows in ([0, 1, 2, 4, 5, 6, 8, 9, 10], [3, 7, 11], [12, 13, 14]):
+            if np.abs(GV[rows][:, slots]).max() > 0:
+                assert common.rel_err(V1[rows][:, slots], GV[rows][:, slots]) < 1e-12
+    if scatter == abi.SCATTER_COLORED:
+        eng.alloc(4); eng.assemble(0, eq, dmn)
+        assert np.array_equal(eng.get_R(), R1) and np.array_equal(eng.get_Val(), V1)
+    eng.thood_val_rc()
+    assert np.array_equal(eng.get_Val()[15], golden["fsi_tet10/Val_rc"][15])
+    assert np.array_equal(eng.get_R()[3] == 0.0, golden["fsi_tet10/R_rc"][3] == 0.0)
+    eng.close()
