@@ -937,7 +937,10 @@ assemble_mesh_hex8_kernel(const __grid_constant__ StructArgs P, const double* __
     r[39] = w;
   }
   __syncwarp();
-  if (!active) return;
+  const unsigned amask = __ballot_sync(0xffffffffu, active);     // lanes with an element (whole elements: 8 lanes each)
+  if (amask == 0u) return;
+  // lanes without an element stay for the transposed scatter of the dof = 3 path (they carry no rows but move other lanes' entries)
+  if (!active && P.dof != 3) return;
   double K[ENON][3][3], lR[3] = {0.0, 0.0, 0.0};
 #pragma unroll
   for (int b = 0; b < ENON; b++)
@@ -946,7 +949,7 @@ assemble_mesh_hex8_kernel(const __grid_constant__ StructArgs P, const double* __
 #pragma unroll
       for (int j = 0; j < 3; j++) K[b][i][j] = 0.0;
 #pragma unroll 1
-  for (int g = 0; g < ENON; g++) {
+  for (int g = 0; g < (active ? ENON : 0); g++) {
     const double* r = sgp[warp][el][g];
     const double w = r[39], wl = w * T1c * mu;
     const double Na = P.N[g][a];
@@ -977,9 +980,34 @@ assemble_mesh_hex8_kernel(const __grid_constant__ StructArgs P, const double* __
           K[b][i][j] += wl * ((i == j ? T1 + (1.0 + lDm) * Nxa[i] * Nxb[i] : lDm * Nxa[i] * Nxb[j] + Nxa[j] * Nxb[i]));
     }
   }
+  if (active)
 #pragma unroll
-  for (int i = 0; i < 3; i++) add64<ATOMIC>(P.R + (size_t)DOF * na + i, lR[i]);
+    for (int i = 0; i < 3; i++) add64<ATOMIC>(P.R + (size_t)DOF * na + i, lR[i]);
   const int* sl = P.slot + (size_t)e * ENON * ENON + a * ENON;
+  if (DOF == 3) {
+    // dof = 3: a block is 9 contiguous doubles.  The 32 blocks (a, b) of the warp for one b go through a 32 x 9 tile (aliased onto the
+    // Gauss-point records, which are dead now) and out as 9 warp-wide adds over contiguous runs: 3 L2 sectors per block instead of 9.
+    double* tile = &sgp[warp][0][0][0];
+    __syncwarp();                                        // every lane of the warp is done with the records
+#pragma unroll
+    for (int b = 0; b < ENON; b++) {
+      const int myslot = active ? __ldg(sl + b) : -1;
+      if (active)
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = 0; j < 3; j++) tile[lane * 9 + 3 * i + j] = K[b][i][j];
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 9; it++) {
+        const int p = it * 32 + lane, src = p / 9, i = p - 9 * src;
+        const int s_ = __shfl_sync(0xffffffffu, myslot, src);
+        if (s_ >= 0) add64<ATOMIC>(P.Val + (size_t)9 * s_ + i, tile[src * 9 + i]);
+      }
+      __syncwarp();
+    }
+    return;
+  }
 #pragma unroll
   for (int b = 0; b < ENON; b++) {
     double* v = P.Val + (size_t)DOF * DOF * sl[b];
