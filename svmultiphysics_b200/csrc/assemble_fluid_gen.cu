@@ -7,7 +7,7 @@
 //
 // Mapping (same idea as the solid kernel): ENON lanes per element, 32/ENON elements per warp, nG == ENON.
 //   phase A  lane g evaluates Gauss point g once: Jacobian, physical first and second derivatives, the interpolated
-//            state, viscosity, tau_M/C/B, the fine-scale velocity — and leaves a FluidGP (45 doubles) plus one
+//            state, viscosity, tau_M/C/B, the fine-scale velocity — and leaves a FluidGP (55 doubles) plus one
 //            FluidNode (11 doubles) per element node in shared memory.  The lane of the LAST Gauss point publishes its
 //            second derivatives first, because the reference's continuity loop uses them at every Gauss point.
 //   phase B  lane a = element node a = one block row of the element matrix: residual row, then FG_NB column nodes at a

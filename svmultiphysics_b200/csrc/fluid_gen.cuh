@@ -8,7 +8,7 @@
 // strong momentum residual (rS), the viscosity gradient mu_x and the fine-scale velocity tangent updu.
 //
 // Layout of the work: everything that does not depend on the node pair (a,b) is evaluated ONCE per Gauss point
-// (FluidGP, ~45 doubles) together with 11 numbers per element node (FluidNode); a tangent block is then a short
+// (FluidGP, 55 doubles) together with 11 numbers per element node (FluidNode); a tangent block is then a short
 // bilinear expression in (FluidNode_a, FluidNode_b) — see fluid_gen_block.
 //
 // Two reference behaviours that parity needs and that are easy to miss:
