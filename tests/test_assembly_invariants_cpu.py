@@ -351,3 +351,74 @@ def test_general_fluid_kernel_algebra_on_skewed_hex8(hostmath):
     print("hex8 tangent-vs-FD at rest:", np.abs(lhs[:3] - rhs[:3]).max() / np.abs(rhs[:3]).max(), np.abs(lhs[3] - rhs[3]).max() / np.abs(rhs[3]).max())
     assert np.abs(lhs[:3] - rhs[:3]).max() < 1e-4 * np.abs(rhs[:3]).max()
     assert np.abs(lhs[3] - rhs[3]).max() < 1e-4 * np.abs(rhs[3]).max()
+
+
+# ---- Taylor-Hood fluid (fluid_thood.cuh): oracle-independent identities -----------------------------------------------------------------
+def _csr_any(m):
+    """CSR graph of any mesh: all node pairs of an element, columns sorted."""
+    E = m.IEN.shape[0]
+    r = np.repeat(m.IEN, E, axis=0).ravel(order="F").astype(np.int64)
+    c = np.tile(m.IEN, (E, 1)).ravel(order="F").astype(np.int64)
+    key = np.unique(r * m.nNo + c)
+    rows, cols = (key // m.nNo).astype(np.int32), (key % m.nNo).astype(np.int32)
+    rowPtr = np.zeros(m.nNo + 1, np.int32)
+    np.add.at(rowPtr, rows + 1, 1)
+    return np.cumsum(rowPtr).astype(np.int32), np.ascontiguousarray(cols)
+
+
+def _fluid_thood(hostmath, m, Ag, Yg, Bf, d, rowPtr, colPtr, dt=0.005):
+    from tests.test_hostmath_cpu import HostThoodArgs
+    golden, tabs = common.load_golden("fluid_thood.npz"), common.load_golden("fluid_hi.npz")
+    w, N, Nx, Nxx = (tabs[f"tables/tet10/{k}"] for k in ("w", "N", "Nx", "Nxx"))
+    t = {k: golden[f"tables/tet10/{k}"] for k in ("eNoNq", "nG1", "nG2", "lShpF_q", "Nq1", "Nqxi1", "w2", "Nw2", "Nwxi2", "Nq2", "Nqxi2")}
+    eq = common.fluid_thood_eq(dt)
+    tr = lambda a: np.ascontiguousarray(np.asarray(a).T)
+    keep = [np.ascontiguousarray(m.IEN.T.astype(np.int32)), tr(m.x), tr(Ag), tr(Yg), tr(Bf), np.ascontiguousarray(w), tr(N), tr(Nx), tr(Nxx),
+            tr(t["Nq1"]), tr(t["Nqxi1"]), np.ascontiguousarray(t["w2"]), tr(t["Nw2"]), tr(t["Nwxi2"]), tr(t["Nq2"]), tr(t["Nqxi2"])]
+    A = HostThoodArgs()
+    (A.IEN, A.x, A.Ag, A.Yg, A.Bf, A.w, A.N, A.Nxi, A.Nxi2, A.Nq1, A.Nqxi1, A.w2, A.Nw2, A.Nwxi2, A.Nq2, A.Nqxi2) = (k.ctypes.data for k in keep)
+    A.eNoN, A.eNoNq, A.nEl, A.nG, A.nG2, A.tDof, A.mvMsh, A.lShpFq = 10, 4, m.nEl, len(w), int(t["nG2"]), 4, 0, int(t["lShpF_q"])
+    A.dt, A.af, A.am, A.gam = eq.dt, eq.af, eq.am, eq.gam
+    A.dm.rho, A.dm.Kd = d.rho, d.K_darcy
+    for i in range(3):
+        A.dm.f[i] = d.f[i]
+    A.dm.mu_i, A.dm.mu_o, A.dm.lam, A.dm.a, A.dm.n = d.mu_i, d.mu_o, d.lam, d.a, d.n
+    A.dm.viscType, A.dm.Id, A.dm.isFluid = d.viscType, -1, 1
+    R = np.zeros((m.nNo, 4)); V = np.zeros((len(colPtr), 16))
+    rc = hostmath.hostmath_fluid_thood(C.byref(A), rowPtr.ctypes.data_as(C.c_void_p), colPtr.ctypes.data_as(C.c_void_p),
+                                       R.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return R.T.copy(), V.T.copy()
+
+
+def test_taylor_hood_tangent_and_continuity_invariants(hostmath):
+    """P2-P1 algebra, no oracle: (i) the continuity rows are linear in the velocity and independent of the pressure, so their tangent is
+    the exact derivative in any state; (ii) at rest the momentum tangent is the derivative of the momentum residual up to the one term
+    the reference keeps from the VMS form — rho N_a (up . grad N_b) in T1 (fluid.cpp:2147), although with vmsFlag false the residual
+    convects with u, not u + up (fluid.cpp:2070-2077, 2097-2099): measured 2 % of the largest entry, bounded at 5 % here; (iii) the continuity residual sums to the integral of div u over the mesh (the pressure shape functions sum to
+    one); (iv) rows 3 of the edge nodes and the whole pressure-pressure block are empty before fs::thood_val_rc."""
+    m = meshgen.elevate(meshgen.box_tet4(2, 2, 2, (1.0, 1.0, 1.0)), "tet10", bend=0.0)       # straight edges: exact quadrature of div u
+    rowPtr, colPtr = _csr_any(m)
+    rng = np.random.default_rng(4)
+    eq = common.fluid_thood_eq(0.005)
+    Bf = np.zeros((3, m.nNo), order="F")
+    d = abi.fluid_domain()
+    c_a, c_y = eq.am, eq.af * eq.gam * eq.dt
+    edge = np.setdiff1d(np.arange(m.nNo), np.unique(m.IEN[:4]))
+    for scale, tol_m in ((0.0, 5e-2), (1.0, None)):
+        A0 = np.asfortranarray(0.1 * rng.standard_normal((4, m.nNo)))
+        Y0 = np.asfortranarray(scale * rng.standard_normal((4, m.nNo))); Y0[3] = rng.standard_normal(m.nNo)
+        delta = np.asfortranarray(rng.standard_normal((4, m.nNo)))
+        R0, V = _fluid_thood(hostmath, m, A0, Y0, Bf, d, rowPtr, colPtr)
+        e = 1e-6
+        Rp, _ = _fluid_thood(hostmath, m, np.asfortranarray(A0 + e * c_a * delta), np.asfortranarray(Y0 + e * c_y * delta), Bf, d, rowPtr, colPtr)
+        Rm, _ = _fluid_thood(hostmath, m, np.asfortranarray(A0 - e * c_a * delta), np.asfortranarray(Y0 - e * c_y * delta), Bf, d, rowPtr, colPtr)
+        lhs, rhs = _csr_matvec(rowPtr, colPtr, V, delta, dof=4), (Rp - Rm) / (2 * e)
+        assert np.abs(lhs[3] - rhs[3]).max() < 1e-7 * np.abs(rhs[3]).max()                   # (i)
+        if tol_m is not None:
+            assert np.abs(lhs[:3] - rhs[:3]).max() < tol_m * np.abs(rhs[:3]).max()           # (ii)
+        assert not R0[3, edge].any() and not V[15].any() and not V[12:15][:, np.isin(np.repeat(np.arange(m.nNo), np.diff(rowPtr)), edge)].any()   # (iv)
+    # (iii) u = (x, 2y, -0.5z): div u = 2.5, volume 1
+    Y = np.zeros((4, m.nNo), order="F"); Y[0], Y[1], Y[2] = m.x[0], 2.0 * m.x[1], -0.5 * m.x[2]
+    R, _ = _fluid_thood(hostmath, m, np.zeros((4, m.nNo), order="F"), Y, Bf, d, rowPtr, colPtr)
+    assert abs(R[3].sum() - 2.5) < 1e-12
