@@ -182,14 +182,21 @@ assemble_fluid_gen_kernel(const __grid_constant__ FluidGenArgs P)
                                   P.mvMsh ? sym : nullptr, sgp[g], snd(g), uF, uV);
   }
   __syncwarp();
-  if (!active || a >= ENON) return;
+  // HEX8: the 4 x 4 blocks leave through a transposition tile (below), which needs every lane of the warp — lanes without an element
+  // stay and move other lanes' entries
+  constexpr bool TILE = (ENON == 8 && NG == 8);
+  if (TILE) {
+    if (__ballot_sync(0xffffffffu, active) == 0u) return;
+  } else if (!active || a >= ENON) return;
+  const int NGa = active ? NG : 0;
 
   // ---- phase B ------------------------------------------------------------------------------------------------
   double lR[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
-  for (int g = 0; g < NG; g++) fluid_gen_residual(sgp[g], fluid_node_expand(sgp[g], snd(g)[a]), lR);
+  for (int g = 0; g < NGa; g++) fluid_gen_residual(sgp[g], fluid_node_expand(sgp[g], snd(g)[a]), lR);
+  if (active)
 #pragma unroll
-  for (int i = 0; i < 4; i++) fg_add<ATOMIC>(P.R + 4 * (size_t)node + i, lR[i]);
+    for (int i = 0; i < 4; i++) fg_add<ATOMIC>(P.R + 4 * (size_t)node + i, lR[i]);
   const int* sl = P.slot + (size_t)e * ENON * ENON;
   constexpr int NB = (ENON % FG_NB == 0) ? FG_NB : (ENON % 2 == 0 ? 2 : 1);
 #pragma unroll 1
@@ -197,25 +204,47 @@ assemble_fluid_gen_kernel(const __grid_constant__ FluidGenArgs P)
     // CSR slots of the NB blocks, requested before the Gauss loop so that the load latency hides behind the FMAs
     int slots[NB];
 #pragma unroll
-    for (int bb = 0; bb < NB; bb++) slots[bb] = __ldg(sl + a * ENON + b0 + bb);
+    for (int bb = 0; bb < NB; bb++) slots[bb] = active ? __ldg(sl + a * ENON + b0 + bb) : -1;
     double K[NB][16];
 #pragma unroll
     for (int bb = 0; bb < NB; bb++)
 #pragma unroll
       for (int i = 0; i < 16; i++) K[bb][i] = 0.0;
 #pragma unroll 1
-    for (int g = 0; g < NG; g++) {
+    for (int g = 0; g < NGa; g++) {
       const FluidNodeC* nd = snd(g);
       FluidRow row;
       fluid_gen_row(sgp[g], fluid_node_expand(sgp[g], nd[a]), row);
 #pragma unroll
       for (int bb = 0; bb < NB; bb++) fluid_gen_block_row(row, fluid_node_expand(sgp[g], nd[b0 + bb]), K[bb]);
     }
+    if (TILE) {
+      // one block = 16 contiguous doubles = one 128-byte line: lane (el, a) parks its block in the dead nodal-input area of its element
+      // (row stride 17), then each half-warp adds one block per step with consecutive lanes on consecutive doubles: 4 L2 sectors per
+      // block instead of 16
+      double* trow = se + a * 17;
+      const double* wbase = sm + (TAB_SMEM ? NG * TLD : 0) + (size_t)(warp * EPW) * PER_EL;
 #pragma unroll
-    for (int bb = 0; bb < NB; bb++) {
-      double* v = P.Val + 16 * (size_t)slots[bb];
+      for (int bb = 0; bb < NB; bb++) {
+        __syncwarp();
+        if (active)
 #pragma unroll
-      for (int i = 0; i < 16; i++) fg_add<ATOMIC>(v + i, K[bb][i]);
+          for (int i = 0; i < 16; i++) trow[i] = K[bb][i];
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 16; it++) {
+          const int src = 2 * it + (lane >> 4), i = lane & 15;
+          const int s_ = __shfl_sync(0xffffffffu, slots[bb], src);
+          if (s_ >= 0) fg_add<ATOMIC>(P.Val + 16 * (size_t)s_ + i, wbase[(size_t)(src >> 3) * PER_EL + (src & 7) * 17 + i]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int bb = 0; bb < NB; bb++) {
+        double* v = P.Val + 16 * (size_t)slots[bb];
+#pragma unroll
+        for (int i = 0; i < 16; i++) fg_add<ATOMIC>(v + i, K[bb][i]);
+      }
     }
   }
 }
