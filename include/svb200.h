@@ -304,7 +304,7 @@ SVB200_API int svb200_thood_val_rc(svb200_ctx* ctx);
  * column-major grisMapList[p].map(2, n): map(0,0), map(1,0), map(0,1), ... (INPUT node order, every node with a twin: -1 is
  * rejected); closed[p] = RIS.clsFlg[p] (closed surfaces add nothing).  The CSR graph must contain the extra connections lhsa adds
  * when com_mod.risFlag is set (lhsa.cpp:168-193).  nProj = 0 removes the plan.  Call after svb200_set_graph and again whenever a
- * surface opens or closes. */
+ * surface opens or closes.  Both nodes of a pair must belong to this partition (the plan is built from the local graph). */
 SVB200_API int svb200_set_ris(svb200_ctx* ctx, int32_t nProj, const int32_t* nMap, const int32_t* maps, const int32_t* closed);
 
 /* Unfitted resistive immersed surfaces (URIS valves): the penalty terms of fluid_3d_m / fluid_3d_c (solver/fluid.cpp:2006-2008,
@@ -325,8 +325,10 @@ typedef struct {
 } svb200_uris;
 /* nUris = 0 removes the valves (com_mod.urisActFlag false).  sdf(nNo, nUris): urisType::sdf of valve i at sdf + i*nNo (signed or
  * not: the absolute value is used); scaffold_udf likewise (NULL if no valve has a scaffold); valve_vel(3, nNo, nUris):
- * urisType::valve_velocity_fluid (NULL if no valve includes its velocity).  INPUT node order.  While valves are set, the fluid
- * elements run through the per-Gauss-point kernel (the closed-form TET4 kernel has no URIS terms). */
+ * urisType::valve_velocity_fluid (NULL if no valve includes its velocity).  INPUT node order.  The URIS terms live in the
+ * per-Gauss-point kernel: on a TET4 mesh (atomic scatter) only the band of elements with a node inside a valve's or scaffold's
+ * thickness runs through it, the rest stays with the closed-form kernel (exact there: the factor is zero); other meshes and the
+ * deterministic scatter take the per-Gauss-point kernel throughout. */
 SVB200_API int svb200_set_uris(svb200_ctx* ctx, int32_t nUris, const svb200_uris* valves, const double* sdf,
                                const double* scaffold_udf, const double* valve_vel);
 
